@@ -1,0 +1,173 @@
+/*
+ * nrb200_ldpc.h -- C ABI of libldpc_b200.so, the B200-native drop-in for OpenAirInterface's
+ * loadable LDPC codec ("libldpc<_version>.so").
+ *
+ * Part 1 declares EXACTLY the four symbols OAI's loader dlsym()s
+ *   (reference openair1/PHY/CODING/nrLDPC_load.c:46-71, prototypes nrLDPC_defs.h:68-87,
+ *    nrLDPC_extern.h:27-44) with layout-compatible parameter structs, so the unmodified
+ *   ldpctest / nr_dlsim / nr_ulsim / nr-softmodem binaries bind them with
+ *   `--loader.ldpc.shlibversion _b200` (or `ldpctest -v _b200`).
+ * Part 2 declares the batched extension entry points (BASELINE config 2 needs batch=1024; the
+ *   per-code-block blocking ABI cannot express a batch).
+ *
+ * Plain C: pointers, sizes and PODs only.  No CUDA or torch types appear in any signature;
+ * `stream` arguments are an opaque `void *` carrying a cudaStream_t (NULL = legacy default stream).
+ */
+#ifndef NRB200_LDPC_H
+#define NRB200_LDPC_H
+
+#include <stdint.h>
+#include <stdbool.h>
+#include <pthread.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1: the OAI loadable-codec ABI
+ * ---------------------------------------------------------------------------------------- */
+
+/* reference common/utils/time_meas.h:61-75 (time_stats_t); only .total of the decoder stats and the
+ * four encoder timers are ever touched by this library (and only when non-NULL). */
+typedef struct nrb200_time_stats {
+  long long in;
+  long long diff;
+  long long p_time;
+  double diff_square;
+  long long max;
+  int trials;
+  int meas_flag;
+  char *meas_name;
+  int meas_index;
+  int meas_enabled;
+  void *tpoolmsg;
+  void *tstatptr;
+} nrb200_time_stats_t;
+
+/* reference nrLDPC_decoder/nrLDPC_types.h:115-127 (t_nrLDPC_time_stats) */
+typedef struct nrb200_ldpc_time_stats {
+  nrb200_time_stats_t llr2llrProcBuf, llr2CnProcBuf, cnProc, cnProcPc, bnProcPc, bnProc, cn2bnProcBuf, bn2cnProcBuf,
+      llrRes2llrOut, llr2bit, total;
+} nrb200_ldpc_time_stats_t;
+
+/* reference nrLDPC_types.h:75-79 (e_nrLDPC_outMode) */
+typedef enum nrb200_ldpc_outmode {
+  NRB200_OUTMODE_BIT = 0,     /* numLLR/8 bytes, MSB-first packed hard bits (nrLDPC_bnProc.h:1344-1380) */
+  NRB200_OUTMODE_BITINT8 = 1, /* one hard bit per int8 */
+  NRB200_OUTMODE_LLRINT8 = 2  /* one a-posteriori LLR per int8 */
+} nrb200_ldpc_outmode_t;
+
+/* reference nrLDPC_types.h:84-97 (t_nrLDPC_dec_params); field order and types are ABI. */
+typedef struct nrb200_ldpc_dec_params {
+  uint8_t BG;         /* base graph 1|2 */
+  uint16_t Z;         /* lifting size */
+  uint8_t R;          /* decoder rate LUT selector: BG1 {13,23,89}, BG2 {15,13,23} */
+  uint16_t F;         /* filler bits (offload convention only) */
+  uint8_t Qm;         /* modulation order (offload convention only) */
+  uint8_t rv;         /* redundancy version (offload convention only) */
+  uint8_t numMaxIter; /* iteration cap */
+  int E;              /* CPU convention: payload length in bits handed to check_crc; offload: rate-matched length */
+  nrb200_ldpc_outmode_t outMode;
+  int crc_type;       /* CRC24_A=0 CRC24_B=1 CRC16=2 CRC8=3 (coding_defs.h:33-36) */
+  int (*check_crc)(uint8_t *decoded_bytes, uint32_t n, uint8_t crc_type); /* NULL => parity-check early stop */
+  uint8_t setCombIn;  /* offload: combine with the stored HARQ soft buffer */
+} nrb200_ldpc_dec_params_t;
+
+/* reference openair1/PHY/defs_common.h:996-1027 (decode_abort_t) */
+typedef struct nrb200_decode_abort {
+  pthread_mutex_t mutex_failure;
+  bool failed;
+} nrb200_decode_abort_t;
+
+/* reference nrLDPC_defs.h:40-66 (encoder_implemparams_t); field order and types are ABI. */
+typedef struct nrb200_ldpc_enc_params {
+  unsigned int n_segments;
+  unsigned int macro_num; /* which group of 8 segments this call encodes */
+  unsigned char gen_code;
+  nrb200_time_stats_t *tinput, *tprep, *tparity, *toutput; /* each may be NULL */
+  int Kr;
+  uint32_t Kb;
+  uint32_t Zc;
+  void *harq;
+  uint8_t BG;
+  unsigned char *output;
+  uint32_t K;
+  uint32_t F;
+  uint8_t Qm;
+  uint32_t E;
+  unsigned int G;
+  uint8_t rv;
+} nrb200_ldpc_enc_params_t;
+
+/* replaces LDPCinit (nrLDPC_decoder.c:162): creates the CUDA context, per-thread streams, pinned staging and
+ * uploads the lifted-graph tables.  Idempotent (ldpctest calls it per segment, ldpctest.c:326).
+ * Returns 0; returns -1 (loader then AssertFatal()s, nrLDPC_load.c:68) when no CUDA device is usable --
+ * there is NO CPU fallback. */
+int32_t LDPCinit(void);
+/* replaces LDPCshutdown (nrLDPC_decoder.c:167) */
+int32_t LDPCshutdown(void);
+/* replaces LDPCdecoder (nrLDPC_decoder.c:172-195), "CPU-compatible" convention: p_llr holds ncol(R)*Z int8 LLRs
+ * (first 2Z punctured = 0, fillers = +127); p_out receives per outMode; returns iterations used,
+ * > numMaxIter means failure (and *ab is set).  harq_pid/ulsch_id/C are ignored in this convention.
+ * Blocking, re-entrant; concurrent callers are micro-batched into one launch. */
+int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p_decParams, uint8_t harq_pid, uint8_t ulsch_id, uint8_t C, int8_t *p_llr,
+                    int8_t *p_out, nrb200_ldpc_time_stats_t *p_profiler, nrb200_decode_abort_t *ab);
+/* replaces LDPCencoder (nrLDPC_encoder/ldpc_encoder_optim8segmulti.c:46-212): encodes segments
+ * 8*macro_num .. min(8*macro_num+8, n_segments) of input[] (K/8 packed bytes each, MSB first) into
+ * output[] as one bit per byte, K-2Z systematic + parity = 66Z (BG1) / 50Z (BG2) bytes.  Returns 0. */
+int32_t LDPCencoder(uint8_t **input, uint8_t **output, nrb200_ldpc_enc_params_t *impp);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2: batched extension (same arithmetic, many code blocks per launch)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Shape of one homogeneous batch of code blocks. */
+typedef struct nrb200_ldpc_batch_desc {
+  uint8_t BG;
+  uint16_t Z;
+  uint8_t R;          /* decoder LUT selector as above */
+  uint8_t numMaxIter;
+  uint8_t outMode;    /* nrb200_ldpc_outmode_t */
+  uint8_t crc_type;   /* used when use_crc != 0 */
+  uint8_t use_crc;    /* 0: parity-check stop (check_crc == NULL); 1: in-kernel CRC stop with reference semantics */
+  uint32_t crc_len_bits; /* the `E` the reference passes to check_crc (payload incl. CRC, bits) */
+  uint32_t n_cb;      /* code blocks in the batch */
+  uint32_t llr_stride; /* bytes between consecutive code blocks' LLR arrays (>= ncol(R)*Z) */
+  uint32_t out_stride; /* bytes between consecutive outputs (BIT: >= ncol(R)*Z/8, else >= ncol(R)*Z) */
+} nrb200_ldpc_batch_desc_t;
+
+/* number of input LLRs per code block for (BG, Z, R): ncol(R)*Z (nrLDPC_init.h:58, nrLDPCdecoder_defs.h:53-84); -1 if invalid */
+int32_t nrb200_ldpc_num_llr(int BG, int Z, int R);
+
+/* Device-resident batch decode: d_llr/d_out/d_iters are device pointers; asynchronous on `stream`.
+ * d_iters[i] receives what LDPCdecoder would return for block i.  Returns 0, or a negative error. */
+int32_t nrb200_ldpc_decode_batch_dev(const nrb200_ldpc_batch_desc_t *desc, const int8_t *d_llr, uint8_t *d_out,
+                                     int32_t *d_iters, void *stream);
+/* Host-buffer batch decode: H2D (pinned staging if the buffers are not pinned), kernel, D2H; blocking. */
+int32_t nrb200_ldpc_decode_batch_host(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters);
+
+/* Batch encode: in = n_cb x K/8 packed bytes (stride in_stride), out = n_cb x (66Z|50Z) bytes, one bit per byte
+ * (stride out_stride).  Same output as LDPCencoder per block. */
+int32_t nrb200_ldpc_encode_batch_dev(int BG, int Z, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
+                                     uint8_t *d_out, uint32_t out_stride, void *stream);
+int32_t nrb200_ldpc_encode_batch_host(int BG, int Z, int K, uint32_t n_cb, const uint8_t *in, uint32_t in_stride, uint8_t *out,
+                                      uint32_t out_stride);
+
+/* CRC of n_blk bit strings of bitlen bits each (MSB first, stride bytes apart): out[i] = reference crc24a/crc24b/
+ * crc24c/crc16/crc12/crc11/crc8/crc6 value (left-aligned in 32 bits exactly as crc_byte.c:148-312 returns it).
+ * poly_id: 0=24A 1=24B 2=24C 3=16 4=12 5=11 6=8 7=6. */
+int32_t nrb200_crc_batch_dev(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out,
+                             void *stream);
+int32_t nrb200_crc_batch_host(int poly_id, uint32_t n_blk, const uint8_t *in, uint32_t stride, uint32_t bitlen, uint32_t *out);
+
+/* Device in use / last CUDA error text (diagnostics; never NULL). */
+int32_t nrb200_device_index(void);
+const char *nrb200_last_error(void);
+/* Kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
+uint64_t nrb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRB200_LDPC_H */

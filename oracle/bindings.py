@@ -1,0 +1,232 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes bindings for the CPU oracle (oracle/liboracle.so, the C restatement) and,
+when present, the compiled unmodified reference (oracle/_ref/libref_*.so, built by oracle/build_ref.sh).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg import this module.
+The product package (openairinterface5g_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(HERE, "_ref")
+
+_u8p = C.POINTER(C.c_uint8)
+_i8p = C.POINTER(C.c_int8)
+_i16p = C.POINTER(C.c_int16)
+
+
+class TimeStats(C.Structure):  # common/utils/time_meas.h:61-75
+    _fields_ = [("in_", C.c_longlong), ("diff", C.c_longlong), ("p_time", C.c_longlong), ("diff_square", C.c_double),
+                ("max", C.c_longlong), ("trials", C.c_int), ("meas_flag", C.c_int), ("meas_name", C.c_char_p),
+                ("meas_index", C.c_int), ("meas_enabled", C.c_int), ("tpoolmsg", C.c_void_p), ("tstatptr", C.c_void_p)]
+
+
+class LdpcTimeStats(C.Structure):  # nrLDPC_types.h:115-127
+    _fields_ = [(n, TimeStats) for n in ("llr2llrProcBuf", "llr2CnProcBuf", "cnProc", "cnProcPc", "bnProcPc", "bnProc",
+                                         "cn2bnProcBuf", "bn2cnProcBuf", "llrRes2llrOut", "llr2bit", "total")]
+
+
+CHECK_CRC_T = C.CFUNCTYPE(C.c_int, _u8p, C.c_uint32, C.c_uint8)
+
+
+class DecParams(C.Structure):  # nrLDPC_types.h:84-97
+    _fields_ = [("BG", C.c_uint8), ("Z", C.c_uint16), ("R", C.c_uint8), ("F", C.c_uint16), ("Qm", C.c_uint8), ("rv", C.c_uint8),
+                ("numMaxIter", C.c_uint8), ("E", C.c_int), ("outMode", C.c_int), ("crc_type", C.c_int),
+                ("check_crc", C.c_void_p), ("setCombIn", C.c_uint8)]
+
+
+class DecodeAbort(C.Structure):  # defs_common.h:996-1000 (pthread_mutex_t is 40 bytes on x86-64 glibc)
+    _fields_ = [("mutex", C.c_uint8 * 40), ("failed", C.c_bool)]
+
+
+class EncParams(C.Structure):  # nrLDPC_defs.h:40-66
+    _fields_ = [("n_segments", C.c_uint), ("macro_num", C.c_uint), ("gen_code", C.c_ubyte),
+                ("tinput", C.c_void_p), ("tprep", C.c_void_p), ("tparity", C.c_void_p), ("toutput", C.c_void_p),
+                ("Kr", C.c_int), ("Kb", C.c_uint32), ("Zc", C.c_uint32), ("harq", C.c_void_p), ("BG", C.c_uint8),
+                ("output", C.c_void_p), ("K", C.c_uint32), ("F", C.c_uint32), ("Qm", C.c_uint8), ("E", C.c_uint32),
+                ("G", C.c_uint), ("rv", C.c_uint8)]
+
+
+def ncols_for_rate(BG, R):
+    return {(1, 13): 68, (1, 23): 35, (1, 89): 27, (2, 15): 52, (2, 13): 32, (2, 23): 17}[(BG, R)]
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+# ------------------------------------------------------------------------------------------------ oracle (C restatement)
+class Oracle:
+    def __init__(self):
+        so = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", HERE, "liboracle.so"])
+        L = self.lib = C.CDLL(so)
+        L.orc_crc.restype = C.c_uint32
+        L.orc_crc.argtypes = [C.c_int, _u8p, C.c_uint32]
+        L.orc_check_crc.argtypes = [_u8p, C.c_uint32, C.c_int]
+        L.orc_ldpc_decode.argtypes = [C.c_int] * 5 + [_i8p, _i8p, C.c_int, C.c_uint32, C.c_int, C.c_int]
+        L.orc_ldpc_encode.argtypes = [C.c_int, C.c_int, C.c_int, _u8p, _u8p]
+        L.orc_rate_matching_tx.argtypes = [C.c_uint32, C.c_int, C.c_int, _u8p, _u8p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
+        L.orc_rate_matching_rx.argtypes = [C.c_uint32, C.c_int, C.c_int, _i16p, _i16p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_interleave.argtypes = [C.c_uint32, C.c_int, _u8p, _u8p]
+        L.orc_interleave.restype = None
+        L.orc_deinterleave.argtypes = [C.c_uint32, C.c_int, _i16p, _i16p]
+        L.orc_deinterleave.restype = None
+        L.orc_get_R_ldpc_decoder.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int), C.c_int]
+        L.orc_segmentation.argtypes = [_u8p, C.POINTER(_u8p), C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint),
+                                       C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_int]
+
+    def ils_of_z(self, Z):
+        return self.lib.orc_ils_of_z(int(Z))
+
+    def crc(self, poly_id, data, bitlen):
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        return int(self.lib.orc_crc(poly_id, _ptr(d, _u8p), bitlen))
+
+    def check_crc(self, data, n, crc_type):
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        return int(self.lib.orc_check_crc(_ptr(d, _u8p), n, crc_type))
+
+    def decode(self, BG, Z, R, max_iter, llr, out_mode=0, use_crc=0, crc_len_bits=0, crc_type=0, abort_in=0):
+        n = ncols_for_rate(BG, R) * Z
+        llr = np.ascontiguousarray(llr, dtype=np.int8)
+        assert llr.size >= n
+        out = np.zeros(n + 64, dtype=np.int8)
+        it = self.lib.orc_ldpc_decode(BG, Z, R, max_iter, out_mode, _ptr(llr, _i8p), _ptr(out, _i8p), use_crc, crc_len_bits, crc_type, abort_in)
+        return it, (out[:(n + 7) // 8].view(np.uint8) if out_mode == 0 else out[:n])
+
+    def encode(self, BG, Z, K, payload):
+        p = np.ascontiguousarray(payload, dtype=np.uint8)
+        out = np.zeros((68 if BG == 1 else 52) * Z, dtype=np.uint8)
+        rc = self.lib.orc_ldpc_encode(BG, Z, K, _ptr(p, _u8p), _ptr(out, _u8p))
+        assert rc == 0, rc
+        return out[:(66 if BG == 1 else 50) * Z]
+
+    def rate_matching_tx(self, Tbslbrm, BG, Z, w, C_, F, Foffset, rv, E):
+        w = np.ascontiguousarray(w, dtype=np.uint8)
+        e = np.zeros(E, dtype=np.uint8)
+        rc = self.lib.orc_rate_matching_tx(Tbslbrm, BG, Z, _ptr(w, _u8p), _ptr(e, _u8p), C_, F, Foffset, rv, E)
+        return rc, e
+
+    def rate_matching_rx(self, Tbslbrm, BG, Z, w, soft, C_, rv, clear, E, F, Foffset):
+        soft = np.ascontiguousarray(soft, dtype=np.int16)
+        assert w.dtype == np.int16 and w.flags.c_contiguous
+        return self.lib.orc_rate_matching_rx(Tbslbrm, BG, Z, _ptr(w, _i16p), _ptr(soft, _i16p), C_, rv, clear, E, F, Foffset)
+
+    def interleave(self, E, Qm, e):
+        e = np.ascontiguousarray(e, dtype=np.uint8)
+        f = np.zeros(E, dtype=np.uint8)
+        self.lib.orc_interleave(E, Qm, _ptr(e, _u8p), _ptr(f, _u8p))
+        return f
+
+    def deinterleave(self, E, Qm, f):
+        f = np.ascontiguousarray(f, dtype=np.int16)
+        e = np.zeros(E, dtype=np.int16)
+        self.lib.orc_deinterleave(E, Qm, _ptr(e, _i16p), _ptr(f, _i16p))
+        return e
+
+    def get_R(self, rv, E, BG, Z, llrLen, rnd):
+        ll = C.c_int(llrLen)
+        r = self.lib.orc_get_R_ldpc_decoder(rv, E, BG, Z, C.byref(ll), rnd)
+        return r, ll.value
+
+    def segmentation(self, data, B, BG):
+        Cc, K, Zo, F = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+        Kb = self.lib.orc_segmentation(None, None, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
+        if Kb < 0:
+            return Kb, 0, 0, 0, 0, None
+        segs = np.zeros((Cc.value, K.value // 8 + 8), dtype=np.uint8)
+        if data is not None:
+            d = np.ascontiguousarray(data, dtype=np.uint8)
+            ptrs = (_u8p * Cc.value)(*[C.cast(segs[r].ctypes.data, _u8p) for r in range(Cc.value)])
+            self.lib.orc_segmentation(_ptr(d, _u8p), ptrs, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
+        return Kb, Cc.value, K.value, Zo.value, F.value, segs[:, :K.value // 8]
+
+
+# ------------------------------------------------------------------------------------------------ compiled reference
+def have_reference():
+    return all(os.path.exists(os.path.join(REFDIR, f)) for f in
+               ("libref_ldpc_dec.so", "libref_ldpc_enc.so", "libref_ldpc_enc_orig.so", "libref_coding.so", "libref_dfts.so"))
+
+
+class Reference:
+    """The unmodified OAI sources compiled by oracle/build_ref.sh."""
+
+    def __init__(self, avx512=False):
+        if not have_reference():
+            raise FileNotFoundError("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
+        self.dec = C.CDLL(os.path.join(REFDIR, "libref_ldpc_dec512.so" if avx512 else "libref_ldpc_dec.so"))
+        self.enc = C.CDLL(os.path.join(REFDIR, "libref_ldpc_enc.so"))
+        self.enc_orig = C.CDLL(os.path.join(REFDIR, "libref_ldpc_enc_orig.so"))
+        self.cod = C.CDLL(os.path.join(REFDIR, "libref_coding.so"))
+        self.cod.crcTableInit()
+        for n in ("crc24a", "crc24b", "crc24c", "crc16", "crc12", "crc11", "crc8", "crc6"):
+            f = getattr(self.cod, n)
+            f.restype = C.c_uint32
+            f.argtypes = [_u8p, C.c_int]
+        self.cod.check_crc.argtypes = [_u8p, C.c_uint32, C.c_uint8]
+        self.dec.LDPCdecoder.argtypes = [C.POINTER(DecParams), C.c_uint8, C.c_uint8, C.c_uint8, _i8p, _i8p, C.c_void_p, C.c_void_p]
+        self.dec.LDPCinit()
+        self._prof = LdpcTimeStats()
+
+    def crc(self, poly_id, data, bitlen):
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        d = np.concatenate([d, np.zeros(8, np.uint8)])
+        name = ("crc24a", "crc24b", "crc24c", "crc16", "crc12", "crc11", "crc8", "crc6")[poly_id]
+        return int(getattr(self.cod, name)(_ptr(d, _u8p), bitlen))
+
+    def decode(self, BG, Z, R, max_iter, llr, out_mode=0, use_crc=0, crc_len_bits=0, crc_type=0, abort_in=0):
+        n = ncols_for_rate(BG, R) * Z
+        # the reference reads whole 32-byte vectors: give it NR_LDPC_MAX_NUM_LLR-sized aligned buffers like its callers do
+        buf = np.zeros(27000 + 64, dtype=np.int8)
+        off = (-buf.ctypes.data) % 64
+        a = buf[off:off + 27000]
+        a[:n] = np.asarray(llr, dtype=np.int8)[:n]
+        out = np.zeros(27000 + 64, dtype=np.int8)
+        offo = (-out.ctypes.data) % 64
+        o = out[offo:offo + 27000]
+        p = DecParams()
+        p.BG, p.Z, p.R, p.numMaxIter, p.outMode, p.E, p.crc_type = BG, Z, R, max_iter, out_mode, crc_len_bits, crc_type
+        p.check_crc = C.cast(self.cod.check_crc, C.c_void_p).value if use_crc else None
+        ab = DecodeAbort()
+        ab.failed = bool(abort_in)
+        it = self.dec.LDPCdecoder(C.byref(p), 0, 0, 0, _ptr(a, _i8p), _ptr(o, _i8p), C.cast(C.byref(self._prof), C.c_void_p),
+                                  C.cast(C.byref(ab), C.c_void_p))
+        self.last_abort = bool(ab.failed)
+        return it, (o[:(n + 7) // 8].view(np.uint8).copy() if out_mode == 0 else o[:n].copy())
+
+    def decode_raw_fn(self):
+        return self.dec.LDPCdecoder
+
+    def encode(self, BG, Z, K, payloads, orig=False):
+        """payloads: (n_seg, K/8) uint8; returns (n_seg, 66Z|50Z) uint8 of 0/1 -- LDPCencoder in groups of 8."""
+        payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+        nseg = payloads.shape[0]
+        nout = (66 if BG == 1 else 50) * Z
+        pad_in = np.zeros((nseg, K // 8 + 64), dtype=np.uint8)
+        pad_in[:, :K // 8] = payloads
+        outs = np.zeros((nseg, 68 * 384 + 64), dtype=np.uint8)
+        inp = (_u8p * nseg)(*[C.cast(pad_in[i].ctypes.data, _u8p) for i in range(nseg)])
+        oup = (_u8p * nseg)(*[C.cast(outs[i].ctypes.data + ((-outs[i].ctypes.data) % 32), _u8p) for i in range(nseg)])
+        ip = EncParams()
+        ip.n_segments, ip.Kb, ip.Zc, ip.BG, ip.K, ip.gen_code = nseg, (22 if BG == 1 else 10), Z, BG, K, 0
+        if orig:
+            for j in range(nseg):
+                one_in = (_u8p * 1)(inp[j])
+                one_out = (_u8p * 1)(oup[j])
+                ip.n_segments = 1
+                rc = self.enc_orig.LDPCencoder(one_in, one_out, C.byref(ip))
+                assert rc == nout, rc  # ldpc_encoder.c:259 returns the coded length
+        else:
+            for m in range((nseg + 7) // 8):
+                ip.macro_num = m
+                rc = self.enc.LDPCencoder(inp, oup, C.byref(ip))
+                assert rc == 0
+        res = np.zeros((nseg, nout), dtype=np.uint8)
+        for i in range(nseg):
+            o = (-outs[i].ctypes.data) % 32
+            res[i] = outs[i, o:o + nout]
+        return res

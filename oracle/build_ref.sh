@@ -1,0 +1,53 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- builds the *unmodified* OpenAirInterface reference sources,
+# in place from /root/reference, into shared objects under oracle/_ref/ (git-ignored).
+# Nothing from the reference tree is copied into this repository; the only generated text
+# is a simde->native intrinsic alias header (simde is absent in this image; on x86 simde is a
+# 1:1 wrapper of the native intrinsics, reference CMakeLists.txt:124-133) and the reference's
+# own code-generator output (nrLDPC_tools/generator_*), both written to oracle/_ref/.
+#
+# Products (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference arm
+# may load them):
+#   oracle/_ref/libref_ldpc_dec.so      LDPCinit/LDPCshutdown/LDPCdecoder  (nrLDPC_decoder.c, AVX2)
+#   oracle/_ref/libref_ldpc_dec512.so   same, -march=native (AVX512 generated kernels) [optional]
+#   oracle/_ref/libref_ldpc_enc.so      LDPCencoder (ldpc_encoder_optim8segmulti.c, default libldpc.so)
+#   oracle/_ref/libref_ldpc_enc_orig.so LDPCencoder (ldpc_encoder.c, scalar "_orig")
+#   oracle/_ref/libref_dfts.so          dft/idft/dfts_autoinit (oai_dfts.c)
+#   oracle/_ref/libref_coding.so        crc_byte.c + nr_rate_matching.c + nr_segmentation.c
+set -euo pipefail
+R=${OAI_REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+W=$HERE/_ref
+if [ ! -d "$R/openair1" ]; then echo "reference tree not present at $R: keeping prebuilt oracle/_ref" >&2; exit 0; fi
+mkdir -p $W/shim/simde/x86 $W/shim/simde/arm $W/gen/{cnProc,bnProc,bnProcPc,cnProc_avx512,bnProc_avx512,bnProcPc_avx512}
+# 1) simde -> native alias header
+grep -rhoE '\bsimde_[_a-zA-Z0-9]+|\bsimde__m[0-9a-z]+|\bSIMDE_[A-Z_0-9]+' $R/openair1 $R/common | sort -u > $W/tokens.txt
+{ echo '#pragma once'; echo '#include <immintrin.h>'; echo '#include <mmintrin.h>';
+  while read t; do case "$t" in simde_*) echo "#define $t ${t#simde}";; SIMDE_MM_SHUFFLE) echo "#define $t _MM_SHUFFLE";; esac; done < $W/tokens.txt; } > $W/shim/simde/x86/shim_all.h
+for f in mmx sse sse2 sse3 ssse3 sse4.1 sse4.2 avx2 fma clmul avx512; do echo '#include "shim_all.h"' > $W/shim/simde/x86/$f.h; done
+echo '#include "x86/shim_all.h"' > $W/shim/simde/simde-common.h; echo '#pragma once' > $W/shim/simde/arm/neon.h
+INC="-I$W/shim -I$W/gen -I$R/openair1/PHY/CODING/nrLDPC_decoder -I$R/openair1 -I$R -I$R/common/utils -I$R/common/utils/LOG -I$R/common/utils/T \
+ -I$R/openair2/COMMON -I$R/nfapi/open-nFAPI/nfapi/public_inc -I$R/openair2 -I$R/openair1/PHY -I$R/common -I$R/radio/COMMON -I$R/executables \
+ -I$R/openair2/NR_UE_PHY_INTERFACE -I$R/openair2/NR_PHY_INTERFACE -I$R/openair2/PHY_INTERFACE -I$R/openair3/COMMON -I$R/openair3"
+DEFS="-DMAX_NUM_CCs=1 -DNB_ANTENNAS_RX=4 -DNB_ANTENNAS_TX=4 -DNUMBER_OF_UE_MAX_NB_IoT=16"
+# 2) the reference's own generated decoder headers
+T=$R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_tools
+if [ ! -f $W/gen/.done ]; then
+  ( cd $W/gen
+    gcc -O1 -mavx2 $INC -DCODEGEN $T/generator_cnProc/{cnProc_gen_BG1_avx2.c,cnProc_gen_BG2_avx2.c,main.c} -o cn_gen && ./cn_gen .
+    gcc -O1 -mavx2 $INC -DCODEGEN $T/generator_bnProc/{bnProc_gen_BG1_avx2.c,bnProc_gen_BG2_avx2.c,bnProcPc_gen_BG1_avx2.c,bnProcPc_gen_BG2_avx2.c,main.c} -o bn_gen && ./bn_gen .
+    gcc -O1 -mavx512bw $INC -DCODEGEN $T/generator_cnProc_avx512/*.c -o cn512 && ./cn512 . || true
+    gcc -O1 -mavx512bw $INC -DCODEGEN $T/generator_bnProc_avx512/*.c -o bn512 && ./bn512 . || true
+    touch .done )
+fi
+# 3) libraries
+cd $W
+F="-O3 -mavx2 -mno-avx512f -fPIC -shared -w"
+gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder.c              -o libref_ldpc_dec.so
+gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/nrLDPC_encoder/ldpc_encoder_optim8segmulti.c -o libref_ldpc_enc.so
+gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/nrLDPC_encoder/ldpc_encoder.c                -o libref_ldpc_enc_orig.so
+gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/TOOLS/oai_dfts.c -lm                                -o libref_dfts.so
+gcc -O3 -march=native -fPIC -shared -w $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder.c -o libref_ldpc_dec512.so || echo "avx512 variant skipped"
+gcc $F -mpclmul $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/crc_byte.c $R/openair1/PHY/CODING/nr_rate_matching.c \
+    $R/openair1/PHY/CODING/nr_segmentation.c -o libref_coding.so || echo "libref_coding.so: FAILED (see DESIGN.md)"
+ls -la $W/*.so

@@ -1,0 +1,59 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the OpenAirInterface NR LDPC hot path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may link or
+ * load this.  The product (libldpc_b200.so) never does.
+ *
+ * Parity status: PINNED.  Every function below is differential-tested bit-exactly against the unmodified
+ * reference compiled by oracle/build_ref.sh (oracle/_ref/libref_*.so) in tests/test_oracle_vs_reference.py,
+ * and against the committed fixtures in tests/golden/ (generated from that compiled reference by
+ * tools/gen_golden.py) on machines where /root/reference is absent.
+ */
+#ifndef NRB200_ORACLE_H
+#define NRB200_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference-defect emulation, see nrb200_oracle.c (bit 0: AVX2 BG2 R15 generator defect) */
+void orc_set_quirks(int q);
+
+/* lifting-set index iLS (0..7) of Z, -1 if Z is not one of the 51 NR lifting sizes */
+int orc_ils_of_z(int Z);
+/* columns the decoder uses for rate selector R: BG1 13->68 23->35 89->27; BG2 15->52 13->32 23->17; -1 if invalid */
+int orc_ncols_for_rate(int BG, int R);
+
+/* MSB-first bitwise CRC, result left-aligned in 32 bits like crc_byte.c:148-312.
+ * poly_id: 0=24A 1=24B 2=24C 3=16 4=12 5=11 6=8 7=6 */
+uint32_t orc_crc(int poly_id, const uint8_t *data, uint32_t bitlen);
+/* crc_byte.c:314-379 */
+int orc_check_crc(const uint8_t *decoded_bytes, uint32_t n, int crc_type);
+
+/* nrLDPC_decoder.c:172-881 flooding int8 min-sum.  out sized per outMode (BIT: ncols*Z/8).
+ * use_crc=0 <=> check_crc==NULL.  abort_in != 0 models a peer segment having set decode_abort_t before the call.
+ * Returns what LDPCdecoder returns. */
+int orc_ldpc_decode(int BG, int Z, int R, int numMaxIter, int outMode, const int8_t *llr, int8_t *out, int use_crc,
+                    uint32_t crc_len_bits, int crc_type, int abort_in);
+
+/* ldpc_encoder_optim8segmulti.c:46-212 for one segment: in = K/8 packed bytes MSB-first, out = 66Z|50Z bytes of 0/1. */
+int orc_ldpc_encode(int BG, int Z, int K, const uint8_t *in, uint8_t *out);
+
+/* nr_segmentation.c:32-180; outputs as the reference; seg_out[r] must hold K/8 bytes when non-NULL. Returns Kb or -1. */
+int orc_segmentation(const uint8_t *in, uint8_t **seg_out, unsigned B, unsigned *C, unsigned *K, unsigned *Zout, unsigned *F, int BG);
+
+/* nr_rate_matching.c:424-505 */
+int orc_rate_matching_tx(uint32_t Tbslbrm, int BG, int Z, const uint8_t *w, uint8_t *e, int C, uint32_t F, uint32_t Foffset, int rv,
+                         uint32_t E);
+/* nr_rate_matching.c:507-603 */
+int orc_rate_matching_rx(uint32_t Tbslbrm, int BG, int Z, int16_t *w, const int16_t *soft, int C, int rv, int clear, uint32_t E,
+                         uint32_t F, uint32_t Foffset);
+/* nr_rate_matching.c:36-305 / 310-388 (f[i+j*Qm] = e[i*E/Qm + j]) */
+void orc_interleave(uint32_t E, int Qm, const uint8_t *e, uint8_t *f);
+void orc_deinterleave(uint32_t E, int Qm, int16_t *e, const int16_t *f);
+/* nr_rate_matching.c:390-422 */
+int orc_get_R_ldpc_decoder(int rv, int E, int BG, int Z, int *llrLen, int round);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
