@@ -1,0 +1,154 @@
+// NR LDPC encoder kernels.  Systematic QC encoding through H's dual-diagonal core: the result is bit-identical to the
+// reference's generator-matrix XOR networks (nrLDPC_encoder/ldpc_encoder_optim8segmulti.c:46-212,
+// ldpc_encode_parity_check.c:90-220) -- any correct systematic encoder of the same code is.  Output layout is the ABI's:
+// one bit per byte, K-2Z systematic bits followed by all parity bits (66Z for BG1, 50Z for BG2).
+#include "nrb200_ctx.h"
+#include "ldpc_common.cuh"
+
+namespace nrb200 {
+
+// one CTA per code block; x = the whole codeword as 0/1 bytes in shared memory
+__global__ void __launch_bounds__(384, 2)
+ldpc_encode_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t n_cb, const uint8_t *__restrict__ in, uint32_t in_stride,
+                   uint8_t *__restrict__ out, uint32_t out_stride)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EncGraphDev &g = *reinterpret_cast<EncGraphDev *>(smem_raw);
+  for (int i = threadIdx.x; i < (int)(sizeof(EncGraphDev) / 4); i += blockDim.x)
+    reinterpret_cast<int *>(smem_raw)[i] = reinterpret_cast<const int *>(gdev)[i];
+  __syncthreads();
+  const int Z = g.Z, nsys = g.nsys, ncols = g.ncols, nrows = g.nrows;
+  uint8_t *x = smem_raw + ((sizeof(EncGraphDev) + 15) & ~15);
+  uint8_t *lam = x + (((size_t)ncols * Z + 15) & ~15);     // 4 x Z systematic partial sums of the core rows
+
+  for (uint32_t cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+    const uint8_t *src = in + (size_t)cb * in_stride;
+    for (int i = threadIdx.x; i < ncols * Z; i += blockDim.x)
+      x[i] = i < K ? (uint8_t)((src[i >> 3] >> (7 - (i & 7))) & 1) : (uint8_t)0;
+    __syncthreads();
+    // lambda_r (r < 4): systematic columns only
+    for (int i = threadIdx.x; i < 4 * Z; i += blockDim.x) {
+      const int r = i / Z, t = i - r * Z;
+      unsigned acc = 0;
+      for (int e = g.row_start[r]; e < g.row_start[r + 1]; e++) {
+        const int c = g.edge_col[e];
+        if (c >= nsys) continue;
+        int v = t + g.edge_shift[e]; if (v >= Z) v -= Z;
+        acc ^= x[c * Z + v];
+      }
+      lam[i] = (uint8_t)acc;
+    }
+    __syncthreads();
+    // p0: sum of the four core rows = x^sigma * p0
+    for (int t = threadIdx.x; t < Z; t += blockDim.x) {
+      int v = t + g.sigma; if (v >= Z) v -= Z;
+      x[nsys * Z + v] = lam[t] ^ lam[Z + t] ^ lam[2 * Z + t] ^ lam[3 * Z + t];
+    }
+    __syncthreads();
+    // the other three core parity columns, in dependency order
+    for (int n = 0; n < 3; n++) {
+      const int r = g.core_row[n], pc = g.core_col[n], psh = g.core_shift[n];
+      for (int t = threadIdx.x; t < Z; t += blockDim.x) {
+        unsigned acc = lam[r * Z + t];
+        for (int e = g.row_start[r]; e < g.row_start[r + 1]; e++) {
+          const int c = g.edge_col[e];
+          if (c < nsys || c == pc) continue;
+          // columns still unknown at this step are all-zero in x, so including them is harmless
+          int v = t + g.edge_shift[e]; if (v >= Z) v -= Z;
+          acc ^= x[c * Z + v];
+        }
+        int v = t + psh; if (v >= Z) v -= Z;
+        x[pc * Z + v] = (uint8_t)acc;
+      }
+      __syncthreads();
+    }
+    // extension rows: the degree-1 diagonal column (shift 0) closes each row
+    for (int i = threadIdx.x; i < (nrows - 4) * Z; i += blockDim.x) {
+      const int r = 4 + i / Z, t = i % Z;
+      unsigned acc = 0;
+      for (int e = g.row_start[r]; e < g.row_start[r + 1]; e++) {
+        const int c = g.edge_col[e];
+        if (c == nsys + r) continue;
+        int v = t + g.edge_shift[e]; if (v >= Z) v -= Z;
+        acc ^= x[c * Z + v];
+      }
+      x[(nsys + r) * Z + t] = (uint8_t)acc;
+    }
+    __syncthreads();
+    uint8_t *dst = out + (size_t)cb * out_stride;
+    const int nout = (ncols - 2) * Z;
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) dst[i] = x[2 * Z + i];
+    __syncthreads();
+  }
+}
+
+int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
+                  uint8_t *d_out, uint32_t out_stride, cudaStream_t stream)
+{
+  if (n_cb == 0) return 0;
+  auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t smem = a16(sizeof(EncGraphDev)) + a16((size_t)h_g.ncols * h_g.Z) + a16((size_t)4 * h_g.Z);
+  static std::atomic<size_t> configured{0};
+  if (smem > configured.load()) {
+    NRB200_CUDA_OK(cudaFuncSetAttribute(ldpc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "enc smem attr");
+    configured.store(smem);
+  }
+  int threads = ((h_g.Z + 31) / 32) * 32;
+  if (threads < 64) threads = 64;
+  if (threads > 384) threads = 384;
+  ldpc_encode_kernel<<<n_cb, threads, smem, stream>>>(d_g, K, n_cb, d_in, in_stride, d_out, out_stride);
+  ctx().launches++;
+  NRB200_CUDA_OK(cudaGetLastError(), "encode launch");
+  return 0;
+}
+
+// ---- CRC: out = data(x) * x^deg mod g, left-aligned like crc_byte.c:148-312.  One CTA per bit string;
+//      remainder = XOR over set bits i of tab[bitlen-1-i+deg].
+__global__ void crc_kernel(const uint32_t *__restrict__ tab, int deg, uint32_t n_blk, const uint8_t *__restrict__ in, uint32_t stride,
+                           uint32_t bitlen, uint32_t *__restrict__ out)
+{
+  __shared__ unsigned s_acc;
+  for (uint32_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
+    if (threadIdx.x == 0) s_acc = 0;
+    __syncthreads();
+    const uint8_t *src = in + (size_t)b * stride;
+    unsigned rem = 0;
+    const uint32_t nbytes = (bitlen + 7) / 8;
+    for (uint32_t j = threadIdx.x; j < nbytes; j += blockDim.x) {
+      unsigned byte = src[j];
+      while (byte) {
+        const int k = 31 - __clz(byte);          // bit k of the byte = stream bit 8j + (7-k)
+        byte &= ~(1u << k);
+        const uint32_t i = 8 * j + (7 - k);
+        if (i < bitlen) rem ^= __ldg(tab + (bitlen - 1 - i + deg));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
+    if ((threadIdx.x & 31) == 0 && rem) atomicXor(&s_acc, rem);
+    __syncthreads();
+    if (threadIdx.x == 0) out[b] = s_acc;
+    __syncthreads();
+  }
+}
+
+int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream)
+{
+  if (poly_id < 0 || poly_id > 7) return -4;
+  const int deg = poly_id <= 2 ? 24 : poly_id == 3 ? 16 : poly_id == 4 ? 12 : poly_id == 5 ? 11 : poly_id == 6 ? 8 : 6;
+  if (bitlen + deg > (uint32_t)kCrcTableLen) return -4;
+  if (n_blk == 0) return 0;
+  crc_kernel<<<n_blk, 256, 0, stream>>>(ctx().crc_tab[poly_id], deg, n_blk, d_in, stride, bitlen, d_out);
+  ctx().launches++;
+  NRB200_CUDA_OK(cudaGetLastError(), "crc launch");
+  return 0;
+}
+
+int quirks_from_env()
+{
+  static int q = -1;
+  if (q < 0) { const char *s = getenv("NRB200_EMULATE_AVX2_BG2R15_DEFECT"); q = (s && *s == '1') ? 1 : 0; }
+  return q;
+}
+
+}  // namespace nrb200

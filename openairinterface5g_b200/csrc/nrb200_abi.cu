@@ -1,0 +1,263 @@
+// C ABI of libldpc_b200.so (include/nrb200_ldpc.h): the four OAI loader symbols plus the batched extension.
+#include "../../include/nrb200_ldpc.h"
+#include "nrb200_ctx.h"
+#include "ldpc_common.cuh"
+#include <cstring>
+
+#define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace nrb200 {
+int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream);
+int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
+                  uint8_t *d_out, uint32_t out_stride, cudaStream_t stream);
+int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
+int quirks_from_env();
+}
+using namespace nrb200;
+
+static inline unsigned long long rdtsc_now()
+{
+#if defined(__x86_64__)
+  unsigned long long a, d;
+  __asm__ volatile("rdtsc" : "=a"(a), "=d"(d));
+  return (d << 32) | a;
+#else
+  return 0;
+#endif
+}
+
+static int ensure_init()
+{
+  Ctx &c = ctx();
+  if (!c.inited) { if (c.init() != 0) return -1; }
+  cudaSetDevice(c.dev);   // the runtime's current device is per host thread
+  return 0;
+}
+
+static int crc_poly_of_type(int crc_type) { return crc_type == 0 ? 0 : crc_type == 1 ? 1 : crc_type == 2 ? 3 : 6; }
+
+static int fill_args(const nrb200_ldpc_batch_desc_t *d, const GraphDev &hg, DecodeArgs *a)
+{
+  const uint32_t numLLR = (uint32_t)hg.ncols * hg.Z;
+  const uint32_t out_bytes = d->outMode == NRB200_OUTMODE_BIT ? (numLLR + 7) / 8 : numLLR;
+  if (d->llr_stride < numLLR || d->out_stride < out_bytes) return -4;
+  if (d->outMode > 2) return -4;
+  std::memset(a, 0, sizeof(*a));
+  a->n_cb = d->n_cb; a->llr_stride = d->llr_stride; a->out_stride = d->out_stride;
+  a->numMaxIter = d->numMaxIter; a->outMode = d->outMode; a->use_crc = d->use_crc ? 1 : 0;
+  a->quirks = (uint8_t)quirks_from_env();
+  if (a->use_crc) {
+    if (d->crc_type > 3 || d->crc_len_bits % 8 || d->crc_len_bits < 32 || d->crc_len_bits > numLLR || d->crc_len_bits >= (uint32_t)kCrcTableLen) return -4;
+    a->crc_len_bits = d->crc_len_bits;
+    a->crc_tab = ctx().crc_tab[crc_poly_of_type(d->crc_type)];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ part 2: batch API
+NRB200_EXPORT int32_t nrb200_ldpc_num_llr(int BG, int Z, int R)
+{
+  const int nc = ncols_for_rate(BG, R);
+  if (nc < 0 || ils_of_z(Z) < 0) return -1;
+  return nc * Z;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_dev(const nrb200_ldpc_batch_desc_t *desc, const int8_t *d_llr, uint8_t *d_out,
+                                                   int32_t *d_iters, void *stream)
+{
+  if (ensure_init()) return -1;
+  const GraphDev *hg = nullptr;
+  const GraphDev *dg = ctx().graph(desc->BG, desc->Z, desc->R, &hg);
+  if (!dg) return -4;
+  DecodeArgs a;
+  if (int rc = fill_args(desc, *hg, &a)) return rc;
+  a.llr = d_llr; a.out = d_out; a.iters = d_iters;
+  return launch_decode(dg, *hg, a, (cudaStream_t)stream);
+}
+
+static int decode_host_impl(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, const uint8_t *abort_flags)
+{
+  if (ensure_init()) return -1;
+  const GraphDev *hg = nullptr;
+  const GraphDev *dg = ctx().graph(desc->BG, desc->Z, desc->R, &hg);
+  if (!dg) return -4;
+  DecodeArgs a;
+  if (int rc = fill_args(desc, *hg, &a)) return rc;
+  const size_t n = desc->n_cb;
+  if (n == 0) return 0;
+  const size_t in_bytes = n * desc->llr_stride, out_bytes = n * desc->out_stride, aux_bytes = n * (sizeof(int32_t) + 1);
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(in_bytes, out_bytes, aux_bytes)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    // caller memory is pageable in general (OAI stack arrays): stage through the pinned buffer
+    std::memcpy(w->h_in, llr, in_bytes);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    int32_t *d_it = (int32_t *)w->d_aux;
+    uint8_t *d_ab = (uint8_t *)w->d_aux + n * sizeof(int32_t);
+    if (abort_flags) {
+      std::memcpy((uint8_t *)w->h_aux + n * sizeof(int32_t), abort_flags, n);
+      cudaMemcpyAsync(d_ab, (uint8_t *)w->h_aux + n * sizeof(int32_t), n, cudaMemcpyHostToDevice, w->stream);
+      a.abort_flags = d_ab;
+    }
+    if (desc->use_crc) {   // the reference leaves p_out untouched until a CRC check runs: round-trip the caller's bytes
+      std::memcpy(w->h_out, out, out_bytes);
+      cudaMemcpyAsync(w->d_out, w->h_out, out_bytes, cudaMemcpyHostToDevice, w->stream);
+    }
+    a.llr = (const int8_t *)w->d_in; a.out = (uint8_t *)w->d_out; a.iters = d_it;
+    if ((rc = launch_decode(dg, *hg, a, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->h_aux, d_it, n * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    cudaError_t e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) { ctx().set_error("decode sync", e); rc = -2; break; }
+    std::memcpy(out, w->h_out, out_bytes);
+    std::memcpy(iters, w->h_aux, n * sizeof(int32_t));
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_host(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters)
+{
+  return decode_host_impl(desc, llr, out, iters, nullptr);
+}
+
+NRB200_EXPORT int32_t nrb200_device_index(void) { return ctx().inited ? ctx().dev : -1; }
+NRB200_EXPORT const char *nrb200_last_error(void) { return ctx().last_error.c_str(); }
+NRB200_EXPORT uint64_t nrb200_launch_count(void) { return ctx().launches.load(); }
+
+// ------------------------------------------------------------------------------------------ part 1: OAI loader ABI
+NRB200_EXPORT int32_t LDPCinit(void) { return ctx().init() == 0 ? 0 : -1; }
+NRB200_EXPORT int32_t LDPCshutdown(void) { ctx().shutdown(); return 0; }
+
+NRB200_EXPORT int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t C, int8_t *p_llr,
+                                  int8_t *p_out, nrb200_ldpc_time_stats_t *prof, nrb200_decode_abort_t *ab)
+{
+  (void)harq_pid; (void)ulsch_id; (void)C;
+  const unsigned long long t0 = prof ? rdtsc_now() : 0;
+  const int32_t numLLR = nrb200_ldpc_num_llr(p->BG, p->Z, p->R);
+  if (numLLR < 0) return -1;
+  nrb200_ldpc_batch_desc_t d;
+  std::memset(&d, 0, sizeof(d));
+  d.BG = p->BG; d.Z = p->Z; d.R = p->R; d.numMaxIter = p->numMaxIter; d.outMode = (uint8_t)p->outMode;
+  d.n_cb = 1; d.llr_stride = (uint32_t)numLLR; d.out_stride = p->outMode == NRB200_OUTMODE_BIT ? (uint32_t)(numLLR + 7) / 8 : (uint32_t)numLLR;
+  uint8_t abort_now = 0;
+  if (ab) {   // check_abort (defs_common.h:1008-1016)
+    pthread_mutex_lock(&ab->mutex_failure);
+    abort_now = ab->failed ? 1 : 0;
+    pthread_mutex_unlock(&ab->mutex_failure);
+  }
+  int32_t it = 0;
+  int rc;
+  if (p->check_crc) {
+    // The reference calls back into the host's check_crc (crc_byte.c:314) from inside the loop; the kernel evaluates the
+    // same CRC on device (types CRC24_A/B, CRC16, CRC8).
+    d.use_crc = 1; d.crc_type = (uint8_t)p->crc_type; d.crc_len_bits = (uint32_t)p->E;
+  }
+  // In CRC mode the reference leaves p_out untouched unless a check ran: decode into a scratch copy of p_out's current bytes
+  rc = decode_host_impl(&d, p_llr, (uint8_t *)p_out, &it, &abort_now);
+  if (rc != 0) return -1;
+  if (it > p->numMaxIter && ab) {   // set_abort (nrLDPC_decoder.c:190-193)
+    pthread_mutex_lock(&ab->mutex_failure);
+    ab->failed = true;
+    pthread_mutex_unlock(&ab->mutex_failure);
+  }
+  if (prof) {   // stop_meas(&p_profiler->total) equivalent (time_meas.h:161-177); fine-grained fields are compiled out upstream
+    const long long dt = (long long)(rdtsc_now() - t0);
+    prof->total.trials++; prof->total.diff += dt; prof->total.p_time = dt; prof->total.diff_square += (double)dt * (double)dt;
+    if (dt > prof->total.max) prof->total.max = dt;
+  }
+  return it;
+}
+
+// ------------------------------------------------------------------------------------------ encoder + CRC
+NRB200_EXPORT int32_t nrb200_ldpc_encode_batch_dev(int BG, int Z, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
+                                                   uint8_t *d_out, uint32_t out_stride, void *stream)
+{
+  if (ensure_init()) return -1;
+  const EncGraphDev *hg = nullptr;
+  const EncGraphDev *dg = ctx().enc_graph(BG, Z, &hg);
+  if (!dg || K != hg->nsys * Z) return -4;
+  if (in_stride < (uint32_t)(K + 7) / 8 || out_stride < (uint32_t)(hg->ncols - 2) * Z) return -4;
+  return launch_encode(dg, *hg, K, n_cb, d_in, in_stride, d_out, out_stride, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_encode_batch_host(int BG, int Z, int K, uint32_t n_cb, const uint8_t *in, uint32_t in_stride, uint8_t *out,
+                                                    uint32_t out_stride)
+{
+  if (ensure_init()) return -1;
+  if (n_cb == 0) return 0;
+  const size_t in_bytes = (size_t)n_cb * in_stride, out_bytes = (size_t)n_cb * out_stride;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(in_bytes, out_bytes, 16)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, in, in_bytes);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = nrb200_ldpc_encode_batch_dev(BG, Z, K, n_cb, (const uint8_t *)w->d_in, in_stride, (uint8_t *)w->d_out, out_stride, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    cudaError_t e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) { ctx().set_error("encode sync", e); rc = -2; break; }
+    std::memcpy(out, w->h_out, out_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+NRB200_EXPORT int32_t LDPCencoder(uint8_t **input, uint8_t **output, nrb200_ldpc_enc_params_t *impp)
+{
+  // segments 8*macro_num .. min(8*macro_num+8, n_segments) (ldpc_encoder_optim8segmulti.c:62-63)
+  if (ensure_init()) return -1;
+  const unsigned s0 = 8 * impp->macro_num;
+  const unsigned s1 = impp->n_segments > 8 * (impp->macro_num + 1) ? 8 * (impp->macro_num + 1) : impp->n_segments;
+  if (s1 <= s0) return 0;
+  const int BG = impp->BG, Z = (int)impp->Zc, K = (int)impp->K;
+  const unsigned long long t0 = impp->tparity ? rdtsc_now() : 0;
+  const uint32_t n = s1 - s0, kin = (uint32_t)(K + 7) / 8, nout = (uint32_t)((BG == 1 ? 66 : 50) * Z);
+  const uint32_t in_stride = (kin + 15) & ~15u, out_stride = (nout + 15) & ~15u;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve((size_t)n * in_stride, (size_t)n * out_stride, 16)) { if (w) ctx().release(w); return -1; }
+  int rc = 0;
+  do {
+    for (uint32_t j = 0; j < n; j++) std::memcpy((uint8_t *)w->h_in + (size_t)j * in_stride, input[s0 + j], kin);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, (size_t)n * in_stride, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -1; break; }
+    if (nrb200_ldpc_encode_batch_dev(BG, Z, K, n, (const uint8_t *)w->d_in, in_stride, (uint8_t *)w->d_out, out_stride, w->stream) != 0) { rc = -1; break; }
+    if (cudaMemcpyAsync(w->h_out, w->d_out, (size_t)n * out_stride, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -1; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -1; break; }
+    for (uint32_t j = 0; j < n; j++) std::memcpy(output[s0 + j], (uint8_t *)w->h_out + (size_t)j * out_stride, nout);
+  } while (0);
+  ctx().release(w);
+  if (impp->tparity && rc == 0) {
+    const long long dt = (long long)(rdtsc_now() - t0);
+    impp->tparity->trials++; impp->tparity->diff += dt; impp->tparity->p_time = dt;
+  }
+  return rc;
+}
+
+NRB200_EXPORT int32_t nrb200_crc_batch_dev(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out,
+                                           void *stream)
+{
+  if (ensure_init()) return -1;
+  if (stride < (bitlen + 7) / 8) return -4;
+  return launch_crc(poly_id, n_blk, d_in, stride, bitlen, d_out, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_crc_batch_host(int poly_id, uint32_t n_blk, const uint8_t *in, uint32_t stride, uint32_t bitlen, uint32_t *out)
+{
+  if (ensure_init()) return -1;
+  if (n_blk == 0) return 0;
+  const size_t in_bytes = (size_t)n_blk * stride, out_bytes = (size_t)n_blk * 4;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(in_bytes, out_bytes, 16)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, in, in_bytes);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = nrb200_crc_batch_dev(poly_id, n_blk, (const uint8_t *)w->d_in, stride, bitlen, (uint32_t *)w->d_out, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(out, w->h_out, out_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}

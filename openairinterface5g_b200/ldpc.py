@@ -1,0 +1,219 @@
+"""Host-side binding of libldpc_b200.so -- the B200-native drop-in for OAI's loadable LDPC codec.
+
+This mirrors the reference's `ldpc_interface_t` (openair1/PHY/CODING/nrLDPC_defs.h:68-87): `LDPCinit`, `LDPCshutdown`,
+`LDPCdecoder`, `LDPCencoder` with the same parameter structs, plus the batched extension declared in
+include/nrb200_ldpc.h.  Everything computes on the GPU; if the shared object or a CUDA device is missing the calls raise --
+there is no CPU fallback.  PyTorch is used only to own device memory / streams for the device-resident entry points.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libldpc_b200.so")
+
+_u8p = C.POINTER(C.c_uint8)
+_i8p = C.POINTER(C.c_int8)
+
+OUTMODE_BIT, OUTMODE_BITINT8, OUTMODE_LLRINT8 = 0, 1, 2
+CRC24_A, CRC24_B, CRC16, CRC8 = 0, 1, 2, 3          # coding_defs.h:33-36
+POLY_24A, POLY_24B, POLY_24C, POLY_16, POLY_12, POLY_11, POLY_8, POLY_6 = range(8)
+
+
+class TimeStats(C.Structure):          # include/nrb200_ldpc.h nrb200_time_stats_t
+    _fields_ = [("in_", C.c_longlong), ("diff", C.c_longlong), ("p_time", C.c_longlong), ("diff_square", C.c_double),
+                ("max", C.c_longlong), ("trials", C.c_int), ("meas_flag", C.c_int), ("meas_name", C.c_char_p),
+                ("meas_index", C.c_int), ("meas_enabled", C.c_int), ("tpoolmsg", C.c_void_p), ("tstatptr", C.c_void_p)]
+
+
+class LdpcTimeStats(C.Structure):
+    _fields_ = [(n, TimeStats) for n in ("llr2llrProcBuf", "llr2CnProcBuf", "cnProc", "cnProcPc", "bnProcPc", "bnProc",
+                                         "cn2bnProcBuf", "bn2cnProcBuf", "llrRes2llrOut", "llr2bit", "total")]
+
+
+class DecParams(C.Structure):          # t_nrLDPC_dec_params
+    _fields_ = [("BG", C.c_uint8), ("Z", C.c_uint16), ("R", C.c_uint8), ("F", C.c_uint16), ("Qm", C.c_uint8), ("rv", C.c_uint8),
+                ("numMaxIter", C.c_uint8), ("E", C.c_int), ("outMode", C.c_int), ("crc_type", C.c_int),
+                ("check_crc", C.c_void_p), ("setCombIn", C.c_uint8)]
+
+
+class DecodeAbort(C.Structure):        # decode_abort_t
+    _fields_ = [("mutex", C.c_uint8 * 40), ("failed", C.c_bool)]
+
+
+class EncParams(C.Structure):          # encoder_implemparams_t
+    _fields_ = [("n_segments", C.c_uint), ("macro_num", C.c_uint), ("gen_code", C.c_ubyte),
+                ("tinput", C.c_void_p), ("tprep", C.c_void_p), ("tparity", C.c_void_p), ("toutput", C.c_void_p),
+                ("Kr", C.c_int), ("Kb", C.c_uint32), ("Zc", C.c_uint32), ("harq", C.c_void_p), ("BG", C.c_uint8),
+                ("output", C.c_void_p), ("K", C.c_uint32), ("F", C.c_uint32), ("Qm", C.c_uint8), ("E", C.c_uint32),
+                ("G", C.c_uint), ("rv", C.c_uint8)]
+
+
+class BatchDesc(C.Structure):          # nrb200_ldpc_batch_desc_t
+    _fields_ = [("BG", C.c_uint8), ("Z", C.c_uint16), ("R", C.c_uint8), ("numMaxIter", C.c_uint8), ("outMode", C.c_uint8),
+                ("crc_type", C.c_uint8), ("use_crc", C.c_uint8), ("crc_len_bits", C.c_uint32), ("n_cb", C.c_uint32),
+                ("llr_stride", C.c_uint32), ("out_stride", C.c_uint32)]
+
+
+class Nrb200Error(RuntimeError):
+    pass
+
+
+def ncols_for_rate(BG, R):
+    """Columns the decoder LUT for rate selector R spans (nrLDPCdecoder_defs.h:53-57,80-84)."""
+    return {(1, 13): 68, (1, 23): 35, (1, 89): 27, (2, 15): 52, (2, 13): 32, (2, 23): 17}[(BG, R)]
+
+
+class LdpcLib:
+    """ldpc_interface_t equivalent bound to libldpc_b200.so."""
+
+    def __init__(self, path=_SO):
+        if not os.path.exists(path):
+            raise Nrb200Error(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)")
+        L = self.lib = C.CDLL(path)
+        L.LDPCinit.restype = C.c_int32
+        L.LDPCshutdown.restype = C.c_int32
+        L.LDPCdecoder.restype = C.c_int32
+        L.LDPCdecoder.argtypes = [C.POINTER(DecParams), C.c_uint8, C.c_uint8, C.c_uint8, _i8p, _i8p, C.c_void_p, C.c_void_p]
+        L.LDPCencoder.restype = C.c_int32
+        L.LDPCencoder.argtypes = [C.POINTER(_u8p), C.POINTER(_u8p), C.POINTER(EncParams)]
+        L.nrb200_ldpc_num_llr.argtypes = [C.c_int] * 3
+        L.nrb200_ldpc_decode_batch_dev.argtypes = [C.POINTER(BatchDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ldpc_decode_batch_host.argtypes = [C.POINTER(BatchDesc), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ldpc_encode_batch_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.nrb200_ldpc_encode_batch_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.nrb200_crc_batch_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.nrb200_crc_batch_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.nrb200_last_error.restype = C.c_char_p
+        L.nrb200_launch_count.restype = C.c_uint64
+        self._inited = False
+
+    # ---- lifecycle (load_LDPClib / free_LDPClib, nrLDPC_load.c:46-76)
+    def init(self):
+        if self.lib.LDPCinit() != 0:
+            raise Nrb200Error("LDPCinit failed: " + self.last_error())
+        self._inited = True
+        return 0
+
+    def shutdown(self):
+        self._inited = False
+        return self.lib.LDPCshutdown()
+
+    def last_error(self):
+        return (self.lib.nrb200_last_error() or b"").decode()
+
+    def launch_count(self):
+        return int(self.lib.nrb200_launch_count())
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise Nrb200Error(f"{what} failed (rc={rc}): {self.last_error()}")
+
+    # ---- the per-code-block ABI, exactly as OAI calls it
+    def LDPCdecoder(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, E=0, crc_type=0, check_crc=None, abort=None, profiler=None):
+        """Returns (iterations, out).  `check_crc`: None => parity-check stop; any truthy value => CRC stop (evaluated on device
+        with the reference's check_crc semantics).  `abort`: optional DecodeAbort shared between segments."""
+        n = ncols_for_rate(BG, R) * Z
+        llr = np.ascontiguousarray(llr, dtype=np.int8)
+        assert llr.size >= n
+        out = np.zeros(n if outMode != OUTMODE_BIT else (n + 7) // 8, dtype=np.int8)
+        p = DecParams()
+        p.BG, p.Z, p.R, p.numMaxIter, p.outMode, p.E, p.crc_type = BG, Z, R, numMaxIter, outMode, E, crc_type
+        p.check_crc = 1 if check_crc else None
+        it = self.lib.LDPCdecoder(C.byref(p), 0, 0, 0, llr.ctypes.data_as(_i8p), out.ctypes.data_as(_i8p),
+                                  C.cast(C.byref(profiler), C.c_void_p) if profiler is not None else None,
+                                  C.cast(C.byref(abort), C.c_void_p) if abort is not None else None)
+        if it < 0:
+            raise Nrb200Error("LDPCdecoder failed: " + self.last_error())
+        return it, (out.view(np.uint8) if outMode == OUTMODE_BIT else out)
+
+    def LDPCencoder(self, BG, Z, K, payloads):
+        """payloads: (n_seg, ceil(K/8)) uint8.  Encodes in groups of 8 (macro_num) like nr_dlsch_coding.c:389-395.
+        Returns (n_seg, 66Z|50Z) uint8, one bit per byte."""
+        payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+        nseg = payloads.shape[0]
+        nout = (66 if BG == 1 else 50) * Z
+        outs = np.zeros((nseg, nout), dtype=np.uint8)
+        inp = (_u8p * nseg)(*[C.cast(payloads[i].ctypes.data, _u8p) for i in range(nseg)])
+        oup = (_u8p * nseg)(*[C.cast(outs[i].ctypes.data, _u8p) for i in range(nseg)])
+        ip = EncParams()
+        ip.n_segments, ip.Kb, ip.Zc, ip.BG, ip.K = nseg, (22 if BG == 1 else 10), Z, BG, K
+        for m in range((nseg + 7) // 8):
+            ip.macro_num = m
+            self._check(self.lib.LDPCencoder(inp, oup, C.byref(ip)), "LDPCencoder")
+        return outs
+
+    # ---- batched extension, host buffers (end-to-end: H2D + kernel + D2H inside the call)
+    def _desc(self, BG, Z, R, numMaxIter, outMode, n_cb, llr_stride, out_stride, use_crc=0, crc_len_bits=0, crc_type=0):
+        d = BatchDesc()
+        d.BG, d.Z, d.R, d.numMaxIter, d.outMode = BG, Z, R, numMaxIter, outMode
+        d.use_crc, d.crc_len_bits, d.crc_type = use_crc, crc_len_bits, crc_type
+        d.n_cb, d.llr_stride, d.out_stride = n_cb, llr_stride, out_stride
+        return d
+
+    def decode_batch_host(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):
+        llr = np.ascontiguousarray(llr, dtype=np.int8)
+        n_cb, stride = llr.shape
+        n = ncols_for_rate(BG, R) * Z
+        ob = (n + 7) // 8 if outMode == OUTMODE_BIT else n
+        if out is None:
+            out = np.zeros((n_cb, ob), dtype=np.uint8)
+        if iters is None:
+            iters = np.zeros(n_cb, dtype=np.int32)
+        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
+        self._check(self.lib.nrb200_ldpc_decode_batch_host(C.byref(d), llr.ctypes.data, out.ctypes.data, iters.ctypes.data), "decode_batch_host")
+        return iters, out
+
+    def encode_batch_host(self, BG, Z, K, payloads):
+        payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+        n_cb, stride = payloads.shape
+        nout = (66 if BG == 1 else 50) * Z
+        out = np.zeros((n_cb, nout), dtype=np.uint8)
+        self._check(self.lib.nrb200_ldpc_encode_batch_host(BG, Z, K, n_cb, payloads.ctypes.data, stride, out.ctypes.data, nout), "encode_batch_host")
+        return out
+
+    def crc_batch_host(self, poly_id, data, bitlen):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        n, stride = data.shape
+        out = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.nrb200_crc_batch_host(poly_id, n, data.ctypes.data, stride, bitlen, out.ctypes.data), "crc_batch_host")
+        return out
+
+    # ---- batched extension, device-resident torch tensors (asynchronous on torch's current stream)
+    def decode_batch_torch(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):
+        import torch
+        assert llr.is_cuda and llr.dtype == torch.int8 and llr.is_contiguous() and llr.dim() == 2
+        n_cb, stride = llr.shape
+        n = ncols_for_rate(BG, R) * Z
+        ob = (n + 7) // 8 if outMode == OUTMODE_BIT else n
+        if out is None:
+            out = torch.empty((n_cb, ob), dtype=torch.uint8, device=llr.device)
+        if iters is None:
+            iters = torch.empty(n_cb, dtype=torch.int32, device=llr.device)
+        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
+        st = torch.cuda.current_stream(llr.device).cuda_stream
+        self._check(self.lib.nrb200_ldpc_decode_batch_dev(C.byref(d), llr.data_ptr(), out.data_ptr(), iters.data_ptr(), st), "decode_batch_dev")
+        return iters, out
+
+    def encode_batch_torch(self, BG, Z, K, payloads, out=None):
+        import torch
+        assert payloads.is_cuda and payloads.dtype == torch.uint8 and payloads.is_contiguous()
+        n_cb, stride = payloads.shape
+        nout = (66 if BG == 1 else 50) * Z
+        if out is None:
+            out = torch.empty((n_cb, nout), dtype=torch.uint8, device=payloads.device)
+        st = torch.cuda.current_stream(payloads.device).cuda_stream
+        self._check(self.lib.nrb200_ldpc_encode_batch_dev(BG, Z, K, n_cb, payloads.data_ptr(), stride, out.data_ptr(), out.shape[1], st), "encode_batch_dev")
+        return out
+
+
+_lib = None
+
+
+def load_LDPClib():
+    """Process-wide instance, initialised (mirrors load_LDPClib + LDPCinit, nrLDPC_load.c:46-71)."""
+    global _lib
+    if _lib is None:
+        _lib = LdpcLib()
+        _lib.init()
+    return _lib
