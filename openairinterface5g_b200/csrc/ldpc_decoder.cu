@@ -2,6 +2,9 @@
 #include "nrb200_ctx.h"
 #include "ldpc_common.cuh"
 #include "ldpc_decoder_generic.cuh"
+#include "ldpc_decoder_packed.cuh"
+#include <map>
+#include <mutex>
 #include <cstdlib>
 
 namespace nrb200 {
@@ -13,11 +16,55 @@ static size_t generic_smem_bytes(const GraphDev &g)
   return a16(sizeof(GraphDev)) + a16(numLLR) + a16((size_t)g.nreal * g.Z) + a16(numLLR) + a16((size_t)g.nrows * g.Z);
 }
 
+// device copies of the packed tables, keyed like Ctx::graphs
+static std::mutex g_pk_mu;
+static std::map<uint32_t, std::pair<PackedGraph *, PackedGraph>> g_pk;
+
+static const PackedGraph *packed_graph(const GraphDev &h_g, const PackedGraph **host)
+{
+  const uint32_t key = ((uint32_t)h_g.BG << 24) | ((uint32_t)h_g.Z << 8) | (uint32_t)h_g.R;
+  std::lock_guard<std::mutex> lk(g_pk_mu);
+  auto it = g_pk.find(key);
+  if (it == g_pk.end()) {
+    PackedGraph pg;
+    PackedGraph *d = nullptr;
+    if (build_packed_graph(h_g, &pg) && (size_t)pg.total_words * 4 + sizeof(PackedGraph) + 64 <= (size_t)ctx().max_smem_optin) {
+      if (cudaMalloc(&d, sizeof(PackedGraph)) != cudaSuccess) d = nullptr;
+      else cudaMemcpy(d, &pg, sizeof(PackedGraph), cudaMemcpyHostToDevice);
+    }
+    it = g_pk.emplace(key, std::make_pair(d, pg)).first;
+  }
+  *host = &it->second.second;
+  return it->second.first;
+}
+
+void packed_graph_cache_clear()
+{
+  std::lock_guard<std::mutex> lk(g_pk_mu);
+  for (auto &kv : g_pk) if (kv.second.first) cudaFree(kv.second.first);
+  g_pk.clear();
+}
+
 // Returns 0 or a negative error.  Asynchronous on `stream`.
 int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream)
 {
   Ctx &c = ctx();
   if (a.n_cb == 0) return 0;
+  static const bool force_generic = getenv("NRB200_FORCE_GENERIC") != nullptr;
+  const PackedGraph *h_pg = nullptr;
+  const PackedGraph *d_pg = (h_g.Z % 4 == 0 && !force_generic) ? packed_graph(h_g, &h_pg) : nullptr;
+  if (d_pg) {
+    const size_t smem = (size_t)h_pg->total_words * 4;
+    static std::atomic<size_t> configured_pk{0};
+    if (smem > configured_pk.load()) {
+      NRB200_CUDA_OK(cudaFuncSetAttribute(ldpc_decode_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
+      configured_pk.store(smem);
+    }
+    ldpc_decode_packed_kernel<<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
+    c.launches++;
+    NRB200_CUDA_OK(cudaGetLastError(), "packed decode launch");
+    return 0;
+  }
   {
     const size_t smem = generic_smem_bytes(h_g);
     if ((int)smem > c.max_smem_optin) return -3;

@@ -117,6 +117,7 @@ ldpc_decode_generic_kernel(const GraphDev *__restrict__ gdev, DecodeArgs a)
         int bad = 0;
         for (int i = threadIdx.x; i < nrows * Z; i += blockDim.x) {
           const int r = i / Z, t = i - r * Z;
+          if (t >= g.row_pc_from[r]) continue;   // lifts the reference's cnProcPc never tests (nrb200_graph.cc)
           int par = g.row_p_col[r] >= 0 ? hdp[i] : 0;
           for (int m = g.row_start[r]; m < g.row_start[r + 1]; m++) {
             int v = t + g.edge_shift[m]; if (v >= Z) v -= Z;

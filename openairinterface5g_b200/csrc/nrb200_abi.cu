@@ -2,6 +2,7 @@
 #include "../../include/nrb200_ldpc.h"
 #include "nrb200_ctx.h"
 #include "ldpc_common.cuh"
+#include <algorithm>
 #include <cstring>
 
 #define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
@@ -75,45 +76,68 @@ NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_dev(const nrb200_ldpc_batch_desc_
   return launch_decode(dg, *hg, a, (cudaStream_t)stream);
 }
 
+static bool is_pinned_host(const void *p)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Host-buffer decode.  Pageable caller memory (OAI's stack arrays) is staged through the workspace's pinned buffers;
+// page-locked caller memory is copied from / to directly.  Large batches are cut into chunks that alternate between two
+// streams so the H2D copy of chunk i+1 overlaps the kernel of chunk i.
 static int decode_host_impl(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, const uint8_t *abort_flags)
 {
   if (ensure_init()) return -1;
   const GraphDev *hg = nullptr;
   const GraphDev *dg = ctx().graph(desc->BG, desc->Z, desc->R, &hg);
   if (!dg) return -4;
-  DecodeArgs a;
-  if (int rc = fill_args(desc, *hg, &a)) return rc;
+  DecodeArgs a0;
+  if (int rc = fill_args(desc, *hg, &a0)) return rc;
   const size_t n = desc->n_cb;
   if (n == 0) return 0;
   const size_t in_bytes = n * desc->llr_stride, out_bytes = n * desc->out_stride, aux_bytes = n * (sizeof(int32_t) + 1);
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(in_bytes, out_bytes, aux_bytes)) { if (w) ctx().release(w); return -5; }
+  Workspace *w2 = n >= 64 ? ctx().acquire() : nullptr;
+  if (!w || !w->reserve(in_bytes, out_bytes, aux_bytes)) { if (w) ctx().release(w); if (w2) ctx().release(w2); return -5; }
+  const bool pin_in = is_pinned_host(llr), pin_out = is_pinned_host(out);
   int rc = 0;
   do {
-    // caller memory is pageable in general (OAI stack arrays): stage through the pinned buffer
-    std::memcpy(w->h_in, llr, in_bytes);
-    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
     int32_t *d_it = (int32_t *)w->d_aux;
     uint8_t *d_ab = (uint8_t *)w->d_aux + n * sizeof(int32_t);
-    if (abort_flags) {
-      std::memcpy((uint8_t *)w->h_aux + n * sizeof(int32_t), abort_flags, n);
-      cudaMemcpyAsync(d_ab, (uint8_t *)w->h_aux + n * sizeof(int32_t), n, cudaMemcpyHostToDevice, w->stream);
-      a.abort_flags = d_ab;
+    uint8_t *h_ab = (uint8_t *)w->h_aux + n * sizeof(int32_t);
+    if (abort_flags) std::memcpy(h_ab, abort_flags, n);
+    const uint8_t *h_src = (const uint8_t *)llr;
+    if (!pin_in) { std::memcpy(w->h_in, llr, in_bytes); h_src = (const uint8_t *)w->h_in; }
+    uint8_t *h_dst = pin_out ? out : (uint8_t *)w->h_out;
+    if (desc->use_crc && !pin_out) std::memcpy(w->h_out, out, out_bytes);   // the reference leaves p_out untouched until a CRC check runs
+    const size_t nchunk = w2 ? 4 : 1;
+    const size_t per = (n + nchunk - 1) / nchunk;
+    cudaStream_t st[2] = {w->stream, w2 ? w2->stream : w->stream};
+    for (size_t ci = 0, c0 = 0; c0 < n; ci++, c0 += per) {
+      const size_t cn = std::min(per, n - c0);
+      cudaStream_t s = st[ci & 1];
+      const size_t io = c0 * desc->llr_stride, oo = c0 * desc->out_stride;
+      if (cudaMemcpyAsync((uint8_t *)w->d_in + io, h_src + io, cn * desc->llr_stride, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = -2; break; }
+      if (abort_flags) cudaMemcpyAsync(d_ab + c0, h_ab + c0, cn, cudaMemcpyHostToDevice, s);
+      if (desc->use_crc) cudaMemcpyAsync((uint8_t *)w->d_out + oo, h_dst + oo, cn * desc->out_stride, cudaMemcpyHostToDevice, s);
+      DecodeArgs a = a0;
+      a.n_cb = (uint32_t)cn;
+      a.llr = (const int8_t *)w->d_in + io; a.out = (uint8_t *)w->d_out + oo; a.iters = d_it + c0;
+      a.abort_flags = abort_flags ? d_ab + c0 : nullptr;
+      if ((rc = launch_decode(dg, *hg, a, s)) != 0) break;
+      if (cudaMemcpyAsync(h_dst + oo, (uint8_t *)w->d_out + oo, cn * desc->out_stride, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
+      if (cudaMemcpyAsync((int32_t *)w->h_aux + c0, d_it + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
     }
-    if (desc->use_crc) {   // the reference leaves p_out untouched until a CRC check runs: round-trip the caller's bytes
-      std::memcpy(w->h_out, out, out_bytes);
-      cudaMemcpyAsync(w->d_out, w->h_out, out_bytes, cudaMemcpyHostToDevice, w->stream);
-    }
-    a.llr = (const int8_t *)w->d_in; a.out = (uint8_t *)w->d_out; a.iters = d_it;
-    if ((rc = launch_decode(dg, *hg, a, w->stream)) != 0) break;
-    if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
-    if (cudaMemcpyAsync(w->h_aux, d_it, n * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
-    cudaError_t e = cudaStreamSynchronize(w->stream);
-    if (e != cudaSuccess) { ctx().set_error("decode sync", e); rc = -2; break; }
-    std::memcpy(out, w->h_out, out_bytes);
+    cudaError_t e = cudaStreamSynchronize(st[0]);
+    cudaError_t e2 = w2 ? cudaStreamSynchronize(st[1]) : cudaSuccess;
+    if (rc != 0) break;
+    if (e != cudaSuccess || e2 != cudaSuccess) { ctx().set_error("decode sync", e != cudaSuccess ? e : e2); rc = -2; break; }
+    if (!pin_out) std::memcpy(out, w->h_out, out_bytes);
     std::memcpy(iters, w->h_aux, n * sizeof(int32_t));
   } while (0);
   ctx().release(w);
+  if (w2) ctx().release(w2);
   return rc;
 }
 

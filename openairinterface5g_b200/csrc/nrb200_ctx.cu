@@ -8,6 +8,8 @@
 
 namespace nrb200 {
 
+void packed_graph_cache_clear();
+
 Ctx &ctx()
 {
   static Ctx c;
@@ -83,6 +85,7 @@ void Ctx::shutdown()
   std::lock_guard<std::mutex> lk(mu);
   if (!inited) return;
   cudaDeviceSynchronize();
+  packed_graph_cache_clear();
   for (auto &kv : graphs) cudaFree(kv.second);
   for (auto &kv : enc_graphs) cudaFree(kv.second);
   graphs.clear(); graphs_host.clear(); enc_graphs.clear(); enc_graphs_host.clear();

@@ -68,6 +68,24 @@ bool build_graph(int BG, int Z, int R, GraphDev *g)
   }
   g->row_start[g->nrows] = (int16_t)m;
   g->nreal = m;
+  // Parity-check coverage of the reference (nrLDPC_cnProc.h:887-1960): each check-node degree group is scanned as
+  // ceil(n_g*Z/32) 32-byte vectors, the last of which is only tested `if (Mrem)` (:964-965) -- when n_g*Z is a multiple
+  // of 32 (always for Z = 384) the final 32 check nodes of the group never take part in the early-stop decision.
+  // Rows sit in ascending order inside a group (lut_startAddrCnGroups layout).  Replicated for bit-exact iteration counts.
+  {
+    int rowdeg[kMaxRows] = {0};
+    for (int ee = 0; ee < ne; ee++) rowdeg[b.row[ee]]++;
+    for (int r = 0; r < g->nrows; r++) g->row_pc_from[r] = (int16_t)Z;
+    for (int d = 1; d <= kMaxRowDeg; d++) {
+      int members[kMaxRows], n = 0;
+      for (int r = 0; r < g->nrows; r++) if (rowdeg[r] == d) members[n++] = r;
+      if (n == 0 || (n * Z) % 32 != 0) continue;
+      for (int idx = n * Z - 32; idx < n * Z; idx++) {
+        const int r = members[idx / Z], t = idx % Z;
+        if (t < g->row_pc_from[r]) g->row_pc_from[r] = (int16_t)t;
+      }
+    }
+  }
   // column lists
   int k = 0;
   for (int c = 0; c < ncols; c++) {

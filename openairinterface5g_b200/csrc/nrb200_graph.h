@@ -29,6 +29,7 @@ struct GraphDev {
   int16_t row_p_col[kMaxRows];       // degree-1 column attached to row r, or -1
   int16_t row_p_shift[kMaxRows];     // its shift (mod Z)
   int16_t row_deg3_idx[kMaxRows];    // index of the row inside the degree-3 group (quirk emulation), else -1
+  int16_t row_pc_from[kMaxRows];     // first lift of row r the reference's parity check does NOT test (Z = all tested), see nrb200_graph.cc
   int16_t edge_col[kMaxEdges];       // per slot
   int16_t edge_shift[kMaxEdges];     // per slot, already reduced mod Z
   int16_t col_start[kMaxCols + 1];   // range into col_edges of column c

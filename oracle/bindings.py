@@ -230,3 +230,63 @@ class Reference:
             o = (-outs[i].ctypes.data) % 32
             res[i] = outs[i, o:o + nout]
         return res
+
+    # ---- coding helpers of the compiled reference (libref_coding.so)
+    def check_crc(self, data, n, crc_type):
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        return int(self.cod.check_crc(_ptr(d, _u8p), n, crc_type))
+
+    def rate_matching_tx(self, Tbslbrm, BG, Z, w, C_, F, Foffset, rv, E):
+        w = np.ascontiguousarray(w, dtype=np.uint8)
+        e = np.zeros(E + 64, dtype=np.uint8)
+        f = self.cod.nr_rate_matching_ldpc
+        f.argtypes = [C.c_uint32, C.c_uint8, C.c_uint16, _u8p, _u8p, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint8, C.c_uint32]
+        rc = f(Tbslbrm, BG, Z, _ptr(w, _u8p), _ptr(e, _u8p), C_, F, Foffset, rv, E)
+        return rc, e[:E]
+
+    def rate_matching_rx(self, Tbslbrm, BG, Z, w, soft, C_, rv, clear, E, F, Foffset):
+        soft = np.ascontiguousarray(soft, dtype=np.int16)
+        assert w.dtype == np.int16 and w.flags.c_contiguous
+        f = self.cod.nr_rate_matching_ldpc_rx
+        f.argtypes = [C.c_uint32, C.c_uint8, C.c_uint16, _i16p, _i16p, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint32]
+        return f(Tbslbrm, BG, Z, _ptr(w, _i16p), _ptr(soft, _i16p), C_, rv, clear, E, F, Foffset)
+
+    def interleave(self, E, Qm, e):
+        e = np.ascontiguousarray(e, dtype=np.uint8)
+        f = np.zeros(E + 64, dtype=np.uint8)
+        fn = self.cod.nr_interleaving_ldpc
+        fn.argtypes = [C.c_uint32, C.c_uint8, _u8p, _u8p]
+        fn.restype = None
+        fn(E, Qm, _ptr(e, _u8p), _ptr(f, _u8p))
+        return f[:E]
+
+    def deinterleave(self, E, Qm, f):
+        f = np.ascontiguousarray(f, dtype=np.int16)
+        e = np.zeros(E + 64, dtype=np.int16)
+        fn = self.cod.nr_deinterleaving_ldpc
+        fn.argtypes = [C.c_uint32, C.c_uint8, _i16p, _i16p]
+        fn.restype = None
+        fn(E, Qm, _ptr(e, _i16p), _ptr(f, _i16p))
+        return e[:E]
+
+    def get_R(self, rv, E, BG, Z, llrLen, rnd):
+        ll = C.c_int(llrLen)
+        fn = self.cod.nr_get_R_ldpc_decoder
+        fn.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int), C.c_int]
+        r = fn(rv, E, BG, Z, C.byref(ll), rnd)
+        return r, ll.value
+
+    def segmentation(self, data, B, BG):
+        Cc, K, Zo, F = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+        fn = self.cod.nr_segmentation
+        fn.argtypes = [_u8p, C.POINTER(_u8p), C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_uint8]
+        fn.restype = C.c_int32
+        Kb = fn(None, None, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
+        if Kb < 0:
+            return Kb, 0, 0, 0, 0, None
+        segs = np.zeros((Cc.value, K.value // 8 + 8), dtype=np.uint8)
+        if data is not None:
+            d = np.ascontiguousarray(data, dtype=np.uint8)
+            ptrs = (_u8p * Cc.value)(*[C.cast(segs[r].ctypes.data, _u8p) for r in range(Cc.value)])
+            fn(_ptr(d, _u8p), ptrs, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
+        return Kb, Cc.value, K.value, Zo.value, F.value, segs[:, :K.value // 8]

@@ -1,0 +1,66 @@
+/*
+ * TEST / BENCH INFRASTRUCTURE ONLY -- multi-threaded driver that times a CPU LDPC decoder on the host cores the way
+ * ldpctest.c:329-340 calls it (one blocking LDPCdecoder call per code block, decode_abort_t reset before each call,
+ * re-entrant decoder, one pthread per core).  `fn` is the reference's LDPCdecoder (oracle/_ref/libref_ldpc_dec.so) or
+ * NULL for the scalar oracle port.  Used only by bench.py's cpu_baseline / --impl reference leg.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "nrb200_oracle.h"
+#include "../include/nrb200_ldpc.h"
+
+typedef int32_t (*dec_fn_t)(nrb200_ldpc_dec_params_t *, uint8_t, uint8_t, uint8_t, int8_t *, int8_t *, void *, nrb200_decode_abort_t *);
+
+typedef struct {
+  dec_fn_t fn; const int8_t *llr; int n, stride, BG, Z, R, maxIter, tid, nthreads; double seconds; long count; long iters;
+} job_t;
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+static void *worker(void *arg)
+{
+  job_t *j = (job_t *)arg;
+  nrb200_ldpc_dec_params_t p;
+  memset(&p, 0, sizeof(p));
+  p.BG = (uint8_t)j->BG; p.Z = (uint16_t)j->Z; p.R = (uint8_t)j->R; p.numMaxIter = (uint8_t)j->maxIter; p.outMode = NRB200_OUTMODE_BIT;
+  p.E = (j->BG == 1 ? 22 : 10) * j->Z;
+  nrb200_decode_abort_t ab;
+  pthread_mutex_init(&ab.mutex_failure, NULL);
+  int8_t *in = aligned_alloc(64, 27008), *out = aligned_alloc(64, 27008);
+  const double t_end = now_s() + j->seconds;
+  int i = j->tid;
+  while (now_s() < t_end) {
+    memcpy(in, j->llr + (size_t)(i % j->n) * j->stride, 27000);   /* callers hand the decoder their own aligned buffer */
+    ab.failed = false;                                            /* set_abort(&dec_abort, false), ldpctest.c:330 */
+    int it = j->fn ? j->fn(&p, 0, 0, 0, in, out, NULL, &ab)
+                   : orc_ldpc_decode(j->BG, j->Z, j->R, j->maxIter, 0, in, out, 0, 0, 0, 0);
+    j->iters += it;
+    j->count++;
+    i += j->nthreads;
+  }
+  free(in); free(out);
+  return NULL;
+}
+
+/* returns total decodes; *elapsed = wall seconds; *mean_iters = mean returned iteration count */
+long orc_bench_ldpc_decoder(void *fn, const int8_t *llr, int n, int stride, int BG, int Z, int R, int maxIter, int threads, double seconds,
+                            double *elapsed, double *mean_iters)
+{
+  pthread_t *th = calloc((size_t)threads, sizeof(*th));
+  job_t *jobs = calloc((size_t)threads, sizeof(*jobs));
+  const double t0 = now_s();
+  for (int t = 0; t < threads; t++) {
+    jobs[t] = (job_t){(dec_fn_t)fn, llr, n, stride, BG, Z, R, maxIter, t, threads, seconds, 0, 0};
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  long total = 0, its = 0;
+  for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); total += jobs[t].count; its += jobs[t].iters; }
+  *elapsed = now_s() - t0;
+  *mean_iters = total ? (double)its / (double)total : 0.0;
+  free(th); free(jobs);
+  return total;
+}

@@ -111,6 +111,17 @@ int orc_ldpc_decode(int BG, int Z, int R, int numMaxIter, int outMode, const int
     for (int t = 0; t < Z; t++) Q[(size_t)e * Z + t] = llr[c * Z + (t + s) % Z];
   }
 
+  /* rows grouped by degree, ascending row order inside a group (the reference's lut_startAddrCnGroups layout) */
+  int pc_from[46], rowdeg[46] = {0};
+  for (int e = 0; e < ne; e++) rowdeg[g.row[e]]++;
+  for (int r = 0; r < nrows; r++) pc_from[r] = Z;
+  for (int d = 1; d <= 19; d++) {
+    int members[46], n = 0;
+    for (int r = 0; r < nrows; r++) if (rowdeg[r] == d) members[n++] = r;
+    if (n == 0 || (n * Z) % 32 != 0) continue;
+    for (int idx = n * Z - 32; idx < n * Z; idx++) { const int r = members[idx / Z], t = idx % Z; if (t < pc_from[r]) pc_from[r] = t; }
+  }
+
   int numIter = 0, pcRes = 1, crc_ok_break = 0;
   for (;;) {
     if (numIter >= 1) {                   /* while ((numIter <= numMaxIter) && (pcRes != 0)) (nrLDPC_decoder.c:552) */
@@ -167,13 +178,16 @@ int orc_ldpc_decode(int BG, int Z, int R, int numMaxIter, int outMode, const int
     if (numIter == 1) continue;          /* no parity check after the first iteration (:541-547) */
 
     if (!use_crc) {
-      /* cnProcPc (nrLDPC_cnProc.h:887-1960): XOR over a check's edges of sign(adds_epi8(cnProcBuf, cnProcBufRes)) */
+      /* cnProcPc (nrLDPC_cnProc.h:887-1960): XOR over a check's edges of sign(adds_epi8(cnProcBuf, cnProcBufRes)).
+         The reference walks each check-node degree group as ceil(n_g*Z/32) 32-byte vectors, checks the first M32-1 of them and
+         ORs in the last one only `if (Mrem)` (:964-965, same in every group) -- so when n_g*Z is a multiple of 32 (always for
+         Z = 384) the final 32 check nodes of the group are never tested.  pc_from[r] = first unchecked lift of row r. */
       pcRes = 0;
       int a0 = 0;
       while (a0 < ne && !pcRes) {
         int a1 = a0;
         while (a1 < ne && g.row[a1] == g.row[a0]) a1++;
-        for (int t = 0; t < Z && !pcRes; t++) {
+        for (int t = 0; t < pc_from[g.row[a0]] && !pcRes; t++) {
           int par = 0;
           for (int k = a0; k < a1; k++) par ^= (sat8(Q[(size_t)k * Z + t] + Rm[(size_t)k * Z + t]) < 0);
           pcRes |= par;

@@ -1,0 +1,76 @@
+"""The CPU oracle against the committed golden vectors (tests/golden/*.npz, produced from the compiled reference by
+tools/gen_golden.py).  Runs anywhere -- this is what pins the oracle on machines without /root/reference."""
+import os
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_decoder_golden(oracle):
+    d = _load("ldpc_decoder.npz")
+    for ci in range(int(d["ncases"][0])):
+        BG, Z, R, n, mi, om, uc, K = [int(x) for x in d[f"c{ci}_par"]]
+        llr = d[f"c{ci}_llr"]
+        for i in range(n):
+            it, out = oracle.decode(BG, Z, R, mi, llr[i], om)
+            # intended arithmetic == the AVX512 build everywhere
+            assert it == d[f"c{ci}_iters_avx512"][i] and np.array_equal(np.asarray(out).view(np.uint8), d[f"c{ci}_out_avx512"][i].view(np.uint8)), (ci, i)
+            oracle.lib.orc_set_quirks(1)   # + the AVX2 generator defect (only changes BG2 R15)
+            it2, out2 = oracle.decode(BG, Z, R, mi, llr[i], om)
+            oracle.lib.orc_set_quirks(0)
+            assert it2 == d[f"c{ci}_iters_avx2"][i] and np.array_equal(np.asarray(out2).view(np.uint8), d[f"c{ci}_out_avx2"][i].view(np.uint8)), (ci, i)
+            if (BG, R) != (2, 15):
+                assert it == it2
+
+
+def test_decoder_crc_mode_golden(oracle):
+    d = _load("ldpc_decoder.npz")
+    BG, Z, R, n, K = [int(x) for x in d["crc_par"]]
+    for mi in (2, 3, 8):
+        for i in range(n):
+            it, out = oracle.decode(BG, Z, R, mi, d["crc_llr"][i], 0, 1, K, 1)
+            assert it == d[f"crc{mi}_iters"][i] and np.array_equal(out, d[f"crc{mi}_out"][i]), (mi, i)
+
+
+def test_encoder_golden(oracle):
+    d = _load("ldpc_encoder.npz")
+    for ci in range(int(d["ncases"][0])):
+        BG, Z, K = [int(x) for x in d[f"e{ci}_par"]]
+        P = d[f"e{ci}_in"]
+        nout = (66 if BG == 1 else 50) * Z
+        orig = np.unpackbits(d[f"e{ci}_orig"], axis=1)[:, :nout]
+        optim = np.unpackbits(d[f"e{ci}_optim"], axis=1)[:, :nout]
+        for i in range(P.shape[0]):
+            assert np.array_equal(oracle.encode(BG, Z, K, P[i]), orig[i]), (BG, Z, i)
+        assert np.array_equal(orig, optim) == ((BG, Z) != (2, 64))   # the reference's BG2 Z=64 default-encoder defect
+
+
+def test_coding_golden(oracle):
+    d = _load("coding.npz")
+    for i, n in enumerate(d["crc_lens"]):
+        for p in range(8):
+            assert oracle.crc(p, d["crc_data"][i], int(n)) == int(d["crc_vals"][i][p])
+    for ci, (BG, Z, F, E, rv, Tb, Cs, Qm) in enumerate(d["rm_cases"].tolist()):
+        K = (22 if BG == 1 else 10) * Z
+        Fo = K - F - 2 * Z
+        N = (66 if BG == 1 else 50) * Z
+        rc, e = oracle.rate_matching_tx(Tb, BG, Z, d[f"rm{ci}_w"], Cs, F, Fo, rv, E)
+        assert rc == 0 and np.array_equal(e, d[f"rm{ci}_e"])
+        assert np.array_equal(oracle.interleave(E, Qm, e), d[f"rm{ci}_f"])
+        dei = oracle.deinterleave(E, Qm, d[f"rm{ci}_soft"])
+        assert np.array_equal(dei, d[f"rm{ci}_dei"])
+        w = np.zeros(N + 16, dtype=np.int16)
+        oracle.rate_matching_rx(Tb, BG, Z, w, dei, Cs, rv, 1, E, F, Fo)
+        assert np.array_equal(w[:N], d[f"rm{ci}_w1"])
+        oracle.rate_matching_rx(Tb, BG, Z, w, dei, Cs, rv, 0, E, F, Fo)
+        assert np.array_equal(w[:N], d[f"rm{ci}_w2"])
+        assert list(oracle.get_R(rv, E, BG, Z, 0, 0)) == d[f"rm{ci}_getR"].tolist()
+    for ci, (BG, B) in enumerate(d["seg_cases"].tolist()):
+        Kb, Cc, K, Zc, F, s = oracle.segmentation(d[f"seg{ci}_in"], B, BG)
+        assert [Kb, Cc, K, Zc, F] == d[f"seg{ci}_par"].tolist()
+        assert np.array_equal(s, d[f"seg{ci}_out"])

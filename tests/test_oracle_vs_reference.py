@@ -1,0 +1,164 @@
+"""Pins the CPU oracle (oracle/nrb200_oracle.c) bit-exactly against the UNMODIFIED reference compiled by oracle/build_ref.sh.
+Runs wherever oracle/_ref exists (this container; the built .so files also travel to the GPU box)."""
+import numpy as np
+import pytest
+from common import ALL_Z, RATES, NCOLS, make_case, payloads
+
+
+def test_lifting_sizes(oracle):
+    assert [z for z in range(0, 400) if oracle.ils_of_z(z) >= 0] == ALL_Z
+
+
+@pytest.mark.parametrize("BG", [1, 2])
+def test_encoder_all_z(oracle, reference, BG):
+    """ldpctest.c:286-292 cross-check, for every lifting size whose K is a whole number of bytes."""
+    for Z in ALL_Z:
+        K, P = payloads(BG, Z, 3, Z)
+        if K % 8:
+            continue
+        orig = reference.encode(BG, Z, K, P, orig=True)
+        optim = reference.encode(BG, Z, K, P)
+        mine = np.stack([oracle.encode(BG, Z, K, P[i]) for i in range(3)])
+        assert np.array_equal(mine, orig), (BG, Z)
+        if (BG, Z) == (2, 64):
+            # reference defect: `case 64: break;` in encode_parity_check_part_optim (ldpc_encode_parity_check.c BG2 switch)
+            # while LDPCencoder routes BG2 Zc>=64 there => the default encoder emits all-zero parity for BG2 Z=64.
+            assert not np.array_equal(optim, orig) and not optim[:, 8 * Z:].any()
+        else:
+            assert np.array_equal(optim, orig), (BG, Z)
+
+
+@pytest.mark.parametrize("BG,R,ebn0", [(1, 13, 1.0), (1, 13, 2.4), (1, 13, 3.0), (1, 23, 4.0), (1, 89, 7.0), (2, 13, 2.5), (2, 23, 5.0)])
+def test_decoder_z384(oracle, reference, BG, R, ebn0):
+    K, P, llr = make_case(oracle, BG, 384, R, 3, ebn0, seed=R)
+    for i in range(3):
+        it_r, out_r = reference.decode(BG, 384, R, 8, llr[i])
+        it_o, out_o = oracle.decode(BG, 384, R, 8, llr[i])
+        assert it_r == it_o and np.array_equal(out_r, out_o)
+
+
+def test_decoder_all_z_all_rates(oracle, reference):
+    for BG in (1, 2):
+        for R in RATES[BG]:
+            if (BG, R) == (2, 15):
+                continue   # AVX2 build has a generator defect there, see test_bg2_r15_avx2_defect
+            for Z in ALL_Z[::3] + [384]:
+                K, P, llr = make_case(oracle, BG, Z, R, 1, 3.0 if R in (13, 15) else 6.0, seed=Z + R)
+                it_r, out_r = reference.decode(BG, Z, R, 8, llr[0])
+                it_o, out_o = oracle.decode(BG, Z, R, 8, llr[0])
+                assert it_r == it_o and np.array_equal(out_r, out_o), (BG, Z, R)
+
+
+def test_bg2_r15_avx2_defect(oracle, reference):
+    """cnProc_gen_BG2_avx2.c emits `i+=2` for the degree-3 group => the AVX2 build never updates odd 32-byte vectors of those
+    check nodes.  The oracle reproduces the AVX2 build bit-exactly with quirk bit 0 and the intended arithmetic without."""
+    for Z, e in ((384, 0.5), (64, 3.0), (7, 3.0)):
+        K, P, llr = make_case(oracle, 2, Z, 15, 2, e, seed=Z)
+        for i in range(2):
+            it_r, out_r = reference.decode(2, Z, 15, 8, llr[i])
+            oracle.lib.orc_set_quirks(1)
+            it_q, out_q = oracle.decode(2, Z, 15, 8, llr[i])
+            oracle.lib.orc_set_quirks(0)
+            assert it_r == it_q and np.array_equal(out_r, out_q)
+
+
+def test_bg2_r15_avx512_is_the_intended_arithmetic(oracle, reference512):
+    for Z, e in ((384, 0.5), (384, 3.0), (64, 3.0), (7, 3.0)):
+        K, P, llr = make_case(oracle, 2, Z, 15, 2, e, seed=Z)
+        for i in range(2):
+            it_r, out_r = reference512.decode(2, Z, 15, 8, llr[i])
+            it_o, out_o = oracle.decode(2, Z, 15, 8, llr[i])
+            assert it_r == it_o and np.array_equal(out_r, out_o)
+
+
+@pytest.mark.parametrize("out_mode", [1, 2])
+def test_output_modes(oracle, reference, out_mode):
+    """LLRINT8 really yields hard bits in the reference (llr2bit runs in place over p_out, nrLDPC_decoder.c:866-877)."""
+    K, P, llr = make_case(oracle, 1, 96, 13, 2, 3.0, seed=3)
+    for i in range(2):
+        it_r, out_r = reference.decode(1, 96, 13, 8, llr[i], out_mode)
+        it_o, out_o = oracle.decode(1, 96, 13, 8, llr[i], out_mode)
+        assert it_r == it_o and np.array_equal(out_r, out_o)
+        assert set(np.unique(out_r)) <= {0, 1}
+
+
+@pytest.mark.parametrize("max_iter", [0, 1, 2, 3, 5, 20])
+def test_iteration_caps_and_crc_mode(oracle, reference, max_iter):
+    BG, Z, R = 1, 128, 13
+    K = 22 * Z
+    rng = np.random.default_rng(max_iter)
+    P = rng.integers(0, 256, size=(4, K // 8), dtype=np.uint8)
+    for i in range(4):   # attach a CRC24B so that check_crc can succeed
+        crc = oracle.crc(1, P[i], K - 24) >> 8
+        P[i, -3:] = [(crc >> 16) & 0xFF, (crc >> 8) & 0xFF, crc & 0xFF]
+    from openairinterface5g_b200.synth import awgn_llr
+    cw = np.stack([oracle.encode(BG, Z, K, P[i]) for i in range(4)])
+    for ebn0 in (1.5, 3.0):
+        llr = awgn_llr(cw, Z, 68, ebn0, 1 / 3, max_iter)
+        for i in range(4):
+            for use_crc in (0, 1):
+                it_r, out_r = reference.decode(BG, Z, R, max_iter, llr[i], 0, use_crc, K, 1)
+                it_o, out_o = oracle.decode(BG, Z, R, max_iter, llr[i], 0, use_crc, K, 1)
+                assert it_r == it_o, (max_iter, ebn0, i, use_crc)
+                assert np.array_equal(out_r, out_o), (max_iter, ebn0, i, use_crc)
+
+
+def test_abort_flag(oracle, reference):
+    K, P, llr = make_case(oracle, 1, 64, 13, 1, 3.0, seed=1)
+    it_r, out_r = reference.decode(1, 64, 13, 8, llr[0], abort_in=1)
+    it_o, out_o = oracle.decode(1, 64, 13, 8, llr[0], abort_in=1)
+    assert it_r == it_o == 10 and np.array_equal(out_r, out_o)
+
+
+def test_crc_all_polys(oracle, reference):
+    rng = np.random.default_rng(0)
+    for n in (8, 24, 32, 100, 1001, 3840, 8424, 8448):
+        d = rng.integers(0, 256, size=(n + 7) // 8 + 4, dtype=np.uint8)
+        for poly in range(8):
+            assert oracle.crc(poly, d, n) == reference.crc(poly, d, n), (poly, n)
+    for crc_type, poly, L in ((0, 0, 24), (1, 1, 24), (2, 3, 16), (3, 6, 8)):
+        d = rng.integers(0, 256, size=64, dtype=np.uint8)
+        c = oracle.crc(poly, d, 8 * 64 - L) >> (32 - L)
+        for b in range(L // 8):
+            d[64 - L // 8 + b] = (c >> (8 * (L // 8 - 1 - b))) & 0xFF
+        assert oracle.check_crc(d, 512, crc_type) == reference.check_crc(d, 512, crc_type) == 1
+        d[3] ^= 4
+        assert oracle.check_crc(d, 512, crc_type) == reference.check_crc(d, 512, crc_type) == 0
+
+
+def test_rate_matching_and_interleaving(oracle, reference):
+    rng = np.random.default_rng(5)
+    for BG, Z, F, E, rv, Tbslbrm, Cseg in ((1, 384, 0, 9072, 0, 0, 1), (1, 384, 88, 9072, 2, 0, 3), (1, 96, 40, 30000, 1, 0, 2), (2, 128, 16, 5000, 3, 0, 1),
+                                           (1, 384, 0, 20000, 0, 200000, 20), (2, 52, 0, 1200, 0, 0, 1), (1, 208, 120, 4100, 3, 90000, 4), (2, 384, 200, 19000, 2, 0, 2)):
+        N = (66 if BG == 1 else 50) * Z
+        K = (22 if BG == 1 else 10) * Z
+        Foffset = K - F - 2 * Z
+        w = rng.integers(0, 2, size=N, dtype=np.uint8)
+        w[Foffset:Foffset + F] = 2   # NR_NULL
+        rc_r, e_r = reference.rate_matching_tx(Tbslbrm, BG, Z, w, Cseg, F, Foffset, rv, E)
+        rc_o, e_o = oracle.rate_matching_tx(Tbslbrm, BG, Z, w, Cseg, F, Foffset, rv, E)
+        assert rc_r == rc_o == 0 and np.array_equal(e_r, e_o), (BG, Z, F, E, rv)
+        for Qm in (2, 4, 6, 8):
+            Eq = E - E % Qm
+            assert np.array_equal(reference.interleave(Eq, Qm, e_r[:Eq]), oracle.interleave(Eq, Qm, e_r[:Eq]))
+            soft = rng.integers(-300, 300, size=Eq, dtype=np.int16)
+            assert np.array_equal(reference.deinterleave(Eq, Qm, soft), oracle.deinterleave(Eq, Qm, soft))
+        soft = rng.integers(-128, 128, size=E, dtype=np.int16)
+        w_r = rng.integers(-50, 50, size=N + 16, dtype=np.int16)
+        w_o = w_r.copy()
+        for clear in (1, 0):
+            assert reference.rate_matching_rx(Tbslbrm, BG, Z, w_r, soft, Cseg, rv, clear, E, F, Foffset) == 0
+            assert oracle.rate_matching_rx(Tbslbrm, BG, Z, w_o, soft, Cseg, rv, clear, E, F, Foffset) == 0
+            assert np.array_equal(w_r, w_o)
+        for rnd in (0, 1):
+            assert reference.get_R(rv, E, BG, Z, 0, rnd) == oracle.get_R(rv, E, BG, Z, 0, rnd)
+
+
+def test_segmentation(oracle, reference):
+    rng = np.random.default_rng(9)
+    for BG, B in ((1, 8448), (1, 8456), (1, 100000), (1, 424), (2, 3840), (2, 3848), (2, 600), (2, 200), (2, 100), (1, 1277992 // 8 * 8), (2, 40000)):
+        data = rng.integers(0, 256, size=B // 8 + 8, dtype=np.uint8)
+        r = reference.segmentation(data, B, BG)
+        o = oracle.segmentation(data, B, BG)
+        assert r[:5] == o[:5], (BG, B, r[:5], o[:5])
+        assert np.array_equal(r[5], o[5]), (BG, B)
