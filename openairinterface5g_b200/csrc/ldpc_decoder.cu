@@ -28,7 +28,9 @@ static const PackedGraph *packed_graph(const GraphDev &h_g, const PackedGraph **
   if (it == g_pk.end()) {
     PackedGraph pg;
     PackedGraph *d = nullptr;
-    if (build_packed_graph(h_g, &pg) && (size_t)pg.total_words * 4 + sizeof(PackedGraph) + 64 <= (size_t)ctx().max_smem_optin) {
+    int maxt = kPackedMaxThreads;
+    if (const char *e = getenv("NRB200_PACKED_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kPackedMaxThreads) maxt = v; }
+    if (build_packed_graph(h_g, &pg, maxt) && (size_t)pg.total_bytes + sizeof(PackedGraph) + 64 <= (size_t)ctx().max_smem_optin) {
       if (cudaMalloc(&d, sizeof(PackedGraph)) != cudaSuccess) d = nullptr;
       else cudaMemcpy(d, &pg, sizeof(PackedGraph), cudaMemcpyHostToDevice);
     }
@@ -54,7 +56,7 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
   const PackedGraph *h_pg = nullptr;
   const PackedGraph *d_pg = (h_g.Z % 4 == 0 && !force_generic) ? packed_graph(h_g, &h_pg) : nullptr;
   if (d_pg) {
-    const size_t smem = (size_t)h_pg->total_words * 4;
+    const size_t smem = (size_t)h_pg->total_bytes;
     static std::atomic<size_t> configured_pk{0};
     if (smem > configured_pk.load()) {
       NRB200_CUDA_OK(cudaFuncSetAttribute(ldpc_decode_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");

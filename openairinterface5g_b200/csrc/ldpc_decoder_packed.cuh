@@ -2,20 +2,22 @@
 // Z = 384 case): one CTA per code block, four lifts per 32-bit register (byte SIMD-in-word), all state in shared memory.
 //
 // Schedule (bit exact with the reference's two-phase flooding decoder, nrLDPC_decoder.c:206-881):
-//   state    Rn[m][t]  = cn->bn message of edge slot m at check lift t           (cnProcBufRes)
-//            A[c][v]   = a-posteriori LLR of bit (c, v), degree >= 2 columns      (llrRes)
-//            L[c][v]   = channel LLR                                              (llrProcBuf)
+//   state    R[m][t]   = cn->bn message of edge slot m at check lift t            (cnProcBufRes)
+//            A[c][v]   = a-posteriori LLR of bit (c, v), degree >= 2 columns       (llrRes)
+//            L[c][v]   = channel LLR                                               (llrProcBuf)
 //   CN phase thread (row r, word k): for every edge  Q = subs_epi8(A[c][t+s], R_old)  -- what bnProc/bn2cnProcBuf
-//            produced at the end of the previous iteration (nrLDPC_bnProc.h:325), formed on the fly from the shifted A
+//            produced at the end of the previous iteration (nrLDPC_bnProc.h:325), formed on the fly from the rotated A
 //            word, so no bn->cn buffer and no circular copies exist -- then exclude-self min / sign product
 //            (nrLDPC_cnProc.h:388-877) written back in place.  The sign bytes of the same A words give the previous
 //            iteration's syndrome (nrLDPC_cnProc.h:887-1960) for free: sign(adds_epi8(Q, R)) == sign(A)  (DESIGN.md).
-//   BN phase thread (column c, word k): A = sat8(L + sum_e R[m_e][v - s_e])      (nrLDPC_bnProc.h:40-263)
-// The quantisation points are the reference's: int16 sum -> sat8 -> subs_epi8 -> |.| clipped to 127.  Clipping Q to
-// [-127,127] instead of [-128,127] is exact because the check node only ever uses min(|Q|,127) and sign(Q).
+//   BN phase thread (column c, word k): A = sat8(L + sum_e R[m_e][v - s_e])       (nrLDPC_bnProc.h:40-263)
+// The quantisation points are the reference's: int16 sum -> sat8 -> subs_epi8 -> |.| clipped to 127.
 //
-// Rows carry one halo word (word Zw repeats word 0) so a circularly shifted 4-lift group is always two consecutive
-// words + one funnel shift; row stride is Zw+4 words to keep every row 16-byte aligned for the bulk (TMA) load of L.
+// Number format: every byte in shared memory is OFFSET BINARY (value + 128).  Then
+//   |A - R|          is one VABSDIFF4.U8 (the only byte-SIMD ALU op sm_100 has in hardware),
+//   min(|Q|,127)     == min(|A - R|, 127): saturating the difference first (subs_epi8) never changes the clipped magnitude,
+//   sign(Q)          == (A' < R') unsigned, 4 logic ops,
+//   sum of messages  is a plain 32-bit add of zero-extended byte pairs (no lane can overflow), bias removed once per column.
 #pragma once
 #include "ldpc_common.cuh"
 #include "ldpc_packed_graph.h"
@@ -23,143 +25,181 @@
 namespace nrb200 {
 
 // ---------------------------------------------------------------------------------------------- byte SIMD helpers
+// The inline-PTX forms pin the instruction selection: one LOP3 per 3-input boolean, one PRMT per byte broadcast.  Left to
+// itself nvcc re-associates the masks of the 7-bit tricks into ~50 % more LOP3s, and the ALU pipe is this kernel's limiter.
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
 }
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return r;
+}
+// a + b emitted as IMAD a*one+b (one == 1 at run time): same result, FMA pipe instead of the saturated ALU pipe
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one)
+{
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+  return r;
+}
+constexpr uint32_t kH = 0x80808080u, kL7 = 0x7f7f7f7fu;
+// LUT bytes: inputs a = 0xF0, b = 0xCC, c = 0xAA
+constexpr int kLutSel = 0xCA;      // a ? b : c
+constexpr int kLutOrAnd = 0xA8;    // (a | b) & c
+constexpr int kLutOrBandC = 0xF8;  // a | (b & c)
+constexpr int kLutXorAnd = 0x28;   // (a ^ b) & c
+constexpr int kLutXorBandC = 0x78; // a ^ (b & c)
+constexpr int kLutXorNBandC = 0xD2; // a ^ (~b & c)
+constexpr int kLutLtu = 0x4D;      // (~a & b) | (~(a ^ b) & ~c)
+constexpr int kLutXor3 = 0x96;     // a ^ b ^ c
+constexpr int kLutMajNot = 0x17;   // ~majority(a, b, c)
 // 0xFF in every byte whose bit 7 is set
 __device__ __forceinline__ uint32_t msb_mask(uint32_t x) { return prmt(x, 0u, 0xba98u); }
-__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }   // one LOP3
+__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return lop3<kLutSel>(m, a, b); }
 
-// per byte, operands in [0,127]: 0xFF where a >= b
-__device__ __forceinline__ uint32_t ge7(uint32_t a, uint32_t b) { return msb_mask((a | 0x80808080u) - b); }
+__device__ __forceinline__ uint32_t lds(const char *smb, uint32_t off) { return *reinterpret_cast<const uint32_t *>(smb + off); }
+__device__ __forceinline__ uint2 lds2(const char *smb, uint32_t off) { return *reinterpret_cast<const uint2 *>(smb + off); }
+__device__ __forceinline__ void sts(char *smb, uint32_t off, uint32_t v) { *reinterpret_cast<uint32_t *>(smb + off) = v; }
 
-// two's complement bytes of +-mag (mag in [0,127]) where neg has bit 7 of a byte set for "negative"; -0 -> 0
-__device__ __forceinline__ uint32_t apply_sign7(uint32_t mag, uint32_t neg)
+// one exclude-self two-minimum step on 7-bit magnitudes (a + 128 - b never borrows across bytes: bit 7 <=> a >= b)
+__device__ __forceinline__ void twomin(uint32_t mag, uint32_t &min1, uint32_t &min2)
 {
-  const uint32_t n = msb_mask(neg);
-  const uint32_t c = (mag ^ (n & 0x7f7f7f7fu)) + (n & 0x01010101u);   // (127-mag)+1 = 128-mag on negative bytes
-  return c ^ (n & 0x80808080u);
+  const uint32_t m1 = msb_mask(mag + kH - min1);   // mag >= min1
+  const uint32_t t = sel4(m1, mag, min1);          // max(mag, min1)
+  min1 = sel4(m1, min1, mag);
+  min2 = sel4(msb_mask(t + kH - min2), min2, t);
 }
 
-__device__ __forceinline__ void unpack_s16x2(uint32_t w, uint32_t &lo, uint32_t &hi)
+// offset-binary cn->bn message (R + 128) from the excluded minimum and the sign word (bit 7 = negative); -0 -> 0
+__device__ __forceinline__ uint32_t make_r(uint32_t qsm, uint32_t min1, uint32_t min2, uint32_t sgn, uint32_t one)
 {
-  lo = prmt(w, 0u, 0x9180u);   // {sext(b1), sext(b0)}
-  hi = prmt(w, 0u, 0xb3a2u);   // {sext(b3), sext(b2)}
+  const uint32_t ne = msb_mask(add_fma(lop3<kLutXorAnd>(qsm, min1, kL7), kL7, one));   // 0xFF where |Q| != min1
+  const uint32_t mag = sel4(ne, min1, min2);
+  const uint32_t n = msb_mask(sgn ^ qsm);                                               // 0xFF where the other signs multiply to -1
+  const uint32_t c = add_fma(lop3<kLutXorBandC>(mag, n, kL7), n & 0x01010101u, one);    // 128 - mag on negative bytes
+  return lop3<kLutXorNBandC>(c, n, kH);                                                 // 128 + mag on the others
 }
 
-template <int D>
-__device__ __forceinline__ void cn_row(const PackedGraph &G, uint32_t *__restrict__ sm, int r, int k, bool first_iter, uint32_t quirk_zero,
-                                       uint32_t &bad)
+template <int D, bool QUIRK>
+__device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool halo,
+                                       bool first_iter, uint32_t quirk_zero, uint32_t &bad)
 {
-  const int e0 = G.row_start[r];
+  const uint32_t one = G.one;
+  const uint32_t e0 = row.e0_deg & 0xFFFu;
+  const uint32_t rb = row.rbase + kb;
   uint32_t q[D];
-  uint32_t min1 = 0x7f7f7f7fu, min2 = 0x7f7f7f7fu, sgn = 0u, synd = 0u;
-  uint32_t *Rrow = sm + G.off_R + e0 * G.RS + k;
+  uint32_t min1 = kL7, min2 = kL7, sgn = 0u, synd = (D & 1) ? kH : 0u;   // sign(A) < 0 <=> bit 7 of A' clear
 #pragma unroll
   for (int j = 0; j < D; j++) {
-    const int m = e0 + j;
-    int w0 = k + G.cn_q[m];
-    if (w0 >= G.Zw) w0 -= G.Zw;
-    const uint32_t *ap = sm + G.cn_abase[m] + w0;
-    const uint32_t aw = __funnelshift_r(ap[0], ap[1], G.cn_rho[m]);       // A at lifts t+s .. t+s+3
-    const uint32_t rold = Rrow[j * G.RS];
+    const uint2 d = *reinterpret_cast<const uint2 *>(G.cn_desc[e0 + j]);
+    const uint32_t aa = kb + d.x;
+    const uint32_t aw = __funnelshift_r(lds(smb, aa), lds(smb, aa + 4), d.y);   // A' at lifts t+s .. t+s+3
+    const uint32_t ro = lds(smb, rb + j * G.RSB);
     synd ^= aw;
-    const uint32_t qq = __vsubss4(aw, rold);                               // subs_epi8(llrRes, cn->bn)  (bnProc)
-    q[j] = qq;
-    const uint32_t mag = __vabsss4(qq);                                    // min(|Q|,127)
-    sgn ^= qq;
-    const uint32_t m1 = ge7(mag, min1);                                    // mag >= min1
-    const uint32_t t = sel4(m1, mag, min1);                                // max(mag, min1)
-    min1 = sel4(m1, min1, mag);
-    min2 = sel4(ge7(t, min2), min2, t);
+    const uint32_t dd = __vabsdiffu4(aw, ro);                                    // |A - R|
+    const uint32_t mag = lop3<kLutOrAnd>(dd, msb_mask(dd), kL7);                 // min(|A - R|, 127)
+    const uint32_t x = (aw | kH) - (ro & kL7);
+    const uint32_t qsm = lop3<kLutOrBandC>(mag, lop3<kLutLtu>(aw, ro, x), kH);   // sign-magnitude Q, sign = (A' < R')
+    q[j] = qsm;
+    sgn ^= qsm;
+    twomin(mag, min1, min2);
   }
-  uint32_t qp = 0u;
-  const int pc = G.row_p_col[r];
-  if (pc >= 0) {                                                           // degree-1 neighbour: Q is the channel LLR forever
-    int w0 = k + G.row_p_q[r];
-    if (w0 >= G.Zw) w0 -= G.Zw;
-    const uint32_t *lp = sm + G.off_L + pc * G.RS + w0;
-    qp = __funnelshift_r(lp[0], lp[1], G.row_p_rho[r]);
-    uint32_t *P = sm + G.off_P + G.row_p_idx[r] * G.Zw + k;
-    synd ^= *P;                                                            // sign(llr + R_p) of the previous iteration
-    const uint32_t mag = __vabsss4(qp);
-    sgn ^= qp;
-    const uint32_t m1 = ge7(mag, min1);
-    const uint32_t t = sel4(m1, mag, min1);
-    min1 = sel4(m1, min1, mag);
-    min2 = sel4(ge7(t, min2), min2, t);
-    // R_p of this iteration -> sign of adds_epi8(llr, R_p) for the next syndrome
-    const uint32_t isMin = ~msb_mask(((mag ^ min1) & 0x7f7f7f7fu) + 0x7f7f7f7fu);   // 0xFF where mag == min1
-    const uint32_t rp = apply_sign7(sel4(isMin, min2, min1), sgn ^ qp) & ~quirk_zero;
-    *P = __vaddss4(qp, rp) & 0x80808080u;
+  if (row.lrow != 0xFFFFFFFFu) {                                           // degree-1 neighbour: Q is the channel LLR forever
+    const uint32_t pa = (row.prow_pcw & 0xFFFFFFu) + kb;
+    const uint32_t qsm = lds(smb, pa + G.ZB);                              // precomputed sign-magnitude of the channel LLR
+    synd ^= lds(smb, pa);                                                  // sign(llr + R_p) of the previous iteration
+    sgn ^= qsm;
+    twomin(qsm & kL7, min1, min2);
+    uint32_t rp = make_r(qsm, min1, min2, sgn, one);
+    if (QUIRK) rp = (rp & ~quirk_zero) | (kH & quirk_zero);
+    // adds_epi8(llr, R_p) < 0  <=>  L' + R' < 256  <=>  no carry out of the byte
+    const uint32_t lp = lds(smb, pa + 2 * G.ZB);                           // the neighbour's channel LLR + 128, already rotated
+    const uint32_t x = (lp & kL7) + (rp & kL7);
+    sts(smb, pa, lop3<kLutMajNot>(lp, rp, x) & kH);
   }
-  if (!first_iter && k < G.row_pc_words[r]) bad |= synd & 0x80808080u;
+  if (!first_iter && (kb >> 2) < (row.prow_pcw >> 24)) bad |= synd & kH;
 #pragma unroll
   for (int j = 0; j < D; j++) {
-    const uint32_t mag = __vabsss4(q[j]);
-    const uint32_t isMin = ~msb_mask(((mag ^ min1) & 0x7f7f7f7fu) + 0x7f7f7f7fu);
-    const uint32_t rn = apply_sign7(sel4(isMin, min2, min1), sgn ^ q[j]) & ~quirk_zero;
-    Rrow[j * G.RS] = rn;
-    if (k == 0) Rrow[j * G.RS + G.Zw] = rn;                                // halo
+    uint32_t rn = make_r(q[j], min1, min2, sgn, one);
+    if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
+    sts(smb, rb + j * G.RSB, rn);
+    if (halo) sts(smb, rb + j * G.RSB + G.ZB, rn);
   }
 }
 
-__device__ __forceinline__ void cn_dispatch(const PackedGraph &G, uint32_t *sm, int r, int k, bool first_iter, uint32_t qz, uint32_t &bad)
+template <bool QUIRK>
+__device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int r, uint32_t kb, bool halo, bool first_iter, uint32_t &bad)
 {
-  switch (G.row_start[r + 1] - G.row_start[r]) {
-    case 2: cn_row<2>(G, sm, r, k, first_iter, qz, bad); break;
-    case 3: cn_row<3>(G, sm, r, k, first_iter, qz, bad); break;
-    case 4: cn_row<4>(G, sm, r, k, first_iter, qz, bad); break;
-    case 5: cn_row<5>(G, sm, r, k, first_iter, qz, bad); break;
-    case 6: cn_row<6>(G, sm, r, k, first_iter, qz, bad); break;
-    case 7: cn_row<7>(G, sm, r, k, first_iter, qz, bad); break;
-    case 8: cn_row<8>(G, sm, r, k, first_iter, qz, bad); break;
-    case 9: cn_row<9>(G, sm, r, k, first_iter, qz, bad); break;
-    case 10: cn_row<10>(G, sm, r, k, first_iter, qz, bad); break;
-    case 19: cn_row<19>(G, sm, r, k, first_iter, qz, bad); break;
+  const PackedRow row = G.rows[r];
+  uint32_t qz = 0u;
+  if (QUIRK && (row.e0_deg >> 20)) {
+    // reference AVX2 generator defect (BG2 R15): odd 32-byte vectors of the degree-3 group are never written
+    const int gi = (int)(row.e0_deg >> 20) - 1;
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (((gi * G.Z + (int)kb + b) >> 5) & 1) qz |= 0xFFu << (8 * b);
+  }
+  switch ((row.e0_deg >> 12) & 0xFFu) {
+    case 2: cn_row<2, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 3: cn_row<3, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 4: cn_row<4, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 5: cn_row<5, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 6: cn_row<6, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 7: cn_row<7, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 8: cn_row<8, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 9: cn_row<9, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 10: cn_row<10, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 19: cn_row<19, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
     default: break;   // build_packed_graph() refuses graphs with other row degrees
   }
 }
 
-// A = sat8(L + sum R) for column c, word k
-__device__ __forceinline__ void bn_col(const PackedGraph &G, uint32_t *__restrict__ sm, int c, int k)
+// one bit-node edge: fetch the rotated R' word and add its four bytes to the four running sums (IDP.4A, FMA pipe)
+__device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__restrict__ smb, int i, uint32_t kb, uint32_t kbs, uint32_t &s0, uint32_t &s1,
+                                        uint32_t &s2, uint32_t &s3)
 {
-  const uint32_t lw = sm[G.off_L + c * G.RS + k];
-  uint32_t lo, hi;
-  unpack_s16x2(lw, lo, hi);
-  for (int i = G.col_start[c]; i < G.col_start[c + 1]; i++) {
-    int w0 = k - G.bn_qq[i];
-    if (w0 < 0) w0 += G.Zw;
-    const uint32_t *rp = sm + G.bn_rbase[i] + w0;
-    const uint32_t rw = __funnelshift_r(rp[0], rp[1], G.bn_sh[i]);
-    uint32_t rl, rh;
-    unpack_s16x2(rw, rl, rh);
-    lo = __vadd2(lo, rl);
-    hi = __vadd2(hi, rh);
-  }
-  // packs_epi16: saturate each 16-bit lane to int8
-  lo = __vmaxs2(__vmins2(lo, 0x007f007fu), 0xff80ff80u);
-  hi = __vmaxs2(__vmins2(hi, 0x007f007fu), 0xff80ff80u);
+  const uint2 d = *reinterpret_cast<const uint2 *>(G.bn_desc[i]);
+  uint32_t a = kb + d.x;
+  if (kbs < d.y) a += G.ZB;                                                 // circular wrap of v - s
+  const uint32_t rw = __funnelshift_r(lds(smb, a), lds(smb, a + 4), d.y);
+  s0 = __dp4a(rw, 0x00000001u, s0);
+  s1 = __dp4a(rw, 0x00000100u, s1);
+  s2 = __dp4a(rw, 0x00010000u, s2);
+  s3 = __dp4a(rw, 0x01000000u, s3);
+}
+
+// A' = clamp(L' + sum R' - 128*deg, 0, 255) for column c, word k   (packs_epi16 of the int16 sum, in offset binary)
+__device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ smb, int c, uint32_t kb, uint32_t kbs)
+{
+  const uint32_t lw = lds(smb, G.off_L + c * G.RSB + kb);
+  uint32_t s0 = lw & 0xFFu, s1 = (lw >> 8) & 0xFFu, s2 = (lw >> 16) & 0xFFu, s3 = lw >> 24;
+  int i = G.col_start[c];
+  const int i1 = G.col_start[c + 1];
+  for (; i + 2 <= i1; i += 2) { bn_edge(G, smb, i, kb, kbs, s0, s1, s2, s3); bn_edge(G, smb, i + 1, kb, kbs, s0, s1, s2, s3); }
+  if (i < i1) bn_edge(G, smb, i, kb, kbs, s0, s1, s2, s3);
+  const uint32_t nb = G.col_negbias[c];
+  const uint32_t lo = __vmins2(__viaddmax_s16x2(prmt(s0, s1, 0x5410u), nb, 0u), 0x00ff00ffu);
+  const uint32_t hi = __vmins2(__viaddmax_s16x2(prmt(s2, s3, 0x5410u), nb, 0u), 0x00ff00ffu);
   const uint32_t a = prmt(lo, hi, 0x6420u);
-  uint32_t *ap = sm + G.off_A + G.col_arow[c] * G.RS;
-  ap[k] = a;
-  if (k == 0) ap[G.Zw] = a;
+  const uint32_t ao = G.off_A + G.col_arow[c] * 2 * G.ZB + kb;
+  sts(smb, ao, a);
+  sts(smb, ao + G.ZB, a);
 }
 
 // hard decision of codeword position i (0/1); degree-1 columns read as 0 like the reference's untouched llrRes
-__device__ __forceinline__ unsigned hd_bit(const PackedGraph &G, const uint32_t *sm, int i)
+__device__ __forceinline__ unsigned hd_bit(const PackedGraph &G, const char *smb, int i)
 {
   const int c = i / G.Z, v = i - c * G.Z;
   const int ar = G.col_arow[c];
   if (ar < 0) return 0u;
-  const uint8_t *row = reinterpret_cast<const uint8_t *>(sm + G.off_A + ar * G.RS);
-  return row[v] >> 7;
+  return (reinterpret_cast<const uint8_t *>(smb + G.off_A + ar * 2 * G.ZB)[v] >> 7) ^ 1u;
 }
 
-__device__ __forceinline__ void packed_write_output(const PackedGraph &G, const uint32_t *sm, const DecodeArgs &a, int cb)
+__device__ __forceinline__ void packed_write_output(const PackedGraph &G, const char *smb, const DecodeArgs &a, int cb)
 {
   uint8_t *o = a.out + (size_t)cb * a.out_stride;
   const int numLLR = G.ncols * G.Z;
@@ -170,8 +210,8 @@ __device__ __forceinline__ void packed_write_output(const PackedGraph &G, const 
         const int i = j * 8, c = i / G.Z, v = i - c * G.Z, ar = G.col_arow[c];
         unsigned b = 0;
         if (ar >= 0) {
-          const uint32_t *w = sm + G.off_A + ar * G.RS + (v >> 2);
-          const uint32_t t0 = (w[0] & 0x80808080u) >> 7, t1 = (w[1] & 0x80808080u) >> 7;
+          const uint32_t wo = G.off_A + ar * 2 * G.ZB + v;
+          const uint32_t t0 = (~lds(smb, wo) & kH) >> 7, t1 = (~lds(smb, wo + 4) & kH) >> 7;
           b = (((t0 * 0x08040201u) >> 24) & 0xFu) << 4 | (((t1 * 0x08040201u) >> 24) & 0xFu);   // lift v first = MSB
         }
         o[j] = (uint8_t)b;
@@ -179,21 +219,21 @@ __device__ __forceinline__ void packed_write_output(const PackedGraph &G, const 
     } else {
       for (int j = threadIdx.x; j < nbytes; j += blockDim.x) {
         unsigned b = 0;
-        for (int kk = 0; kk < 8; kk++) { const int i = j * 8 + kk; if (i < numLLR) b |= hd_bit(G, sm, i) << (7 - kk); }
+        for (int kk = 0; kk < 8; kk++) { const int i = j * 8 + kk; if (i < numLLR) b |= hd_bit(G, smb, i) << (7 - kk); }
         o[j] = (uint8_t)b;
       }
     }
   } else {
-    for (int i = threadIdx.x; i < numLLR; i += blockDim.x) o[i] = (uint8_t)hd_bit(G, sm, i);
+    for (int i = threadIdx.x; i < numLLR; i += blockDim.x) o[i] = (uint8_t)hd_bit(G, smb, i);
   }
 }
 
-__device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const uint32_t *sm, const DecodeArgs &a, int *scratch)
+__device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const char *smb, const DecodeArgs &a, int *scratch)
 {
   const int n = (int)a.crc_len_bits;
   unsigned rem = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (hd_bit(G, sm, i)) rem ^= __ldg(a.crc_tab + (n - 1 - i));
+    if (hd_bit(G, smb, i)) rem ^= __ldg(a.crc_tab + (n - 1 - i));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
   if (threadIdx.x == 0) *scratch = 0;
@@ -211,15 +251,20 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ PackedGraph G;
   __shared__ int s_flag;
+  char *smb = reinterpret_cast<char *>(sm);
   for (int i = threadIdx.x; i < (int)(sizeof(PackedGraph) / 4); i += blockDim.x)
     reinterpret_cast<int *>(&G)[i] = reinterpret_cast<const int *>(gdev)[i];
   __syncthreads();
-  const int Zw = G.Zw, RS = G.RS;
+  const int Zw = G.Zw;
   const int bin = threadIdx.x / Zw, kw = threadIdx.x - bin * Zw;
+  const uint32_t kb = 4u * (uint32_t)kw;
+  const uint32_t kbs = (kb << 8) | 0xFFu;
   const bool worker = bin < G.nbins;
+  const bool halo = kw == 0;
+  const bool quirks = (a.quirks & 1) != 0;
 
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
-    // ---- load channel LLRs (global int8, coalesced 32-bit) into L rows with halo; A := L for degree>=2 columns; R := 0
+    // ---- load channel LLRs (global int8, coalesced 32-bit) as offset binary into L rows with halo; A := L; R := 0; P := 0
     const int8_t *gl = a.llr + (size_t)cb * a.llr_stride;
     const bool al4 = ((reinterpret_cast<uintptr_t>(gl) & 3) == 0);
     for (int i = threadIdx.x; i < G.ncols * Zw; i += blockDim.x) {
@@ -230,13 +275,30 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
         const uint8_t *b = reinterpret_cast<const uint8_t *>(gl) + 4 * i;
         w = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
       }
-      sm[G.off_L + c * RS + k] = w;
-      if (k == 0) sm[G.off_L + c * RS + Zw] = w;
+      w ^= kH;
+      const uint32_t lo = G.off_L + c * G.RSB + 4 * k;
+      sts(smb, lo, w);
+      if (k == 0) sts(smb, lo + G.ZB, w);
       const int ar = G.col_arow[c];
-      if (ar >= 0) { sm[G.off_A + ar * RS + k] = w; if (k == 0) sm[G.off_A + ar * RS + Zw] = w; }
+      if (ar >= 0) { const uint32_t ao = G.off_A + ar * 2 * G.ZB + 4 * k; sts(smb, ao, w); sts(smb, ao + G.ZB, w); }
     }
-    for (int i = threadIdx.x; i < G.nreal * RS; i += blockDim.x) sm[G.off_R + i] = 0u;
-    for (int i = threadIdx.x; i < G.nrowP * Zw; i += blockDim.x) sm[G.off_P + i] = 0u;
+    for (int i = threadIdx.x; i < G.nreal * (G.RSB >> 2); i += blockDim.x) sts(smb, G.off_R + 4 * i, kH);
+    __syncthreads();
+    // P rows: word k = sign(llr_p + R_p) flags (start clear), word Zw+k = sign-magnitude of the degree-1 neighbour's channel LLR,
+    // word 2Zw+k = that LLR + 128 itself (rotated)
+    for (int i = threadIdx.x; i < G.nrows * Zw; i += blockDim.x) {
+      const int r = i / Zw, k = i - r * Zw;
+      const PackedRow row = G.rows[r];
+      if (row.lrow == 0xFFFFFFFFu) continue;
+      uint32_t w0 = 4u * (uint32_t)(k + G.row_p_q[r]);
+      if (w0 >= (uint32_t)G.ZB) w0 -= G.ZB;
+      const uint32_t lp = __funnelshift_r(lds(smb, row.lrow + w0), lds(smb, row.lrow + w0 + 4), (uint32_t)G.row_p_rho[r]);
+      const uint32_t dd = __vabsdiffu4(lp, kH);
+      const uint32_t pa = (row.prow_pcw & 0xFFFFFFu) + 4u * (uint32_t)k;
+      sts(smb, pa, 0u);
+      sts(smb, pa + G.ZB, lop3<kLutOrAnd>(dd, msb_mask(dd), kL7) | (~lp & kH));
+      sts(smb, pa + 2 * G.ZB, lp);
+    }
     __syncthreads();
 
     const int maxIter = a.numMaxIter;
@@ -248,21 +310,16 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
     while (!done) {
       // CN phase of iteration numIter+1 (also yields the syndrome of iteration numIter when numIter >= 2)
       uint32_t bad = 0;
-      if (worker) for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) {
-        const int r = G.cn_bin_rows[i], k = kw;
-        uint32_t qz = 0u;
-        if ((a.quirks & 1) && G.row_deg3_idx[r] >= 0) {
-          // reference AVX2 generator defect (BG2 R15): odd 32-byte vectors of the degree-3 group are never written
-#pragma unroll
-          for (int b = 0; b < 4; b++) if (((G.row_deg3_idx[r] * G.Z + 4 * k + b) >> 5) & 1) qz |= 0xFFu << (8 * b);
-        }
-        cn_dispatch(G, sm, r, k, numIter == 0, qz, bad);
+      if (worker) {
+        if (!quirks) for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<false>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
+        else for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<true>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
       }
       const int pcRes = __syncthreads_or(bad != 0);   // also the CN->BN barrier
       if (numIter >= 2 && !a.use_crc && pcRes == 0) break;          // iteration numIter passed its parity check (:552)
       numIter++;
       // BN phase
-      if (worker) for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) bn_col(G, sm, G.bn_bin_cols[i], kw);
+      if (worker)
+        for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) bn_col(G, smb, G.bn_bin_cols[i], kb, kbs);
       __syncthreads();
       // loop control, mirroring `while (numIter <= numMaxIter && pcRes != 0)` evaluated before each further iteration
       if (numIter == 1) {
@@ -271,8 +328,8 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       } else {
         if (a.use_crc) {
           if (numIter > 2) {                                         // :850-862
-            packed_write_output(G, sm, a, cb);
-            if (packed_crc_check(G, sm, a, &s_flag)) break;
+            packed_write_output(G, smb, a, cb);
+            if (packed_crc_check(G, smb, a, &s_flag)) break;
           }
           if (!(numIter <= maxIter)) done = true;
         } else {
@@ -280,7 +337,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
         }
       }
     }
-    if (!a.use_crc) packed_write_output(G, sm, a, cb);               // :865-877
+    if (!a.use_crc) packed_write_output(G, smb, a, cb);               // :865-877
     if (threadIdx.x == 0) a.iters[cb] = numIter;
     __syncthreads();
   }

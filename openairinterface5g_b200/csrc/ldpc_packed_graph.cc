@@ -1,4 +1,4 @@
-// Host-side construction of the packed decoder's tables (ldpc_decoder_packed.cuh: PackedGraph).
+// Host-side construction of the packed decoder's tables (ldpc_packed_graph.h).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -31,47 +31,55 @@ bool build_packed_graph(const GraphDev &g, PackedGraph *p, int max_threads)
 {
   if (g.Z % 4) return false;
   std::memset(p, 0, sizeof(*p));
-  p->Z = g.Z; p->Zw = g.Z / 4; p->RS = p->Zw + 4;
+  p->Z = g.Z; p->Zw = g.Z / 4; p->ZB = 4 * p->Zw; p->RSB = 4 * (p->Zw + 4);
   p->ncols = g.ncols; p->nrows = g.nrows; p->nreal = g.nreal;
-  // A rows for degree>=2 columns
   int na = 0;
-  for (int c = 0; c < g.ncols; c++) p->col_arow[c] = (int16_t)(g.col_deg[c] >= 2 ? na++ : -1);
+  for (int c = 0; c < g.ncols; c++) {
+    p->col_arow[c] = (int16_t)(g.col_deg[c] >= 2 ? na++ : -1);
+    const uint32_t nb = (uint32_t)(-(128 * g.col_deg[c])) & 0xFFFFu;
+    p->col_negbias[c] = nb | (nb << 16);
+  }
   p->ncolA = na;
   int np = 0;
+  for (int r = 0; r < g.nrows; r++) if (g.row_p_col[r] >= 0) np++;
+  p->nrowP = np;
+  p->off_A = 0;
+  p->off_R = p->off_A + na * 2 * p->ZB;
+  p->off_L = p->off_R + g.nreal * p->RSB;
+  p->off_P = p->off_L + g.ncols * p->RSB;
+  p->total_bytes = p->off_P + np * 3 * p->ZB;
+  p->one = 1u;
+  np = 0;
   for (int r = 0; r < g.nrows; r++) {
-    p->row_start[r] = g.row_start[r];
-    p->row_p_col[r] = g.row_p_col[r];
-    p->row_deg3_idx[r] = g.row_deg3_idx[r];
-    p->row_pc_words[r] = (int16_t)(g.row_pc_from[r] / 4);
-    if (g.row_pc_from[r] % 4) return false;
-    p->row_p_idx[r] = -1;
-    if (g.row_p_col[r] >= 0) {
-      p->row_p_idx[r] = (int16_t)np++;
-      p->row_p_q[r] = (int16_t)(g.row_p_shift[r] / 4);
-      p->row_p_rho[r] = (int16_t)(8 * (g.row_p_shift[r] % 4));
-    }
     const int d = g.row_start[r + 1] - g.row_start[r];
     if (!((d >= 2 && d <= 10) || d == 19)) return false;   // cn_dispatch() instantiations
+    if (g.row_pc_from[r] % 4) return false;
+    PackedRow &pr = p->rows[r];
+    pr.e0_deg = (uint32_t)g.row_start[r] | ((uint32_t)d << 12) | ((uint32_t)(g.row_deg3_idx[r] + 1) << 20);
+    pr.rbase = (uint32_t)(p->off_R + g.row_start[r] * p->RSB);
+    pr.lrow = 0xFFFFFFFFu;
+    pr.prow_pcw = (uint32_t)(g.row_pc_from[r] / 4) << 24;
+    if (g.row_p_col[r] >= 0) {
+      pr.lrow = (uint32_t)(p->off_L + g.row_p_col[r] * p->RSB);
+      pr.prow_pcw |= (uint32_t)(p->off_P + np * 3 * p->ZB);
+      p->row_p_q[r] = (int16_t)(g.row_p_shift[r] / 4);
+      p->row_p_rho[r] = (int16_t)(8 * (g.row_p_shift[r] % 4));
+      np++;
+    }
   }
-  p->row_start[g.nrows] = g.row_start[g.nrows];
-  p->nrowP = np;
-  p->off_R = 0;
-  p->off_A = p->off_R + g.nreal * p->RS;
-  p->off_L = p->off_A + na * p->RS;
-  p->off_P = p->off_L + g.ncols * p->RS;
-  p->total_words = p->off_P + np * p->Zw;
   for (int m = 0; m < g.nreal; m++) {
     const int c = g.edge_col[m], s = g.edge_shift[m];
-    p->cn_abase[m] = p->off_A + p->col_arow[c] * p->RS;
-    p->cn_q[m] = (int16_t)(s / 4);
-    p->cn_rho[m] = (int16_t)(8 * (s % 4));
+    const uint32_t aoff = (uint32_t)(p->off_A + p->col_arow[c] * 2 * p->ZB + 4 * (s / 4));
+    p->cn_desc[m][0] = aoff;
+    p->cn_desc[m][1] = (uint32_t)(8 * (s % 4));
   }
   for (int c = 0; c <= g.ncols; c++) p->col_start[c] = g.col_start[c];
   for (int i = 0; i < g.nreal; i++) {
     const int m = g.col_edges[i], s = g.edge_shift[m], q = s / 4, rho = s % 4;
-    p->bn_rbase[i] = p->off_R + m * p->RS;
-    p->bn_qq[i] = (int16_t)(q + (rho ? 1 : 0));
-    p->bn_sh[i] = (int16_t)(8 * ((4 - rho) & 3));
+    const int qq4 = 4 * (q + (rho ? 1 : 0));
+    const uint32_t base_minus = (uint32_t)(p->off_R + m * p->RSB - qq4);   // off_R > 4*(Zw+1) always (A region precedes)
+    p->bn_desc[i][0] = base_minus;
+    p->bn_desc[i][1] = ((uint32_t)qq4 << 8) | (uint32_t)(8 * ((4 - rho) & 3));
   }
   // thread geometry: bins of Zw threads
   int nbins = max_threads / p->Zw;
@@ -79,7 +87,7 @@ bool build_packed_graph(const GraphDev &g, PackedGraph *p, int max_threads)
   p->nbins = nbins;
   p->nthreads = std::min(max_threads, std::max(32, ((nbins * p->Zw + 31) / 32) * 32));
   std::vector<std::pair<int, int>> rows, cols;
-  for (int r = 0; r < g.nrows; r++) rows.push_back({g.row_start[r + 1] - g.row_start[r] + (g.row_p_col[r] >= 0 ? 1 : 0) + 1, r});
+  for (int r = 0; r < g.nrows; r++) rows.push_back({3 * (g.row_start[r + 1] - g.row_start[r]) + (g.row_p_col[r] >= 0 ? 3 : 0) + 2, r});
   for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) cols.push_back({g.col_deg[c] + 1, c});
   lpt(rows, nbins, p->cn_bin_start, p->cn_bin_rows);
   lpt(cols, nbins, p->bn_bin_start, p->bn_bin_cols);

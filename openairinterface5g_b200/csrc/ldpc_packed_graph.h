@@ -8,30 +8,40 @@ namespace nrb200 {
 constexpr int kPackedMaxThreads = 768;
 constexpr int kMaxBins = 24;
 
-// Host-built tables for the packed kernel (copied to shared memory at kernel start).
+// Per check row, one 16-byte record (read with a single LDS.128).
+struct PackedRow {
+  uint32_t e0_deg;     // bits[11:0] first slot, bits[19:12] number of stored edges D, bits[27:20] degree-3 group index + 1
+  uint32_t rbase;      // byte offset of R row of the first slot
+  uint32_t lrow;       // byte offset of the L row of the degree-1 neighbour column, 0xFFFFFFFF when the row has none
+  uint32_t prow_pcw;   // bits[23:0] byte offset of the row's P (degree-1 sign) words, bits[31:24] words taking part in the parity check
+};
+
+// Shared-memory image (all offsets in bytes from the start of the dynamic shared buffer):
+//   A  ncolA rows of 2*Zw words : a-posteriori LLRs + 128 (offset binary), stored twice so a rotation never wraps
+//   R  nreal rows of Zw+4 words : cn->bn messages + 128, word Zw repeats word 0 (halo)
+//   L  ncols rows of Zw+4 words : channel LLRs + 128, with halo
+//   P  nrowP rows of 3*Zw words : word k: 0x80 per byte where sat8(llr_p + R_p) < 0; word Zw+k: sign-magnitude of the neighbour's
+//                                 channel LLR; word 2Zw+k: that LLR + 128 (rotated)
 struct PackedGraph {
-  int32_t Z, Zw, RS;                 // lifts, words per row, row stride in words (Zw + 4)
+  int32_t Z, Zw, ZB, RSB;            // lifts, words per row, 4*Zw, R/L row stride in bytes
   int32_t ncols, nrows, nreal, ncolA, nrowP;
-  int32_t off_R, off_A, off_L, off_P, total_words;   // region offsets (words) inside the dynamic shared buffer
+  int32_t off_A, off_R, off_L, off_P, total_bytes;
   int32_t nbins, nthreads;           // thread t works for bin t / Zw on word t % Zw; bins own whole rows / columns
-  int16_t cn_bin_start[kMaxBins + 1]; // LPT-balanced row lists per bin (heavy rows first)
+  int16_t cn_bin_start[kMaxBins + 1];
   int16_t cn_bin_rows[kMaxRows];
-  int16_t bn_bin_start[kMaxBins + 1]; // LPT-balanced column lists per bin
+  int16_t bn_bin_start[kMaxBins + 1];
   int16_t bn_bin_cols[kMaxCols];
-  int16_t row_start[kMaxRows + 1];   // slot range per row
-  int16_t row_p_col[kMaxRows];       // degree-1 column of the row or -1
-  int16_t row_p_q[kMaxRows], row_p_rho[kMaxRows];
-  int16_t row_p_idx[kMaxRows];       // row index inside the P (degree-1 sign) region
-  int16_t row_deg3_idx[kMaxRows];
-  int16_t row_pc_words[kMaxRows];    // words of the row that take part in the parity check (reference cnProcPc coverage)
+  int16_t row_p_q[kMaxRows], row_p_rho[kMaxRows];   // rotation of the degree-1 neighbour (0 for every NR base graph)
   int16_t col_start[kMaxCols + 1];
   int16_t col_arow[kMaxCols];        // row of column c inside the A region, -1 for degree-1 columns
-  // per slot, CN side: where the edge's bit node lives in A and how far it is rotated
-  int32_t cn_abase[kMaxEdges];       // word offset of A row of the edge's column
-  int16_t cn_q[kMaxEdges], cn_rho[kMaxEdges];
-  // per column-edge entry, BN side
-  int32_t bn_rbase[kMaxEdges];       // word offset of R row of the slot
-  int16_t bn_qq[kMaxEdges], bn_sh[kMaxEdges];   // word back-shift and funnel byte shift*8
+  uint32_t col_negbias[kMaxCols];    // two 16-bit lanes of -(128 * degree): removes the offset-binary bias of the summed messages
+  alignas(16) PackedRow rows[kMaxRows];
+  // per slot, CN side: .x = byte offset of A row + 4*(shift / 4), .y = 8*(shift % 4) (funnel amount)
+  alignas(8) uint32_t cn_desc[kMaxEdges][2];
+  // per column-edge entry, BN side: .x = byte offset of R row - 4*qq, .y = (4*qq << 8) | 8*((4 - shift%4) & 3)
+  // (.y is compared against (kb << 8) | 0xFF for the circular wrap and used as-is as the funnel amount: only bits[4:0] count)
+  alignas(8) uint32_t bn_desc[kMaxEdges][2];
+  uint32_t one;                      // == 1, read at run time so that selected adds are emitted as IMAD (FMA pipe), see DESIGN.md
 };
 
 bool build_packed_graph(const GraphDev &g, PackedGraph *p, int max_threads = kPackedMaxThreads);

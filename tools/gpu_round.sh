@@ -1,21 +1,27 @@
 #!/usr/bin/env bash
 # One gpurun call: GPU parity tests, the bench line, the ncu launch list and one full capture of the decode kernel.
-# Usage (from the CPU box): gpurun --timeout 1800 -- 'bash tools/gpu_round.sh [tag]'
+# Usage (from the CPU box): gpurun --timeout 1800 -- 'bash tools/gpu_round.sh [tag] [quick]'
 set -u
 TAG=${1:-r01}
+MODE=${2:-full}
 mkdir -p gpurun_out
 make -C oracle liboracle.so >/dev/null 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_${TAG}.txt
-nproc >> gpurun_out/gpu_${TAG}.txt; lscpu | grep -E "Model name|^CPU\(s\)|Flags" | cut -c1-300 >> gpurun_out/gpu_${TAG}.txt
+nproc >> gpurun_out/gpu_${TAG}.txt; lscpu | grep -E "Model name|^CPU\(s\)" | cut -c1-200 >> gpurun_out/gpu_${TAG}.txt
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_${TAG}.txt
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+echo "== variants"
+for t in 768 672 576 480 384; do NRB200_PACKED_THREADS=$t timeout 120 python tools/kernel_time.py 1.0 2>&1 | tail -1; done | tee gpurun_out/variants_${TAG}.txt
+timeout 120 python tools/kernel_time.py 3.0 2>&1 | tail -1 | tee -a gpurun_out/variants_${TAG}.txt
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json
+if [ "$MODE" = "full" ]; then
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== bench point B (Eb/N0 3 dB, early stop)"; timeout 300 python bench.py --steps 50 --warmup 5 --ebn0 3.0 --no-cpu 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_pointB.json
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_reference.json
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
   python bench.py --steps 5 --warmup 3 --no-cpu --no-check --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
+fi
 echo "== ncu full (decode kernel)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 2 -f -o gpurun_out/prof_decode_${TAG} \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-check --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
-ls -la gpurun_out | tail -15
+ls -la gpurun_out | tail -8
