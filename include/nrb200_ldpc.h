@@ -161,6 +161,38 @@ int32_t nrb200_crc_batch_dev(int poly_id, uint32_t n_blk, const uint8_t *d_in, u
                              void *stream);
 int32_t nrb200_crc_batch_host(int poly_id, uint32_t n_blk, const uint8_t *in, uint32_t stride, uint32_t bitlen, uint32_t *out);
 
+/* ------------------------------------------------------------------------------------------
+ * Part 3: rate matching / interleaving around the codec (one transport block = n_seg code block segments per call)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Parameters shared by all segments of a transport block (reference nr_rate_matching.c:424-603 argument lists). */
+typedef struct nrb200_rm_desc {
+  uint8_t BG;
+  uint16_t Z;
+  uint8_t Qm;        /* modulation order 2|4|6|8 */
+  uint8_t rv;        /* redundancy version 0..3 */
+  uint8_t clear;     /* RX: 1 = new data, zero the first Ncb soft values before accumulating (d_to_be_cleared) */
+  uint32_t C;        /* number of segments of the TB (enters Nref = 3*Tbslbrm/(2C)) */
+  uint32_t Tbslbrm;  /* 0 = no limited-buffer rate matching */
+  uint32_t F;        /* filler bits per segment */
+  uint32_t K;        /* segment length incl. fillers (22Z | 10Z); Foffset = K - F - 2Z */
+  uint32_t n_seg;    /* segments handled by this call (normally == C) */
+} nrb200_rm_desc_t;
+
+/* TX: replaces nr_rate_matching_ldpc + nr_interleaving_ldpc (nr_dlsch_coding.c:204-245).  d = n_seg encoder outputs (one bit per
+ * byte, 66Z|50Z each, stride d_stride); E[r] = rate-matched length of segment r; f receives the segments back to back
+ * (offset of segment r = sum of E[0..r)), one bit per byte. */
+int32_t nrb200_ldpc_rm_tx_batch_dev(const nrb200_rm_desc_t *desc, const uint8_t *d_d, uint32_t d_stride, const uint32_t *d_E,
+                                    const uint32_t *d_foff, uint8_t *d_f, void *stream);
+int32_t nrb200_ldpc_rm_tx_batch_host(const nrb200_rm_desc_t *desc, const uint8_t *d, uint32_t d_stride, const uint32_t *E, uint8_t *f);
+/* RX: replaces nr_deinterleaving_ldpc + nr_rate_matching_ldpc_rx + the decoder-input packing of nr_ulsch_decoding.c:153-210.
+ * soft = the segments' E[r] int16 LLRs back to back; harq = n_seg persistent int16 soft buffers (>= 66Z|50Z each, stride
+ * harq_stride elements), updated in place; llr receives 68Z|52Z int8 decoder inputs per segment (stride llr_stride bytes). */
+int32_t nrb200_ldpc_rm_rx_batch_dev(const nrb200_rm_desc_t *desc, const int16_t *d_soft, const uint32_t *d_E, const uint32_t *d_soff,
+                                    int16_t *d_harq, uint32_t harq_stride, int8_t *d_llr, uint32_t llr_stride, void *stream);
+int32_t nrb200_ldpc_rm_rx_batch_host(const nrb200_rm_desc_t *desc, const int16_t *soft, const uint32_t *E, int16_t *harq, uint32_t harq_stride,
+                                     int8_t *llr, uint32_t llr_stride);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

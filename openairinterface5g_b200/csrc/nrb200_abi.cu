@@ -4,6 +4,7 @@
 #include "ldpc_common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -13,6 +14,9 @@ int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_
                   uint8_t *d_out, uint32_t out_stride, cudaStream_t stream);
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
 int quirks_from_env();
+int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
+int launch_rm_rx(const nrb200_rm_desc_t &p, const int16_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
+                 int8_t *llr, uint32_t llr_stride, cudaStream_t st);
 }
 using namespace nrb200;
 
@@ -281,6 +285,97 @@ NRB200_EXPORT int32_t nrb200_crc_batch_host(int poly_id, uint32_t n_blk, const u
     if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
     if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
     std::memcpy(out, w->h_out, out_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ part 3: rate matching
+static int rm_check(const nrb200_rm_desc_t *d)
+{
+  if ((d->BG != 1 && d->BG != 2) || ils_of_z(d->Z) < 0 || d->rv > 3) return -4;
+  if (d->Qm != 1 && d->Qm != 2 && d->Qm != 4 && d->Qm != 6 && d->Qm != 8) return -4;
+  if (d->K != (uint32_t)(d->BG == 1 ? 22 : 10) * d->Z || d->F + 2u * d->Z > d->K || d->C == 0) return -4;
+  return 0;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_rm_tx_batch_dev(const nrb200_rm_desc_t *desc, const uint8_t *d_d, uint32_t d_stride, const uint32_t *d_E,
+                                                  const uint32_t *d_foff, uint8_t *d_f, void *stream)
+{
+  if (ensure_init()) return -1;
+  if (int rc = rm_check(desc)) return rc;
+  if (d_stride < (uint32_t)(desc->BG == 1 ? 66 : 50) * desc->Z) return -4;
+  return launch_rm_tx(*desc, d_d, d_stride, d_E, d_foff, d_f, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_rm_tx_batch_host(const nrb200_rm_desc_t *desc, const uint8_t *d, uint32_t d_stride, const uint32_t *E, uint8_t *f)
+{
+  if (ensure_init()) return -1;
+  if (int rc = rm_check(desc)) return rc;
+  const uint32_t n = desc->n_seg;
+  if (n == 0) return 0;
+  std::vector<uint32_t> tab(2 * (size_t)n);
+  size_t tot = 0;
+  const uint32_t Foffset = desc->K - desc->F - 2u * desc->Z;
+  for (uint32_t r = 0; r < n; r++) { if (E[r] < Foffset) return -4; tab[r] = E[r]; tab[n + r] = (uint32_t)tot; tot += E[r]; }   // "Foffset > E" is an error upstream (:454)
+  const size_t in_bytes = (size_t)n * d_stride;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(in_bytes, tot, 8 * (size_t)n)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, d, in_bytes);
+    std::memcpy(w->h_aux, tab.data(), 8 * (size_t)n);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->d_aux, w->h_aux, 8 * (size_t)n, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = launch_rm_tx(*desc, (const uint8_t *)w->d_in, d_stride, (const uint32_t *)w->d_aux, (const uint32_t *)w->d_aux + n, (uint8_t *)w->d_out, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, tot, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(f, w->h_out, tot);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_rm_rx_batch_dev(const nrb200_rm_desc_t *desc, const int16_t *d_soft, const uint32_t *d_E, const uint32_t *d_soff,
+                                                  int16_t *d_harq, uint32_t harq_stride, int8_t *d_llr, uint32_t llr_stride, void *stream)
+{
+  if (ensure_init()) return -1;
+  if (int rc = rm_check(desc)) return rc;
+  if (harq_stride < (uint32_t)(desc->BG == 1 ? 66 : 50) * desc->Z || llr_stride < (uint32_t)(desc->BG == 1 ? 68 : 52) * desc->Z) return -4;
+  return launch_rm_rx(*desc, d_soft, d_E, d_soff, d_harq, harq_stride, d_llr, llr_stride, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_rm_rx_batch_host(const nrb200_rm_desc_t *desc, const int16_t *soft, const uint32_t *E, int16_t *harq,
+                                                   uint32_t harq_stride, int8_t *llr, uint32_t llr_stride)
+{
+  if (ensure_init()) return -1;
+  if (int rc = rm_check(desc)) return rc;
+  const uint32_t n = desc->n_seg;
+  if (n == 0) return 0;
+  if (harq_stride < (uint32_t)(desc->BG == 1 ? 66 : 50) * desc->Z || llr_stride < (uint32_t)(desc->BG == 1 ? 68 : 52) * desc->Z) return -4;
+  std::vector<uint32_t> tab(2 * (size_t)n);
+  size_t tot = 0;
+  const uint32_t Foffset = desc->K - desc->F - 2u * desc->Z;
+  for (uint32_t r = 0; r < n; r++) { if (E[r] < Foffset || E[r] % desc->Qm) return -4; tab[r] = E[r]; tab[n + r] = (uint32_t)tot; tot += E[r]; }
+  const size_t soft_bytes = 2 * tot, harq_bytes = 2 * (size_t)n * harq_stride, llr_bytes = (size_t)n * llr_stride;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(soft_bytes + harq_bytes + 64, llr_bytes, 8 * (size_t)n)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    const size_t hoff = (soft_bytes + 15) & ~(size_t)15;
+    std::memcpy(w->h_in, soft, soft_bytes);
+    std::memcpy((uint8_t *)w->h_in + hoff, harq, harq_bytes);
+    std::memcpy(w->h_aux, tab.data(), 8 * (size_t)n);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, hoff + harq_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->d_aux, w->h_aux, 8 * (size_t)n, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    int16_t *d_harq = (int16_t *)((uint8_t *)w->d_in + hoff);
+    if ((rc = launch_rm_rx(*desc, (const int16_t *)w->d_in, (const uint32_t *)w->d_aux, (const uint32_t *)w->d_aux + n, d_harq, harq_stride,
+                           (int8_t *)w->d_out, llr_stride, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, llr_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync((uint8_t *)w->h_in + hoff, d_harq, harq_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(llr, w->h_out, llr_bytes);
+    std::memcpy(harq, (uint8_t *)w->h_in + hoff, harq_bytes);
   } while (0);
   ctx().release(w);
   return rc;

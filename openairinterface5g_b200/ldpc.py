@@ -55,6 +55,11 @@ class BatchDesc(C.Structure):          # nrb200_ldpc_batch_desc_t
                 ("llr_stride", C.c_uint32), ("out_stride", C.c_uint32)]
 
 
+class RmDesc(C.Structure):             # nrb200_rm_desc_t
+    _fields_ = [("BG", C.c_uint8), ("Z", C.c_uint16), ("Qm", C.c_uint8), ("rv", C.c_uint8), ("clear", C.c_uint8), ("C", C.c_uint32),
+                ("Tbslbrm", C.c_uint32), ("F", C.c_uint32), ("K", C.c_uint32), ("n_seg", C.c_uint32)]
+
+
 class Nrb200Error(RuntimeError):
     pass
 
@@ -84,6 +89,8 @@ class LdpcLib:
         L.nrb200_ldpc_encode_batch_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_crc_batch_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.nrb200_crc_batch_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.nrb200_ldpc_rm_tx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_last_error.restype = C.c_char_p
         L.nrb200_launch_count.restype = C.c_uint64
         self._inited = False
@@ -178,6 +185,35 @@ class LdpcLib:
         out = np.zeros(n, dtype=np.uint32)
         self._check(self.lib.nrb200_crc_batch_host(poly_id, n, data.ctypes.data, stride, bitlen, out.ctypes.data), "crc_batch_host")
         return out
+
+    # ---- rate matching / interleaving around the codec (nr_rate_matching.c), one transport block per call
+    def _rmdesc(self, BG, Z, Qm, rv, C_, Tbslbrm, F, n_seg, clear=0):
+        d = RmDesc()
+        d.BG, d.Z, d.Qm, d.rv, d.clear, d.C, d.Tbslbrm, d.F, d.K, d.n_seg = BG, Z, Qm, rv, clear, C_, Tbslbrm, F, (22 if BG == 1 else 10) * Z, n_seg
+        return d
+
+    def rm_tx_host(self, BG, Z, Qm, rv, C_, Tbslbrm, F, d, E):
+        """nr_rate_matching_ldpc + nr_interleaving_ldpc for the n_seg segments of a TB.  d: (n_seg, 66Z|50Z) 0/1 bytes, E: per-segment
+        lengths.  Returns the concatenated f (sum(E) bytes)."""
+        d = np.ascontiguousarray(d, dtype=np.uint8)
+        E = np.ascontiguousarray(E, dtype=np.uint32)
+        f = np.zeros(int(E.sum()), dtype=np.uint8)
+        desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, d.shape[0])
+        self._check(self.lib.nrb200_ldpc_rm_tx_batch_host(C.byref(desc), d.ctypes.data, d.shape[1], E.ctypes.data, f.ctypes.data), "rm_tx_batch_host")
+        return f
+
+    def rm_rx_host(self, BG, Z, Qm, rv, C_, Tbslbrm, F, soft, E, harq, clear):
+        """nr_deinterleaving_ldpc + nr_rate_matching_ldpc_rx + decoder-input packing.  soft: concatenated int16 LLRs, harq: (n_seg, >=N)
+        int16 updated in place.  Returns (n_seg, 68Z|52Z) int8 decoder inputs."""
+        soft = np.ascontiguousarray(soft, dtype=np.int16)
+        E = np.ascontiguousarray(E, dtype=np.uint32)
+        assert harq.dtype == np.int16 and harq.flags.c_contiguous
+        n = harq.shape[0]
+        kcz = (68 if BG == 1 else 52) * Z
+        llr = np.zeros((n, kcz), dtype=np.int8)
+        desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, n, clear)
+        self._check(self.lib.nrb200_ldpc_rm_rx_batch_host(C.byref(desc), soft.ctypes.data, E.ctypes.data, harq.ctypes.data, harq.shape[1], llr.ctypes.data, kcz), "rm_rx_batch_host")
+        return llr
 
     # ---- batched extension, device-resident torch tensors (asynchronous on torch's current stream)
     def decode_batch_torch(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):
