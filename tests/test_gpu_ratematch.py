@@ -97,11 +97,11 @@ def test_dl_ul_chain_roundtrip(ldpc, oracle):
         crc = oracle.crc(1, P[r], K - 24) >> 8
         P[r, -3:] = [(crc >> 16) & 0xFF, (crc >> 8) & 0xFF, crc & 0xFF]
     cw = ldpc.encode_batch_host(BG, Z, K, P)
-    Es = [12000] * C_
+    Es = [20000] * C_
     f = ldpc.rm_tx_host(BG, Z, Qm, rv, C_, 0, 0, cw, Es)
-    sigma = 0.6
+    sigma = 0.55
     y = (1.0 - 2.0 * f.astype(np.float64)) + sigma * rng.standard_normal(f.size)
-    soft = np.clip(np.floor(y * 8 / sigma / sigma / 4), -127, 127).astype(np.int16)
+    soft = np.clip(np.floor(y * 8 / sigma / sigma), -127, 127).astype(np.int16)
     harq = np.zeros((C_, 66 * Z), dtype=np.int16)
     llr = ldpc.rm_rx_host(BG, Z, Qm, rv, C_, 0, 0, soft, Es, harq, 1)
     R = oracle.get_R(rv, Es[0], BG, Z, 0, 0)[0]
