@@ -133,6 +133,13 @@ class Oracle:
         r = self.lib.orc_get_R_ldpc_decoder(rv, E, BG, Z, C.byref(ll), rnd)
         return r, ll.value
 
+    def dft(self, N, inverse, x, scale=1):
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        y = np.zeros(2 * N, dtype=np.int16)
+        rc = self.lib.orc_dft(N, int(inverse), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), scale)
+        assert rc == 0, rc
+        return y
+
     def segmentation(self, data, B, BG):
         Cc, K, Zo, F = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
         Kb = self.lib.orc_segmentation(None, None, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
@@ -290,3 +297,18 @@ class Reference:
             ptrs = (_u8p * Cc.value)(*[C.cast(segs[r].ctypes.data, _u8p) for r in range(Cc.value)])
             fn(_ptr(d, _u8p), ptrs, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
         return Kb, Cc.value, K.value, Zo.value, F.value, segs[:, :K.value // 8]
+
+    # ---- DFT library of the reference (libref_dfts.so): the per-size entry points and the dft()/idft() dispatchers
+    def dft(self, N, inverse, x, scale=1):
+        if not hasattr(self, "_dfts"):
+            self._dfts = C.CDLL(os.path.join(REFDIR, "libref_dfts.so"))
+            self._dfts.dfts_autoinit()
+        buf = np.zeros(2 * N + 64, dtype=np.int16)
+        o = ((-buf.ctypes.data) % 32) // 2
+        xin = buf[o:o + 2 * N]
+        xin[:] = np.asarray(x, dtype=np.int16)
+        out = np.zeros(2 * N + 64, dtype=np.int16)
+        oo = ((-out.ctypes.data) % 32) // 2
+        y = out[oo:oo + 2 * N]
+        getattr(self._dfts, ("idft" if inverse else "dft") + str(N))(xin.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_ubyte(scale))
+        return y.copy()

@@ -162,3 +162,19 @@ def test_segmentation(oracle, reference):
         o = oracle.segmentation(data, B, BG)
         assert r[:5] == o[:5], (BG, B, r[:5], o[:5])
         assert np.array_equal(r[5], o[5]), (BG, B)
+
+
+DFT_SIZES = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192]
+
+
+@pytest.mark.parametrize("N", DFT_SIZES)
+def test_dft_idft_q15(oracle, reference, N):
+    """Bit-exact Q15 DFT/IDFT restatement vs oai_dfts.c for the OFDM sizes, over amplitudes that do and do not saturate."""
+    rng = np.random.default_rng(N)
+    for inverse in (False, True):
+        for amp in (300, 3000, 20000, 32767):
+            for scale in (1, 0):
+                x = rng.integers(-amp, amp + 1, size=2 * N).astype(np.int16)
+                assert np.array_equal(oracle.dft(N, inverse, x, scale), reference.dft(N, inverse, x, scale)), (N, inverse, amp, scale)
+        x = rng.choice(np.array([-32768, 32767, 0], dtype=np.int16), size=2 * N)
+        assert np.array_equal(oracle.dft(N, inverse, x, 1), reference.dft(N, inverse, x, 1))
