@@ -1,0 +1,393 @@
+// libdfts_b200.so -- batched bit-exact Q15 DFT/IDFT kernels + the OAI `dft`/`idft` plug-in ABI (include/nrb200_dfts.h).
+//
+// Arithmetic restated from the reference openair1/PHY/TOOLS/oai_dfts.c: N = r3 * r2 * N4 with r3 in {1,3}, r2 in {1,2},
+// N4 = 16 * 4^D, decimation in time: 16-point saturating kernel (:1190-1458), radix-4 levels (16-bit saturating butterfly with
+// hand-rounded tables for 64 and forward 256 :803-948, 32-bit butterfly + wrapping add of x0 otherwise :633-721), optional
+// radix-2 level (:390-476) and radix-3 level (:477-540); per-level scaling >>3 (64), >>1 (256+), mulhrs 1/sqrt2, 1/sqrt3.
+// Here the recursion is unrolled into in-place passes over one shared-memory buffer: leaves are written in digit-reversed order
+// so every later butterfly reads and writes the same 4 (2, 3) addresses.  One CTA handles `tpb` transforms of N points.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/nrb200_dfts.h"
+#include "nr_dft_tables.h"
+
+#define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct cx { int r, i; };
+
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+__device__ __forceinline__ int wrap16(int v) { return (int)(short)v; }
+__device__ __forceinline__ int neg16(int v) { return v == -32768 ? -32768 : -v; }
+__device__ __forceinline__ cx mjn(cx a) { return {a.i, neg16(a.r)}; }
+__device__ __forceinline__ cx sadd(cx a, cx b) { return {sat16(a.r + b.r), sat16(a.i + b.i)}; }
+__device__ __forceinline__ cx ssub(cx a, cx b) { return {sat16(a.r - b.r), sat16(a.i - b.i)}; }
+__device__ __forceinline__ int sra15(unsigned v) { return ((int)v) >> 15; }
+__device__ __forceinline__ cx unpack(unsigned w) { return {(int)(short)(w & 0xFFFFu), (int)(short)(w >> 16)}; }
+__device__ __forceinline__ unsigned pack(cx a) { return ((unsigned)a.r & 0xFFFFu) | ((unsigned)a.i << 16); }
+// packed_cmult2: (a . ta, a . tb) >> 15, packs
+__device__ __forceinline__ cx cmult2(cx a, const short *ta, const short *tb)
+{
+  return {sat16(sra15((unsigned)(a.r * ta[0]) + (unsigned)(a.i * ta[1]))), sat16(sra15((unsigned)(a.r * tb[0]) + (unsigned)(a.i * tb[1])))};
+}
+__device__ __forceinline__ int mulhrs(int a, int b) { return wrap16((a * b + 0x4000) >> 15); }
+
+__device__ __forceinline__ void bfly4_sat(cx x0, cx a1, cx a2, cx a3, bool inv, cx &y0, cx &y1, cx &y2, cx &y3)
+{
+  cx x02 = sadd(x0, a2), x13 = sadd(a1, a3);
+  y0 = sadd(x02, x13);
+  y2 = ssub(x02, x13);
+  x02 = ssub(x0, a2);
+  x13 = ssub(mjn(a1), mjn(a3));
+  const cx ya = sadd(x02, x13), yb = ssub(x02, x13);
+  y1 = inv ? yb : ya;
+  y3 = inv ? ya : yb;
+}
+// 32-bit product by w (forward) or conj(w) (inverse); unsigned arithmetic wraps like the reference's epi32 adds
+__device__ __forceinline__ void cm32(cx x, int wr, int wi, bool inv, unsigned &re, unsigned &im)
+{
+  if (inv) { re = (unsigned)(x.r * wr) + (unsigned)(x.i * wi); im = (unsigned)(x.i * wr) - (unsigned)(x.r * wi); }
+  else { re = (unsigned)(x.r * wr) - (unsigned)(x.i * wi); im = (unsigned)(x.r * wi) + (unsigned)(x.i * wr); }
+}
+__device__ __forceinline__ cx pk32(unsigned r, unsigned i) { return {sat16(sra15(r)), sat16(sra15(i))}; }
+
+__device__ __forceinline__ void bfly4_32(cx x0, cx x1, cx x2, cx x3, const short *w1, const short *w2, const short *w3, bool inv, cx &y0, cx &y1,
+                                         cx &y2, cx &y3)
+{
+  unsigned x1r, x1i, x2r, x2i, x3r, x3i;
+  cm32(x1, w1[0], w1[1], inv, x1r, x1i);
+  cm32(x2, w2[0], w2[1], inv, x2r, x2i);
+  cm32(x3, w3[0], w3[1], inv, x3r, x3i);
+  const cx d0 = pk32(x1r + x2r + x3r, x1i + x2i + x3i);
+  const cx da = pk32(x1i - (x2r + x3i), (x3r - x2i) - x1r);
+  const cx d2 = pk32((x2r - x3r) - x1r, (x2i - x3i) - x1i);
+  const cx db = pk32((x3i - x2r) - x1i, x1r - (x2i + x3r));
+  y0 = {wrap16(x0.r + d0.r), wrap16(x0.i + d0.i)};
+  y2 = {wrap16(x0.r + d2.r), wrap16(x0.i + d2.i)};
+  const cx oa = {wrap16(x0.r + da.r), wrap16(x0.i + da.i)}, ob = {wrap16(x0.r + db.r), wrap16(x0.i + db.i)};
+  y1 = inv ? ob : oa;
+  y3 = inv ? oa : ob;
+}
+
+// Device-resident twiddle blob (int16): the hand-rounded tables of nr_dft_tables.h followed by the generated ones.
+struct TwOffsets {
+  int tw16, tw16a, tw16b, tw16c, tw64, tw64a, tw64b, tw64c, tw128, tw128a, tw128b, tw256, tw256a, tw256b, tw512;
+  int rad4_1024, rad4_4096, rad2_2048, rad2_8192, rad3[4];   // rad3: 768, 1536, 3072, 6144 (twa then twb)
+};
+
+struct DftPlan {
+  int N, r3, r2, N4, D;       // N = r3 * r2 * N4, N4 = 16 * 4^D
+  int inverse, scale;
+  int tpb;                    // transforms per CTA
+  int top4_tw;                // offset of the generated radix-4 table of the largest 4^k level (-1 if none)
+  int rad2_tw, rad3_tw;       // offsets, -1 if unused
+};
+
+__global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const short *__restrict__ tw, const unsigned *__restrict__ in,
+                                                  unsigned *__restrict__ out, unsigned n)
+{
+  extern __shared__ unsigned sm[];          // [tpb][N] natural-order input copy, then [tpb][N] work buffer
+  const int N = P.N, tpb = P.tpb;
+  unsigned *xin = sm, *buf = sm + tpb * N;
+  const bool inv = P.inverse != 0;
+  const unsigned t0 = blockIdx.x * tpb;
+  const int nt = min((unsigned)tpb, n - t0);
+  for (int i = threadIdx.x; i < nt * N; i += blockDim.x) xin[i] = in[(size_t)t0 * N + i];
+  __syncthreads();
+  // ---- leaves: 16-point kernels, output slot = digit-reversed leaf id so that all later passes are in place
+  const int T = P.r3 * P.r2, leaves4 = P.N4 >> 4, D = P.D;
+  const short *ta16 = tw + (inv ? O.tw16 : O.tw16a), *tb16 = tw + (inv ? O.tw16c : O.tw16b);
+  for (int w = threadIdx.x; w < nt * T * leaves4; w += blockDim.x) {
+    const int tr = w / (T * leaves4), rem = w - tr * (T * leaves4);
+    const int t = rem / leaves4, s = rem - t * leaves4;
+    const int q3 = t / P.r2, q2 = t - q3 * P.r2;
+    int mo = 0;                                            // m' = d1 + 4 d2 + ...; s = dD + 4 d(D-1) + ... + 4^(D-1) d1
+    for (int l = 0, ss = s; l < D; l++, ss >>= 2) mo = (mo << 2) | (ss & 3);
+    const unsigned *x = xin + tr * N;
+    cx v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) v[m] = unpack(x[q3 + P.r3 * (q2 + P.r2 * (mo + (m << (2 * D))))]);
+    cx A[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) bfly4_sat(v[c], v[4 + c], v[8 + c], v[12 + c], inv, A[0][c], A[1][c], A[2][c], A[3][c]);
+    unsigned *y = buf + tr * N + t * P.N4 + s * 16;
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+      cx b1 = cmult2(A[k1][1], ta16 + 2 * k1, tb16 + 2 * k1), b2 = cmult2(A[k1][2], ta16 + 8 + 2 * k1, tb16 + 8 + 2 * k1),
+         b3 = cmult2(A[k1][3], ta16 + 16 + 2 * k1, tb16 + 16 + 2 * k1);
+      cx y0, y1, y2, y3;
+      bfly4_sat(A[k1][0], b1, b2, b3, inv, y0, y1, y2, y3);
+      y[k1] = pack(y0); y[k1 + 4] = pack(y1); y[k1 + 8] = pack(y2); y[k1 + 12] = pack(y3);
+    }
+  }
+  __syncthreads();
+  // ---- radix-4 levels: sub-size M -> 4M, in place
+  for (int l = 1, M = 16; l <= D; l++, M <<= 2) {
+    const int size = 4 * M;
+    const bool last_overall = (l == D) && T == 1;
+    const int sh = size == 64 ? 3 : 1;
+    const bool do_scale = last_overall ? (P.scale != 0) : true;
+    const int nb = nt * (N >> 2);
+    for (int w = threadIdx.x; w < nb; w += blockDim.x) {
+      const int tr = w / (N >> 2), rem = w - tr * (N >> 2);
+      const int g = rem / M, k = rem - g * M;              // g enumerates (t, s') groups: base = g * 4M
+      unsigned *p = buf + tr * N + g * size + k;
+      const cx x0 = unpack(p[0]), x1 = unpack(p[M]), x2 = unpack(p[2 * M]), x3 = unpack(p[3 * M]);
+      cx y0, y1, y2, y3;
+      if (size == 64) {
+        const short *ta = tw + (inv ? O.tw64 : O.tw64a), *tb = tw + (inv ? O.tw64c : O.tw64b);
+        bfly4_sat(x0, cmult2(x1, ta + 2 * k, tb + 2 * k), cmult2(x2, ta + 32 + 2 * k, tb + 32 + 2 * k), cmult2(x3, ta + 64 + 2 * k, tb + 64 + 2 * k), inv,
+                  y0, y1, y2, y3);
+      } else if (size == 256 && !inv) {
+        const short *ta = tw + O.tw256a, *tb = tw + O.tw256b;
+        bfly4_sat(x0, cmult2(x1, ta + 2 * k, tb + 2 * k), cmult2(x2, ta + 128 + 2 * k, tb + 128 + 2 * k), cmult2(x3, ta + 256 + 2 * k, tb + 256 + 2 * k),
+                  false, y0, y1, y2, y3);
+      } else {
+        const short *t4 = tw + (size == 256 ? O.tw256 : size == 1024 ? O.rad4_1024 : O.rad4_4096);
+        bfly4_32(x0, x1, x2, x3, t4 + 2 * k, t4 + 2 * M + 2 * k, t4 + 4 * M + 2 * k, inv, y0, y1, y2, y3);
+      }
+      if (do_scale) { y0.r >>= sh; y0.i >>= sh; y1.r >>= sh; y1.i >>= sh; y2.r >>= sh; y2.i >>= sh; y3.r >>= sh; y3.i >>= sh; }
+      p[0] = pack(y0); p[M] = pack(y1); p[2 * M] = pack(y2); p[3 * M] = pack(y3);
+    }
+    __syncthreads();
+  }
+  // ---- radix-2 level
+  if (P.r2 == 2) {
+    const int M = P.N4, size = 2 * M;
+    const bool do_scale = P.r3 == 1 ? (P.scale != 0) : true;
+    for (int w = threadIdx.x; w < nt * (N >> 1); w += blockDim.x) {
+      const int tr = w / (N >> 1), rem = w - tr * (N >> 1);
+      const int g = rem / M, k = rem - g * M;
+      unsigned *p = buf + tr * N + g * size + k;
+      const cx x0 = unpack(p[0]), x1 = unpack(p[M]);
+      cx y0, y1;
+      if (size == 128 && !inv) {
+        const cx t = cmult2(x1, tw + O.tw128a + 2 * k, tw + O.tw128b + 2 * k);
+        y0 = sadd(x0, t); y1 = ssub(x0, t);
+      } else {
+        const short *t2 = tw + (size == 128 ? O.tw128 : size == 512 ? O.tw512 : P.rad2_tw) + 2 * k;
+        unsigned br, bi;
+        cm32(x1, t2[0], t2[1], inv, br, bi);
+        const unsigned ar = (unsigned)(x0.r * 32767), ai = (unsigned)(x0.i * 32767);
+        y0 = pk32(ar + br, ai + bi); y1 = pk32(ar - br, ai - bi);
+      }
+      if (do_scale) { y0.r = mulhrs(y0.r, 23170); y0.i = mulhrs(y0.i, 23170); y1.r = mulhrs(y1.r, 23170); y1.i = mulhrs(y1.i, 23170); }
+      p[0] = pack(y0); p[M] = pack(y1);
+    }
+    __syncthreads();
+  }
+  // ---- radix-3 level
+  if (P.r3 == 3) {
+    const int M = N / 3;
+    const short *twa = tw + P.rad3_tw, *twb = twa + 2 * M;
+    for (int w = threadIdx.x; w < nt * M; w += blockDim.x) {
+      const int tr = w / M, k = w - tr * M;
+      unsigned *p = buf + tr * N + k;
+      const cx x0 = unpack(p[0]);
+      unsigned r, i, r2, i2;
+      cm32(unpack(p[M]), twa[2 * k], twa[2 * k + 1], inv, r, i);
+      const cx x1 = pk32(r, i);
+      cm32(unpack(p[2 * M]), twb[2 * k], twb[2 * k + 1], inv, r, i);
+      const cx x2 = pk32(r, i);
+      cx y0 = sadd(x0, sadd(x1, x2));
+      cm32(x1, -16384, -28378, inv, r, i); cm32(x2, -16384, 28378, inv, r2, i2);
+      cx y1 = sadd(x0, pk32(r + r2, i + i2));
+      cm32(x1, -16384, 28378, inv, r, i); cm32(x2, -16384, -28378, inv, r2, i2);
+      cx y2 = sadd(x0, pk32(r + r2, i + i2));
+      if (P.scale == 1) {
+        y0.r = mulhrs(y0.r, 18919); y0.i = mulhrs(y0.i, 18919); y1.r = mulhrs(y1.r, 18919); y1.i = mulhrs(y1.i, 18919);
+        y2.r = mulhrs(y2.r, 18919); y2.i = mulhrs(y2.i, 18919);
+      }
+      p[0] = pack(y0); p[M] = pack(y1); p[2 * M] = pack(y2);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < nt * N; i += blockDim.x) out[(size_t)t0 * N + i] = buf[i];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct DftCtx {
+  std::mutex mu;
+  bool inited = false;
+  int dev = 0;
+  short *d_tw = nullptr;
+  TwOffsets off;
+  cudaStream_t stream = nullptr;
+  void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
+  size_t cap = 0;
+  std::atomic<uint64_t> launches{0};
+  std::string last_error;
+};
+DftCtx &dctx() { static DftCtx c; return c; }
+
+short rnd16(double v) { return (short)std::round(v); }
+
+int dft_init()
+{
+  DftCtx &c = dctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.inited) return 0;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { c.last_error = "no CUDA device"; return -1; }
+  int want = 0;
+  if (const char *s = getenv("NRB200_DEVICE")) want = atoi(s);
+  else if (const char *s2 = getenv("LOCAL_RANK")) want = atoi(s2) % n;
+  if (want < 0 || want >= n) want = 0;
+  if (cudaSetDevice(want) != cudaSuccess) { c.last_error = "cudaSetDevice failed"; return -1; }
+  c.dev = want;
+  std::vector<short> blob;
+  auto put = [&](const int16_t *p, int len) { int o = (int)blob.size(); blob.insert(blob.end(), p, p + len); return o; };
+  TwOffsets &O = c.off;
+  O.tw16 = put(NRB200_TW16, 24); O.tw16a = put(NRB200_TW16A, 24); O.tw16b = put(NRB200_TW16B, 24); O.tw16c = put(NRB200_TW16C, 24);
+  O.tw64 = put(NRB200_TW64, 96); O.tw64a = put(NRB200_TW64A, 96); O.tw64b = put(NRB200_TW64B, 96); O.tw64c = put(NRB200_TW64C, 96);
+  O.tw128 = put(NRB200_TW128, 128); O.tw128a = put(NRB200_TW128A, 128); O.tw128b = put(NRB200_TW128B, 128);
+  O.tw256 = put(NRB200_TW256, 384); O.tw256a = put(NRB200_TW256A, 384); O.tw256b = put(NRB200_TW256B, 384);
+  O.tw512 = put(NRB200_TW512, 512);
+  auto rad4 = [&](int N) {   // init_rad4 (oai_dfts.c:7709-7722): three planes W^k, W^2k, W^3k of N/4 entries
+    int o = (int)blob.size();
+    for (int p = 1; p <= 3; p++)
+      for (int i = 0; i < N / 4; i++) { blob.push_back(rnd16(32767.0 * cos(2 * M_PI * p * i / N))); blob.push_back((short)-rnd16(32767.0 * sin(2 * M_PI * p * i / N))); }
+    return o;
+  };
+  auto rad2 = [&](int N) {   // init_rad2 (:7747-7756)
+    int o = (int)blob.size();
+    for (int i = 0; i < N / 2; i++) { blob.push_back(rnd16(32767.0 * cos(2 * M_PI * i / N))); blob.push_back((short)-rnd16(32767.0 * sin(2 * M_PI * i / N))); }
+    return o;
+  };
+  auto rad3 = [&](int N) {   // init_rad3 (:7772-7782): twa then twb
+    int o = (int)blob.size();
+    for (int p = 1; p <= 2; p++)
+      for (int i = 0; i < N / 3; i++) { blob.push_back(rnd16(32767.0 * cos(2 * M_PI * p * i / N))); blob.push_back((short)-rnd16(32767.0 * sin(2 * M_PI * p * i / N))); }
+    return o;
+  };
+  O.rad4_1024 = rad4(1024); O.rad4_4096 = rad4(4096); O.rad2_2048 = rad2(2048); O.rad2_8192 = rad2(8192);
+  const int r3n[4] = {768, 1536, 3072, 6144};
+  for (int i = 0; i < 4; i++) O.rad3[i] = rad3(r3n[i]);
+  if (cudaMalloc(&c.d_tw, blob.size() * sizeof(short)) != cudaSuccess) { c.last_error = "cudaMalloc twiddles"; return -1; }
+  cudaMemcpy(c.d_tw, blob.data(), blob.size() * sizeof(short), cudaMemcpyHostToDevice);
+  if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) { c.last_error = "stream"; return -1; }
+  cudaFuncSetAttribute(dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  c.inited = true;
+  return 0;
+}
+
+bool make_plan(int N, int inverse, int scale, DftPlan *P)
+{
+  const DftCtx &c = dctx();
+  int r3 = (N % 3 == 0) ? 3 : 1, rest = N / r3, r2 = 1, D = -1;
+  for (int d = 1, n4 = 64; d <= 4; d++, n4 *= 4) {
+    if (rest == n4) { D = d; break; }
+    if (rest == 2 * n4) { D = d; r2 = 2; break; }
+  }
+  if (D < 0 || N > 8192) return false;
+  P->N = N; P->r3 = r3; P->r2 = r2; P->N4 = rest / r2; P->D = D; P->inverse = inverse; P->scale = scale;
+  P->tpb = N >= 2048 ? 1 : 2048 / N;
+  P->top4_tw = -1;
+  P->rad2_tw = r2 == 2 ? (2 * P->N4 == 2048 ? c.off.rad2_2048 : 2 * P->N4 == 8192 ? c.off.rad2_8192 : -1) : -1;
+  P->rad3_tw = r3 == 3 ? c.off.rad3[N == 768 ? 0 : N == 1536 ? 1 : N == 3072 ? 2 : 3] : -1;
+  return true;
+}
+
+int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
+{
+  DftPlan P;
+  if (!make_plan(N, inverse, scale, &P)) return -4;
+  if (n == 0) return 0;
+  DftCtx &c = dctx();
+  const unsigned grid = (n + P.tpb - 1) / P.tpb;
+  const size_t smem = (size_t)2 * P.tpb * N * 4;
+  dft_kernel<<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n);
+  c.launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft launch: ") + cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+const int kDftSizes[] = {12, 24, 36, 48, 60, 64, 72, 96, 108, 120, 128, 144, 180, 192, 216, 240, 256, 288, 300, 324, 360, 384, 432, 480, 512, 540, 576, 600,
+                         648, 720, 768, 864, 900, 960, 972, 1024, 1080, 1152, 1200, 1296, 1440, 1500, 1536, 1620, 1728, 1800, 1920, 1944, 2048, 2160,
+                         2304, 2400, 2592, 2700, 2880, 2916, 3000, 3072, 3240, 4096, 6144, 8192, 9216, 12288, 18432, 24576, 36864, 49152, 73728, 98304};
+const int kIdftSizes[] = {64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 9216, 12288, 16384, 18432, 24576, 32768, 36864, 49152, 65536,
+                          73728, 98304};
+
+void one_transform(bool inverse, uint8_t sizeidx, int16_t *in, int16_t *out, unsigned char scale)
+{
+  const int N = nrb200_dft_size_of_index(inverse, sizeidx);
+  if (N < 0 || !nrb200_dft_supported(N) || dft_init() != 0) {
+    fprintf(stderr, "[nrb200 dfts] %s size index %d (N=%d) is not available in libdfts_b200.so: %s\n", inverse ? "idft" : "dft", sizeidx, N,
+            dctx().inited ? "size not implemented yet" : dctx().last_error.c_str());
+    abort();   // fail loudly: this library has no CPU fallback
+  }
+  if (nrb200_dft_batch_host(N, inverse, 1, in, out, scale) != 0) {
+    fprintf(stderr, "[nrb200 dfts] transform failed: %s\n", dctx().last_error.c_str());
+    abort();
+  }
+}
+
+}  // namespace
+
+NRB200_EXPORT int32_t nrb200_dft_size_of_index(int inverse, int sizeidx)
+{
+  if (sizeidx < 0) return -1;
+  if (inverse) return sizeidx < (int)(sizeof(kIdftSizes) / sizeof(int)) ? kIdftSizes[sizeidx] : -1;
+  return sizeidx < (int)(sizeof(kDftSizes) / sizeof(int)) ? kDftSizes[sizeidx] : -1;
+}
+
+NRB200_EXPORT int32_t nrb200_dft_supported(int N)
+{
+  DftPlan P;
+  int r3 = (N % 3 == 0) ? 3 : 1, rest = N / r3;
+  (void)P;
+  for (int n4 = 64; n4 <= 4096; n4 *= 4) if (rest == n4 || rest == 2 * n4) return N <= 8192 ? 1 : 0;
+  return 0;
+}
+
+NRB200_EXPORT int dfts_autoinit(void) { return dft_init(); }
+
+NRB200_EXPORT int32_t nrb200_dft_batch_dev(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, void *stream)
+{
+  if (dft_init() != 0) return -1;
+  cudaSetDevice(dctx().dev);
+  return launch_dft(N, inverse, n, d_in, d_out, scale, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, const int16_t *in, int16_t *out, int scale)
+{
+  if (dft_init() != 0) return -1;
+  if (!nrb200_dft_supported(N)) return -4;
+  if (n == 0) return 0;
+  DftCtx &c = dctx();
+  std::lock_guard<std::mutex> lk(c.mu);   // one staging buffer: host-buffer calls are serialised (the batched entry point is the fast path)
+  cudaSetDevice(c.dev);
+  const size_t bytes = (size_t)n * N * 4;
+  if (bytes > c.cap) {
+    if (c.d_in) { cudaFree(c.d_in); cudaFree(c.d_out); cudaFreeHost(c.h_in); cudaFreeHost(c.h_out); }
+    c.cap = bytes + bytes / 4 + 65536;
+    if (cudaMalloc(&c.d_in, c.cap) != cudaSuccess || cudaMalloc(&c.d_out, c.cap) != cudaSuccess || cudaHostAlloc(&c.h_in, c.cap, 0) != cudaSuccess ||
+        cudaHostAlloc(&c.h_out, c.cap, 0) != cudaSuccess) { c.cap = 0; c.last_error = "staging alloc"; return -5; }
+  }
+  std::memcpy(c.h_in, in, bytes);
+  cudaMemcpyAsync(c.d_in, c.h_in, bytes, cudaMemcpyHostToDevice, c.stream);
+  DftPlan P;
+  if (!make_plan(N, inverse, scale, &P)) return -4;
+  const unsigned grid = (n + P.tpb - 1) / P.tpb;
+  dft_kernel<<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n);
+  c.launches++;
+  cudaMemcpyAsync(c.h_out, c.d_out, bytes, cudaMemcpyDeviceToHost, c.stream);
+  cudaError_t e = cudaStreamSynchronize(c.stream);
+  if (e != cudaSuccess) { c.last_error = std::string("dft: ") + cudaGetErrorString(e); return -2; }
+  std::memcpy(out, c.h_out, bytes);
+  return 0;
+}
+
+NRB200_EXPORT void dft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag) { one_transform(false, sizeidx, sigF, sig, scale_flag); }
+NRB200_EXPORT void idft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag) { one_transform(true, sizeidx, sigF, sig, scale_flag); }
+NRB200_EXPORT const char *nrb200_dfts_last_error(void) { return dctx().last_error.c_str(); }
+NRB200_EXPORT uint64_t nrb200_dfts_launch_count(void) { return dctx().launches.load(); }

@@ -1,0 +1,91 @@
+"""Host-side binding of libdfts_b200.so -- the B200-native drop-in for OAI's loadable DFT library (`dft`/`idft` function-pointer
+pair, openair1/PHY/TOOLS/dfts_load.c:47-61, tools_defs.h:404-676).  Bit-exact Q15 arithmetic of oai_dfts.c for the OFDM sizes."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdfts_b200.so")
+
+DFT_SIZES = [12, 24, 36, 48, 60, 64, 72, 96, 108, 120, 128, 144, 180, 192, 216, 240, 256, 288, 300, 324, 360, 384, 432, 480, 512, 540, 576, 600, 648, 720,
+             768, 864, 900, 960, 972, 1024, 1080, 1152, 1200, 1296, 1440, 1500, 1536, 1620, 1728, 1800, 1920, 1944, 2048, 2160, 2304, 2400, 2592, 2700,
+             2880, 2916, 3000, 3072, 3240, 4096, 6144, 8192, 9216, 12288, 18432, 24576, 36864, 49152, 73728, 98304]      # FOREACH_DFTSZ
+IDFT_SIZES = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 9216, 12288, 16384, 18432, 24576, 32768, 36864, 49152, 65536, 73728,
+              98304]                                                                                                      # FOREACH_IDFTSZ
+SUPPORTED = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192]
+
+
+def get_dft(N):
+    """dft_size_idx_t of N (tools_defs.h:547-610)."""
+    return DFT_SIZES.index(N)
+
+
+def get_idft(N):
+    return IDFT_SIZES.index(N)
+
+
+class DftsLib:
+    def __init__(self, path=_SO):
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = self.lib = C.CDLL(path)
+        L.dft.argtypes = [C.c_uint8, C.c_void_p, C.c_void_p, C.c_ubyte]
+        L.dft.restype = None
+        L.idft.argtypes = [C.c_uint8, C.c_void_p, C.c_void_p, C.c_ubyte]
+        L.idft.restype = None
+        L.nrb200_dft_batch_dev.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.nrb200_dft_batch_host.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.nrb200_dfts_last_error.restype = C.c_char_p
+        L.nrb200_dfts_launch_count.restype = C.c_uint64
+
+    def autoinit(self):
+        if self.lib.dfts_autoinit() != 0:
+            raise RuntimeError("dfts_autoinit failed: " + (self.lib.nrb200_dfts_last_error() or b"").decode())
+
+    def dft(self, sizeidx, x, scale=1):
+        """The plug-in call OAI makes: dft(get_dft(N), in, out, scale_flag), one transform."""
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        y = np.zeros_like(x)
+        self.lib.dft(sizeidx, x.ctypes.data, y.ctypes.data, scale)
+        return y
+
+    def idft(self, sizeidx, x, scale=1):
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        y = np.zeros_like(x)
+        self.lib.idft(sizeidx, x.ctypes.data, y.ctypes.data, scale)
+        return y
+
+    def batch_host(self, N, inverse, x, scale=1):
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        n = x.size // (2 * N)
+        y = np.zeros_like(x)
+        rc = self.lib.nrb200_dft_batch_host(N, int(inverse), n, x.ctypes.data, y.ctypes.data, scale)
+        if rc != 0:
+            raise RuntimeError(f"nrb200_dft_batch_host rc={rc}: " + (self.lib.nrb200_dfts_last_error() or b"").decode())
+        return y
+
+    def batch_torch(self, N, inverse, x, scale=1, out=None):
+        import torch
+        assert x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
+        n = x.numel() // (2 * N)
+        if out is None:
+            out = torch.empty_like(x)
+        rc = self.lib.nrb200_dft_batch_dev(N, int(inverse), n, x.data_ptr(), out.data_ptr(), scale, torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"nrb200_dft_batch_dev rc={rc}")
+        return out
+
+    def launch_count(self):
+        return int(self.lib.nrb200_dfts_launch_count())
+
+
+_lib = None
+
+
+def load_dftslib():
+    """load_dftslib() equivalent (dfts_load.c:47-61): dlopen + dfts_autoinit."""
+    global _lib
+    if _lib is None:
+        _lib = DftsLib()
+        _lib.autoinit()
+    return _lib

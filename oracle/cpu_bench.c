@@ -64,3 +64,39 @@ long orc_bench_ldpc_decoder(void *fn, const int8_t *llr, int n, int stride, int 
   free(th); free(jobs);
   return total;
 }
+
+/* ---- same idea for the DFT library: `fn` is the reference's per-size entry point (e.g. idft4096 of oracle/_ref/libref_dfts.so) */
+typedef void (*dft_fn_t)(int16_t *, int16_t *, unsigned char);
+typedef struct { dft_fn_t fn; const int16_t *x; int N, n, tid, nthreads; double seconds; long count; } djob_t;
+static void *dworker(void *arg)
+{
+  djob_t *j = (djob_t *)arg;
+  int16_t *in = aligned_alloc(64, (size_t)j->N * 4 + 64), *out = aligned_alloc(64, (size_t)j->N * 4 + 64);
+  const double t_end = now_s() + j->seconds;
+  int i = j->tid;
+  while (now_s() < t_end) {
+    for (int r = 0; r < 16; r++) {
+      memcpy(in, j->x + (size_t)(i % j->n) * j->N * 2, (size_t)j->N * 4);
+      j->fn(in, out, 1);
+      j->count++;
+      i += j->nthreads;
+    }
+  }
+  free(in); free(out);
+  return NULL;
+}
+long orc_bench_dft(void *fn, const int16_t *x, int N, int n, int threads, double seconds, double *elapsed)
+{
+  pthread_t *th = calloc((size_t)threads, sizeof(*th));
+  djob_t *jobs = calloc((size_t)threads, sizeof(*jobs));
+  const double t0 = now_s();
+  for (int t = 0; t < threads; t++) {
+    jobs[t] = (djob_t){(dft_fn_t)fn, x, N, n, t, threads, seconds, 0};
+    pthread_create(&th[t], NULL, dworker, &jobs[t]);
+  }
+  long total = 0;
+  for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); total += jobs[t].count; }
+  *elapsed = now_s() - t0;
+  free(th); free(jobs);
+  return total;
+}

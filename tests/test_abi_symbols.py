@@ -21,12 +21,23 @@ def test_ldpc_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
 
 
+def test_dfts_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(ROOT, "openairinterface5g_b200", "libdfts_b200.so"))
+    names = _declared("nrb200_dfts.h")
+    assert {"dft", "idft", "dfts_autoinit"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
 def test_only_abi_symbols_are_exported():
     """-fvisibility=hidden + -Bsymbolic: ldpctest loads two LDPC libraries RTLD_GLOBAL in one process."""
     import subprocess
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "openairinterface5g_b200", "libldpc_b200.so")], text=True)
     syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
     assert all(s.startswith(("LDPC", "nrb200_")) for s in syms), syms
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "openairinterface5g_b200", "libdfts_b200.so")], text=True)
+    syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert all(s in ("dft", "idft", "dfts_autoinit") or s.startswith("nrb200_") for s in syms), syms
 
 
 def test_struct_layouts_match_reference_abi():

@@ -74,3 +74,11 @@ def test_coding_golden(oracle):
         Kb, Cc, K, Zc, F, s = oracle.segmentation(d[f"seg{ci}_in"], B, BG)
         assert [Kb, Cc, K, Zc, F] == d[f"seg{ci}_par"].tolist()
         assert np.array_equal(s, d[f"seg{ci}_out"])
+
+
+def test_dft_golden(oracle):
+    d = _load("dft.npz")
+    for N in (64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192):
+        for i in range(d[f"x{N}"].shape[0]):
+            assert np.array_equal(oracle.dft(N, False, d[f"x{N}"][i], 1), d[f"dft{N}"][i]), N
+            assert np.array_equal(oracle.dft(N, True, d[f"x{N}"][i], 1), d[f"idft{N}"][i]), N

@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Secondary measurements (not the headline bench line): Q15 IDFT/DFT 4096 throughput (one 100 MHz slot = 28 transforms for 2 antennas),
+LDPC encoder and rate-matching throughput, each with the reference's CPU path timed on the host cores where a compiled reference
+exists.  Prints one JSON object per line; used by tools/gpu_round.sh and summarised under profiles/."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openairinterface5g_b200.ldpc import load_LDPClib          # noqa: E402
+from openairinterface5g_b200.dfts import load_dftslib           # noqa: E402
+
+
+def peaks():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def cpu_dft(N, inverse, seconds=5.0):
+    from oracle import bindings as ob
+    if not ob.have_reference():
+        return None
+    ref = C.CDLL(os.path.join(ob.REFDIR, "libref_dfts.so"))
+    ref.dfts_autoinit()
+    orc = ob.Oracle()
+    f = orc.lib.orc_bench_dft
+    f.restype = C.c_long
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    x = np.random.default_rng(0).integers(-3000, 3000, size=(64, 2 * N)).astype(np.int16)
+    el = C.c_double()
+    cores = os.cpu_count() or 1
+    n = f(C.cast(getattr(ref, ("idft" if inverse else "dft") + str(N)), C.c_void_p), x.ctypes.data, N, 64, cores, seconds, C.byref(el))
+    return {"value": n / el.value, "unit": "transforms/s", "cores": cores, "kind": "reference", "sample": f"{n} {N}-point transforms in {el.value:.1f} s"}
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    lib, dl = load_LDPClib(), load_dftslib()
+    hbm = peaks()
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    # ---- DFT 4096: 1024 slots' worth? keep it at 28 transforms x 64 slots = 1792 transforms (29 MB in, 29 MB out)
+    for N, inverse, nb in ((4096, True, 1792), (4096, False, 1792), (2048, True, 3584), (1536, False, 3584)):
+        bufs = [torch.randint(-3000, 3000, (nb, 2 * N), dtype=torch.int16, device=dev, generator=g) for _ in range(5)]   # 5 x 29 MB > L2
+        out = torch.empty_like(bufs[0])
+        i = [0]
+
+        def run():
+            dl.batch_torch(N, inverse, bufs[i[0] % 5], 1, out=out); i[0] += 1
+        ms = timeit(run, n=40)
+        algo = nb * N * 4 * 2
+        line = {"what": f"{'idft' if inverse else 'dft'}{N}", "batch": nb, "ms": ms, "value": nb / ms * 1e3, "unit": "transforms/s",
+                "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo / ms / 1e6 / hbm, "algorithmic_bytes_per_transform": N * 8}}
+        if N == 4096:
+            line["cpu_baseline"] = cpu_dft(N, inverse)
+            h = bufs[0].cpu().numpy()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                dl.batch_host(N, inverse, h, 1)
+            line["e2e_transforms_per_s"] = 5 * nb / (time.perf_counter() - t0)
+        print(json.dumps(line), flush=True)
+    # ---- encoder + rate matching (BG1 Z=384, batch 1024)
+    B, Z, K = 1024, 384, 8448
+    payload = torch.randint(0, 256, (B, K // 8), dtype=torch.uint8, device=dev, generator=g)
+    cw = torch.empty((B, 66 * Z), dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: lib.encode_batch_torch(1, Z, K, payload, out=cw), n=20)
+    algo = B * (K // 8 + 66 * Z)
+    print(json.dumps({"what": "ldpc_encode BG1 Z=384", "batch": B, "ms": ms, "value": B / ms * 1e3, "unit": "CB/s",
+                      "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo / ms / 1e6 / hbm, "algorithmic_bytes_per_cb": K // 8 + 66 * Z}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
