@@ -193,6 +193,19 @@ int32_t nrb200_ldpc_rm_rx_batch_dev(const nrb200_rm_desc_t *desc, const int16_t 
 int32_t nrb200_ldpc_rm_rx_batch_host(const nrb200_rm_desc_t *desc, const int16_t *soft, const uint32_t *E, int16_t *harq, uint32_t harq_stride,
                                      int8_t *llr, uint32_t llr_stride);
 
+/* ------------------------------------------------------------------------------------------
+ * Part 4: demodulation -- single-layer max-log LLRs (no plug-in boundary exists for this in OAI: a maintainer interposes
+ * nr_ulsch_compute_llr / nr_dlsch_*_llr)
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces nr_ulsch_compute_llr (nr_ulsch_llr_computation.c:316-373): rxF = nb_re compensated symbols {re, im} int16, mag_a/b/c =
+ * the |h|^2-scaled decision thresholds (unused planes may be NULL), llr = nb_re * Qm int16, Qm in {2, 4, 6, 8}.
+ * All pointers 16-byte aligned for the _dev variant. */
+int32_t nrb200_pusch_llr_dev(int Qm, uint32_t nb_re, const int16_t *d_rxF, const int16_t *d_mag_a, const int16_t *d_mag_b,
+                             const int16_t *d_mag_c, int16_t *d_llr, void *stream);
+int32_t nrb200_pusch_llr_host(int Qm, uint32_t nb_re, const int16_t *rxF, const int16_t *mag_a, const int16_t *mag_b, const int16_t *mag_c,
+                              int16_t *llr);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

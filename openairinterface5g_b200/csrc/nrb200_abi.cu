@@ -14,6 +14,7 @@ int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_
                   uint8_t *d_out, uint32_t out_stride, cudaStream_t stream);
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
 int quirks_from_env();
+int launch_pusch_llr(int Qm, uint32_t nb_re, const int16_t *y, const int16_t *ma, const int16_t *mb, const int16_t *mc, int16_t *out, cudaStream_t st);
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
 int launch_rm_rx(const nrb200_rm_desc_t &p, const int16_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
                  int8_t *llr, uint32_t llr_stride, cudaStream_t st);
@@ -376,6 +377,44 @@ NRB200_EXPORT int32_t nrb200_ldpc_rm_rx_batch_host(const nrb200_rm_desc_t *desc,
     if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
     std::memcpy(llr, w->h_out, llr_bytes);
     std::memcpy(harq, (uint8_t *)w->h_in + hoff, harq_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ part 4: demodulation LLRs
+NRB200_EXPORT int32_t nrb200_pusch_llr_dev(int Qm, uint32_t nb_re, const int16_t *d_rxF, const int16_t *d_mag_a, const int16_t *d_mag_b,
+                                           const int16_t *d_mag_c, int16_t *d_llr, void *stream)
+{
+  if (ensure_init()) return -1;
+  if ((Qm >= 4 && !d_mag_a) || (Qm >= 6 && !d_mag_b) || (Qm >= 8 && !d_mag_c)) return -4;
+  return launch_pusch_llr(Qm, nb_re, d_rxF, d_mag_a, d_mag_b, d_mag_c, d_llr, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_pusch_llr_host(int Qm, uint32_t nb_re, const int16_t *rxF, const int16_t *mag_a, const int16_t *mag_b, const int16_t *mag_c,
+                                            int16_t *llr)
+{
+  if (ensure_init()) return -1;
+  if (Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) return -4;
+  if ((Qm >= 4 && !mag_a) || (Qm >= 6 && !mag_b) || (Qm >= 8 && !mag_c)) return -4;
+  if (nb_re == 0) return 0;
+  const size_t plane = ((size_t)nb_re * 4 + 15) & ~(size_t)15, out_bytes = (size_t)nb_re * Qm * 2;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(4 * plane, out_bytes + 16, 16)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    uint8_t *h = (uint8_t *)w->h_in;
+    std::memcpy(h, rxF, (size_t)nb_re * 4);
+    if (Qm >= 4) std::memcpy(h + plane, mag_a, (size_t)nb_re * 4);
+    if (Qm >= 6) std::memcpy(h + 2 * plane, mag_b, (size_t)nb_re * 4);
+    if (Qm >= 8) std::memcpy(h + 3 * plane, mag_c, (size_t)nb_re * 4);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, 4 * plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    const uint8_t *d = (const uint8_t *)w->d_in;
+    if ((rc = launch_pusch_llr(Qm, nb_re, (const int16_t *)d, (const int16_t *)(d + plane), (const int16_t *)(d + 2 * plane), (const int16_t *)(d + 3 * plane),
+                               (int16_t *)w->d_out, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(llr, w->h_out, out_bytes);
   } while (0);
   ctx().release(w);
   return rc;

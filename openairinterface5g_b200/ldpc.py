@@ -91,6 +91,8 @@ class LdpcLib:
         L.nrb200_crc_batch_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.nrb200_ldpc_rm_tx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.nrb200_pusch_llr_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_llr_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_last_error.restype = C.c_char_p
         L.nrb200_launch_count.restype = C.c_uint64
         self._inited = False
@@ -214,6 +216,27 @@ class LdpcLib:
         desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, n, clear)
         self._check(self.lib.nrb200_ldpc_rm_rx_batch_host(C.byref(desc), soft.ctypes.data, E.ctypes.data, harq.ctypes.data, harq.shape[1], llr.ctypes.data, kcz), "rm_rx_batch_host")
         return llr
+
+    # ---- demodulation: nr_ulsch_compute_llr (single layer, max-log)
+    def pusch_llr_host(self, Qm, rxF, mag_a=None, mag_b=None, mag_c=None):
+        rxF = np.ascontiguousarray(rxF, dtype=np.int16)
+        n = rxF.size // 2
+        mk = lambda a: np.ascontiguousarray(a, dtype=np.int16) if a is not None else None
+        a, b, c = mk(mag_a), mk(mag_b), mk(mag_c)
+        out = np.zeros(n * Qm, dtype=np.int16)
+        p = lambda v: v.ctypes.data if v is not None else None
+        self._check(self.lib.nrb200_pusch_llr_host(Qm, n, rxF.ctypes.data, p(a), p(b), p(c), out.ctypes.data), "pusch_llr_host")
+        return out
+
+    def pusch_llr_torch(self, Qm, rxF, mag_a=None, mag_b=None, mag_c=None, out=None):
+        import torch
+        n = rxF.numel() // 2
+        if out is None:
+            out = torch.empty(n * Qm, dtype=torch.int16, device=rxF.device)
+        p = lambda v: v.data_ptr() if v is not None else None
+        st = torch.cuda.current_stream(rxF.device).cuda_stream
+        self._check(self.lib.nrb200_pusch_llr_dev(Qm, n, rxF.data_ptr(), p(mag_a), p(mag_b), p(mag_c), out.data_ptr(), st), "pusch_llr_dev")
+        return out
 
     # ---- batched extension, device-resident torch tensors (asynchronous on torch's current stream)
     def decode_batch_torch(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):

@@ -133,6 +133,15 @@ class Oracle:
         r = self.lib.orc_get_R_ldpc_decoder(rv, E, BG, Z, C.byref(ll), rnd)
         return r, ll.value
 
+    def ulsch_llr(self, Qm, rxF, maga, magb, magc):
+        rxF = np.ascontiguousarray(rxF, dtype=np.int16)
+        n = rxF.size // 2
+        out = np.zeros(n * Qm, dtype=np.int16)
+        mk = lambda a: np.ascontiguousarray(a, dtype=np.int16).ctypes.data_as(C.c_void_p) if a is not None else None
+        self.lib.orc_ulsch_llr.restype = None
+        self.lib.orc_ulsch_llr(Qm, rxF.ctypes.data_as(C.c_void_p), mk(maga), mk(magb), mk(magc), out.ctypes.data_as(C.c_void_p), C.c_uint32(n))
+        return out
+
     def dft(self, N, inverse, x, scale=1):
         x = np.ascontiguousarray(x, dtype=np.int16)
         y = np.zeros(2 * N, dtype=np.int16)
@@ -312,3 +321,23 @@ class Reference:
         y = out[oo:oo + 2 * N]
         getattr(self._dfts, ("idft" if inverse else "dft") + str(N))(xin.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_ubyte(scale))
         return y.copy()
+
+    # ---- PUSCH LLR computation of the reference (libref_llr.so: nr_ulsch_compute_llr)
+    def ulsch_llr(self, Qm, rxF, maga, magb, magc):
+        if not hasattr(self, "_llr"):
+            self._llr = C.CDLL(os.path.join(REFDIR, "libref_llr.so"))
+        n = np.asarray(rxF).size // 2
+        def al(a):
+            buf = np.zeros(2 * n + 64, dtype=np.int16)
+            o = ((-buf.ctypes.data) % 32) // 2
+            v = buf[o:o + 2 * n + 32]
+            if a is not None:
+                v[:2 * n] = np.asarray(a, dtype=np.int16)
+            return v
+        x, a, b, c = al(rxF), al(maga), al(magb), al(magc)
+        out = np.zeros(n * Qm + 128, dtype=np.int16)
+        oo = ((-out.ctypes.data) % 32) // 2
+        o = out[oo:oo + n * Qm + 64]
+        p = lambda v: v.ctypes.data_as(C.c_void_p)
+        self._llr.nr_ulsch_compute_llr(p(x), p(a), p(b), p(c), p(o), C.c_uint32(n), C.c_uint8(0), C.c_uint8(Qm))
+        return o[:n * Qm].copy()

@@ -14,6 +14,7 @@
 #   oracle/_ref/libref_ldpc_enc_orig.so LDPCencoder (ldpc_encoder.c, scalar "_orig")
 #   oracle/_ref/libref_dfts.so          dft/idft/dfts_autoinit (oai_dfts.c)
 #   oracle/_ref/libref_coding.so        crc_byte.c + nr_rate_matching.c + nr_segmentation.c
+#   oracle/_ref/libref_llr.so           nr_ulsch_llr_computation.c (PUSCH max-log LLRs)
 set -euo pipefail
 R=${OAI_REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -50,4 +51,5 @@ gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/TOOLS/oai_dfts.c -lm        
 gcc -O3 -march=native -fPIC -shared -w $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder.c -o libref_ldpc_dec512.so || echo "avx512 variant skipped"
 gcc $F -mpclmul $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/crc_byte.c $R/openair1/PHY/CODING/nr_rate_matching.c \
     $R/openair1/PHY/CODING/nr_segmentation.c -o libref_coding.so || echo "libref_coding.so: FAILED (see DESIGN.md)"
+gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_llr_computation.c $R/openair1/PHY/TOOLS/simde_operations.c -o libref_llr.so || echo "libref_llr.so: FAILED"
 ls -la $W/*.so

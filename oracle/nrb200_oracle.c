@@ -369,3 +369,23 @@ int orc_get_R_ldpc_decoder(int rv, int E, int BG, int Z, int *llrLen, int round)
   if (BG == 2) return decoderR < 0.3333 ? 15 : decoderR < 0.6667 ? 13 : 23;
   return decoderR < 0.6667 ? 13 : decoderR < 0.8889 ? 23 : 89;
 }
+
+/* ---- PUSCH single-layer max-log LLRs (openair1/PHY/NR_TRANSPORT/nr_ulsch_llr_computation.c:45-312) ----
+ * rxF, mag*: nb_re complex int16 {re, im}; out: nb_re * Qm int16.  abs_epi16(-32768) stays -32768; subs_epi16 saturates. */
+static inline int orc_abs16(int v) { return v == -32768 ? -32768 : (v < 0 ? -v : v); }
+static inline int orc_subs16(int a, int b) { int d = a - b; return d > 32767 ? 32767 : d < -32768 ? -32768 : d; }
+void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_t *magb, const int16_t *magc, int16_t *out, uint32_t nb_re)
+{
+  for (uint32_t i = 0; i < nb_re; i++) {
+    const int yr = rxF[2 * i], yi = rxF[2 * i + 1];
+    int16_t *o = out + (size_t)i * Qm;
+    if (Qm == 2) { o[0] = (int16_t)(yr >> 3); o[1] = (int16_t)(yi >> 3); continue; }   /* :45-58 */
+    const int ar = orc_subs16(maga[2 * i], orc_abs16(yr)), ai = orc_subs16(maga[2 * i + 1], orc_abs16(yi));
+    o[0] = (int16_t)yr; o[1] = (int16_t)yi; o[2] = (int16_t)ar; o[3] = (int16_t)ai;
+    if (Qm == 4) continue;                                                                /* :64-118 */
+    const int br = orc_subs16(magb[2 * i], orc_abs16(ar)), bi = orc_subs16(magb[2 * i + 1], orc_abs16(ai));
+    o[4] = (int16_t)br; o[5] = (int16_t)bi;
+    if (Qm == 6) continue;                                                                /* :124-196 */
+    o[6] = (int16_t)orc_subs16(magc[2 * i], orc_abs16(br)); o[7] = (int16_t)orc_subs16(magc[2 * i + 1], orc_abs16(bi));   /* :198-282 */
+  }
+}

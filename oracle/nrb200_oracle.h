@@ -53,6 +53,9 @@ void orc_deinterleave(uint32_t E, int Qm, int16_t *e, const int16_t *f);
 /* nr_rate_matching.c:390-422 */
 int orc_get_R_ldpc_decoder(int rv, int E, int BG, int Z, int *llrLen, int round);
 
+/* nr_ulsch_llr_computation.c:45-312: single-layer max-log LLRs for Qm = 2, 4, 6, 8 */
+void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_t *magb, const int16_t *magc, int16_t *out, uint32_t nb_re);
+
 /* Q15 DFT/IDFT of the OFDM sizes (nrb200_dft_oracle.c restates openair1/PHY/TOOLS/oai_dfts.c); interleaved {re,im} int16. */
 int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale);
 

@@ -178,3 +178,14 @@ def test_dft_idft_q15(oracle, reference, N):
                 assert np.array_equal(oracle.dft(N, inverse, x, scale), reference.dft(N, inverse, x, scale)), (N, inverse, amp, scale)
         x = rng.choice(np.array([-32768, 32767, 0], dtype=np.int16), size=2 * N)
         assert np.array_equal(oracle.dft(N, inverse, x, 1), reference.dft(N, inverse, x, 1))
+
+
+@pytest.mark.parametrize("Qm", [2, 4, 6, 8])
+def test_pusch_llr(oracle, reference, Qm):
+    """nr_ulsch_compute_llr (AVX2 path) vs the restatement, for RE counts that are and are not multiples of 8."""
+    rng = np.random.default_rng(Qm)
+    for n in (8, 96, 3276, 3272):
+        y = rng.integers(-32768, 32768, size=2 * n).astype(np.int16)
+        y[:16] = rng.choice(np.array([-32768, 32767, 0, -1], dtype=np.int16), size=16)
+        mags = [rng.integers(0, 20000, size=2 * n).astype(np.int16) for _ in range(3)]
+        assert np.array_equal(oracle.ulsch_llr(Qm, y, *mags), reference.ulsch_llr(Qm, y, *mags)), (Qm, n)

@@ -88,5 +88,41 @@ def main():
                       "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo / ms / 1e6 / hbm, "algorithmic_bytes_per_cb": K // 8 + 66 * Z}}), flush=True)
 
 
+    # ---- PUSCH max-log LLRs, 64QAM, 64 slots x 13 symbols x 3276 REs (HBM bound: 12 B in + 12 B out per RE)
+    for Qm in (6, 8, 2):
+        n = 3276 * 13 * 64
+        ys = [torch.randint(-8000, 8000, (2 * n,), dtype=torch.int16, device=dev, generator=g) for _ in range(6)]
+        ma, mb, mc = (torch.randint(0, 20000, (2 * n,), dtype=torch.int16, device=dev, generator=g) for _ in range(3))
+        out = torch.empty(n * Qm, dtype=torch.int16, device=dev)
+        i = [0]
+
+        def run():
+            lib.pusch_llr_torch(Qm, ys[i[0] % 6], ma, mb, mc, out=out); i[0] += 1
+        ms = timeit(run, n=40)
+        planes = {2: 1, 4: 2, 6: 3, 8: 4}[Qm]
+        algo = n * (4 * planes + 2 * Qm)
+        print(json.dumps({"what": f"pusch_llr Qm={Qm}", "re": n, "ms": ms, "value": n / ms * 1e3, "unit": "RE/s",
+                          "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo / ms / 1e6 / hbm, "algorithmic_bytes_per_re": 4 * planes + 2 * Qm}}), flush=True)
+    # ---- the per-code-block OAI ABI under tpool-style concurrency: T host threads, one blocking LDPCdecoder call per segment
+    import threading
+    from openairinterface5g_b200.synth import awgn_llr, random_payloads
+    P = random_payloads(64, K, 3)
+    cwn = lib.encode_batch_host(1, Z, K, P)
+    llr = awgn_llr(cwn, Z, 68, 1.0, 1.0 / 3.0, 3)
+    for T in (1, 8, 32):
+        cnt = [0] * T
+        stop = time.perf_counter() + 2.0
+
+        def work(t):
+            j = t
+            while time.perf_counter() < stop:
+                lib.LDPCdecoder(1, Z, 13, 8, llr[j % 64]); cnt[t] += 1; j += T
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+        t0 = time.perf_counter()
+        [t.start() for t in ths]; [t.join() for t in ths]
+        dt = time.perf_counter() - t0
+        print(json.dumps({"what": "LDPCdecoder per-call ABI", "host_threads": T, "value": sum(cnt) / dt, "unit": "CB/s", "us_per_call": 1e6 * dt * T / max(1, sum(cnt))}), flush=True)
+
+
 if __name__ == "__main__":
     main()
