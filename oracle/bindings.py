@@ -133,6 +133,26 @@ class Oracle:
         r = self.lib.orc_get_R_ldpc_decoder(rv, E, BG, Z, C.byref(ll), rnd)
         return r, ll.value
 
+    def scramble(self, in_bits, q, Nid, rnti):
+        x = np.ascontiguousarray(in_bits, dtype=np.uint8)
+        out = np.zeros((x.size + 31) // 32, dtype=np.uint32)
+        self.lib.orc_scramble.restype = None
+        self.lib.orc_scramble(x.ctypes.data_as(C.c_void_p), C.c_uint32(x.size), C.c_uint32(q), C.c_uint32(Nid), C.c_uint32(rnti), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def unscramble_llr(self, llr, q, Nid, rnti):
+        y = np.ascontiguousarray(llr, dtype=np.int16).copy()
+        self.lib.orc_unscramble_llr.restype = None
+        self.lib.orc_unscramble_llr(y.ctypes.data_as(C.c_void_p), C.c_uint32(y.size), C.c_uint32(q), C.c_uint32(Nid), C.c_uint32(rnti))
+        return y
+
+    def modulate(self, packed_bits, length, Qm):
+        x = np.ascontiguousarray(packed_bits).view(np.uint8)
+        out = np.zeros(2 * (length // Qm), dtype=np.int16)
+        self.lib.orc_modulate.restype = None
+        self.lib.orc_modulate(x.ctypes.data_as(C.c_void_p), C.c_uint32(length), Qm, out.ctypes.data_as(C.c_void_p))
+        return out
+
     def ulsch_llr(self, Qm, rxF, maga, magb, magc):
         rxF = np.ascontiguousarray(rxF, dtype=np.int16)
         n = rxF.size // 2
@@ -341,3 +361,43 @@ class Reference:
         p = lambda v: v.ctypes.data_as(C.c_void_p)
         self._llr.nr_ulsch_compute_llr(p(x), p(a), p(b), p(c), p(o), C.c_uint32(n), C.c_uint8(0), C.c_uint8(Qm))
         return o[:n * Qm].copy()
+
+    # ---- scrambling + QAM mapper of the reference (libref_mod.so: nr_scrambling.c, nr_modulation.c, nr_gen_mod_table.c)
+    def _mod(self):
+        if not hasattr(self, "_modlib"):
+            self._modlib = C.CDLL(os.path.join(REFDIR, "libref_mod.so"))
+            self._modlib.nr_generate_modulation_table()
+            self._modlib.init_byte2m128i()
+        return self._modlib
+
+    def scramble(self, in_bits, q, Nid, rnti):
+        L = self._mod()
+        x = np.asarray(in_bits, dtype=np.uint8)
+        buf = np.zeros(x.size + 128, dtype=np.uint8)
+        o = (-buf.ctypes.data) % 32
+        v = buf[o:o + x.size + 64]
+        v[:x.size] = x
+        out = np.zeros((x.size + 31) // 32 + 8, dtype=np.uint32)
+        L.nr_codeword_scrambling(v.ctypes.data_as(C.c_void_p), C.c_uint32(x.size), C.c_uint8(q), C.c_uint32(Nid), C.c_uint32(rnti), out.ctypes.data_as(C.c_void_p))
+        return out[:(x.size + 31) // 32].copy()
+
+    def unscramble_llr(self, llr, q, Nid, rnti):
+        L = self._mod()
+        x = np.asarray(llr, dtype=np.int16)
+        buf = np.zeros(x.size + 128, dtype=np.int16)
+        o = ((-buf.ctypes.data) % 32) // 2
+        v = buf[o:o + x.size + 64]
+        v[:x.size] = x
+        L.nr_codeword_unscrambling(v.ctypes.data_as(C.c_void_p), C.c_uint32(x.size), C.c_uint8(q), C.c_uint32(Nid), C.c_uint32(rnti))
+        return v[:x.size].copy()
+
+    def modulate(self, packed_bits, length, Qm):
+        L = self._mod()
+        x = np.ascontiguousarray(packed_bits).view(np.uint8)
+        buf = np.zeros(x.size + 64, dtype=np.uint8)
+        buf[:x.size] = x
+        out = np.zeros(2 * (length // Qm) + 64, dtype=np.int16)
+        oo = ((-out.ctypes.data) % 32) // 2
+        o = out[oo:oo + 2 * (length // Qm) + 16]
+        L.nr_modulation(buf.ctypes.data_as(C.c_void_p), C.c_uint32(length), C.c_uint16(Qm), o.ctypes.data_as(C.c_void_p))
+        return o[:2 * (length // Qm)].copy()

@@ -14,6 +14,7 @@
 #   oracle/_ref/libref_ldpc_enc_orig.so LDPCencoder (ldpc_encoder.c, scalar "_orig")
 #   oracle/_ref/libref_dfts.so          dft/idft/dfts_autoinit (oai_dfts.c)
 #   oracle/_ref/libref_coding.so        crc_byte.c + nr_rate_matching.c + nr_segmentation.c
+#   oracle/_ref/libref_mod.so           nr_modulation.c + nr_gen_mod_table.c (QAM mapper)
 #   oracle/_ref/libref_llr.so           nr_ulsch_llr_computation.c (PUSCH max-log LLRs)
 set -euo pipefail
 R=${OAI_REF:-/root/reference}
@@ -24,7 +25,13 @@ mkdir -p $W/shim/simde/x86 $W/shim/simde/arm $W/gen/{cnProc,bnProc,bnProcPc,cnPr
 # 1) simde -> native alias header
 grep -rhoE '\bsimde_[_a-zA-Z0-9]+|\bsimde__m[0-9a-z]+|\bSIMDE_[A-Z_0-9]+' $R/openair1 $R/common | sort -u > $W/tokens.txt
 { echo '#pragma once'; echo '#include <immintrin.h>'; echo '#include <mmintrin.h>';
-  while read t; do case "$t" in simde_*) echo "#define $t ${t#simde}";; SIMDE_MM_SHUFFLE) echo "#define $t _MM_SHUFFLE";; esac; done < $W/tokens.txt; } > $W/shim/simde/x86/shim_all.h
+  while read t; do case "$t" in
+    # AVX512VL-only spellings that simde emulates on AVX2: same unaligned 128/256-bit move
+    simde_mm256_loadu_epi32|simde_mm256_loadu_epi16|simde_mm256_loadu_epi8) echo "#define $t(p) _mm256_loadu_si256((const __m256i *)(p))";;
+    simde_mm_loadu_epi32|simde_mm_loadu_epi16|simde_mm_loadu_epi8) echo "#define $t(p) _mm_loadu_si128((const __m128i *)(p))";;
+    simde_mm256_storeu_epi32|simde_mm256_storeu_epi16|simde_mm256_storeu_epi8) echo "#define $t(p, v) _mm256_storeu_si256((__m256i *)(p), (v))";;
+    simde_mm_storeu_epi32|simde_mm_storeu_epi16|simde_mm_storeu_epi8) echo "#define $t(p, v) _mm_storeu_si128((__m128i *)(p), (v))";;
+    simde_*) echo "#define $t ${t#simde}";; SIMDE_MM_SHUFFLE) echo "#define $t _MM_SHUFFLE";; esac; done < $W/tokens.txt; } > $W/shim/simde/x86/shim_all.h
 for f in mmx sse sse2 sse3 ssse3 sse4.1 sse4.2 avx2 fma clmul avx512; do echo '#include "shim_all.h"' > $W/shim/simde/x86/$f.h; done
 echo '#include "x86/shim_all.h"' > $W/shim/simde/simde-common.h; echo '#pragma once' > $W/shim/simde/arm/neon.h
 INC="-I$W/shim -I$W/gen -I$R/openair1/PHY/CODING/nrLDPC_decoder -I$R/openair1 -I$R -I$R/common/utils -I$R/common/utils/LOG -I$R/common/utils/T \
@@ -52,4 +59,5 @@ gcc -O3 -march=native -fPIC -shared -w $INC $DEFS $HERE/ref_stubs.c $R/openair1/
 gcc $F -mpclmul $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/crc_byte.c $R/openair1/PHY/CODING/nr_rate_matching.c \
     $R/openair1/PHY/CODING/nr_segmentation.c -o libref_coding.so || echo "libref_coding.so: FAILED (see DESIGN.md)"
 gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_llr_computation.c $R/openair1/PHY/TOOLS/simde_operations.c -o libref_llr.so || echo "libref_llr.so: FAILED"
+gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_mod.c $R/openair1/PHY/MODULATION/nr_modulation.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c $R/openair1/PHY/NR_TRANSPORT/nr_scrambling.c $R/openair1/PHY/NR_REFSIG/scrambling_luts.c -lm -o libref_mod.so || echo "libref_mod.so: FAILED"
 ls -la $W/*.so

@@ -389,3 +389,59 @@ void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_
     o[6] = (int16_t)orc_subs16(magc[2 * i], orc_abs16(br)); o[7] = (int16_t)orc_subs16(magc[2 * i + 1], orc_abs16(bi));   /* :198-282 */
   }
 }
+
+/* ---- Gold sequence, (un)scrambling, QAM mapper ----
+ * lte_gold_generic (openair1/PHY/LTE_TRANSPORT/transport_proto.h:633-680): c(n) = x1(n+1600) ^ x2(n+1600), produced 32 bits per call
+ * (bit i of the word = c(32w + i)); nr_codeword_scrambling / _unscrambling (NR_TRANSPORT/nr_scrambling.c:30-96);
+ * nr_modulation (MODULATION/nr_modulation.c:115-244) with the tables of NR_REFSIG/nr_gen_mod_table.c:33-98. */
+static void orc_gold_step(uint32_t *x1, uint32_t *x2)
+{
+  *x1 = (*x1 >> 1) ^ (*x1 >> 4);
+  *x1 = *x1 ^ (*x1 << 31) ^ (*x1 << 28);
+  *x2 = (*x2 >> 1) ^ (*x2 >> 2) ^ (*x2 >> 3) ^ (*x2 >> 4);
+  *x2 = *x2 ^ (*x2 << 31) ^ (*x2 << 30) ^ (*x2 << 29) ^ (*x2 << 28);
+}
+void orc_gold_words(uint32_t c_init, uint32_t n_words, uint32_t *out)
+{
+  uint32_t x1 = 1u + (1u << 31), x2 = c_init;
+  x2 = x2 ^ ((x2 ^ (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3)) << 31);
+  for (int n = 1; n < 50; n++) orc_gold_step(&x1, &x2);
+  for (uint32_t w = 0; w < n_words; w++) { orc_gold_step(&x1, &x2); out[w] = x1 ^ x2; }
+}
+/* in: one bit per byte (the rate matcher's output); out: ceil(size/32) words, bit i of word w = in[32w+i] ^ c(32w+i) */
+void orc_scramble(const uint8_t *in, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, uint32_t *out)
+{
+  const uint32_t nw = (size + 31) >> 5;
+  orc_gold_words((n_RNTI << 15) + (q << 14) + Nid, nw, out);
+  for (uint32_t w = 0; w < nw; w++) {
+    uint32_t v = 0;
+    for (int i = 0; i < 32; i++) if (32 * w + i < size) v |= (uint32_t)(in[32 * w + i] & 1) << i;   /* movemask(slli_epi16(c, 7)) */
+    out[w] ^= v;
+  }
+}
+/* llr[i] *= (1 - 2 c(i)) with mullo_epi16 (so -32768 stays -32768) */
+void orc_unscramble_llr(int16_t *llr, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI)
+{
+  const uint32_t nw = (size + 31) >> 5;
+  uint32_t *c = malloc(4 * (size_t)nw + 4);
+  orc_gold_words((n_RNTI << 15) + (q << 14) + Nid, nw, c);
+  for (uint32_t i = 0; i < size; i++) if ((c[i >> 5] >> (i & 31)) & 1) llr[i] = (int16_t)(uint16_t)(0u - (uint16_t)llr[i]);
+  free(c);
+}
+/* bits: packed LSB-first (what orc_scramble produces); out: length/Qm symbols {re, im} */
+void orc_modulate(const uint8_t *bits, uint32_t length, int Qm, int16_t *out)
+{
+  const float val = 32768.0f, s2 = 0.70711f, s10 = 0.31623f, s42 = 0.15430f, s170 = 0.076696f;
+  for (uint32_t i = 0; i < length / Qm; i++) {
+    int b[8];
+    for (int j = 0; j < Qm; j++) { const uint32_t n = i * Qm + j; b[j] = 1 - 2 * ((bits[n >> 3] >> (n & 7)) & 1); }
+    short lr, li;
+    float sc;
+    if (Qm == 2) { lr = (short)b[0]; li = (short)b[1]; sc = s2; }
+    else if (Qm == 4) { lr = (short)(b[0] * (2 - b[2])); li = (short)(b[1] * (2 - b[3])); sc = s10; }
+    else if (Qm == 6) { lr = (short)(b[0] * (4 - b[2] * (2 - b[4]))); li = (short)(b[1] * (4 - b[3] * (2 - b[5]))); sc = s42; }
+    else { lr = (short)(b[0] * (8 - b[2] * (4 - b[4] * (2 - b[6])))); li = (short)(b[1] * (8 - b[3] * (4 - b[5] * (2 - b[7])))); sc = s170; }
+    out[2 * i] = (short)(lr * val * sc * s2);        /* float32, evaluated left to right like nr_gen_mod_table.c */
+    out[2 * i + 1] = (short)(li * val * sc * s2);
+  }
+}

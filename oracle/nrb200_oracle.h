@@ -53,6 +53,12 @@ void orc_deinterleave(uint32_t E, int Qm, int16_t *e, const int16_t *f);
 /* nr_rate_matching.c:390-422 */
 int orc_get_R_ldpc_decoder(int rv, int E, int BG, int Z, int *llrLen, int round);
 
+/* Gold sequence words, nr_codeword_scrambling / _unscrambling, nr_modulation */
+void orc_gold_words(uint32_t c_init, uint32_t n_words, uint32_t *out);
+void orc_scramble(const uint8_t *in, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, uint32_t *out);
+void orc_unscramble_llr(int16_t *llr, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI);
+void orc_modulate(const uint8_t *bits, uint32_t length, int Qm, int16_t *out);
+
 /* nr_ulsch_llr_computation.c:45-312: single-layer max-log LLRs for Qm = 2, 4, 6, 8 */
 void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_t *magb, const int16_t *magc, int16_t *out, uint32_t nb_re);
 

@@ -189,3 +189,23 @@ def test_pusch_llr(oracle, reference, Qm):
         y[:16] = rng.choice(np.array([-32768, 32767, 0, -1], dtype=np.int16), size=16)
         mags = [rng.integers(0, 20000, size=2 * n).astype(np.int16) for _ in range(3)]
         assert np.array_equal(oracle.ulsch_llr(Qm, y, *mags), reference.ulsch_llr(Qm, y, *mags)), (Qm, n)
+
+
+def test_scrambling_and_modulation(oracle, reference):
+    rng = np.random.default_rng(6)
+    for size, q, Nid, rnti in ((64, 0, 0, 1), (1000, 0, 123, 0x1234), (9072 * 6, 1, 1007, 65535), (33, 0, 5, 77)):
+        bits = rng.integers(0, 2, size=size, dtype=np.uint8)
+        sc_o, sc_r = oracle.scramble(bits, q, Nid, rnti), reference.scramble(bits, q, Nid, rnti)
+        assert np.array_equal(sc_o, sc_r), (size, q, Nid, rnti)
+        for Qm in (2, 4, 6, 8):
+            length = (size // (Qm * 8)) * Qm * 8 if Qm != 6 else (size // 24) * 24
+            if length < Qm * 8 * 4:
+                continue
+            assert np.array_equal(oracle.modulate(sc_o, length, Qm), reference.modulate(sc_r, length, Qm)), (size, Qm)
+
+
+def test_unscrambling(oracle, reference):
+    rng = np.random.default_rng(8)
+    for size, q, Nid, rnti in ((64, 0, 0, 1), (9072, 1, 1007, 65535), (12 * 273 * 6, 0, 500, 4660)):
+        llr = rng.integers(-32768, 32768, size=size).astype(np.int16)
+        assert np.array_equal(oracle.unscramble_llr(llr, q, Nid, rnti), reference.unscramble_llr(llr, q, Nid, rnti))
