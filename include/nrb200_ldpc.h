@@ -206,6 +206,19 @@ int32_t nrb200_pusch_llr_dev(int Qm, uint32_t nb_re, const int16_t *d_rxF, const
 int32_t nrb200_pusch_llr_host(int Qm, uint32_t nb_re, const int16_t *rxF, const int16_t *mag_a, const int16_t *mag_b, const int16_t *mag_c,
                               int16_t *llr);
 
+/* ---- Part 5: scrambling and the QAM mapper ---------------------------------------------------------------------------
+ * replaces nr_codeword_scrambling (nr_scrambling.c:30-51): in = `size` bits, one per byte (the rate matcher's f); out = ceil(size/32)
+ * words, bit i of word w = in[32w+i] ^ c(32w+i), c = Gold sequence with c_init = (n_RNTI << 15) + (q << 14) + Nid. */
+int32_t nrb200_scramble_dev(const uint8_t *d_in, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, uint32_t *d_out, void *stream);
+int32_t nrb200_scramble_host(const uint8_t *in, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, uint32_t *out);
+/* replaces nr_codeword_unscrambling (nr_scrambling.c:53-80): llr[i] *= (1 - 2 c(i)) in place (mullo_epi16: -32768 stays -32768) */
+int32_t nrb200_unscramble_llr_dev(int16_t *d_llr, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, void *stream);
+int32_t nrb200_unscramble_llr_host(int16_t *llr, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI);
+/* replaces nr_modulation (nr_modulation.c:115-244): bits packed LSB-first (what the scrambler writes; the device buffer must be
+ * readable one byte past the last bit), length_bits / Qm symbols {re, im} int16 out. */
+int32_t nrb200_modulate_dev(const uint32_t *d_bits, uint32_t length_bits, int Qm, int16_t *d_out, void *stream);
+int32_t nrb200_modulate_host(const uint32_t *bits, uint32_t length_bits, int Qm, int16_t *out);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

@@ -14,6 +14,8 @@ int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_
                   uint8_t *d_out, uint32_t out_stride, cudaStream_t stream);
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
 int quirks_from_env();
+int launch_gold(int mode, uint32_t c_init, uint32_t size, const uint8_t *in, uint32_t *out, int16_t *llr, cudaStream_t st);
+int launch_modulate(int Qm, uint32_t length_bits, const uint8_t *bits, int16_t *out, cudaStream_t st);
 int launch_pusch_llr(int Qm, uint32_t nb_re, const int16_t *y, const int16_t *ma, const int16_t *mb, const int16_t *mc, int16_t *out, cudaStream_t st);
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
 int launch_rm_rx(const nrb200_rm_desc_t &p, const int16_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
@@ -418,4 +420,65 @@ NRB200_EXPORT int32_t nrb200_pusch_llr_host(int Qm, uint32_t nb_re, const int16_
   } while (0);
   ctx().release(w);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------ scrambling + QAM mapper
+static inline uint32_t gold_cinit(uint32_t q, uint32_t Nid, uint32_t n_RNTI) { return (n_RNTI << 15) + (q << 14) + Nid; }
+
+NRB200_EXPORT int32_t nrb200_scramble_dev(const uint8_t *d_in, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, uint32_t *d_out, void *stream)
+{
+  if (ensure_init()) return -1;
+  return launch_gold(0, gold_cinit(q, Nid, n_RNTI), size, d_in, d_out, nullptr, (cudaStream_t)stream);
+}
+NRB200_EXPORT int32_t nrb200_unscramble_llr_dev(int16_t *d_llr, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, void *stream)
+{
+  if (ensure_init()) return -1;
+  return launch_gold(1, gold_cinit(q, Nid, n_RNTI), size, nullptr, nullptr, d_llr, (cudaStream_t)stream);
+}
+NRB200_EXPORT int32_t nrb200_modulate_dev(const uint32_t *d_bits, uint32_t length_bits, int Qm, int16_t *d_out, void *stream)
+{
+  if (ensure_init()) return -1;
+  return launch_modulate(Qm, length_bits, (const uint8_t *)d_bits, d_out, (cudaStream_t)stream);
+}
+
+// "copy in, run, copy out" for the small host-buffer variants (64 zero bytes of slack after the input)
+template <typename F>
+static int host_roundtrip(const void *in, size_t in_bytes, void *out, size_t out_bytes, bool inplace, F &&run)
+{
+  if (ensure_init()) return -1;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(in_bytes + 64, out_bytes + 64, 16)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, in, in_bytes);
+    std::memset((uint8_t *)w->h_in + in_bytes, 0, 64);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes + 64, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = run(w)) != 0) break;
+    void *src = inplace ? w->d_in : w->d_out;
+    if (cudaMemcpyAsync(w->h_out, src, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(out, w->h_out, out_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+NRB200_EXPORT int32_t nrb200_scramble_host(const uint8_t *in, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI, uint32_t *out)
+{
+  if (size == 0) return 0;
+  return host_roundtrip(in, size, out, 4 * (size_t)((size + 31) >> 5), false, [&](Workspace *w) {
+    return launch_gold(0, gold_cinit(q, Nid, n_RNTI), size, (const uint8_t *)w->d_in, (uint32_t *)w->d_out, nullptr, w->stream); });
+}
+NRB200_EXPORT int32_t nrb200_unscramble_llr_host(int16_t *llr, uint32_t size, uint32_t q, uint32_t Nid, uint32_t n_RNTI)
+{
+  if (size == 0) return 0;
+  return host_roundtrip(llr, 2 * (size_t)size, llr, 2 * (size_t)size, true, [&](Workspace *w) {
+    return launch_gold(1, gold_cinit(q, Nid, n_RNTI), size, nullptr, nullptr, (int16_t *)w->d_in, w->stream); });
+}
+NRB200_EXPORT int32_t nrb200_modulate_host(const uint32_t *bits, uint32_t length_bits, int Qm, int16_t *out)
+{
+  if (Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) return -4;
+  if (length_bits / Qm == 0) return 0;
+  return host_roundtrip(bits, (length_bits + 7) / 8, out, 4 * (size_t)(length_bits / Qm), false, [&](Workspace *w) {
+    return launch_modulate(Qm, length_bits, (const uint8_t *)w->d_in, (int16_t *)w->d_out, w->stream); });
 }

@@ -3,17 +3,19 @@
 //   lte_gold_generic                                    reference openair1/PHY/LTE_TRANSPORT/transport_proto.h:633-680
 //   nr_modulation + nr_generate_modulation_table        reference MODULATION/nr_modulation.c:115-244, NR_REFSIG/nr_gen_mod_table.c:33-98
 // The reference produces the Gold sequence 32 bits at a time with a serial word recurrence (state' = L(state), GF(2)-linear on the
-// 32-bit word).  Here every thread jumps straight to its own run of words with precomputed powers L^(2^k) (binary 32x32 matrices),
-// then walks 16 words with the same recurrence -- identical bits, no serial dependence across the code word.
+// 32-bit word).  Here every thread jumps straight to its own word with precomputed powers L^(2^k) (binary 32x32 matrices),
+// (nibble-indexed tables: 8 loads per product) -- identical bits, no serial dependence across the code word.
 #include "nrb200_ctx.h"
+#include <cstring>
 #include <vector>
 
 namespace nrb200 {
 
 constexpr int kGoldPow = 22;     // jump distances up to 2^22 words = 2^27 bits
-constexpr int kGoldRun = 16;     // words per thread
+constexpr int kGoldBlk = 256;    // words (= threads) per CTA
 
-struct GoldTables { uint32_t m[2][kGoldPow][32]; };   // m[g][k][i] = image of bit i under 2^k word steps of generator g
+// L^(2^k) as 8 nibble tables: t[g][k][j][v] = image of (v << 4j).  One matrix-vector product = 8 loads + 8 XORs.
+struct GoldTables { uint32_t t[2][kGoldPow][8][16]; };
 static GoldTables *d_gold = nullptr;
 static uint32_t *d_modtab = nullptr;                   // per Qm: 2^Qm symbols {re | im << 16}; offsets 0, 4, 20, 84
 
@@ -27,14 +29,22 @@ int scramble_mod_init()
   if (d_gold) return 0;
   std::vector<GoldTables> h(1);
   for (int g = 0; g < 2; g++) {
-    for (int i = 0; i < 32; i++) h[0].m[g][0][i] = g == 0 ? step1(1u << i) : step2(1u << i);
-    for (int k = 1; k < kGoldPow; k++)
-      for (int i = 0; i < 32; i++) {          // M^(2^k) e_i = M^(2^(k-1)) (M^(2^(k-1)) e_i)
-        const uint32_t v = h[0].m[g][k - 1][i];
+    uint32_t col[32], nxt[32];
+    for (int i = 0; i < 32; i++) col[i] = g == 0 ? step1(1u << i) : step2(1u << i);
+    for (int k = 0; k < kGoldPow; k++) {
+      for (int j = 0; j < 8; j++)
+        for (int v = 0; v < 16; v++) {
+          uint32_t y = 0;
+          for (int b = 0; b < 4; b++) if ((v >> b) & 1) y ^= col[4 * j + b];
+          h[0].t[g][k][j][v] = y;
+        }
+      for (int i = 0; i < 32; i++) {            // M^(2^(k+1)) e_i = M^(2^k) (M^(2^k) e_i)
         uint32_t y = 0;
-        for (int b = 0; b < 32; b++) if ((v >> b) & 1) y ^= h[0].m[g][k - 1][b];
-        h[0].m[g][k][i] = y;
+        for (int b = 0; b < 32; b++) if ((col[i] >> b) & 1) y ^= col[b];
+        nxt[i] = y;
       }
+      std::memcpy(col, nxt, sizeof(col));
+    }
   }
   if (cudaMalloc(&d_gold, sizeof(GoldTables)) != cudaSuccess) return -1;
   cudaMemcpy(d_gold, h.data(), sizeof(GoldTables), cudaMemcpyHostToDevice);
@@ -55,44 +65,66 @@ int scramble_mod_init()
 
 __device__ __forceinline__ uint32_t dstep1(uint32_t x) { x = (x >> 1) ^ (x >> 4); return x ^ (x << 31) ^ (x << 28); }
 __device__ __forceinline__ uint32_t dstep2(uint32_t x) { x = (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4); return x ^ (x << 31) ^ (x << 30) ^ (x << 29) ^ (x << 28); }
-__device__ __forceinline__ uint32_t matvec(const uint32_t *__restrict__ col, uint32_t x)
+__device__ __forceinline__ uint32_t matvec(const uint32_t (*__restrict__ t)[16], uint32_t x)
 {
   uint32_t y = 0;
-#pragma unroll 8
-  for (int b = 0; b < 32; b++) y ^= ((x >> b) & 1u) ? __ldg(col + b) : 0u;
+#pragma unroll
+  for (int j = 0; j < 8; j++) y ^= __ldg(&t[j][(x >> (4 * j)) & 15u]);
   return y;
 }
-// generator states after `steps` word steps from the reset values (x1 = 1 + 2^31, x2 = c_init with bit 31 completed)
-__device__ __forceinline__ void gold_jump(const GoldTables *__restrict__ T, uint32_t c_init, uint32_t steps, uint32_t &x1, uint32_t &x2)
+// Gold word number w of the sequence started from c_init: the reset loop performs 49 word steps, every call one more
+// (transport_proto.h:655-676), so word w is the XOR of both generator states after 50 + w steps.
+__device__ __forceinline__ uint32_t gold_word(const GoldTables *__restrict__ T, uint32_t c_init, uint32_t w)
 {
-  x1 = 1u + (1u << 31);
-  x2 = c_init ^ ((c_init ^ (c_init >> 1) ^ (c_init >> 2) ^ (c_init >> 3)) << 31);
+  uint32_t x1 = 1u + (1u << 31);
+  uint32_t x2 = c_init ^ ((c_init ^ (c_init >> 1) ^ (c_init >> 2) ^ (c_init >> 3)) << 31);
+  uint32_t steps = 50u + w;
   for (int k = 0; steps; k++, steps >>= 1)
-    if (steps & 1u) { x1 = matvec(T->m[0][k], x1); x2 = matvec(T->m[1][k], x2); }
+    if (steps & 1u) { x1 = matvec(T->t[0][k], x1); x2 = matvec(T->t[1][k], x2); }
+  return x1 ^ x2;
 }
 
-// mode 0: scramble (in = one bit per byte, out = packed words)   mode 1: unscramble int16 LLRs in place
-__global__ void __launch_bounds__(256) gold_kernel(const GoldTables *__restrict__ T, int mode, uint32_t c_init, uint32_t size,
-                                                   const uint8_t *__restrict__ in, uint32_t *__restrict__ out, int16_t *__restrict__ llr)
+// One CTA = 256 words of the sequence (8192 bits).  Phase 1: thread t produces word t.  Phase 2: the CTA sweeps its 8192 elements
+// with coalesced accesses.   mode 0: scramble (in = one bit per byte, out = packed words)   mode 1: unscramble int16 LLRs in place
+__global__ void __launch_bounds__(kGoldBlk) gold_kernel(const GoldTables *__restrict__ T, int mode, int aligned, uint32_t c_init, uint32_t size,
+                                                        const uint8_t *__restrict__ in, uint32_t *__restrict__ out, int16_t *__restrict__ llr)
 {
-  const uint32_t nw = (size + 31) >> 5;
-  const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) * kGoldRun;
-  if (w0 >= nw) return;
-  uint32_t x1, x2;
-  gold_jump(T, c_init, 49u + w0, x1, x2);                 // the reset loop performs 49 steps, every call one more (transport_proto.h:655-676)
-  for (uint32_t w = w0; w < w0 + kGoldRun && w < nw; w++) {
-    x1 = dstep1(x1); x2 = dstep2(x2);
-    const uint32_t s = x1 ^ x2;
-    if (mode == 0) {
-      uint32_t v = 0;
-#pragma unroll 8
-      for (int i = 0; i < 32; i++) if (32 * w + i < size) v |= (uint32_t)(in[32 * w + i] & 1u) << i;
-      out[w] = v ^ s;
-    } else {
-#pragma unroll 8
-      for (int i = 0; i < 32; i++) {
-        const uint32_t n = 32 * w + i;
-        if (n < size && ((s >> i) & 1u)) llr[n] = (int16_t)(uint16_t)(0u - (uint16_t)llr[n]);   // mullo_epi16 by -1 wraps
+  __shared__ uint32_t s_gold[kGoldBlk];
+  const uint32_t nw = (size + 31) >> 5, wb = blockIdx.x * kGoldBlk, t = threadIdx.x;
+  if (wb + t < nw) s_gold[t] = gold_word(T, c_init, wb + t);
+  __syncthreads();
+  const uint32_t e0 = wb * 32u;
+  if (mode == 0) {
+#pragma unroll 2
+    for (int k = 0; k < 8; k++) {                         // 4 input bytes per thread per pass, 8 lanes make one word
+      const uint32_t e = e0 + 4u * t + 1024u * k;
+      uint32_t nib = 0;
+      if (aligned && e + 4 <= size) {
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(in + e) & 0x01010101u;
+        nib = (v | (v >> 7) | (v >> 14) | (v >> 21)) & 15u;
+      } else {
+        for (int i = 0; i < 4; i++) if (e + i < size) nib |= (uint32_t)(in[e + i] & 1u) << i;
+      }
+      uint32_t v = nib << (4u * (t & 7u));
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      v |= __shfl_xor_sync(0xffffffffu, v, 4);
+      if ((t & 7u) == 0 && e < size) out[e >> 5] = v ^ s_gold[(e - e0) >> 5];
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < 16; k++) {                        // 2 LLRs per thread per pass
+      const uint32_t e = e0 + 2u * t + 512u * k;
+      if (e >= size) break;
+      const uint32_t g = s_gold[(e - e0) >> 5] >> (e & 31u);
+      if (aligned && e + 2 <= size) {
+        uint32_t v = *reinterpret_cast<uint32_t *>(llr + e);
+        // 16-bit wrapping negation of the halves selected by the two sequence bits (mullo_epi16 by -1: -32768 stays)
+        const uint32_t m = ((g & 1u) ? 0xffffu : 0u) | ((g & 2u) ? 0xffff0000u : 0u);
+        v = __vsub2(v ^ m, m);                            // (x ^ -1) - (-1) = -x per halfword, wrapping
+        *reinterpret_cast<uint32_t *>(llr + e) = v;
+      } else {
+        for (int i = 0; i < 2; i++) if (e + i < size && ((g >> i) & 1u)) llr[e + i] = (int16_t)(uint16_t)(0u - (uint16_t)llr[e + i]);
       }
     }
   }
@@ -114,8 +146,9 @@ int launch_gold(int mode, uint32_t c_init, uint32_t size, const uint8_t *in, uin
 {
   if (scramble_mod_init() != 0) return -5;
   if (size == 0) return 0;
-  const uint32_t nw = (size + 31) >> 5, nthreads = (nw + kGoldRun - 1) / kGoldRun;
-  gold_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(d_gold, mode, c_init, size, in, out, llr);
+  const uint32_t nw = (size + 31) >> 5;
+  const int aligned = mode == 0 ? ((uintptr_t)in & 3u) == 0 : ((uintptr_t)llr & 3u) == 0;
+  gold_kernel<<<(nw + kGoldBlk - 1) / kGoldBlk, kGoldBlk, 0, st>>>(d_gold, mode, aligned, c_init, size, in, out, llr);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "gold launch");
   return 0;

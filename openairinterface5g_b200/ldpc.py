@@ -93,6 +93,9 @@ class LdpcLib:
         L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_pusch_llr_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_pusch_llr_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_scramble_host.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.nrb200_unscramble_llr_host.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.nrb200_modulate_host.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.nrb200_last_error.restype = C.c_char_p
         L.nrb200_launch_count.restype = C.c_uint64
         self._inited = False
@@ -216,6 +219,24 @@ class LdpcLib:
         desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, n, clear)
         self._check(self.lib.nrb200_ldpc_rm_rx_batch_host(C.byref(desc), soft.ctypes.data, E.ctypes.data, harq.ctypes.data, harq.shape[1], llr.ctypes.data, kcz), "rm_rx_batch_host")
         return llr
+
+    # ---- scrambling (nr_scrambling.c) and QAM mapper (nr_modulation.c)
+    def scramble_host(self, in_bits, q, Nid, n_RNTI):
+        x = np.ascontiguousarray(in_bits, dtype=np.uint8)
+        out = np.zeros((x.size + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.nrb200_scramble_host(x.ctypes.data, x.size, q, Nid, n_RNTI, out.ctypes.data), "scramble_host")
+        return out
+
+    def unscramble_llr_host(self, llr, q, Nid, n_RNTI):
+        y = np.ascontiguousarray(llr, dtype=np.int16).copy()
+        self._check(self.lib.nrb200_unscramble_llr_host(y.ctypes.data, y.size, q, Nid, n_RNTI), "unscramble_llr_host")
+        return y
+
+    def modulate_host(self, packed_words, length_bits, Qm):
+        x = np.ascontiguousarray(packed_words, dtype=np.uint32)
+        out = np.zeros(2 * (length_bits // Qm), dtype=np.int16)
+        self._check(self.lib.nrb200_modulate_host(x.ctypes.data, length_bits, Qm, out.ctypes.data), "modulate_host")
+        return out
 
     # ---- demodulation: nr_ulsch_compute_llr (single layer, max-log)
     def pusch_llr_host(self, Qm, rxF, mag_a=None, mag_b=None, mag_c=None):
