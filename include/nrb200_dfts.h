@@ -29,6 +29,35 @@ int32_t nrb200_dft_supported(int N);
 const char *nrb200_dfts_last_error(void);
 uint64_t nrb200_dfts_launch_count(void);
 
+/* Part 3: slot-level OFDM front end -- one launch per slot instead of one dft()/idft() call per symbol and antenna, with the work the
+ * reference does around each transform fused into the kernel's load and store phases.  All buffers are interleaved {re, im} int16
+ * ("c16"); offsets and strides count c16 elements.
+ *   nrb200_ofdm_mod_slot_*   replaces apply_nr_rotation_TX + nr_feptx0/PHY_ofdm_mod(CYCLIC_PREFIX)   (ofdm_mod.c:337-376, :130-281;
+ *                            nr_ru_procedures.c:52-140): rotate -> IDFT -> cyclic prefix.  The rotated txdataF is not written back.
+ *   nrb200_ofdm_demod_slot_* replaces the nr_slot_fep_ul loop of nr_fep_full + apply_nr_rotation_RX  (slot_fep_nr.c:223-332;
+ *                            nr_ru_procedures.c:228-262): FFT-window gather (1/ofdm_offset_divisor of the CP early, frame ring wrap)
+ *                            -> DFT -> phase and timeshift compensation. */
+typedef struct nrb200_ofdm_slot_s {
+  uint32_t fft_size;             /* fp->ofdm_symbol_size: one of the sizes nrb200_dft_supported() accepts */
+  uint32_t n_symb;               /* symbols handled by this call (1..14), symbol l uses entry l of the arrays below */
+  uint32_t n_ant;
+  uint32_t f_stride;             /* _dev: c16 between antennas in the frequency-domain buffer (symbol l at l * fft_size) */
+  uint32_t t_stride;             /* _dev: c16 between antennas in the time-domain buffer */
+  uint32_t t_off[14];            /* TX: first CP sample of symbol l; RX: first sample of symbol l's FFT window */
+  uint32_t prefix[14];           /* TX: CP length of symbol l (fp->nb_prefix_samples0 or nb_prefix_samples) */
+  uint32_t t_ring;               /* RX: when non-zero, time-domain indices are taken modulo t_ring (fp->samples_per_frame) */
+  uint32_t rotate;               /* 0: transform (+CP) only; 1: also apply_nr_rotation_TX / apply_nr_rotation_RX */
+  uint32_t nb_rb;                /* N_RB_DL / N_RB_UL: the rotation covers the two half-band ranges the reference covers */
+  uint32_t first_carrier_offset; /* fp->first_carrier_offset */
+  int16_t rot[14][2];            /* fp->symbol_rotation[link][(slot % slots_per_subframe) * 14 + l] as stored (RX conjugates it itself) */
+} nrb200_ofdm_slot_t;
+int32_t nrb200_ofdm_mod_slot_dev(const nrb200_ofdm_slot_t *d, const int16_t *d_txdataF, int16_t *d_txdata, void *stream);
+int32_t nrb200_ofdm_demod_slot_dev(const nrb200_ofdm_slot_t *d, const int16_t *d_rxdata, const int16_t *d_timeshift, int16_t *d_rxdataF, void *stream);
+/* host buffers, one pointer per antenna like ru->common.txdataF_BF[aa] / txdata[aa] / rxdata[aa] / rxdataF[aa]; f_stride / t_stride are
+ * ignored; timeshift = fp->timeshift_symbol_rotation (fft_size c16; may be NULL when rotate == 0) */
+int32_t nrb200_ofdm_mod_slot_host(const nrb200_ofdm_slot_t *d, const int16_t *const *txdataF, int16_t *const *txdata);
+int32_t nrb200_ofdm_demod_slot_host(const nrb200_ofdm_slot_t *d, const int16_t *const *rxdata, const int16_t *timeshift, int16_t *const *rxdataF);
+
 #ifdef __cplusplus
 }
 #endif

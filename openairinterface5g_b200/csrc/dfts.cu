@@ -6,6 +6,7 @@
 // radix-2 level (:390-476) and radix-3 level (:477-540); per-level scaling >>3 (64), >>1 (256+), mulhrs 1/sqrt2, 1/sqrt3.
 // Here the recursion is unrolled into in-place passes over one shared-memory buffer: leaves are written in digit-reversed order
 // so every later butterfly reads and writes the same 4 (2, 3) addresses.  One CTA handles `tpb` transforms of N points.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -91,8 +92,46 @@ struct DftPlan {
   int rad2_tw, rad3_tw;       // offsets, -1 if unused
 };
 
+// Slot-level OFDM front end fused into the transform's load / store phases (include/nrb200_dfts.h Part 3):
+//   mode 1 (TX): apply_nr_rotation_TX on load, IDFT, cyclic-prefix insertion on store      (ofdm_mod.c:130-281, 337-376)
+//   mode 2 (RX): FFT-window gather from the frame ring on load, DFT, apply_nr_rotation_RX on store (slot_fep_nr.c:223-332)
+struct SlotIO {
+  int n_symb, rotate;
+  unsigned f_stride, t_stride, t_ring;
+  unsigned t_off[14], prefix[14];
+  unsigned r_start[2], r_len;               // the two sub-carrier ranges the reference rotates
+  short rot[14][2];
+  const unsigned *timeshift;                // RX: fp->timeshift_symbol_rotation (N c16)
+};
+
+// rotate_cpx_vector (cmult_sv.c:77-145, AVX2 branch): 8-element vector body saturates, the scalar tail truncates
+__device__ __forceinline__ unsigned rotate_c16(unsigned w, int ar, int ai, bool body)
+{
+  const cx x = unpack(w);
+  if (body) {
+    const int nai = wrap16(-ai);
+    return pack(cx{sat16(sra15((unsigned)(x.r * ar) + (unsigned)(x.i * nai))), sat16(sra15((unsigned)(x.r * ai) + (unsigned)(x.i * ar)))});
+  }
+  return pack(cx{wrap16(sra15((unsigned)(x.r * ar) - (unsigned)(x.i * ai))), wrap16(sra15((unsigned)(x.r * ai) + (unsigned)(x.i * ar)))});
+}
+// multadd_cpx_vector(zero_flag = 1) (cmult_vv.c:158-213): plain product >> 15, saturating
+__device__ __forceinline__ unsigned mult_c16(unsigned w, unsigned t)
+{
+  const cx a = unpack(w), b = unpack(t);
+  const int nai = wrap16(-a.i);
+  return pack(cx{sat16(sra15((unsigned)(a.r * b.r) + (unsigned)(nai * b.i))), sat16(sra15((unsigned)(a.i * b.r) + (unsigned)(a.r * b.i)))});
+}
+// position of sub-carrier i inside the rotated ranges: -1 outside, else offset j within its range
+__device__ __forceinline__ int range_pos(const SlotIO &S, unsigned i)
+{
+  if (i - S.r_start[0] < S.r_len) return (int)(i - S.r_start[0]);
+  if (i - S.r_start[1] < S.r_len) return (int)(i - S.r_start[1]);
+  return -1;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const short *__restrict__ tw, const unsigned *__restrict__ in,
-                                                  unsigned *__restrict__ out, unsigned n)
+                                                  unsigned *__restrict__ out, unsigned n, SlotIO S)
 {
   extern __shared__ unsigned sm[];          // [tpb][N] natural-order input copy, then [tpb][N] work buffer
   const int N = P.N, tpb = P.tpb;
@@ -100,7 +139,25 @@ __global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const 
   const bool inv = P.inverse != 0;
   const unsigned t0 = blockIdx.x * tpb;
   const int nt = min((unsigned)tpb, n - t0);
-  for (int i = threadIdx.x; i < nt * N; i += blockDim.x) xin[i] = in[(size_t)t0 * N + i];
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < nt * N; i += blockDim.x) xin[i] = in[(size_t)t0 * N + i];
+  } else {
+    for (int w = threadIdx.x; w < nt * N; w += blockDim.x) {
+      const unsigned tr = w / N, i = w - tr * N, t = t0 + tr, ant = t / S.n_symb, l = t - ant * S.n_symb;
+      if (MODE == 1) {
+        unsigned v = in[(size_t)ant * S.f_stride + (size_t)l * N + i];
+        if (S.rotate) {
+          const int j = range_pos(S, i);
+          if (j >= 0) v = rotate_c16(v, S.rot[l][0], S.rot[l][1], (unsigned)j < (S.r_len & ~7u));
+        }
+        xin[w] = v;
+      } else {
+        unsigned k = S.t_off[l] + i;
+        if (S.t_ring) k %= S.t_ring;
+        xin[w] = in[(size_t)ant * S.t_stride + k];
+      }
+    }
+  }
   __syncthreads();
   // ---- leaves: 16-point kernels, output slot = digit-reversed leaf id so that all later passes are in place
   const int T = P.r3 * P.r2, leaves4 = P.N4 >> 4, D = P.D;
@@ -210,7 +267,29 @@ __global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const 
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < nt * N; i += blockDim.x) out[(size_t)t0 * N + i] = buf[i];
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < nt * N; i += blockDim.x) out[(size_t)t0 * N + i] = buf[i];
+  } else {
+    for (int w = threadIdx.x; w < nt * N; w += blockDim.x) {
+      const unsigned tr = w / N, i = w - tr * N, t = t0 + tr, ant = t / S.n_symb, l = t - ant * S.n_symb;
+      unsigned v = buf[w];
+      if (MODE == 1) {
+        unsigned *o = out + (size_t)ant * S.t_stride + S.t_off[l];
+        const unsigned cp = S.prefix[l];
+        o[cp + i] = v;
+        if (i >= (unsigned)N - cp) o[i - ((unsigned)N - cp)] = v;        // cyclic prefix = the last cp samples
+      } else {
+        if (S.rotate) {
+          const int j = range_pos(S, i);
+          if (j >= 0) {
+            v = rotate_c16(v, S.rot[l][0], wrap16(-S.rot[l][1]), (unsigned)j < (S.r_len & ~7u));
+            if ((unsigned)j < (S.r_len & ~3u)) v = mult_c16(v, __ldg(S.timeshift + i));
+          }
+        }
+        out[(size_t)ant * S.f_stride + (size_t)l * N + i] = v;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -274,7 +353,9 @@ int dft_init()
   if (cudaMalloc(&c.d_tw, blob.size() * sizeof(short)) != cudaSuccess) { c.last_error = "cudaMalloc twiddles"; return -1; }
   cudaMemcpy(c.d_tw, blob.data(), blob.size() * sizeof(short), cudaMemcpyHostToDevice);
   if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) { c.last_error = "stream"; return -1; }
-  cudaFuncSetAttribute(dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
   c.inited = true;
   return 0;
 }
@@ -304,7 +385,7 @@ int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_o
   DftCtx &c = dctx();
   const unsigned grid = (n + P.tpb - 1) / P.tpb;
   const size_t smem = (size_t)2 * P.tpb * N * 4;
-  dft_kernel<<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n);
+  dft_kernel<0><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
   c.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft launch: ") + cudaGetErrorString(e); return -2; }
@@ -378,12 +459,143 @@ NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, cons
   DftPlan P;
   if (!make_plan(N, inverse, scale, &P)) return -4;
   const unsigned grid = (n + P.tpb - 1) / P.tpb;
-  dft_kernel<<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n);
+  dft_kernel<0><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
   c.launches++;
   cudaMemcpyAsync(c.h_out, c.d_out, bytes, cudaMemcpyDeviceToHost, c.stream);
   cudaError_t e = cudaStreamSynchronize(c.stream);
   if (e != cudaSuccess) { c.last_error = std::string("dft: ") + cudaGetErrorString(e); return -2; }
   std::memcpy(out, c.h_out, bytes);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ slot-level OFDM
+namespace {
+bool slot_io(const nrb200_ofdm_slot_t *d, bool rx, const unsigned *d_timeshift, SlotIO *S)
+{
+  if (!d || d->n_symb < 1 || d->n_symb > 14 || d->n_ant < 1) return false;
+  const unsigned N = d->fft_size;
+  S->n_symb = (int)d->n_symb; S->rotate = d->rotate ? 1 : 0;
+  S->f_stride = d->f_stride; S->t_stride = d->t_stride; S->t_ring = rx ? d->t_ring : 0;
+  for (unsigned l = 0; l < 14; l++) {
+    S->t_off[l] = d->t_off[l]; S->prefix[l] = d->prefix[l]; S->rot[l][0] = d->rot[l][0]; S->rot[l][1] = d->rot[l][1];
+    if (!rx && l < d->n_symb && d->prefix[l] > N) return false;
+  }
+  // the two ranges of apply_nr_rotation_TX/RX (odd nb_rb: one extra half PRB on both sides)
+  const unsigned odd = d->nb_rb & 1u;
+  S->r_len = (d->nb_rb + odd) * 6;
+  S->r_start[0] = 0; S->r_start[1] = d->first_carrier_offset - (odd ? 6 : 0);
+  if (S->rotate && (S->r_len > N || S->r_start[1] + S->r_len > N)) return false;
+  S->timeshift = d_timeshift;
+  if (rx && S->rotate && !d_timeshift) return false;
+  return true;
+}
+
+int launch_slot(const nrb200_ofdm_slot_t *d, bool rx, const void *d_in, void *d_out, const unsigned *d_timeshift, cudaStream_t st)
+{
+  DftPlan P;
+  SlotIO S;
+  if (!make_plan((int)d->fft_size, rx ? 0 : 1, 1, &P)) return -4;
+  if (!slot_io(d, rx, d_timeshift, &S)) return -4;
+  DftCtx &c = dctx();
+  const unsigned n = d->n_symb * d->n_ant, grid = (n + P.tpb - 1) / P.tpb;
+  const size_t smem = (size_t)2 * P.tpb * P.N * 4;
+  if (rx) dft_kernel<2><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+  else dft_kernel<1><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+  c.launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("ofdm slot launch: ") + cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+bool stage_reserve(DftCtx &c, size_t bytes)
+{
+  if (bytes <= c.cap) return true;
+  if (c.d_in) { cudaFree(c.d_in); cudaFree(c.d_out); cudaFreeHost(c.h_in); cudaFreeHost(c.h_out); }
+  c.cap = bytes + bytes / 4 + 65536;
+  if (cudaMalloc(&c.d_in, c.cap) != cudaSuccess || cudaMalloc(&c.d_out, c.cap) != cudaSuccess || cudaHostAlloc(&c.h_in, c.cap, 0) != cudaSuccess ||
+      cudaHostAlloc(&c.h_out, c.cap, 0) != cudaSuccess) { c.cap = 0; c.d_in = nullptr; c.last_error = "staging alloc"; return false; }
+  return true;
+}
+}  // namespace
+
+NRB200_EXPORT int32_t nrb200_ofdm_mod_slot_dev(const nrb200_ofdm_slot_t *d, const int16_t *d_txdataF, int16_t *d_txdata, void *stream)
+{
+  if (dft_init() != 0) return -1;
+  cudaSetDevice(dctx().dev);
+  return launch_slot(d, false, d_txdataF, d_txdata, nullptr, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_ofdm_demod_slot_dev(const nrb200_ofdm_slot_t *d, const int16_t *d_rxdata, const int16_t *d_timeshift, int16_t *d_rxdataF,
+                                                 void *stream)
+{
+  if (dft_init() != 0) return -1;
+  cudaSetDevice(dctx().dev);
+  return launch_slot(d, true, d_rxdata, d_rxdataF, (const unsigned *)d_timeshift, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_ofdm_mod_slot_host(const nrb200_ofdm_slot_t *d, const int16_t *const *txdataF, int16_t *const *txdata)
+{
+  if (dft_init() != 0) return -1;
+  if (!d || d->n_symb < 1 || d->n_symb > 14 || d->n_ant < 1 || !nrb200_dft_supported((int)d->fft_size)) return -4;
+  DftCtx &c = dctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaSetDevice(c.dev);
+  const unsigned N = d->fft_size, ns = d->n_symb, na = d->n_ant;
+  // time-domain span written by this call, relative to txdata[a]
+  unsigned lo = d->t_off[0], hi = 0;
+  for (unsigned l = 0; l < ns; l++) { lo = std::min(lo, d->t_off[l]); hi = std::max(hi, d->t_off[l] + d->prefix[l] + N); }
+  const size_t fin = (size_t)ns * N, tout = hi - lo;
+  if (!stage_reserve(c, 4 * std::max(fin, tout) * na)) return -5;
+  for (unsigned a = 0; a < na; a++) std::memcpy((uint8_t *)c.h_in + 4 * fin * a, txdataF[a], 4 * fin);
+  cudaMemcpyAsync(c.d_in, c.h_in, 4 * fin * na, cudaMemcpyHostToDevice, c.stream);
+  nrb200_ofdm_slot_t e = *d;
+  e.f_stride = (uint32_t)fin; e.t_stride = (uint32_t)tout;
+  for (unsigned l = 0; l < ns; l++) e.t_off[l] -= lo;
+  const int rc = launch_slot(&e, false, c.d_in, c.d_out, nullptr, c.stream);
+  if (rc != 0) return rc;
+  cudaMemcpyAsync(c.h_out, c.d_out, 4 * tout * na, cudaMemcpyDeviceToHost, c.stream);
+  cudaError_t er = cudaStreamSynchronize(c.stream);
+  if (er != cudaSuccess) { c.last_error = std::string("ofdm mod: ") + cudaGetErrorString(er); return -2; }
+  for (unsigned a = 0; a < na; a++) {
+    // only the samples this call produced are written back (symbols may be non-contiguous when n_symb < 14)
+    for (unsigned l = 0; l < ns; l++)
+      std::memcpy(txdata[a] + 2 * (size_t)d->t_off[l], (uint8_t *)c.h_out + 4 * (tout * a + e.t_off[l]), 4 * (size_t)(d->prefix[l] + N));
+  }
+  return 0;
+}
+
+NRB200_EXPORT int32_t nrb200_ofdm_demod_slot_host(const nrb200_ofdm_slot_t *d, const int16_t *const *rxdata, const int16_t *timeshift,
+                                                  int16_t *const *rxdataF)
+{
+  if (dft_init() != 0) return -1;
+  if (!d || d->n_symb < 1 || d->n_symb > 14 || d->n_ant < 1 || !nrb200_dft_supported((int)d->fft_size)) return -4;
+  if (d->rotate && !timeshift) return -4;
+  DftCtx &c = dctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaSetDevice(c.dev);
+  const unsigned N = d->fft_size, ns = d->n_symb, na = d->n_ant, ring = d->t_ring;
+  // Only the FFT windows travel: window l of antenna a lands at (a * ns + l) * N in the staging buffer (the ring wrap is resolved here).
+  const size_t win = (size_t)ns * N;
+  if (!stage_reserve(c, 4 * (win * na + N))) return -5;
+  for (unsigned a = 0; a < na; a++)
+    for (unsigned l = 0; l < ns; l++) {
+      uint8_t *dst = (uint8_t *)c.h_in + 4 * (win * a + (size_t)l * N);
+      const size_t k = ring ? d->t_off[l] % ring : d->t_off[l];
+      const size_t first = ring ? std::min<size_t>(N, ring - k) : N;
+      std::memcpy(dst, rxdata[a] + 2 * k, 4 * first);
+      if (first < N) std::memcpy(dst + 4 * first, rxdata[a], 4 * (N - first));
+    }
+  if (d->rotate) std::memcpy((uint8_t *)c.h_in + 4 * win * na, timeshift, 4 * (size_t)N);
+  cudaMemcpyAsync(c.d_in, c.h_in, 4 * (win * na + N), cudaMemcpyHostToDevice, c.stream);
+  nrb200_ofdm_slot_t e = *d;
+  e.t_ring = 0; e.t_stride = (uint32_t)win; e.f_stride = (uint32_t)win;
+  for (unsigned l = 0; l < ns; l++) e.t_off[l] = l * N;
+  const int rc = launch_slot(&e, true, c.d_in, c.d_out, (const unsigned *)c.d_in + win * na, c.stream);
+  if (rc != 0) return rc;
+  cudaMemcpyAsync(c.h_out, c.d_out, 4 * win * na, cudaMemcpyDeviceToHost, c.stream);
+  cudaError_t er = cudaStreamSynchronize(c.stream);
+  if (er != cudaSuccess) { c.last_error = std::string("ofdm demod: ") + cudaGetErrorString(er); return -2; }
+  for (unsigned a = 0; a < na; a++) std::memcpy(rxdataF[a], (uint8_t *)c.h_out + 4 * win * a, 4 * win);
   return 0;
 }
 

@@ -35,6 +35,10 @@ class DftsLib:
         L.idft.restype = None
         L.nrb200_dft_batch_dev.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.nrb200_dft_batch_host.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.nrb200_ofdm_mod_slot_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ofdm_demod_slot_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ofdm_mod_slot_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ofdm_demod_slot_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_dfts_last_error.restype = C.c_char_p
         L.nrb200_dfts_launch_count.restype = C.c_uint64
 
@@ -74,6 +78,52 @@ class DftsLib:
         if rc != 0:
             raise RuntimeError(f"nrb200_dft_batch_dev rc={rc}")
         return out
+
+    # ---- slot-level OFDM front end (include/nrb200_dfts.h Part 3)
+    def _err(self, what, rc):
+        raise RuntimeError(f"{what} rc={rc}: " + (self.lib.nrb200_dfts_last_error() or b"").decode())
+
+    def ofdm_mod_slot_host(self, parms, slot, txdataF, rot=None):
+        """txdataF[n_ant][14*N*2] int16 -> txdata[n_ant][slot samples * 2]; apply_nr_rotation_TX + PHY_ofdm_mod in one launch."""
+        F = np.ascontiguousarray(txdataF, dtype=np.int16).reshape(len(txdataF), -1)
+        na = F.shape[0]
+        d = parms.desc(slot, na, rot)
+        out = np.zeros((na, 2 * d.t_stride), np.int16)
+        pin = (C.c_void_p * na)(*[F[a].ctypes.data for a in range(na)])
+        pout = (C.c_void_p * na)(*[out[a].ctypes.data for a in range(na)])
+        rc = self.lib.nrb200_ofdm_mod_slot_host(C.addressof(d), pin, pout)
+        if rc != 0:
+            self._err("nrb200_ofdm_mod_slot_host", rc)
+        return out
+
+    def ofdm_demod_slot_host(self, parms, slot, rxdata, rot=None, sample_offset=0):
+        """rxdata[n_ant][samples_per_frame*2] (frame ring) -> rxdataF[n_ant][14*N*2]; nr_slot_fep_ul x 14 + apply_nr_rotation_RX."""
+        X = np.ascontiguousarray(rxdata, dtype=np.int16).reshape(len(rxdata), -1)
+        na = X.shape[0]
+        d = parms.desc(slot, na, rot, rx=True, sample_offset=sample_offset)
+        ts = np.ascontiguousarray(parms.timeshift_rotation()) if rot is not None else None
+        out = np.zeros((na, 2 * 14 * parms.N), np.int16)
+        pin = (C.c_void_p * na)(*[X[a].ctypes.data for a in range(na)])
+        pout = (C.c_void_p * na)(*[out[a].ctypes.data for a in range(na)])
+        rc = self.lib.nrb200_ofdm_demod_slot_host(C.addressof(d), pin, None if ts is None else ts.ctypes.data, pout)
+        if rc != 0:
+            self._err("nrb200_ofdm_demod_slot_host", rc)
+        return out
+
+    def ofdm_mod_slot_torch(self, desc, txdataF, txdata):
+        import torch
+        rc = self.lib.nrb200_ofdm_mod_slot_dev(C.addressof(desc), txdataF.data_ptr(), txdata.data_ptr(), torch.cuda.current_stream(txdataF.device).cuda_stream)
+        if rc != 0:
+            self._err("nrb200_ofdm_mod_slot_dev", rc)
+        return txdata
+
+    def ofdm_demod_slot_torch(self, desc, rxdata, timeshift, rxdataF):
+        import torch
+        rc = self.lib.nrb200_ofdm_demod_slot_dev(C.addressof(desc), rxdata.data_ptr(), 0 if timeshift is None else timeshift.data_ptr(), rxdataF.data_ptr(),
+                                                 torch.cuda.current_stream(rxdata.device).cuda_stream)
+        if rc != 0:
+            self._err("nrb200_ofdm_demod_slot_dev", rc)
+        return rxdataF
 
     def launch_count(self):
         return int(self.lib.nrb200_dfts_launch_count())

@@ -162,6 +162,40 @@ class Oracle:
         self.lib.orc_ulsch_llr(Qm, rxF.ctypes.data_as(C.c_void_p), mk(maga), mk(magb), mk(magc), out.ctypes.data_as(C.c_void_p), C.c_uint32(n))
         return out
 
+    # ---- slot-level OFDM front end
+    def ofdm_geometry(self, N, mu, slot):
+        pre = np.zeros(14, np.uint32); cps = np.zeros(14, np.uint32); ss = C.c_uint32(); fl = C.c_uint32()
+        self.lib.orc_ofdm_geometry(N, mu, slot, pre.ctypes.data_as(C.c_void_p), cps.ctypes.data_as(C.c_void_p), C.byref(ss), C.byref(fl))
+        return pre, cps, ss.value, fl.value
+
+    def symbol_rotation(self, mu, f0):
+        out = np.zeros(2 * (14 << mu), np.int16)
+        self.lib.orc_symbol_rotation.argtypes = [C.c_int, C.c_double, C.c_void_p]
+        self.lib.orc_symbol_rotation(mu, float(f0), out.ctypes.data)
+        return out
+
+    def timeshift_rotation(self, N, sample_offset):
+        out = np.zeros(2 * N, np.int16)
+        self.lib.orc_timeshift_rotation(N, sample_offset, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def ofdm_tx_slot(self, N, mu, nb_rb, slot, nsymb, rot, txdataF):
+        pre, cps, _, _ = self.ofdm_geometry(N, mu, slot)
+        F = np.ascontiguousarray(txdataF, dtype=np.int16).copy()
+        out = np.zeros(2 * int(cps[13] + pre[13] + N), np.int16)
+        r = None if rot is None else np.ascontiguousarray(rot, dtype=np.int16)
+        self.lib.orc_ofdm_tx_slot(N, mu, nb_rb, slot, nsymb, None if r is None else r.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p),
+                                  out.ctypes.data_as(C.c_void_p))
+        return out, F
+
+    def ofdm_rx_slot(self, N, mu, nb_rb, slot, divisor, sample_offset, rot, rxdata):
+        x = np.ascontiguousarray(rxdata, dtype=np.int16)
+        out = np.zeros(2 * 14 * N, np.int16)
+        r = None if rot is None else np.ascontiguousarray(rot, dtype=np.int16)
+        self.lib.orc_ofdm_rx_slot(N, mu, nb_rb, slot, divisor, sample_offset, None if r is None else r.ctypes.data_as(C.c_void_p),
+                                  x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
     def dft(self, N, inverse, x, scale=1):
         x = np.ascontiguousarray(x, dtype=np.int16)
         y = np.zeros(2 * N, dtype=np.int16)
@@ -363,6 +397,40 @@ class Reference:
         return o[:n * Qm].copy()
 
     # ---- scrambling + QAM mapper of the reference (libref_mod.so: nr_scrambling.c, nr_modulation.c, nr_gen_mod_table.c)
+    def _ofdm(self):
+        if not hasattr(self, "_ofdmlib"):
+            self._ofdmlib = C.CDLL(os.path.join(REFDIR, "libref_ofdm.so"))
+            rc = self._ofdmlib.refh_ofdm_init(os.path.join(REFDIR, "libref_dfts.so").encode())
+            assert rc == 0, rc
+            self._ofdmlib.refh_rotation_tables.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        return self._ofdmlib
+
+    def rotation_tables(self, N, mu, nb_rb, divisor, dl_freq, ul_freq):
+        L = self._ofdm()
+        dl = np.zeros(448, np.int16); ul = np.zeros(448, np.int16); ts = np.zeros(2 * N, np.int16)
+        L.refh_rotation_tables(N, mu, nb_rb, divisor, float(dl_freq), float(ul_freq), dl.ctypes.data, ul.ctypes.data, ts.ctypes.data)
+        return dl, ul, ts
+
+    def ofdm_tx_slot(self, N, mu, nb_rb, slot, nsymb, rot224, txdataF, out_len):
+        L = self._ofdm()
+        F = np.ascontiguousarray(txdataF, dtype=np.int16).copy()
+        out = np.zeros(2 * out_len + 64, np.int16)
+        r = None if rot224 is None else np.ascontiguousarray(rot224, dtype=np.int16)
+        L.refh_ofdm_tx_slot(N, mu, nb_rb, slot, nsymb, None if r is None else r.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p),
+                            out.ctypes.data_as(C.c_void_p))
+        return out[:2 * out_len], F
+
+    def ofdm_rx_slot(self, N, mu, nb_rb, slot, divisor, sample_offset, rot224, rxdata):
+        L = self._ofdm()
+        x = np.ascontiguousarray(rxdata, dtype=np.int16).copy()
+        buf = np.zeros(2 * 14 * N + 32, np.int16)
+        off = ((-buf.ctypes.data) % 32) // 2           # dft() asserts a 32-byte aligned output
+        out = buf[off:off + 2 * 14 * N]
+        r = None if rot224 is None else np.ascontiguousarray(rot224, dtype=np.int16)
+        L.refh_ofdm_rx_slot(N, mu, nb_rb, slot, divisor, sample_offset, None if r is None else r.ctypes.data_as(C.c_void_p),
+                            x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out.copy()
+
     def _mod(self):
         if not hasattr(self, "_modlib"):
             self._modlib = C.CDLL(os.path.join(REFDIR, "libref_mod.so"))

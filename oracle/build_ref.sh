@@ -60,4 +60,8 @@ gcc $F -mpclmul $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/CODING/crc_byte.c $
     $R/openair1/PHY/CODING/nr_segmentation.c -o libref_coding.so || echo "libref_coding.so: FAILED (see DESIGN.md)"
 gcc $F $INC $DEFS $HERE/ref_stubs.c $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_llr_computation.c $R/openair1/PHY/TOOLS/simde_operations.c -o libref_llr.so || echo "libref_llr.so: FAILED"
 gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_mod.c $R/openair1/PHY/MODULATION/nr_modulation.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c $R/openair1/PHY/NR_TRANSPORT/nr_scrambling.c $R/openair1/PHY/NR_REFSIG/scrambling_luts.c -lm -o libref_mod.so || echo "libref_mod.so: FAILED"
+# slot-level OFDM front end; dft/idft stay function pointers bound at run time to libref_dfts.so (ref_harness_ofdm.c)
+gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_ofdm.c $R/openair1/PHY/MODULATION/ofdm_mod.c $R/openair1/PHY/MODULATION/slot_fep_nr.c \
+    $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/TOOLS/cmult_vv.c $R/openair1/PHY/MODULATION/nr_modulation.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c \
+    -lm -ldl -o libref_ofdm.so || echo "libref_ofdm.so: FAILED"
 ls -la $W/*.so

@@ -65,6 +65,15 @@ void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_
 /* Q15 DFT/IDFT of the OFDM sizes (nrb200_dft_oracle.c restates openair1/PHY/TOOLS/oai_dfts.c); interleaved {re,im} int16. */
 int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale);
 
+/* slot-level OFDM front end (nrb200_ofdm_oracle.c) */
+void orc_rotate_cpx_vector(const int16_t *x, int16_t ar, int16_t ai, int16_t *y, uint32_t N);
+void orc_mult_cpx_vector(const int16_t *x1, const int16_t *x2, int16_t *y, uint32_t N);
+void orc_symbol_rotation(int mu, double f0, int16_t *rot);
+void orc_timeshift_rotation(int N, int sample_offset, int16_t *out);
+void orc_ofdm_geometry(int N, int mu, int slot, uint32_t *prefix, uint32_t *cp_start, uint32_t *slot_start, uint32_t *frame_len);
+void orc_ofdm_tx_slot(int N, int mu, int nb_rb, int slot, int nsymb, const int16_t *rot, int16_t *txdataF, int16_t *txdata);
+void orc_ofdm_rx_slot(int N, int mu, int nb_rb, int slot, int divisor, int sample_offset, const int16_t *rot, const int16_t *rxdata, int16_t *rxdataF);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,3 +82,17 @@ def test_dft_golden(oracle):
         for i in range(d[f"x{N}"].shape[0]):
             assert np.array_equal(oracle.dft(N, False, d[f"x{N}"][i], 1), d[f"dft{N}"][i]), N
             assert np.array_equal(oracle.dft(N, True, d[f"x{N}"][i], 1), d[f"idft{N}"][i]), N
+
+
+def test_ofdm_parms_mirror(oracle):
+    """openairinterface5g_b200/ofdm.py (product host code) derives the same slot geometry and rotation tables as the oracle restatement
+    (itself pinned to nr_parms.c / nr_modulation.c through the compiled reference)."""
+    from openairinterface5g_b200.ofdm import NrOfdmParms
+    for N, mu, nb in ((4096, 1, 273), (2048, 2, 66), (1024, 0, 52), (1536, 1, 78)):
+        P = NrOfdmParms(N, mu, nb)
+        for slot in range(10 << mu):
+            pre, cps, ss, fl = oracle.ofdm_geometry(N, mu, slot)
+            p2, s2 = P.slot_geometry(slot)
+            assert list(pre) == p2 and list(cps) == s2 and ss == P.slot_timestamp(slot) and fl == P.samples_per_frame
+        assert np.array_equal(oracle.symbol_rotation(mu, 3.6192e9).reshape(-1, 2), P.symbol_rotation(3.6192e9))
+        assert np.array_equal(oracle.timeshift_rotation(N, P.nb_prefix_samples // 8).reshape(-1, 2), P.timeshift_rotation())

@@ -209,3 +209,51 @@ def test_unscrambling(oracle, reference):
     for size, q, Nid, rnti in ((64, 0, 0, 1), (9072, 1, 1007, 65535), (12 * 273 * 6, 0, 500, 4660)):
         llr = rng.integers(-32768, 32768, size=size).astype(np.int16)
         assert np.array_equal(oracle.unscramble_llr(llr, q, Nid, rnti), reference.unscramble_llr(llr, q, Nid, rnti))
+
+
+# ------------------------------------------------------------------------------------------ slot-level OFDM front end (a20)
+OFDM_CASES = [  # N, mu, nb_rb, slot
+    (4096, 1, 273, 0), (4096, 1, 273, 3), (2048, 1, 106, 1), (1024, 0, 52, 2), (1536, 1, 78, 4), (512, 0, 25, 0), (3072, 1, 162, 2), (2048, 2, 66, 5),
+]
+
+
+def test_rotation_tables(oracle, reference):
+    for N, mu, nb_rb, _ in OFDM_CASES:
+        for div in (8, 4):
+            dl, ul, ts = reference.rotation_tables(N, mu, nb_rb, div, 3619200000.0, 3619200000.0 - 1e7)
+            n = 2 * (14 << mu)
+            assert np.array_equal(oracle.symbol_rotation(mu, 3619200000.0), dl[:n])
+            assert np.array_equal(oracle.symbol_rotation(mu, 3619200000.0 - 1e7), ul[:n])
+            assert np.array_equal(oracle.timeshift_rotation(N, (N // 128 * 9) // div), ts)
+
+
+def test_ofdm_tx_slot(oracle, reference):
+    rng = np.random.default_rng(20)
+    for N, mu, nb_rb, slot in OFDM_CASES:
+        rot = oracle.symbol_rotation(mu, 3619200000.0)
+        rot224 = np.zeros(448, np.int16); rot224[:rot.size] = rot
+        F = np.zeros((14, N, 2), np.int16)
+        fco = N - nb_rb * 6
+        amp = 32767 if slot == 3 else 4000               # one case drives the saturating / truncating corners of rotate_cpx_vector
+        F[:, :nb_rb * 6] = rng.integers(-amp, amp + 1, size=(14, nb_rb * 6, 2))
+        F[:, fco:] = rng.integers(-amp, amp + 1, size=(14, nb_rb * 6, 2))
+        for use_rot in (True, False):
+            y_o, F_o = oracle.ofdm_tx_slot(N, mu, nb_rb, slot, 14, rot if use_rot else None, F)
+            y_r, F_r = reference.ofdm_tx_slot(N, mu, nb_rb, slot, 14, rot224 if use_rot else None, F, y_o.size // 2)
+            assert np.array_equal(F_o, F_r), (N, mu, nb_rb, slot, "rotated txdataF")
+            assert np.array_equal(y_o, y_r), (N, mu, nb_rb, slot, use_rot)
+
+
+def test_ofdm_rx_slot(oracle, reference):
+    rng = np.random.default_rng(21)
+    for N, mu, nb_rb, slot in OFDM_CASES:
+        _, _, _, frame_len = oracle.ofdm_geometry(N, mu, slot)
+        rot = oracle.symbol_rotation(mu, 3609200000.0)
+        rot224 = np.zeros(448, np.int16); rot224[:rot.size] = rot
+        amp = 32767 if slot == 3 else 3000
+        rx = rng.integers(-amp, amp + 1, size=2 * frame_len).astype(np.int16)
+        for div, ta in ((8, 0), (8, N // 8), (4, N // 32 + 3), (8, N // 4 + 5)):   # in slot 0 a timing offset wraps around the frame buffer
+            for use_rot in (True, False):
+                y_o = oracle.ofdm_rx_slot(N, mu, nb_rb, slot, div, ta, rot if use_rot else None, rx)
+                y_r = reference.ofdm_rx_slot(N, mu, nb_rb, slot, div, ta, rot224 if use_rot else None, rx)
+                assert np.array_equal(y_o, y_r), (N, mu, nb_rb, slot, div, ta, use_rot)
