@@ -93,6 +93,9 @@ class LdpcLib:
         L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_pusch_llr_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_pusch_llr_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_scramble_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.nrb200_unscramble_llr_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.nrb200_modulate_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         L.nrb200_scramble_host.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.nrb200_unscramble_llr_host.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.nrb200_modulate_host.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
@@ -236,6 +239,24 @@ class LdpcLib:
         x = np.ascontiguousarray(packed_words, dtype=np.uint32)
         out = np.zeros(2 * (length_bits // Qm), dtype=np.int16)
         self._check(self.lib.nrb200_modulate_host(x.ctypes.data, length_bits, Qm, out.ctypes.data), "modulate_host")
+        return out
+
+    def scramble_torch(self, in_bits, q, Nid, n_RNTI, out):
+        import torch
+        self._check(self.lib.nrb200_scramble_dev(in_bits.data_ptr(), in_bits.numel(), q, Nid, n_RNTI, out.data_ptr(),
+                                                 torch.cuda.current_stream(in_bits.device).cuda_stream), "scramble_dev")
+        return out
+
+    def unscramble_llr_torch(self, llr, q, Nid, n_RNTI):
+        import torch
+        self._check(self.lib.nrb200_unscramble_llr_dev(llr.data_ptr(), llr.numel(), q, Nid, n_RNTI, torch.cuda.current_stream(llr.device).cuda_stream),
+                    "unscramble_llr_dev")
+        return llr
+
+    def modulate_torch(self, packed_words, length_bits, Qm, out):
+        import torch
+        self._check(self.lib.nrb200_modulate_dev(packed_words.data_ptr(), length_bits, Qm, out.data_ptr(),
+                                                 torch.cuda.current_stream(out.device).cuda_stream), "modulate_dev")
         return out
 
     # ---- demodulation: nr_ulsch_compute_llr (single layer, max-log)

@@ -58,6 +58,11 @@ def _ptr(a, t):
 
 
 # ------------------------------------------------------------------------------------------------ oracle (C restatement)
+class PuschParms(C.Structure):       # orc_pusch_t
+    _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "Qm", "ul_dmrs_symb_pos",
+                                         "dmrs_config_type", "num_dmrs_cdm_grps_no_data")]
+
+
 class Oracle:
     def __init__(self):
         so = os.path.join(HERE, "liboracle.so")
@@ -161,6 +166,25 @@ class Oracle:
         self.lib.orc_ulsch_llr.restype = None
         self.lib.orc_ulsch_llr(Qm, rxF.ctypes.data_as(C.c_void_p), mk(maga), mk(magb), mk(magc), out.ctypes.data_as(C.c_void_p), C.c_uint32(n))
         return out
+
+    # ---- single-layer PUSCH inner receiver
+    def pusch_nb_re(self, P, symbol):
+        return int(self.lib.orc_pusch_nb_re(C.byref(P), symbol))
+
+    def pusch_log2_maxh(self, P, meas_symbol, ch_symbol, rxdataF, ch_est):
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(ch_est, dtype=np.int16)
+        avg = np.zeros(8, np.int32)
+        r = self.lib.orc_pusch_log2_maxh(C.byref(P), meas_symbol, ch_symbol, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p))
+        return int(r), avg[:P.nb_rx].copy()
+
+    def pusch_inner_rx_symbol(self, P, symbol, ch_symbol, shift, rxdataF, ch_est):
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(ch_est, dtype=np.int16)
+        blen = (P.rb_size * 12 + 15) & ~15
+        valid = self.pusch_nb_re(P, symbol)
+        llr = np.zeros(valid * P.Qm, np.int16); comp = np.zeros(2 * blen, np.int16)
+        self.lib.orc_pusch_inner_rx_symbol(C.byref(P), symbol, ch_symbol, shift, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p),
+                                           llr.ctypes.data_as(C.c_void_p), comp.ctypes.data_as(C.c_void_p))
+        return llr, comp
 
     # ---- slot-level OFDM front end
     def ofdm_geometry(self, N, mu, slot):
@@ -397,6 +421,35 @@ class Reference:
         return o[:n * Qm].copy()
 
     # ---- scrambling + QAM mapper of the reference (libref_mod.so: nr_scrambling.c, nr_modulation.c, nr_gen_mod_table.c)
+    def _pusch(self):
+        if not hasattr(self, "_puschlib"):
+            self._puschlib = C.CDLL(os.path.join(REFDIR, "libref_pusch.so"))
+        return self._puschlib
+
+    @staticmethod
+    def _pusch_params(P, nb_layer, symbol, ch_symbol, shift, nvar, valid):
+        return np.array([P.fft_size, P.nb_rx, nb_layer, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.Qm, symbol, ch_symbol, P.ul_dmrs_symb_pos,
+                         P.num_dmrs_cdm_grps_no_data, P.dmrs_config_type, shift, nvar, valid], dtype=np.int32)
+
+    def pusch_inner_rx_symbol(self, P, symbol, ch_symbol, shift, rxdataF, ch_est, valid):
+        L = self._pusch()
+        prm = self._pusch_params(P, 1, symbol, ch_symbol, shift, 0, valid)
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(ch_est, dtype=np.int16).copy()
+        blen = (P.rb_size * 12 + 15) & ~15
+        llr = np.zeros(valid * P.Qm + 64, np.int16); comp = np.zeros(2 * blen, np.int16)
+        L.refh_pusch_inner_rx(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+                              comp.ctypes.data_as(C.c_void_p))
+        return llr[:valid * P.Qm], comp
+
+    def pusch_log2_maxh(self, P, meas_symbol, ch_symbol, rxdataF, ch_est):
+        L = self._pusch()
+        prm = self._pusch_params(P, 1, meas_symbol, ch_symbol, 0, 0, 0)
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(ch_est, dtype=np.int16).copy()
+        avg = np.zeros(8, np.int32)
+        raw = L.refh_pusch_log2_maxh(prm.ctypes.data_as(C.c_void_p), 0, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p))
+        # the final rule of nr_rx_pusch_tp for one layer (:1642-1646): + 1 + log2_approx(nb_rx >> 2), floored at 0
+        return max(0, int(raw) + 1 + int(P.nb_rx >> 2).bit_length()), avg[:P.nb_rx].copy()
+
     def _ofdm(self):
         if not hasattr(self, "_ofdmlib"):
             self._ofdmlib = C.CDLL(os.path.join(REFDIR, "libref_ofdm.so"))

@@ -64,4 +64,7 @@ gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_mod.c $R/openair1/PHY/MODULA
 gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_ofdm.c $R/openair1/PHY/MODULATION/ofdm_mod.c $R/openair1/PHY/MODULATION/slot_fep_nr.c \
     $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/TOOLS/cmult_vv.c $R/openair1/PHY/MODULATION/nr_modulation.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c \
     -lm -ldl -o libref_ofdm.so || echo "libref_ofdm.so: FAILED"
+# PUSCH inner receiver: ref_harness_pusch.c textually includes nr_ulsch_demodulation.c (its per-symbol functions are static)
+gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pusch.c $HERE/ref_harness_pusch.c $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_llr_computation.c \
+    $R/openair1/PHY/TOOLS/simde_operations.c $R/openair1/PHY/TOOLS/log2_approx.c -lm -o libref_pusch.so || echo "libref_pusch.so: FAILED"
 ls -la $W/*.so

@@ -65,6 +65,16 @@ void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_
 /* Q15 DFT/IDFT of the OFDM sizes (nrb200_dft_oracle.c restates openair1/PHY/TOOLS/oai_dfts.c); interleaved {re,im} int16. */
 int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale);
 
+/* single-layer PUSCH inner receiver (nrb200_pusch_oracle.c) */
+typedef struct {
+  int32_t fft_size, nb_rx, rb_start, bwp_start, rb_size, first_carrier_offset, Qm, ul_dmrs_symb_pos, dmrs_config_type, num_dmrs_cdm_grps_no_data;
+} orc_pusch_t;
+int orc_pusch_nb_re(const orc_pusch_t *p, int symbol);
+int orc_pusch_extract(const orc_pusch_t *p, int is_dmrs_symbol, const int16_t *rxF, const int16_t *ch, int16_t *rx_ext, int16_t *ch_ext);
+int orc_pusch_log2_maxh(const orc_pusch_t *p, int meas_symbol, int ch_symbol, const int16_t *rxdataF, const int16_t *ch_est, int32_t *avg_out);
+int orc_pusch_inner_rx_symbol(const orc_pusch_t *p, int symbol, int ch_symbol, int output_shift, const int16_t *rxdataF, const int16_t *ch_est,
+                              int16_t *llr, int16_t *comp_out);
+
 /* slot-level OFDM front end (nrb200_ofdm_oracle.c) */
 void orc_rotate_cpx_vector(const int16_t *x, int16_t ar, int16_t ai, int16_t *y, uint32_t N);
 void orc_mult_cpx_vector(const int16_t *x1, const int16_t *x2, int16_t *y, uint32_t N);

@@ -257,3 +257,40 @@ def test_ofdm_rx_slot(oracle, reference):
                 y_o = oracle.ofdm_rx_slot(N, mu, nb_rb, slot, div, ta, rot if use_rot else None, rx)
                 y_r = reference.ofdm_rx_slot(N, mu, nb_rb, slot, div, ta, rot224 if use_rot else None, rx)
                 assert np.array_equal(y_o, y_r), (N, mu, nb_rb, slot, div, ta, use_rot)
+
+
+# ------------------------------------------------------------------------------------------ single-layer PUSCH inner receiver (a23 + a25)
+def _pusch_case(rng, N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm, nb_rb_carrier, amp_y=2000, amp_h=1500):
+    from oracle.bindings import PuschParms
+    P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - nb_rb_carrier * 6, Qm, dmrs_pos, dmrs_type, cdm)
+    rx = rng.integers(-amp_y, amp_y + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    h = rng.integers(-amp_h, amp_h + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    return P, rx, h
+
+
+PUSCH_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm_no_data, carrier PRBs
+    (4096, 4, 0, 273, 6, 1 << 2, 0, 2, 273), (4096, 2, 0, 273, 8, 1 << 2, 0, 1, 273), (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106),
+    (2048, 2, 30, 76, 2, 1 << 3, 0, 1, 106), (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52), (512, 8, 3, 11, 8, 1 << 0, 0, 1, 25),
+    (4096, 4, 100, 173, 6, 1 << 2, 1, 1, 273),
+]
+
+
+def test_pusch_inner_rx(oracle, reference):
+    rng = np.random.default_rng(40)
+    for case in PUSCH_CASES:
+        big = case[1] == 8
+        P, rx, h = _pusch_case(rng, *case, amp_y=32767 if big else 2000, amp_h=32767 if big else 1500)
+        dm = [s for s in range(14) if (P.ul_dmrs_symb_pos >> s) & 1]
+        sh_o, avg_o = oracle.pusch_log2_maxh(P, dm[0] if oracle.pusch_nb_re(P, dm[0]) > 0 else dm[0] + 1, dm[0], rx, h)
+        meas = dm[0] if oracle.pusch_nb_re(P, dm[0]) > 0 else dm[0] + 1
+        sh_r, avg_r = reference.pusch_log2_maxh(P, meas, dm[0], rx, h)
+        assert np.array_equal(avg_o, avg_r) and sh_o == sh_r, (case, avg_o, avg_r, sh_o, sh_r)
+        for symbol in (dm[0], dm[0] + 1, 13):
+            valid = oracle.pusch_nb_re(P, symbol)
+            if valid == 0:
+                continue
+            for shift in {sh_o, 0 if big else max(0, sh_o - 3)}:
+                llr_o, comp_o = oracle.pusch_inner_rx_symbol(P, symbol, dm[0], shift, rx, h)
+                llr_r, comp_r = reference.pusch_inner_rx_symbol(P, symbol, dm[0], shift, rx, h, valid)
+                assert np.array_equal(comp_o, comp_r), (case, symbol, shift, "comp")
+                assert np.array_equal(llr_o, llr_r), (case, symbol, shift, "llr")

@@ -103,6 +103,65 @@ def main():
         algo = n * (4 * planes + 2 * Qm)
         print(json.dumps({"what": f"pusch_llr Qm={Qm}", "re": n, "ms": ms, "value": n / ms * 1e3, "unit": "RE/s",
                           "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo / ms / 1e6 / hbm, "algorithmic_bytes_per_re": 4 * planes + 2 * Qm}}), flush=True)
+    # ---- slot-level OFDM front end at 100 MHz (N=4096, mu=1, 273 PRB): 64 antenna-slots per launch = 896 transforms
+    from openairinterface5g_b200.ofdm import NrOfdmParms
+    Pm = NrOfdmParms(4096, 1, 273)
+    rot = Pm.symbol_rotation(3619200000.0)
+    na = 64
+    dtx = Pm.desc(1, na, rot)
+    Fs = [torch.randint(-3000, 3000, (na, 14 * 4096 * 2), dtype=torch.int16, device=dev, generator=g) for _ in range(5)]
+    tx = torch.empty((na, 2 * dtx.t_stride), dtype=torch.int16, device=dev)
+    i = [0]
+
+    def run_tx():
+        dl.ofdm_mod_slot_torch(dtx, Fs[i[0] % 5], tx); i[0] += 1
+    ms = timeit(run_tx, n=40)
+    algo = na * (14 * 4096 * 4 + dtx.t_stride * 4)
+    line = {"what": "ofdm_mod_slot 4096/273PRB (rotation + IDFT + CP)", "antenna_slots": na, "ms": ms, "value": na / ms * 1e3, "unit": "antenna-slots/s",
+            "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo / ms / 1e6 / hbm,
+                         "algorithmic_bytes_per_antenna_slot": algo // na}}
+    print(json.dumps(line), flush=True)
+    drx = Pm.desc(1, na, rot, rx=True, t_stride=2 * Pm.samples_per_slot0)
+    drx.t_ring = 0
+    base = Pm.slot_timestamp(1) - 64
+    for l in range(14):
+        drx.t_off[l] = drx.t_off[l] - base
+    Xs = [torch.randint(-3000, 3000, (na, 2 * 2 * Pm.samples_per_slot0), dtype=torch.int16, device=dev, generator=g) for _ in range(3)]
+    ts = torch.from_numpy(Pm.timeshift_rotation()).to(dev)
+    rxF = torch.empty((na, 14 * 4096 * 2), dtype=torch.int16, device=dev)
+
+    def run_rx():
+        dl.ofdm_demod_slot_torch(drx, Xs[i[0] % 3], ts, rxF); i[0] += 1
+    ms = timeit(run_rx, n=40)
+    algo = na * (14 * 4096 * 4 * 2)
+    print(json.dumps({"what": "ofdm_demod_slot 4096/273PRB (window + DFT + rotation/timeshift)", "antenna_slots": na, "ms": ms, "value": na / ms * 1e3,
+                      "unit": "antenna-slots/s", "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                                               "frac": algo / ms / 1e6 / hbm, "algorithmic_bytes_per_antenna_slot": algo // na}}), flush=True)
+    try:
+        from oracle import bindings as ob
+        if ob.have_reference():
+            ref = ob.Reference()
+            Fh = Fs[0][0].cpu().numpy()
+            rot224 = np.zeros(448, np.int16); rot224[:rot.size] = rot.reshape(-1)
+            t0 = time.perf_counter(); k = 0
+            while time.perf_counter() - t0 < 2.0:
+                ref.ofdm_tx_slot(4096, 1, 273, 1, 14, rot224, Fh, dtx.t_stride); k += 1
+            print(json.dumps({"what": "reference apply_nr_rotation_TX + nr_normal_prefix_mod (1 host thread)", "value": k / (time.perf_counter() - t0),
+                              "unit": "antenna-slots/s", "kind": "reference"}), flush=True)
+    except Exception as e:                                    # the CPU comparison is optional
+        print(json.dumps({"what": "reference ofdm", "unavailable": str(e)}), flush=True)
+    # ---- scrambling + QAM mapper on a full-band 2-layer 64QAM PDSCH codeword (G = 471744 bits), 64 codewords per timing loop
+    G = 471744
+    bits = torch.randint(0, 2, (G,), dtype=torch.uint8, device=dev, generator=g)
+    words = torch.empty((G + 31) // 32 + 1, dtype=torch.int32, device=dev)
+    sym = torch.empty(2 * (G // 6), dtype=torch.int16, device=dev)
+    llrs = torch.randint(-3000, 3000, (G,), dtype=torch.int16, device=dev, generator=g)
+    ms = timeit(lambda: lib.scramble_torch(bits, 0, 42, 4660, words), n=50)
+    print(json.dumps({"what": "nr_codeword_scrambling G=471744", "us": ms * 1e3, "value": G / ms * 1e3, "unit": "bits/s"}), flush=True)
+    ms = timeit(lambda: lib.modulate_torch(words, G, 6, sym), n=50)
+    print(json.dumps({"what": "nr_modulation 64QAM G=471744", "us": ms * 1e3, "value": G / 6 / ms * 1e3, "unit": "symbols/s"}), flush=True)
+    ms = timeit(lambda: lib.unscramble_llr_torch(llrs, 0, 42, 4660), n=50)
+    print(json.dumps({"what": "nr_codeword_unscrambling G=471744", "us": ms * 1e3, "value": G / ms * 1e3, "unit": "LLR/s"}), flush=True)
     # ---- the per-code-block OAI ABI under tpool-style concurrency: T host threads, one blocking LDPCdecoder call per segment
     import threading
     from openairinterface5g_b200.synth import awgn_llr, random_payloads

@@ -12,7 +12,7 @@ echo "== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | 
 echo "== variants"
 for t in 768 672 576 480 384; do NRB200_PACKED_THREADS=$t timeout 120 python tools/kernel_time.py 1.0 2>&1 | tail -1; done | tee gpurun_out/variants_${TAG}.txt
 timeout 120 python tools/kernel_time.py 3.0 2>&1 | tail -1 | tee -a gpurun_out/variants_${TAG}.txt
-echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -14 | tee gpurun_out/extras_${TAG}.jsonl
+echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -24 | tee gpurun_out/extras_${TAG}.jsonl
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json
 if [ "$MODE" = "full" ]; then
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
