@@ -219,6 +219,33 @@ int32_t nrb200_unscramble_llr_host(int16_t *llr, uint32_t size, uint32_t q, uint
 int32_t nrb200_modulate_dev(const uint32_t *d_bits, uint32_t length_bits, int Qm, int16_t *d_out, void *stream);
 int32_t nrb200_modulate_host(const uint32_t *bits, uint32_t length_bits, int Qm, int16_t *out);
 
+/* ---- Part 6: single-layer PUSCH inner receiver ------------------------------------------------------------------------
+ * One launch per slot replaces, for nrOfLayers == 1 without PT-RS / transform precoding, the per-symbol chain
+ *   nr_ulsch_extract_rbs -> nr_ulsch_channel_compensation (MRC over rx antennas, QAM magnitude thresholds) -> nr_ulsch_compute_llr
+ *   -> descrambling                                   (nr_ulsch_demodulation.c inner_rx :1262-1384, nr_pusch_symbol_processing :1386-1436)
+ * and nrb200_pusch_log2_maxh_* replaces the measurement that precedes it (nr_ulsch_scale_channel + nr_ulsch_channel_level + the
+ * log2_maxh rule, :1595-1647).  Field names follow nfapi_nr_pusch_pdu_t / NR_DL_FRAME_PARMS.  rxdataF: [nb_rx][14][fft_size] c16 (the
+ * slot's rxdataF, soffset applied by the caller); ul_ch_estimates: [nb_rx][14][fft_size] c16, the estimates of DMRS symbol s stored at
+ * symbol s from index 0 for the first allocated sub-carrier (nr_pusch_channel_estimation's layout).  LLR order and the per-symbol offsets
+ * are pusch_vars->llr_offset[] (:1659-1664); the symbol of the estimates is the latest DMRS symbol at or before the data symbol. */
+typedef struct nrb200_pusch_rx_s {
+  uint32_t fft_size, nb_rx;                 /* ofdm_symbol_size, nb_antennas_rx (1..8) */
+  uint32_t rb_start, bwp_start, rb_size, first_carrier_offset;
+  uint32_t qam_mod_order;                   /* 2 4 6 8 */
+  uint32_t start_symbol_index, nr_of_symbols, ul_dmrs_symb_pos, dmrs_config_type /* 0 = type 1 */, num_dmrs_cdm_grps_no_data;
+  uint32_t log2_maxh;                       /* compensation shift (ignored by _dev when d_log2_maxh != NULL) */
+  uint32_t rx_stride, ch_stride;            /* _dev: c16 between antennas of rxdataF / ul_ch_estimates */
+  uint32_t unscramble, rnti, data_scrambling_id;   /* unscramble != 0: LLRs are multiplied by 1 - 2 c(i), c_init = (rnti << 15) + id */
+} nrb200_pusch_rx_t;
+uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
+/* d_out: 9 int32 on the device: [0..nb_rx) = avg per antenna, [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
+int32_t nrb200_pusch_log2_maxh_dev(const nrb200_pusch_rx_t *d, const int16_t *d_ul_ch_estimates, int32_t *d_out, void *stream);
+int32_t nrb200_pusch_inner_rx_dev(const nrb200_pusch_rx_t *d, const int16_t *d_rxdataF, const int16_t *d_ul_ch_estimates, const int32_t *d_log2_maxh,
+                                  int16_t *d_llr, void *stream);
+/* host buffers, contiguous [nb_rx][14][fft_size]; computes log2_maxh itself when d->log2_maxh == 0xFFFFFFFF and returns it in *log2_maxh_out */
+int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, const int16_t *rxdataF, const int16_t *ul_ch_estimates, int16_t *llr,
+                                   int32_t *log2_maxh_out);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

@@ -15,6 +15,9 @@ int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
 int quirks_from_env();
 int launch_gold(int mode, uint32_t c_init, uint32_t size, const uint8_t *in, uint32_t *out, int16_t *llr, cudaStream_t st);
+uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d);
+int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d_out9, uint32_t *d_count, cudaStream_t st);
+int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st);
 int launch_modulate(int Qm, uint32_t length_bits, const uint8_t *bits, int16_t *out, cudaStream_t st);
 int launch_pusch_llr(int Qm, uint32_t nb_re, const int16_t *y, const int16_t *ma, const int16_t *mb, const int16_t *mc, int16_t *out, cudaStream_t st);
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
@@ -481,4 +484,67 @@ NRB200_EXPORT int32_t nrb200_modulate_host(const uint32_t *bits, uint32_t length
   if (length_bits / Qm == 0) return 0;
   return host_roundtrip(bits, (length_bits + 7) / 8, out, 4 * (size_t)(length_bits / Qm), false, [&](Workspace *w) {
     return launch_modulate(Qm, length_bits, (const uint8_t *)w->d_in, (int16_t *)w->d_out, w->stream); });
+}
+
+// ------------------------------------------------------------------------------------------ PUSCH inner receiver (one layer)
+static uint32_t *pusch_counter()
+{
+  static uint32_t *d = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!d && cudaMalloc(&d, 64) == cudaSuccess) cudaMemset(d, 0, 64);
+  return d;
+}
+
+NRB200_EXPORT uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d) { return d ? pusch_num_llr(*d) : 0; }
+
+NRB200_EXPORT int32_t nrb200_pusch_log2_maxh_dev(const nrb200_pusch_rx_t *d, const int16_t *d_ch, int32_t *d_out, void *stream)
+{
+  if (ensure_init() || !d) return -1;
+  uint32_t *cnt = pusch_counter();
+  if (!cnt) return -5;
+  return launch_pusch_level(*d, d_ch, d_out, cnt, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_pusch_inner_rx_dev(const nrb200_pusch_rx_t *d, const int16_t *d_rxF, const int16_t *d_ch, const int32_t *d_log2_maxh,
+                                                int16_t *d_llr, void *stream)
+{
+  if (ensure_init() || !d) return -1;
+  return launch_pusch_rx(*d, d_rxF, d_ch, d_log2_maxh, d_llr, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, const int16_t *rxdataF, const int16_t *ul_ch_estimates, int16_t *llr,
+                                                 int32_t *log2_maxh_out)
+{
+  if (ensure_init() || !d) return -1;
+  const uint32_t n_llr = pusch_num_llr(*d);
+  if (n_llr == 0) return -4;
+  const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(2 * plane, (size_t)n_llr * 2 + 64, 64)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, rxdataF, plane);
+    std::memcpy((uint8_t *)w->h_in + plane, ul_ch_estimates, plane);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, 2 * plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    nrb200_pusch_rx_t e = *d;
+    e.rx_stride = e.ch_stride = 14 * d->fft_size;
+    const int16_t *d_rx = (const int16_t *)w->d_in, *d_ch = (const int16_t *)((uint8_t *)w->d_in + plane);
+    const bool measure = d->log2_maxh == 0xFFFFFFFFu;
+    int32_t *d_lvl = (int32_t *)w->d_aux;
+    if (measure) {
+      e.log2_maxh = 0;
+      // one workspace, one stream: give the level kernel its own completion counter slot in the workspace
+      if (cudaMemsetAsync((uint8_t *)w->d_aux + 40, 0, 4, w->stream) != cudaSuccess) { rc = -2; break; }
+      if ((rc = launch_pusch_level(e, d_ch, d_lvl, (uint32_t *)((uint8_t *)w->d_aux + 40), w->stream)) != 0) break;
+    }
+    if ((rc = launch_pusch_rx(e, d_rx, d_ch, measure ? d_lvl + 8 : nullptr, (int16_t *)w->d_out, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, (size_t)n_llr * 2, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (measure && cudaMemcpyAsync(w->h_aux, d_lvl, 36, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(llr, w->h_out, (size_t)n_llr * 2);
+    if (log2_maxh_out) *log2_maxh_out = measure ? ((int32_t *)w->h_aux)[8] : (int32_t)d->log2_maxh;
+  } while (0);
+  ctx().release(w);
+  return rc;
 }

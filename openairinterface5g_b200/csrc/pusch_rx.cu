@@ -1,0 +1,233 @@
+// Single-layer PUSCH inner receiver: resource extraction, MRC channel compensation, QAM magnitude thresholds, max-log LLRs and
+// (optionally) descrambling in ONE launch per slot, plus the channel-level measurement that fixes the compensation shift.
+// Reference: openair1/PHY/NR_TRANSPORT/nr_ulsch_demodulation.c -- nr_ulsch_extract_rbs :279-380, nr_ulsch_scale_channel :382-414,
+// get_nb_re_pusch :416-432, nr_ulsch_channel_level :434-466, nr_ulsch_channel_compensation :468-578, inner_rx :1262-1384,
+// log2_maxh rule and llr_offset bookkeeping of nr_rx_pusch_tp :1595-1700, unscrambling in nr_pusch_symbol_processing :1430-1433.
+// The reference walks symbol by symbol through four intermediate buffers (rxFext, chFext, rxdataF_comp, the three magnitude planes);
+// here one thread owns one resource element of one symbol: it gathers y and h of every rx antenna straight from rxdataF /
+// ul_ch_estimates (12 B per antenna and RE in, 2 * Qm B out), so nothing but the LLRs is ever written.  HBM bound.
+#include "nrb200_ctx.h"
+#include "gold_seq.cuh"
+#include "../../include/nrb200_ldpc.h"
+
+namespace nrb200 {
+
+struct PuschGeom {
+  int N, nb_rx, start_re, nb_re, Qm, dmrs_type, shift_from_dev, shift;
+  unsigned rx_stride, ch_stride;
+  int n_sym;                       // symbols with at least one valid RE
+  int sym[14], ch_sym[14], is_dmrs[14], valid[14];
+  unsigned llr_off[14];
+  unsigned unscramble, c_init;
+};
+
+__device__ __forceinline__ int p_sat16(int v) { return max(-32768, min(32767, v)); }
+__device__ __forceinline__ int p_wrap16(int v) { return (int)(short)v; }
+__device__ __forceinline__ int p_lo(unsigned w) { return (int)(short)(w & 0xFFFFu); }
+__device__ __forceinline__ int p_hi(unsigned w) { return (int)(short)(w >> 16); }
+__device__ __forceinline__ int p_abs16w(int v) { return v == -32768 ? -32768 : abs(v); }
+__device__ __forceinline__ int p_subs16(int a, int b) { return max(-32768, min(32767, a - b)); }
+__device__ __forceinline__ int p_mulhrs(int a, int b) { return p_wrap16((a * b + 0x4000) >> 15); }
+
+// i-th extracted RE of a symbol -> (sub-carrier in the symbol, index into the channel estimates), exactly the reference's loops
+// (including the type-2 branch that forgets start_re when the allocation does not wrap, :345-351)
+__device__ __forceinline__ void re_source(const PuschGeom &G, int is_dmrs, int i, int &rx_idx, int &ch_idx)
+{
+  const int N = G.N, s = G.start_re;
+  if (!is_dmrs) { rx_idx = s + i; if (rx_idx >= N) rx_idx -= N; ch_idx = i; return; }
+  const bool nowrap = s + G.nb_re < N;
+  const int neg = N - s;
+  if (G.dmrs_type == 0) {
+    const int idx = 2 * i + 1;
+    if (nowrap || idx < neg) { rx_idx = s + idx; ch_idx = idx; return; }
+    const int n1 = neg >> 1;                     // odd indices below neg
+    const int j = i - n1;
+    rx_idx = 2 * j + 1; ch_idx = (neg | 1) + 2 * j;
+    return;
+  }
+  int idx = 6 * (i >> 2) + 2 + (i & 3);
+  if (nowrap) { rx_idx = idx; ch_idx = idx; return; }
+  const int c1 = 4 * (neg / 6) + max(0, neg % 6 - 2);
+  if (i < c1) { rx_idx = s + idx; ch_idx = idx; return; }
+  const int j = i - c1;
+  idx = 6 * (j >> 2) + 2 + (j & 3);
+  rx_idx = idx; ch_idx = neg + idx;
+}
+
+template <int QM>
+__global__ void __launch_bounds__(256) pusch_rx_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift, const unsigned *__restrict__ rxF,
+                                                       const unsigned *__restrict__ ch, short *__restrict__ llr)
+{
+  __shared__ uint32_t s_gold[(256 * QM) / 32 + 2];
+  const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
+  const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
+  if (i0 >= valid) return;
+  const unsigned bit0 = G.llr_off[k] + (unsigned)i0 * QM;          // first LLR (= scrambling bit) index handled by this CTA
+  if (G.unscramble) {
+    const unsigned w0 = bit0 >> 5, nw = ((bit0 + 256u * QM + 31u) >> 5) - w0;
+    if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
+    __syncthreads();
+  }
+  if (i >= valid) return;
+  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  int rx_idx, ch_idx;
+  re_source(G, is_dmrs, i, rx_idx, ch_idx);
+  constexpr int ampa = QM == 4 ? 20724 : QM == 6 ? 20225 : QM == 8 ? 20106 : 0;     // QAM16_n1 / QAM64_n1 / QAM256_n1 (impl_defs_top.h:205-222)
+  constexpr int ampb = QM == 6 ? 10112 : QM == 8 ? 10053 : 0;
+  constexpr int ampc = QM == 8 ? 5026 : 0;
+  int cr = 0, ci = 0, ma = 0, mb = 0, mc = 0;
+  for (int a = 0; a < G.nb_rx; a++) {
+    const unsigned y = __ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx);
+    const unsigned h = __ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx);
+    const int hr = p_lo(h), hi = p_hi(h), yr = p_lo(y), yi = p_hi(y), nhi = p_wrap16(-hi);
+    // madd_epi16 wraps in 32 bits, srai, packs_epi32 saturates; the MRC sum over antennas is add_epi16 (wraps)
+    cr = p_wrap16(cr + p_sat16(((int)((unsigned)(hr * yr) + (unsigned)(hi * yi))) >> shift));
+    ci = p_wrap16(ci + p_sat16(((int)((unsigned)(nhi * yr) + (unsigned)(hr * yi))) >> shift));
+    if (QM > 2) {
+      const int m = p_sat16(((int)((unsigned)(hr * hr) + (unsigned)(hi * hi))) >> shift);
+      ma = p_wrap16(ma + p_mulhrs(m, ampa));
+      if (QM > 4) mb = p_wrap16(mb + p_mulhrs(m, ampb));
+      if (QM > 6) mc = p_wrap16(mc + p_mulhrs(m, ampc));
+    }
+  }
+  int o[8];
+  if (QM == 2) { o[0] = cr >> 3; o[1] = ci >> 3; }
+  else {
+    o[0] = cr; o[1] = ci;
+    o[2] = p_subs16(ma, p_abs16w(cr)); o[3] = p_subs16(ma, p_abs16w(ci));
+    if (QM > 4) { o[4] = p_subs16(mb, p_abs16w(o[2])); o[5] = p_subs16(mb, p_abs16w(o[3])); }
+    if (QM > 6) { o[6] = p_subs16(mc, p_abs16w(o[4])); o[7] = p_subs16(mc, p_abs16w(o[5])); }
+  }
+  const unsigned b = G.llr_off[k] + (unsigned)i * QM;
+  if (G.unscramble) {
+    const unsigned rel = b - ((bit0 >> 5) << 5);
+#pragma unroll
+    for (int m = 0; m < QM; m++) {
+      const unsigned r = rel + m;
+      if ((s_gold[r >> 5] >> (r & 31u)) & 1u) o[m] = p_wrap16(-o[m]);           // llr * s with s = -1: -32768 stays (int16 wrap)
+    }
+  }
+  // Qm int16 per RE; b * 2 bytes is 4-byte aligned because Qm is even
+  unsigned *dst = reinterpret_cast<unsigned *>(llr + b);
+#pragma unroll
+  for (int m = 0; m < QM / 2; m++) dst[m] = ((unsigned)o[2 * m] & 0xFFFFu) | ((unsigned)o[2 * m + 1] << 16);
+}
+
+// nr_ulsch_scale_channel (shift_ch_ext = 0) + nr_ulsch_channel_level on the measurement symbol, one CTA per rx antenna, then the
+// log2_maxh rule for one layer.  avg[a] and the final shift are left in d_out[0..nb_rx) and d_out[8].
+__global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_k, int len, const unsigned *__restrict__ ch, int *__restrict__ d_out,
+                                                          unsigned *__restrict__ d_count)
+{
+  __shared__ unsigned s_sum[256];
+  const int a = blockIdx.x, is_dmrs = G.is_dmrs[meas_k];
+  int x = 0;
+  while (x < 31 && !((len >> x) & 1)) x++;                       // factor2(len)
+  const int y = len >> x;
+  // number of REs the extraction writes for this symbol (everything beyond stays zero and adds nothing)
+  const int n_ext = !is_dmrs ? G.nb_re : G.dmrs_type == 0 ? G.nb_re / 2 : (G.nb_re / 6) * 4;
+  unsigned acc = 0;
+  for (int i = threadIdx.x; i < min(n_ext, len & ~3); i += blockDim.x) {
+    int rx_idx, ch_idx;
+    re_source(G, is_dmrs, i, rx_idx, ch_idx);
+    const unsigned h = __ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[meas_k] * G.N + ch_idx);
+    const int r = p_wrap16(((p_lo(h) * 8192) >> 16) << 3), im = p_wrap16(((p_hi(h) * 8192) >> 16) << 3);   // mulhi by 8192, slli 3
+    acc += (unsigned)(((int)((unsigned)(r * r) + (unsigned)(im * im))) >> x);
+  }
+  s_sum[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) s_sum[threadIdx.x] += s_sum[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) {
+    d_out[a] = (int)s_sum[0] / y;
+    __threadfence();
+    if (atomicAdd(d_count, 1u) == (unsigned)G.nb_rx - 1) {       // last antenna: combine
+      int avgs = 0;
+      for (int k = 0; k < G.nb_rx; k++) avgs = max(avgs, ((volatile int *)d_out)[k]);
+      auto l2 = [](unsigned v) { return v ? 32 - __clz(v) : 0; };  // log2_approx: bit length (values < 2^31)
+      int l = (l2((unsigned)avgs) >> 1) + 1 + l2((unsigned)G.nb_rx >> 2);
+      d_out[8] = l < 0 ? 0 : l;
+      *d_count = 0;
+    }
+  }
+}
+
+static int nb_re_symbol(const nrb200_pusch_rx_t &d, int symbol)
+{
+  if ((d.ul_dmrs_symb_pos >> symbol) & 1) return d.rb_size * (12 - d.num_dmrs_cdm_grps_no_data * (d.dmrs_config_type == 0 ? 6 : 4));
+  return d.rb_size * 12;
+}
+
+static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_llr)
+{
+  const int Qm = d.qam_mod_order;
+  if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
+      d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || d.log2_maxh > 31)
+    return -4;
+  G->N = d.fft_size; G->nb_rx = d.nb_rx; G->nb_re = 12 * d.rb_size; G->Qm = Qm; G->dmrs_type = d.dmrs_config_type;
+  G->start_re = (d.first_carrier_offset + (d.rb_start + d.bwp_start) * 12) % d.fft_size;
+  G->shift = d.log2_maxh; G->shift_from_dev = 0;
+  G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
+  G->unscramble = d.unscramble; G->c_init = (d.rnti << 15) + d.data_scrambling_id;
+  int first_dmrs = -1;
+  for (uint32_t s = d.start_symbol_index; s < d.start_symbol_index + d.nr_of_symbols; s++)
+    if ((d.ul_dmrs_symb_pos >> s) & 1) { first_dmrs = s; break; }
+  if (first_dmrs < 0) return -4;
+  G->n_sym = 0;
+  unsigned off = 0;
+  int cur = first_dmrs;
+  for (uint32_t s = d.start_symbol_index; s < d.start_symbol_index + d.nr_of_symbols; s++) {
+    const int dm = (d.ul_dmrs_symb_pos >> s) & 1;
+    if (dm) cur = s;                                            // nr_pusch_symbol_processing :1398-1404
+    const int v = nb_re_symbol(d, s);
+    if (v > 0) {
+      const int k = G->n_sym++;
+      G->sym[k] = s; G->ch_sym[k] = cur; G->is_dmrs[k] = dm; G->valid[k] = v; G->llr_off[k] = off;
+    }
+    off += (unsigned)v * Qm;
+  }
+  if (total_llr) *total_llr = off;
+  return G->n_sym > 0 ? 0 : -4;
+}
+
+uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d)
+{
+  PuschGeom G;
+  uint32_t n = 0;
+  return make_geom(d, &G, &n) == 0 ? n : 0;
+}
+
+int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d_out9, uint32_t *d_count, cudaStream_t st)
+{
+  PuschGeom G;
+  int rc = make_geom(d, &G, nullptr);
+  if (rc) return rc;
+  const int len = (G.valid[0] + 15) & ~15;                      // first symbol with data (:1601-1611)
+  pusch_level_kernel<<<G.nb_rx, 256, 0, st>>>(G, 0, len, (const unsigned *)ch, d_out9, d_count);
+  ctx().launches++;
+  NRB200_CUDA_OK(cudaGetLastError(), "pusch_level launch");
+  return 0;
+}
+
+int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st)
+{
+  PuschGeom G;
+  int rc = make_geom(d, &G, nullptr);
+  if (rc) return rc;
+  if (d.unscramble && scramble_mod_init() != 0) return -5;
+  G.shift_from_dev = d_shift != nullptr;
+  const GoldTables *T = d.unscramble ? gold_tables_dev() : nullptr;
+  int vmax = 0;
+  for (int k = 0; k < G.n_sym; k++) vmax = std::max(vmax, G.valid[k]);
+  const dim3 grid((vmax + 255) / 256, G.n_sym);
+  const unsigned *R = (const unsigned *)rxF, *C = (const unsigned *)ch;
+  switch (G.Qm) {
+    case 2: pusch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    case 4: pusch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    case 6: pusch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    default: pusch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+  }
+  ctx().launches++;
+  NRB200_CUDA_OK(cudaGetLastError(), "pusch_rx launch");
+  return 0;
+}
+
+}  // namespace nrb200

@@ -6,21 +6,21 @@
 // 32-bit word).  Here every thread jumps straight to its own word with precomputed powers L^(2^k) (binary 32x32 matrices),
 // (nibble-indexed tables: 8 loads per product) -- identical bits, no serial dependence across the code word.
 #include "nrb200_ctx.h"
+#include "gold_seq.cuh"
 #include <cstring>
 #include <vector>
 
 namespace nrb200 {
 
-constexpr int kGoldPow = 22;     // jump distances up to 2^22 words = 2^27 bits
 constexpr int kGoldBlk = 256;    // words (= threads) per CTA
 
-// L^(2^k) as 8 nibble tables: t[g][k][j][v] = image of (v << 4j).  One matrix-vector product = 8 loads + 8 XORs.
-struct GoldTables { uint32_t t[2][kGoldPow][8][16]; };
 static GoldTables *d_gold = nullptr;
 static uint32_t *d_modtab = nullptr;                   // per Qm: 2^Qm symbols {re | im << 16}; offsets 0, 4, 20, 84
 
 static inline uint32_t step1(uint32_t x) { x = (x >> 1) ^ (x >> 4); return x ^ (x << 31) ^ (x << 28); }
 static inline uint32_t step2(uint32_t x) { x = (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4); return x ^ (x << 31) ^ (x << 30) ^ (x << 29) ^ (x << 28); }
+
+const GoldTables *gold_tables_dev() { return d_gold; }
 
 int scramble_mod_init()
 {
@@ -65,25 +65,6 @@ int scramble_mod_init()
 
 __device__ __forceinline__ uint32_t dstep1(uint32_t x) { x = (x >> 1) ^ (x >> 4); return x ^ (x << 31) ^ (x << 28); }
 __device__ __forceinline__ uint32_t dstep2(uint32_t x) { x = (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4); return x ^ (x << 31) ^ (x << 30) ^ (x << 29) ^ (x << 28); }
-__device__ __forceinline__ uint32_t matvec(const uint32_t (*__restrict__ t)[16], uint32_t x)
-{
-  uint32_t y = 0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) y ^= __ldg(&t[j][(x >> (4 * j)) & 15u]);
-  return y;
-}
-// Gold word number w of the sequence started from c_init: the reset loop performs 49 word steps, every call one more
-// (transport_proto.h:655-676), so word w is the XOR of both generator states after 50 + w steps.
-__device__ __forceinline__ uint32_t gold_word(const GoldTables *__restrict__ T, uint32_t c_init, uint32_t w)
-{
-  uint32_t x1 = 1u + (1u << 31);
-  uint32_t x2 = c_init ^ ((c_init ^ (c_init >> 1) ^ (c_init >> 2) ^ (c_init >> 3)) << 31);
-  uint32_t steps = 50u + w;
-  for (int k = 0; steps; k++, steps >>= 1)
-    if (steps & 1u) { x1 = matvec(T->t[0][k], x1); x2 = matvec(T->t[1][k], x2); }
-  return x1 ^ x2;
-}
-
 // One CTA = 256 words of the sequence (8192 bits).  Phase 1: thread t produces word t.  Phase 2: the CTA sweeps its 8192 elements
 // with coalesced accesses.   mode 0: scramble (in = one bit per byte, out = packed words)   mode 1: unscramble int16 LLRs in place
 __global__ void __launch_bounds__(kGoldBlk) gold_kernel(const GoldTables *__restrict__ T, int mode, int aligned, uint32_t c_init, uint32_t size,

@@ -69,6 +69,12 @@ def ncols_for_rate(BG, R):
     return {(1, 13): 68, (1, 23): 35, (1, 89): 27, (2, 15): 52, (2, 13): 32, (2, 23): 17}[(BG, R)]
 
 
+class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_nr_pusch_pdu_t / NR_DL_FRAME_PARMS)
+    _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order",
+                                          "start_symbol_index", "nr_of_symbols", "ul_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data",
+                                          "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id")]
+
+
 class LdpcLib:
     """ldpc_interface_t equivalent bound to libldpc_b200.so."""
 
@@ -93,6 +99,11 @@ class LdpcLib:
         L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_pusch_llr_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_pusch_llr_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_num_llr.argtypes = [C.c_void_p]
+        L.nrb200_pusch_num_llr.restype = C.c_uint32
+        L.nrb200_pusch_log2_maxh_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_inner_rx_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_inner_rx_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_scramble_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.nrb200_unscramble_llr_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.nrb200_modulate_dev.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
@@ -258,6 +269,33 @@ class LdpcLib:
         self._check(self.lib.nrb200_modulate_dev(packed_words.data_ptr(), length_bits, Qm, out.data_ptr(),
                                                  torch.cuda.current_stream(out.device).cuda_stream), "modulate_dev")
         return out
+
+    # ---- single-layer PUSCH inner receiver (nr_ulsch_demodulation.c inner_rx + log2_maxh measurement)
+    def pusch_num_llr(self, desc):
+        return int(self.lib.nrb200_pusch_num_llr(C.addressof(desc)))
+
+    def pusch_inner_rx_host(self, desc, rxdataF, ul_ch_estimates):
+        """rxdataF, ul_ch_estimates: [nb_rx][14][N][2] int16.  desc.log2_maxh == 0xFFFFFFFF: measure it like nr_rx_pusch_tp does.
+        Returns (llr int16[G], log2_maxh)."""
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16)
+        h = np.ascontiguousarray(ul_ch_estimates, dtype=np.int16)
+        n = self.pusch_num_llr(desc)
+        if n == 0:
+            raise ValueError("invalid PUSCH descriptor")
+        llr = np.zeros(n, dtype=np.int16)
+        sh = C.c_int32(-1)
+        self._check(self.lib.nrb200_pusch_inner_rx_host(C.addressof(desc), x.ctypes.data, h.ctypes.data, llr.ctypes.data, C.addressof(sh)), "pusch_inner_rx_host")
+        return llr, sh.value
+
+    def pusch_inner_rx_torch(self, desc, rxdataF, ul_ch_estimates, llr, level=None):
+        """Device-resident variant; `level` = int32[9] scratch: when given, log2_maxh is measured on the device first (stream ordered)."""
+        import torch
+        st = torch.cuda.current_stream(rxdataF.device).cuda_stream
+        if level is not None:
+            self._check(self.lib.nrb200_pusch_log2_maxh_dev(C.addressof(desc), ul_ch_estimates.data_ptr(), level.data_ptr(), st), "pusch_log2_maxh_dev")
+        self._check(self.lib.nrb200_pusch_inner_rx_dev(C.addressof(desc), rxdataF.data_ptr(), ul_ch_estimates.data_ptr(),
+                                                       0 if level is None else level.data_ptr() + 32, llr.data_ptr(), st), "pusch_inner_rx_dev")
+        return llr
 
     # ---- demodulation: nr_ulsch_compute_llr (single layer, max-log)
     def pusch_llr_host(self, Qm, rxF, mag_a=None, mag_b=None, mag_c=None):

@@ -1,0 +1,58 @@
+"""GPU parity of the fused single-layer PUSCH inner receiver (extract + MRC compensation + LLR + descrambling, one launch per slot)
+against the CPU oracle, which tests/test_oracle_vs_reference.py pins symbol by symbol to the compiled reference inner_rx."""
+import numpy as np
+import pytest
+
+from oracle.bindings import PuschParms
+from openairinterface5g_b200.ldpc import PuschRxDesc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm_no_data, carrier PRBs, start_symbol, nr_of_symbols
+    (4096, 4, 0, 273, 6, 1 << 2, 0, 2, 273, 0, 14), (4096, 2, 0, 273, 8, 1 << 2, 0, 1, 273, 0, 14), (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 0, 14),
+    (2048, 2, 30, 76, 2, 1 << 3, 0, 1, 106, 2, 10), (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 0, 14), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 1, 12),
+    (512, 8, 3, 11, 8, 1 << 0, 0, 1, 25, 0, 7), (4096, 4, 100, 173, 6, (1 << 2) | (1 << 7) | (1 << 11), 1, 1, 273, 0, 14),
+    (2048, 4, 56, 50, 6, 1 << 2, 0, 1, 106, 0, 14),   # allocation wraps around DC (start_re + nb_re > N)
+]
+
+
+def _oracle_slot(oracle, P, start, nsym, rx, h, shift, unscr=None):
+    """Compose the per-symbol oracle the way nr_rx_pusch_tp / nr_pusch_symbol_processing do."""
+    dm = [s for s in range(start, start + nsym) if (P.ul_dmrs_symb_pos >> s) & 1]
+    cur, out = dm[0], []
+    for s in range(start, start + nsym):
+        if (P.ul_dmrs_symb_pos >> s) & 1:
+            cur = s
+        if oracle.pusch_nb_re(P, s) == 0:
+            continue
+        out.append(oracle.pusch_inner_rx_symbol(P, s, cur, shift, rx, h)[0])
+    llr = np.concatenate(out)
+    if unscr is not None:
+        llr = oracle.unscramble_llr(llr, 0, unscr[1], unscr[0])
+    return llr
+
+
+def test_pusch_inner_rx_vs_oracle(ldpc, oracle):
+    rng = np.random.default_rng(50)
+    for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym in CASES:
+        big = nb_rx == 8
+        ay, ah = (32767, 32767) if big else (2000, 1500)
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        fco = N - carrier * 6
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, dtype_, cdm)
+        dm0 = [s for s in range(start, start + nsym) if (dpos >> s) & 1][0]
+        meas = [s for s in range(start, start + nsym) if oracle.pusch_nb_re(P, s) > 0][0]
+        cur = dm0 if meas < dm0 else max(s for s in range(start, meas + 1) if (dpos >> s) & 1)
+        sh_o, _ = oracle.pusch_log2_maxh(P, meas, cur, rx, h)
+        for unscr in (None, (0x1234, 77)):
+            d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0,
+                            0 if unscr is None else 1, 0 if unscr is None else unscr[0], 0 if unscr is None else unscr[1])
+            llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+            assert sh == sh_o, (N, nb_rx, Qm, sh, sh_o)
+            ref = _oracle_slot(oracle, P, start, nsym, rx, h, sh_o, unscr)
+            assert llr.size == ref.size and np.array_equal(llr, ref), (N, nb_rx, rb_start, rb_size, Qm, unscr)
+        # explicit shift (the caller's own log2_maxh)
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 3, 0, 0, 0, 0, 0)
+        llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+        assert sh == 3 and np.array_equal(llr, _oracle_slot(oracle, P, start, nsym, rx, h, 3))
