@@ -160,7 +160,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
 {
   const int Qm = d.qam_mod_order;
   if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
-      d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || d.log2_maxh > 31)
+      d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || (d.log2_maxh > 31 && d.log2_maxh != 0xFFFFFFFFu))
     return -4;
   G->N = d.fft_size; G->nb_rx = d.nb_rx; G->nb_re = 12 * d.rb_size; G->Qm = Qm; G->dmrs_type = d.dmrs_config_type;
   G->start_re = (d.first_carrier_offset + (d.rb_start + d.bwp_start) * 12) % d.fft_size;

@@ -46,3 +46,19 @@ def test_struct_layouts_match_reference_abi():
     assert ldpc.DecParams.E.offset == 12 and ldpc.DecParams.check_crc.offset == 24
     assert ctypes.sizeof(ldpc.TimeStats) == 80 and ctypes.sizeof(ldpc.LdpcTimeStats) == 880
     assert ldpc.EncParams.Zc.offset == 56 and ldpc.EncParams.K.offset == 88
+
+
+def test_pusch_num_llr_matches_oracle_bookkeeping(oracle):
+    """nrb200_pusch_num_llr is host arithmetic (no GPU): G = sum over symbols of get_nb_re_pusch * Qm (nr_ulsch_demodulation.c:416-432, :1659-1664)."""
+    from oracle.bindings import PuschParms
+    from openairinterface5g_b200.ldpc import LdpcLib, PuschRxDesc
+    lib = LdpcLib()
+    for N, nb_rx, rb_size, Qm, dpos, dtype_, cdm, start, nsym in ((4096, 4, 273, 6, 1 << 2, 0, 2, 0, 14), (2048, 2, 50, 4, (1 << 2) | (1 << 11), 0, 1, 0, 14),
+                                                                  (1024, 2, 32, 8, 1 << 2, 1, 2, 1, 12), (1024, 1, 52, 2, 1 << 3, 1, 1, 2, 10)):
+        P = PuschParms(N, nb_rx, 0, 0, rb_size, N - 6 * rb_size, Qm, dpos, dtype_, cdm)
+        want = sum(oracle.pusch_nb_re(P, s) for s in range(start, start + nsym)) * Qm
+        for shift in (5, 0xFFFFFFFF):
+            d = PuschRxDesc(N, nb_rx, 0, 0, rb_size, N - 6 * rb_size, Qm, start, nsym, dpos, dtype_, cdm, shift, 0, 0, 0, 0, 0)
+            assert lib.pusch_num_llr(d) == want
+    bad = PuschRxDesc(4096, 4, 0, 0, 273, 2458, 5, 0, 14, 4, 0, 2, 0, 0, 0, 0, 0, 0)       # Qm = 5
+    assert lib.pusch_num_llr(bad) == 0
