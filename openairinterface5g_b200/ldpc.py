@@ -95,6 +95,8 @@ class LdpcLib:
         L.nrb200_ldpc_encode_batch_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_crc_batch_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.nrb200_crc_batch_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.nrb200_ldpc_rm_tx_batch_dev.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ldpc_rm_rx_batch_dev.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.nrb200_ldpc_rm_tx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_pusch_llr_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -205,6 +207,16 @@ class LdpcLib:
         self._check(self.lib.nrb200_crc_batch_host(poly_id, n, data.ctypes.data, stride, bitlen, out.ctypes.data), "crc_batch_host")
         return out
 
+    def crc_batch_torch(self, poly_id, data, bitlen, out=None):
+        """data: (n, stride) uint8 on the device; returns uint32 (n,) left-aligned CRCs like crc_byte.c."""
+        import torch
+        n, stride = data.shape
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=data.device)
+        self._check(self.lib.nrb200_crc_batch_dev(poly_id, n, data.data_ptr(), stride, bitlen, out.data_ptr(),
+                                                  torch.cuda.current_stream(data.device).cuda_stream), "crc_batch_dev")
+        return out
+
     # ---- rate matching / interleaving around the codec (nr_rate_matching.c), one transport block per call
     def _rmdesc(self, BG, Z, Qm, rv, C_, Tbslbrm, F, n_seg, clear=0):
         d = RmDesc()
@@ -232,6 +244,22 @@ class LdpcLib:
         llr = np.zeros((n, kcz), dtype=np.int8)
         desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, n, clear)
         self._check(self.lib.nrb200_ldpc_rm_rx_batch_host(C.byref(desc), soft.ctypes.data, E.ctypes.data, harq.ctypes.data, harq.shape[1], llr.ctypes.data, kcz), "rm_rx_batch_host")
+        return llr
+
+    def rm_tx_torch(self, BG, Z, Qm, rv, C_, Tbslbrm, F, d, E, foff, f):
+        """Device-resident rm_tx: d (n_seg, 66Z|50Z) uint8, E / foff uint32 device vectors (lengths, offsets into f), f uint8 out."""
+        import torch
+        desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, d.shape[0])
+        self._check(self.lib.nrb200_ldpc_rm_tx_batch_dev(C.byref(desc), d.data_ptr(), d.shape[1], E.data_ptr(), foff.data_ptr(), f.data_ptr(),
+                                                         torch.cuda.current_stream(d.device).cuda_stream), "rm_tx_batch_dev")
+        return f
+
+    def rm_rx_torch(self, BG, Z, Qm, rv, C_, Tbslbrm, F, soft, E, soff, harq, llr, clear=1):
+        """Device-resident rm_rx: soft int16 (sum E), harq (n_seg, >= 66Z|50Z) int16 in place, llr (n_seg, >= 68Z|52Z) int8 out."""
+        import torch
+        desc = self._rmdesc(BG, Z, Qm, rv, C_, Tbslbrm, F, harq.shape[0], clear)
+        self._check(self.lib.nrb200_ldpc_rm_rx_batch_dev(C.byref(desc), soft.data_ptr(), E.data_ptr(), soff.data_ptr(), harq.data_ptr(), harq.shape[1],
+                                                         llr.data_ptr(), llr.shape[1], torch.cuda.current_stream(soft.device).cuda_stream), "rm_rx_batch_dev")
         return llr
 
     # ---- scrambling (nr_scrambling.c) and QAM mapper (nr_modulation.c)

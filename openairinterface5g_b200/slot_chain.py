@@ -1,0 +1,109 @@
+"""Device-resident PUSCH slot chains built from the library's kernels -- the order of calls mirrors the reference's procedures:
+  receive : nr_fep_full (OFDM demodulation) -> nr_rx_pusch_tp (level, compensation, LLR, descrambling) -> nr_ulsch_decoding
+            (de-interleave / rate recover / HARQ combine -> LDPC decode with CRC24B stop) -> nr_postDecode (TB CRC)
+            openair1/SCHED_NR/phy_procedures_nr_gNB.c:271-300, NR_TRANSPORT/nr_ulsch_demodulation.c:1447, nr_ulsch_decoding.c:320
+  transmit: nr_ulsch_encoding-style coding chain (TB CRC, segmentation, LDPC encode, rate match + interleave), scrambling, modulation,
+            resource mapping and OFDM modulation -- used here to synthesise a standards-shaped slot for tests and benchmarks.
+Channel estimation is not implemented yet: the receive chain takes ul_ch_estimates as an input.
+torch is used for buffers, index plumbing (resource mapping) and the synthetic channel only."""
+import numpy as np
+import torch
+
+from . import transport as T
+from .ldpc import CRC24_B, PuschRxDesc
+from .ofdm import NrOfdmParms
+
+
+class PuschSlotChain:
+    def __init__(self, lib, dl, device, A=235624, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_rx=4, Qm=6, slot=1, rnti=0x1234, nid=77,
+                 ul_freq=3609200000.0, max_iter=8):
+        self.lib, self.dl, self.dev = lib, dl, device
+        self.P = NrOfdmParms(N, mu, carrier_rb)
+        self.N, self.nb_rx, self.Qm, self.slot, self.rnti, self.nid, self.max_iter = N, nb_rx, Qm, slot, rnti, nid, max_iter
+        self.rb_start, self.rb_size, self.A = rb_start, rb_size, A
+        self.dmrs_pos, self.dmrs_type, self.cdm = 1 << 2, 0, 2                     # one type-1 DMRS symbol, no data on it
+        self.seg = T.nr_segmentation(A + 24, 1)
+        assert (A + 24 + self.seg["C"] * self.seg["L"]) % (8 * self.seg["C"]) == 0, "pick A like a real TBS: whole bytes per segment"
+        self.C, self.K, self.Z, self.F = self.seg["C"], self.seg["K"], self.seg["Z"], self.seg["F"]
+        self.G = T.nr_get_G(rb_size, 14, 12, 1, 0, Qm, 1)
+        E = [T.nr_get_E(self.G, self.C, Qm, 1, r) for r in range(self.C)]
+        self.R = T.nr_get_R_ldpc_decoder(0, E[0], 1, self.Z)[0]
+        self.E = torch.tensor(E, dtype=torch.int32, device=device)
+        self.Eoff = torch.tensor(np.concatenate([[0], np.cumsum(E)[:-1]]), dtype=torch.int32, device=device)
+        self.rot = self.P.symbol_rotation(ul_freq)
+        self.ts = torch.from_numpy(self.P.timeshift_rotation()).to(device)
+        self.desc = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, self.P.first_carrier_offset, Qm, 0, 14, self.dmrs_pos, self.dmrs_type, self.cdm,
+                                0, 14 * N, 14 * N, 1, rnti, nid)
+        assert lib.pusch_num_llr(self.desc) == self.G
+        # receive-side buffers (allocated once, like the reference's per-UE pusch_vars)
+        self.rxF = torch.empty((nb_rx, 14 * N, 2), dtype=torch.int16, device=device)
+        self.level = torch.zeros(9, dtype=torch.int32, device=device)
+        self.llr16 = torch.empty(self.G, dtype=torch.int16, device=device)
+        self.harq = torch.zeros((self.C, 66 * self.Z), dtype=torch.int16, device=device)
+        self.llr8 = torch.empty((self.C, 68 * self.Z), dtype=torch.int8, device=device)
+        self.hard = torch.empty((self.C, 68 * self.Z // 8), dtype=torch.uint8, device=device)
+        self.iters = torch.empty(self.C, dtype=torch.int32, device=device)
+        self.tb = torch.empty((1, (A + 24) // 8), dtype=torch.uint8, device=device)
+        self.tbcrc = torch.empty(1, dtype=torch.int32, device=device)
+        self.drx = self.P.desc(slot, nb_rx, self.rot, rx=True)
+        # data resource elements in transmission order: symbol-major, sub-carriers from start_re, wrapping at N
+        start_re = (self.P.first_carrier_offset + rb_start * 12) % N
+        sc = (start_re + np.arange(12 * rb_size)) % N
+        syms = [s for s in range(14) if not (self.dmrs_pos >> s) & 1]
+        self.re_index = torch.tensor(np.concatenate([s * N + sc for s in syms]), dtype=torch.int64, device=device)
+
+    # ------------------------------------------------------------------ synthesis (not timed)
+    def synthesize(self, seed=1, snr_db=30.0, h_amp=724.0, tx_amp=724):
+        """Returns (payload bytes uint8[A/8], rxdata int16 [nb_rx, samples_per_frame, 2], ul_ch_estimates int16 [nb_rx, 14*N, 2])."""
+        lib, dl, dev, N = self.lib, self.dl, self.dev, self.N
+        rng = np.random.default_rng(seed)
+        payload = rng.integers(0, 256, size=self.A // 8, dtype=np.uint8)
+        crc = int(lib.crc_batch_host(0, payload[None, :], self.A)[0]) >> 8                  # crc24a
+        tb = np.concatenate([payload, np.array([(crc >> 16) & 255, (crc >> 8) & 255, crc & 255], np.uint8)])
+        segs, _ = T.segment_transport_block(lib, tb, 1)
+        cw = lib.encode_batch_torch(1, self.Z, self.K, torch.from_numpy(segs).to(dev))
+        f = torch.empty(self.G, dtype=torch.uint8, device=dev)
+        lib.rm_tx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, cw, self.E, self.Eoff, f)
+        words = torch.zeros((self.G + 31) // 32 + 1, dtype=torch.int32, device=dev)
+        lib.scramble_torch(f, 0, self.nid, self.rnti, words)
+        sym = torch.empty((self.G // self.Qm, 2), dtype=torch.int16, device=dev)
+        lib.modulate_torch(words, self.G, self.Qm, sym)
+        x = (sym.to(torch.int32) * tx_amp) >> 15                                           # the amp scaling of the TX resource mapper
+        g = torch.Generator(device=dev); g.manual_seed(seed)
+        ph = torch.rand(self.nb_rx, generator=g, device=dev) * 6.2831853
+        h = torch.stack([torch.cos(ph), torch.sin(ph)], dim=1) * h_amp                     # flat channel per rx antenna
+        hi = torch.round(h).to(torch.int32)
+        est = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.int16, device=dev)
+        dm = 2
+        est[:, dm * N:dm * N + 12 * self.rb_size, 0] = hi[:, 0:1].to(torch.int16)
+        est[:, dm * N:dm * N + 12 * self.rb_size, 1] = hi[:, 1:2].to(torch.int16)
+        sigma = float(tx_amp) * 0.70711 * 10.0 ** (-snr_db / 20.0) * 0.70711 * (h_amp / 1024.0)
+        grid = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.float32, device=dev)
+        for a in range(self.nb_rx):
+            yr = (hi[a, 0] * x[:, 0] - hi[a, 1] * x[:, 1]).to(torch.float32) / 1024.0
+            yi = (hi[a, 0] * x[:, 1] + hi[a, 1] * x[:, 0]).to(torch.float32) / 1024.0
+            y = torch.stack([yr, yi], dim=1) + sigma * torch.randn((x.shape[0], 2), generator=g, device=dev)
+            grid[a].index_copy_(0, self.re_index, y)
+        gridF = torch.clamp(torch.round(grid), -32768, 32767).to(torch.int16).contiguous()
+        # to the time domain with the library's own modulator (phase pre-compensation on, as a UE would transmit)
+        dtx = self.P.desc(self.slot, self.nb_rx, self.rot)
+        t = torch.zeros((self.nb_rx, dtx.t_stride, 2), dtype=torch.int16, device=dev)
+        dl.ofdm_mod_slot_torch(dtx, gridF, t)
+        rxdata = torch.zeros((self.nb_rx, self.P.samples_per_frame, 2), dtype=torch.int16, device=dev)
+        ss = self.P.slot_timestamp(self.slot)
+        rxdata[:, ss:ss + dtx.t_stride] = t
+        torch.cuda.synchronize()
+        return payload, rxdata, est
+
+    # ------------------------------------------------------------------ receive chain (the timed part)
+    def receive(self, rxdata, est):
+        lib, dl = self.lib, self.dl
+        dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)
+        lib.pusch_inner_rx_torch(self.desc, self.rxF, est, self.llr16, level=self.level)
+        lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
+        lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
+                               out=self.hard, iters=self.iters)
+        nbytes = (self.seg["Kprime"] - self.seg["L"]) // 8
+        self.tb.view(-1).copy_(self.hard[:, :nbytes].reshape(-1))                             # nr_postDecode: concatenate the segments
+        lib.crc_batch_torch(0, self.tb, self.A + 24, out=self.tbcrc)                       # CRC over payload + CRC24A == 0 when intact
+        return self.tb, self.iters, self.tbcrc

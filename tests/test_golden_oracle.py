@@ -96,3 +96,28 @@ def test_ofdm_parms_mirror(oracle):
             assert list(pre) == p2 and list(cps) == s2 and ss == P.slot_timestamp(slot) and fl == P.samples_per_frame
         assert np.array_equal(oracle.symbol_rotation(mu, 3.6192e9).reshape(-1, 2), P.symbol_rotation(3.6192e9))
         assert np.array_equal(oracle.timeshift_rotation(N, P.nb_prefix_samples // 8).reshape(-1, 2), P.timeshift_rotation())
+
+
+def test_transport_arithmetic_mirror(oracle):
+    """openairinterface5g_b200/transport.py (product host code) against the oracle's nr_segmentation / nr_get_R_ldpc_decoder restatements."""
+    import ctypes as C
+    from openairinterface5g_b200 import transport as T
+    L = oracle.lib
+    for BG in (1, 2):
+        for B in list(range(24, 9000, 137)) + [8448, 8449, 3840, 3841, 100000, 235848, 471696, 1000000]:
+            c, k, z, f = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+            kb = L.orc_segmentation(None, None, B, C.byref(c), C.byref(k), C.byref(z), C.byref(f), BG)
+            if kb < 0:
+                with pytest.raises(ValueError):
+                    T.nr_segmentation(B, BG)
+                continue
+            s = T.nr_segmentation(B, BG)
+            assert (s["C"], s["K"], s["Z"], s["F"], s["Kb"]) == (c.value, k.value, z.value, f.value, kb), (BG, B)
+        for Z in (384, 208, 64, 22):
+            for rv in range(4):
+                for E in (500, 3000, 9072, 9126, 12000, 26000, 40000):
+                    ll = C.c_int(0)
+                    r = L.orc_get_R_ldpc_decoder(rv, E, BG, Z, C.byref(ll), 0)
+                    assert T.nr_get_R_ldpc_decoder(rv, E, BG, Z) == (r, ll.value), (BG, Z, rv, E)
+    G = T.nr_get_G(273, 14, 12, 1, 0, 6, 1)
+    assert G == 255528 and sum(T.nr_get_E(G, 28, 6, 1, r) for r in range(28)) == G
