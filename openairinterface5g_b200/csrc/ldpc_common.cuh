@@ -7,6 +7,8 @@
 namespace nrb200 {
 
 constexpr int kCrcTableLen = 8448 + 32;   // longest code block (bits) the CRC-stop mode can see
+constexpr int kCrcChunk = 8192;           // long messages are folded in chunks of this many bits, counted from the END of the message
+constexpr int kCrcMaxChunks = 256;        // => up to 2 097 152 bits (a transport block is <= ~1.3 Mbit)
 
 // Launch arguments of the decode kernels (POD, passed by value).
 struct DecodeArgs {

@@ -132,12 +132,54 @@ __global__ void crc_kernel(const uint32_t *__restrict__ tab, int deg, uint32_t n
   }
 }
 
+// Long messages: CTA (k, b) takes chunk k of block b -- the bits whose distance from the end lies in [k L, (k+1) L) -- reduces it with the
+// short table, then moves the deg-bit remainder to its place with shift[k] and XORs it into out[b] (zeroed by the launcher).
+__global__ void crc_long_kernel(const uint32_t *__restrict__ tab, const uint32_t *__restrict__ shift, int deg, const uint8_t *__restrict__ in,
+                                uint32_t stride, uint32_t bitlen, uint32_t *__restrict__ out)
+{
+  __shared__ unsigned s_acc;
+  const uint32_t k = blockIdx.x, b = blockIdx.y;
+  if (threadIdx.x == 0) s_acc = 0;
+  __syncthreads();
+  const uint8_t *src = in + (size_t)b * stride;
+  // message bit i (0 = first) has distance e = bitlen - 1 - i from the end; this chunk: e in [kL, (k+1)L)
+  const uint32_t e_lo = k * kCrcChunk, e_hi = min(bitlen, (k + 1) * (uint32_t)kCrcChunk);      // [e_lo, e_hi)
+  const uint32_t i_lo = bitlen - e_hi, i_hi = bitlen - e_lo;                                   // bits [i_lo, i_hi)
+  unsigned rem = 0;
+  for (uint32_t j = (i_lo >> 3) + threadIdx.x; j <= ((i_hi - 1) >> 3); j += blockDim.x) {
+    unsigned byte = src[j];
+    while (byte) {
+      const int kk = 31 - __clz(byte);
+      byte &= ~(1u << kk);
+      const uint32_t i = 8 * j + (7 - kk);
+      if (i >= i_lo && i < i_hi) rem ^= __ldg(tab + (bitlen - 1 - i - e_lo + deg));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
+  if ((threadIdx.x & 31) == 0 && rem) atomicXor(&s_acc, rem);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned r = s_acc, folded = 0;
+    for (int bb = 0; bb < deg; bb++) if ((r >> (32 - deg + bb)) & 1u) folded ^= __ldg(shift + k * 32 + bb);
+    if (folded) atomicXor(out + b, folded);
+  }
+}
+
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream)
 {
   if (poly_id < 0 || poly_id > 7) return -4;
   const int deg = poly_id <= 2 ? 24 : poly_id == 3 ? 16 : poly_id == 4 ? 12 : poly_id == 5 ? 11 : poly_id == 6 ? 8 : 6;
-  if (bitlen + deg > (uint32_t)kCrcTableLen) return -4;
   if (n_blk == 0) return 0;
+  if (bitlen + deg > (uint32_t)kCrcTableLen) {
+    const uint32_t nchunks = (bitlen + kCrcChunk - 1) / kCrcChunk;
+    if (nchunks > (uint32_t)kCrcMaxChunks || n_blk > 65535) return -4;
+    NRB200_CUDA_OK(cudaMemsetAsync(d_out, 0, (size_t)n_blk * 4, stream), "crc memset");
+    crc_long_kernel<<<dim3(nchunks, n_blk), 256, 0, stream>>>(ctx().crc_tab[poly_id], ctx().crc_shift[poly_id], deg, d_in, stride, bitlen, d_out);
+    ctx().launches++;
+    NRB200_CUDA_OK(cudaGetLastError(), "crc launch");
+    return 0;
+  }
   crc_kernel<<<n_blk, 256, 0, stream>>>(ctx().crc_tab[poly_id], deg, n_blk, d_in, stride, bitlen, d_out);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "crc launch");

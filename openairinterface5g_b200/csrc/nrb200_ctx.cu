@@ -75,6 +75,21 @@ int Ctx::init()
     }
     if (cudaMalloc(&crc_tab[pi], kCrcTableLen * sizeof(uint32_t)) != cudaSuccess) { last_error = "cudaMalloc crc table"; return -1; }
     cudaMemcpy(crc_tab[pi], t.data(), kCrcTableLen * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    // long messages (transport-block CRC): shift[k][b] = x^(b + k * kCrcChunk) mod g, so a chunk's remainder can be moved to its place
+    std::vector<uint32_t> sh((size_t)kCrcMaxChunks * 32, 0u);
+    v = 1u << (32 - deg);
+    for (int k = 0; k < kCrcMaxChunks; k++) {
+      uint32_t u = v;
+      for (int b = 0; b < deg; b++) {
+        sh[(size_t)k * 32 + b] = u;
+        const uint32_t top = u & 0x80000000u;
+        u <<= 1;
+        if (top) u ^= kPoly[pi];
+      }
+      for (int j = 0; j < kCrcChunk; j++) { const uint32_t top = v & 0x80000000u; v <<= 1; if (top) v ^= kPoly[pi]; }
+    }
+    if (cudaMalloc(&crc_shift[pi], sh.size() * sizeof(uint32_t)) != cudaSuccess) { last_error = "cudaMalloc crc shift table"; return -1; }
+    cudaMemcpy(crc_shift[pi], sh.data(), sh.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   }
   inited = true;
   return 0;
@@ -97,6 +112,7 @@ void Ctx::shutdown()
   }
   pool.clear();
   for (auto &p : crc_tab) { cudaFree(p); p = nullptr; }
+  for (auto &p : crc_shift) { cudaFree(p); p = nullptr; }
   inited = false;
 }
 

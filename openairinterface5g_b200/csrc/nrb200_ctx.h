@@ -32,6 +32,7 @@ struct Ctx {
   std::map<uint32_t, EncGraphDev *> enc_graphs;  // key BG<<16 | Z
   std::map<uint32_t, EncGraphDev> enc_graphs_host;
   uint32_t *crc_tab[8] = {nullptr};              // device: x^j mod g for the 8 polynomials
+  uint32_t *crc_shift[8] = {nullptr};            // device: x^(b + k * kCrcChunk) mod g, [k][32] (long-message CRC)
   std::vector<Workspace *> pool;
   std::atomic<uint64_t> launches{0};
   std::string last_error;

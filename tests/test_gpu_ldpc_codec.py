@@ -192,3 +192,13 @@ def test_batch1024_properties(ldpc):
     # empty batch
     it0, out0 = ldpc.decode_batch_host(1, Z, 13, 8, np.zeros((0, 68 * Z), dtype=np.int8))
     assert it0.size == 0
+
+
+def test_crc_long_messages(ldpc, oracle):
+    """Transport-block sized CRCs (nr_postDecode / nr_dlsch_encoding call crc24a / crc16 on the whole TB): chunk-folded kernel vs oracle."""
+    rng = np.random.default_rng(12)
+    for bitlen in (8456, 8457, 16384, 16385, 24584 + 5, 235648, 1277992):
+        data = rng.integers(0, 256, size=(3, (bitlen + 7) // 8 + 3), dtype=np.uint8)
+        for p in (0, 1, 3):
+            got = ldpc.crc_batch_host(p, data, bitlen)
+            assert [int(x) for x in got] == [oracle.crc(p, data[i], bitlen) for i in range(3)], (p, bitlen)
