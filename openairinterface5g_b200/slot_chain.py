@@ -73,10 +73,15 @@ class PuschSlotChain:
         ph = torch.rand(self.nb_rx, generator=g, device=dev) * 6.2831853
         h = torch.stack([torch.cos(ph), torch.sin(ph)], dim=1) * h_amp                     # flat channel per rx antenna
         hi = torch.round(h).to(torch.int32)
+        # Genie estimate in the reference's convention: rxdataF = h_est * x_unit with x_unit the unit-energy constellation (the estimator
+        # divides by unit-amplitude pilots, so the transmit amplitude is part of h_est).  Here rxdataF = hi * x / 1024 and
+        # x = x_unit * 23170 * tx_amp / 32768.
+        unit = 23170.0 * tx_amp / 32768.0
+        he = torch.round(hi.to(torch.float32) * (unit / 1024.0)).to(torch.int16)
         est = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.int16, device=dev)
         dm = 2
-        est[:, dm * N:dm * N + 12 * self.rb_size, 0] = hi[:, 0:1].to(torch.int16)
-        est[:, dm * N:dm * N + 12 * self.rb_size, 1] = hi[:, 1:2].to(torch.int16)
+        est[:, dm * N:dm * N + 12 * self.rb_size, 0] = he[:, 0:1]
+        est[:, dm * N:dm * N + 12 * self.rb_size, 1] = he[:, 1:2]
         sigma = float(tx_amp) * 0.70711 * 10.0 ** (-snr_db / 20.0) * 0.70711 * (h_amp / 1024.0)
         grid = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.float32, device=dev)
         for a in range(self.nb_rx):

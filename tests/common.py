@@ -24,3 +24,79 @@ def make_case(oracle, BG, Z, R, n, ebn0_db, seed):
     rate = (22 if BG == 1 else 10) / (nc - 2)
     cw = np.stack([oracle.encode(BG, Z, K, P[i]) for i in range(n)])
     return K, P, awgn_llr(cw, Z, nc, ebn0_db, rate, seed)
+
+
+# ------------------------------------------------------------------------------------------------ oracle-only PUSCH slot chain
+def oracle_pusch_transmit(oracle, P, A, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, seed, tx_amp=724, h_amp=724.0, snr_db=30.0):
+    """CPU restatement chain (oracle functions only) that produces one slot of time-domain samples per rx antenna: TB CRC, segmentation,
+    LDPC encoding, rate matching + interleaving, scrambling, QAM mapping, resource mapping (one type-1 DMRS symbol at l = 2 without data),
+    flat channel + noise, OFDM modulation.  Returns (payload, frame [nb_rx, 2 * samples_per_frame], genie estimates [nb_rx, 14, N, 2], info)."""
+    from openairinterface5g_b200 import transport as T
+    rng = np.random.default_rng(seed)
+    N = P.N
+    payload = rng.integers(0, 256, size=A // 8, dtype=np.uint8)
+    crc = oracle.crc(0, payload, A) >> 8
+    tb = np.concatenate([payload, np.array([(crc >> 16) & 255, (crc >> 8) & 255, crc & 255], np.uint8)])
+    _, C_, K, Z, F, segs = oracle.segmentation(tb, A + 24, 1)
+    G = T.nr_get_G(rb_size, 14, 12, 1, 0, Qm, 1)
+    E = [T.nr_get_E(G, C_, Qm, 1, r) for r in range(C_)]
+    f = []
+    for r in range(C_):
+        d = oracle.encode(1, Z, K, segs[r]).copy()
+        d[K - F - 2 * Z:K - 2 * Z] = 2                                     # NR_NULL filler marks (nr_dlsch_coding.c)
+        rc, e = oracle.rate_matching_tx(0, 1, Z, d, C_, F, K - F - 2 * Z, 0, E[r])
+        assert rc == 0
+        f.append(oracle.interleave(E[r], Qm, e))
+    f = np.concatenate(f)
+    words = oracle.scramble(f, 0, nid, rnti)
+    sym = oracle.modulate(words, G, Qm).reshape(-1, 2).astype(np.int64)
+    x = (sym * tx_amp) >> 15
+    start_re = (P.first_carrier_offset + rb_start * 12) % N
+    sc = (start_re + np.arange(12 * rb_size)) % N
+    data_syms = [s for s in range(14) if s != 2]
+    ph = rng.uniform(0, 2 * np.pi, nb_rx)
+    hi = np.round(np.stack([np.cos(ph), np.sin(ph)], axis=1) * h_amp).astype(np.int64)
+    unit = 23170.0 * tx_amp / 32768.0
+    est = np.zeros((nb_rx, 14, N, 2), np.int16)
+    est[:, 2, :12 * rb_size, :] = np.round(hi * (unit / 1024.0)).astype(np.int16)[:, None, :]
+    sigma = unit * (h_amp / 1024.0) * 10.0 ** (-snr_db / 20.0) * 0.70711
+    frame = np.zeros((nb_rx, 2 * P.samples_per_frame), np.int16)
+    ss = P.slot_timestamp(slot)
+    for a in range(nb_rx):
+        yr = (hi[a, 0] * x[:, 0] - hi[a, 1] * x[:, 1]) / 1024.0
+        yi = (hi[a, 0] * x[:, 1] + hi[a, 1] * x[:, 0]) / 1024.0
+        y = np.stack([yr, yi], axis=1) + sigma * rng.standard_normal((x.shape[0], 2))
+        grid = np.zeros((14, N, 2), np.int16)
+        yq = np.clip(np.round(y), -32768, 32767).astype(np.int16).reshape(len(data_syms), 12 * rb_size, 2)
+        for j, s in enumerate(data_syms):
+            grid[s, sc] = yq[j]
+        t, _ = oracle.ofdm_tx_slot(N, P.mu, P.nb_rb, slot, 14, rot.reshape(-1), grid.reshape(-1))
+        frame[a, 2 * ss:2 * ss + t.size] = t
+    return payload, frame, est, dict(C=C_, K=K, Z=Z, F=F, E=E, G=G)
+
+
+def oracle_pusch_receive(oracle, P, info, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, frame, est, max_iter=8):
+    """The receive chain with oracle functions: OFDM demod, level, inner receiver, descrambling, de-interleaving, rate recovery,
+    decoder-input packing (nr_ulsch_decoding.c:195-210), decoding with CRC24B stop.  Returns (tb bytes, iterations, llr16, log2_maxh)."""
+    from oracle.bindings import PuschParms
+    from openairinterface5g_b200 import transport as T
+    N = P.N
+    rxF = np.stack([oracle.ofdm_rx_slot(N, P.mu, P.nb_rb, slot, P.divisor, 0, rot.reshape(-1), frame[a]).reshape(14, N, 2) for a in range(nb_rx)])
+    PP = PuschParms(N, nb_rx, rb_start, 0, rb_size, P.first_carrier_offset, Qm, 1 << 2, 0, 2)
+    shift, _ = oracle.pusch_log2_maxh(PP, 0, 2, rxF, est)
+    llr = np.concatenate([oracle.pusch_inner_rx_symbol(PP, s, 2, shift, rxF, est)[0] for s in range(14) if s != 2])
+    llr = oracle.unscramble_llr(llr, 0, nid, rnti)
+    C_, K, Z, F, E = info["C"], info["K"], info["Z"], info["F"], info["E"]
+    R = T.nr_get_R_ldpc_decoder(0, E[0], 1, Z)[0]
+    off, out, its = 0, [], []
+    for r in range(C_):
+        e = oracle.deinterleave(E[r], Qm, llr[off:off + E[r]]); off += E[r]
+        w = np.zeros(66 * Z, np.int16)
+        assert oracle.rate_matching_rx(0, 1, Z, w, e, C_, 0, 1, E[r], F, K - F - 2 * Z) == 0
+        z = np.zeros(68 * Z, np.int16)
+        z[2 * Z:K - F] = w[:K - F - 2 * Z]
+        z[K - F:K] = 127
+        z[K:] = w[K - 2 * Z:]
+        it, hard = oracle.decode(1, Z, R, max_iter, np.clip(z, -128, 127).astype(np.int8), use_crc=1, crc_len_bits=K - F, crc_type=1)
+        its.append(it); out.append(np.asarray(hard, dtype=np.uint8)[:(K - F - 24) // 8])
+    return np.concatenate(out), np.array(its), llr, shift

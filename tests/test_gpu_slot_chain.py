@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(A=18696, N=2048, carrier_rb=106, rb_start=20, rb_size=50, nb_rx=2, Qm=4, slot=3)])
-def test_pusch_slot_roundtrip(ldpc, cfg):
+def test_pusch_slot_roundtrip(ldpc, oracle, cfg):
     dev = torch.device("cuda", 0)
     chain = PuschSlotChain(ldpc, load_dftslib(), dev, **cfg)
     payload, rxdata, est = chain.synthesize(seed=5)
@@ -25,3 +25,13 @@ def test_pusch_slot_roundtrip(ldpc, cfg):
     assert np.array_equal(got[:payload.size], payload)
     assert int(tbcrc.cpu()[0]) == 0
     assert int(chain.level.cpu()[8]) > 0
+    if cfg:
+        # the same slot through the oracle-only chain: LLRs, iteration counts and the transport block must agree bit for bit
+        from common import oracle_pusch_receive
+        info = dict(C=chain.C, K=chain.K, Z=chain.Z, F=chain.F, E=[int(e) for e in chain.E.cpu()])
+        frame = rxdata.cpu().numpy().reshape(chain.nb_rx, -1)
+        tb_o, its_o, llr_o, shift_o = oracle_pusch_receive(oracle, chain.P, info, chain.Qm, chain.rb_start, chain.rb_size, chain.nb_rx, chain.slot,
+                                                           chain.rnti, chain.nid, chain.rot, frame, est.cpu().numpy().reshape(chain.nb_rx, 14, chain.N, 2))
+        assert shift_o == int(chain.level.cpu()[8])
+        assert np.array_equal(chain.llr16.cpu().numpy(), llr_o)
+        assert np.array_equal(it, its_o) and np.array_equal(got[:tb_o.size], tb_o)
