@@ -246,6 +246,29 @@ int32_t nrb200_pusch_inner_rx_dev(const nrb200_pusch_rx_t *d, const int16_t *d_r
 int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, const int16_t *rxdataF, const int16_t *ul_ch_estimates, int16_t *llr,
                                    int32_t *log2_maxh_out);
 
+/* ---- Part 7: PUSCH channel estimation, DMRS configuration type 1, frequency-domain interpolation -------------------------
+ * replaces nr_pusch_channel_estimation (nr_ul_channel_estimation.c:67-243) for one DMRS symbol and one antenna port with
+ * transform precoding disabled and chest_freq == 0: DMRS generation, least-squares estimate, delay estimation (IDFT peak, running
+ * maximum across the rx antennas), delay compensation, 16-tap interpolation, delay reversal, noise variance.  Other configurations
+ * (DMRS type 2, chest_freq == 1, low-PAPR DMRS) return -4: the library never falls back.
+ * rxdataF [nb_rx][14][fft_size] c16; ul_ch_estimates [nb_rx][14][fft_size] c16: symbol `symbol` of every antenna is rewritten.
+ * state (5 int32): max_ch, nvar, est_delay, delay_max_pos, delay_max_val -- what the reference returns through *max_ch, *nvar and delay_t. */
+typedef struct nrb200_pusch_chest_s {
+  uint32_t fft_size, nb_rx;
+  uint32_t slot, symbol;                    /* Ns and l of the DMRS symbol */
+  uint32_t port;                            /* antenna port p - 1000 (0..3): get_dmrs_port(nl, dmrs_ports) */
+  uint32_t rb_start, bwp_start, rb_size, first_carrier_offset;
+  uint32_t scid, ul_dmrs_scrambling_id;
+  uint32_t rx_stride, ch_stride;            /* _dev: c16 between antennas */
+} nrb200_pusch_chest_t;
+/* the 6 * rb_size conjugated DMRS symbols {re, im} the estimator correlates with (nr_pusch_dmrs_rx output); host arithmetic, no GPU needed */
+int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots);
+uint64_t nrb200_pusch_chest_scratch_bytes(const nrb200_pusch_chest_t *d);
+/* d_scratch: nrb200_pusch_chest_scratch_bytes() bytes; d_state: 18 int32 on the device, [0..5) as described above */
+int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, const int16_t *d_rxdataF, int16_t *d_ul_ch_estimates, void *d_scratch, int32_t *d_state,
+                               void *stream);
+int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

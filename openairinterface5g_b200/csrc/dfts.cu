@@ -19,7 +19,12 @@
 #include "../../include/nrb200_dfts.h"
 #include "nr_dft_tables.h"
 
+// dfts_internal.cu compiles this file a second time into libldpc_b200.so (the PUSCH delay estimator needs an IDFT): there the C ABI stays hidden.
+#ifdef NRB200_DFTS_INTERNAL
+#define NRB200_EXPORT extern "C" __attribute__((visibility("hidden")))
+#else
 #define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
+#endif
 
 namespace {
 
@@ -603,3 +608,13 @@ NRB200_EXPORT void dft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned ch
 NRB200_EXPORT void idft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag) { one_transform(true, sizeidx, sigF, sig, scale_flag); }
 NRB200_EXPORT const char *nrb200_dfts_last_error(void) { return dctx().last_error.c_str(); }
 NRB200_EXPORT uint64_t nrb200_dfts_launch_count(void) { return dctx().launches.load(); }
+
+#ifdef NRB200_DFTS_INTERNAL
+namespace nrb200 {
+int dft_batch_internal(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
+{
+  if (dft_init() != 0) return -1;
+  return launch_dft(N, inverse, n, d_in, d_out, scale, st);
+}
+}  // namespace nrb200
+#endif

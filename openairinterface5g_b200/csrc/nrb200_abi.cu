@@ -18,6 +18,9 @@ int launch_gold(int mode, uint32_t c_init, uint32_t size, const uint8_t *in, uin
 uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d);
 int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d_out9, uint32_t *d_count, cudaStream_t st);
 int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st);
+size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
+int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil);
+int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol);
 int launch_modulate(int Qm, uint32_t length_bits, const uint8_t *bits, int16_t *out, cudaStream_t st);
 int launch_pusch_llr(int Qm, uint32_t nb_re, const int16_t *y, const int16_t *ma, const int16_t *mb, const int16_t *mc, int16_t *out, cudaStream_t st);
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
@@ -544,6 +547,46 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
     if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
     std::memcpy(llr, w->h_out, (size_t)n_llr * 2);
     if (log2_maxh_out) *log2_maxh_out = measure ? ((int32_t *)w->h_aux)[8] : (int32_t)d->log2_maxh;
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ PUSCH channel estimation
+NRB200_EXPORT int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots) { return d && pilots ? pusch_dmrs_pilots_host(*d, pilots) : -4; }
+
+NRB200_EXPORT uint64_t nrb200_pusch_chest_scratch_bytes(const nrb200_pusch_chest_t *d) { return d ? pusch_chest_scratch_bytes(*d) : 0; }
+
+NRB200_EXPORT int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, const int16_t *d_rxF, int16_t *d_est, void *d_scratch, int32_t *d_state, void *stream)
+{
+  if (ensure_init() || !d) return -1;
+  return launch_pusch_chest(*d, d_rxF, d_est, d_scratch, d_state, (cudaStream_t)stream, -1);
+}
+
+NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5)
+{
+  if (ensure_init() || !d) return -1;
+  if (d->nb_rx < 1 || d->nb_rx > 8 || d->symbol > 13) return -4;
+  // only the DMRS symbol travels: [nb_rx][N] in, [nb_rx][N] out
+  const size_t sym = (size_t)d->fft_size * 4, plane = sym * d->nb_rx, scratch = pusch_chest_scratch_bytes(*d);
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(plane, plane, scratch + 128)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    for (uint32_t a = 0; a < d->nb_rx; a++)
+      std::memcpy((uint8_t *)w->h_in + sym * a, (const uint8_t *)rxdataF + ((size_t)a * 14 + d->symbol) * sym, sym);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    nrb200_pusch_chest_t e = *d;
+    e.rx_stride = e.ch_stride = d->fft_size;                                 // staged as a one-symbol slot (buffer symbol 0)
+    int32_t *d_state = (int32_t *)((uint8_t *)w->d_aux + scratch);
+    rc = launch_pusch_chest(e, (const int16_t *)w->d_in, (int16_t *)w->d_out, w->d_aux, d_state, w->stream, 0);
+    if (rc != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, plane, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->h_aux, d_state, 20, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    for (uint32_t a = 0; a < d->nb_rx; a++)
+      std::memcpy((uint8_t *)ul_ch_estimates + ((size_t)a * 14 + d->symbol) * sym, (uint8_t *)w->h_out + sym * a, sym);
+    if (state5) std::memcpy(state5, w->h_aux, 20);
   } while (0);
   ctx().release(w);
   return rc;

@@ -1,0 +1,257 @@
+// PUSCH channel estimation, DMRS configuration type 1, frequency-domain interpolation (the reference's default, chest_freq == 0).
+// Reference: nr_pusch_channel_estimation (openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c:67-243, 483-487) with nr_gold_pusch /
+// nr_pusch_dmrs_rx (NR_REFSIG/nr_gold.c:99-116, nr_dmrs_rx.c:44-116), nr_est_delay / get_delay_idx / init_delay_table
+// (common/utils/nr/nr_common.c:906-990), c16multaddVectRealComplex and filt16_ul_* (tools_defs.h:266-297, filt16a_32.h:242-249).
+// The reference walks the pilots serially and overlap-adds a 16-tap window per pilot into the estimate.  Here:
+//   chest_ls_kernel      one thread per pilot pair: DMRS bits from the Gold jump-ahead tables, LS estimate held over 4 REs, max_ch
+//   (IDFT)               the library's own Q15 transform kernel on the zero-padded LS estimates of all antennas (nr_est_delay / freq2time)
+//   chest_peak_kernel    peak of |h(t)|^2 >> 1 per antenna, then the reference's running maximum ACROSS antennas (delay_t is only reset per call)
+//   chest_interp_kernel  one thread per output sub-carrier GATHERS the <= 8 pilot windows that cover it, in pilot order, with the same saturating
+//                        adds; then reverts the delay and accumulates the noise estimate.
+// All four are stream ordered; nothing returns to the host.
+#include "nrb200_ctx.h"
+#include "gold_seq.cuh"
+#include "../../include/nrb200_ldpc.h"
+#include <cmath>
+#include <map>
+
+namespace nrb200 {
+
+int dft_batch_internal(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);   // dfts_internal.cu
+
+struct ChestGeom {
+  int N, nb_rx, symbol, nb, np, k0, delta, wsign_odd, dmrs_offset;
+  unsigned rx_stride, ch_stride, x2;
+};
+
+__device__ __forceinline__ int c_sat16(int v) { return max(-32768, min(32767, v)); }
+__device__ __forceinline__ int c_wrap16(int v) { return (int)(short)v; }
+__device__ __forceinline__ int c_lo(unsigned w) { return (int)(short)(w & 0xFFFFu); }
+__device__ __forceinline__ int c_hi(unsigned w) { return (int)(short)(w >> 16); }
+__device__ __forceinline__ unsigned c_pk(int r, int i) { return ((unsigned)r & 0xFFFFu) | ((unsigned)i << 16); }
+__device__ __forceinline__ int c_mulhrs(int a, int b) { return c_wrap16((a * b + 0x4000) >> 15); }
+// c16mulShift(a, b, 8): truncating casts
+__device__ __forceinline__ unsigned c_mul8(unsigned a, unsigned b)
+{
+  const int ar = c_lo(a), ai = c_hi(a), br = c_lo(b), bi = c_hi(b);
+  return c_pk(c_wrap16((ar * br - ai * bi) >> 8), c_wrap16((ar * bi + ai * br) >> 8));
+}
+
+// state[0] = max_ch, state[1] = nvar, state[2] = est_delay (last antenna), [3] = delay_max_pos, [4] = delay_max_val, [8 + a] = est_delay seen by antenna a,
+// state[16..17] = 64-bit noise accumulator
+__global__ void __launch_bounds__(256) chest_ls_kernel(ChestGeom G, const GoldTables *__restrict__ T, const unsigned *__restrict__ rxF, unsigned *__restrict__ ls,
+                                                       int *__restrict__ state)
+{
+  __shared__ uint32_t s_gold[40];
+  const int a = blockIdx.y, n0 = blockIdx.x * 256, n = n0 + threadIdx.x;
+  const unsigned bit0 = 2u * (unsigned)(G.dmrs_offset + 2 * n0);            // first DMRS bit this CTA needs (2 bits per pilot, 2 pilots per thread)
+  const unsigned w0 = bit0 >> 5;
+  if (n0 < 3 * G.nb) {
+    if (threadIdx.x < 34) s_gold[threadIdx.x] = gold_word(T, G.x2, w0 + threadIdx.x);
+  }
+  __syncthreads();
+  unsigned *dst = ls + (size_t)a * G.N;
+  if (4 * n >= G.N) return;
+  unsigned v = 0;
+  if (n < 3 * G.nb) {
+    const unsigned *rx = rxF + (size_t)a * G.rx_stride + (size_t)G.symbol * G.N;
+    int cr = 0, ci = 0;
+#pragma unroll
+    for (int kl = 0; kl < 2; kl++) {
+      const int i = G.dmrs_offset + 2 * n + kl;                            // pilot index in the sequence
+      const unsigned r0 = 2u * (unsigned)i - (w0 << 5);
+      const int b0 = (s_gold[r0 >> 5] >> (r0 & 31u)) & 1u, b1 = (s_gold[(r0 + 1) >> 5] >> ((r0 + 1) & 31u)) & 1u;
+      const int w = (i & 1) ? G.wsign_odd : 1;
+      // conj of the QPSK symbol (nr_rx_mod_table): re = +A for b0 = 0, im = -A for b1 = 0, negated when w = -1
+      const int pr = w * (b0 ? -23170 : 23170), pi = w * (b1 ? 23170 : -23170);
+      int re = G.k0 + (n << 2) + (kl << 1) + G.delta;
+      re %= G.N;
+      const unsigned y = __ldg(rx + re);
+      cr += (pr * c_lo(y) - pi * c_hi(y)) >> 16;
+      ci += (pr * c_hi(y) + pi * c_lo(y)) >> 16;
+    }
+    const int m = max(abs(cr), abs(ci));
+    if (m > 0) atomicMax(state, m);
+    v = c_pk(c_wrap16(cr), c_wrap16(ci));
+  }
+  reinterpret_cast<uint4 *>(dst)[n] = make_uint4(v, v, v, v);
+}
+
+__global__ void __launch_bounds__(256) chest_peak_kernel(ChestGeom G, const unsigned *__restrict__ tim, int *__restrict__ state)
+{
+  __shared__ int s_val[256], s_pos[256];
+  int max_pos = 0, max_val = 0;
+  for (int a = 0; a < G.nb_rx; a++) {
+    const unsigned *t = tim + (size_t)a * G.N;
+    int bv = -1, bp = 0;
+    for (int i = threadIdx.x; i < G.N; i += blockDim.x) {
+      const unsigned w = t[i];
+      const int v = (int)(((unsigned)(c_lo(w) * c_lo(w) + c_hi(w) * c_hi(w))) >> 1);
+      if (v > bv) { bv = v; bp = i; }                                       // ascending i per thread: keeps the first maximum
+    }
+    s_val[threadIdx.x] = bv; s_pos[threadIdx.x] = bp;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        const int ov = s_val[threadIdx.x + s], op = s_pos[threadIdx.x + s];
+        if (ov > s_val[threadIdx.x] || (ov == s_val[threadIdx.x] && op < s_pos[threadIdx.x])) { s_val[threadIdx.x] = ov; s_pos[threadIdx.x] = op; }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (s_val[0] > max_val) { max_val = s_val[0]; max_pos = s_pos[0]; }   // strict: an earlier antenna's peak wins ties
+      if (max_pos > G.N / 2) max_pos -= G.N;
+      state[8 + a] = max_pos;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { state[2] = max_pos; state[3] = max_pos; state[4] = max_val; }
+}
+
+__device__ __forceinline__ int filt_tap(int pc, int np, int t)
+{
+  if (pc == 0) return t < 8 ? 4096 : 0;                                      // filt16_ul_p0
+  if (pc <= 2) return t < 4 ? 4096 : t < 12 ? 2048 : 0;                      // filt16_ul_p1p2
+  if (pc == np - 1) return t < 4 ? 4096 : t < 8 ? 8192 : 0;                  // filt16_ul_last
+  return 2048;                                                               // filt16_ul_middle
+}
+
+__global__ void __launch_bounds__(256) chest_interp_kernel(ChestGeom G, const unsigned *__restrict__ ls, const unsigned *__restrict__ dtab /* [41][N] */,
+                                                           unsigned *__restrict__ est, int *__restrict__ state)
+{
+  const int a = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+  const int nre = 12 * G.nb, kmax = min(nre + 8, G.N);
+  const unsigned *l = ls + (size_t)a * G.N;
+  const int ed = state[8 + a];
+  const unsigned *tb = dtab + (size_t)min(max(20 + ed, 0), 40) * G.N, *ti = dtab + (size_t)min(max(20 - ed, 0), 40) * G.N;
+  unsigned long long noise = 0;
+  if (k < G.N) {
+    unsigned out = 0;
+    if (k < kmax) {
+      int yr = 0, yi = 0;
+      const int bq = k >> 2;
+      for (int b = max(0, bq - 3); b <= bq; b++) {
+        const int p_lo = b == 0 ? 0 : 2 * b + 3, p_hi = min(2 * b + 4, G.np - 1);
+        for (int pc = p_lo; pc <= p_hi; pc++) {
+          const int f = filt_tap(pc, G.np, k - 4 * b);
+          if (f == 0) continue;
+          const unsigned c = c_mul8(l[2 * pc], __ldg(tb + 2 * pc));          // delay-compensated LS estimate of pilot pc
+          const int mr = c_mulhrs(c_lo(c), f), mi = c_mulhrs(c_hi(c), f);
+          yr = c_sat16(yr + c_sat16(2 * mr)); yi = c_sat16(yi + c_sat16(2 * mi));
+        }
+      }
+      out = c_pk(yr, yi);
+      if (k < nre) {
+        out = c_mul8(out, __ldg(ti + k));                                    // revert the delay
+        const unsigned lv = l[k];
+        const int dr = c_wrap16(c_lo(lv) - c_lo(out)), di = c_wrap16(c_hi(lv) - c_hi(out));
+        noise = (unsigned)(dr * dr + di * di);
+      }
+    }
+    est[(size_t)a * G.ch_stride + (size_t)G.symbol * G.N + k] = out;        // the whole symbol is rewritten (memset in the reference)
+  }
+  // block reduction of the noise power
+  __shared__ unsigned long long s_n[256];
+  s_n[threadIdx.x] = noise;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) s_n[threadIdx.x] += s_n[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0 && s_n[0]) atomicAdd(reinterpret_cast<unsigned long long *>(state + 16), s_n[0]);
+}
+
+__global__ void chest_finish_kernel(ChestGeom G, int *state)
+{
+  const unsigned long long n = *reinterpret_cast<unsigned long long *>(state + 16);
+  const int nest = 12 * G.nb * G.nb_rx;
+  state[1] = (int)(unsigned)(n / (unsigned long long)nest);
+}
+
+// fp->delay_table (init_delay_table): round(256 e^{j 2 pi k d / N}) for d = -20..20, built once per N
+static const unsigned *delay_table_dev(int N)
+{
+  static std::mutex mu;
+  static std::map<int, unsigned *> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(N);
+  if (it != cache.end()) return it->second;
+  std::vector<unsigned> h((size_t)41 * N);
+  for (int d = -20; d <= 20; d++)
+    for (int k = 0; k < N; k++) {
+      const double ang = 2.0 * M_PI * k * d / N;
+      const short r = (short)std::round(256 * std::cos(ang)), i = (short)std::round(256 * std::sin(ang));
+      h[(size_t)(20 + d) * N + k] = ((unsigned)(unsigned short)r) | ((unsigned)(unsigned short)i << 16);
+    }
+  unsigned *dptr = nullptr;
+  if (cudaMalloc(&dptr, h.size() * 4) != cudaSuccess) return nullptr;
+  cudaMemcpy(dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  cache[N] = dptr;
+  return dptr;
+}
+
+static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
+{
+  if (d.nb_rx < 1 || d.nb_rx > 8 || d.symbol > 13 || d.port > 3 || d.rb_size < 1 || 12 * d.rb_size > d.fft_size || d.scid > 1 || (d.fft_size & 3)) return -4;
+  G->N = d.fft_size; G->nb_rx = d.nb_rx; G->symbol = d.symbol; G->nb = d.rb_size; G->np = 6 * d.rb_size;
+  G->k0 = ((d.rb_start + d.bwp_start) * 12 + d.first_carrier_offset) % d.fft_size;
+  G->delta = (d.port >> 1) & 1;                                              // delta1[p]
+  G->wsign_odd = (d.port & 1) ? -1 : 1;                                      // wf1[p][1]
+  G->dmrs_offset = ((d.bwp_start + d.rb_start) * 12) / 2;
+  G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
+  const unsigned long long nid = d.ul_dmrs_scrambling_id;
+  const unsigned long long t = ((1ULL << 17) * (unsigned long long)(14 * d.slot + d.symbol + 1) * ((nid << 1) + 1) + ((nid << 1) + d.scid));
+  G->x2 = (unsigned)(t % (1ULL << 31));
+  return 0;
+}
+
+// Host-side DMRS generation (nr_gold_pusch + nr_pusch_dmrs_rx, serial word recurrence like the reference): 6 * rb_size conjugated pilots {re, im}.
+// The estimator kernel derives the same bits from the jump-ahead tables; this entry point serves transmit-side synthesis and tests.
+int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil)
+{
+  ChestGeom G;
+  int rc = chest_geom(d, &G);
+  if (rc) return rc;
+  uint32_t x1 = 1u + (1u << 31), x2 = G.x2;
+  x2 = x2 ^ ((x2 ^ (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3)) << 31);
+  auto step = [&]() {
+    x1 = (x1 >> 1) ^ (x1 >> 4); x1 = x1 ^ (x1 << 31) ^ (x1 << 28);
+    x2 = (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3) ^ (x2 >> 4); x2 = x2 ^ (x2 << 31) ^ (x2 << 30) ^ (x2 << 29) ^ (x2 << 28);
+  };
+  for (int n = 1; n < 50; n++) step();
+  const int last = G.dmrs_offset + G.np;
+  std::vector<uint32_t> g((size_t)(2 * last + 31) / 32 + 1);
+  for (auto &w : g) { step(); w = x1 ^ x2; }
+  for (int i = G.dmrs_offset; i < last; i++) {
+    const int b0 = (g[(2 * i) >> 5] >> ((2 * i) & 31)) & 1, b1 = (g[(2 * i + 1) >> 5] >> ((2 * i + 1) & 31)) & 1;
+    const int w = (i & 1) ? G.wsign_odd : 1;
+    pil[2 * (i - G.dmrs_offset)] = (int16_t)(w * (b0 ? -23170 : 23170));
+    pil[2 * (i - G.dmrs_offset) + 1] = (int16_t)(w * (b1 ? 23170 : -23170));
+  }
+  return 0;
+}
+
+size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d) { return (size_t)2 * d.nb_rx * d.fft_size * 4 + 128; }
+
+// d_scratch: pusch_chest_scratch_bytes(); d_state: 18 int32 (see chest_ls_kernel), zeroed here
+// buf_symbol >= 0: the buffers hold the DMRS symbol at that index (the host entry point stages a one-symbol slot); the DMRS sequence always uses d.symbol
+int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol)
+{
+  ChestGeom G;
+  int rc = chest_geom(d, &G);
+  if (rc) return rc;
+  if (buf_symbol >= 0) G.symbol = buf_symbol;
+  if (scramble_mod_init() != 0) return -5;
+  const unsigned *dtab = delay_table_dev(G.N);
+  if (!dtab) return -5;
+  unsigned *ls = (unsigned *)d_scratch, *tim = ls + (size_t)G.nb_rx * G.N;
+  NRB200_CUDA_OK(cudaMemsetAsync(d_state, 0, 18 * 4, st), "chest memset");
+  chest_ls_kernel<<<dim3((G.N / 4 + 255) / 256, G.nb_rx), 256, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, ls, d_state);
+  NRB200_CUDA_OK(cudaGetLastError(), "chest_ls launch");
+  if ((rc = dft_batch_internal(G.N, 1, G.nb_rx, (const int16_t *)ls, (int16_t *)tim, 1, st)) != 0) return rc;
+  chest_peak_kernel<<<1, 256, 0, st>>>(G, tim, d_state);
+  chest_interp_kernel<<<dim3((G.N + 255) / 256, G.nb_rx), 256, 0, st>>>(G, ls, dtab, (unsigned *)est, d_state);
+  chest_finish_kernel<<<1, 1, 0, st>>>(G, d_state);
+  ctx().launches += 5;
+  NRB200_CUDA_OK(cudaGetLastError(), "chest launch");
+  return 0;
+}
+
+}  // namespace nrb200

@@ -75,6 +75,11 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
                                           "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id")]
 
 
+class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
+    _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
+                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride")]
+
+
 class LdpcLib:
     """ldpc_interface_t equivalent bound to libldpc_b200.so."""
 
@@ -101,6 +106,11 @@ class LdpcLib:
         L.nrb200_ldpc_rm_rx_batch_host.argtypes = [C.POINTER(RmDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_pusch_llr_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_pusch_llr_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_dmrs_pilots_host.argtypes = [C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_chest_scratch_bytes.argtypes = [C.c_void_p]
+        L.nrb200_pusch_chest_scratch_bytes.restype = C.c_uint64
+        L.nrb200_pusch_chest_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_pusch_chest_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_pusch_num_llr.argtypes = [C.c_void_p]
         L.nrb200_pusch_num_llr.restype = C.c_uint32
         L.nrb200_pusch_log2_maxh_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -297,6 +307,29 @@ class LdpcLib:
         self._check(self.lib.nrb200_modulate_dev(packed_words.data_ptr(), length_bits, Qm, out.data_ptr(),
                                                  torch.cuda.current_stream(out.device).cuda_stream), "modulate_dev")
         return out
+
+    # ---- PUSCH channel estimation, DMRS type 1 (nr_ul_channel_estimation.c)
+    def pusch_dmrs_pilots(self, desc):
+        pil = np.zeros(2 * 6 * desc.rb_size, dtype=np.int16)
+        self._check(self.lib.nrb200_pusch_dmrs_pilots_host(C.addressof(desc), pil.ctypes.data), "pusch_dmrs_pilots_host")
+        return pil
+
+    def pusch_chest_host(self, desc, rxdataF, ul_ch_estimates=None):
+        """rxdataF [nb_rx][14][N][2] int16 -> (ul_ch_estimates with symbol desc.symbol rewritten, state int32[5] = max_ch, nvar, est_delay, pos, val)."""
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16)
+        est = np.zeros_like(x) if ul_ch_estimates is None else np.ascontiguousarray(ul_ch_estimates, dtype=np.int16)
+        st = np.zeros(5, dtype=np.int32)
+        self._check(self.lib.nrb200_pusch_chest_host(C.addressof(desc), x.ctypes.data, est.ctypes.data, st.ctypes.data), "pusch_chest_host")
+        return est, st
+
+    def pusch_chest_torch(self, desc, rxdataF, ul_ch_estimates, scratch, state):
+        import torch
+        self._check(self.lib.nrb200_pusch_chest_dev(C.addressof(desc), rxdataF.data_ptr(), ul_ch_estimates.data_ptr(), scratch.data_ptr(), state.data_ptr(),
+                                                    torch.cuda.current_stream(rxdataF.device).cuda_stream), "pusch_chest_dev")
+        return ul_ch_estimates
+
+    def pusch_chest_scratch_bytes(self, desc):
+        return int(self.lib.nrb200_pusch_chest_scratch_bytes(C.addressof(desc)))
 
     # ---- single-layer PUSCH inner receiver (nr_ulsch_demodulation.c inner_rx + log2_maxh measurement)
     def pusch_num_llr(self, desc):

@@ -4,19 +4,19 @@
             openair1/SCHED_NR/phy_procedures_nr_gNB.c:271-300, NR_TRANSPORT/nr_ulsch_demodulation.c:1447, nr_ulsch_decoding.c:320
   transmit: nr_ulsch_encoding-style coding chain (TB CRC, segmentation, LDPC encode, rate match + interleave), scrambling, modulation,
             resource mapping and OFDM modulation -- used here to synthesise a standards-shaped slot for tests and benchmarks.
-Channel estimation is not implemented yet: the receive chain takes ul_ch_estimates as an input.
+Channel estimation runs on the DMRS symbol the synthesiser transmits (type 1, port 0, one symbol, no data on it).
 torch is used for buffers, index plumbing (resource mapping) and the synthetic channel only."""
 import numpy as np
 import torch
 
 from . import transport as T
-from .ldpc import CRC24_B, PuschRxDesc
+from .ldpc import CRC24_B, PuschChestDesc, PuschRxDesc
 from .ofdm import NrOfdmParms
 
 
 class PuschSlotChain:
     def __init__(self, lib, dl, device, A=235624, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_rx=4, Qm=6, slot=1, rnti=0x1234, nid=77,
-                 ul_freq=3609200000.0, max_iter=8):
+                 ul_freq=3609200000.0, max_iter=8, dmrs_id=55):
         self.lib, self.dl, self.dev = lib, dl, device
         self.P = NrOfdmParms(N, mu, carrier_rb)
         self.N, self.nb_rx, self.Qm, self.slot, self.rnti, self.nid, self.max_iter = N, nb_rx, Qm, slot, rnti, nid, max_iter
@@ -35,6 +35,10 @@ class PuschSlotChain:
         self.desc = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, self.P.first_carrier_offset, Qm, 0, 14, self.dmrs_pos, self.dmrs_type, self.cdm,
                                 0, 14 * N, 14 * N, 1, rnti, nid)
         assert lib.pusch_num_llr(self.desc) == self.G
+        self.cdesc = PuschChestDesc(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N)
+        self.est = torch.zeros((nb_rx, 14 * N, 2), dtype=torch.int16, device=device)
+        self.chest_scratch = torch.empty(lib.pusch_chest_scratch_bytes(self.cdesc), dtype=torch.uint8, device=device)
+        self.chest_state = torch.zeros(18, dtype=torch.int32, device=device)
         # receive-side buffers (allocated once, like the reference's per-UE pusch_vars)
         self.rxF = torch.empty((nb_rx, 14 * N, 2), dtype=torch.int16, device=device)
         self.level = torch.zeros(9, dtype=torch.int32, device=device)
@@ -82,13 +86,21 @@ class PuschSlotChain:
         dm = 2
         est[:, dm * N:dm * N + 12 * self.rb_size, 0] = he[:, 0:1]
         est[:, dm * N:dm * N + 12 * self.rb_size, 1] = he[:, 1:2]
-        sigma = float(tx_amp) * 0.70711 * 10.0 ** (-snr_db / 20.0) * 0.70711 * (h_amp / 1024.0)
+        sigma = unit * (h_amp / 1024.0) * 10.0 ** (-snr_db / 20.0) * 0.70711
         grid = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.float32, device=dev)
+        # DMRS (type 1, port 0: every second sub-carrier of symbol 2) = conj of the receiver's pilot table at the data's unit amplitude
+        pil = torch.from_numpy(lib.pusch_dmrs_pilots(self.cdesc).reshape(-1, 2).astype(np.float32)).to(dev) * (unit / 32767.0)
+        k0 = (self.P.first_carrier_offset + self.rb_start * 12) % N
+        dm_index = torch.tensor(2 * N + (k0 + 2 * np.arange(6 * self.rb_size)) % N, dtype=torch.int64, device=dev)
+        hf = hi.to(torch.float32) / 1024.0
         for a in range(self.nb_rx):
             yr = (hi[a, 0] * x[:, 0] - hi[a, 1] * x[:, 1]).to(torch.float32) / 1024.0
             yi = (hi[a, 0] * x[:, 1] + hi[a, 1] * x[:, 0]).to(torch.float32) / 1024.0
             y = torch.stack([yr, yi], dim=1) + sigma * torch.randn((x.shape[0], 2), generator=g, device=dev)
             grid[a].index_copy_(0, self.re_index, y)
+            dr = hf[a, 0] * pil[:, 0] + hf[a, 1] * pil[:, 1]                               # h * conj(pil)
+            di = hf[a, 1] * pil[:, 0] - hf[a, 0] * pil[:, 1]
+            grid[a].index_copy_(0, dm_index, torch.stack([dr, di], dim=1) + sigma * torch.randn((pil.shape[0], 2), generator=g, device=dev))
         gridF = torch.clamp(torch.round(grid), -32768, 32767).to(torch.int16).contiguous()
         # to the time domain with the library's own modulator (phase pre-compensation on, as a UE would transmit)
         dtx = self.P.desc(self.slot, self.nb_rx, self.rot)
@@ -101,9 +113,12 @@ class PuschSlotChain:
         return payload, rxdata, est
 
     # ------------------------------------------------------------------ receive chain (the timed part)
-    def receive(self, rxdata, est):
+    def receive(self, rxdata, est=None):
+        """est=None: estimate the channel from the DMRS symbol (the normal path); otherwise use the caller's ul_ch_estimates."""
         lib, dl = self.lib, self.dl
         dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)
+        if est is None:
+            est = lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)
         lib.pusch_inner_rx_torch(self.desc, self.rxF, est, self.llr16, level=self.level)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
         lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,

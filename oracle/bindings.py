@@ -58,6 +58,11 @@ def _ptr(a, t):
 
 
 # ------------------------------------------------------------------------------------------------ oracle (C restatement)
+class ChestParms(C.Structure):       # orc_chest_t
+    _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
+                                         "dmrs_scrambling_id")]
+
+
 class PuschParms(C.Structure):       # orc_pusch_t
     _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "Qm", "ul_dmrs_symb_pos",
                                          "dmrs_config_type", "num_dmrs_cdm_grps_no_data")]
@@ -166,6 +171,19 @@ class Oracle:
         self.lib.orc_ulsch_llr.restype = None
         self.lib.orc_ulsch_llr(Qm, rxF.ctypes.data_as(C.c_void_p), mk(maga), mk(magb), mk(magc), out.ctypes.data_as(C.c_void_p), C.c_uint32(n))
         return out
+
+    # ---- PUSCH channel estimation (DMRS type 1)
+    def pusch_dmrs_pilots(self, P):
+        pil = np.zeros(2 * 6 * P.rb_size, np.int16)
+        self.lib.orc_pusch_dmrs_pilots(C.byref(P), pil.ctypes.data_as(C.c_void_p))
+        return pil
+
+    def pusch_channel_estimation(self, P, rxdataF):
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16)
+        est = np.zeros(P.nb_rx * 14 * P.fft_size * 2, np.int16)
+        out = np.zeros(5, np.int32)
+        self.lib.orc_pusch_channel_estimation(C.byref(P), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return est.reshape(P.nb_rx, 14, P.fft_size, 2), out
 
     # ---- single-layer PUSCH inner receiver
     def pusch_nb_re(self, P, symbol):
@@ -421,6 +439,20 @@ class Reference:
         return o[:n * Qm].copy()
 
     # ---- scrambling + QAM mapper of the reference (libref_mod.so: nr_scrambling.c, nr_modulation.c, nr_gen_mod_table.c)
+    def pusch_channel_estimation(self, P, rxdataF, n_rb_ul, chest_freq=0, dmrs_type=0):
+        if not hasattr(self, "_chestlib"):
+            self._chestlib = C.CDLL(os.path.join(REFDIR, "libref_chest.so"))
+            assert self._chestlib.refh_chest_init(os.path.join(REFDIR, "libref_dfts.so").encode()) == 0
+        prm = np.array([P.fft_size, P.nb_rx, n_rb_ul, P.slot, P.symbol, P.port, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.scid,
+                        P.dmrs_scrambling_id, dmrs_type, chest_freq], dtype=np.int32)
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy()
+        est = np.zeros(P.nb_rx * 14 * P.fft_size * 2, np.int16)
+        out = np.zeros(5, np.int32)
+        pil = np.zeros(2 * 6 * P.rb_size, np.int16)
+        self._chestlib.refh_pusch_chest(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p),
+                                        out.ctypes.data_as(C.c_void_p), pil.ctypes.data_as(C.c_void_p))
+        return est.reshape(P.nb_rx, 14, P.fft_size, 2), out, pil
+
     def _pusch(self):
         if not hasattr(self, "_puschlib"):
             self._puschlib = C.CDLL(os.path.join(REFDIR, "libref_pusch.so"))

@@ -1,0 +1,123 @@
+/* TEST INFRASTRUCTURE ONLY (see nrb200_oracle.h).  CPU restatement of the PUSCH channel estimator of the reference for DMRS
+ * configuration type 1 with frequency-domain interpolation (chest_freq == 0), transform precoding disabled:
+ *   nr_pusch_channel_estimation    openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c:67-243, 483-487
+ *   nr_gold_pusch / nr_pusch_dmrs_rx  NR_REFSIG/nr_gold.c:99-116, NR_REFSIG/nr_dmrs_rx.c:44-116
+ *   nr_est_delay, get_delay_idx, init_delay_table   common/utils/nr/nr_common.c:906-990
+ *   c16multaddVectRealComplex + filt16_ul_*          PHY/TOOLS/tools_defs.h:266-297, NR_UE_ESTIMATION/filt16a_32.h:242-249
+ * Pinned against the compiled reference (oracle/_ref/libref_chest.so) by tests/test_oracle_vs_reference.py. */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "nrb200_oracle.h"
+
+static inline int16_t sat16(int32_t v) { return v > 32767 ? 32767 : v < -32768 ? -32768 : (int16_t)v; }
+static inline int16_t wrap16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
+static inline int16_t mulhrs16(int a, int b) { return wrap16(((a * b) + 0x4000) >> 15); }
+
+static const int16_t F_P0[16] = {4096, 4096, 4096, 4096, 4096, 4096, 4096, 4096, 0, 0, 0, 0, 0, 0, 0, 0};
+static const int16_t F_P1P2[16] = {4096, 4096, 4096, 4096, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 0, 0, 0, 0};
+static const int16_t F_MID[16] = {2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048};
+static const int16_t F_LAST[16] = {4096, 4096, 4096, 4096, 8192, 8192, 8192, 8192, 0, 0, 0, 0, 0, 0, 0, 0};
+
+/* conjugated DMRS of one symbol: 6 * rb_size c16 */
+void orc_pusch_dmrs_pilots(const orc_chest_t *p, int16_t *pil)
+{
+  static const int wf1[8][2] = {{1, 1}, {1, -1}, {1, 1}, {1, -1}, {1, 1}, {1, -1}, {1, 1}, {1, -1}};
+  const uint32_t nid = (uint32_t)p->dmrs_scrambling_id;
+  const uint64_t t = ((1ULL << 17) * (uint64_t)(14 * p->slot + p->symbol + 1) * ((nid << 1) + 1) + ((nid << 1) + (uint32_t)p->scid));
+  const uint32_t x2 = (uint32_t)(t % (1ULL << 31));
+  const int dmrs_offset = ((p->bwp_start + p->rb_start) * 12) / 2, n = 6 * p->rb_size;
+  const uint32_t nw = (uint32_t)((2 * (dmrs_offset + n) + 31) / 32 + 1);
+  uint32_t *g = malloc(4 * (size_t)nw);
+  orc_gold_words(x2, nw, g);
+  for (int i = dmrs_offset; i < dmrs_offset + n; i++) {
+    const int w = wf1[p->port][i & 1];                          /* wt1[p][l' = 0] = 1 */
+    const int b0 = (g[(2 * i) >> 5] >> ((2 * i) & 31)) & 1, b1 = (g[(2 * i + 1) >> 5] >> ((2 * i + 1) & 31)) & 1;
+    const int idx = (b0 << 1) ^ b1;
+    /* nr_rx_mod_table QPSK entries = conj of the transmitted symbol: idx 0 (+,-) 1 (+,+) 2 (-,-) 3 (-,+), negated when w == -1 */
+    static const int sr[4] = {1, 1, -1, -1}, si[4] = {-1, 1, -1, 1};
+    pil[2 * (i - dmrs_offset)] = (int16_t)(w * sr[idx] * 23170);
+    pil[2 * (i - dmrs_offset) + 1] = (int16_t)(w * si[idx] * 23170);
+  }
+  free(g);
+}
+
+static void multadd16(const int16_t *filt, int16_t ar, int16_t ai, int16_t *y)
+{
+  for (int t = 0; t < 16; t++) {
+    const int16_t mr = mulhrs16(ar, filt[t]), mi = mulhrs16(ai, filt[t]);
+    y[2 * t] = sat16((int32_t)y[2 * t] + sat16(2 * (int32_t)mr));
+    y[2 * t + 1] = sat16((int32_t)y[2 * t + 1] + sat16(2 * (int32_t)mi));
+  }
+}
+
+/* rxdataF [nb_rx][14 N] c16; ul_ch_est [nb_rx][14 N] c16 (symbol p->symbol is rewritten, N entries + up to 8 beyond the allocation stay 0);
+ * out: max_ch, nvar, est_delay, delay_max_pos, delay_max_val */
+int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out)
+{
+  static const int delta1[8] = {0, 0, 1, 1, 0, 0, 1, 1};
+  const int N = p->fft_size, nb = p->rb_size, np = 6 * nb, delta = delta1[p->port];
+  const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
+  int16_t *pil = malloc(4 * (size_t)np), *ls = malloc(4 * (size_t)N), *tim = malloc(4 * (size_t)N), *acc = malloc(4 * (size_t)(N + 16));
+  orc_pusch_dmrs_pilots(p, pil);
+  int max_ch = 0, max_pos = 0, max_val = 0;
+  uint64_t noise = 0;
+  int nest = 0;
+  for (int a = 0; a < p->nb_rx; a++) {
+    const int16_t *rx = rxdataF + 2 * ((size_t)a * 14 + p->symbol) * N;
+    int16_t *ul = ul_ch_est + 2 * ((size_t)a * 14 + p->symbol) * N;
+    memset(ls, 0, 4 * (size_t)N);
+    memset(acc, 0, 4 * (size_t)(N + 16));
+    for (int n = 0; n < 3 * nb; n++) {                                       /* LS estimate: average of two pilots, held over 4 REs */
+      int32_t cr = 0, ci = 0;
+      for (int kl = 0; kl < 2; kl++) {
+        const int re = (k0 + (n << 2) + (kl << 1) + delta) % N;
+        const int32_t pr = pil[2 * (2 * n + kl)], pi = pil[2 * (2 * n + kl) + 1], yr = rx[2 * re], yi = rx[2 * re + 1];
+        cr += (pr * yr - pi * yi) >> 16;
+        ci += (pr * yi + pi * yr) >> 16;
+      }
+      const int acr = cr < 0 ? -cr : cr, aci = ci < 0 ? -ci : ci;
+      if (acr > max_ch) max_ch = acr;
+      if (aci > max_ch) max_ch = aci;
+      for (int k = 4 * n; k < 4 * n + 4; k++) { ls[2 * k] = (int16_t)cr; ls[2 * k + 1] = (int16_t)ci; }
+    }
+    orc_dft(N, 1, ls, tim, 1);                                                /* nr_est_delay: peak of the impulse response */
+    for (int i = 0; i < N; i++) {
+      const int temp = (int)(((uint32_t)((int32_t)tim[2 * i] * tim[2 * i] + (int32_t)tim[2 * i + 1] * tim[2 * i + 1])) >> 1);
+      if (temp > max_val) { max_pos = i; max_val = temp; }
+    }
+    if (max_pos > N / 2) max_pos -= N;
+    const int est_delay = max_pos;
+    int d_idx = 20 + est_delay; d_idx = d_idx < 0 ? 0 : d_idx > 40 ? 40 : d_idx;
+    int i_idx = 20 - est_delay; i_idx = i_idx < 0 ? 0 : i_idx > 40 ? 40 : i_idx;
+    const int dly = d_idx - 20, idly = i_idx - 20;
+    int base = 0;
+    for (int pc = 0; pc < np; pc++) {                                         /* delay compensation + 16-tap interpolation, overlap-added */
+      const int k = pc << 1;
+      const double ang = 2.0 * M_PI * k * dly / N;
+      const int16_t tr = (int16_t)round(256 * cos(ang)), ti = (int16_t)round(256 * sin(ang));
+      const int32_t lr = ls[2 * k], li = ls[2 * k + 1];
+      const int16_t cr = (int16_t)((lr * tr - li * ti) >> 8), ci = (int16_t)((lr * ti + li * tr) >> 8);
+      if (pc == 0) multadd16(F_P0, cr, ci, acc + 2 * base);
+      else if (pc == 1 || pc == 2) multadd16(F_P1P2, cr, ci, acc + 2 * base);
+      else if (pc == np - 1) multadd16(F_LAST, cr, ci, acc + 2 * base);
+      else { multadd16(F_MID, cr, ci, acc + 2 * base); if (pc % 2 == 0) base += 4; }
+    }
+    for (int k = 0; k < 12 * nb; k++) {                                       /* revert the delay, accumulate the noise estimate */
+      const double ang = 2.0 * M_PI * k * idly / N;
+      const int16_t tr = (int16_t)round(256 * cos(ang)), ti = (int16_t)round(256 * sin(ang));
+      const int32_t ar = acc[2 * k], ai = acc[2 * k + 1];
+      const int16_t cr = (int16_t)((ar * tr - ai * ti) >> 8), ci = (int16_t)((ar * ti + ai * tr) >> 8);
+      acc[2 * k] = cr; acc[2 * k + 1] = ci;
+      const int16_t dr = (int16_t)(ls[2 * k] - cr), di = (int16_t)(ls[2 * k + 1] - ci);
+      noise += (uint32_t)((int32_t)dr * dr + (int32_t)di * di);
+    }
+    nest += 12 * nb;
+    memset(ul, 0, 4 * (size_t)N);
+    memcpy(ul, acc, 4 * (size_t)(12 * nb + 8 <= N ? 12 * nb + 8 : N));
+  }
+  out[0] = max_ch; out[1] = nest > 0 ? (int32_t)(uint32_t)(noise / (uint64_t)nest) : 0; out[2] = max_pos; out[3] = max_pos; out[4] = max_val;
+  free(pil); free(ls); free(tim); free(acc);
+  return 0;
+}

@@ -65,6 +65,13 @@ void orc_ulsch_llr(int Qm, const int16_t *rxF, const int16_t *maga, const int16_
 /* Q15 DFT/IDFT of the OFDM sizes (nrb200_dft_oracle.c restates openair1/PHY/TOOLS/oai_dfts.c); interleaved {re,im} int16. */
 int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale);
 
+/* PUSCH channel estimation, DMRS type 1, frequency-domain interpolation (nrb200_chest_oracle.c) */
+typedef struct {
+  int32_t fft_size, nb_rx, slot, symbol, port, rb_start, bwp_start, rb_size, first_carrier_offset, scid, dmrs_scrambling_id;
+} orc_chest_t;
+void orc_pusch_dmrs_pilots(const orc_chest_t *p, int16_t *pil);
+int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);
+
 /* single-layer PUSCH inner receiver (nrb200_pusch_oracle.c) */
 typedef struct {
   int32_t fft_size, nb_rx, rb_start, bwp_start, rb_size, first_carrier_offset, Qm, ul_dmrs_symb_pos, dmrs_config_type, num_dmrs_cdm_grps_no_data;

@@ -27,7 +27,7 @@ def make_case(oracle, BG, Z, R, n, ebn0_db, seed):
 
 
 # ------------------------------------------------------------------------------------------------ oracle-only PUSCH slot chain
-def oracle_pusch_transmit(oracle, P, A, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, seed, tx_amp=724, h_amp=724.0, snr_db=30.0):
+def oracle_pusch_transmit(oracle, P, A, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, seed, tx_amp=724, h_amp=724.0, snr_db=30.0, dmrs_id=55):
     """CPU restatement chain (oracle functions only) that produces one slot of time-domain samples per rx antenna: TB CRC, segmentation,
     LDPC encoding, rate matching + interleaving, scrambling, QAM mapping, resource mapping (one type-1 DMRS symbol at l = 2 without data),
     flat channel + noise, OFDM modulation.  Returns (payload, frame [nb_rx, 2 * samples_per_frame], genie estimates [nb_rx, 14, N, 2], info)."""
@@ -60,6 +60,10 @@ def oracle_pusch_transmit(oracle, P, A, Qm, rb_start, rb_size, nb_rx, slot, rnti
     est = np.zeros((nb_rx, 14, N, 2), np.int16)
     est[:, 2, :12 * rb_size, :] = np.round(hi * (unit / 1024.0)).astype(np.int16)[:, None, :]
     sigma = unit * (h_amp / 1024.0) * 10.0 ** (-snr_db / 20.0) * 0.70711
+    from oracle.bindings import ChestParms
+    CP = ChestParms(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, P.first_carrier_offset, 0, dmrs_id)
+    pil = oracle.pusch_dmrs_pilots(CP).reshape(-1, 2).astype(np.float64) * (unit / 32767.0)
+    dm_sc = (start_re + 2 * np.arange(6 * rb_size)) % N
     frame = np.zeros((nb_rx, 2 * P.samples_per_frame), np.int16)
     ss = P.slot_timestamp(slot)
     for a in range(nb_rx):
@@ -70,18 +74,25 @@ def oracle_pusch_transmit(oracle, P, A, Qm, rb_start, rb_size, nb_rx, slot, rnti
         yq = np.clip(np.round(y), -32768, 32767).astype(np.int16).reshape(len(data_syms), 12 * rb_size, 2)
         for j, s in enumerate(data_syms):
             grid[s, sc] = yq[j]
+        hc = (hi[a, 0] + 1j * hi[a, 1]) / 1024.0
+        d = hc * (pil[:, 0] - 1j * pil[:, 1])                                # DMRS = conj of the receiver's table, data amplitude
+        dn = np.stack([d.real, d.imag], axis=1) + sigma * rng.standard_normal((pil.shape[0], 2))
+        grid[2, dm_sc] = np.clip(np.round(dn), -32768, 32767).astype(np.int16)
         t, _ = oracle.ofdm_tx_slot(N, P.mu, P.nb_rb, slot, 14, rot.reshape(-1), grid.reshape(-1))
         frame[a, 2 * ss:2 * ss + t.size] = t
     return payload, frame, est, dict(C=C_, K=K, Z=Z, F=F, E=E, G=G)
 
 
-def oracle_pusch_receive(oracle, P, info, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, frame, est, max_iter=8):
+def oracle_pusch_receive(oracle, P, info, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, frame, est=None, max_iter=8, dmrs_id=55):
     """The receive chain with oracle functions: OFDM demod, level, inner receiver, descrambling, de-interleaving, rate recovery,
     decoder-input packing (nr_ulsch_decoding.c:195-210), decoding with CRC24B stop.  Returns (tb bytes, iterations, llr16, log2_maxh)."""
     from oracle.bindings import PuschParms
     from openairinterface5g_b200 import transport as T
     N = P.N
     rxF = np.stack([oracle.ofdm_rx_slot(N, P.mu, P.nb_rb, slot, P.divisor, 0, rot.reshape(-1), frame[a]).reshape(14, N, 2) for a in range(nb_rx)])
+    if est is None:                                                          # estimate from the DMRS symbol (nr_pusch_channel_estimation)
+        from oracle.bindings import ChestParms
+        est, _ = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, P.first_carrier_offset, 0, dmrs_id), rxF)
     PP = PuschParms(N, nb_rx, rb_start, 0, rb_size, P.first_carrier_offset, Qm, 1 << 2, 0, 2)
     shift, _ = oracle.pusch_log2_maxh(PP, 0, 2, rxF, est)
     llr = np.concatenate([oracle.pusch_inner_rx_symbol(PP, s, 2, shift, rxF, est)[0] for s in range(14) if s != 2])

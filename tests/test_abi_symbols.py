@@ -1,4 +1,5 @@
 """The C-ABI library loads and exports every symbol include/*.h declares (no compute call: works without a GPU)."""
+import numpy as np
 import ctypes
 import os
 import re
@@ -62,3 +63,15 @@ def test_pusch_num_llr_matches_oracle_bookkeeping(oracle):
             assert lib.pusch_num_llr(d) == want
     bad = PuschRxDesc(4096, 4, 0, 0, 273, 2458, 5, 0, 14, 4, 0, 2, 0, 0, 0, 0, 0, 0)       # Qm = 5
     assert lib.pusch_num_llr(bad) == 0
+
+
+def test_pusch_dmrs_pilots_match_oracle(oracle):
+    """nrb200_pusch_dmrs_pilots_host is host arithmetic (nr_gold_pusch + nr_pusch_dmrs_rx): no GPU needed."""
+    from oracle.bindings import ChestParms
+    from openairinterface5g_b200.ldpc import LdpcLib, PuschChestDesc
+    lib = LdpcLib()
+    for N, slot, symbol, port, rb_start, rb_size, scid, nid in ((4096, 1, 2, 0, 0, 273, 0, 77), (2048, 19, 11, 1, 30, 76, 1, 65535), (1024, 0, 2, 2, 0, 52, 1, 0),
+                                                                (1024, 5, 0, 3, 20, 32, 0, 300)):
+        P = ChestParms(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid)
+        d = PuschChestDesc(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid, 14 * N, 14 * N)
+        assert np.array_equal(lib.pusch_dmrs_pilots(d), oracle.pusch_dmrs_pilots(P))

@@ -294,3 +294,35 @@ def test_pusch_inner_rx(oracle, reference):
                 llr_r, comp_r = reference.pusch_inner_rx_symbol(P, symbol, dm[0], shift, rx, h, valid)
                 assert np.array_equal(comp_o, comp_r), (case, symbol, shift, "comp")
                 assert np.array_equal(llr_o, llr_r), (case, symbol, shift, "llr")
+
+
+# ------------------------------------------------------------------------------------------ PUSCH channel estimation (a22), DMRS type 1
+CHEST_CASES = [  # N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier PRBs, scid, dmrs id, delay (samples) of the synthetic channel
+    (4096, 4, 1, 2, 0, 0, 273, 273, 0, 77, 0), (4096, 2, 8, 2, 0, 0, 273, 273, 1, 1007, 3), (2048, 2, 3, 3, 0, 10, 50, 106, 0, 5, -2),
+    (2048, 1, 19, 11, 1, 30, 76, 106, 0, 65535, 1), (1024, 4, 0, 2, 2, 0, 52, 52, 1, 0, 7), (1024, 2, 5, 0, 3, 20, 32, 52, 0, 300, -30), (512, 8, 2, 2, 0, 3, 11, 25, 0, 9, 0),
+]
+
+
+def test_pusch_channel_estimation(oracle, reference):
+    from oracle.bindings import ChestParms
+    rng = np.random.default_rng(60)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay in CHEST_CASES:
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, scid, nid)
+        big = nb_rx == 8
+        # a channel with a linear phase (time delay) on the pilots + noise, so that the delay estimator has a peak to find
+        pil = oracle.pusch_dmrs_pilots(P).reshape(-1, 2).astype(np.float64)
+        rx = rng.integers(-300, 301, size=(nb_rx, 14, N, 2)).astype(np.int16) if not big else rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        if not big:
+            k0 = ((rb_start * 12) + P.first_carrier_offset) % N
+            delta = (0, 0, 1, 1)[port]
+            for a in range(nb_rx):
+                h = (900 + 100 * a) * np.exp(1j * (0.3 * a - 2 * np.pi * delay * np.arange(6 * rb_size) * 2 / N))
+                tx = (pil[:, 0] - 1j * pil[:, 1]) / 23170.0 / np.sqrt(2)          # transmitted DMRS = conj of the rx table
+                y = h * tx
+                idx = (k0 + 2 * np.arange(6 * rb_size) + delta) % N
+                rx[a, symbol, idx, 0] += np.round(y.real).astype(np.int16); rx[a, symbol, idx, 1] += np.round(y.imag).astype(np.int16)
+        est_r, out_r, pil_r = reference.pusch_channel_estimation(P, rx, carrier)
+        assert np.array_equal(oracle.pusch_dmrs_pilots(P), pil_r), (N, slot, symbol, port, "pilots")
+        est_o, out_o = oracle.pusch_channel_estimation(P, rx)
+        assert np.array_equal(out_o, out_r), (N, nb_rx, slot, symbol, port, out_o, out_r)
+        assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """PUSCH slot receive chain throughput (SURVEY 8d "Metric 2" analogue for the uplink, hot-path stages only): one full-band 100 MHz slot
-(273 PRB, 64QAM, 4 rx antennas, 28 code blocks) through OFDM demod -> level -> compensation/LLR/descrambling -> rate recovery -> LDPC decode
+(273 PRB, 64QAM, 4 rx antennas, 28 code blocks) through OFDM demod -> channel estimation -> level -> compensation/LLR/descrambling -> rate recovery -> LDPC decode
 -> TB CRC, device resident, eager launches and replayed from a CUDA graph, plus the same with the slot's samples copied from pinned host
 memory and the transport block copied back.  Prints JSON lines; summarised under profiles/."""
 import json
@@ -34,20 +34,21 @@ def main():
     lib, dl = load_LDPClib(), load_dftslib()
     ch = PuschSlotChain(lib, dl, dev)
     payload, rxdata, est = ch.synthesize(seed=3, snr_db=30.0)
-    tb, iters, crc = ch.receive(rxdata, est)
+    tb, iters, crc = ch.receive(rxdata)
     torch.cuda.synchronize()
     ok = bool((iters <= ch.max_iter).all()) and int(crc[0]) == 0 and bool((tb.view(-1)[:payload.size].cpu() == torch.from_numpy(payload)).all())
     base = {"workload": "PUSCH slot rx 100MHz 273PRB 64QAM 4rx 1 layer, 28 CB K=8448 (TB 235624 bit)", "decoded_ok": ok,
             "mean_iterations": float(iters.float().mean())}
     l0 = lib.launch_count() + dl.launch_count()
-    ms = timed(lambda: ch.receive(rxdata, est), 200)
+    ms = timed(lambda: ch.receive(rxdata), 200)
     launches = (lib.launch_count() + dl.launch_count() - l0) / 205
     print(json.dumps(dict(base, mode="device-resident, eager", ms_per_slot=ms, slots_per_s=1e3 / ms, kernels_per_slot=launches,
                           realtime_factor_vs_2000_slots_per_s=1e3 / ms / 2000.0)), flush=True)
     # per-stage times (each stage alone, back to back 200x)
     st = {
         "ofdm_demod": lambda: dl.ofdm_demod_slot_torch(ch.drx, rxdata, ch.ts, ch.rxF),
-        "level+inner_rx": lambda: lib.pusch_inner_rx_torch(ch.desc, ch.rxF, est, ch.llr16, level=ch.level),
+        "channel_estimation": lambda: lib.pusch_chest_torch(ch.cdesc, ch.rxF, ch.est, ch.chest_scratch, ch.chest_state),
+        "level+inner_rx": lambda: lib.pusch_inner_rx_torch(ch.desc, ch.rxF, ch.est, ch.llr16, level=ch.level),
         "rm_rx": lambda: lib.rm_rx_torch(1, ch.Z, ch.Qm, 0, ch.C, 0, ch.F, ch.llr16, ch.E, ch.Eoff, ch.harq, ch.llr8, clear=1),
         "ldpc_decode": lambda: lib.decode_batch_torch(1, ch.Z, ch.R, ch.max_iter, ch.llr8, use_crc=1, crc_len_bits=ch.K - ch.F, crc_type=1, out=ch.hard, iters=ch.iters),
     }
@@ -56,10 +57,10 @@ def main():
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
-            ch.receive(rxdata, est)
+            ch.receive(rxdata)
             torch.cuda.synchronize()
             with torch.cuda.graph(g, stream=s):
-                ch.receive(rxdata, est)
+                ch.receive(rxdata)
         ms_g = timed(g.replay, 500)
         print(json.dumps(dict(base, mode="device-resident, CUDA graph replay", ms_per_slot=ms_g, slots_per_s=1e3 / ms_g)), flush=True)
     except Exception as e:                                           # graph capture is an optimisation, not a requirement
@@ -72,7 +73,7 @@ def main():
 
     def e2e():
         rxdata[:, ss:ss + nsamp].copy_(h_slot, non_blocking=True)
-        t, _, _ = ch.receive(rxdata, est)
+        t, _, _ = ch.receive(rxdata)
         h_tb.copy_(t, non_blocking=True)
     t0 = time.perf_counter()
     ms_e = timed(e2e, 200)
