@@ -269,6 +269,20 @@ int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, const int16_t *d_r
                                void *stream);
 int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5);
 
+/* ---- Part 8: the "offload" calling convention of the codec ABI -----------------------------------------------------------
+ * OAI's second LDPC interface (ldpc_interface_offload, loaded as version "_t2" when --ldpc-offload-enable is given; reference
+ * implementation nrLDPC_decoder_offload.c:1034-1145 in front of a T2 accelerator) uses the same four prototypes with different
+ * semantics: the decoder receives the E raw int8 LLRs of ONE segment and does de-interleaving, rate recovery and HARQ combining
+ * itself, keeping the soft buffers inside the library keyed by (ulsch_id, segment); the encoder returns E rate-matched, interleaved
+ * bits.  libldpc_b200_t2.so exports LDPCinit/LDPCshutdown/LDPCdecoder/LDPCencoder with these semantics and forwards to the two entry
+ * points below.  The arithmetic is this library's (the reference's arithmetic here lives in the accelerator): int16 HARQ accumulation as
+ * nr_rate_matching_ldpc_rx, the bit-exact flooding decoder with parity-check stop, numMaxIter from the parameter block.
+ * decode: p->{BG,Z,R,F,Qm,rv,E,numMaxIter,setCombIn}; llr = E int8; out = K/8 bytes (K = 22Z | 10Z); returns iterations, < 0 on error.
+ * encode: impp->{BG,Zc,K,F,Qm,rv,E}; in = K/8 bytes; out = E bytes, one bit each. */
+int32_t nrb200_ldpc_offload_init(void);   /* = LDPCinit of libldpc_b200.so under a name the shim can link to */
+int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t r, const int8_t *llr, uint8_t *out);
+int32_t nrb200_ldpc_offload_encode(const uint8_t *in, uint8_t *out, const nrb200_ldpc_enc_params_t *impp);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

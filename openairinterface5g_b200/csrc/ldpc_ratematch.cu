@@ -60,14 +60,16 @@ __global__ void rm_tx_kernel(nrb200_rm_desc_t p, const uint8_t *__restrict__ d, 
 }
 
 // ---- RX: soft (E_r interleaved int16 per segment) -> HARQ buffer d (int16, += with wrap) -> decoder input llr (int8)
-__global__ void rm_rx_kernel(nrb200_rm_desc_t p, const int16_t *__restrict__ soft, const uint32_t *__restrict__ E_seg,
+// SoftT = int16_t (the CPU-compatible convention: demodulator LLRs) or int8_t (the offload convention: the caller already packed to int8)
+template <typename SoftT>
+__global__ void rm_rx_kernel(nrb200_rm_desc_t p, const SoftT *__restrict__ soft, const uint32_t *__restrict__ E_seg,
                              const uint32_t *__restrict__ s_off, int16_t *__restrict__ harq, uint32_t harq_stride, int8_t *__restrict__ llr,
                              uint32_t llr_stride)
 {
   const uint32_t r = blockIdx.x;
   const uint32_t E = E_seg[r], EQm = E / p.Qm;
   const RmGeom g = rm_geom(p.BG, p.Z, p.Tbslbrm, p.C, p.F, p.K, p.rv);
-  const int16_t *in = soft + s_off[r];
+  const SoftT *in = soft + s_off[r];
   int16_t *w = harq + (size_t)r * harq_stride;
   // rate recovery: every ring slot sums the soft values of all its repetitions (int16 arithmetic wraps like the reference's +=)
   for (uint32_t slot = threadIdx.x; slot < g.L; slot += blockDim.x) {
@@ -75,7 +77,7 @@ __global__ void rm_rx_kernel(nrb200_rm_desc_t p, const int16_t *__restrict__ sof
     uint32_t acc = p.clear ? 0u : (uint32_t)(uint16_t)w[pos];
     for (uint32_t k = (slot + g.L - g.r0) % g.L; k < E; k += g.L) {
       const uint32_t i = k / EQm, j = k - i * EQm;           // e[i*EQm + j] = f[j*Qm + i]
-      acc += (uint32_t)(uint16_t)in[j * p.Qm + i];
+      acc += (uint32_t)(uint16_t)(int16_t)in[j * p.Qm + i];
     }
     w[pos] = (int16_t)(uint16_t)acc;
   }
@@ -107,7 +109,17 @@ int launch_rm_rx(const nrb200_rm_desc_t &p, const int16_t *soft, const uint32_t 
                  int8_t *llr, uint32_t llr_stride, cudaStream_t st)
 {
   if (p.n_seg == 0) return 0;
-  rm_rx_kernel<<<p.n_seg, 512, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
+  rm_rx_kernel<int16_t><<<p.n_seg, 512, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
+  ctx().launches++;
+  NRB200_CUDA_OK(cudaGetLastError(), "rm_rx launch");
+  return 0;
+}
+
+int launch_rm_rx8(const nrb200_rm_desc_t &p, const int8_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
+                  int8_t *llr, uint32_t llr_stride, cudaStream_t st)
+{
+  if (p.n_seg == 0) return 0;
+  rm_rx_kernel<int8_t><<<p.n_seg, 512, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "rm_rx launch");
   return 0;

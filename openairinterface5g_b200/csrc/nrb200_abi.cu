@@ -4,6 +4,8 @@
 #include "ldpc_common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
@@ -21,6 +23,8 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
 int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil);
 int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol);
+int launch_rm_rx8(const nrb200_rm_desc_t &p, const int8_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
+                  int8_t *llr, uint32_t llr_stride, cudaStream_t st);
 int launch_modulate(int Qm, uint32_t length_bits, const uint8_t *bits, int16_t *out, cudaStream_t st);
 int launch_pusch_llr(int Qm, uint32_t nb_re, const int16_t *y, const int16_t *ma, const int16_t *mb, const int16_t *mc, int16_t *out, cudaStream_t st);
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
@@ -587,6 +591,107 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, con
     for (uint32_t a = 0; a < d->nb_rx; a++)
       std::memcpy((uint8_t *)ul_ch_estimates + ((size_t)a * 14 + d->symbol) * sym, (uint8_t *)w->h_out + sym * a, sym);
     if (state5) std::memcpy(state5, w->h_aux, 20);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ offload calling convention
+// Library-owned HARQ soft buffers, one per (ulsch_id, segment) like the accelerator's internal HARQ memory
+// (harq_combined_input.offset = ulsch_id * 64 * LDPC_MAX_CB_SIZE + r * LDPC_MAX_CB_SIZE, nrLDPC_decoder_offload.c:545-546).
+static int16_t *offload_harq(uint8_t ulsch_id, uint8_t r)
+{
+  static std::mutex mu;
+  static std::map<uint32_t, int16_t *> store;
+  std::lock_guard<std::mutex> lk(mu);
+  const uint32_t key = ((uint32_t)ulsch_id << 8) | r;
+  auto it = store.find(key);
+  if (it != store.end()) return it->second;
+  int16_t *d = nullptr;
+  if (cudaMalloc(&d, (size_t)66 * 384 * 2) != cudaSuccess) return nullptr;
+  cudaMemset(d, 0, (size_t)66 * 384 * 2);
+  store[key] = d;
+  return d;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_offload_init(void) { return LDPCinit(); }
+
+NRB200_EXPORT int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t r, const int8_t *llr,
+                                                 uint8_t *out)
+{
+  (void)harq_pid;
+  if (ensure_init() || !p) return -1;
+  const int32_t numLLR = nrb200_ldpc_num_llr(p->BG, p->Z, p->R);
+  if (numLLR < 0 || p->E <= 0 || p->E > 32768 * 4) return -4;
+  nrb200_rm_desc_t rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.BG = p->BG; rd.Z = p->Z; rd.Qm = p->Qm; rd.rv = p->rv; rd.clear = p->setCombIn ? 0 : 1; rd.C = 1; rd.Tbslbrm = 0; rd.F = p->F;
+  rd.K = (uint32_t)(p->BG == 1 ? 22 : 10) * p->Z; rd.n_seg = 1;
+  if (int rc = rm_check(&rd)) return rc;
+  nrb200_ldpc_batch_desc_t d;
+  std::memset(&d, 0, sizeof(d));
+  const uint32_t kcZ = (uint32_t)(p->BG == 1 ? 68 : 52) * p->Z;
+  d.BG = p->BG; d.Z = p->Z; d.R = p->R; d.numMaxIter = p->numMaxIter; d.outMode = NRB200_OUTMODE_BIT; d.n_cb = 1; d.llr_stride = kcZ;
+  d.out_stride = ((uint32_t)numLLR + 7) / 8;
+  const GraphDev *hg = nullptr;
+  const GraphDev *dg = ctx().graph(d.BG, d.Z, d.R, &hg);
+  if (!dg) return -4;
+  DecodeArgs a;
+  if (int rc = fill_args(&d, *hg, &a)) return rc;
+  int16_t *harq = offload_harq(ulsch_id, r);
+  if (!harq) return -5;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve((size_t)p->E + 64, kcZ + d.out_stride + 64, 64)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  int32_t it = -1;
+  do {
+    std::memcpy(w->h_in, llr, (size_t)p->E);
+    uint32_t *h_meta = (uint32_t *)w->h_aux;
+    h_meta[0] = (uint32_t)p->E; h_meta[1] = 0;
+    if (cudaMemcpyAsync(w->d_in, w->h_in, (size_t)p->E, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->d_aux, w->h_aux, 8, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    int8_t *d_llr8 = (int8_t *)w->d_out;
+    uint8_t *d_hard = (uint8_t *)w->d_out + ((kcZ + 63) & ~63u);
+    if ((rc = launch_rm_rx8(rd, (const int8_t *)w->d_in, (const uint32_t *)w->d_aux, (const uint32_t *)w->d_aux + 1, harq, 66 * 384, d_llr8, kcZ, w->stream)) != 0) break;
+    a.llr = d_llr8; a.out = d_hard; a.iters = (int32_t *)((uint8_t *)w->d_aux + 16);
+    if ((rc = launch_decode(dg, *hg, a, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, d_hard, rd.K / 8, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync((uint8_t *)w->h_aux + 16, (uint8_t *)w->d_aux + 16, 4, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(out, w->h_out, rd.K / 8);
+    it = *(int32_t *)((uint8_t *)w->h_aux + 16);
+  } while (0);
+  ctx().release(w);
+  return rc != 0 ? (rc < 0 ? rc : -1) : it;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_offload_encode(const uint8_t *in, uint8_t *out, const nrb200_ldpc_enc_params_t *impp)
+{
+  if (ensure_init() || !impp || !in || !out) return -1;
+  const int BG = impp->BG, Z = (int)impp->Zc;
+  const EncGraphDev *hg = nullptr;
+  const EncGraphDev *dg = ctx().enc_graph(BG, Z, &hg);
+  if (!dg || impp->K != (uint32_t)hg->nsys * Z || impp->E == 0) return -4;
+  nrb200_rm_desc_t rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.BG = (uint8_t)BG; rd.Z = (uint16_t)Z; rd.Qm = impp->Qm; rd.rv = impp->rv; rd.C = 1; rd.Tbslbrm = 0; rd.F = impp->F; rd.K = impp->K; rd.n_seg = 1;
+  if (int rc = rm_check(&rd)) return rc;
+  const uint32_t nout = (uint32_t)(hg->ncols - 2) * Z, kin = impp->K / 8;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(kin + 64, (size_t)nout + impp->E + 128, 64)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, in, kin);
+    uint32_t *h_meta = (uint32_t *)w->h_aux;
+    h_meta[0] = impp->E; h_meta[1] = 0;
+    if (cudaMemcpyAsync(w->d_in, w->h_in, kin, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->d_aux, w->h_aux, 8, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    uint8_t *d_d = (uint8_t *)w->d_out, *d_f = (uint8_t *)w->d_out + ((nout + 63) & ~63u);
+    if ((rc = launch_encode(dg, *hg, (int)impp->K, 1, (const uint8_t *)w->d_in, kin, d_d, nout, w->stream)) != 0) break;
+    if ((rc = launch_rm_tx(rd, d_d, nout, (const uint32_t *)w->d_aux, (const uint32_t *)w->d_aux + 1, d_f, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, d_f, impp->E, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(out, w->h_out, impp->E);
   } while (0);
   ctx().release(w);
   return rc;

@@ -407,6 +407,44 @@ class LdpcLib:
         return out
 
 
+class OffloadLdpcLib:
+    """libldpc_b200_t2.so: the same four symbols with OAI's "offload" semantics (ldpc_interface_offload, nr_ulsch_decoding.c:230-300,
+    nr_dlsch_coding.c:362-384): one segment per call, the library de-interleaves, rate-recovers and HARQ-combines."""
+
+    def __init__(self, path=os.path.join(_HERE, "libldpc_b200_t2.so"), init=True):
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = self.lib = C.CDLL(path)
+        L.LDPCdecoder.argtypes = [C.POINTER(DecParams), C.c_uint8, C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.LDPCencoder.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(EncParams)]
+        if init and L.LDPCinit() != 0:
+            raise Nrb200Error("LDPCinit (offload) failed: no usable CUDA device")
+
+    def LDPCdecoder(self, BG, Z, R, numMaxIter, E, Qm, rv, F, llr_E, ulsch_id=0, r=0, harq_pid=0, setCombIn=0):
+        p = DecParams()
+        p.BG, p.Z, p.R, p.F, p.Qm, p.rv, p.numMaxIter, p.E, p.outMode, p.setCombIn = BG, Z, R, F, Qm, rv, numMaxIter, E, OUTMODE_BIT, setCombIn
+        x = np.ascontiguousarray(llr_E, dtype=np.int8)
+        assert x.size >= E
+        K = (22 if BG == 1 else 10) * Z
+        out = np.zeros(K // 8, dtype=np.uint8)
+        it = self.lib.LDPCdecoder(C.byref(p), harq_pid, ulsch_id, r, x.ctypes.data, out.ctypes.data, None, None)
+        if it < 0:
+            raise Nrb200Error(f"offload LDPCdecoder rc={it}")
+        return it, out
+
+    def LDPCencoder(self, BG, Z, K, F, Qm, rv, E, segment):
+        ip = EncParams()
+        ip.n_segments, ip.BG, ip.Zc, ip.K, ip.F, ip.Qm, ip.rv, ip.E = 1, BG, Z, K, F, Qm, rv, E
+        seg = np.ascontiguousarray(segment, dtype=np.uint8)
+        out = np.zeros(E, dtype=np.uint8)
+        inp = (C.c_void_p * 1)(seg.ctypes.data)
+        oup = (C.c_void_p * 1)(out.ctypes.data)
+        rc = self.lib.LDPCencoder(inp, oup, C.byref(ip))
+        if rc != 0:
+            raise Nrb200Error(f"offload LDPCencoder rc={rc}")
+        return out
+
+
 _lib = None
 
 

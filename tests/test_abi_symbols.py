@@ -75,3 +75,11 @@ def test_pusch_dmrs_pilots_match_oracle(oracle):
         P = ChestParms(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid)
         d = PuschChestDesc(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid, 14 * N, 14 * N)
         assert np.array_equal(lib.pusch_dmrs_pilots(d), oracle.pusch_dmrs_pilots(P))
+
+
+def test_offload_flavour_exports_the_loader_symbols():
+    """libldpc_b200_t2.so (offload calling convention) loads next to libldpc_b200.so and exports exactly the four names the loader dlsym()s."""
+    from openairinterface5g_b200.ldpc import OffloadLdpcLib
+    lib = OffloadLdpcLib(init=False).lib
+    for name in ("LDPCinit", "LDPCshutdown", "LDPCdecoder", "LDPCencoder"):
+        assert getattr(lib, name) is not None
