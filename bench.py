@@ -30,6 +30,17 @@ METRIC = "LDPC code-blocks/sec (BG1 Z=384 K=8448 8-iter)"
 WORKLOAD = "ldpctest BG1 Z=384 K=8448 R=1/3 8-iter batch=1024 int8 LLR, Eb/N0 1.0 dB (all blocks run 9 passes)"
 
 
+
+def ncu_traffic(n_cb):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the decode kernel, from the committed `ncu --set full` capture
+    (profiles/ncu_decode_traffic.json, taken with the same 1024-block launch); scaled if this run's batch differs.  None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_decode_traffic.json")))
+        return int((d["dram_bytes_read"] + d["dram_bytes_write"]) * n_cb / 1024)
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,7 +280,7 @@ def run_b200(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "numMaxIter": MAX_ITER, "ebn0_db": args.ebn0, "mean_returned_iters": mean_iters,
                        "l2": f"inputs rotate over {NB} distinct batches ({NB * B * NUM_LLR / 1e6:.0f} MB > 126 MB L2)", "parallelism": f"cb-shard x{world}"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(B),
                          "peak_source": peak_src, "kernel": "ldpc_decode_packed_kernel", "kernel_ms": 1000.0 * kernel_s,
                          "note": "on-chip bound: message state lives in shared memory; see edge_updates_per_s",
                          "edge_updates_per_s": value / world * EDGE_UPDATES_PER_PASS * passes},

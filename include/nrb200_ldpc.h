@@ -236,9 +236,13 @@ typedef struct nrb200_pusch_rx_s {
   uint32_t log2_maxh;                       /* compensation shift (ignored by _dev when d_log2_maxh != NULL) */
   uint32_t rx_stride, ch_stride;            /* _dev: c16 between antennas of rxdataF / ul_ch_estimates */
   uint32_t unscramble, rnti, data_scrambling_id;   /* unscramble != 0: LLRs are multiplied by 1 - 2 c(i), c_init = (rnti << 15) + id */
+  uint32_t nrOfLayers;                      /* 0 or 1: one layer.  2: MMSE receiver (nr_ulsch_mmse_2layers), qam_mod_order >= 6, nb_rx 2 or 4;
+                                             * ul_ch_estimates then holds [2 * nb_rx] planes, index layer * nb_rx + rx, LLRs are layer de-mapped */
+  uint32_t noise_var;                       /* 2 layers: nvar of the channel estimator, added to the diagonal of H^H H */
+  uint32_t max_ch;                          /* 2 layers: the estimator's max_ch (scales the level measurement, nr_ulsch_scale_channel) */
 } nrb200_pusch_rx_t;
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
-/* d_out: 9 int32 on the device: [0..nb_rx) = avg per antenna, [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
+/* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
 int32_t nrb200_pusch_log2_maxh_dev(const nrb200_pusch_rx_t *d, const int16_t *d_ul_ch_estimates, int32_t *d_out, void *stream);
 int32_t nrb200_pusch_inner_rx_dev(const nrb200_pusch_rx_t *d, const int16_t *d_rxdataF, const int16_t *d_ul_ch_estimates, const int32_t *d_log2_maxh,
                                   int16_t *d_llr, void *stream);

@@ -128,8 +128,11 @@ static int decode_host_impl(const nrb200_ldpc_batch_desc_t *desc, const int8_t *
     if (!pin_in) { std::memcpy(w->h_in, llr, in_bytes); h_src = (const uint8_t *)w->h_in; }
     uint8_t *h_dst = pin_out ? out : (uint8_t *)w->h_out;
     if (desc->use_crc && !pin_out) std::memcpy(w->h_out, out, out_bytes);   // the reference leaves p_out untouched until a CRC check runs
-    const size_t nchunk = w2 ? 4 : 1;
-    const size_t per = (n + nchunk - 1) / nchunk;
+    // Chunks of one wave (one CTA per SM) alternate between the two streams: the first kernel starts after 1/7 of the input has crossed
+    // PCIe, later chunks' CTAs fill the SMs the previous chunk's tail frees, and only the last wave's output is copied after the kernels.
+    // NRB200_HOST_CHUNK_WAVES = waves per chunk (default 1).
+    static const size_t waves = []() { const char *e = getenv("NRB200_HOST_CHUNK_WAVES"); const int v = e ? atoi(e) : 1; return (size_t)(v > 0 ? v : 1); }();
+    const size_t per = w2 ? std::max<size_t>(1, (size_t)ctx().sm_count * waves) : n;
     cudaStream_t st[2] = {w->stream, w2 ? w2->stream : w->stream};
     for (size_t ci = 0, c0 = 0; c0 < n; ci++, c0 += per) {
       const size_t cn = std::min(per, n - c0);

@@ -9,6 +9,7 @@
 #include "nrb200_ctx.h"
 #include "gold_seq.cuh"
 #include "../../include/nrb200_ldpc.h"
+#include <climits>
 
 namespace nrb200 {
 
@@ -19,6 +20,9 @@ struct PuschGeom {
   int sym[14], ch_sym[14], is_dmrs[14], valid[14];
   unsigned llr_off[14];
   unsigned unscramble, c_init;
+  int nl;                          // layers (1 | 2)
+  unsigned nvar;                   // noise variance added to the diagonal of H^H H (2 layers)
+  int lvl_amp, lvl_b;              // nr_ulsch_scale_channel constants of the level measurement
 };
 
 __device__ __forceinline__ int p_sat16(int v) { return max(-32768, min(32767, v)); }
@@ -113,13 +117,110 @@ __global__ void __launch_bounds__(256) pusch_rx_kernel(PuschGeom G, const GoldTa
   for (int m = 0; m < QM / 2; m++) dst[m] = ((unsigned)o[2 * m] & 0xFFFFu) | ((unsigned)o[2 * m + 1] << 16);
 }
 
+// ---- two layers, MMSE (Qm >= 6): matched filter per layer, H^H H + nvar I from the same estimates, determinant, 2x2 adjugate, per-layer LLRs,
+// layer de-mapping and descrambling (nr_ulsch_mmse_2layers :870-1260 and helpers, nr_pusch_symbol_processing :1420-1433).  One thread per RE;
+// the scaling exponent b is shared by groups of 4 consecutive REs (one SSE vector in the reference): 4-lane shuffle sum.
+__device__ __forceinline__ int p_log2_approx(unsigned v) { return v ? 32 - __clz(v) : 0; }      // bit length; the reference scans bits 0..30 only
+__device__ __forceinline__ int p_mad(int ar, int br, int ai, int bi) { return (int)((unsigned)(ar * br) + (unsigned)(ai * bi)); }
+
+template <int QM>
+__global__ void __launch_bounds__(256) pusch_rx2_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift,
+                                                        const unsigned *__restrict__ rxF, const unsigned *__restrict__ ch, short *__restrict__ llr)
+{
+  __shared__ uint32_t s_gold[(256 * 2 * QM) / 32 + 2];
+  const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
+  const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
+  if (i0 >= valid) return;
+  const unsigned bit0 = 2u * G.llr_off[k] + (unsigned)i0 * 2 * QM;      // both layers interleaved per RE after de-mapping
+  if (G.unscramble) {
+    const unsigned w0 = bit0 >> 5, nw = ((bit0 + 256u * 2 * QM + 31u) >> 5) - w0;
+    if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
+    __syncthreads();
+  }
+  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  // number of REs the extraction writes (beyond it the reference's buffers hold zeros)
+  const int n_ext = !is_dmrs ? G.nb_re : G.dmrs_type == 0 ? G.nb_re / 2 : (G.nb_re / 6) * 4;
+  int c0r = 0, c0i = 0, c1r = 0, c1i = 0;
+  int af[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};                       // 00, 01, 10, 11
+  if (i < n_ext) {
+    int rx_idx, ch_idx;
+    re_source(G, is_dmrs, i, rx_idx, ch_idx);
+    for (int a = 0; a < G.nb_rx; a++) {
+      const unsigned y = __ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx);
+      const unsigned h0 = __ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx);
+      const unsigned h1 = __ldg(ch + (size_t)(G.nb_rx + a) * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx);
+      const int yr = p_lo(y), yi = p_hi(y), h0r = p_lo(h0), h0i = p_hi(h0), h1r = p_lo(h1), h1i = p_hi(h1);
+      c0r = p_wrap16(c0r + p_sat16(p_mad(h0r, yr, h0i, yi) >> shift)); c0i = p_wrap16(c0i + p_sat16(p_mad(p_wrap16(-h0i), yr, h0r, yi) >> shift));
+      c1r = p_wrap16(c1r + p_sat16(p_mad(h1r, yr, h1i, yi) >> shift)); c1i = p_wrap16(c1i + p_sat16(p_mad(p_wrap16(-h1i), yr, h1r, yi) >> shift));
+      const int hr[2] = {h0r, h1r}, hi[2] = {h0i, h1i};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {                                      // conj(h_first) * h_second, first = e >> 1, second = e & 1
+        const int ar = hr[e >> 1], ai = hi[e >> 1], br = hr[e & 1], bi = hi[e & 1];
+        const int re = p_sat16(p_mad(ar, br, ai, bi) >> shift), im = p_sat16(p_mad(p_wrap16(-ai), br, ar, bi) >> shift);
+        if (a == 0) { af[e][0] = re; af[e][1] = im; } else { af[e][0] = p_sat16(af[e][0] + re); af[e][1] = p_sat16(af[e][1] + im); }
+      }
+    }
+  }
+  if (G.nvar) {                                                          // add_epi32 on the packed {re, im} word (carries into im)
+#pragma unroll
+    for (int e = 0; e < 4; e += 3) {
+      const unsigned w = (((unsigned)af[e][0] & 0xFFFFu) | ((unsigned)af[e][1] << 16)) + G.nvar;
+      af[e][0] = p_lo(w); af[e][1] = p_hi(w);
+    }
+  }
+  const int ad = p_mad(af[0][0], af[3][0], p_wrap16(-af[0][1]), af[3][1]);
+  const int bc = p_mad(af[1][0], af[2][0], p_wrap16(-af[1][1]), af[2][1]);
+  int det = (int)((unsigned)ad - (unsigned)bc);
+  det = det == INT_MIN ? det : abs(det);
+  int sum = det >> 2;
+  sum = (int)((unsigned)sum + (unsigned)__shfl_xor_sync(0xffffffffu, sum, 1));
+  sum = (int)((unsigned)sum + (unsigned)__shfl_xor_sync(0xffffffffu, sum, 2));
+  if (i >= valid) return;
+  const int b = p_log2_approx((unsigned)sum & 0x7FFFFFFFu) - 8;
+  const int m = p_sat16(b > 0 ? det >> b : (int)((unsigned)det << (-b)));
+  constexpr int ampa = QM == 6 ? 20225 : 20106, ampb = QM == 6 ? 10112 : 10053, ampc = QM == 8 ? 5026 : 0;
+  const int ma = p_wrap16(((m * ampa) >> 16) << 1), mb = p_wrap16(((m * ampb) >> 16) << 1), mc = p_wrap16(((m * ampc) >> 16) << 1);
+  // x0 = comp0 * d - comp1 * b ; x1 = comp1 * a - comp0 * c  (complex products, 32-bit wrap, shift by the group's exponent, pack)
+  int xr[2], xi[2];
+  {
+    const int in[2][4][2] = {{{c0r, c0i}, {af[3][0], af[3][1]}, {c1r, c1i}, {af[1][0], af[1][1]}}, {{c1r, c1i}, {af[0][0], af[0][1]}, {c0r, c0i}, {af[2][0], af[2][1]}}};
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      int re = (int)((unsigned)p_mad(in[l][0][0], in[l][1][0], p_wrap16(-in[l][0][1]), in[l][1][1]) - (unsigned)p_mad(in[l][2][0], in[l][3][0], p_wrap16(-in[l][2][1]), in[l][3][1]));
+      int im = (int)((unsigned)p_mad(in[l][0][1], in[l][1][0], in[l][0][0], in[l][1][1]) - (unsigned)p_mad(in[l][2][1], in[l][3][0], in[l][2][0], in[l][3][1]));
+      if (b > 0) { re >>= b; im >>= b; } else { re = (int)((unsigned)re << (-b)); im = (int)((unsigned)im << (-b)); }
+      xr[l] = p_sat16(re); xi[l] = p_sat16(im);
+    }
+  }
+  const unsigned bb = 2u * G.llr_off[k] + (unsigned)i * 2 * QM;
+  const unsigned rel = bb - ((bit0 >> 5) << 5);
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    int o[8];
+    o[0] = xr[l]; o[1] = xi[l];
+    o[2] = p_subs16(ma, p_abs16w(o[0])); o[3] = p_subs16(ma, p_abs16w(o[1]));
+    o[4] = p_subs16(mb, p_abs16w(o[2])); o[5] = p_subs16(mb, p_abs16w(o[3]));
+    if (QM > 6) { o[6] = p_subs16(mc, p_abs16w(o[4])); o[7] = p_subs16(mc, p_abs16w(o[5])); }
+    if (G.unscramble) {
+#pragma unroll
+      for (int mm = 0; mm < QM; mm++) {
+        const unsigned r = rel + l * QM + mm;
+        if ((s_gold[r >> 5] >> (r & 31u)) & 1u) o[mm] = p_wrap16(-o[mm]);
+      }
+    }
+    unsigned *dst = reinterpret_cast<unsigned *>(llr + bb + l * QM);
+#pragma unroll
+    for (int mm = 0; mm < QM / 2; mm++) dst[mm] = ((unsigned)o[2 * mm] & 0xFFFFu) | ((unsigned)o[2 * mm + 1] << 16);
+  }
+}
+
 // nr_ulsch_scale_channel (shift_ch_ext = 0) + nr_ulsch_channel_level on the measurement symbol, one CTA per rx antenna, then the
 // log2_maxh rule for one layer.  avg[a] and the final shift are left in d_out[0..nb_rx) and d_out[8].
 __global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_k, int len, const unsigned *__restrict__ ch, int *__restrict__ d_out,
                                                           unsigned *__restrict__ d_count)
 {
   __shared__ unsigned s_sum[256];
-  const int a = blockIdx.x, is_dmrs = G.is_dmrs[meas_k];
+  const int a = blockIdx.x, is_dmrs = G.is_dmrs[meas_k];          // a = layer * nb_rx + rx
   int x = 0;
   while (x < 31 && !((len >> x) & 1)) x++;                       // factor2(len)
   const int y = len >> x;
@@ -130,7 +231,7 @@ __global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_
     int rx_idx, ch_idx;
     re_source(G, is_dmrs, i, rx_idx, ch_idx);
     const unsigned h = __ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[meas_k] * G.N + ch_idx);
-    const int r = p_wrap16(((p_lo(h) * 8192) >> 16) << 3), im = p_wrap16(((p_hi(h) * 8192) >> 16) << 3);   // mulhi by 8192, slli 3
+    const int r = p_wrap16(((p_lo(h) * G.lvl_amp) >> 16) << G.lvl_b), im = p_wrap16(((p_hi(h) * G.lvl_amp) >> 16) << G.lvl_b);   // mulhi by ch_amp, slli b
     acc += (unsigned)(((int)((unsigned)(r * r) + (unsigned)(im * im))) >> x);
   }
   s_sum[threadIdx.x] = acc;
@@ -139,11 +240,11 @@ __global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_
   if (threadIdx.x == 0) {
     d_out[a] = (int)s_sum[0] / y;
     __threadfence();
-    if (atomicAdd(d_count, 1u) == (unsigned)G.nb_rx - 1) {       // last antenna: combine
+    if (atomicAdd(d_count, 1u) == (unsigned)(G.nb_rx * G.nl) - 1) {   // last (layer, antenna) pair: combine
       int avgs = 0;
-      for (int k = 0; k < G.nb_rx; k++) avgs = max(avgs, ((volatile int *)d_out)[k]);
+      for (int k = 0; k < G.nb_rx * G.nl; k++) avgs = max(avgs, ((volatile int *)d_out)[k]);
       auto l2 = [](unsigned v) { return v ? 32 - __clz(v) : 0; };  // log2_approx: bit length (values < 2^31)
-      int l = (l2((unsigned)avgs) >> 1) + 1 + l2((unsigned)G.nb_rx >> 2);
+      int l = G.nl == 2 ? (l2((unsigned)avgs) >> 1) - 3 : (l2((unsigned)avgs) >> 1) + 1 + l2((unsigned)G.nb_rx >> 2);
       d_out[8] = l < 0 ? 0 : l;
       *d_count = 0;
     }
@@ -159,6 +260,8 @@ static int nb_re_symbol(const nrb200_pusch_rx_t &d, int symbol)
 static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_llr)
 {
   const int Qm = d.qam_mod_order;
+  const int nl = d.nrOfLayers == 0 ? 1 : (int)d.nrOfLayers;
+  if (nl > 2 || (nl == 2 && (Qm < 6 || (d.nb_rx != 2 && d.nb_rx != 4)))) return -4;   // 2 layers: MMSE receiver only, like the reference for Qm >= 6
   if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
       d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || (d.log2_maxh > 31 && d.log2_maxh != 0xFFFFFFFFu))
     return -4;
@@ -167,6 +270,15 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
   G->shift = d.log2_maxh; G->shift_from_dev = 0;
   G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
   G->unscramble = d.unscramble; G->c_init = (d.rnti << 15) + d.data_scrambling_id;
+  G->nl = nl; G->nvar = d.noise_var;
+  {
+    // nr_ulsch_scale_channel: shift_ch_ext = log2_approx(max_ch >> 11) for 2 layers, 0 for one
+    int sce = 0;
+    if (nl > 1) { const unsigned v = d.max_ch >> 11; sce = v ? 32 - __builtin_clz(v) : 0; }
+    int b = 3, amp = 8192;
+    if (sce > 3) { b = 0; amp = (short)(amp >> (sce - 3)); if (amp == 0) amp = 1; } else b -= sce;
+    G->lvl_amp = amp; G->lvl_b = b;
+  }
   int first_dmrs = -1;
   for (uint32_t s = d.start_symbol_index; s < d.start_symbol_index + d.nr_of_symbols; s++)
     if ((d.ul_dmrs_symb_pos >> s) & 1) { first_dmrs = s; break; }
@@ -184,7 +296,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
     }
     off += (unsigned)v * Qm;
   }
-  if (total_llr) *total_llr = off;
+  if (total_llr) *total_llr = off * (unsigned)nl;
   return G->n_sym > 0 ? 0 : -4;
 }
 
@@ -201,7 +313,7 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
   int rc = make_geom(d, &G, nullptr);
   if (rc) return rc;
   const int len = (G.valid[0] + 15) & ~15;                      // first symbol with data (:1601-1611)
-  pusch_level_kernel<<<G.nb_rx, 256, 0, st>>>(G, 0, len, (const unsigned *)ch, d_out9, d_count);
+  pusch_level_kernel<<<G.nb_rx * G.nl, 256, 0, st>>>(G, 0, len, (const unsigned *)ch, d_out9, d_count);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "pusch_level launch");
   return 0;
@@ -217,13 +329,18 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
   const GoldTables *T = d.unscramble ? gold_tables_dev() : nullptr;
   int vmax = 0;
   for (int k = 0; k < G.n_sym; k++) vmax = std::max(vmax, G.valid[k]);
-  const dim3 grid((vmax + 255) / 256, G.n_sym);
+  const dim3 grid((((vmax + 3) & ~3) + 255) / 256, G.n_sym);
   const unsigned *R = (const unsigned *)rxF, *C = (const unsigned *)ch;
-  switch (G.Qm) {
-    case 2: pusch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-    case 4: pusch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-    case 6: pusch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-    default: pusch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+  if (G.nl == 2) {
+    if (G.Qm == 6) pusch_rx2_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
+    else pusch_rx2_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
+  } else {
+    switch (G.Qm) {
+      case 2: pusch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 4: pusch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 6: pusch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      default: pusch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    }
   }
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "pusch_rx launch");

@@ -204,6 +204,22 @@ class Oracle:
                                            llr.ctypes.data_as(C.c_void_p), comp.ctypes.data_as(C.c_void_p))
         return llr, comp
 
+    def pusch_log2_maxh_2l(self, P, meas_symbol, ch_symbol, max_ch, rxdataF, ch_est):
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(ch_est, dtype=np.int16)
+        avg = np.zeros(8, np.int32)
+        r = self.lib.orc_pusch_log2_maxh_2l(C.byref(P), meas_symbol, ch_symbol, max_ch, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p))
+        return int(r), avg[:2 * P.nb_rx].copy()
+
+    def pusch_inner_rx_symbol_2l(self, P, symbol, ch_symbol, shift, nvar, rxdataF, ch_est):
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(ch_est, dtype=np.int16)
+        blen = (P.rb_size * 12 + 15) & ~15
+        valid = self.pusch_nb_re(P, symbol)
+        llr = np.zeros((2, valid * P.Qm), np.int16); comp = np.zeros((2, 2 * blen), np.int16)
+        self.lib.orc_pusch_inner_rx_symbol_2l.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.lib.orc_pusch_inner_rx_symbol_2l(C.addressof(P), symbol, ch_symbol, shift, nvar, x.ctypes.data, h.ctypes.data, llr.ctypes.data, comp.ctypes.data)
+        assert rc == valid, rc
+        return llr, comp
+
     # ---- slot-level OFDM front end
     def ofdm_geometry(self, N, mu, slot):
         pre = np.zeros(14, np.uint32); cps = np.zeros(14, np.uint32); ss = C.c_uint32(); fl = C.c_uint32()
@@ -463,23 +479,27 @@ class Reference:
         return np.array([P.fft_size, P.nb_rx, nb_layer, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.Qm, symbol, ch_symbol, P.ul_dmrs_symb_pos,
                          P.num_dmrs_cdm_grps_no_data, P.dmrs_config_type, shift, nvar, valid], dtype=np.int32)
 
-    def pusch_inner_rx_symbol(self, P, symbol, ch_symbol, shift, rxdataF, ch_est, valid):
+    def pusch_inner_rx_symbol(self, P, symbol, ch_symbol, shift, rxdataF, ch_est, valid, nb_layer=1, nvar=0):
         L = self._pusch()
-        prm = self._pusch_params(P, 1, symbol, ch_symbol, shift, 0, valid)
+        prm = self._pusch_params(P, nb_layer, symbol, ch_symbol, shift, nvar, valid)
         x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(ch_est, dtype=np.int16).copy()
         blen = (P.rb_size * 12 + 15) & ~15
-        llr = np.zeros(valid * P.Qm + 64, np.int16); comp = np.zeros(2 * blen, np.int16)
+        llr = np.zeros(nb_layer * valid * P.Qm + 64, np.int16); comp = np.zeros(nb_layer * 2 * blen, np.int16)
         L.refh_pusch_inner_rx(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                               comp.ctypes.data_as(C.c_void_p))
+        if nb_layer == 2:
+            return llr[:2 * valid * P.Qm].reshape(2, -1), comp.reshape(2, -1)
         return llr[:valid * P.Qm], comp
 
-    def pusch_log2_maxh(self, P, meas_symbol, ch_symbol, rxdataF, ch_est):
+    def pusch_log2_maxh(self, P, meas_symbol, ch_symbol, rxdataF, ch_est, nb_layer=1, max_ch=0):
         L = self._pusch()
-        prm = self._pusch_params(P, 1, meas_symbol, ch_symbol, 0, 0, 0)
+        prm = self._pusch_params(P, nb_layer, meas_symbol, ch_symbol, 0, 0, 0)
         x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(ch_est, dtype=np.int16).copy()
         avg = np.zeros(8, np.int32)
-        raw = L.refh_pusch_log2_maxh(prm.ctypes.data_as(C.c_void_p), 0, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p))
+        raw = L.refh_pusch_log2_maxh(prm.ctypes.data_as(C.c_void_p), max_ch, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p))
         # the final rule of nr_rx_pusch_tp for one layer (:1642-1646): + 1 + log2_approx(nb_rx >> 2), floored at 0
+        if nb_layer == 2:                                         # MMSE rule (:1640-1641)
+            return max(0, int(raw) - 3), avg[:2 * P.nb_rx].copy()
         return max(0, int(raw) + 1 + int(P.nb_rx >> 2).bit_length()), avg[:P.nb_rx].copy()
 
     def _ofdm(self):

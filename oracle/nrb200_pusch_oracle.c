@@ -3,6 +3,7 @@
  * get_nb_re_pusch :416-432, nr_ulsch_channel_level :434-466, nr_ulsch_channel_compensation :468-578 (rho == NULL), the log2_maxh rule
  * of nr_rx_pusch_tp :1595-1647 and the per-symbol composition inner_rx :1262-1384 followed by nr_ulsch_compute_llr.
  * Pinned against the compiled reference (oracle/_ref/libref_pusch.so) by tests/test_oracle_vs_reference.py. */
+#include <limits.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -118,4 +119,126 @@ int orc_pusch_inner_rx_symbol(const orc_pusch_t *p, int symbol, int ch_symbol, i
   if (comp_out) memcpy(comp_out, comp, 4 * (size_t)blen);
   free(rx); free(ch); free(comp); free(ma); free(mb); free(mc);
   return valid;
+}
+
+/* ---- two layers, MMSE receiver (Qm >= 6): nr_ulsch_channel_compensation per layer + nr_ulsch_mmse_2layers (:870-1260) with its helpers
+ * nr_ulsch_conjch0_mult_ch1 :651-695, nr_ulsch_construct_HhH_elements :761-868, nr_ulsch_det_HhH :579-644, nr_ulsch_comp_muli_sum :697-759.
+ * ch_est: [2 * nb_rx][14 N] c16, index layer * nb_rx + rx.  llr: [2][valid * Qm].  comp_out (optional): [2][buffer_length] c16 after MMSE.
+ * Returns the number of valid REs, or -1 for configurations the reference itself rejects (nb_rx not 2 or 4). */
+static inline int32_t abs32w(int32_t v) { return v == INT32_MIN ? v : (v < 0 ? -v : v); }
+static int log2a(uint32_t x) { return log2_approx_(x); }
+
+int orc_pusch_inner_rx_symbol_2l(const orc_pusch_t *p, int symbol, int ch_symbol, int shift, uint32_t nvar, const int16_t *rxdataF, const int16_t *ch_est,
+                                 int16_t *llr, int16_t *comp_out)
+{
+  const int N = p->fft_size, blen = (p->rb_size * 12 + 15) & ~15, Qm = p->Qm, nrx = p->nb_rx;
+  if (nrx != 2 && nrx != 4) return -1;
+  const int is_dmrs = (p->ul_dmrs_symb_pos >> symbol) & 1;
+  const int valid = orc_pusch_nb_re(p, symbol);
+  const size_t B = 2 * (size_t)blen;
+  int16_t *rx = calloc(B * nrx, 2), *ch = calloc(B * nrx * 2, 2), *comp = calloc(B * 2, 2), *mag[3];
+  for (int i = 0; i < 3; i++) mag[i] = calloc(B * 2, 2);
+  for (int a = 0; a < nrx; a++)
+    for (int l = 0; l < 2; l++)
+      orc_pusch_extract(p, is_dmrs, rxdataF + 2 * ((size_t)a * 14 + symbol) * N, ch_est + 2 * ((size_t)(l * nrx + a) * 14 + ch_symbol) * N, rx + B * a,
+                        ch + B * (l * nrx + a));
+  /* matched filter per layer (MRC sum wraps) */
+  for (int l = 0; l < 2; l++)
+    for (int a = 0; a < nrx; a++)
+      for (int i = 0; i < (blen >> 3) * 8; i++) {
+        const int32_t hr = ch[B * (l * nrx + a) + 2 * i], hi = ch[B * (l * nrx + a) + 2 * i + 1], yr = rx[B * a + 2 * i], yi = rx[B * a + 2 * i + 1];
+        const int32_t nhi = wrap16(-hi);
+        comp[B * l + 2 * i] = wrap16(comp[B * l + 2 * i] + sat16(wrap32((int64_t)hr * yr + (int64_t)hi * yi) >> shift));
+        comp[B * l + 2 * i + 1] = wrap16(comp[B * l + 2 * i + 1] + sat16(wrap32((int64_t)nhi * yr + (int64_t)hr * yi) >> shift));
+      }
+  const int ampv[3] = {Qm == 4 ? 20724 : Qm == 6 ? 20225 : Qm == 8 ? 20106 : 0, Qm == 6 ? 10112 : Qm == 8 ? 10053 : 0, Qm == 8 ? 5026 : 0};
+  const int nb_rb_0 = valid / 12 + ((valid % 12) ? 1 : 0);
+  for (int g = 0; g < 3 * nb_rb_0; g++) {
+    int32_t det[4], af[4][4][2];                                        /* af[k][00,01,10,11][re,im] */
+    for (int k = 0; k < 4; k++) {
+      const int i = 4 * g + k;
+      int16_t s[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      for (int a = 0; a < nrx; a++) {
+        const int16_t *h0 = ch + B * (0 * nrx + a) + 2 * i, *h1 = ch + B * (1 * nrx + a) + 2 * i;
+        const int16_t *pair[4][2] = {{h0, h0}, {h0, h1}, {h1, h0}, {h1, h1}};   /* conj(first) * second: 00, 01, 10, 11 */
+        for (int e = 0; e < 4; e++) {
+          const int32_t ar = pair[e][0][0], ai = pair[e][0][1], br = pair[e][1][0], bi = pair[e][1][1];
+          const int32_t nai = wrap16(-ai);
+          const int16_t re = sat16(wrap32((int64_t)ar * br + (int64_t)ai * bi) >> shift), im = sat16(wrap32((int64_t)nai * br + (int64_t)ar * bi) >> shift);
+          if (a == 0) { s[e][0] = re; s[e][1] = im; } else { s[e][0] = sat16((int32_t)s[e][0] + re); s[e][1] = sat16((int32_t)s[e][1] + im); }
+        }
+      }
+      for (int e = 0; e < 4; e++) { af[k][e][0] = s[e][0]; af[k][e][1] = s[e][1]; }
+      if (nvar != 0)                                                     /* add_epi32 on the packed {re, im} word: carries into im */
+        for (int e = 0; e < 4; e += 3) {
+          uint32_t w = ((uint32_t)(uint16_t)af[k][e][0]) | ((uint32_t)(uint16_t)af[k][e][1] << 16);
+          w += nvar;
+          af[k][e][0] = (int16_t)(w & 0xFFFF); af[k][e][1] = (int16_t)(w >> 16);
+        }
+      const int32_t ad = wrap32((int64_t)af[k][0][0] * af[k][3][0] + (int64_t)wrap16(-af[k][0][1]) * af[k][3][1]);
+      const int32_t bc = wrap32((int64_t)af[k][1][0] * af[k][2][0] + (int64_t)wrap16(-af[k][1][1]) * af[k][2][1]);
+      det[k] = abs32w(wrap32((int64_t)ad - bc));
+    }
+    int32_t sum_det = 0;
+    for (int k = 0; k < 4; k++) sum_det = wrap32((int64_t)sum_det + (det[k] >> 2));
+    const int b = log2a((uint32_t)sum_det) - 8;
+    for (int k = 0; k < 4; k++) {
+      const int i = 4 * g + k;
+      const int32_t dm = b > 0 ? det[k] >> b : (int32_t)((uint32_t)det[k] << (-b));
+      const int16_t m = sat16(dm);
+      for (int l = 0; l < 2; l++)
+        for (int t = 0; t < 3; t++) {
+          const int16_t v = wrap16(((m * ampv[t]) >> 16) << 1);
+          mag[t][B * l + 2 * i] = v; mag[t][B * l + 2 * i + 1] = v;
+        }
+      /* x0 = comp0 * d - comp1 * b ; x1 = comp1 * a - comp0 * c */
+      const int32_t c0r = comp[2 * i], c0i = comp[2 * i + 1], c1r = comp[B + 2 * i], c1i = comp[B + 2 * i + 1];
+      const int32_t in[2][4][2] = {{{c0r, c0i}, {af[k][3][0], af[k][3][1]}, {c1r, c1i}, {af[k][1][0], af[k][1][1]}},
+                                   {{c1r, c1i}, {af[k][0][0], af[k][0][1]}, {c0r, c0i}, {af[k][2][0], af[k][2][1]}}};
+      for (int l = 0; l < 2; l++) {
+        const int32_t xr = in[l][0][0], xi = in[l][0][1], yr = in[l][1][0], yi = in[l][1][1], wr = in[l][2][0], wi = in[l][2][1], zr = in[l][3][0], zi = in[l][3][1];
+        int32_t re = wrap32((int64_t)wrap32((int64_t)xr * yr + (int64_t)wrap16(-xi) * yi) - wrap32((int64_t)wr * zr + (int64_t)wrap16(-wi) * zi));
+        int32_t im = wrap32((int64_t)wrap32((int64_t)xi * yr + (int64_t)xr * yi) - wrap32((int64_t)wi * zr + (int64_t)wr * zi));
+        if (b > 0) { re >>= b; im >>= b; } else { re = (int32_t)((uint32_t)re << (-b)); im = (int32_t)((uint32_t)im << (-b)); }
+        comp[B * l + 2 * i] = sat16(re); comp[B * l + 2 * i + 1] = sat16(im);
+      }
+    }
+  }
+  for (int l = 0; l < 2; l++) orc_ulsch_llr(Qm, comp + B * l, mag[0] + B * l, mag[1] + B * l, mag[2] + B * l, llr + (size_t)l * valid * Qm, (uint32_t)valid);
+  if (comp_out) memcpy(comp_out, comp, B * 2 * 2);
+  free(rx); free(ch); free(comp);
+  for (int i = 0; i < 3; i++) free(mag[i]);
+  return valid;
+}
+
+/* log2_maxh for two layers with the MMSE receiver (Qm >= 6): the estimates of both layers are scaled by shift_ch_ext = log2_approx(max_ch >> 11)
+ * (nr_ulsch_scale_channel :382-414) before the level, the rule is (log2_approx(max avg) >> 1) - 3, floored at 0 (:1640-1647).
+ * ch_est [2 * nb_rx][14 N]; avg_out (optional) 2 * nb_rx values, index layer * nb_rx + rx. */
+int orc_pusch_log2_maxh_2l(const orc_pusch_t *p, int meas_symbol, int ch_symbol, int max_ch, const int16_t *rxdataF, const int16_t *ch_est, int32_t *avg_out)
+{
+  const int N = p->fft_size, nrx = p->nb_rx;
+  const int len = (orc_pusch_nb_re(p, meas_symbol) + 15) & ~15, cap = (p->rb_size * 12 + 15) & ~15;
+  const int shift_ch_ext = log2_approx_((uint32_t)(max_ch >> 11));
+  int b = 3, amp = 8192;
+  if (shift_ch_ext > 3) { b = 0; amp = (int16_t)(amp >> (shift_ch_ext - 3)); if (amp == 0) amp = 1; } else b -= shift_ch_ext;
+  int16_t *rx = calloc(2 * (size_t)cap, 2), *ch = calloc(2 * (size_t)cap, 2);
+  const int x = factor2_(len), y = len >> x;
+  int avgs = 0;
+  for (int l = 0; l < 2; l++)
+    for (int a = 0; a < nrx; a++) {
+      memset(rx, 0, 4 * (size_t)cap); memset(ch, 0, 4 * (size_t)cap);
+      orc_pusch_extract(p, (p->ul_dmrs_symb_pos >> meas_symbol) & 1, rxdataF + 2 * ((size_t)a * 14 + meas_symbol) * N,
+                        ch_est + 2 * ((size_t)(l * nrx + a) * 14 + ch_symbol) * N, rx, ch);
+      int32_t lane[4] = {0, 0, 0, 0};
+      for (int i = 0; i < (len >> 2) * 4; i++) {
+        const int16_t r = wrap16((((int32_t)ch[2 * i] * amp) >> 16) << b), im = wrap16((((int32_t)ch[2 * i + 1] * amp) >> 16) << b);
+        lane[i & 3] = wrap32((int64_t)lane[i & 3] + (wrap32((int64_t)r * r + (int64_t)im * im) >> x));
+      }
+      const int32_t avg = wrap32((int64_t)lane[0] + lane[1] + lane[2] + lane[3]) / y;
+      if (avg_out) avg_out[l * nrx + a] = avg;
+      if (avg > avgs) avgs = avg;
+    }
+  free(rx); free(ch);
+  const int l2 = (log2_approx_((uint32_t)avgs) >> 1) - 3;
+  return l2 < 0 ? 0 : l2;
 }

@@ -47,8 +47,8 @@ def test_offload_encoder_decoder_vs_oracle(ldpc, oracle):
         # ---- decoder: first transmission (rv 0, new data), then a retransmission (rv 2) combined with the stored soft buffer
         w = np.zeros((kc - 2) * Z, np.int16)
         for rnd, rv in enumerate((0, 2)):
-            noise = rng.normal(0, 14.0, size=E)
-            llr = np.clip(np.round((1 - 2 * tx[rv].astype(np.float64)) * 10 + noise), -128, 127).astype(np.int8)
+            noise = rng.normal(0, 6.0, size=E)
+            llr = np.clip(np.round((1 - 2 * tx[rv].astype(np.float64)) * 24 + noise), -128, 127).astype(np.int8)
             R = oracle.get_R(rv, E, BG, Z, 0, 0)[0]
             e16 = oracle.deinterleave(E, Qm, llr.astype(np.int16))
             assert oracle.rate_matching_rx(0, BG, Z, w, e16, 1, rv, 1 if rnd == 0 else 0, E, F, K - F - 2 * Z) == 0

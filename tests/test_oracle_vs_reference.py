@@ -326,3 +326,26 @@ def test_pusch_channel_estimation(oracle, reference):
         est_o, out_o = oracle.pusch_channel_estimation(P, rx)
         assert np.array_equal(out_o, out_r), (N, nb_rx, slot, symbol, port, out_o, out_r)
         assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
+
+
+def test_pusch_inner_rx_two_layers_mmse(oracle, reference):
+    """nb_layer == 2, Qm >= 6: matched filter per layer + nr_ulsch_mmse_2layers + per-layer LLRs, through the reference's inner_rx."""
+    from oracle.bindings import PuschParms
+    rng = np.random.default_rng(41)
+    for N, nb_rx, rb_start, rb_size, Qm, carrier, nvar in ((4096, 4, 0, 273, 6, 273, 40), (2048, 2, 10, 50, 8, 106, 7), (1024, 4, 20, 32, 6, 52, 0), (2048, 2, 30, 76, 8, 106, 1000),
+                                                           (1024, 2, 0, 52, 6, 52, 90000)):
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, 1 << 2, 0, 2)
+        rx = rng.integers(-2000, 2001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-1500, 1501, size=(2 * nb_rx, 14, N, 2)).astype(np.int16)
+        for max_ch in (0, 1500, 30000, 200000):
+            sh_o, avg_o = oracle.pusch_log2_maxh_2l(P, 0, 2, max_ch, rx, h)
+            sh_r, avg_r = reference.pusch_log2_maxh(P, 0, 2, rx, h, nb_layer=2, max_ch=max_ch)
+            assert np.array_equal(avg_o, avg_r) and sh_o == sh_r, (N, nb_rx, max_ch, avg_o, avg_r, sh_o, sh_r)
+        for symbol, shift in ((3, 8), (13, 6), (0, 11)):
+            valid = oracle.pusch_nb_re(P, symbol)
+            if nvar == 0:
+                nvar = 1                     # the reference AssertFatal()s on a zero determinant (zero-padded REs) unless noise is added
+            llr_o, comp_o = oracle.pusch_inner_rx_symbol_2l(P, symbol, 2, shift, nvar, rx, h)
+            llr_r, comp_r = reference.pusch_inner_rx_symbol(P, symbol, 2, shift, rx, h, valid, nb_layer=2, nvar=nvar)
+            assert np.array_equal(comp_o, comp_r), (N, nb_rx, Qm, symbol, shift, nvar, "comp")
+            assert np.array_equal(llr_o, llr_r), (N, nb_rx, Qm, symbol, shift, nvar, "llr")
