@@ -529,14 +529,14 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   if (ensure_init() || !d) return -1;
   const uint32_t n_llr = pusch_num_llr(*d);
   if (n_llr == 0) return -4;
-  const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4;
+  const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers == 2 ? 2 : 1);
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(2 * plane, (size_t)n_llr * 2 + 64, 64)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     std::memcpy(w->h_in, rxdataF, plane);
-    std::memcpy((uint8_t *)w->h_in + plane, ul_ch_estimates, plane);
-    if (cudaMemcpyAsync(w->d_in, w->h_in, 2 * plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy((uint8_t *)w->h_in + plane, ul_ch_estimates, est_plane);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, plane + est_plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
     nrb200_pusch_rx_t e = *d;
     e.rx_stride = e.ch_stride = 14 * d->fft_size;
     const int16_t *d_rx = (const int16_t *)w->d_in, *d_ch = (const int16_t *)((uint8_t *)w->d_in + plane);

@@ -336,7 +336,8 @@ class LdpcLib:
         return int(self.lib.nrb200_pusch_num_llr(C.addressof(desc)))
 
     def pusch_inner_rx_host(self, desc, rxdataF, ul_ch_estimates):
-        """rxdataF, ul_ch_estimates: [nb_rx][14][N][2] int16.  desc.log2_maxh == 0xFFFFFFFF: measure it like nr_rx_pusch_tp does.
+        """rxdataF: [nb_rx][14][N][2] int16; ul_ch_estimates: [nb_rx * layers][14][N][2] (index layer * nb_rx + rx).
+        desc.log2_maxh == 0xFFFFFFFF: measure it like nr_rx_pusch_tp does.
         Returns (llr int16[G], log2_maxh)."""
         x = np.ascontiguousarray(rxdataF, dtype=np.int16)
         h = np.ascontiguousarray(ul_ch_estimates, dtype=np.int16)

@@ -56,3 +56,38 @@ def test_pusch_inner_rx_vs_oracle(ldpc, oracle):
         d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 3, 0, 0, 0, 0, 0)
         llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
         assert sh == 3 and np.array_equal(llr, _oracle_slot(oracle, P, start, nsym, rx, h, 3))
+
+
+def test_pusch_inner_rx_two_layers_vs_oracle(ldpc, oracle):
+    """nrOfLayers = 2, Qm >= 6: matched filter per layer + MMSE + per-layer LLRs + layer de-mapping + descrambling in one launch."""
+    rng = np.random.default_rng(51)
+    for N, nb_rx, rb_start, rb_size, Qm, carrier, nvar, max_ch, dpos, cdm in ((4096, 4, 0, 273, 6, 273, 40, 1400, 1 << 2, 2), (2048, 2, 10, 50, 8, 106, 7, 30000, 1 << 2, 2),
+                                                                             (1024, 4, 20, 32, 6, 52, 1, 0, 1 << 3, 2), (2048, 2, 30, 75, 8, 106, 1000, 9000, 1 << 2, 1),
+                                                                             (4096, 4, 3, 11, 6, 273, 90000, 200000, (1 << 2) | (1 << 11), 2)):
+        fco = N - carrier * 6
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, 0, cdm)
+        rx = rng.integers(-2000, 2001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-1500, 1501, size=(2 * nb_rx, 14, N, 2)).astype(np.int16)
+        dms = [s for s in range(14) if (dpos >> s) & 1]
+        meas = [s for s in range(14) if oracle.pusch_nb_re(P, s) > 0][0]
+        sh_o, _ = oracle.pusch_log2_maxh_2l(P, meas, dms[0], max_ch, rx, h)
+        for shift in (0xFFFFFFFF, 7):
+            for unscr in (None, (0x4321, 99)):
+                d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, 0, 14, dpos, 0, cdm, shift, 0, 0, 0 if unscr is None else 1,
+                                0 if unscr is None else unscr[0], 0 if unscr is None else unscr[1], 2, nvar, max_ch)
+                llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+                use = sh_o if shift == 0xFFFFFFFF else 7
+                assert sh == use, (N, nb_rx, Qm, sh, use)
+                cur, out = dms[0], []
+                for s in range(14):
+                    if (dpos >> s) & 1:
+                        cur = s
+                    v = oracle.pusch_nb_re(P, s)
+                    if v == 0:
+                        continue
+                    l2, _ = oracle.pusch_inner_rx_symbol_2l(P, s, cur, use, nvar, rx, h)
+                    out.append(np.stack([l2[0].reshape(v, Qm), l2[1].reshape(v, Qm)], axis=1).reshape(-1))       # layer de-mapping (:1422-1428)
+                ref = np.concatenate(out)
+                if unscr is not None:
+                    ref = oracle.unscramble_llr(ref, 0, unscr[1], unscr[0])
+                assert llr.size == ref.size and np.array_equal(llr, ref), (N, nb_rx, rb_size, Qm, shift, unscr)
