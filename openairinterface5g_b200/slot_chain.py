@@ -16,29 +16,31 @@ from .ofdm import NrOfdmParms
 
 class PuschSlotChain:
     def __init__(self, lib, dl, device, A=235624, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_rx=4, Qm=6, slot=1, rnti=0x1234, nid=77,
-                 ul_freq=3609200000.0, max_iter=8, dmrs_id=55):
+                 ul_freq=3609200000.0, max_iter=8, dmrs_id=55, n_layers=1):
         self.lib, self.dl, self.dev = lib, dl, device
         self.P = NrOfdmParms(N, mu, carrier_rb)
         self.N, self.nb_rx, self.Qm, self.slot, self.rnti, self.nid, self.max_iter = N, nb_rx, Qm, slot, rnti, nid, max_iter
-        self.rb_start, self.rb_size, self.A = rb_start, rb_size, A
+        self.rb_start, self.rb_size, self.A, self.nl = rb_start, rb_size, A, n_layers
+        assert n_layers in (1, 2)
         self.dmrs_pos, self.dmrs_type, self.cdm = 1 << 2, 0, 2                     # one type-1 DMRS symbol, no data on it
         self.seg = T.nr_segmentation(A + 24, 1)
         assert (A + 24 + self.seg["C"] * self.seg["L"]) % (8 * self.seg["C"]) == 0, "pick A like a real TBS: whole bytes per segment"
         self.C, self.K, self.Z, self.F = self.seg["C"], self.seg["K"], self.seg["Z"], self.seg["F"]
-        self.G = T.nr_get_G(rb_size, 14, 12, 1, 0, Qm, 1)
-        E = [T.nr_get_E(self.G, self.C, Qm, 1, r) for r in range(self.C)]
+        self.G = T.nr_get_G(rb_size, 14, 12, 1, 0, Qm, n_layers)
+        E = [T.nr_get_E(self.G, self.C, Qm, n_layers, r) for r in range(self.C)]
         self.R = T.nr_get_R_ldpc_decoder(0, E[0], 1, self.Z)[0]
         self.E = torch.tensor(E, dtype=torch.int32, device=device)
         self.Eoff = torch.tensor(np.concatenate([[0], np.cumsum(E)[:-1]]), dtype=torch.int32, device=device)
         self.rot = self.P.symbol_rotation(ul_freq)
         self.ts = torch.from_numpy(self.P.timeshift_rotation()).to(device)
         self.desc = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, self.P.first_carrier_offset, Qm, 0, 14, self.dmrs_pos, self.dmrs_type, self.cdm,
-                                0, 14 * N, 14 * N, 1, rnti, nid)
+                                0, 14 * N, 14 * N, 1, rnti, nid, n_layers, 0, 0)
         assert lib.pusch_num_llr(self.desc) == self.G
-        self.cdesc = PuschChestDesc(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N)
-        self.est = torch.zeros((nb_rx, 14 * N, 2), dtype=torch.int16, device=device)
+        self.cdescs = [PuschChestDesc(N, nb_rx, slot, 2, p, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N) for p in range(n_layers)]
+        self.cdesc = self.cdescs[0]
+        self.est = torch.zeros((n_layers * nb_rx, 14 * N, 2), dtype=torch.int16, device=device)   # ul_ch_estimates[p * nb_rx + aarx]
         self.chest_scratch = torch.empty(lib.pusch_chest_scratch_bytes(self.cdesc), dtype=torch.uint8, device=device)
-        self.chest_state = torch.zeros(18, dtype=torch.int32, device=device)
+        self.chest_state = torch.zeros((n_layers, 18), dtype=torch.int32, device=device)
         # receive-side buffers (allocated once, like the reference's per-UE pusch_vars)
         self.rxF = torch.empty((nb_rx, 14 * N, 2), dtype=torch.int16, device=device)
         self.level = torch.zeros(9, dtype=torch.int32, device=device)
@@ -73,34 +75,40 @@ class PuschSlotChain:
         sym = torch.empty((self.G // self.Qm, 2), dtype=torch.int16, device=dev)
         lib.modulate_torch(words, self.G, self.Qm, sym)
         x = (sym.to(torch.int32) * tx_amp) >> 15                                           # the amp scaling of the TX resource mapper
+        nl = self.nl
+        xl = x.reshape(-1, nl, 2)                                                          # layer mapping: x^(l)(i) = d(nl * i + l)
         g = torch.Generator(device=dev); g.manual_seed(seed)
-        ph = torch.rand(self.nb_rx, generator=g, device=dev) * 6.2831853
-        h = torch.stack([torch.cos(ph), torch.sin(ph)], dim=1) * h_amp                     # flat channel per rx antenna
-        hi = torch.round(h).to(torch.int32)
+        # flat nb_rx x nl channel: random phases, layer 1 orthogonal-ish to layer 0 across antenna pairs
+        ph = torch.rand((self.nb_rx, nl), generator=g, device=dev) * 6.2831853
+        if nl == 2:
+            ph[:, 1] = ph[:, 0] + 3.14159265 * (torch.arange(self.nb_rx, device=dev) % 2) + 0.3 * torch.arange(self.nb_rx, device=dev)
+        hi = torch.round(torch.stack([torch.cos(ph), torch.sin(ph)], dim=2) * h_amp).to(torch.int32)      # [rx][layer][re/im]
         # Genie estimate in the reference's convention: rxdataF = h_est * x_unit with x_unit the unit-energy constellation (the estimator
         # divides by unit-amplitude pilots, so the transmit amplitude is part of h_est).  Here rxdataF = hi * x / 1024 and
         # x = x_unit * 23170 * tx_amp / 32768.
         unit = 23170.0 * tx_amp / 32768.0
         he = torch.round(hi.to(torch.float32) * (unit / 1024.0)).to(torch.int16)
-        est = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.int16, device=dev)
+        est = torch.zeros((nl * self.nb_rx, 14 * N, 2), dtype=torch.int16, device=dev)
         dm = 2
-        est[:, dm * N:dm * N + 12 * self.rb_size, 0] = he[:, 0:1]
-        est[:, dm * N:dm * N + 12 * self.rb_size, 1] = he[:, 1:2]
+        for l in range(nl):
+            est[l * self.nb_rx:(l + 1) * self.nb_rx, dm * N:dm * N + 12 * self.rb_size, :] = he[:, l, None, :]
         sigma = unit * (h_amp / 1024.0) * 10.0 ** (-snr_db / 20.0) * 0.70711
         grid = torch.zeros((self.nb_rx, 14 * N, 2), dtype=torch.float32, device=dev)
-        # DMRS (type 1, port 0: every second sub-carrier of symbol 2) = conj of the receiver's pilot table at the data's unit amplitude
-        pil = torch.from_numpy(lib.pusch_dmrs_pilots(self.cdesc).reshape(-1, 2).astype(np.float32)).to(dev) * (unit / 32767.0)
+        # DMRS (type 1, ports 0..nl-1 on every second sub-carrier of symbol 2, CDM-separated by the w_f cover) = conj of the receiver's pilot
+        # tables at the data's unit amplitude
+        pils = [torch.from_numpy(lib.pusch_dmrs_pilots(cd).reshape(-1, 2).astype(np.float32)).to(dev) * (unit / 32767.0) for cd in self.cdescs]
         k0 = (self.P.first_carrier_offset + self.rb_start * 12) % N
         dm_index = torch.tensor(2 * N + (k0 + 2 * np.arange(6 * self.rb_size)) % N, dtype=torch.int64, device=dev)
         hf = hi.to(torch.float32) / 1024.0
+        xf = xl.to(torch.float32)
         for a in range(self.nb_rx):
-            yr = (hi[a, 0] * x[:, 0] - hi[a, 1] * x[:, 1]).to(torch.float32) / 1024.0
-            yi = (hi[a, 0] * x[:, 1] + hi[a, 1] * x[:, 0]).to(torch.float32) / 1024.0
-            y = torch.stack([yr, yi], dim=1) + sigma * torch.randn((x.shape[0], 2), generator=g, device=dev)
+            yr = sum(hf[a, l, 0] * xf[:, l, 0] - hf[a, l, 1] * xf[:, l, 1] for l in range(nl))
+            yi = sum(hf[a, l, 0] * xf[:, l, 1] + hf[a, l, 1] * xf[:, l, 0] for l in range(nl))
+            y = torch.stack([yr, yi], dim=1) + sigma * torch.randn((xf.shape[0], 2), generator=g, device=dev)
             grid[a].index_copy_(0, self.re_index, y)
-            dr = hf[a, 0] * pil[:, 0] + hf[a, 1] * pil[:, 1]                               # h * conj(pil)
-            di = hf[a, 1] * pil[:, 0] - hf[a, 0] * pil[:, 1]
-            grid[a].index_copy_(0, dm_index, torch.stack([dr, di], dim=1) + sigma * torch.randn((pil.shape[0], 2), generator=g, device=dev))
+            dr = sum(hf[a, l, 0] * pils[l][:, 0] + hf[a, l, 1] * pils[l][:, 1] for l in range(nl))       # sum_l h_l * conj(pil_l)
+            di = sum(hf[a, l, 1] * pils[l][:, 0] - hf[a, l, 0] * pils[l][:, 1] for l in range(nl))
+            grid[a].index_copy_(0, dm_index, torch.stack([dr, di], dim=1) + sigma * torch.randn((pils[0].shape[0], 2), generator=g, device=dev))
         gridF = torch.clamp(torch.round(grid), -32768, 32767).to(torch.int16).contiguous()
         # to the time domain with the library's own modulator (phase pre-compensation on, as a UE would transmit)
         dtx = self.P.desc(self.slot, self.nb_rx, self.rot)
@@ -118,7 +126,14 @@ class PuschSlotChain:
         lib, dl = self.lib, self.dl
         dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)
         if est is None:
-            est = lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)
+            for p, cd in enumerate(self.cdescs):                                       # one estimator call per DMRS port (:1473-1486)
+                lib.pusch_chest_torch(cd, self.rxF, self.est[p * self.nb_rx:], self.chest_scratch, self.chest_state[p])
+            est = self.est
+            if self.nl == 2:
+                # the MMSE receiver needs two scalars of the estimator on the host side of the ABI: max_ch and nvar (:1470-1512)
+                st = self.chest_state[:, :2].cpu().numpy()
+                self.desc.max_ch = int(st[:, 0].max())
+                self.desc.noise_var = int(int(st[:, 1].astype(np.int64).sum()) // (14 * self.nl * self.nb_rx))
         lib.pusch_inner_rx_torch(self.desc, self.rxF, est, self.llr16, level=self.level)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
         lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
