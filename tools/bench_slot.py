@@ -32,12 +32,17 @@ def timed(fn, n, warm=5):
 def main():
     dev = torch.device("cuda", 0)
     lib, dl = load_LDPClib(), load_dftslib()
-    ch = PuschSlotChain(lib, dl, dev)
+    for nl in (1, 2):
+        run(lib, dl, dev, nl)
+
+
+def run(lib, dl, dev, nl):
+    ch = PuschSlotChain(lib, dl, dev) if nl == 1 else PuschSlotChain(lib, dl, dev, A=471272, n_layers=2)
     payload, rxdata, est = ch.synthesize(seed=3, snr_db=30.0)
     tb, iters, crc = ch.receive(rxdata)
     torch.cuda.synchronize()
     ok = bool((iters <= ch.max_iter).all()) and int(crc[0]) == 0 and bool((tb.view(-1)[:payload.size].cpu() == torch.from_numpy(payload)).all())
-    base = {"workload": "PUSCH slot rx 100MHz 273PRB 64QAM 4rx 1 layer, 28 CB K=8448 (TB 235624 bit)", "decoded_ok": ok,
+    base = {"workload": f"PUSCH slot rx 100MHz 273PRB 64QAM 4rx {nl} layer(s), {ch.C} CB K=8448 (TB {ch.A} bit)", "decoded_ok": ok,
             "mean_iterations": float(iters.float().mean())}
     l0 = lib.launch_count() + dl.launch_count()
     ms = timed(lambda: ch.receive(rxdata), 200)
@@ -47,7 +52,7 @@ def main():
     # per-stage times (each stage alone, back to back 200x)
     st = {
         "ofdm_demod": lambda: dl.ofdm_demod_slot_torch(ch.drx, rxdata, ch.ts, ch.rxF),
-        "channel_estimation": lambda: lib.pusch_chest_torch(ch.cdesc, ch.rxF, ch.est, ch.chest_scratch, ch.chest_state),
+        "channel_estimation": lambda: [lib.pusch_chest_torch(cd, ch.rxF, ch.est[p * ch.nb_rx:], ch.chest_scratch, ch.chest_state[p]) for p, cd in enumerate(ch.cdescs)],
         "level+inner_rx": lambda: lib.pusch_inner_rx_torch(ch.desc, ch.rxF, ch.est, ch.llr16, level=ch.level),
         "rm_rx": lambda: lib.rm_rx_torch(1, ch.Z, ch.Qm, 0, ch.C, 0, ch.F, ch.llr16, ch.E, ch.Eoff, ch.harq, ch.llr8, clear=1),
         "ldpc_decode": lambda: lib.decode_batch_torch(1, ch.Z, ch.R, ch.max_iter, ch.llr8, use_crc=1, crc_len_bits=ch.K - ch.F, crc_type=1, out=ch.hard, iters=ch.iters),

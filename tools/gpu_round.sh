@@ -18,7 +18,7 @@ if [ "$MODE" = "full" ]; then
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== bench point B (Eb/N0 3 dB, early stop)"; timeout 300 python bench.py --steps 50 --warmup 5 --ebn0 3.0 --no-cpu 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_pointB.json
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_reference.json
-echo "== slot chain"; timeout 200 python tools/bench_slot.py 2>&1 | tail -6 | tee gpurun_out/slot_${TAG}.jsonl
+echo "== slot chain"; timeout 200 python tools/bench_slot.py 2>&1 | tail -10 | tee gpurun_out/slot_${TAG}.jsonl
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
   python bench.py --steps 5 --warmup 3 --no-cpu --no-check --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
