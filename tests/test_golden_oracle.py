@@ -121,3 +121,38 @@ def test_transport_arithmetic_mirror(oracle):
                     assert T.nr_get_R_ldpc_decoder(rv, E, BG, Z) == (r, ll.value), (BG, Z, rv, E)
     G = T.nr_get_G(273, 14, 12, 1, 0, 6, 1)
     assert G == 255528 and sum(T.nr_get_E(G, 28, 6, 1, r) for r in range(28)) == G
+
+
+def test_phy_golden(oracle):
+    """Oracle restatements against tests/golden/phy.npz (outputs of the compiled reference, tools/gen_golden_phy.py): scrambling, mapper, slot-level OFDM,
+    channel estimation, one- and two-layer PUSCH receivers.  This is what pins the oracle on a machine without /root/reference."""
+    from oracle.bindings import ChestParms, PuschParms
+    g = _load("phy.npz")
+    q, nid, rnti = [int(x) for x in g["scr_par"]]
+    sc = oracle.scramble(g["scr_bits"], q, nid, rnti)
+    assert np.array_equal(sc, g["scr_out"])
+    for Qm in (2, 4, 6, 8):
+        assert np.array_equal(oracle.modulate(sc, (3001 // Qm) * Qm, Qm), g[f"mod{Qm}"])
+    assert np.array_equal(oracle.unscramble_llr(g["unscr_in"], q, nid, rnti), g["unscr_out"])
+    N, mu, nb_rb, slot, div, ta = [int(x) for x in g["ofdm_par"]]
+    assert np.array_equal(oracle.symbol_rotation(mu, 3619200000.0), g["ofdm_rot_dl"]) and np.array_equal(oracle.symbol_rotation(mu, 3609200000.0), g["ofdm_rot_ul"])
+    assert np.array_equal(oracle.timeshift_rotation(N, (N // 128 * 9) // div), g["ofdm_timeshift"])
+    y, Frot = oracle.ofdm_tx_slot(N, mu, nb_rb, slot, 14, g["ofdm_rot_dl"], g["ofdm_txF"])
+    assert np.array_equal(y, g["ofdm_tx_out"]) and np.array_equal(Frot.reshape(-1), g["ofdm_tx_rotated"].reshape(-1))
+    assert np.array_equal(oracle.ofdm_rx_slot(N, mu, nb_rb, slot, div, ta, g["ofdm_rot_ul"], g["ofdm_rx_in"]), g["ofdm_rx_out"])
+    P = ChestParms(*[int(x) for x in g["chest_par"]])
+    assert np.array_equal(oracle.pusch_dmrs_pilots(P), g["chest_pilots"])
+    est, st = oracle.pusch_channel_estimation(P, g["chest_rx"])
+    assert np.array_equal(st, g["chest_state"]) and np.array_equal(est[:, P.symbol], g["chest_est"])
+    PP = PuschParms(*[int(x) for x in g["rx1_par"]])
+    sh, avg = oracle.pusch_log2_maxh(PP, 2, 2, g["rx1_rx"], g["rx1_h"])
+    assert sh == int(g["rx1_shift"][0]) and np.array_equal(avg, g["rx1_avg"])
+    for s in (2, 5):
+        l, c = oracle.pusch_inner_rx_symbol(PP, s, 2, sh, g["rx1_rx"], g["rx1_h"])
+        assert np.array_equal(l, g[f"rx1_llr{s}"]) and np.array_equal(c, g[f"rx1_comp{s}"])
+    par2 = [int(x) for x in g["rx2_par"]]
+    PP2 = PuschParms(*par2[:10])
+    l, c = oracle.pusch_inner_rx_symbol_2l(PP2, 4, 2, par2[11], par2[10], g["rx1_rx"], g["rx2_h"])
+    assert np.array_equal(l, g["rx2_llr"]) and np.array_equal(c, g["rx2_comp"])
+    sh2, avg2 = oracle.pusch_log2_maxh_2l(PP2, 0, 2, par2[12], g["rx1_rx"], g["rx2_h"])
+    assert sh2 == int(g["rx2_shift"][0]) and np.array_equal(avg2, g["rx2_avg"])
