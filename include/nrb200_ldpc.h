@@ -264,11 +264,13 @@ typedef struct nrb200_pusch_chest_s {
   uint32_t rb_start, bwp_start, rb_size, first_carrier_offset;
   uint32_t scid, ul_dmrs_scrambling_id;
   uint32_t rx_stride, ch_stride;            /* _dev: c16 between antennas */
+  uint32_t n_ports;                         /* 0 or 1: port `port` only.  2: ports `port` and `port + 1` in the same launches; estimates of port q go to
+                                             * plane (q * nb_rx + rx), state of port q to d_state + 18 q (state5 + 5 q for the host entry point) */
 } nrb200_pusch_chest_t;
 /* the 6 * rb_size conjugated DMRS symbols {re, im} the estimator correlates with (nr_pusch_dmrs_rx output); host arithmetic, no GPU needed */
 int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots);
 uint64_t nrb200_pusch_chest_scratch_bytes(const nrb200_pusch_chest_t *d);
-/* d_scratch: nrb200_pusch_chest_scratch_bytes() bytes; d_state: 18 int32 on the device, [0..5) as described above */
+/* d_scratch: nrb200_pusch_chest_scratch_bytes() bytes; d_state: 18 int32 per port on the device, [0..5) of each as described above */
 int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, const int16_t *d_rxdataF, int16_t *d_ul_ch_estimates, void *d_scratch, int32_t *d_state,
                                void *stream);
 int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5);

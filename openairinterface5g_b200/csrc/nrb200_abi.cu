@@ -573,11 +573,12 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, cons
 NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5)
 {
   if (ensure_init() || !d) return -1;
-  if (d->nb_rx < 1 || d->nb_rx > 8 || d->symbol > 13) return -4;
-  // only the DMRS symbol travels: [nb_rx][N] in, [nb_rx][N] out
+  if (d->nb_rx < 1 || d->nb_rx > 8 || d->symbol > 13 || d->n_ports > 2) return -4;
+  const uint32_t np = d->n_ports == 0 ? 1 : d->n_ports;
+  // only the DMRS symbol travels: [nb_rx][N] in, [n_ports * nb_rx][N] out
   const size_t sym = (size_t)d->fft_size * 4, plane = sym * d->nb_rx, scratch = pusch_chest_scratch_bytes(*d);
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(plane, plane, scratch + 128)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(plane, plane * np, scratch + 256)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     for (uint32_t a = 0; a < d->nb_rx; a++)
@@ -588,12 +589,13 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, con
     int32_t *d_state = (int32_t *)((uint8_t *)w->d_aux + scratch);
     rc = launch_pusch_chest(e, (const int16_t *)w->d_in, (int16_t *)w->d_out, w->d_aux, d_state, w->stream, 0);
     if (rc != 0) break;
-    if (cudaMemcpyAsync(w->h_out, w->d_out, plane, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
-    if (cudaMemcpyAsync(w->h_aux, d_state, 20, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->h_out, w->d_out, plane * np, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->h_aux, d_state, 18 * 4 * np, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
     if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
-    for (uint32_t a = 0; a < d->nb_rx; a++)
-      std::memcpy((uint8_t *)ul_ch_estimates + ((size_t)a * 14 + d->symbol) * sym, (uint8_t *)w->h_out + sym * a, sym);
-    if (state5) std::memcpy(state5, w->h_aux, 20);
+    for (uint32_t q = 0; q < np; q++)
+      for (uint32_t a = 0; a < d->nb_rx; a++)
+        std::memcpy((uint8_t *)ul_ch_estimates + ((size_t)(q * d->nb_rx + a) * 14 + d->symbol) * sym, (uint8_t *)w->h_out + sym * (q * d->nb_rx + a), sym);
+    if (state5) for (uint32_t q = 0; q < np; q++) std::memcpy(state5 + 5 * q, (int32_t *)w->h_aux + 18 * q, 20);
   } while (0);
   ctx().release(w);
   return rc;

@@ -20,9 +20,11 @@ namespace nrb200 {
 int dft_batch_internal(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);   // dfts_internal.cu
 
 struct ChestGeom {
-  int N, nb_rx, symbol, nb, np, k0, delta, wsign_odd, dmrs_offset;
+  int N, nb_rx, symbol, nb, np, k0, dmrs_offset;
+  int n_ports, delta[2], wsign_odd[2];      // ports handled by one call (DMRS ports p, p+1 share the Gold sequence, differ in delta / w_f)
   unsigned rx_stride, ch_stride, x2;
 };
+constexpr int kChestState = 18;             // int32 per port, see chest_ls_kernel
 
 __device__ __forceinline__ int c_sat16(int v) { return max(-32768, min(32767, v)); }
 __device__ __forceinline__ int c_wrap16(int v) { return (int)(short)v; }
@@ -37,20 +39,21 @@ __device__ __forceinline__ unsigned c_mul8(unsigned a, unsigned b)
   return c_pk(c_wrap16((ar * br - ai * bi) >> 8), c_wrap16((ar * bi + ai * br) >> 8));
 }
 
-// state[0] = max_ch, state[1] = nvar, state[2] = est_delay (last antenna), [3] = delay_max_pos, [4] = delay_max_val, [8 + a] = est_delay seen by antenna a,
-// state[16..17] = 64-bit noise accumulator
+// per port: state[0] = max_ch, [1] = nvar, [2] = est_delay (after the last antenna), [3] = delay_max_pos, [4] = delay_max_val, [5] = CTA completion counter,
+// [6..7] = 64-bit noise accumulator, [8 + a] = est_delay seen by antenna a (diagnostic).  raw (scratch): per (port, antenna) {peak value, peak position}.
 __global__ void __launch_bounds__(256) chest_ls_kernel(ChestGeom G, const GoldTables *__restrict__ T, const unsigned *__restrict__ rxF, unsigned *__restrict__ ls,
                                                        int *__restrict__ state)
 {
   __shared__ uint32_t s_gold[40];
-  const int a = blockIdx.y, n0 = blockIdx.x * 256, n = n0 + threadIdx.x;
+  const int pa = blockIdx.y, port = pa / G.nb_rx, a = pa - port * G.nb_rx, n0 = blockIdx.x * 256, n = n0 + threadIdx.x;
+  state += port * kChestState;
   const unsigned bit0 = 2u * (unsigned)(G.dmrs_offset + 2 * n0);            // first DMRS bit this CTA needs (2 bits per pilot, 2 pilots per thread)
   const unsigned w0 = bit0 >> 5;
   if (n0 < 3 * G.nb) {
     if (threadIdx.x < 34) s_gold[threadIdx.x] = gold_word(T, G.x2, w0 + threadIdx.x);
   }
   __syncthreads();
-  unsigned *dst = ls + (size_t)a * G.N;
+  unsigned *dst = ls + (size_t)pa * G.N;
   if (4 * n >= G.N) return;
   unsigned v = 0;
   if (n < 3 * G.nb) {
@@ -61,10 +64,10 @@ __global__ void __launch_bounds__(256) chest_ls_kernel(ChestGeom G, const GoldTa
       const int i = G.dmrs_offset + 2 * n + kl;                            // pilot index in the sequence
       const unsigned r0 = 2u * (unsigned)i - (w0 << 5);
       const int b0 = (s_gold[r0 >> 5] >> (r0 & 31u)) & 1u, b1 = (s_gold[(r0 + 1) >> 5] >> ((r0 + 1) & 31u)) & 1u;
-      const int w = (i & 1) ? G.wsign_odd : 1;
+      const int w = (i & 1) ? G.wsign_odd[port] : 1;
       // conj of the QPSK symbol (nr_rx_mod_table): re = +A for b0 = 0, im = -A for b1 = 0, negated when w = -1
       const int pr = w * (b0 ? -23170 : 23170), pi = w * (b1 ? 23170 : -23170);
-      int re = G.k0 + (n << 2) + (kl << 1) + G.delta;
+      int re = G.k0 + (n << 2) + (kl << 1) + G.delta[port];
       re %= G.N;
       const unsigned y = __ldg(rx + re);
       cr += (pr * c_lo(y) - pi * c_hi(y)) >> 16;
@@ -77,35 +80,38 @@ __global__ void __launch_bounds__(256) chest_ls_kernel(ChestGeom G, const GoldTa
   reinterpret_cast<uint4 *>(dst)[n] = make_uint4(v, v, v, v);
 }
 
-__global__ void __launch_bounds__(256) chest_peak_kernel(ChestGeom G, const unsigned *__restrict__ tim, int *__restrict__ state)
+// peak of |h(t)|^2 >> 1 of one (port, antenna): {value, first position}.  The reference's running maximum across antennas is applied by the consumers.
+__global__ void __launch_bounds__(256) chest_peak_kernel(ChestGeom G, const unsigned *__restrict__ tim, int *__restrict__ raw)
 {
   __shared__ int s_val[256], s_pos[256];
-  int max_pos = 0, max_val = 0;
-  for (int a = 0; a < G.nb_rx; a++) {
-    const unsigned *t = tim + (size_t)a * G.N;
-    int bv = -1, bp = 0;
-    for (int i = threadIdx.x; i < G.N; i += blockDim.x) {
-      const unsigned w = t[i];
-      const int v = (int)(((unsigned)(c_lo(w) * c_lo(w) + c_hi(w) * c_hi(w))) >> 1);
-      if (v > bv) { bv = v; bp = i; }                                       // ascending i per thread: keeps the first maximum
-    }
-    s_val[threadIdx.x] = bv; s_pos[threadIdx.x] = bp;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if (threadIdx.x < s) {
-        const int ov = s_val[threadIdx.x + s], op = s_pos[threadIdx.x + s];
-        if (ov > s_val[threadIdx.x] || (ov == s_val[threadIdx.x] && op < s_pos[threadIdx.x])) { s_val[threadIdx.x] = ov; s_pos[threadIdx.x] = op; }
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      if (s_val[0] > max_val) { max_val = s_val[0]; max_pos = s_pos[0]; }   // strict: an earlier antenna's peak wins ties
-      if (max_pos > G.N / 2) max_pos -= G.N;
-      state[8 + a] = max_pos;
+  const unsigned *t = tim + (size_t)blockIdx.x * G.N;
+  int bv = -1, bp = 0;
+  for (int i = threadIdx.x; i < G.N; i += blockDim.x) {
+    const unsigned w = t[i];
+    const int v = (int)(((unsigned)(c_lo(w) * c_lo(w) + c_hi(w) * c_hi(w))) >> 1);
+    if (v > bv) { bv = v; bp = i; }                                       // ascending i per thread: keeps the first maximum
+  }
+  s_val[threadIdx.x] = bv; s_pos[threadIdx.x] = bp;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const int ov = s_val[threadIdx.x + s], op = s_pos[threadIdx.x + s];
+      if (ov > s_val[threadIdx.x] || (ov == s_val[threadIdx.x] && op < s_pos[threadIdx.x])) { s_val[threadIdx.x] = ov; s_pos[threadIdx.x] = op; }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { state[2] = max_pos; state[3] = max_pos; state[4] = max_val; }
+  if (threadIdx.x == 0) { raw[2 * blockIdx.x] = s_val[0]; raw[2 * blockIdx.x + 1] = s_pos[0]; }
+}
+
+// nr_est_delay's state after antennas 0..a of one port: delay_t is reset once per call, so the maximum runs ACROSS antennas (strict >: an earlier
+// antenna's peak wins ties) and the wrap to negative delays is applied after every antenna.
+__device__ __forceinline__ void running_delay(const ChestGeom &G, const int *__restrict__ raw_port, int a, int &max_pos, int &max_val)
+{
+  max_pos = 0; max_val = 0;
+  for (int k = 0; k <= a; k++) {
+    if (raw_port[2 * k] > max_val) { max_val = raw_port[2 * k]; max_pos = raw_port[2 * k + 1]; }
+    if (max_pos > G.N / 2) max_pos -= G.N;
+  }
 }
 
 __device__ __forceinline__ int filt_tap(int pc, int np, int t)
@@ -117,12 +123,14 @@ __device__ __forceinline__ int filt_tap(int pc, int np, int t)
 }
 
 __global__ void __launch_bounds__(256) chest_interp_kernel(ChestGeom G, const unsigned *__restrict__ ls, const unsigned *__restrict__ dtab /* [41][N] */,
-                                                           unsigned *__restrict__ est, int *__restrict__ state)
+                                                           const int *__restrict__ raw, unsigned *__restrict__ est, int *__restrict__ state)
 {
-  const int a = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+  const int pa = blockIdx.y, port = pa / G.nb_rx, a = pa - port * G.nb_rx, k = blockIdx.x * 256 + threadIdx.x;
+  state += port * kChestState;
   const int nre = 12 * G.nb, kmax = min(nre + 8, G.N);
-  const unsigned *l = ls + (size_t)a * G.N;
-  const int ed = state[8 + a];
+  const unsigned *l = ls + (size_t)pa * G.N;
+  int ed, mv;
+  running_delay(G, raw + 2 * port * G.nb_rx, a, ed, mv);
   const unsigned *tb = dtab + (size_t)min(max(20 + ed, 0), 40) * G.N, *ti = dtab + (size_t)min(max(20 - ed, 0), 40) * G.N;
   unsigned long long noise = 0;
   if (k < G.N) {
@@ -148,21 +156,27 @@ __global__ void __launch_bounds__(256) chest_interp_kernel(ChestGeom G, const un
         noise = (unsigned)(dr * dr + di * di);
       }
     }
-    est[(size_t)a * G.ch_stride + (size_t)G.symbol * G.N + k] = out;        // the whole symbol is rewritten (memset in the reference)
+    est[(size_t)pa * G.ch_stride + (size_t)G.symbol * G.N + k] = out;        // the whole symbol is rewritten (memset in the reference)
   }
   // block reduction of the noise power
   __shared__ unsigned long long s_n[256];
   s_n[threadIdx.x] = noise;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) s_n[threadIdx.x] += s_n[threadIdx.x + s]; __syncthreads(); }
-  if (threadIdx.x == 0 && s_n[0]) atomicAdd(reinterpret_cast<unsigned long long *>(state + 16), s_n[0]);
-}
-
-__global__ void chest_finish_kernel(ChestGeom G, int *state)
-{
-  const unsigned long long n = *reinterpret_cast<unsigned long long *>(state + 16);
-  const int nest = 12 * G.nb * G.nb_rx;
-  state[1] = (int)(unsigned)(n / (unsigned long long)nest);
+  if (threadIdx.x == 0) {
+    if (s_n[0]) atomicAdd(reinterpret_cast<unsigned long long *>(state + 6), s_n[0]);
+    if (blockIdx.x == 0) state[8 + a] = ed;
+    __threadfence();
+    // the last CTA of this port publishes nvar and the final delay_t
+    if (atomicAdd(reinterpret_cast<unsigned *>(state + 5), 1u) == gridDim.x * (unsigned)G.nb_rx - 1) {
+      __threadfence();
+      const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(state + 6);
+      state[1] = (int)(unsigned)(n / (unsigned long long)(12 * G.nb * G.nb_rx));
+      int fp, fv;
+      running_delay(G, raw + 2 * port * G.nb_rx, G.nb_rx - 1, fp, fv);
+      state[2] = fp; state[3] = fp; state[4] = fv;
+    }
+  }
 }
 
 // fp->delay_table (init_delay_table): round(256 e^{j 2 pi k d / N}) for d = -20..20, built once per N
@@ -192,8 +206,13 @@ static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
   if (d.nb_rx < 1 || d.nb_rx > 8 || d.symbol > 13 || d.port > 3 || d.rb_size < 1 || 12 * d.rb_size > d.fft_size || d.scid > 1 || (d.fft_size & 3)) return -4;
   G->N = d.fft_size; G->nb_rx = d.nb_rx; G->symbol = d.symbol; G->nb = d.rb_size; G->np = 6 * d.rb_size;
   G->k0 = ((d.rb_start + d.bwp_start) * 12 + d.first_carrier_offset) % d.fft_size;
-  G->delta = (d.port >> 1) & 1;                                              // delta1[p]
-  G->wsign_odd = (d.port & 1) ? -1 : 1;                                      // wf1[p][1]
+  G->n_ports = d.n_ports == 0 ? 1 : (int)d.n_ports;
+  if (G->n_ports > 2 || d.port + G->n_ports > 4) return -4;
+  for (int q = 0; q < G->n_ports; q++) {
+    const unsigned pp = d.port + q;
+    G->delta[q] = (pp >> 1) & 1;                                            // delta1[p]
+    G->wsign_odd[q] = (pp & 1) ? -1 : 1;                                    // wf1[p][1]
+  }
   G->dmrs_offset = ((d.bwp_start + d.rb_start) * 12) / 2;
   G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
   const unsigned long long nid = d.ul_dmrs_scrambling_id;
@@ -221,16 +240,16 @@ int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil)
   for (auto &w : g) { step(); w = x1 ^ x2; }
   for (int i = G.dmrs_offset; i < last; i++) {
     const int b0 = (g[(2 * i) >> 5] >> ((2 * i) & 31)) & 1, b1 = (g[(2 * i + 1) >> 5] >> ((2 * i + 1) & 31)) & 1;
-    const int w = (i & 1) ? G.wsign_odd : 1;
+    const int w = (i & 1) ? G.wsign_odd[0] : 1;
     pil[2 * (i - G.dmrs_offset)] = (int16_t)(w * (b0 ? -23170 : 23170));
     pil[2 * (i - G.dmrs_offset) + 1] = (int16_t)(w * (b1 ? 23170 : -23170));
   }
   return 0;
 }
 
-size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d) { return (size_t)2 * d.nb_rx * d.fft_size * 4 + 128; }
+size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d) { return (size_t)2 * 2 * d.nb_rx * d.fft_size * 4 + 256; }   // LS + time planes for up to 2 ports, raw peaks
 
-// d_scratch: pusch_chest_scratch_bytes(); d_state: 18 int32 (see chest_ls_kernel), zeroed here
+// d_scratch: pusch_chest_scratch_bytes(); d_state: 18 int32 per port (see chest_ls_kernel), zeroed here
 // buf_symbol >= 0: the buffers hold the DMRS symbol at that index (the host entry point stages a one-symbol slot); the DMRS sequence always uses d.symbol
 int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol)
 {
@@ -241,15 +260,16 @@ int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_
   if (scramble_mod_init() != 0) return -5;
   const unsigned *dtab = delay_table_dev(G.N);
   if (!dtab) return -5;
-  unsigned *ls = (unsigned *)d_scratch, *tim = ls + (size_t)G.nb_rx * G.N;
-  NRB200_CUDA_OK(cudaMemsetAsync(d_state, 0, 18 * 4, st), "chest memset");
-  chest_ls_kernel<<<dim3((G.N / 4 + 255) / 256, G.nb_rx), 256, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, ls, d_state);
+  const int npa = G.n_ports * G.nb_rx;
+  unsigned *ls = (unsigned *)d_scratch, *tim = ls + (size_t)npa * G.N;
+  int *raw = (int *)(tim + (size_t)npa * G.N);
+  NRB200_CUDA_OK(cudaMemsetAsync(d_state, 0, (size_t)G.n_ports * kChestState * 4, st), "chest memset");
+  chest_ls_kernel<<<dim3((G.N / 4 + 255) / 256, npa), 256, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, ls, d_state);
   NRB200_CUDA_OK(cudaGetLastError(), "chest_ls launch");
-  if ((rc = dft_batch_internal(G.N, 1, G.nb_rx, (const int16_t *)ls, (int16_t *)tim, 1, st)) != 0) return rc;
-  chest_peak_kernel<<<1, 256, 0, st>>>(G, tim, d_state);
-  chest_interp_kernel<<<dim3((G.N + 255) / 256, G.nb_rx), 256, 0, st>>>(G, ls, dtab, (unsigned *)est, d_state);
-  chest_finish_kernel<<<1, 1, 0, st>>>(G, d_state);
-  ctx().launches += 5;
+  if ((rc = dft_batch_internal(G.N, 1, npa, (const int16_t *)ls, (int16_t *)tim, 1, st)) != 0) return rc;
+  chest_peak_kernel<<<npa, 256, 0, st>>>(G, tim, raw);
+  chest_interp_kernel<<<dim3((G.N + 255) / 256, npa), 256, 0, st>>>(G, ls, dtab, raw, (unsigned *)est, d_state);
+  ctx().launches += 4;
   NRB200_CUDA_OK(cudaGetLastError(), "chest launch");
   return 0;
 }

@@ -77,7 +77,7 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
 
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
-                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride")]
+                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports")]
 
 
 class LdpcLib:
@@ -317,8 +317,9 @@ class LdpcLib:
     def pusch_chest_host(self, desc, rxdataF, ul_ch_estimates=None):
         """rxdataF [nb_rx][14][N][2] int16 -> (ul_ch_estimates with symbol desc.symbol rewritten, state int32[5] = max_ch, nvar, est_delay, pos, val)."""
         x = np.ascontiguousarray(rxdataF, dtype=np.int16)
-        est = np.zeros_like(x) if ul_ch_estimates is None else np.ascontiguousarray(ul_ch_estimates, dtype=np.int16)
-        st = np.zeros(5, dtype=np.int32)
+        np_ = max(1, int(desc.n_ports))
+        est = np.zeros((np_ * x.shape[0],) + x.shape[1:], np.int16) if ul_ch_estimates is None else np.ascontiguousarray(ul_ch_estimates, dtype=np.int16)
+        st = np.zeros(5 * np_, dtype=np.int32)
         self._check(self.lib.nrb200_pusch_chest_host(C.addressof(desc), x.ctypes.data, est.ctypes.data, st.ctypes.data), "pusch_chest_host")
         return est, st
 

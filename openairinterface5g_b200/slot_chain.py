@@ -36,8 +36,8 @@ class PuschSlotChain:
         self.desc = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, self.P.first_carrier_offset, Qm, 0, 14, self.dmrs_pos, self.dmrs_type, self.cdm,
                                 0, 14 * N, 14 * N, 1, rnti, nid, n_layers, 0, 0)
         assert lib.pusch_num_llr(self.desc) == self.G
-        self.cdescs = [PuschChestDesc(N, nb_rx, slot, 2, p, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N) for p in range(n_layers)]
-        self.cdesc = self.cdescs[0]
+        self.cdescs = [PuschChestDesc(N, nb_rx, slot, 2, p, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N, 1) for p in range(n_layers)]
+        self.cdesc = PuschChestDesc(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N, n_layers)   # all ports in one call
         self.est = torch.zeros((n_layers * nb_rx, 14 * N, 2), dtype=torch.int16, device=device)   # ul_ch_estimates[p * nb_rx + aarx]
         self.chest_scratch = torch.empty(lib.pusch_chest_scratch_bytes(self.cdesc), dtype=torch.uint8, device=device)
         self.chest_state = torch.zeros((n_layers, 18), dtype=torch.int32, device=device)
@@ -126,8 +126,7 @@ class PuschSlotChain:
         lib, dl = self.lib, self.dl
         dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)
         if est is None:
-            for p, cd in enumerate(self.cdescs):                                       # one estimator call per DMRS port (:1473-1486)
-                lib.pusch_chest_torch(cd, self.rxF, self.est[p * self.nb_rx:], self.chest_scratch, self.chest_state[p])
+            lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)   # every DMRS port of the PDU (:1473-1486)
             est = self.est
             if self.nl == 2:
                 # the MMSE receiver needs two scalars of the estimator on the host side of the ABI: max_ch and nvar (:1470-1512)

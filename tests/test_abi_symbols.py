@@ -73,7 +73,7 @@ def test_pusch_dmrs_pilots_match_oracle(oracle):
     for N, slot, symbol, port, rb_start, rb_size, scid, nid in ((4096, 1, 2, 0, 0, 273, 0, 77), (2048, 19, 11, 1, 30, 76, 1, 65535), (1024, 0, 2, 2, 0, 52, 1, 0),
                                                                 (1024, 5, 0, 3, 20, 32, 0, 300)):
         P = ChestParms(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid)
-        d = PuschChestDesc(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid, 14 * N, 14 * N)
+        d = PuschChestDesc(N, 2, slot, symbol, port, rb_start, 0, rb_size, N - 6 * 52, scid, nid, 14 * N, 14 * N, 1)
         assert np.array_equal(lib.pusch_dmrs_pilots(d), oracle.pusch_dmrs_pilots(P))
 
 

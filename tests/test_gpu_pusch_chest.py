@@ -20,7 +20,7 @@ def test_pusch_chest_vs_oracle(ldpc, oracle):
     for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay in CASES:
         fco = N - carrier * 6
         P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid)
-        d = PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N)
+        d = PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 1)
         big = nb_rx == 8
         if big:
             rx = rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
@@ -40,3 +40,18 @@ def test_pusch_chest_vs_oracle(ldpc, oracle):
         assert np.array_equal(est[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port)
         other = [s for s in range(14) if s != symbol]
         assert np.array_equal(est[:, other], prev[:, other])                          # nothing else is touched
+
+
+def test_pusch_chest_two_ports_in_one_call(ldpc, oracle):
+    """n_ports = 2: both DMRS ports of a 2-layer PUSCH in the same launches == two single-port estimations."""
+    rng = np.random.default_rng(62)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid in ((4096, 4, 1, 2, 0, 0, 273, 273, 0, 77), (2048, 2, 3, 3, 2, 10, 50, 106, 1, 5), (1024, 8, 9, 2, 0, 4, 40, 52, 0, 900)):
+        fco = N - carrier * 6
+        rx = rng.integers(-2500, 2501, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        d = PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 2)
+        est, st = ldpc.pusch_chest_host(d, rx)
+        assert est.shape[0] == 2 * nb_rx and st.size == 10
+        for q in range(2):
+            est_o, out_o = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, symbol, port + q, rb_start, 0, rb_size, fco, scid, nid), rx)
+            assert np.array_equal(st[5 * q:5 * q + 5], out_o), (N, nb_rx, q, st, out_o)
+            assert np.array_equal(est[q * nb_rx:(q + 1) * nb_rx, symbol], est_o[:, symbol]), (N, nb_rx, q)

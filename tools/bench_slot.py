@@ -52,7 +52,7 @@ def run(lib, dl, dev, nl):
     # per-stage times (each stage alone, back to back 200x)
     st = {
         "ofdm_demod": lambda: dl.ofdm_demod_slot_torch(ch.drx, rxdata, ch.ts, ch.rxF),
-        "channel_estimation": lambda: [lib.pusch_chest_torch(cd, ch.rxF, ch.est[p * ch.nb_rx:], ch.chest_scratch, ch.chest_state[p]) for p, cd in enumerate(ch.cdescs)],
+        "channel_estimation": lambda: lib.pusch_chest_torch(ch.cdesc, ch.rxF, ch.est, ch.chest_scratch, ch.chest_state),
         "level+inner_rx": lambda: lib.pusch_inner_rx_torch(ch.desc, ch.rxF, ch.est, ch.llr16, level=ch.level),
         "rm_rx": lambda: lib.rm_rx_torch(1, ch.Z, ch.Qm, 0, ch.C, 0, ch.F, ch.llr16, ch.E, ch.Eoff, ch.harq, ch.llr8, clear=1),
         "ldpc_decode": lambda: lib.decode_batch_torch(1, ch.Z, ch.R, ch.max_iter, ch.llr8, use_crc=1, crc_len_bits=ch.K - ch.F, crc_type=1, out=ch.hard, iters=ch.iters),
