@@ -240,6 +240,9 @@ typedef struct nrb200_pusch_rx_s {
                                              * ul_ch_estimates then holds [2 * nb_rx] planes, index layer * nb_rx + rx, LLRs are layer de-mapped */
   uint32_t noise_var;                       /* 2 layers: nvar of the channel estimator, added to the diagonal of H^H H */
   uint32_t max_ch;                          /* 2 layers: the estimator's max_ch (scales the level measurement, nr_ulsch_scale_channel) */
+  uint32_t pdsch_ue;                        /* 1: the UE's single-layer PDSCH receiver instead (nr_rx_pdsch, NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684): its own
+                                             * extraction patterns, estimate scaling, saturating MRC, thresholds and log2_maxh rule; ul_dmrs_symb_pos = dlDmrsSymbPos,
+                                             * num_dmrs_cdm_grps_no_data = n_dmrs_cdm_groups, the estimates' symbol = get_valid_dmrs_idx_for_channel_est; nb_rx <= 4 */
 } nrb200_pusch_rx_t;
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
 /* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
@@ -266,6 +269,9 @@ typedef struct nrb200_pusch_chest_s {
   uint32_t rx_stride, ch_stride;            /* _dev: c16 between antennas */
   uint32_t n_ports;                         /* 0 or 1: port `port` only.  2: ports `port` and `port + 1` in the same launches; estimates of port q go to
                                              * plane (q * nb_rx + rx), state of port q to d_state + 18 q (state5 + 5 q for the host entry point) */
+  uint32_t pdsch_ue;                        /* 1: the UE's PDSCH estimator instead (nr_pdsch_channel_estimation + NFAPI_NR_DMRS_TYPE1_linear_interp,
+                                             * NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1305-1385, 1614-1735): same DMRS, delay handling and filters, its own
+                                             * least-squares arithmetic; max_ch and nvar are not produced (0).  rb_start + bwp_start = the PDSCH's rb_offset. */
 } nrb200_pusch_chest_t;
 /* the 6 * rb_size conjugated DMRS symbols {re, im} the estimator correlates with (nr_pusch_dmrs_rx output); host arithmetic, no GPU needed */
 int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots);

@@ -21,6 +21,7 @@ int dft_batch_internal(int N, int inverse, uint32_t n, const int16_t *d_in, int1
 
 struct ChestGeom {
   int N, nb_rx, symbol, nb, np, k0, dmrs_offset;
+  int ue;                                   // 1: the UE's PDSCH estimator (least-squares step of NFAPI_NR_DMRS_TYPE1_linear_interp)
   int n_ports, delta[2], wsign_odd[2];      // ports handled by one call (DMRS ports p, p+1 share the Gold sequence, differ in delta / w_f)
   unsigned rx_stride, ch_stride, x2;
 };
@@ -67,14 +68,21 @@ __global__ void __launch_bounds__(256) chest_ls_kernel(ChestGeom G, const GoldTa
       const int w = (i & 1) ? G.wsign_odd[port] : 1;
       // conj of the QPSK symbol (nr_rx_mod_table): re = +A for b0 = 0, im = -A for b1 = 0, negated when w = -1
       const int pr = w * (b0 ? -23170 : 23170), pi = w * (b1 ? 23170 : -23170);
-      int re = G.k0 + (n << 2) + (kl << 1) + G.delta[port];
-      re %= G.N;
+      int re = G.k0 + (n << 2) + (kl << 1);
+      if (!G.ue) { re += G.delta[port]; re %= G.N; }
+      else { re %= G.N; re += G.delta[port]; }                             // UE: the comb offset moves the symbol pointer, it does not wrap (:1689)
       const unsigned y = __ldg(rx + re);
-      cr += (pr * c_lo(y) - pi * c_hi(y)) >> 16;
-      ci += (pr * c_hi(y) + pi * c_lo(y)) >> 16;
+      if (!G.ue) {
+        cr += (pr * c_lo(y) - pi * c_hi(y)) >> 16;
+        ci += (pr * c_hi(y) + pi * c_lo(y)) >> 16;
+      } else {                                                             // c16mulShift / c16maddShift: int16 accumulation, >> 15 per product
+        cr = c_wrap16(((pr * c_lo(y) - pi * c_hi(y)) >> 15) + cr);
+        ci = c_wrap16(((pr * c_hi(y) + pi * c_lo(y)) >> 15) + ci);
+      }
     }
+    if (G.ue) { cr >>= 1; ci >>= 1; }                                      // c16Shift(ch, 1)
     const int m = max(abs(cr), abs(ci));
-    if (m > 0) atomicMax(state, m);
+    if (m > 0 && !G.ue) atomicMax(state, m);
     v = c_pk(c_wrap16(cr), c_wrap16(ci));
   }
   reinterpret_cast<uint4 *>(dst)[n] = make_uint4(v, v, v, v);
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(256) chest_interp_kernel(ChestGeom G, const un
         out = c_mul8(out, __ldg(ti + k));                                    // revert the delay
         const unsigned lv = l[k];
         const int dr = c_wrap16(c_lo(lv) - c_lo(out)), di = c_wrap16(c_hi(lv) - c_hi(out));
-        noise = (unsigned)(dr * dr + di * di);
+        noise = G.ue ? 0u : (unsigned)(dr * dr + di * di);
       }
     }
     est[(size_t)pa * G.ch_stride + (size_t)G.symbol * G.N + k] = out;        // the whole symbol is rewritten (memset in the reference)
@@ -206,6 +214,7 @@ static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
   if (d.nb_rx < 1 || d.nb_rx > 8 || d.symbol > 13 || d.port > 3 || d.rb_size < 1 || 12 * d.rb_size > d.fft_size || d.scid > 1 || (d.fft_size & 3)) return -4;
   G->N = d.fft_size; G->nb_rx = d.nb_rx; G->symbol = d.symbol; G->nb = d.rb_size; G->np = 6 * d.rb_size;
   G->k0 = ((d.rb_start + d.bwp_start) * 12 + d.first_carrier_offset) % d.fft_size;
+  G->ue = d.pdsch_ue ? 1 : 0;
   G->n_ports = d.n_ports == 0 ? 1 : (int)d.n_ports;
   if (G->n_ports > 2 || d.port + G->n_ports > 4) return -4;
   for (int q = 0; q < G->n_ports; q++) {

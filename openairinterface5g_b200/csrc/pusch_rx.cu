@@ -21,6 +21,8 @@ struct PuschGeom {
   unsigned llr_off[14];
   unsigned unscramble, c_init;
   int nl;                          // layers (1 | 2)
+  int ue, cdm;                     // 1: the UE's PDSCH receiver (nr_rx_pdsch); cdm = n_dmrs_cdm_groups
+  int last_is_dmrs, last_ch_sym, last_span;   // UE: the symbol whose magnitude buffers survive until the LLRs are computed
   unsigned nvar;                   // noise variance added to the diagonal of H^H H (2 layers)
   int lvl_amp, lvl_b;              // nr_ulsch_scale_channel constants of the level measurement
 };
@@ -214,6 +216,120 @@ __global__ void __launch_bounds__(256) pusch_rx2_kernel(PuschGeom G, const GoldT
   }
 }
 
+// ---- UE side, one layer: nr_rx_pdsch (NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684).  Same structure as pusch_rx_kernel with the UE's arithmetic:
+// estimates scaled (mulhi 8192, << 3) before the matched filter, per-antenna outputs packed and combined with SATURATING adds, thresholds mulhi << 1, and --
+// because the reference computes the slot's LLRs after the last symbol with that call's local magnitude buffers -- the thresholds of EVERY symbol come from
+// the LAST symbol's extraction (zero beyond its span).
+__device__ __forceinline__ void ue_source(const PuschGeom &G, int is_dmrs, int i, int &rx_idx, int &ch_idx)
+{
+  const int N = G.N, s = G.start_re;
+  if (!is_dmrs) { rx_idx = s + i; if (rx_idx >= N) rx_idx -= N; ch_idx = i; return; }
+  int per, first;                                  // data REs per 6-RE group and the first of them (nr_dlsch_extract_rbs :1233-1297)
+  if (G.dmrs_type == 0) { per = 3; first = 1; } else if (G.cdm == 1) { per = 4; first = 2; } else { per = 2; first = 4; }
+  const int g = i / per, r = i - g * per;
+  int k = s + 6 * g;
+  if (k >= N) k -= N;
+  const int o = G.dmrs_type == 0 ? 2 * r + first : r + first;
+  rx_idx = k + o; ch_idx = 6 * g + o;
+}
+__device__ __forceinline__ unsigned ue_scale(unsigned h)
+{
+  return ((unsigned)(unsigned short)p_wrap16(((p_lo(h) * 8192) >> 16) << 3)) | ((unsigned)(unsigned short)p_wrap16(((p_hi(h) * 8192) >> 16) << 3) << 16);
+}
+
+template <int QM>
+__global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift, const unsigned *__restrict__ rxF,
+                                                       const unsigned *__restrict__ ch, short *__restrict__ llr)
+{
+  __shared__ uint32_t s_gold[(256 * QM) / 32 + 2];
+  const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
+  const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
+  if (i0 >= valid) return;
+  const unsigned bit0 = G.llr_off[k] + (unsigned)i0 * QM;
+  if (G.unscramble) {
+    const unsigned w0 = bit0 >> 5, nw = ((bit0 + 256u * QM + 31u) >> 5) - w0;
+    if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
+    __syncthreads();
+  }
+  if (i >= valid) return;
+  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  int rx_idx, ch_idx, mch_idx, dummy;
+  ue_source(G, is_dmrs, i, rx_idx, ch_idx);
+  ue_source(G, G.last_is_dmrs, i, dummy, mch_idx);
+  const bool mag_ok = i < G.last_span;
+  constexpr int ampa = QM == 4 ? 20724 : QM == 6 ? 20225 : QM == 8 ? 20106 : 0, ampb = QM == 6 ? 10112 : QM == 8 ? 10053 : 0, ampc = QM == 8 ? 5026 : 0;
+  int cr = 0, ci = 0, ma = 0, mb = 0, mc = 0;
+  for (int a = 0; a < G.nb_rx; a++) {
+    const unsigned y = __ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx);
+    const unsigned h = ue_scale(__ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx));
+    const int hr = p_lo(h), hi = p_hi(h), yr = p_lo(y), yi = p_hi(y);
+    const int r = p_sat16(((int)((unsigned)(hr * yr) + (unsigned)(hi * yi))) >> shift), im = p_sat16(((int)((unsigned)(p_wrap16(-hi) * yr) + (unsigned)(hr * yi))) >> shift);
+    if (a == 0) { cr = r; ci = im; } else { cr = p_sat16(cr + r); ci = p_sat16(ci + im); }
+    if (QM > 2 && mag_ok) {
+      const unsigned hm = ue_scale(__ldg(ch + (size_t)a * G.ch_stride + (size_t)G.last_ch_sym * G.N + mch_idx));
+      const int m = p_sat16(((int)((unsigned)(p_lo(hm) * p_lo(hm)) + (unsigned)(p_hi(hm) * p_hi(hm)))) >> shift);
+      const int va = p_wrap16(((m * ampa) >> 16) << 1), vb = p_wrap16(((m * ampb) >> 16) << 1), vc = p_wrap16(((m * ampc) >> 16) << 1);
+      if (a == 0) { ma = va; mb = vb; mc = vc; } else { ma = p_sat16(ma + va); mb = p_sat16(mb + vb); mc = p_sat16(mc + vc); }
+    }
+  }
+  int o[8];
+  if (QM == 2) { o[0] = cr >> 3; o[1] = ci >> 3; }
+  else {
+    o[0] = cr; o[1] = ci;
+    o[2] = p_subs16(ma, p_abs16w(cr)); o[3] = p_subs16(ma, p_abs16w(ci));
+    if (QM > 4) { o[4] = p_subs16(mb, p_abs16w(o[2])); o[5] = p_subs16(mb, p_abs16w(o[3])); }
+    if (QM > 6) { o[6] = p_subs16(mc, p_abs16w(o[4])); o[7] = p_subs16(mc, p_abs16w(o[5])); }
+  }
+  const unsigned b = G.llr_off[k] + (unsigned)i * QM;
+  if (G.unscramble) {
+    const unsigned rel = b - ((bit0 >> 5) << 5);
+#pragma unroll
+    for (int m = 0; m < QM; m++) { const unsigned r = rel + m; if ((s_gold[r >> 5] >> (r & 31u)) & 1u) o[m] = p_wrap16(-o[m]); }
+  }
+  unsigned *dst = reinterpret_cast<unsigned *>(llr + b);
+#pragma unroll
+  for (int m = 0; m < QM / 2; m++) dst[m] = ((unsigned)o[2 * m] & 0xFFFFu) | ((unsigned)o[2 * m + 1] << 16);
+}
+
+// UE: nr_dlsch_scale_channel + nr_dlsch_channel_level on the first symbol with data, log2_maxh = log2_approx(max avg) / 2 + 1 (:433-452)
+__global__ void __launch_bounds__(256) pdsch_level_kernel(PuschGeom G, int meas_k, const unsigned *__restrict__ ch, int *__restrict__ d_out, unsigned *__restrict__ d_count)
+{
+  __shared__ unsigned s_lane[4][64];
+  const int a = blockIdx.x, is_dmrs = G.is_dmrs[meas_k], len = G.valid[meas_k];
+  int x = 0;
+  while (x < 31 && !((len >> x) & 1)) x++;
+  const int y = len >> x, span = (len / 12 + ((len % 12) ? 1 : 0)) * 12;
+  const int n_ext = !is_dmrs ? G.nb_re : G.dmrs_type == 0 ? (G.cdm == 1 ? G.nb_re / 2 : 0) : (G.cdm == 1 ? (G.nb_re / 6) * 4 : G.cdm == 2 ? (G.nb_re / 6) * 2 : 0);
+  // four 32-bit lanes like the SSE accumulator: lane = i & 3; thread t owns lane t & 3 (stride 256 keeps the lane)
+  unsigned acc = 0;
+  for (int i = threadIdx.x; i < min(n_ext, span); i += blockDim.x) {
+    int rx_idx, ch_idx;
+    ue_source(G, is_dmrs, i, rx_idx, ch_idx);
+    const unsigned h = ue_scale(__ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[meas_k] * G.N + ch_idx));
+    acc += (unsigned)(((int)((unsigned)(p_lo(h) * p_lo(h)) + (unsigned)(p_hi(h) * p_hi(h)))) >> x);
+  }
+  s_lane[threadIdx.x & 3][threadIdx.x >> 2] = acc;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned s = 0;
+    for (int j = 0; j < 64; j++) s += s_lane[threadIdx.x][j];
+    s_lane[threadIdx.x][0] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long tot = (long long)(int)s_lane[0][0] + (int)s_lane[1][0] + (int)s_lane[2][0] + (int)s_lane[3][0];
+    d_out[a] = (int)(tot / y);
+    __threadfence();
+    if (atomicAdd(d_count, 1u) == (unsigned)G.nb_rx - 1) {
+      int avgs = 0;
+      for (int q = 0; q < G.nb_rx; q++) avgs = max(avgs, ((volatile int *)d_out)[q]);
+      const unsigned v = (unsigned)avgs & 0x7FFFFFFFu;
+      d_out[8] = ((v ? 32 - __clz(v) : 0) / 2) + 1;
+      *d_count = 0;
+    }
+  }
+}
+
 // nr_ulsch_scale_channel (shift_ch_ext = 0) + nr_ulsch_channel_level on the measurement symbol, one CTA per rx antenna, then the
 // log2_maxh rule for one layer.  avg[a] and the final shift are left in d_out[0..nb_rx) and d_out[8].
 __global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_k, int len, const unsigned *__restrict__ ch, int *__restrict__ d_out,
@@ -271,6 +387,8 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
   G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
   G->unscramble = d.unscramble; G->c_init = (d.rnti << 15) + d.data_scrambling_id;
   G->nl = nl; G->nvar = d.noise_var;
+  G->ue = d.pdsch_ue ? 1 : 0; G->cdm = d.num_dmrs_cdm_grps_no_data;
+  if (G->ue && (nl != 1 || d.nb_rx > 4)) return -4;
   {
     // nr_ulsch_scale_channel: shift_ch_ext = log2_approx(max_ch >> 11) for 2 layers, 0 for one
     int sce = 0;
@@ -289,12 +407,19 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
   for (uint32_t s = d.start_symbol_index; s < d.start_symbol_index + d.nr_of_symbols; s++) {
     const int dm = (d.ul_dmrs_symb_pos >> s) & 1;
     if (dm) cur = s;                                            // nr_pusch_symbol_processing :1398-1404
+    int chs = cur;
+    if (G->ue) {                                                // get_valid_dmrs_idx_for_channel_est (dmrs_nr.c:321-340): this, previous, else next DMRS symbol
+      chs = -1;
+      for (int q = (int)s; q >= 0 && chs < 0; q--) if ((d.ul_dmrs_symb_pos >> q) & 1) chs = q;
+      for (int q = (int)s; q < 14 && chs < 0; q++) if ((d.ul_dmrs_symb_pos >> q) & 1) chs = q;
+    }
     const int v = nb_re_symbol(d, s);
     if (v > 0) {
       const int k = G->n_sym++;
-      G->sym[k] = s; G->ch_sym[k] = cur; G->is_dmrs[k] = dm; G->valid[k] = v; G->llr_off[k] = off;
+      G->sym[k] = s; G->ch_sym[k] = chs; G->is_dmrs[k] = dm; G->valid[k] = v; G->llr_off[k] = off;
     }
     off += (unsigned)v * Qm;
+    if (s == d.start_symbol_index + d.nr_of_symbols - 1) { G->last_is_dmrs = dm; G->last_ch_sym = chs; G->last_span = (v / 12 + ((v % 12) ? 1 : 0)) * 12; }
   }
   if (total_llr) *total_llr = off * (unsigned)nl;
   return G->n_sym > 0 ? 0 : -4;
@@ -312,6 +437,12 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
   PuschGeom G;
   int rc = make_geom(d, &G, nullptr);
   if (rc) return rc;
+  if (G.ue) {
+    pdsch_level_kernel<<<G.nb_rx, 256, 0, st>>>(G, 0, (const unsigned *)ch, d_out9, d_count);
+    ctx().launches++;
+    NRB200_CUDA_OK(cudaGetLastError(), "pdsch_level launch");
+    return 0;
+  }
   const int len = (G.valid[0] + 15) & ~15;                      // first symbol with data (:1601-1611)
   pusch_level_kernel<<<G.nb_rx * G.nl, 256, 0, st>>>(G, 0, len, (const unsigned *)ch, d_out9, d_count);
   ctx().launches++;
@@ -331,7 +462,14 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
   for (int k = 0; k < G.n_sym; k++) vmax = std::max(vmax, G.valid[k]);
   const dim3 grid((((vmax + 3) & ~3) + 255) / 256, G.n_sym);
   const unsigned *R = (const unsigned *)rxF, *C = (const unsigned *)ch;
-  if (G.nl == 2) {
+  if (G.ue) {
+    switch (G.Qm) {
+      case 2: pdsch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 4: pdsch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 6: pdsch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      default: pdsch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    }
+  } else if (G.nl == 2) {
     if (G.Qm == 6) pusch_rx2_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
     else pusch_rx2_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
   } else {

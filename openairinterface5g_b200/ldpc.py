@@ -72,12 +72,12 @@ def ncols_for_rate(BG, R):
 class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_nr_pusch_pdu_t / NR_DL_FRAME_PARMS)
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order",
                                           "start_symbol_index", "nr_of_symbols", "ul_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data",
-                                          "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id", "nrOfLayers", "noise_var", "max_ch")]
+                                          "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id", "nrOfLayers", "noise_var", "max_ch", "pdsch_ue")]
 
 
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
-                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports")]
+                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue")]
 
 
 class LdpcLib:

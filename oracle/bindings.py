@@ -185,6 +185,12 @@ class Oracle:
         self.lib.orc_pusch_channel_estimation(C.byref(P), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         return est.reshape(P.nb_rx, 14, P.fft_size, 2), out
 
+    def pdsch_channel_estimation(self, P, rxdataF):
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16)
+        est = np.zeros(P.nb_rx * 14 * P.fft_size * 2, np.int16)
+        self.lib.orc_pdsch_channel_estimation(C.byref(P), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p))
+        return est.reshape(P.nb_rx, 14, P.fft_size, 2)
+
     # ---- single-layer PUSCH inner receiver
     def pusch_nb_re(self, P, symbol):
         return int(self.lib.orc_pusch_nb_re(C.byref(P), symbol))
@@ -219,6 +225,15 @@ class Oracle:
         rc = self.lib.orc_pusch_inner_rx_symbol_2l(C.addressof(P), symbol, ch_symbol, shift, nvar, x.ctypes.data, h.ctypes.data, llr.ctypes.data, comp.ctypes.data)
         assert rc == valid, rc
         return llr, comp
+
+    def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est):
+        """UE-side single-layer PDSCH receiver for a whole slot.  Returns (llr int16[G], log2_maxh)."""
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16)
+        llr = np.zeros(14 * 12 * P.rb_size * P.Qm + 64, np.int16)
+        sh = C.c_int32(0)
+        n = self.lib.orc_pdsch_rx_slot(C.byref(P), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+                                       C.byref(sh))
+        return llr[:n].copy(), sh.value
 
     # ---- slot-level OFDM front end
     def ofdm_geometry(self, N, mu, slot):
@@ -468,6 +483,28 @@ class Reference:
         self._chestlib.refh_pusch_chest(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p),
                                         out.ctypes.data_as(C.c_void_p), pil.ctypes.data_as(C.c_void_p))
         return est.reshape(P.nb_rx, 14, P.fft_size, 2), out, pil
+
+    def pdsch_channel_estimation(self, P, rxdataF, n_rb_dl, chest_freq=0, dmrs_type=0):
+        if not hasattr(self, "_uechestlib"):
+            self._uechestlib = C.CDLL(os.path.join(REFDIR, "libref_uechest.so"))
+            assert self._uechestlib.refh_uechest_init(os.path.join(REFDIR, "libref_dfts.so").encode()) == 0
+        prm = np.array([P.fft_size, P.nb_rx, n_rb_dl, P.slot, P.symbol, P.port, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.scid,
+                        P.dmrs_scrambling_id, dmrs_type, chest_freq], dtype=np.int32)
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy()
+        est = np.zeros(P.nb_rx * 14 * P.fft_size * 2, np.int16)
+        self._uechestlib.refh_pdsch_chest(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p))
+        return est.reshape(P.nb_rx, 14, P.fft_size, 2)
+
+    def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est, G):
+        if not hasattr(self, "_pdschlib"):
+            self._pdschlib = C.CDLL(os.path.join(REFDIR, "libref_pdsch.so"))
+        prm = np.array([P.fft_size, P.nb_rx, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.Qm, start_symbol, nr_symbols, P.ul_dmrs_symb_pos,
+                        P.dmrs_config_type, P.num_dmrs_cdm_grps_no_data, G], dtype=np.int32)
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16).copy()
+        llr = np.zeros(G + 64, np.int16); valid = np.zeros(14, np.int32)
+        sh = self._pdschlib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+                                               valid.ctypes.data_as(C.c_void_p), None)
+        return llr[:G].copy(), int(sh), valid
 
     def _pusch(self):
         if not hasattr(self, "_puschlib"):

@@ -121,3 +121,66 @@ int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, i
   free(pil); free(ls); free(tim); free(acc);
   return 0;
 }
+
+/* ---- UE side: nr_pdsch_channel_estimation with NFAPI_NR_DMRS_TYPE1_linear_interp (NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1305-1385,
+ * 1614-1735), DMRS type 1, chest_freq == 0.  Same pilots (nr_pdsch_dmrs_rx / nr_gold_pdsch use the PUSCH formulas), same delay estimation,
+ * filters and delay reversal as the gNB estimator; the least-squares step differs: 16-bit accumulation with >> 15 per product and a final >> 1,
+ * the port's comb offset is added to the symbol pointer (not wrapped with the sub-carrier index), and there is no max_ch / noise output.
+ * p->slot, symbol, port, scid, dmrs_scrambling_id as for the gNB; rb_start + bwp_start = rb_offset of the PDSCH.  dl_ch_est [nb_rx][14 N]. */
+int orc_pdsch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *dl_ch_est)
+{
+  const int N = p->fft_size, nb = p->rb_size, np = 6 * nb, nushift = (p->port >> 1) & 1;
+  const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
+  int16_t *pil = malloc(4 * (size_t)np), *ls = malloc(4 * (size_t)N), *tim = malloc(4 * (size_t)N), *acc = malloc(4 * (size_t)(N + 16));
+  orc_pusch_dmrs_pilots(p, pil);
+  int max_pos = 0, max_val = 0;
+  for (int a = 0; a < p->nb_rx; a++) {
+    const int16_t *rx = rxdataF + 2 * (((size_t)a * 14 + p->symbol) * N + nushift);
+    int16_t *dl = dl_ch_est + 2 * ((size_t)a * 14 + p->symbol) * N;
+    memset(ls, 0, 4 * (size_t)N);
+    memset(acc, 0, 4 * (size_t)(N + 16));
+    int re = k0;
+    for (int pc = 0; pc < np; pc += 2) {
+      const int32_t p0r = pil[2 * pc], p0i = pil[2 * pc + 1], p1r = pil[2 * pc + 2], p1i = pil[2 * pc + 3];
+      const int32_t y0r = rx[2 * re], y0i = rx[2 * re + 1];
+      re = (re + 2) % N;
+      const int32_t y1r = rx[2 * re], y1i = rx[2 * re + 1];
+      re = (re + 2) % N;
+      int16_t cr = (int16_t)((p0r * y0r - p0i * y0i) >> 15), ci = (int16_t)((p0r * y0i + p0i * y0r) >> 15);          /* c16mulShift */
+      cr = (int16_t)(((p1r * y1r - p1i * y1i) >> 15) + cr); ci = (int16_t)(((p1r * y1i + p1i * y1r) >> 15) + ci);     /* c16maddShift */
+      cr = (int16_t)(cr >> 1); ci = (int16_t)(ci >> 1);                                                               /* c16Shift */
+      for (int k = 2 * pc; k < 2 * pc + 4; k++) { ls[2 * k] = cr; ls[2 * k + 1] = ci; }
+    }
+    orc_dft(N, 1, ls, tim, 1);
+    for (int i = 0; i < N; i++) {
+      const int temp = (int)(((uint32_t)((int32_t)tim[2 * i] * tim[2 * i] + (int32_t)tim[2 * i + 1] * tim[2 * i + 1])) >> 1);
+      if (temp > max_val) { max_pos = i; max_val = temp; }
+    }
+    if (max_pos > N / 2) max_pos -= N;
+    int d_idx = 20 + max_pos; d_idx = d_idx < 0 ? 0 : d_idx > 40 ? 40 : d_idx;
+    int i_idx = 20 - max_pos; i_idx = i_idx < 0 ? 0 : i_idx > 40 ? 40 : i_idx;
+    const int dly = d_idx - 20, idly = i_idx - 20;
+    int base = 0;
+    for (int pc = 0; pc < np; pc++) {
+      const int k = pc << 1;
+      const double ang = 2.0 * M_PI * k * dly / N;
+      const int16_t tr = (int16_t)round(256 * cos(ang)), ti = (int16_t)round(256 * sin(ang));
+      const int32_t lr = ls[2 * k], li = ls[2 * k + 1];
+      const int16_t cr = (int16_t)((lr * tr - li * ti) >> 8), ci = (int16_t)((lr * ti + li * tr) >> 8);
+      if (pc == 0) multadd16(F_P0, cr, ci, acc + 2 * base);
+      else if (pc == 1 || pc == 2) multadd16(F_P1P2, cr, ci, acc + 2 * base);
+      else if (pc == np - 1) multadd16(F_LAST, cr, ci, acc + 2 * base);
+      else { multadd16(F_MID, cr, ci, acc + 2 * base); if (pc % 2 == 0) base += 4; }
+    }
+    for (int k = 0; k < 12 * nb; k++) {
+      const double ang = 2.0 * M_PI * k * idly / N;
+      const int16_t tr = (int16_t)round(256 * cos(ang)), ti = (int16_t)round(256 * sin(ang));
+      const int32_t ar = acc[2 * k], ai = acc[2 * k + 1];
+      acc[2 * k] = (int16_t)((ar * tr - ai * ti) >> 8); acc[2 * k + 1] = (int16_t)((ar * ti + ai * tr) >> 8);
+    }
+    memset(dl, 0, 4 * (size_t)N);
+    memcpy(dl, acc, 4 * (size_t)(12 * nb + 8 <= N ? 12 * nb + 8 : N));
+  }
+  free(pil); free(ls); free(tim); free(acc);
+  return 0;
+}

@@ -242,3 +242,95 @@ int orc_pusch_log2_maxh_2l(const orc_pusch_t *p, int meas_symbol, int ch_symbol,
   const int l2 = (log2_approx_((uint32_t)avgs) >> 1) - 3;
   return l2 < 0 ? 0 : l2;
 }
+
+/* ---- UE side: nr_rx_pdsch for one layer (NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684 with nr_dlsch_extract_rbs :1182-1301, nr_dlsch_scale_channel
+ * :1052-1101, nr_dlsch_channel_level :1104-1142, nr_dlsch_channel_compensation :737-1050, nr_dlsch_detection_mrc :1303-1368, nr_dlsch_llr :1909-1990,
+ * get_valid_dmrs_idx_for_channel_est NR_REFSIG/dmrs_nr.c:321-340).  Differences to the gNB receiver: the estimates are scaled (mulhi 8192, << 3) BEFORE the
+ * matched filter, every antenna's output is packed on its own and the antennas are combined with SATURATING adds, the magnitude thresholds use mulhi << 1,
+ * and the LLRs of the whole slot are computed at the last symbol with the magnitudes of that LAST symbol (the per-symbol magnitude buffers are locals of
+ * nr_rx_pdsch).  p->ul_dmrs_symb_pos = dlDmrsSymbPos, p->num_dmrs_cdm_grps_no_data = n_dmrs_cdm_groups.  Returns the number of LLRs written. */
+static int valid_dmrs_idx(int pos, int symbol)
+{
+  if ((pos >> symbol) & 1) return symbol;
+  for (int s = symbol; s >= 0; s--) if ((pos >> s) & 1) return s;
+  for (int s = symbol; s < 14; s++) if ((pos >> s) & 1) return s;
+  return -1;
+}
+
+int orc_pdsch_rx_slot(const orc_pusch_t *p, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out)
+{
+  const int N = p->fft_size, nrx = p->nb_rx, nb = p->rb_size, Qm = p->Qm, pos = p->ul_dmrs_symb_pos, type = p->dmrs_config_type, cdm = p->num_dmrs_cdm_grps_no_data;
+  const int sz = (nb * 12 + 15) & ~15;
+  const int start_re = (p->first_carrier_offset + (p->rb_start + p->bwp_start) * 12) % N;
+  const int ampv[3] = {Qm == 4 ? 20724 : Qm == 6 ? 20225 : Qm == 8 ? 20106 : 0, Qm == 6 ? 10112 : Qm == 8 ? 10053 : 0, Qm == 8 ? 5026 : 0};
+  int16_t *rx = malloc(4 * (size_t)sz * nrx), *ch = malloc(4 * (size_t)sz * nrx), *comp = calloc((size_t)14 * nb * 12 * 2, 2), *mag[3], *cm = malloc(4 * (size_t)sz);
+  for (int t = 0; t < 3; t++) mag[t] = calloc(2 * (size_t)sz, 2);
+  int valid[14] = {0}, log2_maxh = 0;
+  int first_with_data = start_symbol;
+  const int dmrs_data_re = type == 0 ? 12 - 6 * cdm : 12 - 4 * cdm;
+  while (dmrs_data_re == 0 && ((pos >> first_with_data) & 1)) first_with_data++;
+  for (int m = start_symbol; m < start_symbol + nr_symbols; m++) {
+    const int pilots = (pos >> m) & 1, vd = valid_dmrs_idx(pos, m);
+    memset(rx, 0, 4 * (size_t)sz * nrx); memset(ch, 0, 4 * (size_t)sz * nrx);
+    for (int t = 0; t < 3; t++) memset(mag[t], 0, 4 * (size_t)sz);      /* the magnitude buffers are per-call locals */
+    for (int a = 0; a < nrx; a++) {
+      const int16_t *rxF = rxdataF + 2 * ((size_t)a * 14 + m) * N, *h = dl_ch_est + 2 * ((size_t)a * 14 + vd) * N;
+      int16_t *re = rx + 2 * (size_t)sz * a, *ce = ch + 2 * (size_t)sz * a;
+      int n = 0;
+#define PUT2(ri, ci) do { re[2 * n] = rxF[2 * (ri)]; re[2 * n + 1] = rxF[2 * (ri) + 1]; ce[2 * n] = h[2 * (ci)]; ce[2 * n + 1] = h[2 * (ci) + 1]; n++; } while (0)
+      if (!pilots) { for (int i = 0; i < 12 * nb; i++) PUT2((start_re + i) % N, i); }
+      else if (type == 0) {
+        if (cdm == 1) { int k = start_re; for (int j = 0; j < 6 * nb; j += 3) { PUT2(k + 1, 2 * j + 1); PUT2(k + 3, 2 * j + 3); PUT2(k + 5, 2 * j + 5); k += 6; if (k >= N) k -= N; } }
+      } else {
+        if (cdm == 1) { int k = start_re; for (int j = 0; j < 8 * nb; j += 4) { const int c0 = 6 * (j / 4); PUT2(k + 2, c0 + 2); PUT2(k + 3, c0 + 3); PUT2(k + 4, c0 + 4); PUT2(k + 5, c0 + 5); k += 6; if (k >= N) k -= N; } }
+        else if (cdm == 2) { int k = start_re; for (int j = 0; j < 4 * nb; j += 2) { const int c0 = 6 * (j / 2); PUT2(k + 4, c0 + 4); PUT2(k + 5, c0 + 5); k += 6; if (k >= N) k -= N; } }
+      }
+#undef PUT2
+    }
+    const int len = pilots ? (type == 0 ? nb * (12 - 6 * cdm) : nb * (12 - 4 * cdm)) : nb * 12;
+    const int nb_rb_0 = len / 12 + ((len % 12) ? 1 : 0), span = nb_rb_0 * 12;
+    for (int a = 0; a < nrx; a++)                                       /* scale */
+      for (int i = 0; i < 2 * span; i++) { int16_t *c = ch + 2 * (size_t)sz * a; c[i] = wrap16((((int32_t)c[i] * 8192) >> 16) << 3); }
+    if (m == first_with_data) {                                         /* level -> log2_maxh */
+      const int x = factor2_((uint32_t)len), y = len >> x;
+      int avgs = 0;
+      for (int a = 0; a < nrx; a++) {
+        const int16_t *c = ch + 2 * (size_t)sz * a;
+        int32_t lane[4] = {0, 0, 0, 0};
+        for (int i = 0; i < span; i++) lane[i & 3] = wrap32((int64_t)lane[i & 3] + (wrap32((int64_t)c[2 * i] * c[2 * i] + (int64_t)c[2 * i + 1] * c[2 * i + 1]) >> x));
+        const int avg = (int)(((int64_t)lane[0] + lane[1] + lane[2] + lane[3]) / y);
+        if (avg > avgs) avgs = avg;
+      }
+      log2_maxh = (log2_approx_((uint32_t)avgs) / 2) + 1;
+    }
+    const int shift = log2_maxh;
+    int16_t *out = comp + 2 * (size_t)m * nb * 12;
+    for (int a = 0; a < nrx; a++) {                                     /* matched filter per antenna, then saturating MRC */
+      const int16_t *c = ch + 2 * (size_t)sz * a, *y = rx + 2 * (size_t)sz * a;
+      for (int i = 0; i < span; i++) {
+        const int32_t hr = c[2 * i], hi = c[2 * i + 1], yr = y[2 * i], yi = y[2 * i + 1];
+        const int16_t cr = sat16(wrap32((int64_t)hr * yr + (int64_t)hi * yi) >> shift), ci = sat16(wrap32((int64_t)wrap16(-hi) * yr + (int64_t)hr * yi) >> shift);
+        const int16_t mm = sat16(wrap32((int64_t)hr * hr + (int64_t)hi * hi) >> shift);
+        if (a == 0) { cm[2 * i] = cr; cm[2 * i + 1] = ci; } else { cm[2 * i] = sat16((int32_t)cm[2 * i] + cr); cm[2 * i + 1] = sat16((int32_t)cm[2 * i + 1] + ci); }
+        if (Qm > 2)
+          for (int t = 0; t < 3; t++) {
+            const int16_t v = wrap16(((mm * ampv[t]) >> 16) << 1);
+            if (a == 0) { mag[t][2 * i] = v; mag[t][2 * i + 1] = v; } else { mag[t][2 * i] = sat16((int32_t)mag[t][2 * i] + v); mag[t][2 * i + 1] = sat16((int32_t)mag[t][2 * i + 1] + v); }
+          }
+      }
+    }
+    /* rxdataF_comp of symbol m lives at m * nb_rb * 12; vectors beyond the last symbol's region are not modelled (span <= nb * 12) */
+    memcpy(out, cm, 4 * (size_t)span);
+    valid[m] = len;
+  }
+  /* LLRs of the whole slot with the magnitudes of the last symbol */
+  size_t off = 0;
+  for (int m = start_symbol; m < start_symbol + nr_symbols; m++) {
+    orc_ulsch_llr(Qm, comp + 2 * (size_t)m * nb * 12, mag[0], mag[1], mag[2], llr + off, (uint32_t)valid[m]);
+    off += (size_t)valid[m] * Qm;
+  }
+  if (log2_maxh_out) *log2_maxh_out = log2_maxh;
+  free(rx); free(ch); free(comp); free(cm);
+  for (int t = 0; t < 3; t++) free(mag[t]);
+  return (int)off;
+}

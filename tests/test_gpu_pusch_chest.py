@@ -55,3 +55,17 @@ def test_pusch_chest_two_ports_in_one_call(ldpc, oracle):
             est_o, out_o = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, symbol, port + q, rb_start, 0, rb_size, fco, scid, nid), rx)
             assert np.array_equal(st[5 * q:5 * q + 5], out_o), (N, nb_rx, q, st, out_o)
             assert np.array_equal(est[q * nb_rx:(q + 1) * nb_rx, symbol], est_o[:, symbol]), (N, nb_rx, q)
+
+
+def test_pdsch_chest_ue_side_vs_oracle(ldpc, oracle):
+    """pdsch_ue = 1: the UE's PDSCH estimator (same kernels, the UE's least-squares arithmetic)."""
+    rng = np.random.default_rng(64)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay in CASES:
+        fco = N - carrier * 6
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid)
+        rx = rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16) if nb_rx == 8 else rng.integers(-3000, 3001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        d = PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 1, 1)
+        est, st = ldpc.pusch_chest_host(d, rx)
+        est_o = oracle.pdsch_channel_estimation(P, rx)
+        assert np.array_equal(est[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port)
+        assert st[0] == 0 and st[1] == 0

@@ -349,3 +349,47 @@ def test_pusch_inner_rx_two_layers_mmse(oracle, reference):
             llr_r, comp_r = reference.pusch_inner_rx_symbol(P, symbol, 2, shift, rx, h, valid, nb_layer=2, nvar=nvar)
             assert np.array_equal(comp_o, comp_r), (N, nb_rx, Qm, symbol, shift, nvar, "comp")
             assert np.array_equal(llr_o, llr_r), (N, nb_rx, Qm, symbol, shift, nvar, "llr")
+
+
+def test_pdsch_channel_estimation_ue(oracle, reference):
+    """UE-side estimator (nr_pdsch_channel_estimation, DMRS type 1 linear interpolation) on the same cases as the gNB one."""
+    from oracle.bindings import ChestParms
+    rng = np.random.default_rng(63)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay in CHEST_CASES:
+        if nb_rx > 4:
+            nb_rx = 4                      # NB_ANTENNAS_RX of the reference build
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, scid, nid)
+        pil = oracle.pusch_dmrs_pilots(P).reshape(-1, 2).astype(np.float64)
+        rx = rng.integers(-300, 301, size=(nb_rx, 14, N, 2)).astype(np.int16) if symbol != 2 or N != 512 else rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        k0 = ((rb_start * 12) + P.first_carrier_offset) % N
+        for a in range(nb_rx):
+            h = (900 + 100 * a) * np.exp(1j * (0.3 * a - 2 * np.pi * delay * np.arange(6 * rb_size) * 2 / N))
+            y = h * (pil[:, 0] - 1j * pil[:, 1]) / 32767.0
+            idx = (k0 + 2 * np.arange(6 * rb_size)) % N + ((port >> 1) & 1)
+            if N != 512:
+                rx[a, symbol].reshape(-1, 2)[idx, 0] += np.round(y.real).astype(np.int16); rx[a, symbol].reshape(-1, 2)[idx, 1] += np.round(y.imag).astype(np.int16)
+        est_r = reference.pdsch_channel_estimation(P, rx, carrier)
+        est_o = oracle.pdsch_channel_estimation(P, rx)
+        assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
+
+
+PDSCH_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols
+    (4096, 2, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13), (4096, 4, 0, 273, 8, 1 << 2, 0, 1, 273, 1, 13), (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13),
+    (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10), (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12), (512, 4, 3, 11, 8, 1 << 1, 0, 1, 25, 1, 6),
+]
+
+
+def test_pdsch_rx_slot_ue(oracle, reference):
+    """UE-side PDSCH receiver, one layer: the reference's own nr_rx_pdsch symbol loop vs the oracle restatement."""
+    from oracle.bindings import PuschParms
+    rng = np.random.default_rng(65)
+    for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym in PDSCH_CASES:
+        big = N == 512
+        ay, ah = (32767, 32767) if big else (2000, 1500)
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        llr_o, sh_o = oracle.pdsch_rx_slot(P, start, nsym, rx, h)
+        llr_r, sh_r, valid = reference.pdsch_rx_slot(P, start, nsym, rx, h, llr_o.size)
+        assert sh_o == sh_r, (N, nb_rx, Qm, sh_o, sh_r)
+        assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
