@@ -156,3 +156,8 @@ def test_phy_golden(oracle):
     assert np.array_equal(l, g["rx2_llr"]) and np.array_equal(c, g["rx2_comp"])
     sh2, avg2 = oracle.pusch_log2_maxh_2l(PP2, 0, 2, par2[12], g["rx1_rx"], g["rx2_h"])
     assert sh2 == int(g["rx2_shift"][0]) and np.array_equal(avg2, g["rx2_avg"])
+    PU = ChestParms(*[int(x) for x in g["uechest_par"]])
+    assert np.array_equal(oracle.pdsch_channel_estimation(PU, g["chest_rx"])[:, PU.symbol], g["uechest_est"])
+    pd = [int(x) for x in g["pdsch_par"]]
+    l, sh = oracle.pdsch_rx_slot(PuschParms(*pd[:10]), pd[10], pd[11], g["rx1_rx"], g["rx1_h"])
+    assert sh == int(g["pdsch_shift"][0]) and np.array_equal(l, g["pdsch_llr"])

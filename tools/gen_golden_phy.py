@@ -72,6 +72,15 @@ def main():
     g["rx2_llr"], g["rx2_comp"] = l, c
     sh2, avg2 = ref.pusch_log2_maxh(PP2, 0, 2, rxF, h2, nb_layer=2, max_ch=9000)
     g["rx2_shift"], g["rx2_avg"] = np.array([sh2], np.int32), avg2
+    # ---- UE side: PDSCH channel estimation (port 2, same geometry) and the single-layer nr_rx_pdsch receiver (16QAM, DMRS with data at symbol 2)
+    PU = ChestParms(N, nrx, 7, 3, 2, 3, 0, 20, N - 25 * 6, 1, 321)
+    g["uechest_par"] = np.array([N, nrx, 7, 3, 2, 3, 0, 20, N - 25 * 6, 1, 321], np.int32)
+    g["uechest_est"] = ref.pdsch_channel_estimation(PU, rxF, 25)[:, 3]
+    PD = PuschParms(N, nrx, 3, 0, 20, N - 25 * 6, 4, 1 << 2, 0, 1)
+    g["pdsch_par"] = np.array([N, nrx, 3, 0, 20, N - 25 * 6, 4, 1 << 2, 0, 1, 1, 13], np.int32)      # ..., start_symbol, nr_symbols
+    G_ = (12 * 12 + 6) * 20 * 4
+    l, sh, _ = ref.pdsch_rx_slot(PD, 1, 13, rxF, h, G_)
+    g["pdsch_llr"], g["pdsch_shift"] = l, np.array([sh], np.int32)
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
