@@ -40,9 +40,12 @@ __device__ __forceinline__ int sra15(unsigned v) { return ((int)v) >> 15; }
 __device__ __forceinline__ cx unpack(unsigned w) { return {(int)(short)(w & 0xFFFFu), (int)(short)(w >> 16)}; }
 __device__ __forceinline__ unsigned pack(cx a) { return ((unsigned)a.r & 0xFFFFu) | ((unsigned)a.i << 16); }
 // packed_cmult2: (a . ta, a . tb) >> 15, packs
+// twiddles are {re, im} int16 pairs at even offsets of the table blob: one 32-bit load each
+__device__ __forceinline__ cx ldtw(const short *p) { return unpack(__ldg(reinterpret_cast<const unsigned *>(p))); }
 __device__ __forceinline__ cx cmult2(cx a, const short *ta, const short *tb)
 {
-  return {sat16(sra15((unsigned)(a.r * ta[0]) + (unsigned)(a.i * ta[1]))), sat16(sra15((unsigned)(a.r * tb[0]) + (unsigned)(a.i * tb[1])))};
+  const cx A = ldtw(ta), B = ldtw(tb);
+  return {sat16(sra15((unsigned)(a.r * A.r) + (unsigned)(a.i * A.i))), sat16(sra15((unsigned)(a.r * B.r) + (unsigned)(a.i * B.i)))};
 }
 __device__ __forceinline__ int mulhrs(int a, int b) { return wrap16((a * b + 0x4000) >> 15); }
 
@@ -69,9 +72,10 @@ __device__ __forceinline__ void bfly4_32(cx x0, cx x1, cx x2, cx x3, const short
                                          cx &y2, cx &y3)
 {
   unsigned x1r, x1i, x2r, x2i, x3r, x3i;
-  cm32(x1, w1[0], w1[1], inv, x1r, x1i);
-  cm32(x2, w2[0], w2[1], inv, x2r, x2i);
-  cm32(x3, w3[0], w3[1], inv, x3r, x3i);
+  const cx W1 = ldtw(w1), W2 = ldtw(w2), W3 = ldtw(w3);
+  cm32(x1, W1.r, W1.i, inv, x1r, x1i);
+  cm32(x2, W2.r, W2.i, inv, x2r, x2i);
+  cm32(x3, W3.r, W3.i, inv, x3r, x3i);
   const cx d0 = pk32(x1r + x2r + x3r, x1i + x2i + x3i);
   const cx da = pk32(x1i - (x2r + x3i), (x3r - x2i) - x1r);
   const cx d2 = pk32((x2r - x3r) - x1r, (x2i - x3i) - x1i);
@@ -134,14 +138,17 @@ __device__ __forceinline__ int range_pos(const SlotIO &S, unsigned i)
   return -1;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const short *__restrict__ tw, const unsigned *__restrict__ in,
+#ifndef NRB200_DFT_MINBLOCKS
+#define NRB200_DFT_MINBLOCKS 2
+#endif
+template <int MODE, bool INV>
+__global__ void __launch_bounds__(256, NRB200_DFT_MINBLOCKS) dft_kernel(DftPlan P, TwOffsets O, const short *__restrict__ tw, const unsigned *__restrict__ in,
                                                   unsigned *__restrict__ out, unsigned n, SlotIO S)
 {
   extern __shared__ unsigned sm[];          // [tpb][N] natural-order input copy, then [tpb][N] work buffer
   const int N = P.N, tpb = P.tpb;
   unsigned *xin = sm, *buf = sm + tpb * N;
-  const bool inv = P.inverse != 0;
+  constexpr bool inv = INV;                 // compile time: the butterflies select their outputs without SEL / ISETP
   const unsigned t0 = blockIdx.x * tpb;
   const int nt = min((unsigned)tpb, n - t0);
   if (MODE == 0) {
@@ -180,15 +187,18 @@ __global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const 
     cx A[4][4];
 #pragma unroll
     for (int c = 0; c < 4; c++) bfly4_sat(v[c], v[4 + c], v[8 + c], v[12 + c], inv, A[0][c], A[1][c], A[2][c], A[3][c]);
-    unsigned *y = buf + tr * N + t * P.N4 + s * 16;
+    unsigned yv[16];
 #pragma unroll
     for (int k1 = 0; k1 < 4; k1++) {
       cx b1 = cmult2(A[k1][1], ta16 + 2 * k1, tb16 + 2 * k1), b2 = cmult2(A[k1][2], ta16 + 8 + 2 * k1, tb16 + 8 + 2 * k1),
          b3 = cmult2(A[k1][3], ta16 + 16 + 2 * k1, tb16 + 16 + 2 * k1);
       cx y0, y1, y2, y3;
       bfly4_sat(A[k1][0], b1, b2, b3, inv, y0, y1, y2, y3);
-      y[k1] = pack(y0); y[k1 + 4] = pack(y1); y[k1 + 8] = pack(y2); y[k1 + 12] = pack(y3);
+      yv[k1] = pack(y0); yv[k1 + 4] = pack(y1); yv[k1 + 8] = pack(y2); yv[k1 + 12] = pack(y3);
     }
+    uint4 *y4 = reinterpret_cast<uint4 *>(buf + tr * N + t * P.N4 + s * 16);       // one leaf = 64 contiguous bytes: four 128-bit stores
+#pragma unroll
+    for (int q = 0; q < 4; q++) y4[q] = make_uint4(yv[4 * q], yv[4 * q + 1], yv[4 * q + 2], yv[4 * q + 3]);
   }
   __syncthreads();
   // ---- radix-4 levels: sub-size M -> 4M, in place
@@ -237,7 +247,8 @@ __global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const 
       } else {
         const short *t2 = tw + (size == 128 ? O.tw128 : size == 512 ? O.tw512 : P.rad2_tw) + 2 * k;
         unsigned br, bi;
-        cm32(x1, t2[0], t2[1], inv, br, bi);
+        const cx T2 = ldtw(t2);
+        cm32(x1, T2.r, T2.i, inv, br, bi);
         const unsigned ar = (unsigned)(x0.r * 32767), ai = (unsigned)(x0.i * 32767);
         y0 = pk32(ar + br, ai + bi); y1 = pk32(ar - br, ai - bi);
       }
@@ -255,9 +266,10 @@ __global__ void __launch_bounds__(256) dft_kernel(DftPlan P, TwOffsets O, const 
       unsigned *p = buf + tr * N + k;
       const cx x0 = unpack(p[0]);
       unsigned r, i, r2, i2;
-      cm32(unpack(p[M]), twa[2 * k], twa[2 * k + 1], inv, r, i);
+      const cx TA = ldtw(twa + 2 * k), TB = ldtw(twb + 2 * k);
+      cm32(unpack(p[M]), TA.r, TA.i, inv, r, i);
       const cx x1 = pk32(r, i);
-      cm32(unpack(p[2 * M]), twb[2 * k], twb[2 * k + 1], inv, r, i);
+      cm32(unpack(p[2 * M]), TB.r, TB.i, inv, r, i);
       const cx x2 = pk32(r, i);
       cx y0 = sadd(x0, sadd(x1, x2));
       cm32(x1, -16384, -28378, inv, r, i); cm32(x2, -16384, 28378, inv, r2, i2);
@@ -358,9 +370,10 @@ int dft_init()
   if (cudaMalloc(&c.d_tw, blob.size() * sizeof(short)) != cudaSuccess) { c.last_error = "cudaMalloc twiddles"; return -1; }
   cudaMemcpy(c.d_tw, blob.data(), blob.size() * sizeof(short), cudaMemcpyHostToDevice);
   if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) { c.last_error = "stream"; return -1; }
-  cudaFuncSetAttribute(dft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
-  cudaFuncSetAttribute(dft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
-  cudaFuncSetAttribute(dft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
   c.inited = true;
   return 0;
 }
@@ -390,7 +403,8 @@ int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_o
   DftCtx &c = dctx();
   const unsigned grid = (n + P.tpb - 1) / P.tpb;
   const size_t smem = (size_t)2 * P.tpb * N * 4;
-  dft_kernel<0><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
+  if (inverse) dft_kernel<0, true><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
+  else dft_kernel<0, false><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
   c.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft launch: ") + cudaGetErrorString(e); return -2; }
@@ -464,7 +478,8 @@ NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, cons
   DftPlan P;
   if (!make_plan(N, inverse, scale, &P)) return -4;
   const unsigned grid = (n + P.tpb - 1) / P.tpb;
-  dft_kernel<0><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
+  if (inverse) dft_kernel<0, true><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
+  else dft_kernel<0, false><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
   c.launches++;
   cudaMemcpyAsync(c.h_out, c.d_out, bytes, cudaMemcpyDeviceToHost, c.stream);
   cudaError_t e = cudaStreamSynchronize(c.stream);
@@ -504,8 +519,8 @@ int launch_slot(const nrb200_ofdm_slot_t *d, bool rx, const void *d_in, void *d_
   DftCtx &c = dctx();
   const unsigned n = d->n_symb * d->n_ant, grid = (n + P.tpb - 1) / P.tpb;
   const size_t smem = (size_t)2 * P.tpb * P.N * 4;
-  if (rx) dft_kernel<2><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
-  else dft_kernel<1><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+  if (rx) dft_kernel<2, false><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+  else dft_kernel<1, true><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
   c.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("ofdm slot launch: ") + cudaGetErrorString(e); return -2; }

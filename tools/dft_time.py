@@ -5,13 +5,14 @@ import sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from openairinterface5g_b200.dfts import load_dftslib   # noqa: E402
+from openairinterface5g_b200.dfts import DftsLib   # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 inv = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 nb = int(sys.argv[3]) if len(sys.argv) > 3 else 1792
 dev = torch.device("cuda", 0)
-dl = load_dftslib()
+dl = DftsLib(os.environ["NRB200_DFTS_SO"]) if os.environ.get("NRB200_DFTS_SO") else DftsLib()
+dl.autoinit()
 g = torch.Generator(device=dev); g.manual_seed(1)
 bufs = [torch.randint(-3000, 3000, (nb, 2 * N), dtype=torch.int16, device=dev, generator=g) for _ in range(5)]
 out = torch.empty_like(bufs[0])
