@@ -240,9 +240,11 @@ typedef struct nrb200_pusch_rx_s {
                                              * ul_ch_estimates then holds [2 * nb_rx] planes, index layer * nb_rx + rx, LLRs are layer de-mapped */
   uint32_t noise_var;                       /* 2 layers: nvar of the channel estimator, added to the diagonal of H^H H */
   uint32_t max_ch;                          /* 2 layers: the estimator's max_ch (scales the level measurement, nr_ulsch_scale_channel) */
-  uint32_t pdsch_ue;                        /* 1: the UE's single-layer PDSCH receiver instead (nr_rx_pdsch, NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684): its own
+  uint32_t pdsch_ue;                        /* 1: the UE's PDSCH receiver instead (nr_rx_pdsch, NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684): its own
                                              * extraction patterns, estimate scaling, saturating MRC, thresholds and log2_maxh rule; ul_dmrs_symb_pos = dlDmrsSymbPos,
-                                             * num_dmrs_cdm_grps_no_data = n_dmrs_cdm_groups, the estimates' symbol = get_valid_dmrs_idx_for_channel_est; nb_rx <= 4 */
+                                             * num_dmrs_cdm_grps_no_data = n_dmrs_cdm_groups, the estimates' symbol = get_valid_dmrs_idx_for_channel_est; nb_rx <= 4.
+                                             * nrOfLayers == 2 (nb_rx >= 2, any qam_mod_order): per-layer MRC + nr_zero_forcing_rx (:1726-1869) + layer
+                                             * de-mapping; dl_ch_estimates holds [2 * nb_rx] planes, index layer * nb_rx + rx */
 } nrb200_pusch_rx_t;
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
 /* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */

@@ -291,10 +291,116 @@ __global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTa
   for (int m = 0; m < QM / 2; m++) dst[m] = ((unsigned)o[2 * m] & 0xFFFFu) | ((unsigned)o[2 * m + 1] << 16);
 }
 
+// ---- UE side, two layers: matched filter + saturating MRC per layer, then nr_zero_forcing_rx (:1726-1869) per resource element: H^H H element by element
+// (each antenna's product packed, antennas combined with saturating adds), determinant and adjugate with products shifted by log2_maxh - 2, the adjugate applied
+// to the two matched-filter outputs, thresholds = determinant * QAM_amp (mulhi, << 1) -- of the LAST symbol, like the one-layer path -- and the LLRs written
+// layer de-mapped (nr_dlsch_layer_demapping :1871-1907) and descrambled.  Estimates: plane layer * nb_rx + rx.
+struct C16 { int r, i; };
+__device__ __forceinline__ int p_sra(int v, int s) { return ((unsigned)s & 0xFFu) > 31u ? (v >> 31) : (v >> (s & 0xFF)); }
+__device__ __forceinline__ C16 c_unpack(unsigned w) { return C16{p_lo(w), p_hi(w)}; }
+__device__ __forceinline__ C16 c_conj0_mult1(C16 a, C16 b, int s)     // conj(a) * b >> s, packed (nr_conjch0_mult_ch1, nr_dlsch_channel_compensation)
+{
+  return C16{p_sat16(p_sra((int)((unsigned)(a.r * b.r) + (unsigned)(a.i * b.i)), s)), p_sat16(p_sra((int)((unsigned)(p_wrap16(-a.i) * b.r) + (unsigned)(a.r * b.i)), s))};
+}
+__device__ __forceinline__ C16 c_mult(C16 a, C16 b, int s)            // a * b >> s, packed (nr_a_mult_b)
+{
+  return C16{p_sat16(p_sra((int)((unsigned)(a.r * b.r) + (unsigned)(p_wrap16(-a.i) * b.i)), s)), p_sat16(p_sra((int)((unsigned)(a.i * b.r) + (unsigned)(a.r * b.i)), s))};
+}
+__device__ __forceinline__ C16 c_adds(C16 a, C16 b) { return C16{p_sat16(a.r + b.r), p_sat16(a.i + b.i)}; }
+__device__ __forceinline__ C16 c_neg(C16 a) { return C16{p_wrap16(-a.r), p_wrap16(-a.i)}; }
+// E[c][r] = sum over rx antennas of conj(H[r][a]) H[c][a] >> shift, H read (and scaled) from plane l * nb_rx + a at (symbol chs, index ci)
+__device__ __forceinline__ void ue_gram(const PuschGeom &G, const unsigned *__restrict__ ch, int chs, int ci, int shift, C16 (&H)[2][4], C16 (&E)[2][2])
+{
+#pragma unroll
+  for (int l = 0; l < 2; l++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      if (a < G.nb_rx) H[l][a] = c_unpack(ue_scale(__ldg(ch + (size_t)(l * G.nb_rx + a) * G.ch_stride + (size_t)chs * G.N + ci)));
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      C16 acc = c_conj0_mult1(H[r][0], H[c][0], shift);
+#pragma unroll
+      for (int a = 1; a < 4; a++)
+        if (a < G.nb_rx) acc = c_adds(acc, c_conj0_mult1(H[r][a], H[c][a], shift));
+      E[c][r] = acc;
+    }
+}
+__device__ __forceinline__ C16 ue_det(const C16 (&E)[2][2], int shift0) { return c_adds(c_mult(E[0][0], E[1][1], shift0), c_mult(E[0][1], c_neg(E[1][0]), shift0)); }
+
+template <int QM>
+__global__ void __launch_bounds__(256) pdsch_rx2_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift, const unsigned *__restrict__ rxF,
+                                                        const unsigned *__restrict__ ch, short *__restrict__ llr)
+{
+  __shared__ uint32_t s_gold[(512 * QM) / 32 + 2];
+  const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
+  const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
+  if (i0 >= valid) return;
+  const unsigned bit0 = 2u * (G.llr_off[k] + (unsigned)i0 * QM);
+  if (G.unscramble) {
+    const unsigned w0 = bit0 >> 5, nw = ((bit0 + 512u * QM + 31u) >> 5) - w0;
+    if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
+    __syncthreads();
+  }
+  if (i >= valid) return;
+  const int shift = G.shift_from_dev ? *d_shift : G.shift, shift0 = shift - 2;
+  int rx_idx, ch_idx, mch_idx, dummy;
+  ue_source(G, is_dmrs, i, rx_idx, ch_idx);
+  ue_source(G, G.last_is_dmrs, i, dummy, mch_idx);
+  C16 H[2][4], E[2][2], mf[2], out[2];
+  ue_gram(G, ch, G.ch_sym[k], ch_idx, shift, H, E);
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+    if (a < G.nb_rx) {
+      const C16 y = c_unpack(__ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx));
+#pragma unroll
+      for (int l = 0; l < 2; l++) { const C16 v = c_conj0_mult1(H[l][a], y, shift); mf[l] = a == 0 ? v : c_adds(mf[l], v); }
+    }
+  // adjugate: inv[r][c] = (-1)^(r + c) E[1 - c][1 - r]; layer r = sum over c of inv[c][r] * mf[c], accumulated from zero with saturating adds
+  for (int r = 0; r < 2; r++) {
+    C16 acc = c_adds(C16{0, 0}, c_mult(r == 0 ? E[1][1] : c_neg(E[0][1]), mf[0], shift0));
+    out[r] = c_adds(acc, c_mult(r == 0 ? c_neg(E[1][0]) : E[0][0], mf[1], shift0));
+  }
+  int ma = 0, mb = 0, mc = 0;
+  if (QM > 2 && i < G.last_span) {
+    constexpr int ampa = QM == 4 ? 20724 : QM == 6 ? 20225 : QM == 8 ? 20106 : 0, ampb = QM == 6 ? 10112 : QM == 8 ? 10053 : 0, ampc = QM == 8 ? 5026 : 0;
+    C16 Hm[2][4], Em[2][2];
+    ue_gram(G, ch, G.last_ch_sym, mch_idx, shift, Hm, Em);
+    const int det = ue_det(Em, shift0).r;
+    ma = p_wrap16(((det * ampa) >> 16) << 1); mb = p_wrap16(((det * ampb) >> 16) << 1); mc = p_wrap16(((det * ampc) >> 16) << 1);
+  }
+  const unsigned b = 2u * (G.llr_off[k] + (unsigned)i * QM);
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    const int cr = out[l].r, ci = out[l].i;
+    int o[8];
+    if (QM == 2) { o[0] = cr >> 3; o[1] = ci >> 3; }
+    else {
+      o[0] = cr; o[1] = ci;
+      o[2] = p_subs16(ma, p_abs16w(cr)); o[3] = p_subs16(ma, p_abs16w(ci));
+      if (QM > 4) { o[4] = p_subs16(mb, p_abs16w(o[2])); o[5] = p_subs16(mb, p_abs16w(o[3])); }
+      if (QM > 6) { o[6] = p_subs16(mc, p_abs16w(o[4])); o[7] = p_subs16(mc, p_abs16w(o[5])); }
+    }
+    const unsigned bl = b + (unsigned)l * QM;
+    if (G.unscramble) {
+      const unsigned rel = bl - ((bit0 >> 5) << 5);
+#pragma unroll
+      for (int m = 0; m < QM; m++) { const unsigned r = rel + m; if ((s_gold[r >> 5] >> (r & 31u)) & 1u) o[m] = p_wrap16(-o[m]); }
+    }
+    unsigned *dst = reinterpret_cast<unsigned *>(llr + bl);
+#pragma unroll
+    for (int m = 0; m < QM / 2; m++) dst[m] = ((unsigned)o[2 * m] & 0xFFFFu) | ((unsigned)o[2 * m + 1] << 16);
+  }
+}
+
 // UE: nr_dlsch_scale_channel + nr_dlsch_channel_level on the first symbol with data, log2_maxh = log2_approx(max avg) / 2 + 1 (:433-452)
+// Two layers: one CTA per (layer, antenna) plane, and nr_dlsch_channel_level_median (:1144-1179) on top: (max + min) / 2 of the 4-RE power sums, both
+// seeded with the plane's average; the plane's entry in d_out is then max(average, median), which is all the log2_maxh rule uses.
 __global__ void __launch_bounds__(256) pdsch_level_kernel(PuschGeom G, int meas_k, const unsigned *__restrict__ ch, int *__restrict__ d_out, unsigned *__restrict__ d_count)
 {
   __shared__ unsigned s_lane[4][64];
+  __shared__ long long s_mx[256], s_mn[256];
   const int a = blockIdx.x, is_dmrs = G.is_dmrs[meas_k], len = G.valid[meas_k];
   int x = 0;
   while (x < 31 && !((len >> x) & 1)) x++;
@@ -318,11 +424,37 @@ __global__ void __launch_bounds__(256) pdsch_level_kernel(PuschGeom G, int meas_
   __syncthreads();
   if (threadIdx.x == 0) {
     const long long tot = (long long)(int)s_lane[0][0] + (int)s_lane[1][0] + (int)s_lane[2][0] + (int)s_lane[3][0];
-    d_out[a] = (int)(tot / y);
+    s_lane[0][1] = (unsigned)(int)(tot / y);
+  }
+  __syncthreads();
+  const int avg = (int)s_lane[0][1];
+  int lvl = avg;
+  if (G.nl > 1) {
+    long long mx = avg, mn = avg;
+    for (int v = threadIdx.x; v < (len >> 2); v += blockDim.x) {
+      long long sum = 0;
+      for (int j = 0; j < 4; j++) {
+        int rx_idx, ch_idx;
+        ue_source(G, is_dmrs, 4 * v + j, rx_idx, ch_idx);
+        const unsigned h = ue_scale(__ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[meas_k] * G.N + ch_idx));
+        sum += ((int)((unsigned)(p_lo(h) * p_lo(h)) + (unsigned)(p_hi(h) * p_hi(h)))) >> 2;
+      }
+      mx = max(mx, sum); mn = min(mn, sum);
+    }
+    s_mx[threadIdx.x] = mx; s_mn[threadIdx.x] = mn;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (threadIdx.x < st) { s_mx[threadIdx.x] = max(s_mx[threadIdx.x], s_mx[threadIdx.x + st]); s_mn[threadIdx.x] = min(s_mn[threadIdx.x], s_mn[threadIdx.x + st]); }
+      __syncthreads();
+    }
+    lvl = max(avg, (int)((s_mx[0] + s_mn[0]) >> 1));
+  }
+  if (threadIdx.x == 0) {
+    d_out[a] = lvl;
     __threadfence();
-    if (atomicAdd(d_count, 1u) == (unsigned)G.nb_rx - 1) {
+    if (atomicAdd(d_count, 1u) == (unsigned)(G.nb_rx * G.nl) - 1) {
       int avgs = 0;
-      for (int q = 0; q < G.nb_rx; q++) avgs = max(avgs, ((volatile int *)d_out)[q]);
+      for (int q = 0; q < G.nb_rx * G.nl; q++) avgs = max(avgs, ((volatile int *)d_out)[q]);
       const unsigned v = (unsigned)avgs & 0x7FFFFFFFu;
       d_out[8] = ((v ? 32 - __clz(v) : 0) / 2) + 1;
       *d_count = 0;
@@ -377,7 +509,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
 {
   const int Qm = d.qam_mod_order;
   const int nl = d.nrOfLayers == 0 ? 1 : (int)d.nrOfLayers;
-  if (nl > 2 || (nl == 2 && (Qm < 6 || (d.nb_rx != 2 && d.nb_rx != 4)))) return -4;   // 2 layers: MMSE receiver only, like the reference for Qm >= 6
+  if (nl > 2 || (nl == 2 && !d.pdsch_ue && (Qm < 6 || (d.nb_rx != 2 && d.nb_rx != 4)))) return -4;   // 2 layers: MMSE receiver only, like the reference for Qm >= 6
   if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
       d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || (d.log2_maxh > 31 && d.log2_maxh != 0xFFFFFFFFu))
     return -4;
@@ -388,7 +520,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
   G->unscramble = d.unscramble; G->c_init = (d.rnti << 15) + d.data_scrambling_id;
   G->nl = nl; G->nvar = d.noise_var;
   G->ue = d.pdsch_ue ? 1 : 0; G->cdm = d.num_dmrs_cdm_grps_no_data;
-  if (G->ue && (nl != 1 || d.nb_rx > 4)) return -4;
+  if (G->ue && (d.nb_rx > 4 || (nl == 2 && d.nb_rx < 2))) return -4;     // the reference applies neither MRC nor zero forcing with one rx antenna
   {
     // nr_ulsch_scale_channel: shift_ch_ext = log2_approx(max_ch >> 11) for 2 layers, 0 for one
     int sce = 0;
@@ -438,7 +570,7 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
   int rc = make_geom(d, &G, nullptr);
   if (rc) return rc;
   if (G.ue) {
-    pdsch_level_kernel<<<G.nb_rx, 256, 0, st>>>(G, 0, (const unsigned *)ch, d_out9, d_count);
+    pdsch_level_kernel<<<G.nb_rx * G.nl, 256, 0, st>>>(G, 0, (const unsigned *)ch, d_out9, d_count);
     ctx().launches++;
     NRB200_CUDA_OK(cudaGetLastError(), "pdsch_level launch");
     return 0;
@@ -462,7 +594,14 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
   for (int k = 0; k < G.n_sym; k++) vmax = std::max(vmax, G.valid[k]);
   const dim3 grid((((vmax + 3) & ~3) + 255) / 256, G.n_sym);
   const unsigned *R = (const unsigned *)rxF, *C = (const unsigned *)ch;
-  if (G.ue) {
+  if (G.ue && G.nl == 2) {
+    switch (G.Qm) {
+      case 2: pdsch_rx2_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 4: pdsch_rx2_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 6: pdsch_rx2_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      default: pdsch_rx2_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    }
+  } else if (G.ue) {
     switch (G.Qm) {
       case 2: pdsch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
       case 4: pdsch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;

@@ -226,12 +226,13 @@ class Oracle:
         assert rc == valid, rc
         return llr, comp
 
-    def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est):
-        """UE-side single-layer PDSCH receiver for a whole slot.  Returns (llr int16[G], log2_maxh)."""
+    def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est, nl=1):
+        """UE-side PDSCH receiver for a whole slot (nl = 1: MRC; nl = 2: zero forcing, dl_ch_est [2 * nb_rx] planes).  Returns (llr int16[G], log2_maxh)."""
         x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16)
-        llr = np.zeros(14 * 12 * P.rb_size * P.Qm + 64, np.int16)
+        llr = np.zeros(nl * 14 * 12 * P.rb_size * P.Qm + 64, np.int16)
         sh = C.c_int32(0)
-        n = self.lib.orc_pdsch_rx_slot(C.byref(P), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+        fn = self.lib.orc_pdsch_rx_slot if nl == 1 else self.lib.orc_pdsch_rx_slot_2l
+        n = fn(C.byref(P), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                                        C.byref(sh))
         return llr[:n].copy(), sh.value
 
@@ -495,11 +496,11 @@ class Reference:
         self._uechestlib.refh_pdsch_chest(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p))
         return est.reshape(P.nb_rx, 14, P.fft_size, 2)
 
-    def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est, G):
+    def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est, G, nl=1):
         if not hasattr(self, "_pdschlib"):
             self._pdschlib = C.CDLL(os.path.join(REFDIR, "libref_pdsch.so"))
         prm = np.array([P.fft_size, P.nb_rx, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.Qm, start_symbol, nr_symbols, P.ul_dmrs_symb_pos,
-                        P.dmrs_config_type, P.num_dmrs_cdm_grps_no_data, G], dtype=np.int32)
+                        P.dmrs_config_type, P.num_dmrs_cdm_grps_no_data, G, nl], dtype=np.int32)
         x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16).copy()
         llr = np.zeros(G + 64, np.int16); valid = np.zeros(14, np.int32)
         sh = self._pdschlib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),

@@ -334,3 +334,151 @@ int orc_pdsch_rx_slot(const orc_pusch_t *p, int start_symbol, int nr_symbols, co
   for (int t = 0; t < 3; t++) free(mag[t]);
   return (int)off;
 }
+
+/* ---- UE side, two layers: nr_rx_pdsch with Nl = 2 (same file: nr_dlsch_channel_level_median :1144-1179, nr_dlsch_detection_mrc :1303-1368 per layer,
+ * nr_zero_forcing_rx :1726-1869 with nr_conjch0_mult_ch1 :1679-1720, nr_matrix_inverse / nr_determin :1460-1506,1549-1610 (fixed-point branch),
+ * nr_a_mult_b :1389-1427, nr_a_sum_b :1370-1383, nr_dlsch_layer_demapping :1871-1907).  dl_ch_est holds 2 * nb_rx planes, index layer * nb_rx + rx.
+ * What differs from one layer: the level also takes the (max + min) / 2 "median" of the 4-RE power sums; after the per-layer matched filter + saturating
+ * MRC, H^H H (2x2, each element packed per antenna and summed with saturating adds) is inverted as adjugate / determinant with products shifted by
+ * log2_maxh - 2, the adjugate is applied to the two matched-filter outputs, and the QAM thresholds become determinant * QAM_amp (mulhi, << 1) -- again only
+ * the LAST symbol's thresholds reach the LLR stage.  nb_rx >= 2 (the reference skips MRC and zero forcing when n_rx == 1). */
+static inline int32_t sra32_(int32_t v, int s) { return ((unsigned)s & 0xFF) > 31 ? (v < 0 ? -1 : 0) : v >> (s & 0xFF); }
+typedef struct { int16_t r, i; } c16o;
+static inline c16o conj0_mult1(c16o a, c16o b, int s)   /* conj(a) * b >> s, packed (nr_conjch0_mult_ch1) */
+{
+  c16o o;
+  o.r = sat16(sra32_(wrap32((int64_t)a.r * b.r + (int64_t)a.i * b.i), s));
+  o.i = sat16(sra32_(wrap32((int64_t)wrap16(-a.i) * b.r + (int64_t)a.r * b.i), s));
+  return o;
+}
+static inline c16o a_mult_b(c16o a, c16o b, int s)      /* a * b >> s, packed (nr_a_mult_b) */
+{
+  c16o o;
+  o.r = sat16(sra32_(wrap32((int64_t)a.r * b.r + (int64_t)wrap16(-a.i) * b.i), s));
+  o.i = sat16(sra32_(wrap32((int64_t)a.i * b.r + (int64_t)a.r * b.i), s));
+  return o;
+}
+static inline c16o adds_c(c16o a, c16o b) { c16o o = {sat16((int32_t)a.r + b.r), sat16((int32_t)a.i + b.i)}; return o; }
+static inline c16o neg_c(c16o a) { c16o o = {wrap16(-a.r), wrap16(-a.i)}; return o; }      /* sign_epi16 by -1: -32768 stays */
+static void ue_src(const orc_pusch_t *p, int start_re, int pilots, int i, int *ri, int *ci)
+{
+  const int N = p->fft_size;
+  if (!pilots) { *ri = (start_re + i) % N; *ci = i; return; }
+  int per, first;
+  if (p->dmrs_config_type == 0) { per = 3; first = 1; } else if (p->num_dmrs_cdm_grps_no_data == 1) { per = 4; first = 2; } else { per = 2; first = 4; }
+  const int g = i / per, r = i - g * per;
+  int k = start_re + 6 * g;
+  while (k >= N) k -= N;
+  const int o = p->dmrs_config_type == 0 ? 2 * r + first : r + first;
+  *ri = k + o; *ci = 6 * g + o;
+}
+
+int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out)
+{
+  enum { NL = 2 };
+  const int N = p->fft_size, nrx = p->nb_rx, nb = p->rb_size, Qm = p->Qm, pos = p->ul_dmrs_symb_pos, type = p->dmrs_config_type, cdm = p->num_dmrs_cdm_grps_no_data;
+  const int sz = (nb * 12 + 15) & ~15;
+  const int start_re = (p->first_carrier_offset + (p->rb_start + p->bwp_start) * 12) % N;
+  const int ampv[3] = {Qm == 4 ? 20724 : Qm == 6 ? 20225 : Qm == 8 ? 20106 : 0, Qm == 6 ? 10112 : Qm == 8 ? 10053 : 0, Qm == 8 ? 5026 : 0};
+  if (nrx < 2) return -1;
+  c16o *rx = malloc(sizeof(c16o) * (size_t)sz * nrx), *ch = malloc(sizeof(c16o) * (size_t)sz * nrx * NL);
+  c16o *comp[NL];
+  int16_t *mag[3], *lay[NL];
+  for (int l = 0; l < NL; l++) { comp[l] = calloc((size_t)14 * nb * 12 + sz, sizeof(c16o)); lay[l] = calloc((size_t)14 * nb * 12 * Qm + 64, 2); }
+  for (int t = 0; t < 3; t++) mag[t] = calloc(2 * (size_t)sz, 2);
+  int valid[14] = {0}, log2_maxh = 0;
+  int first_with_data = start_symbol;
+  const int dmrs_data_re = type == 0 ? 12 - 6 * cdm : 12 - 4 * cdm;
+  while (dmrs_data_re == 0 && ((pos >> first_with_data) & 1)) first_with_data++;
+  for (int m = start_symbol; m < start_symbol + nr_symbols; m++) {
+    const int pilots = (pos >> m) & 1, vd = valid_dmrs_idx(pos, m);
+    const int len = pilots ? (type == 0 ? nb * (12 - 6 * cdm) : nb * (12 - 4 * cdm)) : nb * 12;
+    const int nb_rb_0 = len / 12 + ((len % 12) ? 1 : 0), span = nb_rb_0 * 12;
+    memset(rx, 0, sizeof(c16o) * (size_t)sz * nrx); memset(ch, 0, sizeof(c16o) * (size_t)sz * nrx * NL);
+    for (int t = 0; t < 3; t++) memset(mag[t], 0, 4 * (size_t)sz);
+    for (int i = 0; i < len; i++) {
+      int ri, ci;
+      ue_src(p, start_re, pilots, i, &ri, &ci);
+      for (int a = 0; a < nrx; a++) {
+        const int16_t *rxF = rxdataF + 2 * ((size_t)a * 14 + m) * N;
+        rx[(size_t)a * sz + i].r = rxF[2 * ri]; rx[(size_t)a * sz + i].i = rxF[2 * ri + 1];
+        for (int l = 0; l < NL; l++) {
+          const int16_t *h = dl_ch_est + 2 * ((size_t)(l * nrx + a) * 14 + vd) * N;
+          ch[(size_t)(l * nrx + a) * sz + i].r = h[2 * ci]; ch[(size_t)(l * nrx + a) * sz + i].i = h[2 * ci + 1];
+        }
+      }
+    }
+    for (int q = 0; q < NL * nrx; q++)                                  /* nr_dlsch_scale_channel */
+      for (int i = 0; i < span; i++) {
+        c16o *c = ch + (size_t)q * sz + i;
+        c->r = wrap16((((int32_t)c->r * 8192) >> 16) << 3); c->i = wrap16((((int32_t)c->i * 8192) >> 16) << 3);
+      }
+    if (m == first_with_data) {                                         /* level + median -> log2_maxh (:433-452) */
+      const int x = factor2_((uint32_t)len), y = len >> x;
+      int avgs = 0;
+      int32_t avg[NL * 8];
+      for (int q = 0; q < NL * nrx; q++) {
+        const c16o *c = ch + (size_t)q * sz;
+        int32_t lane[4] = {0, 0, 0, 0};
+        for (int i = 0; i < span; i++) lane[i & 3] = wrap32((int64_t)lane[i & 3] + (wrap32((int64_t)c[i].r * c[i].r + (int64_t)c[i].i * c[i].i) >> x));
+        avg[q] = (int32_t)(((int64_t)lane[0] + lane[1] + lane[2] + lane[3]) / y);
+        if (avg[q] > avgs) avgs = avg[q];
+      }
+      for (int q = 0; q < NL * nrx; q++) {
+        const c16o *c = ch + (size_t)q * sz;
+        int64_t mx = avg[q], mn = avg[q];
+        for (int v = 0; v < (len >> 2); v++) {
+          int64_t s = 0;
+          for (int j = 0; j < 4; j++) s += wrap32((int64_t)c[4 * v + j].r * c[4 * v + j].r + (int64_t)c[4 * v + j].i * c[4 * v + j].i) >> 2;
+          if (s > mx) mx = s;
+          if (s < mn) mn = s;
+        }
+        const int32_t med = (int32_t)((mx + mn) >> 1);
+        if (med > avgs) avgs = med;
+      }
+      log2_maxh = (log2_approx_((uint32_t)avgs) / 2) + 1;
+    }
+    const int shift = log2_maxh, shift0 = shift - 2;
+    for (int i = 0; i < span; i++) {
+      c16o mf[NL], E[NL][NL];                                           /* E[c][r] = sum_a conj(H[r][a]) H[c][a] */
+      for (int l = 0; l < NL; l++)
+        for (int a = 0; a < nrx; a++) {
+          const c16o v = conj0_mult1(ch[(size_t)(l * nrx + a) * sz + i], rx[(size_t)a * sz + i], shift);
+          mf[l] = a == 0 ? v : adds_c(mf[l], v);
+        }
+      for (int r = 0; r < NL; r++)
+        for (int c = 0; c < NL; c++)
+          for (int a = 0; a < nrx; a++) {
+            const c16o v = conj0_mult1(ch[(size_t)(r * nrx + a) * sz + i], ch[(size_t)(c * nrx + a) * sz + i], shift);
+            E[c][r] = a == 0 ? v : adds_c(E[c][r], v);
+          }
+      /* determinant: a44[0][0] * a44[1][1] + a44[0][1] * (-a44[1][0]), each product >> shift0 and packed */
+      const c16o det = adds_c(a_mult_b(E[0][0], E[1][1], shift0), a_mult_b(E[0][1], neg_c(E[1][0]), shift0));
+      /* adjugate: inv[r][c] = (-1)^(r+c) a44[1-c][1-r]; output layer r = sum_c inv[c][r] * mf[c] */
+      c16o inv[NL][NL];
+      for (int r = 0; r < NL; r++) for (int c = 0; c < NL; c++) inv[r][c] = ((r + c) & 1) ? neg_c(E[1 - c][1 - r]) : E[1 - c][1 - r];
+      for (int r = 0; r < NL; r++) {
+        c16o acc = {0, 0};
+        for (int c = 0; c < NL; c++) acc = adds_c(acc, a_mult_b(inv[c][r], mf[c], shift0));
+        comp[r][(size_t)m * nb * 12 + i] = acc;
+      }
+      if (Qm > 2)
+        for (int t = 0; t < 3; t++) { const int16_t v = wrap16(((det.r * ampv[t]) >> 16) << 1); mag[t][2 * i] = v; mag[t][2 * i + 1] = v; }
+    }
+    valid[m] = len;
+  }
+  size_t off = 0;
+  for (int m = start_symbol; m < start_symbol + nr_symbols; m++) {
+    for (int l = 0; l < NL; l++) orc_ulsch_llr(Qm, (const int16_t *)(comp[l] + (size_t)m * nb * 12), mag[0], mag[1], mag[2], lay[l] + off, (uint32_t)valid[m]);
+    off += (size_t)valid[m] * Qm;
+  }
+  const size_t n_re = off / Qm;
+  for (size_t i = 0; i < n_re; i++)
+    for (int l = 0; l < NL; l++)
+      for (int q = 0; q < Qm; q++) llr[NL * Qm * i + l * Qm + q] = lay[l][i * Qm + q];
+  if (log2_maxh_out) *log2_maxh_out = log2_maxh;
+  free(rx); free(ch);
+  for (int l = 0; l < NL; l++) { free(comp[l]); free(lay[l]); }
+  for (int t = 0; t < 3; t++) free(mag[t]);
+  return (int)(NL * off);
+}

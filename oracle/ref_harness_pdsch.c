@@ -9,12 +9,12 @@
 #include "PHY/defs_nr_UE.h"
 #include "PHY/NR_UE_TRANSPORT/nr_transport_proto_ue.h"
 
-enum { D_N, D_NB_RX, D_RB_START, D_BWP_START, D_RB_SIZE, D_FCO, D_QM, D_START_SYMBOL, D_NR_SYMBOLS, D_DMRS_POS, D_DMRS_TYPE, D_CDM_GROUPS, D_G, D_COUNT };
+enum { D_N, D_NB_RX, D_RB_START, D_BWP_START, D_RB_SIZE, D_FCO, D_QM, D_START_SYMBOL, D_NR_SYMBOLS, D_DMRS_POS, D_DMRS_TYPE, D_CDM_GROUPS, D_G, D_NL, D_COUNT };
 
-/* rxdataF: [nb_rx][14 N] c16; dl_ch_est: [nb_rx][14 N] c16; llr out: G int16.  Returns log2_maxh; valid_re_out (14) and comp_out (nb_rb*12*14 c16 of rx 0) optional. */
+/* rxdataF: [nb_rx][14 N] c16; dl_ch_est: [nl * nb_rx][14 N] c16 (plane layer * nb_rx + rx); llr out: G int16 (layer de-mapped).  Returns log2_maxh; valid_re_out (14) and comp_out (nb_rb*12*14 c16 of rx 0) optional. */
 int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr_out, int32_t *valid_re_out, int16_t *comp_out)
 {
-  const int N = p[D_N], nrx = p[D_NB_RX], nb_rb = p[D_RB_SIZE];
+  const int N = p[D_N], nrx = p[D_NB_RX], nb_rb = p[D_RB_SIZE], nl = p[D_NL] > 1 ? p[D_NL] : 1;
   PHY_VARS_NR_UE *ue = calloc(1, sizeof(*ue));
   NR_DL_FRAME_PARMS *fp = &ue->frame_parms;
   fp->ofdm_symbol_size = N; fp->symbols_per_slot = 14; fp->nb_antennas_rx = nrx; fp->N_RB_DL = 273; fp->first_carrier_offset = p[D_FCO];
@@ -22,7 +22,7 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
   ue->chest_time = 0;
   NR_UE_DLSCH_t dlsch[2];
   memset(dlsch, 0, sizeof(dlsch));
-  dlsch[0].Nl = 1; dlsch[0].active = true; dlsch[0].rnti_type = 0;
+  dlsch[0].Nl = nl; dlsch[0].active = true; dlsch[0].rnti_type = 0;
   fapi_nr_dl_config_dlsch_pdu_rel15_t *c = &dlsch[0].dlsch_config;
   c->BWPStart = p[D_BWP_START]; c->start_rb = p[D_RB_START]; c->number_rbs = nb_rb; c->start_symbol = p[D_START_SYMBOL]; c->number_symbols = p[D_NR_SYMBOLS];
   c->dlDmrsSymbPos = p[D_DMRS_POS]; c->dmrsConfigType = p[D_DMRS_TYPE]; c->n_dmrs_cdm_groups = p[D_CDM_GROUPS]; c->qamModOrder = p[D_QM]; c->pduBitmap = 0;
@@ -32,13 +32,13 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
   UE_nr_rxtx_proc_t proc;
   memset(&proc, 0, sizeof(proc));
   const int est_size = 14 * N, rx_size_symbol = (nb_rb * 12 + 15) & ~15;
-  int32_t (*est)[est_size] = calloc(nrx, sizeof(int32_t) * est_size);
+  int32_t (*est)[est_size] = calloc((size_t)nl * nrx, sizeof(int32_t) * est_size);
   c16_t (*rx)[est_size] = calloc(nrx, sizeof(c16_t) * est_size);
-  memcpy(est, dl_ch_est, (size_t)nrx * est_size * 4);
+  memcpy(est, dl_ch_est, (size_t)nl * nrx * est_size * 4);
   memcpy(rx, rxdataF, (size_t)nrx * est_size * 4);
   int32_t (*comp)[nrx][rx_size_symbol * 14];
-  posix_memalign((void **)&comp, 32, sizeof(int32_t) * 1 * nrx * rx_size_symbol * 14);
-  memset(comp, 0, sizeof(int32_t) * 1 * nrx * rx_size_symbol * 14);
+  posix_memalign((void **)&comp, 32, sizeof(int32_t) * nl * nrx * rx_size_symbol * 14);
+  memset(comp, 0, sizeof(int32_t) * nl * nrx * rx_size_symbol * 14);
   int16_t *llr[2];
   posix_memalign((void **)&llr[0], 64, 2 * (size_t)p[D_G] + 4096); memset(llr[0], 0, 2 * (size_t)p[D_G] + 4096);
   llr[1] = NULL;

@@ -393,3 +393,25 @@ def test_pdsch_rx_slot_ue(oracle, reference):
         llr_r, sh_r, valid = reference.pdsch_rx_slot(P, start, nsym, rx, h, llr_o.size)
         assert sh_o == sh_r, (N, nb_rx, Qm, sh_o, sh_r)
         assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
+
+
+PDSCH_2L_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, amplitude (rx, h)
+    (4096, 2, 0, 273, 6, 1 << 2, 0, 1, 273, 1, 13, (2000, 1500)), (4096, 4, 0, 273, 8, 1 << 2, 0, 2, 273, 1, 13, (900, 700)),
+    (2048, 2, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, (4000, 6000)), (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, (300, 200)),
+    (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, (2000, 1500)), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12, (12000, 9000)),
+    (512, 4, 3, 11, 8, 1 << 1, 0, 1, 25, 1, 6, (32767, 32767)), (512, 2, 0, 25, 6, 1 << 2, 0, 1, 25, 0, 14, (60, 40)),
+]
+
+
+def test_pdsch_rx_slot_ue_2layers(oracle, reference):
+    """UE-side PDSCH receiver, two layers (MRC per layer + nr_zero_forcing_rx + layer de-mapping): nr_rx_pdsch symbol loop vs the oracle."""
+    from oracle.bindings import PuschParms
+    rng = np.random.default_rng(66)
+    for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, (ay, ah) in PDSCH_2L_CASES:
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(2 * nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        llr_o, sh_o = oracle.pdsch_rx_slot(P, start, nsym, rx, h, nl=2)
+        llr_r, sh_r, valid = reference.pdsch_rx_slot(P, start, nsym, rx, h, llr_o.size, nl=2)
+        assert sh_o == sh_r, (N, nb_rx, Qm, sh_o, sh_r)
+        assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
