@@ -68,6 +68,17 @@ class PuschParms(C.Structure):       # orc_pusch_t
                                          "dmrs_config_type", "num_dmrs_cdm_grps_no_data")]
 
 
+class PdschTxParms(C.Structure):     # orc_pdsch_tx_t
+    _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "Qm", "nrOfLayers", "start_symbol",
+                                         "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports", "scid",
+                                         "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp")]
+
+    def G(self):
+        n_dmrs_sym = bin(self.dl_dmrs_symb_pos & (((1 << self.nr_of_symbols) - 1) << self.start_symbol)).count("1")
+        per = self.num_dmrs_cdm_grps_no_data * (6 if self.dmrs_config_type == 0 else 4)
+        return (12 * self.nr_of_symbols - per * bin(self.dl_dmrs_symb_pos).count("1")) * self.rb_size * self.nrOfLayers * self.Qm
+
+
 class Oracle:
     def __init__(self):
         so = os.path.join(HERE, "liboracle.so")
@@ -235,6 +246,16 @@ class Oracle:
         n = fn(C.byref(P), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                                        C.byref(sh))
         return llr[:n].copy(), sh.value
+
+    def pdsch_tx_slot(self, P, bits):
+        """gNB PDSCH transmitter after the encoder: bits (uint8, one per element, P.G() of them) -> txdataF [nb_tx][14][N][2] (zeros where nothing is mapped)."""
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        assert b.size == P.G(), (b.size, P.G())
+        out = np.zeros((P.nb_tx, 14, P.fft_size, 2), np.int16)
+        self.lib.orc_pdsch_tx_slot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.lib.orc_pdsch_tx_slot(C.addressof(P), b.ctypes.data, out.ctypes.data)
+        assert rc == b.size, rc
+        return out
 
     # ---- slot-level OFDM front end
     def ofdm_geometry(self, N, mu, slot):
@@ -506,6 +527,18 @@ class Reference:
         sh = self._pdschlib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                                                valid.ctypes.data_as(C.c_void_p), None)
         return llr[:G].copy(), int(sh), valid
+
+    def pdsch_tx_slot(self, P, bits, n_rb_dl):
+        if not hasattr(self, "_pdschtxlib"):
+            self._pdschtxlib = C.CDLL(os.path.join(REFDIR, "libref_pdschtx.so"))
+        prm = np.array([P.fft_size, n_rb_dl, P.nb_tx, P.slot, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.Qm, P.nrOfLayers, P.start_symbol,
+                        P.nr_of_symbols, P.dl_dmrs_symb_pos, P.dmrs_config_type, P.num_dmrs_cdm_grps_no_data, P.dmrs_ports, P.scid, P.dl_dmrs_scrambling_id,
+                        P.data_scrambling_id, P.rnti, P.amp], dtype=np.int32)
+        b = np.ascontiguousarray(bits, dtype=np.uint8).copy()
+        out = np.zeros((P.nb_tx, 14, P.fft_size, 2), np.int16)
+        self._pdschtxlib.refh_pdsch_tx_slot.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        self._pdschtxlib.refh_pdsch_tx_slot(prm.ctypes.data, b.ctypes.data, b.size, out.ctypes.data)
+        return out
 
     def _pusch(self):
         if not hasattr(self, "_puschlib"):

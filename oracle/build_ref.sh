@@ -78,4 +78,9 @@ gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_uechest.c 
 # UE-side PDSCH receiver: the real nr_rx_pdsch, symbol by symbol
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdsch.c $HERE/ref_harness_pdsch.c $R/openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_demodulation.c \
     $R/openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_llr_computation.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/TOOLS/log2_approx.c -lm -o libref_pdsch.so || echo "libref_pdsch.so: FAILED"
+# gNB-side PDSCH transmitter after the encoder: the real nr_generate_pdsch with nr_dlsch_encoding replaced by the harness (bits in)
+gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdschtx.c $HERE/ref_harness_pdschtx.c $R/openair1/PHY/NR_TRANSPORT/nr_dlsch.c \
+    $R/openair1/PHY/NR_REFSIG/nr_gold.c $R/openair1/PHY/NR_TRANSPORT/nr_sch_dmrs.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/NR_REFSIG/ptrs_nr.c \
+    $R/common/utils/nr/nr_common.c $R/openair1/PHY/MODULATION/nr_modulation.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c $R/openair1/PHY/NR_TRANSPORT/nr_scrambling.c \
+    $R/openair1/PHY/NR_REFSIG/scrambling_luts.c -lm -o libref_pdschtx.so || echo "libref_pdschtx.so: FAILED"
 ls -la $W/*.so

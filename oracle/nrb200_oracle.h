@@ -97,6 +97,14 @@ void orc_ofdm_geometry(int N, int mu, int slot, uint32_t *prefix, uint32_t *cp_s
 void orc_ofdm_tx_slot(int N, int mu, int nb_rb, int slot, int nsymb, const int16_t *rot, int16_t *txdataF, int16_t *txdata);
 void orc_ofdm_rx_slot(int N, int mu, int nb_rb, int slot, int divisor, int sample_offset, const int16_t *rot, const int16_t *rxdata, int16_t *rxdataF);
 
+/* gNB PDSCH transmitter after the encoder (nrb200_pdschtx_oracle.c): bits (one per byte, G of them) -> txdataF [nb_tx][14][fft_size] c16; only the
+ * allocation's REs of the PDSCH symbols are written.  Returns G (= the length nr_generate_pdsch derives) or < 0. */
+typedef struct {
+  int32_t fft_size, nb_tx, slot, rb_start, bwp_start, rb_size, first_carrier_offset, Qm, nrOfLayers, start_symbol, nr_of_symbols, dl_dmrs_symb_pos,
+          dmrs_config_type, num_dmrs_cdm_grps_no_data, dmrs_ports, scid, dl_dmrs_scrambling_id, data_scrambling_id, rnti, amp;
+} orc_pdsch_tx_t;
+int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txdataF);
+
 #ifdef __cplusplus
 }
 #endif

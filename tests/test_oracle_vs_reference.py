@@ -415,3 +415,25 @@ def test_pdsch_rx_slot_ue_2layers(oracle, reference):
         llr_r, sh_r, valid = reference.pdsch_rx_slot(P, start, nsym, rx, h, llr_o.size, nl=2)
         assert sh_o == sh_r, (N, nb_rx, Qm, sh_o, sh_r)
         assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
+
+
+PDSCH_TX_CASES = [  # N, carrier PRBs, nb_tx, slot, rb_start, rb_size, Qm, layers, start_symbol, nr_symbols, dmrs_pos, dmrs_type, cdm groups, dmrs_ports, scid, amp
+    (4096, 273, 2, 1, 0, 273, 6, 2, 1, 13, 1 << 2, 0, 1, 0b0011, 0, 512), (4096, 273, 4, 7, 0, 273, 8, 1, 1, 13, 1 << 2, 0, 2, 0b0001, 0, 512),
+    (2048, 106, 2, 3, 10, 50, 4, 2, (1), 13, (1 << 2) | (1 << 11), 0, 2, 0b1100, 1, 700), (2048, 106, 4, 19, 30, 76, 2, 4, 2, 10, 1 << 3, 0, 2, 0b1111, 0, 1000),
+    (1024, 52, 2, 5, 0, 52, 6, 2, 1, 13, 1 << 2, 1, 1, 0b000011, 0, 512), (2048, 106, 4, 0, 20, 31, 4, 3, 2, 12, 1 << 2, 1, 2, 0b001101, 1, 300),
+    (512, 25, 1, 9, 3, 11, 8, 1, 1, 6, 1 << 1, 0, 1, 0, 0, 512), (512, 25, 2, 11, 0, 25, 6, 2, 0, 14, (1 << 2) | (1 << 3), 0, 2, 0b0101, 0, 2047),
+    (1536, 79, 2, 2, 0, 79, 6, 2, 1, 13, (1 << 2) | (1 << 7) | (1 << 11), 1, 3, 0b110000, 0, 512),
+]
+
+
+def test_pdsch_tx_slot(oracle, reference):
+    """gNB PDSCH transmitter after the encoder: the reference's nr_generate_pdsch (scrambling ... txdataF) vs the oracle restatement."""
+    from oracle.bindings import PdschTxParms
+    rng = np.random.default_rng(70)
+    for N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp in PDSCH_TX_CASES:
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234, amp)
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        t_o = oracle.pdsch_tx_slot(P, bits)
+        t_r = reference.pdsch_tx_slot(P, bits, carrier)
+        assert np.array_equal(t_o, t_r), (N, nrb, Qm, nl, dpos, dtype_, cdm, ports, [tuple(x) for x in np.argwhere(t_o != t_r)[:5]])
+        assert np.count_nonzero(t_o) > 0
