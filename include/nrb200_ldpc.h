@@ -297,6 +297,30 @@ int32_t nrb200_ldpc_offload_init(void);   /* = LDPCinit of libldpc_b200.so under
 int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t r, const int8_t *llr, uint8_t *out);
 int32_t nrb200_ldpc_offload_encode(const uint8_t *in, uint8_t *out, const nrb200_ldpc_enc_params_t *impp);
 
+/* ---- Part 9: gNB PDSCH transmitter after the encoder -------------------------------------------------------------------
+ * One launch replaces, for one code word on 1..4 layers without PT-RS and with the identity precoder (pm_idx 0), everything nr_generate_pdsch
+ * (openair1/PHY/NR_TRANSPORT/nr_dlsch.c:56-583) does after nr_dlsch_encoding: nr_pdsch_codeword_scrambling (:160), nr_modulation (:175), nr_layer_mapping
+ * (:192), DMRS generation and resource mapping (:236-478) and the copy into txdataF (:490-530).  Field names follow nfapi_nr_dl_tti_pdsch_pdu_rel15_t /
+ * NR_DL_FRAME_PARMS / PHY_VARS_gNB.  f: the encoder's output, nrb200_pdsch_tx_num_bits() rate-matched and interleaved bits, one per byte (what
+ * nrb200_ldpc_rm_tx_batch_* writes).  txdataF: [nb_tx][14][fft_size] c16 of the slot (txdataF_offset applied by the caller); only the allocation's REs of
+ * the PDSCH symbols are written (antennas beyond the layers get zeros there).  DMRS ports 0..3 (type 1) / 0..5 (type 2) in CDM groups without data; the
+ * amplitude quirks of the reference's resource mapping are reproduced.  Anything else returns -4. */
+typedef struct nrb200_pdsch_tx_s {
+  uint32_t fft_size, nb_tx;                 /* ofdm_symbol_size, nb_antennas_tx */
+  uint32_t slot;                            /* slot in the frame (DMRS sequence) */
+  uint32_t rb_start, bwp_start, rb_size, first_carrier_offset;
+  uint32_t qam_mod_order, nrOfLayers;
+  uint32_t start_symbol_index, nr_of_symbols, dl_dmrs_symb_pos, dmrs_config_type /* 0 = type 1 */, num_dmrs_cdm_grps_no_data;
+  uint32_t dmrs_ports;                      /* bitmap; 0 = port 0 (DCI 1_0), layer l uses the l-th set bit (get_dmrs_port) */
+  uint32_t scid, dl_dmrs_scrambling_id, data_scrambling_id, rnti;
+  uint32_t amp;                             /* gNB->TX_AMP */
+  uint32_t tx_stride;                       /* _dev: c16 between antennas of txdataF */
+} nrb200_pdsch_tx_t;
+uint32_t nrb200_pdsch_tx_num_bits(const nrb200_pdsch_tx_t *d);                 /* G = nb_re * Qm as nr_generate_pdsch derives it, 0 if invalid */
+int32_t nrb200_pdsch_tx_slot_dev(const nrb200_pdsch_tx_t *d, const uint8_t *d_f, int16_t *d_txdataF, void *stream);
+/* host buffers; txdataF is contiguous [nb_tx][14][fft_size] and is read and written back (REs outside the allocation keep their values) */
+int32_t nrb200_pdsch_tx_slot_host(const nrb200_pdsch_tx_t *d, const uint8_t *f, int16_t *txdataF);
+
 /* Device in use / last CUDA error text (diagnostics; never NULL). */
 int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);

@@ -12,6 +12,7 @@ struct GoldTables { uint32_t t[2][kGoldPow][8][16]; };
 
 int scramble_mod_init();                    // builds the tables on first use; 0 ok
 const GoldTables *gold_tables_dev();        // device pointer (valid after scramble_mod_init)
+const uint32_t *mod_tables_dev();           // QAM tables {re | im << 16}: QPSK at 0, 16QAM at 4, 64QAM at 20, 256QAM at 84
 
 __device__ __forceinline__ uint32_t gold_matvec(const uint32_t (*__restrict__ t)[16], uint32_t x)
 {

@@ -26,6 +26,8 @@ int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_
 int launch_rm_rx8(const nrb200_rm_desc_t &p, const int8_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
                   int8_t *llr, uint32_t llr_stride, cudaStream_t st);
 int launch_modulate(int Qm, uint32_t length_bits, const uint8_t *bits, int16_t *out, cudaStream_t st);
+uint32_t pdsch_tx_num_bits(const nrb200_pdsch_tx_t &d);
+int launch_pdsch_tx(const nrb200_pdsch_tx_t &d, const uint8_t *f, int16_t *txF, cudaStream_t st);
 int launch_pusch_llr(int Qm, uint32_t nb_re, const int16_t *y, const int16_t *ma, const int16_t *mb, const int16_t *mc, int16_t *out, cudaStream_t st);
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st);
 int launch_rm_rx(const nrb200_rm_desc_t &p, const int16_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
@@ -494,6 +496,40 @@ NRB200_EXPORT int32_t nrb200_modulate_host(const uint32_t *bits, uint32_t length
   if (length_bits / Qm == 0) return 0;
   return host_roundtrip(bits, (length_bits + 7) / 8, out, 4 * (size_t)(length_bits / Qm), false, [&](Workspace *w) {
     return launch_modulate(Qm, length_bits, (const uint8_t *)w->d_in, (int16_t *)w->d_out, w->stream); });
+}
+
+// ------------------------------------------------------------------------------------------ PDSCH transmitter after the encoder
+NRB200_EXPORT uint32_t nrb200_pdsch_tx_num_bits(const nrb200_pdsch_tx_t *d) { return d ? pdsch_tx_num_bits(*d) : 0; }
+
+NRB200_EXPORT int32_t nrb200_pdsch_tx_slot_dev(const nrb200_pdsch_tx_t *d, const uint8_t *d_f, int16_t *d_txF, void *stream)
+{
+  if (ensure_init() || !d) return -1;
+  return launch_pdsch_tx(*d, d_f, d_txF, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_pdsch_tx_slot_host(const nrb200_pdsch_tx_t *d, const uint8_t *f, int16_t *txdataF)
+{
+  if (ensure_init() || !d) return -1;
+  const uint32_t G = pdsch_tx_num_bits(*d);
+  if (G == 0) return -4;
+  const size_t tx_bytes = (size_t)d->nb_tx * 14 * d->fft_size * 4;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(G + 64, tx_bytes, 16)) { if (w) ctx().release(w); return -5; }
+  nrb200_pdsch_tx_t dd = *d;
+  dd.tx_stride = 14 * d->fft_size;
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, f, G);
+    std::memcpy(w->h_out, txdataF, tx_bytes);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, G, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync(w->d_out, w->h_out, tx_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = launch_pdsch_tx(dd, (const uint8_t *)w->d_in, (int16_t *)w->d_out, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, tx_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(txdataF, w->h_out, tx_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------ PUSCH inner receiver (one layer)

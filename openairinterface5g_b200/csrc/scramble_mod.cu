@@ -21,6 +21,7 @@ static inline uint32_t step1(uint32_t x) { x = (x >> 1) ^ (x >> 4); return x ^ (
 static inline uint32_t step2(uint32_t x) { x = (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4); return x ^ (x << 31) ^ (x << 30) ^ (x << 29) ^ (x << 28); }
 
 const GoldTables *gold_tables_dev() { return d_gold; }
+const uint32_t *mod_tables_dev() { return d_modtab; }
 
 int scramble_mod_init()
 {

@@ -80,6 +80,12 @@ class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
                                           "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue")]
 
 
+class PdschTxDesc(C.Structure):       # nrb200_pdsch_tx_t (field names of nfapi_nr_dl_tti_pdsch_pdu_rel15_t / NR_DL_FRAME_PARMS)
+    _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order", "nrOfLayers",
+                                          "start_symbol_index", "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports",
+                                          "scid", "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "tx_stride")]
+
+
 class LdpcLib:
     """ldpc_interface_t equivalent bound to libldpc_b200.so."""
 
@@ -359,6 +365,31 @@ class LdpcLib:
         self._check(self.lib.nrb200_pusch_inner_rx_dev(C.addressof(desc), rxdataF.data_ptr(), ul_ch_estimates.data_ptr(),
                                                        0 if level is None else level.data_ptr() + 32, llr.data_ptr(), st), "pusch_inner_rx_dev")
         return llr
+
+    # ---- gNB PDSCH transmitter after the encoder (nr_generate_pdsch from scrambling to txdataF)
+    def pdsch_tx_num_bits(self, desc):
+        self.lib.nrb200_pdsch_tx_num_bits.restype = C.c_uint32
+        return int(self.lib.nrb200_pdsch_tx_num_bits(C.c_void_p(C.addressof(desc))))
+
+    def pdsch_tx_slot_host(self, desc, f, txdataF=None):
+        """f: uint8 bits (one per element); txdataF [nb_tx][14][N][2] int16 in/out (zeros when None).  Returns txdataF."""
+        G = self.pdsch_tx_num_bits(desc)
+        if G == 0:
+            raise ValueError("invalid PDSCH descriptor")
+        b = np.ascontiguousarray(f, dtype=np.uint8)
+        assert b.size == G, (b.size, G)
+        out = np.zeros((desc.nb_tx, 14, desc.fft_size, 2), np.int16) if txdataF is None else np.ascontiguousarray(txdataF, dtype=np.int16).copy()
+        self.lib.nrb200_pdsch_tx_slot_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.nrb200_pdsch_tx_slot_host(C.addressof(desc), b.ctypes.data, out.ctypes.data), "pdsch_tx_slot_host")
+        return out
+
+    def pdsch_tx_slot_torch(self, desc, f, txdataF):
+        """Device-resident variant: f uint8[G], txdataF int16 [nb_tx][14][N][2] (desc.tx_stride must be set)."""
+        import torch
+        st = torch.cuda.current_stream(f.device).cuda_stream
+        self.lib.nrb200_pdsch_tx_slot_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.lib.nrb200_pdsch_tx_slot_dev(C.addressof(desc), f.data_ptr(), txdataF.data_ptr(), st), "pdsch_tx_slot_dev")
+        return txdataF
 
     # ---- demodulation: nr_ulsch_compute_llr (single layer, max-log)
     def pusch_llr_host(self, Qm, rxF, mag_a=None, mag_b=None, mag_c=None):

@@ -1,0 +1,42 @@
+"""GPU parity of the fused PDSCH transmitter kernel (scrambling + QAM mapping + layer mapping + DMRS + resource mapping + identity precoding, one launch)
+against the CPU oracle, which tests/test_oracle_vs_reference.py pins to the reference's own nr_generate_pdsch."""
+import numpy as np
+import pytest
+
+from oracle.bindings import PdschTxParms
+from openairinterface5g_b200.ldpc import PdschTxDesc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # N, carrier PRBs, nb_tx, slot, rb_start, rb_size, Qm, layers, start_symbol, nr_symbols, dmrs_pos, dmrs_type, cdm groups, dmrs_ports, scid, amp
+    (4096, 273, 2, 1, 0, 273, 6, 2, 1, 13, 1 << 2, 0, 1, 0b0011, 0, 512), (4096, 273, 4, 7, 0, 273, 8, 1, 1, 13, 1 << 2, 0, 2, 0b0001, 0, 512),
+    (2048, 106, 2, 3, 10, 50, 4, 2, 1, 13, (1 << 2) | (1 << 11), 0, 2, 0b1100, 1, 700), (2048, 106, 4, 19, 30, 76, 2, 4, 2, 10, 1 << 3, 0, 2, 0b1111, 0, 1000),
+    (1024, 52, 2, 5, 0, 52, 6, 2, 1, 13, 1 << 2, 1, 1, 0b000011, 0, 512), (2048, 106, 4, 0, 20, 31, 4, 3, 2, 12, 1 << 2, 1, 2, 0b001101, 1, 300),
+    (512, 25, 1, 9, 3, 11, 8, 1, 1, 6, 1 << 1, 0, 1, 0, 0, 512), (512, 25, 2, 11, 0, 25, 6, 2, 0, 14, (1 << 2) | (1 << 3), 0, 2, 0b0101, 0, 2047),
+    (1536, 79, 2, 2, 0, 79, 6, 2, 1, 13, (1 << 2) | (1 << 7) | (1 << 11), 1, 3, 0b110000, 0, 512), (4096, 273, 4, 4, 0, 273, 8, 4, 1, 13, 1 << 2, 0, 2, 0b1111, 0, 512),
+]
+
+
+def test_pdsch_tx_vs_oracle(ldpc, oracle):
+    rng = np.random.default_rng(71)
+    for N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp in CASES:
+        fco = N - carrier * 6
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234, amp)
+        d = PdschTxDesc(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234, amp, 0)
+        assert ldpc.pdsch_tx_num_bits(d) == P.G()
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        want = oracle.pdsch_tx_slot(P, bits)
+        got = ldpc.pdsch_tx_slot_host(d, bits)
+        assert np.array_equal(got, want), (N, nrb, Qm, nl, dpos, dtype_, cdm, ports, [tuple(x) for x in np.argwhere(got != want)[:6]])
+        # REs outside the allocation keep what the caller had there
+        pre = rng.integers(-100, 100, size=want.shape).astype(np.int16)
+        got2 = ldpc.pdsch_tx_slot_host(d, bits, pre)
+        mask = np.zeros(want.shape[1:3], bool)
+        ks = (fco + rb0 * 12 + np.arange(nrb * 12)) % N
+        mask[s0:s0 + ns, :][:, ks] = True
+        assert np.array_equal(got2[:, mask], want[:, mask]) and np.array_equal(got2[:, ~mask], pre[:, ~mask])
+
+
+def test_pdsch_tx_rejects_unsupported(ldpc):
+    bad = PdschTxDesc(1024, 4, 0, 20, 0, 31, 1024 - 52 * 6, 4, 3, 2, 12, 1 << 2, 1, 2, 0b001101, 1, 40, 501, 0x1234, 300, 0)   # the reference's over-mapping case
+    assert ldpc.pdsch_tx_num_bits(bad) == 0
