@@ -517,6 +517,18 @@ class Reference:
         self._uechestlib.refh_pdsch_chest(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p))
         return est.reshape(P.nb_rx, 14, P.fft_size, 2)
 
+    def ue_slot_fep(self, N, mu, nb_rb, nrx, slot, divisor, rot_dl224, timeshift, rxdata):
+        """the UE's nr_slot_fep for the 14 symbols of a slot.  rxdata [nrx][samples][2]; returns rxdataF [nrx][14 N 2]."""
+        if not hasattr(self, "_uechestlib"):
+            self._uechestlib = C.CDLL(os.path.join(REFDIR, "libref_uechest.so"))
+            assert self._uechestlib.refh_uechest_init(os.path.join(REFDIR, "libref_dfts.so").encode()) == 0
+        x = np.ascontiguousarray(rxdata, dtype=np.int16).reshape(nrx, -1)
+        out = np.zeros((nrx, 2 * 14 * N), np.int16)
+        r = np.ascontiguousarray(rot_dl224, dtype=np.int16); t = np.ascontiguousarray(timeshift, dtype=np.int16)
+        self._uechestlib.refh_ue_slot_fep.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        self._uechestlib.refh_ue_slot_fep(N, mu, nb_rb, nrx, slot, divisor, r.ctypes.data, t.ctypes.data, x.ctypes.data, x.shape[1] // 2, out.ctypes.data)
+        return out
+
     def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est, G, nl=1):
         if not hasattr(self, "_pdschlib"):
             self._pdschlib = C.CDLL(os.path.join(REFDIR, "libref_pdsch.so"))

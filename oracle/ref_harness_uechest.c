@@ -66,3 +66,46 @@ int refh_pdsch_chest(const int32_t *p, const int16_t *rxdataF, int16_t *dl_ch_es
   free(ue->nr_gold_pdsch[0]); free(est); free(rx); free(ue);
   return 0;
 }
+
+/* UE OFDM front end: the real nr_slot_fep (MODULATION/slot_fep_nr.c:37-113) for the 14 symbols of slot Ns of a synchronised UE: dft + apply_nr_rotation_RX
+ * with the DL rotation table.  rxdata: [nb_rx][samples] c16 starting at sample 0 of the frame; rot_dl: 224 pairs; timeshift: N pairs; rxdataF out [nb_rx][14 N]. */
+static uint32_t u_samples_per_slot(int slot, const NR_DL_FRAME_PARMS *fp)
+{
+  if (fp->numerology_index == 0) return fp->samples_per_subframe;
+  return (slot % (fp->slots_per_subframe / 2)) ? fp->samples_per_slotN0 : fp->samples_per_slot0;
+}
+static uint32_t u_slot_timestamp(int slot, const NR_DL_FRAME_PARMS *fp, uint8_t ahead)
+{
+  uint32_t s = 0;
+  for (int i = ahead ? slot : 0; i < (ahead ? slot + ahead : slot); i++) s += u_samples_per_slot(i, fp);
+  return s;
+}
+int refh_ue_slot_fep(int N, int mu, int nb_rb, int nrx, int Ns, int divisor, const int16_t *rot_dl, const int16_t *timeshift, const int16_t *rxdata, uint32_t n_samples,
+                     int16_t *rxdataF)
+{
+  PHY_VARS_NR_UE *ue = calloc(1, sizeof(*ue));
+  NR_DL_FRAME_PARMS *fp = &ue->frame_parms;
+  fp->ofdm_symbol_size = N; fp->numerology_index = mu; fp->slots_per_subframe = 1 << mu; fp->slots_per_frame = 10 << mu; fp->symbols_per_slot = 14;
+  fp->N_RB_DL = fp->N_RB_UL = nb_rb; fp->first_carrier_offset = N - nb_rb * 6; fp->nb_antennas_rx = nrx;
+  fp->nb_prefix_samples = N / 128 * 9; fp->nb_prefix_samples0 = N / 128 * (9 + (1 << mu));
+  fp->samples_per_slotN0 = (fp->nb_prefix_samples + N) * 14; fp->samples_per_slot0 = fp->nb_prefix_samples0 + 13 * fp->nb_prefix_samples + 14 * N;
+  fp->samples_per_subframe = (fp->nb_prefix_samples0 + N) * 2 + (fp->nb_prefix_samples + N) * (14 * fp->slots_per_subframe - 2);
+  fp->samples_per_frame = 10 * fp->samples_per_subframe; fp->samples_per_slot_wCP = 14 * N;
+  fp->get_samples_per_slot = u_samples_per_slot; fp->get_samples_slot_timestamp = u_slot_timestamp; fp->ofdm_offset_divisor = divisor;
+  memcpy(fp->symbol_rotation[0], rot_dl, 224 * 4);
+  memcpy(fp->timeshift_symbol_rotation, timeshift, (size_t)N * 4);
+  ue->is_synchronized = 1;
+  ue->common_vars.rxdata = calloc(nrx, sizeof(c16_t *));
+  for (int a = 0; a < nrx; a++) { posix_memalign((void **)&ue->common_vars.rxdata[a], 32, 4 * (size_t)n_samples + 64); memcpy(ue->common_vars.rxdata[a], rxdata + 2 * (size_t)a * n_samples, 4 * (size_t)n_samples); }
+  UE_nr_rxtx_proc_t proc;
+  memset(&proc, 0, sizeof(proc));
+  proc.nr_slot_rx = Ns;
+  c16_t (*rxF)[14 * N];
+  posix_memalign((void **)&rxF, 32, sizeof(c16_t) * (size_t)nrx * 14 * N);
+  memset(rxF, 0, sizeof(c16_t) * (size_t)nrx * 14 * N);
+  for (int l = 0; l < 14; l++) nr_slot_fep(ue, &proc, (unsigned char)l, rxF);
+  memcpy(rxdataF, rxF, sizeof(c16_t) * (size_t)nrx * 14 * N);
+  for (int a = 0; a < nrx; a++) free(ue->common_vars.rxdata[a]);
+  free(ue->common_vars.rxdata); free(rxF); free(ue);
+  return 0;
+}

@@ -5,3 +5,4 @@
 char openair0_cfg[65536];
 #define REFH_DEAD(name) void name(void) { fprintf(stderr, "ref_harness_uechest: unexpected call of " #name "\n"); abort(); }
 REFH_DEAD(dB_fixed) REFH_DEAD(nr_ptrs_cpe_estimation) REFH_DEAD(nr_ptrs_process_slot) REFH_DEAD(set_ptrs_symb_idx)
+REFH_DEAD(signal_energy)

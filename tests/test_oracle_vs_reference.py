@@ -259,6 +259,21 @@ def test_ofdm_rx_slot(oracle, reference):
                 assert np.array_equal(y_o, y_r), (N, mu, nb_rb, slot, div, ta, use_rot)
 
 
+def test_ue_slot_fep(oracle, reference):
+    """The UE's OFDM front end nr_slot_fep (synchronised UE) is the gNB's with no timing offset and the DL rotation table: same oracle function."""
+    rng = np.random.default_rng(22)
+    for N, mu, nb_rb, slot in OFDM_CASES:
+        _, _, _, frame_len = oracle.ofdm_geometry(N, mu, slot)
+        rot = oracle.symbol_rotation(mu, 3619200000.0)
+        rot224 = np.zeros(448, np.int16); rot224[:rot.size] = rot
+        rx = rng.integers(-3000, 3001, size=(2, 2 * frame_len)).astype(np.int16)
+        for div in (8, 4):
+            ts = reference.rotation_tables(N, mu, nb_rb, div, 3619200000.0, 3619200000.0)[2]
+            y_r = reference.ue_slot_fep(N, mu, nb_rb, 2, slot, div, rot224, ts, rx)
+            for a in range(2):
+                assert np.array_equal(oracle.ofdm_rx_slot(N, mu, nb_rb, slot, div, 0, rot, rx[a]), y_r[a]), (N, mu, nb_rb, slot, div, a)
+
+
 # ------------------------------------------------------------------------------------------ single-layer PUSCH inner receiver (a23 + a25)
 def _pusch_case(rng, N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm, nb_rb_carrier, amp_y=2000, amp_h=1500):
     from oracle.bindings import PuschParms
