@@ -161,6 +161,14 @@ int32_t nrb200_crc_batch_dev(int poly_id, uint32_t n_blk, const uint8_t *d_in, u
                              void *stream);
 int32_t nrb200_crc_batch_host(int poly_id, uint32_t n_blk, const uint8_t *in, uint32_t stride, uint32_t bitlen, uint32_t *out);
 
+/* Transport-block CRC attachment + code block segmentation on the device: what nr_dlsch_encoding does before the encoder (nr_dlsch_coding.c:300-336: crc24a
+ * for A > 3824, else crc16) followed by nr_segmentation (nr_segmentation.c:32-180: equal payload pieces, CRC24B per segment when C > 1, zero filler bytes).
+ * payload: A / 8 bytes (A a multiple of 8); segs: C rows of K / 8 bytes, seg_stride apart -- exactly the encoder's input.  d_scratch: 4 bytes on the device.
+ * nrb200_tb_segment_parms is the scalar part (host arithmetic): out = {C, K, Z, F, Kprime, L}, returns Kb or -1. */
+int32_t nrb200_tb_segment_parms(int BG, uint32_t A, uint32_t out[6]);
+int32_t nrb200_tb_segment_dev(int BG, uint32_t A, const uint8_t *d_payload, uint8_t *d_segs, uint32_t seg_stride, uint32_t *d_scratch, void *stream);
+int32_t nrb200_tb_segment_host(int BG, uint32_t A, const uint8_t *payload, uint8_t *segs, uint32_t seg_stride);
+
 /* ------------------------------------------------------------------------------------------
  * Part 3: rate matching / interleaving around the codec (one transport block = n_seg code block segments per call)
  * ---------------------------------------------------------------------------------------- */

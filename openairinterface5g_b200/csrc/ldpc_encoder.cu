@@ -186,6 +186,78 @@ int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride
   return 0;
 }
 
+// ---- transport block CRC attachment + nr_segmentation on the device (nr_dlsch_coding.c:300-336, nr_segmentation.c:143-175): CTA r copies its (Kprime - L) / 8
+// payload bytes (the last segment ends with the TB CRC, read from d_tbcrc), computes CRC24B over them while copying (C > 1), appends it and zeroes the filler
+// bytes.  The TB CRC itself is one launch_crc before this kernel (stream ordered).
+__global__ void __launch_bounds__(256) segment_kernel(const uint32_t *__restrict__ tab24b, const uint32_t *__restrict__ d_tbcrc, const uint8_t *__restrict__ payload,
+                                                      uint32_t a_bytes, uint32_t crc_bytes, uint32_t nbytes, int add_crc, uint32_t kp_bytes, uint32_t k_bytes,
+                                                      uint8_t *__restrict__ segs, uint32_t stride)
+{
+  __shared__ unsigned s_acc;
+  const uint32_t r = blockIdx.x, bitlen = nbytes * 8;
+  if (threadIdx.x == 0) s_acc = 0;
+  __syncthreads();
+  uint8_t *dst = segs + (size_t)r * stride;
+  const uint32_t tbcrc = *d_tbcrc;                       // left aligned: byte q of the attached CRC = bits 31 - 8q .. 24 - 8q
+  unsigned rem = 0;
+  for (uint32_t j = threadIdx.x; j < nbytes; j += blockDim.x) {
+    const uint32_t q = r * nbytes + j;
+    unsigned byte = q < a_bytes ? payload[q] : (q - a_bytes < crc_bytes ? (tbcrc >> (24 - 8 * (q - a_bytes))) & 255u : 0u);
+    dst[j] = (uint8_t)byte;
+    if (add_crc)
+      while (byte) {
+        const int k = 31 - __clz(byte);
+        byte &= ~(1u << k);
+        rem ^= __ldg(tab24b + (bitlen - 1 - (8 * j + (7 - k)) + 24));
+      }
+  }
+  for (uint32_t j = kp_bytes + threadIdx.x; j < k_bytes; j += blockDim.x) dst[j] = 0;      // filler bytes
+  if (!add_crc) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
+  if ((threadIdx.x & 31) == 0 && rem) atomicXor(&s_acc, rem);
+  __syncthreads();
+  if (threadIdx.x < 3) dst[nbytes + threadIdx.x] = (uint8_t)(s_acc >> (24 - 8 * threadIdx.x));
+}
+
+// nr_segmentation's scalar part (nr_segmentation.c:32-141).  out: C, K, Z, F, Kprime, L.  Returns Kb or -1.
+int tb_segment_parms(int BG, uint32_t A, uint32_t out[6])
+{
+  const uint32_t B = A + (A > 3824 ? 24 : 16), Kcb = BG == 1 ? 8448 : 3840;
+  uint32_t L = 0, Cn = 1, Bp = B;
+  if (B > Kcb) { L = 24; Cn = B / (Kcb - L); if ((Kcb - L) * Cn < B) Cn++; Bp = B + Cn * L; }
+  const uint32_t Kp = Bp / Cn;
+  const uint32_t Kb = BG == 1 ? 22 : (B > 640 ? 10 : B > 560 ? 9 : B > 192 ? 8 : 6);
+  const uint32_t Zmin = Kp / Kb + ((Kp % Kb) ? 1 : 0);
+  uint32_t Z;
+  if (Zmin <= 2) Z = 2;
+  else if (Zmin <= 16) Z = Zmin;
+  else {
+    uint32_t step = Zmin <= 32 ? 2 : Zmin <= 64 ? 4 : Zmin <= 128 ? 8 : Zmin <= 256 ? 16 : Zmin <= 384 ? 32 : 0;
+    if (!step) return -1;
+    Z = (Zmin / step) * step;
+    if (Z < Zmin) Z += step;
+  }
+  const uint32_t K = Z * (BG == 1 ? 22 : 10);
+  out[0] = Cn; out[1] = K; out[2] = Z; out[3] = K - Kp; out[4] = Kp; out[5] = L;
+  return (int)Kb;
+}
+
+int launch_tb_segment(int BG, uint32_t A, const uint8_t *d_payload, uint8_t *d_segs, uint32_t seg_stride, uint32_t *d_scratch, cudaStream_t stream)
+{
+  uint32_t q[6];
+  if ((BG != 1 && BG != 2) || A == 0 || (A & 7) || tb_segment_parms(BG, A, q) < 0) return -4;
+  const uint32_t Cn = q[0], K = q[1], Kp = q[4], L = q[5];
+  if (((Kp - L) & 7) || seg_stride < K / 8 || K + 24 > (uint32_t)kCrcTableLen) return -4;      // the reference's byte copy assumes whole bytes per segment too
+  const int tb_poly = A > 3824 ? 0 : 3;
+  int rc = launch_crc(tb_poly, 1, d_payload, (A + 7) / 8, A, d_scratch, stream);
+  if (rc) return rc;
+  segment_kernel<<<Cn, 256, 0, stream>>>(ctx().crc_tab[1], d_scratch, d_payload, A / 8, tb_poly == 0 ? 3 : 2, (Kp - L) / 8, Cn > 1, Kp / 8, K / 8, d_segs, seg_stride);
+  ctx().launches++;
+  NRB200_CUDA_OK(cudaGetLastError(), "segment launch");
+  return 0;
+}
+
 int quirks_from_env()
 {
   static int q = -1;

@@ -15,6 +15,8 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
 int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
                   uint8_t *d_out, uint32_t out_stride, cudaStream_t stream);
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
+int tb_segment_parms(int BG, uint32_t A, uint32_t out[6]);
+int launch_tb_segment(int BG, uint32_t A, const uint8_t *d_payload, uint8_t *d_segs, uint32_t seg_stride, uint32_t *d_scratch, cudaStream_t stream);
 int quirks_from_env();
 int launch_gold(int mode, uint32_t c_init, uint32_t size, const uint8_t *in, uint32_t *out, int16_t *llr, cudaStream_t st);
 uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d);
@@ -303,6 +305,36 @@ NRB200_EXPORT int32_t nrb200_crc_batch_host(int poly_id, uint32_t n_blk, const u
     if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
     if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
     std::memcpy(out, w->h_out, out_bytes);
+  } while (0);
+  ctx().release(w);
+  return rc;
+}
+
+NRB200_EXPORT int32_t nrb200_tb_segment_parms(int BG, uint32_t A, uint32_t out[6]) { return (BG == 1 || BG == 2) && out ? tb_segment_parms(BG, A, out) : -1; }
+
+NRB200_EXPORT int32_t nrb200_tb_segment_dev(int BG, uint32_t A, const uint8_t *d_payload, uint8_t *d_segs, uint32_t seg_stride, uint32_t *d_scratch, void *stream)
+{
+  if (ensure_init()) return -1;
+  return launch_tb_segment(BG, A, d_payload, d_segs, seg_stride, d_scratch, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_tb_segment_host(int BG, uint32_t A, const uint8_t *payload, uint8_t *segs, uint32_t seg_stride)
+{
+  uint32_t q[6];
+  if ((BG != 1 && BG != 2) || A == 0 || (A & 7) || tb_segment_parms(BG, A, q) < 0) return -4;
+  if (ensure_init()) return -1;
+  const size_t in_bytes = A / 8, out_bytes = (size_t)q[0] * seg_stride;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(in_bytes + 64, out_bytes, 16)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, payload, in_bytes);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, in_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemsetAsync(w->d_out, 0, out_bytes, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = launch_tb_segment(BG, A, (const uint8_t *)w->d_in, (uint8_t *)w->d_out, seg_stride, (uint32_t *)w->d_aux, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_bytes, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(segs, w->h_out, out_bytes);
   } while (0);
   ctx().release(w);
   return rc;

@@ -1,0 +1,113 @@
+"""Device-resident PDSCH slot chain (the nr_dlsim path, BASELINE config 3: 100 MHz, 273 PRB, 2 x 2, two layers, MCS 28) built from the library's kernels.
+The order of calls mirrors the reference's procedures:
+  gNB transmit : nr_generate_pdsch (NR_TRANSPORT/nr_dlsch.c:56-583) = nr_dlsch_encoding (TB CRC24A, nr_segmentation + CRC24B, LDPC encode, rate matching +
+                 interleaving; nr_dlsch_coding.c:280-420) -> scrambling -> modulation -> layer mapping -> DMRS + resource mapping -> precoding, then
+                 nr_feptx0 (apply_nr_rotation_TX + PHY_ofdm_mod, SCHED_NR/nr_ru_procedures.c:55-140)
+  UE receive   : nr_slot_fep (MODULATION/slot_fep_nr.c:37-113) -> nr_pdsch_channel_estimation per DMRS port (NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1614)
+                 -> nr_rx_pdsch (level, compensation, MRC, zero forcing, LLRs, layer de-mapping; NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684)
+                 -> nr_dlsch_unscrambling -> nr_dlsch_decoding (de-interleave / rate recover -> LDPC decode with CRC24B stop -> TB CRC;
+                 NR_UE_TRANSPORT/nr_dlsch_decoding.c:235-420), as nr_ue_pdsch_procedures / nr_ue_dlsch_procedures sequence them
+                 (SCHED_NR_UE/phy_procedures_nr_ue.c:520-760).
+Between the two sits nr_dlsim's double-precision channel model (multipath_channel + add_noise, dlsim.c:1098-1099), which is simulator code and not on the path:
+`channel()` is a small flat 2 x 2 mix plus noise in torch and is never timed.  torch is used for buffers, the byte plumbing of the segmentation and the channel."""
+import numpy as np
+import torch
+
+from . import transport as T
+from .ldpc import CRC24_B, PdschTxDesc, PuschChestDesc, PuschRxDesc
+from .ofdm import NrOfdmParms
+
+
+class PdschSlotChain:
+    def __init__(self, lib, dl, device, A=434280, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_ant=2, Qm=6, slot=1, rnti=0x1234, nid=77,
+                 dl_freq=3619200000.0, max_iter=8, dmrs_id=55, n_layers=2, tx_amp=512, start_symbol=1, nr_symbols=13):
+        self.lib, self.dl, self.dev = lib, dl, device
+        self.P = NrOfdmParms(N, mu, carrier_rb)
+        self.N, self.nb, self.Qm, self.slot, self.rnti, self.nid, self.max_iter, self.nl = N, nb_ant, Qm, slot, rnti, nid, max_iter, n_layers
+        self.rb_start, self.rb_size, self.A = rb_start, rb_size, A
+        assert n_layers in (1, 2) and nb_ant >= n_layers
+        self.dmrs_pos, self.dmrs_type, self.cdm = 1 << 2, 0, 2                     # one type-1 DMRS symbol (ports 0, 1 share CDM group 0), no data on it
+        self.seg = T.nr_segmentation(A + 24, 1)
+        assert (A + 24 + self.seg["C"] * self.seg["L"]) % (8 * self.seg["C"]) == 0, "pick A like a real TBS: whole bytes per segment"
+        self.C, self.K, self.Z, self.F = self.seg["C"], self.seg["K"], self.seg["Z"], self.seg["F"]
+        fco = self.P.first_carrier_offset
+        self.txd = PdschTxDesc(N, nb_ant, slot, rb_start, 0, rb_size, fco, Qm, n_layers, start_symbol, nr_symbols, self.dmrs_pos, self.dmrs_type, self.cdm,
+                               (1 << n_layers) - 1, 0, dmrs_id, nid, rnti, tx_amp, 14 * N)
+        self.G = lib.pdsch_tx_num_bits(self.txd)
+        assert self.G == T.nr_get_G(rb_size, nr_symbols, 12, 1, 0, Qm, n_layers)
+        E = [T.nr_get_E(self.G, self.C, Qm, n_layers, r) for r in range(self.C)]
+        self.R = T.nr_get_R_ldpc_decoder(0, E[0], 1, self.Z)[0]
+        self.E = torch.tensor(E, dtype=torch.int32, device=device)
+        self.Eoff = torch.tensor(np.concatenate([[0], np.cumsum(E)[:-1]]), dtype=torch.int32, device=device)
+        self.rot = self.P.symbol_rotation(dl_freq)
+        self.ts = torch.from_numpy(self.P.timeshift_rotation()).to(device)
+        # ---- transmit-side buffers
+        self.nbytes = (self.seg["Kprime"] - self.seg["L"]) // 8                      # payload bytes per segment
+        self.tb_tx = torch.zeros((1, (A + 24) // 8), dtype=torch.uint8, device=device)
+        self.crc1 = torch.empty(1, dtype=torch.int32, device=device)
+        self.crcC = torch.empty(self.C, dtype=torch.int32, device=device)
+        self.segs = torch.zeros((self.C, self.K // 8), dtype=torch.uint8, device=device)
+        self.cw = torch.empty((self.C, 66 * self.Z), dtype=torch.uint8, device=device)
+        self.f = torch.empty(self.G, dtype=torch.uint8, device=device)
+        self.txF = torch.zeros((nb_ant, 14 * N, 2), dtype=torch.int16, device=device)
+        self.dtx = self.P.desc(slot, nb_ant, self.rot)
+        self.txdata = torch.zeros((nb_ant, self.dtx.t_stride, 2), dtype=torch.int16, device=device)
+        self.shifts = torch.tensor([24, 16, 8], dtype=torch.int32, device=device)
+        # ---- receive-side buffers
+        self.rxd = PuschRxDesc(N, nb_ant, rb_start, 0, rb_size, fco, Qm, start_symbol, nr_symbols, self.dmrs_pos, self.dmrs_type, self.cdm,
+                               0, 14 * N, 14 * N, 1, rnti, nid, n_layers, 0, 0, 1)
+        assert lib.pusch_num_llr(self.rxd) == self.G
+        self.cdesc = PuschChestDesc(N, nb_ant, slot, 2, 0, rb_start, 0, rb_size, fco, 0, dmrs_id, 14 * N, 14 * N, n_layers, 1)   # UE estimator, all ports in one call
+        self.est = torch.zeros((n_layers * nb_ant, 14 * N, 2), dtype=torch.int16, device=device)      # dl_ch_estimates[p * nb_rx + aarx]
+        self.chest_scratch = torch.empty(lib.pusch_chest_scratch_bytes(self.cdesc), dtype=torch.uint8, device=device)
+        self.chest_state = torch.zeros((n_layers, 18), dtype=torch.int32, device=device)
+        self.rxF = torch.empty((nb_ant, 14 * N, 2), dtype=torch.int16, device=device)
+        self.level = torch.zeros(9, dtype=torch.int32, device=device)
+        self.llr16 = torch.empty(self.G, dtype=torch.int16, device=device)
+        self.harq = torch.zeros((self.C, 66 * self.Z), dtype=torch.int16, device=device)
+        self.llr8 = torch.empty((self.C, 68 * self.Z), dtype=torch.int8, device=device)
+        self.hard = torch.empty((self.C, 68 * self.Z // 8), dtype=torch.uint8, device=device)
+        self.iters = torch.empty(self.C, dtype=torch.int32, device=device)
+        self.tb = torch.empty((1, (A + 24) // 8), dtype=torch.uint8, device=device)
+        self.tbcrc = torch.empty(1, dtype=torch.int32, device=device)
+        self.drx = self.P.desc(slot, nb_ant, self.rot, rx=True)
+
+    # ------------------------------------------------------------------ gNB transmit chain (timed)
+    def transmit(self, payload):
+        """payload: uint8[A / 8] on the device.  Returns the slot's time-domain samples int16 [nb_tx, samples, 2]."""
+        lib, dl = self.lib, self.dl
+        lib.tb_segment_torch(1, self.A, payload, self.segs, self.crc1)                      # TB CRC24A + nr_segmentation + CRC24B per segment
+        lib.encode_batch_torch(1, self.Z, self.K, self.segs, out=self.cw)
+        lib.rm_tx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.cw, self.E, self.Eoff, self.f)
+        lib.pdsch_tx_slot_torch(self.txd, self.f, self.txF)                                 # scrambling ... txdataF in one launch
+        dl.ofdm_mod_slot_torch(self.dtx, self.txF, self.txdata)                             # rotation + IDFT + CP
+        return self.txdata
+
+    # ------------------------------------------------------------------ the simulator's channel (never timed)
+    def channel(self, txdata, seed=1, snr_db=35.0, gain=4.0, coupling=0.35):
+        """Flat nb_rx x nb_tx mix + white noise in the time domain, placed at the slot's position of a frame buffer.  Returns int16 [nb_rx, samples_per_frame, 2]."""
+        dev, nb = self.dev, self.nb
+        g = torch.Generator(device=dev); g.manual_seed(seed)
+        x = torch.view_as_complex(txdata.to(torch.float32).contiguous())
+        ph = torch.rand((nb, nb), generator=g, device=dev) * 6.2831853
+        H = torch.polar(torch.full((nb, nb), coupling, device=dev) + (1.0 - coupling) * torch.eye(nb, device=dev), ph) * gain
+        y = H.to(torch.complex64) @ x
+        sig = torch.sqrt(torch.mean(torch.abs(y) ** 2)) * 10.0 ** (-snr_db / 20.0) * 0.70711
+        yr = torch.view_as_real(y) + sig * torch.randn(y.shape + (2,), generator=g, device=dev)
+        rxdata = torch.zeros((nb, self.P.samples_per_frame, 2), dtype=torch.int16, device=dev)
+        ss = self.P.slot_timestamp(self.slot)
+        rxdata[:, ss:ss + txdata.shape[1]] = torch.clamp(torch.round(yr), -32768, 32767).to(torch.int16)
+        return rxdata
+
+    # ------------------------------------------------------------------ UE receive chain (timed)
+    def receive(self, rxdata):
+        lib, dl = self.lib, self.dl
+        dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)                       # nr_slot_fep x 14
+        lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)   # nr_pdsch_channel_estimation, every port
+        lib.pusch_inner_rx_torch(self.rxd, self.rxF, self.est, self.llr16, level=self.level)   # nr_rx_pdsch (+ unscrambling)
+        lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
+        lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
+                               out=self.hard, iters=self.iters)
+        self.tb.view(-1).copy_(self.hard[:, :self.nbytes].reshape(-1))
+        lib.crc_batch_torch(0, self.tb, self.A + 24, out=self.tbcrc)
+        return self.tb, self.iters, self.tbcrc

@@ -233,6 +233,32 @@ class LdpcLib:
                                                   torch.cuda.current_stream(data.device).cuda_stream), "crc_batch_dev")
         return out
 
+    # ---- TB CRC attachment + nr_segmentation on the device
+    def tb_segment_parms(self, BG, A):
+        """Scalar part of nr_segmentation for a transport block of A payload bits (host arithmetic).  Returns dict(C, K, Z, F, Kprime, L, Kb)."""
+        q = (C.c_uint32 * 6)()
+        kb = self.lib.nrb200_tb_segment_parms(BG, A, q)
+        if kb < 0:
+            raise ValueError("transport block too large")
+        return {"C": q[0], "K": q[1], "Z": q[2], "F": q[3], "Kprime": q[4], "L": q[5], "Kb": kb}
+
+    def tb_segment_host(self, BG, payload):
+        """payload: uint8[A / 8].  Returns (C, K / 8) uint8 segments: TB CRC attached, per-segment CRC24B, zero filler."""
+        p = np.ascontiguousarray(payload, dtype=np.uint8)
+        q = self.tb_segment_parms(BG, p.size * 8)
+        out = np.zeros((q["C"], q["K"] // 8), dtype=np.uint8)
+        self.lib.nrb200_tb_segment_host.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        self._check(self.lib.nrb200_tb_segment_host(BG, p.size * 8, p.ctypes.data, out.ctypes.data, out.shape[1]), "tb_segment_host")
+        return out
+
+    def tb_segment_torch(self, BG, A, payload, segs, scratch):
+        """Device-resident: payload uint8[A / 8], segs (C, >= K / 8) uint8 out, scratch int32[1]."""
+        import torch
+        self.lib.nrb200_tb_segment_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        self._check(self.lib.nrb200_tb_segment_dev(BG, A, payload.data_ptr(), segs.data_ptr(), segs.shape[1], scratch.data_ptr(),
+                                                   torch.cuda.current_stream(payload.device).cuda_stream), "tb_segment_dev")
+        return segs
+
     # ---- rate matching / interleaving around the codec (nr_rate_matching.c), one transport block per call
     def _rmdesc(self, BG, Z, Qm, rv, C_, Tbslbrm, F, n_seg, clear=0):
         d = RmDesc()
