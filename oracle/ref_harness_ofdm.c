@@ -9,6 +9,11 @@
 #include <string.h>
 #include "PHY/defs_nr_common.h"
 #include "PHY/TOOLS/tools_defs.h"
+#include <time.h>
+/* wall time of the last call into the reference function(s), excluding the harness's own allocation and copying (cpu_baseline of the DL slot chain) */
+static double g_last_s;
+static inline double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
 
 void nr_normal_prefix_mod(c16_t *txdataF, c16_t *txdata, uint8_t nsymb, const NR_DL_FRAME_PARMS *frame_parms, uint32_t slot);
 void apply_nr_rotation_TX(const NR_DL_FRAME_PARMS *fp, c16_t *txdataF, const c16_t *symbol_rotation, int slot, int nb_rb, int first_symbol, int nsymb);
@@ -88,9 +93,12 @@ void refh_rotation_tables(int N, int mu, int nb_rb, int divisor, double dl_freq,
 void refh_ofdm_tx_slot(int N, int mu, int nb_rb, int slot, int nsymb, const int16_t *rot /* 224 pairs or NULL */, int16_t *txdataF, int16_t *txdata)
 {
   NR_DL_FRAME_PARMS *fp = fill(N, mu, nb_rb, 8);
+  const double t0 = now_s();
   if (rot) apply_nr_rotation_TX(fp, (c16_t *)txdataF, (const c16_t *)rot, slot, nb_rb, 0, nsymb);
   nr_normal_prefix_mod((c16_t *)txdataF, (c16_t *)txdata, (uint8_t)nsymb, fp, (uint32_t)slot);
+  g_last_s = now_s() - t0;
 }
+double refh_ofdm_last_seconds(void) { return g_last_s; }
 
 /* nr_fep_full order: nr_slot_fep_ul for the 14 symbols of `slot`, then apply_nr_rotation_RX (phase + timeshift compensation).
  * rxdata = one frame of samples (samples_per_frame c16); returns samples_per_frame. */

@@ -8,6 +8,13 @@
 #include <string.h>
 #include "PHY/defs_nr_UE.h"
 #include "PHY/NR_UE_TRANSPORT/nr_transport_proto_ue.h"
+#include <time.h>
+/* wall time of the last call into the reference function(s), excluding the harness's own allocation and copying (cpu_baseline of the DL slot chain) */
+static double g_last_s;
+static inline double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+
+double refh_pdsch_last_seconds(void) { return g_last_s; }
 
 enum { D_N, D_NB_RX, D_RB_START, D_BWP_START, D_RB_SIZE, D_FCO, D_QM, D_START_SYMBOL, D_NR_SYMBOLS, D_DMRS_POS, D_DMRS_TYPE, D_CDM_GROUPS, D_G, D_NL, D_COUNT };
 
@@ -52,11 +59,13 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
   int first_symbol_with_data = p[D_START_SYMBOL];
   const int dmrs_data_re = p[D_DMRS_TYPE] == 0 ? 12 - 6 * p[D_CDM_GROUPS] : 12 - 4 * p[D_CDM_GROUPS];
   while (dmrs_data_re == 0 && (p[D_DMRS_POS] & (1 << first_symbol_with_data))) first_symbol_with_data++;
+  const double t0 = now_s();
   for (int m = p[D_START_SYMBOL]; m < p[D_START_SYMBOL] + p[D_NR_SYMBOLS]; m++) {
     const int first_symbol_flag = m == first_symbol_with_data;
     if (nr_rx_pdsch(ue, &proc, dlsch, (unsigned char)m, (unsigned char)first_symbol_flag, harq_pid, est_size, est, llr, dl_valid_re, rx, llr_offset, &log2_maxh,
                     rx_size_symbol, nrx, comp, ptrs_phase, ptrs_re) < 0) { fprintf(stderr, "nr_rx_pdsch failed at symbol %d\n", m); break; }
   }
+  g_last_s = now_s() - t0;
   memcpy(llr_out, llr[0], 2 * (size_t)p[D_G]);
   if (valid_re_out) for (int m = 0; m < 14; m++) valid_re_out[m] = (int32_t)dl_valid_re_buf[m];     /* index m holds symbol m (stored at [symbol - 1] + 1) */
   if (comp_out) memcpy(comp_out, comp[0][0], 4 * (size_t)rx_size_symbol * 14);

@@ -11,6 +11,11 @@
 #include "PHY/NR_TRANSPORT/nr_dlsch.h"
 #include "PHY/NR_REFSIG/nr_refsig.h"
 #include "PHY/NR_REFSIG/nr_mod_table.h"
+#include <time.h>
+/* wall time of the last call into the reference function(s), excluding the harness's own allocation and copying (cpu_baseline of the DL slot chain) */
+static double g_last_s;
+static inline double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
 
 static const uint8_t *g_bits;
 static uint32_t g_nbits;
@@ -23,6 +28,8 @@ int nr_dlsch_encoding(PHY_VARS_gNB *gNB, int frame, uint8_t slot, NR_DL_gNB_HARQ
   memcpy(output, g_bits, g_nbits);
   return 0;
 }
+
+double refh_pdschtx_last_seconds(void) { return g_last_s; }
 
 enum { X_N, X_N_RB_DL, X_NB_TX, X_SLOT, X_RB_START, X_BWP_START, X_RB_SIZE, X_FCO, X_QM, X_NL, X_START_SYMBOL, X_NR_SYMBOLS, X_DMRS_POS, X_DMRS_TYPE,
        X_CDM_GROUPS, X_DMRS_PORTS, X_SCID, X_DMRS_ID, X_DATA_ID, X_RNTI, X_AMP, X_COUNT };
@@ -67,7 +74,9 @@ int refh_pdsch_tx_slot(const int32_t *p, const uint8_t *bits, uint32_t nbits, in
   processingData_L1tx_t *msgTx = calloc(1, sizeof(*msgTx));
   msgTx->gNB = gNB; msgTx->dlsch = dlv; msgTx->num_pdsch_slot = 1; msgTx->slot = slot;
   g_bits = bits; g_nbits = nbits;
+  const double t0 = now_s();
   nr_generate_pdsch(msgTx, 0, slot);
+  g_last_s = now_s() - t0;
   for (int a = 0; a < ntx; a++) memcpy(txdataF_out + 2 * (size_t)a * 14 * N, gNB->common_vars.txdataF[a] + (size_t)slot * 14 * N, sizeof(c16_t) * 14 * N);
   for (int s = 0; s < fp->slots_per_frame; s++) { for (int l = 0; l < 14; l++) { for (int q = 0; q < 2; q++) free(gNB->nr_gold_pdsch_dmrs[s][l][q]); free(gNB->nr_gold_pdsch_dmrs[s][l]); } free(gNB->nr_gold_pdsch_dmrs[s]); }
   free(gNB->nr_gold_pdsch_dmrs);

@@ -9,6 +9,11 @@
 #include <string.h>
 #include "PHY/defs_nr_UE.h"
 #include "PHY/NR_UE_ESTIMATION/nr_estimation.h"
+#include <time.h>
+/* wall time of the last call into the reference function(s), excluding the harness's own allocation and copying (cpu_baseline of the DL slot chain) */
+static double g_last_s;
+static inline double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
 
 void init_delay_table(uint16_t ofdm_symbol_size, int max_delay_comp, int max_ofdm_symbol_size, c16_t delay_table[][max_ofdm_symbol_size]);
 
@@ -26,6 +31,8 @@ int refh_uechest_init(const char *dfts_so)
   autoinit();
   return 0;
 }
+
+double refh_uechest_last_seconds(void) { return g_last_s; }
 
 enum { U_N, U_NB_RX, U_N_RB_DL, U_SLOT, U_SYMBOL, U_PORT, U_RB_START, U_BWP_START, U_RB_SIZE, U_FCO, U_SCID, U_DMRS_ID, U_DMRS_TYPE, U_CHEST_FREQ, U_COUNT };
 
@@ -58,9 +65,11 @@ int refh_pdsch_chest(const int32_t *p, const int16_t *rxdataF, int16_t *dl_ch_es
   memcpy(rx, rxdataF, (size_t)nrx * est_size * 4);
   /* arguments as nr_ue_pdsch_procedures passes them (phy_procedures_nr_ue.c): BWPStart, rb_offset, bwp_start_subcarrier */
   const unsigned short k0 = ((p[U_RB_START] + p[U_BWP_START]) * 12 + p[U_FCO]) % N;
+  const double t0 = now_s();
   nr_pdsch_channel_estimation(ue, &proc, (unsigned short)port, (unsigned char)p[U_SYMBOL], (unsigned char)p[U_SCID], (unsigned short)p[U_DMRS_ID],
                               (unsigned short)p[U_BWP_START], (uint8_t)p[U_DMRS_TYPE], (uint16_t)(p[U_RB_START] + p[U_BWP_START]), k0, (unsigned short)p[U_RB_SIZE], est_size, est,
                               est_size, rx);
+  g_last_s = now_s() - t0;
   for (int a = 0; a < nrx; a++) memcpy(dl_ch_est + 2 * (size_t)a * est_size, est[port * nrx + a], 4 * (size_t)est_size);
   for (int ns = 0; ns < fp->slots_per_frame; ns++) { for (int l = 0; l < 14; l++) { for (int s = 0; s < 2; s++) free(ue->nr_gold_pdsch[0][ns][l][s]); free(ue->nr_gold_pdsch[0][ns][l]); } free(ue->nr_gold_pdsch[0][ns]); }
   free(ue->nr_gold_pdsch[0]); free(est); free(rx); free(ue);
@@ -103,7 +112,9 @@ int refh_ue_slot_fep(int N, int mu, int nb_rb, int nrx, int Ns, int divisor, con
   c16_t (*rxF)[14 * N];
   posix_memalign((void **)&rxF, 32, sizeof(c16_t) * (size_t)nrx * 14 * N);
   memset(rxF, 0, sizeof(c16_t) * (size_t)nrx * 14 * N);
+  const double t0 = now_s();
   for (int l = 0; l < 14; l++) nr_slot_fep(ue, &proc, (unsigned char)l, rxF);
+  g_last_s = now_s() - t0;
   memcpy(rxdataF, rxF, sizeof(c16_t) * (size_t)nrx * 14 * N);
   for (int a = 0; a < nrx; a++) free(ue->common_vars.rxdata[a]);
   free(ue->common_vars.rxdata); free(rxF); free(ue);

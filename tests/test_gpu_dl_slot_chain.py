@@ -48,3 +48,33 @@ def test_pdsch_slot_roundtrip(ldpc, oracle, cfg):
     llr_o, sh_o = oracle.pdsch_rx_slot(PP, r.start_symbol_index, r.nr_of_symbols, rxF, est, nl=chain.nl)
     assert sh_o == int(chain.level.cpu()[8])
     assert np.array_equal(chain.llr16.cpu().numpy(), oracle.unscramble_llr(llr_o, 0, chain.nid, chain.rnti))
+
+
+@pytest.mark.parametrize("cfg", [dict(max_iter=16), dict(A=33816, N=1024, mu=0, carrier_rb=52, rb_size=52, slot=1, Qm=6)])
+def test_pdsch_slot_vs_reference_chain(ldpc, reference, cfg):
+    """The whole slot against the UNMODIFIED reference functions (oracle/dl_slot_ref.py): same payload -> identical time-domain samples out of the gNB chain;
+    same received frame -> identical rxdataF, channel estimates, log2_maxh, LLRs, iteration counts and transport block out of the UE chain."""
+    from oracle.dl_slot_ref import RefDlSlot
+    dev = torch.device("cuda", 0)
+    chain = PdschSlotChain(ldpc, load_dftslib(), dev, **cfg)
+    refc = RefDlSlot(**cfg)
+    payload = np.random.default_rng(11).integers(0, 256, size=chain.A // 8, dtype=np.uint8)
+    tx_ref = refc.transmit(payload)
+    tx = chain.transmit(torch.from_numpy(payload).to(dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(chain.f.cpu().numpy(), refc.f)                                        # CRC, segmentation, encoder, rate matching, interleaver
+    assert np.array_equal(chain.txF.cpu().numpy().reshape(refc.txF.shape), refc.txF)            # scrambling ... precoding
+    assert np.array_equal(tx.cpu().numpy().reshape(tx_ref.shape), tx_ref)                       # rotation, IDFT, cyclic prefix
+    frame = refc.channel(tx_ref, seed=4)
+    tb_ref, its_ref, crc_ref = refc.receive(frame)
+    tb, iters, tbcrc = chain.receive(torch.from_numpy(frame).to(dev))
+    torch.cuda.synchronize()
+    N = chain.N
+    assert np.array_equal(chain.rxF.cpu().numpy().reshape(refc.rxF.shape), refc.rxF)            # nr_slot_fep
+    dm = 2
+    assert np.array_equal(chain.est.cpu().numpy().reshape(refc.est.shape)[:, dm], refc.est[:, dm])   # nr_pdsch_channel_estimation, both ports
+    assert int(chain.level.cpu()[8]) == refc.shift
+    assert np.array_equal(chain.llr16.cpu().numpy(), refc.llr)                                  # nr_rx_pdsch + unscrambling
+    assert np.array_equal(iters.cpu().numpy(), its_ref)
+    assert np.array_equal(tb.cpu().numpy().reshape(-1)[:tb_ref.size], tb_ref) and crc_ref == 0 and int(tbcrc.cpu()[0]) == 0
+    assert np.array_equal(tb_ref[:payload.size], payload)
