@@ -148,7 +148,103 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": v, "unit": "CB/s", "cores": cores, "kind": kind,
                              "sample": f"{sample} distinct code blocks decoded round-robin on {cores} threads, {per_step_s:.1f} s per step, mean returned iterations {mi:.2f}"},
             "e2e": {"value": v, "unit": "CB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if not args.no_slot:
+        try:
+            cb = slot_cpu_baseline(args.slot_cpu_seconds)
+            if cb is not None:
+                line["nr_dlsim_slot"] = {"metric": SLOT_METRIC, "value": cb["value"], "unit": "slots/s", "config": {"workload": SLOT_WORKLOAD}, "cpu_baseline": cb}
+        except Exception as e:
+            line["nr_dlsim_slot"] = {"metric": SLOT_METRIC, "unavailable": repr(e)[:300]}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ second half of BASELINE.json's metric: nr_dlsim slots/s
+SLOT_METRIC = "nr_dlsim slots/sec @100MHz (hot-path stages of one slot: gNB PDSCH transmit + UE PDSCH receive)"
+SLOT_WORKLOAD = "273 PRB mu=1 2x2, 2 layers, 64QAM, MCS28-shaped TB 434280 bit = 52 code blocks K=8448 E=9072, 1 DMRS symbol, 8-iter CRC-stop decode"
+
+
+def slot_cpu_baseline(seconds):
+    """The same slot through the unmodified reference functions (oracle/dl_slot_ref.py; timers around the reference calls only): one process per host core, each
+    running whole slots on its own thread the way nr_dlsim runs them; the aggregate is the sum over processes."""
+    from oracle import bindings as ob
+    if not ob.have_reference():
+        return None
+    cores = os.cpu_count() or 1
+    procs = [subprocess.Popen([sys.executable, "-m", "oracle.dl_slot_ref", str(seconds)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for _ in range(cores)]
+    res = []
+    for p in procs:
+        out, _ = p.communicate()
+        try:
+            res.append(json.loads(out.strip().splitlines()[-1]))
+        except Exception:
+            pass
+    if not res:
+        return None
+    one = max(r["slots_per_s"] for r in res)
+    return {"value": sum(r["slots_per_s"] for r in res), "unit": "slots/s", "cores": len(res), "kind": "reference", "decoded_ok": all(r["decoded_ok"] for r in res),
+            "one_thread_slots_per_s": one,
+            "sample": f"{sum(r['slots'] for r in res)} slots on {len(res)} processes x 1 thread, {seconds:.0f} s each; per process the stages of a slot run in sequence as in nr_dlsim; "
+                      "time counted inside the reference functions only",
+            "stages_us": {k: round(v, 1) for k, v in res[0]["stages_us"].items()}}
+
+
+def slot_b200(lib, dev, cpu_seconds):
+    """Device-resident slot chain (openairinterface5g_b200/dl_slot_chain.py): CUDA-event timing of transmit + receive, then the same with the payload coming from
+    pinned host memory and the decoded transport block going back inside the timed region."""
+    import torch
+    from openairinterface5g_b200.dfts import load_dftslib
+    from openairinterface5g_b200.dl_slot_chain import PdschSlotChain
+    dl = load_dftslib()
+    ch = PdschSlotChain(lib, dl, dev)
+    h_payload = torch.from_numpy(np.random.default_rng(5).integers(0, 256, size=ch.A // 8, dtype=np.uint8)).pin_memory()
+    payload = h_payload.to(dev)
+    rx = ch.channel(ch.transmit(payload), seed=3)
+    tb, iters, crc = ch.receive(rx)
+    torch.cuda.synchronize()
+    ok = bool((iters <= ch.max_iter).all()) and int(crc[0]) == 0 and bool((tb.view(-1)[:payload.numel()] == payload).all())
+    h_tb = torch.empty_like(tb, device="cpu").pin_memory()
+
+    def timed(fn, n, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def slot():
+        ch.transmit(payload)
+        ch.receive(rx)
+
+    def e2e():
+        payload.copy_(h_payload, non_blocking=True)
+        ch.transmit(payload)
+        t, _, _ = ch.receive(rx)
+        h_tb.copy_(t, non_blocking=True)
+    l0 = lib.launch_count() + dl.launch_count()
+    ms = timed(slot, 200)
+    launches = (lib.launch_count() + dl.launch_count() - l0) / 205
+    ms_e = timed(e2e, 200)
+    # compulsory HBM traffic of one slot: samples out and in, both grids, estimates, LLRs, soft buffers, code words (SURVEY.md 8d: "2-3 MB/slot")
+    nsamp = ch.txdata.shape[1]
+    algo = (2 * ch.nb * nsamp * 4 + 2 * ch.nb * 14 * ch.N * 4 + ch.nl * ch.nb * ch.N * 4 + 2 * ch.G * 2 + ch.G + ch.C * (66 + 68 + 66 * 2) * ch.Z + 2 * ch.A // 8)
+    out = {"metric": SLOT_METRIC, "value": 1e3 / ms, "unit": "slots/s", "ms_per_slot": ms, "config": {"workload": SLOT_WORKLOAD}, "decoded_ok": ok,
+           "mean_iterations": float(iters.float().mean()), "gpu_launches_per_slot": launches,
+           "e2e": {"value": 1e3 / ms_e, "unit": "slots/s", "h2d_bytes_per_step": int(h_payload.numel()), "d2h_bytes_per_step": int(h_tb.numel())},
+           "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": _peaks()[0], "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / _peaks()[0],
+                        "algorithmic_bytes_per_slot": int(algo), "note": "16 dependent launches of 10-70 us each on 52 code blocks: launch- and latency-bound, not bandwidth-bound"},
+           "realtime_factor_vs_2000_slots_per_s": 1e3 / ms / 2000.0,
+           "parity": "bit-exact end to end against the unmodified reference functions (tests/test_gpu_dl_slot_chain.py::test_pdsch_slot_vs_reference_chain)"}
+    if cpu_seconds > 0:
+        cb = slot_cpu_baseline(cpu_seconds)
+        if cb is not None:
+            out["cpu_baseline"] = cb
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ this repo's CUDA arm
@@ -289,6 +385,11 @@ def run_b200(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_slot:
+            try:
+                line["nr_dlsim_slot"] = slot_b200(lib, dev, 0.0 if args.no_cpu else args.slot_cpu_seconds)
+            except Exception as e:                                # the second metric must never take the headline line down with it
+                line["nr_dlsim_slot"] = {"metric": SLOT_METRIC, "unavailable": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -306,6 +407,8 @@ def main():
     ap.add_argument("--ebn0", type=float, default=1.0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-slot", action="store_true", help="skip the nr_dlsim slot chain (second half of the BASELINE metric)")
+    ap.add_argument("--slot-cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -218,4 +218,5 @@ def time_slot(seconds=15.0, **kw):
 
 if __name__ == "__main__":
     import json
-    print(json.dumps(time_slot(10.0)))
+    import sys
+    print(json.dumps(time_slot(float(sys.argv[1]) if len(sys.argv) > 1 else 10.0)))
