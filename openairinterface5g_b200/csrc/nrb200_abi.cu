@@ -565,13 +565,17 @@ NRB200_EXPORT int32_t nrb200_pdsch_tx_slot_host(const nrb200_pdsch_tx_t *d, cons
 }
 
 // ------------------------------------------------------------------------------------------ PUSCH inner receiver (one layer)
+// completion counters of the level kernels ("last CTA combines"): one per launch in flight, handed out round robin so that slots processed concurrently on
+// different streams never share one (the kernel leaves its counter at zero)
 static uint32_t *pusch_counter()
 {
+  constexpr uint32_t kCounters = 4096;
   static uint32_t *d = nullptr;
   static std::mutex mu;
+  static uint32_t ticket = 0;
   std::lock_guard<std::mutex> lk(mu);
-  if (!d && cudaMalloc(&d, 64) == cudaSuccess) cudaMemset(d, 0, 64);
-  return d;
+  if (!d && cudaMalloc(&d, kCounters * 4) == cudaSuccess) cudaMemset(d, 0, kCounters * 4);
+  return d ? d + (ticket++ % kCounters) : nullptr;
 }
 
 NRB200_EXPORT uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d) { return d ? pusch_num_llr(*d) : 0; }

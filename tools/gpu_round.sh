@@ -9,9 +9,11 @@ make -C oracle liboracle.so >/dev/null 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_${TAG}.txt
 nproc >> gpurun_out/gpu_${TAG}.txt; lscpu | grep -E "Model name|^CPU\(s\)" | cut -c1-200 >> gpurun_out/gpu_${TAG}.txt
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_${TAG}.txt
+if [ "$MODE" = "variants" ]; then
 echo "== variants"
 for t in 768 672 576 480 384; do NRB200_PACKED_THREADS=$t timeout 120 python tools/kernel_time.py 1.0 2>&1 | tail -1; done | tee gpurun_out/variants_${TAG}.txt
 timeout 120 python tools/kernel_time.py 3.0 2>&1 | tail -1 | tee -a gpurun_out/variants_${TAG}.txt
+fi
 echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -24 | tee gpurun_out/extras_${TAG}.jsonl
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json
 if [ "$MODE" = "full" ]; then
@@ -19,6 +21,9 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench point B (Eb/N0 3 dB, early stop)"; timeout 300 python bench.py --steps 50 --warmup 5 --ebn0 3.0 --no-cpu 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_pointB.json
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_reference.json
 echo "== slot chain"; timeout 200 python tools/bench_slot.py 2>&1 | tail -10 | tee gpurun_out/slot_${TAG}.jsonl
+echo "== DL slot chain"; timeout 200 python tools/bench_dl_slot.py 2>&1 | tail -6 | tee gpurun_out/dlslot_${TAG}.jsonl
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_dlslot_${TAG}.csv \
+  python tools/bench_dl_slot.py once > gpurun_out/ncu_launches_dlslot_${TAG}.log 2>&1
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
   python bench.py --steps 5 --warmup 3 --no-cpu --no-check --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
