@@ -113,7 +113,7 @@ class RefDlSlot:
         return txdata
 
     # ---------------------------------------------------------------- the simulator's channel (not timed, not on the path)
-    def channel(self, txdata, seed=1, snr_db=35.0, gain=4.0, coupling=0.35):
+    def channel(self, txdata, seed=1, snr_db=35.0, gain=3.0, coupling=0.15):
         rng = np.random.default_rng(seed)
         nb = self.nb
         x = txdata.reshape(nb, -1, 2).astype(np.float64)
