@@ -4,6 +4,7 @@
 // one bit per byte, K-2Z systematic bits followed by all parity bits (66Z for BG1, 50Z for BG2).
 #include "nrb200_ctx.h"
 #include "ldpc_common.cuh"
+#include <cstdlib>
 
 namespace nrb200 {
 
@@ -82,10 +83,126 @@ ldpc_encode_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t n_cb, c
   }
 }
 
+// ---- bit-packed variant for lifting sizes that are a multiple of 32 (the hot Z = 384 and every Z = 32 k): a column of the code word is W = Z / 32 words
+//      (bit b of word w = lift 32 w + b), a circular shift is one funnel shift of two neighbouring words, and a row of H is an XOR of a few words.  The whole
+//      code word is 68 W words (3.2 KB at Z = 384), so a block costs ~4 k word operations instead of ~120 k byte operations; one CTA of 128 threads per block.
+//      Same schedule as above: lambda of the four core rows -> p0 -> the other three core columns -> extension rows -> one-bit-per-byte store.
+__device__ __forceinline__ uint32_t rotw(const uint32_t *col, int W, int w, int s)
+{
+  const int q = s >> 5, r = s & 31;
+  int a = w + q; if (a >= W) a -= W;
+  int b = a + 1; if (b >= W) b -= W;
+  return __funnelshift_r(col[a], col[b], r);       // bits (32 w + s) mod Z ... of the column
+}
+
+__global__ void __launch_bounds__(128)
+ldpc_encode_packed_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t n_cb, const uint8_t *__restrict__ in, uint32_t in_stride,
+                          uint8_t *__restrict__ out, uint32_t out_stride)
+{
+  __shared__ EncGraphDev g;
+  __shared__ __align__(16) uint32_t x[68 * 12];
+  __shared__ uint32_t lam[4 * 12];
+  for (int i = threadIdx.x; i < (int)(sizeof(EncGraphDev) / 4); i += blockDim.x)
+    reinterpret_cast<int *>(&g)[i] = reinterpret_cast<const int *>(gdev)[i];
+  __syncthreads();
+  const int Z = g.Z, W = Z >> 5, nsys = g.nsys, ncols = g.ncols, nrows = g.nrows;
+  for (uint32_t cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+    const uint8_t *src = in + (size_t)cb * in_stride;
+    for (int i = threadIdx.x; i < ncols * W; i += blockDim.x) {
+      uint32_t v = 0;
+      const int bit0 = i << 5;
+      if (bit0 < K) {                                                        // MSB-first source bits (ldpc_encoder_optim8segmulti.c:132-149)
+        const uint32_t be = ((uint32_t)src[(bit0 >> 3)] << 24) | ((uint32_t)src[(bit0 >> 3) + 1] << 16) | ((uint32_t)src[(bit0 >> 3) + 2] << 8) | src[(bit0 >> 3) + 3];
+        v = __brev(be);
+        if (bit0 + 32 > K) v &= (1u << (K - bit0)) - 1u;
+      }
+      x[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) {
+      const int r = i / W, w = i - r * W;
+      uint32_t acc = 0;
+      for (int e = g.row_start[r]; e < g.row_start[r + 1]; e++) {
+        const int c = g.edge_col[e];
+        if (c < nsys) acc ^= rotw(x + c * W, W, w, g.edge_shift[e]);
+      }
+      lam[i] = acc;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < W) {                                             // x^sigma p0 = sum of the four core rows
+      const int w = threadIdx.x;
+      uint32_t *y = x + (nsys + 4) * W;                                      // scratch: the first extension column is still unused here
+      y[w] = lam[w] ^ lam[W + w] ^ lam[2 * W + w] ^ lam[3 * W + w];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < W) {
+      int s = Z - g.sigma; if (s >= Z) s -= Z;
+      x[nsys * W + threadIdx.x] = rotw(x + (nsys + 4) * W, W, threadIdx.x, s);
+    }
+    __syncthreads();
+    for (int n = 0; n < 3; n++) {
+      const int r = g.core_row[n], pc = g.core_col[n];
+      uint32_t *y = x + (nsys + 4) * W;
+      if ((int)threadIdx.x < W) {
+        const int w = threadIdx.x;
+        uint32_t acc = lam[r * W + w];
+        for (int e = g.row_start[r]; e < g.row_start[r + 1]; e++) {
+          const int c = g.edge_col[e];
+          if (c < nsys || c == pc) continue;                                 // columns still unknown at this step are all-zero in x
+          acc ^= rotw(x + c * W, W, w, g.edge_shift[e]);
+        }
+        y[w] = acc;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < W) {
+        int s = Z - g.core_shift[n]; if (s >= Z) s -= Z;
+        x[pc * W + threadIdx.x] = rotw(y, W, threadIdx.x, s);
+      }
+      __syncthreads();
+    }
+    if ((int)threadIdx.x < W) x[(nsys + 4) * W + threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (nrows - 4) * W; i += blockDim.x) {
+      const int r = 4 + i / W, w = i % W;
+      uint32_t acc = 0;
+      for (int e = g.row_start[r]; e < g.row_start[r + 1]; e++) {
+        const int c = g.edge_col[e];
+        if (c < nsys + 4) acc ^= rotw(x + c * W, W, w, g.edge_shift[e]);     // systematic + core columns; the diagonal column closes the row
+      }
+      x[(nsys + r) * W + w] = acc;
+    }
+    __syncthreads();
+    uint8_t *dst = out + (size_t)cb * out_stride;
+    const int n16 = (ncols - 2) * Z / 16;                                    // 16 code bits -> one 16-byte store, consecutive lanes contiguous
+    const bool al16 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+      const uint32_t h = (x[2 * W + (i >> 1)] >> ((i & 1) * 16)) & 0xFFFFu;
+      uint4 v;
+      v.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
+      v.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+      v.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+      v.w = ((h >> 12) * 0x00204081u) & 0x01010101u;
+      if (al16) *reinterpret_cast<uint4 *>(dst + 16 * (size_t)i) = v;
+      else {
+        uint32_t a[4] = {v.x, v.y, v.z, v.w};
+        for (int k = 0; k < 16; k++) dst[16 * (size_t)i + k] = (uint8_t)(a[k >> 2] >> (8 * (k & 3)));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
                   uint8_t *d_out, uint32_t out_stride, cudaStream_t stream)
 {
   if (n_cb == 0) return 0;
+  static const bool force_bytes = getenv("NRB200_ENCODE_BYTES") != nullptr;
+  if (h_g.Z % 32 == 0 && K % 32 == 0 && !force_bytes) {
+    ldpc_encode_packed_kernel<<<n_cb, 128, 0, stream>>>(d_g, K, n_cb, d_in, in_stride, d_out, out_stride);
+    ctx().launches++;
+    NRB200_CUDA_OK(cudaGetLastError(), "packed encode launch");
+    return 0;
+  }
   auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   const size_t smem = a16(sizeof(EncGraphDev)) + a16((size_t)h_g.ncols * h_g.Z) + a16((size_t)4 * h_g.Z);
   static std::atomic<size_t> configured{0};
