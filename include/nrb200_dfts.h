@@ -2,10 +2,14 @@
  * nrb200_dfts.h -- C ABI of libdfts_b200.so, the B200-native drop-in for OpenAirInterface's loadable DFT library
  * ("libdfts.so": openair1/PHY/TOOLS/dfts_load.c:47-61 dlsym()s `dft` and `idft`, the loader calls `dfts_autoinit`).
  *
- * Arithmetic: the reference's Q15 fixed point, bit exact (oai_dfts.c), for the OFDM sizes
- *   64 128 256 512 768 1024 1536 2048 3072 4096 6144 8192   (both directions).
- * The DFT-s-OFDM / PRACH sizes of FOREACH_DFTSZ (12..3240 and > 8192) are not implemented yet: calling them aborts loudly
- * (there is no CPU fallback in this library).
+ * Arithmetic: the reference's Q15 fixed point, bit exact (oai_dfts.c), for
+ *   the OFDM sizes 64 128 256 512 768 1024 1536 2048 3072 4096 6144 8192 (both directions, one transform per call), and
+ *   the DFT-s-OFDM family 12 24 36 48 60 72 96 108 120 144 180 192 216 240 288 300 324 360 384 432 480 540 576 600 648 720 864 900 960 972 1080 1152 1200
+ *   1296 1440 1500 1620 1728 1800 1920 1944 2160 2304 2400 2592 2700 2880 2916 3000 3240 (forward only, as in the reference; like the reference's entry
+ *   points oai_dfts.c:4352-7706 every call transforms FOUR interleaved sequences: c16 number 4 n + l is element n of transform l, 4 N c16 in and out).
+ *   DFT_2304: the reference's function combines uninitialised stack (it calls the single-transform dft768 on four-way data, oai_dfts.c:7288-7310) and is not
+ *   reproducible; this library returns the 768 x 3 transform the function documents.
+ * The sizes above 8192 of FOREACH_DFTSZ / FOREACH_IDFTSZ are not implemented yet: calling them aborts loudly (there is no CPU fallback in this library).
  */
 #ifndef NRB200_DFTS_H
 #define NRB200_DFTS_H
@@ -20,7 +24,7 @@ void dft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag)
 void idft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag);
 int dfts_autoinit(void);   /* called by load_module_shlib when present (load_module_shlib.c:174-191); returns 0, -1 without a GPU */
 
-/* Part 2: batched extension -- n transforms of the same size, contiguous (2*N int16 each). */
+/* Part 2: batched extension -- n calls of the same size, contiguous (2*N int16 each; 8*N int16 each for the four-way DFT-s-OFDM sizes). */
 int32_t nrb200_dft_batch_dev(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, void *stream);
 int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, const int16_t *in, int16_t *out, int scale);
 /* N for a reference size index (dft_size_idx_t / idft_size_idx_t), -1 if out of range */

@@ -349,13 +349,163 @@ __global__ void __launch_bounds__(256, NRB200_DFT_MINBLOCKS) dft_kernel(DftPlan 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ four-way DFT-s-OFDM family (12 ... 3240)
+// oai_dfts.c:4352-7706: entry points that work on 128-bit vectors holding four independent transforms (element n of transform l is c16 number 4 n + l).
+// N = 12 * R[L-1] * ... * R[0], decimation in time at every level: M-point transforms of x[m + R n], then per k < M one radix-R butterfly (bfly{2,3,4,5}_tw1 for
+// k = 0, bfly{2,3,4,5} with generated twiddles otherwise) writing y[k + q M], then mulhrs by the level's constant when that level is called with scale 1.
+// Here: one CTA per call (4 N c16 in shared memory, lanes interleaved as in memory, so consecutive threads touch consecutive words), the 12-point kernels
+// read their digit-reversed inputs straight from global memory, every later level runs in place.
+struct SmallPlan {
+  int N, L;
+  int R[5], norm[5], apply[5], tw[5];   // level 0 = top; tw: blob offset (shorts) of (R-1) planes of (M-1) {re, im} pairs, plane p-1, entry k-1
+};
+
+__device__ __forceinline__ cx pcm(cx x, cx w) { unsigned r, i; cm32(x, w.r, w.i, false, r, i); return pk32(r, i); }   // packed_cmult
+__device__ __forceinline__ void bfly3_fwd(cx x0, cx x1, cx x2, cx &y0, cx &y1, cx &y2)
+{
+  unsigned r, i, r2, i2;
+  y0 = sadd(x0, sadd(x1, x2));
+  cm32(x1, -16384, -28378, false, r, i); cm32(x2, -16384, 28378, false, r2, i2);
+  y1 = sadd(x0, pk32(r + r2, i + i2));
+  cm32(x1, -16384, 28378, false, r, i); cm32(x2, -16384, -28378, false, r2, i2);
+  y2 = sadd(x0, pk32(r + r2, i + i2));
+}
+__device__ __forceinline__ void bfly5_fwd(cx x0, const cx (&x)[4], cx (&y)[5])
+{
+  const int W[4][2] = {{10126, -31163}, {-26509, -19260}, {-26510, 19260}, {10126, 31163}};   // W15 .. W45 (oai_dfts.c:324-327)
+  const int sel[4][4] = {{0, 1, 2, 3}, {1, 3, 0, 2}, {2, 0, 3, 1}, {3, 2, 1, 0}};
+  y[0] = sadd(x0, sadd(x[0], sadd(x[1], sadd(x[2], x[3]))));
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    unsigned r = 0, i = 0;
+#pragma unroll
+    for (int p = 0; p < 4; p++) { unsigned a, b; cm32(x[p], W[sel[q][p]][0], W[sel[q][p]][1], false, a, b); r += a; i += b; }
+    y[q + 1] = sadd(x0, pk32(r, i));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dft_small_kernel(SmallPlan P, const short *__restrict__ tw, const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned n_calls)
+{
+  extern __shared__ unsigned sm[];
+  const int N = P.N, L = P.L;
+  for (unsigned call = blockIdx.x; call < n_calls; call += gridDim.x) {
+    const unsigned *src = in + (size_t)call * 4 * N;
+    // ---- 12-point kernels (dft12f :4365-4470): three bfly4_tw1, then bfly3_tw1 and three bfly3 with the hand-entered W12 constants
+    for (int w = threadIdx.x; w < 4 * (N / 12); w += blockDim.x) {
+      const int l = w & 3, b = w >> 2;
+      int stride = 1, first = 0;                      // input index of element n12 of block b: first + stride * n12
+      {
+        int bb = b;
+        // digits of b, innermost level last: n = m0 + R0 (m1 + R1 (... + R[L-1] n12))
+        int mult = 1, digs[5];
+        for (int j = L - 1; j >= 0; j--) { digs[j] = bb % P.R[j]; bb /= P.R[j]; }
+        for (int j = 0; j < L; j++) { first += digs[j] * mult; mult *= P.R[j]; }
+        stride = mult;
+      }
+      cx x[12], t[12], y[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) x[i] = unpack(__ldg(src + 4 * (first + stride * i) + l));
+#pragma unroll
+      for (int c = 0; c < 3; c++) bfly4_sat(x[c], x[c + 3], x[c + 6], x[c + 9], false, t[c], t[c + 3], t[c + 6], t[c + 9]);
+      bfly3_fwd(t[0], t[1], t[2], y[0], y[4], y[8]);
+      bfly3_fwd(t[3], pcm(t[4], {28377, -16383}), pcm(t[5], {16383, -28377}), y[1], y[5], y[9]);
+      bfly3_fwd(t[6], pcm(t[7], {16383, -28377}), pcm(t[8], {-16383, -28377}), y[2], y[6], y[10]);
+      bfly3_fwd(t[9], pcm(t[10], {0, -32767}), pcm(t[11], {-32767, 0}), y[3], y[7], y[11]);
+#pragma unroll
+      for (int k = 0; k < 12; k++) sm[(b * 12 + k) * 4 + l] = pack(y[k]);
+    }
+    __syncthreads();
+    int M = 12;
+    for (int j = L - 1; j >= 0; j--) {
+      const int R = P.R[j], NJ = R * M, norm = P.norm[j];
+      const bool sc = P.apply[j] != 0;
+      const short *t0 = tw + P.tw[j];
+      for (int w = threadIdx.x; w < 4 * (N / R); w += blockDim.x) {
+        const int l = w & 3, t = w >> 2, g = t / M, k = t - g * M;
+        unsigned *base = sm + (size_t)(g * NJ + k) * 4 + l;
+        cx v[5], o[5];
+#pragma unroll
+        for (int p = 0; p < 5; p++) if (p < R) v[p] = unpack(base[p * M * 4]);
+        cx W[4];
+        if (k) {
+#pragma unroll
+          for (int p = 1; p < 5; p++) if (p < R) W[p - 1] = ldtw(t0 + 2 * ((p - 1) * (M - 1) + (k - 1)));
+        }
+        if (R == 2) {
+          if (!k) { o[0] = sadd(v[0], v[1]); o[1] = ssub(v[0], v[1]); }
+          else {
+            unsigned br, bi;
+            const unsigned ar = (unsigned)(v[0].r * 32767), ai = (unsigned)(v[0].i * 32767);
+            cm32(v[1], W[0].r, W[0].i, false, br, bi);
+            o[0] = pk32(ar + br, ai + bi); o[1] = pk32(ar - br, ai - bi);
+          }
+        } else if (R == 3) {
+          if (!k) bfly3_fwd(v[0], v[1], v[2], o[0], o[1], o[2]);
+          else bfly3_fwd(v[0], pcm(v[1], W[0]), pcm(v[2], W[1]), o[0], o[1], o[2]);
+        } else if (R == 4) {
+          if (!k) bfly4_sat(v[0], v[1], v[2], v[3], false, o[0], o[1], o[2], o[3]);
+          else {
+            unsigned x1r, x1i, x2r, x2i, x3r, x3i;
+            cm32(v[1], W[0].r, W[0].i, false, x1r, x1i);
+            cm32(v[2], W[1].r, W[1].i, false, x2r, x2i);
+            cm32(v[3], W[2].r, W[2].i, false, x3r, x3i);
+            const cx d0 = pk32(x1r + x2r + x3r, x1i + x2i + x3i), da = pk32(x1i - (x2r + x3i), (x3r - x2i) - x1r);
+            const cx d2 = pk32((x2r - x3r) - x1r, (x2i - x3i) - x1i), db = pk32((x3i - x2r) - x1i, x1r - (x2i + x3r));
+            o[0] = {wrap16(v[0].r + d0.r), wrap16(v[0].i + d0.i)}; o[1] = {wrap16(v[0].r + da.r), wrap16(v[0].i + da.i)};
+            o[2] = {wrap16(v[0].r + d2.r), wrap16(v[0].i + d2.i)}; o[3] = {wrap16(v[0].r + db.r), wrap16(v[0].i + db.i)};
+          }
+        } else {
+          cx xx[4];
+#pragma unroll
+          for (int p = 0; p < 4; p++) xx[p] = k ? pcm(v[p + 1], W[p]) : v[p + 1];
+          bfly5_fwd(v[0], xx, o);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+          if (q < R) {
+            cx r = o[q];
+            if (sc) { r.r = mulhrs(r.r, norm); r.i = mulhrs(r.i, norm); }
+            base[q * M * 4] = pack(r);
+          }
+      }
+      __syncthreads();
+      M = NJ;
+    }
+    unsigned *dst = out + (size_t)call * 4 * N;
+    for (int i = threadIdx.x; i < 4 * N; i += blockDim.x) dst[i] = sm[i];
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
+// the four-way family: N = R x M, whether the M-point transforms are called with scale 1, and the mulhrs constant applied at this level when ITS scale is 1
+// (dft_norm_table oai_dfts.c:352-368 for 24 ... 300, 1/sqrt(R) in Q15 above; read off every dftN :4680-7706).  768 is dft768p (:6330), reachable only through
+// 2304: the reference's dft2304 (:7288) calls the single-transform dft768 on four-way data and then combines uninitialised stack, so its result is not a function
+// of its input; this library returns the "768 x 3" transform its comment describes (defect 11).
+struct SmallSize { int N, R, M, subscale, norm; };
+const SmallSize kSmall[] = {
+    {24, 2, 12, 0, 6689}, {36, 3, 12, 0, 5461}, {48, 4, 12, 0, 4729}, {60, 5, 12, 0, 4230}, {72, 2, 36, 1, 23170}, {96, 2, 48, 0, 3344}, {108, 3, 36, 0, 3153},
+    {120, 2, 60, 0, 2991}, {144, 3, 48, 1, 18918}, {180, 3, 60, 1, 18918}, {192, 4, 48, 1, 16384}, {216, 3, 72, 1, 18918}, {240, 4, 60, 1, 16384},
+    {288, 3, 96, 1, 18918}, {300, 5, 60, 1, 14654}, {324, 3, 108, 1, 18918}, {360, 3, 120, 1, 18918}, {384, 4, 96, 1, 16384}, {432, 4, 108, 1, 16384},
+    {480, 4, 120, 1, 16384}, {540, 3, 180, 1, 18918}, {576, 3, 192, 1, 18918}, {600, 2, 300, 1, 23170}, {648, 3, 216, 1, 18918}, {720, 4, 180, 1, 16384},
+    {768, 4, 192, 1, 16384}, {864, 3, 288, 1, 18918}, {900, 3, 300, 1, 18918}, {960, 4, 240, 1, 16384}, {972, 3, 324, 1, 18918}, {1080, 3, 360, 1, 18918},
+    {1152, 4, 288, 1, 16384}, {1200, 4, 300, 1, 16384}, {1296, 3, 432, 1, 18918}, {1440, 3, 480, 1, 18918}, {1500, 5, 300, 1, 14654}, {1620, 3, 540, 1, 18918},
+    {1728, 3, 576, 1, 18918}, {1800, 3, 600, 1, 18918}, {1920, 4, 480, 1, 16384}, {1944, 3, 648, 1, 18918}, {2160, 3, 720, 1, 18918}, {2304, 3, 768, 1, 18918},
+    {2400, 4, 600, 1, 16384}, {2592, 3, 864, 1, 18918}, {2700, 3, 900, 1, 18918}, {2880, 3, 960, 1, 18918}, {2916, 3, 972, 1, 18918}, {3000, 5, 600, 1, 14654},
+    {3240, 3, 1080, 1, 18918}};
+constexpr int kNumSmall = (int)(sizeof(kSmall) / sizeof(kSmall[0]));
+int small_index(int N) { for (int i = 0; i < kNumSmall; i++) if (kSmall[i].N == N) return i; return -1; }
+// sizes the `dft` table serves with the four-way entry points (768 is the OFDM transform there)
+bool is_fourway(int N) { return N == 12 || (N != 768 && small_index(N) >= 0); }
+
 struct DftCtx {
   std::mutex mu;
   bool inited = false;
   int dev = 0;
   short *d_tw = nullptr;
   TwOffsets off;
+  int small_tw[51];                       // blob offset of the level twiddles of four-way size kSmall[i].N (-1: none)
   cudaStream_t stream = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
   size_t cap = 0;
@@ -407,6 +557,12 @@ int dft_init()
   O.rad4_1024 = rad4(1024); O.rad4_4096 = rad4(4096); O.rad2_2048 = rad2(2048); O.rad2_8192 = rad2(8192);
   const int r3n[4] = {768, 1536, 3072, 6144};
   for (int i = 0; i < 4; i++) O.rad3[i] = rad3(r3n[i]);
+  for (int i = 0; i < kNumSmall; i++) {   // init_rad{2,3,4,5}_rep (:7725-7828): entries k = 1 .. M-1 of W^(p k), p = 1 .. R-1, one copy instead of four
+    const int N = kSmall[i].N, R = kSmall[i].R, M = kSmall[i].M;
+    c.small_tw[i] = (int)blob.size();
+    for (int p = 1; p < R; p++)
+      for (int k = 1; k < M; k++) { blob.push_back(rnd16(32767.0 * cos(2 * M_PI * p * k / N))); blob.push_back((short)-rnd16(32767.0 * sin(2 * M_PI * p * k / N))); }
+  }
   if (cudaMalloc(&c.d_tw, blob.size() * sizeof(short)) != cudaSuccess) { c.last_error = "cudaMalloc twiddles"; return -1; }
   cudaMemcpy(c.d_tw, blob.data(), blob.size() * sizeof(short), cudaMemcpyHostToDevice);
   if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) { c.last_error = "stream"; return -1; }
@@ -414,6 +570,7 @@ int dft_init()
   cudaFuncSetAttribute(dft_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
   cudaFuncSetAttribute(dft_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
   cudaFuncSetAttribute(dft_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3240 * 4);
   c.inited = true;
   return 0;
 }
@@ -435,8 +592,12 @@ bool make_plan(int N, int inverse, int scale, DftPlan *P)
   return true;
 }
 
+int launch_dft_small(int N, uint32_t n_calls, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);
+bool is_fourway(int N);
+
 int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
 {
+  if (is_fourway(N)) return inverse ? -4 : launch_dft_small(N, n, d_in, d_out, scale, st);
   DftPlan P;
   if (!make_plan(N, inverse, scale, &P)) return -4;
   if (n == 0) return 0;
@@ -448,6 +609,36 @@ int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_o
   c.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft launch: ") + cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+bool make_small_plan(int N, int scale, SmallPlan *P)
+{
+  const DftCtx &c = dctx();
+  if (!is_fourway(N)) return false;
+  P->N = N; P->L = 0;
+  int n = N, apply = scale == 1;
+  while (n != 12) {
+    const int i = small_index(n);
+    if (i < 0 || P->L >= 5) return false;
+    P->R[P->L] = kSmall[i].R; P->norm[P->L] = kSmall[i].norm; P->apply[P->L] = apply; P->tw[P->L] = c.small_tw[i];
+    apply = kSmall[i].subscale; n = kSmall[i].M; P->L++;
+  }
+  for (int j = P->L; j < 5; j++) { P->R[j] = 1; P->norm[j] = 0; P->apply[j] = 0; P->tw[j] = 0; }
+  return true;
+}
+
+// n_calls x (4 N c16 in, 4 N c16 out)
+int launch_dft_small(int N, uint32_t n_calls, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
+{
+  SmallPlan P;
+  if (!make_small_plan(N, scale, &P)) return -4;
+  if (n_calls == 0) return 0;
+  DftCtx &c = dctx();
+  dft_small_kernel<<<n_calls, 256, (size_t)4 * N * 4, st>>>(P, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n_calls);
+  c.launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft_small launch: ") + cudaGetErrorString(e); return -2; }
   return 0;
 }
 
@@ -486,7 +677,7 @@ NRB200_EXPORT int32_t nrb200_dft_supported(int N)
   int r3 = (N % 3 == 0) ? 3 : 1, rest = N / r3;
   (void)P;
   for (int n4 = 64; n4 <= 4096; n4 *= 4) if (rest == n4 || rest == 2 * n4) return N <= 8192 ? 1 : 0;
-  return 0;
+  return is_fourway(N) ? 1 : 0;
 }
 
 NRB200_EXPORT int dfts_autoinit(void) { return dft_init(); }
@@ -506,7 +697,9 @@ NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, cons
   DftCtx &c = dctx();
   std::lock_guard<std::mutex> lk(c.mu);   // one staging buffer: host-buffer calls are serialised (the batched entry point is the fast path)
   cudaSetDevice(c.dev);
-  const size_t bytes = (size_t)n * N * 4;
+  const bool four = is_fourway(N);
+  if (four && inverse) return -4;
+  const size_t bytes = (size_t)n * N * 4 * (four ? 4 : 1);   // the four-way sizes move 4 N c16 per call
   if (bytes > c.cap) {
     if (c.d_in) { cudaFree(c.d_in); cudaFree(c.d_out); cudaFreeHost(c.h_in); cudaFreeHost(c.h_out); }
     c.cap = bytes + bytes / 4 + 65536;
@@ -515,11 +708,17 @@ NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, cons
   }
   std::memcpy(c.h_in, in, bytes);
   cudaMemcpyAsync(c.d_in, c.h_in, bytes, cudaMemcpyHostToDevice, c.stream);
-  DftPlan P;
-  if (!make_plan(N, inverse, scale, &P)) return -4;
-  const unsigned grid = (n + P.tpb - 1) / P.tpb;
-  if (inverse) dft_kernel<0, true><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
-  else dft_kernel<0, false><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
+  if (four) {
+    SmallPlan SP;
+    if (!make_small_plan(N, scale, &SP)) return -4;
+    dft_small_kernel<<<n, 256, (size_t)4 * N * 4, c.stream>>>(SP, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n);
+  } else {
+    DftPlan P;
+    if (!make_plan(N, inverse, scale, &P)) return -4;
+    const unsigned grid = (n + P.tpb - 1) / P.tpb;
+    if (inverse) dft_kernel<0, true><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
+    else dft_kernel<0, false><<<grid, 256, (size_t)2 * P.tpb * N * 4, c.stream>>>(P, c.off, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n, SlotIO{});
+  }
   c.launches++;
   cudaMemcpyAsync(c.h_out, c.d_out, bytes, cudaMemcpyDeviceToHost, c.stream);
   cudaError_t e = cudaStreamSynchronize(c.stream);

@@ -12,7 +12,14 @@ DFT_SIZES = [12, 24, 36, 48, 60, 64, 72, 96, 108, 120, 128, 144, 180, 192, 216, 
              2880, 2916, 3000, 3072, 3240, 4096, 6144, 8192, 9216, 12288, 18432, 24576, 36864, 49152, 73728, 98304]      # FOREACH_DFTSZ
 IDFT_SIZES = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 9216, 12288, 16384, 18432, 24576, 32768, 36864, 49152, 65536, 73728,
               98304]                                                                                                      # FOREACH_IDFTSZ
-SUPPORTED = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192]
+SUPPORTED = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192]          # one transform per call, both directions
+# the DFT-s-OFDM family (PUSCH transform precoding): forward only, every call transforms FOUR interleaved sequences (c16 number 4 n + l = element n of
+# transform l, oai_dfts.c:4352), i.e. 4 N c16 in and out
+FOURWAY = [N for N in DFT_SIZES if N <= 3240 and N not in SUPPORTED]
+
+
+def c16_per_call(N):
+    return 4 * N if N in FOURWAY else N
 
 
 def get_dft(N):
@@ -61,7 +68,8 @@ class DftsLib:
 
     def batch_host(self, N, inverse, x, scale=1):
         x = np.ascontiguousarray(x, dtype=np.int16)
-        n = x.size // (2 * N)
+        n = x.size // (2 * c16_per_call(N))
+        assert n * 2 * c16_per_call(N) == x.size
         y = np.zeros_like(x)
         rc = self.lib.nrb200_dft_batch_host(N, int(inverse), n, x.ctypes.data, y.ctypes.data, scale)
         if rc != 0:
@@ -71,7 +79,7 @@ class DftsLib:
     def batch_torch(self, N, inverse, x, scale=1, out=None):
         import torch
         assert x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()
-        n = x.numel() // (2 * N)
+        n = x.numel() // (2 * c16_per_call(N))
         if out is None:
             out = torch.empty_like(x)
         rc = self.lib.nrb200_dft_batch_dev(N, int(inverse), n, x.data_ptr(), out.data_ptr(), scale, torch.cuda.current_stream(x.device).cuda_stream)

@@ -298,6 +298,15 @@ class Oracle:
         assert rc == 0, rc
         return y
 
+    def dft4(self, N, x, scale=1):
+        """Four-way sizes 12 ... 3240 (DFT-s-OFDM): x = int16[2 * 4 * N], transform l at c16 positions 4 n + l."""
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        assert x.size == 8 * N
+        y = np.zeros(8 * N, dtype=np.int16)
+        rc = self.lib.orc_dft4(N, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), scale)
+        assert rc == 0, rc
+        return y
+
     def segmentation(self, data, B, BG):
         Cc, K, Zo, F = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
         Kb = self.lib.orc_segmentation(None, None, B, C.byref(Cc), C.byref(K), C.byref(Zo), C.byref(F), BG)
@@ -469,6 +478,19 @@ class Reference:
         oo = ((-out.ctypes.data) % 32) // 2
         y = out[oo:oo + 2 * N]
         getattr(self._dfts, ("idft" if inverse else "dft") + str(N))(xin.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_ubyte(scale))
+        return y.copy()
+
+    def dft4(self, N, x, scale=1, name=None):
+        """The four-way entry points dft12 ... dft3240 (4 N c16 in and out)."""
+        self.dft(64, False, np.zeros(128, np.int16))                                   # loads the library
+        buf = np.zeros(8 * N + 64, dtype=np.int16)
+        o = ((-buf.ctypes.data) % 32) // 2
+        xin = buf[o:o + 8 * N]
+        xin[:] = np.asarray(x, dtype=np.int16)
+        out = np.zeros(8 * N + 64, dtype=np.int16)
+        oo = ((-out.ctypes.data) % 32) // 2
+        y = out[oo:oo + 8 * N]
+        getattr(self._dfts, name or ("dft" + str(N)))(xin.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_ubyte(scale))
         return y.copy()
 
     # ---- PUSCH LLR computation of the reference (libref_llr.so: nr_ulsch_compute_llr)

@@ -170,6 +170,125 @@ static void dft_3x(const cx *x, cx *y, int N, int inverse, int scale)
   free(Y);
 }
 
+/* ------------------------------------------------------------------------------------------------------------------------------------------------
+ * The DFT-s-OFDM family 12 ... 3240 (PUSCH transform precoding; oai_dfts.c:4352-7706).  These entry points work on 128-bit vectors holding FOUR independent
+ * transforms ("4-way parallel DFTS (i.e. 4 DFTS with interleaved input/output)", :4352): element n of transform l is c16 number 4 n + l, in and out.
+ * Every size is N = R x M, decimation in time: M-point transforms of x[m], x[m + R], ... (m < R) in natural order, then for every k < M one radix-R butterfly
+ *   k = 0: bfly{2,3,4,5}_tw1 (no twiddles: saturating 16-bit sums for R = 2, 4; 32-bit W products for R = 3, 5)
+ *   k > 0: bfly{2,3,4,5} with twiddles (int16)round(32767 cos/sin(2 pi p k / N)), p = 1 .. R-1 (init_rad{2,3,4,5}_rep :7725-7828)
+ * writing y[k + q M], q < R, followed by mulhrs with a per-size constant when scale_flag == 1.  The 12-point kernel (dft12f :4365-4470) is three bfly4_tw1 and
+ * four bfly3 with hand-entered constants and never scales.  Sub-transforms are called with scale 1 except 96 -> 48, 108 -> 36 and 120 -> 60 (scale 0).
+ * dft2304 (:7288) calls the single-transform dft768 on the four-way data and combines uninitialised stack: not reproducible; orc_dft4 returns the transform
+ * the function's comment ("768 x 3") describes, built on the four-way 768 (dft768p :6330). */
+typedef struct { int R, M, subscale, norm; } small_t;
+static int small_plan(int N, small_t *p)
+{
+  static const int tab[][5] = {
+    {24, 2, 12, 0, 6689}, {36, 3, 12, 0, 5461}, {48, 4, 12, 0, 4729}, {60, 5, 12, 0, 4230}, {72, 2, 36, 1, 23170}, {96, 2, 48, 0, 3344}, {108, 3, 36, 0, 3153},
+    {120, 2, 60, 0, 2991}, {144, 3, 48, 1, 18918}, {180, 3, 60, 1, 18918}, {192, 4, 48, 1, 16384}, {216, 3, 72, 1, 18918}, {240, 4, 60, 1, 16384},
+    {288, 3, 96, 1, 18918}, {300, 5, 60, 1, 14654}, {324, 3, 108, 1, 18918}, {360, 3, 120, 1, 18918}, {384, 4, 96, 1, 16384}, {432, 4, 108, 1, 16384},
+    {480, 4, 120, 1, 16384}, {540, 3, 180, 1, 18918}, {576, 3, 192, 1, 18918}, {600, 2, 300, 1, 23170}, {648, 3, 216, 1, 18918}, {720, 4, 180, 1, 16384},
+    {768, 4, 192, 1, 16384}, {864, 3, 288, 1, 18918}, {900, 3, 300, 1, 18918}, {960, 4, 240, 1, 16384}, {972, 3, 324, 1, 18918}, {1080, 3, 360, 1, 18918},
+    {1152, 4, 288, 1, 16384}, {1200, 4, 300, 1, 16384}, {1296, 3, 432, 1, 18918}, {1440, 3, 480, 1, 18918}, {1500, 5, 300, 1, 14654}, {1620, 3, 540, 1, 18918},
+    {1728, 3, 576, 1, 18918}, {1800, 3, 600, 1, 18918}, {1920, 4, 480, 1, 16384}, {1944, 3, 648, 1, 18918}, {2160, 3, 720, 1, 18918}, {2304, 3, 768, 1, 18918},
+    {2400, 4, 600, 1, 16384}, {2592, 3, 864, 1, 18918}, {2700, 3, 900, 1, 18918}, {2880, 3, 960, 1, 18918}, {2916, 3, 972, 1, 18918}, {3000, 5, 600, 1, 14654},
+    {3240, 3, 1080, 1, 18918}};
+  for (unsigned i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
+    if (tab[i][0] == N) { p->R = tab[i][1]; p->M = tab[i][2]; p->subscale = tab[i][3]; p->norm = tab[i][4]; return 1; }
+  return 0;
+}
+
+/* packed_cmult: cmult then cpack (oai_dfts.c:246-256) */
+static inline cx pcm(cx x, int32_t wr, int32_t wi) { int64_t r, i; cm32(x, wr, wi, 0, &r, &i); return pk32(r, i); }
+/* sum_p x_p * W_p in 32 bit, cpack, saturating add of x0: the y1.. outputs of bfly3 / bfly5 (:477-500, :949-1000) */
+static inline cx wsum(cx x0, const cx *x, const int16_t (*W)[2], const int *sel, int n)
+{
+  int64_t r = 0, i = 0;
+  for (int p = 0; p < n; p++) { int64_t a, b; cm32(x[p], W[sel[p]][0], W[sel[p]][1], 0, &a, &b); r += a; i += b; }
+  return sadd(x0, pk32(r, i));
+}
+static const int16_t W3C[2][2] = {{-16384, -28378}, {-16384, 28378}};                                     /* W13, W23 (:321-322) */
+static const int16_t W5C[4][2] = {{10126, -31163}, {-26509, -19260}, {-26510, 19260}, {10126, 31163}};    /* W15 .. W45 (:324-327) */
+
+static void bfly3_fwd(cx x0, cx x1, cx x2, cx *y0, cx *y1, cx *y2)   /* x1, x2 already multiplied by their twiddles (or taken as they are for k = 0) */
+{
+  const cx x[2] = {x1, x2};
+  static const int s1[2] = {0, 1}, s2[2] = {1, 0};
+  *y0 = sadd(x0, sadd(x1, x2));
+  *y1 = wsum(x0, x, W3C, s1, 2);
+  *y2 = wsum(x0, x, W3C, s2, 2);
+}
+static void bfly5_fwd(cx x0, const cx *x /* 4 */, cx *y /* 5 */)
+{
+  static const int s[4][4] = {{0, 1, 2, 3}, {1, 3, 0, 2}, {2, 0, 3, 1}, {3, 2, 1, 0}};
+  y[0] = sadd(x0, sadd(x[0], sadd(x[1], sadd(x[2], x[3]))));
+  for (int q = 0; q < 4; q++) y[q + 1] = wsum(x0, x, W5C, s[q], 4);
+}
+
+static void dft12_lane(const cx *x, int stride, cx *y)
+{
+  static const int16_t W12[5][2] = {{28377, -16383}, {16383, -28377}, {0, -32767}, {-16383, -28377}, {-32767, 0}};   /* W1, W2, W3, W4, W6 (:4353-4357) */
+  cx t[12];
+  for (int c = 0; c < 3; c++)
+    bfly4_sat(x[c * stride], x[(c + 3) * stride], x[(c + 6) * stride], x[(c + 9) * stride], 0, &t[c], &t[c + 3], &t[c + 6], &t[c + 9]);
+  bfly3_fwd(t[0], t[1], t[2], &y[0], &y[4], &y[8]);
+  bfly3_fwd(t[3], pcm(t[4], W12[0][0], W12[0][1]), pcm(t[5], W12[1][0], W12[1][1]), &y[1], &y[5], &y[9]);
+  bfly3_fwd(t[6], pcm(t[7], W12[1][0], W12[1][1]), pcm(t[8], W12[3][0], W12[3][1]), &y[2], &y[6], &y[10]);
+  bfly3_fwd(t[9], pcm(t[10], W12[2][0], W12[2][1]), pcm(t[11], W12[4][0], W12[4][1]), &y[3], &y[7], &y[11]);
+}
+
+static void dft_small(const cx *x, int stride, cx *y, int N, int scale)
+{
+  if (N == 12) { dft12_lane(x, stride, y); return; }
+  small_t P = {0, 0, 0, 0};
+  small_plan(N, &P);
+  const int R = P.R, M = P.M;
+  cx *Y = malloc(sizeof(cx) * (size_t)N);
+  for (int m = 0; m < R; m++) dft_small(x + m * stride, R * stride, Y + m * M, M, P.subscale);
+  for (int k = 0; k < M; k++) {
+    cx in[5], out[5];
+    int32_t w[8];
+    for (int p = 0; p < R; p++) in[p] = Y[p * M + k];
+    for (int p = 1; p < R; p++) { w[2 * p - 2] = rnd(32767.0 * cos(2 * M_PI * p * k / N)); w[2 * p - 1] = -rnd(32767.0 * sin(2 * M_PI * p * k / N)); }
+    if (R == 2) {
+      if (k == 0) { out[0] = sadd(in[0], in[1]); out[1] = ssub(in[0], in[1]); }                /* bfly2_tw1 (:438-443) */
+      else {                                                                                     /* bfly2 (:362-390) */
+        int64_t br, bi, ar = (int64_t)in[0].r * 32767, ai = (int64_t)in[0].i * 32767;
+        cm32(in[1], w[0], w[1], 0, &br, &bi);
+        out[0] = pk32(ar + br, ai + bi); out[1] = pk32(ar - br, ai - bi);
+      }
+    } else if (R == 3) {
+      if (k == 0) bfly3_fwd(in[0], in[1], in[2], &out[0], &out[1], &out[2]);
+      else bfly3_fwd(in[0], pcm(in[1], w[0], w[1]), pcm(in[2], w[2], w[3]), &out[0], &out[1], &out[2]);
+    } else if (R == 4) {
+      if (k == 0) bfly4_sat(in[0], in[1], in[2], in[3], 0, &out[0], &out[1], &out[2], &out[3]);   /* bfly4_tw1 (:709-745) */
+      else bfly4_32(in[0], in[1], in[2], in[3], w, 0, &out[0], &out[1], &out[2], &out[3]);        /* bfly4 (:584-632) */
+    } else {
+      cx t[4];
+      for (int p = 1; p < 5; p++) t[p - 1] = k == 0 ? in[p] : pcm(in[p], w[2 * p - 2], w[2 * p - 1]);
+      bfly5_fwd(in[0], t, out);
+    }
+    for (int q = 0; q < R; q++) y[k + q * M] = out[q];
+  }
+  if (scale == 1) for (int k = 0; k < N; k++) { y[k].r = mulhrs(y[k].r, P.norm); y[k].i = mulhrs(y[k].i, P.norm); }
+  free(Y);
+}
+
+/* dft(DFT_<N>, in, out, scale_flag) for the four-way sizes: in/out hold 4 N c16, transform l at c16 positions 4 n + l.  768 here is dft768p. */
+int orc_dft4(int N, const int16_t *in, int16_t *out, int scale)
+{
+  small_t P = {0, 0, 0, 0};
+  if (N != 12 && !small_plan(N, &P)) return -1;
+  cx *x = malloc(sizeof(cx) * (size_t)N), *y = malloc(sizeof(cx) * (size_t)N);
+  for (int l = 0; l < 4; l++) {
+    for (int n = 0; n < N; n++) { x[n].r = in[2 * (4 * n + l)]; x[n].i = in[2 * (4 * n + l) + 1]; }
+    dft_small(x, 1, y, N, scale);
+    for (int n = 0; n < N; n++) { out[2 * (4 * n + l)] = (int16_t)y[n].r; out[2 * (4 * n + l) + 1] = (int16_t)y[n].i; }
+  }
+  free(x); free(y);
+  return 0;
+}
+
 /* in/out: interleaved {re, im} int16 like the reference's dft()/idft() (tools_defs.h:514-521); returns 0, -1 for an unsupported size */
 int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale)
 {

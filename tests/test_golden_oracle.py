@@ -161,3 +161,12 @@ def test_phy_golden(oracle):
     pd = [int(x) for x in g["pdsch_par"]]
     l, sh = oracle.pdsch_rx_slot(PuschParms(*pd[:10]), pd[10], pd[11], g["rx1_rx"], g["rx1_h"])
     assert sh == int(g["pdsch_shift"][0]) and np.array_equal(l, g["pdsch_llr"])
+
+
+def test_dft_fourway_golden(oracle):
+    """The DFT-s-OFDM entry points (four interleaved transforms per call) against fixtures produced by the compiled reference (tools/gen_golden_dft4.py)."""
+    d = _load("dft4.npz")
+    for N in d["sizes"]:
+        N = int(N)
+        assert np.array_equal(oracle.dft4(N, d[f"x{N}"], 1), d[f"y{N}_s1"]), N
+        assert np.array_equal(oracle.dft4(N, d[f"x{N}"], 0), d[f"y{N}_s0"]), N

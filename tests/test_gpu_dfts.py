@@ -2,6 +2,7 @@
 import os
 import numpy as np
 import pytest
+import torch
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -65,3 +66,36 @@ def test_slot_of_ofdm_symbols_properties(dfts):
     assert (xr.to(torch.int32) - x.to(torch.int32)).abs().max().item() < 80
     # determinism
     assert torch.equal(X, dfts.batch_torch(4096, False, x, 1))
+
+
+FOURWAY = [12, 24, 36, 48, 60, 72, 96, 108, 120, 144, 180, 192, 216, 240, 288, 300, 324, 360, 384, 432, 480, 540, 576, 600, 648, 720, 864, 900, 960, 972, 1080,
+           1152, 1200, 1296, 1440, 1500, 1620, 1728, 1800, 1920, 1944, 2160, 2304, 2400, 2592, 2700, 2880, 2916, 3000, 3240]
+
+
+@pytest.mark.parametrize("N", FOURWAY)
+def test_fourway_vs_oracle(dfts, oracle, N):
+    """DFT-s-OFDM family: 3 calls per launch (4 N c16 each), amplitudes that do and do not saturate, scale_flag 1 / 0, and the plug-in call dft(DFT_<N>, ...)."""
+    from openairinterface5g_b200.dfts import get_dft
+    rng = np.random.default_rng(N)
+    for amp in (300, 3000, 32767):
+        for scale in (1, 0):
+            x = rng.integers(-amp, amp + 1, size=(3, 8 * N)).astype(np.int16)
+            got = dfts.batch_host(N, False, x, scale)
+            for b in range(3):
+                assert np.array_equal(got[b], oracle.dft4(N, x[b], scale)), (N, amp, scale, b)
+    x = rng.choice(np.array([-32768, 32767, 0], dtype=np.int16), size=8 * N)
+    assert np.array_equal(dfts.dft(get_dft(N), x, 1), oracle.dft4(N, x, 1))
+
+
+def test_fourway_golden_and_device_batch(dfts):
+    d = np.load(os.path.join(G, "dft4.npz"))
+    for N in d["sizes"]:
+        N = int(N)
+        assert np.array_equal(dfts.batch_host(N, False, d[f"x{N}"], 1), d[f"y{N}_s1"]), N
+        assert np.array_equal(dfts.batch_host(N, False, d[f"x{N}"], 0), d[f"y{N}_s0"]), N
+    # a PUSCH-sized batch on the device: 273 PRB = 3240 + 36 is not one DFT size, 270 PRB = 3240 is; 13 symbols x 4 layers = 52 calls in one launch
+    N = 3240
+    x = torch.from_numpy(np.tile(d[f"x{N}"], (52, 1))).cuda()
+    y = dfts.batch_torch(N, False, x, 1)
+    torch.cuda.synchronize()
+    assert all(np.array_equal(y[i].cpu().numpy(), d[f"y{N}_s1"]) for i in (0, 25, 51))

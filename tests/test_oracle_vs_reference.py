@@ -180,6 +180,39 @@ def test_dft_idft_q15(oracle, reference, N):
         assert np.array_equal(oracle.dft(N, inverse, x, 1), reference.dft(N, inverse, x, 1))
 
 
+FOURWAY_SIZES = [12, 24, 36, 48, 60, 72, 96, 108, 120, 144, 180, 192, 216, 240, 288, 300, 324, 360, 384, 432, 480, 540, 576, 600, 648, 720, 864, 900, 960, 972,
+                 1080, 1152, 1200, 1296, 1440, 1500, 1620, 1728, 1800, 1920, 1944, 2160, 2400, 2592, 2700, 2880, 2916, 3000, 3240]
+
+
+@pytest.mark.parametrize("N", FOURWAY_SIZES + [768])
+def test_dft_fourway_q15(oracle, reference, N):
+    """The DFT-s-OFDM entry points dft12 ... dft3240 (four interleaved transforms per call) vs the restatement; 768 is the internal dft768p."""
+    rng = np.random.default_rng(N)
+    name = "dft768p" if N == 768 else None
+    for amp in (300, 3000, 20000, 32767):
+        for scale in (1, 0):
+            x = rng.integers(-amp, amp + 1, size=8 * N).astype(np.int16)
+            assert np.array_equal(oracle.dft4(N, x, scale), reference.dft4(N, x, scale, name=name)), (N, amp, scale)
+    x = rng.choice(np.array([-32768, 32767, 0], dtype=np.int16), size=8 * N)
+    assert np.array_equal(oracle.dft4(N, x, 1), reference.dft4(N, x, 1, name=name))
+
+
+def test_dft2304_reference_is_not_reproducible(oracle, reference):
+    """dft2304 (oai_dfts.c:7288) runs the single-transform dft768 over four-way data and combines stack it never wrote: two calls on the same input differ.
+    The restatement returns the 768 x 3 transform instead; it is checked against a float DFT."""
+    N = 2304
+    x = np.random.default_rng(1).integers(-300, 301, size=8 * N).astype(np.int16)
+    b1 = reference.dft4(N, x, 1)
+    reference.dft4(3240, np.random.default_rng(2).integers(-30000, 30001, size=8 * 3240).astype(np.int16), 1)     # leaves other bytes on the stack
+    b2 = reference.dft4(N, x, 1)
+    assert not np.array_equal(b1, b2)
+    a = oracle.dft4(N, x, 1)
+    X = (x[0::2] + 1j * x[1::2]).reshape(N, 4)
+    Y = np.fft.fft(X, axis=0) / np.sqrt(N)
+    ya = (a[0::2] + 1j * a[1::2]).reshape(N, 4)
+    assert np.abs(ya - Y).max() < 0.06 * np.sqrt((np.abs(Y) ** 2).mean())
+
+
 @pytest.mark.parametrize("Qm", [2, 4, 6, 8])
 def test_pusch_llr(oracle, reference, Qm):
     """nr_ulsch_compute_llr (AVX2 path) vs the restatement, for RE counts that are and are not multiples of 8."""
