@@ -478,11 +478,92 @@ dft_small_kernel(SmallPlan P, const short *__restrict__ tw, const unsigned *__re
   }
 }
 
+// ------------------------------------------------------------------------------------------------ sizes above 8192 (12288 ... 98304)
+// oai_dfts.c:2846-3138, :3614-4350: radix-3 / radix-4 / radix-2 levels on top of a transform that fits in shared memory (4096, 6144 or 8192 points).  Here:
+// one gather pass that puts every base transform's decimated input in a row, the batched shared-memory kernel over the rows, then one in-place pass over
+// global memory per top level (a transform of 98304 points is 384 KB: L2 resident).
+struct BigPlan {
+  int N, B, T, L;                 // N = T * B, T = R[0] * ... * R[L-1], level 0 = top
+  int R[3], sval[3], tw[3];       // radix, the scale argument that level's function receives, blob offset of its (R-1) planes of NJ/R twiddles (k from 0)
+  int base_scale;
+};
+
+__global__ void big_gather_kernel(BigPlan P, const unsigned *__restrict__ in, unsigned *__restrict__ rows, unsigned n_calls)
+{
+  const size_t total = (size_t)n_calls * P.N;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+    const unsigned call = (unsigned)(w / P.N), rem = (unsigned)(w - (size_t)call * P.N);
+    const unsigned srow = rem / P.B, n = rem - srow * P.B;
+    unsigned first = 0, mult = 1, ss = srow, digs[3];
+    for (int j = P.L - 1; j >= 0; j--) { digs[j] = ss % P.R[j]; ss /= P.R[j]; }       // row id = ((m0 R1 + m1) R2 + m2); input index m0 + R0 (m1 + R1 (m2 + R2 n))
+    for (int j = 0; j < P.L; j++) { first += digs[j] * mult; mult *= P.R[j]; }
+    rows[w] = in[(size_t)call * P.N + first + (size_t)P.T * n];
+  }
+}
+
+template <bool INV>
+__global__ void big_combine_kernel(int N, int NJ, int R, int sval, const short *__restrict__ tw, const unsigned *src, unsigned *dst, unsigned n_calls)
+{
+  constexpr bool inv = INV;
+  const int M = NJ / R;
+  const size_t total = (size_t)n_calls * (N / R);
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+    const unsigned call = (unsigned)(w / (N / R)), rem = (unsigned)(w - (size_t)call * (N / R));
+    const unsigned g = rem / M, k = rem - g * M;
+    const size_t base = (size_t)call * N + (size_t)g * NJ + k;
+    if (R == 3) {                                                          // bfly3 / ibfly3 (:477-560), twiddles from init_rad3
+      const cx x0 = unpack(src[base]), a = unpack(src[base + M]), b = unpack(src[base + 2 * M]);
+      const cx T1 = ldtw(tw + 2 * k), T2 = ldtw(tw + 2 * (M + k));
+      unsigned r, i, r2, i2;
+      cm32(a, T1.r, T1.i, inv, r, i);
+      const cx x1 = pk32(r, i);
+      cm32(b, T2.r, T2.i, inv, r, i);
+      const cx x2 = pk32(r, i);
+      cx y0 = sadd(x0, sadd(x1, x2));
+      cm32(x1, -16384, -28378, inv, r, i); cm32(x2, -16384, 28378, inv, r2, i2);
+      cx y1 = sadd(x0, pk32(r + r2, i + i2));
+      cm32(x1, -16384, 28378, inv, r, i); cm32(x2, -16384, -28378, inv, r2, i2);
+      cx y2 = sadd(x0, pk32(r + r2, i + i2));
+      if (sval == 1) {
+        y0 = {mulhrs(y0.r, 18919), mulhrs(y0.i, 18919)}; y1 = {mulhrs(y1.r, 18919), mulhrs(y1.i, 18919)}; y2 = {mulhrs(y2.r, 18919), mulhrs(y2.i, 18919)};
+      }
+      dst[base] = pack(y0); dst[base + M] = pack(y1); dst[base + 2 * M] = pack(y2);
+    } else if (R == 4) {                                                   // bfly4_256 / ibfly4_256 (:633-721), twiddles from init_rad4
+      const cx x0 = unpack(src[base]), x1 = unpack(src[base + M]), x2 = unpack(src[base + 2 * M]), x3 = unpack(src[base + 3 * M]);
+      cx y0, y1, y2, y3;
+      bfly4_32(x0, x1, x2, x3, tw + 2 * k, tw + 2 * (M + k), tw + 2 * (2 * M + k), inv, y0, y1, y2, y3);
+      if (sval > 0) {
+        const int sh = NJ == 65536 ? sval : 1;
+        y0.r >>= sh; y0.i >>= sh; y1.r >>= sh; y1.i >>= sh; y2.r >>= sh; y2.i >>= sh; y3.r >>= sh; y3.i >>= sh;
+      }
+      dst[base] = pack(y0); dst[base + M] = pack(y1); dst[base + 2 * M] = pack(y2); dst[base + 3 * M] = pack(y3);
+    } else {                                                               // bfly2_256 / ibfly2_256 (:390-476), twiddles from init_rad2
+      const cx x0 = unpack(src[base]), x1 = unpack(src[base + M]);
+      const cx T2 = ldtw(tw + 2 * k);
+      unsigned br, bi;
+      cm32(x1, T2.r, T2.i, inv, br, bi);
+      const unsigned ar = (unsigned)(x0.r * 32767), ai = (unsigned)(x0.i * 32767);
+      cx y0 = pk32(ar + br, ai + bi), y1 = pk32(ar - br, ai - bi);
+      if (sval > 0) { y0 = {mulhrs(y0.r, 23170), mulhrs(y0.i, 23170)}; y1 = {mulhrs(y1.r, 23170), mulhrs(y1.i, 23170)}; }
+      dst[base] = pack(y0); dst[base + M] = pack(y1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 // the four-way family: N = R x M, whether the M-point transforms are called with scale 1, and the mulhrs constant applied at this level when ITS scale is 1
 // (dft_norm_table oai_dfts.c:352-368 for 24 ... 300, 1/sqrt(R) in Q15 above; read off every dftN :4680-7706).  768 is dft768p (:6330), reachable only through
 // 2304: the reference's dft2304 (:7288) calls the single-transform dft768 on four-way data and then combines uninitialised stack, so its result is not a function
 // of its input; this library returns the "768 x 3" transform its comment describes (defect 11).
+// sizes above 8192: the radix of the top level (the rest is the next smaller size).  9216 and 73728 are AssertFatal("Need to do this") in the reference;
+// dft32768/idft32768 overrun their stack buffers (:2966-3004: 256 x 64 input vectors read from a 4096-vector array) and crash, dft98304/idft98304 call them,
+// idft65536 reads its second and third twiddle planes at twice the right offset, the third beyond the table (:4200-4202): for these four sizes this library
+// computes the transform the code intends (same level arithmetic as the sizes that work), which cannot be pinned against the reference.
+struct BigSize { int N, R; };
+const BigSize kBig[] = {{12288, 3}, {16384, 4}, {18432, 3}, {24576, 3}, {32768, 2}, {36864, 3}, {49152, 3}, {65536, 4}, {98304, 3}};
+constexpr int kNumBig = (int)(sizeof(kBig) / sizeof(kBig[0]));
+int big_index(int N) { for (int i = 0; i < kNumBig; i++) if (kBig[i].N == N) return i; return -1; }
+
 struct SmallSize { int N, R, M, subscale, norm; };
 const SmallSize kSmall[] = {
     {24, 2, 12, 0, 6689}, {36, 3, 12, 0, 5461}, {48, 4, 12, 0, 4729}, {60, 5, 12, 0, 4230}, {72, 2, 36, 1, 23170}, {96, 2, 48, 0, 3344}, {108, 3, 36, 0, 3153},
@@ -500,11 +581,12 @@ int small_index(int N) { for (int i = 0; i < kNumSmall; i++) if (kSmall[i].N == 
 bool is_fourway(int N) { return N == 12 || (N != 768 && small_index(N) >= 0); }
 
 struct DftCtx {
-  std::mutex mu;
+  std::recursive_mutex mu;
   bool inited = false;
   int dev = 0;
   short *d_tw = nullptr;
   TwOffsets off;
+  int big_tw[9];                          // blob offsets of the top-level twiddles of kBig[i]
   int small_tw[51];                       // blob offset of the level twiddles of four-way size kSmall[i].N (-1: none)
   cudaStream_t stream = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
@@ -519,7 +601,7 @@ short rnd16(double v) { return (short)std::round(v); }
 int dft_init()
 {
   DftCtx &c = dctx();
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
   if (c.inited) return 0;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { c.last_error = "no CUDA device"; return -1; }
@@ -557,6 +639,7 @@ int dft_init()
   O.rad4_1024 = rad4(1024); O.rad4_4096 = rad4(4096); O.rad2_2048 = rad2(2048); O.rad2_8192 = rad2(8192);
   const int r3n[4] = {768, 1536, 3072, 6144};
   for (int i = 0; i < 4; i++) O.rad3[i] = rad3(r3n[i]);
+  for (int i = 0; i < kNumBig; i++) c.big_tw[i] = kBig[i].R == 3 ? rad3(kBig[i].N) : kBig[i].R == 4 ? rad4(kBig[i].N) : rad2(kBig[i].N);
   for (int i = 0; i < kNumSmall; i++) {   // init_rad{2,3,4,5}_rep (:7725-7828): entries k = 1 .. M-1 of W^(p k), p = 1 .. R-1, one copy instead of four
     const int N = kSmall[i].N, R = kSmall[i].R, M = kSmall[i].M;
     c.small_tw[i] = (int)blob.size();
@@ -593,11 +676,13 @@ bool make_plan(int N, int inverse, int scale, DftPlan *P)
 }
 
 int launch_dft_small(int N, uint32_t n_calls, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);
+int launch_dft_big(int N, int inverse, uint32_t n_calls, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);
 bool is_fourway(int N);
 
 int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
 {
   if (is_fourway(N)) return inverse ? -4 : launch_dft_small(N, n, d_in, d_out, scale, st);
+  if (N > 8192) return launch_dft_big(N, inverse, n, d_in, d_out, scale, st);
   DftPlan P;
   if (!make_plan(N, inverse, scale, &P)) return -4;
   if (n == 0) return 0;
@@ -608,8 +693,59 @@ int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_o
   else dft_kernel<0, false><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
   c.launches++;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft launch: ") + cudaGetErrorString(e); return -2; }
+  if (e != cudaSuccess) { std::lock_guard<std::recursive_mutex> lk(c.mu); c.last_error = std::string("dft launch: ") + cudaGetErrorString(e); return -2; }
   return 0;
+}
+
+bool make_big_plan(int N, int inverse, int scale, BigPlan *P)
+{
+  const DftCtx &c = dctx();
+  if (big_index(N) < 0) return false;
+  if (N == 65536 && !inverse) return false;                 // the reference has no dft65536
+  P->N = N; P->L = 0; P->T = 1;
+  int n = N, sv = scale;
+  while (n > 8192) {
+    const int i = big_index(n);
+    if (i < 0 || P->L >= 3) return false;
+    const int R = kBig[i].R;
+    P->R[P->L] = R; P->sval[P->L] = sv; P->tw[P->L] = c.big_tw[i];
+    sv = (n == 12288 || n == 18432) ? sv : 1;                 // dft12288 / dft18432 hand their scale argument down (:3641, :3755), every other level passes 1
+    n /= R; P->T *= R; P->L++;
+  }
+  for (int j = P->L; j < 3; j++) { P->R[j] = 1; P->sval[j] = 0; P->tw[j] = 0; }
+  P->B = n; P->base_scale = sv;
+  return true;
+}
+
+int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);
+
+int launch_dft_big(int N, int inverse, uint32_t n_calls, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
+{
+  BigPlan P;
+  if (!make_big_plan(N, inverse, scale, &P)) return -4;
+  if (n_calls == 0) return 0;
+  DftCtx &c = dctx();
+  unsigned *rows = nullptr;
+  const size_t total = (size_t)n_calls * N;
+  if (cudaMallocAsync((void **)&rows, total * 4, st) != cudaSuccess) { std::lock_guard<std::recursive_mutex> lk(c.mu); c.last_error = "dft_big scratch"; return -5; }
+  const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  big_gather_kernel<<<grid, 256, 0, st>>>(P, (const unsigned *)d_in, rows, n_calls);
+  c.launches++;
+  int rc = launch_dft(P.B, inverse, n_calls * P.T, (const int16_t *)rows, d_out, P.base_scale, st);
+  int M = P.B;
+  for (int j = P.L - 1; j >= 0 && rc == 0; j--) {
+    const int NJ = M * P.R[j];
+    const size_t work = total / P.R[j];
+    const unsigned g2 = (unsigned)std::min<size_t>((work + 255) / 256, 148 * 16);
+    if (inverse) big_combine_kernel<true><<<g2, 256, 0, st>>>(N, NJ, P.R[j], P.sval[j], c.d_tw + P.tw[j], (const unsigned *)d_out, (unsigned *)d_out, n_calls);
+    else big_combine_kernel<false><<<g2, 256, 0, st>>>(N, NJ, P.R[j], P.sval[j], c.d_tw + P.tw[j], (const unsigned *)d_out, (unsigned *)d_out, n_calls);
+    c.launches++;
+    M = NJ;
+  }
+  cudaFreeAsync(rows, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { std::lock_guard<std::recursive_mutex> lk(c.mu); c.last_error = std::string("dft_big launch: ") + cudaGetErrorString(e); return -2; }
+  return rc;
 }
 
 bool make_small_plan(int N, int scale, SmallPlan *P)
@@ -638,7 +774,7 @@ int launch_dft_small(int N, uint32_t n_calls, const int16_t *d_in, int16_t *d_ou
   dft_small_kernel<<<n_calls, 256, (size_t)4 * N * 4, st>>>(P, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n_calls);
   c.launches++;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("dft_small launch: ") + cudaGetErrorString(e); return -2; }
+  if (e != cudaSuccess) { std::lock_guard<std::recursive_mutex> lk(c.mu); c.last_error = std::string("dft_small launch: ") + cudaGetErrorString(e); return -2; }
   return 0;
 }
 
@@ -676,8 +812,9 @@ NRB200_EXPORT int32_t nrb200_dft_supported(int N)
   DftPlan P;
   int r3 = (N % 3 == 0) ? 3 : 1, rest = N / r3;
   (void)P;
-  for (int n4 = 64; n4 <= 4096; n4 *= 4) if (rest == n4 || rest == 2 * n4) return N <= 8192 ? 1 : 0;
-  return is_fourway(N) ? 1 : 0;
+  if (N <= 8192)
+    for (int n4 = 64; n4 <= 4096; n4 *= 4) if (rest == n4 || rest == 2 * n4) return 1;
+  return (is_fourway(N) || big_index(N) >= 0) ? 1 : 0;
 }
 
 NRB200_EXPORT int dfts_autoinit(void) { return dft_init(); }
@@ -695,7 +832,7 @@ NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, cons
   if (!nrb200_dft_supported(N)) return -4;
   if (n == 0) return 0;
   DftCtx &c = dctx();
-  std::lock_guard<std::mutex> lk(c.mu);   // one staging buffer: host-buffer calls are serialised (the batched entry point is the fast path)
+  std::lock_guard<std::recursive_mutex> lk(c.mu);   // one staging buffer: host-buffer calls are serialised (the batched entry point is the fast path)
   cudaSetDevice(c.dev);
   const bool four = is_fourway(N);
   if (four && inverse) return -4;
@@ -708,7 +845,11 @@ NRB200_EXPORT int32_t nrb200_dft_batch_host(int N, int inverse, uint32_t n, cons
   }
   std::memcpy(c.h_in, in, bytes);
   cudaMemcpyAsync(c.d_in, c.h_in, bytes, cudaMemcpyHostToDevice, c.stream);
-  if (four) {
+  if (!four && N > 8192) {
+    const int rc = launch_dft_big(N, inverse, n, (const int16_t *)c.d_in, (int16_t *)c.d_out, scale, c.stream);
+    if (rc != 0) return rc;
+    c.launches--;   // counted inside
+  } else if (four) {
     SmallPlan SP;
     if (!make_small_plan(N, scale, &SP)) return -4;
     dft_small_kernel<<<n, 256, (size_t)4 * N * 4, c.stream>>>(SP, c.d_tw, (const unsigned *)c.d_in, (unsigned *)c.d_out, n);
@@ -762,7 +903,7 @@ int launch_slot(const nrb200_ofdm_slot_t *d, bool rx, const void *d_in, void *d_
   else dft_kernel<1, true><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
   c.launches++;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.last_error = std::string("ofdm slot launch: ") + cudaGetErrorString(e); return -2; }
+  if (e != cudaSuccess) { std::lock_guard<std::recursive_mutex> lk(c.mu); c.last_error = std::string("ofdm slot launch: ") + cudaGetErrorString(e); return -2; }
   return 0;
 }
 
@@ -797,7 +938,7 @@ NRB200_EXPORT int32_t nrb200_ofdm_mod_slot_host(const nrb200_ofdm_slot_t *d, con
   if (dft_init() != 0) return -1;
   if (!d || d->n_symb < 1 || d->n_symb > 14 || d->n_ant < 1 || !nrb200_dft_supported((int)d->fft_size)) return -4;
   DftCtx &c = dctx();
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
   cudaSetDevice(c.dev);
   const unsigned N = d->fft_size, ns = d->n_symb, na = d->n_ant;
   // time-domain span written by this call, relative to txdata[a]
@@ -830,7 +971,7 @@ NRB200_EXPORT int32_t nrb200_ofdm_demod_slot_host(const nrb200_ofdm_slot_t *d, c
   if (!d || d->n_symb < 1 || d->n_symb > 14 || d->n_ant < 1 || !nrb200_dft_supported((int)d->fft_size)) return -4;
   if (d->rotate && !timeshift) return -4;
   DftCtx &c = dctx();
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
   cudaSetDevice(c.dev);
   const unsigned N = d->fft_size, ns = d->n_symb, na = d->n_ant, ring = d->t_ring;
   // Only the FFT windows travel: window l of antenna a lands at (a * ns + l) * N in the staging buffer (the ring wrap is resolved here).

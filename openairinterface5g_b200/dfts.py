@@ -16,6 +16,7 @@ SUPPORTED = [64, 128, 256, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192]  
 # the DFT-s-OFDM family (PUSCH transform precoding): forward only, every call transforms FOUR interleaved sequences (c16 number 4 n + l = element n of
 # transform l, oai_dfts.c:4352), i.e. 4 N c16 in and out
 FOURWAY = [N for N in DFT_SIZES if N <= 3240 and N not in SUPPORTED]
+LARGE = [12288, 16384, 18432, 24576, 32768, 36864, 49152, 65536, 98304]               # 65536: inverse only; 9216 and 73728 do not exist in the reference either
 
 
 def c16_per_call(N):

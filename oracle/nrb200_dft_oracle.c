@@ -118,14 +118,15 @@ static void dft_pow4(const cx *x, int stride, cx *y, int N, int inverse, int sca
       bfly4_32(Y[k], Y[M + k], Y[2 * M + k], Y[3 * M + k], w, inverse, &y[k], &y[k + M], &y[k + 2 * M], &y[k + 3 * M]);
     }
   }
-  if (scale) for (int k = 0; k < N; k++) { y[k].r >>= 1; y[k].i >>= 1; }
+  if (scale > 0) { const int sh = N == 65536 ? scale : 1;   /* idft65536 shifts by `scale` itself (oai_dfts.c:4206-4226), every other level by 1 */
+    for (int k = 0; k < N; k++) { y[k].r >>= sh; y[k].i >>= sh; } }
   free(Y);
 }
 
-/* radix-2 on top: 128, 512, 2048, 8192 (oai_dfts.c:1775-1900, 2093-2255, 2372-2550, 2665-2842) */
+/* radix-2 on top: 128, 512, 2048, 8192, 32768 (oai_dfts.c:1775-1900, 2093-2255, 2372-2550, 2665-2842, 2958-3138) */
 static void dft_pow2(const cx *x, int stride, cx *y, int N, int inverse, int scale)
 {
-  if (N == 64 || N == 256 || N == 1024 || N == 4096) { dft_pow4(x, stride, y, N, inverse, scale); return; }
+  if (N == 64 || N == 256 || N == 1024 || N == 4096 || N == 16384 || N == 65536) { dft_pow4(x, stride, y, N, inverse, scale); return; }
   const int M = N / 2;
   cx *Y = malloc(sizeof(cx) * (size_t)N);
   dft_pow4(x, 2 * stride, Y, M, inverse, 1);
@@ -148,12 +149,16 @@ static void dft_pow2(const cx *x, int stride, cx *y, int N, int inverse, int sca
   free(Y);
 }
 
-/* radix-3 on top: 768, 1536, 3072, 6144 (bfly3/ibfly3 oai_dfts.c:477-540, drivers :3140-3600) */
-static void dft_3x(const cx *x, cx *y, int N, int inverse, int scale)
+/* radix-3 on top: 768, 1536, 3072, 6144 and the large sizes 12288, 18432, 24576, 36864, 49152, 98304 (bfly3/ibfly3 oai_dfts.c:477-540, drivers :3140-3600,
+ * :3614-4350).  The M-point transforms are called with scale 1, except by 12288 and 18432, which hand their own scale argument down (:3641-3643, :3755-3757). */
+static void dft_3x(const cx *x, int stride, cx *y, int N, int inverse, int scale)
 {
-  const int M = N / 3;
+  const int M = N / 3, sub = (N == 12288 || N == 18432) ? scale : 1;
   cx *Y = malloc(sizeof(cx) * (size_t)N);
-  for (int q = 0; q < 3; q++) dft_pow2(x + q, 3, Y + q * M, M, inverse, 1);
+  for (int q = 0; q < 3; q++) {
+    if (M % 3 == 0) dft_3x(x + q * stride, 3 * stride, Y + q * M, M, inverse, sub);
+    else dft_pow2(x + q * stride, 3 * stride, Y + q * M, M, inverse, sub);
+  }
   for (int k = 0; k < M; k++) {
     int64_t r, i, r2, i2;
     cm32(Y[M + k], rnd(32767.0 * cos(2 * M_PI * k / N)), -rnd(32767.0 * sin(2 * M_PI * k / N)), inverse, &r, &i);            /* init_rad3 :7772-7782 */
@@ -292,10 +297,12 @@ int orc_dft4(int N, const int16_t *in, int16_t *out, int scale)
 /* in/out: interleaved {re, im} int16 like the reference's dft()/idft() (tools_defs.h:514-521); returns 0, -1 for an unsupported size */
 int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale)
 {
-  if (!(N == 64 || N == 128 || N == 256 || N == 512 || N == 768 || N == 1024 || N == 1536 || N == 2048 || N == 3072 || N == 4096 || N == 6144 || N == 8192)) return -1;
+  /* 9216 and 73728 are AssertFatal("Need to do this") in the reference (:3601-3610, :4240-4250); 65536 exists only as idft65536 */
+  if (!(N == 64 || N == 128 || N == 256 || N == 512 || N == 768 || N == 1024 || N == 1536 || N == 2048 || N == 3072 || N == 4096 || N == 6144 || N == 8192 ||
+        N == 12288 || N == 16384 || N == 18432 || N == 24576 || N == 32768 || N == 36864 || N == 49152 || N == 65536 || N == 98304)) return -1;
   cx *x = malloc(sizeof(cx) * (size_t)N), *y = malloc(sizeof(cx) * (size_t)N);
   for (int n = 0; n < N; n++) { x[n].r = in[2 * n]; x[n].i = in[2 * n + 1]; }
-  if (N % 3 == 0) dft_3x(x, y, N, inverse, scale);
+  if (N % 3 == 0) dft_3x(x, 1, y, N, inverse, scale);
   else dft_pow2(x, 1, y, N, inverse, scale);
   for (int n = 0; n < N; n++) { out[2 * n] = (int16_t)y[n].r; out[2 * n + 1] = (int16_t)y[n].i; }
   free(x); free(y);

@@ -99,3 +99,30 @@ def test_fourway_golden_and_device_batch(dfts):
     y = dfts.batch_torch(N, False, x, 1)
     torch.cuda.synchronize()
     assert all(np.array_equal(y[i].cpu().numpy(), d[f"y{N}_s1"]) for i in (0, 25, 51))
+
+
+@pytest.mark.parametrize("N", [12288, 16384, 18432, 24576, 32768, 36864, 49152, 65536, 98304])
+def test_large_sizes_vs_oracle(dfts, oracle, N):
+    """Sizes above 8192: gather + batched shared-memory transforms + one global pass per top level; 2 transforms per launch, both directions."""
+    rng = np.random.default_rng(N)
+    for inverse in (False, True):
+        if N == 65536 and not inverse:
+            continue                                   # the reference has no dft65536
+        for amp, scale in ((300, 1), (3000, 0), (32767, 1), (3000, 2)):
+            x = rng.integers(-amp, amp + 1, size=(2, 2 * N)).astype(np.int16)
+            got = dfts.batch_host(N, inverse, x, scale)
+            for b in range(2):
+                assert np.array_equal(got[b], oracle.dft(N, inverse, x[b], scale)), (N, inverse, amp, scale, b)
+
+
+def test_large_plugin_abi_and_device_batch(dfts, oracle):
+    from openairinterface5g_b200.dfts import get_dft, get_idft
+    rng = np.random.default_rng(77)
+    x = rng.integers(-2000, 2001, size=2 * 24576).astype(np.int16)
+    assert np.array_equal(dfts.dft(get_dft(24576), x, 1), oracle.dft(24576, False, x, 1))
+    assert np.array_equal(dfts.idft(get_idft(24576), x, 1), oracle.dft(24576, True, x, 1))
+    xd = torch.from_numpy(np.tile(x, (5, 1))).cuda()
+    y = dfts.batch_torch(24576, True, xd, 1)
+    torch.cuda.synchronize()
+    want = oracle.dft(24576, True, x, 1)
+    assert all(np.array_equal(y[i].cpu().numpy(), want) for i in range(5))

@@ -180,6 +180,30 @@ def test_dft_idft_q15(oracle, reference, N):
         assert np.array_equal(oracle.dft(N, inverse, x, 1), reference.dft(N, inverse, x, 1))
 
 
+@pytest.mark.parametrize("N", [12288, 16384, 18432, 24576, 36864, 49152])
+def test_dft_idft_large_q15(oracle, reference, N):
+    """The sizes above 8192 that work in the reference (radix-3 / radix-4 levels over 4096, 6144, 8192; 12288 and 18432 hand their scale argument down).
+    9216 / 73728 are AssertFatal there, 32768 / 98304 overrun their stack buffers and 65536 reads beyond its twiddle table: those cannot be pinned."""
+    rng = np.random.default_rng(N)
+    for inverse in (False, True):
+        for amp, scale in ((300, 1), (3000, 0), (32767, 1), (3000, 2)):
+            x = rng.integers(-amp, amp + 1, size=2 * N).astype(np.int16)
+            assert np.array_equal(oracle.dft(N, inverse, x, scale), reference.dft(N, inverse, x, scale)), (N, inverse, amp, scale)
+
+
+@pytest.mark.parametrize("N,inverse", [(32768, False), (32768, True), (65536, True), (98304, False), (98304, True)])
+def test_dft_large_unpinned_sizes_are_dfts(oracle, N, inverse):
+    """Sizes whose reference implementation is broken (see above): the restatement applies the same level arithmetic as the working sizes; checked against a
+    float transform (gain 1/sqrt(N) with scale 1)."""
+    x = np.random.default_rng(N).integers(-300, 301, size=2 * N).astype(np.int16)
+    y = oracle.dft(N, inverse, x, 1)
+    X = x[0::2] + 1j * x[1::2]
+    Y = (np.fft.ifft(X) * N if inverse else np.fft.fft(X)) / np.sqrt(N)
+    ya = y[0::2] + 1j * y[1::2]
+    # the truncating >> 15 of every level leaves a bias that piles up in the bins around DC, so compare in the rms sense (measured: 1.1-1.2 %)
+    assert np.sqrt((np.abs(ya - Y) ** 2).mean()) < 0.02 * np.sqrt((np.abs(Y) ** 2).mean())
+
+
 FOURWAY_SIZES = [12, 24, 36, 48, 60, 72, 96, 108, 120, 144, 180, 192, 216, 240, 288, 300, 324, 360, 384, 432, 480, 540, 576, 600, 648, 720, 864, 900, 960, 972,
                  1080, 1152, 1200, 1296, 1440, 1500, 1620, 1728, 1800, 1920, 1944, 2160, 2400, 2592, 2700, 2880, 2916, 3000, 3240]
 
