@@ -603,8 +603,8 @@ class Reference:
         avg = np.zeros(8, np.int32)
         raw = L.refh_pusch_log2_maxh(prm.ctypes.data_as(C.c_void_p), max_ch, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p))
         # the final rule of nr_rx_pusch_tp for one layer (:1642-1646): + 1 + log2_approx(nb_rx >> 2), floored at 0
-        if nb_layer == 2:                                         # MMSE rule (:1640-1641)
-            return max(0, int(raw) - 3), avg[:2 * P.nb_rx].copy()
+        if nb_layer == 2:                                         # - 3 for the MMSE receiver only (:1640-1641)
+            return max(0, int(raw) - (3 if P.Qm >= 6 else 0)), avg[:2 * P.nb_rx].copy()
         return max(0, int(raw) + 1 + int(P.nb_rx >> 2).bit_length()), avg[:P.nb_rx].copy()
 
     def _ofdm(self):

@@ -49,6 +49,7 @@ int refh_pusch_inner_rx(const int32_t *p, const int16_t *rxdataF, const int16_t 
   for (int l = 0; l < nl; l++) { posix_memalign((void **)&llrp[l], 64, 2 * llr_n + 1024); memset(llrp[l], 0, 2 * llr_n + 1024); }   /* the LLR kernels use aligned vector stores */
   valid[symbol] = (int16_t)p[P_VALID_RE];
   pv.ul_ch_estimates = est; pv.rxdataF_comp = cmp; pv.ul_valid_re_per_slot = valid;
+  pv.llr_layers = llrp;                                                   /* nr_ulsch_shift_llr (QPSK ML path) works on these; llr_offset stays 0 */
   pv.dmrs_symbol = (uint8_t)p[P_DMRS_SYMBOL]; pv.log2_maxh = (int16_t)p[P_SHIFT];
   inner_rx(gNB, 0, 0, &fp, &pv, &pdu, rxF, NULL, llrp, 0, p[P_VALID_RE], symbol, p[P_SHIFT], (uint32_t)p[P_NVAR]);
   for (int l = 0; l < nl; l++) memcpy(comp + (size_t)l * 2 * buffer_length, &cmp[l * nrx][symbol * buffer_length], 4 * (size_t)buffer_length);

@@ -423,6 +423,29 @@ def test_pusch_inner_rx_two_layers_mmse(oracle, reference):
             assert np.array_equal(llr_o, llr_r), (N, nb_rx, Qm, symbol, shift, nvar, "llr")
 
 
+def test_pusch_inner_rx_two_layers_ml(oracle, reference):
+    """nb_layer == 2, Qm < 6: matched filter per layer, rho and magnitudes, joint max-log ML LLRs (nr_ulsch_qpsk_qpsk / nr_ulsch_qam16_qam16), through inner_rx."""
+    from oracle.bindings import PuschParms
+    rng = np.random.default_rng(43)
+    for N, nb_rx, rb_start, rb_size, Qm, carrier, amp in ((4096, 4, 0, 273, 4, 273, 1500), (2048, 2, 10, 50, 2, 106, 1500), (1024, 4, 20, 32, 4, 52, 6000), (2048, 1, 30, 77, 2, 106, 4000),
+                                                          (1024, 2, 0, 51, 4, 52, 300), (1024, 3, 3, 9, 2, 52, 32767)):
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, 1 << 2, 0, 2)
+        rx = rng.integers(-2000, 2001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-amp, amp + 1, size=(2 * nb_rx, 14, N, 2)).astype(np.int16)
+        for max_ch in (0, 1500, 200000):
+            sh_o, avg_o = oracle.pusch_log2_maxh_2l(P, 0, 2, max_ch, rx, h)
+            sh_r, avg_r = reference.pusch_log2_maxh(P, 0, 2, rx, h, nb_layer=2, max_ch=max_ch)
+            assert np.array_equal(avg_o, avg_r) and sh_o == sh_r, (N, nb_rx, max_ch, avg_o, avg_r, sh_o, sh_r)
+        for symbol, shift in ((3, 8), (13, 5), (0, 11), (2, 7)):
+            valid = oracle.pusch_nb_re(P, symbol)
+            if valid == 0:
+                continue
+            llr_o, comp_o = oracle.pusch_inner_rx_symbol_2l(P, symbol, 2, shift, 0, rx, h)
+            llr_r, comp_r = reference.pusch_inner_rx_symbol(P, symbol, 2, shift, rx, h, valid, nb_layer=2, nvar=0)
+            assert np.array_equal(comp_o, comp_r), (N, nb_rx, Qm, symbol, shift, "comp")
+            assert np.array_equal(llr_o, llr_r), (N, nb_rx, Qm, symbol, shift, "llr", int((llr_o != llr_r).sum()))
+
+
 def test_pdsch_channel_estimation_ue(oracle, reference):
     """UE-side estimator (nr_pdsch_channel_estimation, DMRS type 1 linear interpolation) on the same cases as the gNB one."""
     from oracle.bindings import ChestParms

@@ -53,7 +53,7 @@ def throughput(lib, dl, dev, K, n_rounds=60, e2e=False):
     return K * n_rounds / (ms * 1e-3), sum(pipe.check(host=e2e))
 
 
-def stage_saturation(lib, dl, dev, K=16, n=40):
+def stage_saturation(lib, dl, dev, K=16, n=20):
     """Where the GPU time of a slot goes when the device is full: every stage alone, K chains each on its own stream, us per slot at saturation."""
     pipe = PdschSlotPipeline(lib, dl, dev, K, use_graphs=False)
     st = {
@@ -71,11 +71,24 @@ def stage_saturation(lib, dl, dev, K=16, n=40):
     }
     out = {}
     cur = torch.cuda.current_stream(dev)
+    REP = 8                                     # each stage 8x per CUDA graph: one replay per chain and round keeps the host out of the measurement
     for name, f in st.items():
+        graphs = []
+        for k in range(K):
+            s = pipe.streams[k]
+            with torch.cuda.stream(s):
+                f(pipe.chains[k], pipe.payload[k], pipe.rx[k])
+                s.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    for _ in range(REP):
+                        f(pipe.chains[k], pipe.payload[k], pipe.rx[k])
+            graphs.append(g)
+
         def rnd():
             for k in range(K):
                 with torch.cuda.stream(pipe.streams[k]):
-                    f(pipe.chains[k], pipe.payload[k], pipe.rx[k])
+                    graphs[k].replay()
         for _ in range(3):
             rnd()
         torch.cuda.synchronize()
@@ -85,7 +98,7 @@ def stage_saturation(lib, dl, dev, K=16, n=40):
             rnd()
         pipe.join(cur); e1.record(cur)
         torch.cuda.synchronize()
-        out[name] = round(1e3 * e0.elapsed_time(e1) / (n * K), 2)
+        out[name] = round(1e3 * e0.elapsed_time(e1) / (n * K * REP), 2)
     out["sum"] = round(sum(out.values()), 2)
     return out
 

@@ -21,14 +21,14 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench point B (Eb/N0 3 dB, early stop)"; timeout 300 python bench.py --steps 50 --warmup 5 --ebn0 3.0 --no-cpu 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_pointB.json
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}_reference.json
 echo "== slot chain"; timeout 200 python tools/bench_slot.py 2>&1 | tail -10 | tee gpurun_out/slot_${TAG}.jsonl
-echo "== DL slot chain"; timeout 200 python tools/bench_dl_slot.py 2>&1 | tail -6 | tee gpurun_out/dlslot_${TAG}.jsonl
+echo "== DL slot chain"; timeout 200 python tools/bench_dl_slot.py 2>&1 | tail -12 | tee gpurun_out/dlslot_${TAG}.jsonl
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_dlslot_${TAG}.csv \
   python tools/bench_dl_slot.py once > gpurun_out/ncu_launches_dlslot_${TAG}.log 2>&1
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
-  python bench.py --steps 5 --warmup 3 --no-cpu --no-check --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
+  python bench.py --steps 5 --warmup 3 --no-cpu --no-check --no-slot --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
 fi
 echo "== ncu full (decode kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
-  python bench.py --steps 3 --warmup 3 --no-cpu --no-check --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
+  python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
