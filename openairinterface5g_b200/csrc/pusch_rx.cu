@@ -216,6 +216,127 @@ __global__ void __launch_bounds__(256) pusch_rx2_kernel(PuschGeom G, const GoldT
   }
 }
 
+// ---- two layers, joint max-log ML detector (Qm < 6): nr_ulsch_compute_ML_llr (nr_ulsch_llr_computation.c:2100-2130) -> nr_ulsch_qpsk_qpsk (:375-525) and
+// nr_ulsch_qam16_qam16 (:903-1135) on the matched-filter outputs, rho[l][1-l] (saturating sum over rx of conj(h_l) h_(1-l)) and, for 16QAM, ul_ch_maga of both
+// layers (wrapping sum over rx of mulhrs(sat(|h|^2 >> shift), QAM16_n1)) as nr_ulsch_channel_compensation (:468-575) leaves them; QPSK LLRs >> 4
+// (nr_ulsch_shift_llr :2064-2098); layer de-mapping and descrambling as in the MMSE kernel.  Element-wise int16 arithmetic, one thread per RE.  The x86
+// build of the reference walks 16 REs per pass for floor(valid / 8) / 2 passes (rounded up): REs beyond that keep what the LLR buffer held -- zeros here.
+__device__ __forceinline__ int m_mulhi(int a, int b) { return (a * b) >> 16; }
+__device__ __forceinline__ int m_sll(int a, int n) { return p_wrap16(a << n); }
+__device__ __forceinline__ int m_adds(int a, int b) { return p_sat16(a + b); }
+__device__ __forceinline__ int m_subs(int a, int b) { return p_sat16(a - b); }
+__device__ __forceinline__ int m_abs(int a) { return p_abs16w(a); }   // abs_epi16: -32768 stays.  NOT (short)(a < 0 ? -a : a): nvcc 12.9 folds that cast into a saturating conversion
+
+__device__ __forceinline__ void ml_qpsk_qpsk(int y0r, int y0i, int y1r, int y1i, int rhor, int rhoi, int (&o)[4])
+{
+  const int y0r2 = m_sll(m_mulhi(y0r, 23170), 1), y0i2 = m_sll(m_mulhi(y0i, 23170), 1), y1r2 = y1r >> 1, y1i2 = y1i >> 1;
+  const int rho_p = m_mulhi(m_adds(rhor, rhoi), 23170), rho_m = m_mulhi(m_subs(rhor, rhoi), 23170);
+  const int rpm = m_abs(m_subs(rho_p, y1r2)), imm = m_abs(m_subs(rho_m, y1i2)), rmm = m_abs(m_subs(rho_m, y1r2)), ipm = m_abs(m_subs(rho_p, y1i2));
+  const int rpp = m_abs(m_adds(rho_p, y1r2)), imp = m_abs(m_adds(rho_m, y1i2)), rmp = m_abs(m_adds(rho_m, y1r2)), ipp = m_abs(m_adds(rho_p, y1i2));
+  const int pp = m_adds(m_adds(m_adds(rpm, imm), y0r2), y0i2);      // x = (+, +)
+  const int pm = m_subs(m_adds(m_adds(rmm, ipp), y0r2), y0i2);      // x = (+, -)
+  const int mp = m_adds(m_subs(m_adds(rmp, ipm), y0r2), y0i2);      // x = (-, +)
+  const int mm = m_subs(m_subs(m_adds(rpp, imp), y0r2), y0i2);      // x = (-, -)
+  o[0] = m_subs(max(pp, pm), max(mp, mm)) >> 4;
+  o[1] = m_subs(max(pp, mp), max(pm, mm)) >> 4;
+}
+
+__device__ __forceinline__ void ml_qam16_qam16(int y0r, int y0i, int y1r, int y1i, int mag_des, int mag_int, int rr, int ri, int (&o)[4])
+{
+  constexpr int C10 = 20724, C10Q15 = 10362, C3 = 31086, CS = 25905, C9 = 23315;
+  const int rpi = m_adds(rr, ri), rmi = m_subs(rr, ri);
+  int rs[8], y0s[8], bm[16];
+  rs[0] = m_mulhi(rpi, C10); rs[4] = m_mulhi(rmi, C10); rs[3] = m_sll(m_mulhi(rpi, C3), 1); rs[7] = m_sll(m_mulhi(rmi, C3), 1);
+  const int x4 = m_mulhi(rr, C10), x5 = m_sll(m_mulhi(ri, C3), 1), x6 = m_sll(m_mulhi(rr, C3), 1), x7 = m_mulhi(ri, C10);
+  rs[1] = m_adds(x4, x5); rs[5] = m_subs(x4, x5); rs[2] = m_adds(x6, x7); rs[6] = m_subs(x6, x7);
+  const int y0r1 = m_mulhi(y0r, C10), y0i1 = m_mulhi(y0i, C10), y0r3 = m_sll(m_mulhi(y0r, C3), 1), y0i3 = m_sll(m_mulhi(y0i, C3), 1);
+  y0s[0] = m_adds(y0r1, y0i1); y0s[4] = m_subs(y0r1, y0i1); y0s[1] = m_adds(y0r1, y0i3); y0s[5] = m_subs(y0r1, y0i3);
+  y0s[2] = m_adds(y0r3, y0i1); y0s[6] = m_subs(y0r3, y0i1); y0s[3] = m_adds(y0r3, y0i3); y0s[7] = m_subs(y0r3, y0i3);
+  const int cc[4] = {m_mulhi(mag_des, C10Q15), m_sll(m_mulhi(mag_des, CS), 1), m_sll(m_mulhi(mag_des, CS), 1), m_sll(m_mulhi(mag_des, C9), 2)};
+  // the two possible values of square_a_epi16 (:741) per component: a = 1/sqrt(10) or 3/sqrt(10)
+  const int sq1 = m_sll(m_mulhi(m_sll(m_mulhi(m_sll(m_mulhi(C10Q15, C10Q15), 1), CS), 1), mag_int), 1);
+  const int sq3 = m_sll(m_mulhi(m_sll(m_mulhi(m_sll(m_mulhi(C3, C3), 1), CS), 1), mag_int), 1);
+  constexpr int idx[16] = {4, 6, 5, 7, 0, 2, 1, 3, 0, 2, 1, 3, 4, 6, 5, 7};
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int psr = j < 8 ? m_abs(m_subs(rs[j], y1r)) : m_abs(m_adds(rs[(j - 4) & 7], y1r));
+    const int psi = (j & 4) ? m_abs(m_adds(rs[idx[j]], y1i)) : m_abs(m_subs(rs[idx[j]], y1i));
+    const bool lr = psr < mag_int, li = psi < mag_int;
+    const int psa = m_adds(m_sll(m_mulhi(psr, lr ? C10Q15 : C3), 1), m_sll(m_mulhi(psi, li ? C10Q15 : C3), 1));
+    const int t = m_subs(psa, m_adds(lr ? sq1 : sq3, li ? sq1 : sq3));
+    bm[j] = j < 8 ? m_subs(m_adds(t, y0s[j]), cc[j & 3]) : m_subs(m_subs(t, y0s[(j + 4) & 7]), cc[j & 3]);
+  }
+#define NRB200_MX8(a, b, c, d, e, f, g, h) max(max(max(bm[a], bm[b]), max(bm[c], bm[d])), max(max(bm[e], bm[f]), max(bm[g], bm[h])))
+  o[0] = m_subs(NRB200_MX8(0, 1, 2, 3, 4, 5, 6, 7), NRB200_MX8(8, 9, 10, 11, 12, 13, 14, 15));
+  o[1] = m_subs(NRB200_MX8(0, 1, 3, 2, 8, 9, 10, 11), NRB200_MX8(4, 5, 6, 7, 12, 13, 14, 15));
+  o[2] = m_subs(NRB200_MX8(0, 1, 4, 5, 8, 9, 12, 13), NRB200_MX8(2, 3, 6, 7, 10, 11, 14, 15));
+  o[3] = m_subs(NRB200_MX8(0, 2, 4, 6, 8, 10, 12, 14), NRB200_MX8(1, 3, 5, 7, 9, 11, 13, 15));
+#undef NRB200_MX8
+}
+
+template <int QM>
+__global__ void __launch_bounds__(256) pusch_rx2ml_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift,
+                                                          const unsigned *__restrict__ rxF, const unsigned *__restrict__ ch, short *__restrict__ llr)
+{
+  __shared__ uint32_t s_gold[(256 * 2 * QM) / 32 + 2];
+  const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
+  const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
+  if (i0 >= valid) return;
+  const unsigned bit0 = 2u * G.llr_off[k] + (unsigned)i0 * 2 * QM;
+  if (G.unscramble) {
+    const unsigned w0 = bit0 >> 5, nw = ((bit0 + 256u * 2 * QM + 31u) >> 5) - w0;
+    if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
+    __syncthreads();
+  }
+  if (i >= valid) return;
+  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  const int covered = 16 * (((valid >> 3) + 1) >> 1);
+  int o[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  if (i < covered) {
+    const int n_ext = !is_dmrs ? G.nb_re : G.dmrs_type == 0 ? G.nb_re / 2 : (G.nb_re / 6) * 4;
+    int c[2][2] = {{0, 0}, {0, 0}}, rho[2][2] = {{0, 0}, {0, 0}}, mg[2] = {0, 0};
+    if (i < n_ext) {
+      int rx_idx, ch_idx;
+      re_source(G, is_dmrs, i, rx_idx, ch_idx);
+      for (int a = 0; a < G.nb_rx; a++) {
+        const unsigned y = __ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx);
+        const unsigned hw[2] = {__ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx),
+                                __ldg(ch + (size_t)(G.nb_rx + a) * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx)};
+        const int yr = p_lo(y), yi = p_hi(y);
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+          const int hr = p_lo(hw[l]), hi = p_hi(hw[l]), gr = p_lo(hw[1 - l]), gi = p_hi(hw[1 - l]), nhi = p_wrap16(-hi);
+          c[l][0] = p_wrap16(c[l][0] + p_sat16(p_mad(hr, yr, hi, yi) >> shift));
+          c[l][1] = p_wrap16(c[l][1] + p_sat16(p_mad(nhi, yr, hr, yi) >> shift));
+          rho[l][0] = p_sat16(rho[l][0] + p_sat16(p_mad(hr, gr, hi, gi) >> shift));
+          rho[l][1] = p_sat16(rho[l][1] + p_sat16(p_mad(nhi, gr, hr, gi) >> shift));
+          if (QM == 4) mg[l] = p_wrap16(mg[l] + p_wrap16((p_sat16(p_mad(hr, hr, hi, hi) >> shift) * 20724 + 0x4000) >> 15));
+        }
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      if (QM == 2) ml_qpsk_qpsk(c[l][0], c[l][1], c[1 - l][0], c[1 - l][1], rho[l][0], rho[l][1], o[l]);
+      else ml_qam16_qam16(c[l][0], c[l][1], c[1 - l][0], c[1 - l][1], mg[l], mg[1 - l], rho[l][0], rho[l][1], o[l]);
+    }
+  }
+  const unsigned bb = 2u * G.llr_off[k] + (unsigned)i * 2 * QM;
+  const unsigned rel = bb - ((bit0 >> 5) << 5);
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    if (G.unscramble) {
+#pragma unroll
+      for (int mm = 0; mm < QM; mm++) {
+        const unsigned r = rel + l * QM + mm;
+        if ((s_gold[r >> 5] >> (r & 31u)) & 1u) o[l][mm] = p_wrap16(-o[l][mm]);
+      }
+    }
+    unsigned *dst = reinterpret_cast<unsigned *>(llr + bb + l * QM);
+#pragma unroll
+    for (int mm = 0; mm < QM / 2; mm++) dst[mm] = ((unsigned)o[l][2 * mm] & 0xFFFFu) | ((unsigned)o[l][2 * mm + 1] << 16);
+  }
+}
+
 // ---- UE side, one layer: nr_rx_pdsch (NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684).  Same structure as pusch_rx_kernel with the UE's arithmetic:
 // estimates scaled (mulhi 8192, << 3) before the matched filter, per-antenna outputs packed and combined with SATURATING adds, thresholds mulhi << 1, and --
 // because the reference computes the slot's LLRs after the last symbol with that call's local magnitude buffers -- the thresholds of EVERY symbol come from
@@ -492,7 +613,7 @@ __global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_
       int avgs = 0;
       for (int k = 0; k < G.nb_rx * G.nl; k++) avgs = max(avgs, ((volatile int *)d_out)[k]);
       auto l2 = [](unsigned v) { return v ? 32 - __clz(v) : 0; };  // log2_approx: bit length (values < 2^31)
-      int l = G.nl == 2 ? (l2((unsigned)avgs) >> 1) - 3 : (l2((unsigned)avgs) >> 1) + 1 + l2((unsigned)G.nb_rx >> 2);
+      int l = G.nl == 2 ? (l2((unsigned)avgs) >> 1) - (G.Qm >= 6 ? 3 : 0) : (l2((unsigned)avgs) >> 1) + 1 + l2((unsigned)G.nb_rx >> 2);   // - 3: MMSE only (:1640)
       d_out[8] = l < 0 ? 0 : l;
       *d_count = 0;
     }
@@ -509,7 +630,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
 {
   const int Qm = d.qam_mod_order;
   const int nl = d.nrOfLayers == 0 ? 1 : (int)d.nrOfLayers;
-  if (nl > 2 || (nl == 2 && !d.pdsch_ue && (Qm < 6 || (d.nb_rx != 2 && d.nb_rx != 4)))) return -4;   // 2 layers: MMSE receiver only, like the reference for Qm >= 6
+  if (nl > 2 || (nl == 2 && !d.pdsch_ue && Qm >= 6 && d.nb_rx != 2 && d.nb_rx != 4)) return -4;   // 2 layers: MMSE receiver (Qm >= 6; 2 or 4 rx like the reference), joint ML below
   if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
       d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || (d.log2_maxh > 31 && d.log2_maxh != 0xFFFFFFFFu))
     return -4;
@@ -609,7 +730,9 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
       default: pdsch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
     }
   } else if (G.nl == 2) {
-    if (G.Qm == 6) pusch_rx2_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
+    if (G.Qm == 2) pusch_rx2ml_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
+    else if (G.Qm == 4) pusch_rx2ml_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
+    else if (G.Qm == 6) pusch_rx2_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
     else pusch_rx2_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
   } else {
     switch (G.Qm) {

@@ -577,3 +577,10 @@ int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols,
   for (int t = 0; t < 3; t++) free(mag[t]);
   return (int)(NL * off);
 }
+
+/* flat entry points of the two ML kernels for unit tests: one resource element */
+void orc_ml_qpsk_qpsk(const int16_t *y0, const int16_t *y1, const int16_t *rho, int16_t *out2) { ml_qpsk_qpsk(y0, y1, rho, out2); out2[0] >>= 4; out2[1] >>= 4; }
+void orc_ml_qam16_qam16(const int16_t *y0, const int16_t *y1, int mag_des, int mag_int, const int16_t *rho, int16_t *out4)
+{
+  ml_qam16_qam16(y0, y1, (int16_t)mag_des, (int16_t)mag_int, rho, out4);
+}

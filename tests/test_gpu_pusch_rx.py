@@ -59,11 +59,16 @@ def test_pusch_inner_rx_vs_oracle(ldpc, oracle):
 
 
 def test_pusch_inner_rx_two_layers_vs_oracle(ldpc, oracle):
-    """nrOfLayers = 2, Qm >= 6: matched filter per layer + MMSE + per-layer LLRs + layer de-mapping + descrambling in one launch."""
+    """nrOfLayers = 2: matched filter per layer + MMSE (Qm >= 6) or joint max-log ML detector (Qm < 6) + layer de-mapping + descrambling in one launch."""
     rng = np.random.default_rng(51)
     for N, nb_rx, rb_start, rb_size, Qm, carrier, nvar, max_ch, dpos, cdm in ((4096, 4, 0, 273, 6, 273, 40, 1400, 1 << 2, 2), (2048, 2, 10, 50, 8, 106, 7, 30000, 1 << 2, 2),
                                                                              (1024, 4, 20, 32, 6, 52, 1, 0, 1 << 3, 2), (2048, 2, 30, 75, 8, 106, 1000, 9000, 1 << 2, 1),
-                                                                             (4096, 4, 3, 11, 6, 273, 90000, 200000, (1 << 2) | (1 << 11), 2)):
+                                                                             (4096, 4, 3, 11, 6, 273, 90000, 200000, (1 << 2) | (1 << 11), 2),
+                                                                             # Qm < 6: the joint max-log ML detector (QPSK-QPSK, 16QAM-16QAM), any number of rx antennas;
+                                                                             # rb_size = 3 mod 4 leaves the last 4 REs of a symbol without LLRs in the reference
+                                                                             (4096, 4, 0, 273, 4, 273, 0, 1400, 1 << 2, 2), (2048, 2, 10, 51, 2, 106, 0, 30000, 1 << 2, 2),
+                                                                             (1024, 3, 20, 31, 4, 52, 0, 0, 1 << 3, 1), (2048, 1, 30, 75, 2, 106, 0, 9000, (1 << 2) | (1 << 11), 2),
+                                                                             (1024, 2, 0, 52, 4, 52, 0, 200000, 1 << 2, 2)):
         fco = N - carrier * 6
         P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, 0, cdm)
         rx = rng.integers(-2000, 2001, size=(nb_rx, 14, N, 2)).astype(np.int16)
