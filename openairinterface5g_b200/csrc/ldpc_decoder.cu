@@ -57,12 +57,16 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
   const PackedGraph *d_pg = (h_g.Z % 4 == 0 && !force_generic) ? packed_graph(h_g, &h_pg) : nullptr;
   if (d_pg) {
     const size_t smem = (size_t)h_pg->total_bytes;
-    static std::atomic<size_t> configured_pk{0};
-    if (smem > configured_pk.load()) {
-      NRB200_CUDA_OK(cudaFuncSetAttribute(ldpc_decode_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
-      configured_pk.store(smem);
+    // Z = 384 (K = 8448, both headline workloads) runs the instantiation with the row geometry as immediates
+    const bool z384 = h_pg->Zw == 96;
+    static std::atomic<size_t> configured_pk[2];
+    if (smem > configured_pk[z384].load()) {
+      NRB200_CUDA_OK(cudaFuncSetAttribute(z384 ? ldpc_decode_packed_kernel<96> : ldpc_decode_packed_kernel<0>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
+      configured_pk[z384].store(smem);
     }
-    ldpc_decode_packed_kernel<<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
+    if (z384) ldpc_decode_packed_kernel<96><<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
+    else ldpc_decode_packed_kernel<0><<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
     c.launches++;
     NRB200_CUDA_OK(cudaGetLastError(), "packed decode launch");
     return 0;

@@ -21,118 +21,73 @@
 #pragma once
 #include "ldpc_common.cuh"
 #include "ldpc_packed_graph.h"
+#include "ldpc_packed_simd.cuh"   // cn_input / twomin / make_r and the LOP3 / PRMT forms (host-checked: tests/host/packed_simd_check.cc)
 
 namespace nrb200 {
-
-// ---------------------------------------------------------------------------------------------- byte SIMD helpers
-// The inline-PTX forms pin the instruction selection: one LOP3 per 3-input boolean, one PRMT per byte broadcast.  Left to
-// itself nvcc re-associates the masks of the 7-bit tricks into ~50 % more LOP3s, and the ALU pipe is this kernel's limiter.
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-template <int LUT>
-__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
-{
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
-  return r;
-}
-// a + b emitted as IMAD a*one+b (one == 1 at run time): same result, FMA pipe instead of the saturated ALU pipe
-__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one)
-{
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
-  return r;
-}
-constexpr uint32_t kH = 0x80808080u, kL7 = 0x7f7f7f7fu;
-// LUT bytes: inputs a = 0xF0, b = 0xCC, c = 0xAA
-constexpr int kLutSel = 0xCA;      // a ? b : c
-constexpr int kLutOrAnd = 0xA8;    // (a | b) & c
-constexpr int kLutOrBandC = 0xF8;  // a | (b & c)
-constexpr int kLutXorAnd = 0x28;   // (a ^ b) & c
-constexpr int kLutXorBandC = 0x78; // a ^ (b & c)
-constexpr int kLutXorNBandC = 0xD2; // a ^ (~b & c)
-constexpr int kLutLtu = 0x4D;      // (~a & b) | (~(a ^ b) & ~c)
-constexpr int kLutXor3 = 0x96;     // a ^ b ^ c
-constexpr int kLutMajNot = 0x17;   // ~majority(a, b, c)
-// 0xFF in every byte whose bit 7 is set
-__device__ __forceinline__ uint32_t msb_mask(uint32_t x) { return prmt(x, 0u, 0xba98u); }
-__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return lop3<kLutSel>(m, a, b); }
 
 __device__ __forceinline__ uint32_t lds(const char *smb, uint32_t off) { return *reinterpret_cast<const uint32_t *>(smb + off); }
 __device__ __forceinline__ uint2 lds2(const char *smb, uint32_t off) { return *reinterpret_cast<const uint2 *>(smb + off); }
 __device__ __forceinline__ void sts(char *smb, uint32_t off, uint32_t v) { *reinterpret_cast<uint32_t *>(smb + off) = v; }
 
-// one exclude-self two-minimum step on 7-bit magnitudes (a + 128 - b never borrows across bytes: bit 7 <=> a >= b)
-__device__ __forceinline__ void twomin(uint32_t mag, uint32_t &min1, uint32_t &min2)
-{
-  const uint32_t m1 = msb_mask(mag + kH - min1);   // mag >= min1
-  const uint32_t t = sel4(m1, mag, min1);          // max(mag, min1)
-  min1 = sel4(m1, min1, mag);
-  min2 = sel4(msb_mask(t + kH - min2), min2, t);
-}
+// Row geometry: ZWC = Z / 4 fixed at compile time (the hot Z = 384 instantiation: every R / L / P row offset becomes an immediate
+// of the LDS / STS instead of a multiply-add per edge), ZWC = 0 reads it from the graph tables (every other lifting size).
+template <int ZWC> __device__ __forceinline__ int geo_zw(const PackedGraph &G) { return ZWC ? ZWC : G.Zw; }
+template <int ZWC> __device__ __forceinline__ uint32_t geo_zb(const PackedGraph &G) { return ZWC ? 4u * ZWC : (uint32_t)G.ZB; }
+template <int ZWC> __device__ __forceinline__ uint32_t geo_rsb(const PackedGraph &G) { return ZWC ? 4u * (ZWC + 4) : (uint32_t)G.RSB; }
 
-// offset-binary cn->bn message (R + 128) from the excluded minimum and the sign word (bit 7 = negative); -0 -> 0
-__device__ __forceinline__ uint32_t make_r(uint32_t qsm, uint32_t min1, uint32_t min2, uint32_t sgn, uint32_t one)
-{
-  const uint32_t ne = msb_mask(add_fma(lop3<kLutXorAnd>(qsm, min1, kL7), kL7, one));   // 0xFF where |Q| != min1
-  const uint32_t mag = sel4(ne, min1, min2);
-  const uint32_t n = msb_mask(sgn ^ qsm);                                               // 0xFF where the other signs multiply to -1
-  const uint32_t c = add_fma(lop3<kLutXorBandC>(mag, n, kL7), n & 0x01010101u, one);    // 128 - mag on negative bytes
-  return lop3<kLutXorNBandC>(c, n, kH);                                                 // 128 + mag on the others
-}
-
-template <int D, bool QUIRK>
+template <int ZWC, int D, bool QUIRK>
 __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool halo,
                                        bool first_iter, uint32_t quirk_zero, uint32_t &bad)
 {
-  const uint32_t one = G.one;
+  const uint32_t one = G.one, mone = 0u - one;
+  const uint32_t ZB = geo_zb<ZWC>(G), RSB = geo_rsb<ZWC>(G);
   const uint32_t e0 = row.e0_deg & 0xFFFu;
   const uint32_t rb = row.rbase + kb;
   uint32_t q[D];
   uint32_t min1 = kL7, min2 = kL7, sgn = 0u, synd = (D & 1) ? kH : 0u;   // sign(A) < 0 <=> bit 7 of A' clear
+  uint32_t aprev = 0u, qprev = 0u;
 #pragma unroll
   for (int j = 0; j < D; j++) {
     const uint2 d = *reinterpret_cast<const uint2 *>(G.cn_desc[e0 + j]);
-    const uint32_t aa = kb + d.x;
+    const uint32_t aa = add_fma(kb, d.x, one);
     const uint32_t aw = __funnelshift_r(lds(smb, aa), lds(smb, aa + 4), d.y);   // A' at lifts t+s .. t+s+3
-    const uint32_t ro = lds(smb, rb + j * G.RSB);
-    synd ^= aw;
-    const uint32_t dd = __vabsdiffu4(aw, ro);                                    // |A - R|
-    const uint32_t mag = lop3<kLutOrAnd>(dd, msb_mask(dd), kL7);                 // min(|A - R|, 127)
-    const uint32_t x = (aw | kH) - (ro & kL7);
-    const uint32_t qsm = lop3<kLutOrBandC>(mag, lop3<kLutLtu>(aw, ro, x), kH);   // sign-magnitude Q, sign = (A' < R')
-    q[j] = qsm;
-    sgn ^= qsm;
+    const uint32_t ro = lds(smb, rb + j * RSB);
+    uint32_t mag;
+    cn_input(aw, ro, mone, mag, q[j]);
+    if (j & 1) {                                                                 // XORs of two edges at a time: one LOP3 each
+      synd = lop3<kLutXor3>(synd, aprev, aw);
+      sgn = lop3<kLutXor3>(sgn, qprev, q[j]);
+    }
+    aprev = aw;
+    qprev = q[j];
     twomin(mag, min1, min2);
   }
+  if (D & 1) { synd ^= aprev; sgn ^= qprev; }
   if (row.lrow != 0xFFFFFFFFu) {                                           // degree-1 neighbour: Q is the channel LLR forever
     const uint32_t pa = (row.prow_pcw & 0xFFFFFFu) + kb;
-    const uint32_t qsm = lds(smb, pa + G.ZB);                              // precomputed sign-magnitude of the channel LLR
+    const uint32_t qsm = lds(smb, pa + ZB);                              // precomputed sign-magnitude of the channel LLR
     synd ^= lds(smb, pa);                                                  // sign(llr + R_p) of the previous iteration
     sgn ^= qsm;
     twomin(qsm & kL7, min1, min2);
-    uint32_t rp = make_r(qsm, min1, min2, sgn, one);
+    uint32_t rp = make_r(qsm, min1, min1 | kH, min2 | kH, sgn, one, mone);
     if (QUIRK) rp = (rp & ~quirk_zero) | (kH & quirk_zero);
     // adds_epi8(llr, R_p) < 0  <=>  L' + R' < 256  <=>  no carry out of the byte
-    const uint32_t lp = lds(smb, pa + 2 * G.ZB);                           // the neighbour's channel LLR + 128, already rotated
+    const uint32_t lp = lds(smb, pa + 2 * ZB);                           // the neighbour's channel LLR + 128, already rotated
     const uint32_t x = (lp & kL7) + (rp & kL7);
     sts(smb, pa, lop3<kLutMajNot>(lp, rp, x) & kH);
   }
   if (!first_iter && (kb >> 2) < (row.prow_pcw >> 24)) bad |= synd & kH;
+  const uint32_t p1 = min1 | kH, p2 = min2 | kH;
 #pragma unroll
   for (int j = 0; j < D; j++) {
-    uint32_t rn = make_r(q[j], min1, min2, sgn, one);
+    uint32_t rn = make_r(q[j], min1, p1, p2, sgn, one, mone);
     if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
-    sts(smb, rb + j * G.RSB, rn);
-    if (halo) sts(smb, rb + j * G.RSB + G.ZB, rn);
+    sts(smb, rb + j * RSB, rn);
+    if (halo) sts(smb, rb + j * RSB + ZB, rn);
   }
 }
 
-template <bool QUIRK>
+template <int ZWC, bool QUIRK>
 __device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int r, uint32_t kb, bool halo, bool first_iter, uint32_t &bad)
 {
   const PackedRow row = G.rows[r];
@@ -144,27 +99,28 @@ __device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int
     for (int b = 0; b < 4; b++) if (((gi * G.Z + (int)kb + b) >> 5) & 1) qz |= 0xFFu << (8 * b);
   }
   switch ((row.e0_deg >> 12) & 0xFFu) {
-    case 2: cn_row<2, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 3: cn_row<3, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 4: cn_row<4, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 5: cn_row<5, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 6: cn_row<6, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 7: cn_row<7, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 8: cn_row<8, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 9: cn_row<9, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 10: cn_row<10, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 19: cn_row<19, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 2: cn_row<ZWC, 2, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 3: cn_row<ZWC, 3, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 4: cn_row<ZWC, 4, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 5: cn_row<ZWC, 5, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 6: cn_row<ZWC, 6, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 7: cn_row<ZWC, 7, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 8: cn_row<ZWC, 8, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 9: cn_row<ZWC, 9, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 10: cn_row<ZWC, 10, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
+    case 19: cn_row<ZWC, 19, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
     default: break;   // build_packed_graph() refuses graphs with other row degrees
   }
 }
 
 // one bit-node edge: fetch the rotated R' word and add its four bytes to the four running sums (IDP.4A, FMA pipe)
+template <int ZWC>
 __device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__restrict__ smb, int i, uint32_t kb, uint32_t kbs, uint32_t &s0, uint32_t &s1,
                                         uint32_t &s2, uint32_t &s3)
 {
   const uint2 d = *reinterpret_cast<const uint2 *>(G.bn_desc[i]);
   uint32_t a = kb + d.x;
-  if (kbs < d.y) a += G.ZB;                                                 // circular wrap of v - s
+  if (kbs < d.y) a += geo_zb<ZWC>(G);                                                 // circular wrap of v - s
   const uint32_t rw = __funnelshift_r(lds(smb, a), lds(smb, a + 4), d.y);
   s0 = __dp4a(rw, 0x00000001u, s0);
   s1 = __dp4a(rw, 0x00000100u, s1);
@@ -173,21 +129,23 @@ __device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__rest
 }
 
 // A' = clamp(L' + sum R' - 128*deg, 0, 255) for column c, word k   (packs_epi16 of the int16 sum, in offset binary)
+template <int ZWC>
 __device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ smb, int c, uint32_t kb, uint32_t kbs)
 {
-  const uint32_t lw = lds(smb, G.off_L + c * G.RSB + kb);
+  const uint32_t ZB = geo_zb<ZWC>(G);
+  const uint32_t lw = lds(smb, G.off_L + c * geo_rsb<ZWC>(G) + kb);
   uint32_t s0 = lw & 0xFFu, s1 = (lw >> 8) & 0xFFu, s2 = (lw >> 16) & 0xFFu, s3 = lw >> 24;
   int i = G.col_start[c];
   const int i1 = G.col_start[c + 1];
-  for (; i + 2 <= i1; i += 2) { bn_edge(G, smb, i, kb, kbs, s0, s1, s2, s3); bn_edge(G, smb, i + 1, kb, kbs, s0, s1, s2, s3); }
-  if (i < i1) bn_edge(G, smb, i, kb, kbs, s0, s1, s2, s3);
+  for (; i + 2 <= i1; i += 2) { bn_edge<ZWC>(G, smb, i, kb, kbs, s0, s1, s2, s3); bn_edge<ZWC>(G, smb, i + 1, kb, kbs, s0, s1, s2, s3); }
+  if (i < i1) bn_edge<ZWC>(G, smb, i, kb, kbs, s0, s1, s2, s3);
   const uint32_t nb = G.col_negbias[c];
   const uint32_t lo = __vmins2(__viaddmax_s16x2(prmt(s0, s1, 0x5410u), nb, 0u), 0x00ff00ffu);
   const uint32_t hi = __vmins2(__viaddmax_s16x2(prmt(s2, s3, 0x5410u), nb, 0u), 0x00ff00ffu);
   const uint32_t a = prmt(lo, hi, 0x6420u);
-  const uint32_t ao = G.off_A + G.col_arow[c] * 2 * G.ZB + kb;
+  const uint32_t ao = G.off_A + G.col_arow[c] * 2 * ZB + kb;
   sts(smb, ao, a);
-  sts(smb, ao + G.ZB, a);
+  sts(smb, ao + ZB, a);
 }
 
 // hard decision of codeword position i (0/1); degree-1 columns read as 0 like the reference's untouched llrRes
@@ -245,6 +203,7 @@ __device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const char
   return r == 0;
 }
 
+template <int ZWC>
 __global__ void __launch_bounds__(kPackedMaxThreads, 1)
 ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
 {
@@ -255,7 +214,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
   for (int i = threadIdx.x; i < (int)(sizeof(PackedGraph) / 4); i += blockDim.x)
     reinterpret_cast<int *>(&G)[i] = reinterpret_cast<const int *>(gdev)[i];
   __syncthreads();
-  const int Zw = G.Zw;
+  const int Zw = geo_zw<ZWC>(G);
   const int bin = threadIdx.x / Zw, kw = threadIdx.x - bin * Zw;
   const uint32_t kb = 4u * (uint32_t)kw;
   const uint32_t kbs = (kb << 8) | 0xFFu;
@@ -293,7 +252,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       uint32_t w0 = 4u * (uint32_t)(k + G.row_p_q[r]);
       if (w0 >= (uint32_t)G.ZB) w0 -= G.ZB;
       const uint32_t lp = __funnelshift_r(lds(smb, row.lrow + w0), lds(smb, row.lrow + w0 + 4), (uint32_t)G.row_p_rho[r]);
-      const uint32_t dd = __vabsdiffu4(lp, kH);
+      const uint32_t dd = vabsdiffu4(lp, kH);
       const uint32_t pa = (row.prow_pcw & 0xFFFFFFu) + 4u * (uint32_t)k;
       sts(smb, pa, 0u);
       sts(smb, pa + G.ZB, lop3<kLutOrAnd>(dd, msb_mask(dd), kL7) | (~lp & kH));
@@ -311,15 +270,15 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       // CN phase of iteration numIter+1 (also yields the syndrome of iteration numIter when numIter >= 2)
       uint32_t bad = 0;
       if (worker) {
-        if (!quirks) for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<false>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
-        else for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<true>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
+        if (!quirks) for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<ZWC, false>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
+        else for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<ZWC, true>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
       }
       const int pcRes = __syncthreads_or(bad != 0);   // also the CN->BN barrier
       if (numIter >= 2 && !a.use_crc && pcRes == 0) break;          // iteration numIter passed its parity check (:552)
       numIter++;
       // BN phase
       if (worker)
-        for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) bn_col(G, smb, G.bn_bin_cols[i], kb, kbs);
+        for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) bn_col<ZWC>(G, smb, G.bn_bin_cols[i], kb, kbs);
       __syncthreads();
       // loop control, mirroring `while (numIter <= numMaxIter && pcRes != 0)` evaluated before each further iteration
       if (numIter == 1) {
