@@ -146,6 +146,15 @@ int32_t nrb200_ldpc_decode_batch_dev(const nrb200_ldpc_batch_desc_t *desc, const
                                      int32_t *d_iters, void *stream);
 /* Host-buffer batch decode: H2D (pinned staging if the buffers are not pinned), kernel, D2H; blocking. */
 int32_t nrb200_ldpc_decode_batch_host(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters);
+/* The same call in two halves, so that a caller can keep several batches in flight and the copies of one batch overlap the
+ * kernels of another -- the enqueue / dequeue shape of the bbdev calls in the reference's T2 offload
+ * (openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder_offload.c:1048-1100: rte_bbdev_enqueue_ldpc_dec_ops / dequeue).
+ * submit() stages pageable buffers, enqueues every H2D copy, kernel and D2H copy and returns a ticket; llr / out / iters must stay
+ * valid and untouched until wait(ticket), which blocks until that batch is complete and frees the ticket.  out and iters hold the
+ * results only after wait() returned 0.  Every ticket must be waited for exactly once. */
+int32_t nrb200_ldpc_decode_batch_host_submit(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters,
+                                             void **ticket);
+int32_t nrb200_ldpc_decode_batch_host_wait(void *ticket);
 
 /* Batch encode: in = n_cb x K/8 packed bytes (stride in_stride), out = n_cb x (66Z|50Z) bytes, one bit per byte
  * (stride out_stride).  Same output as LDPCencoder per block. */

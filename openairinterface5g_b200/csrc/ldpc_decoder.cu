@@ -17,6 +17,7 @@ static size_t generic_smem_bytes(const GraphDev &g)
 }
 
 // device copies of the packed tables, keyed like Ctx::graphs
+constexpr int kPackedDefaultThreadsZ384 = 768;
 static std::mutex g_pk_mu;
 static std::map<uint32_t, std::pair<PackedGraph *, PackedGraph>> g_pk;
 
@@ -28,8 +29,9 @@ static const PackedGraph *packed_graph(const GraphDev &h_g, const PackedGraph **
   if (it == g_pk.end()) {
     PackedGraph pg;
     PackedGraph *d = nullptr;
-    int maxt = kPackedMaxThreads;
-    if (const char *e = getenv("NRB200_PACKED_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kPackedMaxThreads) maxt = v; }
+    const int cap = h_g.Z == 384 ? kPackedMaxThreadsZ384 : kPackedMaxThreads;
+    int maxt = h_g.Z == 384 ? kPackedDefaultThreadsZ384 : kPackedMaxThreads;
+    if (const char *e = getenv("NRB200_PACKED_THREADS")) { int v = atoi(e); if (v >= 32 && v <= cap) maxt = v; }
     if (build_packed_graph(h_g, &pg, maxt) && (size_t)pg.total_bytes + sizeof(PackedGraph) + 64 <= (size_t)ctx().max_smem_optin) {
       if (cudaMalloc(&d, sizeof(PackedGraph)) != cudaSuccess) d = nullptr;
       else cudaMemcpy(d, &pg, sizeof(PackedGraph), cudaMemcpyHostToDevice);
@@ -57,16 +59,20 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
   const PackedGraph *d_pg = (h_g.Z % 4 == 0 && !force_generic) ? packed_graph(h_g, &h_pg) : nullptr;
   if (d_pg) {
     const size_t smem = (size_t)h_pg->total_bytes;
-    // Z = 384 (K = 8448, both headline workloads) runs the instantiation with the row geometry as immediates
-    const bool z384 = h_pg->Zw == 96;
-    static std::atomic<size_t> configured_pk[2];
-    if (smem > configured_pk[z384].load()) {
-      NRB200_CUDA_OK(cudaFuncSetAttribute(z384 ? ldpc_decode_packed_kernel<96> : ldpc_decode_packed_kernel<0>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
-      configured_pk[z384].store(smem);
+    // Z = 384 (K = 8448, both headline workloads) runs an instantiation with the row geometry as immediates
+    void (*kern)(const PackedGraph *, DecodeArgs) = ldpc_decode_packed_kernel<0, kPackedMaxThreads>;
+    int variant = 0;
+    if (h_pg->Zw == 96) {
+      if (h_pg->nthreads > 864) { kern = ldpc_decode_packed_kernel<96, 960>; variant = 3; }
+      else if (h_pg->nthreads > 768) { kern = ldpc_decode_packed_kernel<96, 864>; variant = 2; }
+      else { kern = ldpc_decode_packed_kernel<96, 768>; variant = 1; }
     }
-    if (z384) ldpc_decode_packed_kernel<96><<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
-    else ldpc_decode_packed_kernel<0><<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
+    static std::atomic<size_t> configured_pk[4];
+    if (smem > configured_pk[variant].load()) {
+      NRB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
+      configured_pk[variant].store(smem);
+    }
+    kern<<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
     c.launches++;
     NRB200_CUDA_OK(cudaGetLastError(), "packed decode launch");
     return 0;

@@ -203,8 +203,10 @@ __device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const char
   return r == 0;
 }
 
-template <int ZWC>
-__global__ void __launch_bounds__(kPackedMaxThreads, 1)
+// MAXT = launch bound: 768 threads leave 80 registers per thread, 864 leave 72, 960 leave 64 (no spills in any of them); more bins
+// of Zw threads = more warps per scheduler to hide the shared-memory latency of the dependent descriptor -> message loads.
+template <int ZWC, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
 {
   extern __shared__ __align__(16) uint32_t sm[];

@@ -5,7 +5,8 @@
 
 namespace nrb200 {
 
-constexpr int kPackedMaxThreads = 768;
+constexpr int kPackedMaxThreads = 768;       // launch bound of the generic instantiation
+constexpr int kPackedMaxThreadsZ384 = 960;   // Z = 384 instantiations exist for 768 / 864 / 960 threads (8 / 9 / 10 bins of 96)
 constexpr int kMaxBins = 24;
 
 // Per check row, one 16-byte record (read with a single LDS.128).

@@ -107,67 +107,115 @@ static bool is_pinned_host(const void *p)
 // Host-buffer decode.  Pageable caller memory (OAI's stack arrays) is staged through the workspace's pinned buffers;
 // page-locked caller memory is copied from / to directly.  Large batches are cut into chunks that alternate between two
 // streams so the H2D copy of chunk i+1 overlaps the kernel of chunk i.
-static int decode_host_impl(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, const uint8_t *abort_flags)
+// The work is split in two halves so that a caller can keep several batches in flight (enqueue / dequeue, the shape of the
+// bbdev calls of the reference's T2 offload, nrLDPC_decoder_offload.c:1048-1100): decode_submit() stages, enqueues every copy and
+// kernel and returns; decode_finish() waits for the batch's two streams and hands the results over.
+struct DecodeTicket {
+  Workspace *w = nullptr, *w2 = nullptr;
+  uint8_t *out = nullptr;
+  int32_t *iters = nullptr;
+  size_t n = 0, out_bytes = 0;
+  bool pin_out = false;
+  int rc = 0;
+};
+
+static DecodeTicket *decode_submit(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, const uint8_t *abort_flags,
+                                   int *rc_out)
 {
-  if (ensure_init()) return -1;
+  *rc_out = 0;
+  if (ensure_init()) { *rc_out = -1; return nullptr; }
   const GraphDev *hg = nullptr;
   const GraphDev *dg = ctx().graph(desc->BG, desc->Z, desc->R, &hg);
-  if (!dg) return -4;
+  if (!dg) { *rc_out = -4; return nullptr; }
   DecodeArgs a0;
-  if (int rc = fill_args(desc, *hg, &a0)) return rc;
+  if (int rc = fill_args(desc, *hg, &a0)) { *rc_out = rc; return nullptr; }
   const size_t n = desc->n_cb;
-  if (n == 0) return 0;
+  DecodeTicket *t = new DecodeTicket();
+  t->out = out; t->iters = iters; t->n = n;
+  if (n == 0) return t;
   const size_t in_bytes = n * desc->llr_stride, out_bytes = n * desc->out_stride, aux_bytes = n * (sizeof(int32_t) + 1);
-  Workspace *w = ctx().acquire();
-  Workspace *w2 = n >= 64 ? ctx().acquire() : nullptr;
-  if (!w || !w->reserve(in_bytes, out_bytes, aux_bytes)) { if (w) ctx().release(w); if (w2) ctx().release(w2); return -5; }
-  const bool pin_in = is_pinned_host(llr), pin_out = is_pinned_host(out);
+  t->out_bytes = out_bytes;
+  Workspace *w = t->w = ctx().acquire();
+  Workspace *w2 = t->w2 = n >= 64 ? ctx().acquire(false) : nullptr;
+  if (!w || !w->reserve(in_bytes, out_bytes, aux_bytes)) { if (w) ctx().release(w); if (w2) ctx().release(w2); delete t; *rc_out = -5; return nullptr; }
+  const bool pin_in = is_pinned_host(llr), pin_out = t->pin_out = is_pinned_host(out);
   int rc = 0;
-  do {
-    int32_t *d_it = (int32_t *)w->d_aux;
-    uint8_t *d_ab = (uint8_t *)w->d_aux + n * sizeof(int32_t);
-    uint8_t *h_ab = (uint8_t *)w->h_aux + n * sizeof(int32_t);
-    if (abort_flags) std::memcpy(h_ab, abort_flags, n);
-    const uint8_t *h_src = (const uint8_t *)llr;
-    if (!pin_in) { std::memcpy(w->h_in, llr, in_bytes); h_src = (const uint8_t *)w->h_in; }
-    uint8_t *h_dst = pin_out ? out : (uint8_t *)w->h_out;
-    if (desc->use_crc && !pin_out) std::memcpy(w->h_out, out, out_bytes);   // the reference leaves p_out untouched until a CRC check runs
-    // Chunks of one wave (one CTA per SM) alternate between the two streams: the first kernel starts after 1/7 of the input has crossed
-    // PCIe, later chunks' CTAs fill the SMs the previous chunk's tail frees, and only the last wave's output is copied after the kernels.
-    // NRB200_HOST_CHUNK_WAVES = waves per chunk (default 1).
-    static const size_t waves = []() { const char *e = getenv("NRB200_HOST_CHUNK_WAVES"); const int v = e ? atoi(e) : 1; return (size_t)(v > 0 ? v : 1); }();
-    const size_t per = w2 ? std::max<size_t>(1, (size_t)ctx().sm_count * waves) : n;
-    cudaStream_t st[2] = {w->stream, w2 ? w2->stream : w->stream};
-    for (size_t ci = 0, c0 = 0; c0 < n; ci++, c0 += per) {
-      const size_t cn = std::min(per, n - c0);
-      cudaStream_t s = st[ci & 1];
-      const size_t io = c0 * desc->llr_stride, oo = c0 * desc->out_stride;
-      if (cudaMemcpyAsync((uint8_t *)w->d_in + io, h_src + io, cn * desc->llr_stride, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = -2; break; }
-      if (abort_flags) cudaMemcpyAsync(d_ab + c0, h_ab + c0, cn, cudaMemcpyHostToDevice, s);
-      if (desc->use_crc) cudaMemcpyAsync((uint8_t *)w->d_out + oo, h_dst + oo, cn * desc->out_stride, cudaMemcpyHostToDevice, s);
-      DecodeArgs a = a0;
-      a.n_cb = (uint32_t)cn;
-      a.llr = (const int8_t *)w->d_in + io; a.out = (uint8_t *)w->d_out + oo; a.iters = d_it + c0;
-      a.abort_flags = abort_flags ? d_ab + c0 : nullptr;
-      if ((rc = launch_decode(dg, *hg, a, s)) != 0) break;
-      if (cudaMemcpyAsync(h_dst + oo, (uint8_t *)w->d_out + oo, cn * desc->out_stride, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
-      if (cudaMemcpyAsync((int32_t *)w->h_aux + c0, d_it + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
+  int32_t *d_it = (int32_t *)w->d_aux;
+  uint8_t *d_ab = (uint8_t *)w->d_aux + n * sizeof(int32_t);
+  uint8_t *h_ab = (uint8_t *)w->h_aux + n * sizeof(int32_t);
+  if (abort_flags) std::memcpy(h_ab, abort_flags, n);
+  const uint8_t *h_src = (const uint8_t *)llr;
+  if (!pin_in) { std::memcpy(w->h_in, llr, in_bytes); h_src = (const uint8_t *)w->h_in; }
+  uint8_t *h_dst = pin_out ? out : (uint8_t *)w->h_out;
+  if (desc->use_crc && !pin_out) std::memcpy(w->h_out, out, out_bytes);   // the reference leaves p_out untouched until a CRC check runs
+  // Chunks of one wave (one CTA per SM) alternate between the two streams: the first kernel starts after 1/7 of the input has crossed
+  // PCIe, later chunks' CTAs fill the SMs the previous chunk's tail frees, and only the last wave's output is copied after the kernels.
+  // NRB200_HOST_CHUNK_WAVES = waves per chunk (default 1).
+  static const size_t waves = []() { const char *e = getenv("NRB200_HOST_CHUNK_WAVES"); const int v = e ? atoi(e) : 1; return (size_t)(v > 0 ? v : 1); }();
+  const size_t per = w2 ? std::max<size_t>(1, (size_t)ctx().sm_count * waves) : n;
+  cudaStream_t st[2] = {w->stream, w2 ? w2->stream : w->stream};
+  for (size_t ci = 0, c0 = 0; c0 < n; ci++, c0 += per) {
+    const size_t cn = std::min(per, n - c0);
+    cudaStream_t s = st[ci & 1];
+    const size_t io = c0 * desc->llr_stride, oo = c0 * desc->out_stride;
+    if (cudaMemcpyAsync((uint8_t *)w->d_in + io, h_src + io, cn * desc->llr_stride, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = -2; break; }
+    if (abort_flags) cudaMemcpyAsync(d_ab + c0, h_ab + c0, cn, cudaMemcpyHostToDevice, s);
+    if (desc->use_crc) cudaMemcpyAsync((uint8_t *)w->d_out + oo, h_dst + oo, cn * desc->out_stride, cudaMemcpyHostToDevice, s);
+    DecodeArgs a = a0;
+    a.n_cb = (uint32_t)cn;
+    a.llr = (const int8_t *)w->d_in + io; a.out = (uint8_t *)w->d_out + oo; a.iters = d_it + c0;
+    a.abort_flags = abort_flags ? d_ab + c0 : nullptr;
+    if ((rc = launch_decode(dg, *hg, a, s)) != 0) break;
+    if (cudaMemcpyAsync(h_dst + oo, (uint8_t *)w->d_out + oo, cn * desc->out_stride, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
+    if (cudaMemcpyAsync((int32_t *)w->h_aux + c0, d_it + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
+  }
+  t->rc = rc;
+  return t;
+}
+
+static int decode_finish(DecodeTicket *t)
+{
+  int rc = t->rc;
+  if (t->w) {
+    cudaError_t e = cudaStreamSynchronize(t->w->stream);
+    cudaError_t e2 = t->w2 ? cudaStreamSynchronize(t->w2->stream) : cudaSuccess;
+    if (rc == 0 && (e != cudaSuccess || e2 != cudaSuccess)) { ctx().set_error("decode sync", e != cudaSuccess ? e : e2); rc = -2; }
+    if (rc == 0) {
+      if (!t->pin_out) std::memcpy(t->out, t->w->h_out, t->out_bytes);
+      std::memcpy(t->iters, t->w->h_aux, t->n * sizeof(int32_t));
     }
-    cudaError_t e = cudaStreamSynchronize(st[0]);
-    cudaError_t e2 = w2 ? cudaStreamSynchronize(st[1]) : cudaSuccess;
-    if (rc != 0) break;
-    if (e != cudaSuccess || e2 != cudaSuccess) { ctx().set_error("decode sync", e != cudaSuccess ? e : e2); rc = -2; break; }
-    if (!pin_out) std::memcpy(out, w->h_out, out_bytes);
-    std::memcpy(iters, w->h_aux, n * sizeof(int32_t));
-  } while (0);
-  ctx().release(w);
-  if (w2) ctx().release(w2);
+    ctx().release(t->w);
+    if (t->w2) ctx().release(t->w2);
+  }
+  delete t;
   return rc;
+}
+
+static int decode_host_impl(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, const uint8_t *abort_flags)
+{
+  int rc = 0;
+  DecodeTicket *t = decode_submit(desc, llr, out, iters, abort_flags, &rc);
+  return t ? decode_finish(t) : rc;
 }
 
 NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_host(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters)
 {
   return decode_host_impl(desc, llr, out, iters, nullptr);
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_host_submit(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters,
+                                                           void **ticket)
+{
+  if (!ticket) return -4;
+  int rc = 0;
+  *ticket = decode_submit(desc, llr, out, iters, nullptr, &rc);
+  return *ticket ? 0 : rc;
+}
+
+NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_host_wait(void *ticket)
+{
+  if (!ticket) return -4;
+  return decode_finish((DecodeTicket *)ticket);
 }
 
 NRB200_EXPORT int32_t nrb200_device_index(void) { return ctx().inited ? ctx().dev : -1; }

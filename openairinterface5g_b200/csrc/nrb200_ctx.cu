@@ -154,11 +154,21 @@ const EncGraphDev *Ctx::enc_graph(int BG, int Z, const EncGraphDev **host)
   return it->second;
 }
 
-Workspace *Ctx::acquire()
+// want_buffers: hand out the pooled workspace with the largest staging buffers (a caller that will reserve()); otherwise the one with the
+// smallest (a caller that only needs the stream).  Keeps the roles stable when several batches are in flight, so no call re-allocates
+// pinned memory in steady state.
+Workspace *Ctx::acquire(bool want_buffers)
 {
   {
     std::lock_guard<std::mutex> lk(mu);
-    if (!pool.empty()) { Workspace *w = pool.back(); pool.pop_back(); return w; }
+    if (!pool.empty()) {
+      size_t best = 0;
+      for (size_t i = 1; i < pool.size(); i++)
+        if (want_buffers ? pool[i]->cap_in > pool[best]->cap_in : pool[i]->cap_in < pool[best]->cap_in) best = i;
+      Workspace *w = pool[best];
+      pool.erase(pool.begin() + (long)best);
+      return w;
+    }
   }
   Workspace *w = new Workspace();
   if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return nullptr; }

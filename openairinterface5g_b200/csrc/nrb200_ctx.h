@@ -41,7 +41,7 @@ struct Ctx {
   void shutdown();
   const GraphDev *graph(int BG, int Z, int R, const GraphDev **host = nullptr);   // nullptr if invalid
   const EncGraphDev *enc_graph(int BG, int Z, const EncGraphDev **host = nullptr);
-  Workspace *acquire();
+  Workspace *acquire(bool want_buffers = true);
   void release(Workspace *w);
   void set_error(const char *where, cudaError_t e);
 };

@@ -102,6 +102,8 @@ class LdpcLib:
         L.nrb200_ldpc_num_llr.argtypes = [C.c_int] * 3
         L.nrb200_ldpc_decode_batch_dev.argtypes = [C.POINTER(BatchDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nrb200_ldpc_decode_batch_host.argtypes = [C.POINTER(BatchDesc), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrb200_ldpc_decode_batch_host_submit.argtypes = [C.POINTER(BatchDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.nrb200_ldpc_decode_batch_host_wait.argtypes = [C.c_void_p]
         L.nrb200_ldpc_encode_batch_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.nrb200_ldpc_encode_batch_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nrb200_crc_batch_dev.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -206,6 +208,23 @@ class LdpcLib:
             iters = np.zeros(n_cb, dtype=np.int32)
         d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
         self._check(self.lib.nrb200_ldpc_decode_batch_host(C.byref(d), llr.ctypes.data, out.ctypes.data, iters.ctypes.data), "decode_batch_host")
+        return iters, out
+
+    def decode_batch_host_submit(self, BG, Z, R, numMaxIter, llr, out, iters, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0):
+        """First half of decode_batch_host (enqueue): returns a ticket for decode_batch_host_wait.  llr (int8, C-contiguous, 2-D), out and
+        iters are used in place and must stay alive and untouched until the wait; results are valid only after it."""
+        assert llr.dtype == np.int8 and llr.flags.c_contiguous and out.flags.c_contiguous and iters.dtype == np.int32
+        n_cb, stride = llr.shape
+        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
+        t = C.c_void_p()
+        self._check(self.lib.nrb200_ldpc_decode_batch_host_submit(C.byref(d), llr.ctypes.data, out.ctypes.data, iters.ctypes.data, C.byref(t)),
+                    "decode_batch_host_submit")
+        return (t, llr, out, iters)   # the tuple keeps the buffers alive
+
+    def decode_batch_host_wait(self, ticket):
+        """Second half (dequeue): blocks until the batch of `ticket` is complete; returns (iters, out)."""
+        t, _, out, iters = ticket
+        self._check(self.lib.nrb200_ldpc_decode_batch_host_wait(t), "decode_batch_host_wait")
         return iters, out
 
     def encode_batch_host(self, BG, Z, K, payloads):
