@@ -276,7 +276,7 @@ int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, const int16_t *rx
  * replaces nr_pusch_channel_estimation (nr_ul_channel_estimation.c:67-243) for one DMRS symbol and one antenna port with
  * transform precoding disabled and chest_freq == 0: DMRS generation, least-squares estimate, delay estimation (IDFT peak, running
  * maximum across the rx antennas), delay compensation, 16-tap interpolation, delay reversal, noise variance.  Other configurations
- * (DMRS type 2, chest_freq == 1, low-PAPR DMRS) return -4: the library never falls back.
+ * (low-PAPR DMRS, i.e. transform precoding) return -4: the library never falls back.  DMRS type 2 and chest_freq == 1: see the last two fields.
  * rxdataF [nb_rx][14][fft_size] c16; ul_ch_estimates [nb_rx][14][fft_size] c16: symbol `symbol` of every antenna is rewritten.
  * state (5 int32): max_ch, nvar, est_delay, delay_max_pos, delay_max_val -- what the reference returns through *max_ch, *nvar and delay_t. */
 typedef struct nrb200_pusch_chest_s {
@@ -291,6 +291,11 @@ typedef struct nrb200_pusch_chest_s {
   uint32_t pdsch_ue;                        /* 1: the UE's PDSCH estimator instead (nr_pdsch_channel_estimation + NFAPI_NR_DMRS_TYPE1_linear_interp,
                                              * NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1305-1385, 1614-1735): same DMRS, delay handling and filters, its own
                                              * least-squares arithmetic; max_ch and nvar are not produced (0).  rb_start + bwp_start = the PDSCH's rb_offset. */
+  uint32_t dmrs_config_type;                /* pusch_pdu->dmrs_config_type: 0 = type 1, 1 = type 2 (nr_ul_channel_estimation.c:258-283) */
+  uint32_t chest_freq;                      /* gNB->chest_freq: 0 = frequency-domain interpolation, 1 = one average per PRB (:285-460; NO_INTERP build).
+                                             * The three variants (type 2, chest_freq 1 of either type) serve the gNB estimator, one port per call
+                                             * (n_ports <= 1, pdsch_ue = 0).  chest_freq = 1 needs rb_size >= 2 and, for type 2, slot % 4 == 0: the reference reads
+                                             * slot-ring position 0 there.  Anything else returns -4. */
 } nrb200_pusch_chest_t;
 /* the 6 * rb_size conjugated DMRS symbols {re, im} the estimator correlates with (nr_pusch_dmrs_rx output); host arithmetic, no GPU needed */
 int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots);

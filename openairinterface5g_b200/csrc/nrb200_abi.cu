@@ -24,7 +24,8 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
 int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st);
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
 int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil);
-int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol);
+int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol,
+                       int tail_override = 0);
 int launch_rm_rx8(const nrb200_rm_desc_t &p, const int8_t *soft, const uint32_t *E, const uint32_t *off, int16_t *harq, uint32_t harq_stride,
                   int8_t *llr, uint32_t llr_stride, cudaStream_t st);
 int launch_modulate(int Qm, uint32_t length_bits, const uint8_t *bits, int16_t *out, cudaStream_t st);
@@ -695,19 +696,23 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, con
   if (ensure_init() || !d) return -1;
   if (d->nb_rx < 1 || d->nb_rx > 8 || d->symbol > 13 || d->n_ports > 2) return -4;
   const uint32_t np = d->n_ports == 0 ? 1 : d->n_ports;
-  // only the DMRS symbol travels: [nb_rx][N] in, [n_ports * nb_rx][N] out
-  const size_t sym = (size_t)d->fft_size * 4, plane = sym * d->nb_rx, scratch = pusch_chest_scratch_bytes(*d);
+  // only the DMRS symbol travels: [nb_rx][N + 4] in (4 c16 of the next symbol follow: the variants' pointer shift can read one of them),
+  // [n_ports * nb_rx][N] out
+  const size_t sym = (size_t)d->fft_size * 4, row = sym + 16, plane = sym * d->nb_rx, scratch = pusch_chest_scratch_bytes(*d);
+  const int tail = d->symbol < 13 ? 4 : 0;
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(plane, plane * np, scratch + 256)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(row * d->nb_rx, plane * np, scratch + 256)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
-    for (uint32_t a = 0; a < d->nb_rx; a++)
-      std::memcpy((uint8_t *)w->h_in + sym * a, (const uint8_t *)rxdataF + ((size_t)a * 14 + d->symbol) * sym, sym);
-    if (cudaMemcpyAsync(w->d_in, w->h_in, plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    for (uint32_t a = 0; a < d->nb_rx; a++) {
+      std::memset((uint8_t *)w->h_in + row * a + sym, 0, 16);
+      std::memcpy((uint8_t *)w->h_in + row * a, (const uint8_t *)rxdataF + ((size_t)a * 14 + d->symbol) * sym, sym + 4 * (size_t)tail);
+    }
+    if (cudaMemcpyAsync(w->d_in, w->h_in, row * d->nb_rx, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
     nrb200_pusch_chest_t e = *d;
-    e.rx_stride = e.ch_stride = d->fft_size;                                 // staged as a one-symbol slot (buffer symbol 0)
+    e.rx_stride = d->fft_size + 4; e.ch_stride = d->fft_size;                // staged as a one-symbol slot (buffer symbol 0)
     int32_t *d_state = (int32_t *)((uint8_t *)w->d_aux + scratch);
-    rc = launch_pusch_chest(e, (const int16_t *)w->d_in, (int16_t *)w->d_out, w->d_aux, d_state, w->stream, 0);
+    rc = launch_pusch_chest(e, (const int16_t *)w->d_in, (int16_t *)w->d_out, w->d_aux, d_state, w->stream, 0, tail);
     if (rc != 0) break;
     if (cudaMemcpyAsync(w->h_out, w->d_out, plane * np, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
     if (cudaMemcpyAsync(w->h_aux, d_state, 18 * 4 * np, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }

@@ -1,4 +1,5 @@
-// PUSCH channel estimation, DMRS configuration type 1, frequency-domain interpolation (the reference's default, chest_freq == 0).
+// PUSCH channel estimation.  Main path: DMRS configuration type 1, frequency-domain interpolation (the reference's default, chest_freq == 0);
+// the other three branches of the reference function (type 2, and chest_freq == 1 for both types) are the "variants" further down.
 // Reference: nr_pusch_channel_estimation (openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c:67-243, 483-487) with nr_gold_pusch /
 // nr_pusch_dmrs_rx (NR_REFSIG/nr_gold.c:99-116, nr_dmrs_rx.c:44-116), nr_est_delay / get_delay_idx / init_delay_table
 // (common/utils/nr/nr_common.c:906-990), c16multaddVectRealComplex and filt16_ul_* (tools_defs.h:266-297, filt16a_32.h:242-249).
@@ -24,6 +25,8 @@ struct ChestGeom {
   int ue;                                   // 1: the UE's PDSCH estimator (least-squares step of NFAPI_NR_DMRS_TYPE1_linear_interp)
   int n_ports, delta[2], wsign_odd[2];      // ports handled by one call (DMRS ports p, p+1 share the Gold sequence, differ in delta / w_f)
   unsigned rx_stride, ch_stride, x2;
+  int type2, chest_freq;                    // DMRS configuration type 2 / one average per PRB (the variants below)
+  int nushift, tail;                        // variants: (p >> 1) & 1 added to the symbol POINTER; c16 readable beyond the symbol's N (0 on the slot's last symbol)
 };
 constexpr int kChestState = 18;             // int32 per port, see chest_ls_kernel
 
@@ -187,6 +190,112 @@ __global__ void __launch_bounds__(256) chest_interp_kernel(ChestGeom G, const un
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Variants of nr_pusch_channel_estimation: DMRS type 2 with chest_freq == 0 (nr_ul_channel_estimation.c:258-283) and one average per PRB,
+// chest_freq == 1 (:285-343 type 1, :343-460 type 2; NO_INTERP is defined to 1 in that file, so a PRB's 12 REs take the average itself).
+// The reference's quirks are part of the arithmetic and are reproduced (oracle/nrb200_chest_oracle.c lists them): nushift = (p >> 1) & 1 moves
+// the symbol pointer for both DMRS types; type 2 accumulates the first four REs of every CDM group ACROSS antennas; type 2 + chest_freq == 1
+// uses the first PRB's third pilot twice and needs slot % 4 == 0.
+
+// conj of DMRS symbol i of the sequence (nr_rx_mod_table / nr_rx_nmod_table) as {re, im}
+__device__ __forceinline__ void dmrs_conj(const GoldTables *__restrict__ T, unsigned x2, int i, int wsign_odd, int &pr, int &pi)
+{
+  const unsigned b = 2u * (unsigned)i;
+  const uint32_t w = gold_word(T, x2, b >> 5);                             // bits 2i, 2i+1 never straddle a word
+  const int b0 = (w >> (b & 31u)) & 1u, b1 = (w >> ((b & 31u) + 1u)) & 1u;
+  const int s = (i & 1) ? wsign_odd : 1;
+  pr = s * (b0 ? -23170 : 23170); pi = s * (b1 ? 23170 : -23170);
+}
+__device__ __forceinline__ unsigned rx_at(const ChestGeom &G, const unsigned *__restrict__ rx, int idx)
+{
+  return idx < G.N + G.tail ? __ldg(rx + idx) : 0u;                        // beyond the slot's last symbol: not ours to read
+}
+
+// type 2, chest_freq == 0: one thread per CDM pair, antennas in sequence (the running saturating sum of the first four REs)
+__global__ void __launch_bounds__(128) chest_t2_ls_kernel(ChestGeom G, const GoldTables *__restrict__ T, const unsigned *__restrict__ rxF, unsigned *__restrict__ ls,
+                                                          int *__restrict__ state)
+{
+  const int m = blockIdx.x * 128 + threadIdx.x;                            // pair index: pilots 2m, 2m + 1, sub-carriers 6m .. 6m + 5
+  unsigned long long noise = 0;
+  if (m < 2 * G.nb) {
+    int p0r, p0i, p1r, p1i;
+    dmrs_conj(T, G.x2, G.dmrs_offset + 2 * m, G.wsign_odd[0], p0r, p0i);
+    dmrs_conj(T, G.x2, G.dmrs_offset + 2 * m + 1, G.wsign_odd[0], p1r, p1i);
+    const int re0 = (G.k0 + 6 * m) % G.N + G.nushift, re1 = (G.k0 + 6 * m + 1) % G.N + G.nushift;
+    int accr = 0, acci = 0, mx = 0;
+    for (int a = 0; a < G.nb_rx; a++) {
+      const unsigned *rx = rxF + (size_t)a * G.rx_stride + (size_t)G.symbol * G.N;
+      const unsigned y0 = rx_at(G, rx, re0), y1 = rx_at(G, rx, re1);
+      const int c0r = c_wrap16((p0r * c_lo(y0) - p0i * c_hi(y0)) >> 15), c0i = c_wrap16((p0r * c_hi(y0) + p0i * c_lo(y0)) >> 15);
+      const int c1r = c_wrap16((p1r * c_lo(y1) - p1i * c_hi(y1)) >> 15), c1i = c_wrap16((p1r * c_hi(y1) + p1i * c_lo(y1)) >> 15);
+      const int cr = c_wrap16((c0r + c1r) >> 1), ci = c_wrap16((c0i + c1i) >> 1);
+      mx = max(mx, max(abs(cr), abs(ci)));
+      accr = c_sat16(accr + c_wrap16((cr >> 2) << 2)); acci = c_sat16(acci + c_wrap16((ci >> 2) << 2));   // mulhi_s1_int16(ch, 16384), adds_epi16
+      unsigned *dst = ls + (size_t)a * G.N + 6 * m;
+      const unsigned va = c_pk(accr, acci), vc = c_pk(cr, ci);
+      dst[0] = va; dst[1] = va; dst[2] = va; dst[3] = va; dst[4] = vc; dst[5] = vc;
+      const int dr = c_wrap16(c0r - cr), di = c_wrap16(c0i - ci);
+      noise += (unsigned)(dr * dr + di * di);
+    }
+    if (mx > 0) atomicMax(state, mx);
+  }
+  __shared__ unsigned long long s_n[128];
+  s_n[threadIdx.x] = noise;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) { if (threadIdx.x < s) s_n[threadIdx.x] += s_n[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0 && s_n[0]) atomicAdd(reinterpret_cast<unsigned long long *>(state + 6), s_n[0]);
+}
+
+// type 2, chest_freq == 0: ul_ch[n] = c16mulShift(ls[n], delay_table[get_delay_idx(-est_delay)][n % 6], 8); the rest of the symbol is cleared
+__global__ void __launch_bounds__(256) chest_t2_apply_kernel(ChestGeom G, const unsigned *__restrict__ ls, const unsigned *__restrict__ dtab, const int *__restrict__ raw,
+                                                             unsigned *__restrict__ est, int *__restrict__ state)
+{
+  const int a = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+  int ed, mv;
+  running_delay(G, raw, a, ed, mv);
+  if (k < G.N) {
+    const unsigned *ti = dtab + (size_t)min(max(20 - ed, 0), 40) * G.N;
+    est[(size_t)a * G.ch_stride + (size_t)G.symbol * G.N + k] = k < 12 * G.nb ? c_mul8(ls[(size_t)a * G.N + k], __ldg(ti + k % 6)) : 0u;
+  }
+  if (k == 0) {
+    state[8 + a] = ed;
+    if (a == G.nb_rx - 1) {                                                 // chest_t2_ls_kernel has completed (stream order): publish nvar and delay_t
+      const unsigned long long n = *reinterpret_cast<const unsigned long long *>(state + 6);
+      state[1] = (int)(unsigned)(n / (unsigned long long)(2 * G.nb * G.nb_rx));
+      state[2] = ed; state[3] = ed; state[4] = mv;
+    }
+  }
+}
+
+// chest_freq == 1: every sub-carrier of PRB j takes the PRB's average; no delay estimation, no noise estimate
+__global__ void __launch_bounds__(256) chest_avg_kernel(ChestGeom G, const GoldTables *__restrict__ T, const unsigned *__restrict__ rxF, unsigned *__restrict__ est,
+                                                        int *__restrict__ state)
+{
+  const int a = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;            // one thread per PRB; PRBs beyond the allocation clear their 12 sub-carriers
+  if (12 * j >= G.N) return;
+  unsigned v = 0;
+  if (j < G.nb) {
+    const unsigned *rx = rxF + (size_t)a * G.rx_stride + (size_t)G.symbol * G.N;
+    const int cnt = G.type2 ? 4 : 6;
+    int sr = 0, si = 0;
+    for (int i = 0; i < cnt; i++) {
+      int pidx, re;
+      if (!G.type2) { pidx = 6 * j + i; re = (G.k0 + 12 * j + 2 * i) % G.N; }
+      else { pidx = j == 0 ? min(i, 2) : 4 * j - 1 + i; re = (G.k0 + 12 * j + (i & 1) + 6 * (i >> 1)) % G.N; }
+      int pr, pi;
+      dmrs_conj(T, G.x2, G.dmrs_offset + pidx, G.wsign_odd[0], pr, pi);
+      const unsigned y = rx_at(G, rx, re + G.nushift);
+      sr += (pr * c_lo(y) - pi * c_hi(y)) >> 15;
+      si += (pr * c_hi(y) + pi * c_lo(y)) >> 15;
+    }
+    const int cr = c_wrap16(sr / cnt), ci = c_wrap16(si / cnt);
+    if (j > 0 && j < G.nb - 1) { const int m = max(abs(cr), abs(ci)); if (m > 0) atomicMax(state, m); }
+    v = c_pk(cr, ci);
+  }
+  unsigned *dst = est + (size_t)a * G.ch_stride + (size_t)G.symbol * G.N + 12 * j;
+  for (int k = 0; k < 12 && 12 * j + k < G.N; k++) dst[k] = v;
+}
+
 // fp->delay_table (init_delay_table): round(256 e^{j 2 pi k d / N}) for d = -20..20, built once per N
 static const unsigned *delay_table_dev(int N)
 {
@@ -222,7 +331,17 @@ static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
     G->delta[q] = (pp >> 1) & 1;                                            // delta1[p]
     G->wsign_odd[q] = (pp & 1) ? -1 : 1;                                    // wf1[p][1]
   }
-  G->dmrs_offset = ((d.bwp_start + d.rb_start) * 12) / 2;
+  G->type2 = d.dmrs_config_type ? 1 : 0; G->chest_freq = d.chest_freq ? 1 : 0;
+  G->nushift = (d.port >> 1) & 1;
+  G->tail = d.symbol < 13 ? 4 : 0;
+  if (G->type2 || G->chest_freq) {
+    // variants: gNB estimator, one port per call; the pointer shift needs an even first sub-carrier to stay inside the symbol (always the case
+    // for an even first_carrier_offset); PRB averages need two PRBs; type 2 averages need slot % 4 == 0 (see the kernels' header)
+    if (G->ue || G->n_ports != 1 || d.dmrs_config_type > 1 || d.chest_freq > 1) return -4;
+    if (G->chest_freq && (d.rb_size < 2 || (G->type2 && (d.slot & 3)))) return -4;
+    G->np = (G->type2 ? 4 : 6) * d.rb_size;
+  }
+  G->dmrs_offset = ((d.bwp_start + d.rb_start) * 12) / (G->type2 ? 3 : 2);
   G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
   const unsigned long long nid = d.ul_dmrs_scrambling_id;
   const unsigned long long t = ((1ULL << 17) * (unsigned long long)(14 * d.slot + d.symbol + 1) * ((nid << 1) + 1) + ((nid << 1) + d.scid));
@@ -244,7 +363,7 @@ int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil)
     x2 = (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3) ^ (x2 >> 4); x2 = x2 ^ (x2 << 31) ^ (x2 << 30) ^ (x2 << 29) ^ (x2 << 28);
   };
   for (int n = 1; n < 50; n++) step();
-  const int last = G.dmrs_offset + G.np;
+  const int last = G.dmrs_offset + G.np;                                     // np = 6 (type 1) or 4 (type 2) pilots per PRB
   std::vector<uint32_t> g((size_t)(2 * last + 31) / 32 + 1);
   for (auto &w : g) { step(); w = x1 ^ x2; }
   for (int i = G.dmrs_offset; i < last; i++) {
@@ -260,7 +379,8 @@ size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d) { return (size_t
 
 // d_scratch: pusch_chest_scratch_bytes(); d_state: 18 int32 per port (see chest_ls_kernel), zeroed here
 // buf_symbol >= 0: the buffers hold the DMRS symbol at that index (the host entry point stages a one-symbol slot); the DMRS sequence always uses d.symbol
-int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol)
+int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol,
+                       int tail_override)
 {
   ChestGeom G;
   int rc = chest_geom(d, &G);
@@ -273,6 +393,24 @@ int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_
   unsigned *ls = (unsigned *)d_scratch, *tim = ls + (size_t)npa * G.N;
   int *raw = (int *)(tim + (size_t)npa * G.N);
   NRB200_CUDA_OK(cudaMemsetAsync(d_state, 0, (size_t)G.n_ports * kChestState * 4, st), "chest memset");
+  if (buf_symbol >= 0) G.tail = tail_override;
+  if (G.chest_freq) {
+    chest_avg_kernel<<<dim3((G.N / 12 + 1 + 255) / 256, G.nb_rx), 256, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, (unsigned *)est, d_state);
+    ctx().launches += 1;
+    NRB200_CUDA_OK(cudaGetLastError(), "chest_avg launch");
+    return 0;
+  }
+  if (G.type2) {
+    NRB200_CUDA_OK(cudaMemsetAsync(ls, 0, (size_t)G.nb_rx * G.N * 4, st), "chest ls memset");
+    chest_t2_ls_kernel<<<(2 * G.nb + 127) / 128, 128, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, ls, d_state);
+    NRB200_CUDA_OK(cudaGetLastError(), "chest_t2_ls launch");
+    if ((rc = dft_batch_internal(G.N, 1, G.nb_rx, (const int16_t *)ls, (int16_t *)tim, 1, st)) != 0) return rc;
+    chest_peak_kernel<<<G.nb_rx, 256, 0, st>>>(G, tim, raw);
+    chest_t2_apply_kernel<<<dim3((G.N + 255) / 256, G.nb_rx), 256, 0, st>>>(G, ls, dtab, raw, (unsigned *)est, d_state);
+    ctx().launches += 4;
+    NRB200_CUDA_OK(cudaGetLastError(), "chest_t2 launch");
+    return 0;
+  }
   chest_ls_kernel<<<dim3((G.N / 4 + 255) / 256, npa), 256, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, ls, d_state);
   NRB200_CUDA_OK(cudaGetLastError(), "chest_ls launch");
   if ((rc = dft_batch_internal(G.N, 1, npa, (const int16_t *)ls, (int16_t *)tim, 1, st)) != 0) return rc;

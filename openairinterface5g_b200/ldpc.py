@@ -77,7 +77,7 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
 
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
-                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue")]
+                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue", "dmrs_config_type", "chest_freq")]
 
 
 class PdschTxDesc(C.Structure):       # nrb200_pdsch_tx_t (field names of nfapi_nr_dl_tti_pdsch_pdu_rel15_t / NR_DL_FRAME_PARMS)

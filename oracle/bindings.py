@@ -60,7 +60,7 @@ def _ptr(a, t):
 # ------------------------------------------------------------------------------------------------ oracle (C restatement)
 class ChestParms(C.Structure):       # orc_chest_t
     _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
-                                         "dmrs_scrambling_id")]
+                                         "dmrs_scrambling_id", "dmrs_type", "chest_freq")]
 
 
 class PuschParms(C.Structure):       # orc_pusch_t

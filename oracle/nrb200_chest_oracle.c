@@ -1,6 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY (see nrb200_oracle.h).  CPU restatement of the PUSCH channel estimator of the reference for DMRS
- * configuration type 1 with frequency-domain interpolation (chest_freq == 0), transform precoding disabled:
- *   nr_pusch_channel_estimation    openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c:67-243, 483-487
+ * configuration types 1 and 2, with frequency-domain interpolation (chest_freq == 0) and with one average per PRB (chest_freq == 1),
+ * transform precoding disabled:
+ *   nr_pusch_channel_estimation    openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c:67-487
  *   nr_gold_pusch / nr_pusch_dmrs_rx  NR_REFSIG/nr_gold.c:99-116, NR_REFSIG/nr_dmrs_rx.c:44-116
  *   nr_est_delay, get_delay_idx, init_delay_table   common/utils/nr/nr_common.c:906-990
  *   c16multaddVectRealComplex + filt16_ul_*          PHY/TOOLS/tools_defs.h:266-297, NR_UE_ESTIMATION/filt16a_32.h:242-249
@@ -20,14 +21,14 @@ static const int16_t F_P1P2[16] = {4096, 4096, 4096, 4096, 2048, 2048, 2048, 204
 static const int16_t F_MID[16] = {2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048};
 static const int16_t F_LAST[16] = {4096, 4096, 4096, 4096, 8192, 8192, 8192, 8192, 0, 0, 0, 0, 0, 0, 0, 0};
 
-/* conjugated DMRS of one symbol: 6 * rb_size c16 */
+/* conjugated DMRS of one symbol: 6 * rb_size c16 (type 1) or 4 * rb_size (type 2) */
 void orc_pusch_dmrs_pilots(const orc_chest_t *p, int16_t *pil)
 {
   static const int wf1[8][2] = {{1, 1}, {1, -1}, {1, 1}, {1, -1}, {1, 1}, {1, -1}, {1, 1}, {1, -1}};
   const uint32_t nid = (uint32_t)p->dmrs_scrambling_id;
   const uint64_t t = ((1ULL << 17) * (uint64_t)(14 * p->slot + p->symbol + 1) * ((nid << 1) + 1) + ((nid << 1) + (uint32_t)p->scid));
   const uint32_t x2 = (uint32_t)(t % (1ULL << 31));
-  const int dmrs_offset = ((p->bwp_start + p->rb_start) * 12) / 2, n = 6 * p->rb_size;
+  const int dmrs_offset = ((p->bwp_start + p->rb_start) * 12) / (p->dmrs_type ? 3 : 2), n = (p->dmrs_type ? 4 : 6) * p->rb_size;   /* wf2 == wf1 for ports 0..7 */
   const uint32_t nw = (uint32_t)((2 * (dmrs_offset + n) + 31) / 32 + 1);
   uint32_t *g = malloc(4 * (size_t)nw);
   orc_gold_words(x2, nw, g);
@@ -54,8 +55,16 @@ static void multadd16(const int16_t *filt, int16_t ar, int16_t ai, int16_t *y)
 
 /* rxdataF [nb_rx][14 N] c16; ul_ch_est [nb_rx][14 N] c16 (symbol p->symbol is rewritten, N entries + up to 8 beyond the allocation stay 0);
  * out: max_ch, nvar, est_delay, delay_max_pos, delay_max_val */
+/* the pointer shift of the variants can address one sample past the symbol: the next symbol's first sub-carrier, as in the reference; past the
+ * slot's last symbol (the reference reads the next slot of its ring there) the restatement and the product read 0 */
+#define RX_AT(rx, idx, c) (((idx) >= N && p->symbol >= 13) ? 0 : (rx)[2 * (idx) + (c)])
+static int chest_type2_freq(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);
+static int chest_prb_average(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);
+
 int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out)
 {
+  if (p->chest_freq) return chest_prb_average(p, rxdataF, ul_ch_est, out);
+  if (p->dmrs_type) return chest_type2_freq(p, rxdataF, ul_ch_est, out);
   static const int delta1[8] = {0, 0, 1, 1, 0, 0, 1, 1};
   const int N = p->fft_size, nb = p->rb_size, np = 6 * nb, delta = delta1[p->port];
   const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
@@ -119,6 +128,112 @@ int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, i
   }
   out[0] = max_ch; out[1] = nest > 0 ? (int32_t)(uint32_t)(noise / (uint64_t)nest) : 0; out[2] = max_pos; out[3] = max_pos; out[4] = max_val;
   free(pil); free(ls); free(tim); free(acc);
+  return 0;
+}
+
+/* ---- DMRS type 2, frequency-domain "interpolation" (nr_ul_channel_estimation.c:258-283): one least-squares value per CDM pair
+ * (two adjacent pilots, >> 15 each, averaged), held over the pair's 6 sub-carriers, delay estimated from the IDFT peak and compensated with
+ * ul_delay_table[n % 6] -- only the first six entries of the table are ever used.  As the reference does:
+ *  - nushift = (p >> 1) & 1 moves the symbol POINTER (ports 2, 3 read one sub-carrier up, not two; the index wraps before the shift is added);
+ *  - ul_ls_est is cleared once per call, and the first four REs of every group are written with a saturating ADD
+ *    (multadd_real_four_symbols_vector_complex_scalar with filt8_rep4 = ch & ~3), so antenna a holds the running sum over antennas 0..a
+ *    there, and the plain value in the last two REs;
+ *  - the noise estimate compares the first pilot's product with the pair's average. */
+static int chest_type2_freq(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out)
+{
+  const int N = p->fft_size, nb = p->rb_size, nushift = (p->port >> 1) & 1;
+  const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
+  int16_t *pil = malloc(4 * (size_t)(4 * nb)), *ls = calloc((size_t)N, 4), *tim = malloc(4 * (size_t)N);
+  orc_pusch_dmrs_pilots(p, pil);
+  int max_ch = 0, max_pos = 0, max_val = 0, nest = 0;
+  uint64_t noise = 0;
+  for (int a = 0; a < p->nb_rx; a++) {
+    const int16_t *rx = rxdataF + 2 * ((size_t)a * 14 + p->symbol) * N;
+    int16_t *ul = ul_ch_est + 2 * ((size_t)a * 14 + p->symbol) * N;
+    for (int n = 0, m = 0; n < 12 * nb; n += 6, m += 2) {
+      int16_t c[2][2];
+      for (int kl = 0; kl < 2; kl++) {
+        const int re = (k0 + n + kl) % N;
+        const int32_t pr = pil[2 * (m + kl)], pi = pil[2 * (m + kl) + 1], yr = RX_AT(rx, re + nushift, 0), yi = RX_AT(rx, re + nushift, 1);
+        c[kl][0] = (int16_t)((pr * yr - pi * yi) >> 15);
+        c[kl][1] = (int16_t)((pr * yi + pi * yr) >> 15);
+      }
+      const int16_t cr = (int16_t)((c[0][0] + c[1][0]) >> 1), ci = (int16_t)((c[0][1] + c[1][1]) >> 1);
+      const int acr = cr < 0 ? -cr : cr, aci = ci < 0 ? -ci : ci;
+      if (acr > max_ch) max_ch = acr;
+      if (aci > max_ch) max_ch = aci;
+      const int16_t fr = wrap16((cr >> 2) << 2), fi = wrap16((ci >> 2) << 2);   /* mulhi_s1_int16(ch, 16384) */
+      for (int k = n; k < n + 4; k++) { ls[2 * k] = sat16((int32_t)ls[2 * k] + fr); ls[2 * k + 1] = sat16((int32_t)ls[2 * k + 1] + fi); }
+      for (int k = n + 4; k < n + 6; k++) { ls[2 * k] = cr; ls[2 * k + 1] = ci; }
+      const int16_t dr = (int16_t)(c[0][0] - cr), di = (int16_t)(c[0][1] - ci);
+      noise += (uint32_t)((int32_t)dr * dr + (int32_t)di * di);
+      nest++;
+    }
+    orc_dft(N, 1, ls, tim, 1);
+    for (int i = 0; i < N; i++) {
+      const int temp = (int)(((uint32_t)((int32_t)tim[2 * i] * tim[2 * i] + (int32_t)tim[2 * i + 1] * tim[2 * i + 1])) >> 1);
+      if (temp > max_val) { max_pos = i; max_val = temp; }
+    }
+    if (max_pos > N / 2) max_pos -= N;
+    int i_idx = 20 - max_pos; i_idx = i_idx < 0 ? 0 : i_idx > 40 ? 40 : i_idx;   /* get_delay_idx(-est_delay, MAX_DELAY_COMP) */
+    memset(ul, 0, 4 * (size_t)N);
+    for (int n = 0; n < 12 * nb; n++) {
+      const double ang = 2.0 * M_PI * (n % 6) * (i_idx - 20) / N;
+      const int16_t tr = (int16_t)round(256 * cos(ang)), ti = (int16_t)round(256 * sin(ang));
+      const int32_t lr = ls[2 * n], li = ls[2 * n + 1];
+      ul[2 * n] = (int16_t)((lr * tr - li * ti) >> 8); ul[2 * n + 1] = (int16_t)((lr * ti + li * tr) >> 8);
+    }
+  }
+  out[0] = max_ch; out[1] = nest > 0 ? (int32_t)(uint32_t)(noise / (uint64_t)nest) : 0; out[2] = max_pos; out[3] = max_pos; out[4] = max_val;
+  free(pil); free(ls); free(tim);
+  return 0;
+}
+
+/* ---- chest_freq == 1: one value per PRB, no delay estimation, no noise estimate (nr_ul_channel_estimation.c:285-343 type 1, :343-460
+ * type 2).  NO_INTERP is defined to 1 at the top of that file, so each PRB's 12 sub-carriers simply take the PRB's average.
+ * Type 1: average of the 6 pilot products (>> 15 each, 32-bit sum, C division by 6).  Type 2: (sum of 4 products) / 4, where, as the
+ * reference does, the first PRB uses its third pilot twice (the pointer is not advanced), so PRB j >= 1 correlates with pilots
+ * 4 j - 1 ... 4 j + 2; every access but the very first omits `soffset`, i.e. reads the slot-ring position 0 -- the restatement (and the
+ * product) therefore requires slot % 4 == 0 for type 2.  max_ch only sees the PRBs between the first and the last.  rb_size >= 2 (with one
+ * PRB the reference runs the "last PRB" code on a second, non-existent PRB). */
+static int chest_prb_average(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out)
+{
+  const int N = p->fft_size, nb = p->rb_size, nushift = (p->port >> 1) & 1, t2 = p->dmrs_type != 0;
+  const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
+  if (nb < 2 || (t2 && (p->slot & 3))) return -1;
+  int16_t *pil = malloc(4 * (size_t)(6 * nb));
+  orc_pusch_dmrs_pilots(p, pil);
+  int max_ch = 0;
+  for (int a = 0; a < p->nb_rx; a++) {
+    const int16_t *rx = rxdataF + 2 * ((size_t)a * 14 + p->symbol) * N;
+    int16_t *ul = ul_ch_est + 2 * ((size_t)a * 14 + p->symbol) * N;
+    memset(ul, 0, 4 * (size_t)N);
+    for (int j = 0; j < nb; j++) {
+      int32_t sr = 0, si = 0;
+      const int cnt = t2 ? 4 : 6;
+      for (int i = 0; i < cnt; i++) {
+        int pi_idx, re;
+        if (!t2) { pi_idx = 6 * j + i; re = (k0 + 12 * j + 2 * i) % N; }
+        else {
+          static const int off[4] = {0, 1, 6, 7};
+          pi_idx = j == 0 ? (i < 3 ? i : 2) : 4 * j - 1 + i;
+          re = (k0 + 12 * j + off[i]) % N;
+        }
+        const int32_t pr = pil[2 * pi_idx], pim = pil[2 * pi_idx + 1], yr = RX_AT(rx, re + nushift, 0), yi = RX_AT(rx, re + nushift, 1);
+        sr += (pr * yr - pim * yi) >> 15;
+        si += (pr * yi + pim * yr) >> 15;
+      }
+      const int16_t cr = (int16_t)(sr / cnt), ci = (int16_t)(si / cnt);
+      if (j > 0 && j < nb - 1) {
+        const int acr = cr < 0 ? -cr : cr, aci = ci < 0 ? -ci : ci;
+        if (acr > max_ch) max_ch = acr;
+        if (aci > max_ch) max_ch = aci;
+      }
+      for (int k = 12 * j; k < 12 * j + 12; k++) { ul[2 * k] = cr; ul[2 * k + 1] = ci; }
+    }
+  }
+  out[0] = max_ch; out[1] = 0; out[2] = 0; out[3] = 0; out[4] = 0;
+  free(pil);
   return 0;
 }
 

@@ -68,6 +68,8 @@ int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale);
 /* PUSCH channel estimation, DMRS type 1, frequency-domain interpolation (nrb200_chest_oracle.c) */
 typedef struct {
   int32_t fft_size, nb_rx, slot, symbol, port, rb_start, bwp_start, rb_size, first_carrier_offset, scid, dmrs_scrambling_id;
+  int32_t dmrs_type;    /* 0: DMRS configuration type 1, 1: type 2 (pusch_dmrs_type_t) */
+  int32_t chest_freq;   /* gNB->chest_freq: 0 = frequency-domain interpolation, 1 = one average per PRB */
 } orc_chest_t;
 void orc_pusch_dmrs_pilots(const orc_chest_t *p, int16_t *pil);
 int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);

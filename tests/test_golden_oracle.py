@@ -170,3 +170,15 @@ def test_dft_fourway_golden(oracle):
         N = int(N)
         assert np.array_equal(oracle.dft4(N, d[f"x{N}"], 1), d[f"y{N}_s1"]), N
         assert np.array_equal(oracle.dft4(N, d[f"x{N}"], 0), d[f"y{N}_s0"]), N
+
+
+def test_chest_variants_golden(oracle):
+    """DMRS type 2 and chest_freq = 1 estimators against vectors of the compiled reference (tools/gen_golden_chest_variants.py)."""
+    from oracle.bindings import ChestParms
+    g = _load("chest_variants.npz")
+    for i in range(int(g["n_cases"][0])):
+        P = ChestParms(*[int(x) for x in g[f"par{i}"]])
+        npil = g[f"pilots{i}"].size
+        assert np.array_equal(oracle.pusch_dmrs_pilots(P)[:npil], g[f"pilots{i}"]), i
+        est, st = oracle.pusch_channel_estimation(P, g["rx"])
+        assert np.array_equal(st, g[f"state{i}"]) and np.array_equal(est[:, P.symbol], g[f"est{i}"]), i

@@ -69,3 +69,65 @@ def test_pdsch_chest_ue_side_vs_oracle(ldpc, oracle):
         est_o = oracle.pdsch_channel_estimation(P, rx)
         assert np.array_equal(est[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port)
         assert st[0] == 0 and st[1] == 0
+
+
+VARIANT_CASES = [  # N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier PRBs, scid, dmrs id, delay
+    (4096, 4, 4, 2, 0, 0, 273, 273, 0, 77, 2), (2048, 2, 8, 3, 1, 10, 50, 106, 1, 1007, -3), (1024, 3, 0, 11, 2, 20, 32, 52, 0, 300, 5),
+    (1024, 2, 12, 2, 3, 0, 52, 52, 1, 0, 0), (512, 8, 16, 5, 0, 3, 11, 25, 0, 9, 1), (2048, 1, 4, 0, 0, 30, 2, 106, 0, 65535, 0),
+    (1024, 2, 8, 13, 3, 0, 52, 52, 0, 41, 1),      # last symbol of the slot, ports 2 / 3: the shifted pointer reaches the symbol's end
+]
+
+
+def _variant_input(rng, oracle, P, N, nb_rx, symbol, port, rb_start, fco, dmrs_type, delay):
+    if nb_rx == 8:
+        return rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    rx = rng.integers(-300, 301, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    npil = (4 if dmrs_type else 6) * P.rb_size
+    pil = oracle.pusch_dmrs_pilots(P).reshape(-1, 2).astype(np.float64)[:npil]
+    k0 = (rb_start * 12 + fco) % N
+    n = np.arange(npil)
+    idx = ((k0 + 2 * n) % N if dmrs_type == 0 else (k0 + 6 * (n // 2) + (n & 1)) % N) + ((port >> 1) & 1)
+    keep = idx < N
+    for a in range(nb_rx):
+        h = (2000 + 300 * a) * np.exp(1j * (0.4 * a - 2 * np.pi * delay * (idx - k0) / N))
+        y = h * (pil[:, 0] - 1j * pil[:, 1]) / 23170.0 / np.sqrt(2)
+        rx[a, symbol, idx[keep], 0] += np.round(y.real).astype(np.int16)[keep]; rx[a, symbol, idx[keep], 1] += np.round(y.imag).astype(np.int16)[keep]
+    return rx
+
+
+@pytest.mark.parametrize("dmrs_type,chest_freq", [(1, 0), (0, 1), (1, 1)])
+def test_pusch_chest_variants_vs_oracle(ldpc, oracle, dmrs_type, chest_freq):
+    """DMRS type 2 (frequency-domain) and the per-PRB averages of both DMRS types, host entry point and device-resident entry point."""
+    import torch
+    rng = np.random.default_rng(70 + 2 * dmrs_type + chest_freq)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay in VARIANT_CASES:
+        fco = N - carrier * 6
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, dmrs_type, chest_freq)
+        d = PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 1, 0, dmrs_type, chest_freq)
+        rx = _variant_input(rng, oracle, P, N, nb_rx, symbol, port, rb_start, fco, dmrs_type, delay)
+        est_o, out_o = oracle.pusch_channel_estimation(P, rx)
+        prev = rng.integers(-5, 6, size=rx.shape).astype(np.int16)
+        est, st = ldpc.pusch_chest_host(d, rx, prev.copy())
+        assert np.array_equal(st, out_o), (N, nb_rx, slot, symbol, port, st, out_o)
+        assert np.array_equal(est[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port)
+        other = [s for s in range(14) if s != symbol]
+        assert np.array_equal(est[:, other], prev[:, other])
+        # device-resident slot buffers
+        t_rx = torch.from_numpy(rx).cuda()
+        t_est = torch.from_numpy(prev.copy()).cuda()
+        scratch = torch.empty(ldpc.pusch_chest_scratch_bytes(d), dtype=torch.uint8, device="cuda")
+        state = torch.zeros(18, dtype=torch.int32, device="cuda")
+        ldpc.pusch_chest_torch(d, t_rx, t_est, scratch, state)
+        torch.cuda.synchronize()
+        assert np.array_equal(state[:5].cpu().numpy(), out_o) and np.array_equal(t_est.cpu().numpy()[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, "dev")
+
+
+def test_pusch_chest_variants_refuse_what_the_reference_cannot_do(ldpc):
+    from openairinterface5g_b200.ldpc import Nrb200Error
+    rx = np.zeros((2, 14, 512, 2), np.int16)
+    for kw in (dict(rb_size=1, chest_freq=1), dict(slot=5, dmrs_config_type=1, chest_freq=1), dict(n_ports=2, dmrs_config_type=1), dict(pdsch_ue=1, chest_freq=1)):
+        f = dict(fft_size=512, nb_rx=2, slot=4, symbol=2, port=0, rb_start=0, bwp_start=0, rb_size=20, first_carrier_offset=362, scid=0, ul_dmrs_scrambling_id=7,
+                 rx_stride=14 * 512, ch_stride=14 * 512, n_ports=1, pdsch_ue=0, dmrs_config_type=0, chest_freq=0)
+        f.update(kw)
+        with pytest.raises(Nrb200Error):
+            ldpc.pusch_chest_host(PuschChestDesc(**f), rx)

@@ -400,6 +400,43 @@ def test_pusch_channel_estimation(oracle, reference):
         assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
 
 
+CHEST_VARIANT_CASES = [  # N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier PRBs, scid, dmrs id, delay
+    (4096, 4, 4, 2, 0, 0, 273, 273, 0, 77, 2), (2048, 2, 8, 3, 1, 10, 50, 106, 1, 1007, -3), (1024, 3, 0, 11, 2, 20, 32, 52, 0, 300, 5),
+    (1024, 2, 12, 2, 3, 0, 52, 52, 1, 0, 0), (512, 8, 16, 5, 0, 3, 11, 25, 0, 9, 1), (2048, 1, 4, 0, 0, 30, 2, 106, 0, 65535, 0),
+]
+
+
+@pytest.mark.parametrize("dmrs_type,chest_freq", [(1, 0), (0, 1), (1, 1)])
+def test_pusch_channel_estimation_variants(oracle, reference, dmrs_type, chest_freq):
+    """DMRS type 2 with frequency-domain interpolation, and the one-average-per-PRB estimators (chest_freq = 1) of both DMRS types
+    (nr_ul_channel_estimation.c:258-460), against the compiled reference.  Type 2 + chest_freq = 1 reads slot-ring position 0 (a missing
+    `soffset`), so those cases use slots that are multiples of 4."""
+    from oracle.bindings import ChestParms
+    rng = np.random.default_rng(61 + 2 * dmrs_type + chest_freq)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay in CHEST_VARIANT_CASES:
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, scid, nid, dmrs_type, chest_freq)
+        big = nb_rx == 8
+        rx = rng.integers(-300, 301, size=(nb_rx, 14, N, 2)).astype(np.int16) if not big else rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        if not big:          # a delayed flat channel on the pilot REs so that the estimators see something coherent
+            pil = oracle.pusch_dmrs_pilots(P).reshape(-1, 2).astype(np.float64)
+            k0 = ((rb_start * 12) + P.first_carrier_offset) % N
+            npil = pil.shape[0]
+            if dmrs_type == 0:
+                idx = (k0 + 2 * np.arange(npil)) % N + ((port >> 1) & 1)
+            else:
+                idx = (k0 + 6 * (np.arange(npil) // 2) + (np.arange(npil) & 1)) % N + ((port >> 1) & 1)
+            for a in range(nb_rx):
+                h = (2000 + 300 * a) * np.exp(1j * (0.4 * a - 2 * np.pi * delay * (idx - k0) / N))
+                y = h * (pil[:, 0] - 1j * pil[:, 1]) / 23170.0 / np.sqrt(2)
+                rx[a, symbol, idx, 0] += np.round(y.real).astype(np.int16); rx[a, symbol, idx, 1] += np.round(y.imag).astype(np.int16)
+        est_r, out_r, pil_r = reference.pusch_channel_estimation(P, rx, carrier, chest_freq=chest_freq, dmrs_type=dmrs_type)
+        npil = (4 if dmrs_type else 6) * rb_size
+        assert np.array_equal(oracle.pusch_dmrs_pilots(P)[:2 * npil], pil_r[:2 * npil]), (N, slot, symbol, port, "pilots")
+        est_o, out_o = oracle.pusch_channel_estimation(P, rx)
+        assert np.array_equal(out_o, out_r), (N, nb_rx, slot, symbol, port, out_o, out_r)
+        assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
+
+
 def test_pusch_inner_rx_two_layers_mmse(oracle, reference):
     """nb_layer == 2, Qm >= 6: matched filter per layer + nr_ulsch_mmse_2layers + per-layer LLRs, through the reference's inner_rx."""
     from oracle.bindings import PuschParms

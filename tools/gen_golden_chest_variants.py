@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/chest_variants.npz from the UNMODIFIED reference nr_pusch_channel_estimation (oracle/_ref/libref_chest.so): DMRS type 2
+with frequency-domain interpolation and the per-PRB averages (chest_freq = 1) of both DMRS types.  Seeded inputs, outputs ONLY from the reference.
+Run where /root/reference exists; tests/test_golden_oracle.py pins the oracle to these vectors where it does not (the GPU box)."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.bindings import Reference, ChestParms  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "chest_variants.npz")
+
+
+def main():
+    ref = Reference()
+    rng = np.random.default_rng(2027)
+    g = {}
+    N, nrx, carrier = 512, 3, 25
+    rx = rng.integers(-4000, 4001, size=(nrx, 14, N, 2)).astype(np.int16)
+    g["rx"] = rx
+    cases = []
+    for i, (dmrs_type, chest_freq, slot, symbol, port, rb_start, rb_size) in enumerate(((1, 0, 7, 3, 0, 3, 20), (1, 0, 2, 11, 3, 0, 25), (0, 1, 5, 2, 2, 1, 22), (1, 1, 8, 4, 1, 0, 25))):
+        par = [N, nrx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, i & 1, 300 + i, dmrs_type, chest_freq]
+        est, out, pil = ref.pusch_channel_estimation(ChestParms(*par), rx, carrier, chest_freq=chest_freq, dmrs_type=dmrs_type)
+        g[f"par{i}"], g[f"est{i}"], g[f"state{i}"] = np.array(par, np.int32), est[:, symbol], out
+        g[f"pilots{i}"] = pil[:2 * (4 if dmrs_type else 6) * rb_size]
+        cases.append(i)
+    g["n_cases"] = np.array([len(cases)], np.int32)
+    np.savez_compressed(OUT, **g)
+    print(OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()
