@@ -52,7 +52,19 @@ def ncu_on_chip(n_cb, kernel_s, sm_mhz, sm_count=148):
         achieved = n_cb * per_cb / kernel_s / 1e9
         peak = sm_count * 4 * 0.5 * float(sm_mhz) * 1e6 / 1e9
         return {"bound": "alu_pipe", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
-                "alu_pipe_warp_inst_per_cb": per_cb, "ncu": {k: d[k] for k in ("alu_pipe_pct", "issue_active_pct", "fmaheavy_pipe_pct", "lsu_pipe_pct", "source") if k in d}}
+                "alu_pipe_warp_inst_per_cb": per_cb, "warp_inst_per_cb": d.get("warp_inst_per_launch", 0) / 1024.0, "ncu": {k: d[k] for k in ("alu_pipe_pct", "issue_active_pct", "fmaheavy_pipe_pct", "lsu_pipe_pct", "source") if k in d}}
+    except Exception:
+        return None
+
+
+def measured_mix_ceiling():
+    """tools/ubench/alu_ceiling (built by __graft_entry__.build()): warp instructions per cycle per scheduler this GPU sustains on the decoder's
+    opcode blend with nothing but the pipes in the way (no barriers, branches or dependent descriptor loads), and on LOP3 alone."""
+    exe = os.path.join(ROOT, "tools", "ubench", "_bin", "alu_ceiling")
+    if not os.path.exists(exe):
+        return None
+    try:
+        return json.loads(subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1])
     except Exception:
         return None
 
@@ -445,6 +457,10 @@ def run_b200(args, rank, world, local_rank):
         }
         oc = ncu_on_chip(B, kernel_s, line["clocks"].get("sm_mhz") or 1965.0)
         if oc is not None:
+            ub = measured_mix_ceiling() if world == 1 else None
+            if ub and "decoder_mix_ipc_per_scheduler" in ub and oc.get("warp_inst_per_cb"):
+                ipc = B * oc["warp_inst_per_cb"] / kernel_s / (148 * 4 * float(line["clocks"].get("sm_mhz") or 1965.0) * 1e6)
+                oc["micro_benchmark"] = dict(ub, decoder_ipc_per_scheduler=ipc, frac_of_measured_mix_ceiling=ipc / ub["decoder_mix_ipc_per_scheduler"])
             line["roofline"]["on_chip"] = oc
         if cpu is not None:
             line["cpu_baseline"] = cpu

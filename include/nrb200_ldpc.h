@@ -156,6 +156,12 @@ int32_t nrb200_ldpc_decode_batch_host_submit(const nrb200_ldpc_batch_desc_t *des
                                              void **ticket);
 int32_t nrb200_ldpc_decode_batch_host_wait(void *ticket);
 
+/* Host arithmetic only (no GPU needed): the work schedule of the packed decoder kernel for (BG, Z, R) with at most max_threads threads per CTA.
+ * info (8 int32): threads per CTA, number of work lists, 1 if a list belongs to a warp (items = 32 words of a row or column) / 0 if to a bin of
+ * Z / 4 threads (items = whole rows or columns), heaviest and mean check-node list, heaviest and mean bit-node list (modelled warp instructions),
+ * 1 if every item appears exactly once.  Returns 0, or -4 when the packed kernel does not serve the configuration (Z not a multiple of 4). */
+int32_t nrb200_ldpc_packed_schedule_info(int BG, int Z, int R, int max_threads, int32_t *info);
+
 /* Batch encode: in = n_cb x K/8 packed bytes (stride in_stride), out = n_cb x (66Z|50Z) bytes, one bit per byte
  * (stride out_stride).  Same output as LDPCencoder per block. */
 int32_t nrb200_ldpc_encode_batch_dev(int BG, int Z, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,

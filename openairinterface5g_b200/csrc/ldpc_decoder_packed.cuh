@@ -44,7 +44,8 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
   const uint32_t e0 = row.e0_deg & 0xFFFu;
   const uint32_t rb = row.rbase + kb;
   uint32_t q[D];
-  uint32_t min1 = kL7, min2 = kL7, sgn = 0u, synd = (D & 1) ? kH : 0u;   // sign(A) < 0 <=> bit 7 of A' clear
+  uint32_t sgn = 0u, synd = (D & 1) ? kH : 0u;                           // sign(A) < 0 <=> bit 7 of A' clear
+  TwoMin tm = twomin_init();
   uint32_t aprev = 0u, qprev = 0u;
 #pragma unroll
   for (int j = 0; j < D; j++) {
@@ -60,7 +61,7 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
     }
     aprev = aw;
     qprev = q[j];
-    twomin(mag, min1, min2);
+    twomin(mag, tm, one, mone);
   }
   if (D & 1) { synd ^= aprev; sgn ^= qprev; }
   if (row.lrow != 0xFFFFFFFFu) {                                           // degree-1 neighbour: Q is the channel LLR forever
@@ -68,8 +69,8 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
     const uint32_t qsm = lds(smb, pa + ZB);                              // precomputed sign-magnitude of the channel LLR
     synd ^= lds(smb, pa);                                                  // sign(llr + R_p) of the previous iteration
     sgn ^= qsm;
-    twomin(qsm & kL7, min1, min2);
-    uint32_t rp = make_r(qsm, min1, min1 | kH, min2 | kH, sgn, one, mone);
+    twomin(qsm & kL7, tm, one, mone);
+    uint32_t rp = make_r(qsm, tm.n1, twomin_min1(tm, mone) | kH, twomin_min2(tm, mone) | kH, sgn, one, mone);
     if (QUIRK) rp = (rp & ~quirk_zero) | (kH & quirk_zero);
     // adds_epi8(llr, R_p) < 0  <=>  L' + R' < 256  <=>  no carry out of the byte
     const uint32_t lp = lds(smb, pa + 2 * ZB);                           // the neighbour's channel LLR + 128, already rotated
@@ -77,10 +78,10 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
     sts(smb, pa, lop3<kLutMajNot>(lp, rp, x) & kH);
   }
   if (!first_iter && (kb >> 2) < (row.prow_pcw >> 24)) bad |= synd & kH;
-  const uint32_t p1 = min1 | kH, p2 = min2 | kH;
+  const uint32_t p1 = twomin_min1(tm, mone) | kH, p2 = twomin_min2(tm, mone) | kH;
 #pragma unroll
   for (int j = 0; j < D; j++) {
-    uint32_t rn = make_r(q[j], min1, p1, p2, sgn, one, mone);
+    uint32_t rn = make_r(q[j], tm.n1, p1, p2, sgn, one, mone);
     if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
     sts(smb, rb + j * RSB, rn);
     if (halo) sts(smb, rb + j * RSB + ZB, rn);
@@ -115,13 +116,13 @@ __device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int
 
 // one bit-node edge: fetch the rotated R' word and add its four bytes to the four running sums (IDP.4A, FMA pipe)
 template <int ZWC>
-__device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__restrict__ smb, int i, uint32_t kb, uint32_t kbs, uint32_t &s0, uint32_t &s1,
+__device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__restrict__ smb, int i, uint32_t kb, uint32_t &s0, uint32_t &s1,
                                         uint32_t &s2, uint32_t &s3)
 {
-  const uint2 d = *reinterpret_cast<const uint2 *>(G.bn_desc[i]);
-  uint32_t a = kb + d.x;
-  if (kbs < d.y) a += geo_zb<ZWC>(G);                                                 // circular wrap of v - s
-  const uint32_t rw = __funnelshift_r(lds(smb, a), lds(smb, a + 4), d.y);
+  const uint4 d = *reinterpret_cast<const uint4 *>(G.bn_desc[i]);
+  const uint32_t x = add_fma(kb, d.x, G.one);                                // kb - 4 qq
+  const uint32_t a = add_fma(__viaddmin_u32(x, geo_zb<ZWC>(G), x), d.y, G.one);   // circular wrap of v - s, then the row's base
+  const uint32_t rw = __funnelshift_r(lds(smb, a), lds(smb, a + 4), d.z);
   s0 = __dp4a(rw, 0x00000001u, s0);
   s1 = __dp4a(rw, 0x00000100u, s1);
   s2 = __dp4a(rw, 0x00010000u, s2);
@@ -130,15 +131,15 @@ __device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__rest
 
 // A' = clamp(L' + sum R' - 128*deg, 0, 255) for column c, word k   (packs_epi16 of the int16 sum, in offset binary)
 template <int ZWC>
-__device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ smb, int c, uint32_t kb, uint32_t kbs)
+__device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ smb, int c, uint32_t kb)
 {
   const uint32_t ZB = geo_zb<ZWC>(G);
   const uint32_t lw = lds(smb, G.off_L + c * geo_rsb<ZWC>(G) + kb);
-  uint32_t s0 = lw & 0xFFu, s1 = (lw >> 8) & 0xFFu, s2 = (lw >> 16) & 0xFFu, s3 = lw >> 24;
+  uint32_t s0 = __dp4a(lw, 0x00000001u, 0u), s1 = __dp4a(lw, 0x00000100u, 0u), s2 = __dp4a(lw, 0x00010000u, 0u), s3 = __dp4a(lw, 0x01000000u, 0u);
   int i = G.col_start[c];
   const int i1 = G.col_start[c + 1];
-  for (; i + 2 <= i1; i += 2) { bn_edge<ZWC>(G, smb, i, kb, kbs, s0, s1, s2, s3); bn_edge<ZWC>(G, smb, i + 1, kb, kbs, s0, s1, s2, s3); }
-  if (i < i1) bn_edge<ZWC>(G, smb, i, kb, kbs, s0, s1, s2, s3);
+  for (; i + 2 <= i1; i += 2) { bn_edge<ZWC>(G, smb, i, kb, s0, s1, s2, s3); bn_edge<ZWC>(G, smb, i + 1, kb, s0, s1, s2, s3); }
+  if (i < i1) bn_edge<ZWC>(G, smb, i, kb, s0, s1, s2, s3);
   const uint32_t nb = G.col_negbias[c];
   const uint32_t lo = __vmins2(__viaddmax_s16x2(prmt(s0, s1, 0x5410u), nb, 0u), 0x00ff00ffu);
   const uint32_t hi = __vmins2(__viaddmax_s16x2(prmt(s2, s3, 0x5410u), nb, 0u), 0x00ff00ffu);
@@ -217,11 +218,12 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
     reinterpret_cast<int *>(&G)[i] = reinterpret_cast<const int *>(gdev)[i];
   __syncthreads();
   const int Zw = geo_zw<ZWC>(G);
-  const int bin = threadIdx.x / Zw, kw = threadIdx.x - bin * Zw;
-  const uint32_t kb = 4u * (uint32_t)kw;
-  const uint32_t kbs = (kb << 8) | 0xFFu;
+  // work lists (ldpc_packed_graph.h): one per bin of Zw threads (item = a whole row / column, this thread's word fixed), or one per warp
+  // (item = 32 words of a row / column: item >> 8 selects which)
+  const bool witems = G.warp_items != 0;
+  const int bin = witems ? (int)(threadIdx.x >> 5) : (int)threadIdx.x / Zw;
+  const uint32_t kb0 = witems ? 4u * (threadIdx.x & 31u) : 4u * (uint32_t)((int)threadIdx.x - bin * Zw);
   const bool worker = bin < G.nbins;
-  const bool halo = kw == 0;
   const bool quirks = (a.quirks & 1) != 0;
 
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
@@ -272,15 +274,23 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       // CN phase of iteration numIter+1 (also yields the syndrome of iteration numIter when numIter >= 2)
       uint32_t bad = 0;
       if (worker) {
-        if (!quirks) for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<ZWC, false>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
-        else for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) cn_dispatch<ZWC, true>(G, smb, G.cn_bin_rows[i], kb, halo, numIter == 0, bad);
+        for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) {
+          const int it = G.cn_bin_rows[i];
+          const uint32_t kb = kb0 + 128u * (uint32_t)(it >> 8);
+          if (!quirks) cn_dispatch<ZWC, false>(G, smb, it & 0xFF, kb, kb == 0u, numIter == 0, bad);
+          else cn_dispatch<ZWC, true>(G, smb, it & 0xFF, kb, kb == 0u, numIter == 0, bad);
+        }
       }
       const int pcRes = __syncthreads_or(bad != 0);   // also the CN->BN barrier
       if (numIter >= 2 && !a.use_crc && pcRes == 0) break;          // iteration numIter passed its parity check (:552)
       numIter++;
       // BN phase
       if (worker)
-        for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) bn_col<ZWC>(G, smb, G.bn_bin_cols[i], kb, kbs);
+        for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) {
+          const int it = G.bn_bin_cols[i];
+          const uint32_t kb = kb0 + 128u * (uint32_t)(it >> 8);
+          bn_col<ZWC>(G, smb, it & 0xFF, kb);
+        }
       __syncthreads();
       // loop control, mirroring `while (numIter <= numMaxIter && pcRes != 0)` evaluated before each further iteration
       if (numIter == 1) {

@@ -19,6 +19,51 @@ static void lpt(const std::vector<std::pair<int, int>> &items /* (weight, id) */
     bins[b].push_back(it.second);
     load[b] += it.first;
   }
+  // LPT leaves the heaviest list up to ~10 % above the mean here (identical chunks of a row land in lockstep); refine by moving an item
+  // off the heaviest list, or swapping it against a lighter item of another list, while that lowers the pair's maximum.
+  std::vector<int> w(1 << 16, 0);
+  for (auto &it : s) w[(size_t)it.second & 0xFFFF] = it.first;
+  for (int round = 0; round < 4000; round++) {
+    int a = 0;
+    for (int i = 1; i < nbins; i++) if (load[i] > load[a]) a = i;
+    bool improved = false;
+    for (int b = 0; b < nbins && !improved; b++) {
+      if (b == a) continue;
+      const int pair_max = load[a];
+      for (size_t i = 0; i < bins[a].size() && !improved; i++) {
+        const int wi = w[(size_t)bins[a][i] & 0xFFFF];
+        if (std::max(load[a] - wi, load[b] + wi) < pair_max) {              // move
+          load[a] -= wi; load[b] += wi;
+          bins[b].push_back(bins[a][i]); bins[a].erase(bins[a].begin() + (long)i);
+          improved = true;
+          break;
+        }
+        for (size_t j = 0; j < bins[b].size(); j++) {                       // swap
+          const int wj = w[(size_t)bins[b][j] & 0xFFFF];
+          if (wj < wi && std::max(load[a] - wi + wj, load[b] + wi - wj) < pair_max) {
+            load[a] += wj - wi; load[b] += wi - wj;
+            std::swap(bins[a][i], bins[b][j]);
+            improved = true;
+            break;
+          }
+          for (size_t k = j + 1; k < bins[b].size(); k++) {                 // one item against two lighter ones
+            const int wjk = wj + w[(size_t)bins[b][k] & 0xFFFF];
+            if (wjk < wi && std::max(load[a] - wi + wjk, load[b] + wi - wjk) < pair_max) {
+              load[a] += wjk - wi; load[b] += wi - wjk;
+              const int x = bins[a][i], y = bins[b][j], z = bins[b][k];
+              bins[a][i] = y; bins[a].push_back(z);
+              bins[b].erase(bins[b].begin() + (long)k); bins[b][j] = x;
+              improved = true;
+              break;
+            }
+          }
+          if (improved) break;
+        }
+      }
+    }
+    if (!improved) break;
+  }
+  for (auto &bl : bins) std::stable_sort(bl.begin(), bl.end(), [&](int x, int y) { return w[(size_t)x & 0xFFFF] > w[(size_t)y & 0xFFFF]; });
   int n = 0;
   for (int b = 0; b < nbins; b++) {
     bin_start[b] = (int16_t)n;
@@ -77,20 +122,37 @@ bool build_packed_graph(const GraphDev &g, PackedGraph *p, int max_threads)
   for (int i = 0; i < g.nreal; i++) {
     const int m = g.col_edges[i], s = g.edge_shift[m], q = s / 4, rho = s % 4;
     const int qq4 = 4 * (q + (rho ? 1 : 0));
-    const uint32_t base_minus = (uint32_t)(p->off_R + m * p->RSB - qq4);   // off_R > 4*(Zw+1) always (A region precedes)
-    p->bn_desc[i][0] = base_minus;
-    p->bn_desc[i][1] = ((uint32_t)qq4 << 8) | (uint32_t)(8 * ((4 - rho) & 3));
+    p->bn_desc[i][0] = (uint32_t)(-qq4);
+    p->bn_desc[i][1] = (uint32_t)(p->off_R + m * p->RSB);
+    p->bn_desc[i][2] = (uint32_t)(8 * ((4 - rho) & 3));
+    p->bn_desc[i][3] = 0u;
   }
-  // thread geometry: bins of Zw threads
-  int nbins = max_threads / p->Zw;
-  nbins = std::max(1, std::min(nbins, std::min(kMaxBins, g.nrows)));
-  p->nbins = nbins;
-  p->nthreads = std::min(max_threads, std::max(32, ((nbins * p->Zw + 31) / 32) * 32));
+  // thread geometry.  Costs are warp instructions per item measured on the Z = 384 kernel (profiles/r01n_*): a row costs 18 (dispatch) +
+  // 32 per stored edge + 51 with a degree-1 neighbour (11 without); a column 65 + 13.5 per edge.
+  auto row_cost = [&](int r) { return 2 * (18 + 32 * (g.row_start[r + 1] - g.row_start[r]) + (g.row_p_col[r] >= 0 ? 51 : 11)); };
+  auto col_cost = [&](int c) { return 130 + 27 * g.col_deg[c]; };
   std::vector<std::pair<int, int>> rows, cols;
-  for (int r = 0; r < g.nrows; r++) rows.push_back({3 * (g.row_start[r + 1] - g.row_start[r]) + (g.row_p_col[r] >= 0 ? 3 : 0) + 2, r});
-  for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) cols.push_back({g.col_deg[c] + 1, c});
-  lpt(rows, nbins, p->cn_bin_start, p->cn_bin_rows);
-  lpt(cols, nbins, p->bn_bin_start, p->bn_bin_cols);
+  if (p->Zw % 32 == 0 && max_threads >= 32) {
+    // work item = 32 words of one row / column, one list per warp
+    const int chunks = p->Zw / 32;
+    int nwarps = std::min(max_threads / 32, kMaxBins);
+    nwarps = std::max(1, std::min(nwarps, g.nrows * chunks));
+    p->warp_items = 1;
+    p->nbins = nwarps;
+    p->nthreads = 32 * nwarps;
+    for (int r = 0; r < g.nrows; r++) for (int k = 0; k < chunks; k++) rows.push_back({row_cost(r), r | (k << 8)});
+    for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) for (int k = 0; k < chunks; k++) cols.push_back({col_cost(c), c | (k << 8)});
+  } else {
+    // bins of Zw threads owning whole rows / columns
+    int nbins = max_threads / p->Zw;
+    nbins = std::max(1, std::min(nbins, std::min(kMaxBins, g.nrows)));
+    p->nbins = nbins;
+    p->nthreads = std::min(max_threads, std::max(32, ((nbins * p->Zw + 31) / 32) * 32));
+    for (int r = 0; r < g.nrows; r++) rows.push_back({row_cost(r), r});
+    for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) cols.push_back({col_cost(c), c});
+  }
+  lpt(rows, p->nbins, p->cn_bin_start, p->cn_bin_rows);
+  lpt(cols, p->nbins, p->bn_bin_start, p->bn_bin_cols);
   return true;
 }
 

@@ -7,7 +7,7 @@ namespace nrb200 {
 
 constexpr int kPackedMaxThreads = 768;       // launch bound of the generic instantiation
 constexpr int kPackedMaxThreadsZ384 = 960;   // Z = 384 instantiations exist for 768 / 864 / 960 threads (8 / 9 / 10 bins of 96)
-constexpr int kMaxBins = 24;
+constexpr int kMaxBins = 32;                 // work lists: bins of Zw threads, or single warps (see PackedGraph::warp_items)
 
 // Per check row, one 16-byte record (read with a single LDS.128).
 struct PackedRow {
@@ -27,11 +27,14 @@ struct PackedGraph {
   int32_t Z, Zw, ZB, RSB;            // lifts, words per row, 4*Zw, R/L row stride in bytes
   int32_t ncols, nrows, nreal, ncolA, nrowP;
   int32_t off_A, off_R, off_L, off_P, total_bytes;
-  int32_t nbins, nthreads;           // thread t works for bin t / Zw on word t % Zw; bins own whole rows / columns
+  int32_t nbins, nthreads;           // warp_items == 0: thread t works for bin t / Zw on word t % Zw; bins own whole rows / columns
+  int32_t warp_items;                // 1 (Zw a multiple of 32): a work item is 32 words of a row / column, every WARP owns a list of items --
+                                     //   138 + 78 items on 24 warps for BG1 Z = 384 balance to ~1 % where 46 rows on 8 bins leave ~9 % at the barriers
+  // list l = items cn_bin_start[l] .. cn_bin_start[l + 1]; item = row (column) | chunk << 8, chunk = which 32 words of the row
   int16_t cn_bin_start[kMaxBins + 1];
-  int16_t cn_bin_rows[kMaxRows];
+  int16_t cn_bin_rows[3 * kMaxRows];
   int16_t bn_bin_start[kMaxBins + 1];
-  int16_t bn_bin_cols[kMaxCols];
+  int16_t bn_bin_cols[3 * kMaxCols];
   int16_t row_p_q[kMaxRows], row_p_rho[kMaxRows];   // rotation of the degree-1 neighbour (0 for every NR base graph)
   int16_t col_start[kMaxCols + 1];
   int16_t col_arow[kMaxCols];        // row of column c inside the A region, -1 for degree-1 columns
@@ -39,9 +42,10 @@ struct PackedGraph {
   alignas(16) PackedRow rows[kMaxRows];
   // per slot, CN side: .x = byte offset of A row + 4*(shift / 4), .y = 8*(shift % 4) (funnel amount)
   alignas(8) uint32_t cn_desc[kMaxEdges][2];
-  // per column-edge entry, BN side: .x = byte offset of R row - 4*qq, .y = (4*qq << 8) | 8*((4 - shift%4) & 3)
-  // (.y is compared against (kb << 8) | 0xFF for the circular wrap and used as-is as the funnel amount: only bits[4:0] count)
-  alignas(8) uint32_t bn_desc[kMaxEdges][2];
+  // per column-edge entry, BN side (one LDS.128): .x = -4*qq (the word offset of lift v - s before the circular wrap, as a 32-bit two's
+  // complement), .y = byte offset of the R row, .z = funnel amount 8*((4 - shift%4) & 3), .w unused.  The wrap is one unsigned
+  // min(x, x + ZB) on x = kb - 4*qq (VIADDMNMX): a negative x is huge as unsigned, x + ZB is then the wrapped offset.
+  alignas(16) uint32_t bn_desc[kMaxEdges][4];
   uint32_t one;                      // == 1, read at run time so that selected adds are emitted as IMAD (FMA pipe), see DESIGN.md
 };
 

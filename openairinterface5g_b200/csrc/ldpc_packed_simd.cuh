@@ -97,21 +97,31 @@ NRB200_SIMD void cn_input(uint32_t aw, uint32_t ro, uint32_t mone, uint32_t &mag
   qsm = lop3<kLutOrBandC>(mag, lop3<kLutBorrow>(aw, ro, diff), kH);
 }
 
-// one exclude-self two-minimum step on 7-bit magnitudes (a + 128 - b never borrows across bytes: bit 7 <=> a >= b)
-NRB200_SIMD void twomin(uint32_t mag, uint32_t &min1, uint32_t &min2)
+// Exclude-self two-minimum tracking on 7-bit magnitudes, state kept NEGATED so that every compare is one multiply-add on the FMA pipe
+// (the ALU pipe is the decoder's limiter, the FMA pipe idles):
+//   n1  = 0x7f - min1            n2p = 0x7f - min2 + 0x7f          (bytes 0..127 / 127..254: no byte ever carries or borrows)
+//   mag > min1  <=>  bit 7 of mag + n1;       max(mag, min1) > min2  <=>  bit 7 of n2p - (0x7f - max(mag, min1))
+// Strict compares are enough: on a tie both orders give the same minimum and the same runner-up.
+struct TwoMin { uint32_t n1, n2p; };
+NRB200_SIMD TwoMin twomin_init() { return TwoMin{0u, kL7}; }                  // min1 = min2 = 127
+NRB200_SIMD void twomin(uint32_t mag, TwoMin &s, uint32_t one, uint32_t mone)
 {
-  const uint32_t m1 = msb_mask(mag + kH - min1);   // mag >= min1
-  const uint32_t t = sel4(m1, mag, min1);          // max(mag, min1)
-  min1 = sel4(m1, min1, mag);
-  min2 = sel4(msb_mask(t + kH - min2), min2, t);
+  const uint32_t nmag = add_fma(mag, kL7, mone);               // 0x7f - mag
+  const uint32_t m1 = msb_mask(add_fma(mag, s.n1, one));       // mag > min1
+  const uint32_t nt = sel4(m1, nmag, s.n1);                    // 0x7f - max(mag, min1)
+  s.n1 = sel4(m1, s.n1, nmag);
+  const uint32_t m2 = msb_mask(add_fma(nt, s.n2p, mone));      // max(mag, min1) > min2
+  s.n2p = sel4(m2, s.n2p, add_fma(nt, kL7, one));
 }
+NRB200_SIMD uint32_t twomin_min1(const TwoMin &s, uint32_t mone) { return add_fma(s.n1, kL7, mone); }
+NRB200_SIMD uint32_t twomin_min2(const TwoMin &s, uint32_t mone) { return add_fma(s.n2p, 0xFEFEFEFEu, mone); }
 
 // offset-binary cn->bn message (R + 128) of one edge from the row's two minima and sign product (bit 7 = negative).
-// p1 = min1 | 0x80, p2 = min2 | 0x80 are formed once per row; the negative message 128 - mag is the per-byte two's complement of
-// 128 + mag, one multiply-add on the FMA pipe (kNegC); -0 comes out as 0x80 like +0.
-NRB200_SIMD uint32_t make_r(uint32_t qsm, uint32_t min1, uint32_t p1, uint32_t p2, uint32_t sgn, uint32_t one, uint32_t mone)
+// p1 = min1 | 0x80, p2 = min2 | 0x80 are formed once per row; |Q| >= min1 always, so |Q| != min1 <=> bit 7 of |Q| + n1; the negative
+// message 128 - mag is the per-byte two's complement of 128 + mag, one multiply-add on the FMA pipe (kNegC); -0 comes out as 0x80 like +0.
+NRB200_SIMD uint32_t make_r(uint32_t qsm, uint32_t n1, uint32_t p1, uint32_t p2, uint32_t sgn, uint32_t one, uint32_t mone)
 {
-  const uint32_t ne = msb_mask(add_fma(lop3<kLutXorAnd>(qsm, min1, kL7), kL7, one));   // 0xFF where |Q| != min1
+  const uint32_t ne = msb_mask(add_fma(qsm & kL7, n1, one));                            // 0xFF where |Q| != min1
   const uint32_t x = sel4(ne, p1, p2);                                                  // 128 + excluded minimum
   const uint32_t n = msb_mask(sgn ^ qsm);                                               // 0xFF where the other signs multiply to -1
   return sel4(n, add_fma(x, kNegC, mone), x);

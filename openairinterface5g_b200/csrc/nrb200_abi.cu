@@ -1,6 +1,7 @@
 // C ABI of libldpc_b200.so (include/nrb200_ldpc.h): the four OAI loader symbols plus the batched extension.
 #include "../../include/nrb200_ldpc.h"
 #include "nrb200_ctx.h"
+#include "ldpc_packed_graph.h"
 #include "ldpc_common.cuh"
 #include <algorithm>
 #include <cstring>
@@ -217,6 +218,50 @@ NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_host_wait(void *ticket)
 {
   if (!ticket) return -4;
   return decode_finish((DecodeTicket *)ticket);
+}
+
+// Host arithmetic only (no GPU): the packed decoder's work schedule for (BG, Z, R) with at most max_threads threads, for inspection and the
+// CPU tests.  info[0] = threads per CTA, [1] = work lists, [2] = 1 when a list belongs to a warp (items of 32 words) and 0 when to a bin of
+// Z / 4 threads (whole rows), [3] / [4] = heaviest / mean check-node list (modelled warp instructions), [5] / [6] = same for the bit-node
+// lists, [7] = 1 when every (row, chunk) and every (column of degree >= 2, chunk) appears in exactly one list.  Returns 0, -4 if the packed
+// kernel does not serve this configuration.
+NRB200_EXPORT int32_t nrb200_ldpc_packed_schedule_info(int BG, int Z, int R, int max_threads, int32_t *info)
+{
+  GraphDev *g = new GraphDev();
+  PackedGraph *p = new PackedGraph();
+  int rc = -4;
+  if (info && build_graph(BG, Z, R, g) && build_packed_graph(*g, p, max_threads)) {
+    const int chunks = p->warp_items ? p->Zw / 32 : 1;
+    auto audit = [&](const int16_t *start, const int16_t *items, bool rows, int32_t *mx, int32_t *mean) {
+      std::vector<int> seen((size_t)256 * 4, 0);
+      long total = 0, worst = 0;
+      for (int l = 0; l < p->nbins; l++) {
+        long load = 0;
+        for (int i = start[l]; i < start[l + 1]; i++) {
+          const int id = items[i] & 0xFF, k = items[i] >> 8;
+          seen[(size_t)id * 4 + k]++;
+          load += rows ? 18 + 32 * (g->row_start[id + 1] - g->row_start[id]) + (g->row_p_col[id] >= 0 ? 51 : 11) : 65 + (27 * g->col_deg[id]) / 2;
+        }
+        total += load; worst = std::max(worst, load);
+      }
+      *mx = (int32_t)worst; *mean = (int32_t)(total / p->nbins);
+      bool ok = true;
+      const int n = rows ? g->nrows : g->ncols;
+      for (int id = 0; id < n; id++)
+        for (int k = 0; k < 4; k++) {
+          const bool want = k < chunks && (rows || g->col_deg[id] >= 2);
+          if (seen[(size_t)id * 4 + k] != (want ? 1 : 0)) ok = false;
+        }
+      return ok;
+    };
+    info[0] = p->nthreads; info[1] = p->nbins; info[2] = p->warp_items;
+    const bool ok_cn = audit(p->cn_bin_start, p->cn_bin_rows, true, info + 3, info + 4);
+    const bool ok_bn = audit(p->bn_bin_start, p->bn_bin_cols, false, info + 5, info + 6);
+    info[7] = ok_cn && ok_bn ? 1 : 0;
+    rc = 0;
+  }
+  delete g; delete p;
+  return rc;
 }
 
 NRB200_EXPORT int32_t nrb200_device_index(void) { return ctx().inited ? ctx().dev : -1; }

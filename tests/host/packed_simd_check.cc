@@ -54,17 +54,25 @@ int main()
           }
         }
         // the kernel's sequence (cn_row): inputs in pairs, three-input XORs for the sign product
-        uint32_t min1 = kL7, min2 = kL7, sgn = 0u, qprev = 0u;
+        uint32_t sgn = 0u, qprev = 0u;
+        TwoMin tm = twomin_init();
         for (int j = 0; j < D; j++) {
           uint32_t mag;
           cn_input(aw[j], ro[j], mone, mag, q[j]);
           if (j & 1) sgn = lop3<kLutXor3>(sgn, qprev, q[j]);
           qprev = q[j];
-          twomin(mag, min1, min2);
+          twomin(mag, tm, one, mone);
         }
         if (D & 1) sgn ^= qprev;
-        const uint32_t p1 = min1 | kH, p2 = min2 | kH;
-        for (int j = 0; j < D; j++) rn[j] = make_r(q[j], min1, p1, p2, sgn, one, mone);
+        const uint32_t p1 = twomin_min1(tm, mone) | kH, p2 = twomin_min2(tm, mone) | kH;
+        for (int j = 0; j < D; j++) rn[j] = make_r(q[j], tm.n1, p1, p2, sgn, one, mone);
+        {   // the tracked minima themselves
+          for (int b = 0; b < 4; b++) {
+            int m1 = 127, m2 = 127;
+            for (int k = 0; k < D; k++) { int a = std::abs(Q[k][b]); if (a > 127) a = 127; if (a < m1) { m2 = m1; m1 = a; } else if (a < m2) m2 = a; }
+            CHECK((int)((twomin_min1(tm, mone) >> (8 * b)) & 0xFF) == m1 && (int)((twomin_min2(tm, mone) >> (8 * b)) & 0xFF) == m2, "two minima D %d", D);
+          }
+        }
         for (int j = 0; j < D; j++)
           for (int b = 0; b < 4; b++) {
             int mn = 127, sg = 1;

@@ -83,3 +83,23 @@ def test_offload_flavour_exports_the_loader_symbols():
     lib = OffloadLdpcLib(init=False).lib
     for name in ("LDPCinit", "LDPCshutdown", "LDPCdecoder", "LDPCencoder"):
         assert getattr(lib, name) is not None
+
+
+def test_packed_decoder_schedule_covers_every_item_and_balances():
+    """Host arithmetic of the packed decoder's work lists (nrb200_ldpc_packed_schedule_info, no GPU): every (row, chunk) and (column, chunk) is
+    owned by exactly one list for every lifting size the packed kernel serves, and the headline configurations balance to a few per cent."""
+    import numpy as np
+    lib = ctypes.CDLL(os.path.join(ROOT, "openairinterface5g_b200", "libldpc_b200.so"))
+    info = np.zeros(8, np.int32)
+    zs = [z for z in (2, 3, 5, 7, 9, 11, 13, 15) for z in [z * (1 << j) for j in range(8)] if z <= 384 and z % 4 == 0]
+    for BG, rates in ((1, (13, 23, 89)), (2, (15, 13, 23))):
+        for R in rates:
+            for Z in sorted(set(zs)):
+                for t in (768, 256):
+                    assert lib.nrb200_ldpc_packed_schedule_info(BG, Z, R, t, info.ctypes.data_as(ctypes.c_void_p)) == 0, (BG, Z, R, t)
+                    assert info[7] == 1 and info[0] <= t and info[0] % 32 == 0, (BG, Z, R, t, info)
+                    assert info[2] == (1 if (Z // 4) % 32 == 0 else 0)
+    assert lib.nrb200_ldpc_packed_schedule_info(1, 6, 13, 768, info.ctypes.data_as(ctypes.c_void_p)) == -4       # generic kernel's territory
+    for BG, Z, R, t in ((1, 384, 13, 768), (1, 384, 13, 960), (1, 384, 23, 768)):
+        lib.nrb200_ldpc_packed_schedule_info(BG, Z, R, t, info.ctypes.data_as(ctypes.c_void_p))
+        assert info[3] <= 1.06 * info[4] and info[5] <= 1.06 * info[6], (BG, Z, R, t, info)
