@@ -62,7 +62,7 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
     // Z = 384 (K = 8448, both headline workloads) runs an instantiation with the row geometry as immediates
     void (*kern)(const PackedGraph *, DecodeArgs) = ldpc_decode_packed_kernel<0, kPackedMaxThreads>;
     int variant = 0;
-    if (h_pg->Zw == 96) {
+    if (h_pg->Zw == 96 && !(a.quirks & 1)) {
       if (h_pg->nthreads > 864) { kern = ldpc_decode_packed_kernel<96, 960>; variant = 3; }
       else if (h_pg->nthreads > 768) { kern = ldpc_decode_packed_kernel<96, 864>; variant = 2; }
       else { kern = ldpc_decode_packed_kernel<96, 768>; variant = 1; }

@@ -35,6 +35,29 @@ template <int ZWC> __device__ __forceinline__ int geo_zw(const PackedGraph &G) {
 template <int ZWC> __device__ __forceinline__ uint32_t geo_zb(const PackedGraph &G) { return ZWC ? 4u * ZWC : (uint32_t)G.ZB; }
 template <int ZWC> __device__ __forceinline__ uint32_t geo_rsb(const PackedGraph &G) { return ZWC ? 4u * (ZWC + 4) : (uint32_t)G.RSB; }
 
+// the row's degree-1 neighbour (extension parity column, no stored message: its Q is the channel LLR forever) and the row's parity check
+template <int ZWC, bool QUIRK>
+__device__ __forceinline__ void cn_row_neighbour(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool first_iter,
+                                                 uint32_t quirk_zero, TwoMin &tm, uint32_t &sgn, uint32_t &synd, uint32_t &bad)
+{
+  const uint32_t one = G.one, mone = 0u - one;
+  const uint32_t ZB = geo_zb<ZWC>(G);
+  if (row.lrow != 0xFFFFFFFFu) {
+    const uint32_t pa = (row.prow_pcw & 0xFFFFFFu) + kb;
+    const uint32_t qsm = lds(smb, pa + ZB);                              // precomputed sign-magnitude of the channel LLR
+    synd ^= lds(smb, pa);                                                  // sign(llr + R_p) of the previous iteration
+    sgn ^= qsm;
+    twomin(qsm & kL7, tm, one, mone);
+    uint32_t rp = make_r(qsm, tm.n1, twomin_min1(tm, mone) | kH, twomin_min2(tm, mone) | kH, sgn, one, mone);
+    if (QUIRK) rp = (rp & ~quirk_zero) | (kH & quirk_zero);
+    // adds_epi8(llr, R_p) < 0  <=>  L' + R' < 256  <=>  no carry out of the byte
+    const uint32_t lp = lds(smb, pa + 2 * ZB);                           // the neighbour's channel LLR + 128, already rotated
+    const uint32_t x = (lp & kL7) + (rp & kL7);
+    sts(smb, pa, lop3<kLutMajNot>(lp, rp, x) & kH);
+  }
+  if (!first_iter && (kb >> 2) < (row.prow_pcw >> 24)) bad |= synd & kH;
+}
+
 template <int ZWC, int D, bool QUIRK>
 __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool halo,
                                        bool first_iter, uint32_t quirk_zero, uint32_t &bad)
@@ -64,20 +87,7 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
     twomin(mag, tm, one, mone);
   }
   if (D & 1) { synd ^= aprev; sgn ^= qprev; }
-  if (row.lrow != 0xFFFFFFFFu) {                                           // degree-1 neighbour: Q is the channel LLR forever
-    const uint32_t pa = (row.prow_pcw & 0xFFFFFFu) + kb;
-    const uint32_t qsm = lds(smb, pa + ZB);                              // precomputed sign-magnitude of the channel LLR
-    synd ^= lds(smb, pa);                                                  // sign(llr + R_p) of the previous iteration
-    sgn ^= qsm;
-    twomin(qsm & kL7, tm, one, mone);
-    uint32_t rp = make_r(qsm, tm.n1, twomin_min1(tm, mone) | kH, twomin_min2(tm, mone) | kH, sgn, one, mone);
-    if (QUIRK) rp = (rp & ~quirk_zero) | (kH & quirk_zero);
-    // adds_epi8(llr, R_p) < 0  <=>  L' + R' < 256  <=>  no carry out of the byte
-    const uint32_t lp = lds(smb, pa + 2 * ZB);                           // the neighbour's channel LLR + 128, already rotated
-    const uint32_t x = (lp & kL7) + (rp & kL7);
-    sts(smb, pa, lop3<kLutMajNot>(lp, rp, x) & kH);
-  }
-  if (!first_iter && (kb >> 2) < (row.prow_pcw >> 24)) bad |= synd & kH;
+  cn_row_neighbour<ZWC, QUIRK>(G, smb, row, kb, first_iter, quirk_zero, tm, sgn, synd, bad);
   const uint32_t p1 = twomin_min1(tm, mone) | kH, p2 = twomin_min2(tm, mone) | kH;
 #pragma unroll
   for (int j = 0; j < D; j++) {
@@ -85,6 +95,53 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
     if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
     sts(smb, rb + j * RSB, rn);
     if (halo) sts(smb, rb + j * RSB + ZB, rn);
+  }
+}
+
+// The same row as a LOOP over its edges: the fallback for row degrees without an unrolled instantiation, and an experiment.  The decoder's
+// instruction stream is straight-line code, and the micro-benchmark (tools/ubench/alu_ceiling.cu) sustains 0.76 warp instructions per cycle and
+// scheduler on this opcode blend while the code stays below ~32 KB but 0.66 at the ~50 KB the unrolled rows of one iteration add up to -- the rate
+// the kernel runs at.  A loop cannot keep the inputs Q in registers between the two passes, so pass 1 parks the sign-magnitude word in the edge's
+// own R slot (R_old is dead once read; only this thread touches this word during the CN phase) and pass 2 reads it back.  Measured: the ~25 % more
+// instructions cost more than the smaller footprint returns (all rows looped 0.79 ms, degrees 7-19 looped 0.72 ms, all unrolled 0.70 ms per 1024
+// blocks), so every NR row degree stays unrolled.
+template <int ZWC, bool QUIRK>
+__device__ __forceinline__ void cn_row_loop(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool halo,
+                                         bool first_iter, uint32_t quirk_zero, uint32_t &bad)
+{
+  const uint32_t one = G.one, mone = 0u - one;
+  const uint32_t ZB = geo_zb<ZWC>(G), RSB = geo_rsb<ZWC>(G);
+  const int D = (int)((row.e0_deg >> 12) & 0xFFu);
+  const uint32_t e0 = row.e0_deg & 0xFFFu;
+  const uint32_t rb = row.rbase + kb;
+  uint32_t sgn = 0u, synd = (D & 1) ? kH : 0u;
+  TwoMin tm = twomin_init();
+  {
+    const uint32_t *dp = G.cn_desc[e0];
+    uint32_t ra = rb;
+#pragma unroll 1
+    for (int j = 0; j < D; j++, dp += 2, ra += RSB) {
+      const uint2 d = *reinterpret_cast<const uint2 *>(dp);
+      const uint32_t aa = add_fma(kb, d.x, one);
+      const uint32_t aw = __funnelshift_r(lds(smb, aa), lds(smb, aa + 4), d.y);
+      const uint32_t ro = lds(smb, ra);
+      uint32_t mag, qsm;
+      cn_input(aw, ro, mone, mag, qsm);
+      sts(smb, ra, qsm);
+      synd ^= aw;
+      sgn ^= qsm;
+      twomin(mag, tm, one, mone);
+    }
+  }
+  cn_row_neighbour<ZWC, QUIRK>(G, smb, row, kb, first_iter, quirk_zero, tm, sgn, synd, bad);
+  const uint32_t p1 = twomin_min1(tm, mone) | kH, p2 = twomin_min2(tm, mone) | kH;
+  uint32_t ra = rb;
+#pragma unroll 1
+  for (int j = 0; j < D; j++, ra += RSB) {
+    uint32_t rn = make_r(lds(smb, ra), tm.n1, p1, p2, sgn, one, mone);
+    if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
+    sts(smb, ra, rn);
+    if (halo) sts(smb, ra + ZB, rn);
   }
 }
 
@@ -99,19 +156,19 @@ __device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int
 #pragma unroll
     for (int b = 0; b < 4; b++) if (((gi * G.Z + (int)kb + b) >> 5) & 1) qz |= 0xFFu << (8 * b);
   }
-  switch ((row.e0_deg >> 12) & 0xFFu) {
-    case 2: cn_row<ZWC, 2, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 3: cn_row<ZWC, 3, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 4: cn_row<ZWC, 4, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 5: cn_row<ZWC, 5, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 6: cn_row<ZWC, 6, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 7: cn_row<ZWC, 7, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 8: cn_row<ZWC, 8, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 9: cn_row<ZWC, 9, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 10: cn_row<ZWC, 10, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    case 19: cn_row<ZWC, 19, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); break;
-    default: break;   // build_packed_graph() refuses graphs with other row degrees
+  // row degrees in NRB200_UNROLL_MASK run unrolled, any other through the loop (see cn_row_loop)
+#ifndef NRB200_UNROLL_MASK
+#define NRB200_UNROLL_MASK 0x807FCu   /* every row degree the NR base graphs have: measured best (profiles/variants_r01n.txt) */
+#endif
+  const uint32_t D = (row.e0_deg >> 12) & 0xFFu;
+#define NRB200_CN_CASE(d) case d: if ((NRB200_UNROLL_MASK >> d) & 1u) { cn_row<ZWC, d, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); return; } break;
+  switch (D) {
+    NRB200_CN_CASE(2) NRB200_CN_CASE(3) NRB200_CN_CASE(4) NRB200_CN_CASE(5) NRB200_CN_CASE(6) NRB200_CN_CASE(7) NRB200_CN_CASE(8) NRB200_CN_CASE(9)
+    NRB200_CN_CASE(10) NRB200_CN_CASE(19)
+    default: break;
   }
+#undef NRB200_CN_CASE
+  cn_row_loop<ZWC, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad);
 }
 
 // one bit-node edge: fetch the rotated R' word and add its four bytes to the four running sums (IDP.4A, FMA pipe)
@@ -119,10 +176,10 @@ template <int ZWC>
 __device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__restrict__ smb, int i, uint32_t kb, uint32_t &s0, uint32_t &s1,
                                         uint32_t &s2, uint32_t &s3)
 {
-  const uint4 d = *reinterpret_cast<const uint4 *>(G.bn_desc[i]);
-  const uint32_t x = add_fma(kb, d.x, G.one);                                // kb - 4 qq
-  const uint32_t a = add_fma(__viaddmin_u32(x, geo_zb<ZWC>(G), x), d.y, G.one);   // circular wrap of v - s, then the row's base
-  const uint32_t rw = __funnelshift_r(lds(smb, a), lds(smb, a + 4), d.z);
+  const uint2 d = *reinterpret_cast<const uint2 *>(G.bn_desc[i]);
+  uint32_t a = kb + d.x;
+  if (((kb << 8) | 0xFFu) < d.y) a += geo_zb<ZWC>(G);                        // circular wrap of v - s
+  const uint32_t rw = __funnelshift_r(lds(smb, a), lds(smb, a + 4), d.y);
   s0 = __dp4a(rw, 0x00000001u, s0);
   s1 = __dp4a(rw, 0x00000100u, s1);
   s2 = __dp4a(rw, 0x00010000u, s2);
@@ -277,8 +334,10 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
         for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) {
           const int it = G.cn_bin_rows[i];
           const uint32_t kb = kb0 + 128u * (uint32_t)(it >> 8);
-          if (!quirks) cn_dispatch<ZWC, false>(G, smb, it & 0xFF, kb, kb == 0u, numIter == 0, bad);
-          else cn_dispatch<ZWC, true>(G, smb, it & 0xFF, kb, kb == 0u, numIter == 0, bad);
+          // the defect-emulation variant (BG2 R15 only) lives in the generic instantiation alone: launch_decode() routes such calls there,
+          // and the Z = 384 kernels carry half the code
+          if (ZWC == 0 && quirks) cn_dispatch<ZWC, ZWC == 0>(G, smb, it & 0xFF, kb, kb == 0u, numIter == 0, bad);
+          else cn_dispatch<ZWC, false>(G, smb, it & 0xFF, kb, kb == 0u, numIter == 0, bad);
         }
       }
       const int pcRes = __syncthreads_or(bad != 0);   // also the CN->BN barrier

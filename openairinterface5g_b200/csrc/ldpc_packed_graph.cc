@@ -122,10 +122,9 @@ bool build_packed_graph(const GraphDev &g, PackedGraph *p, int max_threads)
   for (int i = 0; i < g.nreal; i++) {
     const int m = g.col_edges[i], s = g.edge_shift[m], q = s / 4, rho = s % 4;
     const int qq4 = 4 * (q + (rho ? 1 : 0));
-    p->bn_desc[i][0] = (uint32_t)(-qq4);
-    p->bn_desc[i][1] = (uint32_t)(p->off_R + m * p->RSB);
-    p->bn_desc[i][2] = (uint32_t)(8 * ((4 - rho) & 3));
-    p->bn_desc[i][3] = 0u;
+    const uint32_t base_minus = (uint32_t)(p->off_R + m * p->RSB - qq4);   // off_R > 4*(Zw+1) always (A region precedes)
+    p->bn_desc[i][0] = base_minus;
+    p->bn_desc[i][1] = ((uint32_t)qq4 << 8) | (uint32_t)(8 * ((4 - rho) & 3));
   }
   // thread geometry.  Costs are warp instructions per item measured on the Z = 384 kernel (profiles/r01n_*): a row costs 18 (dispatch) +
   // 32 per stored edge + 51 with a degree-1 neighbour (11 without); a column 65 + 13.5 per edge.

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libldpc_b200.so")
+_SO = os.environ.get("NRB200_LIB") or os.path.join(_HERE, "libldpc_b200.so")   # NRB200_LIB: A/B builds of tools/ (never set in production)
 
 _u8p = C.POINTER(C.c_uint8)
 _i8p = C.POINTER(C.c_int8)

@@ -24,7 +24,7 @@
 
 constexpr int kChains = 8;
 
-template <int MODE>
+template <int MODE, int UNROLL>
 __global__ void __launch_bounds__(768, 1) body(uint32_t *out, int iters, uint32_t one)
 {
   extern __shared__ uint32_t sm[];
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(768, 1) body(uint32_t *out, int iters, uint32_
   for (int i = threadIdx.x; i < 12288; i += blockDim.x) sm[i] = i * 747796405u;
   __syncthreads();
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm) + 4u * threadIdx.x;
-#pragma unroll 1
+#pragma unroll UNROLL
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int c = 0; c < kChains; c++) {
@@ -62,21 +62,21 @@ __global__ void __launch_bounds__(768, 1) body(uint32_t *out, int iters, uint32_
   if (r == 0x12345u) out[threadIdx.x] = r;
 }
 
-template <int MODE>
+template <int MODE, int UNROLL>
 static double run(int per_iter, int sms, int clock_khz)
 {
   uint32_t *d;
   cudaMalloc(&d, 4096);
-  cudaFuncSetAttribute(body<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);
+  cudaFuncSetAttribute(body<MODE, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);
   const int iters = 4000;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  body<MODE><<<sms, 768, 49152>>>(d, 200, 1u);
+  body<MODE, UNROLL><<<sms, 768, 49152>>>(d, 200, 1u);
   cudaDeviceSynchronize();
   float best = 1e30f;
   for (int rep = 0; rep < 5; rep++) {
     cudaEventRecord(e0);
-    body<MODE><<<sms, 768, 49152>>>(d, iters, 1u);
+    body<MODE, UNROLL><<<sms, 768, 49152>>>(d, iters, 1u);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -97,8 +97,17 @@ int main()
   // SASS instructions per loop iteration, counted with cuobjdump (sm_100a, nvcc 12.9): 67 = 64 LOP3 + 3 loop; 131 = 72 LOP3 + 32 PRMT + 8 IADD3 + 8 SHF +
   // 8 VABSDIFF4 + 3 loop; 243 = 128 ALU (80 LOP3, 24 PRMT, 8 IADD3, 8 SHF, 8 VABSDIFF4) + 56 IMAD + 16 IDP.4A + 32 LDS + 8 STS + 3 loop
   // (ALU share 52.7 %, the decoder's is 52.6 %; LSU 16.5 % vs 17.2 %; FMA pipe 29.6 % vs 21 %)
-  const double lop3 = run<0>(67, p.multiProcessorCount, clk), alu = run<1>(131, p.multiProcessorCount, clk), mix = run<2>(243, p.multiProcessorCount, clk);
+  const double lop3 = run<0, 1>(67, p.multiProcessorCount, clk), alu = run<1, 1>(131, p.multiProcessorCount, clk), mix = run<2, 1>(243, p.multiProcessorCount, clk);
+  // the same blend as straight-line code: the loop unrolled 40 times = ~9 600 instructions = 150 KB of SASS per trip, as large as the decoder's
+  // unrolled row code -- what instruction fetch costs when nothing is re-used from the L0 instruction cache
+  const double mix_big = run<2, 40>(240, p.multiProcessorCount, clk);
+  // footprint sweep of the same blend: instruction-cache knees (3.9 KB of SASS per unrolled iteration)
+  const double f2 = run<2, 2>(240, p.multiProcessorCount, clk), f4 = run<2, 4>(240, p.multiProcessorCount, clk), f8 = run<2, 8>(240, p.multiProcessorCount, clk),
+               f16 = run<2, 16>(240, p.multiProcessorCount, clk), f25 = run<2, 25>(240, p.multiProcessorCount, clk), f32 = run<2, 32>(240, p.multiProcessorCount, clk),
+               f80 = run<2, 80>(240, p.multiProcessorCount, clk);
   printf("{\"sm_count\": %d, \"clock_khz\": %d, \"lop3_ipc_per_scheduler\": %.4f, \"alu_mix_ipc_per_scheduler\": %.4f, \"decoder_mix_ipc_per_scheduler\": %.4f, "
-         "\"decoder_mix_alu_share\": %.4f}\n", p.multiProcessorCount, clk, lop3, alu, mix, 128.0 / 243.0);
+         "\"decoder_mix_straight_line_ipc_per_scheduler\": %.4f, \"decoder_mix_alu_share\": %.4f, "
+         "\"ipc_vs_code_kb\": {\"3.9\": %.4f, \"7.7\": %.4f, \"15\": %.4f, \"31\": %.4f, \"61\": %.4f, \"96\": %.4f, \"123\": %.4f, \"154\": %.4f, \"307\": %.4f}}\n",
+         p.multiProcessorCount, clk, lop3, alu, mix, mix_big, 128.0 / 243.0, mix, f2, f4, f8, f16, f25, f32, mix_big, f80);
   return 0;
 }
