@@ -457,7 +457,7 @@ def run_b200(args, rank, world, local_rank):
         }
         oc = ncu_on_chip(B, kernel_s, line["clocks"].get("sm_mhz") or 1965.0)
         if oc is not None:
-            ub = measured_mix_ceiling() if world == 1 else None
+            ub = measured_mix_ceiling() if (world == 1 and not args.no_ubench) else None
             if ub and "decoder_mix_ipc_per_scheduler" in ub and oc.get("warp_inst_per_cb"):
                 ipc = B * oc["warp_inst_per_cb"] / kernel_s / (148 * 4 * float(line["clocks"].get("sm_mhz") or 1965.0) * 1e6)
                 oc["micro_benchmark"] = dict(ub, decoder_ipc_per_scheduler=ipc, frac_of_measured_mix_ceiling=ipc / ub["decoder_mix_ipc_per_scheduler"])
@@ -486,6 +486,7 @@ def main():
     ap.add_argument("--ebn0", type=float, default=1.0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ubench", action="store_true", help="skip tools/ubench/alu_ceiling (e.g. under ncu, so that the launch list holds the step's kernels only)")
     ap.add_argument("--no-slot", action="store_true", help="skip the nr_dlsim slot chain (second half of the BASELINE metric)")
     ap.add_argument("--slot-cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-check", action="store_true")

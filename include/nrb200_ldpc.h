@@ -310,6 +310,15 @@ uint64_t nrb200_pusch_chest_scratch_bytes(const nrb200_pusch_chest_t *d);
 int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, const int16_t *d_rxdataF, int16_t *d_ul_ch_estimates, void *d_scratch, int32_t *d_state,
                                void *stream);
 int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5);
+/* nr_chest_time_domain_avg (openair1/PHY/NR_REFSIG/dmrs_nr.c:343-417; called with gNB->chest_time == 1 from nr_rx_pusch_tp, nr_ulsch_demodulation.c:1527-1538,
+ * and by the UE, SCHED_NR_UE/phy_procedures_nr_ue.c:560): the estimates of the allocation's DMRS symbols are averaged into the first DMRS symbol (first
+ * 12 * rb_size entries of the symbol; saturating sums; / 2 and / 4 as arithmetic shifts, / 3 towards zero).  est: [nb_rx][14][fft_size] c16, planes ch_stride
+ * c16 apart (_dev), rewritten in place; with several layers only layer 0's planes are averaged, as in the reference.  Returns the index of the first DMRS
+ * symbol (what the caller then uses as pusch_vars->dmrs_symbol), or a negative error (-4: no DMRS symbol in the allocation or more than four). */
+int32_t nrb200_chest_time_avg_dev(uint32_t fft_size, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos,
+                                  uint32_t rb_size, int16_t *d_est, void *stream);
+int32_t nrb200_chest_time_avg_host(uint32_t fft_size, uint32_t nb_rx, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos, uint32_t rb_size,
+                                   int16_t *est);
 
 /* ---- Part 8: the "offload" calling convention of the codec ABI -----------------------------------------------------------
  * OAI's second LDPC interface (ldpc_interface_offload, loaded as version "_t2" when --ldpc-offload-enable is given; reference

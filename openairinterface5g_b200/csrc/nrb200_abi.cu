@@ -24,6 +24,8 @@ uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d);
 int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d_out9, uint32_t *d_count, cudaStream_t st);
 int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st);
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
+int launch_chest_time_avg(uint32_t N, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos, uint32_t rb_size,
+                          int16_t *d_est, cudaStream_t st);
 int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil);
 int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_t *est, void *d_scratch, int32_t *d_state, cudaStream_t st, int buf_symbol,
                        int tail_override = 0);
@@ -734,6 +736,38 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_dev(const nrb200_pusch_chest_t *d, cons
 {
   if (ensure_init() || !d) return -1;
   return launch_pusch_chest(*d, d_rxF, d_est, d_scratch, d_state, (cudaStream_t)stream, -1);
+}
+
+NRB200_EXPORT int32_t nrb200_chest_time_avg_dev(uint32_t fft_size, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols,
+                                                uint32_t dmrs_symb_pos, uint32_t rb_size, int16_t *d_est, void *stream)
+{
+  if (ensure_init()) return -1;
+  return launch_chest_time_avg(fft_size, nb_rx, ch_stride, start_symbol, nr_of_symbols, dmrs_symb_pos, rb_size, d_est, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_chest_time_avg_host(uint32_t fft_size, uint32_t nb_rx, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos,
+                                                 uint32_t rb_size, int16_t *est)
+{
+  if (ensure_init() || !est) return -1;
+  if (nb_rx < 1 || nb_rx > 64 || fft_size < 12) return -4;
+  const size_t sym = (size_t)fft_size * 4, plane = 14 * sym, all = plane * nb_rx;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(all, 16, 16)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, est, all);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, all, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    rc = launch_chest_time_avg(fft_size, nb_rx, 14 * fft_size, start_symbol, nr_of_symbols, dmrs_symb_pos, rb_size, (int16_t *)w->d_in, w->stream);
+    if (rc < 0) break;
+    const int first = rc;
+    for (uint32_t a = 0; a < nb_rx; a++)      // only the first DMRS symbol changes
+      if (cudaMemcpyAsync((uint8_t *)w->h_in + a * plane + first * sym, (uint8_t *)w->d_in + a * plane + first * sym, sym, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }
+    if (rc < 0) break;
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    for (uint32_t a = 0; a < nb_rx; a++) std::memcpy((uint8_t *)est + a * plane + first * sym, (uint8_t *)w->h_in + a * plane + first * sym, sym);
+  } while (0);
+  ctx().release(w);
+  return rc;
 }
 
 NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, const int16_t *rxdataF, int16_t *ul_ch_estimates, int32_t *state5)

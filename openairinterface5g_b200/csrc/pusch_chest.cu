@@ -296,6 +296,45 @@ __global__ void __launch_bounds__(256) chest_avg_kernel(ChestGeom G, const GoldT
   for (int k = 0; k < 12 && 12 * j + k < G.N; k++) dst[k] = v;
 }
 
+// nr_chest_time_domain_avg (NR_REFSIG/dmrs_nr.c:343-417): the slot's DMRS-symbol estimates summed (adds_epi16) into the first DMRS symbol over the
+// first 12 * num_rbs entries of the symbol and divided by their number (>> 1, / 3 towards zero, >> 2).  One thread per antenna and entry; the
+// reference makes one pass over the symbol per additional DMRS symbol plus one for the division.
+__global__ void __launch_bounds__(256) chest_time_avg_kernel(int N, unsigned plane_stride, int first, unsigned later_mask, int ndmrs, int n, unsigned *__restrict__ est)
+{
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= n) return;
+  unsigned *plane = est + (size_t)blockIdx.y * plane_stride;
+  const unsigned v = plane[(size_t)first * N + k];
+  int r = c_lo(v), i = c_hi(v);
+  for (int s = first + 1; s < 14; s++)
+    if ((later_mask >> s) & 1u) {
+      const unsigned x = plane[(size_t)s * N + k];
+      r = c_sat16(r + c_lo(x)); i = c_sat16(i + c_hi(x));
+    }
+  if (ndmrs == 2) { r >>= 1; i >>= 1; }
+  else if (ndmrs == 4) { r >>= 2; i >>= 2; }
+  else if (ndmrs == 3) { r /= 3; i /= 3; }
+  plane[(size_t)first * N + k] = c_pk(r, i);
+}
+
+// returns the first DMRS symbol (>= 0) or a negative error
+int launch_chest_time_avg(uint32_t N, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos, uint32_t rb_size,
+                          int16_t *d_est, cudaStream_t st)
+{
+  const uint32_t total = start_symbol + nr_of_symbols;
+  if (total > 14 || nb_rx < 1 || 12 * rb_size > N || rb_size < 1) return -4;
+  int ndmrs = 0, first = -1;
+  for (uint32_t s = 0; s < total; s++) ndmrs += (dmrs_symb_pos >> s) & 1u;          // get_dmrs_symbols_in_slot counts from symbol 0
+  for (uint32_t s = start_symbol; s < total; s++) if ((dmrs_symb_pos >> s) & 1u) { first = (int)s; break; }
+  if (first < 0 || ndmrs < 1 || ndmrs > 4) return -4;                                // AssertFatal in the reference
+  const unsigned later = dmrs_symb_pos & ((1u << total) - 1u) & ~((2u << first) - 1u);
+  const int n = 12 * (int)rb_size;
+  chest_time_avg_kernel<<<dim3((n + 255) / 256, nb_rx), 256, 0, st>>>((int)N, ch_stride, first, later, ndmrs, n, (unsigned *)d_est);
+  ctx().launches += 1;
+  NRB200_CUDA_OK(cudaGetLastError(), "chest_time_avg launch");
+  return first;
+}
+
 // fp->delay_table (init_delay_table): round(256 e^{j 2 pi k d / N}) for d = -20..20, built once per N
 static const unsigned *delay_table_dev(int N)
 {

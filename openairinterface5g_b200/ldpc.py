@@ -380,6 +380,22 @@ class LdpcLib:
                                                     torch.cuda.current_stream(rxdataF.device).cuda_stream), "pusch_chest_dev")
         return ul_ch_estimates
 
+    def chest_time_avg_host(self, est, num_symbols, start_symbol, dmrs_bitmap, num_rbs):
+        """nr_chest_time_domain_avg: est [nb_rx][14][N][2] int16 -> (averaged copy, first DMRS symbol)."""
+        e = np.ascontiguousarray(est, dtype=np.int16).copy()
+        rc = self.lib.nrb200_chest_time_avg_host(e.shape[2], e.shape[0], start_symbol, num_symbols, dmrs_bitmap, num_rbs, C.c_void_p(e.ctypes.data))
+        if rc < 0:
+            self._check(rc, "chest_time_avg_host")
+        return e, rc
+
+    def chest_time_avg_torch(self, est, num_symbols, start_symbol, dmrs_bitmap, num_rbs):
+        import torch
+        rc = self.lib.nrb200_chest_time_avg_dev(est.shape[2], est.shape[0], 14 * est.shape[2], start_symbol, num_symbols, dmrs_bitmap, num_rbs,
+                                                C.c_void_p(est.data_ptr()), C.c_void_p(torch.cuda.current_stream(est.device).cuda_stream))
+        if rc < 0:
+            self._check(rc, "chest_time_avg_dev")
+        return rc
+
     def pusch_chest_scratch_bytes(self, desc):
         return int(self.lib.nrb200_pusch_chest_scratch_bytes(C.addressof(desc)))
 

@@ -196,6 +196,13 @@ class Oracle:
         self.lib.orc_pusch_channel_estimation(C.byref(P), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         return est.reshape(P.nb_rx, 14, P.fft_size, 2), out
 
+    def chest_time_domain_avg(self, est, num_symbols, start_symbol, dmrs_bitmap, num_rbs):
+        """est [nb_rx][14][N][2] int16 -> averaged copy (nr_chest_time_domain_avg)."""
+        e = np.ascontiguousarray(est, dtype=np.int16).copy()
+        rc = self.lib.orc_chest_time_domain_avg(e.shape[2], e.shape[0], num_symbols, start_symbol, dmrs_bitmap, num_rbs, e.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return e
+
     def pdsch_channel_estimation(self, P, rxdataF):
         x = np.ascontiguousarray(rxdataF, dtype=np.int16)
         est = np.zeros(P.nb_rx * 14 * P.fft_size * 2, np.int16)
@@ -550,6 +557,13 @@ class Reference:
         self._uechestlib.refh_ue_slot_fep.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         self._uechestlib.refh_ue_slot_fep(N, mu, nb_rb, nrx, slot, divisor, r.ctypes.data, t.ctypes.data, x.ctypes.data, x.shape[1] // 2, out.ctypes.data)
         return out
+
+    def chest_time_domain_avg(self, est, num_symbols, start_symbol, dmrs_bitmap, num_rbs):
+        if not hasattr(self, "_pdschlib"):
+            self._pdschlib = C.CDLL(os.path.join(REFDIR, "libref_pdsch.so"))
+        e = np.ascontiguousarray(est, dtype=np.int16).copy()
+        self._pdschlib.refh_chest_time_avg(e.shape[2], e.shape[0], num_symbols, start_symbol, dmrs_bitmap, num_rbs, e.ctypes.data_as(C.c_void_p))
+        return e
 
     def pdsch_rx_slot(self, P, start_symbol, nr_symbols, rxdataF, dl_ch_est, G, nl=1):
         if not hasattr(self, "_pdschlib"):

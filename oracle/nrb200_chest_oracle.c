@@ -299,3 +299,32 @@ int orc_pdsch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, i
   free(pil); free(ls); free(tim); free(acc);
   return 0;
 }
+
+
+/* ---- nr_chest_time_domain_avg (openair1/PHY/NR_REFSIG/dmrs_nr.c:343-417; gNB: nr_rx_pusch_tp with chest_time == 1, nr_ulsch_demodulation.c:1527-1538;
+ * UE: phy_procedures_nr_ue.c:560): the estimates of the slot's DMRS symbols are summed (saturating) into the FIRST DMRS symbol over the first
+ * 12 * num_rbs entries of the symbol (from the symbol's start, whatever the allocation's first sub-carrier is) and divided by their number:
+ * 2 -> >> 1, 4 -> >> 2 (arithmetic shifts), 3 -> C division (towards zero), 1 -> unchanged.  Only planes 0 .. nb_rx-1 are touched (with several
+ * layers: layer 0 only, as in the reference).  est [nb_rx][14][N] c16 in place.  Returns -1 for 0 or more than 4 DMRS symbols (AssertFatal there). */
+int orc_chest_time_domain_avg(int N, int nb_rx, int num_symbols, int start_symbol, int dmrs_bitmap, int num_rbs, int16_t *est)
+{
+  const int total = start_symbol + num_symbols;
+  int ndmrs = 0, first = -1;
+  for (int s = 0; s < total; s++) ndmrs += (dmrs_bitmap >> s) & 1;
+  for (int s = start_symbol; s < total; s++) if ((dmrs_bitmap >> s) & 1) { first = s; break; }
+  if (first < 0 || ndmrs < 1 || ndmrs > 4) return -1;
+  for (int a = 0; a < nb_rx; a++) {
+    int16_t *d = est + 2 * ((size_t)a * 14 + first) * N;
+    for (int s = first + 1; s < total; s++) {
+      if (!((dmrs_bitmap >> s) & 1)) continue;
+      const int16_t *x = est + 2 * ((size_t)a * 14 + s) * N;
+      for (int k = 0; k < 24 * num_rbs; k++) d[k] = sat16((int32_t)d[k] + x[k]);
+    }
+    for (int k = 0; k < 24 * num_rbs; k++) {
+      if (ndmrs == 2) d[k] = (int16_t)(d[k] >> 1);
+      else if (ndmrs == 4) d[k] = (int16_t)(d[k] >> 2);
+      else if (ndmrs == 3) d[k] = (int16_t)(d[k] / 3);
+    }
+  }
+  return 0;
+}

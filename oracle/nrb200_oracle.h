@@ -74,6 +74,7 @@ typedef struct {
 void orc_pusch_dmrs_pilots(const orc_chest_t *p, int16_t *pil);
 int orc_pusch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);
 int orc_pdsch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *dl_ch_est);
+int orc_chest_time_domain_avg(int N, int nb_rx, int num_symbols, int start_symbol, int dmrs_bitmap, int num_rbs, int16_t *est);
 
 /* single-layer PUSCH inner receiver (nrb200_pusch_oracle.c) */
 typedef struct {

@@ -72,3 +72,18 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
   free(est); free(rx); free(comp); free(llr[0]); free(ue);
   return log2_maxh;
 }
+
+
+/* nr_chest_time_domain_avg (openair1/PHY/NR_REFSIG/dmrs_nr.c:343-417), the real function: est is [nb_rx][14][N] c16, rewritten in place. */
+void nr_chest_time_domain_avg(NR_DL_FRAME_PARMS *frame_parms, int32_t **ch_estimates, uint8_t num_symbols, uint8_t start_symbol, uint16_t dmrs_bitmap, uint16_t num_rbs);
+int refh_chest_time_avg(int N, int nb_rx, int num_symbols, int start_symbol, int dmrs_bitmap, int num_rbs, int16_t *est)
+{
+  NR_DL_FRAME_PARMS *fp = calloc(1, sizeof(*fp));
+  fp->ofdm_symbol_size = N; fp->nb_antennas_rx = nb_rx;
+  int32_t **planes = calloc(nb_rx, sizeof(int32_t *));
+  for (int a = 0; a < nb_rx; a++) { posix_memalign((void **)&planes[a], 32, 4 * (size_t)14 * N); memcpy(planes[a], est + 2 * (size_t)a * 14 * N, 4 * (size_t)14 * N); }
+  nr_chest_time_domain_avg(fp, planes, (uint8_t)num_symbols, (uint8_t)start_symbol, (uint16_t)dmrs_bitmap, (uint16_t)num_rbs);
+  for (int a = 0; a < nb_rx; a++) { memcpy(est + 2 * (size_t)a * 14 * N, planes[a], 4 * (size_t)14 * N); free(planes[a]); }
+  free(planes); free(fp);
+  return 0;
+}

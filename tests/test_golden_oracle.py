@@ -182,3 +182,13 @@ def test_chest_variants_golden(oracle):
         assert np.array_equal(oracle.pusch_dmrs_pilots(P)[:npil], g[f"pilots{i}"]), i
         est, st = oracle.pusch_channel_estimation(P, g["rx"])
         assert np.array_equal(st, g[f"state{i}"]) and np.array_equal(est[:, P.symbol], g[f"est{i}"]), i
+
+
+def test_chest_time_avg_golden(oracle):
+    g = _load("chest_variants.npz")
+    for i in range(3):
+        nsym, start, bitmap, nrb = [int(x) for x in g[f"tavg_par{i}"]]
+        out = oracle.chest_time_domain_avg(g["tavg_in"], nsym, start, bitmap, nrb)
+        first = min(s for s in range(start, start + nsym) if (bitmap >> s) & 1)
+        assert np.array_equal(out[:, first], g[f"tavg_out{i}"]), i
+        assert np.array_equal(np.delete(out, first, axis=1), np.delete(g["tavg_in"], first, axis=1)), i

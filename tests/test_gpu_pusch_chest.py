@@ -131,3 +131,26 @@ def test_pusch_chest_variants_refuse_what_the_reference_cannot_do(ldpc):
         f.update(kw)
         with pytest.raises(Nrb200Error):
             ldpc.pusch_chest_host(PuschChestDesc(**f), rx)
+
+
+def test_chest_time_domain_avg_vs_oracle(ldpc, oracle):
+    """nr_chest_time_domain_avg: host and device entry points, 1-4 DMRS symbols, full-scale inputs (saturating sums)."""
+    import torch
+    rng = np.random.default_rng(78)
+    for N, nb_rx, start, nsym, bitmap, nrb in ((512, 2, 0, 14, 0b00000000000100, 25), (512, 3, 0, 14, 0b00100000000100, 20), (1024, 2, 2, 12, 0b00101000001000, 52),
+                                               (1024, 4, 0, 14, 0b00100100100100, 40), (4096, 4, 0, 14, 0b00100000000100, 273), (512, 2, 4, 8, 0b11000000110000, 11)):
+        est = rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        est[:, :, ::5] //= 50
+        want = oracle.chest_time_domain_avg(est, nsym, start, bitmap, nrb)
+        got, first = ldpc.chest_time_avg_host(est, nsym, start, bitmap, nrb)
+        assert first == min(s for s in range(start, start + nsym) if (bitmap >> s) & 1)
+        assert np.array_equal(got, want), (N, nb_rx, start, nsym, bin(bitmap), nrb)
+        t = torch.from_numpy(est.copy()).cuda()
+        assert ldpc.chest_time_avg_torch(t, nsym, start, bitmap, nrb) == first
+        torch.cuda.synchronize()
+        assert np.array_equal(t.cpu().numpy(), want)
+    from openairinterface5g_b200.ldpc import Nrb200Error
+    with pytest.raises(Nrb200Error):
+        ldpc.chest_time_avg_host(est, 14, 0, 0, 11)             # no DMRS symbol: AssertFatal in the reference
+    with pytest.raises(Nrb200Error):
+        ldpc.chest_time_avg_host(est, 14, 0, 0b11111, 11)       # five DMRS symbols

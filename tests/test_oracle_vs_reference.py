@@ -437,6 +437,19 @@ def test_pusch_channel_estimation_variants(oracle, reference, dmrs_type, chest_f
         assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
 
 
+def test_chest_time_domain_avg(oracle, reference):
+    """nr_chest_time_domain_avg (dmrs_nr.c:343-417): 1-4 DMRS symbols, saturating sums, the three division rules, full-scale inputs."""
+    rng = np.random.default_rng(77)
+    for N, nb_rx, start, nsym, bitmap, nrb in ((512, 2, 0, 14, 0b00000000000100, 25), (512, 3, 0, 14, 0b00100000000100, 20), (1024, 2, 2, 12, 0b00101000001000, 52),
+                                               (1024, 4, 0, 14, 0b00100100100100, 40), (2048, 1, 1, 10, 0b00000010000100, 106), (512, 2, 4, 8, 0b11000000110000, 11)):
+        est = rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        est[:, :, ::7] //= 64                                  # a share of small values so that not every sum saturates
+        r = reference.chest_time_domain_avg(est, nsym, start, bitmap, nrb)
+        o = oracle.chest_time_domain_avg(est, nsym, start, bitmap, nrb)
+        assert np.array_equal(o, r), (N, nb_rx, start, nsym, bin(bitmap), nrb)
+        assert not np.array_equal(o, est) or bin(bitmap & ((1 << (start + nsym)) - 1)).count("1") == 1
+
+
 def test_pusch_inner_rx_two_layers_mmse(oracle, reference):
     """nb_layer == 2, Qm >= 6: matched filter per layer + nr_ulsch_mmse_2layers + per-layer LLRs, through the reference's inner_rx."""
     from oracle.bindings import PuschParms

@@ -27,6 +27,16 @@ def main():
         g[f"par{i}"], g[f"est{i}"], g[f"state{i}"] = np.array(par, np.int32), est[:, symbol], out
         g[f"pilots{i}"] = pil[:2 * (4 if dmrs_type else 6) * rb_size]
         cases.append(i)
+    # nr_chest_time_domain_avg: 2, 3 and 4 DMRS symbols on full-scale estimates
+    est = rng.integers(-32768, 32768, size=(2, 14, N, 2)).astype(np.int16)
+    est[:, :, ::5] //= 50
+    g["tavg_in"] = est
+    for i, (start, nsym, bitmap, nrb) in enumerate(((0, 14, 0b00100000000100, 25), (2, 12, 0b00101000001000, 20), (0, 14, 0b00100100100100, 22))):
+        g[f"tavg_par{i}"] = np.array([nsym, start, bitmap, nrb], np.int32)
+        out = ref.chest_time_domain_avg(est, nsym, start, bitmap, nrb)
+        first = min(s for s in range(start, start + nsym) if (bitmap >> s) & 1)
+        g[f"tavg_out{i}"] = out[:, first]
+        assert np.array_equal(np.delete(out, first, axis=1), np.delete(est, first, axis=1))
     g["n_cases"] = np.array([len(cases)], np.int32)
     np.savez_compressed(OUT, **g)
     print(OUT, os.path.getsize(OUT), "bytes")

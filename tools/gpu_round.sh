@@ -14,6 +14,7 @@ echo "== variants"
 for t in 768 672 576 480 384; do NRB200_PACKED_THREADS=$t timeout 120 python tools/kernel_time.py 1.0 2>&1 | tail -1; done | tee gpurun_out/variants_${TAG}.txt
 timeout 120 python tools/kernel_time.py 3.0 2>&1 | tail -1 | tee -a gpurun_out/variants_${TAG}.txt
 fi
+echo "== micro-benchmark (ALU pipe / opcode-blend / code-footprint ceilings)"; timeout 120 tools/ubench/_bin/alu_ceiling | tee gpurun_out/alu_ceiling_${TAG}.json
 echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -24 | tee gpurun_out/extras_${TAG}.jsonl
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json
 if [ "$MODE" = "full" ]; then
@@ -26,9 +27,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
   python tools/bench_dl_slot.py once > gpurun_out/ncu_launches_dlslot_${TAG}.log 2>&1
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
-  python bench.py --steps 5 --warmup 3 --no-cpu --no-check --no-slot --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
+  python bench.py --steps 5 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
 fi
 echo "== ncu full (decode kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
-  python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
+  python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
