@@ -302,6 +302,8 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from openairinterface5g_b200.ldpc import load_LDPClib
     lib = load_LDPClib()
