@@ -141,3 +141,70 @@ class PuschSlotChain:
         self.tb.view(-1).copy_(self.hard[:, :nbytes].reshape(-1))                             # nr_postDecode: concatenate the segments
         lib.crc_batch_torch(0, self.tb, self.A + 24, out=self.tbcrc)                       # CRC over payload + CRC24A == 0 when intact
         return self.tb, self.iters, self.tbcrc
+
+
+class PuschSlotPipeline:
+    """K PUSCH slots in flight on one GPU, the uplink counterpart of dl_slot_chain.PdschSlotPipeline: K independent PuschSlotChain instances (own buffers,
+    own stream, own received samples), each slot's receive launches captured once into a CUDA graph and replayed.  One slot alone is latency bound (11 dependent
+    launches, 28 code blocks on 148 SMs); a gNB serves several users and carriers, whose slots are independent.  One layer per slot (the two-layer receiver takes
+    max_ch / nvar through the host side of the ABI and is not capturable yet)."""
+
+    def __init__(self, lib, dl, device, n_inflight, use_graphs=True, seed0=200, **cfg):
+        self.K, self.dev = n_inflight, device
+        self.chains, self.graphs, self.streams, self.rx, self.payload, self.h_rx, self.h_tb = [], [], [], [], [], [], []
+        for k in range(n_inflight):
+            st = torch.cuda.Stream(device=device)
+            with torch.cuda.stream(st):
+                ch = PuschSlotChain(lib, dl, device, **cfg)
+                payload, rxdata, _ = ch.synthesize(seed=seed0 + k, snr_db=30.0)
+                ch.receive(rxdata)                                   # warm-up outside the capture
+                st.synchronize()
+                g = None
+                if use_graphs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=st):
+                        ch.receive(rxdata)
+            self.chains.append(ch); self.graphs.append(g); self.streams.append(st); self.rx.append(rxdata); self.payload.append(payload)
+            ss, ns = ch.P.slot_timestamp(ch.slot), ch.P.samples_per_slot(ch.slot)
+            self.slot_span = (ss, ss + ns)
+            self.h_rx.append(rxdata[:, ss:ss + ns].contiguous().cpu().pin_memory())       # the slot's samples only (983 KB at 4 rx)
+            self.h_tb.append(torch.empty_like(ch.tb, device="cpu").pin_memory())
+        torch.cuda.synchronize(device)
+
+    def round(self, e2e=False):
+        for k in range(self.K):
+            with torch.cuda.stream(self.streams[k]):
+                if e2e:
+                    self.rx[k][:, self.slot_span[0]:self.slot_span[1]].copy_(self.h_rx[k], non_blocking=True)   # the slot's time-domain samples of every rx antenna
+                if self.graphs[k] is not None:
+                    self.graphs[k].replay()
+                else:
+                    self.chains[k].receive(self.rx[k])
+                if e2e:
+                    self.h_tb[k].copy_(self.chains[k].tb, non_blocking=True)
+
+    def timed_rounds(self, n_rounds, e2e=False, warm=3):
+        """CUDA-event time (ms) of n_rounds x K slots; events on the current stream, every slot stream forks from it and joins back."""
+        for _ in range(warm):
+            self.round(e2e)
+        torch.cuda.synchronize(self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for st in self.streams:
+            st.wait_event(e0)
+        for _ in range(n_rounds):
+            self.round(e2e)
+        for st in self.streams:
+            ev = torch.cuda.Event(); ev.record(st); cur.wait_event(ev)
+        e1.record(cur)
+        torch.cuda.synchronize(self.dev)
+        return e0.elapsed_time(e1)
+
+    def check(self, host=False):
+        ok = []
+        for k, ch in enumerate(self.chains):
+            tb = self.h_tb[k] if host else ch.tb.cpu()
+            want = torch.from_numpy(self.payload[k])
+            ok.append(bool((ch.iters <= ch.max_iter).all()) and int(ch.tbcrc.cpu()[0]) == 0 and bool((tb.view(-1)[:want.numel()] == want).all()))
+        return ok

@@ -36,3 +36,25 @@ def test_pusch_slot_roundtrip(ldpc, oracle, cfg):
         assert shift_o == int(chain.level.cpu()[8])
         assert np.array_equal(chain.llr16.cpu().numpy(), llr_o)
         assert np.array_equal(it, its_o) and np.array_equal(got[:tb_o.size], tb_o)
+
+
+def test_pusch_slots_in_flight_match_single_slot(ldpc):
+    """PuschSlotPipeline: every stream's slot (CUDA graph replay, device resident and with the samples / transport block crossing PCIe) decodes its own
+    payload, and gives the LLRs and iteration counts the same slot gives when run alone."""
+    import torch
+    from openairinterface5g_b200.dfts import load_dftslib
+    from openairinterface5g_b200.slot_chain import PuschSlotChain, PuschSlotPipeline
+    dl = load_dftslib()
+    dev = torch.device("cuda", 0)
+    cfg = dict(A=18696, N=2048, carrier_rb=106, rb_start=20, rb_size=50, nb_rx=2, Qm=4, slot=3)
+    pipe = PuschSlotPipeline(ldpc, dl, dev, 3, seed0=300, **cfg)
+    pipe.timed_rounds(2)
+    assert all(pipe.check())
+    pipe.timed_rounds(2, e2e=True)
+    assert all(pipe.check(host=True))
+    for k in (0, 2):
+        alone = PuschSlotChain(ldpc, dl, dev, **cfg)
+        payload, rxdata, _ = alone.synthesize(seed=300 + k, snr_db=30.0)
+        alone.receive(rxdata)
+        torch.cuda.synchronize()
+        assert torch.equal(alone.llr16, pipe.chains[k].llr16) and torch.equal(alone.iters, pipe.chains[k].iters) and torch.equal(alone.tb, pipe.chains[k].tb)
