@@ -268,6 +268,12 @@ typedef struct nrb200_pusch_rx_s {
                                              * num_dmrs_cdm_grps_no_data = n_dmrs_cdm_groups, the estimates' symbol = get_valid_dmrs_idx_for_channel_est; nb_rx <= 4.
                                              * nrOfLayers == 2 (nb_rx >= 2, any qam_mod_order): per-layer MRC + nr_zero_forcing_rx (:1726-1869) + layer
                                              * de-mapping; dl_ch_estimates holds [2 * nb_rx] planes, index layer * nb_rx + rx */
+  uint64_t d_est_state;                     /* _dev, 2 layers, optional: DEVICE address of the channel estimator's state (nrb200_pusch_chest_dev's d_state, 18 int32 per
+                                             * port).  When non-zero, max_ch and noise_var are taken from it ON THE DEVICE (max over the ports' max_ch; sum of the ports'
+                                             * nvar / (nr_of_symbols * nrOfLayers * nb_rx), nr_ulsch_demodulation.c:1470-1524) and the two fields above are ignored:
+                                             * estimator -> level -> receiver then run stream ordered with no host round trip (and can be captured in a CUDA graph). */
+  uint32_t est_state_ports;                 /* number of ports in d_est_state (1 or 2) */
+  uint32_t reserved0;
 } nrb200_pusch_rx_t;
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
 /* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */

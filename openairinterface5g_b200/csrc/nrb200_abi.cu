@@ -695,6 +695,7 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
                                                  int32_t *log2_maxh_out)
 {
   if (ensure_init() || !d) return -1;
+  if (d->d_est_state != 0) return -4;                                     // a device address: the _dev entry points only
   const uint32_t n_llr = pusch_num_llr(*d);
   if (n_llr == 0) return -4;
   const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers == 2 ? 2 : 1);

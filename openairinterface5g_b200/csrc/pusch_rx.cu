@@ -25,6 +25,8 @@ struct PuschGeom {
   int last_is_dmrs, last_ch_sym, last_span;   // UE: the symbol whose magnitude buffers survive until the LLRs are computed
   unsigned nvar;                   // noise variance added to the diagonal of H^H H (2 layers)
   int lvl_amp, lvl_b;              // nr_ulsch_scale_channel constants of the level measurement
+  const int *est_state;            // optional (device): the channel estimator's state, 18 int32 per port; replaces nvar / lvl_amp / lvl_b (est_scalars)
+  int est_ports, est_div;          // ports in est_state; nr_of_symbols * nrOfLayers * nb_rx
 };
 
 __device__ __forceinline__ int p_sat16(int v) { return max(-32768, min(32767, v)); }
@@ -34,6 +36,23 @@ __device__ __forceinline__ int p_hi(unsigned w) { return (int)(short)(w >> 16); 
 __device__ __forceinline__ int p_abs16w(int v) { return v == -32768 ? -32768 : abs(v); }
 __device__ __forceinline__ int p_subs16(int a, int b) { return max(-32768, min(32767, a - b)); }
 __device__ __forceinline__ int p_mulhrs(int a, int b) { return p_wrap16((a * b + 0x4000) >> 15); }
+
+// nvar and the nr_ulsch_scale_channel constants, from the descriptor or -- stream ordered behind the estimator, no host round trip -- from the
+// estimator's device state: max_ch = max over ports, nvar = sum over ports / (symbols * layers * antennas) (nr_ulsch_demodulation.c:1470-1524),
+// shift_ch_ext = log2_approx(max_ch >> 11) (:382-432)
+__device__ __forceinline__ void est_scalars(const PuschGeom &G, unsigned &nvar, int &amp, int &b)
+{
+  nvar = G.nvar; amp = G.lvl_amp; b = G.lvl_b;
+  if (G.est_state == nullptr) return;
+  int mx = 0;
+  unsigned long long nv = 0;
+  for (int p = 0; p < G.est_ports; p++) { mx = max(mx, __ldg(G.est_state + 18 * p)); nv += (unsigned)__ldg(G.est_state + 18 * p + 1); }
+  nvar = (unsigned)(nv / (unsigned long long)G.est_div);
+  const unsigned v = (unsigned)mx >> 11;
+  const int sce = v ? 32 - __clz(v) : 0;
+  b = 3; amp = 8192;
+  if (sce > 3) { b = 0; amp = (short)(amp >> (sce - 3)); if (amp == 0) amp = 1; } else b -= sce;
+}
 
 // i-th extracted RE of a symbol -> (sub-carrier in the symbol, index into the channel estimates), exactly the reference's loops
 // (including the type-2 branch that forgets start_re when the allocation does not wrap, :345-351)
@@ -163,10 +182,12 @@ __global__ void __launch_bounds__(256) pusch_rx2_kernel(PuschGeom G, const GoldT
       }
     }
   }
-  if (G.nvar) {                                                          // add_epi32 on the packed {re, im} word (carries into im)
+  unsigned nvar; int lvl_amp_unused, lvl_b_unused;
+  est_scalars(G, nvar, lvl_amp_unused, lvl_b_unused);
+  if (nvar) {                                                            // add_epi32 on the packed {re, im} word (carries into im)
 #pragma unroll
     for (int e = 0; e < 4; e += 3) {
-      const unsigned w = (((unsigned)af[e][0] & 0xFFFFu) | ((unsigned)af[e][1] << 16)) + G.nvar;
+      const unsigned w = (((unsigned)af[e][0] & 0xFFFFu) | ((unsigned)af[e][1] << 16)) + nvar;
       af[e][0] = p_lo(w); af[e][1] = p_hi(w);
     }
   }
@@ -595,12 +616,14 @@ __global__ void __launch_bounds__(256) pusch_level_kernel(PuschGeom G, int meas_
   const int y = len >> x;
   // number of REs the extraction writes for this symbol (everything beyond stays zero and adds nothing)
   const int n_ext = !is_dmrs ? G.nb_re : G.dmrs_type == 0 ? G.nb_re / 2 : (G.nb_re / 6) * 4;
+  unsigned nvar_unused; int lvl_amp, lvl_b;
+  est_scalars(G, nvar_unused, lvl_amp, lvl_b);
   unsigned acc = 0;
   for (int i = threadIdx.x; i < min(n_ext, len & ~3); i += blockDim.x) {
     int rx_idx, ch_idx;
     re_source(G, is_dmrs, i, rx_idx, ch_idx);
     const unsigned h = __ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[meas_k] * G.N + ch_idx);
-    const int r = p_wrap16(((p_lo(h) * G.lvl_amp) >> 16) << G.lvl_b), im = p_wrap16(((p_hi(h) * G.lvl_amp) >> 16) << G.lvl_b);   // mulhi by ch_amp, slli b
+    const int r = p_wrap16(((p_lo(h) * lvl_amp) >> 16) << lvl_b), im = p_wrap16(((p_hi(h) * lvl_amp) >> 16) << lvl_b);   // mulhi by ch_amp, slli b
     acc += (unsigned)(((int)((unsigned)(r * r) + (unsigned)(im * im))) >> x);
   }
   s_sum[threadIdx.x] = acc;
@@ -640,6 +663,12 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
   G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
   G->unscramble = d.unscramble; G->c_init = (d.rnti << 15) + d.data_scrambling_id;
   G->nl = nl; G->nvar = d.noise_var;
+  G->est_state = nullptr; G->est_ports = 0; G->est_div = 1;
+  if (d.d_est_state != 0) {
+    if (nl != 2 || d.pdsch_ue || d.est_state_ports < 1 || d.est_state_ports > 2) return -4;
+    G->est_state = reinterpret_cast<const int *>((uintptr_t)d.d_est_state);
+    G->est_ports = (int)d.est_state_ports; G->est_div = (int)(d.nr_of_symbols * nl * d.nb_rx);
+  }
   G->ue = d.pdsch_ue ? 1 : 0; G->cdm = d.num_dmrs_cdm_grps_no_data;
   if (G->ue && (d.nb_rx > 4 || (nl == 2 && d.nb_rx < 2))) return -4;     // the reference applies neither MRC nor zero forcing with one rx antenna
   {

@@ -72,7 +72,8 @@ def ncols_for_rate(BG, R):
 class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_nr_pusch_pdu_t / NR_DL_FRAME_PARMS)
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order",
                                           "start_symbol_index", "nr_of_symbols", "ul_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data",
-                                          "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id", "nrOfLayers", "noise_var", "max_ch", "pdsch_ue")]
+                                          "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id", "nrOfLayers", "noise_var", "max_ch", "pdsch_ue")] + \
+               [("d_est_state", C.c_uint64), ("est_state_ports", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t

@@ -21,6 +21,7 @@ class PuschSlotChain:
         self.P = NrOfdmParms(N, mu, carrier_rb)
         self.N, self.nb_rx, self.Qm, self.slot, self.rnti, self.nid, self.max_iter = N, nb_rx, Qm, slot, rnti, nid, max_iter
         self.rb_start, self.rb_size, self.A, self.nl = rb_start, rb_size, A, n_layers
+        self.host_scalars = False
         assert n_layers in (1, 2)
         self.dmrs_pos, self.dmrs_type, self.cdm = 1 << 2, 0, 2                     # one type-1 DMRS symbol, no data on it
         self.seg = T.nr_segmentation(A + 24, 1)
@@ -129,10 +130,15 @@ class PuschSlotChain:
             lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)   # every DMRS port of the PDU (:1473-1486)
             est = self.est
             if self.nl == 2:
-                # the MMSE receiver needs two scalars of the estimator on the host side of the ABI: max_ch and nvar (:1470-1512)
-                st = self.chest_state[:, :2].cpu().numpy()
-                self.desc.max_ch = int(st[:, 0].max())
-                self.desc.noise_var = int(int(st[:, 1].astype(np.int64).sum()) // (14 * self.nl * self.nb_rx))
+                # the MMSE receiver needs two scalars of the estimator, max_ch and nvar (:1470-1512): read on the device from the estimator's state
+                # (host_scalars = True keeps the older path through the descriptor, one device-to-host read per slot)
+                if self.host_scalars:
+                    st = self.chest_state[:, :2].cpu().numpy()
+                    self.desc.d_est_state = 0
+                    self.desc.max_ch = int(st[:, 0].max())
+                    self.desc.noise_var = int(int(st[:, 1].astype(np.int64).sum()) // (14 * self.nl * self.nb_rx))
+                else:
+                    self.desc.d_est_state, self.desc.est_state_ports = self.chest_state.data_ptr(), self.nl
         lib.pusch_inner_rx_torch(self.desc, self.rxF, est, self.llr16, level=self.level)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
         lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
@@ -146,8 +152,8 @@ class PuschSlotChain:
 class PuschSlotPipeline:
     """K PUSCH slots in flight on one GPU, the uplink counterpart of dl_slot_chain.PdschSlotPipeline: K independent PuschSlotChain instances (own buffers,
     own stream, own received samples), each slot's receive launches captured once into a CUDA graph and replayed.  One slot alone is latency bound (11 dependent
-    launches, 28 code blocks on 148 SMs); a gNB serves several users and carriers, whose slots are independent.  One layer per slot (the two-layer receiver takes
-    max_ch / nvar through the host side of the ABI and is not capturable yet)."""
+    launches, 28 code blocks on 148 SMs); a gNB serves several users and carriers, whose slots are independent.  Two layers work the same way: the MMSE
+    receiver reads the estimator's max_ch / nvar from device memory (nrb200_pusch_rx_t.d_est_state), so the whole slot is stream ordered and capturable."""
 
     def __init__(self, lib, dl, device, n_inflight, use_graphs=True, seed0=200, **cfg):
         self.K, self.dev = n_inflight, device

@@ -58,3 +58,22 @@ def test_pusch_slots_in_flight_match_single_slot(ldpc):
         alone.receive(rxdata)
         torch.cuda.synchronize()
         assert torch.equal(alone.llr16, pipe.chains[k].llr16) and torch.equal(alone.iters, pipe.chains[k].iters) and torch.equal(alone.tb, pipe.chains[k].tb)
+
+
+def test_two_layer_receiver_reads_estimator_state_on_device(ldpc):
+    """nrb200_pusch_rx_t.d_est_state: max_ch / nvar taken from the estimator's device state give the LLRs, level and transport block of the path that
+    carries them through the host side of the descriptor; and the two-layer slot is capturable (PuschSlotPipeline with n_layers = 2)."""
+    from openairinterface5g_b200.slot_chain import PuschSlotPipeline
+    dl = load_dftslib()
+    dev = torch.device("cuda", 0)
+    cfg = dict(A=33640, N=1024, mu=0, carrier_rb=52, rb_size=52, nb_rx=2, Qm=6, slot=1, n_layers=2)
+    a, b = PuschSlotChain(ldpc, dl, dev, **cfg), PuschSlotChain(ldpc, dl, dev, **cfg)
+    payload, rxdata, _ = a.synthesize(seed=9)
+    b.host_scalars = True
+    a.receive(rxdata); b.receive(rxdata)
+    torch.cuda.synchronize()
+    assert torch.equal(a.level, b.level) and torch.equal(a.llr16, b.llr16) and torch.equal(a.iters, b.iters) and torch.equal(a.tb, b.tb)
+    assert b.desc.noise_var > 0 and np.array_equal(a.tb.cpu().numpy().reshape(-1)[:payload.size], payload)
+    pipe = PuschSlotPipeline(ldpc, dl, dev, 2, seed0=400, **cfg)
+    pipe.timed_rounds(2, e2e=True)
+    assert all(pipe.check(host=True))

@@ -36,14 +36,14 @@ def main():
         run(lib, dl, dev, nl)
     # throughput: K independent slots in flight (one stream + one CUDA graph per slot), device resident and with the samples / transport block crossing PCIe
     from openairinterface5g_b200.slot_chain import PuschSlotPipeline
-    for K in (4, 8, 16):
-        pipe = PuschSlotPipeline(lib, dl, dev, K)
+    for K, nl in ((4, 1), (8, 1), (16, 1), (4, 2), (8, 2), (16, 2)):
+        pipe = PuschSlotPipeline(lib, dl, dev, K) if nl == 1 else PuschSlotPipeline(lib, dl, dev, K, A=471272, n_layers=2)
         rounds = max(4, 256 // K)
         ms = pipe.timed_rounds(rounds) / (rounds * K)
         ok = pipe.check()
         ms_e = pipe.timed_rounds(rounds, e2e=True) / (rounds * K)
         ok_e = pipe.check(host=True)
-        print(json.dumps({"workload": "PUSCH slot rx 100MHz 273PRB 64QAM 4rx 1 layer, 28 CB K=8448 (TB 235624 bit)", "mode": f"{K} slots in flight (one stream + CUDA graph per slot)",
+        print(json.dumps({"workload": f"PUSCH slot rx 100MHz 273PRB 64QAM 4rx {nl} layer(s), {pipe.chains[0].C} CB K=8448 (TB {pipe.chains[0].A} bit)", "mode": f"{K} slots in flight (one stream + CUDA graph per slot)",
                           "slots_per_s": 1e3 / ms, "decoded_ok": f"{sum(ok)}/{K}", "e2e_slots_per_s": 1e3 / ms_e, "e2e_decoded_ok": f"{sum(ok_e)}/{K}",
                           "h2d_bytes_per_slot": int(pipe.h_rx[0].numel() * 2), "d2h_bytes_per_slot": int(pipe.h_tb[0].numel()),
                           "realtime_factor_vs_2000_slots_per_s": 1e3 / ms / 2000.0}), flush=True)
