@@ -100,6 +100,9 @@ typedef struct nrb200_ldpc_enc_params {
   uint8_t rv;
 } nrb200_ldpc_enc_params_t;
 
+/* A translation unit that also includes OAI's own nrLDPC_extern.h (an interposer compiled against OAI headers, integration/) defines
+ * NRB200_NO_OAI_LOADER_PROTOTYPES: the four loader symbols are then declared by OAI, with OAI's layout-identical types. */
+#ifndef NRB200_NO_OAI_LOADER_PROTOTYPES
 /* replaces LDPCinit (nrLDPC_decoder.c:162): creates the CUDA context, per-thread streams, pinned staging and
  * uploads the lifted-graph tables.  Idempotent (ldpctest calls it per segment, ldpctest.c:326).
  * Returns 0; returns -1 (loader then AssertFatal()s, nrLDPC_load.c:68) when no CUDA device is usable --
@@ -117,6 +120,7 @@ int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p_decParams, uint8_t harq_pid, uin
  * 8*macro_num .. min(8*macro_num+8, n_segments) of input[] (K/8 packed bytes each, MSB first) into
  * output[] as one bit per byte, K-2Z systematic + parity = 66Z (BG1) / 50Z (BG2) bytes.  Returns 0. */
 int32_t LDPCencoder(uint8_t **input, uint8_t **output, nrb200_ldpc_enc_params_t *impp);
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * Part 2: batched extension (same arithmetic, many code blocks per launch)

@@ -1,0 +1,25 @@
+#!/usr/bin/env bash
+# Builds the OAI-side interposers of integration/ against the reference's own headers (they define OAI symbols, so they need OAI's types):
+#   integration/_build/libnrb200_shim_chest.so      LD_PRELOAD-able nr_pusch_channel_estimation -> libldpc_b200.so
+#   oracle/_ref/libshimtest_chest.so                the reference-side caller harness (oracle/ref_harness_chest.c, test infrastructure) linked against the
+#                                                   interposer INSTEAD of nr_ul_channel_estimation.c: what tests/test_gpu_interpose.py drives on the GPU box
+# Needs oracle/build_ref.sh to have run (simde alias headers) and openairinterface5g_b200/libldpc_b200.so to exist.  Where /root/reference is absent the
+# prebuilt files are kept (they travel to the GPU box like every other built artefact).
+set -euo pipefail
+R=${OAI_REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+ROOT=$(dirname "$HERE")
+W=$ROOT/oracle/_ref
+if [ ! -d "$R/openair1" ]; then echo "reference tree not present at $R: keeping prebuilt interposers" >&2; exit 0; fi
+mkdir -p $HERE/_build
+INC="-I$W/shim -I$R/openair1 -I$R -I$R/common/utils -I$R/common/utils/LOG -I$R/common/utils/T \
+ -I$R/openair2/COMMON -I$R/nfapi/open-nFAPI/nfapi/public_inc -I$R/openair2 -I$R/openair1/PHY -I$R/common -I$R/radio/COMMON -I$R/executables \
+ -I$R/openair2/NR_UE_PHY_INTERFACE -I$R/openair2/NR_PHY_INTERFACE -I$R/openair2/PHY_INTERFACE -I$R/openair3/COMMON -I$R/openair3 -I$ROOT/include"
+DEFS="-DMAX_NUM_CCs=1 -DNB_ANTENNAS_RX=4 -DNB_ANTENNAS_TX=4 -DNUMBER_OF_UE_MAX_NB_IoT=16"
+F="-O2 -mavx2 -mno-avx512f -fPIC -shared -w -include limits.h"
+LIB="-L$ROOT/openairinterface5g_b200 -l:libldpc_b200.so"
+gcc $F $INC $DEFS $HERE/oai_shim_pusch_chest.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_chest.so
+gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_chest.c $ROOT/oracle/ref_harness_chest.c $HERE/oai_shim_pusch_chest.c \
+    $R/openair1/PHY/NR_REFSIG/nr_dmrs_rx.c $R/openair1/PHY/NR_REFSIG/nr_gold.c $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/cmult_sv.c \
+    $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -o $W/libshimtest_chest.so
+ls -la $HERE/_build/libnrb200_shim_chest.so $W/libshimtest_chest.so
