@@ -84,3 +84,5 @@ gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdschtx.c 
     $R/common/utils/nr/nr_common.c $R/openair1/PHY/MODULATION/nr_modulation.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c $R/openair1/PHY/NR_TRANSPORT/nr_scrambling.c \
     $R/openair1/PHY/NR_REFSIG/scrambling_luts.c -lm -o libref_pdschtx.so || echo "libref_pdschtx.so: FAILED"
 ls -la $W/*.so
+# the reference's side of the LDPC loader boundary (OAI's own types; dlopens the library under test at run time)
+gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_loader.c -ldl -lpthread -o libref_loader.so || echo "libref_loader.so: FAILED"

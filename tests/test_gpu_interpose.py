@@ -42,3 +42,57 @@ def test_oai_caller_reaches_the_gpu_through_the_interposed_symbol(oracle):
         est_o, out_o = oracle.pusch_channel_estimation(P, rx)
         assert np.array_equal(out, out_o), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq, out, out_o)
         assert np.array_equal(est.reshape(nb_rx, 14, N, 2)[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq)
+
+
+@pytest.mark.parametrize("so", ["libldpc_b200.so"])
+def test_reference_loader_side_with_oai_types(oracle, so):
+    """The LDPC plug-in boundary from OAI's side: oracle/ref_harness_loader.c is compiled against OAI's own nrLDPC_defs.h / nrLDPC_types.h, looks the four
+    symbols up like load_LDPClib (dlopen RTLD_LAZY | RTLD_NODELETE | RTLD_GLOBAL, dlclose after the lookup), and calls them like ldpctest -- LDPCinit again
+    before every segment, one blocking LDPCdecoder call per segment, encoder in groups of 8 segments via macro_num.  Code words, decoded bits and returned
+    iteration counts must be the oracle's."""
+    from common import make_case
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_loader.so")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run oracle/build_ref.sh where /root/reference exists")
+    h = C.CDLL(path)
+    assert h.refh_loader_open(os.path.join(ROOT, "openairinterface5g_b200", so).encode()) == 0
+    for BG, Z, R, n_seg, ebn0 in ((1, 384, 13, 11, 2.3), (2, 96, 15, 3, 1.5), (1, 176, 23, 9, 4.5)):
+        K, P, llr = make_case(oracle, BG, Z, R, n_seg, ebn0, seed=Z + n_seg)
+        Kb = 22 if BG == 1 else 10
+        nout = (66 if BG == 1 else 50) * Z
+        cw = np.zeros((n_seg, nout), np.uint8)
+        pay = np.ascontiguousarray(P, dtype=np.uint8)
+        assert h.refh_loader_encode(BG, Z, Kb, K, n_seg, pay.ctypes.data_as(C.c_void_p), cw.ctypes.data_as(C.c_void_p)) == 0
+        for j in range(n_seg):
+            assert np.array_equal(cw[j], oracle.encode(BG, Z, K, P[j])), (BG, Z, j)
+        ncol = llr.shape[1] // Z
+        out = np.zeros((n_seg, ncol * Z // 8), np.uint8)
+        iters = np.zeros(n_seg, np.int32)
+        llr = np.ascontiguousarray(llr, dtype=np.int8)
+        h.refh_loader_decode(BG, Z, R, 8, K, n_seg, llr.shape[1], llr.ctypes.data_as(C.c_void_p), out.shape[1], out.ctypes.data_as(C.c_void_p),
+                             iters.ctypes.data_as(C.c_void_p))
+        for j in range(n_seg):
+            it_o, out_o = oracle.decode(BG, Z, R, 8, llr[j], 0)
+            assert iters[j] == it_o and np.array_equal(out[j], np.asarray(out_o).view(np.uint8)), (BG, Z, R, j, iters[j], it_o)
+    # LDPCshutdown (free_LDPClib) is exercised in its own process below: this one shares the library instance with the other tests' fixtures
+
+
+def test_reference_loader_lifecycle_in_its_own_process():
+    """load -> decode -> free_LDPClib -> load again -> decode, as two physim runs in one process would (ldpctest.c:503-504, dlsim.c:1306)."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes as C, numpy as np, os, sys; sys.path.insert(0, 'tests'); from common import make_case; from oracle.bindings import Oracle\n"
+        "orc = Oracle(); h = C.CDLL('oracle/_ref/libref_loader.so'); so = os.path.abspath('openairinterface5g_b200/libldpc_b200.so').encode()\n"
+        "K, P, llr = make_case(orc, 1, 384, 13, 2, 2.4, 5); llr = np.ascontiguousarray(llr, dtype=np.int8)\n"
+        "for rnd in range(2):\n"
+        "    assert h.refh_loader_open(so) == 0\n"
+        "    out = np.zeros((2, 68 * 384 // 8), np.uint8); it = np.zeros(2, np.int32)\n"
+        "    h.refh_loader_decode(1, 384, 13, 8, K, 2, llr.shape[1], llr.ctypes.data_as(C.c_void_p), out.shape[1], out.ctypes.data_as(C.c_void_p), it.ctypes.data_as(C.c_void_p))\n"
+        "    for j in range(2):\n"
+        "        io, oo = orc.decode(1, 384, 13, 8, llr[j], 0)\n"
+        "        assert it[j] == io and np.array_equal(out[j], np.asarray(oo).view(np.uint8))\n"
+        "    assert h.refh_loader_close() == 0\n"
+        "print('LIFECYCLE_OK')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert "LIFECYCLE_OK" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
