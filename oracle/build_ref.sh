@@ -86,3 +86,5 @@ gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdschtx.c 
 ls -la $W/*.so
 # the reference's side of the LDPC loader boundary (OAI's own types; dlopens the library under test at run time)
 gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_loader.c -ldl -lpthread -o libref_loader.so || echo "libref_loader.so: FAILED"
+# OAI's dft_size_idx_t / idft_size_idx_t enumerator order (pins the size index the dft()/idft() drop-in receives)
+gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_dftidx.c -o libref_dftidx.so || echo "libref_dftidx.so: FAILED"

@@ -582,3 +582,25 @@ def test_pdsch_tx_slot(oracle, reference):
         t_r = reference.pdsch_tx_slot(P, bits, carrier)
         assert np.array_equal(t_o, t_r), (N, nrb, Qm, nl, dpos, dtype_, cdm, ports, [tuple(x) for x in np.argwhere(t_o != t_r)[:5]])
         assert np.count_nonzero(t_o) > 0
+
+
+def test_dft_size_index_enumerators_match_oai_header():
+    """The size index dft() / idft() receive is OAI's dft_size_idx_t / idft_size_idx_t enumerator: the library's table (nrb200_dft_size_of_index, no GPU needed) and
+    the Python mirror are pinned to get_dft / get_idft compiled from OAI's own tools_defs.h (oracle/ref_harness_dftidx.c)."""
+    import ctypes as C
+    import os
+    from openairinterface5g_b200 import dfts
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_dftidx.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_dftidx.so not built (needs /root/reference)")
+    ref = C.CDLL(path)
+    lib = C.CDLL(os.path.join(ROOT, "openairinterface5g_b200", "libdfts_b200.so"))
+    assert ref.refh_dft_count() == len(dfts.DFT_SIZES) and ref.refh_idft_count() == len(dfts.IDFT_SIZES)
+    for i, n in enumerate(dfts.DFT_SIZES):
+        assert ref.refh_dft_size_at(i) == n and dfts.get_dft(n) == i, (i, n)
+        assert lib.nrb200_dft_size_of_index(0, i) == n, (i, n)
+    for i, n in enumerate(dfts.IDFT_SIZES):
+        assert ref.refh_idft_size_at(i) == n and dfts.get_idft(n) == i, (i, n)
+        assert lib.nrb200_dft_size_of_index(1, i) == n, (i, n)
+    assert ref.refh_get_dft4096() == dfts.get_dft(4096) and ref.refh_get_idft4096() == dfts.get_idft(4096)
