@@ -309,9 +309,10 @@ typedef struct nrb200_pusch_chest_s {
                                              * least-squares arithmetic; max_ch and nvar are not produced (0).  rb_start + bwp_start = the PDSCH's rb_offset. */
   uint32_t dmrs_config_type;                /* pusch_pdu->dmrs_config_type: 0 = type 1, 1 = type 2 (nr_ul_channel_estimation.c:258-283) */
   uint32_t chest_freq;                      /* gNB->chest_freq: 0 = frequency-domain interpolation, 1 = one average per PRB (:285-460; NO_INTERP build).
-                                             * The three variants (type 2, chest_freq 1 of either type) serve the gNB estimator, one port per call
-                                             * (n_ports <= 1, pdsch_ue = 0).  chest_freq = 1 needs rb_size >= 2 and, for type 2, slot % 4 == 0: the reference reads
-                                             * slot-ring position 0 there.  Anything else returns -4. */
+                                             * The three variants (type 2, chest_freq 1 of either type) serve one port per call (n_ports <= 1), for the gNB estimator
+                                             * and, with pdsch_ue = 1, for the UE's (NFAPI_NR_DMRS_TYPE2_linear_interp / TYPE1_average_prb / TYPE2_average_prb,
+                                             * nr_dl_channel_estimation.c:1378-1612; type 2: ports 0..5).  chest_freq = 1 needs rb_size >= 2 and, for the gNB's type 2,
+                                             * slot % 4 == 0: the reference reads slot-ring position 0 there.  Anything else returns -4. */
 } nrb200_pusch_chest_t;
 /* the 6 * rb_size conjugated DMRS symbols {re, im} the estimator correlates with (nr_pusch_dmrs_rx output); host arithmetic, no GPU needed */
 int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots);

@@ -1,5 +1,6 @@
 // PUSCH channel estimation.  Main path: DMRS configuration type 1, frequency-domain interpolation (the reference's default, chest_freq == 0);
-// the other three branches of the reference function (type 2, and chest_freq == 1 for both types) are the "variants" further down.
+// the other three branches of the reference function (type 2, and chest_freq == 1 for both types) are the "variants" further down, and so are the UE's
+// (nr_pdsch_channel_estimation's NFAPI_NR_DMRS_TYPE2_linear_interp / TYPE1_average_prb / TYPE2_average_prb, pdsch_ue = 1).
 // Reference: nr_pusch_channel_estimation (openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c:67-243, 483-487) with nr_gold_pusch /
 // nr_pusch_dmrs_rx (NR_REFSIG/nr_gold.c:99-116, nr_dmrs_rx.c:44-116), nr_est_delay / get_delay_idx / init_delay_table
 // (common/utils/nr/nr_common.c:906-990), c16multaddVectRealComplex and filt16_ul_* (tools_defs.h:266-297, filt16a_32.h:242-249).
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(256) chest_interp_kernel(ChestGeom G, const un
         for (int pc = p_lo; pc <= p_hi; pc++) {
           const int f = filt_tap(pc, G.np, k - 4 * b);
           if (f == 0) continue;
-          const unsigned c = c_mul8(l[2 * pc], __ldg(tb + 2 * pc));          // delay-compensated LS estimate of pilot pc
+          const int si = (G.ue && G.type2) ? (pc / 3) * 6 : 2 * pc;          // UE type 2: three "pilots" share a CDM pair's value (:1499-1501)
+          const unsigned c = c_mul8(l[si], __ldg(tb + si));                  // delay-compensated LS estimate of pilot pc
           const int mr = c_mulhrs(c_lo(c), f), mi = c_mulhrs(c_hi(c), f);
           yr = c_sat16(yr + c_sat16(2 * mr)); yi = c_sat16(yi + c_sat16(2 * mi));
         }
@@ -246,6 +248,25 @@ __global__ void __launch_bounds__(128) chest_t2_ls_kernel(ChestGeom G, const Gol
   if (threadIdx.x == 0 && s_n[0]) atomicAdd(reinterpret_cast<unsigned long long *>(state + 6), s_n[0]);
 }
 
+// UE, type 2, chest_freq == 0 (NFAPI_NR_DMRS_TYPE2_linear_interp, nr_dl_channel_estimation.c:1463-1490): one thread per CDM pair and antenna,
+// the pair's average held over its 6 sub-carriers; the interpolation that follows is the type 1 one (chest_interp_kernel)
+__global__ void __launch_bounds__(128) chest_ue_t2_ls_kernel(ChestGeom G, const GoldTables *__restrict__ T, const unsigned *__restrict__ rxF, unsigned *__restrict__ ls)
+{
+  const int m = blockIdx.x * 128 + threadIdx.x, a = blockIdx.y;
+  if (m >= 2 * G.nb) return;
+  int p0r, p0i, p1r, p1i;
+  dmrs_conj(T, G.x2, G.dmrs_offset + 2 * m, G.wsign_odd[0], p0r, p0i);
+  dmrs_conj(T, G.x2, G.dmrs_offset + 2 * m + 1, G.wsign_odd[0], p1r, p1i);
+  const unsigned *rx = rxF + (size_t)a * G.rx_stride + (size_t)G.symbol * G.N;
+  const unsigned y0 = rx_at(G, rx, (G.k0 + 6 * m) % G.N + G.nushift), y1 = rx_at(G, rx, (G.k0 + 6 * m + 1) % G.N + G.nushift);
+  const int lr = c_wrap16((p0r * c_lo(y0) - p0i * c_hi(y0)) >> 15), li = c_wrap16((p0r * c_hi(y0) + p0i * c_lo(y0)) >> 15);
+  const int rr = c_wrap16((p1r * c_lo(y1) - p1i * c_hi(y1)) >> 15), ri = c_wrap16((p1r * c_hi(y1) + p1i * c_lo(y1)) >> 15);
+  const unsigned v = c_pk(c_wrap16((lr + rr) >> 1), c_wrap16((li + ri) >> 1));
+  unsigned *dst = ls + (size_t)a * G.N + 6 * m;
+#pragma unroll
+  for (int k = 0; k < 6; k++) dst[k] = v;
+}
+
 // type 2, chest_freq == 0: ul_ch[n] = c16mulShift(ls[n], delay_table[get_delay_idx(-est_delay)][n % 6], 8); the rest of the symbol is cleared
 __global__ void __launch_bounds__(256) chest_t2_apply_kernel(ChestGeom G, const unsigned *__restrict__ ls, const unsigned *__restrict__ dtab, const int *__restrict__ raw,
                                                              unsigned *__restrict__ est, int *__restrict__ state)
@@ -281,7 +302,8 @@ __global__ void __launch_bounds__(256) chest_avg_kernel(ChestGeom G, const GoldT
     for (int i = 0; i < cnt; i++) {
       int pidx, re;
       if (!G.type2) { pidx = 6 * j + i; re = (G.k0 + 12 * j + 2 * i) % G.N; }
-      else { pidx = j == 0 ? min(i, 2) : 4 * j - 1 + i; re = (G.k0 + 12 * j + (i & 1) + 6 * (i >> 1)) % G.N; }
+      else if (!G.ue) { pidx = j == 0 ? min(i, 2) : 4 * j - 1 + i; re = (G.k0 + 12 * j + (i & 1) + 6 * (i >> 1)) % G.N; }
+      else { pidx = 4 * j + i; re = (j == 0 ? G.k0 + i : G.k0 + 4 + 20 * (j - 1) + 5 * i) % G.N; }   // the UE's walk (:1541-1575): 4 consecutive, then 5 apart
       int pr, pi;
       dmrs_conj(T, G.x2, G.dmrs_offset + pidx, G.wsign_odd[0], pr, pi);
       const unsigned y = rx_at(G, rx, re + G.nushift);
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(256) chest_avg_kernel(ChestGeom G, const GoldT
       si += (pr * c_hi(y) + pi * c_lo(y)) >> 15;
     }
     const int cr = c_wrap16(sr / cnt), ci = c_wrap16(si / cnt);
-    if (j > 0 && j < G.nb - 1) { const int m = max(abs(cr), abs(ci)); if (m > 0) atomicMax(state, m); }
+    if (!G.ue && j > 0 && j < G.nb - 1) { const int m = max(abs(cr), abs(ci)); if (m > 0) atomicMax(state, m); }
     v = c_pk(cr, ci);
   }
   unsigned *dst = est + (size_t)a * G.ch_stride + (size_t)G.symbol * G.N + 12 * j;
@@ -359,12 +381,12 @@ static const unsigned *delay_table_dev(int N)
 
 static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
 {
-  if (d.nb_rx < 1 || d.nb_rx > 8 || d.symbol > 13 || d.port > 3 || d.rb_size < 1 || 12 * d.rb_size > d.fft_size || d.scid > 1 || (d.fft_size & 3)) return -4;
+  if (d.nb_rx < 1 || d.nb_rx > 8 || d.symbol > 13 || d.port > ((d.pdsch_ue && d.dmrs_config_type) ? 5u : 3u) || d.rb_size < 1 || 12 * d.rb_size > d.fft_size || d.scid > 1 || (d.fft_size & 3)) return -4;
   G->N = d.fft_size; G->nb_rx = d.nb_rx; G->symbol = d.symbol; G->nb = d.rb_size; G->np = 6 * d.rb_size;
   G->k0 = ((d.rb_start + d.bwp_start) * 12 + d.first_carrier_offset) % d.fft_size;
   G->ue = d.pdsch_ue ? 1 : 0;
   G->n_ports = d.n_ports == 0 ? 1 : (int)d.n_ports;
-  if (G->n_ports > 2 || d.port + G->n_ports > 4) return -4;
+  if (G->n_ports > 2 || d.port + G->n_ports > ((d.pdsch_ue && d.dmrs_config_type) ? 6u : 4u)) return -4;
   for (int q = 0; q < G->n_ports; q++) {
     const unsigned pp = d.port + q;
     G->delta[q] = (pp >> 1) & 1;                                            // delta1[p]
@@ -376,9 +398,10 @@ static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
   if (G->type2 || G->chest_freq) {
     // variants: gNB estimator, one port per call; the pointer shift needs an even first sub-carrier to stay inside the symbol (always the case
     // for an even first_carrier_offset); PRB averages need two PRBs; type 2 averages need slot % 4 == 0 (see the kernels' header)
-    if (G->ue || G->n_ports != 1 || d.dmrs_config_type > 1 || d.chest_freq > 1) return -4;
-    if (G->chest_freq && (d.rb_size < 2 || (G->type2 && (d.slot & 3)))) return -4;
-    G->np = (G->type2 ? 4 : 6) * d.rb_size;
+    if (G->n_ports != 1 || d.dmrs_config_type > 1 || d.chest_freq > 1) return -4;
+    if (G->chest_freq && (d.rb_size < 2 || (G->type2 && !G->ue && (d.slot & 3)))) return -4;
+    G->np = (G->type2 && !G->ue ? 4 : 6) * d.rb_size;                       // the UE's type 2 branch feeds the type 1 interpolation: 6 "pilots" per PRB
+    if (G->ue && G->type2) { static const int delta2[6] = {0, 0, 2, 2, 4, 4}; G->nushift = delta2[d.port]; }   // get_delta(p, NFAPI_NR_DMRS_TYPE2)
   }
   G->dmrs_offset = ((d.bwp_start + d.rb_start) * 12) / (G->type2 ? 3 : 2);
   G->rx_stride = d.rx_stride; G->ch_stride = d.ch_stride;
@@ -402,7 +425,7 @@ int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil)
     x2 = (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3) ^ (x2 >> 4); x2 = x2 ^ (x2 << 31) ^ (x2 << 30) ^ (x2 << 29) ^ (x2 << 28);
   };
   for (int n = 1; n < 50; n++) step();
-  const int last = G.dmrs_offset + G.np;                                     // np = 6 (type 1) or 4 (type 2) pilots per PRB
+  const int last = G.dmrs_offset + (G.type2 ? 4 : 6) * G.nb;                 // 6 (type 1) or 4 (type 2) pilots per PRB
   std::vector<uint32_t> g((size_t)(2 * last + 31) / 32 + 1);
   for (auto &w : g) { step(); w = x1 ^ x2; }
   for (int i = G.dmrs_offset; i < last; i++) {
@@ -437,6 +460,17 @@ int launch_pusch_chest(const nrb200_pusch_chest_t &d, const int16_t *rxF, int16_
     chest_avg_kernel<<<dim3((G.N / 12 + 1 + 255) / 256, G.nb_rx), 256, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, (unsigned *)est, d_state);
     ctx().launches += 1;
     NRB200_CUDA_OK(cudaGetLastError(), "chest_avg launch");
+    return 0;
+  }
+  if (G.type2 && G.ue) {
+    NRB200_CUDA_OK(cudaMemsetAsync(ls, 0, (size_t)G.nb_rx * G.N * 4, st), "chest ls memset");
+    chest_ue_t2_ls_kernel<<<dim3((2 * G.nb + 127) / 128, G.nb_rx), 128, 0, st>>>(G, gold_tables_dev(), (const unsigned *)rxF, ls);
+    NRB200_CUDA_OK(cudaGetLastError(), "chest_ue_t2_ls launch");
+    if ((rc = dft_batch_internal(G.N, 1, G.nb_rx, (const int16_t *)ls, (int16_t *)tim, 1, st)) != 0) return rc;
+    chest_peak_kernel<<<G.nb_rx, 256, 0, st>>>(G, tim, raw);
+    chest_interp_kernel<<<dim3((G.N + 255) / 256, G.nb_rx), 256, 0, st>>>(G, ls, dtab, raw, (unsigned *)est, d_state);
+    ctx().launches += 4;
+    NRB200_CUDA_OK(cudaGetLastError(), "chest_ue_t2 launch");
     return 0;
   }
   if (G.type2) {

@@ -16,6 +16,10 @@ static inline int16_t sat16(int32_t v) { return v > 32767 ? 32767 : v < -32768 ?
 static inline int16_t wrap16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
 static inline int16_t mulhrs16(int a, int b) { return wrap16(((a * b) + 0x4000) >> 15); }
 
+/* the pointer shift of some branches can address a few samples past the symbol: the next symbol's first sub-carriers, as in the reference; past the
+ * slot's last symbol (the reference reads the next slot of its ring there) the restatement and the product read 0 */
+#define RX_AT(rx, idx, c) (((idx) >= N && p->symbol >= 13) ? 0 : (rx)[2 * (idx) + (c)])
+
 static const int16_t F_P0[16] = {4096, 4096, 4096, 4096, 4096, 4096, 4096, 4096, 0, 0, 0, 0, 0, 0, 0, 0};
 static const int16_t F_P1P2[16] = {4096, 4096, 4096, 4096, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 0, 0, 0, 0};
 static const int16_t F_MID[16] = {2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048};
@@ -55,9 +59,6 @@ static void multadd16(const int16_t *filt, int16_t ar, int16_t ai, int16_t *y)
 
 /* rxdataF [nb_rx][14 N] c16; ul_ch_est [nb_rx][14 N] c16 (symbol p->symbol is rewritten, N entries + up to 8 beyond the allocation stay 0);
  * out: max_ch, nvar, est_delay, delay_max_pos, delay_max_val */
-/* the pointer shift of the variants can address one sample past the symbol: the next symbol's first sub-carrier, as in the reference; past the
- * slot's last symbol (the reference reads the next slot of its ring there) the restatement and the product read 0 */
-#define RX_AT(rx, idx, c) (((idx) >= N && p->symbol >= 13) ? 0 : (rx)[2 * (idx) + (c)])
 static int chest_type2_freq(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);
 static int chest_prb_average(const orc_chest_t *p, const int16_t *rxdataF, int16_t *ul_ch_est, int32_t *out);
 
@@ -242,29 +243,80 @@ static int chest_prb_average(const orc_chest_t *p, const int16_t *rxdataF, int16
  * filters and delay reversal as the gNB estimator; the least-squares step differs: 16-bit accumulation with >> 15 per product and a final >> 1,
  * the port's comb offset is added to the symbol pointer (not wrapped with the sub-carrier index), and there is no max_ch / noise output.
  * p->slot, symbol, port, scid, dmrs_scrambling_id as for the gNB; rb_start + bwp_start = rb_offset of the PDSCH.  dl_ch_est [nb_rx][14 N]. */
+/* UE, chest_freq == 1 (NFAPI_NR_DMRS_TYPE1_average_prb / TYPE2_average_prb, nr_dl_channel_estimation.c:1378-1612; NO_INTERP is 1 there too): every PRB's 12
+ * sub-carriers take the average of the PRB's pilot products.  Type 1 is the gNB's arithmetic.  Type 2 walks the sub-carriers its own way: the first PRB reads four
+ * CONSECUTIVE sub-carriers k0 .. k0+3, every later PRB four sub-carriers 5 apart continuing from there (k0 + 4 + 20 (j - 1) + 5 i) -- reproduced as written.
+ * The pointer shift is (p >> 1) & 1 for type 1 and delta2[p] (0, 2, 4) for type 2. */
+static int ue_prb_average(const orc_chest_t *p, const int16_t *rxdataF, int16_t *dl_ch_est)
+{
+  static const int delta2[6] = {0, 0, 2, 2, 4, 4};
+  const int N = p->fft_size, nb = p->rb_size, t2 = p->dmrs_type != 0, nushift = t2 ? delta2[p->port] : (p->port >> 1) & 1, cnt = t2 ? 4 : 6;
+  const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
+  if (nb < 2) return -1;
+  int16_t *pil = malloc(4 * (size_t)(6 * nb));
+  orc_pusch_dmrs_pilots(p, pil);
+  for (int a = 0; a < p->nb_rx; a++) {
+    const int16_t *rx = rxdataF + 2 * ((size_t)a * 14 + p->symbol) * N;
+    int16_t *dl = dl_ch_est + 2 * ((size_t)a * 14 + p->symbol) * N;
+    memset(dl, 0, 4 * (size_t)N);
+    for (int j = 0; j < nb; j++) {
+      int32_t sr = 0, si = 0;
+      for (int i = 0; i < cnt; i++) {
+        const int re = !t2 ? (k0 + 12 * j + 2 * i) % N : j == 0 ? (k0 + i) % N : (k0 + 4 + 20 * (j - 1) + 5 * i) % N;
+        const int32_t pr = pil[2 * (cnt * j + i)], pim = pil[2 * (cnt * j + i) + 1], yr = RX_AT(rx, re + nushift, 0), yi = RX_AT(rx, re + nushift, 1);
+        sr += (pr * yr - pim * yi) >> 15;
+        si += (pr * yi + pim * yr) >> 15;
+      }
+      const int16_t cr = (int16_t)(sr / cnt), ci = (int16_t)(si / cnt);
+      for (int k = 12 * j; k < 12 * j + 12; k++) { dl[2 * k] = cr; dl[2 * k + 1] = ci; }
+    }
+  }
+  free(pil);
+  return 0;
+}
+
 int orc_pdsch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, int16_t *dl_ch_est)
 {
-  const int N = p->fft_size, nb = p->rb_size, np = 6 * nb, nushift = (p->port >> 1) & 1;
+  static const int delta2[6] = {0, 0, 2, 2, 4, 4};
+  if (p->chest_freq) return ue_prb_average(p, rxdataF, dl_ch_est);
+  /* DMRS type 2 (NFAPI_NR_DMRS_TYPE2_linear_interp, :1463-1528): one least-squares value per CDM pair held over the pair's 6 sub-carriers, then the TYPE 1
+   * machinery on top of it -- 6 "pilots" per PRB, three of them sharing a value (k = (pilot / 3) * 6), the same four 16-tap filters, delay compensation and reversal */
+  const int t2 = p->dmrs_type != 0;
+  const int N = p->fft_size, nb = p->rb_size, np = 6 * nb, nushift = t2 ? delta2[p->port] : (p->port >> 1) & 1;
   const int k0 = ((p->rb_start + p->bwp_start) * 12 + p->first_carrier_offset) % N;
   int16_t *pil = malloc(4 * (size_t)np), *ls = malloc(4 * (size_t)N), *tim = malloc(4 * (size_t)N), *acc = malloc(4 * (size_t)(N + 16));
   orc_pusch_dmrs_pilots(p, pil);
   int max_pos = 0, max_val = 0;
   for (int a = 0; a < p->nb_rx; a++) {
-    const int16_t *rx = rxdataF + 2 * (((size_t)a * 14 + p->symbol) * N + nushift);
+    const int16_t *rx = rxdataF + 2 * ((size_t)a * 14 + p->symbol) * N;
     int16_t *dl = dl_ch_est + 2 * ((size_t)a * 14 + p->symbol) * N;
     memset(ls, 0, 4 * (size_t)N);
     memset(acc, 0, 4 * (size_t)(N + 16));
     int re = k0;
-    for (int pc = 0; pc < np; pc += 2) {
-      const int32_t p0r = pil[2 * pc], p0i = pil[2 * pc + 1], p1r = pil[2 * pc + 2], p1i = pil[2 * pc + 3];
-      const int32_t y0r = rx[2 * re], y0i = rx[2 * re + 1];
-      re = (re + 2) % N;
-      const int32_t y1r = rx[2 * re], y1i = rx[2 * re + 1];
-      re = (re + 2) % N;
-      int16_t cr = (int16_t)((p0r * y0r - p0i * y0i) >> 15), ci = (int16_t)((p0r * y0i + p0i * y0r) >> 15);          /* c16mulShift */
-      cr = (int16_t)(((p1r * y1r - p1i * y1i) >> 15) + cr); ci = (int16_t)(((p1r * y1i + p1i * y1r) >> 15) + ci);     /* c16maddShift */
-      cr = (int16_t)(cr >> 1); ci = (int16_t)(ci >> 1);                                                               /* c16Shift */
-      for (int k = 2 * pc; k < 2 * pc + 4; k++) { ls[2 * k] = cr; ls[2 * k + 1] = ci; }
+    if (!t2) {
+      for (int pc = 0; pc < np; pc += 2) {
+        const int32_t p0r = pil[2 * pc], p0i = pil[2 * pc + 1], p1r = pil[2 * pc + 2], p1i = pil[2 * pc + 3];
+        const int32_t y0r = RX_AT(rx, re + nushift, 0), y0i = RX_AT(rx, re + nushift, 1);
+        re = (re + 2) % N;
+        const int32_t y1r = RX_AT(rx, re + nushift, 0), y1i = RX_AT(rx, re + nushift, 1);
+        re = (re + 2) % N;
+        int16_t cr = (int16_t)((p0r * y0r - p0i * y0i) >> 15), ci = (int16_t)((p0r * y0i + p0i * y0r) >> 15);          /* c16mulShift */
+        cr = (int16_t)(((p1r * y1r - p1i * y1i) >> 15) + cr); ci = (int16_t)(((p1r * y1i + p1i * y1r) >> 15) + ci);     /* c16maddShift */
+        cr = (int16_t)(cr >> 1); ci = (int16_t)(ci >> 1);                                                               /* c16Shift */
+        for (int k = 2 * pc; k < 2 * pc + 4; k++) { ls[2 * k] = cr; ls[2 * k + 1] = ci; }
+      }
+    } else {
+      for (int pc = 0; pc < 4 * nb; pc += 2) {
+        const int32_t p0r = pil[2 * pc], p0i = pil[2 * pc + 1], p1r = pil[2 * pc + 2], p1i = pil[2 * pc + 3];
+        const int32_t y0r = RX_AT(rx, re + nushift, 0), y0i = RX_AT(rx, re + nushift, 1);
+        re = (re + 1) % N;
+        const int32_t y1r = RX_AT(rx, re + nushift, 0), y1i = RX_AT(rx, re + nushift, 1);
+        re = (re + 5) % N;
+        const int16_t lr = (int16_t)((p0r * y0r - p0i * y0i) >> 15), li = (int16_t)((p0r * y0i + p0i * y0r) >> 15);
+        const int16_t rr = (int16_t)((p1r * y1r - p1i * y1i) >> 15), ri = (int16_t)((p1r * y1i + p1i * y1r) >> 15);
+        const int16_t cr = (int16_t)((lr + rr) >> 1), ci = (int16_t)((li + ri) >> 1);                                   /* c16addShift */
+        for (int k = 3 * pc; k < 3 * pc + 6; k++) { ls[2 * k] = cr; ls[2 * k + 1] = ci; }
+      }
     }
     orc_dft(N, 1, ls, tim, 1);
     for (int i = 0; i < N; i++) {
@@ -277,7 +329,7 @@ int orc_pdsch_channel_estimation(const orc_chest_t *p, const int16_t *rxdataF, i
     const int dly = d_idx - 20, idly = i_idx - 20;
     int base = 0;
     for (int pc = 0; pc < np; pc++) {
-      const int k = pc << 1;
+      const int k = t2 ? (pc / 3) * 6 : pc << 1;
       const double ang = 2.0 * M_PI * k * dly / N;
       const int16_t tr = (int16_t)round(256 * cos(ang)), ti = (int16_t)round(256 * sin(ang));
       const int32_t lr = ls[2 * k], li = ls[2 * k + 1];

@@ -192,3 +192,11 @@ def test_chest_time_avg_golden(oracle):
         first = min(s for s in range(start, start + nsym) if (bitmap >> s) & 1)
         assert np.array_equal(out[:, first], g[f"tavg_out{i}"]), i
         assert np.array_equal(np.delete(out, first, axis=1), np.delete(g["tavg_in"], first, axis=1)), i
+
+
+def test_ue_chest_variants_golden(oracle):
+    from oracle.bindings import ChestParms
+    g = _load("chest_variants.npz")
+    for i in range(4):
+        P = ChestParms(*[int(x) for x in g[f"ue_par{i}"]])
+        assert np.array_equal(oracle.pdsch_channel_estimation(P, g["rx"])[:, P.symbol], g[f"ue_est{i}"]), i

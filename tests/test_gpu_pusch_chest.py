@@ -125,7 +125,8 @@ def test_pusch_chest_variants_vs_oracle(ldpc, oracle, dmrs_type, chest_freq):
 def test_pusch_chest_variants_refuse_what_the_reference_cannot_do(ldpc):
     from openairinterface5g_b200.ldpc import Nrb200Error
     rx = np.zeros((2, 14, 512, 2), np.int16)
-    for kw in (dict(rb_size=1, chest_freq=1), dict(slot=5, dmrs_config_type=1, chest_freq=1), dict(n_ports=2, dmrs_config_type=1), dict(pdsch_ue=1, chest_freq=1)):
+    for kw in (dict(rb_size=1, chest_freq=1), dict(slot=5, dmrs_config_type=1, chest_freq=1), dict(n_ports=2, dmrs_config_type=1), dict(pdsch_ue=1, chest_freq=1, rb_size=1),
+               dict(port=4, dmrs_config_type=1), dict(pdsch_ue=1, port=4)):
         f = dict(fft_size=512, nb_rx=2, slot=4, symbol=2, port=0, rb_start=0, bwp_start=0, rb_size=20, first_carrier_offset=362, scid=0, ul_dmrs_scrambling_id=7,
                  rx_stride=14 * 512, ch_stride=14 * 512, n_ports=1, pdsch_ue=0, dmrs_config_type=0, chest_freq=0)
         f.update(kw)
@@ -154,3 +155,22 @@ def test_chest_time_domain_avg_vs_oracle(ldpc, oracle):
         ldpc.chest_time_avg_host(est, 14, 0, 0, 11)             # no DMRS symbol: AssertFatal in the reference
     with pytest.raises(Nrb200Error):
         ldpc.chest_time_avg_host(est, 14, 0, 0b11111, 11)       # five DMRS symbols
+
+
+@pytest.mark.parametrize("dmrs_type,chest_freq", [(1, 0), (0, 1), (1, 1)])
+def test_pdsch_chest_ue_variants_vs_oracle(ldpc, oracle, dmrs_type, chest_freq):
+    """pdsch_ue = 1 with DMRS type 2 (ports 0-5) and with the per-PRB averages: the UE's own walks over the pilots (oracle pinned to nr_pdsch_channel_estimation)."""
+    rng = np.random.default_rng(80 + 2 * dmrs_type + chest_freq)
+    cases = [(4096, 2, 4, 2, 0, 0, 273, 273, 0, 77), (2048, 2, 8, 3, 1, 10, 50, 106, 1, 1007), (1024, 3, 0, 11, 2, 20, 32, 52, 0, 300), (1024, 2, 12, 2, 3, 0, 52, 52, 1, 0),
+             (512, 4, 16, 5, 0, 3, 11, 25, 0, 9), (2048, 1, 5, 0, 1, 30, 2, 106, 0, 65535), (1024, 2, 9, 13, 3, 0, 52, 52, 0, 41)]
+    if dmrs_type == 1:
+        cases += [(1024, 2, 3, 4, 4, 0, 52, 52, 0, 21), (1024, 2, 7, 6, 5, 8, 30, 52, 1, 22), (1024, 2, 7, 13, 5, 0, 52, 52, 1, 23)]
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid in cases:
+        fco = N - carrier * 6
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, dmrs_type, chest_freq)
+        d = PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 1, 1, dmrs_type, chest_freq)
+        rx = rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16) if N == 512 else rng.integers(-3000, 3001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        est, st = ldpc.pusch_chest_host(d, rx)
+        est_o = oracle.pdsch_channel_estimation(P, rx)
+        assert np.array_equal(est[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq)
+        assert st[0] == 0 and st[1] == 0

@@ -518,6 +518,24 @@ def test_pdsch_channel_estimation_ue(oracle, reference):
         assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
 
 
+@pytest.mark.parametrize("dmrs_type,chest_freq", [(1, 0), (0, 1), (1, 1)])
+def test_pdsch_channel_estimation_ue_variants(oracle, reference, dmrs_type, chest_freq):
+    """UE estimator, DMRS type 2 (NFAPI_NR_DMRS_TYPE2_linear_interp) and the per-PRB averages of both types, against the real nr_pdsch_channel_estimation.
+    Type 2 ports 0-5 (pointer shift 0 / 2 / 4)."""
+    from oracle.bindings import ChestParms
+    rng = np.random.default_rng(65 + 2 * dmrs_type + chest_freq)
+    cases = [(4096, 2, 4, 2, 0, 0, 273, 273, 0, 77), (2048, 2, 8, 3, 1, 10, 50, 106, 1, 1007), (1024, 3, 0, 11, 2, 20, 32, 52, 0, 300), (1024, 2, 12, 2, 3, 0, 52, 52, 1, 0),
+             (512, 4, 16, 5, 0, 3, 11, 25, 0, 9), (2048, 1, 5, 0, 1, 30, 2, 106, 0, 65535)]
+    if dmrs_type == 1:
+        cases += [(1024, 2, 3, 4, 4, 0, 52, 52, 0, 21), (1024, 2, 7, 6, 5, 8, 30, 52, 1, 22)]
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid in cases:
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, scid, nid, dmrs_type, chest_freq)
+        rx = rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16) if N == 512 else rng.integers(-3000, 3001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        est_r = reference.pdsch_channel_estimation(P, rx, carrier, chest_freq=chest_freq, dmrs_type=dmrs_type)
+        est_o = oracle.pdsch_channel_estimation(P, rx)
+        assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq)
+
+
 PDSCH_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols
     (4096, 2, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13), (4096, 4, 0, 273, 8, 1 << 2, 0, 1, 273, 1, 13), (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13),
     (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10), (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12), (512, 4, 3, 11, 8, 1 << 1, 0, 1, 25, 1, 6),

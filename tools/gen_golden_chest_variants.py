@@ -27,6 +27,11 @@ def main():
         g[f"par{i}"], g[f"est{i}"], g[f"state{i}"] = np.array(par, np.int32), est[:, symbol], out
         g[f"pilots{i}"] = pil[:2 * (4 if dmrs_type else 6) * rb_size]
         cases.append(i)
+    # UE estimator variants (nr_pdsch_channel_estimation): type 2 linear interpolation (ports 1 and 4) and both per-PRB averages
+    for i, (dmrs_type, chest_freq, slot, symbol, port, rb_start, rb_size) in enumerate(((1, 0, 7, 3, 1, 3, 20), (1, 0, 2, 11, 4, 0, 25), (0, 1, 5, 2, 2, 1, 22), (1, 1, 9, 4, 5, 0, 25))):
+        par = [N, nrx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, i & 1, 400 + i, dmrs_type, chest_freq]
+        g[f"ue_par{i}"] = np.array(par, np.int32)
+        g[f"ue_est{i}"] = ref.pdsch_channel_estimation(ChestParms(*par), rx, carrier, chest_freq=chest_freq, dmrs_type=dmrs_type)[:, symbol]
     # nr_chest_time_domain_avg: 2, 3 and 4 DMRS symbols on full-scale estimates
     est = rng.integers(-32768, 32768, size=(2, 14, N, 2)).astype(np.int16)
     est[:, :, ::5] //= 50
