@@ -302,9 +302,20 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL printf()s its version banner to stdout when the first communicator is created; rank 0's stdout carries exactly one JSON line, so file
+        # descriptor 1 points at stderr until that has happened (C stdio flushed before it is restored)
+        import ctypes
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            ctypes.CDLL(None).fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
     from openairinterface5g_b200.ldpc import load_LDPClib
     lib = load_LDPClib()
 

@@ -32,9 +32,18 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        import ctypes
+        saved = os.dup(1)                     # NCCL's version banner goes to stderr (see bench.py)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            ctypes.CDLL(None).fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
     lib, dl = load_LDPClib(), load_dftslib()
     mine = [ue for ue in range(args.ues) if sticky_gpu(ue, 0, world) == rank]
     pipe = PuschSlotPipeline(lib, dl, dev, len(mine), seed0=500 + 100 * rank, A=471272, n_layers=2) if mine else None
