@@ -71,7 +71,17 @@ class PuschParms(C.Structure):       # orc_pusch_t
 class PdschTxParms(C.Structure):     # orc_pdsch_tx_t
     _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "Qm", "nrOfLayers", "start_symbol",
                                          "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports", "scid",
-                                         "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp")]
+                                         "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "pm_idx")] + [("pm_weights", C.c_int16 * 32)]
+
+    def set_precoding(self, pm_idx, weights):
+        """weights [4 layers][4 antennas][2] int16 (nfapi_nr_pm_pdu_t.weights); pm_idx 0 = identity."""
+        self.pm_idx = pm_idx
+        w = np.zeros((4, 4, 2), np.int16)
+        if weights is not None:
+            a = np.asarray(weights, dtype=np.int16)
+            w[:a.shape[0], :a.shape[1]] = a
+        self.pm_weights = (C.c_int16 * 32)(*[int(x) for x in w.reshape(-1)])
+        return self
 
     def G(self):
         n_dmrs_sym = bin(self.dl_dmrs_symb_pos & (((1 << self.nr_of_symbols) - 1) << self.start_symbol)).count("1")
@@ -585,7 +595,11 @@ class Reference:
         b = np.ascontiguousarray(bits, dtype=np.uint8).copy()
         out = np.zeros((P.nb_tx, 14, P.fft_size, 2), np.int16)
         self._pdschtxlib.refh_pdsch_tx_slot.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        self._pdschtxlib.refh_pdschtx_set_precoding.argtypes = [C.c_int, C.c_void_p]
+        w = np.array(list(P.pm_weights), dtype=np.int16)
+        self._pdschtxlib.refh_pdschtx_set_precoding(int(P.pm_idx), w.ctypes.data)
         self._pdschtxlib.refh_pdsch_tx_slot(prm.ctypes.data, b.ctypes.data, b.size, out.ctypes.data)
+        self._pdschtxlib.refh_pdschtx_set_precoding(0, None)
         return out
 
     def _pusch(self):

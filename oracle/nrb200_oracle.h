@@ -105,6 +105,8 @@ void orc_ofdm_rx_slot(int N, int mu, int nb_rb, int slot, int divisor, int sampl
 typedef struct {
   int32_t fft_size, nb_tx, slot, rb_start, bwp_start, rb_size, first_carrier_offset, Qm, nrOfLayers, start_symbol, nr_of_symbols, dl_dmrs_symb_pos,
           dmrs_config_type, num_dmrs_cdm_grps_no_data, dmrs_ports, scid, dl_dmrs_scrambling_id, data_scrambling_id, rnti, amp;
+  int32_t pm_idx;               /* 0: identity precoding; > 0: the wideband precoding matrix below (one PRG spanning the allocation) */
+  int16_t pm_weights[4][4][2];  /* nfapi_nr_pm_pdu_t.weights[layer][antenna] {Re, Im} */
 } orc_pdsch_tx_t;
 int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txdataF);
 

@@ -95,6 +95,31 @@ int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txd
       }
     }
   }
+  if (p->pm_idx > 0) {
+    /* non-identity precoding (:536-590, nr_layer_precoder_simd / nr_layer_precoder_cm, MODULATION/nr_modulation.c:702-815): with one PRG the RBs are taken two at a
+     * time (the last one alone when rb_size is odd); a group whose last sub-carrier stays below the end of the symbol (subCarrier + re_cnt < N) goes through
+     * the SIMD routine -- per-layer products truncated to 16 bits, SATURATING accumulation over the layers -- any other group through the scalar one, whose
+     * c16maddShift accumulation WRAPS.  (The SIMD routine conjugates the weight in 16 bits; a weight with Im = -32768 is not restated.) */
+    int16_t *lay = malloc(4 * (size_t)nl * 14 * N);
+    memcpy(lay, txdataF, 4 * (size_t)nl * 14 * N);
+    for (int ant = 0; ant < p->nb_tx; ant++)
+      for (int l = p->start_symbol; l < p->start_symbol + p->nr_of_symbols; l++)
+        for (int i = 0; i < p->rb_size * 12; i++) {
+          const int g = i / 24, cnt = (p->rb_size * 12 - 24 * g) >= 24 ? 24 : 12, sc_g = (start_sc + 24 * g) % N, wraps = sc_g + cnt >= N;
+          const int k = (start_sc + i) % N;
+          int32_t yr = 0, yi = 0;
+          for (int al = 0; al < nl; al++) {
+            const int32_t xr = lay[2 * (((size_t)al * 14 + l) * N + k)], xi = lay[2 * (((size_t)al * 14 + l) * N + k) + 1];
+            const int32_t wr = p->pm_weights[al][ant][0], wi = p->pm_weights[al][ant][1];
+            const int16_t pr = wrap16_((xr * wr - xi * wi) >> 15), pi = wrap16_((xr * wi + xi * wr) >> 15);
+            if (wraps) { yr = wrap16_(yr + pr); yi = wrap16_(yi + pi); }
+            else { yr = yr + pr > 32767 ? 32767 : yr + pr < -32768 ? -32768 : yr + pr; yi = yi + pi > 32767 ? 32767 : yi + pi < -32768 ? -32768 : yi + pi; }
+          }
+          txdataF[2 * (((size_t)ant * 14 + l) * N + k)] = (int16_t)yr; txdataF[2 * (((size_t)ant * 14 + l) * N + k) + 1] = (int16_t)yi;
+        }
+    free(lay); free(scr); free(mod); free(mod_dmrs); free(gold);
+    return G;
+  }
   /* antennas beyond the layers: zero over the allocation (identity precoding, :497-523) */
   for (int ant = nl; ant < p->nb_tx; ant++)
     for (int l = p->start_symbol; l < p->start_symbol + p->nr_of_symbols; l++)

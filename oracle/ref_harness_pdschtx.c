@@ -31,6 +31,12 @@ int nr_dlsch_encoding(PHY_VARS_gNB *gNB, int frame, uint8_t slot, NR_DL_gNB_HARQ
 
 double refh_pdschtx_last_seconds(void) { return g_last_s; }
 
+/* wideband precoding for the next refh_pdsch_tx_slot calls: pm_idx = 0 restores the identity; weights [layer][antenna]{re, im} (nfapi_nr_pm_pdu_t.weights).
+ * One PRG spanning the allocation: precodingAndBeamforming.prgs_list has a single entry in the reference's nFAPI structures (nfapi_nr_interface_scf.h:704). */
+static int g_pm_idx;
+static int16_t g_pm_w[4][4][2];
+void refh_pdschtx_set_precoding(int pm_idx, const int16_t *weights) { g_pm_idx = pm_idx; if (weights) memcpy(g_pm_w, weights, sizeof(g_pm_w)); }
+
 enum { X_N, X_N_RB_DL, X_NB_TX, X_SLOT, X_RB_START, X_BWP_START, X_RB_SIZE, X_FCO, X_QM, X_NL, X_START_SYMBOL, X_NR_SYMBOLS, X_DMRS_POS, X_DMRS_TYPE,
        X_CDM_GROUPS, X_DMRS_PORTS, X_SCID, X_DMRS_ID, X_DATA_ID, X_RNTI, X_AMP, X_COUNT };
 
@@ -71,6 +77,15 @@ int refh_pdsch_tx_slot(const int32_t *p, const uint8_t *bits, uint32_t nbits, in
   rel15->numDmrsCdmGrpsNoData = p[X_CDM_GROUPS]; rel15->dmrsPorts = p[X_DMRS_PORTS]; rel15->SCID = p[X_SCID]; rel15->dlDmrsScramblingId = p[X_DMRS_ID];
   rel15->dataScramblingId = p[X_DATA_ID]; rel15->rnti = p[X_RNTI]; rel15->nrOfLayers = p[X_NL]; rel15->NrOfCodewords = 1; rel15->qamModOrder[0] = p[X_QM];
   rel15->pduBitmap = 0; rel15->precodingAndBeamforming.prg_size = 0;
+  nfapi_nr_pm_pdu_t *pm_pdus = NULL;
+  if (g_pm_idx > 0) {
+    rel15->precodingAndBeamforming.num_prgs = 1; rel15->precodingAndBeamforming.prg_size = rel15->rbSize; rel15->precodingAndBeamforming.prgs_list[0].pm_idx = g_pm_idx;
+    pm_pdus = calloc(g_pm_idx, sizeof(*pm_pdus));
+    gNB->gNB_config.pmi_list.num_pm_idx = g_pm_idx; gNB->gNB_config.pmi_list.pmi_pdu = pm_pdus;
+    nfapi_nr_pm_pdu_t *e = &pm_pdus[g_pm_idx - 1];
+    e->pm_idx = g_pm_idx; e->numLayers = rel15->nrOfLayers; e->num_ant_ports = ntx;
+    for (int l = 0; l < 4; l++) for (int a = 0; a < 4; a++) { e->weights[l][a].precoder_weight_Re = g_pm_w[l][a][0]; e->weights[l][a].precoder_weight_Im = g_pm_w[l][a][1]; }
+  }
   processingData_L1tx_t *msgTx = calloc(1, sizeof(*msgTx));
   msgTx->gNB = gNB; msgTx->dlsch = dlv; msgTx->num_pdsch_slot = 1; msgTx->slot = slot;
   g_bits = bits; g_nbits = nbits;
@@ -81,6 +96,6 @@ int refh_pdsch_tx_slot(const int32_t *p, const uint8_t *bits, uint32_t nbits, in
   for (int s = 0; s < fp->slots_per_frame; s++) { for (int l = 0; l < 14; l++) { for (int q = 0; q < 2; q++) free(gNB->nr_gold_pdsch_dmrs[s][l][q]); free(gNB->nr_gold_pdsch_dmrs[s][l]); } free(gNB->nr_gold_pdsch_dmrs[s]); }
   free(gNB->nr_gold_pdsch_dmrs);
   for (int a = 0; a < ntx; a++) free(gNB->common_vars.txdataF[a]);
-  free(gNB->common_vars.txdataF); free(gNB->common_vars.beam_id[0]); free(gNB->common_vars.beam_id); free(harq->f); free(dl); free(msgTx); free(gNB);
+  free(gNB->common_vars.txdataF); free(gNB->common_vars.beam_id[0]); free(gNB->common_vars.beam_id); free(harq->f); free(dl); free(msgTx); free(gNB); free(pm_pdus);
   return 0;
 }

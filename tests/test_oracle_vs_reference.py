@@ -602,6 +602,29 @@ def test_pdsch_tx_slot(oracle, reference):
         assert np.count_nonzero(t_o) > 0
 
 
+def test_pdsch_tx_slot_wideband_precoding(oracle, reference):
+    """Non-identity precoding (pm_idx > 0, one PRG over the allocation): nr_layer_precoder_simd for RB pairs that end below the symbol's last sub-carrier
+    (saturating accumulation over the layers), nr_layer_precoder_cm for the others (wrapping).  Weights near full scale provoke both behaviours; odd and even
+    rb_size, allocations that wrap around DC and ones that end exactly at the symbol's last sub-carrier."""
+    from oracle.bindings import PdschTxParms
+    rng = np.random.default_rng(71)
+    cases = [  # N, carrier, ntx, slot, rb0, nrb, Qm, nl
+        (4096, 273, 4, 1, 0, 273, 6, 2), (4096, 273, 2, 3, 0, 272, 8, 2), (2048, 106, 4, 5, 10, 51, 4, 1), (1024, 52, 4, 0, 3, 40, 6, 4), (1024, 52, 2, 7, 0, 26, 2, 2),
+        (512, 25, 4, 2, 2, 21, 6, 3), (512, 25, 4, 2, 0, 12, 6, 2),
+    ]
+    for N, carrier, ntx, slot, rb0, nrb, Qm, nl in cases:
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, 1, 13, 1 << 2, 0, 2, (1 << nl) - 1, 0, 40 + slot, 501, 0x1234, 512 if Qm < 8 else 30000)
+        w = rng.integers(-32767, 32768, size=(4, 4, 2)).astype(np.int16)
+        if Qm < 8:
+            w //= 3
+        P.set_precoding(1 + (slot % 3), w)
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        t_o = oracle.pdsch_tx_slot(P, bits)
+        t_r = reference.pdsch_tx_slot(P, bits, carrier)
+        assert np.array_equal(t_o, t_r), (N, nrb, Qm, nl, ntx, [tuple(x) for x in np.argwhere(t_o != t_r)[:5]])
+        assert np.count_nonzero(t_o[ntx - 1]) > 0                       # every antenna radiates
+
+
 def test_dft_size_index_enumerators_match_oai_header():
     """The size index dft() / idft() receive is OAI's dft_size_idx_t / idft_size_idx_t enumerator: the library's table (nrb200_dft_size_of_index, no GPU needed) and
     the Python mirror are pinned to get_dft / get_idft compiled from OAI's own tools_defs.h (oracle/ref_harness_dftidx.c)."""
