@@ -363,6 +363,10 @@ typedef struct nrb200_pdsch_tx_s {
   uint32_t scid, dl_dmrs_scrambling_id, data_scrambling_id, rnti;
   uint32_t amp;                             /* gNB->TX_AMP */
   uint32_t tx_stride;                       /* _dev: c16 between antennas of txdataF */
+  uint32_t pm_idx;                          /* precodingAndBeamforming.prgs_list[0].pm_idx: 0 = identity (layer l -> antenna l, the others zeroed); > 0 = the
+                                             * matrix below on every RB of the allocation (one PRG: the reference's nFAPI structure holds a single prgs_list entry),
+                                             * nr_dlsch.c:536-590 with nr_layer_precoder_simd / nr_layer_precoder_cm; nb_tx <= 4 */
+  int16_t pm_weights[4][4][2];              /* gNB_config.pmi_list.pmi_pdu[pm_idx - 1].weights[layer][antenna] {precoder_weight_Re, precoder_weight_Im} */
 } nrb200_pdsch_tx_t;
 uint32_t nrb200_pdsch_tx_num_bits(const nrb200_pdsch_tx_t *d);                 /* G = nb_re * Qm as nr_generate_pdsch derives it, 0 if invalid */
 int32_t nrb200_pdsch_tx_slot_dev(const nrb200_pdsch_tx_t *d, const uint8_t *d_f, int16_t *d_txdataF, void *stream);

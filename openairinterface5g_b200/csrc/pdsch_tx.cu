@@ -20,6 +20,8 @@ struct PdschTxGeom {
   unsigned m_base[14], dmrs_cinit[14];
   int delta[4], wf1[4];            // per layer: DMRS comb offset and Wf(1) (Wf(0) = Wt = 1 for the supported ports)
   int dmrs_idx0;
+  int pm;                          // > 0: wideband non-identity precoding with pmw (one PRG over the allocation)
+  short pmw[4][4][2];              // nfapi_nr_pm_pdu_t.weights[layer][antenna] {Re, Im}
 };
 
 __device__ __forceinline__ int t_wrap16(int v) { return (int)(short)v; }
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(256) pdsch_tx_kernel(PdschTxGeom G, const Gold
   }
   __syncthreads();
   if (i >= G.nb_re) return;
+  unsigned lay[4] = {0u, 0u, 0u, 0u};                                              // this RE's value on every layer (txdataF_precoding[layer][symbol][k])
   int kk = G.start_sc + i;
   if (kk >= G.N) kk -= G.N;
   const size_t o = (size_t)symbol * G.N + kk;
@@ -70,19 +73,24 @@ __global__ void __launch_bounds__(256) pdsch_tx_kernel(PdschTxGeom G, const Gold
     const unsigned m = G.m_base[k] + (unsigned)i;
     const int j = i < G.upper ? i : i - G.upper, len = i < G.upper ? G.upper : G.rem;
     const bool body = j < (len & ~3);
-    for (int l = 0; l < G.nl; l++) {
-      const unsigned x = modsym(m * G.nl + l);
-      const int xr = (int)(short)(x & 0xFFFFu), xi = (int)(short)(x >> 16);
-      const int r = body ? t_wrap16((xr * G.amp + 0x4000) >> 15) : t_wrap16(((xr * G.amp) >> 14) + 1);
-      const int im = body ? t_wrap16((xi * G.amp + 0x4000) >> 15) : t_wrap16(((xi * G.amp) >> 14) + 1);
-      txF[(size_t)l * G.tx_stride + o] = ((unsigned)r & 0xFFFFu) | ((unsigned)im << 16);
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      if (l < G.nl) {
+        const unsigned x = modsym(m * G.nl + l);
+        const int xr = (int)(short)(x & 0xFFFFu), xi = (int)(short)(x >> 16);
+        const int r = body ? t_wrap16((xr * G.amp + 0x4000) >> 15) : t_wrap16(((xr * G.amp) >> 14) + 1);
+        const int im = body ? t_wrap16((xi * G.amp + 0x4000) >> 15) : t_wrap16(((xi * G.amp) >> 14) + 1);
+        lay[l] = ((unsigned)r & 0xFFFFu) | ((unsigned)im << 16);
+      }
     }
   } else {
     int g6 = 0, r;
     if (G.type == 0) r = i & 1; else { g6 = i / 6; r = i - 6 * g6; }
     const bool data_ok = G.type == 0 ? r >= G.cdm : r >= 2 * G.cdm;
     const unsigned m = G.m_base[k] + (unsigned)rank_below(i);
-    for (int l = 0; l < G.nl; l++) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      if (l >= G.nl) continue;
       const int d = r - G.delta[l];
       unsigned v = 0;
       if (G.type == 0 ? d == 0 : (d == 0 || d == 1)) {
@@ -95,10 +103,35 @@ __global__ void __launch_bounds__(256) pdsch_tx_kernel(PdschTxGeom G, const Gold
         const unsigned x = modsym(m * G.nl + l);
         v = ((unsigned)t_wrap16(((int)(short)(x & 0xFFFFu) * G.amp) >> 15) & 0xFFFFu) | ((unsigned)t_wrap16(((int)(short)(x >> 16) * G.amp) >> 15) << 16);
       }
-      txF[(size_t)l * G.tx_stride + o] = v;
+      lay[l] = v;
     }
   }
-  for (int a = G.nl; a < G.nb_tx; a++) txF[(size_t)a * G.tx_stride + o] = 0;     // identity precoding: antennas beyond the layers are zeroed over the allocation
+  if (G.pm == 0) {                                                                 // identity precoding: layer l -> antenna l, antennas beyond the layers are zeroed
+#pragma unroll
+    for (int l = 0; l < 4; l++) if (l < G.nl) txF[(size_t)l * G.tx_stride + o] = lay[l];
+    for (int a = G.nl; a < G.nb_tx; a++) txF[(size_t)a * G.tx_stride + o] = 0;
+    return;
+  }
+  // Non-identity precoding (nr_dlsch.c:536-590): with one PRG the reference takes the RBs two at a time (the last one alone when rb_size is odd).  A group
+  // that ends below the symbol's last sub-carrier runs nr_layer_precoder_simd -- per-layer products truncated to 16 bits, SATURATING sum over the layers --
+  // any other group nr_layer_precoder_cm, whose c16maddShift sum WRAPS (MODULATION/nr_modulation.c:702-815).
+  const int g = i / 24, cnt = (G.nb_re - 24 * g) >= 24 ? 24 : 12;
+  int sc_g = G.start_sc + 24 * g;
+  if (sc_g >= G.N) sc_g -= G.N;
+  const bool wraps = sc_g + cnt >= G.N;
+  for (int a = 0; a < G.nb_tx; a++) {
+    int yr = 0, yi = 0;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      if (l < G.nl) {
+        const int xr = (int)(short)(lay[l] & 0xFFFFu), xi = (int)(short)(lay[l] >> 16), wr = G.pmw[l][a][0], wi = G.pmw[l][a][1];
+        const int pr = t_wrap16((xr * wr - xi * wi) >> 15), pi = t_wrap16((xr * wi + xi * wr) >> 15);
+        if (wraps) { yr = t_wrap16(yr + pr); yi = t_wrap16(yi + pi); }
+        else { yr = max(-32768, min(32767, yr + pr)); yi = max(-32768, min(32767, yi + pi)); }
+      }
+    }
+    txF[(size_t)a * G.tx_stride + o] = ((unsigned)yr & 0xFFFFu) | ((unsigned)yi << 16);
+  }
 }
 
 static int make_tx_geom(const nrb200_pdsch_tx_t &d, PdschTxGeom *G, uint32_t *n_bits)
@@ -118,6 +151,11 @@ static int make_tx_geom(const nrb200_pdsch_tx_t &d, PdschTxGeom *G, uint32_t *n_
   if (sc + G->nb_re > G->N) { G->rem = G->nb_re + sc - G->N; G->upper = G->N - sc; }
   G->tx_stride = d.tx_stride; G->c_init = (d.rnti << 15) + d.data_scrambling_id;
   G->dmrs_idx0 = (d.rb_start + d.bwp_start) * (type == 0 ? 6 : 4);
+  G->pm = (int)d.pm_idx;
+  if (G->pm > 0) {
+    if (d.nb_tx > 4 || d.nb_tx < 2) return -4;                              // weights[4][4]; "No precoding can be done with a single antenna port"
+    for (int l = 0; l < 4; l++) for (int a = 0; a < 4; a++) { G->pmw[l][a][0] = d.pm_weights[l][a][0]; G->pmw[l][a][1] = d.pm_weights[l][a][1]; }
+  }
   for (int l = 0; l < nl; l++) {
     int port = 0;
     if (d.dmrs_ports) { int found = -1; port = -1; for (int i = 0; i < 12; i++) if ((d.dmrs_ports >> i) & 1) { if (++found == l) { port = i; break; } } }   // get_dmrs_port

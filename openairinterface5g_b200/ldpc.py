@@ -84,7 +84,17 @@ class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
 class PdschTxDesc(C.Structure):       # nrb200_pdsch_tx_t (field names of nfapi_nr_dl_tti_pdsch_pdu_rel15_t / NR_DL_FRAME_PARMS)
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order", "nrOfLayers",
                                           "start_symbol_index", "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports",
-                                          "scid", "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "tx_stride")]
+                                          "scid", "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "tx_stride", "pm_idx")] + [("pm_weights", C.c_int16 * 32)]
+
+    def set_precoding(self, pm_idx, weights):
+        """Wideband precoding matrix: weights [layers <= 4][antennas <= 4][2] int16 (nfapi_nr_pm_pdu_t.weights); pm_idx 0 = identity."""
+        w = np.zeros((4, 4, 2), np.int16)
+        if weights is not None:
+            a = np.asarray(weights, dtype=np.int16)
+            w[:a.shape[0], :a.shape[1]] = a
+        self.pm_idx = pm_idx
+        self.pm_weights = (C.c_int16 * 32)(*[int(x) for x in w.reshape(-1)])
+        return self
 
 
 class LdpcLib:

@@ -40,3 +40,33 @@ def test_pdsch_tx_vs_oracle(ldpc, oracle):
 def test_pdsch_tx_rejects_unsupported(ldpc):
     bad = PdschTxDesc(1024, 4, 0, 20, 0, 31, 1024 - 52 * 6, 4, 3, 2, 12, 1 << 2, 1, 2, 0b001101, 1, 40, 501, 0x1234, 300, 0)   # the reference's over-mapping case
     assert ldpc.pdsch_tx_num_bits(bad) == 0
+
+
+def test_pdsch_tx_wideband_precoding_vs_oracle(ldpc, oracle):
+    """pm_idx > 0: the precoding stage of the fused kernel (saturating accumulation for RB pairs inside the symbol, wrapping for the pair that reaches or crosses
+    its last sub-carrier), DMRS types 1 and 2, 1-4 layers on 2-4 antennas, odd and even rb_size; then back to the identity with the same descriptor."""
+    rng = np.random.default_rng(72)
+    cases = [  # N, carrier, ntx, slot, rb0, nrb, Qm, nl, dmrs_type, cdm, ports, amp
+        (4096, 273, 4, 1, 0, 273, 6, 2, 0, 2, 0b0011, 512), (4096, 273, 2, 3, 0, 272, 8, 2, 0, 2, 0b0011, 30000), (2048, 106, 4, 5, 10, 51, 4, 1, 0, 2, 0b0001, 700),
+        (1024, 52, 4, 0, 3, 40, 6, 4, 0, 2, 0b1111, 30000), (1024, 52, 2, 7, 0, 26, 2, 2, 1, 1, 0b000011, 512), (512, 25, 4, 2, 2, 21, 6, 3, 1, 2, 0b001101, 20000),
+        (512, 25, 4, 2, 0, 12, 8, 2, 0, 1, 0b0011, 30000),
+    ]
+    for N, carrier, ntx, slot, rb0, nrb, Qm, nl, dtype_, cdm, ports, amp in cases:
+        fco = N - carrier * 6
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, 1, 13, 1 << 2, dtype_, cdm, ports, 0, 40 + slot, 501, 0x1234, amp)
+        d = PdschTxDesc(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, 1, 13, 1 << 2, dtype_, cdm, ports, 0, 40 + slot, 501, 0x1234, amp, 0)
+        w = rng.integers(-32767, 32768, size=(4, 4, 2)).astype(np.int16)
+        if amp < 1000:
+            w //= 3
+        P.set_precoding(2, w); d.set_precoding(2, w)
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        want = oracle.pdsch_tx_slot(P, bits)
+        got = ldpc.pdsch_tx_slot_host(d, bits)
+        assert np.array_equal(got, want), (N, nrb, Qm, nl, ntx, [tuple(x) for x in np.argwhere(got != want)[:6]])
+        assert np.count_nonzero(got[ntx - 1]) > 0
+        P.set_precoding(0, None); d.set_precoding(0, None)
+        assert np.array_equal(ldpc.pdsch_tx_slot_host(d, bits), oracle.pdsch_tx_slot(P, bits))
+    from openairinterface5g_b200.ldpc import Nrb200Error
+    d1 = PdschTxDesc(512, 1, 2, 0, 0, 12, 362, 6, 1, 1, 13, 1 << 2, 0, 1, 0b0001, 0, 42, 501, 0x1234, 512, 0).set_precoding(1, np.ones((1, 1, 2), np.int16))
+    with pytest.raises((Nrb200Error, ValueError)):                  # rejected when the descriptor is validated
+        ldpc.pdsch_tx_slot_host(d1, np.zeros(10, np.uint8))          # "No precoding can be done with a single antenna port"
