@@ -200,3 +200,14 @@ def test_ue_chest_variants_golden(oracle):
     for i in range(4):
         P = ChestParms(*[int(x) for x in g[f"ue_par{i}"]])
         assert np.array_equal(oracle.pdsch_channel_estimation(P, g["rx"])[:, P.symbol], g[f"ue_est{i}"]), i
+
+
+def test_pdsch_tx_precoding_golden(oracle):
+    """nr_generate_pdsch after the encoder, identity and wideband non-identity precoding, against vectors of the compiled reference."""
+    from oracle.bindings import PdschTxParms
+    g = _load("chest_variants.npz")
+    for i in range(2):
+        P = PdschTxParms(*[int(x) for x in g[f"tx_par{i}"]])
+        pm = int(g[f"tx_pm{i}"][0])
+        P.set_precoding(pm, g[f"tx_w{i}"] if pm else None)
+        assert np.array_equal(oracle.pdsch_tx_slot(P, g[f"tx_bits{i}"]), g[f"tx_out{i}"]), i

@@ -8,7 +8,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.bindings import Reference, ChestParms  # noqa: E402
+from oracle.bindings import Reference, ChestParms, PdschTxParms  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "chest_variants.npz")
 
@@ -42,6 +42,16 @@ def main():
         first = min(s for s in range(start, start + nsym) if (bitmap >> s) & 1)
         g[f"tavg_out{i}"] = out[:, first]
         assert np.array_equal(np.delete(out, first, axis=1), np.delete(est, first, axis=1))
+    # gNB PDSCH transmitter (nr_generate_pdsch after the encoder): identity and wideband non-identity precoding, 2 layers on 4 antennas, allocation ending at the
+    # symbol's last sub-carrier region so that both the saturating (SIMD) and the wrapping (scalar) accumulation occur
+    for i, (pm, amp) in enumerate(((0, 512), (3, 30000))):
+        par = [N, 4, 6, 2, 0, 21, N - carrier * 6, 6, 2, 1, 13, 1 << 2, 0, 2, 0b0011, 0, 46, 501, 0x1234, amp]
+        P = PdschTxParms(*par)
+        w = np.random.default_rng(77).integers(-32767, 32768, size=(4, 4, 2)).astype(np.int16)
+        P.set_precoding(pm, w if pm else None)
+        bits = np.random.default_rng(78 + i).integers(0, 2, size=P.G(), dtype=np.uint8)
+        g[f"tx_par{i}"], g[f"tx_pm{i}"], g[f"tx_w{i}"], g[f"tx_bits{i}"] = np.array(par, np.int32), np.array([pm], np.int32), w, bits
+        g[f"tx_out{i}"] = ref.pdsch_tx_slot(P, bits, carrier)
     g["n_cases"] = np.array([len(cases)], np.int32)
     np.savez_compressed(OUT, **g)
     print(OUT, os.path.getsize(OUT), "bytes")
