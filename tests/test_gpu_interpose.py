@@ -96,3 +96,25 @@ def test_reference_loader_lifecycle_in_its_own_process():
         "print('LIFECYCLE_OK')\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert "LIFECYCLE_OK" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
+
+
+def test_ue_caller_reaches_the_gpu_through_the_interposed_symbol(oracle):
+    """The UE-side twin: oracle/ref_harness_uechest.c (the caller, as nr_ue_pdsch_procedures passes the arguments) linked against
+    integration/oai_shim_pdsch_chest.c instead of nr_dl_channel_estimation.c -- DMRS types 1 / 2, chest_freq 0 / 1."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libshimtest_uechest.so")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run integration/build_shims.sh where /root/reference exists")
+    lib = C.CDLL(path)
+    assert lib.refh_uechest_init(os.path.join(ROOT, "oracle", "_ref", "libref_dfts.so").encode()) == 0
+    rng = np.random.default_rng(92)
+    for N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, dmrs_type, chest_freq in (
+            (4096, 2, 1, 2, 0, 0, 273, 273, 0, 77, 0, 0), (2048, 2, 7, 3, 1, 10, 50, 106, 1, 1007, 0, 0), (1024, 4, 6, 11, 2, 20, 32, 52, 0, 300, 1, 0),
+            (1024, 2, 3, 4, 4, 0, 52, 52, 0, 21, 1, 0), (2048, 2, 9, 3, 1, 10, 50, 106, 1, 1007, 0, 1), (512, 2, 8, 4, 5, 0, 25, 25, 1, 303, 1, 1)):
+        fco = N - carrier * 6
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, dmrs_type, chest_freq)
+        rx = rng.integers(-3000, 3001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        prm = np.array([N, nb_rx, carrier, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, dmrs_type, chest_freq], dtype=np.int32)
+        est = np.zeros(nb_rx * 14 * N * 2, np.int16)
+        assert lib.refh_pdsch_chest(prm.ctypes.data_as(C.c_void_p), rx.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p)) == 0
+        est_o = oracle.pdsch_channel_estimation(P, rx)
+        assert np.array_equal(est.reshape(nb_rx, 14, N, 2)[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq)
