@@ -38,7 +38,7 @@ class DecParams(C.Structure):          # t_nrLDPC_dec_params
 
 
 class DecodeAbort(C.Structure):        # decode_abort_t
-    _fields_ = [("mutex", C.c_uint8 * 40), ("failed", C.c_bool)]
+    _fields_ = [("mutex", C.c_uint64 * 5), ("failed", C.c_bool)]     # pthread_mutex_t: 40 bytes, 8-byte aligned (x86-64 glibc) -> sizeof 48 like the C struct
 
 
 class EncParams(C.Structure):          # encoder_implemparams_t

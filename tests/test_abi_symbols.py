@@ -103,3 +103,26 @@ def test_packed_decoder_schedule_covers_every_item_and_balances():
     for BG, Z, R, t in ((1, 384, 13, 768), (1, 384, 13, 960), (1, 384, 23, 768)):
         lib.nrb200_ldpc_packed_schedule_info(BG, Z, R, t, info.ctypes.data_as(ctypes.c_void_p))
         assert info[3] <= 1.06 * info[4] and info[5] <= 1.06 * info[6], (BG, Z, R, t, info)
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every descriptor in include/nrb200_ldpc.h, as gcc lays them out, against the ctypes mirrors the tests and bench.py call through."""
+    import subprocess
+    from openairinterface5g_b200 import ldpc
+    pairs = [("nrb200_ldpc_dec_params_t", ldpc.DecParams, None), ("nrb200_ldpc_enc_params_t", ldpc.EncParams, None), ("nrb200_decode_abort_t", ldpc.DecodeAbort, None),
+             ("nrb200_ldpc_batch_desc_t", ldpc.BatchDesc, "out_stride"), ("nrb200_rm_desc_t", ldpc.RmDesc, None), ("nrb200_pusch_rx_t", ldpc.PuschRxDesc, "d_est_state"),
+             ("nrb200_pusch_chest_t", ldpc.PuschChestDesc, "chest_freq"), ("nrb200_pdsch_tx_t", ldpc.PdschTxDesc, "pm_weights")]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrb200_ldpc.h"', 'int main(void) {']
+    for cname, _, field in pairs:
+        src.append(f'  printf("{cname} %zu %zu\\n", sizeof({cname}), {"offsetof(" + cname + ", " + field + ")" if field else "(size_t)0"});')
+    src += ['  return 0;', '}']
+    c = tmp_path / "abi_layout.c"
+    c.write_text("\n".join(src))
+    exe = str(tmp_path / "abi_layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(c)])
+    out = subprocess.check_output([exe], text=True).split("\n")
+    got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
+    for cname, cls, field in pairs:
+        assert got[cname][0] == ctypes.sizeof(cls), (cname, got[cname][0], ctypes.sizeof(cls))
+        if field:
+            assert got[cname][1] == getattr(cls, field).offset, (cname, field, got[cname][1], getattr(cls, field).offset)
