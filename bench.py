@@ -472,7 +472,7 @@ def run_b200(args, rank, world, local_rank):
         if oc is not None:
             ub = measured_mix_ceiling() if (world == 1 and not args.no_ubench) else None
             if ub and "decoder_mix_ipc_per_scheduler" in ub and oc.get("warp_inst_per_cb"):
-                ipc = B * oc["warp_inst_per_cb"] / kernel_s / (148 * 4 * float(line["clocks"].get("sm_mhz") or 1965.0) * 1e6)
+                ipc = B * oc["warp_inst_per_cb"] / kernel_s / (int(ub.get("sm_count", 148)) * 4 * float(line["clocks"].get("sm_mhz") or 1965.0) * 1e6)
                 oc["micro_benchmark"] = dict(ub, decoder_ipc_per_scheduler=ipc, frac_of_measured_mix_ceiling=ipc / ub["decoder_mix_ipc_per_scheduler"])
             line["roofline"]["on_chip"] = oc
         if cpu is not None:
