@@ -3,6 +3,7 @@
 #include "ldpc_common.cuh"
 #include "ldpc_decoder_generic.cuh"
 #include "ldpc_decoder_packed.cuh"
+#include "ldpc_decoder_cluster.cuh"
 #include <map>
 #include <mutex>
 #include <cstdlib>
@@ -42,11 +43,46 @@ static const PackedGraph *packed_graph(const GraphDev &h_g, const PackedGraph **
   return it->second.first;
 }
 
+// cluster work partitions, keyed by graph and cluster size
+static std::map<uint64_t, std::pair<ClusterSched *, ClusterSched>> g_cl;
+
+static const ClusterSched *cluster_sched(const GraphDev &h_g, const PackedGraph &h_pg, int C, const ClusterSched **host)
+{
+  const uint64_t key = ((uint64_t)C << 32) | ((uint32_t)h_g.BG << 24) | ((uint32_t)h_g.Z << 8) | (uint32_t)h_g.R;
+  std::lock_guard<std::mutex> lk(g_pk_mu);
+  auto it = g_cl.find(key);
+  if (it == g_cl.end()) {
+    ClusterSched cs;
+    ClusterSched *d = nullptr;
+    int T = C >= 8 ? 12 : C >= 4 ? 16 : 24;                 // warps per CTA: ~1-2 work items per warp and phase
+    if (const char *e = getenv("NRB200_CLUSTER_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= kClMaxWarps && C * v <= kClMaxLists) T = v; }
+    if (build_cluster_sched(h_g, h_pg, C, T, &cs)) {
+      if (cudaMalloc(&d, sizeof(ClusterSched)) != cudaSuccess) d = nullptr;
+      else cudaMemcpy(d, &cs, sizeof(ClusterSched), cudaMemcpyHostToDevice);
+    }
+    it = g_cl.emplace(key, std::make_pair(d, cs)).first;
+  }
+  *host = &it->second.second;
+  return it->second.first;
+}
+
 void packed_graph_cache_clear()
 {
   std::lock_guard<std::mutex> lk(g_pk_mu);
   for (auto &kv : g_pk) if (kv.second.first) cudaFree(kv.second.first);
   g_pk.clear();
+  for (auto &kv : g_cl) if (kv.second.first) cudaFree(kv.second.first);
+  g_cl.clear();
+}
+
+// CTAs per code block for a launch of n_cb blocks: a cluster per block while every cluster of the launch can be resident at once (the GPCs
+// of a B200 hold 16 clusters of 8, 33 of 4, 74 of 2 with one 205 KB CTA per SM), one CTA per block beyond that -- there throughput, not the
+// time of one block, is what matters and the single-CTA kernel spends the fewest SM-cycles per block.  NRB200_CLUSTER = 0 / 2 / 4 / 8 forces.
+static int pick_cluster(uint32_t n_cb)
+{
+  static const int forced = []() { const char *e = getenv("NRB200_CLUSTER"); return e ? atoi(e) : -1; }();
+  if (forced == 0 || forced == 2 || forced == 4 || forced == 8) return forced;
+  return n_cb <= 16 ? 8 : n_cb <= 33 ? 4 : n_cb <= 74 ? 2 : 0;
 }
 
 // Returns 0 or a negative error.  Asynchronous on `stream`.
@@ -57,6 +93,33 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
   static const bool force_generic = getenv("NRB200_FORCE_GENERIC") != nullptr;
   const PackedGraph *h_pg = nullptr;
   const PackedGraph *d_pg = (h_g.Z % 4 == 0 && !force_generic) ? packed_graph(h_g, &h_pg) : nullptr;
+  const int C = d_pg && h_pg->warp_items && !(a.quirks & 1) ? pick_cluster(a.n_cb) : 0;
+  if (C >= 2) {
+    const ClusterSched *h_cs = nullptr;
+    const ClusterSched *d_cs = cluster_sched(h_g, *h_pg, C, &h_cs);
+    if (d_cs) {
+      const size_t smem = (size_t)h_pg->total_bytes;
+      void (*kern)(const PackedGraph *, const ClusterSched *, DecodeArgs) = h_pg->Zw == 96 ? ldpc_decode_cluster_kernel<96> : ldpc_decode_cluster_kernel<0>;
+      static std::atomic<size_t> configured_cl[2];
+      const int v = h_pg->Zw == 96 ? 1 : 0;
+      if (smem > configured_cl[v].load()) {
+        NRB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cluster smem attr");
+        configured_cl[v].store(smem);
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(a.n_cb * (unsigned)C, 1, 1);
+      cfg.blockDim = dim3((unsigned)h_cs->nthreads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      NRB200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, d_pg, d_cs, a), "cluster decode launch");
+      c.launches++;
+      return 0;
+    }
+  }
   if (d_pg) {
     const size_t smem = (size_t)h_pg->total_bytes;
     // Z = 384 (K = 8448, both headline workloads) runs an instantiation with the row geometry as immediates

@@ -33,7 +33,8 @@ ldpc_decode_generic_kernel(const GraphDev *__restrict__ gdev, DecodeArgs a)
   __shared__ int s_flag;
 
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
-    const int8_t *gl = a.llr + (size_t)cb * a.llr_stride;
+    const BlockIo io = block_io(a, cb);
+    const int8_t *gl = io.llr;
     for (int i = threadIdx.x; i < numLLR; i += blockDim.x) { llr[i] = gl[i]; hd[i] = 0; }
     __syncthreads();
     // llr2CnProcBuf (nrLDPC_mPass.h:128-169)
@@ -45,13 +46,18 @@ ldpc_decode_generic_kernel(const GraphDev *__restrict__ gdev, DecodeArgs a)
     __syncthreads();
 
     const int maxIter = a.numMaxIter;
-    const bool abort_in = a.abort_flags != nullptr && a.abort_flags[cb] != 0;
     int numIter = 0, pc = 1;
     bool wrote_out = false;
     for (;;) {
       if (numIter >= 1 && !(numIter <= maxIter && pc != 0)) break;      // nrLDPC_decoder.c:552
       numIter++;
-      if (numIter > 1 && abort_in) { numIter = maxIter + 2; break; }    // :557-560
+      if (numIter > 1 && io.abort) {                                    // check_abort(ab), polled at the top of every iteration (:557-560)
+        if (threadIdx.x == 0) s_flag = *io.abort;
+        __syncthreads();
+        const int ab = s_flag;
+        __syncthreads();
+        if (ab) { numIter = maxIter + 2; break; }
+      }
 
       // ---- check nodes
       for (int i = threadIdx.x; i < nrows * Z; i += blockDim.x) {
@@ -127,15 +133,15 @@ ldpc_decode_generic_kernel(const GraphDev *__restrict__ gdev, DecodeArgs a)
         }
         pc = __syncthreads_or(bad);
       } else if (numIter > 2) {                                          // :850-862
-        write_output(a, cb, hd, numLLR);
+        write_output(a, io.out, hd, numLLR);
         wrote_out = true;
         const int ok = crc_check_block(a, hd, &s_flag);
         if (ok) break;
       }
     }
-    if (!a.use_crc) write_output(a, cb, hd, numLLR);                     // :865-877
+    if (!a.use_crc) write_output(a, io.out, hd, numLLR);                 // :865-877
     (void)wrote_out;
-    if (threadIdx.x == 0) a.iters[cb] = numIter;
+    block_finish(io, a, numIter, 0);
     __syncthreads();
   }
 }

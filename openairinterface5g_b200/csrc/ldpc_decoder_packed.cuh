@@ -215,14 +215,15 @@ __device__ __forceinline__ unsigned hd_bit(const PackedGraph &G, const char *smb
   return (reinterpret_cast<const uint8_t *>(smb + G.off_A + ar * 2 * G.ZB)[v] >> 7) ^ 1u;
 }
 
-__device__ __forceinline__ void packed_write_output(const PackedGraph &G, const char *smb, const DecodeArgs &a, int cb)
+// part/nparts: the share of the output this CTA stores (cluster kernel: every CTA of the cluster holds the whole a-posteriori state)
+__device__ __forceinline__ void packed_write_output(const PackedGraph &G, const char *smb, const DecodeArgs &a, uint8_t *o, int part = 0, int nparts = 1)
 {
-  uint8_t *o = a.out + (size_t)cb * a.out_stride;
   const int numLLR = G.ncols * G.Z;
+  const int tid = (int)threadIdx.x + part * (int)blockDim.x, nthr = nparts * (int)blockDim.x;
   if (a.outMode == 0) {
     const int nbytes = (numLLR + 7) >> 3;
     if ((G.Z & 7) == 0) {
-      for (int j = threadIdx.x; j < nbytes; j += blockDim.x) {
+      for (int j = tid; j < nbytes; j += nthr) {
         const int i = j * 8, c = i / G.Z, v = i - c * G.Z, ar = G.col_arow[c];
         unsigned b = 0;
         if (ar >= 0) {
@@ -233,14 +234,14 @@ __device__ __forceinline__ void packed_write_output(const PackedGraph &G, const 
         o[j] = (uint8_t)b;
       }
     } else {
-      for (int j = threadIdx.x; j < nbytes; j += blockDim.x) {
+      for (int j = tid; j < nbytes; j += nthr) {
         unsigned b = 0;
         for (int kk = 0; kk < 8; kk++) { const int i = j * 8 + kk; if (i < numLLR) b |= hd_bit(G, smb, i) << (7 - kk); }
         o[j] = (uint8_t)b;
       }
     }
   } else {
-    for (int i = threadIdx.x; i < numLLR; i += blockDim.x) o[i] = (uint8_t)hd_bit(G, smb, i);
+    for (int i = tid; i < numLLR; i += nthr) o[i] = (uint8_t)hd_bit(G, smb, i);
   }
 }
 
@@ -248,8 +249,13 @@ __device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const char
 {
   const int n = (int)a.crc_len_bits;
   unsigned rem = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (hd_bit(G, smb, i)) rem ^= __ldg(a.crc_tab + (n - 1 - i));
+  if (a.outMode == 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (hd_bit(G, smb, i)) rem ^= __ldg(a.crc_tab + (n - 1 - i));
+  } else {   // the reference checks the one-bit-per-byte array as it stands (nrLDPC_decoder.c:852-858): message bit 8j+7 = hard bit j
+    for (int j = threadIdx.x; 8 * j + 7 < n; j += blockDim.x)
+      if (hd_bit(G, smb, j)) rem ^= __ldg(a.crc_tab + (n - 8 - 8 * j));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
   if (threadIdx.x == 0) *scratch = 0;
@@ -269,7 +275,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
 {
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ PackedGraph G;
-  __shared__ int s_flag;
+  __shared__ int s_flag, s_abort;
   char *smb = reinterpret_cast<char *>(sm);
   for (int i = threadIdx.x; i < (int)(sizeof(PackedGraph) / 4); i += blockDim.x)
     reinterpret_cast<int *>(&G)[i] = reinterpret_cast<const int *>(gdev)[i];
@@ -285,7 +291,8 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
 
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
     // ---- load channel LLRs (global int8, coalesced 32-bit) as offset binary into L rows with halo; A := L; R := 0; P := 0
-    const int8_t *gl = a.llr + (size_t)cb * a.llr_stride;
+    const BlockIo io = block_io(a, cb);
+    const int8_t *gl = io.llr;
     const bool al4 = ((reinterpret_cast<uintptr_t>(gl) & 3) == 0);
     for (int i = threadIdx.x; i < G.ncols * Zw; i += blockDim.x) {
       const int c = i / Zw, k = i - c * Zw;
@@ -322,7 +329,6 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
     __syncthreads();
 
     const int maxIter = a.numMaxIter;
-    const bool abort_in = a.abort_flags != nullptr && a.abort_flags[cb] != 0;
     // Reference control flow (nrLDPC_decoder.c:541-863), restated for the fused schedule: after BN phase n the state
     // equals the reference's after iteration n.  The parity check of iteration n is a by-product of CN phase n+1.
     int numIter = 0;
@@ -330,6 +336,9 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
     while (!done) {
       // CN phase of iteration numIter+1 (also yields the syndrome of iteration numIter when numIter >= 2)
       uint32_t bad = 0;
+      // check_abort(ab) is polled at the top of every iteration from the second on (nrLDPC_decoder.c:557-560): thread 0 samples the flag while
+      // the check-node phase runs (the load's latency hides behind it), everybody reads it after the barrier
+      if (io.abort && threadIdx.x == 0) s_abort = *io.abort;
       if (worker) {
         for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) {
           const int it = G.cn_bin_rows[i];
@@ -343,6 +352,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       const int pcRes = __syncthreads_or(bad != 0);   // also the CN->BN barrier
       if (numIter >= 2 && !a.use_crc && pcRes == 0) break;          // iteration numIter passed its parity check (:552)
       numIter++;
+      if (numIter >= 2 && io.abort && s_abort) { numIter = maxIter + 2; break; }   // the state (A) is still that of the previous iteration
       // BN phase
       if (worker)
         for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) {
@@ -354,11 +364,10 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       // loop control, mirroring `while (numIter <= numMaxIter && pcRes != 0)` evaluated before each further iteration
       if (numIter == 1) {
         if (!(1 <= maxIter)) done = true;                            // the while condition fails straight away
-        else if (abort_in) { numIter = maxIter + 2; done = true; }   // :557-560, checked when entering iteration 2
       } else {
         if (a.use_crc) {
           if (numIter > 2) {                                         // :850-862
-            packed_write_output(G, smb, a, cb);
+            packed_write_output(G, smb, a, io.out);
             if (packed_crc_check(G, smb, a, &s_flag)) break;
           }
           if (!(numIter <= maxIter)) done = true;
@@ -367,8 +376,8 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
         }
       }
     }
-    if (!a.use_crc) packed_write_output(G, smb, a, cb);               // :865-877
-    if (threadIdx.x == 0) a.iters[cb] = numIter;
+    if (!a.use_crc) packed_write_output(G, smb, a, io.out);           // :865-877
+    block_finish(io, a, numIter, 0);
     __syncthreads();
   }
 }

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <vector>
 #include "ldpc_packed_graph.h"
+#include "ldpc_cluster.h"
 
 namespace nrb200 {
 
@@ -152,6 +153,38 @@ bool build_packed_graph(const GraphDev &g, PackedGraph *p, int max_threads)
   }
   lpt(rows, p->nbins, p->cn_bin_start, p->cn_bin_rows);
   lpt(cols, p->nbins, p->bn_bin_start, p->bn_bin_cols);
+  return true;
+}
+
+bool build_cluster_sched(const GraphDev &g, const PackedGraph &p, int C, int T, ClusterSched *s)
+{
+  if (p.Zw % 32 || C < 2 || C > kClMaxCtas || T < 1 || T > kClMaxWarps || C * T > kClMaxLists) return false;
+  std::memset(s, 0, sizeof(*s));
+  const int chunks = p.Zw / 32;
+  if (chunks > 3) return false;
+  s->C = C; s->T = T; s->nthreads = 32 * T; s->chunks = chunks;
+  // same cost model as the single-CTA lists; a column additionally pays the broadcast of its a-posteriori word to the C CTAs
+  auto row_cost = [&](int r) { return 2 * (18 + 32 * (g.row_start[r + 1] - g.row_start[r]) + (g.row_p_col[r] >= 0 ? 51 : 11)); };
+  auto col_cost = [&](int c) { return 130 + 44 * g.col_deg[c] + 6 * C; };
+  std::vector<std::pair<int, int>> rows, cols;
+  for (int r = 0; r < g.nrows; r++) for (int k = 0; k < chunks; k++) rows.push_back({row_cost(r), r | (k << 8)});
+  for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) for (int k = 0; k < chunks; k++) cols.push_back({col_cost(c), c | (k << 8)});
+  lpt(rows, C * T, s->cn_start, s->cn_items);
+  lpt(cols, C * T, s->bn_start, s->bn_items);
+  // owner CTA of every (row, chunk)
+  std::vector<int> owner((size_t)kMaxRows * 4, 0);
+  for (int l = 0; l < C * T; l++)
+    for (int i = s->cn_start[l]; i < s->cn_start[l + 1]; i++) owner[(size_t)(s->cn_items[i] & 0xFF) * 4 + (s->cn_items[i] >> 8)] = l / T;
+  std::vector<int> row_of_slot(g.nreal, 0);
+  for (int r = 0; r < g.nrows; r++) for (int m = g.row_start[r]; m < g.row_start[r + 1]; m++) row_of_slot[m] = r;
+  for (int i = 0; i < g.nreal; i++) {
+    const int r = row_of_slot[g.col_edges[i]];
+    uint32_t own = 0;
+    for (int k = 0; k < chunks; k++) own |= (uint32_t)owner[(size_t)r * 4 + k] << (3 * k);
+    own |= (uint32_t)owner[(size_t)r * 4] << (3 * chunks);
+    s->bn_desc[i][0] = p.bn_desc[i][0];
+    s->bn_desc[i][1] = (p.bn_desc[i][1] & 0xFFFFFu) | (own << 20);
+  }
   return true;
 }
 

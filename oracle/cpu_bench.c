@@ -100,3 +100,47 @@ long orc_bench_dft(void *fn, const int16_t *x, int N, int n, int threads, double
   free(th); free(jobs);
   return total;
 }
+
+/* ---- decode EVERY block of a batch once on `threads` host threads (large-sample differential tests: tests/test_gpu_parity_scale.py).
+ * `fn` = the reference's LDPCdecoder (or NULL for the scalar port), `crc_fn` = the reference's check_crc (crc_byte.c:314) or NULL for the
+ * parity-check stop ldpctest uses.  Outputs land in out[n][out_stride] / iters[n]; returns n. */
+typedef struct { dec_fn_t fn; void *crc_fn; const int8_t *llr; int n, stride, BG, Z, R, maxIter, crc_type, crc_len, tid, nthreads; uint8_t *out; int out_stride;
+                 int32_t *iters; } ajob_t;
+static void *aworker(void *arg)
+{
+  ajob_t *j = (ajob_t *)arg;
+  nrb200_ldpc_dec_params_t p;
+  memset(&p, 0, sizeof(p));
+  p.BG = (uint8_t)j->BG; p.Z = (uint16_t)j->Z; p.R = (uint8_t)j->R; p.numMaxIter = (uint8_t)j->maxIter; p.outMode = NRB200_OUTMODE_BIT;
+  p.E = j->crc_fn ? j->crc_len : (j->BG == 1 ? 22 : 10) * j->Z;
+  p.crc_type = (uint8_t)j->crc_type;
+  p.check_crc = (int (*)(uint8_t *, uint32_t, uint8_t))j->crc_fn;
+  nrb200_decode_abort_t ab;
+  pthread_mutex_init(&ab.mutex_failure, NULL);
+  int8_t *in = aligned_alloc(64, 27008), *out = aligned_alloc(64, 27008);
+  const int nb = j->out_stride < 27000 ? j->out_stride : 27000;
+  for (int i = j->tid; i < j->n; i += j->nthreads) {
+    memset(in, 0, 27008);
+    memcpy(in, j->llr + (size_t)i * j->stride, (size_t)(j->stride < 27000 ? j->stride : 27000));
+    memset(out, 0, 27008);
+    ab.failed = false;
+    j->iters[i] = j->fn ? j->fn(&p, 0, 0, 0, in, out, NULL, &ab)
+                        : orc_ldpc_decode(j->BG, j->Z, j->R, j->maxIter, 0, in, out, j->crc_fn != NULL, (uint32_t)j->crc_len, j->crc_type, 0);
+    memcpy(j->out + (size_t)i * j->out_stride, out, (size_t)nb);
+  }
+  free(in); free(out);
+  return NULL;
+}
+long orc_decode_all(void *fn, void *crc_fn, const int8_t *llr, int n, int stride, int BG, int Z, int R, int maxIter, int crc_type, int crc_len,
+                    uint8_t *out, int out_stride, int32_t *iters, int threads)
+{
+  pthread_t *th = calloc((size_t)threads, sizeof(*th));
+  ajob_t *jobs = calloc((size_t)threads, sizeof(*jobs));
+  for (int t = 0; t < threads; t++) {
+    jobs[t] = (ajob_t){(dec_fn_t)fn, crc_fn, llr, n, stride, BG, Z, R, maxIter, crc_type, crc_len, t, threads, out, out_stride, iters};
+    pthread_create(&th[t], NULL, aworker, &jobs[t]);
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+  return n;
+}

@@ -17,6 +17,27 @@ def payloads(BG, Z, n, seed):
     return K, P
 
 
+def decode_all_reference(oracle, reference, llr, BG, Z, R, max_iter, crc=None, threads=None):
+    """Every row of llr through the UNMODIFIED reference LDPCdecoder (oracle/_ref/libref_ldpc_dec.so), one blocking call per block on all host
+    cores (oracle/cpu_bench.c:orc_decode_all).  crc = (crc_type, crc_len_bits) selects the check_crc stop (nrLDPC_decoder.c:850-862), None the
+    parity-check stop of ldpctest.  Returns (iters[n], out[n, ncols*Z/8])."""
+    import ctypes as C
+    import os
+    llr = np.ascontiguousarray(llr, dtype=np.int8)
+    n, stride = llr.shape
+    ob = NCOLS[(BG, R)] * Z // 8
+    out = np.zeros((n, ob), np.uint8)
+    its = np.zeros(n, np.int32)
+    f = oracle.lib.orc_decode_all
+    f.restype = C.c_long
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    fn = C.cast(reference.dec.LDPCdecoder, C.c_void_p)
+    crc_fn = C.cast(reference.cod.check_crc, C.c_void_p) if crc else None
+    f(fn, crc_fn, llr.ctypes.data, n, stride, BG, Z, R, max_iter, crc[0] if crc else 0, crc[1] if crc else 0, out.ctypes.data, ob, its.ctypes.data,
+      threads or os.cpu_count() or 8)
+    return its, out
+
+
 def make_case(oracle, BG, Z, R, n, ebn0_db, seed):
     """payload -> oracle encoder -> BPSK/AWGN -> int8 LLRs.  Returns (K, payload bytes, llr[n, ncols*Z])."""
     K, P = payloads(BG, Z, n, seed)

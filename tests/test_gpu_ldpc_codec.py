@@ -78,6 +78,27 @@ def test_decoder_crc_stop_mode(ldpc, oracle):
                 assert iters[i] == it_o and np.array_equal(out[i], out_o), (BG, Z, mi, i)
 
 
+@pytest.mark.parametrize("out_mode", [1, 2])
+def test_decoder_crc_stop_one_bit_per_byte_modes(ldpc, oracle, out_mode):
+    """check_crc with outMode BITINT8 / LLRINT8: the reference runs the CRC over the one-bit-per-byte output array as it stands
+    (nrLDPC_decoder.c:852-858).  An all-zero code word makes that array's CRC pass (early stop), random payloads never pass (numMaxIter + 1)."""
+    from openairinterface5g_b200.synth import awgn_llr
+    for BG, Z, R in ((1, 384, 13), (2, 96, 13), (1, 10, 13)):
+        K = (22 if BG == 1 else 10) * Z
+        if K % 8:
+            continue
+        rng = np.random.default_rng(Z + out_mode)
+        P = rng.integers(0, 256, size=(4, K // 8), dtype=np.uint8)
+        P[:2] = 0
+        cw = np.stack([oracle.encode(BG, Z, K, P[i]) for i in range(4)])
+        llr = awgn_llr(cw, Z, NCOLS[(BG, R)], 3.5, (22 if BG == 1 else 10) / (NCOLS[(BG, R)] - 2), Z)
+        iters, out = ldpc.decode_batch_host(BG, Z, R, 6, llr, outMode=out_mode, use_crc=1, crc_len_bits=K, crc_type=1)
+        for i in range(4):
+            it_o, out_o = oracle.decode(BG, Z, R, 6, llr[i], out_mode, 1, K, 1)
+            assert iters[i] == it_o and np.array_equal(out[i].view(np.uint8), np.asarray(out_o).view(np.uint8)), (BG, Z, i, iters[i], it_o)
+        assert iters[0] <= 6 and iters[3] == 7
+
+
 def test_oai_per_block_abi(ldpc, oracle):
     """LDPCdecoder exactly as nr_ulsch_decoding.c:218-222 / ldpctest.c:329-340 call it."""
     from openairinterface5g_b200.ldpc import DecodeAbort, LdpcTimeStats
@@ -159,8 +180,8 @@ def test_avx2_bg2_r15_defect_emulation(oracle):
     subprocess.check_call([sys.executable, "-c", code], env=e)
 
 
-def test_batch1024_properties(ldpc):
-    """BASELINE size (batch 1024, BG1 Z=384): encode -> noiseless/noisy channel -> decode round trip on the GPU only."""
+def test_batch1024_properties(ldpc, oracle, reference):
+    """BASELINE size (batch 1024, BG1 Z=384): encode -> noisy channel -> decode; size-independent properties AND every block against the compiled reference."""
     import torch
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev); g.manual_seed(3)
@@ -182,6 +203,16 @@ def test_batch1024_properties(ldpc):
     torch.cuda.synchronize()
     assert int(iters.max()) <= 8                         # every block converges at 4 dB (ldpctest: BLER 0 well below this SNR)
     assert torch.equal(out[:, :K // 8], payload)
+    # every one of the 1024 blocks against the unmodified reference decoder (all host cores), here and at the bench's operating point A (1 dB)
+    from common import decode_all_reference
+    it_c, out_c = decode_all_reference(oracle, reference, llr.cpu().numpy(), 1, Z, 13, 8)
+    assert np.array_equal(iters.cpu().numpy(), it_c) and np.array_equal(out.cpu().numpy(), out_c)
+    sigma1 = 1.0 / np.sqrt(2.0 * 10 ** 0.1 / 3.0)
+    llr1 = torch.zeros((B, 68 * Z), dtype=torch.int8, device=dev)
+    llr1[:, 2 * Z:] = torch.clamp(torch.floor(((1.0 - 2.0 * cw.float()) + sigma1 * torch.randn(cw.shape, device=dev, generator=g)) / (sigma1 / 16)), -128, 127).to(torch.int8)
+    it1, out1 = ldpc.decode_batch_torch(1, Z, 13, 8, llr1)
+    it1_c, out1_c = decode_all_reference(oracle, reference, llr1.cpu().numpy(), 1, Z, 13, 8)
+    assert np.array_equal(it1.cpu().numpy(), it1_c) and np.array_equal(out1.cpu().numpy(), out1_c)
     # idempotence / determinism: same input, same output and iteration counts
     iters2, out2 = ldpc.decode_batch_torch(1, Z, 13, 8, llr)
     torch.cuda.synchronize()

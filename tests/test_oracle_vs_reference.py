@@ -645,3 +645,19 @@ def test_dft_size_index_enumerators_match_oai_header():
         assert ref.refh_idft_size_at(i) == n and dfts.get_idft(n) == i, (i, n)
         assert lib.nrb200_dft_size_of_index(1, i) == n, (i, n)
     assert ref.refh_get_dft4096() == dfts.get_dft(4096) and ref.refh_get_idft4096() == dfts.get_idft(4096)
+
+
+def test_decode_all_driver_matches_single_calls(oracle, reference):
+    """oracle/cpu_bench.c:orc_decode_all (the all-cores driver of the large-sample GPU differential tests) returns what one-by-one calls return,
+    in both stop modes."""
+    from common import decode_all_reference, make_case
+    K, P, llr = make_case(oracle, 1, 384, 13, 12, 2.2, 99)
+    its, out = decode_all_reference(oracle, reference, llr, 1, 384, 13, 8, threads=4)
+    for i in range(12):
+        it_r, out_r = reference.decode(1, 384, 13, 8, llr[i])
+        assert its[i] == it_r and np.array_equal(out[i], out_r)
+    K, P, llr = make_case(oracle, 1, 384, 23, 6, 4.0, 98)
+    its, out = decode_all_reference(oracle, reference, llr, 1, 384, 23, 8, crc=(1, K), threads=3)
+    for i in range(6):
+        it_r, out_r = reference.decode(1, 384, 23, 8, llr[i], use_crc=1, crc_len_bits=K, crc_type=1)
+        assert its[i] == it_r and np.array_equal(out[i], out_r)
