@@ -31,14 +31,23 @@ WORKLOAD = "ldpctest BG1 Z=384 K=8448 R=1/3 8-iter batch=1024 int8 LLR, Eb/N0 1.
 
 
 
-def ncu_traffic(n_cb):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the decode kernel, from the committed `ncu --set full` capture
-    (profiles/ncu_decode_traffic.json, taken with the same 1024-block launch); scaled if this run's batch differs.  None if absent."""
+def _ncu_capture():
+    """profiles/ncu_decode_traffic.json (written by tools/ncu_traffic_json.py from an `ncu --set full` capture of the same 1024-block launch), but only
+    if it was taken from the kernel sources this run executes: the file carries their SHA-1 and a stale capture is not reported."""
     try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from ncu_traffic_json import kernel_source_sha1
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_decode_traffic.json")))
-        return int((d["dram_bytes_read"] + d["dram_bytes_write"]) * n_cb / 1024)
+        return d if d.get("kernel_source_sha1") == kernel_source_sha1() else None
     except Exception:
         return None
+
+
+def ncu_traffic(n_cb):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the decode kernel from the ncu capture; scaled if this run's batch differs.
+    None if there is no capture of the current kernel sources."""
+    d = _ncu_capture()
+    return int((d["dram_bytes_read"] + d["dram_bytes_write"]) * n_cb / 1024) if d else None
 
 
 def ncu_on_chip(n_cb, kernel_s, sm_mhz, sm_count=148):
@@ -47,12 +56,14 @@ def ncu_on_chip(n_cb, kernel_s, sm_mhz, sm_count=148):
     (sm__pipe_alu_cycles_active of the same 1024-block launch, profiles/ncu_decode_traffic.json); rate = this run's blocks / this run's
     kernel time, peak = SMs x 4 schedulers x 0.5 x the SM clock sampled during the timed region."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_decode_traffic.json")))
+        d = _ncu_capture()
+        if d is None:
+            return None
         per_cb = float(d["alu_pipe_warp_inst_per_cb"])
         achieved = n_cb * per_cb / kernel_s / 1e9
         peak = sm_count * 4 * 0.5 * float(sm_mhz) * 1e6 / 1e9
         return {"bound": "alu_pipe", "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
-                "alu_pipe_warp_inst_per_cb": per_cb, "warp_inst_per_cb": d.get("warp_inst_per_launch", 0) / 1024.0, "ncu": {k: d[k] for k in ("alu_pipe_pct", "issue_active_pct", "fmaheavy_pipe_pct", "lsu_pipe_pct", "source") if k in d}}
+                "alu_pipe_warp_inst_per_cb": per_cb, "warp_inst_per_cb": d.get("warp_inst_per_launch", 0) / 1024.0, "ncu": {k: d[k] for k in ("alu_pipe_pct", "issue_active_pct", "fmaheavy_pipe_pct", "lsu_pipe_pct", "source", "kernel_source_sha1") if k in d}}
     except Exception:
         return None
 
@@ -292,6 +303,30 @@ def slot_b200(lib, dev, cpu_seconds, inflight=16):
     return out
 
 
+def plugin_abi(with_reference):
+    """The drop-in boundary itself: unmodified host code makes ONE blocking LDPCdecoder call per code block through the four dlsym'ed symbols
+    (ldpctest.c:329-340 serially, nr_ulsch_decoding.c:435-468 from tpool workers).  tools/abi_bench.c does exactly that from 1 and from `cores` host
+    threads against libldpc_b200.so and -- same binary, inputs, threads: the cpu_baseline of this key -- against the compiled reference decoder; every
+    call's output and iteration count is checked against the reference's."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_abi
+    cores = os.cpu_count() or 8
+    ours, ref = bench_abi.sweep(seconds=1.5, ebn0=1.0, ours_threads=(1, cores), ref_threads=(1, cores), with_reference=with_reference)
+    keep = ("host_threads", "value", "us_per_call_mean", "us_per_call_p50", "us_per_call_p99", "mismatches", "checked", "blocks_per_launch", "us_device")
+    out = {"metric": "LDPCdecoder calls/s through the OAI loader ABI (one code block per blocking call)", "unit": "CB/s", "workload": WORKLOAD.replace("batch=1024 ", ""),
+           "b200": [{k: d.get(k) for k in keep} | ({"error": d["error"]} if "error" in d else {}) for d in ours],
+           "path": "mapped pinned staging row read / written by the kernel, callers combined at the launch lock, 8-CTA cluster kernel (csrc/nrb200_ll.cu)"}
+    if ref:
+        out["cpu_baseline"] = {"kind": "reference", "cores": cores, "rows": [{k: d.get(k) for k in keep[:7]} for d in ref],
+                               "sample": "same harness, same 64 blocks, 1.5 s per point"}
+        try:
+            out["ratio_1_thread"] = ours[0]["value"] / ref[0]["value"]
+            out["ratio_all_cores"] = ours[-1]["value"] / ref[-1]["value"]
+        except Exception:
+            pass
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ this repo's CUDA arm
 def run_b200(args, rank, world, local_rank):
     import torch
@@ -477,6 +512,11 @@ def run_b200(args, rank, world, local_rank):
             line["roofline"]["on_chip"] = oc
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_abi:
+            try:
+                line["e2e_plugin_abi"] = plugin_abi(not args.no_cpu)
+            except Exception as e:
+                line["e2e_plugin_abi"] = {"unavailable": repr(e)[:300]}
         if world == 1 and not args.no_slot:
             try:
                 line["nr_dlsim_slot"] = slot_b200(lib, dev, 0.0 if args.no_cpu else args.slot_cpu_seconds)
@@ -503,6 +543,7 @@ def main():
     ap.add_argument("--no-slot", action="store_true", help="skip the nr_dlsim slot chain (second half of the BASELINE metric)")
     ap.add_argument("--slot-cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-abi", action="store_true", help="skip the per-call loader-ABI measurement (tools/abi_bench)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

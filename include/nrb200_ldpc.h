@@ -113,7 +113,12 @@ int32_t LDPCshutdown(void);
 /* replaces LDPCdecoder (nrLDPC_decoder.c:172-195), "CPU-compatible" convention: p_llr holds ncol(R)*Z int8 LLRs
  * (first 2Z punctured = 0, fillers = +127); p_out receives per outMode; returns iterations used,
  * > numMaxIter means failure (and *ab is set).  harq_pid/ulsch_id/C are ignored in this convention.
- * Blocking, re-entrant; concurrent callers are micro-batched into one launch. */
+ * An internal failure (no device, invalid parameters, CUDA error) is reported the same way: numMaxIter + 1 with *ab set, cause in
+ * nrb200_last_error() -- never a negative value, OAI's callers test `<= numMaxIter` only.
+ * Blocking, re-entrant.  Low-latency path (csrc/nrb200_ll.cu): the LLRs are staged in mapped pinned memory that the kernel reads and
+ * answers into directly (no copy engine, no stream synchronisation); callers that arrive while another caller is issuing a launch are
+ * combined into the next launch; one code block runs on a thread-block cluster of up to 8 SMs; *ab is re-read while the call waits and
+ * polled by the kernel once per iteration (check_abort, nrLDPC_decoder.c:557-560).  NRB200_LL=0 selects the copy-engine path. */
 int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p_decParams, uint8_t harq_pid, uint8_t ulsch_id, uint8_t C, int8_t *p_llr,
                     int8_t *p_out, nrb200_ldpc_time_stats_t *p_profiler, nrb200_decode_abort_t *ab);
 /* replaces LDPCencoder (nrLDPC_encoder/ldpc_encoder_optim8segmulti.c:46-212): encodes segments
@@ -378,6 +383,13 @@ int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);
 /* Kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
 uint64_t nrb200_launch_count(void);
+/* low-latency path statistics: kernel launches and code blocks so far (blocks / launches = callers combined per launch) */
+void nrb200_ll_stats(uint64_t *launches, uint64_t *blocks);
+/* where the low-latency calls spent their time, sums in nanoseconds: [0] staging (memcpy into the mapped row), [1] queue + kernel launch,
+ * [2] waiting for the kernel's completion bytes, [3] copying the result out, [4] device-side time of the block (%globaltimer) */
+void nrb200_ll_timing(uint64_t *out5);
+/* debug: clock64() phase marks of the cluster decoder (64 per CTA of code block 0) when NRB200_CLUSTER_TIMERS=1; out512 = int64[8 * 64] */
+int32_t nrb200_debug_cluster_marks(long long *out512);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
 // Work partition of ONE code block over a thread-block cluster (ldpc_decoder_cluster.cuh): which warp of which CTA owns which
-// 32-word piece of which check row / bit column, and -- for the bit-node phase -- which CTA holds the cn->bn messages it has to pull.
+// 32-word piece of which check row / bit column, and which CTA owns each bit column (the check-node phase pushes messages there).
 #pragma once
 #include <cstdint>
 #include "ldpc_packed_graph.h"
@@ -9,18 +9,23 @@ namespace nrb200 {
 constexpr int kClMaxCtas = 8;        // portable cluster size limit
 constexpr int kClMaxWarps = 24;      // warps per CTA (launch bound 768 threads)
 constexpr int kClMaxLists = kClMaxCtas * 16;   // C * T <= 128 work lists
+constexpr int kClSplitItem = 0x1000;          // item flag: 16-word piece shared by the two halves of a warp
+constexpr int kClSplitRowDeg = 19, kClSplitColDeg = 16;
 
-struct ClusterSched {
+struct alignas(16) ClusterSched {
   int32_t C, T, nthreads, chunks;    // CTAs per code block, warps per CTA, 32 * T, Zw / 32
-  // list l = rank * T + warp; items cn_start[l] .. cn_start[l + 1]; item = row (column) | chunk << 8 as in PackedGraph
+  // list l = rank * T + warp; items cn_start[l] .. cn_start[l + 1]; item = row (column) | chunk << 8 as in PackedGraph, or -- the heavy rows
+  // (19 stored edges) and columns (>= kClSplitColDeg edges) -- row (column) | piece << 8 | kClSplitItem: 16 words, the two halves of the warp
+  // take one half of the edges each and combine their partial results by shuffle, which halves the longest dependent chain of the phase
   int16_t cn_start[kClMaxLists + 1];
-  int16_t cn_items[3 * kMaxRows];
+  int16_t cn_items[6 * kMaxRows];
   int16_t bn_start[kClMaxLists + 1];
-  int16_t bn_items[3 * kMaxCols];
-  // per column-edge entry (index as PackedGraph::bn_desc): .x = byte offset of the R row - 4*qq (same as PackedGraph), .y = bits[4:0] funnel
-  // amount, bits[16:8] 4*qq, bits[31:20] four 3-bit cluster ranks: the CTA that owns words 32*k .. 32*k+31 of this edge's R row for k = 0, 1, 2
-  // and, in field `chunks`, the owner of word 0 again (the halo word Zw)
-  alignas(8) uint32_t bn_desc[kMaxEdges][2];
+  int16_t bn_items[6 * kMaxCols];
+  // bit columns are owned whole (all chunks) by one CTA: col_rank[c]; edge_rank[m] = col_rank[column of stored edge m] is where the check-node
+  // phase pushes the edge's new cn->bn message (patched into bits[10:8] of the kernel's copy of PackedGraph::cn_desc[m][1])
+  uint8_t col_rank[kMaxCols];
+  uint8_t edge_rank[kMaxEdges];
+  uint8_t pad[16 - (kMaxCols + kMaxEdges) % 16];
 };
 
 // C CTAs of T warps each; false when the configuration cannot be split this way (Zw not a multiple of 32, too many lists).

@@ -13,12 +13,13 @@ constexpr int kCrcMaxChunks = 256;        // => up to 2 097 152 bits (a transpor
 constexpr int kLlMaxBatch = 32;           // code blocks one low-latency launch can carry (their row numbers travel in the launch arguments)
 
 // Control record of one staging row of the low-latency path (mapped pinned host memory, written by the kernel, polled by the host thread
-// that waits for the block: no stream synchronisation, no copy engine on the way).  16 bytes.
+// that waits for the block: no stream synchronisation, no copy engine on the way).  32 bytes.
 struct LlCtrl {
   uint8_t done[8];     // done[rank] = the launch's sequence byte once CTA `rank` of the block's cluster has stored its share of the output
   int32_t iters;       // what LDPCdecoder returns
   uint8_t abort;       // host -> device: decode_abort_t::failed as the waiting host thread last saw it (polled every iteration, nrLDPC_decoder.c:557)
   uint8_t pad[3];
+  uint64_t t_begin, t_end;   // %globaltimer (ns) when CTA 0 of the block started and when it stored its completion byte: device-side time of the block
 };
 
 // Launch arguments of the decode kernels (POD, passed by value).
@@ -45,6 +46,9 @@ struct BlockIo {
   LlCtrl *ctrl;                      // nullptr outside the low-latency mode
   const volatile uint8_t *abort;     // nullptr when the caller gave no abort flag
 };
+// low-latency mode: CTA 0 of a block stamps its start time
+__device__ __forceinline__ void block_begin(const BlockIo &io, int rank);
+
 __device__ __forceinline__ BlockIo block_io(const DecodeArgs &a, int cb)
 {
   BlockIo io;
@@ -57,6 +61,11 @@ __device__ __forceinline__ BlockIo block_io(const DecodeArgs &a, int cb)
   return io;
 }
 
+__device__ __forceinline__ void block_begin(const BlockIo &io, int rank)
+{
+  if (io.ctrl && rank == 0 && threadIdx.x == 0) { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); io.ctrl->t_begin = t; }
+}
+
 // End of a block: hand the result over.  Low-latency mode: every thread has fenced its output stores to host memory (system scope); the
 // barrier orders them before thread 0's iteration count and completion byte, which the host thread is spinning on.
 __device__ __forceinline__ void block_finish(const BlockIo &io, const DecodeArgs &a, int numIter, int rank)
@@ -65,7 +74,12 @@ __device__ __forceinline__ void block_finish(const BlockIo &io, const DecodeArgs
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      if (rank == 0) { io.ctrl->iters = numIter; __threadfence_system(); }
+      if (rank == 0) {
+        io.ctrl->iters = numIter;
+        uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        io.ctrl->t_end = t;
+        __threadfence_system();
+      }
       *reinterpret_cast<volatile uint8_t *>(&io.ctrl->done[rank]) = a.ll_seq;
     }
   } else if (threadIdx.x == 0 && rank == 0) {

@@ -66,6 +66,12 @@ static const ClusterSched *cluster_sched(const GraphDev &h_g, const PackedGraph 
   return it->second.first;
 }
 
+// debug: the cluster kernel's phase marks (64 per CTA of code block 0), see NRB200_CL_MARK
+int debug_cluster_marks(long long *out)
+{
+  return cudaMemcpyFromSymbol(out, g_cl_marks, sizeof(long long) * kClMaxCtas * 64) == cudaSuccess ? 0 : -2;
+}
+
 void packed_graph_cache_clear()
 {
   std::lock_guard<std::mutex> lk(g_pk_mu);
@@ -82,26 +88,44 @@ static int pick_cluster(uint32_t n_cb)
 {
   static const int forced = []() { const char *e = getenv("NRB200_CLUSTER"); return e ? atoi(e) : -1; }();
   if (forced == 0 || forced == 2 || forced == 4 || forced == 8) return forced;
-  return n_cb <= 16 ? 8 : n_cb <= 33 ? 4 : n_cb <= 74 ? 2 : 0;
+  return n_cb <= 15 ? 8 : n_cb <= 33 ? 4 : n_cb <= 74 ? 2 : 0;   // launch__cluster_max_active of the 8-CTA kernel is 15 on a B200 (ncu, profiles/)
 }
+
+int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream, uint32_t load, int *cluster_out);
 
 // Returns 0 or a negative error.  Asynchronous on `stream`.
 int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream)
 {
+  return launch_decode_impl(d_g, h_g, a, stream, a.n_cb, nullptr);
+}
+
+// The low-latency path's launch: `load` = code blocks in flight on the device including this launch's (several small launches share the
+// SMs, the cluster size is chosen for all of them together); *cluster_out = CTAs per block of the kernel that was launched (1 = no cluster).
+int launch_decode_ll(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream, uint32_t load, int *cluster_out)
+{
+  return launch_decode_impl(d_g, h_g, a, stream, load, cluster_out);
+}
+
+int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream, uint32_t load, int *cluster_out)
+{
   Ctx &c = ctx();
+  if (cluster_out) *cluster_out = 1;
   if (a.n_cb == 0) return 0;
   static const bool force_generic = getenv("NRB200_FORCE_GENERIC") != nullptr;
   const PackedGraph *h_pg = nullptr;
   const PackedGraph *d_pg = (h_g.Z % 4 == 0 && !force_generic) ? packed_graph(h_g, &h_pg) : nullptr;
-  const int C = d_pg && h_pg->warp_items && !(a.quirks & 1) ? pick_cluster(a.n_cb) : 0;
+  const int C = d_pg && h_pg->warp_items && !(a.quirks & 1) ? pick_cluster(load) : 0;
   if (C >= 2) {
     const ClusterSched *h_cs = nullptr;
     const ClusterSched *d_cs = cluster_sched(h_g, *h_pg, C, &h_cs);
     if (d_cs) {
       const size_t smem = (size_t)h_pg->total_bytes;
-      void (*kern)(const PackedGraph *, const ClusterSched *, DecodeArgs) = h_pg->Zw == 96 ? ldpc_decode_cluster_kernel<96> : ldpc_decode_cluster_kernel<0>;
-      static std::atomic<size_t> configured_cl[2];
-      const int v = h_pg->Zw == 96 ? 1 : 0;
+      const bool wide = h_cs->nthreads > 512;
+      void (*kern)(const PackedGraph *, const ClusterSched *, DecodeArgs) =
+          h_pg->Zw == 96 ? (wide ? ldpc_decode_cluster_kernel<96, 768> : ldpc_decode_cluster_kernel<96, 512>)
+                         : (wide ? ldpc_decode_cluster_kernel<0, 768> : ldpc_decode_cluster_kernel<0, 512>);
+      static std::atomic<size_t> configured_cl[4];
+      const int v = (h_pg->Zw == 96 ? 2 : 0) + (wide ? 1 : 0);
       if (smem > configured_cl[v].load()) {
         NRB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cluster smem attr");
         configured_cl[v].store(smem);
@@ -117,6 +141,7 @@ int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a,
       cfg.attrs = at; cfg.numAttrs = 1;
       NRB200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, d_pg, d_cs, a), "cluster decode launch");
       c.launches++;
+      if (cluster_out) *cluster_out = C;
       return 0;
     }
   }

@@ -34,6 +34,7 @@ ldpc_decode_generic_kernel(const GraphDev *__restrict__ gdev, DecodeArgs a)
 
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
     const BlockIo io = block_io(a, cb);
+    block_begin(io, 0);
     const int8_t *gl = io.llr;
     for (int i = threadIdx.x; i < numLLR; i += blockDim.x) { llr[i] = gl[i]; hd[i] = 0; }
     __syncthreads();

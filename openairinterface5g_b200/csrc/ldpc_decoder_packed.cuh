@@ -29,6 +29,22 @@ __device__ __forceinline__ uint32_t lds(const char *smb, uint32_t off) { return 
 __device__ __forceinline__ uint2 lds2(const char *smb, uint32_t off) { return *reinterpret_cast<const uint2 *>(smb + off); }
 __device__ __forceinline__ void sts(char *smb, uint32_t off, uint32_t v) { *reinterpret_cast<uint32_t *>(smb + off) = v; }
 
+// ---- distributed shared memory (thread-block clusters): the cluster decoder (ldpc_decoder_cluster.cuh) pushes every new cn->bn message into
+//      the CTA that owns the edge's bit column
+__device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cl_map(uint32_t saddr, uint32_t rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cl_st(uint32_t caddr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(caddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void cl_st8(uint32_t caddr, uint32_t v) { asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(caddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void cl_sync()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Row geometry: ZWC = Z / 4 fixed at compile time (the hot Z = 384 instantiation: every R / L / P row offset becomes an immediate
 // of the LDS / STS instead of a multiply-add per edge), ZWC = 0 reads it from the graph tables (every other lifting size).
 template <int ZWC> __device__ __forceinline__ int geo_zw(const PackedGraph &G) { return ZWC ? ZWC : G.Zw; }
@@ -58,9 +74,11 @@ __device__ __forceinline__ void cn_row_neighbour(const PackedGraph &G, char *__r
   if (!first_iter && (kb >> 2) < (row.prow_pcw >> 24)) bad |= synd & kH;
 }
 
-template <int ZWC, int D, bool QUIRK>
+// CL (cluster decoder): sbase = shared-window address of smb; bits[10:8] of an edge's cn_desc .y hold the cluster rank of the CTA that owns the
+// edge's bit column, and every new message is also stored into that CTA's copy of the R row (same offset), where its bit-node phase reads it.
+template <int ZWC, int D, bool QUIRK, bool CL = false>
 __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool halo,
-                                       bool first_iter, uint32_t quirk_zero, uint32_t &bad)
+                                       bool first_iter, uint32_t quirk_zero, uint32_t &bad, uint32_t sbase = 0u)
 {
   const uint32_t one = G.one, mone = 0u - one;
   const uint32_t ZB = geo_zb<ZWC>(G), RSB = geo_rsb<ZWC>(G);
@@ -94,7 +112,11 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
     uint32_t rn = make_r(q[j], tm.n1, p1, p2, sgn, one, mone);
     if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
     sts(smb, rb + j * RSB, rn);
-    if (halo) sts(smb, rb + j * RSB + ZB, rn);
+    if (CL) {
+      const uint32_t ra = cl_map(sbase + rb + j * RSB, prmt(G.cn_desc[e0 + j][1], 0u, 0x4441u));
+      cl_st(ra, rn);
+      if (halo) cl_st(ra + ZB, rn);
+    } else if (halo) sts(smb, rb + j * RSB + ZB, rn);
   }
 }
 
@@ -105,9 +127,9 @@ __device__ __forceinline__ void cn_row(const PackedGraph &G, char *__restrict__ 
 // own R slot (R_old is dead once read; only this thread touches this word during the CN phase) and pass 2 reads it back.  Measured: the ~25 % more
 // instructions cost more than the smaller footprint returns (all rows looped 0.79 ms, degrees 7-19 looped 0.72 ms, all unrolled 0.70 ms per 1024
 // blocks), so every NR row degree stays unrolled.
-template <int ZWC, bool QUIRK>
+template <int ZWC, bool QUIRK, bool CL = false>
 __device__ __forceinline__ void cn_row_loop(const PackedGraph &G, char *__restrict__ smb, const PackedRow &row, uint32_t kb, bool halo,
-                                         bool first_iter, uint32_t quirk_zero, uint32_t &bad)
+                                         bool first_iter, uint32_t quirk_zero, uint32_t &bad, uint32_t sbase = 0u)
 {
   const uint32_t one = G.one, mone = 0u - one;
   const uint32_t ZB = geo_zb<ZWC>(G), RSB = geo_rsb<ZWC>(G);
@@ -141,12 +163,16 @@ __device__ __forceinline__ void cn_row_loop(const PackedGraph &G, char *__restri
     uint32_t rn = make_r(lds(smb, ra), tm.n1, p1, p2, sgn, one, mone);
     if (QUIRK) rn = (rn & ~quirk_zero) | (kH & quirk_zero);
     sts(smb, ra, rn);
-    if (halo) sts(smb, ra + ZB, rn);
+    if (CL) {
+      const uint32_t rr = cl_map(sbase + ra, prmt(G.cn_desc[e0 + j][1], 0u, 0x4441u));
+      cl_st(rr, rn);
+      if (halo) cl_st(rr + ZB, rn);
+    } else if (halo) sts(smb, ra + ZB, rn);
   }
 }
 
-template <int ZWC, bool QUIRK>
-__device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int r, uint32_t kb, bool halo, bool first_iter, uint32_t &bad)
+template <int ZWC, bool QUIRK, bool CL = false>
+__device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int r, uint32_t kb, bool halo, bool first_iter, uint32_t &bad, uint32_t sbase = 0u)
 {
   const PackedRow row = G.rows[r];
   uint32_t qz = 0u;
@@ -161,14 +187,14 @@ __device__ __forceinline__ void cn_dispatch(const PackedGraph &G, char *smb, int
 #define NRB200_UNROLL_MASK 0x807FCu   /* every row degree the NR base graphs have: measured best (profiles/variants_r01n.txt) */
 #endif
   const uint32_t D = (row.e0_deg >> 12) & 0xFFu;
-#define NRB200_CN_CASE(d) case d: if ((NRB200_UNROLL_MASK >> d) & 1u) { cn_row<ZWC, d, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad); return; } break;
+#define NRB200_CN_CASE(d) case d: if ((NRB200_UNROLL_MASK >> d) & 1u) { cn_row<ZWC, d, QUIRK, CL>(G, smb, row, kb, halo, first_iter, qz, bad, sbase); return; } break;
   switch (D) {
     NRB200_CN_CASE(2) NRB200_CN_CASE(3) NRB200_CN_CASE(4) NRB200_CN_CASE(5) NRB200_CN_CASE(6) NRB200_CN_CASE(7) NRB200_CN_CASE(8) NRB200_CN_CASE(9)
     NRB200_CN_CASE(10) NRB200_CN_CASE(19)
     default: break;
   }
 #undef NRB200_CN_CASE
-  cn_row_loop<ZWC, QUIRK>(G, smb, row, kb, halo, first_iter, qz, bad);
+  cn_row_loop<ZWC, QUIRK, CL>(G, smb, row, kb, halo, first_iter, qz, bad, sbase);
 }
 
 // one bit-node edge: fetch the rotated R' word and add its four bytes to the four running sums (IDP.4A, FMA pipe)
@@ -187,8 +213,9 @@ __device__ __forceinline__ void bn_edge(const PackedGraph &G, const char *__rest
 }
 
 // A' = clamp(L' + sum R' - 128*deg, 0, 255) for column c, word k   (packs_epi16 of the int16 sum, in offset binary)
+// CL > 0 (cluster decoder): the word goes into the A replica of every one of the CL CTAs
 template <int ZWC>
-__device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ smb, int c, uint32_t kb)
+__device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ smb, int c, uint32_t kb, int CL = 0, uint32_t sbase = 0u)
 {
   const uint32_t ZB = geo_zb<ZWC>(G);
   const uint32_t lw = lds(smb, G.off_L + c * geo_rsb<ZWC>(G) + kb);
@@ -202,8 +229,16 @@ __device__ __forceinline__ void bn_col(const PackedGraph &G, char *__restrict__ 
   const uint32_t hi = __vmins2(__viaddmax_s16x2(prmt(s2, s3, 0x5410u), nb, 0u), 0x00ff00ffu);
   const uint32_t a = prmt(lo, hi, 0x6420u);
   const uint32_t ao = G.off_A + G.col_arow[c] * 2 * ZB + kb;
-  sts(smb, ao, a);
-  sts(smb, ao + ZB, a);
+  if (CL > 0) {
+    for (int r = 0; r < CL; r++) {
+      const uint32_t ra = cl_map(sbase + ao, (uint32_t)r);
+      cl_st(ra, a);
+      cl_st(ra + ZB, a);
+    }
+  } else {
+    sts(smb, ao, a);
+    sts(smb, ao + ZB, a);
+  }
 }
 
 // hard decision of codeword position i (0/1); degree-1 columns read as 0 like the reference's untouched llrRes
@@ -292,6 +327,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
     // ---- load channel LLRs (global int8, coalesced 32-bit) as offset binary into L rows with halo; A := L; R := 0; P := 0
     const BlockIo io = block_io(a, cb);
+    block_begin(io, 0);
     const int8_t *gl = io.llr;
     const bool al4 = ((reinterpret_cast<uintptr_t>(gl) & 3) == 0);
     for (int i = threadIdx.x; i < G.ncols * Zw; i += blockDim.x) {

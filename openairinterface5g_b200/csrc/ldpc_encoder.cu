@@ -11,7 +11,7 @@ namespace nrb200 {
 // one CTA per code block; x = the whole codeword as 0/1 bytes in shared memory
 __global__ void __launch_bounds__(384, 2)
 ldpc_encode_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t n_cb, const uint8_t *__restrict__ in, uint32_t in_stride,
-                   uint8_t *__restrict__ out, uint32_t out_stride)
+                   uint8_t *__restrict__ out, uint32_t out_stride, volatile uint8_t *done)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EncGraphDev &g = *reinterpret_cast<EncGraphDev *>(smem_raw);
@@ -79,7 +79,9 @@ ldpc_encode_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t n_cb, c
     uint8_t *dst = out + (size_t)cb * out_stride;
     const int nout = (ncols - 2) * Z;
     for (int i = threadIdx.x; i < nout; i += blockDim.x) dst[i] = x[2 * Z + i];
+    if (done) __threadfence_system();
     __syncthreads();
+    if (done && threadIdx.x == 0) done[cb] = 1;
   }
 }
 
@@ -97,7 +99,7 @@ __device__ __forceinline__ uint32_t rotw(const uint32_t *col, int W, int w, int 
 
 __global__ void __launch_bounds__(128)
 ldpc_encode_packed_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t n_cb, const uint8_t *__restrict__ in, uint32_t in_stride,
-                          uint8_t *__restrict__ out, uint32_t out_stride)
+                          uint8_t *__restrict__ out, uint32_t out_stride, volatile uint8_t *done)
 {
   __shared__ EncGraphDev g;
   __shared__ __align__(16) uint32_t x[68 * 12];
@@ -188,17 +190,20 @@ ldpc_encode_packed_kernel(const EncGraphDev *__restrict__ gdev, int K, uint32_t 
         for (int k = 0; k < 16; k++) dst[16 * (size_t)i + k] = (uint8_t)(a[k >> 2] >> (8 * (k & 3)));
       }
     }
+    if (done) __threadfence_system();        // low-latency mode: out is mapped host memory, done[cb] is what the calling thread spins on
     __syncthreads();
+    if (done && threadIdx.x == 0) done[cb] = 1;
   }
 }
 
+// done != nullptr (low-latency mode): in / out / done are mapped host memory, done[cb] := 1 once block cb's output is stored
 int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
-                  uint8_t *d_out, uint32_t out_stride, cudaStream_t stream)
+                  uint8_t *d_out, uint32_t out_stride, cudaStream_t stream, uint8_t *done)
 {
   if (n_cb == 0) return 0;
   static const bool force_bytes = getenv("NRB200_ENCODE_BYTES") != nullptr;
   if (h_g.Z % 32 == 0 && K % 32 == 0 && !force_bytes) {
-    ldpc_encode_packed_kernel<<<n_cb, 128, 0, stream>>>(d_g, K, n_cb, d_in, in_stride, d_out, out_stride);
+    ldpc_encode_packed_kernel<<<n_cb, 128, 0, stream>>>(d_g, K, n_cb, d_in, in_stride, d_out, out_stride, done);
     ctx().launches++;
     NRB200_CUDA_OK(cudaGetLastError(), "packed encode launch");
     return 0;
@@ -213,7 +218,7 @@ int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_
   int threads = ((h_g.Z + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > 384) threads = 384;
-  ldpc_encode_kernel<<<n_cb, threads, smem, stream>>>(d_g, K, n_cb, d_in, in_stride, d_out, out_stride);
+  ldpc_encode_kernel<<<n_cb, threads, smem, stream>>>(d_g, K, n_cb, d_in, in_stride, d_out, out_stride, done);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "encode launch");
   return 0;
@@ -378,7 +383,10 @@ int launch_tb_segment(int BG, uint32_t A, const uint8_t *d_payload, uint8_t *d_s
 int quirks_from_env()
 {
   static int q = -1;
-  if (q < 0) { const char *s = getenv("NRB200_EMULATE_AVX2_BG2R15_DEFECT"); q = (s && *s == '1') ? 1 : 0; }
+  if (q < 0) {
+    const char *s = getenv("NRB200_EMULATE_AVX2_BG2R15_DEFECT"), *t = getenv("NRB200_CLUSTER_TIMERS");
+    q = ((s && *s == '1') ? 1 : 0) | ((t && *t == '1') ? 2 : 0);   // bit 1: the cluster decoder records clock64() phase marks (tools/cluster_phases.py)
+  }
   return q;
 }
 

@@ -163,28 +163,46 @@ bool build_cluster_sched(const GraphDev &g, const PackedGraph &p, int C, int T, 
   const int chunks = p.Zw / 32;
   if (chunks > 3) return false;
   s->C = C; s->T = T; s->nthreads = 32 * T; s->chunks = chunks;
-  // same cost model as the single-CTA lists; a column additionally pays the broadcast of its a-posteriori word to the C CTAs
-  auto row_cost = [&](int r) { return 2 * (18 + 32 * (g.row_start[r + 1] - g.row_start[r]) + (g.row_p_col[r] >= 0 ? 51 : 11)); };
-  auto col_cost = [&](int c) { return 130 + 44 * g.col_deg[c] + 6 * C; };
-  std::vector<std::pair<int, int>> rows, cols;
-  for (int r = 0; r < g.nrows; r++) for (int k = 0; k < chunks; k++) rows.push_back({row_cost(r), r | (k << 8)});
-  for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) for (int k = 0; k < chunks; k++) cols.push_back({col_cost(c), c | (k << 8)});
-  lpt(rows, C * T, s->cn_start, s->cn_items);
-  lpt(cols, C * T, s->bn_start, s->bn_items);
-  // owner CTA of every (row, chunk)
-  std::vector<int> owner((size_t)kMaxRows * 4, 0);
-  for (int l = 0; l < C * T; l++)
-    for (int i = s->cn_start[l]; i < s->cn_start[l + 1]; i++) owner[(size_t)(s->cn_items[i] & 0xFF) * 4 + (s->cn_items[i] >> 8)] = l / T;
-  std::vector<int> row_of_slot(g.nreal, 0);
-  for (int r = 0; r < g.nrows; r++) for (int m = g.row_start[r]; m < g.row_start[r + 1]; m++) row_of_slot[m] = r;
-  for (int i = 0; i < g.nreal; i++) {
-    const int r = row_of_slot[g.col_edges[i]];
-    uint32_t own = 0;
-    for (int k = 0; k < chunks; k++) own |= (uint32_t)owner[(size_t)r * 4 + k] << (3 * k);
-    own |= (uint32_t)owner[(size_t)r * 4] << (3 * chunks);
-    s->bn_desc[i][0] = p.bn_desc[i][0];
-    s->bn_desc[i][1] = (p.bn_desc[i][1] & 0xFFFFFu) | (own << 20);
+  // cost model of the single-CTA lists; a row additionally pays the push of every message (4 per edge), a column the broadcast of its word
+  auto row_cost = [&](int r) { return 2 * (18 + 36 * (g.row_start[r + 1] - g.row_start[r]) + (g.row_p_col[r] >= 0 ? 51 : 11)); };
+  auto col_cost = [&](int c) { return 130 + 27 * g.col_deg[c] + 6 * C; };
+  // check rows: any warp of any CTA (their messages travel to the column owners anyway)
+  const int pieces = p.Zw / 16;
+  std::vector<std::pair<int, int>> rows;
+  for (int r = 0; r < g.nrows; r++) {
+    if (g.row_start[r + 1] - g.row_start[r] == kClSplitRowDeg)
+      for (int k = 0; k < pieces; k++) rows.push_back({row_cost(r) / 2 + 80, r | (k << 8) | kClSplitItem});
+    else
+      for (int k = 0; k < chunks; k++) rows.push_back({row_cost(r), r | (k << 8)});
   }
+  lpt(rows, C * T, s->cn_start, s->cn_items);
+  // bit columns: whole columns to CTAs (longest first onto the lightest CTA), then each CTA's (column, chunk) items onto its T warps
+  std::vector<std::pair<int, int>> cols;
+  for (int c = 0; c < g.ncols; c++) if (g.col_deg[c] >= 2) cols.push_back({col_cost(c), c});
+  std::stable_sort(cols.begin(), cols.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+  std::vector<int> load(C, 0);
+  std::vector<std::vector<std::pair<int, int>>> mine(C);
+  for (auto &cc : cols) {
+    int b = 0;
+    for (int i = 1; i < C; i++) if (load[i] < load[b]) b = i;
+    load[b] += cc.first;
+    s->col_rank[cc.second] = (uint8_t)b;
+    if (g.col_start[cc.second + 1] - g.col_start[cc.second] >= kClSplitColDeg)
+      for (int k = 0; k < pieces; k++) mine[b].push_back({cc.first / 2 + 40, cc.second | (k << 8) | kClSplitItem});
+    else
+      for (int k = 0; k < chunks; k++) mine[b].push_back({cc.first, cc.second | (k << 8)});
+  }
+  int n = 0;
+  for (int r = 0; r < C; r++) {
+    int16_t st[kClMaxWarps + 1], items[6 * kMaxCols];
+    lpt(mine[r], T, st, items);
+    for (int w = 0; w < T; w++) {
+      s->bn_start[r * T + w] = (int16_t)n;
+      for (int i = st[w]; i < st[w + 1]; i++) s->bn_items[n++] = items[i];
+    }
+  }
+  s->bn_start[C * T] = (int16_t)n;
+  for (int m = 0; m < g.nreal; m++) s->edge_rank[m] = s->col_rank[g.edge_col[m]];
   return true;
 }
 

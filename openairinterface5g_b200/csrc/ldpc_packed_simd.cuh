@@ -115,6 +115,13 @@ NRB200_SIMD void twomin(uint32_t mag, TwoMin &s, uint32_t one, uint32_t mone)
 }
 NRB200_SIMD uint32_t twomin_min1(const TwoMin &s, uint32_t mone) { return add_fma(s.n1, kL7, mone); }
 NRB200_SIMD uint32_t twomin_min2(const TwoMin &s, uint32_t mone) { return add_fma(s.n2p, 0xFEFEFEFEu, mone); }
+// two minima of the union of two edge sets: feed the other set's two minima through the tracker (the cluster decoder splits the degree-19
+// rows between the two halves of a warp)
+NRB200_SIMD void twomin_merge(TwoMin &s, const TwoMin &o, uint32_t one, uint32_t mone)
+{
+  twomin(twomin_min1(o, mone), s, one, mone);
+  twomin(twomin_min2(o, mone), s, one, mone);
+}
 
 // offset-binary cn->bn message (R + 128) of one edge from the row's two minima and sign product (bit 7 = negative).
 // p1 = min1 | 0x80, p2 = min2 | 0x80 are formed once per row; |Q| >= min1 always, so |Q| != min1 <=> bit 7 of |Q| + n1; the negative

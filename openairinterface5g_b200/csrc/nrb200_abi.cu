@@ -13,8 +13,15 @@
 
 namespace nrb200 {
 int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream);
+int ll_decode_one(const GraphDev *dg, const GraphDev *hg, const DecodeArgs &a0, uint64_t sig, size_t in_bytes, size_t out_bytes, const int8_t *llr,
+                  uint8_t *out, int32_t *iters, nrb200_decode_abort_t *ab);
+void ll_stats(uint64_t *launches, uint64_t *blocks);
+int ll_warm();
+void ll_timing(uint64_t out[5]);
+int debug_cluster_marks(long long *out);
 int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
-                  uint8_t *d_out, uint32_t out_stride, cudaStream_t stream);
+                  uint8_t *d_out, uint32_t out_stride, cudaStream_t stream, uint8_t *done = nullptr);
+int ll_encode(const EncGraphDev *dg, const EncGraphDev *hg, int K, uint32_t n, uint8_t **input, uint8_t **output, uint32_t kin, uint32_t nout);
 int launch_crc(int poly_id, uint32_t n_blk, const uint8_t *d_in, uint32_t stride, uint32_t bitlen, uint32_t *d_out, cudaStream_t stream);
 int tb_segment_parms(int BG, uint32_t A, uint32_t out[6]);
 int launch_tb_segment(int BG, uint32_t A, const uint8_t *d_payload, uint8_t *d_segs, uint32_t seg_stride, uint32_t *d_scratch, cudaStream_t stream);
@@ -267,12 +274,37 @@ NRB200_EXPORT int32_t nrb200_ldpc_packed_schedule_info(int BG, int Z, int R, int
 }
 
 NRB200_EXPORT int32_t nrb200_device_index(void) { return ctx().inited ? ctx().dev : -1; }
-NRB200_EXPORT const char *nrb200_last_error(void) { return ctx().last_error.c_str(); }
+NRB200_EXPORT const char *nrb200_last_error(void)
+{
+  static thread_local std::string copy;       // other threads may replace Ctx::last_error at any time
+  std::lock_guard<std::mutex> lk(ctx().mu);
+  copy = ctx().last_error;
+  return copy.c_str();
+}
 NRB200_EXPORT uint64_t nrb200_launch_count(void) { return ctx().launches.load(); }
 
 // ------------------------------------------------------------------------------------------ part 1: OAI loader ABI
-NRB200_EXPORT int32_t LDPCinit(void) { return ctx().init() == 0 ? 0 : -1; }
+NRB200_EXPORT int32_t LDPCinit(void)
+{
+  if (ctx().init() != 0) return -1;
+  cudaSetDevice(ctx().dev);
+  return ll_warm() == 0 ? 0 : -1;
+}
 NRB200_EXPORT int32_t LDPCshutdown(void) { ctx().shutdown(); return 0; }
+
+// Failure inside the library: OAI's callers decide success with `decodeIterations <= numMaxIter` (nr_ulsch_decoding.c:221,
+// nr_dlsch_decoding.c:90) and know no negative return in this convention, so an internal error is reported the way the reference reports
+// a block it could not decode: numMaxIter + 1 with the abort flag set; the cause is kept for nrb200_last_error().
+static int32_t decoder_failure(const nrb200_ldpc_dec_params_t *p, nrb200_decode_abort_t *ab, const char *why)
+{
+  ctx().set_error(why, cudaPeekAtLastError());
+  if (ab) {
+    pthread_mutex_lock(&ab->mutex_failure);
+    ab->failed = true;
+    pthread_mutex_unlock(&ab->mutex_failure);
+  }
+  return (int32_t)p->numMaxIter + 1;
+}
 
 NRB200_EXPORT int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t C, int8_t *p_llr,
                                   int8_t *p_out, nrb200_ldpc_time_stats_t *prof, nrb200_decode_abort_t *ab)
@@ -280,27 +312,39 @@ NRB200_EXPORT int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p, uint8_t harq_pid,
   (void)harq_pid; (void)ulsch_id; (void)C;
   const unsigned long long t0 = prof ? rdtsc_now() : 0;
   const int32_t numLLR = nrb200_ldpc_num_llr(p->BG, p->Z, p->R);
-  if (numLLR < 0) return -1;
+  if (numLLR < 0) return decoder_failure(p, ab, "LDPCdecoder: (BG, Z, R) is not an NR decoder configuration");
+  if (ensure_init()) return decoder_failure(p, ab, "LDPCdecoder: no CUDA device");
   nrb200_ldpc_batch_desc_t d;
   std::memset(&d, 0, sizeof(d));
   d.BG = p->BG; d.Z = p->Z; d.R = p->R; d.numMaxIter = p->numMaxIter; d.outMode = (uint8_t)p->outMode;
   d.n_cb = 1; d.llr_stride = (uint32_t)numLLR; d.out_stride = p->outMode == NRB200_OUTMODE_BIT ? (uint32_t)(numLLR + 7) / 8 : (uint32_t)numLLR;
-  uint8_t abort_now = 0;
-  if (ab) {   // check_abort (defs_common.h:1008-1016)
-    pthread_mutex_lock(&ab->mutex_failure);
-    abort_now = ab->failed ? 1 : 0;
-    pthread_mutex_unlock(&ab->mutex_failure);
-  }
-  int32_t it = 0;
-  int rc;
   if (p->check_crc) {
     // The reference calls back into the host's check_crc (crc_byte.c:314) from inside the loop; the kernel evaluates the
     // same CRC on device (types CRC24_A/B, CRC16, CRC8).
     d.use_crc = 1; d.crc_type = (uint8_t)p->crc_type; d.crc_len_bits = (uint32_t)p->E;
   }
-  // In CRC mode the reference leaves p_out untouched unless a check ran: decode into a scratch copy of p_out's current bytes
-  rc = decode_host_impl(&d, p_llr, (uint8_t *)p_out, &it, &abort_now);
-  if (rc != 0) return -1;
+  int32_t it = 0;
+  int rc;
+  static const bool use_ll = []() { const char *e = getenv("NRB200_LL"); return !(e && atoi(e) == 0); }();
+  if (use_ll) {
+    // low-latency path (nrb200_ll.cu): mapped staging row, concurrent callers combined into one launch, cluster kernel, abort flag polled per iteration
+    const GraphDev *hg = nullptr;
+    const GraphDev *dg = ctx().graph(d.BG, d.Z, d.R, &hg);
+    DecodeArgs a0;
+    if (!dg || fill_args(&d, *hg, &a0) != 0) return decoder_failure(p, ab, "LDPCdecoder: invalid decode parameters");
+    const uint64_t sig = ((uint64_t)d.BG << 56) | ((uint64_t)d.Z << 40) | ((uint64_t)d.R << 32) | ((uint64_t)d.numMaxIter << 24) | ((uint64_t)d.outMode << 22) |
+                         ((uint64_t)d.use_crc << 21) | ((uint64_t)d.crc_type << 18) | (uint64_t)(d.crc_len_bits & 0x3FFFFu);
+    rc = ll_decode_one(dg, hg, a0, sig, (size_t)numLLR, d.out_stride, p_llr, (uint8_t *)p_out, &it, ab);
+  } else {
+    uint8_t abort_now = 0;
+    if (ab) {   // check_abort (defs_common.h:1008-1016)
+      pthread_mutex_lock(&ab->mutex_failure);
+      abort_now = ab->failed ? 1 : 0;
+      pthread_mutex_unlock(&ab->mutex_failure);
+    }
+    rc = decode_host_impl(&d, p_llr, (uint8_t *)p_out, &it, &abort_now);
+  }
+  if (rc != 0) return decoder_failure(p, ab, "LDPCdecoder: device error");
   if (it > p->numMaxIter && ab) {   // set_abort (nrLDPC_decoder.c:190-193)
     pthread_mutex_lock(&ab->mutex_failure);
     ab->failed = true;
@@ -313,6 +357,12 @@ NRB200_EXPORT int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p, uint8_t harq_pid,
   }
   return it;
 }
+
+NRB200_EXPORT void nrb200_ll_timing(uint64_t *out5) { if (out5) ll_timing(out5); }
+NRB200_EXPORT int32_t nrb200_debug_cluster_marks(long long *out512) { return ensure_init() ? -1 : debug_cluster_marks(out512); }
+
+// launches / code blocks of the low-latency path so far: blocks / launches = how many concurrent callers rode on one launch on average
+NRB200_EXPORT void nrb200_ll_stats(uint64_t *launches, uint64_t *blocks) { if (launches && blocks) ll_stats(launches, blocks); }
 
 // ------------------------------------------------------------------------------------------ encoder + CRC
 NRB200_EXPORT int32_t nrb200_ldpc_encode_batch_dev(int BG, int Z, int K, uint32_t n_cb, const uint8_t *d_in, uint32_t in_stride,
@@ -359,6 +409,19 @@ NRB200_EXPORT int32_t LDPCencoder(uint8_t **input, uint8_t **output, nrb200_ldpc
   const unsigned long long t0 = impp->tparity ? rdtsc_now() : 0;
   const uint32_t n = s1 - s0, kin = (uint32_t)(K + 7) / 8, nout = (uint32_t)((BG == 1 ? 66 : 50) * Z);
   const uint32_t in_stride = (kin + 15) & ~15u, out_stride = (nout + 15) & ~15u;
+  static const bool use_ll = []() { const char *e = getenv("NRB200_LL"); return !(e && atoi(e) == 0); }();
+  if (use_ll) {
+    // low-latency path (nrb200_ll.cu): payloads and code words live in mapped pinned memory, the kernel reads and writes them over PCIe itself
+    const EncGraphDev *hg = nullptr;
+    const EncGraphDev *dg = ctx().enc_graph(BG, Z, &hg);
+    if (!dg || K != hg->nsys * Z) return -1;
+    const int rc = ll_encode(dg, hg, K, n, input + s0, output + s0, kin, nout);
+    if (impp->tparity && rc == 0) {
+      const long long dt = (long long)(rdtsc_now() - t0);
+      impp->tparity->trials++; impp->tparity->diff += dt; impp->tparity->p_time = dt;
+    }
+    return rc == 0 ? 0 : -1;
+  }
   Workspace *w = ctx().acquire();
   if (!w || !w->reserve((size_t)n * in_stride, (size_t)n * out_stride, 16)) { if (w) ctx().release(w); return -1; }
   int rc = 0;

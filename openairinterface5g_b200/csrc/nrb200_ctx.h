@@ -23,7 +23,7 @@ struct Workspace {
 
 struct Ctx {
   std::mutex mu;
-  bool inited = false;
+  std::atomic<bool> inited{false};             // read without the mutex by every entry point
   int dev = -1;
   int sm_count = 0;
   int max_smem_optin = 0;

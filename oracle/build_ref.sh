@@ -88,3 +88,20 @@ ls -la $W/*.so
 gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_loader.c -ldl -lpthread -o libref_loader.so || echo "libref_loader.so: FAILED"
 # OAI's dft_size_idx_t / idft_size_idx_t enumerator order (pins the size index the dft()/idft() drop-in receives)
 gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_dftidx.c -o libref_dftidx.so || echo "libref_dftidx.so: FAILED"
+# ---- the reference's OWN physim executable: ldpctest (openair1/PHY/CODING/TESTBENCH/ldpctest.c) with the reference's module loader
+#      (load_module_shlib.c), command-line-only config module, logging and noise generators, linked like CMakeLists.txt:2205-2217 does, plus the
+#      two LDPC modules it always loads (CMakeLists.txt:816-844): libldpc_orig.so (ldpc_encoder.c) and libldpc.so (ldpc_encoder_optim8segmulti.c),
+#      both with nrLDPC_decoder.c.  `ldpctest -v _b200` then dlopens libldpc_b200.so through the unmodified loader (tests/test_gpu_ldpctest.py).
+mkdir -p $W/oai_libs $W/ldpctest_obj
+LT_DEFS="$DEFS -DPACKAGE_VERSION=\"oracle-build\" -DT_TRACER=0"
+LT_SRCS="openair1/PHY/CODING/TESTBENCH/ldpctest.c openair1/PHY/CODING/nrLDPC_load.c common/utils/load_module_shlib.c common/config/config_load_configmodule.c
+ common/config/config_userapi.c common/config/config_cmdline.c common/config/config_common.c common/utils/LOG/log.c common/utils/time_meas.c
+ openair1/SIMULATION/TOOLS/rangen_double.c openair1/SIMULATION/TOOLS/taus.c common/utils/utils.c"
+ok=1
+for f in $LT_SRCS; do gcc -O2 -mavx2 -w -c $INC $LT_DEFS $R/$f -o $W/ldpctest_obj/$(basename $f .c).o || { echo "ldpctest: FAILED compiling $f"; ok=0; }; done
+if [ $ok = 1 ]; then
+  gcc -o $W/ldpctest $W/ldpctest_obj/*.o -lm -lpthread -ldl -rdynamic || echo "ldpctest: FAILED linking"
+  gcc $F $INC $DEFS $R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder.c $R/openair1/PHY/CODING/nrLDPC_encoder/ldpc_encoder.c -o $W/oai_libs/libldpc_orig.so
+  gcc $F $INC $DEFS $R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder.c $R/openair1/PHY/CODING/nrLDPC_encoder/ldpc_encoder_optim8segmulti.c -o $W/oai_libs/libldpc.so
+  ls -la $W/ldpctest $W/oai_libs
+fi

@@ -66,6 +66,17 @@ int main()
         if (D & 1) sgn ^= qprev;
         const uint32_t p1 = twomin_min1(tm, mone) | kH, p2 = twomin_min2(tm, mone) | kH;
         for (int j = 0; j < D; j++) rn[j] = make_r(q[j], tm.n1, p1, p2, sgn, one, mone);
+        if (D >= 4) {   // the cluster decoder's split rows: two halves tracked separately, then merged either way round (twomin_merge)
+          const int h = (D + 1) / 2;
+          TwoMin ta = twomin_init(), tb = twomin_init();
+          for (int j = 0; j < D; j++) { uint32_t mag, qq; cn_input(aw[j], ro[j], mone, mag, qq); twomin(mag, j < h ? ta : tb, one, mone); }
+          TwoMin ma = ta, mb = tb;
+          twomin_merge(ma, tb, one, mone);
+          twomin_merge(mb, ta, one, mone);
+          CHECK(twomin_min1(ma, mone) == twomin_min1(tm, mone) && twomin_min2(ma, mone) == twomin_min2(tm, mone), "merge a<-b D %d", D);
+          CHECK(twomin_min1(mb, mone) == twomin_min1(tm, mone) && twomin_min2(mb, mone) == twomin_min2(tm, mone), "merge b<-a D %d", D);
+          CHECK(ma.n1 == tm.n1 && mb.n1 == tm.n1, "merged n1 D %d", D);
+        }
         {   // the tracked minima themselves
           for (int b = 0; b < 4; b++) {
             int m1 = 127, m2 = 127;

@@ -32,4 +32,6 @@ fi
 echo "== ncu full (decode kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu -i gpurun_out/prof_decode_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_decode_${TAG}_raw.csv 2>/dev/null \
+  && python tools/ncu_traffic_json.py gpurun_out/prof_decode_${TAG}_raw.csv gpurun_out/ncu_decode_traffic_${TAG}.json 1024 "gpurun_out/prof_decode_${TAG}.ncu-rep" | cut -c1-300
 ls -la gpurun_out | tail -8
