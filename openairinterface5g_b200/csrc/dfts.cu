@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(256, NRB200_DFT_MINBLOCKS) dft_kernel(DftPlan 
   }
 }
 
+#include "dft4096_tma.cuh"
+
 // ------------------------------------------------------------------------------------------------ four-way DFT-s-OFDM family (12 ... 3240)
 // oai_dfts.c:4352-7706: entry points that work on 128-bit vectors holding four independent transforms (element n of transform l is c16 number 4 n + l).
 // N = 12 * R[L-1] * ... * R[0], decimation in time at every level: M-point transforms of x[m + R n], then per k < M one radix-R butterfly (bfly{2,3,4,5}_tw1 for
@@ -583,7 +585,7 @@ bool is_fourway(int N) { return N == 12 || (N != 768 && small_index(N) >= 0); }
 struct DftCtx {
   std::recursive_mutex mu;
   bool inited = false;
-  int dev = 0;
+  int dev = 0, sm_count = 148;
   short *d_tw = nullptr;
   TwOffsets off;
   int big_tw[9];                          // blob offsets of the top-level twiddles of kBig[i]
@@ -653,6 +655,15 @@ int dft_init()
   cudaFuncSetAttribute(dft_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
   cudaFuncSetAttribute(dft_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
   cudaFuncSetAttribute(dft_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4);
+  cudaFuncSetAttribute(dft4096_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft4096::kSmemBytes);
+  cudaFuncSetAttribute(dft4096_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft4096::kSmemBytes);
+  cudaFuncSetAttribute(dft4096_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft4096::kSmemBytes);
+  cudaFuncSetAttribute(dft4096_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft4096::kSmemBytes);
+  {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, c.dev);
+    c.sm_count = prop.multiProcessorCount;
+  }
   cudaFuncSetAttribute(dft_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3240 * 4);
   c.inited = true;
   return 0;
@@ -679,6 +690,13 @@ int launch_dft_small(int N, uint32_t n_calls, const int16_t *d_in, int16_t *d_ou
 int launch_dft_big(int N, int inverse, uint32_t n_calls, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);
 bool is_fourway(int N);
 
+// the 4096-point bulk-copy kernel needs 16-byte aligned sample arrays (NRB200_DFT_TMA=0 keeps the generic kernel, for A/B runs)
+static bool use_tma4096(int N, const void *a, const void *b)
+{
+  static const bool on = []() { const char *e = getenv("NRB200_DFT_TMA"); return !(e && atoi(e) == 0); }();
+  return on && N == 4096 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st)
 {
   if (is_fourway(N)) return inverse ? -4 : launch_dft_small(N, n, d_in, d_out, scale, st);
@@ -689,7 +707,11 @@ int launch_dft(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_o
   DftCtx &c = dctx();
   const unsigned grid = (n + P.tpb - 1) / P.tpb;
   const size_t smem = (size_t)2 * P.tpb * N * 4;
-  if (inverse) dft_kernel<0, true><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
+  if (use_tma4096(N, d_in, d_out)) {   // persistent, bulk-copy fed, conflict-free layouts (dft4096_tma.cuh)
+    const unsigned g4 = std::min<unsigned>(n, 3u * (unsigned)c.sm_count);
+    if (inverse) dft4096_kernel<0, true><<<g4, 256, dft4096::kSmemBytes, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
+    else dft4096_kernel<0, false><<<g4, 256, dft4096::kSmemBytes, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
+  } else if (inverse) dft_kernel<0, true><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
   else dft_kernel<0, false><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, SlotIO{});
   c.launches++;
   cudaError_t e = cudaGetLastError();
@@ -899,7 +921,13 @@ int launch_slot(const nrb200_ofdm_slot_t *d, bool rx, const void *d_in, void *d_
   DftCtx &c = dctx();
   const unsigned n = d->n_symb * d->n_ant, grid = (n + P.tpb - 1) / P.tpb;
   const size_t smem = (size_t)2 * P.tpb * P.N * 4;
-  if (rx) dft_kernel<2, false><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+  // bulk copies carry the frequency-domain side (always whole, contiguous symbols) when its base and antenna stride are 16-byte multiples; the
+  // time-domain side is checked per symbol inside the kernel (timing offsets are arbitrary sample counts)
+  if (use_tma4096((int)d->fft_size, rx ? d_out : d_in, nullptr) && (S.f_stride & 3u) == 0u) {
+    const unsigned g4 = std::min<unsigned>(n, 3u * (unsigned)c.sm_count);
+    if (rx) dft4096_kernel<2, false><<<g4, 256, dft4096::kSmemBytes, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+    else dft4096_kernel<1, true><<<g4, 256, dft4096::kSmemBytes, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
+  } else if (rx) dft_kernel<2, false><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
   else dft_kernel<1, true><<<grid, 256, smem, st>>>(P, c.off, c.d_tw, (const unsigned *)d_in, (unsigned *)d_out, n, S);
   c.launches++;
   cudaError_t e = cudaGetLastError();
