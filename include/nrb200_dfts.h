@@ -32,6 +32,9 @@ int32_t nrb200_dft_size_of_index(int inverse, int sizeidx);
 int32_t nrb200_dft_supported(int N);
 const char *nrb200_dfts_last_error(void);
 uint64_t nrb200_dfts_launch_count(void);
+/* one process, several GPUs: the library keeps one context per device; selects the device the CALLING THREAD's following calls run on
+ * (default NRB200_DEVICE, else LOCAL_RANK, else 0).  Device pointers handed to the *_dev entry points must belong to it. */
+int32_t nrb200_dfts_set_device(int dev);
 
 /* Part 3: slot-level OFDM front end -- one launch per slot instead of one dft()/idft() call per symbol and antenna, with the work the
  * reference does around each transform fused into the kernel's load and store phases.  All buffers are interleaved {re, im} int16

@@ -383,6 +383,20 @@ int32_t nrb200_device_index(void);
 const char *nrb200_last_error(void);
 /* Kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
 uint64_t nrb200_launch_count(void);
+
+/* ---- one process, several GPUs (OAI is one process; SURVEY 8e: code blocks are independent, no data-path collective) ----
+ * The library keeps one context per visible device.  nrb200_set_device() selects the device the CALLING THREAD's following calls run on
+ * (default: NRB200_DEVICE, else LOCAL_RANK, else 0); device pointers handed to the *_dev entry points must belong to it.
+ * With NRB200_DEVICES=all|<n> in the environment the OAI-facing entry points spread their calls themselves: LDPCdecoder / LDPCencoder
+ * round robin (the host owns the HARQ state in that convention), the offload convention by nrb200_sticky_device(ulsch_id, r) so that a
+ * segment's library-owned soft buffer stays on one GPU across HARQ rounds. */
+/* the constant tables of (BG, Z, R) as one byte blob (size returned; min(size, cap) bytes copied): what a multi-rank job broadcasts at init */
+int32_t nrb200_ldpc_graph_blob(int BG, int Z, int R, void *out, uint32_t cap);
+int32_t nrb200_device_count(void);
+int32_t nrb200_set_device(int dev);
+int32_t nrb200_sticky_device(uint32_t ulsch_id, uint32_t r, uint32_t n_dev);
+/* nrb200_ldpc_decode_batch_host over devices 0 .. n_dev-1 of this process: contiguous shards, all devices' copies and kernels in flight together */
+int32_t nrb200_ldpc_decode_batch_host_multi(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, int32_t n_dev);
 /* low-latency path statistics: kernel launches and code blocks so far (blocks / launches = callers combined per launch) */
 void nrb200_ll_stats(uint64_t *launches, uint64_t *blocks);
 /* where the low-latency calls spent their time, sums in nanoseconds: [0] staging (memcpy into the mapped row), [1] queue + kernel launch,

@@ -596,7 +596,29 @@ struct DftCtx {
   std::atomic<uint64_t> launches{0};
   std::string last_error;
 };
-DftCtx &dctx() { static DftCtx c; return c; }
+// one context per device; the calling thread's current device selects it (nrb200_dfts_set_device; inside libldpc_b200.so the thread's
+// nrb200_set_device selection; default NRB200_DEVICE / LOCAL_RANK / 0)
+#ifdef NRB200_DFTS_INTERNAL
+}  // namespace
+namespace nrb200 { int current_device(); }
+namespace {
+int cur_ddev() { return nrb200::current_device(); }
+#else
+thread_local int tls_ddev = -1;
+int cur_ddev()
+{
+  if (tls_ddev < 0) {
+    int n = 0, want = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (const char *s = getenv("NRB200_DEVICE")) want = atoi(s);
+    else if (const char *s2 = getenv("LOCAL_RANK")) want = n > 0 ? atoi(s2) % n : 0;
+    if (want < 0 || want >= (n > 0 ? n : 1) || want >= 16) want = 0;
+    tls_ddev = want;
+  }
+  return tls_ddev;
+}
+#endif
+DftCtx &dctx() { static DftCtx c[16]; return c[cur_ddev()]; }
 
 short rnd16(double v) { return (short)std::round(v); }
 
@@ -607,10 +629,8 @@ int dft_init()
   if (c.inited) return 0;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { c.last_error = "no CUDA device"; return -1; }
-  int want = 0;
-  if (const char *s = getenv("NRB200_DEVICE")) want = atoi(s);
-  else if (const char *s2 = getenv("LOCAL_RANK")) want = atoi(s2) % n;
-  if (want < 0 || want >= n) want = 0;
+  const int want = cur_ddev();
+  if (want < 0 || want >= n) { c.last_error = "no such CUDA device"; return -1; }
   if (cudaSetDevice(want) != cudaSuccess) { c.last_error = "cudaSetDevice failed"; return -1; }
   c.dev = want;
   std::vector<short> blob;
@@ -1029,6 +1049,16 @@ NRB200_EXPORT int32_t nrb200_ofdm_demod_slot_host(const nrb200_ofdm_slot_t *d, c
 
 NRB200_EXPORT void dft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag) { one_transform(false, sizeidx, sigF, sig, scale_flag); }
 NRB200_EXPORT void idft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag) { one_transform(true, sizeidx, sigF, sig, scale_flag); }
+#ifndef NRB200_DFTS_INTERNAL
+// one process, several GPUs: selects the device the calling thread's following calls run on (see include/nrb200_dfts.h)
+NRB200_EXPORT int32_t nrb200_dfts_set_device(int dev)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || dev < 0 || dev >= n || dev >= 16) return -1;
+  tls_ddev = dev;
+  return 0;
+}
+#endif
 NRB200_EXPORT const char *nrb200_dfts_last_error(void) { return dctx().last_error.c_str(); }
 NRB200_EXPORT uint64_t nrb200_dfts_launch_count(void) { return dctx().launches.load(); }
 

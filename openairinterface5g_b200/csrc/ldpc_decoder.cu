@@ -20,11 +20,11 @@ static size_t generic_smem_bytes(const GraphDev &g)
 // device copies of the packed tables, keyed like Ctx::graphs
 constexpr int kPackedDefaultThreadsZ384 = 768;
 static std::mutex g_pk_mu;
-static std::map<uint32_t, std::pair<PackedGraph *, PackedGraph>> g_pk;
+static std::map<uint64_t, std::pair<PackedGraph *, PackedGraph>> g_pk;   // key includes the device: tables live in that device's memory
 
 static const PackedGraph *packed_graph(const GraphDev &h_g, const PackedGraph **host)
 {
-  const uint32_t key = ((uint32_t)h_g.BG << 24) | ((uint32_t)h_g.Z << 8) | (uint32_t)h_g.R;
+  const uint64_t key = ((uint64_t)ctx().dev << 40) | ((uint32_t)h_g.BG << 24) | ((uint32_t)h_g.Z << 8) | (uint32_t)h_g.R;
   std::lock_guard<std::mutex> lk(g_pk_mu);
   auto it = g_pk.find(key);
   if (it == g_pk.end()) {
@@ -48,7 +48,7 @@ static std::map<uint64_t, std::pair<ClusterSched *, ClusterSched>> g_cl;
 
 static const ClusterSched *cluster_sched(const GraphDev &h_g, const PackedGraph &h_pg, int C, const ClusterSched **host)
 {
-  const uint64_t key = ((uint64_t)C << 32) | ((uint32_t)h_g.BG << 24) | ((uint32_t)h_g.Z << 8) | (uint32_t)h_g.R;
+  const uint64_t key = ((uint64_t)ctx().dev << 40) | ((uint64_t)C << 32) | ((uint32_t)h_g.BG << 24) | ((uint32_t)h_g.Z << 8) | (uint32_t)h_g.R;
   std::lock_guard<std::mutex> lk(g_pk_mu);
   auto it = g_cl.find(key);
   if (it == g_cl.end()) {
@@ -124,11 +124,11 @@ int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArg
       void (*kern)(const PackedGraph *, const ClusterSched *, DecodeArgs) =
           h_pg->Zw == 96 ? (wide ? ldpc_decode_cluster_kernel<96, 768> : ldpc_decode_cluster_kernel<96, 512>)
                          : (wide ? ldpc_decode_cluster_kernel<0, 768> : ldpc_decode_cluster_kernel<0, 512>);
-      static std::atomic<size_t> configured_cl[4];
+      static std::atomic<size_t> configured_cl[kMaxDevices][4];
       const int v = (h_pg->Zw == 96 ? 2 : 0) + (wide ? 1 : 0);
-      if (smem > configured_cl[v].load()) {
+      if (smem > configured_cl[c.dev][v].load()) {
         NRB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cluster smem attr");
-        configured_cl[v].store(smem);
+        configured_cl[c.dev][v].store(smem);
       }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(a.n_cb * (unsigned)C, 1, 1);
@@ -155,10 +155,10 @@ int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArg
       else if (h_pg->nthreads > 768) { kern = ldpc_decode_packed_kernel<96, 864>; variant = 2; }
       else { kern = ldpc_decode_packed_kernel<96, 768>; variant = 1; }
     }
-    static std::atomic<size_t> configured_pk[4];
-    if (smem > configured_pk[variant].load()) {
+    static std::atomic<size_t> configured_pk[kMaxDevices][4];
+    if (smem > configured_pk[c.dev][variant].load()) {
       NRB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
-      configured_pk[variant].store(smem);
+      configured_pk[c.dev][variant].store(smem);
     }
     kern<<<a.n_cb, h_pg->nthreads, smem, stream>>>(d_pg, a);
     c.launches++;
@@ -168,10 +168,10 @@ int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArg
   {
     const size_t smem = generic_smem_bytes(h_g);
     if ((int)smem > c.max_smem_optin) return -3;
-    static std::atomic<size_t> configured{0};
-    if (smem > configured.load()) {
+    static std::atomic<size_t> configured[kMaxDevices];
+    if (smem > configured[c.dev].load()) {
       NRB200_CUDA_OK(cudaFuncSetAttribute(ldpc_decode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-      configured.store(smem);
+      configured[c.dev].store(smem);
     }
     int threads = h_g.Z * 2;
     threads = ((threads + 31) / 32) * 32;

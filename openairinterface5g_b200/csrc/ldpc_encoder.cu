@@ -210,10 +210,10 @@ int launch_encode(const EncGraphDev *d_g, const EncGraphDev &h_g, int K, uint32_
   }
   auto a16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   const size_t smem = a16(sizeof(EncGraphDev)) + a16((size_t)h_g.ncols * h_g.Z) + a16((size_t)4 * h_g.Z);
-  static std::atomic<size_t> configured{0};
-  if (smem > configured.load()) {
+  static std::atomic<size_t> configured[kMaxDevices];
+  if (smem > configured[ctx().dev].load()) {
     NRB200_CUDA_OK(cudaFuncSetAttribute(ldpc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "enc smem attr");
-    configured.store(smem);
+    configured[ctx().dev].store(smem);
   }
   int threads = ((h_g.Z + 31) / 32) * 32;
   if (threads < 64) threads = 64;

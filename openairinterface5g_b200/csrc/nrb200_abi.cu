@@ -274,6 +274,86 @@ NRB200_EXPORT int32_t nrb200_ldpc_packed_schedule_info(int BG, int Z, int R, int
 }
 
 NRB200_EXPORT int32_t nrb200_device_index(void) { return ctx().inited ? ctx().dev : -1; }
+
+// ------------------------------------------------------------------------------------------ one process, several GPUs
+NRB200_EXPORT int32_t nrb200_device_count(void) { return device_count(); }
+NRB200_EXPORT int32_t nrb200_set_device(int dev) { return set_current_device(dev) == 0 ? 0 : -4; }
+
+// How many devices the OAI-facing entry points (LDPCdecoder / LDPCencoder / the offload convention) spread their calls over:
+// NRB200_DEVICES = "all" or a count; default 1 (the thread's current device only).
+static int abi_devices()
+{
+  static const int n = []() {
+    const char *e = getenv("NRB200_DEVICES");
+    if (!e) return 1;
+    const int have = device_count();
+    const int v = strcmp(e, "all") == 0 ? have : atoi(e);
+    return v < 1 ? 1 : (v > have ? (have > 0 ? have : 1) : v);
+  }();
+  return n;
+}
+
+// The constant tables the decode kernels read for (BG, Z, R) -- lifted-graph descriptor + the packed decoder's shared-memory image description -- as
+// one byte blob (host copy of what sits in device memory).  bench.py broadcasts rank 0's blob over NCCL at init and every rank compares its own
+// against it ("NCCL broadcast of the base-graph matrices only at init").  Returns the blob size, or a negative error; copies min(size, cap) bytes.
+NRB200_EXPORT int32_t nrb200_ldpc_graph_blob(int BG, int Z, int R, void *out, uint32_t cap)
+{
+  GraphDev *g = new GraphDev();
+  PackedGraph *p = new PackedGraph();
+  int32_t rc = -4;
+  if (build_graph(BG, Z, R, g)) {
+    const bool packed = (Z % 4 == 0) && build_packed_graph(*g, p, Z == 384 ? 768 : kPackedMaxThreads);
+    const uint32_t total = (uint32_t)sizeof(GraphDev) + (packed ? (uint32_t)sizeof(PackedGraph) : 0u);
+    if (out) {
+      std::vector<uint8_t> b(total);
+      std::memcpy(b.data(), g, sizeof(GraphDev));
+      if (packed) std::memcpy(b.data() + sizeof(GraphDev), p, sizeof(PackedGraph));
+      std::memcpy(out, b.data(), std::min(total, cap));
+    }
+    rc = (int32_t)total;
+  }
+  delete g; delete p;
+  return rc;
+}
+
+// a code block (ulsch_id, segment r) goes to GPU hash(ulsch_id, r) mod nGPU, STICKY across HARQ rounds so that the library-owned int16
+// soft buffer of the offload convention stays on one device.
+NRB200_EXPORT int32_t nrb200_sticky_device(uint32_t ulsch_id, uint32_t r, uint32_t n_dev)
+{
+  if (n_dev == 0) return 0;
+  uint32_t h = ulsch_id * 0x9E3779B1u + r * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  return (int32_t)(h % n_dev);
+}
+
+// Blocking decode of one batch spread over `n_dev` GPUs (device 0 .. n_dev-1) of this process: contiguous shards of the batch, every device's
+// copies and kernels enqueued before the first is waited for.  No collective: code blocks are independent.
+NRB200_EXPORT int32_t nrb200_ldpc_decode_batch_host_multi(const nrb200_ldpc_batch_desc_t *desc, const int8_t *llr, uint8_t *out, int32_t *iters, int32_t n_dev)
+{
+  if (!desc || n_dev < 1 || n_dev > device_count()) return -4;
+  const int saved = current_device();
+  DecodeTicket *tk[kMaxDevices] = {nullptr};
+  int rc = 0;
+  const uint32_t n = desc->n_cb, per = (n + (uint32_t)n_dev - 1) / (uint32_t)n_dev;
+  for (int d = 0; d < n_dev && rc == 0; d++) {
+    const uint32_t c0 = std::min(n, (uint32_t)d * per), c1 = std::min(n, c0 + per);
+    if (c1 == c0) continue;
+    set_current_device(d);
+    nrb200_ldpc_batch_desc_t sd = *desc;
+    sd.n_cb = c1 - c0;
+    tk[d] = decode_submit(&sd, llr + (size_t)c0 * desc->llr_stride, out + (size_t)c0 * desc->out_stride, iters + c0, nullptr, &rc);
+  }
+  for (int d = 0; d < n_dev; d++) {
+    if (!tk[d]) continue;
+    set_current_device(d);
+    cudaSetDevice(ctx().dev);
+    const int r2 = decode_finish(tk[d]);
+    if (rc == 0) rc = r2;
+  }
+  set_current_device(saved);
+  if (ctx().inited) cudaSetDevice(ctx().dev);
+  return rc;
+}
 NRB200_EXPORT const char *nrb200_last_error(void)
 {
   static thread_local std::string copy;       // other threads may replace Ctx::last_error at any time
@@ -313,6 +393,10 @@ NRB200_EXPORT int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p, uint8_t harq_pid,
   const unsigned long long t0 = prof ? rdtsc_now() : 0;
   const int32_t numLLR = nrb200_ldpc_num_llr(p->BG, p->Z, p->R);
   if (numLLR < 0) return decoder_failure(p, ab, "LDPCdecoder: (BG, Z, R) is not an NR decoder configuration");
+  if (abi_devices() > 1) {   // CPU-compatible convention: the host keeps the HARQ state, any device will do -- calls go round the GPUs
+    static std::atomic<unsigned> rr{0};
+    set_current_device((int)(rr++ % (unsigned)abi_devices()));
+  }
   if (ensure_init()) return decoder_failure(p, ab, "LDPCdecoder: no CUDA device");
   nrb200_ldpc_batch_desc_t d;
   std::memset(&d, 0, sizeof(d));
@@ -401,6 +485,7 @@ NRB200_EXPORT int32_t nrb200_ldpc_encode_batch_host(int BG, int Z, int K, uint32
 NRB200_EXPORT int32_t LDPCencoder(uint8_t **input, uint8_t **output, nrb200_ldpc_enc_params_t *impp)
 {
   // segments 8*macro_num .. min(8*macro_num+8, n_segments) (ldpc_encoder_optim8segmulti.c:62-63)
+  if (abi_devices() > 1) set_current_device((int)(impp->macro_num % (unsigned)abi_devices()));   // groups of 8 segments go round the GPUs
   if (ensure_init()) return -1;
   const unsigned s0 = 8 * impp->macro_num;
   const unsigned s1 = impp->n_segments > 8 * (impp->macro_num + 1) ? 8 * (impp->macro_num + 1) : impp->n_segments;
@@ -729,10 +814,11 @@ NRB200_EXPORT int32_t nrb200_pdsch_tx_slot_host(const nrb200_pdsch_tx_t *d, cons
 static uint32_t *pusch_counter()
 {
   constexpr uint32_t kCounters = 4096;
-  static uint32_t *d = nullptr;
+  static uint32_t *dd[kMaxDevices] = {nullptr};
   static std::mutex mu;
   static uint32_t ticket = 0;
   std::lock_guard<std::mutex> lk(mu);
+  uint32_t *&d = dd[ctx().dev];
   if (!d && cudaMalloc(&d, kCounters * 4) == cudaSuccess) cudaMemset(d, 0, kCounters * 4);
   return d ? d + (ticket++ % kCounters) : nullptr;
 }
@@ -877,7 +963,7 @@ static int16_t *offload_harq(uint8_t ulsch_id, uint8_t r)
   static std::mutex mu;
   static std::map<uint32_t, int16_t *> store;
   std::lock_guard<std::mutex> lk(mu);
-  const uint32_t key = ((uint32_t)ulsch_id << 8) | r;
+  const uint32_t key = ((uint32_t)ctx().dev << 16) | ((uint32_t)ulsch_id << 8) | r;   // a buffer lives on the device its (ulsch_id, r) is pinned to
   auto it = store.find(key);
   if (it != store.end()) return it->second;
   int16_t *d = nullptr;
@@ -893,6 +979,7 @@ NRB200_EXPORT int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t 
                                                  uint8_t *out)
 {
   (void)harq_pid;
+  if (abi_devices() > 1) set_current_device(nrb200_sticky_device(ulsch_id, r, (uint32_t)abi_devices()));   // the segment's soft buffer lives there
   if (ensure_init() || !p) return -1;
   const int32_t numLLR = nrb200_ldpc_num_llr(p->BG, p->Z, p->R);
   if (numLLR < 0 || p->E <= 0 || p->E > 32768 * 4) return -4;

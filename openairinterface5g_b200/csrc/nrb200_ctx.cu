@@ -10,11 +10,36 @@ namespace nrb200 {
 
 void packed_graph_cache_clear();
 
-Ctx &ctx()
+static Ctx g_ctx[kMaxDevices];
+static thread_local int tls_dev = -1;
+
+int device_count()
 {
-  static Ctx c;
-  return c;
+  static const int n = []() { int k = 0; if (cudaGetDeviceCount(&k) != cudaSuccess) { cudaGetLastError(); k = 0; } return k < kMaxDevices ? k : kMaxDevices; }();
+  return n;
 }
+
+int current_device()
+{
+  if (tls_dev < 0) {
+    const int n = device_count();
+    int want = 0;
+    if (const char *s = getenv("NRB200_DEVICE")) want = atoi(s);
+    else if (const char *s2 = getenv("LOCAL_RANK")) want = n > 0 ? atoi(s2) % n : 0;   // one process per GPU under torchrun
+    if (want < 0 || want >= (n > 0 ? n : 1)) want = 0;
+    tls_dev = want;
+  }
+  return tls_dev;
+}
+
+int set_current_device(int dev)
+{
+  if (dev < 0 || dev >= device_count()) return -1;
+  tls_dev = dev;
+  return 0;
+}
+
+Ctx &ctx() { return g_ctx[current_device()]; }
 
 void Ctx::set_error(const char *where, cudaError_t e)
 {
@@ -51,10 +76,8 @@ int Ctx::init()
     last_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     return -1;
   }
-  int want = 0;
-  if (const char *s = getenv("NRB200_DEVICE")) want = atoi(s);
-  else if (const char *s2 = getenv("LOCAL_RANK")) want = atoi(s2) % n;   // one process per GPU under torchrun
-  if (want < 0 || want >= n) want = 0;
+  const int want = (int)(this - g_ctx);                 // Ctx i drives device i
+  if (want < 0 || want >= n) { last_error = "no such CUDA device"; return -1; }
   if ((e = cudaSetDevice(want)) != cudaSuccess) { last_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return -1; }
   dev = want;
   cudaDeviceProp p;

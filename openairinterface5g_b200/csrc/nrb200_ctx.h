@@ -1,4 +1,6 @@
-// Process-wide CUDA context of libldpc_b200.so: device selection, lifted-graph cache, CRC tables, workspace pool.
+// Per-device CUDA context of libldpc_b200.so: lifted-graph cache, CRC tables, workspace pool.  One process can drive every visible GPU:
+// there is one Ctx per device and ctx() returns the one of the calling thread's CURRENT device (nrb200_set_device(); default NRB200_DEVICE /
+// LOCAL_RANK / 0), so all per-device state behind the entry points follows the thread's selection.
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
@@ -46,7 +48,11 @@ struct Ctx {
   void set_error(const char *where, cudaError_t e);
 };
 
-Ctx &ctx();
+constexpr int kMaxDevices = 16;
+Ctx &ctx();                 // the calling thread's current device
+int current_device();       // its index
+int set_current_device(int dev);   // 0, or -1 if there is no such device
+int device_count();         // visible CUDA devices (0 without a driver)
 
 #define NRB200_CUDA_OK(call, where)                                  \
   do {                                                               \

@@ -84,10 +84,10 @@ struct Pool {
   }
 };
 
-Pool &pool()
+Pool &pool()                                     // one per device: the streams belong to it
 {
-  static Pool p;
-  return p;
+  static Pool p[kMaxDevices];
+  return p[current_device()];
 }
 
 inline void cpu_relax()
@@ -236,7 +236,7 @@ struct EncPool {
     return ok = true;
   }
 };
-EncPool &enc_pool() { static EncPool p; return p; }
+EncPool &enc_pool() { static EncPool p[kMaxDevices]; return p[current_device()]; }
 }  // namespace
 
 int ll_encode(const EncGraphDev *dg, const EncGraphDev *hg, int K, uint32_t n, uint8_t **input, uint8_t **output, uint32_t kin, uint32_t nout)

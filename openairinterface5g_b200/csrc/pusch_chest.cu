@@ -363,7 +363,8 @@ static const unsigned *delay_table_dev(int N)
   static std::mutex mu;
   static std::map<int, unsigned *> cache;
   std::lock_guard<std::mutex> lk(mu);
-  auto it = cache.find(N);
+  const int key = N | (ctx().dev << 20);                 // one table per size and device
+  auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   std::vector<unsigned> h((size_t)41 * N);
   for (int d = -20; d <= 20; d++)
@@ -375,7 +376,7 @@ static const unsigned *delay_table_dev(int N)
   unsigned *dptr = nullptr;
   if (cudaMalloc(&dptr, h.size() * 4) != cudaSuccess) return nullptr;
   cudaMemcpy(dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
-  cache[N] = dptr;
+  cache[key] = dptr;
   return dptr;
 }
 

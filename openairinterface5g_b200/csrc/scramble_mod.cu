@@ -14,12 +14,14 @@ namespace nrb200 {
 
 constexpr int kGoldBlk = 256;    // words (= threads) per CTA
 
-static GoldTables *d_gold = nullptr;
-static uint32_t *d_modtab = nullptr;                   // per Qm: 2^Qm symbols {re | im << 16}; offsets 0, 4, 20, 84
+static GoldTables *d_gold_dev[kMaxDevices] = {nullptr};  // per device
+static uint32_t *d_modtab_dev[kMaxDevices] = {nullptr};                  // per Qm: 2^Qm symbols {re | im << 16}; offsets 0, 4, 20, 84
 
 static inline uint32_t step1(uint32_t x) { x = (x >> 1) ^ (x >> 4); return x ^ (x << 31) ^ (x << 28); }
 static inline uint32_t step2(uint32_t x) { x = (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4); return x ^ (x << 31) ^ (x << 30) ^ (x << 29) ^ (x << 28); }
 
+#define d_gold (d_gold_dev[ctx().dev])
+#define d_modtab (d_modtab_dev[ctx().dev])
 const GoldTables *gold_tables_dev() { return d_gold; }
 const uint32_t *mod_tables_dev() { return d_modtab; }
 

@@ -156,6 +156,32 @@ class LdpcLib:
         self._inited = False
         return self.lib.LDPCshutdown()
 
+    # ---- one process, several GPUs
+    def device_count(self):
+        return int(self.lib.nrb200_device_count())
+
+    def set_device(self, dev):
+        """Selects the device the calling thread's following calls run on."""
+        self._check(self.lib.nrb200_set_device(int(dev)), "set_device")
+
+    def sticky_device(self, ulsch_id, r, n_dev):
+        return int(self.lib.nrb200_sticky_device(int(ulsch_id), int(r), int(n_dev)))
+
+    def decode_batch_host_multi(self, BG, Z, R, numMaxIter, llr, n_dev, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):
+        """decode_batch_host spread over devices 0 .. n_dev-1 of this process."""
+        llr = np.ascontiguousarray(llr, dtype=np.int8)
+        n_cb, stride = llr.shape
+        n = ncols_for_rate(BG, R) * Z
+        ob = (n + 7) // 8 if outMode == OUTMODE_BIT else n
+        if out is None:
+            out = np.zeros((n_cb, ob), dtype=np.uint8)
+        if iters is None:
+            iters = np.zeros(n_cb, dtype=np.int32)
+        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
+        self._check(self.lib.nrb200_ldpc_decode_batch_host_multi(C.byref(d), llr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                                iters.ctypes.data_as(C.c_void_p), int(n_dev)), "decode_batch_host_multi")
+        return iters, out
+
     def last_error(self):
         return (self.lib.nrb200_last_error() or b"").decode()
 

@@ -12,5 +12,11 @@ def shard_range(n_items, rank, world):
 
 
 def sticky_gpu(ulsch_id, segment, world):
-    """GPU that owns the HARQ soft buffer of (ulsch_id, segment) for the lifetime of the HARQ process."""
-    return (ulsch_id * 131 + segment) % world
+    """GPU that owns the HARQ soft buffer of (ulsch_id, segment) for the lifetime of the HARQ process: the library's rule
+    (nrb200_sticky_device in csrc/nrb200_abi.cu -- the C entry points of the offload convention use the same function), restated here for
+    the one-process-per-GPU tools so that both agree; tests/test_abi_symbols.py checks the two against each other."""
+    h = (ulsch_id * 0x9E3779B1 + segment * 0x85EBCA77) & 0xFFFFFFFF
+    h ^= h >> 15
+    h = (h * 0x2C1B3C6D) & 0xFFFFFFFF
+    h ^= h >> 12
+    return h % world if world else 0

@@ -126,3 +126,21 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
         assert got[cname][0] == ctypes.sizeof(cls), (cname, got[cname][0], ctypes.sizeof(cls))
         if field:
             assert got[cname][1] == getattr(cls, field).offset, (cname, field, got[cname][1], getattr(cls, field).offset)
+
+
+def test_sticky_device_rule_matches_the_python_tools():
+    """nrb200_sticky_device (the rule the offload convention's C entry points use to pin (ulsch_id, segment) to a GPU) == shard.sticky_gpu (what the
+    one-process-per-GPU tools use); host arithmetic only.  Every device index is in range and all devices get work."""
+    import ctypes as C
+    from openairinterface5g_b200.ldpc import LdpcLib
+    from openairinterface5g_b200.shard import sticky_gpu
+    lib = LdpcLib().lib
+    lib.nrb200_sticky_device.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    for world in (1, 2, 3, 4, 8):
+        seen = set()
+        for u in range(64):
+            for r in range(40):
+                d = lib.nrb200_sticky_device(u, r, world)
+                assert d == sticky_gpu(u, r, world) and 0 <= d < world
+                seen.add(d)
+        assert len(seen) == world
