@@ -140,6 +140,9 @@ typedef struct nrb200_ldpc_batch_desc {
   uint8_t outMode;    /* nrb200_ldpc_outmode_t */
   uint8_t crc_type;   /* used when use_crc != 0 */
   uint8_t use_crc;    /* 0: parity-check stop (check_crc == NULL); 1: in-kernel CRC stop with reference semantics */
+  uint8_t latency_mode; /* 0: throughput -- one CTA per code block, the fewest SM-cycles per block (what a caller with many batches / slots in flight wants);
+                         * 1: latency -- when the whole batch fits on the GPU at once, every code block gets a thread-block cluster of 2 / 4 / 8 SMs
+                         * (<= 74 / 33 / 15 blocks): a lone slot's 28-52 code blocks finish sooner, at more SM-cycles per block */
   uint32_t crc_len_bits; /* the `E` the reference passes to check_crc (payload incl. CRC, bits) */
   uint32_t n_cb;      /* code blocks in the batch */
   uint32_t llr_stride; /* bytes between consecutive code blocks' LLR arrays (>= ncol(R)*Z) */

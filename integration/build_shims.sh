@@ -29,3 +29,8 @@ gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_uechest.c $ROO
     $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/TOOLS/cmult_vv.c \
     $R/openair1/PHY/MODULATION/slot_fep_nr.c $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -o $W/libshimtest_uechest.so
 ls -la $HERE/_build/*.so $W/libshimtest_chest.so $W/libshimtest_uechest.so
+# the UE's PDSCH receiver: nr_rx_pdsch (the caller harness drives it symbol by symbol like nr_ue_pdsch_procedures)
+gcc $F $INC $DEFS $HERE/oai_shim_rx_pdsch.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_rx_pdsch.so
+gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_pdsch.c $ROOT/oracle/ref_harness_pdsch.c $HERE/oai_shim_rx_pdsch.c \
+    $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -o $W/libshimtest_pdsch.so
+ls -la $HERE/_build/libnrb200_shim_rx_pdsch.so $W/libshimtest_pdsch.so

@@ -32,6 +32,7 @@ struct DecodeArgs {
   uint32_t n_cb, llr_stride, out_stride;
   uint32_t crc_len_bits;    // the reference's p_decParams->E handed to check_crc (nrLDPC_decoder.c:858)
   uint8_t numMaxIter, outMode, use_crc, quirks;
+  uint8_t latency;          // batch API: 1 = a cluster per code block when the launch fits (nrb200_ldpc_batch_desc_t::latency_mode)
   // low-latency mode (ll_ctrl != nullptr): block b works on staging row ll_rows[b] of llr / out / ll_ctrl instead of row b, `iters` is unused
   LlCtrl *ll_ctrl;
   uint8_t ll_seq;

@@ -96,7 +96,7 @@ int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArg
 // Returns 0 or a negative error.  Asynchronous on `stream`.
 int launch_decode(const GraphDev *d_g, const GraphDev &h_g, const DecodeArgs &a, cudaStream_t stream)
 {
-  return launch_decode_impl(d_g, h_g, a, stream, a.n_cb, nullptr);
+  return launch_decode_impl(d_g, h_g, a, stream, a.latency ? a.n_cb : 0xFFFFFFFFu, nullptr);   // throughput mode: never a cluster
 }
 
 // The low-latency path's launch: `load` = code blocks in flight on the device including this launch's (several small launches share the

@@ -77,7 +77,7 @@ static int fill_args(const nrb200_ldpc_batch_desc_t *d, const GraphDev &hg, Deco
   if (d->outMode > 2) return -4;
   std::memset(a, 0, sizeof(*a));
   a->n_cb = d->n_cb; a->llr_stride = d->llr_stride; a->out_stride = d->out_stride;
-  a->numMaxIter = d->numMaxIter; a->outMode = d->outMode; a->use_crc = d->use_crc ? 1 : 0;
+  a->numMaxIter = d->numMaxIter; a->outMode = d->outMode; a->use_crc = d->use_crc ? 1 : 0; a->latency = d->latency_mode ? 1 : 0;
   a->quirks = (uint8_t)quirks_from_env();
   if (a->use_crc) {
     if (d->crc_type > 3 || d->crc_len_bits % 8 || d->crc_len_bits < 32 || d->crc_len_bits > numLLR || d->crc_len_bits >= (uint32_t)kCrcTableLen) return -4;

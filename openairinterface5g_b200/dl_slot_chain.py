@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import transport as T
+from . import ldpc as _L
 from .ldpc import CRC24_B, PdschTxDesc, PuschChestDesc, PuschRxDesc
 from .ofdm import NrOfdmParms
 
@@ -22,6 +23,7 @@ class PdschSlotChain:
     def __init__(self, lib, dl, device, A=434280, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_ant=2, Qm=6, slot=1, rnti=0x1234, nid=77,
                  dl_freq=3619200000.0, max_iter=8, dmrs_id=55, n_layers=2, tx_amp=512, start_symbol=1, nr_symbols=13):
         self.lib, self.dl, self.dev = lib, dl, device
+        self.latency_mode = 1            # decoder: a cluster of SMs per code block (one slot alone); the pipelines below run many slots and set 0
         self.P = NrOfdmParms(N, mu, carrier_rb)
         self.N, self.nb, self.Qm, self.slot, self.rnti, self.nid, self.max_iter, self.nl = N, nb_ant, Qm, slot, rnti, nid, max_iter, n_layers
         self.rb_start, self.rb_size, self.A = rb_start, rb_size, A
@@ -73,9 +75,48 @@ class PdschSlotChain:
         self.drx = self.P.desc(slot, nb_ant, self.rot, rx=True)
 
     # ------------------------------------------------------------------ gNB transmit chain (timed)
-    def transmit(self, payload):
-        """payload: uint8[A / 8] on the device.  Returns the slot's time-domain samples int16 [nb_tx, samples, 2]."""
+    def _c_tx(self, payload):
+        _L._late_fields()
+        C_ = _L.C
+        d = _L.PdschTxSlotDesc()
+        C_.memmove(C_.addressof(d.tx), C_.addressof(self.txd), C_.sizeof(self.txd))
+        C_.memmove(C_.addressof(d.ofdm), C_.addressof(self.dtx), C_.sizeof(self.dtx))
+        d.rm = self.lib._rmdesc(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.C)
+        d.A, d.K = self.A, self.K
+        b = _L.PdschTxBufs()
+        b.d_payload, b.d_segs, b.d_seg_scratch, b.d_cw = payload.data_ptr(), self.segs.data_ptr(), self.crc1.data_ptr(), self.cw.data_ptr()
+        b.d_E, b.d_Eoff, b.d_f, b.d_txdataF, b.d_txdata = self.E.data_ptr(), self.Eoff.data_ptr(), self.f.data_ptr(), self.txF.data_ptr(), self.txdata.data_ptr()
+        b.seg_stride, b.cw_stride = self.segs.shape[1], self.cw.shape[1]
+        return d, b
+
+    def _c_rx(self, rxdata):
+        _L._late_fields()
+        C_ = _L.C
+        d = _L.SchRxSlotDesc()
+        C_.memmove(C_.addressof(d.ofdm), C_.addressof(self.drx), C_.sizeof(self.drx))
+        C_.memmove(C_.addressof(d.chest), C_.addressof(self.cdesc), C_.sizeof(self.cdesc))
+        C_.memmove(C_.addressof(d.rx), C_.addressof(self.rxd), C_.sizeof(self.rxd))
+        d.rm = self.lib._rmdesc(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.C, 1)
+        d.R, d.numMaxIter, d.use_estimates, d.latency_mode = self.R, self.max_iter, 0, self.latency_mode
+        d.crc_len_bits, d.seg_crc_type = self.K - self.F, CRC24_B
+        d.A, d.tb_crc_bits, d.seg_payload_bytes = self.A, 24, self.nbytes
+        b = _L.SchRxBufs()
+        b.d_rxdata, b.d_timeshift, b.d_rxdataF, b.d_est = rxdata.data_ptr(), self.ts.data_ptr(), self.rxF.data_ptr(), self.est.data_ptr()
+        b.d_chest_scratch, b.d_chest_state, b.d_level, b.d_llr16 = self.chest_scratch.data_ptr(), self.chest_state.data_ptr(), self.level.data_ptr(), self.llr16.data_ptr()
+        b.d_E, b.d_Eoff, b.d_harq, b.d_llr8, b.d_hard = self.E.data_ptr(), self.Eoff.data_ptr(), self.harq.data_ptr(), self.llr8.data_ptr(), self.hard.data_ptr()
+        b.d_iters, b.d_tb, b.d_tbcrc = self.iters.data_ptr(), self.tb.data_ptr(), self.tbcrc.data_ptr()
+        b.harq_stride, b.llr8_stride, b.hard_stride = self.harq.shape[1], self.llr8.shape[1], self.hard.shape[1]
+        return d, b
+
+    def transmit(self, payload, staged=False):
+        """payload: uint8[A / 8] on the device.  Returns the slot's time-domain samples int16 [nb_tx, samples, 2].  ONE library call
+        (nrb200_pdsch_slot_tx_dev); staged=True issues the stages one entry point at a time from here (compared in the tests)."""
         lib, dl = self.lib, self.dl
+        if not staged:
+            d, b = self._c_tx(payload)
+            self._keep_tx = (d, b)
+            lib.pdsch_slot_tx_torch(d, b, self.dev)
+            return self.txdata
         lib.tb_segment_torch(1, self.A, payload, self.segs, self.crc1)                      # TB CRC24A + nr_segmentation + CRC24B per segment
         lib.encode_batch_torch(1, self.Z, self.K, self.segs, out=self.cw)
         lib.rm_tx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.cw, self.E, self.Eoff, self.f)
@@ -103,14 +144,19 @@ class PdschSlotChain:
         return rxdata
 
     # ------------------------------------------------------------------ UE receive chain (timed)
-    def receive(self, rxdata):
+    def receive(self, rxdata, staged=False):
         lib, dl = self.lib, self.dl
+        if not staged:
+            d, b = self._c_rx(rxdata)
+            self._keep_rx = (d, b)
+            lib.sch_slot_rx_torch(d, b, self.dev)
+            return self.tb, self.iters, self.tbcrc
         dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)                       # nr_slot_fep x 14
         lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)   # nr_pdsch_channel_estimation, every port
         lib.pusch_inner_rx_torch(self.rxd, self.rxF, self.est, self.llr16, level=self.level)   # nr_rx_pdsch (+ unscrambling)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
         lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
-                               out=self.hard, iters=self.iters)
+                               out=self.hard, iters=self.iters, latency_mode=self.latency_mode)
         self.tb.view(-1).copy_(self.hard[:, :self.nbytes].reshape(-1))
         lib.crc_batch_torch(0, self.tb, self.A + 24, out=self.tbcrc)
         return self.tb, self.iters, self.tbcrc
@@ -129,6 +175,7 @@ class PdschSlotPipeline:
             s = torch.cuda.Stream(device=device)
             with torch.cuda.stream(s):
                 ch = PdschSlotChain(lib, dl, device, **cfg)
+                ch.latency_mode = 0                                  # many slots in flight: one CTA per code block spends the fewest SM-cycles
                 hp = torch.from_numpy(np.random.default_rng(seed0 + k).integers(0, 256, size=ch.A // 8, dtype=np.uint8)).pin_memory()
                 p = hp.to(device)
                 rx = ch.channel(ch.transmit(p), seed=seed0 + k)

@@ -51,7 +51,7 @@ class EncParams(C.Structure):          # encoder_implemparams_t
 
 class BatchDesc(C.Structure):          # nrb200_ldpc_batch_desc_t
     _fields_ = [("BG", C.c_uint8), ("Z", C.c_uint16), ("R", C.c_uint8), ("numMaxIter", C.c_uint8), ("outMode", C.c_uint8),
-                ("crc_type", C.c_uint8), ("use_crc", C.c_uint8), ("crc_len_bits", C.c_uint32), ("n_cb", C.c_uint32),
+                ("crc_type", C.c_uint8), ("use_crc", C.c_uint8), ("latency_mode", C.c_uint8), ("crc_len_bits", C.c_uint32), ("n_cb", C.c_uint32),
                 ("llr_stride", C.c_uint32), ("out_stride", C.c_uint32)]
 
 
@@ -95,6 +95,40 @@ class PdschTxDesc(C.Structure):       # nrb200_pdsch_tx_t (field names of nfapi_
         self.pm_idx = pm_idx
         self.pm_weights = (C.c_int16 * 32)(*[int(x) for x in w.reshape(-1)])
         return self
+
+
+def _ofdm_desc_cls():
+    from .ofdm import OfdmSlotDesc
+    return OfdmSlotDesc
+
+
+class SchRxSlotDesc(C.Structure):     # nrb200_sch_rx_slot_t (include/nrb200_slot.h)
+    pass
+
+
+class SchRxBufs(C.Structure):         # nrb200_sch_rx_bufs_t
+    _fields_ = [(n, C.c_void_p) for n in ("d_rxdata", "d_timeshift", "d_rxdataF", "d_est", "d_chest_scratch", "d_chest_state", "d_level", "d_llr16", "d_E", "d_Eoff",
+                                          "d_harq", "d_llr8", "d_hard", "d_iters", "d_tb", "d_tbcrc")] + \
+               [(n, C.c_uint32) for n in ("harq_stride", "llr8_stride", "hard_stride", "reserved")]
+
+
+class PdschTxSlotDesc(C.Structure):   # nrb200_pdsch_tx_slot_t
+    pass
+
+
+class PdschTxBufs(C.Structure):       # nrb200_pdsch_tx_bufs_t
+    _fields_ = [(n, C.c_void_p) for n in ("d_payload", "d_segs", "d_seg_scratch", "d_cw", "d_E", "d_Eoff", "d_f", "d_txdataF", "d_txdata")] + \
+               [("seg_stride", C.c_uint32), ("cw_stride", C.c_uint32)]
+
+
+def _late_fields():
+    """The slot descriptors embed nrb200_ofdm_slot_t, whose mirror lives in ofdm.py (which imports nothing from here)."""
+    if not hasattr(SchRxSlotDesc, "ofdm"):
+        O = _ofdm_desc_cls()
+        SchRxSlotDesc._fields_ = [("ofdm", O), ("chest", PuschChestDesc), ("rx", PuschRxDesc), ("rm", RmDesc), ("R", C.c_uint8), ("numMaxIter", C.c_uint8),
+                                  ("use_estimates", C.c_uint8), ("latency_mode", C.c_uint8), ("crc_len_bits", C.c_uint32), ("seg_crc_type", C.c_uint32),
+                                  ("A", C.c_uint32), ("tb_crc_bits", C.c_uint32), ("seg_payload_bytes", C.c_uint32)]
+        PdschTxSlotDesc._fields_ = [("tx", PdschTxDesc), ("ofdm", O), ("rm", RmDesc), ("A", C.c_uint32), ("K", C.c_uint32)]
 
 
 class LdpcLib:
@@ -155,6 +189,15 @@ class LdpcLib:
     def shutdown(self):
         self._inited = False
         return self.lib.LDPCshutdown()
+
+    # ---- slot-level entry points (include/nrb200_slot.h): one call per slot, device resident, stream ordered
+    def sch_slot_rx_torch(self, desc, bufs, device):
+        import torch
+        self._check(self.lib.nrb200_sch_slot_rx_dev(C.byref(desc), C.byref(bufs), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "sch_slot_rx_dev")
+
+    def pdsch_slot_tx_torch(self, desc, bufs, device):
+        import torch
+        self._check(self.lib.nrb200_pdsch_slot_tx_dev(C.byref(desc), C.byref(bufs), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "pdsch_slot_tx_dev")
 
     # ---- one process, several GPUs
     def device_count(self):
@@ -227,14 +270,14 @@ class LdpcLib:
         return outs
 
     # ---- batched extension, host buffers (end-to-end: H2D + kernel + D2H inside the call)
-    def _desc(self, BG, Z, R, numMaxIter, outMode, n_cb, llr_stride, out_stride, use_crc=0, crc_len_bits=0, crc_type=0):
+    def _desc(self, BG, Z, R, numMaxIter, outMode, n_cb, llr_stride, out_stride, use_crc=0, crc_len_bits=0, crc_type=0, latency_mode=0):
         d = BatchDesc()
-        d.BG, d.Z, d.R, d.numMaxIter, d.outMode = BG, Z, R, numMaxIter, outMode
+        d.BG, d.Z, d.R, d.numMaxIter, d.outMode, d.latency_mode = BG, Z, R, numMaxIter, outMode, latency_mode
         d.use_crc, d.crc_len_bits, d.crc_type = use_crc, crc_len_bits, crc_type
         d.n_cb, d.llr_stride, d.out_stride = n_cb, llr_stride, out_stride
         return d
 
-    def decode_batch_host(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):
+    def decode_batch_host(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None, latency_mode=0):
         llr = np.ascontiguousarray(llr, dtype=np.int8)
         n_cb, stride = llr.shape
         n = ncols_for_rate(BG, R) * Z
@@ -243,7 +286,7 @@ class LdpcLib:
             out = np.zeros((n_cb, ob), dtype=np.uint8)
         if iters is None:
             iters = np.zeros(n_cb, dtype=np.int32)
-        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
+        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type, latency_mode)
         self._check(self.lib.nrb200_ldpc_decode_batch_host(C.byref(d), llr.ctypes.data, out.ctypes.data, iters.ctypes.data), "decode_batch_host")
         return iters, out
 
@@ -511,7 +554,7 @@ class LdpcLib:
         return out
 
     # ---- batched extension, device-resident torch tensors (asynchronous on torch's current stream)
-    def decode_batch_torch(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None):
+    def decode_batch_torch(self, BG, Z, R, numMaxIter, llr, outMode=OUTMODE_BIT, use_crc=0, crc_len_bits=0, crc_type=0, out=None, iters=None, latency_mode=0):
         import torch
         assert llr.is_cuda and llr.dtype == torch.int8 and llr.is_contiguous() and llr.dim() == 2
         n_cb, stride = llr.shape
@@ -521,7 +564,7 @@ class LdpcLib:
             out = torch.empty((n_cb, ob), dtype=torch.uint8, device=llr.device)
         if iters is None:
             iters = torch.empty(n_cb, dtype=torch.int32, device=llr.device)
-        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type)
+        d = self._desc(BG, Z, R, numMaxIter, outMode, n_cb, stride, out.shape[1], use_crc, crc_len_bits, crc_type, latency_mode)
         st = torch.cuda.current_stream(llr.device).cuda_stream
         self._check(self.lib.nrb200_ldpc_decode_batch_dev(C.byref(d), llr.data_ptr(), out.data_ptr(), iters.data_ptr(), st), "decode_batch_dev")
         return iters, out

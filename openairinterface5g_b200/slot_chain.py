@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import transport as T
+from . import ldpc as _L
 from .ldpc import CRC24_B, PuschChestDesc, PuschRxDesc
 from .ofdm import NrOfdmParms
 
@@ -18,6 +19,7 @@ class PuschSlotChain:
     def __init__(self, lib, dl, device, A=235624, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_rx=4, Qm=6, slot=1, rnti=0x1234, nid=77,
                  ul_freq=3609200000.0, max_iter=8, dmrs_id=55, n_layers=1):
         self.lib, self.dl, self.dev = lib, dl, device
+        self.latency_mode = 1            # decoder: a cluster of SMs per code block (one slot alone); the pipelines below run many slots and set 0
         self.P = NrOfdmParms(N, mu, carrier_rb)
         self.N, self.nb_rx, self.Qm, self.slot, self.rnti, self.nid, self.max_iter = N, nb_rx, Qm, slot, rnti, nid, max_iter
         self.rb_start, self.rb_size, self.A, self.nl = rb_start, rb_size, A, n_layers
@@ -58,6 +60,29 @@ class PuschSlotChain:
         sc = (start_re + np.arange(12 * rb_size)) % N
         syms = [s for s in range(14) if not (self.dmrs_pos >> s) & 1]
         self.re_index = torch.tensor(np.concatenate([s * N + sc for s in syms]), dtype=torch.int64, device=device)
+        self._slot_desc = None
+
+    def _c_slot(self, rxdata, use_estimates, est):
+        """nrb200_sch_rx_slot_t / nrb200_sch_rx_bufs_t for this chain (include/nrb200_slot.h): the library sequences the slot's launches itself."""
+        _L._late_fields()
+        d = _L.SchRxSlotDesc()
+        C_ = _L.C
+        C_.memmove(C_.addressof(d.ofdm), C_.addressof(self.drx), C_.sizeof(self.drx))
+        C_.memmove(C_.addressof(d.chest), C_.addressof(self.cdesc), C_.sizeof(self.cdesc))
+        C_.memmove(C_.addressof(d.rx), C_.addressof(self.desc), C_.sizeof(self.desc))
+        d.rx.d_est_state, d.rx.est_state_ports = 0, 0
+        d.rm = self.lib._rmdesc(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.C, 1)
+        d.R, d.numMaxIter, d.use_estimates, d.latency_mode = self.R, self.max_iter, 1 if use_estimates else 0, self.latency_mode
+        d.crc_len_bits, d.seg_crc_type = self.K - self.F, CRC24_B
+        d.A, d.tb_crc_bits, d.seg_payload_bytes = self.A, 24, (self.seg["Kprime"] - self.seg["L"]) // 8
+        b = _L.SchRxBufs()
+        e = est if use_estimates else self.est
+        b.d_rxdata, b.d_timeshift, b.d_rxdataF, b.d_est = rxdata.data_ptr(), self.ts.data_ptr(), self.rxF.data_ptr(), e.data_ptr()
+        b.d_chest_scratch, b.d_chest_state, b.d_level, b.d_llr16 = self.chest_scratch.data_ptr(), self.chest_state.data_ptr(), self.level.data_ptr(), self.llr16.data_ptr()
+        b.d_E, b.d_Eoff, b.d_harq, b.d_llr8, b.d_hard = self.E.data_ptr(), self.Eoff.data_ptr(), self.harq.data_ptr(), self.llr8.data_ptr(), self.hard.data_ptr()
+        b.d_iters, b.d_tb, b.d_tbcrc = self.iters.data_ptr(), self.tb.data_ptr(), self.tbcrc.data_ptr()
+        b.harq_stride, b.llr8_stride, b.hard_stride = self.harq.shape[1], self.llr8.shape[1], self.hard.shape[1]
+        return d, b
 
     # ------------------------------------------------------------------ synthesis (not timed)
     def synthesize(self, seed=1, snr_db=30.0, h_amp=724.0, tx_amp=724):
@@ -122,9 +147,16 @@ class PuschSlotChain:
         return payload, rxdata, est
 
     # ------------------------------------------------------------------ receive chain (the timed part)
-    def receive(self, rxdata, est=None):
-        """est=None: estimate the channel from the DMRS symbol (the normal path); otherwise use the caller's ul_ch_estimates."""
+    def receive(self, rxdata, est=None, staged=False):
+        """est=None: estimate the channel from the DMRS symbol (the normal path); otherwise use the caller's ul_ch_estimates.
+        The slot is ONE library call (nrb200_sch_slot_rx_dev); staged=True issues the same stages one entry point at a time from here (the round-1 form, kept
+        for the test that compares the two)."""
         lib, dl = self.lib, self.dl
+        if not staged and not self.host_scalars:
+            d, b = self._c_slot(rxdata, est is not None, est)
+            self._keep = (d, b)
+            lib.sch_slot_rx_torch(d, b, self.dev)
+            return self.tb, self.iters, self.tbcrc
         dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)
         if est is None:
             lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)   # every DMRS port of the PDU (:1473-1486)
@@ -142,7 +174,7 @@ class PuschSlotChain:
         lib.pusch_inner_rx_torch(self.desc, self.rxF, est, self.llr16, level=self.level)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
         lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
-                               out=self.hard, iters=self.iters)
+                               out=self.hard, iters=self.iters, latency_mode=self.latency_mode)
         nbytes = (self.seg["Kprime"] - self.seg["L"]) // 8
         self.tb.view(-1).copy_(self.hard[:, :nbytes].reshape(-1))                             # nr_postDecode: concatenate the segments
         lib.crc_batch_torch(0, self.tb, self.A + 24, out=self.tbcrc)                       # CRC over payload + CRC24A == 0 when intact
@@ -162,6 +194,7 @@ class PuschSlotPipeline:
             st = torch.cuda.Stream(device=device)
             with torch.cuda.stream(st):
                 ch = PuschSlotChain(lib, dl, device, **cfg)
+                ch.latency_mode = 0                                  # many slots in flight: one CTA per code block spends the fewest SM-cycles
                 payload, rxdata, _ = ch.synthesize(seed=seed0 + k, snr_db=30.0)
                 ch.receive(rxdata)                                   # warm-up outside the capture
                 st.synchronize()

@@ -99,3 +99,24 @@ def test_pdsch_slots_in_flight_match_single_slot(ldpc):
         ch = pipe.chains[k]
         assert torch.equal(solo.txdata, ch.txdata) and torch.equal(solo.llr16, ch.llr16)
         assert torch.equal(iters, ch.iters) and torch.equal(tb, ch.tb) and int(crc[0]) == 0
+
+
+def test_slot_entry_points_equal_staged_calls(ldpc):
+    """nrb200_pdsch_slot_tx_dev / nrb200_sch_slot_rx_dev (one library call per direction) against the stages issued one entry point at a time."""
+    dev = torch.device("cuda", 0)
+    dl = load_dftslib()
+    a, b = PdschSlotChain(ldpc, dl, dev), PdschSlotChain(ldpc, dl, dev)
+    payload = torch.from_numpy(np.random.default_rng(4).integers(0, 256, size=a.A // 8, dtype=np.uint8)).to(dev)
+    ta, tb_ = a.transmit(payload), b.transmit(payload, staged=True)
+    torch.cuda.synchronize()
+    for name in ("segs", "cw", "f", "txF", "txdata"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    rx = a.channel(ta, seed=3)
+    a.receive(rx)
+    b.receive(rx, staged=True)
+    torch.cuda.synchronize()
+    for name in ("rxF", "est", "level", "llr16", "llr8", "iters", "tb", "tbcrc"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    nb = (a.K - a.F) // 8
+    assert torch.equal(a.hard[:, :nb], b.hard[:, :nb])
+    assert torch.equal(a.tb.view(-1)[:payload.numel()], payload)

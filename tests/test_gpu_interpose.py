@@ -118,3 +118,34 @@ def test_ue_caller_reaches_the_gpu_through_the_interposed_symbol(oracle):
         assert lib.refh_pdsch_chest(prm.ctypes.data_as(C.c_void_p), rx.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p)) == 0
         est_o = oracle.pdsch_channel_estimation(P, rx)
         assert np.array_equal(est.reshape(nb_rx, 14, N, 2)[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq)
+
+
+def test_oai_ue_caller_reaches_the_gpu_through_nr_rx_pdsch(oracle):
+    """integration/oai_shim_rx_pdsch.c defines OAI's `nr_rx_pdsch`; the reference-side caller (oracle/ref_harness_pdsch.c: fills PHY_VARS_NR_UE / NR_UE_DLSCH_t and
+    calls the function symbol by symbol like nr_ue_pdsch_procedures) is linked against it instead of nr_dlsch_demodulation.c (oracle/_ref/libshimtest_pdsch.so).
+    LLRs, log2_maxh and dl_valid_re that the unchanged host C gets back must be the pinned oracle's, one and two layers."""
+    from oracle.bindings import PuschParms
+    so = os.path.join(ROOT, "oracle", "_ref", "libshimtest_pdsch.so")
+    if not os.path.exists(so):
+        pytest.fail(f"{so} missing: run integration/build_shims.sh where /root/reference exists (the file travels with the repo snapshot)")
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(17)
+    cases = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, layers, amplitudes
+        (4096, 2, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13, 1, (2000, 1500)), (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, 1, (2000, 1500)),
+        (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, 1, (2000, 1500)), (4096, 2, 0, 273, 6, 1 << 2, 0, 1, 273, 1, 13, 2, (2000, 1500)),
+        (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, 2, (300, 200)), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12, 2, (12000, 9000))]
+    for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, nl, (ay, ah) in cases:
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        llr_o, sh_o = oracle.pdsch_rx_slot(P, start, nsym, rx, h, nl=nl)
+        G = llr_o.size
+        prm = np.array([N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, start, nsym, dpos, dtype_, cdm, G, nl], dtype=np.int32)
+        llr = np.zeros(G + 64, np.int16)
+        valid = np.zeros(14, np.int32)
+        sh = lib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), rx.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+                                    valid.ctypes.data_as(C.c_void_p), None)
+        assert sh == sh_o, (N, nb_rx, Qm, nl, sh, sh_o)
+        assert np.array_equal(llr[:G], llr_o), (N, nb_rx, rb_size, Qm, nl, np.nonzero(llr[:G] != llr_o)[0][:5])
+        per = [(rb_size * ((12 - 6 * cdm) if dtype_ == 0 else (12 - 4 * cdm)) if (dpos >> s) & 1 else rb_size * 12) for s in range(start, start + nsym)]
+        assert [int(v) for v in valid[start:start + nsym]] == per and int(valid.sum()) * Qm * nl == G

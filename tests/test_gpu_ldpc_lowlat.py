@@ -25,7 +25,7 @@ def _check_batch(ldpc, oracle, BG, Z, R, n, ebn0, seed, max_iter=8, out_mode=0, 
         from openairinterface5g_b200.synth import awgn_llr
         cw = np.stack([oracle.encode(BG, Z, K, P[i]) for i in range(n)])
         llr = awgn_llr(cw, Z, NCOLS[(BG, R)], ebn0, (22 if BG == 1 else 10) / (NCOLS[(BG, R)] - 2), seed)
-    iters, out = ldpc.decode_batch_host(BG, Z, R, max_iter, llr, outMode=out_mode, **kw)
+    iters, out = ldpc.decode_batch_host(BG, Z, R, max_iter, llr, outMode=out_mode, latency_mode=1, **kw)
     for i in range(n):
         it_o, out_o = oracle.decode(BG, Z, R, max_iter, llr[i], out_mode, *( (1, K, 1) if crc else ()))
         assert iters[i] == it_o, (BG, Z, R, n, i, iters[i], it_o)
@@ -34,7 +34,8 @@ def _check_batch(ldpc, oracle, BG, Z, R, n, ebn0, seed, max_iter=8, out_mode=0, 
 
 @pytest.mark.parametrize("n", [1, 5, 16, 17, 30, 40, 74])
 def test_cluster_sizes_headline_graph(ldpc, oracle, n):
-    """launch_decode picks 8 / 4 / 2 CTAs per block from the batch size (<= 16 / <= 33 / <= 74); every size against the oracle at the waterfall."""
+    """latency_mode = 1: launch_decode picks 8 / 4 / 2 CTAs per block from the batch size (<= 15 / <= 33 / <= 74); every size against the oracle at the
+    waterfall."""
     _check_batch(ldpc, oracle, 1, 384, 13, n, 2.2, seed=100 + n)
 
 
@@ -59,7 +60,7 @@ def test_single_cta_kernel_still_covered_for_small_batches(oracle):
             "from openairinterface5g_b200.ldpc import load_LDPClib; lib = load_LDPClib(); orc = Oracle();"
             "ok = True\n"
             "for (BG, Z, R, e) in ((1, 384, 13, 2.3), (2, 384, 15, 1.0), (1, 256, 23, 4.0)):\n"
-            "    K, P, llr = make_case(orc, BG, Z, R, 3, e, 77); it, out = lib.decode_batch_host(BG, Z, R, 8, llr)\n"
+            "    K, P, llr = make_case(orc, BG, Z, R, 3, e, 77); it, out = lib.decode_batch_host(BG, Z, R, 8, llr, latency_mode=1)\n"
             "    for i in range(3):\n"
             "        a = orc.decode(BG, Z, R, 8, llr[i], 0); ok = ok and a[0] == it[i] and np.array_equal(np.asarray(a[1]).view(np.uint8), out[i])\n"
             "print('VARIANT_OK' if ok else 'VARIANT_BAD')")

@@ -77,3 +77,21 @@ def test_two_layer_receiver_reads_estimator_state_on_device(ldpc):
     pipe = PuschSlotPipeline(ldpc, dl, dev, 2, seed0=400, **cfg)
     pipe.timed_rounds(2, e2e=True)
     assert all(pipe.check(host=True))
+
+
+@pytest.mark.parametrize("cfg", [dict(A=18696, N=2048, carrier_rb=106, rb_start=20, rb_size=50, nb_rx=2, Qm=4, slot=3), dict(A=471272, n_layers=2)])
+def test_slot_entry_point_equals_staged_calls(ldpc, cfg):
+    """nrb200_sch_slot_rx_dev (the whole PUSCH slot in one library call, include/nrb200_slot.h) against the same stages issued one entry point at a
+    time: every intermediate and the result identical."""
+    dev = torch.device("cuda", 0)
+    dl = load_dftslib()
+    a, b = PuschSlotChain(ldpc, dl, dev, **cfg), PuschSlotChain(ldpc, dl, dev, **cfg)
+    payload, rxdata, _ = a.synthesize(seed=9)
+    a.receive(rxdata)
+    b.receive(rxdata, staged=True)
+    torch.cuda.synchronize()
+    for name in ("rxF", "est", "level", "llr16", "llr8", "iters", "tb", "tbcrc"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    nb = (a.K - a.F) // 8                                      # the decoder writes ncols(R) * Z / 8 bytes per segment; the rows are wider
+    assert torch.equal(a.hard[:, :nb], b.hard[:, :nb])
+    assert np.array_equal(a.tb.cpu().numpy().reshape(-1)[:payload.size], payload)

@@ -23,7 +23,7 @@ def main():
     llr = torch.zeros((n, 68 * Z), dtype=torch.int8, device=dev)
     llr[:, 2 * Z:] = torch.clamp(torch.floor(y / (sigma / 16)), -128, 127).to(torch.int8)
     for _ in range(5):
-        it, out = lib.decode_batch_torch(1, Z, 13, 8, llr)
+        it, out = lib.decode_batch_torch(1, Z, 13, 8, llr, latency_mode=1)
     torch.cuda.synchronize()
     marks = np.zeros(8 * 64, np.int64)
     assert lib.lib.nrb200_debug_cluster_marks(marks.ctypes.data_as(C.c_void_p)) == 0

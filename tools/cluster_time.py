@@ -24,12 +24,12 @@ def main():
     for n in ns:
         l = llr[:n].contiguous()
         out = torch.empty((n, 68 * Z // 8), dtype=torch.uint8, device=dev); it = torch.empty(n, dtype=torch.int32, device=dev)
-        for _ in range(5): lib.decode_batch_torch(1, Z, 13, 8, l, out=out, iters=it)
+        for _ in range(5): lib.decode_batch_torch(1, Z, 13, 8, l, out=out, iters=it, latency_mode=1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 50
         e0.record()
-        for _ in range(reps): lib.decode_batch_torch(1, Z, 13, 8, l, out=out, iters=it)
+        for _ in range(reps): lib.decode_batch_torch(1, Z, 13, 8, l, out=out, iters=it, latency_mode=1)
         e1.record(); torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / reps
         print(f"cluster={os.environ.get('NRB200_CLUSTER','auto')} warps={os.environ.get('NRB200_CLUSTER_WARPS','default')} n={n} ebn0={ebn0} "
