@@ -34,3 +34,10 @@ gcc $F $INC $DEFS $HERE/oai_shim_rx_pdsch.c $LIB -Wl,-rpath,'$ORIGIN/../../opena
 gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_pdsch.c $ROOT/oracle/ref_harness_pdsch.c $HERE/oai_shim_rx_pdsch.c \
     $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -o $W/libshimtest_pdsch.so
 ls -la $HERE/_build/libnrb200_shim_rx_pdsch.so $W/libshimtest_pdsch.so
+# the gNB's PUSCH receiver: nr_rx_pusch_tp (+ the estimator it calls by name), driven by a caller harness that fills PHY_VARS_gNB like phy_init_nr_gNB does
+gcc $F $INC $DEFS $HERE/oai_shim_rx_pusch.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_rx_pusch.so
+gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_harness_rxpusch.c $HERE/oai_shim_rx_pusch.c $HERE/oai_shim_pusch_chest.c \
+    $R/openair1/PHY/NR_ESTIMATION/nr_measurements_gNB.c $R/openair1/PHY/TOOLS/signal_energy.c $R/openair1/PHY/TOOLS/dB_routines.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c \
+    $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/NR_TRANSPORT/nr_tbs_tools.c \
+    $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -Wl,--no-undefined -o $W/libshimtest_rxpusch.so || echo "libshimtest_rxpusch.so: FAILED"
+ls -la $HERE/_build/libnrb200_shim_rx_pusch.so $W/libshimtest_rxpusch.so

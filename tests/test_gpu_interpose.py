@@ -149,3 +149,68 @@ def test_oai_ue_caller_reaches_the_gpu_through_nr_rx_pdsch(oracle):
         assert np.array_equal(llr[:G], llr_o), (N, nb_rx, rb_size, Qm, nl, np.nonzero(llr[:G] != llr_o)[0][:5])
         per = [(rb_size * ((12 - 6 * cdm) if dtype_ == 0 else (12 - 4 * cdm)) if (dpos >> s) & 1 else rb_size * 12) for s in range(start, start + nsym)]
         assert [int(v) for v in valid[start:start + nsym]] == per and int(valid.sum()) * Qm * nl == G
+
+
+def test_oai_gnb_caller_reaches_the_gpu_through_nr_rx_pusch_tp(oracle):
+    """integration/oai_shim_rx_pusch.c defines OAI's `nr_rx_pusch_tp`; the reference-side caller (oracle/ref_harness_rxpusch.c: PHY_VARS_gNB with the rxdataF ring,
+    pusch_vars and the ULSCH PDU as phy_init_nr_gNB / the scheduler leave them) is linked against it and against the interposed channel estimator
+    (oracle/_ref/libshimtest_rxpusch.so).  What the unchanged host C reads afterwards -- pusch_vars->llr (layer de-mapped, unscrambled), ul_ch_estimates, log2_maxh,
+    dmrs_symbol, ul_valid_re_per_slot, llr_offset -- must be what the pinned oracle functions give when chained the way the reference chains them
+    (nr_ulsch_demodulation.c:1447-1700), one layer and two (MMSE with the estimator's max_ch / nvar)."""
+    from oracle.bindings import ChestParms, PuschParms
+    so = os.path.join(ROOT, "oracle", "_ref", "libshimtest_rxpusch.so")
+    if not os.path.exists(so):
+        pytest.fail(f"{so} missing: run integration/build_shims.sh where /root/reference exists (the file travels with the repo snapshot)")
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(23)
+    cases = [  # N, nb_rx, carrier PRBs, slot, rb_start, rb_size, Qm, dmrs_pos, cdm groups, layers, dmrs id, rnti, data scrambling id
+        (4096, 4, 273, 1, 0, 273, 6, 1 << 2, 2, 1, 55, 0x1234, 77), (2048, 2, 106, 7, 20, 50, 4, 1 << 2, 2, 1, 1007, 0x4321, 99),
+        (1024, 2, 52, 6, 3, 32, 2, (1 << 2) | (1 << 11), 1, 1, 300, 0x1001, 5),
+        (4096, 4, 273, 1, 0, 273, 6, 1 << 2, 2, 2, 55, 0x1234, 77), (2048, 2, 106, 9, 10, 50, 8, 1 << 3, 2, 2, 1007, 0x2222, 512)]
+    for N, nb_rx, carrier, slot, rb_start, rb_size, Qm, dpos, cdm, nl, dmrs_id, rnti, nid in cases:
+        fco = N - carrier * 6
+        rx = rng.integers(-1500, 1501, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, 0, cdm)
+        dms = [s for s in range(14) if (dpos >> s) & 1]
+        # ---- expected: the oracle functions chained like the reference chains them
+        est = np.zeros((nl * nb_rx, 14, N, 2), np.int16)
+        max_ch, nvar = 0, 0
+        for s in dms:
+            for p in range(nl):
+                e, st = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, s, p, rb_start, 0, rb_size, fco, 0, dmrs_id, 0, 0), rx)
+                est[p * nb_rx:(p + 1) * nb_rx, s] = e[:, s]
+                max_ch = max(max_ch, int(st[0])); nvar += int(st[1])
+        nvar //= 14 * nl * nb_rx
+        valid = [oracle.pusch_nb_re(P, s) for s in range(14)]
+        meas = [s for s in range(14) if valid[s] > 0][0]
+        if nl == 1:
+            sh_o, _ = oracle.pusch_log2_maxh(P, meas, dms[0], rx, est)
+        else:
+            sh_o, _ = oracle.pusch_log2_maxh_2l(P, meas, dms[0], max_ch, rx, est)
+        cur, out = dms[0], []
+        for s in range(14):
+            if (dpos >> s) & 1:
+                cur = s
+            if valid[s] == 0:
+                continue
+            if nl == 1:
+                out.append(oracle.pusch_inner_rx_symbol(P, s, cur, sh_o, rx, est)[0])
+            else:
+                l2, _ = oracle.pusch_inner_rx_symbol_2l(P, s, cur, sh_o, nvar, rx, est)
+                out.append(np.stack([l2[0].reshape(valid[s], Qm), l2[1].reshape(valid[s], Qm)], axis=1).reshape(-1))
+        want = oracle.unscramble_llr(np.concatenate(out), 0, nid, rnti)
+        G = want.size
+        # ---- the unchanged caller
+        prm = np.array([N, nb_rx, carrier, slot, rb_start, 0, rb_size, fco, Qm, 0, 14, dpos, 0, cdm, nl, (1 << nl) - 1, 0, dmrs_id, rnti, nid, 0, 0], dtype=np.int32)
+        llr = np.zeros(G, np.int16)
+        est_out = np.zeros((nl * nb_rx, 14, N, 2), np.int16)
+        info = np.zeros(40, np.int32)
+        assert lib.refh_rx_pusch(prm.ctypes.data_as(C.c_void_p), rx.ctypes.data_as(C.c_void_p), G, llr.ctypes.data_as(C.c_void_p), est_out.ctypes.data_as(C.c_void_p),
+                                 info.ctypes.data_as(C.c_void_p)) == 0
+        for s in dms:
+            assert np.array_equal(est_out[:, s], est[:, s]), (N, nl, "estimates", s)
+        assert info[0] == sh_o and info[1] == dms[0], (N, nl, info[:2], sh_o)
+        assert [int(v) for v in info[2:16]] == valid
+        assert [int(v) for v in info[16:30]] == [int(x) for x in np.concatenate([[0], np.cumsum(np.array(valid) * Qm)[:-1]])]
+        assert np.array_equal(llr, want), (N, nb_rx, Qm, nl, np.nonzero(llr != want)[0][:5])
+        assert all(int(v) > 0 for v in info[30:30 + nb_rx])
