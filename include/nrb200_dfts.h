@@ -20,9 +20,13 @@ extern "C" {
 
 /* Part 1: the OAI plug-in ABI (tools_defs.h:514-521).  sizeidx = position in FOREACH_DFTSZ / FOREACH_IDFTSZ (tools_defs.h:404-499);
  * sigF/sig = interleaved {re, im} int16, one transform; scale_flag as in the reference (0 = none, 1 = 1/sqrt(N) overall). */
+/* (a translation unit that also includes OAI's own tools_defs.h -- an interposer under integration/ -- defines NRB200_NO_OAI_LOADER_PROTOTYPES: there
+ * `dft` / `idft` are OAI's function-pointer globals) */
+#ifndef NRB200_NO_OAI_LOADER_PROTOTYPES
 void dft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag);
 void idft(uint8_t sizeidx, int16_t *sigF, int16_t *sig, unsigned char scale_flag);
 int dfts_autoinit(void);   /* called by load_module_shlib when present (load_module_shlib.c:174-191); returns 0, -1 without a GPU */
+#endif
 
 /* Part 2: batched extension -- n calls of the same size, contiguous (2*N int16 each; 8*N int16 each for the four-way DFT-s-OFDM sizes). */
 int32_t nrb200_dft_batch_dev(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, void *stream);

@@ -41,3 +41,9 @@ gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_harness_rxpusch.c $H
     $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/NR_TRANSPORT/nr_tbs_tools.c \
     $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -Wl,--no-undefined -o $W/libshimtest_rxpusch.so || echo "libshimtest_rxpusch.so: FAILED"
 ls -la $HERE/_build/libnrb200_shim_rx_pusch.so $W/libshimtest_rxpusch.so
+# the RU front end: nr_feptx0 / nr_fep_full -> the slot-level OFDM entry points of libdfts_b200.so
+LIBD="-L$ROOT/openairinterface5g_b200 -l:libdfts_b200.so"
+gcc $F $INC $DEFS $HERE/oai_shim_ru_ofdm.c $LIBD -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_ru_ofdm.so
+gcc $F $INC $DEFS $ROOT/oracle/ref_harness_ru.c $HERE/oai_shim_ru_ofdm.c $LIBD -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -Wl,--no-undefined \
+    -o $W/libshimtest_ru.so || echo "libshimtest_ru.so: FAILED"
+ls -la $HERE/_build/libnrb200_shim_ru_ofdm.so $W/libshimtest_ru.so

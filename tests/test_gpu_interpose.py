@@ -214,3 +214,33 @@ def test_oai_gnb_caller_reaches_the_gpu_through_nr_rx_pusch_tp(oracle):
         assert [int(v) for v in info[16:30]] == [int(x) for x in np.concatenate([[0], np.cumsum(np.array(valid) * Qm)[:-1]])]
         assert np.array_equal(llr, want), (N, nb_rx, Qm, nl, np.nonzero(llr != want)[0][:5])
         assert all(int(v) > 0 for v in info[30:30 + nb_rx])
+
+
+def test_oai_ru_callers_reach_the_gpu_through_nr_feptx0_and_nr_fep_full(oracle):
+    """integration/oai_shim_ru_ofdm.c defines OAI's RU front-end functions `nr_feptx0` (IDFT + cyclic prefix of a tx antenna's symbols) and `nr_fep_full` (the 14 DFTs
+    of every rx antenna of a slot); the reference-side caller (oracle/ref_harness_ru.c: an RU_t with frame parameters and buffers as init_nr_ru leaves them) is linked
+    against it (oracle/_ref/libshimtest_ru.so).  The samples / sub-carriers the unchanged host C finds in ru->common afterwards must be the pinned oracle's (which is
+    pinned against the real PHY_ofdm_mod / nr_slot_fep_ul)."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libshimtest_ru.so")
+    if not os.path.exists(so):
+        pytest.fail(f"{so} missing: run integration/build_shims.sh where /root/reference exists (the file travels with the repo snapshot)")
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(29)
+    for N, mu, nb_rb, slot, nant, chunks, n_ta, divisor in ((4096, 1, 273, 1, 2, 1, 0, 8), (4096, 1, 273, 4, 2, 2, 800, 8), (2048, 1, 106, 19, 1, 1, 0, 8),
+                                                             (1024, 0, 52, 3, 2, 2, 0, 8), (2048, 2, 66, 7, 1, 1, 400, 16)):
+        spf = lib.refh_ru_fep_full(N, mu, nb_rb, slot, nant, divisor, n_ta, None, None)
+        pre, cps, ss, _ = oracle.ofdm_geometry(N, mu, slot)
+        # ---- transmit: every antenna's slot, in `chunks` nr_feptx0 calls per antenna
+        F = rng.integers(-2000, 2001, size=(nant, 14 * N * 2)).astype(np.int16)
+        txdata = np.zeros((nant, spf * 2), np.int16)
+        assert lib.refh_ru_feptx(N, mu, nb_rb, slot, nant, chunks, F.ctypes.data_as(C.c_void_p), txdata.ctypes.data_as(C.c_void_p)) == spf
+        for a in range(nant):
+            t_o, _ = oracle.ofdm_tx_slot(N, mu, nb_rb, slot, 14, None, F[a])
+            assert np.array_equal(txdata[a, 2 * ss:2 * ss + t_o.size], t_o), (N, mu, slot, a, "feptx0")
+            assert not txdata[a, :2 * ss].any() and not txdata[a, 2 * ss + t_o.size:].any()
+        # ---- receive: a frame of samples, timing advance offset (wraps the frame ring when the slot is early in the frame)
+        rx = rng.integers(-3000, 3001, size=(nant, spf * 2)).astype(np.int16)
+        rxF = np.zeros((nant, 14 * N * 2), np.int16)
+        assert lib.refh_ru_fep_full(N, mu, nb_rb, slot, nant, divisor, n_ta, rx.ctypes.data_as(C.c_void_p), rxF.ctypes.data_as(C.c_void_p)) == spf
+        for a in range(nant):
+            assert np.array_equal(rxF[a], oracle.ofdm_rx_slot(N, mu, nb_rb, slot, divisor, n_ta, None, rx[a])), (N, mu, slot, a, "fep_full")
