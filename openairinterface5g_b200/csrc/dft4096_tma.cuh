@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256, 3) dft4096_kernel(DftPlan P, TwOffsets O,
     {
       const int g = t & 15, k = t >> 4;
       const unsigned *p = Y + k * 304 + g;
+      unsigned *q = X + g * 258 + k;
       cx v[4][4];
 #pragma unroll
       for (int b = 0; b < 4; b++)
@@ -155,33 +156,48 @@ __global__ void __launch_bounds__(256, 3) dft4096_kernel(DftPlan P, TwOffsets O,
         for (int a = 0; a < 4; a++) v[a][b] = unpack(p[16 * a + 80 * b]);
 #pragma unroll
       for (int b = 0; b < 4; b++) r4_level<INV>(O, tw, 16, k, true, v[0][b], v[1][b], v[2][b], v[3][b]);
+      if (inv) {                                            // inverse: level 256 is the 32-bit butterfly -> packed form, straight to shared memory
+        const short *t4 = tw + O.tw256;
 #pragma unroll
-      for (int a = 0; a < 4; a++) r4_level<INV>(O, tw, 64, k + 16 * a, true, v[a][0], v[a][1], v[a][2], v[a][3]);
-      unsigned *q = X + g * 258 + k;
+        for (int a = 0; a < 4; a++) {
+          const int kk = k + 16 * a;
+          unsigned y0, y1, y2, y3;
+          bfly4_32p(pack(v[a][0]), pack(v[a][1]), pack(v[a][2]), pack(v[a][3]), t4 + 2 * kk, t4 + 128 + 2 * kk, t4 + 256 + 2 * kk, true, true, y0, y1, y2, y3);
+          q[16 * a] = y0; q[16 * a + 64] = y1; q[16 * a + 128] = y2; q[16 * a + 192] = y3;
+        }
+      } else {
 #pragma unroll
-      for (int b = 0; b < 4; b++)
+        for (int a = 0; a < 4; a++) r4_level<INV>(O, tw, 64, k + 16 * a, true, v[a][0], v[a][1], v[a][2], v[a][3]);
 #pragma unroll
-        for (int a = 0; a < 4; a++) q[16 * a + 64 * b] = pack(v[a][b]);
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int a = 0; a < 4; a++) q[16 * a + 64 * b] = pack(v[a][b]);
+      }
     }
     __syncthreads();
-    // ---- pass B: levels 1024 and 4096.  Thread k' holds element k' of the 16 sub-transforms; results in natural order
+    // ---- pass B: levels 1024 and 4096 (32-bit butterflies on packed words).  Thread k' holds element k' of the 16 sub-transforms; results in natural order
     {
       const int k = t;
-      cx v[4][4];
+      unsigned v[4][4];
 #pragma unroll
       for (int b = 0; b < 4; b++)
 #pragma unroll
-        for (int a = 0; a < 4; a++) v[a][b] = unpack(X[(a + 4 * b) * 258 + k]);
+        for (int a = 0; a < 4; a++) v[a][b] = X[(a + 4 * b) * 258 + k];
+      const short *t1 = tw + O.rad4_1024, *t2 = tw + O.rad4_4096;
 #pragma unroll
-      for (int b = 0; b < 4; b++) r4_level<INV>(O, tw, 256, k, true, v[0][b], v[1][b], v[2][b], v[3][b]);
+      for (int b = 0; b < 4; b++)
+        bfly4_32p(v[0][b], v[1][b], v[2][b], v[3][b], t1 + 2 * k, t1 + 512 + 2 * k, t1 + 1024 + 2 * k, inv, true, v[0][b], v[1][b], v[2][b], v[3][b]);
 #pragma unroll
-      for (int a = 0; a < 4; a++) r4_level<INV>(O, tw, 1024, k + 256 * a, P.scale != 0, v[a][0], v[a][1], v[a][2], v[a][3]);
+      for (int a = 0; a < 4; a++) {
+        const int kk = k + 256 * a;
+        bfly4_32p(v[a][0], v[a][1], v[a][2], v[a][3], t2 + 2 * kk, t2 + 2048 + 2 * kk, t2 + 4096 + 2 * kk, inv, P.scale != 0, v[a][0], v[a][1], v[a][2], v[a][3]);
+      }
 #pragma unroll
       for (int b = 0; b < 4; b++)
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           const unsigned i = (unsigned)(k + 256 * a + 1024 * b);
-          unsigned w = pack(v[a][b]);
+          unsigned w = v[a][b];
           if (MODE == 2 && S.rotate) {
             const int j = range_pos(S, i);
             if (j >= 0) {

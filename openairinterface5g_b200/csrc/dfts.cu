@@ -34,11 +34,20 @@ __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v));
 __device__ __forceinline__ int wrap16(int v) { return (int)(short)v; }
 __device__ __forceinline__ int neg16(int v) { return v == -32768 ? -32768 : -v; }
 __device__ __forceinline__ cx mjn(cx a) { return {a.i, neg16(a.r)}; }
-__device__ __forceinline__ cx sadd(cx a, cx b) { return {sat16(a.r + b.r), sat16(a.i + b.i)}; }
-__device__ __forceinline__ cx ssub(cx a, cx b) { return {sat16(a.r - b.r), sat16(a.i - b.i)}; }
+// adds_epi16 / subs_epi16 on values held sign-extended in 32-bit registers: add-then-min is one VIADDMNMX, the max a VIMNMX.  (Written as max(min(a + b))
+// the compiler recognises a 16-bit saturating add and expands it into a seven-instruction overflow test.)
+__device__ __forceinline__ int sadd16(int a, int b) { return max(__viaddmin_s32(a, b, 32767), -32768); }
+__device__ __forceinline__ cx sadd(cx a, cx b) { return {sadd16(a.r, b.r), sadd16(a.i, b.i)}; }
+__device__ __forceinline__ cx ssub(cx a, cx b) { return {sadd16(a.r, -b.r), sadd16(a.i, -b.i)}; }
 __device__ __forceinline__ int sra15(unsigned v) { return ((int)v) >> 15; }
 __device__ __forceinline__ cx unpack(unsigned w) { return {(int)(short)(w & 0xFFFFu), (int)(short)(w >> 16)}; }
-__device__ __forceinline__ unsigned pack(cx a) { return ((unsigned)a.r & 0xFFFFu) | ((unsigned)a.i << 16); }
+// both components are int16 values: cvt.pack.sat (one I2IP) packs them, the saturation never acts
+__device__ __forceinline__ unsigned pack(cx a)
+{
+  unsigned r;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(a.i), "r"(a.r));
+  return r;
+}
 // packed_cmult2: (a . ta, a . tb) >> 15, packs
 // twiddles are {re, im} int16 pairs at even offsets of the table blob: one 32-bit load each
 __device__ __forceinline__ cx ldtw(const short *p) { return unpack(__ldg(reinterpret_cast<const unsigned *>(p))); }
@@ -85,6 +94,36 @@ __device__ __forceinline__ void bfly4_32(cx x0, cx x1, cx x2, cx x3, const short
   const cx oa = {wrap16(x0.r + da.r), wrap16(x0.i + da.i)}, ob = {wrap16(x0.r + db.r), wrap16(x0.i + db.i)};
   y1 = inv ? ob : oa;
   y3 = inv ? oa : ob;
+}
+
+// The same butterfly on PACKED {re, im} int16 words (the 4096-point kernel): x0 is only ever added with 16-bit wrap-around, so it stays packed
+// (one VIADD.16x2 per output instead of two adds + two sign extensions), and the four 32-bit sums are shifted, saturated and packed by one I2IP each
+// (cvt.pack.sat.s16.s32 = packs_epi32).  Identical results to bfly4_32.
+__device__ __forceinline__ unsigned pk32p(unsigned r, unsigned i)
+{
+  unsigned o;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o) : "r"(sra15(i)), "r"(sra15(r)));
+  return o;
+}
+__device__ __forceinline__ unsigned sra1_16x2(unsigned p) { return ((p >> 1) & 0x7FFF7FFFu) | (p & 0x80008000u); }   // >> 1 of both int16 lanes
+__device__ __forceinline__ void bfly4_32p(unsigned x0, unsigned p1, unsigned p2, unsigned p3, const short *w1, const short *w2, const short *w3, bool inv, bool half,
+                                          unsigned &y0, unsigned &y1, unsigned &y2, unsigned &y3)
+{
+  unsigned x1r, x1i, x2r, x2i, x3r, x3i;
+  const cx W1 = ldtw(w1), W2 = ldtw(w2), W3 = ldtw(w3);
+  cm32(unpack(p1), W1.r, W1.i, inv, x1r, x1i);
+  cm32(unpack(p2), W2.r, W2.i, inv, x2r, x2i);
+  cm32(unpack(p3), W3.r, W3.i, inv, x3r, x3i);
+  const unsigned d0 = pk32p(x1r + x2r + x3r, x1i + x2i + x3i);
+  const unsigned da = pk32p(x1i - (x2r + x3i), (x3r - x2i) - x1r);
+  const unsigned d2 = pk32p((x2r - x3r) - x1r, (x2i - x3i) - x1i);
+  const unsigned db = pk32p((x3i - x2r) - x1i, x1r - (x2i + x3r));
+  y0 = __vadd2(x0, d0);
+  y2 = __vadd2(x0, d2);
+  const unsigned oa = __vadd2(x0, da), ob = __vadd2(x0, db);
+  y1 = inv ? ob : oa;
+  y3 = inv ? oa : ob;
+  if (half) { y0 = sra1_16x2(y0); y1 = sra1_16x2(y1); y2 = sra1_16x2(y2); y3 = sra1_16x2(y3); }
 }
 
 // Device-resident twiddle blob (int16): the hand-rounded tables of nr_dft_tables.h followed by the generated ones.

@@ -29,6 +29,20 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv \
   python bench.py --steps 5 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
 fi
+echo "== per-call loader ABI (tools/abi_bench.c: this library and the compiled reference, same harness)"
+timeout 300 python tools/bench_abi.py 2.0 1.0 2>&1 | tail -16 | tee gpurun_out/abi_${TAG}.jsonl
+echo "== cluster decoder: time of one small launch, phase marks"
+for c in 8 4 2 0; do NRB200_CLUSTER=$c timeout 120 python tools/cluster_time.py 1.0 1 8 2>&1 | tail -2; done | tee gpurun_out/cluster_time_${TAG}.txt
+timeout 120 python tools/cluster_time.py 1.0 2>&1 | tail -6 | tee -a gpurun_out/cluster_time_${TAG}.txt
+timeout 120 python tools/cluster_phases.py 1.0 1 2>&1 | tail -9 | tee gpurun_out/cluster_phases_${TAG}.txt
+echo "== DFT"
+for inv in 1 0; do timeout 120 python tools/dft_time.py 4096 $inv 8880; NRB200_DFT_TMA=0 timeout 120 python tools/dft_time.py 4096 $inv 8880; done 2>&1 | tee gpurun_out/dft_${TAG}.txt
+if [ "$MODE" = "full" ]; then
+echo "== ncu full (cluster decoder, one block on 8 CTAs)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cluster -s 6 -c 1 -f -o gpurun_out/prof_cluster_${TAG} python tools/cluster_time.py 1.0 1 > gpurun_out/ncu_cluster_${TAG}.log 2>&1
+echo "== ncu full (4096-point TMA kernel)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dft4096 -s 3 -c 1 -f -o gpurun_out/prof_dft4096_${TAG} python tools/dft_time.py 4096 1 8880 > gpurun_out/ncu_dft_${TAG}.log 2>&1
+fi
 echo "== ncu full (decode kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
