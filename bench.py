@@ -463,24 +463,26 @@ def run_b200(args, rank, world, local_rank):
 
     e2e_blocking_value = timed_e2e(e2e_blocking)
     e2e_value = timed_e2e(e2e_pipelined)
+    # what the last pipelined step returned (checked against the oracle below), taken before anything else touches the host buffers
+    e2e_last_iters = h_its[(args.steps - 1) % DEPTH].copy()
+    e2e_last_out = np_outs[(args.steps - 1) % DEPTH][:3].copy()
+    e2e_last_llr = np_llr[(args.steps - 1) % len(np_llr)][:3]
 
     # ---- platform ceiling for that traffic: the same bytes per step (H2D of the LLRs, D2H of the hard bits) moved by plain cudaMemcpyAsync on all
     # ranks at once, no kernel at all.  e2e / ceiling = how much of what this host's PCIe / memory system delivers to N GPUs the decode path uses.
     d_llr_c = torch.empty((B, NUM_LLR), dtype=torch.int8, device=dev)
     d_out_c = torch.empty((B, NUM_LLR // 8), dtype=torch.uint8, device=dev)
+    h_out_c = [torch.empty((B, NUM_LLR // 8), dtype=torch.uint8).pin_memory() for _ in range(2)]
     cs = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
     def copies_only(n):
         for i in range(n):
             with torch.cuda.stream(cs[i & 1]):
                 d_llr_c.copy_(h_llr[i % len(h_llr)], non_blocking=True)
-                h_outs[i % DEPTH].copy_(d_out_c, non_blocking=True)
+                h_out_c[i & 1].copy_(d_out_c, non_blocking=True)
         for s_ in cs:
             s_.synchronize()
     copy_ceiling = timed_e2e(copies_only)
-    e2e_last_iters = h_its[(args.steps - 1) % DEPTH].copy()
-    e2e_last_out = np_outs[(args.steps - 1) % DEPTH][:3].copy()
-    e2e_last_llr = np_llr[(args.steps - 1) % len(np_llr)][:3]
 
     # ---- sanity: the timed kernel really decodes (parity of a few blocks of the last batch against the CPU oracle)
     check = e2e_check = None

@@ -39,6 +39,9 @@ __device__ __forceinline__ cx mjn(cx a) { return {a.i, neg16(a.r)}; }
 __device__ __forceinline__ int sadd16(int a, int b) { return max(__viaddmin_s32(a, b, 32767), -32768); }
 __device__ __forceinline__ cx sadd(cx a, cx b) { return {sadd16(a.r, b.r), sadd16(a.i, b.i)}; }
 __device__ __forceinline__ cx ssub(cx a, cx b) { return {sadd16(a.r, -b.r), sadd16(a.i, -b.i)}; }
+// The butterflies are bound by the integer ALU pipe (SHF / VIMNMX / PRMT / LOP3: 87 % busy in ncu, FMA pipe 15 %).  Issuing the arithmetic shifts as IMAD.HI
+// (x * 2^(32-n) >> 32) to move them to the FMA pipe was measured and is SLOWER (49.3 -> 47.0 M IDFT-4096/s for the >> 15 alone, 40.4 M with the sign
+// extensions too): IMAD.HI does not issue at the IMAD rate.  Plain shifts stay.
 __device__ __forceinline__ int sra15(unsigned v) { return ((int)v) >> 15; }
 __device__ __forceinline__ cx unpack(unsigned w) { return {(int)(short)(w & 0xFFFFu), (int)(short)(w >> 16)}; }
 // both components are int16 values: cvt.pack.sat (one I2IP) packs them, the saturation never acts

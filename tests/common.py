@@ -104,19 +104,37 @@ def oracle_pusch_transmit(oracle, P, A, Qm, rb_start, rb_size, nb_rx, slot, rnti
     return payload, frame, est, dict(C=C_, K=K, Z=Z, F=F, E=E, G=G)
 
 
-def oracle_pusch_receive(oracle, P, info, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, frame, est=None, max_iter=8, dmrs_id=55):
-    """The receive chain with oracle functions: OFDM demod, level, inner receiver, descrambling, de-interleaving, rate recovery,
-    decoder-input packing (nr_ulsch_decoding.c:195-210), decoding with CRC24B stop.  Returns (tb bytes, iterations, llr16, log2_maxh)."""
+def oracle_pusch_receive(oracle, P, info, Qm, rb_start, rb_size, nb_rx, slot, rnti, nid, rot, frame, est=None, max_iter=8, dmrs_id=55, n_layers=1, cdm=2):
+    """The receive chain with oracle functions: OFDM demod, channel estimation (every DMRS port), level, inner receiver (one layer: MRC; two layers: the MMSE
+    receiver with the estimator's max_ch / nvar, nr_ulsch_demodulation.c:1470-1524, and layer de-mapping :1422-1428), descrambling, de-interleaving, rate
+    recovery, decoder-input packing (nr_ulsch_decoding.c:195-210), decoding with CRC24B stop.  Returns (tb bytes, iterations, llr16, log2_maxh)."""
     from oracle.bindings import PuschParms
     from openairinterface5g_b200 import transport as T
     N = P.N
     rxF = np.stack([oracle.ofdm_rx_slot(N, P.mu, P.nb_rb, slot, P.divisor, 0, rot.reshape(-1), frame[a]).reshape(14, N, 2) for a in range(nb_rx)])
+    max_ch, nvar = 0, 0
     if est is None:                                                          # estimate from the DMRS symbol (nr_pusch_channel_estimation)
         from oracle.bindings import ChestParms
-        est, _ = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, P.first_carrier_offset, 0, dmrs_id), rxF)
-    PP = PuschParms(N, nb_rx, rb_start, 0, rb_size, P.first_carrier_offset, Qm, 1 << 2, 0, 2)
-    shift, _ = oracle.pusch_log2_maxh(PP, 0, 2, rxF, est)
-    llr = np.concatenate([oracle.pusch_inner_rx_symbol(PP, s, 2, shift, rxF, est)[0] for s in range(14) if s != 2])
+        ests = []
+        for p in range(n_layers):
+            e, st = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, 2, p, rb_start, 0, rb_size, P.first_carrier_offset, 0, dmrs_id), rxF)
+            ests.append(e); max_ch = max(max_ch, int(st[0])); nvar += int(st[1]) & 0xFFFFFFFF
+        est = np.concatenate(ests)                                          # ul_ch_estimates[p * nb_rx + aarx]
+        nvar //= 14 * n_layers * nb_rx
+    PP = PuschParms(N, nb_rx, rb_start, 0, rb_size, P.first_carrier_offset, Qm, 1 << 2, 0, cdm)
+    if n_layers == 1:
+        shift, _ = oracle.pusch_log2_maxh(PP, 0, 2, rxF, est)
+        llr = np.concatenate([oracle.pusch_inner_rx_symbol(PP, s, 2, shift, rxF, est)[0] for s in range(14) if s != 2])
+    else:
+        shift, _ = oracle.pusch_log2_maxh_2l(PP, 0, 2, max_ch, rxF, est)
+        out = []
+        for s in range(14):
+            v = oracle.pusch_nb_re(PP, s)
+            if v == 0:
+                continue
+            l2, _ = oracle.pusch_inner_rx_symbol_2l(PP, s, 2, shift, nvar, rxF, est)
+            out.append(np.stack([l2[0].reshape(v, Qm), l2[1].reshape(v, Qm)], axis=1).reshape(-1))
+        llr = np.concatenate(out)
     llr = oracle.unscramble_llr(llr, 0, nid, rnti)
     C_, K, Z, F, E = info["C"], info["K"], info["Z"], info["F"], info["E"]
     R = T.nr_get_R_ldpc_decoder(0, E[0], 1, Z)[0]

@@ -26,13 +26,13 @@ def test_pusch_slot_roundtrip(ldpc, oracle, cfg):
     assert np.array_equal(got[:payload.size], payload)
     assert int(tbcrc.cpu()[0]) == 0
     assert int(chain.level.cpu()[8]) > 0
-    if cfg and cfg.get("n_layers", 1) == 1:
-        # the same slot through the oracle-only chain: LLRs, iteration counts and the transport block must agree bit for bit
+    if cfg:
+        # the same slot through the oracle-only chain (one and two layers): LLRs, iteration counts and the transport block must agree bit for bit
         from common import oracle_pusch_receive
         info = dict(C=chain.C, K=chain.K, Z=chain.Z, F=chain.F, E=[int(e) for e in chain.E.cpu()])
         frame = rxdata.cpu().numpy().reshape(chain.nb_rx, -1)
         tb_o, its_o, llr_o, shift_o = oracle_pusch_receive(oracle, chain.P, info, chain.Qm, chain.rb_start, chain.rb_size, chain.nb_rx, chain.slot,
-                                                           chain.rnti, chain.nid, chain.rot, frame, None)
+                                                           chain.rnti, chain.nid, chain.rot, frame, None, n_layers=chain.nl, cdm=chain.cdm)
         assert shift_o == int(chain.level.cpu()[8])
         assert np.array_equal(chain.llr16.cpu().numpy(), llr_o)
         assert np.array_equal(it, its_o) and np.array_equal(got[:tb_o.size], tb_o)

@@ -20,7 +20,9 @@ def main():
     raw = list(csv.reader(open(sys.argv[1])))
     n_cb = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
     d = dict(zip(raw[0], raw[2]))
-    f = lambda k: float(d[k].replace(",", ""))
+    unit = dict(zip(raw[0], raw[1]))                 # the raw page prints byte counts in scaled units ("Mbyte")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    f = lambda k: float(d[k].replace(",", "")) * scale.get(unit.get(k, ""), 1.0)
     cyc = f("sm__cycles_active.avg") if "sm__cycles_active.avg" in d else f("sm__cycles_elapsed.max")
     alu = f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
     out = {"kernel": d.get("Kernel Name", "ldpc_decode_packed_kernel"), "launch": f"{n_cb} code blocks, BG1 Z=384 R13, 8 iterations (bench.py under ncu --set full)",
@@ -30,7 +32,7 @@ def main():
            "lsu_pipe_pct": f("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
            "sm_cycles_active": cyc, "warp_inst_per_launch": int(f("smsp__inst_executed.sum")),
            "alu_pipe_warp_inst_per_cb": alu / 100.0 * cyc * 148 * 4 * 0.5 / n_cb,
-           "gpu_time_us": f("gpu__time_duration.sum"),
+           "gpu_time_us": f("gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(unit.get("gpu__time_duration.sum", "us"), 1.0),
            "kernel_source_sha1": kernel_source_sha1(),
            "source": sys.argv[4] if len(sys.argv) > 4 else os.path.basename(sys.argv[1]),
            "note": "alu_pipe_warp_inst_per_cb = sm__inst_executed_pipe_alu (% of peak, active cycles) x active cycles x 148 SMs x 4 schedulers x 0.5 inst/cycle / blocks"}
