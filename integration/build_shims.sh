@@ -21,7 +21,7 @@ LIB="-L$ROOT/openairinterface5g_b200 -l:libldpc_b200.so"
 gcc $F $INC $DEFS $HERE/oai_shim_pusch_chest.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_chest.so
 gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_chest.c $ROOT/oracle/ref_harness_chest.c $HERE/oai_shim_pusch_chest.c \
     $R/openair1/PHY/NR_REFSIG/nr_dmrs_rx.c $R/openair1/PHY/NR_REFSIG/nr_gold.c $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/cmult_sv.c \
-    $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -o $W/libshimtest_chest.so
+    $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/NR_REFSIG/ul_ref_seq_nr.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -o $W/libshimtest_chest.so
 # the UE-side twin: nr_pdsch_channel_estimation
 gcc $F $INC $DEFS $HERE/oai_shim_pdsch_chest.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_uechest.so
 gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_uechest.c $ROOT/oracle/ref_harness_uechest.c $HERE/oai_shim_pdsch_chest.c \

@@ -219,6 +219,25 @@ class Oracle:
         self.lib.orc_pdsch_channel_estimation(C.byref(P), x.ctypes.data_as(C.c_void_p), est.ctypes.data_as(C.c_void_p))
         return est.reshape(P.nb_rx, 14, P.fft_size, 2)
 
+    # ---- transform precoding (DFT-s-OFDM): low-PAPR DMRS for the estimator, frequency equalisation + nr_idft in the one-layer inner receiver
+    def lowpapr_seq(self, u, v, M_ZC, scaling=32767):
+        out = np.zeros(2 * M_ZC, np.int16)
+        rc = self.lib.orc_lowpapr_seq(u, v, M_ZC, scaling, out.ctypes.data_as(C.c_void_p))
+        return out if rc == 0 else None
+
+    def chest_set_lowpapr(self, seq):
+        """seq: the 6 * rb_size c16 low-PAPR sequence the estimator correlates with from now on; None switches back to the Gold-sequence DMRS."""
+        self._lowpapr = None if seq is None else np.ascontiguousarray(seq, dtype=np.int16)
+        self.lib.orc_chest_set_lowpapr(None if seq is None else self._lowpapr.ctypes.data_as(C.c_void_p))
+
+    def pusch_set_transform_precoding(self, on):
+        self.lib.orc_pusch_set_transform_precoding(int(on))
+
+    def nr_idft(self, z, M):
+        y = np.ascontiguousarray(z, dtype=np.int16).copy()
+        rc = self.lib.orc_nr_idft(y.ctypes.data_as(C.c_void_p), M)
+        return y if rc == 0 else None
+
     # ---- single-layer PUSCH inner receiver
     def pusch_nb_re(self, P, symbol):
         return int(self.lib.orc_pusch_nb_re(C.byref(P), symbol))
@@ -531,10 +550,25 @@ class Reference:
         return o[:n * Qm].copy()
 
     # ---- scrambling + QAM mapper of the reference (libref_mod.so: nr_scrambling.c, nr_modulation.c, nr_gen_mod_table.c)
-    def pusch_channel_estimation(self, P, rxdataF, n_rb_ul, chest_freq=0, dmrs_type=0):
+    def _chest(self):
         if not hasattr(self, "_chestlib"):
             self._chestlib = C.CDLL(os.path.join(REFDIR, "libref_chest.so"))
             assert self._chestlib.refh_chest_init(os.path.join(REFDIR, "libref_dfts.so").encode()) == 0
+        return self._chestlib
+
+    def lowpapr_seq(self, u, v, n_re):
+        """gNB_dmrs_lowpaprtype1_sequence[u][v][index(n_re)] of the compiled reference (ul_ref_seq_nr.c), None when n_re is not 6 * 2^a 3^b 5^c."""
+        out = np.zeros(2 * n_re, np.int16)
+        return out if self._chest().refh_lowpapr_seq(u, v, n_re, out.ctypes.data_as(C.c_void_p)) >= 0 else None
+
+    def chest_set_transform_precoding(self, on, u=0, v=0):
+        self._chest().refh_chest_set_transform_precoding(int(on), u, v)
+
+    def pusch_set_transform_precoding(self, on):
+        assert self._pusch().refh_pusch_set_transform_precoding(int(on), os.path.join(REFDIR, "libref_dfts.so").encode()) == 0
+
+    def pusch_channel_estimation(self, P, rxdataF, n_rb_ul, chest_freq=0, dmrs_type=0):
+        self._chest()
         prm = np.array([P.fft_size, P.nb_rx, n_rb_ul, P.slot, P.symbol, P.port, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.scid,
                         P.dmrs_scrambling_id, dmrs_type, chest_freq], dtype=np.int32)
         x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy()

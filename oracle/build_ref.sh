@@ -66,11 +66,11 @@ gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_ofdm.c $R/openair1/PHY/MOD
     -lm -ldl -o libref_ofdm.so || echo "libref_ofdm.so: FAILED"
 # PUSCH inner receiver: ref_harness_pusch.c textually includes nr_ulsch_demodulation.c (its per-symbol functions are static)
 gcc $F $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pusch.c $HERE/ref_harness_pusch.c $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_llr_computation.c \
-    $R/openair1/PHY/TOOLS/simde_operations.c $R/openair1/PHY/TOOLS/log2_approx.c -lm -o libref_pusch.so || echo "libref_pusch.so: FAILED"
+    $R/openair1/PHY/TOOLS/simde_operations.c $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/NR_ESTIMATION/nr_freq_equalization.c -lm -ldl -o libref_pusch.so || echo "libref_pusch.so: FAILED"
 # PUSCH channel estimation (nr_common.c needs <limits.h> for UINT_MAX; dft/idft are bound to libref_dfts.so at run time)
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_chest.c $HERE/ref_harness_chest.c $R/openair1/PHY/NR_ESTIMATION/nr_ul_channel_estimation.c \
     $R/openair1/PHY/NR_REFSIG/nr_dmrs_rx.c $R/openair1/PHY/NR_REFSIG/nr_gold.c $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/cmult_sv.c \
-    $R/openair1/PHY/TOOLS/log2_approx.c -lm -ldl -o libref_chest.so || echo "libref_chest.so: FAILED"
+    $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/NR_REFSIG/ul_ref_seq_nr.c -lm -ldl -o libref_chest.so || echo "libref_chest.so: FAILED"
 # UE-side PDSCH channel estimation
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_uechest.c $HERE/ref_harness_uechest.c $R/openair1/PHY/NR_UE_ESTIMATION/nr_dl_channel_estimation.c \
     $R/openair1/PHY/NR_REFSIG/nr_dmrs_rx.c $R/openair1/PHY/NR_REFSIG/nr_gold_ue.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/NR_TRANSPORT/nr_sch_dmrs.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c \

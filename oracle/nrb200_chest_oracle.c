@@ -26,8 +26,42 @@ static const int16_t F_MID[16] = {2048, 2048, 2048, 2048, 2048, 2048, 2048, 2048
 static const int16_t F_LAST[16] = {4096, 4096, 4096, 4096, 8192, 8192, 8192, 8192, 0, 0, 0, 0, 0, 0, 0, 0};
 
 /* conjugated DMRS of one symbol: 6 * rb_size c16 (type 1) or 4 * rb_size (type 2) */
+/* Transform precoding: the estimator correlates with the conjugate of the low-PAPR type-1 sequence of (u, v), whatever the port, starting at element 0
+ * whatever rb_start (nr_ul_channel_estimation.c:122-133 -> nr_pusch_lowpaprtype1_dmrs_rx(p = 1000, re_offset = 0), nr_dmrs_rx.c:258-300). */
+static const int16_t *g_lowpapr_seq;
+void orc_chest_set_lowpapr(const int16_t *seq) { g_lowpapr_seq = seq; }
+/* base sequences of TS 38.211 5.2.2 as ul_ref_seq_nr.c:55-196 computes them (double precision, floor): M_ZC = 30 (5.2.2.2, closed form) and M_ZC >= 36
+ * (5.2.2.1, Zadoff-Chu of the largest prime below M_ZC, cyclically extended).  The shorter ones (6, 12, 18, 24) are table look-ups of the specification
+ * (phi tables) and are not restated: returns -1. */
+int orc_lowpapr_seq(int u, int v, int M_ZC, int scaling, int16_t *out)
+{
+  if (M_ZC == 30) {
+    for (int n = 0; n < M_ZC; n++) {
+      const double x = -(M_PI * (u + 1) * (n + 1) * (n + 2)) / (double)31;
+      out[2 * n] = (int16_t)floor(scaling * cos(x)); out[2 * n + 1] = (int16_t)floor(scaling * sin(x));
+    }
+    return 0;
+  }
+  if (M_ZC < 36) return -1;
+  int N_ZC = M_ZC - 1;
+  for (;; N_ZC--) { int pr = 1; for (int d = 2; d * d <= N_ZC; d++) if (N_ZC % d == 0) { pr = 0; break; } if (pr) break; }
+  const double q_overbar = N_ZC * (u + 1) / (double)31;
+  unsigned q = (((int)floor(2 * q_overbar)) & 1) == 0 ? (unsigned)((int)floor(q_overbar + .5) - v) : (unsigned)((int)floor(q_overbar + .5) + v);
+  for (unsigned n = 0; n < (unsigned)M_ZC; n++) {
+    const unsigned m = n % (unsigned)N_ZC;
+    const double x = (double)q * m * (m + 1) / N_ZC;
+    out[2 * n] = (int16_t)floor(scaling * cos(M_PI * x));
+    out[2 * n + 1] = (int16_t)-(int16_t)floor(scaling * sin(M_PI * x));
+  }
+  return 0;
+}
+
 void orc_pusch_dmrs_pilots(const orc_chest_t *p, int16_t *pil)
 {
+  if (g_lowpapr_seq) {
+    for (int k = 0; k < 6 * p->rb_size; k++) { pil[2 * k] = g_lowpapr_seq[2 * k]; pil[2 * k + 1] = (int16_t)-g_lowpapr_seq[2 * k + 1]; }
+    return;
+  }
   static const int wf1[8][2] = {{1, 1}, {1, -1}, {1, 1}, {1, -1}, {1, 1}, {1, -1}, {1, 1}, {1, -1}};
   const uint32_t nid = (uint32_t)p->dmrs_scrambling_id;
   const uint64_t t = ((1ULL << 17) * (uint64_t)(14 * p->slot + p->symbol + 1) * ((nid << 1) + 1) + ((nid << 1) + (uint32_t)p->scid));

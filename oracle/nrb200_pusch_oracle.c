@@ -88,6 +88,53 @@ int orc_pusch_log2_maxh(const orc_pusch_t *p, int meas_symbol, int ch_symbol, co
   return l < 0 ? 0 : l;
 }
 
+/* ---- transform precoding (DFT-s-OFDM), one layer, Qm <= 6: inner_rx :1326-1336 runs nr_freq_equalization (NR_ESTIMATION/nr_freq_equalization.c:37-71, Qm > 2)
+ * and nr_idft (:16-265) on the compensated symbol before the LLRs.
+ *   equalisation: per group of 4 REs, amp = the FIRST int16 of the group's magnitude vector (clipped to 4095), comp = mullo(comp, 4096 / amp) >> 3 for all 8
+ *   int16 of the group (amp == 0: the table entry is 0), magnitudes replaced by the constants 324 (16QAM) / 316, 158 (64QAM);
+ *   nr_idft: conj -> four-way dft(DFT_<M>) with the data in lane 0 -> conj; M = 12: scale 0 then mulhi(9459) << 1; M = 1536 / 3072: idft() in place, no conj.
+ * M = 768 and 2304 reach the single-transform dft768 / the broken dft2304 with four-way data (uninitialised lanes mix in): not reproducible, rejected here. */
+int orc_dft4(int N, const int16_t *in, int16_t *out, int scale);
+int orc_dft(int N, int inverse, const int16_t *in, int16_t *out, int scale);
+static int g_transform_precoding;
+void orc_pusch_set_transform_precoding(int on) { g_transform_precoding = on; }
+static int16_t conj16(int16_t v) { return wrap16(-(int32_t)v); }                 /* sign_epi16 by -1: -32768 stays */
+int orc_nr_idft(int16_t *z, int M)
+{
+  if (M == 1536 || M == 3072) {
+    int16_t *t = malloc(4 * (size_t)M);
+    const int rc = orc_dft(M, 1, z, t, 1);
+    if (rc == 0) memcpy(z, t, 4 * (size_t)M);
+    free(t);
+    return rc;
+  }
+  if (M == 768 || M == 2304 || M < 12) return -1;
+  int16_t *in = calloc(16 * (size_t)M, 1), *out = calloc(16 * (size_t)M, 1);
+  for (int i = 0; i < M; i++) { in[8 * i] = z[2 * i]; in[8 * i + 1] = conj16(z[2 * i + 1]); }
+  const int rc = orc_dft4(M, in, out, M == 12 ? 0 : 1);
+  if (rc == 0)
+    for (int i = 0; i < M; i++) {
+      int16_t r = out[8 * i], q = out[8 * i + 1];
+      if (M == 12) { r = wrap16(((r * 9459) >> 16) << 1); q = wrap16(((q * 9459) >> 16) << 1); }
+      z[2 * i] = r; z[2 * i + 1] = conj16(q);
+    }
+  free(in); free(out);
+  return rc;
+}
+static void freq_equalization(int16_t *comp, int16_t *ma, int16_t *mb, int M, int Qm)
+{
+  for (int g = 0; g < (M >> 2); g++) {
+    int amp = ma[8 * g];
+    if (amp > 4095) amp = 4095;
+    const int inv = amp > 0 ? 4096 / amp : 0;                                    /* amp < 0 indexes before nr_inv_ch[] in the reference: undefined there */
+    for (int k = 0; k < 8; k++) {
+      comp[8 * g + k] = (int16_t)(wrap16(comp[8 * g + k] * inv) >> 3);
+      if (Qm == 4) ma[8 * g + k] = 324;
+      else if (Qm == 6) { ma[8 * g + k] = 316; mb[8 * g + k] = 158; }
+    }
+  }
+}
+
 /* One symbol of inner_rx, one layer.  Outputs: llr (valid_re * Qm int16), comp/maga/magb/magc (buffer_length c16 each, may be NULL). */
 int orc_pusch_inner_rx_symbol(const orc_pusch_t *p, int symbol, int ch_symbol, int output_shift, const int16_t *rxdataF, const int16_t *ch_est,
                               int16_t *llr, int16_t *comp_out)
@@ -115,10 +162,15 @@ int orc_pusch_inner_rx_symbol(const orc_pusch_t *p, int symbol, int ch_symbol, i
       if (Qm > 6) { const int16_t v = mulhrs16(m, ampc); mc[2 * i] = wrap16(mc[2 * i] + v); mc[2 * i + 1] = wrap16(mc[2 * i + 1] + v); }
     }
   }
-  orc_ulsch_llr(Qm, comp, ma, mb, mc, llr, (uint32_t)valid);
+  int rc = valid;
+  if (g_transform_precoding && Qm <= 6) {
+    if (Qm > 2) freq_equalization(comp, ma, mb, valid, Qm);
+    if (orc_nr_idft(comp, valid) != 0) rc = -1;
+  }
+  if (rc >= 0) orc_ulsch_llr(Qm, comp, ma, mb, mc, llr, (uint32_t)valid);
   if (comp_out) memcpy(comp_out, comp, 4 * (size_t)blen);
   free(rx); free(ch); free(comp); free(ma); free(mb); free(mc);
-  return valid;
+  return rc;
 }
 
 /* ---- two layers, MMSE receiver (Qm >= 6): nr_ulsch_channel_compensation per layer + nr_ulsch_mmse_2layers (:870-1260) with its helpers

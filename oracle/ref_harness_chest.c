@@ -27,6 +27,26 @@ int refh_chest_init(const char *dfts_so)
   return 0;
 }
 
+/* transform precoding (DFT-s-OFDM): the estimator then correlates with the low-PAPR type-1 sequence of group u, base sequence v
+ * (nr_ul_channel_estimation.c:122-133) instead of the Gold-sequence DMRS.  The sequences come from the reference's own generator
+ * (ul_ref_seq_nr.c, compiled in). */
+#include "PHY/NR_REFSIG/ul_ref_seq_nr.h"
+static int g_tp_on, g_tp_u, g_tp_v;
+void refh_chest_set_transform_precoding(int on, int u, int v)
+{
+  generate_lowpapr_typ1_refsig_sequences(SHRT_MAX);
+  g_tp_on = on; g_tp_u = u; g_tp_v = v;
+}
+/* the 2 * n_re int16 of gNB_dmrs_lowpaprtype1_sequence[u][v][index(n_re)]; returns the index or -1 (n_re not of the form 6 * 2^a 3^b 5^c) */
+int refh_lowpapr_seq(int u, int v, int n_re, int16_t *out)
+{
+  generate_lowpapr_typ1_refsig_sequences(SHRT_MAX);
+  const int idx = get_index_for_dmrs_lowpapr_seq((int16_t)n_re);
+  if (idx < 0 || !gNB_dmrs_lowpaprtype1_sequence[u][v][idx]) return -1;
+  memcpy(out, gNB_dmrs_lowpaprtype1_sequence[u][v][idx], 4 * (size_t)n_re);
+  return idx;
+}
+
 enum { C_N, C_NB_RX, C_N_RB_UL, C_SLOT, C_SYMBOL, C_PORT, C_RB_START, C_BWP_START, C_RB_SIZE, C_FCO, C_SCID, C_DMRS_ID, C_DMRS_TYPE, C_CHEST_FREQ, C_COUNT };
 
 /* rxdataF: [nb_rx][14*N] c16 (the slot).  ul_ch_est out: [nb_rx][14*N] c16 (only symbol `symbol` is written).
@@ -72,7 +92,8 @@ int refh_pusch_chest(const int32_t *p, const int16_t *rxdataF, int16_t *ul_ch_es
   memset(&pdu, 0, sizeof(pdu));
   pdu.rb_size = p[C_RB_SIZE]; pdu.rb_start = p[C_RB_START]; pdu.bwp_start = p[C_BWP_START];
   pdu.scid = p[C_SCID]; pdu.ul_dmrs_scrambling_id = p[C_DMRS_ID]; pdu.dmrs_config_type = p[C_DMRS_TYPE];
-  pdu.transform_precoding = transformPrecoder_disabled;
+  pdu.transform_precoding = g_tp_on ? transformPrecoder_enabled : transformPrecoder_disabled;
+  pdu.dfts_ofdm.low_papr_group_number = (uint8_t)g_tp_u; pdu.dfts_ofdm.low_papr_sequence_number = (uint8_t)g_tp_v;
   int max_ch = 0;
   uint32_t nvar = 0;
   const unsigned short k0 = ((p[C_RB_START] + p[C_BWP_START]) * 12 + p[C_FCO]) % N;

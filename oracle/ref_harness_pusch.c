@@ -5,6 +5,29 @@
  * nr_ulsch_channel_level with the few fields of PHY_VARS_gNB, NR_gNB_PUSCH, nfapi_nr_pusch_pdu_t and NR_DL_FRAME_PARMS they read. */
 #include "PHY/NR_TRANSPORT/nr_ulsch_demodulation.c"
 
+/* transform precoding: inner_rx then runs nr_freq_equalization (Qm > 2) and nr_idft on the compensated symbol (:1326-1336); dft / idft are bound to
+ * the compiled reference libref_dfts.so */
+#include <dlfcn.h>
+void nr_init_fde(void);
+static int g_tp_on;
+int refh_pusch_set_transform_precoding(int on, const char *dfts_so)
+{
+  static int bound;
+  if (on && !bound) {
+    void *h = dlopen(dfts_so, RTLD_NOW | RTLD_LOCAL);
+    if (!h) { fprintf(stderr, "refh_pusch_set_transform_precoding: %s\n", dlerror()); return -1; }
+    int (*autoinit)(void) = (int (*)(void))dlsym(h, "dfts_autoinit");
+    dft = (dftfunc_t)dlsym(h, "dft");
+    idft = (idftfunc_t)dlsym(h, "idft");
+    if (!autoinit || !dft || !idft) return -2;
+    autoinit();
+    nr_init_fde();
+    bound = 1;
+  }
+  g_tp_on = on;
+  return 0;
+}
+
 enum { P_N, P_NB_RX, P_NB_LAYER, P_RB_START, P_BWP_START, P_RB_SIZE, P_FCO, P_QM, P_SYMBOL, P_DMRS_SYMBOL, P_DMRS_POS, P_CDM_NO_DATA, P_DMRS_TYPE,
        P_SHIFT, P_NVAR, P_VALID_RE, P_COUNT };
 
@@ -16,10 +39,11 @@ static void fill(const int32_t *p, NR_DL_FRAME_PARMS *fp, nfapi_nr_pusch_pdu_t *
   fp->first_carrier_offset = p[P_FCO];
   fp->nb_antennas_rx = p[P_NB_RX];
   fp->symbols_per_slot = 14;
+  fp->N_RB_UL = 275;                                   /* only read by an assertion of nr_freq_equalization */
   pdu->rb_start = p[P_RB_START]; pdu->bwp_start = p[P_BWP_START]; pdu->rb_size = p[P_RB_SIZE];
   pdu->qam_mod_order = p[P_QM]; pdu->nrOfLayers = p[P_NB_LAYER];
   pdu->ul_dmrs_symb_pos = p[P_DMRS_POS]; pdu->dmrs_config_type = p[P_DMRS_TYPE]; pdu->num_dmrs_cdm_grps_no_data = p[P_CDM_NO_DATA];
-  pdu->transform_precoding = transformPrecoder_disabled;
+  pdu->transform_precoding = g_tp_on ? transformPrecoder_enabled : transformPrecoder_disabled;
 }
 
 /* One OFDM symbol through inner_rx.  rxdataF: [nb_rx][14*N] c16.  ch_est: [nb_layer*nb_rx][14*N] c16 (ul_ch_estimates layout).

@@ -211,3 +211,30 @@ def test_pdsch_tx_precoding_golden(oracle):
         pm = int(g[f"tx_pm{i}"][0])
         P.set_precoding(pm, g[f"tx_w{i}"] if pm else None)
         assert np.array_equal(oracle.pdsch_tx_slot(P, g[f"tx_bits{i}"]), g[f"tx_out{i}"]), i
+
+
+def test_transform_precoding_golden(oracle):
+    """DFT-s-OFDM: computed low-PAPR sequences, the estimator with low-PAPR pilots and the one-layer inner receiver with nr_freq_equalization + nr_idft,
+    against vectors of the compiled reference (tools/gen_golden_tp.py)."""
+    from oracle.bindings import ChestParms, PuschParms
+    g = _load("transform_precoding.npz")
+    for M, u in ((30, 4), (36, 0), (150, 17), (1620, 29)):
+        assert np.array_equal(oracle.lowpapr_seq(u, 0, M), g[f"seq_{M}_u{u}"]), (M, u)
+    assert oracle.lowpapr_seq(0, 0, 24) is None                             # table-driven lengths are the caller's (see the header)
+    for i in range(3):
+        P = ChestParms(*[int(x) for x in g[f"chest_par{i}"]])
+        oracle.chest_set_lowpapr(g[f"chest_seq{i}"])
+        try:
+            est, st = oracle.pusch_channel_estimation(P, g["rx"])
+        finally:
+            oracle.chest_set_lowpapr(None)
+        assert np.array_equal(st, g[f"chest_state{i}"]) and np.array_equal(est[:, P.symbol], g[f"chest_est{i}"]), i
+    oracle.pusch_set_transform_precoding(1)
+    try:
+        for i in range(5):
+            P = PuschParms(*[int(x) for x in g[f"rx_par{i}"]])
+            symbol, shift = [int(x) for x in g[f"rx_sym{i}"]]
+            llr, comp = oracle.pusch_inner_rx_symbol(P, symbol, 2, shift, g["rx"], g["h"])
+            assert np.array_equal(llr, g[f"rx_llr{i}"]) and np.array_equal(comp[:24 * P.rb_size], g[f"rx_comp{i}"]), i
+    finally:
+        oracle.pusch_set_transform_precoding(0)

@@ -661,3 +661,46 @@ def test_decode_all_driver_matches_single_calls(oracle, reference):
     for i in range(6):
         it_r, out_r = reference.decode(1, 384, 23, 8, llr[i], use_crc=1, crc_len_bits=K, crc_type=1)
         assert its[i] == it_r and np.array_equal(out[i], out_r)
+
+
+def test_transform_precoding_sequences_chest_and_inner_rx(oracle, reference):
+    """DFT-s-OFDM (transform precoding enabled): every computed low-PAPR type-1 sequence (M_ZC = 30 and >= 36, 3 groups), nr_pusch_channel_estimation with the
+    low-PAPR pilots, and inner_rx with nr_freq_equalization + nr_idft (incl. M = 12 with its own scaling and M = 1536 / 3072 through idft())."""
+    from oracle.bindings import ChestParms, PuschParms
+    n = 0
+    for k in range(5, 274):
+        for u in (0, 7, 29):
+            a = reference.lowpapr_seq(u, 0, 6 * k)
+            if a is not None:
+                assert np.array_equal(a, oracle.lowpapr_seq(u, 0, 6 * k)), (k, u)
+                n += 1
+    assert n == 3 * 49
+    rng = np.random.default_rng(3)
+    carrier = {1024: 52, 2048: 106, 4096: 273}
+    for N, nb_rx, rb_start, nb, slot, u in ((2048, 2, 10, 25, 3, 5), (4096, 4, 0, 270, 1, 0), (1024, 1, 7, 6, 0, 29), (2048, 2, 0, 5, 2, 11), (1024, 2, 3, 2, 4, 3)):
+        rx = rng.integers(-3000, 3001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        P = ChestParms(N, nb_rx, slot, 2, 0, rb_start, 0, nb, N - 6 * carrier[N], 0, 55)
+        reference.chest_set_transform_precoding(1, u, 0)
+        oracle.chest_set_lowpapr(reference.lowpapr_seq(u, 0, 6 * nb))
+        try:
+            e_r, st_r, _ = reference.pusch_channel_estimation(P, rx, carrier[N])
+            e_o, st_o = oracle.pusch_channel_estimation(P, rx)
+        finally:
+            reference.chest_set_transform_precoding(0)
+            oracle.chest_set_lowpapr(None)
+        assert np.array_equal(e_r, e_o) and np.array_equal(st_r, st_o[:5]), (N, nb)
+    reference.pusch_set_transform_precoding(1)
+    oracle.pusch_set_transform_precoding(1)
+    try:
+        for N, nb_rx, rb_start, nb, Qm in ((2048, 2, 10, 25, 6), (4096, 4, 0, 270, 4), (1024, 1, 7, 6, 2), (2048, 2, 0, 5, 6), (1024, 2, 3, 1, 4), (4096, 2, 5, 128, 6),
+                                          (4096, 1, 0, 256, 2), (1024, 2, 3, 2, 6), (4096, 2, 0, 135, 4)):
+            P = PuschParms(N, nb_rx, rb_start, 0, nb, N - 6 * carrier[N], Qm, 1 << 2, 0, 2)
+            rx = rng.integers(-2000, 2001, size=(nb_rx, 14, N, 2)).astype(np.int16)
+            h = rng.integers(-1500, 1501, size=(nb_rx, 14, N, 2)).astype(np.int16)
+            for sym, shift in ((0, 7), (5, 9)):
+                l_o, c_o = oracle.pusch_inner_rx_symbol(P, sym, 2, shift, rx, h)
+                l_r, c_r = reference.pusch_inner_rx_symbol(P, sym, 2, shift, rx, h, 12 * nb)
+                assert np.array_equal(l_o, l_r) and np.array_equal(c_o, c_r[:c_o.size]), (N, nb, Qm, sym)
+    finally:
+        reference.pusch_set_transform_precoding(0)
+        oracle.pusch_set_transform_precoding(0)
