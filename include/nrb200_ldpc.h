@@ -285,8 +285,14 @@ typedef struct nrb200_pusch_rx_s {
                                              * nvar / (nr_of_symbols * nrOfLayers * nb_rx), nr_ulsch_demodulation.c:1470-1524) and the two fields above are ignored:
                                              * estimator -> level -> receiver then run stream ordered with no host round trip (and can be captured in a CUDA graph). */
   uint32_t est_state_ports;                 /* number of ports in d_est_state (1 or 2) */
-  uint32_t reserved0;
+  uint32_t transform_precoding;             /* 1: pusch_pdu->transform_precoding == transformPrecoder_enabled (DFT-s-OFDM).  For one layer and qam_mod_order <= 6 the
+                                             * receiver then equalises the compensated symbol (nr_freq_equalization, Qm > 2) and takes the 12 * rb_size point transform
+                                             * of nr_idft across it before the LLRs (nr_ulsch_demodulation.c:1326-1336, :16-265); two layers and 256QAM are untouched,
+                                             * as in the reference.  Needs num_dmrs_cdm_grps_no_data = 2 (no data on DMRS symbols) and 12 * rb_size one of nr_idft's
+                                             * sizes other than 768 and 2304 (the reference's own output is not reproducible there): anything else returns -4. */
+  uint64_t d_tp_scratch;                    /* _dev, transform precoding: DEVICE scratch of nrb200_pusch_tp_scratch_bytes() bytes (the host entry point has its own) */
 } nrb200_pusch_rx_t;
+uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d);
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
 /* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
 int32_t nrb200_pusch_log2_maxh_dev(const nrb200_pusch_rx_t *d, const int16_t *d_ul_ch_estimates, int32_t *d_out, void *stream);
@@ -299,8 +305,8 @@ int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, const int16_t *rx
 /* ---- Part 7: PUSCH channel estimation, DMRS configuration type 1, frequency-domain interpolation -------------------------
  * replaces nr_pusch_channel_estimation (nr_ul_channel_estimation.c:67-243) for one DMRS symbol and one antenna port with
  * transform precoding disabled and chest_freq == 0: DMRS generation, least-squares estimate, delay estimation (IDFT peak, running
- * maximum across the rx antennas), delay compensation, 16-tap interpolation, delay reversal, noise variance.  Other configurations
- * (low-PAPR DMRS, i.e. transform precoding) return -4: the library never falls back.  DMRS type 2 and chest_freq == 1: see the last two fields.
+ * maximum across the rx antennas), delay compensation, 16-tap interpolation, delay reversal, noise variance.  Configurations outside the
+ * ones described here return -4: the library never falls back.  DMRS type 2, chest_freq == 1 and transform precoding (low-PAPR DMRS): see the last fields.
  * rxdataF [nb_rx][14][fft_size] c16; ul_ch_estimates [nb_rx][14][fft_size] c16: symbol `symbol` of every antenna is rewritten.
  * state (5 int32): max_ch, nvar, est_delay, delay_max_pos, delay_max_val -- what the reference returns through *max_ch, *nvar and delay_t. */
 typedef struct nrb200_pusch_chest_s {
@@ -321,7 +327,16 @@ typedef struct nrb200_pusch_chest_s {
                                              * and, with pdsch_ue = 1, for the UE's (NFAPI_NR_DMRS_TYPE2_linear_interp / TYPE1_average_prb / TYPE2_average_prb,
                                              * nr_dl_channel_estimation.c:1378-1612; type 2: ports 0..5).  chest_freq = 1 needs rb_size >= 2 and, for the gNB's type 2,
                                              * slot % 4 == 0: the reference reads slot-ring position 0 there.  Anything else returns -4. */
+  uint32_t transform_precoding;             /* 1: pusch_pdu->transform_precoding == transformPrecoder_enabled: the estimator correlates with the conjugate of the
+                                             * low-PAPR type-1 sequence below instead of the Gold-sequence DMRS, from element 0 whatever rb_start and with w = +1
+                                             * whatever the port (nr_ul_channel_estimation.c:122-133, nr_dmrs_rx.c:258-300).  DMRS type 1, gNB only. */
+  uint64_t lowpapr_seq;                     /* transform precoding: address of the 6 * rb_size c16 of gNB_dmrs_lowpaprtype1_sequence[u][v][index] -- DEVICE memory for
+                                             * the _dev entry point, host memory for _host.  nrb200_lowpapr_sequence_host() computes it for 6 * rb_size >= 30. */
 } nrb200_pusch_chest_t;
+/* base sequence r_{u,v} of TS 38.211 5.2.2 as the reference generates it (ul_ref_seq_nr.c:55-196: double precision, floor(scaling * cos / sin)), n_re = 30 or
+ * >= 36 elements, {re, im} int16 each.  The lengths 6, 12, 18 and 24 are look-ups in the specification's phi tables and stay with the caller (OAI builds all of
+ * them at start-up: generate_lowpapr_typ1_refsig_sequences); returns -4 for them.  Host arithmetic, no GPU needed. */
+int32_t nrb200_lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq);
 /* the 6 * rb_size conjugated DMRS symbols {re, im} the estimator correlates with (nr_pusch_dmrs_rx output); host arithmetic, no GPU needed */
 int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots);
 uint64_t nrb200_pusch_chest_scratch_bytes(const nrb200_pusch_chest_t *d);

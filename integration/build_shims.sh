@@ -38,7 +38,7 @@ ls -la $HERE/_build/libnrb200_shim_rx_pdsch.so $W/libshimtest_pdsch.so
 gcc $F $INC $DEFS $HERE/oai_shim_rx_pusch.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_rx_pusch.so
 gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_harness_rxpusch.c $HERE/oai_shim_rx_pusch.c $HERE/oai_shim_pusch_chest.c \
     $R/openair1/PHY/NR_ESTIMATION/nr_measurements_gNB.c $R/openair1/PHY/TOOLS/signal_energy.c $R/openair1/PHY/TOOLS/dB_routines.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c \
-    $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/NR_TRANSPORT/nr_tbs_tools.c \
+    $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/log2_approx.c $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/NR_TRANSPORT/nr_tbs_tools.c $R/openair1/PHY/NR_REFSIG/ul_ref_seq_nr.c \
     $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -Wl,--no-undefined -o $W/libshimtest_rxpusch.so || echo "libshimtest_rxpusch.so: FAILED"
 ls -la $HERE/_build/libnrb200_shim_rx_pusch.so $W/libshimtest_rxpusch.so
 # the RU front end: nr_feptx0 / nr_fep_full -> the slot-level OFDM entry points of libdfts_b200.so

@@ -7,14 +7,15 @@
  *   - LD_PRELOAD=libnrb200_shim_chest.so nr-softmodem ...      (the softmodem is linked -rdynamic, CMakeLists.txt:164)
  * routes every call to the B200 library.  It is compiled against the reference's own headers (integration/build_shims.sh), reads exactly the
  * fields the reference function reads (frame_parms, common_vars.rxdataF, pusch_vars[ul_id].ul_ch_estimates, the PDU) and writes exactly what it
- * writes (the DMRS symbol of ul_ch_estimates for every rx antenna, *max_ch, *nvar, gNB->ulsch[ul_id].delay).  Configurations the library does not
- * serve (transform precoding) abort loudly like any other AssertFatal in this code base: there is no CPU fallback.
+ * writes (the DMRS symbol of ul_ch_estimates for every rx antenna, *max_ch, *nvar, gNB->ulsch[ul_id].delay).  Transform precoding is served with OAI's
+ * own low-PAPR sequence table.  A configuration the library refuses aborts loudly like any other AssertFatal in this code base: there is no CPU fallback.
  * Test: tests/test_gpu_interpose.py drives it through the reference-side caller harness and compares with the pinned oracle. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "PHY/defs_gNB.h"
 #include "PHY/NR_ESTIMATION/nr_ul_estimation.h"
+#include "PHY/NR_REFSIG/ul_ref_seq_nr.h"
 #define NRB200_NO_OAI_LOADER_PROTOTYPES
 #include "nrb200_ldpc.h"
 
@@ -24,10 +25,6 @@ int nr_pusch_channel_estimation(PHY_VARS_gNB *gNB, unsigned char Ns, unsigned sh
   const NR_DL_FRAME_PARMS *fp = &gNB->frame_parms;
   const int N = fp->ofdm_symbol_size, nrx = fp->nb_antennas_rx;
   const int soffset = (Ns & 3) * fp->symbols_per_slot * N;
-  if (pusch_pdu->transform_precoding != transformPrecoder_disabled) {
-    fprintf(stderr, "nrb200 shim: nr_pusch_channel_estimation with transform precoding is not served by libldpc_b200\n");
-    abort();
-  }
   (void)bwp_start_subcarrier;   /* = ((rb_start + bwp_start) * 12 + first_carrier_offset) % N, recomputed by the library from the PDU */
   nrb200_pusch_chest_t d;
   memset(&d, 0, sizeof(d));
@@ -35,6 +32,14 @@ int nr_pusch_channel_estimation(PHY_VARS_gNB *gNB, unsigned char Ns, unsigned sh
   d.rb_start = pusch_pdu->rb_start; d.bwp_start = pusch_pdu->bwp_start; d.rb_size = pusch_pdu->rb_size; d.first_carrier_offset = fp->first_carrier_offset;
   d.scid = pusch_pdu->scid; d.ul_dmrs_scrambling_id = pusch_pdu->ul_dmrs_scrambling_id;
   d.n_ports = 1; d.dmrs_config_type = pusch_pdu->dmrs_config_type; d.chest_freq = gNB->chest_freq;
+  if (pusch_pdu->transform_precoding != transformPrecoder_disabled) {
+    /* DFT-s-OFDM: the low-PAPR type-1 sequence OAI generated at start-up (generate_lowpapr_typ1_refsig_sequences), selected as the reference
+     * selects it (nr_ul_channel_estimation.c:125-131) */
+    const int16_t index = get_index_for_dmrs_lowpapr_seq(pusch_pdu->rb_size * (NR_NB_SC_PER_RB / 2));
+    const int16_t *dmrs_seq = index >= 0 ? gNB_dmrs_lowpaprtype1_sequence[pusch_pdu->dfts_ofdm.low_papr_group_number][pusch_pdu->dfts_ofdm.low_papr_sequence_number][index] : NULL;
+    if (!dmrs_seq) { fprintf(stderr, "nrb200 shim: no low-PAPR DMRS sequence for %d PRBs\n", pusch_pdu->rb_size); abort(); }
+    d.transform_precoding = 1; d.lowpapr_seq = (uint64_t)(uintptr_t)dmrs_seq;
+  }
   /* the library's host entry point takes the slot as [nb_rx][14][N] c16; OAI keeps one buffer per antenna with a 4-slot ring */
   const size_t plane = (size_t)14 * N;
   int16_t *rx = malloc(4 * plane * nrx), *est = malloc(4 * plane * nrx);

@@ -33,8 +33,8 @@ int nr_rx_pusch_tp(PHY_VARS_gNB *gNB, uint8_t ulsch_id, uint32_t frame, uint8_t 
   nfapi_nr_pusch_pdu_t *pdu = &gNB->ulsch[ulsch_id].harq_process->ulsch_pdu;
   NR_gNB_PUSCH *pv = &gNB->pusch_vars[ulsch_id];
   const int N = fp->ofdm_symbol_size, nrx = fp->nb_antennas_rx, nl = pdu->nrOfLayers;
-  if ((pdu->pdu_bit_map & PUSCH_PDU_BITMAP_PUSCH_PTRS) || pdu->transform_precoding != transformPrecoder_disabled || nl < 1 || nl > 2) {
-    fprintf(stderr, "nrb200 shim: nr_rx_pusch_tp: PT-RS / transform precoding / %d layers are not served by libldpc_b200\n", nl);
+  if ((pdu->pdu_bit_map & PUSCH_PDU_BITMAP_PUSCH_PTRS) || nl < 1 || nl > 2) {
+    fprintf(stderr, "nrb200 shim: nr_rx_pusch_tp: PT-RS / %d layers are not served by libldpc_b200\n", nl);
     abort();
   }
   pv->dmrs_symbol = INVALID_VALUE;
@@ -81,6 +81,7 @@ int nr_rx_pusch_tp(PHY_VARS_gNB *gNB, uint8_t ulsch_id, uint32_t frame, uint8_t 
   d.dmrs_config_type = pdu->dmrs_config_type == pusch_dmrs_type1 ? 0 : 1; d.num_dmrs_cdm_grps_no_data = pdu->num_dmrs_cdm_grps_no_data;
   d.log2_maxh = 0xFFFFFFFFu; d.unscramble = 1; d.rnti = pdu->rnti; d.data_scrambling_id = pdu->data_scrambling_id;
   d.nrOfLayers = nl; d.noise_var = nvar; d.max_ch = (uint32_t)max_ch;
+  d.transform_precoding = pdu->transform_precoding == transformPrecoder_enabled;   /* DFT-s-OFDM: equalisation + nr_idft inside the library call (inner_rx :1326-1336) */
   const uint32_t G = nrb200_pusch_num_llr(&d);
   const size_t plane = (size_t)14 * N;
   const int soffset = (slot % RU_RX_SLOT_DEPTH) * fp->symbols_per_slot * N;

@@ -31,6 +31,8 @@ uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d);
 int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d_out9, uint32_t *d_count, cudaStream_t st);
 int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st);
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
+size_t pusch_tp_scratch_bytes(const nrb200_pusch_rx_t &d);
+int lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq);
 int launch_chest_time_avg(uint32_t N, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos, uint32_t rb_size,
                           int16_t *d_est, cudaStream_t st);
 int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil);
@@ -848,8 +850,9 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   const uint32_t n_llr = pusch_num_llr(*d);
   if (n_llr == 0) return -4;
   const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers == 2 ? 2 : 1);
+  const size_t tp_bytes = d->transform_precoding ? pusch_tp_scratch_bytes(*d) : 0;        // the transforms' input / output planes, behind the level slots
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     std::memcpy(w->h_in, rxdataF, plane);
@@ -857,6 +860,7 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
     if (cudaMemcpyAsync(w->d_in, w->h_in, plane + est_plane, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
     nrb200_pusch_rx_t e = *d;
     e.rx_stride = e.ch_stride = 14 * d->fft_size;
+    e.d_tp_scratch = tp_bytes ? (uint64_t)(uintptr_t)((uint8_t *)w->d_aux + 64) : 0;
     const int16_t *d_rx = (const int16_t *)w->d_in, *d_ch = (const int16_t *)((uint8_t *)w->d_in + plane);
     const bool measure = d->log2_maxh == 0xFFFFFFFFu;
     int32_t *d_lvl = (int32_t *)w->d_aux;
@@ -877,7 +881,10 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   return rc;
 }
 
+NRB200_EXPORT uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d) { return d ? pusch_tp_scratch_bytes(*d) : 0; }
+
 // ------------------------------------------------------------------------------------------ PUSCH channel estimation
+NRB200_EXPORT int32_t nrb200_lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq) { return lowpapr_sequence_host(u, v, n_re, scaling, seq); }
 NRB200_EXPORT int32_t nrb200_pusch_dmrs_pilots_host(const nrb200_pusch_chest_t *d, int16_t *pilots) { return d && pilots ? pusch_dmrs_pilots_host(*d, pilots) : -4; }
 
 NRB200_EXPORT uint64_t nrb200_pusch_chest_scratch_bytes(const nrb200_pusch_chest_t *d) { return d ? pusch_chest_scratch_bytes(*d) : 0; }
@@ -929,8 +936,10 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, con
   // [n_ports * nb_rx][N] out
   const size_t sym = (size_t)d->fft_size * 4, row = sym + 16, plane = sym * d->nb_rx, scratch = pusch_chest_scratch_bytes(*d);
   const int tail = d->symbol < 13 ? 4 : 0;
+  const size_t seq_bytes = d->transform_precoding ? (size_t)24 * d->rb_size : 0;     // the caller's low-PAPR sequence travels behind the state
+  if (d->transform_precoding && d->lowpapr_seq == 0) return -4;
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(row * d->nb_rx, plane * np, scratch + 256)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(row * d->nb_rx, plane * np, scratch + 256 + seq_bytes)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     for (uint32_t a = 0; a < d->nb_rx; a++) {
@@ -941,6 +950,11 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, con
     nrb200_pusch_chest_t e = *d;
     e.rx_stride = d->fft_size + 4; e.ch_stride = d->fft_size;                // staged as a one-symbol slot (buffer symbol 0)
     int32_t *d_state = (int32_t *)((uint8_t *)w->d_aux + scratch);
+    if (seq_bytes) {
+      std::memcpy((uint8_t *)w->h_aux + scratch + 256, reinterpret_cast<const void *>((uintptr_t)d->lowpapr_seq), seq_bytes);
+      if (cudaMemcpyAsync((uint8_t *)w->d_aux + scratch + 256, (uint8_t *)w->h_aux + scratch + 256, seq_bytes, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+      e.lowpapr_seq = (uint64_t)(uintptr_t)((uint8_t *)w->d_aux + scratch + 256);
+    }
     rc = launch_pusch_chest(e, (const int16_t *)w->d_in, (int16_t *)w->d_out, w->d_aux, d_state, w->stream, 0, tail);
     if (rc != 0) break;
     if (cudaMemcpyAsync(w->h_out, w->d_out, plane * np, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }

@@ -28,6 +28,7 @@ struct ChestGeom {
   unsigned rx_stride, ch_stride, x2;
   int type2, chest_freq;                    // DMRS configuration type 2 / one average per PRB (the variants below)
   int nushift, tail;                        // variants: (p >> 1) & 1 added to the symbol POINTER; c16 readable beyond the symbol's N (0 on the slot's last symbol)
+  const unsigned *lowpapr;                  // transform precoding: the 6 * nb c16 low-PAPR type-1 sequence (device); pilots = its conjugate, w = +1, index from 0
 };
 constexpr int kChestState = 18;             // int32 per port, see chest_ls_kernel
 
@@ -67,11 +68,17 @@ __global__ void __launch_bounds__(256) chest_ls_kernel(ChestGeom G, const GoldTa
 #pragma unroll
     for (int kl = 0; kl < 2; kl++) {
       const int i = G.dmrs_offset + 2 * n + kl;                            // pilot index in the sequence
-      const unsigned r0 = 2u * (unsigned)i - (w0 << 5);
-      const int b0 = (s_gold[r0 >> 5] >> (r0 & 31u)) & 1u, b1 = (s_gold[(r0 + 1) >> 5] >> ((r0 + 1) & 31u)) & 1u;
-      const int w = (i & 1) ? G.wsign_odd[port] : 1;
-      // conj of the QPSK symbol (nr_rx_mod_table): re = +A for b0 = 0, im = -A for b1 = 0, negated when w = -1
-      const int pr = w * (b0 ? -23170 : 23170), pi = w * (b1 ? 23170 : -23170);
+      int pr, pi;
+      if (G.lowpapr != nullptr) {                                          // nr_pusch_lowpaprtype1_dmrs_rx(p = 1000, re_offset = 0): conj, int16 wrap
+        const unsigned sq = __ldg(G.lowpapr + 2 * n + kl);
+        pr = c_lo(sq); pi = c_wrap16(-c_hi(sq));
+      } else {
+        const unsigned r0 = 2u * (unsigned)i - (w0 << 5);
+        const int b0 = (s_gold[r0 >> 5] >> (r0 & 31u)) & 1u, b1 = (s_gold[(r0 + 1) >> 5] >> ((r0 + 1) & 31u)) & 1u;
+        const int w = (i & 1) ? G.wsign_odd[port] : 1;
+        // conj of the QPSK symbol (nr_rx_mod_table): re = +A for b0 = 0, im = -A for b1 = 0, negated when w = -1
+        pr = w * (b0 ? -23170 : 23170); pi = w * (b1 ? 23170 : -23170);
+      }
       int re = G.k0 + (n << 2) + (kl << 1);
       if (!G.ue) { re += G.delta[port]; re %= G.N; }
       else { re %= G.N; re += G.delta[port]; }                             // UE: the comb offset moves the symbol pointer, it does not wrap (:1689)
@@ -305,7 +312,8 @@ __global__ void __launch_bounds__(256) chest_avg_kernel(ChestGeom G, const GoldT
       else if (!G.ue) { pidx = j == 0 ? min(i, 2) : 4 * j - 1 + i; re = (G.k0 + 12 * j + (i & 1) + 6 * (i >> 1)) % G.N; }
       else { pidx = 4 * j + i; re = (j == 0 ? G.k0 + i : G.k0 + 4 + 20 * (j - 1) + 5 * i) % G.N; }   // the UE's walk (:1541-1575): 4 consecutive, then 5 apart
       int pr, pi;
-      dmrs_conj(T, G.x2, G.dmrs_offset + pidx, G.wsign_odd[0], pr, pi);
+      if (G.lowpapr != nullptr) { const unsigned sq = __ldg(G.lowpapr + pidx); pr = c_lo(sq); pi = c_wrap16(-c_hi(sq)); }
+      else dmrs_conj(T, G.x2, G.dmrs_offset + pidx, G.wsign_odd[0], pr, pi);
       const unsigned y = rx_at(G, rx, re + G.nushift);
       sr += (pr * c_lo(y) - pi * c_hi(y)) >> 15;
       si += (pr * c_hi(y) + pi * c_lo(y)) >> 15;
@@ -394,6 +402,11 @@ static int chest_geom(const nrb200_pusch_chest_t &d, ChestGeom *G)
     G->wsign_odd[q] = (pp & 1) ? -1 : 1;                                    // wf1[p][1]
   }
   G->type2 = d.dmrs_config_type ? 1 : 0; G->chest_freq = d.chest_freq ? 1 : 0;
+  G->lowpapr = nullptr;
+  if (d.transform_precoding) {                                              // NR_SC_FDMA supports type 1 DMRS only (:123); the sequence is the caller's
+    if (d.dmrs_config_type || d.pdsch_ue || d.lowpapr_seq == 0) return -4;
+    G->lowpapr = reinterpret_cast<const unsigned *>((uintptr_t)d.lowpapr_seq);
+  }
   G->nushift = (d.port >> 1) & 1;
   G->tail = d.symbol < 13 ? 4 : 0;
   if (G->type2 || G->chest_freq) {
@@ -419,6 +432,11 @@ int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil)
   ChestGeom G;
   int rc = chest_geom(d, &G);
   if (rc) return rc;
+  if (d.transform_precoding) {                                               // here lowpapr_seq is a HOST address
+    const int16_t *sq = reinterpret_cast<const int16_t *>((uintptr_t)d.lowpapr_seq);
+    for (int k = 0; k < 6 * G.nb; k++) { pil[2 * k] = sq[2 * k]; pil[2 * k + 1] = (int16_t)-sq[2 * k + 1]; }
+    return 0;
+  }
   uint32_t x1 = 1u + (1u << 31), x2 = G.x2;
   x2 = x2 ^ ((x2 ^ (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3)) << 31);
   auto step = [&]() {
@@ -434,6 +452,31 @@ int pusch_dmrs_pilots_host(const nrb200_pusch_chest_t &d, int16_t *pil)
     const int w = (i & 1) ? G.wsign_odd[0] : 1;
     pil[2 * (i - G.dmrs_offset)] = (int16_t)(w * (b0 ? -23170 : 23170));
     pil[2 * (i - G.dmrs_offset) + 1] = (int16_t)(w * (b1 ? 23170 : -23170));
+  }
+  return 0;
+}
+
+// r_{u,v}(n) of TS 38.211 5.2.2 with the reference's arithmetic (ul_ref_seq_nr.c:55-196): length 30 in closed form (5.2.2.2), 36 and longer as the cyclic
+// extension of the Zadoff-Chu sequence of the largest prime below the length (5.2.2.1); double precision, floor.
+int lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq)
+{
+  if (u > 29 || v > 1 || !seq || (n_re != 30 && n_re < 36) || n_re > 12 * 275) return -4;
+  if (n_re == 30) {
+    for (uint32_t n = 0; n < n_re; n++) {
+      const double x = -(M_PI * (u + 1) * (n + 1) * (n + 2)) / (double)31;
+      seq[2 * n] = (int16_t)std::floor(scaling * std::cos(x)); seq[2 * n + 1] = (int16_t)std::floor(scaling * std::sin(x));
+    }
+    return 0;
+  }
+  uint32_t nzc = n_re - 1;
+  for (;; nzc--) { bool pr = true; for (uint32_t q = 2; q * q <= nzc; q++) if (nzc % q == 0) { pr = false; break; } if (pr) break; }
+  const double qb = nzc * (u + 1) / (double)31;
+  const unsigned q = (((int)std::floor(2 * qb)) & 1) == 0 ? (unsigned)((int)std::floor(qb + .5) - (int)v) : (unsigned)((int)std::floor(qb + .5) + (int)v);
+  for (uint32_t n = 0; n < n_re; n++) {
+    const unsigned m = n % nzc;
+    const double x = (double)q * m * (m + 1) / nzc;
+    seq[2 * n] = (int16_t)std::floor(scaling * std::cos(M_PI * x));
+    seq[2 * n + 1] = (int16_t)-(int16_t)std::floor(scaling * std::sin(M_PI * x));
   }
   return 0;
 }

@@ -27,6 +27,7 @@ struct PuschGeom {
   int lvl_amp, lvl_b;              // nr_ulsch_scale_channel constants of the level measurement
   const int *est_state;            // optional (device): the channel estimator's state, 18 int32 per port; replaces nvar / lvl_amp / lvl_b (est_scalars)
   int est_ports, est_div;          // ports in est_state; nr_of_symbols * nrOfLayers * nb_rx
+  int tp_direct;                   // transform precoding with M = 1536 / 3072: plain [symbol][M] layout for idft(), no conjugation
 };
 
 __device__ __forceinline__ int p_sat16(int v) { return max(-32768, min(32767, v)); }
@@ -79,29 +80,49 @@ __device__ __forceinline__ void re_source(const PuschGeom &G, int is_dmrs, int i
   rx_idx = idx; ch_idx = neg + idx;
 }
 
-template <int QM>
+// Transform precoding (DFT-s-OFDM, one layer, Qm <= 6; inner_rx :1326-1336): between the compensation and the LLRs the reference equalises the symbol
+// (nr_freq_equalization, Qm > 2: every group of 4 REs is multiplied by 4096 / amp of the group's FIRST magnitude and shifted by 3, the thresholds become
+// constants) and takes an M-point transform across the symbol's REs (nr_idft: conj -> four-way dft(DFT_M) with the data in lane 0 -> conj; M = 12 has its
+// own scaling, M = 1536 / 3072 go through idft() directly).  The kernel runs twice around the library's own batched transform:
+//   MODE 1: extraction + MRC + equalisation + conj, written into the transform's input layout -- symbol k is lane (k & 3) of four-way call (k >> 2), so
+//           four symbols share one four-way transform instead of using one lane of four (the lanes are independent);
+//   MODE 2: reads the transform's output, undoes the layout, conj, LLRs with the constant thresholds, descrambling.
+// MODE 0 is the ordinary receiver.
+__device__ __forceinline__ size_t tp_slot(const PuschGeom &G, int k, int i)
+{
+  return G.tp_direct ? (size_t)k * G.nb_re + i : (size_t)(k >> 2) * 4 * G.nb_re + 4 * (size_t)i + (k & 3);
+}
+
+template <int QM, int MODE>
 __global__ void __launch_bounds__(256) pusch_rx_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift, const unsigned *__restrict__ rxF,
-                                                       const unsigned *__restrict__ ch, short *__restrict__ llr)
+                                                       const unsigned *__restrict__ ch, short *__restrict__ llr, unsigned *__restrict__ tp)
 {
   __shared__ uint32_t s_gold[(256 * QM) / 32 + 2];
   const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
   const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
   if (i0 >= valid) return;
   const unsigned bit0 = G.llr_off[k] + (unsigned)i0 * QM;          // first LLR (= scrambling bit) index handled by this CTA
-  if (G.unscramble) {
+  if (MODE != 1 && G.unscramble) {
     const unsigned w0 = bit0 >> 5, nw = ((bit0 + 256u * QM + 31u) >> 5) - w0;
     if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
     __syncthreads();
   }
   if (i >= valid) return;
-  const int shift = G.shift_from_dev ? *d_shift : G.shift;
-  int rx_idx, ch_idx;
-  re_source(G, is_dmrs, i, rx_idx, ch_idx);
   constexpr int ampa = QM == 4 ? 20724 : QM == 6 ? 20225 : QM == 8 ? 20106 : 0;     // QAM16_n1 / QAM64_n1 / QAM256_n1 (impl_defs_top.h:205-222)
   constexpr int ampb = QM == 6 ? 10112 : QM == 8 ? 10053 : 0;
   constexpr int ampc = QM == 8 ? 5026 : 0;
   int cr = 0, ci = 0, ma = 0, mb = 0, mc = 0;
-  for (int a = 0; a < G.nb_rx; a++) {
+  if (MODE == 2) {
+    const unsigned z = tp[tp_slot(G, k, i)];
+    cr = p_lo(z); ci = p_hi(z);
+    if (G.nb_re == 12) { cr = p_wrap16(((cr * 9459) >> 16) << 1); ci = p_wrap16(((ci * 9459) >> 16) << 1); }   // DFT_12 is called unscaled: mulhi(9459) << 1 (:41-48)
+    if (!G.tp_direct) ci = p_wrap16(-ci);                                              // conjugate output (:254-257)
+    ma = QM == 4 ? 324 : 316; mb = 158;                                                 // 512 * 2 / sqrt(10); 512 * 4 / sqrt(42), 512 * 2 / sqrt(42)
+  }
+  const int shift = MODE == 2 ? 0 : (G.shift_from_dev ? *d_shift : G.shift);
+  int rx_idx = 0, ch_idx = 0;
+  if (MODE != 2) re_source(G, is_dmrs, i, rx_idx, ch_idx);
+  for (int a = 0; MODE != 2 && a < G.nb_rx; a++) {
     const unsigned y = __ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx);
     const unsigned h = __ldg(ch + (size_t)a * G.ch_stride + (size_t)G.ch_sym[k] * G.N + ch_idx);
     const int hr = p_lo(h), hi = p_hi(h), yr = p_lo(y), yi = p_hi(y), nhi = p_wrap16(-hi);
@@ -114,6 +135,18 @@ __global__ void __launch_bounds__(256) pusch_rx_kernel(PuschGeom G, const GoldTa
       if (QM > 4) mb = p_wrap16(mb + p_mulhrs(m, ampb));
       if (QM > 6) mc = p_wrap16(mc + p_mulhrs(m, ampc));
     }
+  }
+  if (MODE == 1) {
+    if (QM > 2) {
+      // the group's first magnitude: RE (i & ~3) sits in lane (lane & ~3) of this warp (valid is a multiple of 4, so groups are never split)
+      int amp = __shfl_sync(__activemask(), ma, (threadIdx.x & 31) & ~3);
+      amp = min(amp, 4095);
+      const int inv = amp > 0 ? 4096 / amp : 0;                                         // nr_inv_ch[0] is 0; a negative amp is out of bounds in the reference
+      cr = p_wrap16(cr * inv) >> 3; ci = p_wrap16(ci * inv) >> 3;                       // mullo_epi16, srai 3
+    }
+    if (!G.tp_direct) ci = p_wrap16(-ci);                                               // conjugate input (:27-31)
+    tp[tp_slot(G, k, i)] = ((unsigned)cr & 0xFFFFu) | ((unsigned)ci << 16);
+    return;
   }
   int o[8];
   if (QM == 2) { o[0] = cr >> 3; o[1] = ci >> 3; }
@@ -669,7 +702,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
     G->est_state = reinterpret_cast<const int *>((uintptr_t)d.d_est_state);
     G->est_ports = (int)d.est_state_ports; G->est_div = (int)(d.nr_of_symbols * nl * d.nb_rx);
   }
-  G->ue = d.pdsch_ue ? 1 : 0; G->cdm = d.num_dmrs_cdm_grps_no_data;
+  G->ue = d.pdsch_ue ? 1 : 0; G->cdm = d.num_dmrs_cdm_grps_no_data; G->tp_direct = 0;
   if (G->ue && (d.nb_rx > 4 || (nl == 2 && d.nb_rx < 2))) return -4;     // the reference applies neither MRC nor zero forcing with one rx antenna
   {
     // nr_ulsch_scale_channel: shift_ch_ext = log2_approx(max_ch >> 11) for 2 layers, 0 for one
@@ -732,6 +765,19 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
   return 0;
 }
 
+// nr_idft's sizes (nr_ulsch_demodulation.c:38-246) without 768 and 2304: there the reference hands four-way data to the single-transform dft768 / to
+// dft2304 (which combines uninitialised stack), so its own output is not reproducible
+bool pusch_tp_supported(int M)
+{
+  static const int sizes[] = {12, 24, 36, 48, 60, 72, 96, 108, 120, 144, 180, 192, 216, 240, 288, 300, 324, 360, 384, 432, 480, 540, 576, 600, 648, 720, 864, 900, 960, 972,
+                              1080, 1152, 1200, 1296, 1440, 1500, 1536, 1620, 1728, 1800, 1920, 1944, 2160, 2400, 2592, 2700, 2880, 2916, 3000, 3072, 3240};
+  for (int v : sizes) if (v == M) return true;
+  return false;
+}
+size_t pusch_tp_scratch_bytes(const nrb200_pusch_rx_t &d) { return (size_t)128 * 12 * d.rb_size; }   // two planes of 16 M c16 (input and output of the transforms)
+
+int dft_batch_internal(int N, int inverse, uint32_t n, const int16_t *d_in, int16_t *d_out, int scale, cudaStream_t st);   // dfts_internal.cu
+
 int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st)
 {
   PuschGeom G;
@@ -763,12 +809,34 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
     else if (G.Qm == 4) pusch_rx2ml_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
     else if (G.Qm == 6) pusch_rx2_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
     else pusch_rx2_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);
+  } else if (d.transform_precoding && G.Qm <= 6) {
+    // inner_rx applies the equalisation / nr_idft step to one layer and Qm <= 6 only (:1326); 256QAM and two layers take the ordinary path like the reference
+    const int M = G.nb_re;
+    if (!pusch_tp_supported(M) || d.d_tp_scratch == 0) return -4;
+    for (int k = 0; k < G.n_sym; k++) if (G.valid[k] != M) return -4;           // data on a DMRS symbol: nr_idft has no such size
+    G.tp_direct = (M == 1536 || M == 3072) ? 1 : 0;
+    unsigned *tin = reinterpret_cast<unsigned *>((uintptr_t)d.d_tp_scratch), *tout = tin + 16 * (size_t)M;
+    switch (G.Qm) {
+      case 2: pusch_rx_kernel<2, 1><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, tin); break;
+      case 4: pusch_rx_kernel<4, 1><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, tin); break;
+      default: pusch_rx_kernel<6, 1><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, tin); break;
+    }
+    NRB200_CUDA_OK(cudaGetLastError(), "pusch_rx (transform precoding, stage 1) launch");
+    rc = G.tp_direct ? dft_batch_internal(M, 1, (uint32_t)G.n_sym, (const int16_t *)tin, (int16_t *)tout, 1, st)
+                     : dft_batch_internal(M, 0, (uint32_t)((G.n_sym + 3) / 4), (const int16_t *)tin, (int16_t *)tout, M == 12 ? 0 : 1, st);
+    if (rc) return rc;
+    switch (G.Qm) {
+      case 2: pusch_rx_kernel<2, 2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, tout); break;
+      case 4: pusch_rx_kernel<4, 2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, tout); break;
+      default: pusch_rx_kernel<6, 2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, tout); break;
+    }
+    ctx().launches += 2;
   } else {
     switch (G.Qm) {
-      case 2: pusch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-      case 4: pusch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-      case 6: pusch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-      default: pusch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+      case 2: pusch_rx_kernel<2, 0><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, nullptr); break;
+      case 4: pusch_rx_kernel<4, 0><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, nullptr); break;
+      case 6: pusch_rx_kernel<6, 0><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, nullptr); break;
+      default: pusch_rx_kernel<8, 0><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, nullptr); break;
     }
   }
   ctx().launches++;

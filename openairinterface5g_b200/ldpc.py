@@ -73,12 +73,24 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order",
                                           "start_symbol_index", "nr_of_symbols", "ul_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data",
                                           "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id", "nrOfLayers", "noise_var", "max_ch", "pdsch_ue")] + \
-               [("d_est_state", C.c_uint64), ("est_state_ports", C.c_uint32), ("reserved0", C.c_uint32)]
+               [("d_est_state", C.c_uint64), ("est_state_ports", C.c_uint32), ("transform_precoding", C.c_uint32), ("d_tp_scratch", C.c_uint64)]
 
 
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
-                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue", "dmrs_config_type", "chest_freq")]
+                                          "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue", "dmrs_config_type", "chest_freq",
+                                          "transform_precoding")] + [("lowpapr_seq", C.c_uint64)]
+
+    def set_lowpapr(self, seq):
+        """Transform precoding: seq = the 6 * rb_size c16 low-PAPR type-1 sequence -- a numpy int16 array (host entry points) or a torch CUDA tensor
+        (_dev entry points); None switches back to the Gold-sequence DMRS.  The descriptor keeps the buffer alive."""
+        self._seq = seq
+        if seq is None:
+            self.transform_precoding, self.lowpapr_seq = 0, 0
+        else:
+            self.transform_precoding = 1
+            self.lowpapr_seq = seq.data_ptr() if hasattr(seq, "data_ptr") else seq.ctypes.data
+        return self
 
 
 class PdschTxDesc(C.Structure):       # nrb200_pdsch_tx_t (field names of nfapi_nr_dl_tti_pdsch_pdu_rel15_t / NR_DL_FRAME_PARMS)
@@ -444,6 +456,16 @@ class LdpcLib:
         pil = np.zeros(2 * 6 * desc.rb_size, dtype=np.int16)
         self._check(self.lib.nrb200_pusch_dmrs_pilots_host(C.addressof(desc), pil.ctypes.data), "pusch_dmrs_pilots_host")
         return pil
+
+    def lowpapr_sequence(self, u, v, n_re, scaling=32767):
+        """Low-PAPR base sequence r_{u,v} as the reference generates it (n_re = 30 or >= 36); None for the table-driven lengths (see the header)."""
+        seq = np.zeros(2 * n_re, dtype=np.int16)
+        rc = self.lib.nrb200_lowpapr_sequence_host(u, v, n_re, scaling, C.c_void_p(seq.ctypes.data))
+        return seq if rc == 0 else None
+
+    def pusch_tp_scratch_bytes(self, desc):
+        self.lib.nrb200_pusch_tp_scratch_bytes.restype = C.c_uint64
+        return int(self.lib.nrb200_pusch_tp_scratch_bytes(C.c_void_p(C.addressof(desc))))
 
     def pusch_chest_host(self, desc, rxdataF, ul_ch_estimates=None):
         """rxdataF [nb_rx][14][N][2] int16 -> (ul_ch_estimates with symbol desc.symbol rewritten, state int32[5] = max_ch, nvar, est_delay, pos, val)."""

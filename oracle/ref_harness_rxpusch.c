@@ -15,6 +15,15 @@ idftfunc_t idft;
 
 void init_delay_table(uint16_t ofdm_symbol_size, int max_delay_comp, int max_ofdm_symbol_size, c16_t delay_table[][max_ofdm_symbol_size]);
 
+/* DFT-s-OFDM: the PDU's transform-precoding fields; the low-PAPR sequence table is built like nr_init.c:249 does */
+#include "PHY/NR_REFSIG/ul_ref_seq_nr.h"
+static int g_tp_on, g_tp_u, g_tp_v;
+void refh_rxpusch_set_transform_precoding(int on, int u, int v)
+{
+  generate_lowpapr_typ1_refsig_sequences(SHRT_MAX);
+  g_tp_on = on; g_tp_u = u; g_tp_v = v;
+}
+
 enum { X_N, X_NB_RX, X_N_RB_UL, X_SLOT, X_RB_START, X_BWP_START, X_RB_SIZE, X_FCO, X_QM, X_START_SYMBOL, X_NR_SYMBOLS, X_DMRS_POS, X_DMRS_TYPE, X_CDM, X_NL, X_DMRS_PORTS,
        X_SCID, X_DMRS_ID, X_RNTI, X_DATA_ID, X_CHEST_FREQ, X_CHEST_TIME, X_COUNT };
 
@@ -37,7 +46,8 @@ int refh_rx_pusch(const int32_t *p, const int16_t *rxdataF, int G, int16_t *llr_
   u->start_symbol_index = p[X_START_SYMBOL]; u->nr_of_symbols = p[X_NR_SYMBOLS]; u->ul_dmrs_symb_pos = p[X_DMRS_POS];
   u->dmrs_config_type = p[X_DMRS_TYPE]; u->num_dmrs_cdm_grps_no_data = p[X_CDM]; u->nrOfLayers = nl; u->dmrs_ports = p[X_DMRS_PORTS];
   u->scid = p[X_SCID]; u->ul_dmrs_scrambling_id = p[X_DMRS_ID]; u->rnti = p[X_RNTI]; u->data_scrambling_id = p[X_DATA_ID];
-  u->transform_precoding = transformPrecoder_disabled; u->pdu_bit_map = 0;
+  u->transform_precoding = g_tp_on ? transformPrecoder_enabled : transformPrecoder_disabled; u->pdu_bit_map = 0;
+  u->dfts_ofdm.low_papr_group_number = (uint8_t)g_tp_u; u->dfts_ofdm.low_papr_sequence_number = (uint8_t)g_tp_v;
   NR_gNB_PUSCH *pv = &gNB->pusch_vars[0];
   pv->ul_ch_estimates = calloc(nl * nrx, sizeof(int32_t *));
   pv->ul_ch_estimates_time = calloc(nrx, sizeof(int32_t *));

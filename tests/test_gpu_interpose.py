@@ -216,6 +216,54 @@ def test_oai_gnb_caller_reaches_the_gpu_through_nr_rx_pusch_tp(oracle):
         assert all(int(v) > 0 for v in info[30:30 + nb_rx])
 
 
+def test_oai_gnb_caller_with_transform_precoding_through_nr_rx_pusch_tp(oracle):
+    """The same caller with pusch_pdu->transform_precoding = enabled (DFT-s-OFDM): the interposed estimator takes OAI's own low-PAPR sequence table
+    (gNB_dmrs_lowpaprtype1_sequence[u][v][index], built by the caller like nr_init.c:249 does) and the interposed receiver runs equalisation + nr_idft inside
+    the library call.  Expected values: the pinned oracle chained like nr_rx_pusch_tp chains the reference functions."""
+    from oracle.bindings import ChestParms, PuschParms
+    so = os.path.join(ROOT, "oracle", "_ref", "libshimtest_rxpusch.so")
+    if not os.path.exists(so):
+        pytest.fail(f"{so} missing: run integration/build_shims.sh where /root/reference exists (the file travels with the repo snapshot)")
+    lib = C.CDLL(so)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "transform_precoding.npz"))
+    rng = np.random.default_rng(37)
+    for N, nb_rx, carrier, slot, rb_start, rb_size, Qm, u, dmrs_id, rnti, nid in ((4096, 4, 273, 1, 0, 270, 6, 0, 55, 0x1234, 77), (2048, 2, 106, 7, 20, 50, 4, 17, 1007, 0x4321, 99),
+                                                                               (1024, 2, 52, 6, 3, 2, 2, 29, 300, 0x1001, 5), (1024, 1, 52, 2, 0, 1, 6, 3, 9, 0x77, 1)):
+        fco = N - carrier * 6
+        dpos, cdm = 1 << 2, 2
+        rx = rng.integers(-1500, 1501, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, 0, cdm)
+        seq = oracle.lowpapr_seq(u, 0, 6 * rb_size)
+        if seq is None:
+            seq = gold[f"seq_{6 * rb_size}"][u].copy()
+        oracle.chest_set_lowpapr(seq)
+        oracle.pusch_set_transform_precoding(1)
+        try:
+            e, st = oracle.pusch_channel_estimation(ChestParms(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, fco, 0, dmrs_id, 0, 0), rx)
+            est = np.zeros((nb_rx, 14, N, 2), np.int16)
+            est[:, 2] = e[:, 2]
+            sh_o, _ = oracle.pusch_log2_maxh(P, 0, 2, rx, est)
+            out = [oracle.pusch_inner_rx_symbol(P, s, 2, sh_o, rx, est)[0] for s in range(14) if s != 2]
+        finally:
+            oracle.chest_set_lowpapr(None)
+            oracle.pusch_set_transform_precoding(0)
+        want = oracle.unscramble_llr(np.concatenate(out), 0, nid, rnti)
+        G = want.size
+        prm = np.array([N, nb_rx, carrier, slot, rb_start, 0, rb_size, fco, Qm, 0, 14, dpos, 0, cdm, 1, 1, 0, dmrs_id, rnti, nid, 0, 0], dtype=np.int32)
+        llr = np.zeros(G, np.int16)
+        est_out = np.zeros((nb_rx, 14, N, 2), np.int16)
+        info = np.zeros(40, np.int32)
+        lib.refh_rxpusch_set_transform_precoding(1, u, 0)
+        try:
+            assert lib.refh_rx_pusch(prm.ctypes.data_as(C.c_void_p), rx.ctypes.data_as(C.c_void_p), G, llr.ctypes.data_as(C.c_void_p), est_out.ctypes.data_as(C.c_void_p),
+                                     info.ctypes.data_as(C.c_void_p)) == 0
+        finally:
+            lib.refh_rxpusch_set_transform_precoding(0, 0, 0)
+        assert np.array_equal(est_out[:, 2], est[:, 2]), (N, rb_size, "estimates")
+        assert info[0] == sh_o and info[1] == 2
+        assert np.array_equal(llr, want), (N, nb_rx, Qm, rb_size, np.nonzero(llr != want)[0][:5])
+
+
 def test_oai_ru_callers_reach_the_gpu_through_nr_feptx0_and_nr_fep_full(oracle):
     """integration/oai_shim_ru_ofdm.c defines OAI's RU front-end functions `nr_feptx0` (IDFT + cyclic prefix of a tx antenna's symbols) and `nr_fep_full` (the 14 DFTs
     of every rx antenna of a slot); the reference-side caller (oracle/ref_harness_ru.c: an RU_t with frame parameters and buffers as init_nr_ru leaves them) is linked

@@ -677,18 +677,20 @@ def test_transform_precoding_sequences_chest_and_inner_rx(oracle, reference):
     assert n == 3 * 49
     rng = np.random.default_rng(3)
     carrier = {1024: 52, 2048: 106, 4096: 273}
-    for N, nb_rx, rb_start, nb, slot, u in ((2048, 2, 10, 25, 3, 5), (4096, 4, 0, 270, 1, 0), (1024, 1, 7, 6, 0, 29), (2048, 2, 0, 5, 2, 11), (1024, 2, 3, 2, 4, 3)):
+    for N, nb_rx, rb_start, nb, slot, u, port, cf in ((2048, 2, 10, 25, 3, 5, 0, 0), (4096, 4, 0, 270, 1, 0, 0, 0), (1024, 1, 7, 6, 0, 29, 1, 0), (2048, 2, 0, 5, 2, 11, 3, 0),
+                                                     (1024, 2, 3, 2, 4, 3, 0, 0), (2048, 2, 10, 25, 3, 5, 0, 1), (512, 3, 1, 4, 7, 20, 2, 1), (1024, 1, 7, 6, 0, 29, 1, 1)):
+        carrier.setdefault(512, 25)
         rx = rng.integers(-3000, 3001, size=(nb_rx, 14, N, 2)).astype(np.int16)
-        P = ChestParms(N, nb_rx, slot, 2, 0, rb_start, 0, nb, N - 6 * carrier[N], 0, 55)
+        P = ChestParms(N, nb_rx, slot, 2, port, rb_start, 0, nb, N - 6 * carrier[N], 0, 55, 0, cf)
         reference.chest_set_transform_precoding(1, u, 0)
         oracle.chest_set_lowpapr(reference.lowpapr_seq(u, 0, 6 * nb))
         try:
-            e_r, st_r, _ = reference.pusch_channel_estimation(P, rx, carrier[N])
+            e_r, st_r, _ = reference.pusch_channel_estimation(P, rx, carrier[N], chest_freq=cf)
             e_o, st_o = oracle.pusch_channel_estimation(P, rx)
         finally:
             reference.chest_set_transform_precoding(0)
             oracle.chest_set_lowpapr(None)
-        assert np.array_equal(e_r, e_o) and np.array_equal(st_r, st_o[:5]), (N, nb)
+        assert np.array_equal(e_r, e_o) and np.array_equal(st_r, st_o[:5]), (N, nb, port, cf)
     reference.pusch_set_transform_precoding(1)
     oracle.pusch_set_transform_precoding(1)
     try:
