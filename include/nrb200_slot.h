@@ -82,6 +82,30 @@ typedef struct nrb200_pdsch_tx_bufs_s {
 /* one PDSCH slot of the gNB: payload in, time-domain samples out */
 int32_t nrb200_pdsch_slot_tx_dev(const nrb200_pdsch_tx_slot_t *d, const nrb200_pdsch_tx_bufs_t *b, void *stream);
 
+/* ---- transport-block level, HOST buffers: what nr_ulsch_decoding does for one PUSCH (nr_ulsch_decoding.c:320-470 + nr_processULSegment :121-230) in ONE call.
+ * The reference queues one job per code-block segment on its thread pool -- de-interleaving, rate recovery with HARQ combining into harq_process->d[r],
+ * decoder-input packing, one blocking LDPCdecoder call with the CRC stop -- and the caller collects the C results.  Here the C segments are one rate-recovery
+ * launch and one decode launch (a cluster of SMs per segment: a TB's 1..56 segments finish in the time of one), then the decoded segments are copied out.
+ * The soft buffers are LIBRARY-OWNED DEVICE MEMORY keyed by `harq_key` (the address of the reference's NR_UL_gNB_HARQ_t is a natural key): they stay on the GPU
+ * across HARQ rounds, like the accelerator-side HARQ memory of the reference's offload path (nrLDPC_decoder_offload.c:545-546); d_mirror returns a copy for
+ * callers (and tests) that want to see them.  integration/oai_shim_ulsch_decoding.c is the interposer that calls this with OAI's structures.
+ * The reference's abort flag (a failed segment stops its siblings early) is an optimisation of a block that is lost anyway and is not reproduced: every
+ * segment is decoded, iters[r] is its own verdict. */
+typedef struct nrb200_ulsch_tb_s {
+  nrb200_rm_desc_t rm;            /* BG, Z, Qm, rv, C, Tbslbrm, F, K as nr_ulsch_decoding sets them; n_seg = C; `clear` is ignored (per segment below) */
+  uint32_t numMaxIter;            /* ulsch->max_ldpc_iterations */
+  uint32_t crc_type, crc_len_bits;/* crcType(C, A), lenWithCrc(C, A): the per-segment check_crc stop (:178-179) */
+  uint64_t harq_key;              /* identifies the TB's soft buffers inside the library */
+} nrb200_ulsch_tb_t;
+/* ulsch_llr: the PUSCH's G int16 LLRs (unscrambled, as nr_rx_pusch_tp leaves them); E[r]: nr_get_E per segment; R[r]: nr_get_R_ldpc_decoder per segment;
+ * clear[r]: harq_process->d_to_be_cleared[r] (1 = new data).  c[r] receives K / 8 bytes when segment r decoded (iters[r] <= numMaxIter) and is left alone
+ * otherwise, as in the reference; iters[r] = the decoder's return value.  d_mirror (optional): C pointers, each receives the segment's soft buffer
+ * (66 Z | 50 Z int16) after combining.  Returns 0, or a negative error (-4 invalid arguments, -5 out of memory, -2 CUDA failure). */
+int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, const int16_t *ulsch_llr, const uint32_t *E, const uint8_t *R, const uint8_t *clear,
+                                    uint8_t *const *c, int32_t *iters, int16_t *const *d_mirror);
+/* frees the soft buffers of one key (free_gNB_ulsch) -- or of every key when harq_key == 0 */
+int32_t nrb200_ulsch_harq_release(uint64_t harq_key);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,3 +47,11 @@ gcc $F $INC $DEFS $HERE/oai_shim_ru_ofdm.c $LIBD -Wl,-rpath,'$ORIGIN/../../opena
 gcc $F $INC $DEFS $ROOT/oracle/ref_harness_ru.c $HERE/oai_shim_ru_ofdm.c $LIBD -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -Wl,--no-undefined \
     -o $W/libshimtest_ru.so || echo "libshimtest_ru.so: FAILED"
 ls -la $HERE/_build/libnrb200_shim_ru_ofdm.so $W/libshimtest_ru.so
+# the gNB's transport-block decoder: nr_ulsch_decoding.  The reference's definition shares its object file with new_gNB_ulsch / free_gNB_ulsch, which the caller
+# keeps using, so the interposer is linked AHEAD of it with --allow-multiple-definition (first definition wins) -- the recipe for a softmodem link line too.
+gcc $F $INC $DEFS $HERE/oai_shim_ulsch_decoding.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_ulsch_decoding.so
+gcc $F -mpclmul -D_GNU_SOURCE $INC $DEFS $HERE/oai_shim_ulsch_decoding.c $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_ulsch.c $ROOT/oracle/ref_harness_ulsch.c \
+    $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_decoding.c $R/openair1/PHY/CODING/nr_segmentation.c $R/openair1/PHY/CODING/nr_rate_matching.c $R/openair1/PHY/CODING/crc_byte.c \
+    $R/openair1/PHY/NR_TRANSPORT/nr_tbs_tools.c $R/openair1/PHY/TOOLS/dB_routines.c $R/common/utils/threadPool/thread-pool.c \
+    -Wl,--allow-multiple-definition $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -ldl -lpthread -Wl,--no-undefined -o $W/libshimtest_ulsch.so || echo "libshimtest_ulsch.so: FAILED"
+ls -la $HERE/_build/libnrb200_shim_ulsch_decoding.so $W/libshimtest_ulsch.so

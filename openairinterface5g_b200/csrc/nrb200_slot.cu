@@ -5,6 +5,9 @@
 #include "../../include/nrb200_slot.h"
 #include "nrb200_ctx.h"
 #include <cstring>
+#include <algorithm>
+#include <map>
+#include <mutex>
 
 #define NRB200_EXPORT extern "C" __attribute__((visibility("default")))
 using namespace nrb200;
@@ -65,4 +68,110 @@ NRB200_EXPORT int32_t nrb200_pdsch_slot_tx_dev(const nrb200_pdsch_tx_slot_t *d, 
   if ((rc = nrb200_ofdm_mod_slot_dev(&d->ofdm, b->d_txdataF, b->d_txdata, stream)) != 0) return rc;
   ctx().launches++;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ transport-block level, host buffers (nr_ulsch_decoding)
+namespace {
+struct HarqBuf { int16_t *d = nullptr; size_t elems = 0; int dev = 0; };
+std::mutex g_harq_mu;
+std::map<uint64_t, HarqBuf> g_harq;
+
+// the TB's soft buffers: n_seg x stride int16 on the calling thread's device, created zeroed; a key that changes shape (a reconfigured HARQ process) starts over
+int16_t *harq_buffers(uint64_t key, size_t elems, bool *fresh)
+{
+  std::lock_guard<std::mutex> lk(g_harq_mu);
+  HarqBuf &h = g_harq[key];
+  *fresh = false;
+  if (h.d != nullptr && (h.elems != elems || h.dev != ctx().dev)) {
+    cudaSetDevice(h.dev); cudaFree(h.d); cudaSetDevice(ctx().dev);
+    h = HarqBuf();
+  }
+  if (h.d == nullptr) {
+    if (cudaMalloc(&h.d, elems * sizeof(int16_t)) != cudaSuccess) { g_harq.erase(key); return nullptr; }
+    h.elems = elems; h.dev = ctx().dev; *fresh = true;
+  }
+  return h.d;
+}
+}  // namespace
+
+NRB200_EXPORT int32_t nrb200_ulsch_harq_release(uint64_t harq_key)
+{
+  std::lock_guard<std::mutex> lk(g_harq_mu);
+  for (auto it = g_harq.begin(); it != g_harq.end();) {
+    if (harq_key == 0 || it->first == harq_key) { cudaSetDevice(it->second.dev); cudaFree(it->second.d); it = g_harq.erase(it); }
+    else ++it;
+  }
+  return 0;
+}
+
+NRB200_EXPORT int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, const int16_t *ulsch_llr, const uint32_t *E, const uint8_t *R, const uint8_t *clear,
+                                                  uint8_t *const *c, int32_t *iters, int16_t *const *d_mirror)
+{
+  if (!d || !ulsch_llr || !E || !R || !clear || !c || !iters) return -4;
+  { Ctx &cx = ctx(); if (!cx.inited && cx.init() != 0) return -1; cudaSetDevice(cx.dev); }
+  const uint32_t n = d->rm.n_seg, Z = d->rm.Z;
+  if (n == 0 || n != d->rm.C || n > 4 * 36 || (d->rm.BG != 1 && d->rm.BG != 2) || d->rm.K % 8) return -4;
+  const uint32_t ncb = (d->rm.BG == 1 ? 66u : 50u) * Z, kc = (d->rm.BG == 1 ? 68u : 52u), llr_stride = (kc * Z + 63u) & ~63u, Kb = d->rm.K / 8;
+  const uint32_t hard_stride = (kc * Z / 8 + 63u) & ~63u;
+  size_t G = 0;
+  for (uint32_t r = 0; r < n; r++) G += E[r];
+  Workspace *w = ctx().acquire();
+  // d_in: LLRs | E / offset table;  d_out: hard bits | iteration counts;  d_aux: decoder inputs
+  const size_t tab_off = (2 * G + 63) & ~(size_t)63, out_it = (size_t)n * hard_stride;
+  // (the optional mirror of the soft buffers travels back through the input staging area once the kernels are done with it)
+  const size_t in_bytes = std::max(tab_off + 8 * (size_t)n, d_mirror ? (size_t)n * ncb * 2 : (size_t)0);
+  if (!w || !w->reserve(in_bytes, out_it + 4 * (size_t)n, (size_t)n * llr_stride)) { if (w) ctx().release(w); return -5; }
+  bool fresh = false;
+  int16_t *d_harq = harq_buffers(d->harq_key, (size_t)n * ncb, &fresh);
+  if (!d_harq) { ctx().release(w); return -5; }
+  int rc = 0;
+  cudaStream_t st = w->stream;
+  do {
+    uint32_t *tab = (uint32_t *)((uint8_t *)w->h_in + tab_off);
+    size_t off = 0;
+    for (uint32_t r = 0; r < n; r++) { tab[r] = E[r]; tab[n + r] = (uint32_t)off; off += E[r]; }
+    std::memcpy(w->h_in, ulsch_llr, 2 * G);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, tab_off + 8 * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+    if (fresh && cudaMemsetAsync(d_harq, 0, (size_t)n * ncb * 2, st) != cudaSuccess) { rc = -2; break; }
+    const uint32_t *d_E = (const uint32_t *)((uint8_t *)w->d_in + tab_off), *d_off = d_E + n;
+    // rate recovery: runs of segments with the same d_to_be_cleared flag (uniform in practice: one launch)
+    for (uint32_t r0 = 0; r0 < n && rc == 0;) {
+      uint32_t r1 = r0 + 1;
+      while (r1 < n && (clear[r1] != 0) == (clear[r0] != 0)) r1++;
+      nrb200_rm_desc_t rm = d->rm;
+      rm.clear = clear[r0] ? 1 : 0; rm.n_seg = r1 - r0;
+      rc = nrb200_ldpc_rm_rx_batch_dev(&rm, (const int16_t *)w->d_in, d_E + r0, d_off + r0, d_harq + (size_t)r0 * ncb, ncb, (int8_t *)w->d_aux + (size_t)r0 * llr_stride,
+                                       llr_stride, st);
+      r0 = r1;
+    }
+    if (rc) break;
+    // decode: runs of segments with the same rate selector (E differs by one modulation symbol between the first and the last segments at most)
+    for (uint32_t r0 = 0; r0 < n && rc == 0;) {
+      uint32_t r1 = r0 + 1;
+      while (r1 < n && R[r1] == R[r0]) r1++;
+      nrb200_ldpc_batch_desc_t dd;
+      std::memset(&dd, 0, sizeof(dd));
+      dd.BG = d->rm.BG; dd.Z = (uint16_t)Z; dd.R = R[r0]; dd.numMaxIter = (uint8_t)d->numMaxIter; dd.outMode = NRB200_OUTMODE_BIT;
+      dd.use_crc = 1; dd.crc_type = (uint8_t)d->crc_type; dd.crc_len_bits = d->crc_len_bits; dd.latency_mode = 1;
+      dd.n_cb = r1 - r0; dd.llr_stride = llr_stride; dd.out_stride = hard_stride;
+      rc = nrb200_ldpc_decode_batch_dev(&dd, (const int8_t *)w->d_aux + (size_t)r0 * llr_stride, (uint8_t *)w->d_out + (size_t)r0 * hard_stride,
+                                        (int32_t *)((uint8_t *)w->d_out + out_it) + r0, st);
+      r0 = r1;
+    }
+    if (rc) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_it + 4 * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -2; break; }
+    const int32_t *it = (const int32_t *)((const uint8_t *)w->h_out + out_it);
+    for (uint32_t r = 0; r < n; r++) {
+      iters[r] = it[r];
+      if (it[r] <= (int32_t)d->numMaxIter && c[r]) std::memcpy(c[r], (const uint8_t *)w->h_out + (size_t)r * hard_stride, Kb);
+    }
+    if (d_mirror) {
+      if (cudaMemcpyAsync(w->h_in, d_harq, (size_t)n * ncb * 2, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = -2; break; }
+      for (uint32_t r = 0; r < n; r++) if (d_mirror[r]) std::memcpy(d_mirror[r], (const int16_t *)w->h_in + (size_t)r * ncb, (size_t)ncb * 2);
+    }
+  } while (0);
+  if (rc == -2) ctx().set_error("ulsch_decode_tb_host", cudaGetLastError());
+  ctx().release(w);
+  return rc;
 }

@@ -105,3 +105,8 @@ if [ $ok = 1 ]; then
   gcc $F $INC $DEFS $R/openair1/PHY/CODING/nrLDPC_decoder/nrLDPC_decoder.c $R/openair1/PHY/CODING/nrLDPC_encoder/ldpc_encoder_optim8segmulti.c -o $W/oai_libs/libldpc.so
   ls -la $W/ldpctest $W/oai_libs
 fi
+# ---- the reference's nr_ulsch_decoding (segment jobs on the thread pool, rate recovery, one LDPCdecoder call per segment) behind a caller harness that
+#      collects the results like phy_procedures_gNB_uespec_RX does; ldpc_interface is bound at run time to oai_libs/libldpc.so (the reference CPU decoder)
+gcc $F -mpclmul -D_GNU_SOURCE -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_ulsch.c $HERE/ref_harness_ulsch.c $R/openair1/PHY/NR_TRANSPORT/nr_ulsch_decoding.c \
+    $R/openair1/PHY/CODING/nr_segmentation.c $R/openair1/PHY/CODING/nr_rate_matching.c $R/openair1/PHY/CODING/crc_byte.c $R/openair1/PHY/NR_TRANSPORT/nr_tbs_tools.c \
+    $R/openair1/PHY/TOOLS/dB_routines.c $R/common/utils/threadPool/thread-pool.c -lm -ldl -lpthread -Wl,--no-undefined -o libref_ulsch.so || echo "libref_ulsch.so: FAILED"

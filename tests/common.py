@@ -150,3 +150,34 @@ def oracle_pusch_receive(oracle, P, info, Qm, rb_start, rb_size, nb_rx, slot, rn
         it, hard = oracle.decode(1, Z, R, max_iter, np.clip(z, -128, 127).astype(np.int8), use_crc=1, crc_len_bits=K - F, crc_type=1)
         its.append(it); out.append(np.asarray(hard, dtype=np.uint8)[:(K - F - 24) // 8])
     return np.concatenate(out), np.array(its), llr, shift
+
+
+def make_tb_llrs(oracle, A, Qm, nl, rb_size, rv, seed, snr_db=8.0, BG=1, nsymb=13):
+    """A transport block through the oracle's transmit chain (TB CRC, segmentation, LDPC encoding, rate matching for redundancy version rv, interleaving) and a
+    BPSK-per-bit AWGN channel: what nr_ulsch_decoding receives from nr_rx_pusch_tp.  Returns (payload bytes, llr int16[G], dict(C, K, Z, F, E, G))."""
+    from openairinterface5g_b200 import transport as T
+    rng = np.random.default_rng(seed)
+    payload = rng.integers(0, 256, size=A // 8, dtype=np.uint8)
+    if A > 3824:
+        crc = oracle.crc(0, payload, A) >> 8
+        tb = np.concatenate([payload, np.array([(crc >> 16) & 255, (crc >> 8) & 255, crc & 255], np.uint8)])
+        B = A + 24
+    else:
+        crc = oracle.crc(3, payload, A) >> 16
+        tb = np.concatenate([payload, np.array([(crc >> 8) & 255, crc & 255], np.uint8)])
+        B = A + 16
+    _, C_, K, Z, F, segs = oracle.segmentation(tb, B, BG)
+    G = T.nr_get_G(rb_size, nsymb, 0, 1, 0, Qm, nl)
+    E = [T.nr_get_E(G, C_, Qm, nl, r) for r in range(C_)]
+    f = []
+    for r in range(C_):
+        d = oracle.encode(BG, Z, K, segs[r]).copy()
+        d[K - F - 2 * Z:K - 2 * Z] = 2
+        rc, e = oracle.rate_matching_tx(0, BG, Z, d, C_, F, K - F - 2 * Z, rv, E[r])
+        assert rc == 0
+        f.append(oracle.interleave(E[r], Qm, e))
+    bits = np.concatenate(f).astype(np.float64)
+    sigma = 10 ** (-snr_db / 20.0)
+    y = (1.0 - 2.0 * bits) + sigma * rng.standard_normal(bits.size)
+    llr = np.clip(np.round(y * 24.0), -32768, 32767).astype(np.int16)
+    return payload, llr, dict(C=C_, K=K, Z=Z, F=F, E=E, G=G)

@@ -292,3 +292,59 @@ def test_oai_ru_callers_reach_the_gpu_through_nr_feptx0_and_nr_fep_full(oracle):
         assert lib.refh_ru_fep_full(N, mu, nb_rb, slot, nant, divisor, n_ta, rx.ctypes.data_as(C.c_void_p), rxF.ctypes.data_as(C.c_void_p)) == spf
         for a in range(nant):
             assert np.array_equal(rxF[a], oracle.ofdm_rx_slot(N, mu, nb_rb, slot, divisor, n_ta, None, rx[a])), (N, mu, slot, a, "fep_full")
+
+
+def _ulsch_lib(name, bind=None):
+    so = os.path.join(ROOT, "oracle", "_ref", name)
+    if not os.path.exists(so):
+        pytest.fail(f"{so} missing: run oracle/build_ref.sh and integration/build_shims.sh where /root/reference exists (the files travel with the repo snapshot)")
+    lib = C.CDLL(so)
+    lib.refh_ulsch_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    if bind:
+        assert lib.refh_ulsch_bind_ldpc(os.path.join(ROOT, "oracle", "_ref", bind).encode()) == 0
+    return lib
+
+
+def _ulsch_call(lib, prm, llr, G, Cn, K, Z, tbs, ncb):
+    inf = np.zeros(8, np.int32); it = np.zeros(Cn, np.int32); c = np.zeros(Cn * K // 8, np.uint8); tb = np.zeros(tbs + 3, np.uint8); d = np.zeros(Cn * ncb, np.int16)
+    rc = lib.refh_ulsch_decode(prm.ctypes.data, llr.ctypes.data, G, inf.ctypes.data, it.ctypes.data, c.ctypes.data, tb.ctypes.data, d.ctypes.data)
+    return rc, inf, it, c, tb, d
+
+
+def test_oai_gnb_caller_reaches_the_gpu_through_nr_ulsch_decoding(oracle, monkeypatch):
+    """integration/oai_shim_ulsch_decoding.c defines OAI's `nr_ulsch_decoding`; the reference-side caller (oracle/ref_harness_ulsch.c: gNB thread pool + response
+    FIFO, a ULSCH from the reference's own new_gNB_ulsch, the collection loop of phy_procedures_gNB_uespec_RX with nr_postDecode's copy) is built twice: around
+    the reference's own function with the compiled CPU decoder (libref_ulsch.so), and with the interposer linked ahead of it (libshimtest_ulsch.so), where the whole
+    transport block is one library call.  Same LLRs into both: C / K / Z / F / llrLen, every segment's iteration count, harq_process->c[r], the assembled
+    transport block and -- with NRB200_SHIM_MIRROR_HARQ=1 -- the combined soft buffers harq_process->d[r] must be identical, for a new transmission (rv 0), for
+    a retransmission that combines (rv 2 after an undecodable rv 0), with fillers, BG2, a single segment and 2 layers x 56 segments."""
+    from common import make_tb_llrs
+    monkeypatch.setenv("NRB200_SHIM_MIRROR_HARQ", "1")
+    ref = _ulsch_lib("libref_ulsch.so", "libref_ldpc_dec.so")
+    shim = _ulsch_lib("libshimtest_ulsch.so")
+    cases = [  # A bits, Qm, layers, PRBs, BG, snr of the first transmission (dB), N_RB_UL
+        (33640, 6, 1, 52, 1, 6.0, 106), (235624, 6, 1, 273, 1, 10.0, 273), (471272, 6, 2, 273, 1, 10.0, 273), (3752, 2, 1, 20, 2, 4.0, 106), (1032, 4, 1, 4, 2, 6.0, 52),
+        (33640, 6, 1, 52, 1, 0.0, 106)]
+    for A, Qm, nl, rb, BG, snr, nrb in cases:
+        pay, llr0, info = make_tb_llrs(oracle, A, Qm, nl, rb, 0, seed=A % 97, snr_db=snr, BG=BG)
+        _, llr2, _ = make_tb_llrs(oracle, A, Qm, nl, rb, 2, seed=A % 97, snr_db=snr + 3.0, BG=BG)        # the same payload, redundancy version 2
+        Cn, K, Z, G = info["C"], info["K"], info["Z"], info["G"]
+        ncb = (66 if BG == 1 else 50) * Z
+        for rnd, (rv, llr, new) in enumerate(((0, llr0, 1), (2, llr2, 0))):
+            prm = np.array([nrb, rb, Qm, nl, A // 8, rv, BG, 0, 8, new, rnd, 2], np.int32)
+            a = _ulsch_call(ref, prm, llr, G, Cn, K, Z, A // 8, ncb)
+            b = _ulsch_call(shim, prm, llr, G, Cn, K, Z, A // 8, ncb)
+            assert a[0] == b[0] == Cn, (A, rnd, a[0], b[0])
+            assert np.array_equal(a[1][:5], b[1][:5]), (A, rnd, a[1], b[1])
+            assert np.array_equal(a[5], b[5]), (A, rnd, "soft buffers")
+            ok = a[2] <= 8
+            if ok.all():                                                    # a lost block: the reference's abort flag cuts siblings short (not reproduced)
+                assert np.array_equal(a[2], b[2]), (A, rnd, a[2], b[2])
+                assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]), (A, rnd)
+                assert np.array_equal(b[4][:A // 8], pay)
+            else:
+                assert (b[2] > 8).any(), (A, rnd, a[2], b[2])
+            if snr > 0.5:
+                assert ok.all(), (A, rnd, a[2])
+        if snr < 0.5:                                                         # rv 0 alone was hopeless; combined with rv 2 the block decodes, on both sides
+            assert (a[2] <= 8).all() and np.array_equal(b[4][:A // 8], pay), (a[2], b[2])
