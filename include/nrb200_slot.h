@@ -96,6 +96,8 @@ typedef struct nrb200_ulsch_tb_s {
   uint32_t numMaxIter;            /* ulsch->max_ldpc_iterations */
   uint32_t crc_type, crc_len_bits;/* crcType(C, A), lenWithCrc(C, A): the per-segment check_crc stop (:178-179) */
   uint64_t harq_key;              /* identifies the TB's soft buffers inside the library */
+  uint32_t llr_pinned;            /* 1: ulsch_llr lies in page-locked memory (nrb200_host_register / cudaHostAlloc): the GPU reads it in place, no staging copy */
+  uint32_t reserved;
 } nrb200_ulsch_tb_t;
 /* ulsch_llr: the PUSCH's G int16 LLRs (unscrambled, as nr_rx_pusch_tp leaves them); E[r]: nr_get_E per segment; R[r]: nr_get_R_ldpc_decoder per segment;
  * clear[r]: harq_process->d_to_be_cleared[r] (1 = new data).  c[r] receives K / 8 bytes when segment r decoded (iters[r] <= numMaxIter) and is left alone
@@ -103,6 +105,10 @@ typedef struct nrb200_ulsch_tb_s {
  * (66 Z | 50 Z int16) after combining.  Returns 0, or a negative error (-4 invalid arguments, -5 out of memory, -2 CUDA failure). */
 int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, const int16_t *ulsch_llr, const uint32_t *E, const uint8_t *R, const uint8_t *clear,
                                     uint8_t *const *c, int32_t *iters, int16_t *const *d_mirror);
+/* page-locks (cudaHostRegister) / releases a caller-owned host buffer that lives as long as the process, e.g. OAI's pusch_vars->llr, so that transfers from it are
+ * direct DMA; 0 on success.  The buffer must not be freed while registered. */
+int32_t nrb200_host_register(void *p, uint64_t bytes);
+int32_t nrb200_host_unregister(void *p);
 /* frees the soft buffers of one key (free_gNB_ulsch) -- or of every key when harq_key == 0 */
 int32_t nrb200_ulsch_harq_release(uint64_t harq_key);
 

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include "PHY/defs_gNB.h"
 #include "PHY/CODING/coding_extern.h"
 #include "PHY/CODING/coding_defs.h"
@@ -24,6 +25,31 @@
 #include "PHY/NR_TRANSPORT/nr_dlsch.h"
 #define NRB200_NO_OAI_LOADER_PROTOTYPES
 #include "nrb200_slot.h"
+
+/* pusch_vars->llr is allocated once per ULSCH at start-up (init_nr_transport): page-lock each such buffer the first time it is seen (and again if a longer
+ * stretch of it is used) so that the GPU reads it in place.  A small table under a mutex: the function is called from several threads for different ULSCHs. */
+static int llr_is_pinned(short *llr, size_t bytes)
+{
+  static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  static struct { short *p; size_t bytes; } tab[64];
+  int ok = 0;
+  pthread_mutex_lock(&mu);
+  int slot = -1;
+  for (int i = 0; i < 64; i++) {
+    if (tab[i].p == llr) { slot = i; break; }
+    if (slot < 0 && tab[i].p == NULL) slot = i;
+  }
+  if (slot >= 0) {
+    if (tab[slot].p == llr && tab[slot].bytes >= bytes) ok = 1;
+    else {
+      if (tab[slot].p == llr) nrb200_host_unregister(llr);
+      tab[slot].p = NULL;
+      if (nrb200_host_register(llr, bytes) == 0) { tab[slot].p = llr; tab[slot].bytes = bytes; ok = 1; }
+    }
+  }
+  pthread_mutex_unlock(&mu);
+  return ok;
+}
 
 int nr_ulsch_decoding(PHY_VARS_gNB *gNB, uint8_t ULSCH_id, short *ulsch_llr, NR_DL_FRAME_PARMS *frame_parms, nfapi_nr_pusch_pdu_t *pusch_pdu, uint32_t frame,
                       uint8_t nr_tti_rx, uint8_t harq_pid, uint32_t G)
@@ -81,10 +107,11 @@ int nr_ulsch_decoding(PHY_VARS_gNB *gNB, uint8_t ULSCH_id, short *ulsch_llr, NR_
     clear[r] = hp->d_to_be_cleared[r];
     memset(hp->c[r], 0, hp->K >> 3);                                  /* nr_processULSegment :177 */
   }
+  d.llr_pinned = llr_is_pinned(ulsch_llr, 2 * (size_t)G);
   static int mirror = -1;
   if (mirror < 0) { const char *e = getenv("NRB200_SHIM_MIRROR_HARQ"); mirror = e && *e == '1'; }
   const int rc = nrb200_ulsch_decode_tb_host(&d, ulsch_llr, E, R, clear, (uint8_t *const *)hp->c, iters, mirror ? (int16_t *const *)hp->d : NULL);
-  if (rc != 0) { fprintf(stderr, "nrb200 shim: nrb200_ulsch_decode_tb_host failed (rc = %d)\n", rc); abort(); }
+  if (rc != 0) { fprintf(stderr, "nrb200 shim: nrb200_ulsch_decode_tb_host failed (rc = %d: %s)\n", rc, nrb200_last_error()); abort(); }
 
   /* one result per segment on the response FIFO, filled like the reference fills its jobs (:437-463) */
   uint32_t offset = 0, r_offset = 0;

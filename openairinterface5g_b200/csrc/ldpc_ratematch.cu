@@ -61,40 +61,45 @@ __global__ void rm_tx_kernel(nrb200_rm_desc_t p, const uint8_t *__restrict__ d, 
 
 // ---- RX: soft (E_r interleaved int16 per segment) -> HARQ buffer d (int16, += with wrap) -> decoder input llr (int8)
 // SoftT = int16_t (the CPU-compatible convention: demodulator LLRs) or int8_t (the offload convention: the caller already packed to int8)
+// One segment is spread over gridDim.y CTAs: a ring slot's thread sums its repetitions, updates the soft buffer AND writes the slot's saturated decoder input
+// itself (decoder position = buffer position + 2 Z), so nothing waits for anything; the positions no ring slot owns (the punctured 2 Z, the fillers, what lies
+// beyond a limited buffer's Ncb) are filled by a second independent sweep.
 template <typename SoftT>
-__global__ void rm_rx_kernel(nrb200_rm_desc_t p, const SoftT *__restrict__ soft, const uint32_t *__restrict__ E_seg,
-                             const uint32_t *__restrict__ s_off, int16_t *__restrict__ harq, uint32_t harq_stride, int8_t *__restrict__ llr,
-                             uint32_t llr_stride)
+__global__ void __launch_bounds__(256) rm_rx_kernel(nrb200_rm_desc_t p, const SoftT *__restrict__ soft, const uint32_t *__restrict__ E_seg,
+                                                    const uint32_t *__restrict__ s_off, int16_t *__restrict__ harq, uint32_t harq_stride, int8_t *__restrict__ llr,
+                                                    uint32_t llr_stride)
 {
-  const uint32_t r = blockIdx.x;
+  const uint32_t r = blockIdx.x, tid = blockIdx.y * blockDim.x + threadIdx.x, nthr = gridDim.y * blockDim.x;
   const uint32_t E = E_seg[r], EQm = E / p.Qm;
   const RmGeom g = rm_geom(p.BG, p.Z, p.Tbslbrm, p.C, p.F, p.K, p.rv);
   const SoftT *in = soft + s_off[r];
   int16_t *w = harq + (size_t)r * harq_stride;
+  const uint32_t kcZ = (uint32_t)(p.BG == 1 ? 68 : 52) * p.Z, twoZ = 2u * p.Z;
+  int8_t *l = llr + (size_t)r * llr_stride;
   // rate recovery: every ring slot sums the soft values of all its repetitions (int16 arithmetic wraps like the reference's +=)
-  for (uint32_t slot = threadIdx.x; slot < g.L; slot += blockDim.x) {
+  for (uint32_t slot = tid; slot < g.L; slot += nthr) {
     const uint32_t pos = rm_slot_to_pos(g, slot);
     uint32_t acc = p.clear ? 0u : (uint32_t)(uint16_t)w[pos];
     for (uint32_t k = (slot + g.L - g.r0) % g.L; k < E; k += g.L) {
       const uint32_t i = k / EQm, j = k - i * EQm;           // e[i*EQm + j] = f[j*Qm + i]
       acc += (uint32_t)(uint16_t)(int16_t)in[j * p.Qm + i];
     }
-    w[pos] = (int16_t)(uint16_t)acc;
+    const int v = (int)(int16_t)(uint16_t)acc;
+    w[pos] = (int16_t)v;
+    l[pos + twoZ] = (int8_t)(v > 127 ? 127 : v < -128 ? -128 : v);     // decoder input: saturate(d) (nr_ulsch_decoding.c:195-210)
   }
-  if (p.clear)   // memset(w, 0, Ncb): the filler span inside Ncb is cleared too
-    for (uint32_t pos = g.Foffset + threadIdx.x; pos < g.Foffset + g.F && pos < g.Ncb; pos += blockDim.x) w[pos] = 0;
-  __syncthreads();
-  // decoder input (kc*Z int8): punctured 2Z = 0, fillers = 127, the rest saturate(d)
-  const uint32_t kcZ = (uint32_t)(p.BG == 1 ? 68 : 52) * p.Z, twoZ = 2u * p.Z;
-  int8_t *l = llr + (size_t)r * llr_stride;
-  for (uint32_t i = threadIdx.x; i < kcZ; i += blockDim.x) {
-    int v;
-    if (i < twoZ) v = 0;
-    else if (i >= p.K - p.F && i < p.K) v = 127;
-    else { v = w[i - twoZ]; v = v > 127 ? 127 : v < -128 ? -128 : v; }
-    l[i] = (int8_t)v;
+  // everything else of the decoder input (kc*Z int8): punctured 2Z = 0, fillers = 127 (their soft-buffer span is cleared with the rest of Ncb on new data),
+  // positions beyond Ncb = whatever the soft buffer holds there
+  for (uint32_t i = tid; i < kcZ; i += nthr) {
+    if (i < twoZ) { l[i] = 0; continue; }
+    const uint32_t pos = i - twoZ;
+    if (i >= p.K - p.F && i < p.K) { l[i] = 127; if (p.clear && pos < g.Ncb) w[pos] = 0; continue; }
+    if (pos >= g.Ncb) { const int v = w[pos]; l[i] = (int8_t)(v > 127 ? 127 : v < -128 ? -128 : v); }
   }
 }
+
+// CTAs per segment: enough to put a transport block's few segments on the whole GPU, one for the hundreds of segments of a multi-user batch
+static inline unsigned rm_rx_parts(uint32_t n_seg) { return n_seg >= 256 ? 1u : n_seg >= 64 ? 4u : n_seg >= 16 ? 8u : 16u; }
 
 int launch_rm_tx(const nrb200_rm_desc_t &p, const uint8_t *d, uint32_t d_stride, const uint32_t *E, const uint32_t *off, uint8_t *f, cudaStream_t st)
 {
@@ -109,7 +114,7 @@ int launch_rm_rx(const nrb200_rm_desc_t &p, const int16_t *soft, const uint32_t 
                  int8_t *llr, uint32_t llr_stride, cudaStream_t st)
 {
   if (p.n_seg == 0) return 0;
-  rm_rx_kernel<int16_t><<<p.n_seg, 512, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
+  rm_rx_kernel<int16_t><<<dim3(p.n_seg, rm_rx_parts(p.n_seg)), 256, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "rm_rx launch");
   return 0;
@@ -119,7 +124,7 @@ int launch_rm_rx8(const nrb200_rm_desc_t &p, const int8_t *soft, const uint32_t 
                   int8_t *llr, uint32_t llr_stride, cudaStream_t st)
 {
   if (p.n_seg == 0) return 0;
-  rm_rx_kernel<int8_t><<<p.n_seg, 512, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
+  rm_rx_kernel<int8_t><<<dim3(p.n_seg, rm_rx_parts(p.n_seg)), 256, 0, st>>>(p, soft, E, off, harq, harq_stride, llr, llr_stride);
   ctx().launches++;
   NRB200_CUDA_OK(cudaGetLastError(), "rm_rx launch");
   return 0;

@@ -6,6 +6,10 @@
 #include "nrb200_ctx.h"
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -72,6 +76,14 @@ NRB200_EXPORT int32_t nrb200_pdsch_slot_tx_dev(const nrb200_pdsch_tx_slot_t *d, 
 
 // ------------------------------------------------------------------------------------------ transport-block level, host buffers (nr_ulsch_decoding)
 namespace {
+// segments of all transport blocks currently inside nrb200_ulsch_decode_tb_host: a lone block gets a cluster of SMs per segment (shortest time to its result);
+// once more segments are in flight than the GPU has room for clusters, every segment takes one SM and the fewest SM-cycles (most blocks per second)
+std::atomic<int> g_tb_segments_in_flight{0};
+struct InFlight {
+  int n, total;
+  explicit InFlight(int n_) : n(n_), total(g_tb_segments_in_flight.fetch_add(n_) + n_) {}
+  ~InFlight() { g_tb_segments_in_flight.fetch_sub(n); }
+};
 struct HarqBuf { int16_t *d = nullptr; size_t elems = 0; int dev = 0; };
 std::mutex g_harq_mu;
 std::map<uint64_t, HarqBuf> g_harq;
@@ -94,6 +106,16 @@ int16_t *harq_buffers(uint64_t key, size_t elems, bool *fresh)
 }
 }  // namespace
 
+NRB200_EXPORT int32_t nrb200_host_register(void *p, uint64_t bytes)
+{
+  { Ctx &cx = ctx(); if (!cx.inited && cx.init() != 0) return -1; cudaSetDevice(cx.dev); }
+  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) { ctx().set_error("host_register", e); cudaGetLastError(); return -2; }
+  return 0;
+}
+NRB200_EXPORT int32_t nrb200_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : (cudaGetLastError(), -2); }
+
 NRB200_EXPORT int32_t nrb200_ulsch_harq_release(uint64_t harq_key)
 {
   std::lock_guard<std::mutex> lk(g_harq_mu);
@@ -115,6 +137,12 @@ NRB200_EXPORT int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, co
   const uint32_t hard_stride = (kc * Z / 8 + 63u) & ~63u;
   size_t G = 0;
   for (uint32_t r = 0; r < n; r++) G += E[r];
+  static const bool timing = [] { const char *e = getenv("NRB200_TB_TIMING"); return e && *e == '1'; }();
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  const auto t0 = now();
+  const InFlight load((int)n);
+  const uint8_t latency_mode = load.total <= 74 ? 1 : 0;
   Workspace *w = ctx().acquire();
   // d_in: LLRs | E / offset table;  d_out: hard bits | iteration counts;  d_aux: decoder inputs
   const size_t tab_off = (2 * G + 63) & ~(size_t)63, out_it = (size_t)n * hard_stride;
@@ -130,8 +158,12 @@ NRB200_EXPORT int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, co
     uint32_t *tab = (uint32_t *)((uint8_t *)w->h_in + tab_off);
     size_t off = 0;
     for (uint32_t r = 0; r < n; r++) { tab[r] = E[r]; tab[n + r] = (uint32_t)off; off += E[r]; }
-    std::memcpy(w->h_in, ulsch_llr, 2 * G);
-    if (cudaMemcpyAsync(w->d_in, w->h_in, tab_off + 8 * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+    if (!d->llr_pinned) std::memcpy(w->h_in, ulsch_llr, 2 * G);
+    const auto t1 = now();
+    if (d->llr_pinned) {                                                    // the LLRs straight from the caller's page-locked buffer, the small table from the staging area
+      if (cudaMemcpyAsync(w->d_in, ulsch_llr, 2 * G, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+      if (cudaMemcpyAsync((uint8_t *)w->d_in + tab_off, tab, 8 * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
+    } else if (cudaMemcpyAsync(w->d_in, w->h_in, tab_off + 8 * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = -2; break; }
     if (fresh && cudaMemsetAsync(d_harq, 0, (size_t)n * ncb * 2, st) != cudaSuccess) { rc = -2; break; }
     const uint32_t *d_E = (const uint32_t *)((uint8_t *)w->d_in + tab_off), *d_off = d_E + n;
     // rate recovery: runs of segments with the same d_to_be_cleared flag (uniform in practice: one launch)
@@ -152,7 +184,7 @@ NRB200_EXPORT int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, co
       nrb200_ldpc_batch_desc_t dd;
       std::memset(&dd, 0, sizeof(dd));
       dd.BG = d->rm.BG; dd.Z = (uint16_t)Z; dd.R = R[r0]; dd.numMaxIter = (uint8_t)d->numMaxIter; dd.outMode = NRB200_OUTMODE_BIT;
-      dd.use_crc = 1; dd.crc_type = (uint8_t)d->crc_type; dd.crc_len_bits = d->crc_len_bits; dd.latency_mode = 1;
+      dd.use_crc = 1; dd.crc_type = (uint8_t)d->crc_type; dd.crc_len_bits = d->crc_len_bits; dd.latency_mode = latency_mode;
       dd.n_cb = r1 - r0; dd.llr_stride = llr_stride; dd.out_stride = hard_stride;
       rc = nrb200_ldpc_decode_batch_dev(&dd, (const int8_t *)w->d_aux + (size_t)r0 * llr_stride, (uint8_t *)w->d_out + (size_t)r0 * hard_stride,
                                         (int32_t *)((uint8_t *)w->d_out + out_it) + r0, st);
@@ -160,7 +192,10 @@ NRB200_EXPORT int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, co
     }
     if (rc) break;
     if (cudaMemcpyAsync(w->h_out, w->d_out, out_it + 4 * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
+    const auto t2 = now();
     if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -2; break; }
+    const auto t3 = now();
+    if (timing) fprintf(stderr, "ulsch_decode_tb_host: %u segments: stage %.1f us, enqueue %.1f us, wait %.1f us\n", n, us(t0, t1), us(t1, t2), us(t2, t3));
     const int32_t *it = (const int32_t *)((const uint8_t *)w->h_out + out_it);
     for (uint32_t r = 0; r < n; r++) {
       iters[r] = it[r];

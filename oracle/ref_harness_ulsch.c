@@ -34,29 +34,32 @@ int refh_ulsch_bind_ldpc(const char *so)
 
 enum { U_N_RB_UL, U_RB_SIZE, U_QM, U_NL, U_TBS_BYTES, U_RV, U_BG, U_TBSLBRM, U_MAX_ITER, U_NEW_DATA, U_ROUND, U_NB_RX, U_COUNT };
 
-static PHY_VARS_gNB *g_gNB;
+#define REFH_MAX_CTX 64
+static PHY_VARS_gNB *g_gNBs[REFH_MAX_CTX];          /* one gNB instance per calling thread of the multi-UE benchmark */
+static int g_n_rb_ul[REFH_MAX_CTX];
 
 /* One PUSCH through nr_ulsch_decoding + the caller's collection loop.  llr: G int16.  Outputs: info[0] = C, [1] = K, [2] = Z, [3] = F, [4] = llrLen;
  * iters[r]; c_out: C x (K / 8) bytes (harq_process->c[r]); tb_out: the transport block as nr_postDecode assembles it (harq_process->b, TBS + 3 bytes);
  * d_out (optional): C x 66 Z | 50 Z int16 (harq_process->d[r]).  p[U_NEW_DATA] = 1 starts a new transport block (harq_to_be_cleared), 0 combines.
  * Returns nr_ulsch_decoding's return value. */
-int refh_ulsch_decode(const int32_t *p, const int16_t *llr, int G, int32_t *info, int32_t *iters, uint8_t *c_out, uint8_t *tb_out, int16_t *d_out)
+int refh_ulsch_decode_ctx(int ctx, const int32_t *p, const int16_t *llr, int G, int32_t *info, int32_t *iters, uint8_t *c_out, uint8_t *tb_out, int16_t *d_out)
 {
-  if (!g_gNB) {
-    g_gNB = calloc(1, sizeof(*g_gNB));
+  if (ctx < 0 || ctx >= REFH_MAX_CTX) return -101;
+  if (!g_gNBs[ctx]) {
+    PHY_VARS_gNB *g_gNB = g_gNBs[ctx] = calloc(1, sizeof(*g_gNB));
     crcTableInit();                                                        /* phy_init_nr_gNB does (PHY/INIT/nr_init.c) */
     initNamedTpool("n", &g_gNB->threadPool, false, "gNB-tpool");          /* no worker threads: jobs run in pushTpool, like nr_ulsim without -C */
     initNotifiedFIFO(&g_gNB->respDecode);
     g_gNB->ulsch = calloc(1, sizeof(NR_gNB_ULSCH_t));
     g_gNB->pusch_vars = calloc(1, sizeof(NR_gNB_PUSCH));
   }
-  PHY_VARS_gNB *gNB = g_gNB;
-  static int n_rb_ul;
+  PHY_VARS_gNB *gNB = g_gNBs[ctx];
+  int n_rb_ul = g_n_rb_ul[ctx];
   if (n_rb_ul != p[U_N_RB_UL]) {                                          /* the ULSCH's segment buffers are sized by the carrier (init_nr_transport) */
     if (n_rb_ul) free_gNB_ulsch(&gNB->ulsch[0], (uint16_t)n_rb_ul);
     gNB->ulsch[0] = new_gNB_ulsch((uint8_t)p[U_MAX_ITER], (uint16_t)p[U_N_RB_UL]);
     gNB->ulsch[0].rnti = 0x1234;
-    n_rb_ul = p[U_N_RB_UL];
+    g_n_rb_ul[ctx] = p[U_N_RB_UL];
   }
   NR_DL_FRAME_PARMS *fp = &gNB->frame_parms;
   fp->nb_antennas_rx = p[U_NB_RX]; fp->N_RB_UL = p[U_N_RB_UL];
@@ -91,4 +94,21 @@ int refh_ulsch_decode(const int32_t *p, const int16_t *llr, int G, int32_t *info
   }
   memcpy(tb_out, hp->b, (size_t)p[U_TBS_BYTES] + 3);
   return rc;
+}
+
+int refh_ulsch_decode(const int32_t *p, const int16_t *llr, int G, int32_t *info, int32_t *iters, uint8_t *c_out, uint8_t *tb_out, int16_t *d_out)
+{
+  return refh_ulsch_decode_ctx(0, p, llr, G, info, iters, c_out, tb_out, d_out);
+}
+
+/* n back-to-back calls on context ctx (new data every time), timed here so that no interpreter sits between the calls; returns seconds, < 0 on error */
+#include <time.h>
+double refh_ulsch_decode_loop(int ctx, int n, const int32_t *p, const int16_t *llr, int G, int32_t *info, int32_t *iters, uint8_t *c_out, uint8_t *tb_out)
+{
+  struct timespec a, b;
+  clock_gettime(CLOCK_MONOTONIC, &a);
+  for (int i = 0; i < n; i++)
+    if (refh_ulsch_decode_ctx(ctx, p, llr, G, info, iters, c_out, tb_out, NULL) < 0) return -1.0;
+  clock_gettime(CLOCK_MONOTONIC, &b);
+  return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
 }
