@@ -1,4 +1,4 @@
-/* Link-time / LD_PRELOAD interposer for the OAI UE: nr_pdsch_channel_estimation on the GPU with host C unchanged (the UE-side twin of
+/* Link-time interposer for the OAI UE: nr_pdsch_channel_estimation on the GPU with host C unchanged (the UE-side twin of
  * oai_shim_pusch_chest.c; see there for how it is used).  Same prototype as openair1/PHY/NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1614-1628, compiled
  * against OAI's headers; called once per DMRS symbol and port from nr_ue_pdsch_procedures (SCHED_NR_UE/phy_procedures_nr_ue.c:527-543).  It reads what the
  * reference function reads (frame_parms, the slot's rxdataF planes, ue->chest_freq) and rewrites the DMRS symbol of dl_ch_estimates[p * nb_rx + aarx]. */

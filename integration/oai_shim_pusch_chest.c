@@ -1,11 +1,11 @@
-/* Link-time / LD_PRELOAD interposer for OpenAirInterface: nr_pusch_channel_estimation on the GPU with host C unchanged.
+/* Link-time interposer for OpenAirInterface: nr_pusch_channel_estimation on the GPU with host C unchanged.
  *
  * OAI has no plug-in boundary for channel estimation: the function is called directly from nr_rx_pusch_tp
  * (openair1/PHY/NR_TRANSPORT/nr_ulsch_demodulation.c:1473-1492).  This file DEFINES the same symbol with the same prototype
- * (openair1/PHY/NR_ESTIMATION/nr_ul_estimation.h, nr_ul_channel_estimation.c:67-75) and forwards to libldpc_b200.so, so that either
- *   - linking it ahead of libPHY_NR (or with -Wl,--wrap), or
- *   - LD_PRELOAD=libnrb200_shim_chest.so nr-softmodem ...      (the softmodem is linked -rdynamic, CMakeLists.txt:164)
- * routes every call to the B200 library.  It is compiled against the reference's own headers (integration/build_shims.sh), reads exactly the
+ * (openair1/PHY/NR_ESTIMATION/nr_ul_estimation.h, nr_ul_channel_estimation.c:67-75) and forwards to libldpc_b200.so, so that
+ * linking it ahead of libPHY_NR with -Wl,--allow-multiple-definition (first definition wins) or with -Wl,--wrap routes every call to the B200 library.
+ * (OAI links the PHY statically into the softmodem, and a definition inside the executable wins over LD_PRELOAD: preloading only works for a build that keeps
+ * the PHY in a shared library.)  It is compiled against the reference's own headers (integration/build_shims.sh), reads exactly the
  * fields the reference function reads (frame_parms, common_vars.rxdataF, pusch_vars[ul_id].ul_ch_estimates, the PDU) and writes exactly what it
  * writes (the DMRS symbol of ul_ch_estimates for every rx antenna, *max_ch, *nvar, gNB->ulsch[ul_id].delay).  Transform precoding is served with OAI's
  * own low-PAPR sequence table.  A configuration the library refuses aborts loudly like any other AssertFatal in this code base: there is no CPU fallback.

@@ -1,4 +1,4 @@
-/* Link-time / LD_PRELOAD interposers for the OAI RU front end: nr_feptx0 and nr_fep_full on the GPU with host C unchanged (hook
+/* Link-time interposers for the OAI RU front end: nr_feptx0 and nr_fep_full on the GPU with host C unchanged (hook
  * the OFDM front end one level above the per-symbol dft()/idft() plug-in, where a whole slot's symbols are visible).  Same prototypes as
  * openair1/SCHED_NR/nr_ru_procedures.c:53 and :228, compiled against OAI's headers.
  *   nr_feptx0(ru, slot, first_symbol, num_symbols, aa)  the IDFT + cyclic prefix of num_symbols symbols of tx antenna aa: txdataF_BF[aa] -> txdata[aa]

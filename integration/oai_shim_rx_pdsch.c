@@ -1,4 +1,4 @@
-/* Link-time / LD_PRELOAD interposer for the OAI UE: nr_rx_pdsch on the GPU with host C unchanged (see oai_shim_pusch_chest.c for how the interposers
+/* Link-time interposer for the OAI UE: nr_rx_pdsch on the GPU with host C unchanged (see oai_shim_pusch_chest.c for how the interposers
  * are used).  Same prototype as openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-258, compiled against OAI's headers.
  *
  * nr_ue_pdsch_procedures calls the function once per PDSCH symbol (SCHED_NR_UE/phy_procedures_nr_ue.c:568-600).  The reference extracts, scales and

@@ -1,4 +1,4 @@
-/* Link-time / LD_PRELOAD interposer for the OAI gNB: nr_rx_pusch_tp on the GPU with host C unchanged (see oai_shim_pusch_chest.c for how the
+/* Link-time interposer for the OAI gNB: nr_rx_pusch_tp on the GPU with host C unchanged (see oai_shim_pusch_chest.c for how the
  * interposers are used).  Same prototype as openair1/PHY/NR_TRANSPORT/nr_ulsch_demodulation.c:1447-1451, compiled against OAI's headers.
  *
  * The reference function (:1447-1700) estimates the channel on every DMRS symbol and layer, measures powers, derives log2_maxh from the first symbol that
