@@ -9,7 +9,9 @@
  *   points oai_dfts.c:4352-7706 every call transforms FOUR interleaved sequences: c16 number 4 n + l is element n of transform l, 4 N c16 in and out).
  *   DFT_2304: the reference's function combines uninitialised stack (it calls the single-transform dft768 on four-way data, oai_dfts.c:7288-7310) and is not
  *   reproducible; this library returns the 768 x 3 transform the function documents.
- * The sizes above 8192 of FOREACH_DFTSZ / FOREACH_IDFTSZ are not implemented yet: calling them aborts loudly (there is no CPU fallback in this library).
+ *   the sizes above 8192 (12288 16384 18432 24576 36864 49152 both directions, 32768 / 98304, idft 65536): radix-3 / 4 / 2 levels over global memory on top of the
+ *   shared-memory transforms; 32768, 65536 and 98304 crash or read beyond their tables in the reference (DESIGN.md defect 12) and are checked against a float DFT only.
+ * 9216 and 73728 are AssertFatal("Need to do this") in the reference and abort here too (there is no CPU fallback in this library).
  */
 #ifndef NRB200_DFTS_H
 #define NRB200_DFTS_H

@@ -364,7 +364,8 @@ int32_t nrb200_chest_time_avg_host(uint32_t fft_size, uint32_t nb_rx, uint32_t s
  * nr_rate_matching_ldpc_rx, the bit-exact flooding decoder with parity-check stop, numMaxIter from the parameter block.
  * decode: p->{BG,Z,R,F,Qm,rv,E,numMaxIter,setCombIn}; llr = E int8; out = K/8 bytes (K = 22Z | 10Z); returns iterations, < 0 on error.
  * encode: impp->{BG,Zc,K,F,Qm,rv,E}; in = K/8 bytes; out = E bytes, one bit each. */
-int32_t nrb200_ldpc_offload_init(void);   /* = LDPCinit of libldpc_b200.so under a name the shim can link to */
+int32_t nrb200_ldpc_offload_init(void);      /* = LDPCinit of libldpc_b200.so under a name the shim can link to */
+int32_t nrb200_ldpc_offload_release(void);   /* frees the library-owned soft buffers (LDPCshutdown of the _t2 module) */
 int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t r, const int8_t *llr, uint8_t *out);
 int32_t nrb200_ldpc_offload_encode(const uint8_t *in, uint8_t *out, const nrb200_ldpc_enc_params_t *impp);
 

@@ -972,19 +972,31 @@ NRB200_EXPORT int32_t nrb200_pusch_chest_host(const nrb200_pusch_chest_t *d, con
 // ------------------------------------------------------------------------------------------ offload calling convention
 // Library-owned HARQ soft buffers, one per (ulsch_id, segment) like the accelerator's internal HARQ memory
 // (harq_combined_input.offset = ulsch_id * 64 * LDPC_MAX_CB_SIZE + r * LDPC_MAX_CB_SIZE, nrLDPC_decoder_offload.c:545-546).
-static int16_t *offload_harq(uint8_t ulsch_id, uint8_t r)
+struct OffloadHarq { int16_t *d = nullptr; int dev = 0; std::mutex mu; };   // mu: the reference serialises calls on one buffer with decode_mutex
+static std::mutex g_oh_mu;
+static std::map<uint32_t, OffloadHarq> g_oh_store;                            // node based: entries never move
+static OffloadHarq *offload_harq(uint8_t ulsch_id, uint8_t r)
 {
-  static std::mutex mu;
-  static std::map<uint32_t, int16_t *> store;
-  std::lock_guard<std::mutex> lk(mu);
+  std::lock_guard<std::mutex> lk(g_oh_mu);
   const uint32_t key = ((uint32_t)ctx().dev << 16) | ((uint32_t)ulsch_id << 8) | r;   // a buffer lives on the device its (ulsch_id, r) is pinned to
-  auto it = store.find(key);
-  if (it != store.end()) return it->second;
-  int16_t *d = nullptr;
-  if (cudaMalloc(&d, (size_t)66 * 384 * 2) != cudaSuccess) return nullptr;
-  cudaMemset(d, 0, (size_t)66 * 384 * 2);
-  store[key] = d;
-  return d;
+  OffloadHarq &h = g_oh_store[key];
+  if (h.d == nullptr) {
+    if (cudaMalloc(&h.d, (size_t)66 * 384 * 2) != cudaSuccess) { h.d = nullptr; return nullptr; }
+    cudaMemset(h.d, 0, (size_t)66 * 384 * 2);
+    h.dev = ctx().dev;
+  }
+  return &h;
+}
+// frees every soft buffer of the offload convention (the _t2 library's LDPCshutdown; at most 65536 keys x 50 KB can accumulate otherwise)
+NRB200_EXPORT int32_t nrb200_ldpc_offload_release(void)
+{
+  std::lock_guard<std::mutex> lk(g_oh_mu);
+  for (auto &kv : g_oh_store) {
+    std::lock_guard<std::mutex> lk2(kv.second.mu);
+    if (kv.second.d) { cudaSetDevice(kv.second.dev); cudaFree(kv.second.d); kv.second.d = nullptr; }
+  }
+  cudaSetDevice(ctx().dev);
+  return 0;
 }
 
 NRB200_EXPORT int32_t nrb200_ldpc_offload_init(void) { return LDPCinit(); }
@@ -1012,7 +1024,10 @@ NRB200_EXPORT int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t 
   if (!dg) return -4;
   DecodeArgs a;
   if (int rc = fill_args(&d, *hg, &a)) return rc;
-  int16_t *harq = offload_harq(ulsch_id, r);
+  OffloadHarq *oh = offload_harq(ulsch_id, r);
+  if (!oh) return -5;
+  std::lock_guard<std::mutex> key_lock(oh->mu);
+  int16_t *harq = oh->d;
   if (!harq) return -5;
   Workspace *w = ctx().acquire();
   if (!w || !w->reserve((size_t)p->E + 64, kcZ + d.out_stride + 64, 64)) { if (w) ctx().release(w); return -5; }

@@ -7,7 +7,7 @@
 #define SHIM_EXPORT extern "C" __attribute__((visibility("default")))
 
 SHIM_EXPORT int32_t LDPCinit(void) { return nrb200_ldpc_offload_init(); }
-SHIM_EXPORT int32_t LDPCshutdown(void) { return 0; }   // the HARQ store outlives a reload, like the accelerator's memory
+SHIM_EXPORT int32_t LDPCshutdown(void) { return nrb200_ldpc_offload_release(); }   // free_LDPClib: the soft buffers go with the module
 
 SHIM_EXPORT int32_t LDPCdecoder(nrb200_ldpc_dec_params_t *p, uint8_t harq_pid, uint8_t ulsch_id, uint8_t C, int8_t *p_llr, int8_t *p_out,
                                 nrb200_ldpc_time_stats_t *prof, nrb200_decode_abort_t *ab)

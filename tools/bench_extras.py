@@ -107,7 +107,7 @@ def main():
     from openairinterface5g_b200.ofdm import NrOfdmParms
     Pm = NrOfdmParms(4096, 1, 273)
     rot = Pm.symbol_rotation(3619200000.0)
-    na = 64
+    na = int(os.environ.get("NRB200_OFDM_ANTENNA_SLOTS", "64"))
     dtx = Pm.desc(1, na, rot)
     Fs = [torch.randint(-3000, 3000, (na, 14 * 4096 * 2), dtype=torch.int16, device=dev, generator=g) for _ in range(5)]
     tx = torch.empty((na, 2 * dtx.t_stride), dtype=torch.int16, device=dev)
@@ -162,25 +162,7 @@ def main():
     print(json.dumps({"what": "nr_modulation 64QAM G=471744", "us": ms * 1e3, "value": G / 6 / ms * 1e3, "unit": "symbols/s"}), flush=True)
     ms = timeit(lambda: lib.unscramble_llr_torch(llrs, 0, 42, 4660), n=50)
     print(json.dumps({"what": "nr_codeword_unscrambling G=471744", "us": ms * 1e3, "value": G / ms * 1e3, "unit": "LLR/s"}), flush=True)
-    # ---- the per-code-block OAI ABI under tpool-style concurrency: T host threads, one blocking LDPCdecoder call per segment
-    import threading
-    from openairinterface5g_b200.synth import awgn_llr, random_payloads
-    P = random_payloads(64, K, 3)
-    cwn = lib.encode_batch_host(1, Z, K, P)
-    llr = awgn_llr(cwn, Z, 68, 1.0, 1.0 / 3.0, 3)
-    for T in (1, 8, 32):
-        cnt = [0] * T
-        stop = time.perf_counter() + 2.0
-
-        def work(t):
-            j = t
-            while time.perf_counter() < stop:
-                lib.LDPCdecoder(1, Z, 13, 8, llr[j % 64]); cnt[t] += 1; j += T
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
-        t0 = time.perf_counter()
-        [t.start() for t in ths]; [t.join() for t in ths]
-        dt = time.perf_counter() - t0
-        print(json.dumps({"what": "LDPCdecoder per-call ABI", "host_threads": T, "value": sum(cnt) / dt, "unit": "CB/s", "us_per_call": 1e6 * dt * T / max(1, sum(cnt))}), flush=True)
+    # (the per-call LDPCdecoder / LDPCencoder ABI is measured by tools/bench_abi.py through a C harness: Python caller threads would measure the interpreter lock)
 
 
 if __name__ == "__main__":

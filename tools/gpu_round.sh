@@ -16,6 +16,7 @@ timeout 120 python tools/kernel_time.py 3.0 2>&1 | tail -1 | tee -a gpurun_out/v
 fi
 echo "== micro-benchmark (ALU pipe / opcode-blend / code-footprint ceilings)"; timeout 120 tools/ubench/_bin/alu_ceiling | tee gpurun_out/alu_ceiling_${TAG}.json
 echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -24 | tee gpurun_out/extras_${TAG}.jsonl
+echo "== extras, OFDM front end with 592 antenna-slots per launch"; NRB200_OFDM_ANTENNA_SLOTS=592 timeout 300 python tools/bench_extras.py 2>&1 | grep ofdm_ | tee gpurun_out/extras_ofdm592_${TAG}.jsonl | cut -c1-260
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json
 if [ "$MODE" = "full" ]; then
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
@@ -31,6 +32,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 fi
 echo "== per-call loader ABI (tools/abi_bench.c: this library and the compiled reference, same harness)"
 timeout 300 python tools/bench_abi.py 2.0 1.0 2>&1 | tail -16 | tee gpurun_out/abi_${TAG}.jsonl
+echo "== nr_ulsch_decoding through the OAI-side caller: reference function + CPU decoder vs interposer"
+timeout 400 python tools/bench_ulsch_tb.py 2.0 2>&1 | tee gpurun_out/ulsch_tb_${TAG}.jsonl | cut -c1-420
 echo "== cluster decoder: time of one small launch, phase marks"
 for c in 8 4 2 0; do NRB200_CLUSTER=$c timeout 120 python tools/cluster_time.py 1.0 1 8 2>&1 | tail -2; done | tee gpurun_out/cluster_time_${TAG}.txt
 timeout 120 python tools/cluster_time.py 1.0 2>&1 | tail -6 | tee -a gpurun_out/cluster_time_${TAG}.txt
