@@ -26,6 +26,10 @@ struct alignas(16) ClusterSched {
   uint8_t col_rank[kMaxCols];
   uint8_t edge_rank[kMaxEdges];
   uint8_t pad[16 - (kMaxCols + kMaxEdges) % 16];
+  // bytes each phase delivers into CTA r through asynchronous stores (what its mbarrier is armed with): check-node phase = (ZB + 4) per stored edge whose
+  // column r owns (Zw message words + the halo word) + one 4-byte verdict word from every CTA; bit-node phase = 2 ZB per broadcast column (the doubled A row)
+  uint32_t cn_tx[kClMaxCtas];
+  uint32_t bn_tx, pad2[3];
 };
 
 // C CTAs of T warps each; false when the configuration cannot be split this way (Zw not a multiple of 32, too many lists).

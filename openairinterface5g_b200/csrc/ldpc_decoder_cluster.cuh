@@ -70,9 +70,10 @@ __device__ __forceinline__ void cn_row_split(const PackedGraph &G, char *__restr
     if ((j == DH - 1) && dummy) continue;
     const uint32_t rn = make_r(q[j], tm.n1, p1, p2, sgn, one, mone);
     sts(smb, rb + j * RSB, rn);
-    const uint32_t ra = cl_map(sbase + rb + j * RSB, prmt(G.cn_desc[e0 + j][1], 0u, 0x4441u));
-    cl_st(ra, rn);
-    if (halo) cl_st(ra + ZB, rn);
+    const uint32_t owner = prmt(G.cn_desc[e0 + j][1], 0u, 0x4441u);
+    const uint32_t ra = cl_map(sbase + rb + j * RSB, owner), mb = cl_mbar_at(0, owner);
+    cl_push(ra, rn, mb);
+    cl_push_if(halo, ra + ZB, rn, mb);
   }
 }
 
@@ -99,9 +100,9 @@ __device__ __forceinline__ void bn_col_split(const PackedGraph &G, char *__restr
   const uint32_t a = prmt(lo, hi, 0x6420u);
   const uint32_t ao = sbase + G.off_A + G.col_arow[c] * 2 * ZB + kb;
   for (int r = (int)half; r < C; r += 2) {
-    const uint32_t ra = cl_map(ao, (uint32_t)r);
-    cl_st(ra, a);
-    cl_st(ra + ZB, a);
+    const uint32_t ra = cl_map(ao, (uint32_t)r), mb = cl_mbar_at(1, (uint32_t)r);
+    cl_push(ra, a, mb);
+    cl_push(ra + ZB, a, mb);
   }
 }
 
@@ -114,7 +115,7 @@ ldpc_decode_cluster_kernel(const PackedGraph *__restrict__ gdev, const ClusterSc
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ __align__(16) PackedGraph G;
   __shared__ __align__(16) ClusterSched S;
-  __shared__ __align__(8) uint8_t s_flags[2][8];
+  __shared__ __align__(16) uint32_t s_flags[2][8];                       // per iteration parity: one verdict word per CTA of the cluster
   __shared__ int s_flag;
   char *smb = reinterpret_cast<char *>(sm);
   static_assert(sizeof(PackedGraph) % 16 == 0 && sizeof(ClusterSched) % 16 == 0, "tables are copied with 16-byte accesses");
@@ -137,7 +138,8 @@ ldpc_decode_cluster_kernel(const PackedGraph *__restrict__ gdev, const ClusterSc
       else reinterpret_cast<uint4 *>(&S)[i - nG] = __ldg(s4 + (i - nG));
     }
   }
-  if (threadIdx.x < 16) reinterpret_cast<uint8_t *>(s_flags)[threadIdx.x] = 0;
+  if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(s_flags)[threadIdx.x] = 0;
+  if (NRB200_CLUSTER_ASYNC && threadIdx.x == 0) cl_mbar_init();           // before the first cluster barrier: nobody stores into this CTA earlier
   __syncthreads();
   const int C = S.C;
   const uint32_t rank = cl_rank();
@@ -231,10 +233,12 @@ ldpc_decode_cluster_kernel(const PackedGraph *__restrict__ gdev, const ClusterSc
   const int maxIter = a.numMaxIter;
   int numIter = 0, par = 0;
   bool done = false, wrote = false;
+  uint32_t phase = 0;                                                    // parity of the two mbarriers' current phase (both complete once per iteration)
   while (!done) {
     // ---- CN phase of iteration numIter + 1 (yields the syndrome of iteration numIter); rank 0 samples the caller's abort flag meanwhile
     uint32_t bad = 0, ab = 0;
     if (io.abort && rank == 0 && threadIdx.x == 0) ab = *io.abort;
+    if (NRB200_CLUSTER_ASYNC && threadIdx.x == 0) cl_mbar_expect(0, S.cn_tx[rank]);   // what this phase delivers to this CTA: messages of its columns + C verdicts
     for (int i = S.cn_start[list]; i < S.cn_start[list + 1]; i++) {
       const int it = S.cn_items[i];
       if (it & kClSplitItem) {
@@ -248,18 +252,21 @@ ldpc_decode_cluster_kernel(const PackedGraph *__restrict__ gdev, const ClusterSc
     NRB200_CL_MARK();
     const int bad_cta = __syncthreads_or(bad != 0);
     if (threadIdx.x == 0) {
+      // the verdict goes out after the CTA-wide barrier above: its arrival tells the receiver that EVERY warp of this CTA is done with the phase
       const uint32_t v = (bad_cta ? 1u : 0u) | (ab ? 2u : 0u);
       const uint32_t fa = (uint32_t)__cvta_generic_to_shared(&s_flags[par][rank]);
-      for (int r = 0; r < C; r++) cl_st8(cl_map(fa, (uint32_t)r), v);
+      for (int r = 0; r < C; r++) cl_push(cl_map(fa, (uint32_t)r), v, cl_mbar_at(0, (uint32_t)r));
     }
-    cl_sync();                                                        // every message of this iteration is delivered, every verdict too
+    if (NRB200_CLUSTER_ASYNC) { if (!cl_mbar_wait(0, phase)) __trap(); }
+    else cl_sync();                                                   // every message of this iteration is delivered, every verdict too
     NRB200_CL_MARK();
-    const uint2 f = *reinterpret_cast<const uint2 *>(s_flags[par]);
+    const uint4 f0 = *reinterpret_cast<const uint4 *>(&s_flags[par][0]), f1 = *reinterpret_cast<const uint4 *>(&s_flags[par][4]);
     par ^= 1;
-    const uint32_t any = f.x | f.y;
-    if (numIter >= 2 && !a.use_crc && (any & 0x01010101u) == 0u) break;   // iteration numIter passed its parity check (nrLDPC_decoder.c:552)
+    const uint32_t any = f0.x | f0.y | f0.z | f0.w | f1.x | f1.y | f1.z | f1.w;
+    if (numIter >= 2 && !a.use_crc && (any & 1u) == 0u) break;          // iteration numIter passed its parity check (nrLDPC_decoder.c:552)
     numIter++;
-    if (numIter >= 2 && (any & 0x02020202u)) { numIter = maxIter + 2; break; }   // check_abort at the top of the iteration (:557-560)
+    if (numIter >= 2 && (any & 2u)) { numIter = maxIter + 2; break; }    // check_abort at the top of the iteration (:557-560)
+    if (NRB200_CLUSTER_ASYNC && threadIdx.x == 0) cl_mbar_expect(1, S.bn_tx);
     // ---- BN phase: the columns this CTA owns, all reads local, the new word into every replica of A
     for (int i = S.bn_start[list]; i < S.bn_start[list + 1]; i++) {
       const int it = S.bn_items[i];
@@ -267,7 +274,8 @@ ldpc_decode_cluster_kernel(const PackedGraph *__restrict__ gdev, const ClusterSc
       else bn_col<ZWC>(G, smb, it & 0xFF, kb0 + 128u * (uint32_t)(it >> 8), C, sbase);
     }
     NRB200_CL_MARK();
-    cl_sync();                                                        // every replica of A is complete
+    if (NRB200_CLUSTER_ASYNC) { if (!cl_mbar_wait(1, phase)) __trap(); phase ^= 1u; }
+    else cl_sync();                                                   // every replica of A is complete
     NRB200_CL_MARK();
     if (numIter == 1) {
       if (!(1 <= maxIter)) done = true;

@@ -203,6 +203,10 @@ bool build_cluster_sched(const GraphDev &g, const PackedGraph &p, int C, int T, 
   }
   s->bn_start[C * T] = (int16_t)n;
   for (int m = 0; m < g.nreal; m++) s->edge_rank[m] = s->col_rank[g.edge_col[m]];
+  const uint32_t ZB = 4u * (uint32_t)p.Zw;
+  for (int r = 0; r < C; r++) s->cn_tx[r] = 4u * (uint32_t)C;
+  for (int m = 0; m < g.nreal; m++) s->cn_tx[s->edge_rank[m]] += ZB + 4u;
+  s->bn_tx = 2u * ZB * (uint32_t)cols.size();
   return true;
 }
 
