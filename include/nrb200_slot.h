@@ -25,7 +25,8 @@ extern "C" {
 typedef struct nrb200_sch_rx_slot_s {
   nrb200_ofdm_slot_t ofdm;        /* the slot's FFT windows (RX form of the descriptor) */
   nrb200_pusch_chest_t chest;     /* every DMRS port of the PDU in one call (n_ports); pdsch_ue selects the UE's estimator */
-  nrb200_pusch_rx_t rx;           /* inner receiver; its log2_maxh is measured on the device, max_ch / nvar are read from the estimator's state */
+  nrb200_pusch_rx_t rx;           /* inner receiver; its log2_maxh is measured on the device, max_ch / nvar are read from the estimator's state.
+                                   * DFT-s-OFDM: chest.transform_precoding + chest.lowpapr_seq (device) and rx.transform_precoding + rx.d_tp_scratch */
   nrb200_rm_desc_t rm;            /* rate recovery of the C segments (n_seg = C) */
   uint8_t R, numMaxIter;          /* decoder LUT (nr_get_R_ldpc_decoder) and iteration cap */
   uint8_t use_estimates;          /* 1: skip channel estimation, d_est holds the caller's estimates */

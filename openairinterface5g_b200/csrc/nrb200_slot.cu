@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -106,6 +107,17 @@ int16_t *harq_buffers(uint64_t key, size_t elems, bool *fresh)
 }
 }  // namespace
 
+// Wait for a stream without monopolising a core: poll, and after a while yield between polls.  With as many blocking callers as host cores a pure spin
+// (cudaStreamSynchronize's default) starves whoever is preparing the next launch.
+static cudaError_t polite_sync(cudaStream_t st)
+{
+  for (unsigned spins = 0;; spins++) {
+    const cudaError_t e = cudaStreamQuery(st);
+    if (e != cudaErrorNotReady) return e;
+    if (spins > 24) std::this_thread::yield();
+  }
+}
+
 NRB200_EXPORT int32_t nrb200_host_register(void *p, uint64_t bytes)
 {
   { Ctx &cx = ctx(); if (!cx.inited && cx.init() != 0) return -1; cudaSetDevice(cx.dev); }
@@ -193,7 +205,7 @@ NRB200_EXPORT int32_t nrb200_ulsch_decode_tb_host(const nrb200_ulsch_tb_t *d, co
     if (rc) break;
     if (cudaMemcpyAsync(w->h_out, w->d_out, out_it + 4 * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = -2; break; }
     const auto t2 = now();
-    if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -2; break; }
+    if (polite_sync(st) != cudaSuccess) { rc = -2; break; }
     const auto t3 = now();
     if (timing) fprintf(stderr, "ulsch_decode_tb_host: %u segments: stage %.1f us, enqueue %.1f us, wait %.1f us\n", n, us(t0, t1), us(t1, t2), us(t2, t3));
     const int32_t *it = (const int32_t *)((const uint8_t *)w->h_out + out_it);

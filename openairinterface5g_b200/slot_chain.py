@@ -11,13 +11,13 @@ import torch
 
 from . import transport as T
 from . import ldpc as _L
-from .ldpc import CRC24_B, PuschChestDesc, PuschRxDesc
+from .ldpc import CRC24_A, CRC24_B, PuschChestDesc, PuschRxDesc
 from .ofdm import NrOfdmParms
 
 
 class PuschSlotChain:
     def __init__(self, lib, dl, device, A=235624, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_rx=4, Qm=6, slot=1, rnti=0x1234, nid=77,
-                 ul_freq=3609200000.0, max_iter=8, dmrs_id=55, n_layers=1):
+                 ul_freq=3609200000.0, max_iter=8, dmrs_id=55, n_layers=1, transform_precoding=None):
         self.lib, self.dl, self.dev = lib, dl, device
         self.latency_mode = 1            # decoder: a cluster of SMs per code block (one slot alone); the pipelines below run many slots and set 0
         self.P = NrOfdmParms(N, mu, carrier_rb)
@@ -29,6 +29,7 @@ class PuschSlotChain:
         self.seg = T.nr_segmentation(A + 24, 1)
         assert (A + 24 + self.seg["C"] * self.seg["L"]) % (8 * self.seg["C"]) == 0, "pick A like a real TBS: whole bytes per segment"
         self.C, self.K, self.Z, self.F = self.seg["C"], self.seg["K"], self.seg["Z"], self.seg["F"]
+        self.seg_crc_type = CRC24_B if self.C > 1 else CRC24_A             # crcType(C, A): a lone segment is checked with the transport block's own CRC
         self.G = T.nr_get_G(rb_size, 14, 12, 1, 0, Qm, n_layers)
         E = [T.nr_get_E(self.G, self.C, Qm, n_layers, r) for r in range(self.C)]
         self.R = T.nr_get_R_ldpc_decoder(0, E[0], 1, self.Z)[0]
@@ -41,6 +42,19 @@ class PuschSlotChain:
         assert lib.pusch_num_llr(self.desc) == self.G
         self.cdescs = [PuschChestDesc(N, nb_rx, slot, 2, p, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N, 1) for p in range(n_layers)]
         self.cdesc = PuschChestDesc(N, nb_rx, slot, 2, 0, rb_start, 0, rb_size, self.P.first_carrier_offset, 0, dmrs_id, 14 * N, 14 * N, n_layers)   # all ports in one call
+        # transform precoding (DFT-s-OFDM): (u, v) of the low-PAPR type-1 DMRS; one layer, Qm <= 6, 12 * rb_size one of nr_idft's sizes
+        self.tp = transform_precoding
+        if self.tp is not None:
+            assert n_layers == 1 and Qm <= 6
+            seq = lib.lowpapr_sequence(self.tp[0], self.tp[1], 6 * rb_size)
+            assert seq is not None, "sequence lengths below 30 are table look-ups the caller provides"
+            self._seq_host, self._seq_dev = seq, torch.from_numpy(seq).to(device)
+            for cd in self.cdescs:
+                cd.set_lowpapr(self._seq_host)                                  # host entry points (pilot generation for the synthesiser)
+            self.cdesc.set_lowpapr(self._seq_dev)
+            self.desc.transform_precoding = 1
+            self._tp_scratch = torch.empty(lib.pusch_tp_scratch_bytes(self.desc), dtype=torch.uint8, device=device)
+            self.desc.d_tp_scratch = self._tp_scratch.data_ptr()
         self.est = torch.zeros((n_layers * nb_rx, 14 * N, 2), dtype=torch.int16, device=device)   # ul_ch_estimates[p * nb_rx + aarx]
         self.chest_scratch = torch.empty(lib.pusch_chest_scratch_bytes(self.cdesc), dtype=torch.uint8, device=device)
         self.chest_state = torch.zeros((n_layers, 18), dtype=torch.int32, device=device)
@@ -73,7 +87,7 @@ class PuschSlotChain:
         d.rx.d_est_state, d.rx.est_state_ports = 0, 0
         d.rm = self.lib._rmdesc(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.C, 1)
         d.R, d.numMaxIter, d.use_estimates, d.latency_mode = self.R, self.max_iter, 1 if use_estimates else 0, self.latency_mode
-        d.crc_len_bits, d.seg_crc_type = self.K - self.F, CRC24_B
+        d.crc_len_bits, d.seg_crc_type = self.K - self.F, self.seg_crc_type
         d.A, d.tb_crc_bits, d.seg_payload_bytes = self.A, 24, (self.seg["Kprime"] - self.seg["L"]) // 8
         b = _L.SchRxBufs()
         e = est if use_estimates else self.est
@@ -127,6 +141,11 @@ class PuschSlotChain:
         dm_index = torch.tensor(2 * N + (k0 + 2 * np.arange(6 * self.rb_size)) % N, dtype=torch.int64, device=dev)
         hf = hi.to(torch.float32) / 1024.0
         xf = xl.to(torch.float32)
+        if self.tp is not None:
+            # what the UE's transform precoder does to every symbol's M modulation symbols (38.211 6.3.1.4): X = DFT_M(x) / sqrt(M)
+            M = 12 * self.rb_size
+            xc = torch.view_as_complex(xf[:, 0, :].reshape(-1, M, 2).contiguous())
+            xf = torch.view_as_real(torch.fft.fft(xc, dim=1) / (M ** 0.5)).reshape(-1, 1, 2).contiguous()
         for a in range(self.nb_rx):
             yr = sum(hf[a, l, 0] * xf[:, l, 0] - hf[a, l, 1] * xf[:, l, 1] for l in range(nl))
             yi = sum(hf[a, l, 0] * xf[:, l, 1] + hf[a, l, 1] * xf[:, l, 0] for l in range(nl))
@@ -173,7 +192,7 @@ class PuschSlotChain:
                     self.desc.d_est_state, self.desc.est_state_ports = self.chest_state.data_ptr(), self.nl
         lib.pusch_inner_rx_torch(self.desc, self.rxF, est, self.llr16, level=self.level)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
-        lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,
+        lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=self.seg_crc_type,
                                out=self.hard, iters=self.iters, latency_mode=self.latency_mode)
         nbytes = (self.seg["Kprime"] - self.seg["L"]) // 8
         self.tb.view(-1).copy_(self.hard[:, :nbytes].reshape(-1))                             # nr_postDecode: concatenate the segments

@@ -238,3 +238,37 @@ def test_transform_precoding_golden(oracle):
             assert np.array_equal(llr, g[f"rx_llr{i}"]) and np.array_equal(comp[:24 * P.rb_size], g[f"rx_comp{i}"]), i
     finally:
         oracle.pusch_set_transform_precoding(0)
+
+
+def test_transform_precoding_64qam_cannot_be_demapped(oracle):
+    """A property of the reference, kept visible: after nr_freq_equalization the compensated symbols sit at 128 k (k = 1, 3, 5, 7 for 64QAM) while the constant
+    thresholds it installs are 316 / 158 (nr_freq_equalization.c:63-67), so a NOISELESS DFT-s-OFDM 64QAM symbol is demapped with bit errors; QPSK and 16QAM are
+    clean.  The oracle (pinned bit-exactly to the reference for this path) and the library reproduce it; the closed-loop slot test therefore runs Qm 2 and 4."""
+    from oracle.bindings import PuschParms
+    N, nb, fco = 1024, 25, 1024 - 6 * 52
+    M = 12 * nb
+    rng = np.random.default_rng(1)
+    errors = {}
+    for Qm in (2, 4, 6):
+        bits = rng.integers(0, 2, size=M * Qm).astype(np.uint8)
+        words = np.zeros((M * Qm + 31) // 32 + 1, np.uint32)
+        for i, b in enumerate(bits):
+            words[i >> 5] |= np.uint32(int(b) << (i & 31))
+        sym = oracle.modulate(words, M * Qm, Qm).reshape(-1, 2).astype(np.float64)
+        x = (sym[:, 0] + 1j * sym[:, 1]) * 724 / 32768.0
+        h = 0.6 + 0.37j
+        y = h * np.fft.fft(x) / np.sqrt(M)                                  # the UE's transform precoder, a flat channel, no noise
+        rx = np.zeros((1, 14, N, 2), np.int16); hh = np.zeros((1, 14, N, 2), np.int16)
+        sc = (fco + np.arange(M)) % N
+        rx[0, 0, sc, 0] = np.round(y.real); rx[0, 0, sc, 1] = np.round(y.imag)
+        unit = 23170.0 * 724 / 32768.0
+        hh[0, 2, :M, 0] = round(h.real * unit); hh[0, 2, :M, 1] = round(h.imag * unit)
+        P = PuschParms(N, 1, 0, 0, nb, fco, Qm, 1 << 2, 0, 2)
+        oracle.pusch_set_transform_precoding(1)
+        try:
+            sh, _ = oracle.pusch_log2_maxh(P, 0, 2, rx, hh)
+            llr, _ = oracle.pusch_inner_rx_symbol(P, 0, 2, sh, rx, hh)
+        finally:
+            oracle.pusch_set_transform_precoding(0)
+        errors[Qm] = int(((llr < 0).astype(np.uint8) != bits).sum())
+    assert errors[2] == 0 and errors[4] == 0 and errors[6] > 100, errors

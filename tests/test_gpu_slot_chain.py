@@ -95,3 +95,25 @@ def test_slot_entry_point_equals_staged_calls(ldpc, cfg):
     nb = (a.K - a.F) // 8                                      # the decoder writes ncols(R) * Z / 8 bytes per segment; the rows are wider
     assert torch.equal(a.hard[:, :nb], b.hard[:, :nb])
     assert np.array_equal(a.tb.cpu().numpy().reshape(-1)[:payload.size], payload)
+
+
+@pytest.mark.parametrize("cfg", [dict(A=19464, N=1024, mu=0, carrier_rb=52, rb_start=2, rb_size=50, nb_rx=2, Qm=4, slot=1, transform_precoding=(7, 0)),
+                                 dict(A=9992, N=2048, carrier_rb=106, rb_start=10, rb_size=25, nb_rx=4, Qm=4, slot=3, transform_precoding=(29, 0)),
+                                 dict(A=3752, N=1024, mu=0, carrier_rb=52, rb_start=0, rb_size=20, nb_rx=2, Qm=2, slot=6, transform_precoding=(0, 0))])
+def test_pusch_slot_with_transform_precoding_roundtrip(ldpc, cfg):
+    """DFT-s-OFDM uplink slot: the synthesiser spreads every symbol's modulation symbols with an M-point DFT and sends the low-PAPR type-1 DMRS; the receive
+    chain (one library call: estimation with the low-PAPR pilots, equalisation + nr_idft + LLRs, rate recovery, decode) must return the payload.
+    QPSK and 16QAM: the reference's 64QAM thresholds after nr_freq_equalization do not fit its own constellation scale (DESIGN.md defect 20,
+    tests/test_golden_oracle.py::test_transform_precoding_64qam_cannot_be_demapped), so a 64QAM DFT-s-OFDM block does not decode there either."""
+    dev = torch.device("cuda", 0)
+    chain = PuschSlotChain(ldpc, load_dftslib(), dev, **cfg)
+    payload, rxdata, _ = chain.synthesize(seed=11)
+    tb, iters, tbcrc = chain.receive(rxdata)
+    torch.cuda.synchronize()
+    assert (iters.cpu().numpy() <= chain.max_iter).all(), iters
+    assert np.array_equal(tb.cpu().numpy().reshape(-1)[:payload.size], payload) and int(tbcrc.cpu()[0]) == 0
+    # the same slot without the flag does not decode: the receiver really takes the other path
+    plain = PuschSlotChain(ldpc, load_dftslib(), dev, **{k: v for k, v in cfg.items() if k != "transform_precoding"})
+    plain.receive(rxdata)
+    torch.cuda.synchronize()
+    assert int(plain.tbcrc.cpu()[0]) != 0
