@@ -153,9 +153,10 @@ int launch_decode_impl(const GraphDev *d_g, const GraphDev &h_g, const DecodeArg
     if (h_pg->Zw == 96 && !(a.quirks & 1)) {
       if (h_pg->nthreads > 864) { kern = ldpc_decode_packed_kernel<96, 960>; variant = 3; }
       else if (h_pg->nthreads > 768) { kern = ldpc_decode_packed_kernel<96, 864>; variant = 2; }
+      else if (a.ll_ctrl == nullptr && a.abort_flags == nullptr) { kern = ldpc_decode_packed_kernel<96, 768, true>; variant = 4; }   // the batch launches
       else { kern = ldpc_decode_packed_kernel<96, 768>; variant = 1; }
     }
-    static std::atomic<size_t> configured_pk[kMaxDevices][4];
+    static std::atomic<size_t> configured_pk[kMaxDevices][5];
     if (smem > configured_pk[c.dev][variant].load()) {
       NRB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "packed smem attr");
       configured_pk[c.dev][variant].store(smem);

@@ -362,7 +362,9 @@ __device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const char
 
 // MAXT = launch bound: 768 threads leave 80 registers per thread, 864 leave 72, 960 leave 64 (no spills in any of them); more bins
 // of Zw threads = more warps per scheduler to hide the shared-memory latency of the dependent descriptor -> message loads.
-template <int ZWC, int MAXT>
+// PLAIN = the batch entry points with no per-block control row and no abort flags (what the bench's 1024-block launches are): the low-latency bookkeeping
+// and the per-iteration abort poll are compiled out.
+template <int ZWC, int MAXT, bool PLAIN = false>
 __global__ void __launch_bounds__(MAXT, 1)
 ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
 {
@@ -384,26 +386,53 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
 
   for (int cb = blockIdx.x; cb < (int)a.n_cb; cb += gridDim.x) {
     // ---- load channel LLRs (global int8, coalesced 32-bit) as offset binary into L rows with halo; A := L; R := 0; P := 0
-    const BlockIo io = block_io(a, cb);
-    block_begin(io, 0);
+    BlockIo io;
+    if (PLAIN) { io.llr = a.llr + (size_t)cb * a.llr_stride; io.out = a.out + (size_t)cb * a.out_stride; io.iters = a.iters + cb; io.ctrl = nullptr; io.abort = nullptr; }
+    else { io = block_io(a, cb); block_begin(io, 0); }
     const int8_t *gl = io.llr;
     const bool al4 = ((reinterpret_cast<uintptr_t>(gl) & 3) == 0);
-    for (int i = threadIdx.x; i < G.ncols * Zw; i += blockDim.x) {
+    auto fetch = [&](int i) -> uint32_t {
+      if (al4) return __ldg(reinterpret_cast<const uint32_t *>(gl) + i);
+      const uint8_t *b = reinterpret_cast<const uint8_t *>(gl) + 4 * i;
+      return b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+    };
+    auto place = [&](int i, uint32_t w) {
       const int c = i / Zw, k = i - c * Zw;
-      uint32_t w;
-      if (al4) w = __ldg(reinterpret_cast<const uint32_t *>(gl) + i);
-      else {
-        const uint8_t *b = reinterpret_cast<const uint8_t *>(gl) + 4 * i;
-        w = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
-      }
       w ^= kH;
       const uint32_t lo = G.off_L + c * G.RSB + 4 * k;
       sts(smb, lo, w);
       if (k == 0) sts(smb, lo + G.ZB, w);
       const int ar = G.col_arow[c];
       if (ar >= 0) { const uint32_t ao = G.off_A + ar * 2 * G.ZB + 4 * k; sts(smb, ao, w); sts(smb, ao + G.ZB, w); }
+    };
+    {
+      // eight loads in flight per thread before the first store: the block's 26 KB arrive in two round trips to HBM instead of nine
+      const int W = G.ncols * Zw, n = (int)blockDim.x;
+      int i = threadIdx.x;
+      for (; i + 7 * n < W; i += 8 * n) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = fetch(i + k * n);
+#pragma unroll
+        for (int k = 0; k < 8; k++) place(i + k * n, w[k]);
+      }
+      for (; i + 3 * n < W; i += 4 * n) {
+        const uint32_t w0 = fetch(i), w1 = fetch(i + n), w2 = fetch(i + 2 * n), w3 = fetch(i + 3 * n);
+        place(i, w0); place(i + n, w1); place(i + 2 * n, w2); place(i + 3 * n, w3);
+      }
+      for (; i < W; i += n) place(i, fetch(i));
     }
-    for (int i = threadIdx.x; i < G.nreal * (G.RSB >> 2); i += blockDim.x) sts(smb, G.off_R + 4 * i, kH);
+    {
+      // R := 0 (offset binary), 16 bytes per store where the rows allow it (every lifting size that is a multiple of 16)
+      if (((G.off_R | (G.nreal * G.RSB)) & 15) == 0) {
+        const uint4 z = make_uint4(kH, kH, kH, kH);
+        uint4 *r4 = reinterpret_cast<uint4 *>(smb + G.off_R);
+        const int n4 = (G.nreal * G.RSB) >> 4;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) r4[i] = z;
+      } else {
+        for (int i = threadIdx.x; i < G.nreal * (G.RSB >> 2); i += blockDim.x) sts(smb, G.off_R + 4 * i, kH);
+      }
+    }
     __syncthreads();
     // P rows: word k = sign(llr_p + R_p) flags (start clear), word Zw+k = sign-magnitude of the degree-1 neighbour's channel LLR,
     // word 2Zw+k = that LLR + 128 itself (rotated)
@@ -432,7 +461,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       uint32_t bad = 0;
       // check_abort(ab) is polled at the top of every iteration from the second on (nrLDPC_decoder.c:557-560): thread 0 samples the flag while
       // the check-node phase runs (the load's latency hides behind it), everybody reads it after the barrier
-      if (io.abort && threadIdx.x == 0) s_abort = *io.abort;
+      if (!PLAIN && io.abort && threadIdx.x == 0) s_abort = *io.abort;
       if (worker) {
         for (int i = G.cn_bin_start[bin]; i < G.cn_bin_start[bin + 1]; i++) {
           const int it = G.cn_bin_rows[i];
@@ -446,7 +475,7 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       const int pcRes = __syncthreads_or(bad != 0);   // also the CN->BN barrier
       if (numIter >= 2 && !a.use_crc && pcRes == 0) break;          // iteration numIter passed its parity check (:552)
       numIter++;
-      if (numIter >= 2 && io.abort && s_abort) { numIter = maxIter + 2; break; }   // the state (A) is still that of the previous iteration
+      if (!PLAIN && numIter >= 2 && io.abort && s_abort) { numIter = maxIter + 2; break; }   // the state (A) is still that of the previous iteration
       // BN phase
       if (worker)
         for (int i = G.bn_bin_start[bin]; i < G.bn_bin_start[bin + 1]; i++) {
@@ -471,7 +500,8 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       }
     }
     if (!a.use_crc) packed_write_output(G, smb, a, io.out);           // :865-877
-    block_finish(io, a, numIter, 0);
+    if (PLAIN) { if (threadIdx.x == 0) *io.iters = numIter; }
+    else block_finish(io, a, numIter, 0);
     __syncthreads();
   }
 }

@@ -17,6 +17,12 @@ fi
 echo "== micro-benchmark (ALU pipe / opcode-blend / code-footprint ceilings)"; timeout 120 tools/ubench/_bin/alu_ceiling | tee gpurun_out/alu_ceiling_${TAG}.json
 echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -24 | tee gpurun_out/extras_${TAG}.jsonl
 echo "== extras, OFDM front end with 592 antenna-slots per launch"; NRB200_OFDM_ANTENNA_SLOTS=592 timeout 300 python tools/bench_extras.py 2>&1 | grep ofdm_ | tee gpurun_out/extras_ofdm592_${TAG}.jsonl | cut -c1-260
+echo "== ncu full (decode kernel): first, so that the bench line of this very run carries roofline.traffic / on_chip of the kernel it times"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
+  python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu -i gpurun_out/prof_decode_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_decode_${TAG}_raw.csv 2>/dev/null \
+  && python tools/ncu_traffic_json.py gpurun_out/prof_decode_${TAG}_raw.csv gpurun_out/ncu_decode_traffic_${TAG}.json 1024 "gpurun_out/prof_decode_${TAG}.ncu-rep" | cut -c1-300 \
+  && cp gpurun_out/ncu_decode_traffic_${TAG}.json profiles/ncu_decode_traffic.json   # the bench below reads it (stamped with the kernel sources' SHA-1)
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 2>gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json
 if [ "$MODE" = "full" ]; then
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
@@ -46,9 +52,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:clus
 echo "== ncu full (4096-point TMA kernel)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dft4096 -s 3 -c 1 -f -o gpurun_out/prof_dft4096_${TAG} python tools/dft_time.py 4096 1 8880 > gpurun_out/ncu_dft_${TAG}.log 2>&1
 fi
-echo "== ncu full (decode kernel)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
-  python bench.py --steps 3 --warmup 3 --no-cpu --no-check --no-slot --no-ubench --nbuf 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
-ncu -i gpurun_out/prof_decode_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_decode_${TAG}_raw.csv 2>/dev/null \
-  && python tools/ncu_traffic_json.py gpurun_out/prof_decode_${TAG}_raw.csv gpurun_out/ncu_decode_traffic_${TAG}.json 1024 "gpurun_out/prof_decode_${TAG}.ncu-rep" | cut -c1-300
 ls -la gpurun_out | tail -8
