@@ -362,6 +362,12 @@ __device__ __forceinline__ int packed_crc_check(const PackedGraph &G, const char
 
 // MAXT = launch bound: 768 threads leave 80 registers per thread, 864 leave 72, 960 leave 64 (no spills in any of them); more bins
 // of Zw threads = more warps per scheduler to hide the shared-memory latency of the dependent descriptor -> message loads.
+// -DNRB200_DECODER_TMA=1: stage the channel LLRs of the batch path with TMA bulk copies (below).  Bit exact and MEASURED SLOWER than eight register loads in flight
+// per thread (0.696 against 0.668 ms per 1024 blocks, r02): the LLRs are not used as they arrive -- offset binary, the halo word and the doubled A rows are made
+// on the way into shared memory, which a bulk copy cannot do, so it costs a second pass over the 26 KB.  Off by default.
+#ifndef NRB200_DECODER_TMA
+#define NRB200_DECODER_TMA 0
+#endif
 // PLAIN = the batch entry points with no per-block control row and no abort flags (what the bench's 1024-block launches are): the low-latency bookkeeping
 // and the per-iteration abort poll are compiled out.
 template <int ZWC, int MAXT, bool PLAIN = false>
@@ -371,9 +377,15 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ PackedGraph G;
   __shared__ int s_flag, s_abort;
+  __shared__ __align__(8) unsigned long long s_mbar;
   char *smb = reinterpret_cast<char *>(sm);
   for (int i = threadIdx.x; i < (int)(sizeof(PackedGraph) / 4); i += blockDim.x)
     reinterpret_cast<int *>(&G)[i] = reinterpret_cast<const int *>(gdev)[i];
+  if (PLAIN && threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t tma_phase = 0;
   __syncthreads();
   const int Zw = geo_zw<ZWC>(G);
   // work lists (ldpc_packed_graph.h): one per bin of Zw threads (item = a whole row / column, this thread's word fixed), or one per warp
@@ -405,7 +417,20 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
       const int ar = G.col_arow[c];
       if (ar >= 0) { const uint32_t ao = G.off_A + ar * 2 * G.ZB + 4 * k; sts(smb, ao, w); sts(smb, ao + G.ZB, w); }
     };
-    {
+    // Z = 384 batch path: the block's int8 LLRs are STAGED BY TMA -- one 1-D bulk copy per bit column (384 B) straight into the column's L row, completing on an
+    // mbarrier -- while the threads clear the message rows; afterwards one pass over shared memory turns them into offset binary and fills the halo and the A rows.
+    const bool tma = PLAIN && ZWC == 96 && NRB200_DECODER_TMA && al4 && ((reinterpret_cast<uintptr_t>(gl) | (uintptr_t)G.off_L | (uintptr_t)G.RSB) & 15) == 0;
+    if (tma) {
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the previous block's reads of the L rows are ordered before the bulk writes
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(G.ncols * 4 * Zw)) : "memory");
+        const uint32_t l0 = (uint32_t)__cvta_generic_to_shared(smb) + (uint32_t)G.off_L;
+        for (int c = 0; c < G.ncols; c++)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(l0 + (uint32_t)(c * G.RSB)),
+                       "l"(gl + (size_t)c * 4 * Zw), "r"((uint32_t)(4 * Zw)), "r"(mb) : "memory");
+      }
+    } else {
       // eight loads in flight per thread before the first store: the block's 26 KB arrive in two round trips to HBM instead of nine
       const int W = G.ncols * Zw, n = (int)blockDim.x;
       int i = threadIdx.x;
@@ -431,6 +456,17 @@ ldpc_decode_packed_kernel(const PackedGraph *__restrict__ gdev, DecodeArgs a)
         for (int i = threadIdx.x; i < n4; i += blockDim.x) r4[i] = z;
       } else {
         for (int i = threadIdx.x; i < G.nreal * (G.RSB >> 2); i += blockDim.x) sts(smb, G.off_R + 4 * i, kH);
+      }
+    }
+    if (tma) {
+      const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(mb), "r"(tma_phase) : "memory");
+      tma_phase ^= 1u;
+      for (int i = threadIdx.x; i < G.ncols * Zw; i += blockDim.x) {
+        const int c = i / Zw, k = i - c * Zw;
+        place(i, lds(smb, G.off_L + c * G.RSB + 4 * k));
       }
     }
     __syncthreads();
