@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, 3) dft4096_kernel(DftPlan P, TwOffsets O,
   unsigned ph0 = 0, ph1 = 0;
   if (t == 0 && blockIdx.x < n && in_bulk(blockIdx.x)) { mbar_expect_tx(&mbar[0], N * 4); bulk_load(sm, src_of(blockIdx.x), N * 4, &mbar[0]); }
 
-  const short *ta16 = tw + (inv ? O.tw16 : O.tw16a), *tb16 = tw + (inv ? O.tw16c : O.tw16b);
+  const uint2 *d16 = reinterpret_cast<const uint2 *>(tw + O.dps16[inv ? 1 : 0]), *d64 = reinterpret_cast<const uint2 *>(tw + O.dps64[inv ? 1 : 0]);
   unsigned it = 0;
   for (unsigned tr = blockIdx.x; tr < n; tr += gridDim.x, it++) {
     const int s = (int)(it & 1u);
@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(256, 3) dft4096_kernel(DftPlan P, TwOffsets O,
       const int slot = 16 * (t >> 6) + 80 * ((t >> 4) & 3) + ((t >> 2) & 3) + 4 * (t & 3);
 #pragma unroll
       for (int k1 = 0; k1 < 4; k1++) {
-        cx b1 = cmult2(A[k1][1], ta16 + 2 * k1, tb16 + 2 * k1), b2 = cmult2(A[k1][2], ta16 + 8 + 2 * k1, tb16 + 8 + 2 * k1),
-           b3 = cmult2(A[k1][3], ta16 + 16 + 2 * k1, tb16 + 16 + 2 * k1);
+        cx b1 = cmult2dp(pack(A[k1][1]), d16 + k1), b2 = cmult2dp(pack(A[k1][2]), d16 + 4 + k1), b3 = cmult2dp(pack(A[k1][3]), d16 + 8 + k1);
         cx y0, y1, y2, y3;
         bfly4_sat(A[k1][0], b1, b2, b3, inv, y0, y1, y2, y3);
         Y[(k1)*304 + slot] = pack(y0); Y[(k1 + 4) * 304 + slot] = pack(y1); Y[(k1 + 8) * 304 + slot] = pack(y2); Y[(k1 + 12) * 304 + slot] = pack(y3);
@@ -151,27 +150,33 @@ __global__ void __launch_bounds__(256, 3) dft4096_kernel(DftPlan P, TwOffsets O,
       unsigned *q = X + g * 258 + k;
       cx v[4][4];
 #pragma unroll
-      for (int b = 0; b < 4; b++)
+      for (int b = 0; b < 4; b++) {
+        // level 64 (saturating butterfly, hand-rounded table pair, >> 3): x0 unpacked for the adds, x1..x3 stay packed for the dot products
+        const cx x0 = unpack(p[80 * b]);
+        const cx a1 = cmult2dp(p[16 + 80 * b], d64 + k), a2 = cmult2dp(p[32 + 80 * b], d64 + 16 + k), a3 = cmult2dp(p[48 + 80 * b], d64 + 32 + k);
+        bfly4_sat(x0, a1, a2, a3, inv, v[0][b], v[1][b], v[2][b], v[3][b]);
 #pragma unroll
-        for (int a = 0; a < 4; a++) v[a][b] = unpack(p[16 * a + 80 * b]);
-#pragma unroll
-      for (int b = 0; b < 4; b++) r4_level<INV>(O, tw, 16, k, true, v[0][b], v[1][b], v[2][b], v[3][b]);
+        for (int a = 0; a < 4; a++) { v[a][b].r >>= 3; v[a][b].i >>= 3; }
+      }
       if (inv) {                                            // inverse: level 256 is the 32-bit butterfly -> packed form, straight to shared memory
-        const short *t4 = tw + O.tw256;
+        const uint2 *t4 = reinterpret_cast<const uint2 *>(tw + O.dp256i);
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           const int kk = k + 16 * a;
           unsigned y0, y1, y2, y3;
-          bfly4_32p(pack(v[a][0]), pack(v[a][1]), pack(v[a][2]), pack(v[a][3]), t4 + 2 * kk, t4 + 128 + 2 * kk, t4 + 256 + 2 * kk, true, true, y0, y1, y2, y3);
+          bfly4_32dp(pack(v[a][0]), pack(v[a][1]), pack(v[a][2]), pack(v[a][3]), t4 + kk, t4 + 64 + kk, t4 + 128 + kk, true, true, y0, y1, y2, y3);
           q[16 * a] = y0; q[16 * a + 64] = y1; q[16 * a + 128] = y2; q[16 * a + 192] = y3;
         }
       } else {
+        const uint2 *d256 = reinterpret_cast<const uint2 *>(tw + O.dps256f);
 #pragma unroll
-        for (int a = 0; a < 4; a++) r4_level<INV>(O, tw, 64, k + 16 * a, true, v[a][0], v[a][1], v[a][2], v[a][3]);
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-          for (int a = 0; a < 4; a++) q[16 * a + 64 * b] = pack(v[a][b]);
+        for (int a = 0; a < 4; a++) {                        // forward level 256: saturating butterfly, >> 1
+          const int kk = k + 16 * a;
+          cx y0, y1, y2, y3;
+          bfly4_sat(v[a][0], cmult2dp(pack(v[a][1]), d256 + kk), cmult2dp(pack(v[a][2]), d256 + 64 + kk), cmult2dp(pack(v[a][3]), d256 + 128 + kk), false, y0, y1, y2, y3);
+          y0.r >>= 1; y0.i >>= 1; y1.r >>= 1; y1.i >>= 1; y2.r >>= 1; y2.i >>= 1; y3.r >>= 1; y3.i >>= 1;
+          q[16 * a] = pack(y0); q[16 * a + 64] = pack(y1); q[16 * a + 128] = pack(y2); q[16 * a + 192] = pack(y3);
+        }
       }
     }
     __syncthreads();
@@ -183,14 +188,14 @@ __global__ void __launch_bounds__(256, 3) dft4096_kernel(DftPlan P, TwOffsets O,
       for (int b = 0; b < 4; b++)
 #pragma unroll
         for (int a = 0; a < 4; a++) v[a][b] = X[(a + 4 * b) * 258 + k];
-      const short *t1 = tw + O.rad4_1024, *t2 = tw + O.rad4_4096;
+      const uint2 *t1 = reinterpret_cast<const uint2 *>(tw + O.dp1024[inv ? 1 : 0]), *t2 = reinterpret_cast<const uint2 *>(tw + O.dp4096[inv ? 1 : 0]);
 #pragma unroll
       for (int b = 0; b < 4; b++)
-        bfly4_32p(v[0][b], v[1][b], v[2][b], v[3][b], t1 + 2 * k, t1 + 512 + 2 * k, t1 + 1024 + 2 * k, inv, true, v[0][b], v[1][b], v[2][b], v[3][b]);
+        bfly4_32dp(v[0][b], v[1][b], v[2][b], v[3][b], t1 + k, t1 + 256 + k, t1 + 512 + k, inv, true, v[0][b], v[1][b], v[2][b], v[3][b]);
 #pragma unroll
       for (int a = 0; a < 4; a++) {
         const int kk = k + 256 * a;
-        bfly4_32p(v[a][0], v[a][1], v[a][2], v[a][3], t2 + 2 * kk, t2 + 2048 + 2 * kk, t2 + 4096 + 2 * kk, inv, P.scale != 0, v[a][0], v[a][1], v[a][2], v[a][3]);
+        bfly4_32dp(v[a][0], v[a][1], v[a][2], v[a][3], t2 + kk, t2 + 1024 + kk, t2 + 2048 + kk, inv, P.scale != 0, v[a][0], v[a][1], v[a][2], v[a][3]);
       }
 #pragma unroll
       for (int b = 0; b < 4; b++)

@@ -129,10 +129,47 @@ __device__ __forceinline__ void bfly4_32p(unsigned x0, unsigned p1, unsigned p2,
   if (half) { y0 = sra1_16x2(y0); y1 = sra1_16x2(y1); y2 = sra1_16x2(y2); y3 = sra1_16x2(y3); }
 }
 
+// The same butterfly with the complex products on the dot-product unit (4096-point kernel).  A twiddle is stored as two words of bytes
+//   B_re = {lo(a), lo(b), hi(a), hi(b)},  B_im = {lo(c), lo(d), hi(c), hi(d)}      with re = xr a + xi b, im = xr c + xi d
+// (forward: a = wr, b = -wi, c = wi, d = wr; inverse: a = wr, b = wi, c = -wi, d = wr), lo = the unsigned low byte, hi = the signed high byte of the int16.
+// Then re = 256 * dp2a.hi.s32.s32(x, B_re) + dp2a.lo.s32.u32(x, B_re) with x the PACKED sample: two IDP + one IMAD on the FMA pipe and no unpacking of the
+// sample or the twiddle on the ALU pipe, which is the pipe that limits the kernel.  All arithmetic is modulo 2^32 like the reference's madd_epi16.
+__device__ __forceinline__ unsigned dp_prod(unsigned x, unsigned B)
+{
+  int lo, hi;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(x), "r"(B), "r"(0));
+  asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(x), "r"(B), "r"(0));
+  return (unsigned)(hi * 256 + lo);
+}
+// packed_cmult2 on the dot-product unit: T = {B_re from table a, B_im from table b}; (x . ta, x . tb) >> 15, saturated
+__device__ __forceinline__ cx cmult2dp(unsigned x, const uint2 *t)
+{
+  const uint2 T = __ldg(t);
+  return {sat16(sra15(dp_prod(x, T.x))), sat16(sra15(dp_prod(x, T.y)))};
+}
+__device__ __forceinline__ void bfly4_32dp(unsigned x0, unsigned p1, unsigned p2, unsigned p3, const uint2 *d1, const uint2 *d2, const uint2 *d3, bool inv, bool half,
+                                           unsigned &y0, unsigned &y1, unsigned &y2, unsigned &y3)
+{
+  const uint2 T1 = __ldg(d1), T2 = __ldg(d2), T3 = __ldg(d3);
+  const unsigned x1r = dp_prod(p1, T1.x), x1i = dp_prod(p1, T1.y), x2r = dp_prod(p2, T2.x), x2i = dp_prod(p2, T2.y), x3r = dp_prod(p3, T3.x), x3i = dp_prod(p3, T3.y);
+  const unsigned d0 = pk32p(x1r + x2r + x3r, x1i + x2i + x3i);
+  const unsigned da = pk32p(x1i - (x2r + x3i), (x3r - x2i) - x1r);
+  const unsigned dd2 = pk32p((x2r - x3r) - x1r, (x2i - x3i) - x1i);
+  const unsigned db = pk32p((x3i - x2r) - x1i, x1r - (x2i + x3r));
+  y0 = __vadd2(x0, d0);
+  y2 = __vadd2(x0, dd2);
+  const unsigned oa = __vadd2(x0, da), ob = __vadd2(x0, db);
+  y1 = inv ? ob : oa;
+  y3 = inv ? oa : ob;
+  if (half) { y0 = sra1_16x2(y0); y1 = sra1_16x2(y1); y2 = sra1_16x2(y2); y3 = sra1_16x2(y3); }
+}
+
 // Device-resident twiddle blob (int16): the hand-rounded tables of nr_dft_tables.h followed by the generated ones.
 struct TwOffsets {
   int tw16, tw16a, tw16b, tw16c, tw64, tw64a, tw64b, tw64c, tw128, tw128a, tw128b, tw256, tw256a, tw256b, tw512;
   int rad4_1024, rad4_4096, rad2_2048, rad2_8192, rad3[4];   // rad3: 768, 1536, 3072, 6144 (twa then twb)
+  int dp256i, dp1024[2], dp4096[2];                           // byte-arranged copies for the dot-product butterflies (dp_tables below): [0] forward, [1] inverse
+  int dps16[2], dps64[2], dps256f;                            // the same for the saturating levels' table pairs (packed_cmult2: re from table a, im from table b)
 };
 
 struct DftPlan {
@@ -701,6 +738,37 @@ int dft_init()
     return o;
   };
   O.rad4_1024 = rad4(1024); O.rad4_4096 = rad4(4096); O.rad2_2048 = rad2(2048); O.rad2_8192 = rad2(8192);
+  // dp_tables: byte-arranged copies of a twiddle table for bfly4_32dp (see there), 4 shorts per twiddle, 8-byte aligned
+  auto dp_table = [&](int src, int count, bool inverse) {
+    while (blob.size() % 4) blob.push_back(0);
+    const int o = (int)blob.size();
+    for (int i = 0; i < count; i++) {
+      const int wr = blob[src + 2 * i], wi = blob[src + 2 * i + 1];
+      const int a = wr, b = inverse ? wi : -wi, cc = inverse ? -wi : wi, d = wr;
+      auto lo = [](int v) { return v & 0xFF; };
+      auto hi = [](int v) { return (v >> 8) & 0xFF; };
+      blob.push_back((short)(lo(a) | (lo(b) << 8))); blob.push_back((short)(hi(a) | (hi(b) << 8)));
+      blob.push_back((short)(lo(cc) | (lo(d) << 8))); blob.push_back((short)(hi(cc) | (hi(d) << 8)));
+    }
+    return o;
+  };
+  auto dp_pair = [&](int srca, int srcb, int count) {       // packed_cmult2's two tables: re = xr a.r + xi a.i, im = xr b.r + xi b.i
+    while (blob.size() % 4) blob.push_back(0);
+    const int o = (int)blob.size();
+    for (int i = 0; i < count; i++) {
+      const int a = blob[srca + 2 * i], b = blob[srca + 2 * i + 1], cc = blob[srcb + 2 * i], d = blob[srcb + 2 * i + 1];
+      auto lo = [](int v) { return v & 0xFF; };
+      auto hi = [](int v) { return (v >> 8) & 0xFF; };
+      blob.push_back((short)(lo(a) | (lo(b) << 8))); blob.push_back((short)(hi(a) | (hi(b) << 8)));
+      blob.push_back((short)(lo(cc) | (lo(d) << 8))); blob.push_back((short)(hi(cc) | (hi(d) << 8)));
+    }
+    return o;
+  };
+  O.dps16[0] = dp_pair(O.tw16a, O.tw16b, 12); O.dps16[1] = dp_pair(O.tw16, O.tw16c, 12);
+  O.dps64[0] = dp_pair(O.tw64a, O.tw64b, 48); O.dps64[1] = dp_pair(O.tw64, O.tw64c, 48);
+  O.dps256f = dp_pair(O.tw256a, O.tw256b, 192);
+  O.dp256i = dp_table(O.tw256, 192, true);
+  for (int dir = 0; dir < 2; dir++) { O.dp1024[dir] = dp_table(O.rad4_1024, 768, dir == 1); O.dp4096[dir] = dp_table(O.rad4_4096, 3072, dir == 1); }
   const int r3n[4] = {768, 1536, 3072, 6144};
   for (int i = 0; i < 4; i++) O.rad3[i] = rad3(r3n[i]);
   for (int i = 0; i < kNumBig; i++) c.big_tw[i] = kBig[i].R == 3 ? rad3(kBig[i].N) : kBig[i].R == 4 ? rad4(kBig[i].N) : rad2(kBig[i].N);
