@@ -68,6 +68,10 @@ class PuschParms(C.Structure):       # orc_pusch_t
                                          "dmrs_config_type", "num_dmrs_cdm_grps_no_data")]
 
 
+class PtrsParms(C.Structure):        # orc_ptrs_t
+    _fields_ = [(n, C.c_int32) for n in ("on", "L", "K", "re_offset", "rnti", "slot", "nscid", "nid")]
+
+
 class PdschTxParms(C.Structure):     # orc_pdsch_tx_t
     _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "Qm", "nrOfLayers", "start_symbol",
                                          "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports", "scid",
@@ -282,6 +286,19 @@ class Oracle:
         n = fn(C.byref(P), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                                        C.byref(sh))
         return llr[:n].copy(), sh.value
+
+    def ptrs_symbols(self, start_symbol, nr_symbols, L_log2, dmrs_pos):
+        self.lib.orc_ptrs_symbols.restype = C.c_uint32
+        return int(self.lib.orc_ptrs_symbols(start_symbol, nr_symbols, 1 << L_log2, C.c_uint32(dmrs_pos)))
+
+    def pdsch_rx_slot_ptrs(self, P, T, start_symbol, nr_symbols, rxdataF, dl_ch_est):
+        """UE-side one-layer PDSCH receiver with PT-RS (T = PtrsParms).  Returns (llr, log2_maxh, phase int16[14][2], ptrs_re int32[14])."""
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16)
+        llr = np.zeros(14 * 12 * P.rb_size * P.Qm + 64, np.int16)
+        sh = C.c_int32(0); ph = np.zeros((14, 2), np.int16); nre = np.zeros(14, np.int32)
+        n = self.lib.orc_pdsch_rx_slot_ptrs(C.byref(P), C.byref(T), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p),
+                                            llr.ctypes.data_as(C.c_void_p), C.byref(sh), ph.ctypes.data_as(C.c_void_p), nre.ctypes.data_as(C.c_void_p))
+        return llr[:n].copy(), sh.value, ph, nre
 
     def pdsch_tx_slot(self, P, bits):
         """gNB PDSCH transmitter after the encoder: bits (uint8, one per element, P.G() of them) -> txdataF [nb_tx][14][N][2] (zeros where nothing is mapped)."""
@@ -619,6 +636,24 @@ class Reference:
         sh = self._pdschlib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                                                valid.ctypes.data_as(C.c_void_p), None)
         return llr[:G].copy(), int(sh), valid
+
+    def pdsch_rx_slot_ptrs(self, P, T, start_symbol, nr_symbols, rxdataF, dl_ch_est, G, n_rb_dl=273):
+        """The real nr_rx_pdsch + nr_pdsch_ptrs_processing (libref_pdsch_ptrs.so).  Returns (llr, log2_maxh, valid[14], phase[14][2], ptrs_re[14])."""
+        if not hasattr(self, "_pdschptrslib"):
+            self._pdschptrslib = C.CDLL(os.path.join(REFDIR, "libref_pdsch_ptrs.so"))
+        L = self._pdschptrslib
+        q = np.array([T.on, T.L, T.K, T.re_offset, T.rnti, T.slot, T.nscid, T.nid, n_rb_dl], dtype=np.int32)
+        L.refh_pdsch_set_ptrs(q.ctypes.data_as(C.c_void_p))
+        prm = np.array([P.fft_size, P.nb_rx, P.rb_start, P.bwp_start, P.rb_size, P.first_carrier_offset, P.Qm, start_symbol, nr_symbols, P.ul_dmrs_symb_pos,
+                        P.dmrs_config_type, P.num_dmrs_cdm_grps_no_data, G, 1], dtype=np.int32)
+        x = np.ascontiguousarray(rxdataF, dtype=np.int16).copy(); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16).copy()
+        llr = np.zeros(G + 64, np.int16); valid = np.zeros(14, np.int32)
+        sh = L.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+                                  valid.ctypes.data_as(C.c_void_p), None)
+        ph = np.zeros((14, 2), np.int16); nre = np.zeros(14, np.int32)
+        L.refh_pdsch_get_ptrs(ph.ctypes.data_as(C.c_void_p), nre.ctypes.data_as(C.c_void_p))
+        L.refh_pdsch_set_ptrs(None)
+        return llr[:G].copy(), int(sh), valid, ph, nre
 
     def pdsch_tx_slot(self, P, bits, n_rb_dl):
         if not hasattr(self, "_pdschtxlib"):

@@ -78,6 +78,12 @@ gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_uechest.c 
 # UE-side PDSCH receiver: the real nr_rx_pdsch, symbol by symbol
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdsch.c $HERE/ref_harness_pdsch.c $R/openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_demodulation.c \
     $R/openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_llr_computation.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/TOOLS/log2_approx.c -lm -o libref_pdsch.so || echo "libref_pdsch.so: FAILED"
+# the same receiver harness with PT-RS: the real nr_pdsch_ptrs_processing (nr_dl_channel_estimation.c) + ptrs_nr.c linked in instead of the abort stub
+gcc $F -DREFH_PTRS -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdsch_ptrs.c $HERE/ref_harness_pdsch.c $R/openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_demodulation.c \
+    $R/openair1/PHY/NR_UE_TRANSPORT/nr_dlsch_llr_computation.c $R/openair1/PHY/NR_UE_ESTIMATION/nr_dl_channel_estimation.c $R/openair1/PHY/NR_REFSIG/ptrs_nr.c \
+    $R/openair1/PHY/NR_REFSIG/nr_dmrs_rx.c $R/openair1/PHY/NR_REFSIG/nr_gold_ue.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/NR_TRANSPORT/nr_sch_dmrs.c $R/openair1/PHY/NR_REFSIG/nr_gen_mod_table.c \
+    $R/common/utils/nr/nr_common.c $R/openair1/PHY/TOOLS/cmult_sv.c $R/openair1/PHY/TOOLS/cmult_vv.c $R/openair1/PHY/MODULATION/slot_fep_nr.c $R/openair1/PHY/TOOLS/log2_approx.c \
+    -lm -ldl -Wl,--no-undefined -o libref_pdsch_ptrs.so || echo "libref_pdsch_ptrs.so: FAILED"
 # gNB-side PDSCH transmitter after the encoder: the real nr_generate_pdsch with nr_dlsch_encoding replaced by the harness (bits in)
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdschtx.c $HERE/ref_harness_pdschtx.c $R/openair1/PHY/NR_TRANSPORT/nr_dlsch.c \
     $R/openair1/PHY/NR_REFSIG/nr_gold.c $R/openair1/PHY/NR_TRANSPORT/nr_sch_dmrs.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/NR_REFSIG/ptrs_nr.c \

@@ -4,6 +4,7 @@
  * of nr_rx_pusch_tp :1595-1647 and the per-symbol composition inner_rx :1262-1384 followed by nr_ulsch_compute_llr.
  * Pinned against the compiled reference (oracle/_ref/libref_pusch.so) by tests/test_oracle_vs_reference.py. */
 #include <limits.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -404,7 +405,134 @@ static int valid_dmrs_idx(int pos, int symbol)
   return -1;
 }
 
+/* ---- PT-RS at the UE (nr_pdsch_ptrs_processing, NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1765-1907, called from nr_rx_pdsch :569-574 after the symbol's
+ * compensation; NR_REFSIG/ptrs_nr.c).  Per PT-RS symbol the common phase error is estimated from the compensated PT-RS REs and those REs are squeezed out of
+ * rxdataF_comp (nr_ptrs_cpe_estimation :181-263); at the slot's last symbol the estimates are interpolated over the symbols without PT-RS
+ * (nr_ptrs_process_slot :281-337, only when PTRSTimeDensity > 0) and every non-DMRS symbol is rotated (rotate_cpx_vector over 12 * nb_rb REs) before the LLRs of
+ * the slot are computed.  The magnitude thresholds are NOT squeezed: LLR j of a PT-RS symbol pairs the j-th data RE with threshold j of the last symbol.
+ * Floating point: plain double arithmetic, no fused multiply-add (oracle/_ref is built with -mavx2 only; a -march=native build of the reference may contract
+ * real * real + imag * imag and differ in the last bit -- DESIGN.md, defect 21).  Out-of-range double -> int16 conversions follow x86's cvttsd2si + truncation. */
+static inline int16_t d2i16(double v)
+{
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;            /* cvttsd2si's "integer indefinite" 0x80000000: low half 0 */
+  return (int16_t)(uint16_t)(uint32_t)(int32_t)v;
+}
+/* set_ptrs_symb_idx (ptrs_nr.c:53-86): L_ptrs = 1 << PTRSTimeDensity */
+uint32_t orc_ptrs_symbols(int start_symbol, int duration, int L_ptrs, uint32_t dmrs_pos)
+{
+  uint32_t out = 0;
+  int i = 0, l_ref = start_symbol;
+  const int last = start_symbol + duration - 1;
+  if (L_ptrs == 0) return 0;
+  while (l_ref + i * L_ptrs <= last) {
+    int is_dmrs = 0, l;
+    const int lo = (l_ref + (i - 1) * L_ptrs + 1) > l_ref ? (l_ref + (i - 1) * L_ptrs + 1) : l_ref;
+    for (l = l_ref + i * L_ptrs; l >= lo; l--) if ((dmrs_pos >> l) & 1) { is_dmrs = 1; break; }
+    if (is_dmrs) { l_ref = l; i = 1; continue; }
+    out |= 1u << (l_ref + i * L_ptrs);
+    i++;
+  }
+  return out;
+}
+/* is_ptrs_subcarrier (ptrs_nr.c:107-129) with start_sc = 0 */
+static int is_ptrs_sc(int k, int rnti, int K, int nb_rb, int k_re_ref)
+{
+  const int k_rb_ref = (nb_rb % K == 0) ? rnti % K : rnti % (nb_rb % K);
+  return (k - k_re_ref - k_rb_ref * 12) % (K * 12) == 0;
+}
+static int next_bit(uint32_t mask, int from, int end) { for (int s = from; s < end; s++) if ((mask >> s) & 1) return s; return -1; }
+static int next_est(uint32_t ptrs, uint32_t dmrs, int from, int end)
+{
+  const int np = next_bit(ptrs, from, end), nd = next_bit(dmrs, from, end);
+  if (nd == -1) return np;
+  if (np == -1) return nd;
+  return np > nd ? nd : np;
+}
+static void slope_from(int start, int end, const int16_t *est, double *sl)
+{
+  const uint8_t distance = (uint8_t)(end - start);
+  sl[0] = (double)(est[2 * end] - est[2 * start]) / distance;
+  sl[1] = (double)(est[2 * end + 1] - est[2 * start + 1]) / distance;
+}
+static void est_from_slope(int16_t *est, const double *sl, int start, int end)
+{
+  for (uint8_t i = 1; i < (end - start); i++) {
+    est[2 * (start + i)] = wrap16((int32_t)est[2 * start] + d2i16(i * sl[0]));
+    est[2 * (start + i) + 1] = wrap16((int32_t)est[2 * start + 1] + d2i16(i * sl[1]));
+  }
+}
+/* nr_ptrs_process_slot (ptrs_nr.c:281-337), its control flow kept literally (int8_t references, the initial leftRef = rightRef = 0) */
+int orc_ptrs_process_slot(uint32_t dmrs, uint32_t ptrs, int16_t *est, int start, int nsym)
+{
+  double slope[2] = {0, 0};
+  const uint8_t end = (uint8_t)(start + nsym);
+  int8_t right = 0, left = 0, tmp = 0;
+  for (uint8_t symb = (uint8_t)start; symb < end; symb++) {
+    if (((ptrs >> symb) & 1) || ((dmrs >> symb) & 1)) {
+      left = (int8_t)symb;
+      right = (int8_t)next_est(ptrs, dmrs, symb + 1, end);
+    } else {
+      if (symb == start && left == -1 && right == -1) return -1;
+      if (right != -1 && ((dmrs >> right) & 1)) {
+        tmp = (int8_t)next_est(ptrs, dmrs, right + 1, end);
+        if (tmp != -1) slope_from(right, tmp, est, slope);
+        est_from_slope(est, slope, left, right);
+        symb = (uint8_t)(right - 1);
+      } else if (right != -1 && ((ptrs >> right) & 1)) {
+        slope_from(left, right, est, slope);
+        est_from_slope(est, slope, left, right);
+        symb = (uint8_t)(right - 1);
+      } else if (right == -1 && symb < end) {
+        est_from_slope(est, slope, symb - 1, end);
+        symb = end;
+      } else return -1;
+    }
+  }
+  return 0;
+}
+/* nr_ptrs_cpe_estimation (ptrs_nr.c:181-263) on one symbol's compensated REs (12 * nb_rb c16, squeezed in place); gold = the symbol's PDSCH DMRS sequence */
+static int ptrs_cpe(const orc_ptrs_t *t, int nb_rb, int16_t *comp, const uint32_t *gold, int16_t *est)
+{
+  const int K = t->K, sc = (nb_rb + K - 1) / K;
+  int32_t sr = 0, si = 0;
+  int re_cnt = 0, cnt = 0;
+  for (int re = 0; re < 12 * nb_rb; re++) {
+    if (is_ptrs_sc(re, t->rnti, K, nb_rb, t->re_offset)) {
+      /* nr_gen_ref_conj_symbols (nr_dmrs_rx.c:240-256): conjugated QPSK symbol of bits 2i, 2i+1 */
+      const int b0 = (gold[(2 * re_cnt) >> 5] >> ((2 * re_cnt) & 31)) & 1, b1 = (gold[(2 * re_cnt + 1) >> 5] >> ((2 * re_cnt + 1) & 31)) & 1;
+      const int32_t pr = b0 ? -23170 : 23170, pi = b1 ? 23170 : -23170, xr = comp[2 * re], xi = comp[2 * re + 1];
+      /* mult_cpx_vector (cmult_vv.c:96-156), shift 15, packs_epi32 */
+      if (re_cnt < sc) {
+        sr += sat16(wrap32((int64_t)xr * pr + (int64_t)wrap16(-xi) * pi) >> 15);
+        si += sat16(wrap32((int64_t)xi * pr + (int64_t)xr * pi) >> 15);
+      }
+      re_cnt++;
+    } else { comp[2 * cnt] = comp[2 * re]; comp[2 * cnt + 1] = comp[2 * re + 1]; cnt++; }
+  }
+  double real = (double)sr, imag = (double)si;
+  real /= sc; imag /= sc;
+  const volatile double rr = real * real, ii = imag * imag;            /* volatile: no contraction into an fma whatever the flags */
+  const double ab = sqrt(rr + ii);
+  est[0] = d2i16((real / ab) * (1 << 15));
+  est[1] = d2i16((-1) * (imag / ab) * (1 << 15));
+  return re_cnt;
+}
+
+static int pdsch_rx_slot_impl(const orc_pusch_t *p, const orc_ptrs_t *t, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr,
+                              int32_t *log2_maxh_out, int16_t *phase_out, int32_t *ptrs_re_out);
 int orc_pdsch_rx_slot(const orc_pusch_t *p, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out)
+{
+  return pdsch_rx_slot_impl(p, NULL, start_symbol, nr_symbols, rxdataF, dl_ch_est, llr, log2_maxh_out, NULL, NULL);
+}
+/* phase_out: 14 {re, im} (ptrs_phase_per_slot[0]); ptrs_re_out: 14 (ptrs_re_per_slot[0]); both optional */
+int orc_pdsch_rx_slot_ptrs(const orc_pusch_t *p, const orc_ptrs_t *t, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr,
+                           int32_t *log2_maxh_out, int16_t *phase_out, int32_t *ptrs_re_out)
+{
+  return pdsch_rx_slot_impl(p, t, start_symbol, nr_symbols, rxdataF, dl_ch_est, llr, log2_maxh_out, phase_out, ptrs_re_out);
+}
+
+static int pdsch_rx_slot_impl(const orc_pusch_t *p, const orc_ptrs_t *t, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr,
+                              int32_t *log2_maxh_out, int16_t *phase_out, int32_t *ptrs_re_out)
 {
   const int N = p->fft_size, nrx = p->nb_rx, nb = p->rb_size, Qm = p->Qm, pos = p->ul_dmrs_symb_pos, type = p->dmrs_config_type, cdm = p->num_dmrs_cdm_grps_no_data;
   const int sz = (nb * 12 + 15) & ~15;
@@ -413,6 +541,9 @@ int orc_pdsch_rx_slot(const orc_pusch_t *p, int start_symbol, int nr_symbols, co
   int16_t *rx = malloc(4 * (size_t)sz * nrx), *ch = malloc(4 * (size_t)sz * nrx), *comp = calloc((size_t)14 * nb * 12 * 2, 2), *mag[3], *cm = malloc(4 * (size_t)sz);
   for (int t = 0; t < 3; t++) mag[t] = calloc(2 * (size_t)sz, 2);
   int valid[14] = {0}, log2_maxh = 0;
+  int16_t phase[28] = {0};
+  int32_t ptrs_re[14] = {0};
+  uint32_t ptrs_pos = 0;
   int first_with_data = start_symbol;
   const int dmrs_data_re = type == 0 ? 12 - 6 * cdm : 12 - 4 * cdm;
   while (dmrs_data_re == 0 && ((pos >> first_with_data) & 1)) first_with_data++;
@@ -469,7 +600,26 @@ int orc_pdsch_rx_slot(const orc_pusch_t *p, int start_symbol, int nr_symbols, co
     /* rxdataF_comp of symbol m lives at m * nb_rb * 12; vectors beyond the last symbol's region are not modelled (span <= nb * 12) */
     memcpy(out, cm, 4 * (size_t)span);
     valid[m] = len;
+    if (t && t->on) {                                                    /* nr_pdsch_ptrs_processing for receive antenna 0 (the plane the LLRs read) */
+      ptrs_re[m] = 0; phase[2 * m + 1] = 0; phase[2 * m] = pilots ? 32767 : 0;
+      if (m == start_symbol) ptrs_pos = orc_ptrs_symbols(start_symbol, nr_symbols, 1 << t->L, (uint32_t)pos);
+      if ((ptrs_pos >> m) & 1) {
+        uint32_t gold[20];
+        const uint64_t x2tmp0 = ((uint64_t)(14 * t->slot + m + 1) * (((uint64_t)t->nid << 1) + 1)) << 17;     /* nr_gold_pdsch (nr_gold_ue.c:75-93) */
+        orc_gold_words((uint32_t)((x2tmp0 + ((uint64_t)t->nid << 1) + t->nscid) % (1U << 31)), 20, gold);
+        ptrs_re[m] = ptrs_cpe(t, nb, out, gold, phase + 2 * m);
+      }
+      valid[m] -= ptrs_re[m];
+      if (m == start_symbol + nr_symbols - 1) {
+        int ret = 0;
+        if (t->L > 0) ret = orc_ptrs_process_slot((uint32_t)pos, ptrs_pos, phase, start_symbol, nr_symbols);
+        for (int i = start_symbol; i < start_symbol + nr_symbols; i++)
+          if (!((pos >> i) & 1) && ret == 0) orc_rotate_cpx_vector(comp + 2 * (size_t)i * nb * 12, phase[2 * i], phase[2 * i + 1], comp + 2 * (size_t)i * nb * 12, nb * 12);
+      }
+    }
   }
+  if (phase_out) memcpy(phase_out, phase, sizeof(phase));
+  if (ptrs_re_out) memcpy(ptrs_re_out, ptrs_re, sizeof(ptrs_re));
   /* LLRs of the whole slot with the magnitudes of the last symbol */
   size_t off = 0;
   for (int m = start_symbol; m < start_symbol + nr_symbols; m++) {

@@ -16,6 +16,19 @@ static inline double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTO
 
 double refh_pdsch_last_seconds(void) { return g_last_s; }
 
+#ifdef REFH_PTRS
+/* PT-RS (libref_pdsch_ptrs.so only: the same harness linked with the real nr_pdsch_ptrs_processing of NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1765-1907
+ * and NR_REFSIG/ptrs_nr.c).  q: enabled, PTRSTimeDensity (log2 of L), PTRSFreqDensity (K), PTRSReOffset, rnti, nr_slot_rx, nscid, scramblingID_dlsch, N_RB_DL */
+enum { Q_ON, Q_L, Q_K, Q_REOFF, Q_RNTI, Q_SLOT, Q_NSCID, Q_NID, Q_NRB, Q_COUNT };
+static int32_t g_ptrs[Q_COUNT];
+static int16_t g_phase[14 * 2];
+static int32_t g_ptrs_re[14];
+void refh_pdsch_set_ptrs(const int32_t *q) { if (q) memcpy(g_ptrs, q, sizeof(g_ptrs)); else memset(g_ptrs, 0, sizeof(g_ptrs)); }
+/* what the last slot left in ptrs_phase_per_slot[0] / ptrs_re_per_slot[0] */
+void refh_pdsch_get_ptrs(int16_t *phase28, int32_t *re14) { memcpy(phase28, g_phase, sizeof(g_phase)); memcpy(re14, g_ptrs_re, sizeof(g_ptrs_re)); }
+void nr_gold_pdsch(PHY_VARS_NR_UE *ue, int nscid, uint32_t nid);
+#endif
+
 enum { D_N, D_NB_RX, D_RB_START, D_BWP_START, D_RB_SIZE, D_FCO, D_QM, D_START_SYMBOL, D_NR_SYMBOLS, D_DMRS_POS, D_DMRS_TYPE, D_CDM_GROUPS, D_G, D_NL, D_COUNT };
 
 /* rxdataF: [nb_rx][14 N] c16; dl_ch_est: [nl * nb_rx][14 N] c16 (plane layer * nb_rx + rx); llr out: G int16 (layer de-mapped).  Returns log2_maxh; valid_re_out (14) and comp_out (nb_rb*12*14 c16 of rx 0) optional. */
@@ -38,6 +51,24 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
   ue->dl_harq_processes[1][harq_pid].status = SCH_IDLE;
   UE_nr_rxtx_proc_t proc;
   memset(&proc, 0, sizeof(proc));
+#ifdef REFH_PTRS
+  if (g_ptrs[Q_ON]) {
+    c->pduBitmap = 1; dlsch[0].rnti_type = TYPE_C_RNTI_; dlsch[0].rnti = (uint16_t)g_ptrs[Q_RNTI];
+    c->PTRSTimeDensity = g_ptrs[Q_L]; c->PTRSFreqDensity = g_ptrs[Q_K]; c->PTRSReOffset = g_ptrs[Q_REOFF]; c->nscid = g_ptrs[Q_NSCID];
+    proc.nr_slot_rx = g_ptrs[Q_SLOT]; proc.gNB_id = 0;
+    fp->N_RB_DL = g_ptrs[Q_NRB]; fp->slots_per_frame = 20;
+    const int words = ((fp->N_RB_DL * 12) >> 5) + 1;
+    ue->nr_gold_pdsch[0] = calloc(fp->slots_per_frame, sizeof(uint32_t ***));
+    for (int ns = 0; ns < fp->slots_per_frame; ns++) {
+      ue->nr_gold_pdsch[0][ns] = calloc(14, sizeof(uint32_t **));
+      for (int l = 0; l < 14; l++) {
+        ue->nr_gold_pdsch[0][ns][l] = calloc(2, sizeof(uint32_t *));
+        for (int s = 0; s < 2; s++) ue->nr_gold_pdsch[0][ns][l][s] = calloc(words + 2, 4);
+      }
+    }
+    nr_gold_pdsch(ue, g_ptrs[Q_NSCID], (uint32_t)g_ptrs[Q_NID]);        /* the reference's own generator (NR_REFSIG/nr_gold_ue.c:75-93) */
+  }
+#endif
   const int est_size = 14 * N, rx_size_symbol = (nb_rb * 12 + 15) & ~15;
   int32_t (*est)[est_size] = calloc((size_t)nl * nrx, sizeof(int32_t) * est_size);
   c16_t (*rx)[est_size] = calloc(nrx, sizeof(c16_t) * est_size);
@@ -69,6 +100,14 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
   memcpy(llr_out, llr[0], 2 * (size_t)p[D_G]);
   if (valid_re_out) for (int m = 0; m < 14; m++) valid_re_out[m] = (int32_t)dl_valid_re_buf[m];     /* index m holds symbol m (stored at [symbol - 1] + 1) */
   if (comp_out) memcpy(comp_out, comp[0][0], 4 * (size_t)rx_size_symbol * 14);
+#ifdef REFH_PTRS
+  memcpy(g_phase, ptrs_phase[0], sizeof(g_phase));
+  memcpy(g_ptrs_re, ptrs_re[0], sizeof(g_ptrs_re));
+  if (g_ptrs[Q_ON]) {
+    for (int ns = 0; ns < fp->slots_per_frame; ns++) { for (int l = 0; l < 14; l++) { for (int s = 0; s < 2; s++) free(ue->nr_gold_pdsch[0][ns][l][s]); free(ue->nr_gold_pdsch[0][ns][l]); } free(ue->nr_gold_pdsch[0][ns]); }
+    free(ue->nr_gold_pdsch[0]);
+  }
+#endif
   free(est); free(rx); free(comp); free(llr[0]); free(ue);
   return log2_maxh;
 }
