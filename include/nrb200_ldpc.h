@@ -291,8 +291,22 @@ typedef struct nrb200_pusch_rx_s {
                                              * as in the reference.  Needs num_dmrs_cdm_grps_no_data = 2 (no data on DMRS symbols) and 12 * rb_size one of nr_idft's
                                              * sizes other than 768 and 2304 (the reference's own output is not reproducible there): anything else returns -4. */
   uint64_t d_tp_scratch;                    /* _dev, transform precoding: DEVICE scratch of nrb200_pusch_tp_scratch_bytes() bytes (the host entry point has its own) */
+  uint32_t ptrs;                            /* 1: PT-RS present (pduBitmap & 1 with a C-RNTI), pdsch_ue = 1 and one layer only: nr_pdsch_ptrs_processing
+                                             * (NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1765-1907, called at nr_dlsch_demodulation.c:569-574) -- common phase error per
+                                             * PT-RS symbol (nr_ptrs_cpe_estimation, NR_REFSIG/ptrs_nr.c:181-263), PT-RS REs removed from the LLR stream, interpolation over
+                                             * the other symbols (nr_ptrs_process_slot :281-337), rotation of every non-DMRS symbol before the LLRs.  `rnti` above is
+                                             * dlsch[0].rnti.  Any other combination (gNB side: DESIGN.md defect 19; two layers) returns -4. */
+  uint32_t ptrs_time_density;               /* dlsch_config.PTRSTimeDensity: 0 1 2 (L_PTRS = 1 << value) */
+  uint32_t ptrs_freq_density;               /* dlsch_config.PTRSFreqDensity: K_PTRS 2 or 4 */
+  uint32_t ptrs_re_offset;                  /* dlsch_config.PTRSReOffset, used as k_RE_ref like the reference does (< 12) */
+  uint32_t ptrs_slot, ptrs_nscid, ptrs_dmrs_scrambling_id;   /* proc->nr_slot_rx, dlsch_config.nscid, ue->scramblingID_dlsch[nscid]: the Gold sequence of nr_gold_pdsch */
+  uint32_t ptrs_reserved;
+  uint64_t d_ptrs_state;                    /* _dev: 64 bytes of DEVICE scratch (14 phases + status); afterwards [0..13] = ptrs_phase_per_slot[0] {re, im} packed */
 } nrb200_pusch_rx_t;
 uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d);
+/* PT-RS bookkeeping of a descriptor with ptrs = 1: *ptrs_symbols = dlsch->ptrs_symbols as set_ptrs_symb_idx leaves it (NR_REFSIG/ptrs_nr.c:53-86), *ptrs_re_per_symbol =
+ * ptrs_re_per_slot[0][l] of every PT-RS symbol (nr_ptrs_cpe_estimation's re_cnt).  0, or -4 for a PT-RS configuration the library does not reproduce. */
+int32_t nrb200_pdsch_ptrs_layout(const nrb200_pusch_rx_t *d, uint32_t *ptrs_symbols, uint32_t *ptrs_re_per_symbol);
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
 /* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
 int32_t nrb200_pusch_log2_maxh_dev(const nrb200_pusch_rx_t *d, const int16_t *d_ul_ch_estimates, int32_t *d_out, void *stream);

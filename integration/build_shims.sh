@@ -31,8 +31,8 @@ gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_uechest.c $ROO
 ls -la $HERE/_build/*.so $W/libshimtest_chest.so $W/libshimtest_uechest.so
 # the UE's PDSCH receiver: nr_rx_pdsch (the caller harness drives it symbol by symbol like nr_ue_pdsch_procedures)
 gcc $F $INC $DEFS $HERE/oai_shim_rx_pdsch.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_rx_pdsch.so
-gcc $F $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_pdsch.c $ROOT/oracle/ref_harness_pdsch.c $HERE/oai_shim_rx_pdsch.c \
-    $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -o $W/libshimtest_pdsch.so
+gcc $F -DREFH_PTRS $INC $DEFS $ROOT/oracle/ref_stubs.c $ROOT/oracle/ref_stubs_pdsch.c $ROOT/oracle/ref_harness_pdsch.c $HERE/oai_shim_rx_pdsch.c \
+    $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/NR_REFSIG/nr_gold_ue.c $R/openair1/PHY/TOOLS/log2_approx.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -lm -o $W/libshimtest_pdsch.so
 ls -la $HERE/_build/libnrb200_shim_rx_pdsch.so $W/libshimtest_pdsch.so
 # the gNB's PUSCH receiver: nr_rx_pusch_tp (+ the estimator it calls by name), driven by a caller harness that fills PHY_VARS_gNB like phy_init_nr_gNB does
 gcc $F $INC $DEFS $HERE/oai_shim_rx_pusch.c $LIB -Wl,-rpath,'$ORIGIN/../../openairinterface5g_b200' -o $HERE/_build/libnrb200_shim_rx_pusch.so

@@ -32,6 +32,7 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
 int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_t *ch, const int32_t *d_shift, int16_t *llr, cudaStream_t st);
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
 size_t pusch_tp_scratch_bytes(const nrb200_pusch_rx_t &d);
+int pusch_ptrs_layout(const nrb200_pusch_rx_t &d, uint32_t *mask, uint32_t *n_re);
 int lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq);
 int launch_chest_time_avg(uint32_t N, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos, uint32_t rb_size,
                           int16_t *d_est, cudaStream_t st);
@@ -852,7 +853,7 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers == 2 ? 2 : 1);
   const size_t tp_bytes = d->transform_precoding ? pusch_tp_scratch_bytes(*d) : 0;        // the transforms' input / output planes, behind the level slots
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes + 64)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     std::memcpy(w->h_in, rxdataF, plane);
@@ -861,6 +862,7 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
     nrb200_pusch_rx_t e = *d;
     e.rx_stride = e.ch_stride = 14 * d->fft_size;
     e.d_tp_scratch = tp_bytes ? (uint64_t)(uintptr_t)((uint8_t *)w->d_aux + 64) : 0;
+    e.d_ptrs_state = (uint64_t)(uintptr_t)((uint8_t *)w->d_aux + 64 + tp_bytes);           // PT-RS: 14 phases + status behind the transforms' planes
     const int16_t *d_rx = (const int16_t *)w->d_in, *d_ch = (const int16_t *)((uint8_t *)w->d_in + plane);
     const bool measure = d->log2_maxh == 0xFFFFFFFFu;
     int32_t *d_lvl = (int32_t *)w->d_aux;
@@ -879,6 +881,11 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   } while (0);
   ctx().release(w);
   return rc;
+}
+
+NRB200_EXPORT int32_t nrb200_pdsch_ptrs_layout(const nrb200_pusch_rx_t *d, uint32_t *ptrs_symbols, uint32_t *ptrs_re_per_symbol)
+{
+  return d ? pusch_ptrs_layout(*d, ptrs_symbols, ptrs_re_per_symbol) : -1;
 }
 
 NRB200_EXPORT uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d) { return d ? pusch_tp_scratch_bytes(*d) : 0; }

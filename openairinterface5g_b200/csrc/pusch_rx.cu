@@ -10,6 +10,8 @@
 #include "gold_seq.cuh"
 #include "../../include/nrb200_ldpc.h"
 #include <climits>
+#include <cstring>
+#include <algorithm>
 
 namespace nrb200 {
 
@@ -412,9 +414,140 @@ __device__ __forceinline__ unsigned ue_scale(unsigned h)
   return ((unsigned)(unsigned short)p_wrap16(((p_lo(h) * 8192) >> 16) << 3)) | ((unsigned)(unsigned short)p_wrap16(((p_hi(h) * 8192) >> 16) << 3) << 16);
 }
 
-template <int QM>
+// ---- PT-RS at the UE (nr_pdsch_ptrs_processing, NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1765-1907; NR_REFSIG/ptrs_nr.c), one layer.
+// The reference estimates a common phase error per PT-RS symbol from the compensated PT-RS REs, squeezes those REs out of rxdataF_comp, interpolates the
+// estimates over the other symbols at the slot's last symbol, rotates every non-DMRS symbol and only then computes the slot's LLRs.  Here:
+//   pdsch_ptrs_kernel  one warp per symbol: matched filter + MRC of the symbol's PT-RS REs only (nb_rb / K of them), product with the conjugated QPSK
+//                      pilot (Gold sequence of the symbol's PDSCH DMRS), integer sum across the warp, lane 0 normalises in IEEE double arithmetic without
+//                      fused multiply-adds (what oracle/_ref is built with); then thread 0 runs nr_ptrs_process_slot's interpolation.  15 words of state.
+//   pdsch_rx_kernel    PTRS = true: output index i of a PT-RS symbol is mapped past the PT-RS REs before it, the MRC output is rotated by the symbol's
+//                      phase (AVX2 body / scalar tail of rotate_cpx_vector by buffer position), thresholds stay at index i like the reference's unsqueezed
+//                      magnitude buffers.  No intermediate buffer, still one pass over the slot.
+struct PtrsGeom {
+  int on, L, K12, q0, n;           // L = PTRSTimeDensity (log2); 12 K; first PT-RS RE of a symbol; PT-RS REs per PT-RS symbol
+  int start, nsym;
+  unsigned pos, dmrs_pos;          // PT-RS symbols (set_ptrs_symb_idx), DMRS symbols
+  unsigned cinit[14];              // nr_gold_pdsch's c_init per symbol
+  int ch_sym[14];                  // symbol of the estimates per symbol
+  unsigned *state;                 // device: [0..13] phase {re, im} packed, [14] nr_ptrs_process_slot's return value
+};
+// data RE i of a PT-RS symbol -> RE of the allocation (the PT-RS REs q0 + j * K12 skipped)
+__device__ __forceinline__ int ptrs_unsqueeze(const PtrsGeom &T, int i)
+{
+  if (i < T.q0) return i;
+  return i + min(T.n, (i - T.q0) / (T.K12 - 1) + 1);
+}
+__device__ __forceinline__ int p_d2i16(double v)                       // x86 cvttsd2si + truncation to 16 bits ("integer indefinite" has a zero low half)
+{
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return 0;
+  return p_wrap16((int)v);
+}
+// matched filter + saturating MRC of RE `re` of non-DMRS symbol `symbol` (the one-layer arithmetic of pdsch_rx_kernel)
+__device__ __forceinline__ void ue_mrc(const PuschGeom &G, const unsigned *__restrict__ rxF, const unsigned *__restrict__ ch, int symbol, int chs, int re, int shift,
+                                       int &cr, int &ci)
+{
+  int rx_idx, ch_idx;
+  ue_source(G, 0, re, rx_idx, ch_idx);
+  cr = 0; ci = 0;
+  for (int a = 0; a < G.nb_rx; a++) {
+    const unsigned y = __ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx);
+    const unsigned h = ue_scale(__ldg(ch + (size_t)a * G.ch_stride + (size_t)chs * G.N + ch_idx));
+    const int hr = p_lo(h), hi = p_hi(h), yr = p_lo(y), yi = p_hi(y);
+    const int r = p_sat16(((int)((unsigned)(hr * yr) + (unsigned)(hi * yi))) >> shift), im = p_sat16(((int)((unsigned)(p_wrap16(-hi) * yr) + (unsigned)(hr * yi))) >> shift);
+    if (a == 0) { cr = r; ci = im; } else { cr = p_sat16(cr + r); ci = p_sat16(ci + im); }
+  }
+}
+__device__ __forceinline__ int ptrs_next(unsigned mask, int from, int end) { for (int s = from; s < end; s++) if ((mask >> s) & 1u) return s; return -1; }
+__device__ __forceinline__ int ptrs_next_est(unsigned ptrs, unsigned dmrs, int from, int end)
+{
+  const int np = ptrs_next(ptrs, from, end), nd = ptrs_next(dmrs, from, end);
+  if (nd == -1) return np;
+  if (np == -1) return nd;
+  return np > nd ? nd : np;
+}
+__device__ void ptrs_slope(int start, int end, const short *est, double *sl)
+{
+  const double distance = (double)(unsigned char)(end - start);
+  sl[0] = (double)((int)est[2 * end] - (int)est[2 * start]) / distance;
+  sl[1] = (double)((int)est[2 * end + 1] - (int)est[2 * start + 1]) / distance;
+}
+__device__ void ptrs_from_slope(short *est, const double *sl, int start, int end)
+{
+  for (int i = 1; i < end - start; i++) {
+    est[2 * (start + i)] = (short)p_wrap16((int)est[2 * start] + p_d2i16(__dmul_rn((double)i, sl[0])));
+    est[2 * (start + i) + 1] = (short)p_wrap16((int)est[2 * start + 1] + p_d2i16(__dmul_rn((double)i, sl[1])));
+  }
+}
+// nr_ptrs_process_slot (ptrs_nr.c:281-337), control flow kept as written (8-bit symbol counters, leftRef = rightRef = 0 to begin with)
+__device__ int ptrs_process_slot(unsigned dmrs, unsigned ptrs, short *est, int start, int nsym)
+{
+  double slope[2] = {0.0, 0.0};
+  const int end = start + nsym;
+  int right = 0, left = 0;
+  for (int symb = start; symb < end; symb++) {
+    if (((ptrs >> symb) & 1u) || ((dmrs >> symb) & 1u)) { left = symb; right = ptrs_next_est(ptrs, dmrs, symb + 1, end); continue; }
+    if (symb == start && left == -1 && right == -1) return -1;
+    if (right != -1 && ((dmrs >> right) & 1u)) {
+      const int tmp = ptrs_next_est(ptrs, dmrs, right + 1, end);
+      if (tmp != -1) ptrs_slope(right, tmp, est, slope);
+      ptrs_from_slope(est, slope, left, right);
+      symb = right - 1;
+    } else if (right != -1 && ((ptrs >> right) & 1u)) {
+      ptrs_slope(left, right, est, slope);
+      ptrs_from_slope(est, slope, left, right);
+      symb = right - 1;
+    } else if (right == -1) {
+      ptrs_from_slope(est, slope, symb - 1, end);
+      symb = end;
+    } else return -1;
+  }
+  return 0;
+}
+__global__ void __launch_bounds__(448) pdsch_ptrs_kernel(PuschGeom G, PtrsGeom T, const GoldTables *__restrict__ GT, const int *__restrict__ d_shift,
+                                                         const unsigned *__restrict__ rxF, const unsigned *__restrict__ ch)
+{
+  __shared__ short s_est[28];
+  const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  const bool in_alloc = m >= T.start && m < T.start + T.nsym;
+  if (lane == 0) { s_est[2 * m] = (in_alloc && ((T.dmrs_pos >> m) & 1u)) ? 32767 : 0; s_est[2 * m + 1] = 0; }
+  if (in_alloc && ((T.pos >> m) & 1u)) {
+    int sr = 0, si = 0;
+    for (int j0 = 0; j0 < T.n; j0 += 32) {
+      const int j = j0 + lane;
+      // the symbol's Gold words, one per lane and 32-RE chunk: word (2 j) >> 5 = j >> 4 holds bits 2 j, 2 j + 1
+      const unsigned gw = gold_word(GT, T.cinit[m], (unsigned)(j >> 4));
+      if (j < T.n) {
+        int cr, ci;
+        ue_mrc(G, rxF, ch, m, T.ch_sym[m], T.q0 + j * T.K12, shift, cr, ci);
+        const int b0 = (gw >> ((2 * j) & 31)) & 1u, b1 = (gw >> ((2 * j + 1) & 31)) & 1u;
+        const int pr = b0 ? -23170 : 23170, pi = b1 ? 23170 : -23170;      // nr_gen_ref_conj_symbols: conjugated QPSK (nr_dmrs_rx.c:54-55, :240-256)
+        sr += p_sat16(((int)((unsigned)(cr * pr) + (unsigned)(p_wrap16(-ci) * pi))) >> 15);   // mult_cpx_vector, shift 15, packs (cmult_vv.c:96-156)
+        si += p_sat16(((int)((unsigned)(ci * pr) + (unsigned)(cr * pi))) >> 15);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+    if (lane == 0) {
+      const double sc = (double)T.n;
+      const double real = (double)sr / sc, imag = (double)si / sc;
+      const double ab = sqrt(__dadd_rn(__dmul_rn(real, real), __dmul_rn(imag, imag)));
+      s_est[2 * m] = (short)p_d2i16(__dmul_rn(real / ab, 32768.0));
+      s_est[2 * m + 1] = (short)p_d2i16(__dmul_rn(-(imag / ab), 32768.0));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ret = 0;
+    if (T.L > 0) ret = ptrs_process_slot(T.dmrs_pos, T.pos, s_est, T.start, T.nsym);
+    for (int q = 0; q < 14; q++) T.state[q] = ((unsigned)(unsigned short)s_est[2 * q]) | ((unsigned)(unsigned short)s_est[2 * q + 1] << 16);
+    T.state[14] = (unsigned)ret;
+  }
+}
+
+template <int QM, bool PTRS = false>
 __global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift, const unsigned *__restrict__ rxF,
-                                                       const unsigned *__restrict__ ch, short *__restrict__ llr)
+                                                       const unsigned *__restrict__ ch, short *__restrict__ llr, PtrsGeom PT)
 {
   __shared__ uint32_t s_gold[(256 * QM) / 32 + 2];
   const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
@@ -429,7 +562,7 @@ __global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTa
   if (i >= valid) return;
   const int shift = G.shift_from_dev ? *d_shift : G.shift;
   int rx_idx, ch_idx, mch_idx, dummy;
-  ue_source(G, is_dmrs, i, rx_idx, ch_idx);
+  ue_source(G, is_dmrs, (PTRS && ((PT.pos >> symbol) & 1u)) ? ptrs_unsqueeze(PT, i) : i, rx_idx, ch_idx);
   ue_source(G, G.last_is_dmrs, i, dummy, mch_idx);
   const bool mag_ok = i < G.last_span;
   constexpr int ampa = QM == 4 ? 20724 : QM == 6 ? 20225 : QM == 8 ? 20106 : 0, ampb = QM == 6 ? 10112 : QM == 8 ? 10053 : 0, ampc = QM == 8 ? 5026 : 0;
@@ -446,6 +579,20 @@ __global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTa
       const int va = p_wrap16(((m * ampa) >> 16) << 1), vb = p_wrap16(((m * ampb) >> 16) << 1), vc = p_wrap16(((m * ampc) >> 16) << 1);
       if (a == 0) { ma = va; mb = vb; mc = vc; } else { ma = p_sat16(ma + va); mb = p_sat16(mb + vb); mc = p_sat16(mc + vc); }
     }
+  }
+  if (PTRS && !is_dmrs && PT.state[14] == 0u) {
+    // rotate_cpx_vector(rxdataF_comp of the symbol, phase, 12 * nb_rb, 15) (cmult_sv.c:77-145): madd + packs for whole groups of 8 REs, c16mulShift for the rest
+    const unsigned ph = PT.state[symbol];
+    const int ar = p_lo(ph), ai = p_hi(ph);
+    int xr, xi;
+    if (i < (G.nb_re & ~7)) {
+      xr = p_sat16(((int)((unsigned)(cr * ar) + (unsigned)(ci * p_wrap16(-ai)))) >> 15);
+      xi = p_sat16(((int)((unsigned)(cr * ai) + (unsigned)(ci * ar))) >> 15);
+    } else {
+      xr = p_wrap16(((int)((unsigned)(cr * ar) - (unsigned)(ci * ai))) >> 15);
+      xi = p_wrap16(((int)((unsigned)(cr * ai) + (unsigned)(ci * ar))) >> 15);
+    }
+    cr = xr; ci = xi;
   }
   int o[8];
   if (QM == 2) { o[0] = cr >> 3; o[1] = ci >> 3; }
@@ -682,10 +829,58 @@ static int nb_re_symbol(const nrb200_pusch_rx_t &d, int symbol)
   return d.rb_size * 12;
 }
 
+// set_ptrs_symb_idx (ptrs_nr.c:53-86)
+static unsigned ptrs_symbol_mask(int start_symbol, int duration, int L_ptrs, unsigned dmrs_pos)
+{
+  unsigned out = 0;
+  int i = 0, l_ref = start_symbol;
+  const int last = start_symbol + duration - 1;
+  while (l_ref + i * L_ptrs <= last) {
+    int is_dmrs = 0, l;
+    const int lo = std::max(l_ref + (i - 1) * L_ptrs + 1, l_ref);
+    for (l = l_ref + i * L_ptrs; l >= lo; l--) if ((dmrs_pos >> l) & 1u) { is_dmrs = 1; break; }
+    if (is_dmrs) { l_ref = l; i = 1; continue; }
+    out |= 1u << (l_ref + i * L_ptrs);
+    i++;
+  }
+  return out;
+}
+// PT-RS geometry of a descriptor (one layer at the UE only): 0 = no PT-RS, 1 = filled, < 0 = not a configuration the library reproduces
+static int make_ptrs(const nrb200_pusch_rx_t &d, PtrsGeom *T)
+{
+  std::memset(T, 0, sizeof(*T));
+  if (!d.ptrs) return 0;
+  const int nl = d.nrOfLayers == 0 ? 1 : (int)d.nrOfLayers;
+  // nr_pdsch_ptrs_processing squeezes and rotates plane [0][aarx] only: with two layers the second layer would be left as it is (not reproduced);
+  // the gNB side has no input -> output function (defect 19)
+  if (!d.pdsch_ue || nl != 1) return -4;
+  const int K = (int)d.ptrs_freq_density, nb = (int)d.rb_size;
+  if ((K != 2 && K != 4) || d.ptrs_time_density > 2 || d.ptrs_re_offset >= 12 || d.ptrs_nscid > 1 || d.ptrs_slot >= 160) return -4;
+  const int k_rb_ref = (nb % K == 0) ? (int)(d.rnti & 0xFFFFu) % K : (int)(d.rnti & 0xFFFFu) % (nb % K);          // is_ptrs_subcarrier (ptrs_nr.c:107-129)
+  T->on = 1; T->L = (int)d.ptrs_time_density; T->K12 = 12 * K; T->q0 = (int)d.ptrs_re_offset + 12 * k_rb_ref;
+  T->n = T->q0 < 12 * nb ? (12 * nb - 1 - T->q0) / T->K12 + 1 : 0;
+  if (T->n < 1) return -4;
+  T->start = (int)d.start_symbol_index; T->nsym = (int)d.nr_of_symbols; T->dmrs_pos = d.ul_dmrs_symb_pos;
+  T->pos = ptrs_symbol_mask(T->start, T->nsym, 1 << T->L, d.ul_dmrs_symb_pos);
+  const uint64_t nid = d.ptrs_dmrs_scrambling_id & 0xFFFFu;
+  for (int l = 0; l < 14; l++) {                                          // nr_gold_pdsch (nr_gold_ue.c:75-93)
+    const uint64_t x2tmp0 = ((uint64_t)(14 * d.ptrs_slot + l + 1) * ((nid << 1) + 1)) << 17;
+    T->cinit[l] = (uint32_t)((x2tmp0 + (nid << 1) + d.ptrs_nscid) % (1ull << 31));
+    int chs = -1;                                                         // get_valid_dmrs_idx_for_channel_est
+    for (int q = l; q >= 0 && chs < 0; q--) if ((d.ul_dmrs_symb_pos >> q) & 1) chs = q;
+    for (int q = l; q < 14 && chs < 0; q++) if ((d.ul_dmrs_symb_pos >> q) & 1) chs = q;
+    T->ch_sym[l] = chs < 0 ? 0 : chs;
+  }
+  T->state = reinterpret_cast<unsigned *>((uintptr_t)d.d_ptrs_state);
+  return 1;
+}
+
 static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_llr)
 {
   const int Qm = d.qam_mod_order;
   const int nl = d.nrOfLayers == 0 ? 1 : (int)d.nrOfLayers;
+  PtrsGeom PT;
+  if (make_ptrs(d, &PT) < 0) return -4;
   if (nl > 2 || (nl == 2 && !d.pdsch_ue && Qm >= 6 && d.nb_rx != 2 && d.nb_rx != 4)) return -4;   // 2 layers: MMSE receiver (Qm >= 6; 2 or 4 rx like the reference), joint ML below
   if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
       d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || (d.log2_maxh > 31 && d.log2_maxh != 0xFFFFFFFFu))
@@ -728,16 +923,28 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
       for (int q = (int)s; q >= 0 && chs < 0; q--) if ((d.ul_dmrs_symb_pos >> q) & 1) chs = q;
       for (int q = (int)s; q < 14 && chs < 0; q++) if ((d.ul_dmrs_symb_pos >> q) & 1) chs = q;
     }
-    const int v = nb_re_symbol(d, s);
+    const int v0 = nb_re_symbol(d, s);                                   // what the symbol's extraction / magnitude buffers span
+    int v = v0;
+    if (PT.on && ((PT.pos >> s) & 1u)) v -= PT.n;                     // dl_valid_re[symbol] -= ptrs_re_per_slot[0][symbol] (nr_dlsch_demodulation.c:573)
     if (v > 0) {
       const int k = G->n_sym++;
       G->sym[k] = s; G->ch_sym[k] = chs; G->is_dmrs[k] = dm; G->valid[k] = v; G->llr_off[k] = off;
     }
     off += (unsigned)v * Qm;
-    if (s == d.start_symbol_index + d.nr_of_symbols - 1) { G->last_is_dmrs = dm; G->last_ch_sym = chs; G->last_span = (v / 12 + ((v % 12) ? 1 : 0)) * 12; }
+    if (s == d.start_symbol_index + d.nr_of_symbols - 1) { G->last_is_dmrs = dm; G->last_ch_sym = chs; G->last_span = (v0 / 12 + ((v0 % 12) ? 1 : 0)) * 12; }
   }
   if (total_llr) *total_llr = off * (unsigned)nl;
   return G->n_sym > 0 ? 0 : -4;
+}
+
+int pusch_ptrs_layout(const nrb200_pusch_rx_t &d, uint32_t *mask, uint32_t *n_re)
+{
+  PtrsGeom T;
+  const int rc = make_ptrs(d, &T);
+  if (rc < 0) return rc;
+  if (mask) *mask = T.on ? T.pos : 0u;
+  if (n_re) *n_re = T.on ? (uint32_t)T.n : 0u;
+  return 0;
 }
 
 uint32_t pusch_num_llr(const nrb200_pusch_rx_t &d)
@@ -752,6 +959,11 @@ int launch_pusch_level(const nrb200_pusch_rx_t &d, const int16_t *ch, int32_t *d
   PuschGeom G;
   int rc = make_geom(d, &G, nullptr);
   if (rc) return rc;
+  if (d.ptrs) {                                                   // the level is measured on the symbol as extracted, PT-RS REs included (nr_dlsch_demodulation.c:436-470)
+    nrb200_pusch_rx_t e = d;
+    e.ptrs = 0;
+    if ((rc = make_geom(e, &G, nullptr)) != 0) return rc;
+  }
   if (G.ue) {
     pdsch_level_kernel<<<G.nb_rx * G.nl, 256, 0, st>>>(G, 0, (const unsigned *)ch, d_out9, d_count);
     ctx().launches++;
@@ -798,11 +1010,27 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
       default: pdsch_rx2_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
     }
   } else if (G.ue) {
-    switch (G.Qm) {
-      case 2: pdsch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-      case 4: pdsch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-      case 6: pdsch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
-      default: pdsch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
+    PtrsGeom PT;
+    const int pt = make_ptrs(d, &PT);
+    if (pt < 0) return pt;
+    if (pt == 1) {
+      if (PT.state == nullptr || scramble_mod_init() != 0) return PT.state == nullptr ? -4 : -5;
+      pdsch_ptrs_kernel<<<1, 448, 0, st>>>(G, PT, gold_tables_dev(), d_shift, R, C);
+      NRB200_CUDA_OK(cudaGetLastError(), "pdsch_ptrs launch");
+      ctx().launches++;
+      switch (G.Qm) {
+        case 2: pdsch_rx_kernel<2, true><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+        case 4: pdsch_rx_kernel<4, true><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+        case 6: pdsch_rx_kernel<6, true><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+        default: pdsch_rx_kernel<8, true><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+      }
+    } else {
+      switch (G.Qm) {
+        case 2: pdsch_rx_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+        case 4: pdsch_rx_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+        case 6: pdsch_rx_kernel<6><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+        default: pdsch_rx_kernel<8><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr, PT); break;
+      }
     }
   } else if (G.nl == 2) {
     if (G.Qm == 2) pusch_rx2ml_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr);

@@ -73,7 +73,15 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order",
                                           "start_symbol_index", "nr_of_symbols", "ul_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data",
                                           "log2_maxh", "rx_stride", "ch_stride", "unscramble", "rnti", "data_scrambling_id", "nrOfLayers", "noise_var", "max_ch", "pdsch_ue")] + \
-               [("d_est_state", C.c_uint64), ("est_state_ports", C.c_uint32), ("transform_precoding", C.c_uint32), ("d_tp_scratch", C.c_uint64)]
+               [("d_est_state", C.c_uint64), ("est_state_ports", C.c_uint32), ("transform_precoding", C.c_uint32), ("d_tp_scratch", C.c_uint64)] + \
+               [(n, C.c_uint32) for n in ("ptrs", "ptrs_time_density", "ptrs_freq_density", "ptrs_re_offset", "ptrs_slot", "ptrs_nscid", "ptrs_dmrs_scrambling_id",
+                                          "ptrs_reserved")] + [("d_ptrs_state", C.c_uint64)]
+
+    def set_ptrs(self, time_density, freq_density, re_offset, slot, nscid, dmrs_scrambling_id, d_state=0):
+        """PT-RS at the UE (one layer): the fields of fapi_nr_dl_config_dlsch_pdu_rel15_t nr_pdsch_ptrs_processing reads; self.rnti is dlsch[0].rnti."""
+        self.ptrs, self.ptrs_time_density, self.ptrs_freq_density, self.ptrs_re_offset = 1, time_density, freq_density, re_offset
+        self.ptrs_slot, self.ptrs_nscid, self.ptrs_dmrs_scrambling_id, self.d_ptrs_state = slot, nscid, dmrs_scrambling_id, d_state
+        return self
 
 
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
@@ -504,6 +512,12 @@ class LdpcLib:
     # ---- single-layer PUSCH inner receiver (nr_ulsch_demodulation.c inner_rx + log2_maxh measurement)
     def pusch_num_llr(self, desc):
         return int(self.lib.nrb200_pusch_num_llr(C.addressof(desc)))
+
+    def pdsch_ptrs_layout(self, desc):
+        """(PT-RS symbol mask, PT-RS REs per PT-RS symbol) of a descriptor with ptrs = 1 (set_ptrs_symb_idx / nr_ptrs_cpe_estimation's bookkeeping)."""
+        mask, n = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.nrb200_pdsch_ptrs_layout(C.c_void_p(C.addressof(desc)), C.byref(mask), C.byref(n)), "pdsch_ptrs_layout")
+        return mask.value, n.value
 
     def pusch_inner_rx_host(self, desc, rxdataF, ul_ch_estimates):
         """rxdataF: [nb_rx][14][N][2] int16; ul_ch_estimates: [nb_rx * layers][14][N][2] (index layer * nb_rx + rx).

@@ -287,6 +287,12 @@ class Oracle:
                                        C.byref(sh))
         return llr[:n].copy(), sh.value
 
+    def gold_words(self, c_init, n_words):
+        """n_words 32-bit words of the Gold sequence lte_gold_generic produces for c_init."""
+        out = np.zeros(n_words, np.uint32)
+        self.lib.orc_gold_words(C.c_uint32(c_init), C.c_uint32(n_words), out.ctypes.data_as(C.c_void_p))
+        return out
+
     def ptrs_symbols(self, start_symbol, nr_symbols, L_log2, dmrs_pos):
         self.lib.orc_ptrs_symbols.restype = C.c_uint32
         return int(self.lib.orc_ptrs_symbols(start_symbol, nr_symbols, 1 << L_log2, C.c_uint32(dmrs_pos)))

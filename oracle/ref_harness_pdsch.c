@@ -56,6 +56,7 @@ int refh_pdsch_rx_slot(const int32_t *p, const int16_t *rxdataF, const int16_t *
     c->pduBitmap = 1; dlsch[0].rnti_type = TYPE_C_RNTI_; dlsch[0].rnti = (uint16_t)g_ptrs[Q_RNTI];
     c->PTRSTimeDensity = g_ptrs[Q_L]; c->PTRSFreqDensity = g_ptrs[Q_K]; c->PTRSReOffset = g_ptrs[Q_REOFF]; c->nscid = g_ptrs[Q_NSCID];
     proc.nr_slot_rx = g_ptrs[Q_SLOT]; proc.gNB_id = 0;
+    ue->scramblingID_dlsch[g_ptrs[Q_NSCID]] = (uint16_t)g_ptrs[Q_NID];
     fp->N_RB_DL = g_ptrs[Q_NRB]; fp->slots_per_frame = 20;
     const int words = ((fp->N_RB_DL * 12) >> 5) + 1;
     ue->nr_gold_pdsch[0] = calloc(fp->slots_per_frame, sizeof(uint32_t ***));

@@ -181,3 +181,46 @@ def make_tb_llrs(oracle, A, Qm, nl, rb_size, rv, seed, snr_db=8.0, BG=1, nsymb=1
     y = (1.0 - 2.0 * bits) + sigma * rng.standard_normal(bits.size)
     llr = np.clip(np.round(y * 24.0), -32768, 32767).astype(np.int16)
     return payload, llr, dict(C=C_, K=K, Z=Z, F=F, E=E, G=G)
+
+
+PTRS_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm, carrier, start, nsym, L (log2), K, re_offset, rnti, slot, nscid, nid
+    (4096, 2, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13, 0, 2, 0, 0x1234, 3, 0, 40),
+    (4096, 4, 0, 272, 8, 1 << 2, 0, 1, 273, 1, 13, 1, 4, 2, 0x4321, 7, 1, 500),
+    (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, 2, 2, 5, 0x0101, 0, 0, 1007),
+    (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, 1, 2, 11, 77, 19, 0, 0),
+    (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, 2, 4, 1, 65535, 5, 1, 3),
+    (1024, 2, 20, 31, 4, 1 << 2, 1, 2, 52, 2, 12, 0, 4, 0, 9, 9, 0, 9),
+    (512, 4, 3, 11, 8, 1 << 1, 0, 1, 25, 1, 6, 1, 2, 3, 1, 1, 1, 65535),
+    (2048, 2, 0, 106, 6, (1 << 2) | (1 << 13), 0, 1, 106, 1, 13, 2, 2, 0, 4242, 2, 0, 123),
+    (2048, 2, 0, 105, 6, (1 << 2) | (1 << 7) | (1 << 11), 0, 2, 106, 0, 14, 1, 4, 7, 31, 2, 0, 123),
+]
+PTRS_SIGNALS = [("random", 2000, 1500), ("random", 32767, 32767), ("coherent", 0, 0.0), ("coherent", 30, 0.05), ("coherent", 0, 0.3)]
+
+
+def ptrs_inputs(oracle, rng, case, kind, a, b):
+    """Inputs of a PDSCH slot with PT-RS for the UE receiver.  kind "random": rx / estimates uniform in +-a / +-b.  kind "coherent": a flat channel per antenna,
+    QPSK on every RE, the PT-RS REs carrying the pilots nr_ptrs_cpe_estimation regenerates (Gold sequence of the symbol's PDSCH DMRS), a common phase error of
+    b rad per symbol and Gaussian noise of sigma a -- so the estimates are a real phase ramp (b = 0, a = 0: zero imaginary part, the 32768 -> -32768 case)."""
+    N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+    if kind == "random":
+        return rng.integers(-a, a + 1, size=(nb_rx, 14, N, 2)).astype(np.int16), rng.integers(-b, b + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    start_re = (N - carrier * 6 + rb_start * 12) % N
+    hh = (rng.normal(size=(nb_rx, 1, 1)) + 1j * rng.normal(size=(nb_rx, 1, 1))) * 600
+    tx = (rng.choice([-1, 1], size=(14, N)) + 1j * rng.choice([-1, 1], size=(14, N))) * 700
+    pos = oracle.ptrs_symbols(start, nsym, L, dpos)
+    krb = rnti % K if rb_size % K == 0 else rnti % (rb_size % K)
+    for m in range(14):
+        if (pos >> m) & 1:
+            g = oracle.gold_words(((((14 * slot + m + 1) * (2 * nid + 1)) << 17) + 2 * nid + nscid) % (1 << 31), 20)
+            j = 0
+            for re in range(12 * rb_size):
+                if (re - reoff - krb * 12) % (K * 12) == 0:
+                    b0 = (int(g[(2 * j) >> 5]) >> ((2 * j) & 31)) & 1
+                    b1 = (int(g[(2 * j + 1) >> 5]) >> ((2 * j + 1) & 31)) & 1
+                    tx[m, (start_re + re) % N] = ((-1 if b0 else 1) + 1j * (-1 if b1 else 1)) * 700
+                    j += 1
+    rot = np.exp(1j * b * np.arange(14))[None, :, None]
+    y = hh * tx[None] * rot / 600 + a * (rng.normal(size=(nb_rx, 14, N)) + 1j * rng.normal(size=(nb_rx, 14, N)))
+    rx = np.stack([np.round(y.real), np.round(y.imag)], -1).clip(-32768, 32767).astype(np.int16)
+    hf = np.broadcast_to(hh, (nb_rx, 14, N))
+    return rx, np.stack([np.round(hf.real), np.round(hf.imag)], -1).astype(np.int16)

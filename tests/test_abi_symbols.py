@@ -110,7 +110,7 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     import subprocess
     from openairinterface5g_b200 import ldpc
     pairs = [("nrb200_ldpc_dec_params_t", ldpc.DecParams, None), ("nrb200_ldpc_enc_params_t", ldpc.EncParams, None), ("nrb200_decode_abort_t", ldpc.DecodeAbort, None),
-             ("nrb200_ldpc_batch_desc_t", ldpc.BatchDesc, "out_stride"), ("nrb200_rm_desc_t", ldpc.RmDesc, None), ("nrb200_pusch_rx_t", ldpc.PuschRxDesc, "d_tp_scratch"),
+             ("nrb200_ldpc_batch_desc_t", ldpc.BatchDesc, "out_stride"), ("nrb200_rm_desc_t", ldpc.RmDesc, None), ("nrb200_pusch_rx_t", ldpc.PuschRxDesc, "d_ptrs_state"),
              ("nrb200_pusch_chest_t", ldpc.PuschChestDesc, "lowpapr_seq"), ("nrb200_pdsch_tx_t", ldpc.PdschTxDesc, "pm_weights")]
     ldpc._late_fields()
     pairs += [("nrb200_sch_rx_slot_t", ldpc.SchRxSlotDesc, "seg_payload_bytes"), ("nrb200_sch_rx_bufs_t", ldpc.SchRxBufs, "hard_stride"),
@@ -147,3 +147,24 @@ def test_sticky_device_rule_matches_the_python_tools():
                 assert d == sticky_gpu(u, r, world) and 0 <= d < world
                 seen.add(d)
         assert len(seen) == world
+
+
+def test_pdsch_ptrs_layout_host_logic(oracle):
+    """nrb200_pdsch_ptrs_layout / nrb200_pusch_num_llr are host arithmetic (no GPU): PT-RS symbol mask = set_ptrs_symb_idx, PT-RS REs per symbol and the slot's
+    LLR count as the pinned oracle leaves them."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from common import PTRS_CASES
+    from oracle.bindings import PuschParms, PtrsParms
+    from openairinterface5g_b200.ldpc import LdpcLib, PuschRxDesc
+    lib = LdpcLib()
+    for case in PTRS_CASES:
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, 0, rnti, 501, 1, 0, 0, 1)
+        d.set_ptrs(L, K, reoff, slot, nscid, nid)
+        mask, n = lib.pdsch_ptrs_layout(d)
+        assert mask == oracle.ptrs_symbols(start, nsym, L, dpos), case
+        z = np.zeros((nb_rx, 14, N, 2), np.int16)
+        llr, _, _, nre = oracle.pdsch_rx_slot_ptrs(PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm), PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid),
+                                                   start, nsym, z, z)
+        assert [n if (mask >> s) & 1 else 0 for s in range(14)] == nre.tolist() and lib.pusch_num_llr(d) == llr.size, case

@@ -240,6 +240,19 @@ def test_transform_precoding_golden(oracle):
         oracle.pusch_set_transform_precoding(0)
 
 
+def test_ptrs_ue_golden(oracle):
+    """PT-RS at the UE (nr_pdsch_ptrs_processing inside nr_rx_pdsch): LLRs, log2_maxh, per-symbol phase estimates and PT-RS RE counts against vectors of the
+    compiled reference (tools/gen_golden_ptrs.py)."""
+    from oracle.bindings import PuschParms, PtrsParms
+    g = _load("ptrs.npz")
+    for i in range(int(g["n"])):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = [int(x) for x in g[f"case{i}"]]
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        llr, sh, ph, nre = oracle.pdsch_rx_slot_ptrs(P, PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid), start, nsym, g[f"rx{i}"], g[f"h{i}"])
+        assert sh == int(g[f"sh{i}"]) and np.array_equal(nre, g[f"nre{i}"]) and np.array_equal(ph, g[f"phase{i}"]), i
+        assert np.array_equal(llr, g[f"llr{i}"]), i
+
+
 def test_transform_precoding_64qam_cannot_be_demapped(oracle):
     """A property of the reference, kept visible: after nr_freq_equalization the compensated symbols sit at 128 k (k = 1, 3, 5, 7 for 64QAM) while the constant
     thresholds it installs are 316 / 158 (nr_freq_equalization.c:63-67), so a NOISELESS DFT-s-OFDM 64QAM symbol is demapped with bit errors; QPSK and 16QAM are

@@ -151,6 +151,40 @@ def test_oai_ue_caller_reaches_the_gpu_through_nr_rx_pdsch(oracle):
         assert [int(v) for v in valid[start:start + nsym]] == per and int(valid.sum()) * Qm * nl == G
 
 
+def test_oai_ue_caller_with_ptrs_reaches_the_gpu_through_nr_rx_pdsch(oracle):
+    """The same caller with PT-RS switched on in the PDU (pduBitmap bit 0, C-RNTI, PTRSTimeDensity / PTRSFreqDensity / PTRSReOffset): the interposer keeps
+    dl_valid_re / ptrs_re_per_slot / dlsch->ptrs_symbols per symbol like nr_pdsch_ptrs_processing and the library estimates, interpolates and rotates inside the
+    slot receiver.  LLRs, log2_maxh, dl_valid_re and the PT-RS RE counts must be the pinned oracle's."""
+    from oracle.bindings import PuschParms, PtrsParms
+    from common import PTRS_CASES, ptrs_inputs
+    so = os.path.join(ROOT, "oracle", "_ref", "libshimtest_pdsch.so")
+    if not os.path.exists(so):
+        pytest.fail(f"{so} missing: run integration/build_shims.sh where /root/reference exists (the file travels with the repo snapshot)")
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(19)
+    for case in (PTRS_CASES[0], PTRS_CASES[2], PTRS_CASES[5], PTRS_CASES[8]):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+        for kind, a, b in (("random", 2000, 1500), ("coherent", 30, 0.05)):
+            rx, h = ptrs_inputs(oracle, rng, case, kind, a, b)
+            P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+            llr_o, sh_o, ph_o, nre_o = oracle.pdsch_rx_slot_ptrs(P, PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid), start, nsym, rx, h)
+            G = llr_o.size
+            q = np.array([1, L, K, reoff, rnti, slot, nscid, nid, carrier], dtype=np.int32)
+            lib.refh_pdsch_set_ptrs(q.ctypes.data_as(C.c_void_p))
+            try:
+                prm = np.array([N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, start, nsym, dpos, dtype_, cdm, G, 1], dtype=np.int32)
+                llr = np.zeros(G + 64, np.int16)
+                valid = np.zeros(14, np.int32)
+                sh = lib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), rx.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
+                                            valid.ctypes.data_as(C.c_void_p), None)
+                ph = np.zeros((14, 2), np.int16); nre = np.zeros(14, np.int32)
+                lib.refh_pdsch_get_ptrs(ph.ctypes.data_as(C.c_void_p), nre.ctypes.data_as(C.c_void_p))
+            finally:
+                lib.refh_pdsch_set_ptrs(None)
+            assert sh == sh_o and np.array_equal(nre, nre_o), (case, kind, sh, sh_o, nre, nre_o)
+            assert int(valid.sum()) * Qm == G and np.array_equal(llr[:G], llr_o), (case, kind, np.nonzero(llr[:G] != llr_o)[0][:5])
+
+
 def test_oai_gnb_caller_reaches_the_gpu_through_nr_rx_pusch_tp(oracle):
     """integration/oai_shim_rx_pusch.c defines OAI's `nr_rx_pusch_tp`; the reference-side caller (oracle/ref_harness_rxpusch.c: PHY_VARS_gNB with the rxdataF ring,
     pusch_vars and the ULSCH PDU as phy_init_nr_gNB / the scheduler leave them) is linked against it and against the interposed channel estimator

@@ -59,3 +59,55 @@ def test_pdsch_rx_ue_2layers_vs_oracle(ldpc, oracle):
             assert sh == sh_o, (N, nb_rx, Qm, sh, sh_o)
             ref = llr_o if unscr is None else oracle.unscramble_llr(llr_o, 0, unscr[1], unscr[0])
             assert llr.size == ref.size and np.array_equal(llr, ref), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, unscr, np.nonzero(llr != ref)[0][:6])
+
+
+def test_pdsch_rx_ue_ptrs_vs_oracle(ldpc, oracle):
+    """PT-RS at the UE (ptrs = 1): per-symbol common phase error from the PT-RS REs (IEEE double arithmetic on the device), PT-RS REs removed from the LLR stream,
+    interpolation over the symbols without PT-RS, rotation of every non-DMRS symbol -- two launches per slot, bit-exact against the oracle that
+    tests/test_oracle_vs_reference.py pins to the real nr_rx_pdsch + nr_pdsch_ptrs_processing.  Random full-scale slots and coherent ones with a phase ramp."""
+    from oracle.bindings import PtrsParms
+    from common import PTRS_CASES, PTRS_SIGNALS, ptrs_inputs
+    rng = np.random.default_rng(72)
+    for case in PTRS_CASES:
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+        fco = N - carrier * 6
+        for kind, a, b in PTRS_SIGNALS:
+            rx, h = ptrs_inputs(oracle, rng, case, kind, a, b)
+            P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, dtype_, cdm)
+            llr_o, sh_o, ph_o, nre_o = oracle.pdsch_rx_slot_ptrs(P, PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid), start, nsym, rx, h)
+            for unscr in (0, 1):
+                d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, unscr, rnti, 501, 1, 0, 0, 1)
+                d.set_ptrs(L, K, reoff, slot, nscid, nid)
+                mask, n_re = ldpc.pdsch_ptrs_layout(d)
+                assert mask == oracle.ptrs_symbols(start, nsym, L, dpos) and [n_re if (mask >> s) & 1 else 0 for s in range(14)] == nre_o.tolist(), (case, mask, n_re)
+                llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+                assert sh == sh_o, (case, kind, sh, sh_o)
+                ref = llr_o if not unscr else oracle.unscramble_llr(llr_o, 0, 501, rnti)
+                assert llr.size == ref.size and np.array_equal(llr, ref), (case, kind, a, b, unscr, np.nonzero(llr != ref)[0][:6])
+
+
+def test_pdsch_rx_ue_ptrs_golden(ldpc):
+    """The same path against the committed vectors of the compiled reference (tests/golden/ptrs.npz, tools/gen_golden_ptrs.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ptrs.npz"))
+    for i in range(int(g["n"])):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = [int(x) for x in g[f"case{i}"]]
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, 0, rnti, 0, 1, 0, 0, 1)
+        d.set_ptrs(L, K, reoff, slot, nscid, nid)
+        llr, sh = ldpc.pusch_inner_rx_host(d, g[f"rx{i}"], g[f"h{i}"])
+        assert sh == int(g[f"sh{i}"]) and np.array_equal(llr, g[f"llr{i}"]), (i, np.nonzero(llr != g[f"llr{i}"])[0][:6])
+
+
+def test_pdsch_rx_ptrs_unsupported_combinations_fail_loudly(ldpc):
+    """PT-RS with two layers (the reference squeezes and rotates layer 0 only) and on the gNB side (DESIGN.md defect 19) return -4: no silent fallback."""
+    N, nb_rx = 512, 2
+    rx = np.zeros((nb_rx, 14, N, 2), np.int16); h2 = np.zeros((2 * nb_rx, 14, N, 2), np.int16)
+    for nl, ue in ((2, 1), (1, 0)):
+        d = PuschRxDesc(N, nb_rx, 0, 0, 25, N - 150, 4, 1, 13, 1 << 2, 0, 1, 5, 0, 0, 0, 7, 0, nl, 0, 0, ue)
+        d.set_ptrs(1, 2, 0, 0, 0, 0)
+        assert ldpc.pusch_num_llr(d) == 0
+        with pytest.raises(Exception):
+            ldpc.pusch_inner_rx_host(d, rx, h2[:nl * nb_rx])
+    d = PuschRxDesc(N, nb_rx, 0, 0, 25, N - 150, 4, 1, 13, 1 << 2, 0, 1, 5, 0, 0, 0, 7, 0, 1, 0, 0, 1)
+    d.set_ptrs(1, 3, 0, 0, 0, 0)                                           # K_PTRS must be 2 or 4
+    assert ldpc.pusch_num_llr(d) == 0

@@ -558,6 +558,26 @@ def test_pdsch_rx_slot_ue(oracle, reference):
         assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
 
 
+def test_pdsch_rx_slot_ue_ptrs(oracle, reference):
+    """PT-RS at the UE: the real nr_rx_pdsch + nr_pdsch_ptrs_processing + ptrs_nr.c (oracle/_ref/libref_pdsch_ptrs.so) vs the oracle restatement -- LLRs of the slot,
+    log2_maxh, the per-symbol phase estimates (incl. interpolated ones) and PT-RS RE counts; random full-scale inputs and coherent slots with a phase ramp."""
+    from oracle.bindings import PuschParms, PtrsParms
+    from common import PTRS_CASES, PTRS_SIGNALS, ptrs_inputs
+    rng = np.random.default_rng(71)
+    for case in PTRS_CASES:
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+        for kind, a, b in PTRS_SIGNALS:
+            rx, h = ptrs_inputs(oracle, rng, case, kind, a, b)
+            P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+            T = PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid)
+            llr_o, sh_o, ph_o, nre_o = oracle.pdsch_rx_slot_ptrs(P, T, start, nsym, rx, h)
+            llr_r, sh_r, valid, ph_r, nre_r = reference.pdsch_rx_slot_ptrs(P, T, start, nsym, rx, h, llr_o.size, n_rb_dl=carrier)
+            assert sh_o == sh_r and np.array_equal(nre_o, nre_r), (case, kind, sh_o, sh_r, nre_o, nre_r)
+            assert np.array_equal(ph_o, ph_r), (case, kind, ph_o.tolist(), ph_r.tolist())
+            assert np.array_equal(llr_o, llr_r), (case, kind, a, b, np.nonzero(llr_o != llr_r)[0][:5])
+            assert int(valid.sum()) * Qm == llr_o.size
+
+
 PDSCH_2L_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, amplitude (rx, h)
     (4096, 2, 0, 273, 6, 1 << 2, 0, 1, 273, 1, 13, (2000, 1500)), (4096, 4, 0, 273, 8, 1 << 2, 0, 2, 273, 1, 13, (900, 700)),
     (2048, 2, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, (4000, 6000)), (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, (300, 200)),
