@@ -384,7 +384,7 @@ int32_t nrb200_ldpc_offload_decode(const nrb200_ldpc_dec_params_t *p, uint8_t ha
 int32_t nrb200_ldpc_offload_encode(const uint8_t *in, uint8_t *out, const nrb200_ldpc_enc_params_t *impp);
 
 /* ---- Part 9: gNB PDSCH transmitter after the encoder -------------------------------------------------------------------
- * One launch replaces, for one code word on 1..4 layers without PT-RS and with the identity precoder (pm_idx 0), everything nr_generate_pdsch
+ * One launch replaces, for one code word on 1..4 layers (PT-RS and one wideband precoding matrix included: last fields), everything nr_generate_pdsch
  * (openair1/PHY/NR_TRANSPORT/nr_dlsch.c:56-583) does after nr_dlsch_encoding: nr_pdsch_codeword_scrambling (:160), nr_modulation (:175), nr_layer_mapping
  * (:192), DMRS generation and resource mapping (:236-478) and the copy into txdataF (:490-530).  Field names follow nfapi_nr_dl_tti_pdsch_pdu_rel15_t /
  * NR_DL_FRAME_PARMS / PHY_VARS_gNB.  f: the encoder's output, nrb200_pdsch_tx_num_bits() rate-matched and interleaved bits, one per byte (what
@@ -405,8 +405,15 @@ typedef struct nrb200_pdsch_tx_s {
                                              * matrix below on every RB of the allocation (one PRG: the reference's nFAPI structure holds a single prgs_list entry),
                                              * nr_dlsch.c:536-590 with nr_layer_precoder_simd / nr_layer_precoder_cm; nb_tx <= 4 */
   int16_t pm_weights[4][4][2];              /* gNB_config.pmi_list.pmi_pdu[pm_idx - 1].weights[layer][antenna] {precoder_weight_Re, precoder_weight_Im} */
+  uint32_t ptrs;                            /* 1: pduBitmap & 1 -- PT-RS (nr_dlsch.c:98-111, :287-352): on the symbols set_ptrs_symb_idx selects, the sub-carriers
+                                             * is_ptrs_subcarrier selects (NR_REFSIG/ptrs_nr.c:53-129, `rnti` above) carry on EVERY layer the QPSK symbols of the first bits
+                                             * of the symbol's DMRS Gold sequence, the data skip them, the symbol's scaling truncates, and the encoder delivers
+                                             * harq->unav_res modulation symbols less per layer (nrb200_pdsch_tx_num_bits accounts for it) */
+  uint32_t ptrs_time_density;               /* PTRSTimeDensity 0 1 2 (L_PTRS = 1 << value) */
+  uint32_t ptrs_freq_density;               /* PTRSFreqDensity: K_PTRS 2 or 4 */
+  uint32_t ptrs_re_offset;                  /* PTRSReOffset, used as k_RE_ref like the reference does (< 12) */
 } nrb200_pdsch_tx_t;
-uint32_t nrb200_pdsch_tx_num_bits(const nrb200_pdsch_tx_t *d);                 /* G = nb_re * Qm as nr_generate_pdsch derives it, 0 if invalid */
+uint32_t nrb200_pdsch_tx_num_bits(const nrb200_pdsch_tx_t *d);                 /* G = nb_re * Qm as nr_generate_pdsch derives it (minus the PT-RS REs), 0 if invalid */
 int32_t nrb200_pdsch_tx_slot_dev(const nrb200_pdsch_tx_t *d, const uint8_t *d_f, int16_t *d_txdataF, void *stream);
 /* host buffers; txdataF is contiguous [nb_tx][14][fft_size] and is read and written back (REs outside the allocation keep their values) */
 int32_t nrb200_pdsch_tx_slot_host(const nrb200_pdsch_tx_t *d, const uint8_t *f, int16_t *txdataF);

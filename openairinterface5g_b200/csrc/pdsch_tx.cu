@@ -7,6 +7,7 @@
 // sub-carrier of one symbol for all layers: it computes which modulation symbol lands there (closed forms for the reference's running counters m, dmrs_idx,
 // k', n), reads the Qm bits per layer, XORs the Gold bits (jump-ahead words staged per CTA), looks the symbol up, scales it exactly as the reference does
 // (mulhrs in groups of four per contiguous piece, the doubled-amplitude leftovers at the end of a piece, truncation in DMRS symbols) and writes txdataF once.
+#include <algorithm>
 #include "nrb200_ctx.h"
 #include "gold_seq.cuh"
 #include "../../include/nrb200_ldpc.h"
@@ -20,6 +21,8 @@ struct PdschTxGeom {
   unsigned m_base[14], dmrs_cinit[14];
   int delta[4], wf1[4];            // per layer: DMRS comb offset and Wf(1) (Wf(0) = Wt = 1 for the supported ports)
   int dmrs_idx0;
+  unsigned ptrs_pos;               // PT-RS symbols (set_ptrs_symb_idx); 0: no PT-RS
+  int ptrs_K12, ptrs_q0, ptrs_n;   // PT-RS REs of such a symbol: q0 + j * K12, j < n (is_ptrs_subcarrier relative to the allocation's first sub-carrier)
   int pm;                          // > 0: wideband non-identity precoding with pmw (one PRG over the allocation)
   short pmw[4][4][2];              // nfapi_nr_pm_pdu_t.weights[layer][antenna] {Re, Im}
 };
@@ -33,10 +36,14 @@ __global__ void __launch_bounds__(256) pdsch_tx_kernel(PdschTxGeom G, const Gold
   __shared__ uint32_t s_gold[(256 * 4 * QM) / 32 + 2];
   __shared__ uint32_t s_dmrs[12];
   const int k = blockIdx.y, symbol = G.sym[k], is_dmrs = G.is_dmrs[k];
+  const bool is_ptrs = (G.ptrs_pos >> symbol) & 1u;                               // never a DMRS symbol
   const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
   const uint32_t *tab = modtab + (QM == 2 ? 0 : QM == 4 ? 4 : QM == 6 ? 20 : 84);
+  // PT-RS REs of this symbol below index j
+  auto ptrs_below = [&](int j) -> int { return j <= G.ptrs_q0 ? 0 : min(G.ptrs_n, (j - G.ptrs_q0 - 1) / G.ptrs_K12 + 1); };
   // number of data REs of this symbol below index j (per layer)
   auto rank_below = [&](int j) -> int {
+    if (is_ptrs) return j - ptrs_below(j);
     if (!is_dmrs) return j;
     if (G.type == 0) return G.cdm == 1 ? (j >> 1) : 0;
     const int g6 = j / 6, r = j - 6 * g6;
@@ -51,6 +58,9 @@ __global__ void __launch_bounds__(256) pdsch_tx_kernel(PdschTxGeom G, const Gold
   if (is_dmrs) {
     const int j0 = G.type == 0 ? (i0 >> 1) : 2 * (i0 / 6);
     dw0 = (2u * (unsigned)(G.dmrs_idx0 + j0)) >> 5;
+    if (threadIdx.x < 12) s_dmrs[threadIdx.x] = gold_word(T, G.dmrs_cinit[k], dw0 + threadIdx.x);
+  } else if (is_ptrs) {                                                            // the pilots are the first 2 n_ptrs bits of the symbol's DMRS sequence (:296)
+    dw0 = (2u * (unsigned)ptrs_below(i0)) >> 5;
     if (threadIdx.x < 12) s_dmrs[threadIdx.x] = gold_word(T, G.dmrs_cinit[k], dw0 + threadIdx.x);
   }
   __syncthreads();
@@ -69,7 +79,27 @@ __global__ void __launch_bounds__(256) pdsch_tx_kernel(PdschTxGeom G, const Gold
     idx ^= (unsigned)(g >> (rel & 31u)) & ((1u << QM) - 1u);
     return __ldg(tab + idx);
   };
-  if (!is_dmrs) {
+  if (is_ptrs) {
+    // PT-RS symbol (:300-376): the per-RE branch of the reference -- pilots on every layer, data with the truncating scaling
+    const int d = i - G.ptrs_q0;
+    const bool pilot = d >= 0 && d % G.ptrs_K12 == 0;
+    unsigned v;
+    if (pilot) {
+      const unsigned b = 2u * (unsigned)(d / G.ptrs_K12), rel = b - (dw0 << 5);
+      const unsigned x = __ldg(modtab + ((s_dmrs[rel >> 5] >> (rel & 31u)) & 3u));
+      v = ((unsigned)t_wrap16(((int)(short)(x & 0xFFFFu) * G.amp) >> 15) & 0xFFFFu) | ((unsigned)t_wrap16(((int)(short)(x >> 16) * G.amp) >> 15) << 16);
+    }
+    const unsigned m = G.m_base[k] + (unsigned)rank_below(i);
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      if (l >= G.nl) continue;
+      if (!pilot) {
+        const unsigned x = modsym(m * G.nl + l);
+        v = ((unsigned)t_wrap16(((int)(short)(x & 0xFFFFu) * G.amp) >> 15) & 0xFFFFu) | ((unsigned)t_wrap16(((int)(short)(x >> 16) * G.amp) >> 15) << 16);
+      }
+      lay[l] = v;
+    }
+  } else if (!is_dmrs) {
     const unsigned m = G.m_base[k] + (unsigned)i;
     const int j = i < G.upper ? i : i - G.upper, len = i < G.upper ? G.upper : G.rem;
     const bool body = j < (len & ~3);
@@ -166,6 +196,22 @@ static int make_tx_geom(const nrb200_pdsch_tx_t &d, PdschTxGeom *G, uint32_t *n_
     // modulation buffer (type 2, two groups, delta != 0, fft_size % 6 == 4: allowed_xlsch_re_in_dmrs_symbol admits k == start_sc) is refused
     if (grp >= cdm || (type == 1 && G->delta[l] != 0 && cdm == 2 && d.fft_size % 6 == 4)) return -4;
   }
+  G->ptrs_pos = 0; G->ptrs_K12 = 24; G->ptrs_q0 = 0; G->ptrs_n = 0;
+  if (d.ptrs) {                                                                   // :98-111; set_ptrs_symb_idx / is_ptrs_subcarrier of NR_REFSIG/ptrs_nr.c
+    const int K = (int)d.ptrs_freq_density, nb = (int)d.rb_size;
+    if ((K != 2 && K != 4) || d.ptrs_time_density > 2 || d.ptrs_re_offset >= 12) return -4;
+    const int L = 1 << d.ptrs_time_density, last = (int)(d.start_symbol_index + d.nr_of_symbols) - 1;
+    int i = 0, l_ref = (int)d.start_symbol_index;
+    while (l_ref + i * L <= last) {
+      int hit = -1;
+      for (int l = l_ref + i * L; l >= std::max(l_ref + (i - 1) * L + 1, l_ref); l--) if ((d.dl_dmrs_symb_pos >> l) & 1u) { hit = l; break; }
+      if (hit >= 0) { l_ref = hit; i = 1; continue; }
+      G->ptrs_pos |= 1u << (l_ref + i * L);
+      i++;
+    }
+    const int k_rb_ref = (nb % K == 0) ? (int)(d.rnti & 0xFFFFu) % K : (int)(d.rnti & 0xFFFFu) % (nb % K);
+    G->ptrs_K12 = 12 * K; G->ptrs_q0 = (int)d.ptrs_re_offset + 12 * k_rb_ref; G->ptrs_n = (nb + K - 1) / K;
+  }
   const int per_dmrs = G->nb_re - d.rb_size * cdm * (type == 0 ? 6 : 4);
   unsigned m = 0;
   G->n_sym = 0;
@@ -174,7 +220,7 @@ static int make_tx_geom(const nrb200_pdsch_tx_t &d, PdschTxGeom *G, uint32_t *n_
     G->sym[kx] = s; G->is_dmrs[kx] = dm; G->m_base[kx] = m;
     const unsigned long long x2 = (1ULL << 17) * (14ULL * d.slot + s + 1) * (((unsigned long long)d.dl_dmrs_scrambling_id << 1) + 1) + (((unsigned long long)d.dl_dmrs_scrambling_id << 1) + d.scid);
     G->dmrs_cinit[kx] = (unsigned)(x2 % (1ULL << 31));
-    m += dm ? per_dmrs : G->nb_re;
+    m += dm ? per_dmrs : G->nb_re - (((G->ptrs_pos >> s) & 1u) ? G->ptrs_n : 0);
   }
   // the reference derives the length from the whole dlDmrsSymbPos mask (get_num_dmrs); DMRS symbols outside the allocation would desynchronise it
   int n_mask = 0, n_in = 0;

@@ -21,7 +21,10 @@ from .ofdm import NrOfdmParms
 
 class PdschSlotChain:
     def __init__(self, lib, dl, device, A=434280, N=4096, mu=1, carrier_rb=273, rb_start=0, rb_size=273, nb_ant=2, Qm=6, slot=1, rnti=0x1234, nid=77,
-                 dl_freq=3619200000.0, max_iter=8, dmrs_id=55, n_layers=2, tx_amp=512, start_symbol=1, nr_symbols=13):
+                 dl_freq=3619200000.0, max_iter=8, dmrs_id=55, n_layers=2, tx_amp=512, start_symbol=1, nr_symbols=13, ptrs=None):
+        """ptrs = (PTRSTimeDensity (log2 of L), PTRSFreqDensity K, PTRSReOffset) switches PT-RS on at both ends (pduBitmap & 1; one layer: the UE side of the
+        reference handles layer 0 only): the gNB inserts the pilots, the encoder's G shrinks by unav_res, the UE estimates / interpolates / compensates the common
+        phase error inside its slot receiver."""
         self.lib, self.dl, self.dev = lib, dl, device
         self.latency_mode = 1            # decoder: a cluster of SMs per code block (one slot alone); the pipelines below run many slots and set 0
         self.P = NrOfdmParms(N, mu, carrier_rb)
@@ -35,8 +38,15 @@ class PdschSlotChain:
         fco = self.P.first_carrier_offset
         self.txd = PdschTxDesc(N, nb_ant, slot, rb_start, 0, rb_size, fco, Qm, n_layers, start_symbol, nr_symbols, self.dmrs_pos, self.dmrs_type, self.cdm,
                                (1 << n_layers) - 1, 0, dmrs_id, nid, rnti, tx_amp, 14 * N)
+        self.ptrs = ptrs
+        unav_res = 0
+        if ptrs is not None:
+            assert n_layers == 1
+            self.txd.set_ptrs(*ptrs)
         self.G = lib.pdsch_tx_num_bits(self.txd)
-        assert self.G == T.nr_get_G(rb_size, nr_symbols, 12, 1, 0, Qm, n_layers)
+        if ptrs is not None:
+            unav_res = (T.nr_get_G(rb_size, nr_symbols, 12, 1, 0, Qm, n_layers) - self.G) // (Qm * n_layers)      # harq->unav_res (nr_dlsch.c:111)
+        assert self.G == T.nr_get_G(rb_size, nr_symbols, 12, 1, unav_res, Qm, n_layers) and self.G > 0
         E = [T.nr_get_E(self.G, self.C, Qm, n_layers, r) for r in range(self.C)]
         self.R = T.nr_get_R_ldpc_decoder(0, E[0], 1, self.Z)[0]
         self.E = torch.tensor(E, dtype=torch.int32, device=device)
@@ -58,6 +68,11 @@ class PdschSlotChain:
         # ---- receive-side buffers
         self.rxd = PuschRxDesc(N, nb_ant, rb_start, 0, rb_size, fco, Qm, start_symbol, nr_symbols, self.dmrs_pos, self.dmrs_type, self.cdm,
                                0, 14 * N, 14 * N, 1, rnti, nid, n_layers, 0, 0, 1)
+        if ptrs is not None:
+            self.ptrs_state = torch.zeros(16, dtype=torch.int32, device=device)     # ptrs_phase_per_slot[0] as the library leaves it, + status
+            self.rxd.set_ptrs(ptrs[0], ptrs[1], ptrs[2], slot, 0, dmrs_id, self.ptrs_state.data_ptr())
+            mask, n_re = lib.pdsch_ptrs_layout(self.rxd)
+            assert bin(mask).count("1") * n_re == unav_res
         assert lib.pusch_num_llr(self.rxd) == self.G
         self.cdesc = PuschChestDesc(N, nb_ant, slot, 2, 0, rb_start, 0, rb_size, fco, 0, dmrs_id, 14 * N, 14 * N, n_layers, 1)   # UE estimator, all ports in one call
         self.est = torch.zeros((n_layers * nb_ant, 14 * N, 2), dtype=torch.int16, device=device)      # dl_ch_estimates[p * nb_rx + aarx]
@@ -125,7 +140,7 @@ class PdschSlotChain:
         return self.txdata
 
     # ------------------------------------------------------------------ the simulator's channel (never timed)
-    def channel(self, txdata, seed=1, snr_db=35.0, gain=3.0, coupling=0.15):
+    def channel(self, txdata, seed=1, snr_db=35.0, gain=3.0, coupling=0.15, cpe_per_symbol=0.0):
         """Flat nb_rx x nb_tx mix + white noise in the time domain, placed at the slot's position of a frame buffer.  Returns int16 [nb_rx, samples_per_frame, 2].
         The default gain puts the receiver's power-of-two LLR scaling (log2_maxh) where ~40 % of the 64QAM LLRs sit at the int8 rail: with the reference's
         unscaled min-sum and the double-amplitude REs of its resource mapper (DESIGN.md defect 9) that is the scaling at which every 273-PRB slot decodes within
@@ -136,6 +151,9 @@ class PdschSlotChain:
         ph = torch.rand((nb, nb), generator=g, device=dev) * 6.2831853
         H = torch.polar(torch.full((nb, nb), coupling, device=dev) + (1.0 - coupling) * torch.eye(nb, device=dev), ph) * gain
         y = H.to(torch.complex64) @ x
+        if cpe_per_symbol:                                                  # a slow common phase drift (rad per OFDM symbol): what PT-RS is there to track
+            n = torch.arange(y.shape[1], device=dev, dtype=torch.float32) * (cpe_per_symbol / (self.N * 1.0703125))
+            y = y * torch.polar(torch.ones_like(n), n)
         sig = torch.sqrt(torch.mean(torch.abs(y) ** 2)) * 10.0 ** (-snr_db / 20.0) * 0.70711
         yr = torch.view_as_real(y) + sig * torch.randn(y.shape + (2,), generator=g, device=dev)
         rxdata = torch.zeros((nb, self.P.samples_per_frame, 2), dtype=torch.int16, device=dev)

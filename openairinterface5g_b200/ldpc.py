@@ -104,7 +104,13 @@ class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
 class PdschTxDesc(C.Structure):       # nrb200_pdsch_tx_t (field names of nfapi_nr_dl_tti_pdsch_pdu_rel15_t / NR_DL_FRAME_PARMS)
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "qam_mod_order", "nrOfLayers",
                                           "start_symbol_index", "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports",
-                                          "scid", "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "tx_stride", "pm_idx")] + [("pm_weights", C.c_int16 * 32)]
+                                          "scid", "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "tx_stride", "pm_idx")] + [("pm_weights", C.c_int16 * 32)] + \
+               [(n, C.c_uint32) for n in ("ptrs", "ptrs_time_density", "ptrs_freq_density", "ptrs_re_offset")]
+
+    def set_ptrs(self, time_density, freq_density, re_offset):
+        """PT-RS insertion (pduBitmap & 1): PTRSTimeDensity (log2 of L), PTRSFreqDensity (K), PTRSReOffset."""
+        self.ptrs, self.ptrs_time_density, self.ptrs_freq_density, self.ptrs_re_offset = 1, time_density, freq_density, re_offset
+        return self
 
     def set_precoding(self, pm_idx, weights):
         """Wideband precoding matrix: weights [layers <= 4][antennas <= 4][2] int16 (nfapi_nr_pm_pdu_t.weights); pm_idx 0 = identity."""

@@ -75,7 +75,26 @@ class PtrsParms(C.Structure):        # orc_ptrs_t
 class PdschTxParms(C.Structure):     # orc_pdsch_tx_t
     _fields_ = [(n, C.c_int32) for n in ("fft_size", "nb_tx", "slot", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "Qm", "nrOfLayers", "start_symbol",
                                          "nr_of_symbols", "dl_dmrs_symb_pos", "dmrs_config_type", "num_dmrs_cdm_grps_no_data", "dmrs_ports", "scid",
-                                         "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "pm_idx")] + [("pm_weights", C.c_int16 * 32)]
+                                         "dl_dmrs_scrambling_id", "data_scrambling_id", "rnti", "amp", "pm_idx")] + [("pm_weights", C.c_int16 * 32)] + \
+               [(n, C.c_int32) for n in ("ptrs_on", "ptrs_L", "ptrs_K", "ptrs_re_offset")]
+
+    def set_ptrs(self, L_log2, K, re_offset):
+        self.ptrs_on, self.ptrs_L, self.ptrs_K, self.ptrs_re_offset = 1, L_log2, K, re_offset
+        return self
+
+    def ptrs_res(self):
+        """PT-RS REs of the slot per layer (harq->unav_res)."""
+        if not self.ptrs_on:
+            return 0
+        i, l_ref, L, last, mask = 0, self.start_symbol, 1 << self.ptrs_L, self.start_symbol + self.nr_of_symbols - 1, 0
+        while l_ref + i * L <= last:                       # set_ptrs_symb_idx
+            hit = [l for l in range(l_ref + i * L, max(l_ref + (i - 1) * L + 1, l_ref) - 1, -1) if (self.dl_dmrs_symb_pos >> l) & 1]
+            if hit:
+                l_ref, i = hit[0], 1
+                continue
+            mask |= 1 << (l_ref + i * L)
+            i += 1
+        return bin(mask).count("1") * ((self.rb_size + self.ptrs_K - 1) // self.ptrs_K)
 
     def set_precoding(self, pm_idx, weights):
         """weights [4 layers][4 antennas][2] int16 (nfapi_nr_pm_pdu_t.weights); pm_idx 0 = identity."""
@@ -90,7 +109,7 @@ class PdschTxParms(C.Structure):     # orc_pdsch_tx_t
     def G(self):
         n_dmrs_sym = bin(self.dl_dmrs_symb_pos & (((1 << self.nr_of_symbols) - 1) << self.start_symbol)).count("1")
         per = self.num_dmrs_cdm_grps_no_data * (6 if self.dmrs_config_type == 0 else 4)
-        return (12 * self.nr_of_symbols - per * bin(self.dl_dmrs_symb_pos).count("1")) * self.rb_size * self.nrOfLayers * self.Qm
+        return ((12 * self.nr_of_symbols - per * bin(self.dl_dmrs_symb_pos).count("1")) * self.rb_size - self.ptrs_res()) * self.nrOfLayers * self.Qm
 
 
 class Oracle:
@@ -673,8 +692,10 @@ class Reference:
         self._pdschtxlib.refh_pdschtx_set_precoding.argtypes = [C.c_int, C.c_void_p]
         w = np.array(list(P.pm_weights), dtype=np.int16)
         self._pdschtxlib.refh_pdschtx_set_precoding(int(P.pm_idx), w.ctypes.data)
+        self._pdschtxlib.refh_pdschtx_set_ptrs(int(P.ptrs_on), int(P.ptrs_L), int(P.ptrs_K), int(P.ptrs_re_offset))
         self._pdschtxlib.refh_pdsch_tx_slot(prm.ctypes.data, b.ctypes.data, b.size, out.ctypes.data)
         self._pdschtxlib.refh_pdschtx_set_precoding(0, None)
+        self._pdschtxlib.refh_pdschtx_set_ptrs(0, 0, 0, 0)
         return out
 
     def _pusch(self):

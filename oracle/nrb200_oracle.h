@@ -113,6 +113,7 @@ typedef struct {
           dmrs_config_type, num_dmrs_cdm_grps_no_data, dmrs_ports, scid, dl_dmrs_scrambling_id, data_scrambling_id, rnti, amp;
   int32_t pm_idx;               /* 0: identity precoding; > 0: the wideband precoding matrix below (one PRG spanning the allocation) */
   int16_t pm_weights[4][4][2];  /* nfapi_nr_pm_pdu_t.weights[layer][antenna] {Re, Im} */
+  int32_t ptrs_on, ptrs_L, ptrs_K, ptrs_re_offset;   /* PT-RS (pduBitmap & 1): PTRSTimeDensity (log2), PTRSFreqDensity, PTRSReOffset; the caller then supplies the reduced G */
 } orc_pdsch_tx_t;
 int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txdataF);
 

@@ -4,7 +4,7 @@
  * (MODULATION/nr_modulation.c:246-270), DMRS generation (nr_init_pdsch_dmrs, NR_REFSIG/nr_gold.c:78-96; port tables NR_TRANSPORT/nr_sch_dmrs.c:35-100;
  * allowed_xlsch_re_in_dmrs_symbol NR_REFSIG/dmrs_nr.c:37-62), resource mapping (:236-478) and identity precoding (:490-530).  Pinned bit-exactly against the
  * compiled reference through oracle/ref_harness_pdschtx.c (tests/test_oracle_vs_reference.py).  Only tests/, smoke() and bench.py's cpu_baseline leg may
- * link this.  One code word, 1..4 layers, no PT-RS, pmi 0; DMRS ports 0..3 (type 1) / 0..5 (type 2) whose CDM group is below numDmrsCdmGrpsNoData.
+ * link this.  One code word, 1..4 layers, PT-RS, one wideband precoding matrix; DMRS ports 0..3 (type 1) / 0..5 (type 2) whose CDM group is below numDmrsCdmGrpsNoData.
  * Reference behaviour restated literally: in symbols without DMRS the data are scaled with mulhrs in groups of four REs per contiguous piece of the allocation
  * and the 1..3 REs left over at the end of a piece get ((x * amp) >> 14) + 1, i.e. twice the amplitude (:421-426, :453-459); in DMRS symbols the scaling
  * truncates ((x * amp) >> 15). */
@@ -34,7 +34,18 @@ int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txd
   const int nb_re_dmrs = cdm * (type == 0 ? 6 : 4);
   int n_dmrs_sym = 0;
   for (int s = 0; s < 14; s++) n_dmrs_sym += (p->dl_dmrs_symb_pos >> s) & 1;
-  const int nb_re = (12 * p->nr_of_symbols - nb_re_dmrs * n_dmrs_sym) * p->rb_size * nl, G = nb_re * Qm;
+  /* PT-RS (:98-111, :287-352): on a PT-RS symbol (set_ptrs_symb_idx) every layer carries the QPSK symbols of the first 2 n_ptrs bits of the symbol's DMRS Gold
+   * sequence on the PT-RS sub-carriers (is_ptrs_subcarrier relative to start_sc), the data skip them, and the whole symbol takes the per-RE branch whose scaling
+   * truncates.  harq->unav_res = PT-RS REs of the slot: the encoder produces that many modulation symbols less per layer. */
+  uint32_t ptrs_pos = 0;
+  int n_ptrs = 0, n_ptrs_sym = 0, k_rb_ref = 0;
+  if (p->ptrs_on) {
+    ptrs_pos = orc_ptrs_symbols(p->start_symbol, p->nr_of_symbols, 1 << p->ptrs_L, (uint32_t)p->dl_dmrs_symb_pos);
+    n_ptrs = (p->rb_size + p->ptrs_K - 1) / p->ptrs_K;
+    for (int s = 0; s < 14; s++) n_ptrs_sym += (ptrs_pos >> s) & 1;
+    k_rb_ref = (p->rb_size % p->ptrs_K == 0) ? (p->rnti & 0xFFFF) % p->ptrs_K : (p->rnti & 0xFFFF) % (p->rb_size % p->ptrs_K);
+  }
+  const int nb_re = ((12 * p->nr_of_symbols - nb_re_dmrs * n_dmrs_sym) * p->rb_size - n_ptrs * n_ptrs_sym) * nl, G = nb_re * Qm;
   const int n_dmrs = (p->bwp_start + p->rb_start + p->rb_size) * nb_re_dmrs;
   uint32_t *scr = calloc((size_t)(G >> 5) + 8, 4);
   int16_t *mod = malloc(4 * (size_t)nb_re + 64);
@@ -43,7 +54,7 @@ int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txd
   int start_sc = p->first_carrier_offset + (p->rb_start + p->bwp_start) * 12;
   if (start_sc >= N) start_sc -= N;
   int16_t *mod_dmrs = malloc(4 * (size_t)n_dmrs + 64);
-  uint32_t *gold = malloc(4 * ((size_t)(n_dmrs >> 4) + 4));
+  uint32_t *gold = malloc(4 * ((size_t)(n_dmrs >> 4) + 16));
   for (int layer = 0; layer < nl; layer++) {
     int port = 0;
     if (p->dmrs_ports) { int found = -1; port = -1; for (int i = 0; i < 12; i++) if ((p->dmrs_ports >> i) & 1) { if (++found == layer) { port = i; break; } } if (port < 0) return -1; }
@@ -78,6 +89,23 @@ int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txd
             out[2 * k] = wrap16_((x[0] * amp) >> 15); out[2 * k + 1] = wrap16_((x[1] * amp) >> 15);
             m++;
           } else { out[2 * k] = 0; out[2 * k + 1] = 0; }
+          if (++k >= N) k -= N;
+        }
+      } else if ((ptrs_pos >> l) & 1) {
+        int16_t mod_ptrs[2 * 140];
+        int ptrs_idx = 0;
+        const uint64_t x2 = ((1ULL << 17) * (14 * p->slot + l + 1) * ((p->dl_dmrs_scrambling_id << 1) + 1) + ((p->dl_dmrs_scrambling_id << 1) + p->scid));
+        orc_gold_words((uint32_t)(x2 % (1ULL << 31)), 10, gold);
+        orc_modulate((const uint8_t *)gold, (uint32_t)(2 * n_ptrs), 2, mod_ptrs);
+        for (int i = 0; i < p->rb_size * 12; i++) {
+          if ((i - p->ptrs_re_offset - k_rb_ref * 12) % (p->ptrs_K * 12) == 0) {
+            out[2 * k] = wrap16_((mod_ptrs[2 * ptrs_idx] * amp) >> 15); out[2 * k + 1] = wrap16_((mod_ptrs[2 * ptrs_idx + 1] * amp) >> 15);
+            ptrs_idx++;
+          } else {
+            const int16_t *x = mod + 2 * ((size_t)m * nl + layer);
+            out[2 * k] = wrap16_((x[0] * amp) >> 15); out[2 * k + 1] = wrap16_((x[1] * amp) >> 15);
+            m++;
+          }
           if (++k >= N) k -= N;
         }
       } else {

@@ -37,6 +37,10 @@ static int g_pm_idx;
 static int16_t g_pm_w[4][4][2];
 void refh_pdschtx_set_precoding(int pm_idx, const int16_t *weights) { g_pm_idx = pm_idx; if (weights) memcpy(g_pm_w, weights, sizeof(g_pm_w)); }
 
+/* PT-RS for the next refh_pdsch_tx_slot calls (pduBitmap bit 0; PTRSTimeDensity = log2 of L, PTRSFreqDensity = K, PTRSReOffset); on = 0 switches it off */
+static int g_ptrs[4];
+void refh_pdschtx_set_ptrs(int on, int L, int K, int re_offset) { g_ptrs[0] = on; g_ptrs[1] = L; g_ptrs[2] = K; g_ptrs[3] = re_offset; }
+
 enum { X_N, X_N_RB_DL, X_NB_TX, X_SLOT, X_RB_START, X_BWP_START, X_RB_SIZE, X_FCO, X_QM, X_NL, X_START_SYMBOL, X_NR_SYMBOLS, X_DMRS_POS, X_DMRS_TYPE,
        X_CDM_GROUPS, X_DMRS_PORTS, X_SCID, X_DMRS_ID, X_DATA_ID, X_RNTI, X_AMP, X_COUNT };
 
@@ -77,6 +81,7 @@ int refh_pdsch_tx_slot(const int32_t *p, const uint8_t *bits, uint32_t nbits, in
   rel15->numDmrsCdmGrpsNoData = p[X_CDM_GROUPS]; rel15->dmrsPorts = p[X_DMRS_PORTS]; rel15->SCID = p[X_SCID]; rel15->dlDmrsScramblingId = p[X_DMRS_ID];
   rel15->dataScramblingId = p[X_DATA_ID]; rel15->rnti = p[X_RNTI]; rel15->nrOfLayers = p[X_NL]; rel15->NrOfCodewords = 1; rel15->qamModOrder[0] = p[X_QM];
   rel15->pduBitmap = 0; rel15->precodingAndBeamforming.prg_size = 0;
+  if (g_ptrs[0]) { rel15->pduBitmap = 1; rel15->PTRSTimeDensity = g_ptrs[1]; rel15->PTRSFreqDensity = g_ptrs[2]; rel15->PTRSReOffset = g_ptrs[3]; }
   nfapi_nr_pm_pdu_t *pm_pdus = NULL;
   if (g_pm_idx > 0) {
     rel15->precodingAndBeamforming.num_prgs = 1; rel15->precodingAndBeamforming.prg_size = rel15->rbSize; rel15->precodingAndBeamforming.prgs_list[0].pm_idx = g_pm_idx;

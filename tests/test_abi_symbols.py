@@ -111,7 +111,7 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     from openairinterface5g_b200 import ldpc
     pairs = [("nrb200_ldpc_dec_params_t", ldpc.DecParams, None), ("nrb200_ldpc_enc_params_t", ldpc.EncParams, None), ("nrb200_decode_abort_t", ldpc.DecodeAbort, None),
              ("nrb200_ldpc_batch_desc_t", ldpc.BatchDesc, "out_stride"), ("nrb200_rm_desc_t", ldpc.RmDesc, None), ("nrb200_pusch_rx_t", ldpc.PuschRxDesc, "d_ptrs_state"),
-             ("nrb200_pusch_chest_t", ldpc.PuschChestDesc, "lowpapr_seq"), ("nrb200_pdsch_tx_t", ldpc.PdschTxDesc, "pm_weights")]
+             ("nrb200_pusch_chest_t", ldpc.PuschChestDesc, "lowpapr_seq"), ("nrb200_pdsch_tx_t", ldpc.PdschTxDesc, "ptrs_re_offset")]
     ldpc._late_fields()
     pairs += [("nrb200_sch_rx_slot_t", ldpc.SchRxSlotDesc, "seg_payload_bytes"), ("nrb200_sch_rx_bufs_t", ldpc.SchRxBufs, "hard_stride"),
               ("nrb200_pdsch_tx_slot_t", ldpc.PdschTxSlotDesc, "K"), ("nrb200_pdsch_tx_bufs_t", ldpc.PdschTxBufs, "cw_stride")]

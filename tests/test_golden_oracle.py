@@ -253,6 +253,18 @@ def test_ptrs_ue_golden(oracle):
         assert np.array_equal(llr, g[f"llr{i}"]), i
 
 
+def test_ptrs_gnb_tx_golden(oracle):
+    """PT-RS insertion in nr_generate_pdsch (pduBitmap & 1), with and without wideband precoding, against vectors of the compiled reference."""
+    from oracle.bindings import PdschTxParms
+    g = _load("ptrs.npz")
+    for j in range(int(g["n_tx"])):
+        N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp, L, K, reoff, pm = [int(x) for x in g[f"tx_case{j}"]]
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp).set_ptrs(L, K, reoff)
+        if pm:
+            P.set_precoding(pm, g[f"tx_w{j}"])
+        assert np.array_equal(oracle.pdsch_tx_slot(P, g[f"tx_bits{j}"]), g[f"tx_out{j}"]), j
+
+
 def test_transform_precoding_64qam_cannot_be_demapped(oracle):
     """A property of the reference, kept visible: after nr_freq_equalization the compensated symbols sit at 128 k (k = 1, 3, 5, 7 for 64QAM) while the constant
     thresholds it installs are 316 / 158 (nr_freq_equalization.c:63-67), so a NOISELESS DFT-s-OFDM 64QAM symbol is demapped with bit errors; QPSK and 16QAM are

@@ -70,3 +70,42 @@ def test_pdsch_tx_wideband_precoding_vs_oracle(ldpc, oracle):
     d1 = PdschTxDesc(512, 1, 2, 0, 0, 12, 362, 6, 1, 1, 13, 1 << 2, 0, 1, 0b0001, 0, 42, 501, 0x1234, 512, 0).set_precoding(1, np.ones((1, 1, 2), np.int16))
     with pytest.raises((Nrb200Error, ValueError)):                  # rejected when the descriptor is validated
         ldpc.pdsch_tx_slot_host(d1, np.zeros(10, np.uint8))          # "No precoding can be done with a single antenna port"
+
+
+PTRS = [(0, 2, 0), (1, 4, 2), (2, 2, 5), (1, 2, 11), (2, 4, 1), (0, 4, 0), (1, 2, 3), (2, 2, 0), (1, 4, 7), (1, 2, 1)]     # per CASES entry: L (log2), K, PTRSReOffset
+
+
+def test_pdsch_tx_ptrs_vs_oracle(ldpc, oracle):
+    """PT-RS insertion (ptrs = 1): pilots on every layer of the PT-RS symbols, data skipping them with the truncating scaling, fewer bits consumed -- still one launch;
+    identity and wideband precoding.  The oracle is pinned to nr_generate_pdsch with pduBitmap & 1 (tests/test_oracle_vs_reference.py::test_pdsch_tx_slot_ptrs)."""
+    rng = np.random.default_rng(74)
+    for (N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp), (L, K, reoff) in zip(CASES, PTRS):
+        fco = N - carrier * 6
+        for pm in (0, 1):
+            if pm and (ntx < 2 or ntx > 4):
+                continue
+            P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp).set_ptrs(L, K, reoff)
+            d = PdschTxDesc(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp, 0).set_ptrs(L, K, reoff)
+            if pm:
+                w = rng.integers(-12000, 12001, size=(4, 4, 2)).astype(np.int16)
+                P.set_precoding(2, w); d.set_precoding(2, w)
+            assert ldpc.pdsch_tx_num_bits(d) == P.G()
+            bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+            want = oracle.pdsch_tx_slot(P, bits)
+            got = ldpc.pdsch_tx_slot_host(d, bits)
+            assert np.array_equal(got, want), (N, nrb, Qm, nl, dpos, L, K, reoff, pm, [tuple(x) for x in np.argwhere(got != want)[:6]])
+    bad = PdschTxDesc(512, 1, 2, 0, 0, 12, 362, 6, 1, 1, 13, 1 << 2, 0, 1, 0b0001, 0, 42, 501, 0x1234, 512, 0).set_ptrs(1, 3, 0)
+    assert ldpc.pdsch_tx_num_bits(bad) == 0
+
+
+def test_pdsch_tx_ptrs_golden(ldpc):
+    """The same path against the committed vectors of the compiled reference (tests/golden/ptrs.npz, tools/gen_golden_ptrs.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ptrs.npz"))
+    for j in range(int(g["n_tx"])):
+        N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp, L, K, reoff, pm = [int(x) for x in g[f"tx_case{j}"]]
+        d = PdschTxDesc(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp, 0).set_ptrs(L, K, reoff)
+        if pm:
+            d.set_precoding(pm, g[f"tx_w{j}"])
+        got = ldpc.pdsch_tx_slot_host(d, g[f"tx_bits{j}"])
+        assert np.array_equal(got, g[f"tx_out{j}"]), (j, [tuple(x) for x in np.argwhere(got != g[f"tx_out{j}"])[:6]])

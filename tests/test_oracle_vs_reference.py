@@ -645,6 +645,30 @@ def test_pdsch_tx_slot_wideband_precoding(oracle, reference):
         assert np.count_nonzero(t_o[ntx - 1]) > 0                       # every antenna radiates
 
 
+PDSCH_TX_PTRS = [(0, 2, 0), (1, 4, 2), (2, 2, 5), (1, 2, 11), (2, 4, 1), (0, 4, 0), (1, 2, 3), (2, 2, 0), (1, 4, 7)]     # per PDSCH_TX_CASES entry: L (log2), K, PTRSReOffset
+
+
+def test_pdsch_tx_slot_ptrs(oracle, reference):
+    """PT-RS insertion in nr_generate_pdsch (pduBitmap & 1: nr_dlsch.c:98-111, :287-352): PT-RS symbols take the per-RE mapping branch (truncating scaling),
+    every layer carries the pilots, the data skip them and the encoder's length shrinks by unav_res; with and without wideband precoding."""
+    from oracle.bindings import PdschTxParms
+    rng = np.random.default_rng(73)
+    for (N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp), (L, K, reoff) in zip(PDSCH_TX_CASES, PDSCH_TX_PTRS):
+        for pm in (0, 1):
+            if pm and ntx < 2:
+                continue
+            P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp)
+            P.set_ptrs(L, K, reoff)
+            if pm:
+                P.set_precoding(2, rng.integers(-12000, 12001, size=(4, 4, 2)).astype(np.int16))
+            bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+            t_o = oracle.pdsch_tx_slot(P, bits)
+            t_r = reference.pdsch_tx_slot(P, bits, carrier)
+            assert np.array_equal(t_o, t_r), (N, nrb, Qm, nl, dpos, L, K, reoff, pm, [tuple(x) for x in np.argwhere(t_o != t_r)[:5]])
+            P.ptrs_on = 0
+            assert P.G() > bits.size
+
+
 def test_dft_size_index_enumerators_match_oai_header():
     """The size index dft() / idft() receive is OAI's dft_size_idx_t / idft_size_idx_t enumerator: the library's table (nrb200_dft_size_of_index, no GPU needed) and
     the Python mirror are pinned to get_dft / get_idft compiled from OAI's own tools_defs.h (oracle/ref_harness_dftidx.c)."""

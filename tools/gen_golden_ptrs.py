@@ -39,6 +39,19 @@ def main():
             g[f"rx{i}"], g[f"h{i}"], g[f"llr{i}"], g[f"sh{i}"], g[f"phase{i}"], g[f"nre{i}"] = rx, h, llr, np.int32(sh), ph, nre
             i += 1
     g["n"] = np.int32(i)
+    # gNB side: nr_generate_pdsch with pduBitmap & 1 (oracle/_ref/libref_pdschtx.so)
+    from oracle.bindings import PdschTxParms
+    tx_cases = [(512, 25, 1, 9, 3, 11, 8, 1, 1, 6, 1 << 1, 0, 1, 0, 0, 512, 1, 2, 3, 0), (512, 25, 2, 11, 0, 25, 6, 2, 0, 14, (1 << 2) | (1 << 3), 0, 2, 0b0101, 0, 2047, 2, 2, 0, 0),
+                (512, 25, 4, 4, 2, 21, 4, 2, 1, 13, 1 << 2, 1, 2, 0b000011, 1, 700, 0, 4, 7, 2)]
+    for j, c in enumerate(tx_cases):
+        N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp, L, K, reoff, pm = c
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp).set_ptrs(L, K, reoff)
+        w = rng.integers(-12000, 12001, size=(4, 4, 2)).astype(np.int16)
+        if pm:
+            P.set_precoding(pm, w)
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        g[f"tx_case{j}"], g[f"tx_w{j}"], g[f"tx_bits{j}"], g[f"tx_out{j}"] = np.array(c, np.int32), w, bits, ref.pdsch_tx_slot(P, bits, carrier)
+    g["n_tx"] = np.int32(len(tx_cases))
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
