@@ -301,9 +301,8 @@ class Oracle:
         x = np.ascontiguousarray(rxdataF, dtype=np.int16); h = np.ascontiguousarray(dl_ch_est, dtype=np.int16)
         llr = np.zeros(nl * 14 * 12 * P.rb_size * P.Qm + 64, np.int16)
         sh = C.c_int32(0)
-        fn = self.lib.orc_pdsch_rx_slot if nl == 1 else self.lib.orc_pdsch_rx_slot_2l
-        n = fn(C.byref(P), start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
-                                       C.byref(sh))
+        args = (start_symbol, nr_symbols, x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p), C.byref(sh))
+        n = self.lib.orc_pdsch_rx_slot(C.byref(P), *args) if nl == 1 else self.lib.orc_pdsch_rx_slot_nl(C.byref(P), nl, *args)
         return llr[:n].copy(), sh.value
 
     def gold_words(self, c_init, n_words):

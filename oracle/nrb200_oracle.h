@@ -90,6 +90,7 @@ uint32_t orc_ptrs_symbols(int start_symbol, int duration, int L_ptrs, uint32_t d
 int orc_ptrs_process_slot(uint32_t dmrs, uint32_t ptrs, int16_t *est, int start, int nsym);
 int orc_pdsch_rx_slot_ptrs(const orc_pusch_t *p, const orc_ptrs_t *t, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr,
                            int32_t *log2_maxh_out, int16_t *phase_out, int32_t *ptrs_re_out);
+int orc_pdsch_rx_slot_nl(const orc_pusch_t *p, int NL, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out);
 int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out);
 int orc_pusch_log2_maxh_2l(const orc_pusch_t *p, int meas_symbol, int ch_symbol, int max_ch, const int16_t *rxdataF, const int16_t *ch_est, int32_t *avg_out);
 int orc_pusch_inner_rx_symbol_2l(const orc_pusch_t *p, int symbol, int ch_symbol, int shift, uint32_t nvar, const int16_t *rxdataF, const int16_t *ch_est,

@@ -670,17 +670,52 @@ static void ue_src(const orc_pusch_t *p, int start_re, int pilots, int i, int *r
   *ri = k + o; *ci = 6 * g + o;
 }
 
-int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out)
+/* nr_determin (:1460-1506) on one resource element: Laplace expansion along column 0 exactly as written -- det = sum over rows rtx of a[0][rtx] * det(minor(rtx, 0))
+ * with the sign (-1)^rtx handed DOWN the recursion (it is applied to the 1 x 1 leaves by nr_element_sign), every product nr_a_mult_b (>> shift0, packed) and every sum
+ * nr_a_sum_b (saturating).  a[c][r] is indexed [column][row] like a44. */
+static c16o det_re(int size, c16o a[4][4], int sign, int shift0)
 {
-  enum { NL = 2 };
+  if (size == 1) return sign < 0 ? neg_c(a[0][0]) : a[0][0];
+  c16o acc = {0, 0};
+  for (int rtx = 0; rtx < size; rtx++) {
+    c16o sub[4][4];
+    int rr[3], cc[3], k = 0;
+    for (int r = 0; r < size; r++) if (r != rtx) rr[k++] = r;
+    k = 0;
+    for (int c = 0; c < size; c++) if (c != 0) cc[k++] = c;
+    for (int ri = 0; ri < size - 1; ri++) for (int ci = 0; ci < size - 1; ci++) sub[ci][ri] = a[cc[ci]][rr[ri]];
+    const c16o prod = a_mult_b(a[0][rtx], det_re(size - 1, sub, ((rtx & 1) ? -1 : 1) * sign, shift0), shift0);
+    acc = rtx == 0 ? prod : adds_c(acc, prod);
+  }
+  return acc;
+}
+/* nr_matrix_inverse, fixed-point branch (:1549-1610): inv[rtx][ctx] = det of the minor without row rtx and column ctx, sign (-1)^(rtx + ctx) */
+static void inverse_re(int size, c16o a[4][4], c16o inv[4][4], int shift0)
+{
+  for (int rtx = 0; rtx < size; rtx++)
+    for (int ctx = 0; ctx < size; ctx++) {
+      c16o sub[4][4];
+      int rr[3], cc[3], k = 0;
+      for (int r = 0; r < size; r++) if (r != rtx) rr[k++] = r;
+      k = 0;
+      for (int c = 0; c < size; c++) if (c != ctx) cc[k++] = c;
+      for (int ri = 0; ri < size - 1; ri++) for (int ci = 0; ci < size - 1; ci++) sub[ci][ri] = a[cc[ci]][rr[ri]];
+      inv[rtx][ctx] = det_re(size - 1, sub, ((rtx & 1) ? -1 : 1) * ((ctx & 1) ? -1 : 1), shift0);
+    }
+}
+
+/* Nl = 2, 3 or 4 layers: the reference's code is generic in n_tx (nr_zero_forcing_rx "for 2, 3, and 4 Tx layers", :528) */
+int orc_pdsch_rx_slot_nl(const orc_pusch_t *p, int NL, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out)
+{
+  if (NL < 2 || NL > 4) return -1;
   const int N = p->fft_size, nrx = p->nb_rx, nb = p->rb_size, Qm = p->Qm, pos = p->ul_dmrs_symb_pos, type = p->dmrs_config_type, cdm = p->num_dmrs_cdm_grps_no_data;
   const int sz = (nb * 12 + 15) & ~15;
   const int start_re = (p->first_carrier_offset + (p->rb_start + p->bwp_start) * 12) % N;
   const int ampv[3] = {Qm == 4 ? 20724 : Qm == 6 ? 20225 : Qm == 8 ? 20106 : 0, Qm == 6 ? 10112 : Qm == 8 ? 10053 : 0, Qm == 8 ? 5026 : 0};
   if (nrx < 2) return -1;
   c16o *rx = malloc(sizeof(c16o) * (size_t)sz * nrx), *ch = malloc(sizeof(c16o) * (size_t)sz * nrx * NL);
-  c16o *comp[NL];
-  int16_t *mag[3], *lay[NL];
+  c16o *comp[4];
+  int16_t *mag[3], *lay[4];
   for (int l = 0; l < NL; l++) { comp[l] = calloc((size_t)14 * nb * 12 + sz, sizeof(c16o)); lay[l] = calloc((size_t)14 * nb * 12 * Qm + 64, 2); }
   for (int t = 0; t < 3; t++) mag[t] = calloc(2 * (size_t)sz, 2);
   int valid[14] = {0}, log2_maxh = 0;
@@ -713,7 +748,7 @@ int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols,
     if (m == first_with_data) {                                         /* level + median -> log2_maxh (:433-452) */
       const int x = factor2_((uint32_t)len), y = len >> x;
       int avgs = 0;
-      int32_t avg[NL * 8];
+      int32_t avg[4 * 8];
       for (int q = 0; q < NL * nrx; q++) {
         const c16o *c = ch + (size_t)q * sz;
         int32_t lane[4] = {0, 0, 0, 0};
@@ -737,7 +772,7 @@ int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols,
     }
     const int shift = log2_maxh, shift0 = shift - 2;
     for (int i = 0; i < span; i++) {
-      c16o mf[NL], E[NL][NL];                                           /* E[c][r] = sum_a conj(H[r][a]) H[c][a] */
+      c16o mf[4], E[4][4];                                              /* E[c][r] = sum_a conj(H[r][a]) H[c][a] */
       for (int l = 0; l < NL; l++)
         for (int a = 0; a < nrx; a++) {
           const c16o v = conj0_mult1(ch[(size_t)(l * nrx + a) * sz + i], rx[(size_t)a * sz + i], shift);
@@ -749,11 +784,11 @@ int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols,
             const c16o v = conj0_mult1(ch[(size_t)(r * nrx + a) * sz + i], ch[(size_t)(c * nrx + a) * sz + i], shift);
             E[c][r] = a == 0 ? v : adds_c(E[c][r], v);
           }
-      /* determinant: a44[0][0] * a44[1][1] + a44[0][1] * (-a44[1][0]), each product >> shift0 and packed */
-      const c16o det = adds_c(a_mult_b(E[0][0], E[1][1], shift0), a_mult_b(E[0][1], neg_c(E[1][0]), shift0));
-      /* adjugate: inv[r][c] = (-1)^(r+c) a44[1-c][1-r]; output layer r = sum_c inv[c][r] * mf[c] */
-      c16o inv[NL][NL];
-      for (int r = 0; r < NL; r++) for (int c = 0; c < NL; c++) inv[r][c] = ((r + c) & 1) ? neg_c(E[1 - c][1 - r]) : E[1 - c][1 - r];
+      /* determinant and adjugate (2 x 2: a44[0][0] * a44[1][1] + a44[0][1] * (-a44[1][0]); inv[r][c] = (-1)^(r+c) a44[1-c][1-r]); output layer r = sum over c of
+       * inv[c][r] * mf[c], accumulated from zero with saturating adds (:1786-1814) */
+      const c16o det = det_re(NL, E, +1, shift0);
+      c16o inv[4][4];
+      inverse_re(NL, E, inv, shift0);
       for (int r = 0; r < NL; r++) {
         c16o acc = {0, 0};
         for (int c = 0; c < NL; c++) acc = adds_c(acc, a_mult_b(inv[c][r], mf[c], shift0));
@@ -778,6 +813,11 @@ int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols,
   for (int l = 0; l < NL; l++) { free(comp[l]); free(lay[l]); }
   for (int t = 0; t < 3; t++) free(mag[t]);
   return (int)(NL * off);
+}
+
+int orc_pdsch_rx_slot_2l(const orc_pusch_t *p, int start_symbol, int nr_symbols, const int16_t *rxdataF, const int16_t *dl_ch_est, int16_t *llr, int32_t *log2_maxh_out)
+{
+  return orc_pdsch_rx_slot_nl(p, 2, start_symbol, nr_symbols, rxdataF, dl_ch_est, llr, log2_maxh_out);
 }
 
 /* flat entry points of the two ML kernels for unit tests: one resource element */

@@ -558,6 +558,31 @@ def test_pdsch_rx_slot_ue(oracle, reference):
         assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
 
 
+PDSCH_NL_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, layers, amplitude (rx, h)
+    (4096, 4, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13, 4, (2000, 1500)), (4096, 4, 0, 273, 8, 1 << 2, 0, 2, 273, 1, 13, 3, (900, 700)),
+    (2048, 4, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, 3, (4000, 6000)), (2048, 3, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, 3, (300, 200)),
+    (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, 4, (2000, 1500)), (1024, 4, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12, 4, (12000, 9000)),
+    (512, 4, 3, 11, 8, 1 << 1, 0, 1, 25, 1, 6, 4, (32767, 32767)), (512, 4, 0, 25, 6, 1 << 2, 0, 1, 25, 0, 14, 3, (60, 40)),
+    (2048, 4, 0, 106, 6, (1 << 2) | (1 << 13), 0, 1, 106, 1, 13, 4, (2000, 1500)), (1024, 2, 0, 52, 6, 1 << 2, 0, 2, 52, 1, 13, 3, (2000, 1500)),
+]
+
+
+def test_pdsch_rx_slot_ue_3_4_layers(oracle, reference):
+    """UE-side PDSCH receiver with three and four layers: nr_rx_pdsch's generic n_tx code (per-layer MRC, nr_zero_forcing_rx with the recursive nr_determin /
+    nr_matrix_inverse in fixed point, determinant thresholds, nr_dlsch_layer_demapping) vs the oracle; incl. fewer rx antennas than layers (singular Gram matrix:
+    the arithmetic is still defined) and full-scale inputs."""
+    from oracle.bindings import PuschParms
+    rng = np.random.default_rng(75)
+    for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, nl, (ay, ah) in PDSCH_NL_CASES:
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        llr_o, sh_o = oracle.pdsch_rx_slot(P, start, nsym, rx, h, nl=nl)
+        llr_r, sh_r, valid = reference.pdsch_rx_slot(P, start, nsym, rx, h, llr_o.size, nl=nl)
+        assert sh_o == sh_r, (N, nb_rx, Qm, nl, sh_o, sh_r)
+        assert np.array_equal(llr_o, llr_r), (N, nb_rx, rb_start, rb_size, Qm, nl, dpos, dtype_, cdm, np.nonzero(llr_o != llr_r)[0][:5])
+
+
 def test_pdsch_rx_slot_ue_ptrs(oracle, reference):
     """PT-RS at the UE: the real nr_rx_pdsch + nr_pdsch_ptrs_processing + ptrs_nr.c (oracle/_ref/libref_pdsch_ptrs.so) vs the oracle restatement -- LLRs of the slot,
     log2_maxh, the per-symbol phase estimates (incl. interpolated ones) and PT-RS RE counts; random full-scale inputs and coherent slots with a phase ramp."""
