@@ -278,8 +278,9 @@ typedef struct nrb200_pusch_rx_s {
   uint32_t pdsch_ue;                        /* 1: the UE's PDSCH receiver instead (nr_rx_pdsch, NR_UE_TRANSPORT/nr_dlsch_demodulation.c:241-684): its own
                                              * extraction patterns, estimate scaling, saturating MRC, thresholds and log2_maxh rule; ul_dmrs_symb_pos = dlDmrsSymbPos,
                                              * num_dmrs_cdm_grps_no_data = n_dmrs_cdm_groups, the estimates' symbol = get_valid_dmrs_idx_for_channel_est; nb_rx <= 4.
-                                             * nrOfLayers == 2 (nb_rx >= 2, any qam_mod_order): per-layer MRC + nr_zero_forcing_rx (:1726-1869) + layer
-                                             * de-mapping; dl_ch_estimates holds [2 * nb_rx] planes, index layer * nb_rx + rx */
+                                             * nrOfLayers == 2, 3 or 4 (nb_rx >= 2, any qam_mod_order): per-layer MRC + nr_zero_forcing_rx (:1726-1869, with the
+                                             * recursive fixed-point nr_determin / nr_matrix_inverse :1460-1610 for 3 and 4 layers) + layer de-mapping;
+                                             * dl_ch_estimates holds [nrOfLayers * nb_rx] planes, index layer * nb_rx + rx */
   uint64_t d_est_state;                     /* _dev, 2 layers, optional: DEVICE address of the channel estimator's state (nrb200_pusch_chest_dev's d_state, 18 int32 per
                                              * port).  When non-zero, max_ch and noise_var are taken from it ON THE DEVICE (max over the ports' max_ch; sum of the ports'
                                              * nvar / (nr_of_symbols * nrOfLayers * nb_rx), nr_ulsch_demodulation.c:1470-1524) and the two fields above are ignored:
@@ -308,7 +309,7 @@ uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d);
  * ptrs_re_per_slot[0][l] of every PT-RS symbol (nr_ptrs_cpe_estimation's re_cnt).  0, or -4 for a PT-RS configuration the library does not reproduce. */
 int32_t nrb200_pdsch_ptrs_layout(const nrb200_pusch_rx_t *d, uint32_t *ptrs_symbols, uint32_t *ptrs_re_per_symbol);
 uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d);                     /* int16 LLRs the slot produces (G for one layer), 0 if invalid */
-/* d_out: 9 int32 on the device: [0..nb_rx * layers) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
+/* d_out: 9 int32 on the device: [0..min(8, nb_rx * layers)) = avg per (layer, antenna), [8] = log2_maxh.  The kernel is stream ordered: pass d_out + 8 as d_log2_maxh. */
 int32_t nrb200_pusch_log2_maxh_dev(const nrb200_pusch_rx_t *d, const int16_t *d_ul_ch_estimates, int32_t *d_out, void *stream);
 int32_t nrb200_pusch_inner_rx_dev(const nrb200_pusch_rx_t *d, const int16_t *d_rxdataF, const int16_t *d_ul_ch_estimates, const int32_t *d_log2_maxh,
                                   int16_t *d_llr, void *stream);

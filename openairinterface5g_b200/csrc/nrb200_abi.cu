@@ -822,8 +822,9 @@ static uint32_t *pusch_counter()
   static uint32_t ticket = 0;
   std::lock_guard<std::mutex> lk(mu);
   uint32_t *&d = dd[ctx().dev];
-  if (!d && cudaMalloc(&d, kCounters * 4) == cudaSuccess) cudaMemset(d, 0, kCounters * 4);
-  return d ? d + (ticket++ % kCounters) : nullptr;
+  // 32 words per launch: [0] the counter, [1..16] the per-plane levels of the UE receiver with up to 4 layers x 4 antennas
+  if (!d && cudaMalloc(&d, kCounters * 128) == cudaSuccess) cudaMemset(d, 0, kCounters * 128);
+  return d ? d + 32 * (ticket++ % kCounters) : nullptr;
 }
 
 NRB200_EXPORT uint32_t nrb200_pusch_num_llr(const nrb200_pusch_rx_t *d) { return d ? pusch_num_llr(*d) : 0; }
@@ -850,10 +851,10 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   if (d->d_est_state != 0) return -4;                                     // a device address: the _dev entry points only
   const uint32_t n_llr = pusch_num_llr(*d);
   if (n_llr == 0) return -4;
-  const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers == 2 ? 2 : 1);
+  const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers >= 2 ? d->nrOfLayers : 1);
   const size_t tp_bytes = d->transform_precoding ? pusch_tp_scratch_bytes(*d) : 0;        // the transforms' input / output planes, behind the level slots
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes + 64)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes + 64 + 128)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     std::memcpy(w->h_in, rxdataF, plane);
@@ -869,8 +870,9 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
     if (measure) {
       e.log2_maxh = 0;
       // one workspace, one stream: give the level kernel its own completion counter slot in the workspace
-      if (cudaMemsetAsync((uint8_t *)w->d_aux + 40, 0, 4, w->stream) != cudaSuccess) { rc = -2; break; }
-      if ((rc = launch_pusch_level(e, d_ch, d_lvl, (uint32_t *)((uint8_t *)w->d_aux + 40), w->stream)) != 0) break;
+      uint32_t *cnt = (uint32_t *)((uint8_t *)w->d_aux + 64 + tp_bytes + 64);              // counter + per-plane levels (32 words)
+      if (cudaMemsetAsync(cnt, 0, 4, w->stream) != cudaSuccess) { rc = -2; break; }
+      if ((rc = launch_pusch_level(e, d_ch, d_lvl, cnt, w->stream)) != 0) break;
     }
     if ((rc = launch_pusch_rx(e, d_rx, d_ch, measure ? d_lvl + 8 : nullptr, (int16_t *)w->d_out, w->stream)) != 0) break;
     if (cudaMemcpyAsync(w->h_out, w->d_out, (size_t)n_llr * 2, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess) { rc = -2; break; }

@@ -716,6 +716,131 @@ __global__ void __launch_bounds__(256) pdsch_rx2_kernel(PuschGeom G, const GoldT
   }
 }
 
+// ---- UE side, three and four layers: the reference's receiver is generic in n_tx (nr_zero_forcing_rx "for 2, 3, and 4 Tx layers", :528; nr_determin :1460-1506 and
+// nr_matrix_inverse :1549-1610 recurse over minors).  Same structure as pdsch_rx2_kernel with the Laplace expansion unrolled at compile time: det = sum over rows r of
+// a[0][r] * det(minor(r, 0)), the sign (-1)^r handed down to the 1 x 1 leaves (nr_element_sign), every product nr_a_mult_b (>> shift0, packed), every sum saturating;
+// inv[r][c] = det(minor(r, c)) with sign (-1)^(r + c); layer r = sum over c of inv[c][r] * mf[c].  a[c][r] is indexed [column][row] like the reference's a44.
+template <int S> struct UeMat { C16 a[S][S]; };
+template <int S>
+__device__ __forceinline__ C16 ue_det_n(const UeMat<S> &A, int sign, int shift0)
+{
+  if constexpr (S == 1) return sign < 0 ? c_neg(A.a[0][0]) : A.a[0][0];
+  else {
+    C16 acc = C16{0, 0};
+#pragma unroll
+    for (int rtx = 0; rtx < S; rtx++) {
+      UeMat<S - 1> sub;
+#pragma unroll
+      for (int ri = 0; ri < S - 1; ri++)
+#pragma unroll
+        for (int ci = 0; ci < S - 1; ci++) sub.a[ci][ri] = A.a[ci + 1][ri < rtx ? ri : ri + 1];
+      const C16 prod = c_mult(A.a[0][rtx], ue_det_n<S - 1>(sub, ((rtx & 1) ? -1 : 1) * sign, shift0), shift0);
+      acc = rtx == 0 ? prod : c_adds(acc, prod);
+    }
+    return acc;
+  }
+}
+template <int S>
+__device__ __forceinline__ C16 ue_cofactor(const UeMat<S> &A, int rtx, int ctx, int shift0)
+{
+  UeMat<S - 1> sub;
+#pragma unroll
+  for (int ri = 0; ri < S - 1; ri++)
+#pragma unroll
+    for (int ci = 0; ci < S - 1; ci++) sub.a[ci][ri] = A.a[ci < ctx ? ci : ci + 1][ri < rtx ? ri : ri + 1];
+  return ue_det_n<S - 1>(sub, ((rtx & 1) ? -1 : 1) * ((ctx & 1) ? -1 : 1), shift0);
+}
+// E.a[c][r] = sum over rx antennas of conj(H[r][a]) H[c][a] >> shift (saturating sum of the packed per-antenna products)
+template <int NL>
+__device__ __forceinline__ void ue_gram_n(const PuschGeom &G, const unsigned *__restrict__ ch, int chs, int ci, int shift, C16 (&H)[NL][4], UeMat<NL> &E)
+{
+#pragma unroll
+  for (int l = 0; l < NL; l++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      if (a < G.nb_rx) H[l][a] = c_unpack(ue_scale(__ldg(ch + (size_t)(l * G.nb_rx + a) * G.ch_stride + (size_t)chs * G.N + ci)));
+#pragma unroll
+  for (int r = 0; r < NL; r++)
+#pragma unroll
+    for (int c = 0; c < NL; c++) {
+      C16 acc = c_conj0_mult1(H[r][0], H[c][0], shift);
+#pragma unroll
+      for (int a = 1; a < 4; a++)
+        if (a < G.nb_rx) acc = c_adds(acc, c_conj0_mult1(H[r][a], H[c][a], shift));
+      E.a[c][r] = acc;
+    }
+}
+
+template <int QM, int NL>
+__global__ void __launch_bounds__(128) pdsch_rxn_kernel(PuschGeom G, const GoldTables *__restrict__ T, const int *__restrict__ d_shift, const unsigned *__restrict__ rxF,
+                                                        const unsigned *__restrict__ ch, short *__restrict__ llr)
+{
+  constexpr int TPB = 128;
+  __shared__ uint32_t s_gold[(TPB * NL * QM) / 32 + 2];
+  const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
+  const int i0 = blockIdx.x * TPB, i = i0 + threadIdx.x;
+  if (i0 >= valid) return;
+  const unsigned bit0 = (unsigned)NL * (G.llr_off[k] + (unsigned)i0 * QM);
+  if (G.unscramble) {
+    const unsigned w0 = bit0 >> 5, nw = ((bit0 + (unsigned)(TPB * NL * QM) + 31u) >> 5) - w0;
+    for (unsigned w = threadIdx.x; w < nw; w += TPB) s_gold[w] = gold_word(T, G.c_init, w0 + w);
+    __syncthreads();
+  }
+  if (i >= valid) return;
+  const int shift = G.shift_from_dev ? *d_shift : G.shift, shift0 = shift - 2;
+  int rx_idx, ch_idx, mch_idx, dummy;
+  ue_source(G, is_dmrs, i, rx_idx, ch_idx);
+  ue_source(G, G.last_is_dmrs, i, dummy, mch_idx);
+  C16 H[NL][4], mf[NL], out[NL];
+  UeMat<NL> E;
+  ue_gram_n<NL>(G, ch, G.ch_sym[k], ch_idx, shift, H, E);
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+    if (a < G.nb_rx) {
+      const C16 y = c_unpack(__ldg(rxF + (size_t)a * G.rx_stride + (size_t)symbol * G.N + rx_idx));
+#pragma unroll
+      for (int l = 0; l < NL; l++) { const C16 v = c_conj0_mult1(H[l][a], y, shift); mf[l] = a == 0 ? v : c_adds(mf[l], v); }
+    }
+#pragma unroll
+  for (int r = 0; r < NL; r++) {
+    C16 acc = C16{0, 0};
+#pragma unroll
+    for (int c = 0; c < NL; c++) acc = c_adds(acc, c_mult(ue_cofactor<NL>(E, c, r, shift0), mf[c], shift0));     // inv[c][r] * mf[c]
+    out[r] = acc;
+  }
+  int ma = 0, mb = 0, mc = 0;
+  if (QM > 2 && i < G.last_span) {
+    constexpr int ampa = QM == 4 ? 20724 : QM == 6 ? 20225 : QM == 8 ? 20106 : 0, ampb = QM == 6 ? 10112 : QM == 8 ? 10053 : 0, ampc = QM == 8 ? 5026 : 0;
+    C16 Hm[NL][4];
+    UeMat<NL> Em;
+    ue_gram_n<NL>(G, ch, G.last_ch_sym, mch_idx, shift, Hm, Em);
+    const int det = ue_det_n<NL>(Em, +1, shift0).r;
+    ma = p_wrap16(((det * ampa) >> 16) << 1); mb = p_wrap16(((det * ampb) >> 16) << 1); mc = p_wrap16(((det * ampc) >> 16) << 1);
+  }
+  const unsigned b = (unsigned)NL * (G.llr_off[k] + (unsigned)i * QM);
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const int cr = out[l].r, ci = out[l].i;
+    int o[8];
+    if (QM == 2) { o[0] = cr >> 3; o[1] = ci >> 3; }
+    else {
+      o[0] = cr; o[1] = ci;
+      o[2] = p_subs16(ma, p_abs16w(cr)); o[3] = p_subs16(ma, p_abs16w(ci));
+      if (QM > 4) { o[4] = p_subs16(mb, p_abs16w(o[2])); o[5] = p_subs16(mb, p_abs16w(o[3])); }
+      if (QM > 6) { o[6] = p_subs16(mc, p_abs16w(o[4])); o[7] = p_subs16(mc, p_abs16w(o[5])); }
+    }
+    const unsigned bl = b + (unsigned)l * QM;
+    if (G.unscramble) {
+      const unsigned rel = bl - ((bit0 >> 5) << 5);
+#pragma unroll
+      for (int m = 0; m < QM; m++) { const unsigned r = rel + m; if ((s_gold[r >> 5] >> (r & 31u)) & 1u) o[m] = p_wrap16(-o[m]); }
+    }
+    unsigned *dst = reinterpret_cast<unsigned *>(llr + bl);
+#pragma unroll
+    for (int m = 0; m < QM / 2; m++) dst[m] = ((unsigned)o[2 * m] & 0xFFFFu) | ((unsigned)o[2 * m + 1] << 16);
+  }
+}
+
 // UE: nr_dlsch_scale_channel + nr_dlsch_channel_level on the first symbol with data, log2_maxh = log2_approx(max avg) / 2 + 1 (:433-452)
 // Two layers: one CTA per (layer, antenna) plane, and nr_dlsch_channel_level_median (:1144-1179) on top: (max + min) / 2 of the 4-RE power sums, both
 // seeded with the plane's average; the plane's entry in d_out is then max(average, median), which is all the log2_maxh rule uses.
@@ -772,11 +897,13 @@ __global__ void __launch_bounds__(256) pdsch_level_kernel(PuschGeom G, int meas_
     lvl = max(avg, (int)((s_mx[0] + s_mn[0]) >> 1));
   }
   if (threadIdx.x == 0) {
-    d_out[a] = lvl;
+    // up to 4 layers x 4 antennas = 16 planes: the levels go through the launch's counter block (d_count[1 + plane]); d_out[0..7] mirrors the first eight
+    reinterpret_cast<int *>(d_count)[1 + a] = lvl;
+    if (a < 8) d_out[a] = lvl;
     __threadfence();
     if (atomicAdd(d_count, 1u) == (unsigned)(G.nb_rx * G.nl) - 1) {
       int avgs = 0;
-      for (int q = 0; q < G.nb_rx * G.nl; q++) avgs = max(avgs, ((volatile int *)d_out)[q]);
+      for (int q = 0; q < G.nb_rx * G.nl; q++) avgs = max(avgs, ((volatile int *)d_count)[1 + q]);
       const unsigned v = (unsigned)avgs & 0x7FFFFFFFu;
       d_out[8] = ((v ? 32 - __clz(v) : 0) / 2) + 1;
       *d_count = 0;
@@ -881,7 +1008,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
   const int nl = d.nrOfLayers == 0 ? 1 : (int)d.nrOfLayers;
   PtrsGeom PT;
   if (make_ptrs(d, &PT) < 0) return -4;
-  if (nl > 2 || (nl == 2 && !d.pdsch_ue && Qm >= 6 && d.nb_rx != 2 && d.nb_rx != 4)) return -4;   // 2 layers: MMSE receiver (Qm >= 6; 2 or 4 rx like the reference), joint ML below
+  if (nl > (d.pdsch_ue ? 4 : 2) || (nl == 2 && !d.pdsch_ue && Qm >= 6 && d.nb_rx != 2 && d.nb_rx != 4)) return -4;   // 2 layers: MMSE receiver (Qm >= 6; 2 or 4 rx like the reference), joint ML below
   if ((Qm != 2 && Qm != 4 && Qm != 6 && Qm != 8) || d.nb_rx < 1 || d.nb_rx > 8 || d.rb_size < 1 || d.fft_size < 12 * d.rb_size ||
       d.start_symbol_index + d.nr_of_symbols > 14 || d.dmrs_config_type > 1 || (d.log2_maxh > 31 && d.log2_maxh != 0xFFFFFFFFu))
     return -4;
@@ -898,7 +1025,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
     G->est_ports = (int)d.est_state_ports; G->est_div = (int)(d.nr_of_symbols * nl * d.nb_rx);
   }
   G->ue = d.pdsch_ue ? 1 : 0; G->cdm = d.num_dmrs_cdm_grps_no_data; G->tp_direct = 0;
-  if (G->ue && (d.nb_rx > 4 || (nl == 2 && d.nb_rx < 2))) return -4;     // the reference applies neither MRC nor zero forcing with one rx antenna
+  if (G->ue && (d.nb_rx > 4 || (nl >= 2 && d.nb_rx < 2))) return -4;     // the reference applies neither MRC nor zero forcing with one rx antenna
   {
     // nr_ulsch_scale_channel: shift_ch_ext = log2_approx(max_ch >> 11) for 2 layers, 0 for one
     int sce = 0;
@@ -1002,7 +1129,13 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
   for (int k = 0; k < G.n_sym; k++) vmax = std::max(vmax, G.valid[k]);
   const dim3 grid((((vmax + 3) & ~3) + 255) / 256, G.n_sym);
   const unsigned *R = (const unsigned *)rxF, *C = (const unsigned *)ch;
-  if (G.ue && G.nl == 2) {
+  if (G.ue && G.nl > 2) {
+    const dim3 gridn((((vmax + 3) & ~3) + 127) / 128, G.n_sym);
+#define NRB200_RXN(QM_) do { if (G.nl == 3) pdsch_rxn_kernel<QM_, 3><<<gridn, 128, 0, st>>>(G, T, d_shift, R, C, llr); \
+                             else pdsch_rxn_kernel<QM_, 4><<<gridn, 128, 0, st>>>(G, T, d_shift, R, C, llr); } while (0)
+    switch (G.Qm) { case 2: NRB200_RXN(2); break; case 4: NRB200_RXN(4); break; case 6: NRB200_RXN(6); break; default: NRB200_RXN(8); break; }
+#undef NRB200_RXN
+  } else if (G.ue && G.nl == 2) {
     switch (G.Qm) {
       case 2: pdsch_rx2_kernel<2><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;
       case 4: pdsch_rx2_kernel<4><<<grid, 256, 0, st>>>(G, T, d_shift, R, C, llr); break;

@@ -123,7 +123,7 @@ def test_ue_caller_reaches_the_gpu_through_the_interposed_symbol(oracle):
 def test_oai_ue_caller_reaches_the_gpu_through_nr_rx_pdsch(oracle):
     """integration/oai_shim_rx_pdsch.c defines OAI's `nr_rx_pdsch`; the reference-side caller (oracle/ref_harness_pdsch.c: fills PHY_VARS_NR_UE / NR_UE_DLSCH_t and
     calls the function symbol by symbol like nr_ue_pdsch_procedures) is linked against it instead of nr_dlsch_demodulation.c (oracle/_ref/libshimtest_pdsch.so).
-    LLRs, log2_maxh and dl_valid_re that the unchanged host C gets back must be the pinned oracle's, one and two layers."""
+    LLRs, log2_maxh and dl_valid_re that the unchanged host C gets back must be the pinned oracle's, one to four layers."""
     from oracle.bindings import PuschParms
     so = os.path.join(ROOT, "oracle", "_ref", "libshimtest_pdsch.so")
     if not os.path.exists(so):
@@ -133,7 +133,8 @@ def test_oai_ue_caller_reaches_the_gpu_through_nr_rx_pdsch(oracle):
     cases = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, layers, amplitudes
         (4096, 2, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13, 1, (2000, 1500)), (2048, 1, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, 1, (2000, 1500)),
         (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, 1, (2000, 1500)), (4096, 2, 0, 273, 6, 1 << 2, 0, 1, 273, 1, 13, 2, (2000, 1500)),
-        (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, 2, (300, 200)), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12, 2, (12000, 9000))]
+        (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, 2, (300, 200)), (1024, 2, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12, 2, (12000, 9000)),
+        (2048, 4, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, 3, (4000, 6000)), (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, 4, (2000, 1500))]
     for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, nl, (ay, ah) in cases:
         rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
         h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)

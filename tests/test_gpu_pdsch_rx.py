@@ -111,3 +111,33 @@ def test_pdsch_rx_ptrs_unsupported_combinations_fail_loudly(ldpc):
     d = PuschRxDesc(N, nb_rx, 0, 0, 25, N - 150, 4, 1, 13, 1 << 2, 0, 1, 5, 0, 0, 0, 7, 0, 1, 0, 0, 1)
     d.set_ptrs(1, 3, 0, 0, 0, 0)                                           # K_PTRS must be 2 or 4
     assert ldpc.pusch_num_llr(d) == 0
+
+
+CASES_NL = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, layers, amplitude (rx, h)
+    (4096, 4, 0, 273, 6, 1 << 2, 0, 2, 273, 1, 13, 4, (2000, 1500)), (4096, 4, 0, 273, 8, 1 << 2, 0, 2, 273, 1, 13, 3, (900, 700)),
+    (2048, 4, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, 3, (4000, 6000)), (2048, 3, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, 3, (300, 200)),
+    (1024, 4, 0, 52, 6, 1 << 2, 1, 1, 52, 1, 13, 4, (2000, 1500)), (1024, 4, 20, 32, 4, 1 << 2, 1, 2, 52, 2, 12, 4, (12000, 9000)),
+    (512, 4, 3, 11, 8, 1 << 1, 0, 1, 25, 1, 6, 4, (32767, 32767)), (512, 4, 0, 25, 6, 1 << 2, 0, 1, 25, 0, 14, 3, (60, 40)),
+    (2048, 4, 0, 106, 6, (1 << 2) | (1 << 13), 0, 1, 106, 1, 13, 4, (2000, 1500)), (1024, 2, 0, 52, 6, 1 << 2, 0, 2, 52, 1, 13, 3, (2000, 1500)),
+    (2048, 4, 4, 100, 2, 1 << 2, 0, 2, 106, 1, 13, 4, (2500, 2500)), (2048, 4, 4, 100, 8, 1 << 2, 0, 2, 106, 1, 13, 4, (2500, 2500)),
+]
+
+
+def test_pdsch_rx_ue_3_4_layers_vs_oracle(ldpc, oracle):
+    """Three and four layers at the UE: per-layer MRC, zero forcing with the reference's recursive fixed-point determinant / adjugate (unrolled at compile time in
+    pdsch_rxn_kernel<QM, NL>), determinant thresholds of the last symbol, layer de-mapping, descrambling -- one launch per slot; up to 16 (layer, antenna) planes in
+    the level measurement.  The oracle is pinned to the real nr_rx_pdsch (tests/test_oracle_vs_reference.py::test_pdsch_rx_slot_ue_3_4_layers)."""
+    rng = np.random.default_rng(76)
+    for N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, nl, (ay, ah) in CASES_NL:
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+        fco = N - carrier * 6
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, dtype_, cdm)
+        llr_o, sh_o = oracle.pdsch_rx_slot(P, start, nsym, rx, h, nl=nl)
+        for unscr in (None, (0x2345, 501)):
+            d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, 0 if unscr is None else 1,
+                            0 if unscr is None else unscr[0], 0 if unscr is None else unscr[1], nl, 0, 0, 1)
+            llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+            assert sh == sh_o, (N, nb_rx, Qm, nl, sh, sh_o)
+            ref = llr_o if unscr is None else oracle.unscramble_llr(llr_o, 0, unscr[1], unscr[0])
+            assert llr.size == ref.size and np.array_equal(llr, ref), (N, nb_rx, rb_start, rb_size, Qm, nl, dpos, dtype_, cdm, unscr, np.nonzero(llr != ref)[0][:6])
