@@ -33,6 +33,14 @@ NRB200_EXPORT int32_t nrb200_sch_slot_rx_dev(const nrb200_sch_rx_slot_t *d, cons
   nrb200_pusch_rx_t rx = d->rx;
   if (!d->use_estimates) {
     if ((rc = nrb200_pusch_chest_dev(&d->chest, b->d_rxdataF, b->d_est, b->d_chest_scratch, b->d_chest_state, stream)) != 0) return rc;
+    if (rx.pdsch_ue && rx.nrOfLayers > 2) {
+      // layers 3 and 4: DMRS ports port + 2 (and + 3) of the second CDM group, one more estimator call (the UE calls nr_pdsch_channel_estimation once per port,
+      // phy_procedures_nr_ue.c); its planes and states go behind those of the first two ports, the scratch is reused in stream order
+      nrb200_pusch_chest_t c2 = d->chest;
+      c2.port = d->chest.port + 2; c2.n_ports = rx.nrOfLayers - 2;
+      if ((rc = nrb200_pusch_chest_dev(&c2, b->d_rxdataF, b->d_est + (size_t)2 * 2 * rx.nb_rx * c2.ch_stride, b->d_chest_scratch, b->d_chest_state + 2 * 18, stream)) != 0)
+        return rc;
+    }
     if (rx.nrOfLayers == 2 && !rx.pdsch_ue) {   // the MMSE receiver takes max_ch / nvar from the estimator's state on the device (:1470-1524)
       rx.d_est_state = (uint64_t)(uintptr_t)b->d_chest_state;
       rx.est_state_ports = 2;

@@ -30,7 +30,7 @@ class PdschSlotChain:
         self.P = NrOfdmParms(N, mu, carrier_rb)
         self.N, self.nb, self.Qm, self.slot, self.rnti, self.nid, self.max_iter, self.nl = N, nb_ant, Qm, slot, rnti, nid, max_iter, n_layers
         self.rb_start, self.rb_size, self.A = rb_start, rb_size, A
-        assert n_layers in (1, 2) and nb_ant >= n_layers
+        assert n_layers in (1, 2, 3, 4) and nb_ant >= n_layers
         self.dmrs_pos, self.dmrs_type, self.cdm = 1 << 2, 0, 2                     # one type-1 DMRS symbol (ports 0, 1 share CDM group 0), no data on it
         self.seg = T.nr_segmentation(A + 24, 1)
         assert (A + 24 + self.seg["C"] * self.seg["L"]) % (8 * self.seg["C"]) == 0, "pick A like a real TBS: whole bytes per segment"
@@ -74,7 +74,9 @@ class PdschSlotChain:
             mask, n_re = lib.pdsch_ptrs_layout(self.rxd)
             assert bin(mask).count("1") * n_re == unav_res
         assert lib.pusch_num_llr(self.rxd) == self.G
-        self.cdesc = PuschChestDesc(N, nb_ant, slot, 2, 0, rb_start, 0, rb_size, fco, 0, dmrs_id, 14 * N, 14 * N, n_layers, 1)   # UE estimator, all ports in one call
+        self.cdesc = PuschChestDesc(N, nb_ant, slot, 2, 0, rb_start, 0, rb_size, fco, 0, dmrs_id, 14 * N, 14 * N, min(n_layers, 2), 1)   # UE estimator, ports 0 (and 1) in one call
+        # layers 3 and 4: ports 2 (and 3) of the second CDM group, a second call
+        self.cdesc2 = PuschChestDesc(N, nb_ant, slot, 2, 2, rb_start, 0, rb_size, fco, 0, dmrs_id, 14 * N, 14 * N, n_layers - 2, 1) if n_layers > 2 else None
         self.est = torch.zeros((n_layers * nb_ant, 14 * N, 2), dtype=torch.int16, device=device)      # dl_ch_estimates[p * nb_rx + aarx]
         self.chest_scratch = torch.empty(lib.pusch_chest_scratch_bytes(self.cdesc), dtype=torch.uint8, device=device)
         self.chest_state = torch.zeros((n_layers, 18), dtype=torch.int32, device=device)
@@ -171,6 +173,8 @@ class PdschSlotChain:
             return self.tb, self.iters, self.tbcrc
         dl.ofdm_demod_slot_torch(self.drx, rxdata, self.ts, self.rxF)                       # nr_slot_fep x 14
         lib.pusch_chest_torch(self.cdesc, self.rxF, self.est, self.chest_scratch, self.chest_state)   # nr_pdsch_channel_estimation, every port
+        if self.cdesc2 is not None:
+            lib.pusch_chest_torch(self.cdesc2, self.rxF, self.est[2 * self.nb:], self.chest_scratch, self.chest_state[2:])
         lib.pusch_inner_rx_torch(self.rxd, self.rxF, self.est, self.llr16, level=self.level)   # nr_rx_pdsch (+ unscrambling)
         lib.rm_rx_torch(1, self.Z, self.Qm, 0, self.C, 0, self.F, self.llr16, self.E, self.Eoff, self.harq, self.llr8, clear=1)
         lib.decode_batch_torch(1, self.Z, self.R, self.max_iter, self.llr8, use_crc=1, crc_len_bits=self.K - self.F, crc_type=CRC24_B,

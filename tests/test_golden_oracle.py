@@ -240,6 +240,27 @@ def test_transform_precoding_golden(oracle):
         oracle.pusch_set_transform_precoding(0)
 
 
+def _ue_layers_inputs(g, i):
+    import zlib
+    N, nb_rx, _, _, _, _, _, _, _, _, _, nl, ay, ah = [int(x) for x in g[f"case{i}"]]
+    rng = np.random.default_rng(3000 + i)
+    rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+    assert zlib.crc32(rx.tobytes() + h.tobytes()) == int(g[f"crc{i}"]), "numpy's seeded stream changed: regenerate with tools/gen_golden_ue_layers.py"
+    return rx, h
+
+
+def test_ue_3_4_layers_golden(oracle):
+    """nr_rx_pdsch with three and four layers against vectors of the compiled reference (tools/gen_golden_ue_layers.py; seeded inputs guarded by a checksum)."""
+    from oracle.bindings import PuschParms
+    g = _load("ue_layers.npz")
+    for i in range(int(g["n"])):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, nl, ay, ah = [int(x) for x in g[f"case{i}"]]
+        rx, h = _ue_layers_inputs(g, i)
+        llr, sh = oracle.pdsch_rx_slot(PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm), start, nsym, rx, h, nl=nl)
+        assert sh == int(g[f"sh{i}"]) and np.array_equal(llr, g[f"llr{i}"]), i
+
+
 def test_ptrs_ue_golden(oracle):
     """PT-RS at the UE (nr_pdsch_ptrs_processing inside nr_rx_pdsch): LLRs, log2_maxh, per-symbol phase estimates and PT-RS RE counts against vectors of the
     compiled reference (tools/gen_golden_ptrs.py)."""

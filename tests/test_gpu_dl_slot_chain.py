@@ -156,3 +156,30 @@ def test_pdsch_slot_with_ptrs_tracks_a_phase_drift(ldpc, oracle):
     tb, iters, tbcrc = plain.receive(rxdata)
     torch.cuda.synchronize()
     assert int(tbcrc.cpu()[0]) != 0, "0.55 rad of uncompensated phase error on 16QAM should not decode"
+
+
+@pytest.mark.parametrize("cfg", [dict(A=60584, N=1024, mu=0, carrier_rb=52, rb_size=52, slot=1, Qm=4, n_layers=4, nb_ant=4, max_iter=16),
+                                 dict(A=45240, N=1024, mu=0, carrier_rb=52, rb_size=52, slot=2, Qm=4, n_layers=3, nb_ant=4, max_iter=16)])
+def test_pdsch_slot_three_four_layers_roundtrip(ldpc, oracle, cfg):
+    """Closed loop with three / four layers on four antennas: the transmitter kernel maps ports 0-3 (two CDM groups), the UE estimates every port (two estimator
+    calls), the zero-forcing receiver with the reference's fixed-point 3 x 3 / 4 x 4 inverse separates the layers, the transport block comes back -- through the slot-level
+    C entry points and through the staged calls, with the LLRs equal to the pinned oracle's."""
+    from oracle.bindings import PuschParms
+    dev = torch.device("cuda", 0)
+    chain = PdschSlotChain(ldpc, load_dftslib(), dev, **cfg)
+    rng = np.random.default_rng(11)
+    payload = rng.integers(0, 256, size=chain.A // 8, dtype=np.uint8)
+    rxdata = chain.channel(chain.transmit(torch.from_numpy(payload).to(dev)), seed=5, coupling=0.1)
+    for staged in (True, False):
+        tb, iters, tbcrc = chain.receive(rxdata, staged=staged)
+        torch.cuda.synchronize()
+        it = iters.cpu().numpy()
+        print("layers", chain.nl, "staged", staged, "iterations", it, "log2_maxh", int(chain.level.cpu()[8]))
+        r = chain.rxd
+        PP = PuschParms(r.fft_size, r.nb_rx, r.rb_start, 0, r.rb_size, r.first_carrier_offset, r.qam_mod_order, r.ul_dmrs_symb_pos, r.dmrs_config_type, r.num_dmrs_cdm_grps_no_data)
+        rxF = chain.rxF.cpu().numpy().reshape(r.nb_rx, 14, r.fft_size, 2)
+        est = chain.est.cpu().numpy().reshape(-1, 14, r.fft_size, 2)
+        llr_o, sh_o = oracle.pdsch_rx_slot(PP, r.start_symbol_index, r.nr_of_symbols, rxF, est, nl=chain.nl)
+        assert sh_o == int(chain.level.cpu()[8])
+        assert np.array_equal(chain.llr16.cpu().numpy(), oracle.unscramble_llr(llr_o, 0, chain.nid, chain.rnti))
+        assert int(tbcrc.cpu()[0]) == 0 and np.array_equal(tb.cpu().numpy().reshape(-1)[:payload.size], payload), (staged, it)

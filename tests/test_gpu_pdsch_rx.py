@@ -141,3 +141,19 @@ def test_pdsch_rx_ue_3_4_layers_vs_oracle(ldpc, oracle):
             assert sh == sh_o, (N, nb_rx, Qm, nl, sh, sh_o)
             ref = llr_o if unscr is None else oracle.unscramble_llr(llr_o, 0, unscr[1], unscr[0])
             assert llr.size == ref.size and np.array_equal(llr, ref), (N, nb_rx, rb_start, rb_size, Qm, nl, dpos, dtype_, cdm, unscr, np.nonzero(llr != ref)[0][:6])
+
+
+def test_pdsch_rx_ue_3_4_layers_golden(ldpc):
+    """The same kernels against the committed vectors of the compiled reference (tests/golden/ue_layers.npz)."""
+    import os
+    import zlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ue_layers.npz"))
+    for i in range(int(g["n"])):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, nl, ay, ah = [int(x) for x in g[f"case{i}"]]
+        rng = np.random.default_rng(3000 + i)
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+        assert zlib.crc32(rx.tobytes() + h.tobytes()) == int(g[f"crc{i}"])
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, 0, 0, 0, nl, 0, 0, 1)
+        llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+        assert sh == int(g[f"sh{i}"]) and np.array_equal(llr, g[f"llr{i}"]), (i, np.nonzero(llr != g[f"llr{i}"])[0][:6])
