@@ -112,6 +112,18 @@ class PdschTxParms(C.Structure):     # orc_pdsch_tx_t
         return ((12 * self.nr_of_symbols - per * bin(self.dl_dmrs_symb_pos).count("1")) * self.rb_size - self.ptrs_res()) * self.nrOfLayers * self.Qm
 
 
+
+def _rfsim_call(fn, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise):
+    fn.restype = None
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p]
+    c = np.ascontiguousarray(ch, dtype=np.float64); s = np.ascontiguousarray(sig, dtype=np.int16)
+    assert c.shape == (nb_tx * nb_rx, L, 2) and s.shape == (cir, 2)
+    o = np.ascontiguousarray(out, dtype=np.int16).copy()
+    n = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+    fn(nb_tx, nb_rx, L, offset, pl_dB, noise_dB, c.ctypes.data, s.ctypes.data, o.ctypes.data, rx_ant, o.shape[0], TS, cir, None if n is None else n.ctypes.data)
+    return o
+
+
 class Oracle:
     def __init__(self):
         so = os.path.join(HERE, "liboracle.so")
@@ -310,6 +322,10 @@ class Oracle:
         out = np.zeros(n_words, np.uint32)
         self.lib.orc_gold_words(C.c_uint32(c_init), C.c_uint32(n_words), out.ctypes.data_as(C.c_void_p))
         return out
+
+    def rfsim_rx_add_input(self, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise=None):
+        """rxAddInput: ch [nb_tx * nb_rx][L][2] float64 (plane rx + tx * nb_rx), sig [CirSize][2] int16 (tx antennas interleaved), out [n][2] int16 accumulated into."""
+        return _rfsim_call(self.lib.orc_rfsim_rx_add_input, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise)
 
     def ptrs_symbols(self, start_symbol, nr_symbols, L_log2, dmrs_pos):
         self.lib.orc_ptrs_symbols.restype = C.c_uint32
@@ -660,6 +676,12 @@ class Reference:
         sh = self._pdschlib.refh_pdsch_rx_slot(prm.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), llr.ctypes.data_as(C.c_void_p),
                                                valid.ctypes.data_as(C.c_void_p), None)
         return llr[:G].copy(), int(sh), valid
+
+    def rfsim_rx_add_input(self, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise=None):
+        """The real rxAddInput (oracle/_ref/libref_rfsim.so); gaussZiggurat returns `noise` in call order."""
+        if not hasattr(self, "_rfsimlib"):
+            self._rfsimlib = C.CDLL(os.path.join(REFDIR, "libref_rfsim.so"))
+        return _rfsim_call(self._rfsimlib.refh_rfsim_rx_add_input, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise)
 
     def pdsch_rx_slot_ptrs(self, P, T, start_symbol, nr_symbols, rxdataF, dl_ch_est, G, n_rb_dl=273):
         """The real nr_rx_pdsch + nr_pdsch_ptrs_processing (libref_pdsch_ptrs.so).  Returns (llr, log2_maxh, valid[14], phase[14][2], ptrs_re[14])."""

@@ -118,6 +118,10 @@ typedef struct {
 } orc_pdsch_tx_t;
 int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txdataF);
 
+/* rfsimulator channel application (nrb200_rfsim_oracle.c): rxAddInput of radio/rfsimulator/apply_channelmod.c */
+void orc_rfsim_rx_add_input(int nb_tx, int nb_rx, int channel_length, int channel_offset, double path_loss_dB, float noise_power_dB, const double *ch,
+                            const int16_t *input_sig, int16_t *out, int rxAnt, int nbSamples, uint64_t TS, uint32_t CirSize, const double *noise);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,20 @@ def ptrs_inputs(oracle, rng, case, kind, a, b):
     rx = np.stack([np.round(y.real), np.round(y.imag)], -1).clip(-32768, 32767).astype(np.int16)
     hf = np.broadcast_to(hh, (nb_rx, 14, N))
     return rx, np.stack([np.round(hf.real), np.round(hf.imag)], -1).astype(np.int16)
+
+
+RFSIM_CASES = [  # nb_tx, nb_rx, channel_length, channel_offset, path_loss_dB, noise_power_dB, samples, TS, CirSize factor, amplitude
+    (1, 1, 1, 0, 0.0, -100.0, 3000, 100000, 4, 3000), (2, 2, 12, 0, -3.0, -20.0, 7680, 123456, 3, 8000), (4, 4, 30, 3, -10.5, -6.0, 5000, 30720 * 7 + 11, 2, 32767),
+    (2, 4, 200, 0, 6.0, -40.0, 2048, 999, 2, 1000), (4, 2, 63, -5, -0.1, 0.0, 4097, 2 ** 33 + 5, 2, 20000), (1, 2, 7, 1, 20.0, -3.0, 1000, 50, 1, 32767),
+]
+
+
+def rfsim_inputs(rng, case):
+    """Channel taps, circular tx buffer, pre-filled output and noise draws for one rxAddInput call (tests, golden generator)."""
+    nb_tx, nb_rx, L, offset, pl, npw, n, TS, cf, amp = case
+    cir = cf * (n + L + 16)
+    ch = rng.normal(size=(nb_tx * nb_rx, L, 2)) * (0.7 / np.sqrt(L))
+    sig = rng.integers(-amp, amp + 1, size=(cir, 2)).astype(np.int16)
+    out = rng.integers(-200, 201, size=(n, 2)).astype(np.int16)
+    noise = rng.normal(size=(n, 2))
+    return cir, ch, sig, out, noise

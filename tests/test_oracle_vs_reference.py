@@ -694,6 +694,22 @@ def test_pdsch_tx_slot_ptrs(oracle, reference):
             assert P.G() > bits.size
 
 
+def test_rfsim_rx_add_input(oracle, reference):
+    """rfsimulator channel application: the real rxAddInput (apply_channelmod.c) with the harness's noise draws vs the oracle restatement, every rx
+    antenna, with and without noise; 1-4 antennas either side, 1-200 taps, wrap-around of the circular buffer, full-scale samples, a time stamp above 2^32."""
+    from common import RFSIM_CASES, rfsim_inputs
+    rng = np.random.default_rng(77)
+    for case in RFSIM_CASES:
+        nb_tx, nb_rx, L, offset, pl, npw, n, TS, cf, amp = case
+        cir, ch, sig, out, noise = rfsim_inputs(rng, case)
+        for a in range(nb_rx):
+            for nz in (noise, None):
+                o = oracle.rfsim_rx_add_input(nb_tx, nb_rx, L, offset, pl, npw, ch, sig, out, a, TS, cir, nz)
+                r = reference.rfsim_rx_add_input(nb_tx, nb_rx, L, offset, pl, npw, ch, sig, out, a, TS, cir, nz)
+                assert np.array_equal(o, r), (case, a, nz is None, np.argwhere(o != r)[:5])
+                assert not np.array_equal(o, out)
+
+
 def test_dft_size_index_enumerators_match_oai_header():
     """The size index dft() / idft() receive is OAI's dft_size_idx_t / idft_size_idx_t enumerator: the library's table (nrb200_dft_size_of_index, no GPU needed) and
     the Python mirror are pinned to get_dft / get_idft compiled from OAI's own tools_defs.h (oracle/ref_harness_dftidx.c)."""
