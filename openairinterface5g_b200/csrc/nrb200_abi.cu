@@ -1,5 +1,6 @@
 // C ABI of libldpc_b200.so (include/nrb200_ldpc.h): the four OAI loader symbols plus the batched extension.
 #include "../../include/nrb200_ldpc.h"
+#include "../../include/nrb200_rfsim.h"
 #include "nrb200_ctx.h"
 #include "ldpc_packed_graph.h"
 #include "ldpc_common.cuh"
@@ -33,6 +34,8 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
 size_t pusch_tp_scratch_bytes(const nrb200_pusch_rx_t &d);
 int pusch_ptrs_layout(const nrb200_pusch_rx_t &d, uint32_t *mask, uint32_t *n_re);
+int launch_rfsim(const nrb200_rfsim_chan_t &c, const double *ch, const int16_t *sig, int16_t *out, uint32_t out_stride, uint32_t n, uint64_t TS, uint32_t CirSize,
+                 const double *noise, cudaStream_t st);
 int lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq);
 int launch_chest_time_avg(uint32_t N, uint32_t nb_rx, uint32_t ch_stride, uint32_t start_symbol, uint32_t nr_of_symbols, uint32_t dmrs_symb_pos, uint32_t rb_size,
                           int16_t *d_est, cudaStream_t st);
@@ -888,6 +891,42 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
 NRB200_EXPORT int32_t nrb200_pdsch_ptrs_layout(const nrb200_pusch_rx_t *d, uint32_t *ptrs_symbols, uint32_t *ptrs_re_per_symbol)
 {
   return d ? pusch_ptrs_layout(*d, ptrs_symbols, ptrs_re_per_symbol) : -1;
+}
+
+// ------------------------------------------------------------------------------------------ rfsimulator channel application (rxAddInput)
+NRB200_EXPORT int32_t nrb200_rfsim_rx_add_input_dev(const nrb200_rfsim_chan_t *c, const double *d_ch, const int16_t *d_input_sig, int16_t *d_out, uint32_t out_stride,
+                                                    uint32_t nbSamples, uint64_t TS, uint32_t CirSize, const double *d_noise, void *stream)
+{
+  if (ensure_init() || !c || !d_ch || !d_input_sig || !d_out) return -1;
+  if (out_stride < nbSamples) return -4;
+  return launch_rfsim(*c, d_ch, d_input_sig, d_out, out_stride, nbSamples, TS, CirSize, d_noise, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_rfsim_rx_add_input_host(const nrb200_rfsim_chan_t *c, const double *ch, const int16_t *input_sig, int16_t *out, uint32_t out_stride,
+                                                     uint32_t nbSamples, uint64_t TS, uint32_t CirSize, const double *noise)
+{
+  if (ensure_init() || !c || !ch || !input_sig || !out) return -1;
+  if (out_stride < nbSamples || c->nb_tx < 1 || c->nb_tx > 8 || c->nb_rx < 1 || c->nb_rx > 8 || c->channel_length < 1 || c->channel_length > 255) return -4;
+  const size_t ch_b = (size_t)c->nb_tx * c->nb_rx * c->channel_length * 16, sig_b = ((size_t)CirSize * 4 + 15) & ~(size_t)15;
+  const size_t nz_b = noise ? (size_t)c->nb_rx * nbSamples * 16 : 0, out_b = (size_t)c->nb_rx * out_stride * 4;
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(ch_b + sig_b + nz_b, out_b + 64, 64)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    uint8_t *h = (uint8_t *)w->h_in, *dv = (uint8_t *)w->d_in;
+    std::memcpy(h, ch, ch_b);
+    std::memcpy(h + ch_b, input_sig, (size_t)CirSize * 4);
+    if (noise) std::memcpy(h + ch_b + sig_b, noise, nz_b);
+    std::memcpy(w->h_out, out, out_b);
+    if (cudaMemcpyAsync(dv, h, ch_b + sig_b + nz_b, cudaMemcpyHostToDevice, w->stream) != cudaSuccess ||
+        cudaMemcpyAsync(w->d_out, w->h_out, out_b, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    if ((rc = launch_rfsim(*c, (const double *)dv, (const int16_t *)(dv + ch_b), (int16_t *)w->d_out, out_stride, nbSamples, TS, CirSize,
+                           noise ? (const double *)(dv + ch_b + sig_b) : nullptr, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, out_b, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess || cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    std::memcpy(out, w->h_out, out_b);
+  } while (0);
+  ctx().release(w);
+  return rc;
 }
 
 NRB200_EXPORT uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d) { return d ? pusch_tp_scratch_bytes(*d) : 0; }

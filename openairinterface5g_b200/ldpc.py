@@ -84,6 +84,11 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
         return self
 
 
+class RfsimChan(C.Structure):         # nrb200_rfsim_chan_t
+    _fields_ = [("nb_tx", C.c_uint32), ("nb_rx", C.c_uint32), ("channel_length", C.c_uint32), ("channel_offset", C.c_int32), ("path_loss_dB", C.c_double),
+                ("noise_power_dB", C.c_float), ("reserved", C.c_uint32)]
+
+
 class PuschChestDesc(C.Structure):    # nrb200_pusch_chest_t
     _fields_ = [(n, C.c_uint32) for n in ("fft_size", "nb_rx", "slot", "symbol", "port", "rb_start", "bwp_start", "rb_size", "first_carrier_offset", "scid",
                                           "ul_dmrs_scrambling_id", "rx_stride", "ch_stride", "n_ports", "pdsch_ue", "dmrs_config_type", "chest_freq",
@@ -518,6 +523,27 @@ class LdpcLib:
     # ---- single-layer PUSCH inner receiver (nr_ulsch_demodulation.c inner_rx + log2_maxh measurement)
     def pusch_num_llr(self, desc):
         return int(self.lib.nrb200_pusch_num_llr(C.addressof(desc)))
+
+    def rfsim_rx_add_input_host(self, nb_tx, nb_rx, offset, pl_dB, noise_dB, ch, sig, out, TS, noise=None):
+        """rxAddInput for every receive antenna: ch [nb_tx * nb_rx][L][2] float64 (plane rx + tx * nb_rx), sig [CirSize][2] int16 (tx antennas interleaved),
+        out [nb_rx][n][2] int16 (accumulated into; a copy is returned), noise [nb_rx][n][2] float64 or None."""
+        c = np.ascontiguousarray(ch, dtype=np.float64); s = np.ascontiguousarray(sig, dtype=np.int16); o = np.ascontiguousarray(out, dtype=np.int16).copy()
+        d = RfsimChan(nb_tx, nb_rx, c.shape[1], offset, pl_dB, noise_dB, 0)
+        nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        f = self.lib.nrb200_rfsim_rx_add_input_host
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
+        self._check(f(C.addressof(d), c.ctypes.data, s.ctypes.data, o.ctypes.data, o.shape[1], o.shape[1], TS, s.shape[0], None if nz is None else nz.ctypes.data),
+                    "rfsim_rx_add_input_host")
+        return o
+
+    def rfsim_rx_add_input_torch(self, d, ch, sig, out, TS, noise=None):
+        """Device-resident variant: torch CUDA tensors with the shapes above; out is updated in place."""
+        import torch
+        f = self.lib.nrb200_rfsim_rx_add_input_dev
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        self._check(f(C.addressof(d), ch.data_ptr(), sig.data_ptr(), out.data_ptr(), out.shape[1], out.shape[1], TS, sig.shape[0],
+                      None if noise is None else noise.data_ptr(), torch.cuda.current_stream(out.device).cuda_stream), "rfsim_rx_add_input_dev")
+        return out
 
     def pdsch_ptrs_layout(self, desc):
         """(PT-RS symbol mask, PT-RS REs per PT-RS symbol) of a descriptor with ptrs = 1 (set_ptrs_symb_idx / nr_ptrs_cpe_estimation's bookkeeping)."""
