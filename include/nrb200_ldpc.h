@@ -302,7 +302,7 @@ typedef struct nrb200_pusch_rx_s {
   uint32_t ptrs_re_offset;                  /* dlsch_config.PTRSReOffset, used as k_RE_ref like the reference does (< 12) */
   uint32_t ptrs_slot, ptrs_nscid, ptrs_dmrs_scrambling_id;   /* proc->nr_slot_rx, dlsch_config.nscid, ue->scramblingID_dlsch[nscid]: the Gold sequence of nr_gold_pdsch */
   uint32_t ptrs_reserved;
-  uint64_t d_ptrs_state;                    /* _dev: 64 bytes of DEVICE scratch (14 phases + status); afterwards [0..13] = ptrs_phase_per_slot[0] {re, im} packed */
+  uint64_t d_ptrs_state;                    /* _dev: 128 bytes of DEVICE scratch; afterwards words [0..13] = ptrs_phase_per_slot[0] {re, im} packed, [14] = status */
 } nrb200_pusch_rx_t;
 uint64_t nrb200_pusch_tp_scratch_bytes(const nrb200_pusch_rx_t *d);
 /* PT-RS bookkeeping of a descriptor with ptrs = 1: *ptrs_symbols = dlsch->ptrs_symbols as set_ptrs_symb_idx leaves it (NR_REFSIG/ptrs_nr.c:53-86), *ptrs_re_per_symbol =

@@ -857,7 +857,7 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
   const size_t plane = (size_t)d->nb_rx * 14 * d->fft_size * 4, est_plane = plane * (d->nrOfLayers >= 2 ? d->nrOfLayers : 1);
   const size_t tp_bytes = d->transform_precoding ? pusch_tp_scratch_bytes(*d) : 0;        // the transforms' input / output planes, behind the level slots
   Workspace *w = ctx().acquire();
-  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes + 64 + 128)) { if (w) ctx().release(w); return -5; }
+  if (!w || !w->reserve(plane + est_plane, (size_t)n_llr * 2 + 64, 64 + tp_bytes + 128 + 128)) { if (w) ctx().release(w); return -5; }
   int rc = 0;
   do {
     std::memcpy(w->h_in, rxdataF, plane);
@@ -873,7 +873,7 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
     if (measure) {
       e.log2_maxh = 0;
       // one workspace, one stream: give the level kernel its own completion counter slot in the workspace
-      uint32_t *cnt = (uint32_t *)((uint8_t *)w->d_aux + 64 + tp_bytes + 64);              // counter + per-plane levels (32 words)
+      uint32_t *cnt = (uint32_t *)((uint8_t *)w->d_aux + 64 + tp_bytes + 128);             // counter + per-plane levels (32 words)
       if (cudaMemsetAsync(cnt, 0, 4, w->stream) != cudaSuccess) { rc = -2; break; }
       if ((rc = launch_pusch_level(e, d_ch, d_lvl, cnt, w->stream)) != 0) break;
     }

@@ -417,10 +417,10 @@ __device__ __forceinline__ unsigned ue_scale(unsigned h)
 // ---- PT-RS at the UE (nr_pdsch_ptrs_processing, NR_UE_ESTIMATION/nr_dl_channel_estimation.c:1765-1907; NR_REFSIG/ptrs_nr.c), one layer.
 // The reference estimates a common phase error per PT-RS symbol from the compensated PT-RS REs, squeezes those REs out of rxdataF_comp, interpolates the
 // estimates over the other symbols at the slot's last symbol, rotates every non-DMRS symbol and only then computes the slot's LLRs.  Here:
-//   pdsch_ptrs_kernel  one warp per symbol: matched filter + MRC of the symbol's PT-RS REs only (nb_rb / K of them), product with the conjugated QPSK
-//                      pilot (Gold sequence of the symbol's PDSCH DMRS), integer sum across the warp, lane 0 normalises in IEEE double arithmetic without
-//                      fused multiply-adds (what oracle/_ref is built with); then thread 0 runs nr_ptrs_process_slot's interpolation.  15 words of state.
-//   pdsch_rx_kernel    PTRS = true: output index i of a PT-RS symbol is mapped past the PT-RS REs before it, the MRC output is rotated by the symbol's
+//   pdsch_ptrs_kernel  one CTA per symbol: matched filter + MRC of the symbol's PT-RS REs only (nb_rb / K of them), product with the conjugated QPSK
+//                      pilot (Gold sequence of the symbol's PDSCH DMRS), exact integer sum across the CTA, thread 0 normalises in IEEE double arithmetic without
+//                      fused multiply-adds (what oracle/_ref is built with).  32 words of state: raw estimates in [16..29].
+//   pdsch_rx_kernel    PTRS = true: one thread per CTA runs nr_ptrs_process_slot's interpolation on the 14 raw estimates; output index i of a PT-RS symbol is mapped past the PT-RS REs before it, the MRC output is rotated by the symbol's
 //                      phase (AVX2 body / scalar tail of rotate_cpx_vector by buffer position), thresholds stay at index i like the reference's unsqueezed
 //                      magnitude buffers.  No intermediate buffer, still one pass over the slot.
 struct PtrsGeom {
@@ -429,7 +429,7 @@ struct PtrsGeom {
   unsigned pos, dmrs_pos;          // PT-RS symbols (set_ptrs_symb_idx), DMRS symbols
   unsigned cinit[14];              // nr_gold_pdsch's c_init per symbol
   int ch_sym[14];                  // symbol of the estimates per symbol
-  unsigned *state;                 // device: [0..13] phase {re, im} packed, [14] nr_ptrs_process_slot's return value
+  unsigned *state;                 // device, 32 words: [0..13] phase {re, im} packed, [14] nr_ptrs_process_slot's return value, [16..29] raw per-symbol estimates
 };
 // data RE i of a PT-RS symbol -> RE of the allocation (the PT-RS REs q0 + j * K12 skipped)
 __device__ __forceinline__ int ptrs_unsqueeze(const PtrsGeom &T, int i)
@@ -503,46 +503,54 @@ __device__ int ptrs_process_slot(unsigned dmrs, unsigned ptrs, short *est, int s
   }
   return 0;
 }
-__global__ void __launch_bounds__(448) pdsch_ptrs_kernel(PuschGeom G, PtrsGeom T, const GoldTables *__restrict__ GT, const int *__restrict__ d_shift,
-                                                         const unsigned *__restrict__ rxF, const unsigned *__restrict__ ch)
+// One CTA per symbol of the slot (grid 14): the symbol's PT-RS REs are spread over the CTA's threads, the integer sums are reduced exactly, thread 0 normalises.
+// state[16 + m] = the symbol's RAW estimate (DMRS symbols: 32767 + 0 j, others 0); the interpolation over the slot is redone by every CTA of the receiver kernel
+// (a few hundred instructions of one thread) instead of a serial tail here, and CTA (0, 0) of the receiver publishes the final phasors in state[0..13], state[14].
+constexpr int kPtrsTpb = 160;
+__global__ void __launch_bounds__(kPtrsTpb) pdsch_ptrs_kernel(PuschGeom G, PtrsGeom T, const GoldTables *__restrict__ GT, const int *__restrict__ d_shift,
+                                                              const unsigned *__restrict__ rxF, const unsigned *__restrict__ ch)
 {
-  __shared__ short s_est[28];
-  const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  __shared__ unsigned s_gw[12];
+  __shared__ int s_sum[2][kPtrsTpb / 32];
+  const int m = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_alloc = m >= T.start && m < T.start + T.nsym;
-  if (lane == 0) { s_est[2 * m] = (in_alloc && ((T.dmrs_pos >> m) & 1u)) ? 32767 : 0; s_est[2 * m + 1] = 0; }
-  if (in_alloc && ((T.pos >> m) & 1u)) {
-    int sr = 0, si = 0;
-    for (int j0 = 0; j0 < T.n; j0 += 32) {
-      const int j = j0 + lane;
-      // the symbol's Gold words, one per lane and 32-RE chunk: word (2 j) >> 5 = j >> 4 holds bits 2 j, 2 j + 1
-      const unsigned gw = gold_word(GT, T.cinit[m], (unsigned)(j >> 4));
-      if (j < T.n) {
-        int cr, ci;
-        ue_mrc(G, rxF, ch, m, T.ch_sym[m], T.q0 + j * T.K12, shift, cr, ci);
-        const int b0 = (gw >> ((2 * j) & 31)) & 1u, b1 = (gw >> ((2 * j + 1) & 31)) & 1u;
-        const int pr = b0 ? -23170 : 23170, pi = b1 ? 23170 : -23170;      // nr_gen_ref_conj_symbols: conjugated QPSK (nr_dmrs_rx.c:54-55, :240-256)
-        sr += p_sat16(((int)((unsigned)(cr * pr) + (unsigned)(p_wrap16(-ci) * pi))) >> 15);   // mult_cpx_vector, shift 15, packs (cmult_vv.c:96-156)
-        si += p_sat16(((int)((unsigned)(ci * pr) + (unsigned)(cr * pi))) >> 15);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
-    if (lane == 0) {
-      const double sc = (double)T.n;
-      const double real = (double)sr / sc, imag = (double)si / sc;
-      const double ab = sqrt(__dadd_rn(__dmul_rn(real, real), __dmul_rn(imag, imag)));
-      s_est[2 * m] = (short)p_d2i16(__dmul_rn(real / ab, 32768.0));
-      s_est[2 * m + 1] = (short)p_d2i16(__dmul_rn(-(imag / ab), 32768.0));
-    }
+  if (!(in_alloc && ((T.pos >> m) & 1u))) {
+    if (threadIdx.x == 0) T.state[16 + m] = (in_alloc && ((T.dmrs_pos >> m) & 1u)) ? 32767u : 0u;
+    return;
   }
+  const int shift = G.shift_from_dev ? *d_shift : G.shift;
+  // the pilots are the first 2 n bits of the symbol's PDSCH-DMRS Gold sequence: at most 9 words for 138 PT-RS REs
+  if (threadIdx.x < 12 && (int)threadIdx.x <= (2 * T.n - 1) >> 5) s_gw[threadIdx.x] = gold_word(GT, T.cinit[m], threadIdx.x);
+  __syncthreads();
+  int sr = 0, si = 0;
+  for (int j = threadIdx.x; j < T.n; j += kPtrsTpb) {
+    int cr, ci;
+    ue_mrc(G, rxF, ch, m, T.ch_sym[m], T.q0 + j * T.K12, shift, cr, ci);
+    const unsigned gw = s_gw[j >> 4];
+    const int b0 = (gw >> ((2 * j) & 31)) & 1u, b1 = (gw >> ((2 * j + 1) & 31)) & 1u;
+    const int pr = b0 ? -23170 : 23170, pi = b1 ? 23170 : -23170;          // nr_gen_ref_conj_symbols: conjugated QPSK (nr_dmrs_rx.c:54-55, :240-256)
+    sr += p_sat16(((int)((unsigned)(cr * pr) + (unsigned)(p_wrap16(-ci) * pi))) >> 15);   // mult_cpx_vector, shift 15, packs (cmult_vv.c:96-156)
+    si += p_sat16(((int)((unsigned)(ci * pr) + (unsigned)(cr * pi))) >> 15);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+  if (lane == 0) { s_sum[0][warp] = sr; s_sum[1][warp] = si; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int ret = 0;
-    if (T.L > 0) ret = ptrs_process_slot(T.dmrs_pos, T.pos, s_est, T.start, T.nsym);
-    for (int q = 0; q < 14; q++) T.state[q] = ((unsigned)(unsigned short)s_est[2 * q]) | ((unsigned)(unsigned short)s_est[2 * q + 1] << 16);
-    T.state[14] = (unsigned)ret;
+    sr = 0; si = 0;
+    for (int w = 0; w < kPtrsTpb / 32; w++) { sr += s_sum[0][w]; si += s_sum[1][w]; }
+    const double sc = (double)T.n;
+    const double real = (double)sr / sc, imag = (double)si / sc;
+    const double ab = sqrt(__dadd_rn(__dmul_rn(real, real), __dmul_rn(imag, imag)));
+    const int er = p_d2i16(__dmul_rn(real / ab, 32768.0)), ei = p_d2i16(__dmul_rn(-(imag / ab), 32768.0));
+    T.state[16 + m] = ((unsigned)er & 0xFFFFu) | ((unsigned)ei << 16);
   }
+}
+// the slot's phasors from the raw per-symbol estimates: nr_ptrs_process_slot when PTRSTimeDensity > 0.  Returns its status; est = 14 {re, im}.
+__device__ __forceinline__ int ptrs_finish(const PtrsGeom &T, short *est)
+{
+  for (int q = 0; q < 14; q++) { const unsigned v = T.state[16 + q]; est[2 * q] = (short)(v & 0xFFFFu); est[2 * q + 1] = (short)(v >> 16); }
+  return T.L > 0 ? ptrs_process_slot(T.dmrs_pos, T.pos, est, T.start, T.nsym) : 0;
 }
 
 template <int QM, bool PTRS = false>
@@ -550,15 +558,28 @@ __global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTa
                                                        const unsigned *__restrict__ ch, short *__restrict__ llr, PtrsGeom PT)
 {
   __shared__ uint32_t s_gold[(256 * QM) / 32 + 2];
+  __shared__ unsigned s_phase;
+  __shared__ int s_ptrs_ret;
   const int k = blockIdx.y, symbol = G.sym[k], valid = G.valid[k], is_dmrs = G.is_dmrs[k];
   const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
   if (i0 >= valid) return;
   const unsigned bit0 = G.llr_off[k] + (unsigned)i0 * QM;
+  if (PTRS && threadIdx.x == 255) {
+    // every CTA redoes the slot's interpolation from the 14 raw estimates (cheap, and no serial tail in the estimator kernel); CTA (0, 0) publishes the result
+    short est[28];
+    const int ret = ptrs_finish(PT, est);
+    s_phase = ((unsigned)(unsigned short)est[2 * symbol]) | ((unsigned)(unsigned short)est[2 * symbol + 1] << 16);
+    s_ptrs_ret = ret;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      for (int q = 0; q < 14; q++) PT.state[q] = ((unsigned)(unsigned short)est[2 * q]) | ((unsigned)(unsigned short)est[2 * q + 1] << 16);
+      PT.state[14] = (unsigned)ret;
+    }
+  }
   if (G.unscramble) {
     const unsigned w0 = bit0 >> 5, nw = ((bit0 + 256u * QM + 31u) >> 5) - w0;
     if (threadIdx.x < nw) s_gold[threadIdx.x] = gold_word(T, G.c_init, w0 + threadIdx.x);
-    __syncthreads();
   }
+  if (G.unscramble || PTRS) __syncthreads();
   if (i >= valid) return;
   const int shift = G.shift_from_dev ? *d_shift : G.shift;
   int rx_idx, ch_idx, mch_idx, dummy;
@@ -580,9 +601,9 @@ __global__ void __launch_bounds__(256) pdsch_rx_kernel(PuschGeom G, const GoldTa
       if (a == 0) { ma = va; mb = vb; mc = vc; } else { ma = p_sat16(ma + va); mb = p_sat16(mb + vb); mc = p_sat16(mc + vc); }
     }
   }
-  if (PTRS && !is_dmrs && PT.state[14] == 0u) {
+  if (PTRS && !is_dmrs && s_ptrs_ret == 0) {
     // rotate_cpx_vector(rxdataF_comp of the symbol, phase, 12 * nb_rb, 15) (cmult_sv.c:77-145): madd + packs for whole groups of 8 REs, c16mulShift for the rest
-    const unsigned ph = PT.state[symbol];
+    const unsigned ph = s_phase;
     const int ar = p_lo(ph), ai = p_hi(ph);
     int xr, xi;
     if (i < (G.nb_re & ~7)) {
@@ -1148,7 +1169,7 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
     if (pt < 0) return pt;
     if (pt == 1) {
       if (PT.state == nullptr || scramble_mod_init() != 0) return PT.state == nullptr ? -4 : -5;
-      pdsch_ptrs_kernel<<<1, 448, 0, st>>>(G, PT, gold_tables_dev(), d_shift, R, C);
+      pdsch_ptrs_kernel<<<14, kPtrsTpb, 0, st>>>(G, PT, gold_tables_dev(), d_shift, R, C);
       NRB200_CUDA_OK(cudaGetLastError(), "pdsch_ptrs launch");
       ctx().launches++;
       switch (G.Qm) {

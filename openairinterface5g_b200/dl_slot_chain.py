@@ -69,7 +69,7 @@ class PdschSlotChain:
         self.rxd = PuschRxDesc(N, nb_ant, rb_start, 0, rb_size, fco, Qm, start_symbol, nr_symbols, self.dmrs_pos, self.dmrs_type, self.cdm,
                                0, 14 * N, 14 * N, 1, rnti, nid, n_layers, 0, 0, 1)
         if ptrs is not None:
-            self.ptrs_state = torch.zeros(16, dtype=torch.int32, device=device)     # ptrs_phase_per_slot[0] as the library leaves it, + status
+            self.ptrs_state = torch.zeros(32, dtype=torch.int32, device=device)     # ptrs_phase_per_slot[0] as the library leaves it, + status
             self.rxd.set_ptrs(ptrs[0], ptrs[1], ptrs[2], slot, 0, dmrs_id, self.ptrs_state.data_ptr())
             mask, n_re = lib.pdsch_ptrs_layout(self.rxd)
             assert bin(mask).count("1") * n_re == unav_res

@@ -162,6 +162,48 @@ def main():
     print(json.dumps({"what": "nr_modulation 64QAM G=471744", "us": ms * 1e3, "value": G / 6 / ms * 1e3, "unit": "symbols/s"}), flush=True)
     ms = timeit(lambda: lib.unscramble_llr_torch(llrs, 0, 42, 4660), n=50)
     print(json.dumps({"what": "nr_codeword_unscrambling G=471744", "us": ms * 1e3, "value": G / ms * 1e3, "unit": "LLR/s"}), flush=True)
+    # ---- rfsimulator channel application (rxAddInput): one 10 ms frame at 61.44 Msps, 2 x 2 and 4 x 4, 40 taps, with noise; FP64, 8 operations per tap and tx antenna
+    from openairinterface5g_b200.ldpc import RfsimChan
+    for nb in (2, 4):
+        L, n = 40, 614400
+        cir = 2 * (n + L + 16)
+        rngn = np.random.default_rng(5)
+        chn = rngn.normal(size=(nb * nb, L, 2)) * 0.1
+        sign = rngn.integers(-6000, 6001, size=(cir, 2)).astype(np.int16)
+        d_ch, d_sig = torch.from_numpy(chn).to(dev), torch.from_numpy(sign).to(dev)
+        d_nz = torch.randn((nb, n, 2), dtype=torch.float64, device=dev, generator=g)
+        d_o = torch.zeros((nb, n, 2), dtype=torch.int16, device=dev)
+        dsc = RfsimChan(nb, nb, L, 0, -2.0, -30.0, 0)
+        ms = timeit(lambda: lib.rfsim_rx_add_input_torch(dsc, d_ch, d_sig, d_o, 614400, d_nz), n=20)
+        line = {"what": f"rfsim rxAddInput {nb}x{nb}, {L} taps, {n} samples per antenna", "ms": ms, "value": nb * n / ms * 1e3, "unit": "rx-antenna samples/s",
+                "fp64_gops": 8.0 * nb * L * nb * n / ms / 1e6, "realtime_factor_61.44Msps": n / ms * 1e3 / 61.44e6}
+        try:
+            from oracle import bindings as ob
+            ref = ob.Reference()
+            k = 30720
+            t0 = time.perf_counter()
+            ref.rfsim_rx_add_input(nb, nb, L, 0, -2.0, -30.0, chn, sign, np.zeros((k, 2), np.int16), 0, 614400, cir, rngn.normal(size=(k, 2)))
+            line["reference_1_thread"] = k / (time.perf_counter() - t0)
+        except Exception as e:      # the compiled reference is absent
+            line["reference_1_thread"] = str(e)
+        print(json.dumps(line), flush=True)
+    # ---- UE slot receiver, 273 PRB, 64QAM, 4 rx: level + receiver launches of one slot, device resident; 1 layer with and without PT-RS, 2, 3 and 4 layers
+    from openairinterface5g_b200.ldpc import PuschRxDesc
+    N, nrx, nbr = 4096, 4, 273
+    rxF = torch.randint(-2000, 2001, (nrx, 14 * N, 2), dtype=torch.int16, device=dev, generator=g)
+    est = torch.randint(-1500, 1501, (4 * nrx, 14 * N, 2), dtype=torch.int16, device=dev, generator=g)
+    lvl = torch.zeros(9, dtype=torch.int32, device=dev)
+    pst = torch.zeros(32, dtype=torch.int32, device=dev)
+    for nl, ptrs in ((1, False), (1, True), (2, False), (3, False), (4, False)):
+        dsc = PuschRxDesc(N, nrx, 0, 0, nbr, N - nbr * 6, 6, 1, 13, 1 << 2, 0, 2, 0, 14 * N, 14 * N, 1, 0x1234, 77, nl, 0, 0, 1)
+        if ptrs:
+            dsc.set_ptrs(1, 2, 0, 3, 0, 55, pst.data_ptr())
+        nllr = lib.pusch_num_llr(dsc)
+        llr16 = torch.empty(nllr, dtype=torch.int16, device=dev)
+        ms = timeit(lambda: lib.pusch_inner_rx_torch(dsc, rxF, est, llr16, level=lvl), n=50)
+        in_b = 12 * nbr * 12 * (nrx + nl * nrx) * 4
+        print(json.dumps({"what": f"UE nr_rx_pdsch slot 273PRB 64QAM 4rx, {nl} layer(s){', PT-RS L=2 K=2' if ptrs else ''} (level + receiver)", "us": ms * 1e3,
+                          "value": 1e3 / ms, "unit": "slots/s", "llr": nllr, "algorithmic_GBps": (in_b + 2 * nllr) / ms / 1e6}), flush=True)
     # (the per-call LDPCdecoder / LDPCencoder ABI is measured by tools/bench_abi.py through a C harness: Python caller threads would measure the interpreter lock)
 
 
