@@ -327,6 +327,17 @@ class Oracle:
         """rxAddInput: ch [nb_tx * nb_rx][L][2] float64 (plane rx + tx * nb_rx), sig [CirSize][2] int16 (tx antennas interleaved), out [n][2] int16 accumulated into."""
         return _rfsim_call(self.lib.orc_rfsim_rx_add_input, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise)
 
+    def db_fixed_times10(self, x):
+        return int(self.lib.orc_db_fixed_times10(C.c_uint32(x)))
+
+    def rx_nr_prach(self, nb_rx, short_sequence, NCS, prach_fmt, mu, xu, rxsigF):
+        """PRACH detector: xu [64][839][2] int16 (gNB->X_u), rxsigF [nb_rx][N_ZC][2] int16.  Returns (max_preamble, max_preamble_energy, max_preamble_delay)."""
+        x = np.ascontiguousarray(xu, dtype=np.int16); r = np.ascontiguousarray(rxsigF, dtype=np.int16)
+        assert x.shape == (64, 839, 2) and r.shape == (nb_rx, 139 if short_sequence else 839, 2)
+        out = np.zeros(3, np.int32)
+        self.lib.orc_rx_nr_prach(nb_rx, short_sequence, NCS, prach_fmt, mu, x.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return tuple(int(v) for v in out)
+
     def ptrs_symbols(self, start_symbol, nr_symbols, L_log2, dmrs_pos):
         self.lib.orc_ptrs_symbols.restype = C.c_uint32
         return int(self.lib.orc_ptrs_symbols(start_symbol, nr_symbols, 1 << L_log2, C.c_uint32(dmrs_pos)))
@@ -682,6 +693,29 @@ class Reference:
         if not hasattr(self, "_rfsimlib"):
             self._rfsimlib = C.CDLL(os.path.join(REFDIR, "libref_rfsim.so"))
         return _rfsim_call(self._rfsimlib.refh_rfsim_rx_add_input, nb_tx, nb_rx, L, offset, pl_dB, noise_dB, ch, sig, out, rx_ant, TS, cir, noise)
+
+    def _prach(self):
+        if not hasattr(self, "_prachlib"):
+            self._prachlib = C.CDLL(os.path.join(REFDIR, "libref_prach.so"))
+            assert self._prachlib.refh_prach_init(os.path.join(REFDIR, "libref_dfts.so").encode()) == 0
+        return self._prachlib
+
+    def prach_seq(self, short_sequence, num_sequences, root_index):
+        """compute_nr_prach_seq: gNB->X_u [64][839][2] int16."""
+        xu = np.zeros((64, 839, 2), np.int16)
+        self._prach().refh_prach_seq(short_sequence, num_sequences, root_index, xu.ctypes.data_as(C.c_void_p))
+        return xu
+
+    def db_fixed_times10(self, x):
+        return int(self._prach().refh_db_fixed_times10(C.c_uint32(x)))
+
+    def rx_nr_prach(self, nb_rx, short_sequence, root_index, num_roots, NCS, prach_fmt, mu, xu, rxsigF):
+        """The real rx_nr_prach (unrestricted set).  Returns (max_preamble, max_preamble_energy, max_preamble_delay)."""
+        x = np.ascontiguousarray(xu, dtype=np.int16); r = np.ascontiguousarray(rxsigF, dtype=np.int16)
+        p = np.array([nb_rx, short_sequence, root_index, num_roots, NCS, prach_fmt, mu], np.int32)
+        out = np.zeros(3, np.int32)
+        self._prach().refh_rx_nr_prach(p.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return tuple(int(v) for v in out)
 
     def pdsch_rx_slot_ptrs(self, P, T, start_symbol, nr_symbols, rxdataF, dl_ch_est, G, n_rb_dl=273):
         """The real nr_rx_pdsch + nr_pdsch_ptrs_processing (libref_pdsch_ptrs.so).  Returns (llr, log2_maxh, valid[14], phase[14][2], ptrs_re[14])."""

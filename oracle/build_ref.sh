@@ -86,6 +86,9 @@ gcc $F -DREFH_PTRS -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stub
     -lm -ldl -Wl,--no-undefined -o libref_pdsch_ptrs.so || echo "libref_pdsch_ptrs.so: FAILED"
 # rfsimulator channel application: the real rxAddInput, noise draws and the debug line's signal_energy supplied by the harness
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_rfsim.c $R/radio/rfsimulator/apply_channelmod.c -lm -Wl,--no-undefined -o libref_rfsim.so || echo "libref_rfsim.so: FAILED"
+# gNB PRACH detector: the real rx_nr_prach + compute_nr_prach_seq + dB_fixed_times10 (idft bound to libref_dfts.so at run time)
+gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_harness_prach.c $R/openair1/PHY/NR_TRANSPORT/nr_prach.c $R/openair1/PHY/NR_TRANSPORT/nr_prach_common.c \
+    $R/openair1/PHY/TOOLS/dB_routines.c $R/openair1/PHY/TOOLS/signal_energy.c -lm -ldl -Wl,--no-undefined -o libref_prach.so || echo "libref_prach.so: FAILED"
 # gNB-side PDSCH transmitter after the encoder: the real nr_generate_pdsch with nr_dlsch_encoding replaced by the harness (bits in)
 gcc $F -include limits.h $INC $DEFS $HERE/ref_stubs.c $HERE/ref_stubs_pdschtx.c $HERE/ref_harness_pdschtx.c $R/openair1/PHY/NR_TRANSPORT/nr_dlsch.c \
     $R/openair1/PHY/NR_REFSIG/nr_gold.c $R/openair1/PHY/NR_TRANSPORT/nr_sch_dmrs.c $R/openair1/PHY/NR_REFSIG/dmrs_nr.c $R/openair1/PHY/NR_REFSIG/ptrs_nr.c \

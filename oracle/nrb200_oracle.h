@@ -122,6 +122,10 @@ int orc_pdsch_tx_slot(const orc_pdsch_tx_t *p, const uint8_t *bits, int16_t *txd
 void orc_rfsim_rx_add_input(int nb_tx, int nb_rx, int channel_length, int channel_offset, double path_loss_dB, float noise_power_dB, const double *ch,
                             const int16_t *input_sig, int16_t *out, int rxAnt, int nbSamples, uint64_t TS, uint32_t CirSize, const double *noise);
 
+/* gNB PRACH detector (nrb200_prach_oracle.c): rx_nr_prach of NR_TRANSPORT/nr_prach.c, unrestricted set */
+int orc_db_fixed_times10(uint32_t x);
+int orc_rx_nr_prach(int nb_rx, int short_sequence, int NCS, int prach_fmt, int mu, const int16_t *xu, const int16_t *rxsigF, int32_t *out3);
+
 #ifdef __cplusplus
 }
 #endif

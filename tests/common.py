@@ -241,3 +241,32 @@ def rfsim_inputs(rng, case):
     out = rng.integers(-200, 201, size=(n, 2)).astype(np.int16)
     noise = rng.normal(size=(n, 2))
     return cir, ch, sig, out, noise
+
+
+PRACH_CASES = [  # nb_rx, short_sequence, rootSequenceIndex, NCS, format, mu, sent preamble (-1: noise only), delay in samples of the ZC sequence, amplitude, noise sigma
+    (1, 0, 10, 13, 0, 1, 5, 2, 3000, 0), (2, 0, 22, 13, 0, 1, 37, 7, 800, 300), (4, 0, 100, 26, 1, 0, 63, 0, 500, 500), (2, 0, 0, 0, 3, 1, 9, 3, 2000, 100),
+    (4, 0, 300, 119, 0, 1, 20, 40, 1200, 400), (1, 1, 5, 12, 8, 1, 11, 1, 4000, 0), (2, 1, 40, 23, 5, 1, 30, 5, 1500, 500), (4, 1, 120, 0, 7, 3, 44, 0, 900, 300),
+    (2, 0, 10, 13, 0, 1, -1, 0, 0, 2000), (3, 1, 1, 34, 4, 1, 2, 10, 32767, 0), (4, 0, 837, 46, 2, 1, 50, 12, 20000, 8000),
+]
+
+
+def prach_num_roots(short_sequence, NCS):
+    N_ZC = 139 if short_sequence else 839
+    return 64 if NCS == 0 else -(-64 // (N_ZC // NCS))
+
+
+def prach_inputs(rng, case, xu):
+    """rxsigF [nb_rx][N_ZC][2] for one PRACH occasion: the sent preamble's root sequence with its cyclic shift and a delay, a random phase per antenna, noise."""
+    nb_rx, short, root, NCS, fmt, mu, pre, delay, amp, sigma = case
+    N_ZC = 139 if short else 839
+    k = np.arange(N_ZC)
+    y = np.zeros((nb_rx, N_ZC), np.complex128)
+    if pre >= 0:
+        per_root = N_ZC // NCS if NCS else 1
+        r, v = pre // per_root, pre % per_root
+        x = xu[r, :N_ZC, 0].astype(np.float64) + 1j * xu[r, :N_ZC, 1]
+        shift = v * NCS - delay * N_ZC / (1024 if not short else 256)
+        for a in range(nb_rx):
+            y[a] = x / 32768.0 * amp * np.exp(2j * np.pi * k * shift / N_ZC) * np.exp(1j * rng.uniform(0, 6.28))
+    y += sigma * (rng.normal(size=y.shape) + 1j * rng.normal(size=y.shape))
+    return np.stack([np.round(y.real), np.round(y.imag)], -1).clip(-32768, 32767).astype(np.int16)

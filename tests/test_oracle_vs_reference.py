@@ -710,6 +710,32 @@ def test_rfsim_rx_add_input(oracle, reference):
                 assert not np.array_equal(o, out)
 
 
+def test_db_fixed_times10(oracle, reference):
+    """dB_fixed_times10 (TOOLS/dB_routines.c:132-155) on the generated table floor(100 log10 n) (tools/gen_db_table.py) vs the compiled reference."""
+    rng = np.random.default_rng(80)
+    xs = list(range(0, 70000)) + [int(v) for v in rng.integers(0, 2 ** 32, size=20000, dtype=np.uint64)] + [2 ** 32 - 1, 2 ** 31, 2 ** 24, 2 ** 24 - 1, 2 ** 16, 2 ** 16 - 1]
+    for x in xs:
+        assert oracle.db_fixed_times10(x) == reference.db_fixed_times10(x), x
+
+
+def test_rx_nr_prach(oracle, reference):
+    """gNB PRACH detector: the real rx_nr_prach on long (839) and short (139) sequences, 1-4 antennas, several NCS / formats / numerologies, with the
+    root sequences of the real compute_nr_prach_seq -- detected preamble, energy and timing advance vs the oracle; a sent preamble is found, and noise-only input gives the
+    same (arbitrary) answer in both."""
+    from common import PRACH_CASES, prach_inputs, prach_num_roots
+    rng = np.random.default_rng(81)
+    for case in PRACH_CASES:
+        nb_rx, short, root, NCS, fmt, mu, pre, delay, amp, sigma = case
+        nroots = prach_num_roots(short, NCS)
+        xu = reference.prach_seq(short, nroots, root)
+        rx = prach_inputs(rng, case, xu)
+        got_r = reference.rx_nr_prach(nb_rx, short, root, nroots, NCS, fmt, mu, xu, rx)
+        got_o = oracle.rx_nr_prach(nb_rx, short, NCS, fmt, mu, xu, rx)
+        assert got_o == got_r, (case, got_o, got_r)
+        if pre >= 0 and sigma * 3 < amp <= 20000:            # full-scale input overflows the transform: equality still holds, detection does not
+            assert got_r[0] == pre, (case, got_r)
+
+
 def test_dft_size_index_enumerators_match_oai_header():
     """The size index dft() / idft() receive is OAI's dft_size_idx_t / idft_size_idx_t enumerator: the library's table (nrb200_dft_size_of_index, no GPU needed) and
     the Python mirror are pinned to get_dft / get_idft compiled from OAI's own tools_defs.h (oracle/ref_harness_dftidx.c)."""
