@@ -1,6 +1,7 @@
 // C ABI of libldpc_b200.so (include/nrb200_ldpc.h): the four OAI loader symbols plus the batched extension.
 #include "../../include/nrb200_ldpc.h"
 #include "../../include/nrb200_rfsim.h"
+#include "../../include/nrb200_prach.h"
 #include "nrb200_ctx.h"
 #include "ldpc_packed_graph.h"
 #include "ldpc_common.cuh"
@@ -34,6 +35,9 @@ int launch_pusch_rx(const nrb200_pusch_rx_t &d, const int16_t *rxF, const int16_
 size_t pusch_chest_scratch_bytes(const nrb200_pusch_chest_t &d);
 size_t pusch_tp_scratch_bytes(const nrb200_pusch_rx_t &d);
 int pusch_ptrs_layout(const nrb200_pusch_rx_t &d, uint32_t *mask, uint32_t *n_re);
+uint32_t prach_num_roots(const nrb200_prach_t &d);
+size_t prach_scratch_bytes(const nrb200_prach_t &d);
+int launch_prach(const nrb200_prach_t &d, const int16_t *xu, const int16_t *rxsigF, int32_t *out3, void *scratch, cudaStream_t st);
 int launch_rfsim(const nrb200_rfsim_chan_t &c, const double *ch, const int16_t *sig, int16_t *out, uint32_t out_stride, uint32_t n, uint64_t TS, uint32_t CirSize,
                  const double *noise, cudaStream_t st);
 int lowpapr_sequence_host(uint32_t u, uint32_t v, uint32_t n_re, uint32_t scaling, int16_t *seq);
@@ -175,7 +179,7 @@ static DecodeTicket *decode_submit(const nrb200_ldpc_batch_desc_t *desc, const i
     const size_t cn = std::min(per, n - c0);
     cudaStream_t s = st[ci & 1];
     const size_t io = c0 * desc->llr_stride, oo = c0 * desc->out_stride;
-    if (cudaMemcpyAsync((uint8_t *)w->d_in + io, h_src + io, cn * desc->llr_stride, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = -2; break; }
+    if (cudaError_t ce = cudaMemcpyAsync((uint8_t *)w->d_in + io, h_src + io, cn * desc->llr_stride, cudaMemcpyHostToDevice, s)) { ctx().set_error("decode submit: H2D", ce); rc = -2; break; }
     if (abort_flags) cudaMemcpyAsync(d_ab + c0, h_ab + c0, cn, cudaMemcpyHostToDevice, s);
     if (desc->use_crc) cudaMemcpyAsync((uint8_t *)w->d_out + oo, h_dst + oo, cn * desc->out_stride, cudaMemcpyHostToDevice, s);
     DecodeArgs a = a0;
@@ -183,8 +187,8 @@ static DecodeTicket *decode_submit(const nrb200_ldpc_batch_desc_t *desc, const i
     a.llr = (const int8_t *)w->d_in + io; a.out = (uint8_t *)w->d_out + oo; a.iters = d_it + c0;
     a.abort_flags = abort_flags ? d_ab + c0 : nullptr;
     if ((rc = launch_decode(dg, *hg, a, s)) != 0) break;
-    if (cudaMemcpyAsync(h_dst + oo, (uint8_t *)w->d_out + oo, cn * desc->out_stride, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
-    if (cudaMemcpyAsync((int32_t *)w->h_aux + c0, d_it + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = -2; break; }
+    if (cudaError_t ce = cudaMemcpyAsync(h_dst + oo, (uint8_t *)w->d_out + oo, cn * desc->out_stride, cudaMemcpyDeviceToHost, s)) { ctx().set_error("decode submit: D2H out", ce); rc = -2; break; }
+    if (cudaError_t ce = cudaMemcpyAsync((int32_t *)w->h_aux + c0, d_it + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s)) { ctx().set_error("decode submit: D2H iters", ce); rc = -2; break; }
   }
   t->rc = rc;
   return t;
@@ -891,6 +895,44 @@ NRB200_EXPORT int32_t nrb200_pusch_inner_rx_host(const nrb200_pusch_rx_t *d, con
 NRB200_EXPORT int32_t nrb200_pdsch_ptrs_layout(const nrb200_pusch_rx_t *d, uint32_t *ptrs_symbols, uint32_t *ptrs_re_per_symbol)
 {
   return d ? pusch_ptrs_layout(*d, ptrs_symbols, ptrs_re_per_symbol) : -1;
+}
+
+// ------------------------------------------------------------------------------------------ gNB PRACH detector (rx_nr_prach)
+NRB200_EXPORT uint32_t nrb200_prach_num_roots(const nrb200_prach_t *d) { return d ? prach_num_roots(*d) : 0; }
+NRB200_EXPORT uint64_t nrb200_prach_scratch_bytes(const nrb200_prach_t *d) { return d ? prach_scratch_bytes(*d) : 0; }
+
+NRB200_EXPORT int32_t nrb200_rx_nr_prach_dev(const nrb200_prach_t *d, const int16_t *d_X_u, const int16_t *d_rxsigF, int32_t *d_out, void *d_scratch, void *stream)
+{
+  if (ensure_init() || !d || !d_X_u || !d_rxsigF || !d_out || !d_scratch) return -1;
+  return launch_prach(*d, d_X_u, d_rxsigF, d_out, d_scratch, (cudaStream_t)stream);
+}
+
+NRB200_EXPORT int32_t nrb200_rx_nr_prach_host(const nrb200_prach_t *d, const int16_t *X_u, const int16_t *rxsigF, uint16_t *max_preamble, uint16_t *max_preamble_energy,
+                                              uint16_t *max_preamble_delay)
+{
+  if (ensure_init() || !d || !X_u || !rxsigF) return -1;
+  const uint32_t roots = prach_num_roots(*d);
+  if (roots == 0) return -4;
+  const uint32_t N_ZC = d->short_sequence ? 139 : 839;
+  const size_t xu_b = (size_t)roots * 839 * 4, rx_b = (size_t)d->nb_rx * N_ZC * 4, sc_b = prach_scratch_bytes(*d);
+  Workspace *w = ctx().acquire();
+  if (!w || !w->reserve(xu_b + rx_b, 64, sc_b + 64)) { if (w) ctx().release(w); return -5; }
+  int rc = 0;
+  do {
+    std::memcpy(w->h_in, X_u, xu_b);
+    std::memcpy((uint8_t *)w->h_in + xu_b, rxsigF, rx_b);
+    if (cudaMemcpyAsync(w->d_in, w->h_in, xu_b + rx_b, cudaMemcpyHostToDevice, w->stream) != cudaSuccess) { rc = -2; break; }
+    nrb200_prach_t e = *d;
+    e.rx_stride = N_ZC;
+    if ((rc = launch_prach(e, (const int16_t *)w->d_in, (const int16_t *)((uint8_t *)w->d_in + xu_b), (int32_t *)w->d_out, w->d_aux, w->stream)) != 0) break;
+    if (cudaMemcpyAsync(w->h_out, w->d_out, 12, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess || cudaStreamSynchronize(w->stream) != cudaSuccess) { rc = -2; break; }
+    const int32_t *o = (const int32_t *)w->h_out;
+    if (max_preamble) *max_preamble = (uint16_t)o[0];
+    if (max_preamble_energy) *max_preamble_energy = (uint16_t)o[1];
+    if (max_preamble_delay) *max_preamble_delay = (uint16_t)o[2];
+  } while (0);
+  ctx().release(w);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------ rfsimulator channel application (rxAddInput)

@@ -84,6 +84,10 @@ class PuschRxDesc(C.Structure):       # nrb200_pusch_rx_t (field names of nfapi_
         return self
 
 
+class PrachDesc(C.Structure):         # nrb200_prach_t
+    _fields_ = [(n, C.c_uint32) for n in ("nb_rx", "short_sequence", "num_cs", "prach_format", "numerology", "restricted_set", "rx_stride", "reserved")]
+
+
 class RfsimChan(C.Structure):         # nrb200_rfsim_chan_t
     _fields_ = [("nb_tx", C.c_uint32), ("nb_rx", C.c_uint32), ("channel_length", C.c_uint32), ("channel_offset", C.c_int32), ("path_loss_dB", C.c_double),
                 ("noise_power_dB", C.c_float), ("reserved", C.c_uint32)]
@@ -523,6 +527,31 @@ class LdpcLib:
     # ---- single-layer PUSCH inner receiver (nr_ulsch_demodulation.c inner_rx + log2_maxh measurement)
     def pusch_num_llr(self, desc):
         return int(self.lib.nrb200_pusch_num_llr(C.addressof(desc)))
+
+    def prach_num_roots(self, desc):
+        self.lib.nrb200_prach_num_roots.restype = C.c_uint32
+        return int(self.lib.nrb200_prach_num_roots(C.c_void_p(C.addressof(desc))))
+
+    def rx_nr_prach_host(self, desc, xu, rxsigF):
+        """rx_nr_prach: xu [>= roots][839][2] int16 (gNB->X_u), rxsigF [nb_rx][N_ZC][2] int16.  Returns (max_preamble, max_preamble_energy, max_preamble_delay)."""
+        x = np.ascontiguousarray(xu, dtype=np.int16); r = np.ascontiguousarray(rxsigF, dtype=np.int16)
+        o = (C.c_uint16 * 3)()
+        f = self.lib.nrb200_rx_nr_prach_host
+        f.argtypes = [C.c_void_p] * 6
+        self._check(f(C.addressof(desc), x.ctypes.data, r.ctypes.data, C.addressof(o), C.addressof(o) + 2, C.addressof(o) + 4), "rx_nr_prach_host")
+        return int(o[0]), int(o[1]), int(o[2])
+
+    def rx_nr_prach_torch(self, desc, xu, rxsigF, out3, scratch):
+        import torch
+        f = self.lib.nrb200_rx_nr_prach_dev
+        f.argtypes = [C.c_void_p] * 6
+        self._check(f(C.addressof(desc), xu.data_ptr(), rxsigF.data_ptr(), out3.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream(xu.device).cuda_stream),
+                    "rx_nr_prach_dev")
+        return out3
+
+    def prach_scratch_bytes(self, desc):
+        self.lib.nrb200_prach_scratch_bytes.restype = C.c_uint64
+        return int(self.lib.nrb200_prach_scratch_bytes(C.c_void_p(C.addressof(desc))))
 
     def rfsim_rx_add_input_host(self, nb_tx, nb_rx, offset, pl_dB, noise_dB, ch, sig, out, TS, noise=None):
         """rxAddInput for every receive antenna: ch [nb_tx * nb_rx][L][2] float64 (plane rx + tx * nb_rx), sig [CirSize][2] int16 (tx antennas interleaved),

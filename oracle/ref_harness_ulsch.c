@@ -73,7 +73,18 @@ int refh_ulsch_decode_ctx(int ctx, const int32_t *p, const int16_t *llr, int G, 
   pdu.rb_size = p[U_RB_SIZE]; pdu.qam_mod_order = p[U_QM]; pdu.nrOfLayers = p[U_NL]; pdu.mcs_index = 9; pdu.target_code_rate = 6160;
   pdu.pusch_data.tb_size = p[U_TBS_BYTES]; pdu.pusch_data.rv_index = p[U_RV];
   pdu.maintenance_parms_v3.ldpcBaseGraph = p[U_BG]; pdu.maintenance_parms_v3.tbSizeLbrmBytes = p[U_TBSLBRM];
-  const int rc = nr_ulsch_decoding(gNB, 0, (short *)llr, fp, &pdu, 100, 4, 0, (uint32_t)G);
+  /* pusch_vars->llr is allocated ONCE per ULSCH at start-up in OAI (init_nr_transport) and lives as long as the gNB: the caller's LLRs are copied into such a
+   * buffer (grow-only, never freed) instead of being handed over in place.  The interposer page-locks the buffer it is given; a numpy array that is freed (and
+   * possibly unmapped) afterwards would leave a stale registration behind that later host buffers at the same address inherit. */
+  static short *g_llr[REFH_MAX_CTX];
+  static size_t g_llr_cap[REFH_MAX_CTX];
+  if ((size_t)G > g_llr_cap[ctx]) {
+    const size_t cap = (size_t)G > ((size_t)3 << 20) ? (size_t)G : ((size_t)3 << 20);        /* 273 PRB x 14 symbols x 256QAM x 4 layers = 2.9 M LLRs */
+    if (posix_memalign((void **)&g_llr[ctx], 4096, cap * sizeof(short)) != 0) return -102;   /* an outgrown buffer stays allocated (and registered) */
+    g_llr_cap[ctx] = cap;
+  }
+  memcpy(g_llr[ctx], llr, (size_t)G * sizeof(short));
+  const int rc = nr_ulsch_decoding(gNB, 0, g_llr[ctx], fp, &pdu, 100, 4, 0, (uint32_t)G);
   if (rc < 0) return rc;
   const int Kb = hp->K >> 3;
   for (int n = 0; n < rc; n++) {

@@ -16,9 +16,9 @@ def _declared(header):
 
 def test_ldpc_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(os.path.join(ROOT, "openairinterface5g_b200", "libldpc_b200.so"))
-    names = _declared("nrb200_ldpc.h") + _declared("nrb200_slot.h") + _declared("nrb200_rfsim.h")
+    names = _declared("nrb200_ldpc.h") + _declared("nrb200_slot.h") + _declared("nrb200_rfsim.h") + _declared("nrb200_prach.h")
     assert {"LDPCinit", "LDPCshutdown", "LDPCdecoder", "LDPCencoder", "nrb200_sch_slot_rx_dev", "nrb200_pdsch_slot_tx_dev", "nrb200_set_device",
-            "nrb200_rfsim_rx_add_input_dev", "nrb200_rfsim_rx_add_input_host"} <= set(names)
+            "nrb200_rfsim_rx_add_input_dev", "nrb200_rfsim_rx_add_input_host", "nrb200_rx_nr_prach_dev", "nrb200_rx_nr_prach_host"} <= set(names)
     for n in names:
         assert hasattr(lib, n), n
 
@@ -113,11 +113,11 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     pairs = [("nrb200_ldpc_dec_params_t", ldpc.DecParams, None), ("nrb200_ldpc_enc_params_t", ldpc.EncParams, None), ("nrb200_decode_abort_t", ldpc.DecodeAbort, None),
              ("nrb200_ldpc_batch_desc_t", ldpc.BatchDesc, "out_stride"), ("nrb200_rm_desc_t", ldpc.RmDesc, None), ("nrb200_pusch_rx_t", ldpc.PuschRxDesc, "d_ptrs_state"),
              ("nrb200_pusch_chest_t", ldpc.PuschChestDesc, "lowpapr_seq"), ("nrb200_pdsch_tx_t", ldpc.PdschTxDesc, "ptrs_re_offset"),
-             ("nrb200_rfsim_chan_t", ldpc.RfsimChan, "reserved")]
+             ("nrb200_rfsim_chan_t", ldpc.RfsimChan, "reserved"), ("nrb200_prach_t", ldpc.PrachDesc, "reserved")]
     ldpc._late_fields()
     pairs += [("nrb200_sch_rx_slot_t", ldpc.SchRxSlotDesc, "seg_payload_bytes"), ("nrb200_sch_rx_bufs_t", ldpc.SchRxBufs, "hard_stride"),
               ("nrb200_pdsch_tx_slot_t", ldpc.PdschTxSlotDesc, "K"), ("nrb200_pdsch_tx_bufs_t", ldpc.PdschTxBufs, "cw_stride")]
-    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrb200_slot.h"', '#include "nrb200_rfsim.h"', 'int main(void) {']
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrb200_slot.h"', '#include "nrb200_rfsim.h"', '#include "nrb200_prach.h"', 'int main(void) {']
     for cname, _, field in pairs:
         src.append(f'  printf("{cname} %zu %zu\\n", sizeof({cname}), {"offsetof(" + cname + ", " + field + ")" if field else "(size_t)0"});')
     src += ['  return 0;', '}']
