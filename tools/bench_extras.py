@@ -187,6 +187,33 @@ def main():
         except Exception as e:      # the compiled reference is absent
             line["reference_1_thread"] = str(e)
         print(json.dumps(line), flush=True)
+    # ---- gNB PRACH detector (rx_nr_prach): long sequences, N_CS 13 (64 roots... 1 root per preamble group), 4 rx antennas; occasions back to back on one stream
+    try:
+        from openairinterface5g_b200.ldpc import PrachDesc
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "prach.npz"))
+        for ci, (nrx, short, ncs, fmt, mu) in ((1, (2, 0, 13, 0, 1)), (7, (4, 1, 0, 7, 3))):
+            xu = gold[f"xu{ci}"]
+            nzc = 139 if short else 839
+            dsc = PrachDesc(nrx, short, ncs, fmt, mu, 0, nzc, 0)
+            d_xu = torch.from_numpy(xu).to(dev)
+            rxs = torch.randint(-800, 801, (nrx, nzc, 2), dtype=torch.int16, device=dev, generator=g)
+            o3 = torch.zeros(3, dtype=torch.int32, device=dev)
+            scr = torch.empty(lib.prach_scratch_bytes(dsc), dtype=torch.uint8, device=dev)
+            ms = timeit(lambda: lib.rx_nr_prach_torch(dsc, d_xu, rxs, o3, scr), n=50)
+            line = {"what": f"rx_nr_prach N_ZC={nzc} N_CS={ncs} {nrx} rx ({lib.prach_num_roots(dsc)} roots)", "us": ms * 1e3, "value": 1e3 / ms, "unit": "occasions/s"}
+            try:
+                from oracle import bindings as ob
+                ref = ob.Reference()
+                hx = rxs.cpu().numpy()
+                t0 = time.perf_counter(); k = 0
+                while time.perf_counter() - t0 < 2.0:
+                    ref.rx_nr_prach(nrx, short, 22, lib.prach_num_roots(dsc), ncs, fmt, mu, xu, hx); k += 1
+                line["reference_1_thread"] = k / (time.perf_counter() - t0)
+            except Exception as e:
+                line["reference_1_thread"] = str(e)
+            print(json.dumps(line), flush=True)
+    except Exception as e:
+        print(json.dumps({"what": "rx_nr_prach", "error": str(e)}), flush=True)
     # ---- UE slot receiver, 273 PRB, 64QAM, 4 rx: level + receiver launches of one slot, device resident; 1 layer with and without PT-RS, 2, 3 and 4 layers
     from openairinterface5g_b200.ldpc import PuschRxDesc
     N, nrx, nbr = 4096, 4, 273

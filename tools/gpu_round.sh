@@ -15,7 +15,7 @@ for t in 768 672 576 480 384; do NRB200_PACKED_THREADS=$t timeout 120 python too
 timeout 120 python tools/kernel_time.py 3.0 2>&1 | tail -1 | tee -a gpurun_out/variants_${TAG}.txt
 fi
 echo "== micro-benchmark (ALU pipe / opcode-blend / code-footprint ceilings)"; timeout 120 tools/ubench/_bin/alu_ceiling | tee gpurun_out/alu_ceiling_${TAG}.json
-echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -24 | tee gpurun_out/extras_${TAG}.jsonl
+echo "== extras"; timeout 400 python tools/bench_extras.py 2>&1 | tail -34 | tee gpurun_out/extras_${TAG}.jsonl
 echo "== extras, OFDM front end with 592 antenna-slots per launch"; NRB200_OFDM_ANTENNA_SLOTS=592 timeout 300 python tools/bench_extras.py 2>&1 | grep ofdm_ | tee gpurun_out/extras_ofdm592_${TAG}.jsonl | cut -c1-260
 echo "== ncu full (decode kernel): first, so that the bench line of this very run carries roofline.traffic / on_chip of the kernel it times"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ldpc_decode -s 3 -c 1 -f -o gpurun_out/prof_decode_${TAG} \
@@ -53,3 +53,9 @@ echo "== ncu full (4096-point TMA kernel)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dft4096 -s 3 -c 1 -f -o gpurun_out/prof_dft4096_${TAG} python tools/dft_time.py 4096 1 8880 > gpurun_out/ncu_dft_${TAG}.log 2>&1
 fi
 ls -la gpurun_out | tail -8
+if [ "$MODE" = "full" ]; then
+echo "== rfsimulator channel kernel: time and one full ncu capture"
+timeout 60 python tools/rfsim_time.py 2 40 614400 | tee gpurun_out/rfsim_${TAG}.txt
+timeout 60 python tools/rfsim_time.py 4 40 614400 | tee -a gpurun_out/rfsim_${TAG}.txt
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rfsim -s 5 -c 1 -f -o gpurun_out/prof_rfsim_${TAG} python tools/rfsim_time.py 2 40 614400 > gpurun_out/ncu_rfsim_${TAG}.log 2>&1
+fi
