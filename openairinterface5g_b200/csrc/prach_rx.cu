@@ -48,7 +48,6 @@ __global__ void __launch_bounds__(256) prach_corr_kernel(PrachGeom G, const unsi
 __global__ void __launch_bounds__(256) prach_window_kernel(PrachGeom G, const unsigned *__restrict__ t, int *__restrict__ res)
 {
   __shared__ int s_pow[1024];
-  __shared__ int s_db[256], s_bin[256];
   const int root = blockIdx.x;
   for (int i = threadIdx.x; i < G.size; i += 256) {
     unsigned acc = 0;
@@ -60,29 +59,26 @@ __global__ void __launch_bounds__(256) prach_window_kernel(PrachGeom G, const un
     s_pow[i] = ((int)acc >> G.lg) / G.nb_rx;
   }
   __syncthreads();
-  for (int v = 0; v < G.per_root; v++) {
+  // one warp per preamble of this root: lanes stride the window, keep (largest dB, first bin) and combine with shuffles -- no block-wide barrier per preamble
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int v = warp; v < G.per_root; v += 8) {
     const int p = root * G.per_root + v;
     if (p >= 64) break;
     int shift = (v * G.NCS) % G.N_ZC;                      // preamble_shift = -v NCS mod N_ZC (:470-474)
     shift = shift == 0 ? 0 : G.N_ZC - shift;
     const unsigned shift2 = shift == 0 ? 0u : (unsigned)((shift << G.lg) / G.N_ZC);
-    int best = -1, bin = 0;
-    for (int i = threadIdx.x; i < G.NCS2; i += 256) {
+    int best = -1, bin = 0x7fffffff;
+    for (int i = lane; i < G.NCS2; i += 32) {
       const unsigned b = shift2 + (unsigned)i;
       const int db = prach_db((unsigned)(b < (unsigned)G.size ? s_pow[b] : 0));
       if (db > best) { best = db; bin = i; }
     }
-    s_db[threadIdx.x] = best; s_bin[threadIdx.x] = bin;
-    __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
-      if (threadIdx.x < st) {
-        const int o = threadIdx.x + st;
-        if (s_db[o] > s_db[threadIdx.x] || (s_db[o] == s_db[threadIdx.x] && s_db[o] >= 0 && s_bin[o] < s_bin[threadIdx.x])) { s_db[threadIdx.x] = s_db[o]; s_bin[threadIdx.x] = s_bin[o]; }
-      }
-      __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bin, o);
+      if (ob > best || (ob == best && oi < bin)) { best = ob; bin = oi; }
     }
-    if (threadIdx.x == 0) { res[2 * p] = s_db[0]; res[2 * p + 1] = s_bin[0]; }
-    __syncthreads();
+    if (lane == 0) { res[2 * p] = best; res[2 * p + 1] = bin; }
   }
 }
 

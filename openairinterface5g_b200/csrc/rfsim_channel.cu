@@ -3,6 +3,8 @@
 // reference's bit for bit (products and sums as separate IEEE operations: __dmul_rn / __dadd_rn / __dsub_rn keep nvcc from contracting them).  A CTA stages the
 // taps of its receive antenna (nb_tx x L complex doubles) and the window of the circular tx buffer its 256 samples reach back into ((256 + L - 1) x nb_tx c16)
 // in shared memory: every tx sample is read from global memory once per CTA instead of L times.  FP64-pipe bound: 8 double operations per tap and tx antenna.
+// (Staging the samples already converted to double -- one I2F per staged sample instead of one per tap -- was measured SLOWER: 77.9 against 69.5 us for the
+// 2 x 2 frame; the 16-byte shared loads per tap cost more than the conversions they save.)
 #include "nrb200_ctx.h"
 #include "../../include/nrb200_rfsim.h"
 #include <cmath>
@@ -18,7 +20,7 @@ __global__ void __launch_bounds__(kRfTpb) rfsim_channel_kernel(int nb_tx, int nb
 {
   extern __shared__ __align__(16) unsigned char rf_smem[];
   double2 *s_ch = reinterpret_cast<double2 *>(rf_smem);                               // [nb_tx][L]
-  unsigned *s_sig = reinterpret_cast<unsigned *>(s_ch + (size_t)nb_tx * L);           // [(kRfTpb + L - 1)][nb_tx], oldest sample first
+  unsigned *s_sig = reinterpret_cast<unsigned *>(s_ch + (size_t)nb_tx * L);           // [nb_tx][kRfTpb + L - 1], oldest sample first
   const int rx = blockIdx.y, i0 = blockIdx.x * kRfTpb, i = i0 + threadIdx.x;
   for (int t = threadIdx.x; t < nb_tx * L; t += kRfTpb) {
     const int tx = t / L, l = t - tx * L;
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(kRfTpb) rfsim_channel_kernel(int nb_tx, int nb
   for (int t = threadIdx.x; t < win * nb_tx; t += kRfTpb) {
     const int w = t / nb_tx, tx = t - w * nb_tx;
     const unsigned idx = (unsigned)(((p0 + (unsigned long long)w) * (unsigned long long)nb_tx + (unsigned long long)tx + CirSize) % CirSize);
-    s_sig[t] = __ldg(sig + idx);
+    s_sig[tx * win + w] = __ldg(sig + idx);                 // [tx][window]: neighbouring threads read neighbouring words (no bank conflicts for any nb_tx)
   }
   __syncthreads();
   if (i >= n) return;
@@ -38,9 +40,9 @@ __global__ void __launch_bounds__(kRfTpb) rfsim_channel_kernel(int nb_tx, int nb
   for (int tx = 0; tx < nb_tx; tx++) {
     const double2 *c = s_ch + (size_t)tx * L;
     // tap l of sample i sits at window position (threadIdx.x + L - 1 - l)
-    const unsigned *x = s_sig + (size_t)(threadIdx.x + L - 1) * nb_tx + tx;
+    const unsigned *x = s_sig + (size_t)tx * win + (threadIdx.x + L - 1);
     for (int l = 0; l < L; l++) {
-      const unsigned v = x[-(long long)l * nb_tx];
+      const unsigned v = x[-l];
       const double xr = (double)(short)(v & 0xFFFFu), xi = (double)(short)(v >> 16);
       const double2 h = c[l];
       rr = __dadd_rn(rr, __dsub_rn(__dmul_rn(xr, h.x), __dmul_rn(xi, h.y)));
