@@ -1079,7 +1079,7 @@ static int make_geom(const nrb200_pusch_rx_t &d, PuschGeom *G, uint32_t *total_l
       G->sym[k] = s; G->ch_sym[k] = chs; G->is_dmrs[k] = dm; G->valid[k] = v; G->llr_off[k] = off;
     }
     off += (unsigned)v * Qm;
-    if (s == d.start_symbol_index + d.nr_of_symbols - 1) { G->last_is_dmrs = dm; G->last_ch_sym = chs; G->last_span = (v0 / 12 + ((v0 % 12) ? 1 : 0)) * 12; }
+    if (s == d.start_symbol_index + d.nr_of_symbols - 1) { G->last_is_dmrs = dm; G->last_ch_sym = chs; G->last_span = v0; }   // thresholds exist for the last symbol's EXTRACTED REs only: the reference's vectors run on to whole PRBs, but over zero-padded estimates (threshold 0, like beyond the span)
   }
   if (total_llr) *total_llr = off * (unsigned)nl;
   return G->n_sym > 0 ? 0 : -4;

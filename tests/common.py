@@ -270,3 +270,42 @@ def prach_inputs(rng, case, xu):
             y[a] = x / 32768.0 * amp * np.exp(2j * np.pi * k * shift / N_ZC) * np.exp(1j * rng.uniform(0, 6.28))
     y += sigma * (rng.normal(size=y.shape) + 1j * rng.normal(size=y.shape))
     return np.stack([np.round(y.real), np.round(y.imag)], -1).clip(-32768, 32767).astype(np.int16)
+
+
+def ptrs_fuzz_cases(rng, n, N=512, carrier=25, safe_tail=True):
+    """Random valid PDSCH + PT-RS configurations on a small carrier (the tuple layout of PTRS_CASES): allocation, DMRS symbols (1-3, at least one inside the
+    allocation, possibly its first symbol), DMRS type / CDM groups, modulation, antennas, PT-RS densities and offsets, RNTI, slot, scrambling."""
+    out = []
+    while len(out) < n:
+        rb_size = int(rng.integers(1, carrier + 1)); rb_start = int(rng.integers(0, carrier - rb_size + 1))
+        start = int(rng.integers(0, 4)); nsym = int(rng.integers(3, 15 - start))
+        k = int(rng.integers(1, 4))
+        syms = rng.choice(np.arange(start, start + nsym), size=min(k, nsym), replace=False)
+        dpos = 0
+        for s_ in syms:
+            dpos |= 1 << int(s_)
+        dtype_ = int(rng.integers(0, 2)); cdm = int(rng.integers(1, 3))
+        L, K = int(rng.integers(0, 3)), int(rng.choice([2, 4]))
+        # The reference's LLR routines round a symbol's RE count up to whole SIMD vectors; the spill lands in the next symbol's LLRs (rewritten right after) except
+        # for the slot's LAST symbol, where it runs past the end of nr_rx_pdsch's own malloc'ed layer_llr buffer -- with PT-RS the count is no longer a multiple
+        # of 12 and glibc aborts with "double free or corruption" (DESIGN.md, defect 22).  Keep the last symbol's count a multiple of 16.
+        last = start + nsym - 1
+        i, l_ref, Ls, mask = 0, start, 1 << L, 0
+        while l_ref + i * Ls <= last:                                       # set_ptrs_symb_idx
+            hit = [l for l in range(l_ref + i * Ls, max(l_ref + (i - 1) * Ls + 1, l_ref) - 1, -1) if (dpos >> l) & 1]
+            if hit:
+                l_ref, i = hit[0], 1
+                continue
+            mask |= 1 << (l_ref + i * Ls)
+            i += 1
+        v_last = 0
+        for l in range(start, last + 1):                                    # the last symbol that carries data
+            v = rb_size * ((12 - 6 * cdm) if dtype_ == 0 else (12 - 4 * cdm)) if (dpos >> l) & 1 else 12 * rb_size - (((rb_size + K - 1) // K) if (mask >> l) & 1 else 0)
+            if v:
+                v_last = v
+        if safe_tail and v_last % 16:
+            continue
+        out.append((N, int(rng.integers(1, 5)), rb_start, rb_size, int(rng.choice([2, 4, 6, 8])), dpos, dtype_, cdm, carrier, start, nsym,
+                    L, K, int(rng.integers(0, 12)), int(rng.integers(0, 65536)), int(rng.integers(0, 20)),
+                    int(rng.integers(0, 2)), int(rng.integers(0, 65536))))
+    return out

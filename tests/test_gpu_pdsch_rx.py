@@ -157,3 +157,55 @@ def test_pdsch_rx_ue_3_4_layers_golden(ldpc):
         d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, 0, 0, 0, nl, 0, 0, 1)
         llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
         assert sh == int(g[f"sh{i}"]) and np.array_equal(llr, g[f"llr{i}"]), (i, np.nonzero(llr != g[f"llr{i}"])[0][:6])
+
+
+def test_pdsch_rx_ue_ptrs_fuzz(ldpc, oracle):
+    """Random PT-RS configurations (tests/common.py:ptrs_fuzz_cases; the CPU suite runs 300 of the tail-safe kind against the real nr_rx_pdsch): 120 that the reference
+    can run and 60 whose last symbol has an RE count off the SIMD grid (where the reference itself overruns its LLR buffer, DESIGN.md defect 22) against the oracle."""
+    from oracle.bindings import PtrsParms
+    from common import ptrs_fuzz_cases, ptrs_inputs
+    rng = np.random.default_rng(84)
+    cases = ptrs_fuzz_cases(rng, 120) + ptrs_fuzz_cases(rng, 60, safe_tail=False)
+    done = 0
+    for n, case in enumerate(cases):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+        kind, a, b = (("random", 2000, 1500), ("coherent", 30, 0.05), ("coherent", 0, 0.2))[n % 3]
+        rx, h = ptrs_inputs(oracle, rng, case, kind, a, b)
+        fco = N - carrier * 6
+        llr_o, sh_o, ph_o, nre_o = oracle.pdsch_rx_slot_ptrs(PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, dtype_, cdm), PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid),
+                                                             start, nsym, rx, h)
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, n & 1, rnti, 77, 1, 0, 0, 1)
+        d.set_ptrs(L, K, reoff, slot, nscid, nid)
+        assert ldpc.pusch_num_llr(d) == llr_o.size, case
+        if llr_o.size == 0:
+            continue                                                          # an allocation of DMRS symbols without data
+        llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+        ref = llr_o if not (n & 1) else oracle.unscramble_llr(llr_o, 0, 77, rnti)
+        assert sh == sh_o and np.array_equal(llr, ref), (case, kind, sh, sh_o, np.nonzero(llr != ref)[0][:6])
+        done += 1
+    assert done > 150
+
+
+def test_pdsch_rx_ue_layers_fuzz(ldpc, oracle):
+    """Random allocations / DMRS layouts with 1 ... 4 layers (no PT-RS) against the oracle: 240 configurations, incl. DMRS symbols with data as the slot's last symbol."""
+    from common import ptrs_fuzz_cases
+    rng = np.random.default_rng(86)
+    done = 0
+    for n, case in enumerate(ptrs_fuzz_cases(rng, 240, safe_tail=False)):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym = case[:11]
+        nl = 1 + n % 4
+        nb_rx = max(nb_rx, 2) if nl > 1 else nb_rx
+        ay, ah = ((2000, 1500), (600, 900), (32767, 32767))[n % 3]
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+        fco = N - carrier * 6
+        llr_o, sh_o = oracle.pdsch_rx_slot(PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, dtype_, cdm), start, nsym, rx, h, nl=nl)
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, n & 1, 0x2345, 501, nl, 0, 0, 1)
+        assert ldpc.pusch_num_llr(d) == llr_o.size, case
+        if llr_o.size == 0:
+            continue
+        llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+        ref = llr_o if not (n & 1) else oracle.unscramble_llr(llr_o, 0, 501, 0x2345)
+        assert sh == sh_o and np.array_equal(llr, ref), (case[:11], nl, sh, sh_o, np.nonzero(llr != ref)[0][:6])
+        done += 1
+    assert done > 200

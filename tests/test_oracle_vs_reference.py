@@ -603,6 +603,45 @@ def test_pdsch_rx_slot_ue_ptrs(oracle, reference):
             assert int(valid.sum()) * Qm == llr_o.size
 
 
+def test_pdsch_rx_slot_ue_ptrs_fuzz(oracle, reference):
+    """300 random PT-RS configurations on a 25-PRB carrier (allocation, 1-3 DMRS symbols anywhere in it, both DMRS types, densities, offsets, RNTI, slot): every branch
+    of set_ptrs_symb_idx / nr_ptrs_process_slot (left and right extrapolation, reused slopes, DMRS as the first symbol) against the real functions."""
+    from oracle.bindings import PuschParms, PtrsParms
+    from common import ptrs_fuzz_cases, ptrs_inputs
+    rng = np.random.default_rng(83)
+    for n, case in enumerate(ptrs_fuzz_cases(rng, 300)):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym, L, K, reoff, rnti, slot, nscid, nid = case
+        kind, a, b = (("random", 2000, 1500), ("coherent", 30, 0.05), ("coherent", 0, 0.2))[n % 3]
+        rx, h = ptrs_inputs(oracle, rng, case, kind, a, b)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        T = PtrsParms(1, L, K, reoff, rnti, slot, nscid, nid)
+        llr_o, sh_o, ph_o, nre_o = oracle.pdsch_rx_slot_ptrs(P, T, start, nsym, rx, h)
+        llr_r, sh_r, valid, ph_r, nre_r = reference.pdsch_rx_slot_ptrs(P, T, start, nsym, rx, h, llr_o.size, n_rb_dl=carrier)
+        assert sh_o == sh_r and np.array_equal(nre_o, nre_r) and np.array_equal(ph_o, ph_r), (case, kind, ph_o.tolist(), ph_r.tolist())
+        assert np.array_equal(llr_o, llr_r) and int(valid.sum()) * Qm == llr_o.size, (case, kind, np.nonzero(llr_o != llr_r)[0][:5])
+
+
+def test_pdsch_rx_slot_ue_layers_fuzz(oracle, reference):
+    """200 random allocations / DMRS layouts on a 25-PRB carrier through the real nr_rx_pdsch with 1 ... 4 layers (no PT-RS): incl. a last symbol that is a DMRS symbol
+    with data whose RE count is not a whole number of PRBs (type 2: 8 or 4 data REs per PRB), where the thresholds exist for the extracted REs only."""
+    from oracle.bindings import PuschParms
+    from common import ptrs_fuzz_cases
+    rng = np.random.default_rng(85)
+    for n, case in enumerate(ptrs_fuzz_cases(rng, 200)):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym = case[:11]
+        nl = 1 + n % 4
+        nb_rx = max(nb_rx, 2) if nl > 1 else nb_rx
+        ay, ah = ((2000, 1500), (600, 900), (32767, 32767))[n % 3]
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nl * nb_rx, 14, N, 2)).astype(np.int16)
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        llr_o, sh_o = oracle.pdsch_rx_slot(P, start, nsym, rx, h, nl=nl)
+        if llr_o.size == 0:
+            continue
+        llr_r, sh_r, valid = reference.pdsch_rx_slot(P, start, nsym, rx, h, llr_o.size, nl=nl)
+        assert sh_o == sh_r and np.array_equal(llr_o, llr_r), (case[:11], nl, sh_o, sh_r, np.nonzero(llr_o != llr_r)[0][:5])
+
+
 PDSCH_2L_CASES = [  # N, nb_rx, rb_start, rb_size, Qm, dmrs_pos, dmrs_type, cdm groups, carrier PRBs, start_symbol, nr_symbols, amplitude (rx, h)
     (4096, 2, 0, 273, 6, 1 << 2, 0, 1, 273, 1, 13, (2000, 1500)), (4096, 4, 0, 273, 8, 1 << 2, 0, 2, 273, 1, 13, (900, 700)),
     (2048, 2, 10, 50, 4, (1 << 2) | (1 << 11), 0, 1, 106, 1, 13, (4000, 6000)), (2048, 2, 30, 76, 2, 1 << 3, 0, 2, 106, 2, 10, (300, 200)),
