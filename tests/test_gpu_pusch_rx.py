@@ -96,3 +96,34 @@ def test_pusch_inner_rx_two_layers_vs_oracle(ldpc, oracle):
                 if unscr is not None:
                     ref = oracle.unscramble_llr(ref, 0, unscr[1], unscr[0])
                 assert llr.size == ref.size and np.array_equal(llr, ref), (N, nb_rx, rb_size, Qm, shift, unscr)
+
+
+def test_pusch_inner_rx_fuzz(ldpc, oracle):
+    """150 random single-layer PUSCH allocations / DMRS layouts on a 25-PRB carrier (the per-symbol oracle is swept against the reference's inner_rx on the same
+    generator by tests/test_oracle_vs_reference.py::test_pusch_inner_rx_fuzz): whole-slot LLRs and the measured log2_maxh."""
+    from common import ptrs_fuzz_cases
+    rng = np.random.default_rng(88)
+    done = 0
+    for n, case in enumerate(ptrs_fuzz_cases(rng, 150, safe_tail=False)):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym = case[:11]
+        if (dpos & (dpos << 1)) or ((dpos >> 13) & dpos & 1):
+            continue                                   # "Double DMRS configuration is not yet supported" (get_nb_re_pusch)
+        ay, ah = ((2000, 1500), (600, 900), (32767, 32767))[n % 3]
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        fco = N - carrier * 6
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, fco, Qm, dpos, dtype_, cdm)
+        dm = [s for s in range(start, start + nsym) if (dpos >> s) & 1]
+        with_data = [s for s in range(start, start + nsym) if oracle.pusch_nb_re(P, s) > 0]
+        d = PuschRxDesc(N, nb_rx, rb_start, 0, rb_size, fco, Qm, start, nsym, dpos, dtype_, cdm, 0xFFFFFFFF, 0, 0, n & 1, 0x1234, 77)
+        if not with_data:
+            assert ldpc.pusch_num_llr(d) == 0
+            continue
+        meas = with_data[0]
+        cur = dm[0] if meas < dm[0] else max(s for s in dm if s <= meas)
+        sh_o, _ = oracle.pusch_log2_maxh(P, meas, cur, rx, h)
+        llr, sh = ldpc.pusch_inner_rx_host(d, rx, h)
+        ref = _oracle_slot(oracle, P, start, nsym, rx, h, sh_o, (0x1234, 77) if n & 1 else None)
+        assert sh == sh_o and llr.size == ref.size and np.array_equal(llr, ref), (case[:11], sh, sh_o, np.nonzero(llr != ref)[0][:6] if llr.size == ref.size else (llr.size, ref.size))
+        done += 1
+    assert done > 100

@@ -368,6 +368,40 @@ def test_pusch_inner_rx(oracle, reference):
                 assert np.array_equal(llr_o, llr_r), (case, symbol, shift, "llr")
 
 
+def test_pusch_inner_rx_fuzz(oracle, reference):
+    """150 random single-layer PUSCH allocations / DMRS layouts on a 25-PRB carrier through the reference's inner_rx, three symbols each (a DMRS symbol, the one after it,
+    the allocation's last), at the measured shift and a smaller one."""
+    from oracle.bindings import PuschParms
+    from common import ptrs_fuzz_cases
+    rng = np.random.default_rng(87)
+    for n, case in enumerate(ptrs_fuzz_cases(rng, 150, safe_tail=False)):
+        N, nb_rx, rb_start, rb_size, Qm, dpos, dtype_, cdm, carrier, start, nsym = case[:11]
+        ay, ah = ((2000, 1500), (600, 900), (32767, 32767))[n % 3]
+        rx = rng.integers(-ay, ay + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        h = rng.integers(-ah, ah + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+        if (dpos & (dpos << 1)) or ((dpos >> 13) & dpos & 1):
+            continue                                   # get_nb_re_pusch AssertFatal()s on neighbouring DMRS symbols ("Double DMRS configuration is not yet supported")
+        P = PuschParms(N, nb_rx, rb_start, 0, rb_size, N - carrier * 6, Qm, dpos, dtype_, cdm)
+        dm = [s for s in range(start, start + nsym) if (dpos >> s) & 1]
+        with_data = [s for s in range(start, start + nsym) if oracle.pusch_nb_re(P, s) > 0]
+        if not with_data:
+            continue
+        meas = with_data[0]
+        cur = dm[0] if meas < dm[0] else max(s for s in dm if s <= meas)
+        sh_o, avg_o = oracle.pusch_log2_maxh(P, meas, cur, rx, h)
+        sh_r, avg_r = reference.pusch_log2_maxh(P, meas, cur, rx, h)
+        assert np.array_equal(avg_o, avg_r) and sh_o == sh_r, (case[:11], avg_o, avg_r, sh_o, sh_r)
+        for symbol in sorted({dm[0], min(dm[0] + 1, start + nsym - 1), with_data[-1]}):
+            valid = oracle.pusch_nb_re(P, symbol)
+            if valid == 0:
+                continue
+            chs = dm[0] if symbol < dm[0] else max(s for s in dm if s <= symbol)
+            for shift in {sh_o, max(0, sh_o - 3)}:
+                llr_o, comp_o = oracle.pusch_inner_rx_symbol(P, symbol, chs, shift, rx, h)
+                llr_r, comp_r = reference.pusch_inner_rx_symbol(P, symbol, chs, shift, rx, h, valid)
+                assert np.array_equal(comp_o, comp_r) and np.array_equal(llr_o, llr_r), (case[:11], symbol, chs, shift)
+
+
 # ------------------------------------------------------------------------------------------ PUSCH channel estimation (a22), DMRS type 1
 CHEST_CASES = [  # N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier PRBs, scid, dmrs id, delay (samples) of the synthetic channel
     (4096, 4, 1, 2, 0, 0, 273, 273, 0, 77, 0), (4096, 2, 8, 2, 0, 0, 273, 273, 1, 1007, 3), (2048, 2, 3, 3, 0, 10, 50, 106, 0, 5, -2),
