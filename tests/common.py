@@ -309,3 +309,24 @@ def ptrs_fuzz_cases(rng, n, N=512, carrier=25, safe_tail=True):
                     L, K, int(rng.integers(0, 12)), int(rng.integers(0, 65536)), int(rng.integers(0, 20)),
                     int(rng.integers(0, 2)), int(rng.integers(0, 65536))))
     return out
+
+
+def pdsch_tx_fuzz_cases(rng, n, N=512, carrier=25):
+    """Random valid PDSCH transmitter configurations: (N, carrier, ntx, slot, rb_start, rb_size, Qm, layers, start, nsym, dmrs_pos, dmrs_type, cdm, ports, scid, amp,
+    ptrs or None, precoding index).  DMRS symbols only inside the allocation (the reference derives its length from the whole mask), ports 0 ... layers - 1."""
+    out = []
+    while len(out) < n:
+        rb_size = int(rng.integers(1, carrier + 1)); rb_start = int(rng.integers(0, carrier - rb_size + 1))
+        start = int(rng.integers(0, 4)); nsym = int(rng.integers(3, 15 - start))
+        syms = rng.choice(np.arange(start, start + nsym), size=min(int(rng.integers(1, 4)), nsym), replace=False)
+        dpos = 0
+        for s_ in syms:
+            dpos |= 1 << int(s_)
+        nl = int(rng.integers(1, 5)); dtype_ = int(rng.integers(0, 2))
+        cdm = int(rng.integers(2 if nl > 2 else 1, 3))
+        ntx = int(rng.integers(nl, 5))
+        ptrs = (int(rng.integers(0, 3)), int(rng.choice([2, 4])), int(rng.integers(0, 12))) if rng.integers(0, 2) else None
+        pm = int(rng.integers(1, 4)) if (ntx >= 2 and rng.integers(0, 2)) else 0
+        out.append((N, carrier, ntx, int(rng.integers(0, 20)), rb_start, rb_size, int(rng.choice([2, 4, 6, 8])), nl, start, nsym, dpos, dtype_, cdm, (1 << nl) - 1,
+                    int(rng.integers(0, 2)), int(rng.choice([300, 512, 2047, 30000])), ptrs, pm))
+    return out

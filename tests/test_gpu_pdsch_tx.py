@@ -109,3 +109,35 @@ def test_pdsch_tx_ptrs_golden(ldpc):
             d.set_precoding(pm, g[f"tx_w{j}"])
         got = ldpc.pdsch_tx_slot_host(d, g[f"tx_bits{j}"])
         assert np.array_equal(got, g[f"tx_out{j}"]), (j, [tuple(x) for x in np.argwhere(got != g[f"tx_out{j}"])[:6]])
+
+
+def test_pdsch_tx_fuzz(ldpc, oracle):
+    """250 random transmitter configurations (1-4 layers, PT-RS on / off, wideband precoding on / off; the same generator sweeps the oracle against the real
+    nr_generate_pdsch on the CPU): txdataF bit for bit, and the library declines exactly the configurations the oracle declines."""
+    import ctypes as C
+    from common import pdsch_tx_fuzz_cases
+    rng = np.random.default_rng(90)
+    oracle.lib.orc_pdsch_tx_slot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    done = 0
+    for N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp, ptrs, pm in pdsch_tx_fuzz_cases(rng, 250):
+        fco = N - carrier * 6
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp)
+        d = PdschTxDesc(N, ntx, slot, rb0, 0, nrb, fco, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp, 0)
+        if ptrs:
+            P.set_ptrs(*ptrs); d.set_ptrs(*ptrs)
+        if pm:
+            w = rng.integers(-12000, 12001, size=(4, 4, 2)).astype(np.int16)
+            P.set_precoding(pm, w); d.set_precoding(pm, w)
+        if P.G() <= 0:
+            continue
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        want = np.zeros((ntx, 14, N, 2), np.int16)
+        rc = oracle.lib.orc_pdsch_tx_slot(C.addressof(P), bits.ctypes.data, want.ctypes.data)
+        if rc < 0:
+            assert ldpc.pdsch_tx_num_bits(d) == 0, (N, nrb, nl, dpos, dtype_, cdm)
+            continue
+        assert ldpc.pdsch_tx_num_bits(d) == P.G() == rc
+        got = ldpc.pdsch_tx_slot_host(d, bits)
+        assert np.array_equal(got, want), (N, nrb, Qm, nl, dpos, dtype_, cdm, ptrs, pm, [tuple(x) for x in np.argwhere(got != want)[:6]])
+        done += 1
+    assert done > 150

@@ -1,5 +1,6 @@
 """Pins the CPU oracle (oracle/nrb200_oracle.c) bit-exactly against the UNMODIFIED reference compiled by oracle/build_ref.sh.
 Runs wherever oracle/_ref exists (this container; the built .so files also travel to the GPU box)."""
+import ctypes as C
 import numpy as np
 import pytest
 from common import ALL_Z, RATES, NCOLS, make_case, payloads
@@ -807,6 +808,34 @@ def test_rx_nr_prach(oracle, reference):
         assert got_o == got_r, (case, got_o, got_r)
         if pre >= 0 and sigma * 3 < amp <= 20000:            # full-scale input overflows the transform: equality still holds, detection does not
             assert got_r[0] == pre, (case, got_r)
+
+
+def test_pdsch_tx_slot_fuzz(oracle, reference):
+    """250 random PDSCH transmitter configurations (allocation, DMRS layout, 1-4 layers, PT-RS on / off, wideband precoding on / off) through the real nr_generate_pdsch.
+    Configurations the oracle declines (a port whose CDM group carries data; the over-mapping case, DESIGN.md defect 10) are skipped."""
+    from oracle.bindings import PdschTxParms
+    from common import pdsch_tx_fuzz_cases
+    rng = np.random.default_rng(89)
+    done = 0
+    oracle.lib.orc_pdsch_tx_slot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    for N, carrier, ntx, slot, rb0, nrb, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, amp, ptrs, pm in pdsch_tx_fuzz_cases(rng, 250):
+        P = PdschTxParms(N, ntx, slot, rb0, 0, nrb, N - carrier * 6, Qm, nl, s0, ns, dpos, dtype_, cdm, ports, scid, 40 + slot, 501, 0x1234 + slot, amp)
+        if ptrs:
+            P.set_ptrs(*ptrs)
+        if pm:
+            P.set_precoding(pm, rng.integers(-12000, 12001, size=(4, 4, 2)).astype(np.int16))
+        if P.G() <= 0:
+            continue
+        bits = rng.integers(0, 2, size=P.G(), dtype=np.uint8)
+        out = np.zeros((P.nb_tx, 14, P.fft_size, 2), np.int16)
+        rc = oracle.lib.orc_pdsch_tx_slot(C.addressof(P), bits.ctypes.data, out.ctypes.data)
+        if rc < 0:
+            continue
+        assert rc == bits.size
+        t_r = reference.pdsch_tx_slot(P, bits, carrier)
+        assert np.array_equal(out, t_r), (N, nrb, Qm, nl, dpos, dtype_, cdm, ptrs, pm, [tuple(x) for x in np.argwhere(out != t_r)[:5]])
+        done += 1
+    assert done > 150
 
 
 def test_dft_size_index_enumerators_match_oai_header():
