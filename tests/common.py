@@ -330,3 +330,29 @@ def pdsch_tx_fuzz_cases(rng, n, N=512, carrier=25):
         out.append((N, carrier, ntx, int(rng.integers(0, 20)), rb_start, rb_size, int(rng.choice([2, 4, 6, 8])), nl, start, nsym, dpos, dtype_, cdm, (1 << nl) - 1,
                     int(rng.integers(0, 2)), int(rng.choice([300, 512, 2047, 30000])), ptrs, pm))
     return out
+
+
+def chest_fuzz_cases(rng, n, N=512, carrier=25, max_rx=4):
+    """Random DMRS type 1 channel-estimation configurations: (N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, dmrs id, delay of the synthetic channel)."""
+    out = []
+    for _ in range(n):
+        rb_size = int(rng.integers(1, carrier + 1)); rb_start = int(rng.integers(0, carrier - rb_size + 1))
+        out.append((N, int(rng.integers(1, max_rx + 1)), int(rng.integers(0, 20)), int(rng.integers(0, 14)), int(rng.integers(0, 4)), rb_start, rb_size, carrier,
+                    int(rng.integers(0, 2)), int(rng.integers(0, 65536)), int(rng.integers(-12, 13))))
+    return out
+
+
+def chest_inputs(oracle, rng, P, port, delay, amp_noise=300):
+    """rxdataF with the port's DMRS through a channel with a linear phase (a delay the estimator can find) plus noise; every third call full-scale noise only."""
+    N, nb_rx, symbol, rb_size = P.fft_size, P.nb_rx, P.symbol, P.rb_size
+    if amp_noise is None:
+        return rng.integers(-32768, 32768, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    rx = rng.integers(-amp_noise, amp_noise + 1, size=(nb_rx, 14, N, 2)).astype(np.int16)
+    pil = oracle.pusch_dmrs_pilots(P).reshape(-1, 2).astype(np.float64)
+    k0 = (P.rb_start * 12 + P.first_carrier_offset) % N
+    idx = (k0 + 2 * np.arange(6 * rb_size) + ((port >> 1) & 1)) % N
+    for a in range(nb_rx):
+        hh = (900 + 100 * a) * np.exp(1j * (0.3 * a - 2 * np.pi * delay * np.arange(6 * rb_size) * 2 / N))
+        y = hh * (pil[:, 0] - 1j * pil[:, 1]) / 32767.0
+        rx[a, symbol, idx, 0] += np.round(y.real).astype(np.int16); rx[a, symbol, idx, 1] += np.round(y.imag).astype(np.int16)
+    return rx

@@ -174,3 +174,19 @@ def test_pdsch_chest_ue_variants_vs_oracle(ldpc, oracle, dmrs_type, chest_freq):
         est_o = oracle.pdsch_channel_estimation(P, rx)
         assert np.array_equal(est[:, symbol], est_o[:, symbol]), (N, nb_rx, slot, symbol, port, dmrs_type, chest_freq)
         assert st[0] == 0 and st[1] == 0
+
+
+def test_channel_estimation_fuzz(ldpc, oracle):
+    """150 random DMRS type 1 configurations (tests/common.py:chest_fuzz_cases; the CPU suite sweeps the oracle against the real estimators with the same generator):
+    the gNB estimator (estimates + state) and the UE estimator, every third case with full-scale noise."""
+    from common import chest_fuzz_cases, chest_inputs
+    rng = np.random.default_rng(92)
+    for n, (N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay) in enumerate(chest_fuzz_cases(rng, 150)):
+        fco = N - carrier * 6
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid)
+        rx = chest_inputs(oracle, rng, P, port, delay, None if n % 3 == 2 else 300)
+        est_o, out_o = oracle.pusch_channel_estimation(P, rx)
+        est, st = ldpc.pusch_chest_host(PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 1), rx)
+        assert np.array_equal(st, out_o) and np.array_equal(est[:, symbol], est_o[:, symbol]), ("gNB", N, nb_rx, slot, symbol, port, rb_start, rb_size, st, out_o)
+        est, st = ldpc.pusch_chest_host(PuschChestDesc(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, fco, scid, nid, 14 * N, 14 * N, 1, 1), rx)
+        assert np.array_equal(est[:, symbol], oracle.pdsch_channel_estimation(P, rx)[:, symbol]), ("UE", N, nb_rx, slot, symbol, port, rb_start, rb_size)

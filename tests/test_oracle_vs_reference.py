@@ -435,6 +435,23 @@ def test_pusch_channel_estimation(oracle, reference):
         assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), (N, nb_rx, slot, symbol, port)
 
 
+def test_channel_estimation_fuzz(oracle, reference):
+    """150 random DMRS type 1 configurations (antennas, slot, symbol, port, allocation, scrambling, channel delay; every third with full-scale noise) through the real
+    nr_pusch_channel_estimation and -- up to 4 antennas -- the UE's nr_pdsch_channel_estimation."""
+    from oracle.bindings import ChestParms
+    from common import chest_fuzz_cases, chest_inputs
+    rng = np.random.default_rng(91)
+    for n, (N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier, scid, nid, delay) in enumerate(chest_fuzz_cases(rng, 150)):
+        P = ChestParms(N, nb_rx, slot, symbol, port, rb_start, 0, rb_size, N - carrier * 6, scid, nid)
+        rx = chest_inputs(oracle, rng, P, port, delay, None if n % 3 == 2 else 300)
+        est_r, out_r, _ = reference.pusch_channel_estimation(P, rx, carrier)
+        est_o, out_o = oracle.pusch_channel_estimation(P, rx)
+        assert np.array_equal(out_o, out_r) and np.array_equal(est_o[:, symbol], est_r[:, symbol]), ("gNB", N, nb_rx, slot, symbol, port, rb_start, rb_size, out_o, out_r)
+        est_r = reference.pdsch_channel_estimation(P, rx, carrier)
+        est_o = oracle.pdsch_channel_estimation(P, rx)
+        assert np.array_equal(est_o[:, symbol], est_r[:, symbol]), ("UE", N, nb_rx, slot, symbol, port, rb_start, rb_size)
+
+
 CHEST_VARIANT_CASES = [  # N, nb_rx, slot, symbol, port, rb_start, rb_size, carrier PRBs, scid, dmrs id, delay
     (4096, 4, 4, 2, 0, 0, 273, 273, 0, 77, 2), (2048, 2, 8, 3, 1, 10, 50, 106, 1, 1007, -3), (1024, 3, 0, 11, 2, 20, 32, 52, 0, 300, 5),
     (1024, 2, 12, 2, 3, 0, 52, 52, 1, 0, 0), (512, 8, 16, 5, 0, 3, 11, 25, 0, 9, 1), (2048, 1, 4, 0, 0, 30, 2, 106, 0, 65535, 0),
