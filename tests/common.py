@@ -356,3 +356,19 @@ def chest_inputs(oracle, rng, P, port, delay, amp_noise=300):
         y = hh * (pil[:, 0] - 1j * pil[:, 1]) / 32767.0
         rx[a, symbol, idx, 0] += np.round(y.real).astype(np.int16); rx[a, symbol, idx, 1] += np.round(y.imag).astype(np.int16)
     return rx
+
+
+def prach_fuzz_cases(rng, n):
+    """Random PRACH occasions (the tuple layout of PRACH_CASES) with N_CS from the 38.211 tables 6.3.3.1-5 / -7 (unrestricted set)."""
+    ncs_long = [0, 13, 15, 18, 22, 26, 32, 38, 46, 59, 76, 93, 119, 167, 279, 419]
+    ncs_short = [0, 2, 4, 6, 8, 10, 12, 13, 15, 17, 19, 23, 27, 34, 46, 69]
+    out = []
+    for _ in range(n):
+        short = int(rng.integers(0, 2))
+        ncs = int(rng.choice(ncs_short if short else ncs_long))
+        fmt = int(rng.integers(4, 13)) if short else int(rng.integers(0, 4))
+        pre = int(rng.integers(-1, 64))
+        amp = int(rng.choice([400, 1500, 6000, 32767]))
+        out.append((int(rng.integers(1, 5)), short, int(rng.integers(0, 137 if short else 837)), ncs, fmt, int(rng.integers(0, 4)), pre, int(rng.integers(0, 8)), amp,
+                    int(rng.choice([0, amp // 8, amp // 2]))))
+    return out

@@ -57,3 +57,22 @@ def test_rx_nr_prach_rejects_restricted_sets(ldpc):
     assert ldpc.prach_num_roots(d) == 0
     with pytest.raises(Exception):
         ldpc.rx_nr_prach_host(d, np.zeros((64, 839, 2), np.int16), np.zeros((2, 839, 2), np.int16))
+
+
+def test_rx_nr_prach_fuzz(ldpc, oracle):
+    """Random occasions on the committed root-sequence sets (X_u depends on sequence length, root index and N_CS only): antennas, formats, numerologies, sent preamble,
+    delay, amplitude and noise drawn at random, 12 per set, against the oracle (which the CPU suite sweeps against the real rx_nr_prach on 150 random occasions)."""
+    g = np.load(GOLD)
+    rng = np.random.default_rng(94)
+    for i, base in enumerate(PRACH_CASES):
+        xu = g[f"xu{i}"]
+        short, root, NCS = base[1], base[2], base[3]
+        for _ in range(12):
+            fmt = int(rng.integers(4, 13)) if short else int(rng.integers(0, 4))
+            amp = int(rng.choice([400, 1500, 6000, 32767]))
+            case = (int(rng.integers(1, 5)), short, root, NCS, fmt, int(rng.integers(0, 4)), int(rng.integers(-1, 64)), int(rng.integers(0, 8)), amp,
+                    int(rng.choice([0, amp // 8, amp // 2])))
+            rx = prach_inputs(rng, case, xu)
+            want = oracle.rx_nr_prach(case[0], short, NCS, fmt, case[5], xu, rx)
+            got = ldpc.rx_nr_prach_host(PrachDesc(case[0], short, NCS, fmt, case[5], 0, 0, 0), xu, rx)
+            assert got == want, (case, got, want)

@@ -855,6 +855,21 @@ def test_pdsch_tx_slot_fuzz(oracle, reference):
     assert done > 150
 
 
+def test_rx_nr_prach_fuzz(oracle, reference):
+    """150 random PRACH occasions (antennas, long / short sequences, root index, every N_CS of the unrestricted tables, formats, numerologies, sent preamble or noise only,
+    amplitudes up to full scale) through the real rx_nr_prach with the real compute_nr_prach_seq."""
+    from common import prach_fuzz_cases, prach_inputs, prach_num_roots
+    rng = np.random.default_rng(93)
+    for case in prach_fuzz_cases(rng, 150):
+        nb_rx, short, root, NCS, fmt, mu, pre, delay, amp, sigma = case
+        nroots = prach_num_roots(short, NCS)
+        xu = reference.prach_seq(short, nroots, root)
+        rx = prach_inputs(rng, case, xu)
+        got_r = reference.rx_nr_prach(nb_rx, short, root, nroots, NCS, fmt, mu, xu, rx)
+        got_o = oracle.rx_nr_prach(nb_rx, short, NCS, fmt, mu, xu, rx)
+        assert got_o == got_r, (case, got_o, got_r)
+
+
 def test_dft_size_index_enumerators_match_oai_header():
     """The size index dft() / idft() receive is OAI's dft_size_idx_t / idft_size_idx_t enumerator: the library's table (nrb200_dft_size_of_index, no GPU needed) and
     the Python mirror are pinned to get_dft / get_idft compiled from OAI's own tools_defs.h (oracle/ref_harness_dftidx.c)."""
