@@ -801,6 +801,24 @@ def test_rfsim_rx_add_input(oracle, reference):
                 assert not np.array_equal(o, out)
 
 
+def test_rfsim_rx_add_input_fuzz(oracle, reference):
+    """120 random rxAddInput calls: 1-4 antennas either side, 1-255 taps, offsets of either sign, path loss / noise power, buffer sizes and time stamps (incl. above 2^32)."""
+    rng = np.random.default_rng(95)
+    for n in range(120):
+        nb_tx, nb_rx, L = int(rng.integers(1, 5)), int(rng.integers(1, 5)), int(rng.choice([1, 2, 7, 33, 100, 255]))
+        ns, offset = int(rng.integers(1, 1500)), int(rng.integers(-6, 7))
+        TS = int(rng.integers(L + 8, 1 << 20)) + (int(rng.integers(1, 4)) << 32 if n % 5 == 0 else 0)
+        cir = int(rng.integers(ns + L + 16, 3 * (ns + L + 16)))
+        ch = rng.normal(size=(nb_tx * nb_rx, L, 2)) * (0.7 / np.sqrt(L))
+        sig = rng.integers(-32768, 32768, size=(cir, 2)).astype(np.int16)
+        out = rng.integers(-30000, 30001, size=(ns, 2)).astype(np.int16)
+        noise = rng.normal(size=(ns, 2)) if n % 2 else None
+        pl, npw, a = float(rng.uniform(-20, 6)), float(rng.uniform(-40, 3)), int(rng.integers(0, nb_rx))
+        o = oracle.rfsim_rx_add_input(nb_tx, nb_rx, L, offset, pl, npw, ch, sig, out, a, TS, cir, noise)
+        r = reference.rfsim_rx_add_input(nb_tx, nb_rx, L, offset, pl, npw, ch, sig, out, a, TS, cir, noise)
+        assert np.array_equal(o, r), (nb_tx, nb_rx, L, ns, offset, TS, cir, a, np.argwhere(o != r)[:5])
+
+
 def test_db_fixed_times10(oracle, reference):
     """dB_fixed_times10 (TOOLS/dB_routines.c:132-155) on the generated table floor(100 log10 n) (tools/gen_db_table.py) vs the compiled reference."""
     rng = np.random.default_rng(80)
