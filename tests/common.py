@@ -372,3 +372,18 @@ def prach_fuzz_cases(rng, n):
         out.append((int(rng.integers(1, 5)), short, int(rng.integers(0, 137 if short else 837)), ncs, fmt, int(rng.integers(0, 4)), pre, int(rng.integers(0, 8)), amp,
                     int(rng.choice([0, amp // 8, amp // 2]))))
     return out
+
+
+def rm_fuzz_cases(rng, n):
+    """Random rate-matching configurations: (BG, Z, F, E list (1-3 segments, multiples of Qm), rv, Tbslbrm, C, Qm)."""
+    zs = [16, 24, 36, 52, 64, 96, 128, 208, 256, 320, 384]
+    out = []
+    for _ in range(n):
+        BG = int(rng.integers(1, 3)); Z = int(rng.choice(zs)); Qm = int(rng.choice([2, 4, 6, 8]))
+        K = (22 if BG == 1 else 10) * Z; N = (66 if BG == 1 else 50) * Z
+        F = int(rng.integers(0, max(1, min(K - 2 * Z - 8, 6 * Z)) // 8 + 1)) * 8
+        ne = int(rng.integers(1, 4))
+        E0 = int(rng.integers(max(60, N // 8), 2 * N)) // Qm * Qm
+        Es = [E0 + Qm * int(rng.integers(0, 2)) for _ in range(ne)]
+        out.append((BG, Z, F, Es, int(rng.integers(0, 4)), 0 if rng.integers(0, 2) else int(rng.integers(3000, 400000)), int(rng.integers(ne, 24)), Qm))
+    return out

@@ -108,3 +108,46 @@ def test_dl_ul_chain_roundtrip(ldpc, oracle):
     iters, out = ldpc.decode_batch_host(BG, Z, R, 8, llr, use_crc=1, crc_len_bits=K, crc_type=1)
     assert (iters <= 8).all()
     assert np.array_equal(out[:, :K // 8], P)
+
+
+def test_rm_fuzz(ldpc, oracle):
+    """100 random rate-matching configurations (tests/common.py:rm_fuzz_cases; the CPU suite sweeps the oracle against nr_rate_matching.c with the same generator):
+    bit selection + interleaving, and de-interleaving + rate recovery + soft combining + decoder-input packing over two rounds."""
+    from common import rm_fuzz_cases
+    rng = np.random.default_rng(97)
+    done = 0
+    for BG, Z, F, Es, rv, Tb, C_, Qm in rm_fuzz_cases(rng, 100):
+        N = (66 if BG == 1 else 50) * Z
+        K = (22 if BG == 1 else 10) * Z
+        kcz = (68 if BG == 1 else 52) * Z
+        Fo = K - F - 2 * Z
+        n = len(Es)
+        d = rng.integers(0, 2, size=(n, N), dtype=np.uint8)
+        d_marked = d.copy()
+        d_marked[:, Fo:Fo + F] = 2
+        d[:, Fo:Fo + F] = 0
+        rcs = [oracle.rate_matching_tx(Tb, BG, Z, d_marked[r], C_, F, Fo, rv, E)[0] for r, E in enumerate(Es)]
+        if any(rcs):
+            continue                                             # a combination nr_rate_matching_ldpc itself refuses
+        got = ldpc.rm_tx_host(BG, Z, Qm, rv, C_, Tb, F, d, Es)
+        want = np.concatenate([_oracle_tx(oracle, BG, Z, F, E, rv, Tb, C_, Qm, d_marked[r]) for r, E in enumerate(Es)])
+        assert np.array_equal(got, want), (BG, Z, F, Es, rv, Tb, C_, Qm)
+        soft = rng.integers(-200, 200, size=sum(Es), dtype=np.int16)
+        harq_gpu = rng.integers(-3000, 3000, size=(n, N + 16), dtype=np.int16)
+        harq_cpu = harq_gpu.copy()
+        for clear in (1, 0):
+            llr = ldpc.rm_rx_host(BG, Z, Qm, rv, C_, Tb, F, soft, Es, harq_gpu, clear)
+            off = 0
+            for r, E in enumerate(Es):
+                e = oracle.deinterleave(E, Qm, soft[off:off + E])
+                assert oracle.rate_matching_rx(Tb, BG, Z, harq_cpu[r], e, C_, rv, clear, E, F, Fo) == 0
+                off += E
+                z = np.zeros(kcz, dtype=np.int16)
+                z[K - F:K] = 127
+                z[2 * Z:K - F] = harq_cpu[r][:K - F - 2 * Z]
+                z[K:] = harq_cpu[r][K - 2 * Z:kcz - 2 * Z]
+                assert np.array_equal(llr[r], np.clip(z, -128, 127).astype(np.int8)), (BG, Z, F, Es, rv, Tb, C_, Qm, clear, r)
+            assert np.array_equal(harq_gpu, harq_cpu), (BG, Z, F, Es, rv, Tb, C_, Qm, clear)
+            soft = rng.integers(-200, 200, size=sum(Es), dtype=np.int16)
+        done += 1
+    assert done > 60

@@ -155,6 +155,35 @@ def test_rate_matching_and_interleaving(oracle, reference):
             assert reference.get_R(rv, E, BG, Z, 0, rnd) == oracle.get_R(rv, E, BG, Z, 0, rnd)
 
 
+def test_rate_matching_fuzz(oracle, reference):
+    """150 random rate-matching configurations (base graph, lifting size, filler bits, E, redundancy version, LBRM on / off, segments, modulation): bit selection,
+    interleaving, de-interleaving and rate recovery with soft combining against nr_rate_matching.c."""
+    from common import rm_fuzz_cases
+    rng = np.random.default_rng(96)
+    for BG, Z, F, Es, rv, Tbslbrm, Cseg, Qm in rm_fuzz_cases(rng, 150):
+        N = (66 if BG == 1 else 50) * Z
+        K = (22 if BG == 1 else 10) * Z
+        Foffset = K - F - 2 * Z
+        E = Es[0]
+        w = rng.integers(0, 2, size=N, dtype=np.uint8)
+        w[Foffset:Foffset + F] = 2
+        rc_r, e_r = reference.rate_matching_tx(Tbslbrm, BG, Z, w, Cseg, F, Foffset, rv, E)
+        rc_o, e_o = oracle.rate_matching_tx(Tbslbrm, BG, Z, w, Cseg, F, Foffset, rv, E)
+        assert rc_r == rc_o and (rc_r != 0 or np.array_equal(e_r, e_o)), (BG, Z, F, E, rv, Tbslbrm, Cseg, rc_r, rc_o)
+        if rc_r != 0:
+            continue
+        assert np.array_equal(reference.interleave(E, Qm, e_r[:E]), oracle.interleave(E, Qm, e_r[:E]))
+        soft = rng.integers(-300, 300, size=E, dtype=np.int16)
+        assert np.array_equal(reference.deinterleave(E, Qm, soft), oracle.deinterleave(E, Qm, soft))
+        w_r = rng.integers(-50, 50, size=N + 16, dtype=np.int16)
+        w_o = w_r.copy()
+        for clear in (1, 0):
+            soft = rng.integers(-128, 128, size=E, dtype=np.int16)
+            rr = reference.rate_matching_rx(Tbslbrm, BG, Z, w_r, soft, Cseg, rv, clear, E, F, Foffset)
+            ro = oracle.rate_matching_rx(Tbslbrm, BG, Z, w_o, soft, Cseg, rv, clear, E, F, Foffset)
+            assert rr == ro and np.array_equal(w_r, w_o), (BG, Z, F, E, rv, Tbslbrm, Cseg, clear, rr, ro)
+
+
 def test_segmentation(oracle, reference):
     rng = np.random.default_rng(9)
     for BG, B in ((1, 8448), (1, 8456), (1, 100000), (1, 424), (2, 3840), (2, 3848), (2, 600), (2, 200), (2, 100), (1, 1277992 // 8 * 8), (2, 40000)):
