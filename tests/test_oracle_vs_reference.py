@@ -291,6 +291,26 @@ def test_scrambling_and_modulation(oracle, reference):
             assert np.array_equal(oracle.modulate(sc_o, length, Qm), reference.modulate(sc_r, length, Qm)), (size, Qm)
 
 
+def test_llr_scrambling_modulation_fuzz(oracle, reference):
+    """Random sizes and seeds: max-log LLRs (any RE count that is a multiple of 4, negative and full-scale thresholds), scrambling, the QAM mapper and unscrambling."""
+    rng = np.random.default_rng(98)
+    for n in range(120):
+        Qm = int(rng.choice([2, 4, 6, 8]))
+        nre = 4 * int(rng.integers(1, 900))
+        y = rng.integers(-32768, 32768, size=2 * nre).astype(np.int16)
+        mags = [rng.integers(-32768 if n % 4 == 0 else 0, 32768, size=2 * nre).astype(np.int16) for _ in range(3)]
+        assert np.array_equal(oracle.ulsch_llr(Qm, y, *mags), reference.ulsch_llr(Qm, y, *mags)), ("llr", Qm, nre)
+        size, q, Nid, rnti = int(rng.integers(1, 60000)), int(rng.integers(0, 2)), int(rng.integers(0, 1024)), int(rng.integers(0, 65536))
+        bits = rng.integers(0, 2, size=size, dtype=np.uint8)
+        sc_o, sc_r = oracle.scramble(bits, q, Nid, rnti), reference.scramble(bits, q, Nid, rnti)
+        assert np.array_equal(sc_o, sc_r), ("scramble", size, q, Nid, rnti)
+        length = (size // (Qm * 8)) * Qm * 8 if Qm != 6 else (size // 24) * 24
+        if length >= Qm * 8 * 4:
+            assert np.array_equal(oracle.modulate(sc_o, length, Qm), reference.modulate(sc_r, length, Qm)), ("modulate", size, Qm)
+        llr = rng.integers(-32768, 32768, size=size).astype(np.int16)
+        assert np.array_equal(oracle.unscramble_llr(llr, q, Nid, rnti), reference.unscramble_llr(llr, q, Nid, rnti)), ("unscramble", size, q, Nid, rnti)
+
+
 def test_unscrambling(oracle, reference):
     rng = np.random.default_rng(8)
     for size, q, Nid, rnti in ((64, 0, 0, 1), (9072, 1, 1007, 65535), (12 * 273 * 6, 0, 500, 4660)):
